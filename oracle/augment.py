@@ -1,0 +1,192 @@
+"""imgaug==0.3.0 augmentation stage restated on numpy + cv2 [DEP]; reference selects augmenters through
+schemas/augmenters.raml:43-133 and the YAML `augmentation:` key (README.md:249-268).
+
+TEST INFRASTRUCTURE.  cv2.warpAffine (the backend imgaug's Affine calls) IS available here, so the
+pixel/index arithmetic is PINNED bit-exactly by cv2 4.13 itself: `warp_cv2` is the oracle, and
+`warp_fixedpoint` is the numpy restatement of cv2's fixed-point rule that the
+CUDA kernel implements -- tests check warp_fixedpoint == warp_cv2 == CUDA.
+Parameter DRAWS are not pinned (imgaug's RNG is not reproducible); they follow oracle/philox.py.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import philox
+
+try:  # cv2 is the real backend; present in this image
+    import cv2
+except Exception:  # pragma: no cover
+    cv2 = None
+
+
+@dataclass
+class AugSpec:
+    """The subset of augmenters.raml the device kernel fuses (Fliplr, Flipud, Affine, Multiply, Add)."""
+    fliplr: float = 0.0
+    flipud: float = 0.0
+    affine: bool = False
+    scale: Tuple[float, float] = (1.0, 1.0)
+    translate_x: Tuple[float, float] = (0.0, 0.0)  # translate_percent
+    translate_y: Tuple[float, float] = (0.0, 0.0)
+    rotate: Tuple[float, float] = (0.0, 0.0)  # degrees
+    shear: Tuple[float, float] = (0.0, 0.0)  # degrees
+    multiply: Optional[Tuple[float, float]] = None
+    add: Optional[Tuple[int, int]] = None
+
+
+@dataclass
+class SampleParams:
+    fliplr: bool
+    flipud: bool
+    matrix: np.ndarray  # forward 2x3 float64 (src->dst), identity if no affine
+    has_affine: bool
+    mul: float  # float32-representable multiplier (1.0 = off)
+    has_mul: bool
+    add: int
+
+
+def affine_matrix(scale, tx_px, ty_px, rot_deg, shear_deg, h, w) -> np.ndarray:
+    """imgaug 0.3.0 Affine matrix = to_center * AffineTransform(scale, rot, shear, translation) * to_topleft
+    (skimage.transform semantics), centre = (w/2-0.5, h/2-0.5).  Scalar fp64 ops, no fused multiply-add."""
+    rot = rot_deg * (math.pi / 180.0)
+    sh = shear_deg * (math.pi / 180.0)
+    a00 = scale * math.cos(rot)
+    a01 = -(scale * math.sin(rot + sh))
+    a10 = scale * math.sin(rot)
+    a11 = scale * math.cos(rot + sh)
+    cx, cy = w / 2.0 - 0.5, h / 2.0 - 0.5
+    # A @ T(-c): third column
+    b0 = (a00 * -cx + a01 * -cy) + tx_px
+    b1 = (a10 * -cx + a11 * -cy) + ty_px
+    # T(+c) @ ...
+    return np.array([[a00, a01, b0 + cx], [a10, a11, b1 + cy]], dtype=np.float64)
+
+
+def _lerp(lo, hi, u):
+    return lo + u * (hi - lo)
+
+
+def draw_params(spec: AugSpec, seed: int, step: int, sample: int, h: int, w: int) -> SampleParams:
+    u_lr, u_ud = philox.uniforms(seed, step, sample, 0)
+    u_sc, u_rot = philox.uniforms(seed, step, sample, 1)
+    u_sh, u_tx = philox.uniforms(seed, step, sample, 2)
+    u_ty, u_mul = philox.uniforms(seed, step, sample, 3)
+    u_add, _ = philox.uniforms(seed, step, sample, 4)
+    M = np.array([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]])
+    if spec.affine:
+        scale = _lerp(spec.scale[0], spec.scale[1], u_sc)
+        rot = _lerp(spec.rotate[0], spec.rotate[1], u_rot)
+        sh = _lerp(spec.shear[0], spec.shear[1], u_sh)
+        tx = _lerp(spec.translate_x[0], spec.translate_x[1], u_tx)
+        ty = _lerp(spec.translate_y[0], spec.translate_y[1], u_ty)
+        # imgaug 0.3.0: translate_percent -> px by int(np.round(p*dim)) (round half to even)
+        tx_px = float(int(np.round(tx * w)))
+        ty_px = float(int(np.round(ty * h)))
+        M = affine_matrix(scale, tx_px, ty_px, rot, sh, h, w)
+    mul = np.float32(1.0)
+    if spec.multiply is not None:
+        mul = np.float32(_lerp(spec.multiply[0], spec.multiply[1], u_mul))
+    add = 0
+    if spec.add is not None:
+        lo, hi = int(spec.add[0]), int(spec.add[1])
+        add = lo + int(math.floor(u_add * (hi - lo + 1)))
+    return SampleParams(u_lr < spec.fliplr, u_ud < spec.flipud, M, spec.affine, float(mul),
+                        spec.multiply is not None, add)
+
+
+# ----------------------------------------------------------------------------------------------
+# pixel arithmetic
+# ----------------------------------------------------------------------------------------------
+def invert_affine(M: np.ndarray):
+    """cv2.warpAffine's in-place inversion of the forward matrix (imgwarp.cpp), fp64, unfused."""
+    M = np.asarray(M, dtype=np.float64)
+    D = M[0, 0] * M[1, 1] - M[0, 1] * M[1, 0]
+    D = 1.0 / D if D != 0 else 0.0
+    A11, A22 = M[1, 1] * D, M[0, 0] * D
+    m0, m1, m3, m4 = A11, M[0, 1] * -D, M[1, 0] * -D, A22
+    b1 = -m0 * M[0, 2] - m1 * M[1, 2]
+    b2 = -m3 * M[0, 2] - m4 * M[1, 2]
+    return m0, m1, b1, m3, m4, b2
+
+
+def warp_fixedpoint(src: np.ndarray, M: np.ndarray, nearest: bool, cval: int = 0) -> np.ndarray:
+    """numpy restatement of cv2.warpAffine(BORDER_CONSTANT) fixed-point sampling."""
+    H, W = src.shape[:2]
+    s = src.reshape(H, W, -1)
+    m0, m1, b1, m3, m4, b2 = invert_affine(M)
+    xs = np.arange(W, dtype=np.float64)
+    ys = np.arange(H, dtype=np.float64)
+    adelta = np.rint(m0 * xs * 1024).astype(np.int64)
+    bdelta = np.rint(m3 * xs * 1024).astype(np.int64)
+    rd = 512 if nearest else 16
+    X0 = np.rint((m1 * ys + b1) * 1024).astype(np.int64) + rd
+    Y0 = np.rint((m4 * ys + b2) * 1024).astype(np.int64) + rd
+    Xf = X0[:, None] + adelta[None, :]
+    Yf = Y0[:, None] + bdelta[None, :]
+
+    def tap(sy, sx):
+        ok = (sx >= 0) & (sx < W) & (sy >= 0) & (sy < H)
+        v = s[np.clip(sy, 0, H - 1), np.clip(sx, 0, W - 1)].astype(np.int64)
+        return np.where(ok[..., None], v, cval)
+
+    if nearest:
+        out = tap(Yf >> 10, Xf >> 10)
+    else:
+        X, Y = Xf >> 5, Yf >> 5
+        sx, ax, sy, ay = X >> 5, (X & 31)[..., None], Y >> 5, (Y & 31)[..., None]
+        w00, w01, w10, w11 = (32 - ay) * (32 - ax) * 32, (32 - ay) * ax * 32, ay * (32 - ax) * 32, ay * ax * 32
+        acc = w00 * tap(sy, sx) + w01 * tap(sy, sx + 1) + w10 * tap(sy + 1, sx) + w11 * tap(sy + 1, sx + 1)
+        out = (acc + 16384) >> 15
+    return out.astype(src.dtype).reshape(src.shape)
+
+
+def warp_cv2(src: np.ndarray, M: np.ndarray, nearest: bool) -> np.ndarray:
+    H, W = src.shape[:2]
+    flag = cv2.INTER_NEAREST if nearest else cv2.INTER_LINEAR
+    out = cv2.warpAffine(src, np.asarray(M, dtype=np.float64), dsize=(W, H), flags=flag,
+                         borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+    return out.reshape(src.shape)
+
+
+def multiply_lut(mul: float, rounding: str = "trunc") -> np.ndarray:
+    """imgaug 0.3.0 Multiply on uint8: LUT = clip(arange(256,f32)*mul,0,255).astype(uint8) (truncation).
+    rounding='rint' is the alternative reading; flag, [DEP] unpinned."""
+    v = np.arange(256, dtype=np.float32) * np.float32(mul)
+    v = np.clip(v, 0, 255)
+    if rounding == "rint":
+        v = np.rint(v)
+    return v.astype(np.uint8)
+
+
+def apply(image: np.ndarray, mask: np.ndarray, p: SampleParams, use_cv2: bool = True, mul_rounding="trunc"):
+    """Sequential([Fliplr, Flipud, Affine, Multiply, Add]) on a uint8 HxWx3 image and HxWx1 mask."""
+    img, msk = image, mask
+    if p.fliplr:
+        img, msk = img[:, ::-1], msk[:, ::-1]
+    if p.flipud:
+        img, msk = img[::-1], msk[::-1]
+    img, msk = np.ascontiguousarray(img), np.ascontiguousarray(msk)
+    if p.has_affine:
+        warp = warp_cv2 if (use_cv2 and cv2 is not None) else warp_fixedpoint
+        img = warp(img, p.matrix, False)
+        msk = warp(msk, p.matrix, True)
+    if p.has_mul:
+        img = multiply_lut(p.mul, mul_rounding)[img]
+    if p.add != 0:
+        img = np.clip(img.astype(np.int32) + p.add, 0, 255).astype(np.uint8)
+    return img, msk
+
+
+def augment_batch(images: np.ndarray, masks: np.ndarray, spec: AugSpec, seed: int, step: int,
+                  sample_ids=None, use_cv2=True):
+    N, H, W = images.shape[:3]
+    oi, om = np.empty_like(images), np.empty_like(masks)
+    for n in range(N):
+        sid = n if sample_ids is None else int(sample_ids[n])
+        p = draw_params(spec, seed, step, sid, H, W)
+        oi[n], om[n] = apply(images[n], masks[n], p, use_cv2)
+    return oi, om

@@ -1,0 +1,287 @@
+"""Model graphs the reference builds at segmentation.py:96-155 (createNet1) restated on the oracle layers.
+
+`segmentation_models.Unet/FPN/Linknet` (==0.2.1, requires.txt:15) and `classification_models` ResNets
+are un-vendored [DEP]; the graphs below follow SURVEY.md section 8 a-4/a-5 and Appendix A/B.
+TEST INFRASTRUCTURE -- parity unpinned (no reference test pins these graphs).
+
+A model is (params: Dict[str, Tensor in Keras layout], forward(x_nhwc_float, training) -> y_nhwc).
+Layer names are the Keras names so weight dicts are exchangeable with the engine.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import nn as L
+
+ENC_BN_EPS = 2e-5  # classification_models get_bn_params(): epsilon=2e-5, momentum=0.99
+DEC_BN_EPS = 1e-3  # keras.layers.BatchNormalization default epsilon
+BN_MOMENTUM = 0.99
+
+RESNET_REPS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3), "resnet50": (3, 4, 6, 3),
+               "resnet101": (3, 4, 23, 3), "resnet152": (3, 8, 36, 3)}
+RESNET_BOTTLENECK = {"resnet18": False, "resnet34": False, "resnet50": True, "resnet101": True, "resnet152": True}
+VGG16_BLOCKS = ((64, 2), (128, 2), (256, 3), (512, 3), (512, 3))
+
+
+class ParamStore:
+    """Creates parameters on first use, in graph order, from one numpy Generator (seeded)."""
+
+    def __init__(self, seed: int = 0, enc_init="he_uniform", dec_init="glorot_uniform"):
+        self.gen = np.random.default_rng(seed)
+        self.params: Dict[str, torch.Tensor] = {}
+        self.buffers: Dict[str, torch.Tensor] = {}  # BN moving stats
+        self.enc_init, self.dec_init = enc_init, dec_init
+        self.encoder_names: List[str] = []
+        self._in_encoder = True
+
+    def conv(self, name, kh, kw, cin, cout, bias, init=None):
+        if name + "/kernel" not in self.params:
+            init = init or (self.enc_init if self._in_encoder else self.dec_init)
+            fn = L.he_uniform if init == "he_uniform" else L.glorot_uniform
+            self.params[name + "/kernel"] = torch.from_numpy(fn((kh, kw, cin, cout), self.gen))
+            if bias:
+                self.params[name + "/bias"] = torch.zeros(cout)
+            if self._in_encoder:
+                self.encoder_names.append(name)
+        return self.params[name + "/kernel"], self.params.get(name + "/bias")
+
+    def bn(self, name, c, scale=True):
+        if name + "/beta" not in self.params:
+            if scale:
+                self.params[name + "/gamma"] = torch.ones(c)
+            self.params[name + "/beta"] = torch.zeros(c)
+            self.buffers[name + "/moving_mean"] = torch.zeros(c)
+            self.buffers[name + "/moving_variance"] = torch.ones(c)
+            if self._in_encoder:
+                self.encoder_names.append(name)
+        return self.params.get(name + "/gamma"), self.params[name + "/beta"]
+
+
+class SegModel:
+    """U-Net / FPN / Linknet over ResNet-{18,34,50,..} or VGG16, Keras semantics, NHWC at the boundary."""
+
+    def __init__(self, architecture="Unet", backbone="resnet34", classes=1, activation="sigmoid",
+                 input_shape=(512, 512, 3), seed=0, storage="fp32",
+                 decoder_filters=(256, 128, 64, 32, 16), decoder_use_batchnorm=True,
+                 decoder_block_type="upsampling", enc_init="he_uniform", dec_init="glorot_uniform",
+                 pyramid_block_filters=256, segmentation_block_filters=128, fpn_dropout=None,
+                 update_moving=True):
+        self.arch, self.backbone = architecture, backbone.lower()
+        self.classes, self.activation = classes, activation
+        self.storage = storage
+        self.decoder_filters = tuple(decoder_filters)
+        self.dec_bn = decoder_use_batchnorm
+        self.block_type = decoder_block_type
+        self.pyr, self.segf = pyramid_block_filters, segmentation_block_filters
+        self.P = ParamStore(seed, enc_init, dec_init)
+        self.training = True
+        self.update_moving = update_moving
+        self.taps: Dict[str, torch.Tensor] = {}
+        # materialise parameters with a dry run on a tiny input of the right channel count
+        h = 64 if self.backbone != "vgg16" else 32
+        um, self.update_moving = self.update_moving, False
+        with torch.no_grad():
+            self.forward(torch.zeros(1, h, h, input_shape[2]), emit_logits=False)
+        self.update_moving = um
+        for p in self.P.params.values():
+            p.requires_grad_(True)
+
+    # -- helpers ---------------------------------------------------------------------------
+    @property
+    def params(self):
+        return self.P.params
+
+    @property
+    def buffers(self):
+        return self.P.buffers
+
+    def _bn(self, x, name, eps, scale=True):
+        gamma, beta = self.P.bn(name, x.shape[1], scale)
+        if self.training:
+            y, mean, var = L.batchnorm_train(x, gamma, beta, eps)
+            if self.update_moving:
+                with torch.no_grad():
+                    m = x.numel() // x.shape[1]
+                    unbiased = var * (m / max(m - 1, 1))
+                    mm, mv = self.P.buffers[name + "/moving_mean"], self.P.buffers[name + "/moving_variance"]
+                    mm.mul_(BN_MOMENTUM).add_(mean.detach() * (1 - BN_MOMENTUM))
+                    mv.mul_(BN_MOMENTUM).add_(unbiased.detach() * (1 - BN_MOMENTUM))
+            return y
+        return L.batchnorm_infer(x, gamma, beta, self.P.buffers[name + "/moving_mean"],
+                                 self.P.buffers[name + "/moving_variance"], eps)
+
+    def _bn_relu(self, x, name, eps, tap=None):
+        y = L.rb(torch.relu(self._bn(x, name, eps)), self.storage)
+        if tap:
+            self.taps[tap] = y
+        return y
+
+    def _conv(self, x, name, k, cout, stride=1, padding="valid", bias=False, residual=None):
+        w, b = self.P.conv(name, k, k, x.shape[1], cout, bias)
+        y = L.conv2d(x, w, b, stride, padding, self.storage)
+        if residual is not None:
+            y = y + residual
+        return L.rb(y, self.storage)
+
+    # -- encoders --------------------------------------------------------------------------
+    def _resnet(self, x):
+        reps, bott = RESNET_REPS[self.backbone], RESNET_BOTTLENECK[self.backbone]
+        x = L.rb(self._bn(x, "bn_data", ENC_BN_EPS, scale=False), self.storage)
+        x = self._conv(x, "conv0", 7, 64, stride=2, padding=3)
+        x = self._bn_relu(x, "bn0", ENC_BN_EPS, tap="relu0")
+        x = L.maxpool(x, 3, 2, 1)
+        for stage, rep in enumerate(reps):
+            f = 64 * 2 ** stage
+            for block in range(rep):
+                pre = "stage%d_unit%d_" % (stage + 1, block + 1)
+                first = block == 0
+                stride = 2 if (first and stage > 0) else 1
+                y = self._bn_relu(x, pre + "bn1", ENC_BN_EPS, tap=pre + "relu1")
+                if bott:
+                    sc = self._conv(y, pre + "sc", 1, 4 * f, stride) if first else x
+                    z = self._conv(y, pre + "conv1", 1, f)
+                    z = self._bn_relu(z, pre + "bn2", ENC_BN_EPS)
+                    z = self._conv(z, pre + "conv2", 3, f, stride, padding=1)
+                    z = self._bn_relu(z, pre + "bn3", ENC_BN_EPS)
+                    x = self._conv(z, pre + "conv3", 1, 4 * f, residual=sc)
+                else:
+                    sc = self._conv(y, pre + "sc", 1, f, stride) if first else x
+                    z = self._conv(y, pre + "conv1", 3, f, stride, padding=1)
+                    z = self._bn_relu(z, pre + "bn2", ENC_BN_EPS)
+                    x = self._conv(z, pre + "conv2", 3, f, padding=1, residual=sc)
+        x = self._bn_relu(x, "bn1", ENC_BN_EPS, tap="relu1")
+        skips = ["stage4_unit1_relu1", "stage3_unit1_relu1", "stage2_unit1_relu1", "relu0"]
+        return x, [self.taps[s] for s in skips]
+
+    def _vgg16(self, x):
+        """keras.applications.VGG16 [DEP]: 3x3 same conv + bias + ReLU, 2x2/2 max pool; raw 0..255 input."""
+        x = L.rb(x, self.storage)
+        skips = []
+        for bi, (f, n) in enumerate(VGG16_BLOCKS):
+            for ci in range(n):
+                name = "block%d_conv%d" % (bi + 1, ci + 1)
+                w, b = self.P.conv(name, 3, 3, x.shape[1], f, True, init="glorot_uniform")
+                x = L.rb(torch.relu(L.conv2d(x, w, b, 1, "same", self.storage)), self.storage)
+            skips.append(x)
+            x = L.maxpool(x, 2, 2, 0)
+        return x, skips[::-1]
+
+    # -- decoders --------------------------------------------------------------------------
+    def _conv_bn_relu(self, x, cname, bname, k, cout, use_bn=True):
+        z = self._conv(x, cname, k, cout, 1, "same", bias=not use_bn)
+        if use_bn:
+            return self._bn_relu(z, bname, DEC_BN_EPS)
+        return L.rb(torch.relu(z), self.storage)
+
+    def _unet_decoder(self, x, skips):
+        for i, f in enumerate(self.decoder_filters):
+            pre = "decoder_stage%d_" % i
+            skip = skips[i] if i < len(skips) else None
+            if self.block_type == "transpose":
+                w, b = self.P.conv(pre + "transpose", 4, 4, f, x.shape[1], not self.dec_bn)  # (kh,kw,Cout,Cin)
+                z = L.rb(L.conv2d_transpose(x, w, b, 2, self.storage), self.storage)
+                x = self._bn_relu(z, pre + "bn1", DEC_BN_EPS) if self.dec_bn else L.rb(torch.relu(z), self.storage)
+                if skip is not None:
+                    x = torch.cat([x, skip], dim=1)
+                x = self._conv_bn_relu(x, pre + "conv2", pre + "bn2", 3, f, self.dec_bn)
+            else:
+                x = L.upsample_nearest(x, 2)
+                if skip is not None:
+                    x = torch.cat([x, skip], dim=1)
+                x = self._conv_bn_relu(x, pre + "conv1", pre + "bn1", 3, f, self.dec_bn)
+                x = self._conv_bn_relu(x, pre + "conv2", pre + "bn2", 3, f, self.dec_bn)
+        return x
+
+    def _fpn_decoder(self, x, skips):
+        """segmentation_models 0.2.1 FPN [DEP]: SURVEY.md 8 a-5."""
+        # pyramid: top + 3 skips (H/32 .. H/4)
+        feats = [x] + skips[:3]
+        p = None
+        pyramid = []
+        for i, c in enumerate(feats):
+            lat = self._conv(c, "pyramid_stage_%d_conv1x1" % i, 1, self.pyr, bias=True)
+            if p is not None:
+                lat = L.rb(L.upsample_nearest(p, 2) + lat, self.storage)
+            p = lat
+            pyramid.append(p)
+        outs = []
+        rates = (8, 4, 2, 1)
+        for i, p in enumerate(pyramid):
+            s = self._conv_bn_relu(p, "segm_stage_%d_conv1" % i, "segm_stage_%d_bn1" % i, 3, self.segf, self.dec_bn)
+            s = self._conv_bn_relu(s, "segm_stage_%d_conv2" % i, "segm_stage_%d_bn2" % i, 3, self.segf, self.dec_bn)
+            if rates[i] > 1:
+                s = L.rb(L.resize_bilinear_tf1(s, s.shape[2] * rates[i], s.shape[3] * rates[i]), self.storage)
+            outs.append(s)
+        x = torch.cat(outs, dim=1)
+        x = self._conv_bn_relu(x, "final_stage_conv", "final_stage_bn", 3, self.segf * 4, self.dec_bn)
+        return x
+
+    def _linknet_decoder(self, x, skips):
+        """segmentation_models 0.2.1 Linknet [DEP]: 1x1(C/4) -> up x2 -> 3x3(C/4) -> 1x1(out) -> Add(skip)."""
+        for i in range(5):
+            pre = "decoder_stage%d_" % i
+            skip = skips[i] if i < len(skips) else None
+            cin = x.shape[1]
+            cout = skip.shape[1] if skip is not None else self.decoder_filters[i] if self.decoder_filters[i] else 16
+            z = self._conv_bn_relu(x, pre + "conv1", pre + "bn1", 1, cin // 4, self.dec_bn)
+            z = L.upsample_nearest(z, 2)
+            z = self._conv_bn_relu(z, pre + "conv2", pre + "bn2", 3, cin // 4, self.dec_bn)
+            z = self._conv_bn_relu(z, pre + "conv3", pre + "bn3", 1, cout, self.dec_bn)
+            x = L.rb(z + skip, self.storage) if skip is not None else z
+        return x
+
+    # -- full graph ------------------------------------------------------------------------
+    def forward(self, x_nhwc: torch.Tensor, emit_logits: bool = False) -> torch.Tensor:
+        """x: float NHWC raw 0..255 (no preprocessing call anywhere in the reference).
+
+        emit_logits=True strips the trailing Activation (what musket compile does for lovasz_loss)."""
+        self.P._in_encoder = True
+        x = x_nhwc.permute(0, 3, 1, 2).contiguous().float()
+        if self.backbone == "vgg16":
+            x, skips = self._vgg16(x)
+        else:
+            x, skips = self._resnet(x)
+        self.P._in_encoder = False
+        if self.arch == "Unet":
+            x = self._unet_decoder(x, skips)
+            w, b = self.P.conv("final_conv", 3, 3, x.shape[1], self.classes, True)
+            logits = L.conv2d(x, w, b, 1, "same", self.storage)
+        elif self.arch == "FPN":
+            x = self._fpn_decoder(x, skips)
+            w, b = self.P.conv("head_conv", 3, 3, x.shape[1], self.classes, True)
+            logits = L.conv2d(x, w, b, 1, "same", self.storage)
+            logits = L.resize_bilinear_tf1(logits, logits.shape[2] * 4, logits.shape[3] * 4)
+        elif self.arch == "Linknet":
+            x = self._linknet_decoder(x, skips)
+            w, b = self.P.conv("final_conv", 3, 3, x.shape[1], self.classes, True)
+            logits = L.conv2d(x, w, b, 1, "same", self.storage)
+        else:
+            raise ValueError("Unknown architecture")
+        self.taps["logits"] = logits
+        if emit_logits or self.activation in (None, "none", "linear"):
+            y = logits
+        elif self.activation == "sigmoid":
+            y = torch.sigmoid(logits)
+        elif self.activation == "softmax":
+            y = torch.softmax(logits, dim=1)
+        else:
+            raise ValueError("unknown activation " + str(self.activation))
+        return y.permute(0, 2, 3, 1)
+
+    __call__ = forward
+
+    def state_numpy(self) -> Dict[str, np.ndarray]:
+        d = {k: v.detach().numpy().copy() for k, v in self.P.params.items()}
+        d.update({k: v.numpy().copy() for k, v in self.P.buffers.items()})
+        return d
+
+    def load_numpy(self, d: Dict[str, np.ndarray]):
+        with torch.no_grad():
+            for k, v in self.P.params.items():
+                v.copy_(torch.from_numpy(np.asarray(d[k])))
+            for k, v in self.P.buffers.items():
+                if k in d:
+                    v.copy_(torch.from_numpy(np.asarray(d[k])))

@@ -1,0 +1,33 @@
+"""Philox4x32-10 counter-based RNG (Salmon et al. 2011), numpy restatement.  TEST INFRASTRUCTURE.
+
+The reference's imgaug stream (SFC64, reseeded per worker process) is not reproducible run-to-run
+(SURVEY.md Appendix B), so the engine defines its own draw: Philox(key=seed, counter=(step, sample,
+call, 0)).  This file is the CPU twin of csrc/philox.cuh so oracle and engine draw identical values.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+M0, M1 = 0xD2511F53, 0xCD9E8D57
+W0, W1 = 0x9E3779B9, 0xBB67AE85
+MASK = 0xFFFFFFFF
+
+
+def philox4x32(counter, key):
+    c0, c1, c2, c3 = [int(c) & MASK for c in counter]
+    k0, k1 = [int(k) & MASK for k in key]
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & MASK, p1 & MASK, ((p0 >> 32) ^ c3 ^ k1) & MASK, p0 & MASK
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    return c0, c1, c2, c3
+
+
+def u53(hi: int, lo: int) -> float:
+    """two uint32 -> uniform double in [0,1) with 53 random bits (exact in fp64)."""
+    return float(((hi << 32) | lo) >> 11) * (2.0 ** -53)
+
+
+def uniforms(seed: int, step: int, sample: int, call: int):
+    x = philox4x32((step & MASK, sample & MASK, call & MASK, (step >> 32) & MASK), (seed & MASK, (seed >> 32) & MASK))
+    return u53(x[0], x[1]), u53(x[2], x[3])
