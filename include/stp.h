@@ -1,0 +1,240 @@
+/*
+ * libstp -- C ABI of the B200-native segmentation training hot path.
+ *
+ * The reference (musket-ml/segmentation_training_pipeline) has no native code and no FFI: its hot path is
+ * Keras `train_on_batch` on a graph built at segmentation_pipeline/segmentation.py:96-155 (createNet1) fed by
+ * the imgaug generator selected at segmentation.py:54.  Each entry point below names the reference
+ * call site / dependency op it replaces.  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  All `void*`/typed pointers are DEVICE pointers
+ *     unless the name starts with `h_`.
+ *   - the caller owns every buffer; the library never allocates device memory, never synchronises,
+ *     never changes the current device.  Work is enqueued on `stream` (a cudaStream_t).
+ *   - returns 0 on success, a negative STP_E_* otherwise; message via stp_last_error() (thread local).
+ *   - activations: NHWC bf16, channel count a multiple of 8, 16-byte aligned, `ld` = elements between
+ *     consecutive pixels (>= c; lets a tensor be a channel slice of a concat buffer -> zero-copy concat).
+ *   - conv weights: bf16 [Cout][R][S][Cin] ("KRSC", Cin == x.c); master weights / gradients fp32 same order.
+ */
+#ifndef STP_H_
+#define STP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STP_VERSION 100
+
+enum {
+  STP_OK = 0,
+  STP_E_INVALID = -1,     /* bad argument / shape */
+  STP_E_UNSUPPORTED = -2, /* shape not covered by any kernel specialisation */
+  STP_E_CUDA = -3,        /* CUDA runtime / driver error (text in stp_last_error) */
+  STP_E_WORKSPACE = -4    /* workspace too small */
+};
+
+enum { STP_BF16 = 0, STP_F32 = 1, STP_U8 = 2 };
+
+typedef void* stp_stream; /* cudaStream_t */
+
+typedef struct stp_tensor {
+  void* ptr;  /* element (0,0,0,0) */
+  int32_t n, h, w, c;
+  int32_t ld;    /* pixel stride in elements */
+  int32_t dtype; /* STP_BF16 | STP_F32 | STP_U8 */
+} stp_tensor;
+
+int stp_version(void);
+const char* stp_last_error(void);
+/* number of kernels this library has enqueued from the calling process since load (bench `gpu_launches`) */
+int64_t stp_launch_count(void);
+/* 1 if the tcgen05/TMA conv path is compiled in and enabled, 0 if only the mma.sync path is used */
+int stp_tc_enabled(void);
+void stp_set_tc_enabled(int on);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  augmentation  -- replaces imgaug.augmenters.{Fliplr,Flipud,Affine,Multiply,Add} run by
+ *     musket_core.datasets.ImageKFoldedDataSet (segmentation.py:54; schemas/augmenters.raml:43-133).
+ *     Sampling arithmetic == cv2.warpAffine fixed point, bit exact.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct stp_aug_spec {
+  double fliplr_p, flipud_p;
+  int32_t affine; /* 0/1 */
+  double scale_lo, scale_hi;
+  double tx_lo, tx_hi, ty_lo, ty_hi; /* translate_percent */
+  double rot_lo, rot_hi;             /* degrees */
+  double shear_lo, shear_hi;         /* degrees */
+  int32_t has_mul;
+  double mul_lo, mul_hi;
+  int32_t has_add;
+  int32_t add_lo, add_hi;
+  int32_t mul_rint; /* 0: imgaug-0.3.0 truncating LUT, 1: round-half-even */
+} stp_aug_spec;
+
+typedef struct stp_aug_sample { /* per-sample drawn parameters, device resident, 128 bytes */
+  double m[6];                 /* forward 2x3 affine (src->dst), row major */
+  double inv[6];               /* cv2.warpAffine's fp64 inverse of m (dst->src) */
+  int32_t fliplr, flipud;
+  int32_t has_affine, has_mul;
+  float mul;
+  int32_t add;
+  int32_t src_index;           /* which pool sample this output is drawn from */
+  int32_t _pad;
+} stp_aug_sample;
+
+/* draw parameters: Philox4x32-10(key=seed, ctr=(step, sample_id, call, step>>32)).  `d_step` is a device
+ * int64 so the call is CUDA-graph replayable; sample_id = (step*n + i) % pool (src_index likewise). */
+int stp_augment_draw(const stp_aug_spec* h_spec, uint64_t seed, const int64_t* d_step, int32_t n,
+                     int32_t pool, int32_t h, int32_t w, stp_aug_sample* d_out, stp_stream stream);
+/* apply: img_pool u8 [pool,h,w,c_img], mask_pool u8 [pool,h,w,c_mask] -> img_out/mask_out u8 [n,h,w,*] */
+int stp_augment_apply(const uint8_t* img_pool, const uint8_t* mask_pool, const stp_aug_sample* d_params,
+                      uint8_t* img_out, uint8_t* mask_out, int32_t n, int32_t h, int32_t w,
+                      int32_t c_img, int32_t c_mask, int32_t mul_rint, stp_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2/K4/K5/K9  convolution -- replaces keras.layers.Conv2D / Conv2DTranspose -> TF Conv2D,
+ *     Conv2DBackpropInput, Conv2DBackpropFilter (graph built by segmentation_models.Unet etc. at
+ *     segmentation.py:109-113,155).
+ * ---------------------------------------------------------------------------------------------- */
+enum { STP_CONV_RELU = 1, STP_CONV_STATS = 2 };
+
+typedef struct stp_conv_desc {
+  int32_t r, s;         /* filter height, width */
+  int32_t stride;       /* output stride */
+  int32_t pad_h, pad_w; /* zero padding BEFORE (top/left); bottom/right implied by the output size */
+  int32_t up;           /* zero-insertion factor on the input (1; >1 = transposed conv / strided dgrad) */
+  int32_t flags;
+} stp_conv_desc;
+
+/* y = conv(x, w) [+ bias] [+ residual];  y bf16 or f32.  STP_CONV_STATS: also write per-channel partial
+ * sums for BatchNorm into `stats_partial` (see stp_bn_stats_finalize). */
+int stp_conv_fwd(const stp_conv_desc* d, const stp_tensor* x, const void* w_krsc, const float* bias,
+                 const stp_tensor* residual, const stp_tensor* y, void* workspace, size_t workspace_bytes,
+                 stp_stream stream);
+/* dx = conv_transpose(dy, w) [+ residual]  for the FORWARD descriptor `d`; `w_dgrad` is the
+ * [Cin][R][S][Cout] tap-flipped copy made by stp_weight_prep. */
+int stp_conv_dgrad(const stp_conv_desc* d, const stp_tensor* dy, const void* w_dgrad,
+                   const stp_tensor* residual, const stp_tensor* dx, void* workspace, size_t workspace_bytes,
+                   stp_stream stream);
+/* dw[Cout][R][S][Cin] (f32) = sum_pixels dy (x) x ; deterministic split reduction through workspace */
+int stp_conv_wgrad(const stp_conv_desc* d, const stp_tensor* x, const stp_tensor* dy, float* dw,
+                   void* workspace, size_t workspace_bytes, stp_stream stream);
+size_t stp_conv_wgrad_workspace(const stp_conv_desc* d, const stp_tensor* x, const stp_tensor* dy);
+/* master f32 [Cout][R][S][Cin] -> bf16 same order (w_fwd) and bf16 [Cin][R][S][Cout] flipped (w_dgrad, may be NULL) */
+int stp_weight_prep(const float* w_master, void* w_fwd, void* w_dgrad, int32_t cout, int32_t r, int32_t s,
+                    int32_t cin, stp_stream stream);
+
+/* small-Cout head (final_conv + sigmoid, classes<=4): CUDA-core, HBM bound.  logits/probabilities f32 [M,classes] */
+int stp_head_fwd(const stp_tensor* x, const float* w_krsc_f32, const float* bias, int32_t classes,
+                 float* logits, stp_stream stream);
+/* dlogits f32 [M,classes] -> dx bf16, dw f32 [classes][3][3][Cin], dbias f32[classes] (workspace reduction) */
+int stp_head_bwd(const stp_tensor* x, const float* w_krsc_f32, const float* dlogits, int32_t classes,
+                 const stp_tensor* dx, float* dw, float* dbias, void* workspace, size_t workspace_bytes,
+                 stp_stream stream);
+size_t stp_head_bwd_workspace(const stp_tensor* x, int32_t classes);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3/K6  BatchNormalization(+ReLU) -- replaces keras BatchNormalization -> TF FusedBatchNorm(+Grad)
+ * ---------------------------------------------------------------------------------------------- */
+#define STP_BN_MAX_PARTIALS 1024
+/* number of partial blocks the stats / bwd-reduce kernels use for a [rows, c] tensor (pure host function) */
+int32_t stp_bn_nblk(int64_t rows, int32_t c);
+/* per-channel sum / sum of squares of x (bf16 or u8) -> partial[2][nblk][c] f32 */
+int stp_bn_stats(const stp_tensor* x, float* partial, stp_stream stream);
+/* partials -> mean, invstd, scale=gamma*invstd, shift=beta-mean*scale; updates moving stats
+ * (momentum, unbiased variance) when moving_mean != NULL.  coef f32 [4][c] = mean, invstd, scale, shift */
+int stp_bn_finalize(const float* partial, int32_t nblk, int32_t c, int64_t count, const float* gamma,
+                    const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
+                    float* coef, stp_stream stream);
+/* y = [relu](x*scale+shift); up=2 writes each value to the 2x2 block of y (UpSampling2D fused) */
+int stp_bn_apply(const stp_tensor* x, const float* coef, int32_t relu, int32_t up, const stp_tensor* y,
+                 stp_stream stream);
+/* inference-mode coefficients from moving stats */
+int stp_bn_coef_infer(const float* gamma, const float* beta, const float* moving_mean, const float* moving_var,
+                      float eps, int32_t c, float* coef, stp_stream stream);
+/* backward: g = dy*(x*scale+shift>0 if relu); partial[2][nblk][c] = sum g, sum g*xhat.  pool=2: dy is the
+ * gradient of the 2x-upsampled tensor (2x2 summed on the fly). */
+int stp_bn_bwd_reduce(const stp_tensor* dy, const stp_tensor* x, const float* coef, int32_t relu,
+                      int32_t pool, float* partial, stp_stream stream);
+/* partials -> dgamma, dbeta (f32, written; may be NULL for scale=False) and bcoef f32 [3][c] (a,b,cc) with dx = a*g + b*x + cc */
+int stp_bn_bwd_finalize(const float* partial, int32_t nblk, int32_t c, int64_t count, const float* coef,
+                        float* dgamma, float* dbeta, float* bcoef, stp_stream stream);
+/* dx = a*g + b*x + cc [+ residual] */
+int stp_bn_bwd_apply(const stp_tensor* dy, const stp_tensor* x, const float* coef, const float* bcoef,
+                     int32_t relu, int32_t pool, const stp_tensor* residual, const stp_tensor* dx,
+                     stp_stream stream);
+/* relu-only backward (VGG path / decoder without BN): dx = dy*(y>0) [+residual] */
+int stp_relu_bwd(const stp_tensor* dy, const stp_tensor* y, int32_t pool, const stp_tensor* residual,
+                 const stp_tensor* dx, stp_stream stream);
+
+/* stem: u8 image -> bn_data (scale=False) normalised bf16 with C padded to 8; channel `c_img` is set to
+ * 1.0 (the "ones" channel whose wgrad column yields d(beta of bn_data)) */
+int stp_stem_prep(const uint8_t* img, int32_t n, int32_t h, int32_t w, int32_t c_img, const float* coef,
+                  const stp_tensor* y, stp_stream stream);
+
+/* after the stem wgrad (dw8 f32 [cout][r][s][cin_pad]): dbeta(bn_data)[c<c_img] from the ones-channel column,
+ * then zero the padded columns c>=c_img in place (DESIGN.md "stem") */
+int stp_stem_wgrad_post(float* dw8, const float* w_master, int32_t cout, int32_t r, int32_t s, int32_t cin_pad,
+                        int32_t c_img, float* dbeta, stp_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K7  MaxPooling2D -- replaces keras MaxPooling2D -> TF MaxPool / MaxPoolGrad
+ * ---------------------------------------------------------------------------------------------- */
+int stp_maxpool_fwd(const stp_tensor* x, int32_t k, int32_t stride, int32_t pad, const stp_tensor* y,
+                    uint8_t* argmax, stp_stream stream);
+int stp_maxpool_bwd(const stp_tensor* dy, const uint8_t* argmax, int32_t k, int32_t stride, int32_t pad,
+                    const stp_tensor* residual, const stp_tensor* dx, stp_stream stream);
+
+/* K8 copy / nearest-upsample a tensor into a (strided) destination: UpSampling2D + Concatenate when the
+ * producer could not write in place */
+int stp_copy_up(const stp_tensor* x, int32_t up, const stp_tensor* y, stp_stream stream);
+/* y = a + b (Add layer; Linknet / FPN) */
+int stp_add(const stp_tensor* a, const stp_tensor* b, const stp_tensor* y, stp_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K11/K14  loss + metrics -- replaces keras binary_crossentropy, musket_core.losses.{dice,iou,...}
+ *     (registered at segmentation.py:15-22).  One pass over (logits f32 [M], mask u8 [M]).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct stp_loss_spec {
+  float w_bce, w_dice, w_iou; /* composite loss weights: w_bce*binary_crossentropy + w_dice*dice_loss + w_iou*iou_loss */
+} stp_loss_spec;
+enum { /* indices into the f32 result vector (16 floats) */
+  STP_L_LOSS = 0, STP_L_BCE = 1, STP_L_DICE = 2, STP_L_IOU = 3, STP_L_ACC = 4, STP_L_IOT = 5,
+  STP_L_SUM_P = 6, STP_L_SUM_T = 7, STP_L_SUM_PT = 8, STP_L_COUNT = 9
+};
+int stp_loss_fwd(const float* logits, const uint8_t* mask, int64_t count, const stp_loss_spec* h_spec,
+                 float* partial, float* result16, stp_stream stream);
+size_t stp_loss_partial_floats(void);
+/* dlogits f32 [count] = dL/dlogit using the sums in result16 */
+int stp_loss_bwd(const float* logits, const uint8_t* mask, int64_t count, const stp_loss_spec* h_spec,
+                 const float* result16, float* dlogits, stp_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K12  optimizer -- replaces keras.optimizers.Adam/SGD/RMSprop update ops (segmentation.raml:77-89)
+ *     Keras formulation (eps outside the bias correction).  `d_step` device int64, incremented by
+ *     stp_step_advance once per iteration (graph replayable).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct stp_grad_xform { /* g' = clipvalue(clipnorm(g * scale)) -- keras clipnorm / clipvalue, DDP mean */
+  float scale;           /* e.g. 1/world_size */
+  float clipnorm;        /* <=0: off.  needs d_sumsq = sum(g^2) of the UNSCALED flat gradient */
+  float clipvalue;       /* <=0: off */
+  const float* d_sumsq;  /* device scalar or NULL */
+} stp_grad_xform;
+int stp_adam(float* p, const float* g, float* m, float* v, int64_t count, float lr, float beta1, float beta2,
+             float eps, const stp_grad_xform* h_gx, const int64_t* d_step, stp_stream stream);
+int stp_sgd(float* p, const float* g, float* v, int64_t count, float lr, float momentum, int32_t nesterov,
+            const stp_grad_xform* h_gx, stp_stream stream);
+int stp_rmsprop(float* p, const float* g, float* a, int64_t count, float lr, float rho, float eps,
+                const stp_grad_xform* h_gx, stp_stream stream);
+int stp_step_advance(int64_t* d_step, stp_stream stream);
+/* sum of squares of g into out[0] (f32, deterministic two-pass through `partial`), for clipnorm */
+int stp_sumsq(const float* g, int64_t count, float* partial, float* out, stp_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STP_H_ */

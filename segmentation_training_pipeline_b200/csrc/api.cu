@@ -1,0 +1,118 @@
+// C-ABI plumbing: error state, version, launch counter and the convolution entry points, which pick a
+// kernel SPECIALISATION by shape (tcgen05/TMA implicit GEMM for the FLOP-heavy layers, mma.sync generic
+// implicit GEMM for the irregular / HBM-bound ones).  No CPU fallback anywhere.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "conv.h"
+
+namespace stp {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+static std::atomic<int> g_tc_enabled{1};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace stp
+
+using namespace stp;
+
+extern "C" int stp_version(void) { return STP_VERSION; }
+extern "C" const char* stp_last_error(void) { return g_err; }
+extern "C" int64_t stp_launch_count(void) { return g_launches.load(); }
+extern "C" int stp_tc_enabled(void) { return g_tc_enabled.load(); }
+extern "C" void stp_set_tc_enabled(int on) { g_tc_enabled.store(on ? 1 : 0); }
+
+static int check_conv_common(const stp_conv_desc* d, const stp_tensor* in, const stp_tensor* out, const char* who) {
+  STP_REQUIRE(d && in && out, "%s: null argument", who);
+  STP_REQUIRE(d->r >= 1 && d->s >= 1 && d->stride >= 1 && d->up >= 1 && d->pad_h >= 0 && d->pad_w >= 0,
+              "%s: bad descriptor", who);
+  STP_REQUIRE(vec_ok(in), "%s: input must be bf16 NHWC, c%%8==0, ld%%8==0, 16B aligned", who);
+  STP_REQUIRE(in->n == out->n, "%s: batch mismatch", who);
+  return STP_OK;
+}
+
+extern "C" int stp_conv_fwd(const stp_conv_desc* d, const stp_tensor* x, const void* w_krsc, const float* bias,
+                            const stp_tensor* residual, const stp_tensor* y, void* workspace, size_t workspace_bytes,
+                            stp_stream stream) {
+  int rc = check_conv_common(d, x, y, "conv_fwd");
+  if (rc) return rc;
+  STP_REQUIRE(w_krsc && y->ptr, "conv_fwd: null weights/output");
+  STP_REQUIRE(y->dtype == STP_BF16 || y->dtype == STP_F32, "conv_fwd: y must be bf16 or f32");
+  STP_REQUIRE(y->ld >= y->c, "conv_fwd: bad output ld");
+  if (residual)
+    STP_REQUIRE(residual->dtype == STP_BF16 && residual->c == y->c && pixels(residual) == pixels(y),
+                "conv_fwd: bad residual");
+  (void)workspace;
+  (void)workspace_bytes;
+  ConvP p;
+  p.x = (const __nv_bfloat16*)x->ptr; p.ldx = x->ld; p.N = x->n; p.H = x->h; p.W = x->w; p.Cin = x->c;
+  p.w = (const __nv_bfloat16*)w_krsc;
+  p.y = y->ptr; p.ldy = y->ld; p.Ho = y->h; p.Wo = y->w; p.Cout = y->c; p.y_f32 = y->dtype == STP_F32;
+  p.res = residual ? (const __nv_bfloat16*)residual->ptr : nullptr; p.ldr = residual ? residual->ld : 0;
+  p.bias = bias;
+  p.R = d->r; p.S = d->s; p.stride = d->stride; p.pad_h = d->pad_h; p.pad_w = d->pad_w; p.up = d->up;
+  p.relu = (d->flags & STP_CONV_RELU) ? 1 : 0;
+  p.M = pixels(y); p.K = d->r * d->s * x->c;
+  if (stp_tc_enabled() && tc_conv_supported(p)) return launch_tc_conv(p, (cudaStream_t)stream);
+  return launch_generic_conv(p, (cudaStream_t)stream);
+}
+
+extern "C" int stp_conv_dgrad(const stp_conv_desc* d, const stp_tensor* dy, const void* w_dgrad,
+                              const stp_tensor* residual, const stp_tensor* dx, void* workspace,
+                              size_t workspace_bytes, stp_stream stream) {
+  int rc = check_conv_common(d, dy, dx, "conv_dgrad");
+  if (rc) return rc;
+  STP_REQUIRE(w_dgrad && dx->ptr && dx->dtype == STP_BF16 && dx->ld >= dx->c, "conv_dgrad: bad dx / weights");
+  STP_REQUIRE(d->up == 1 || d->stride == 1, "conv_dgrad: stride and up cannot both be > 1");
+  STP_REQUIRE(d->r - 1 - d->pad_h >= 0 && d->s - 1 - d->pad_w >= 0, "conv_dgrad: pad > filter-1 unsupported");
+  if (residual)
+    STP_REQUIRE(residual->dtype == STP_BF16 && residual->c == dx->c && pixels(residual) == pixels(dx),
+                "conv_dgrad: bad residual");
+  (void)workspace;
+  (void)workspace_bytes;
+  ConvP p;
+  p.x = (const __nv_bfloat16*)dy->ptr; p.ldx = dy->ld; p.N = dy->n; p.H = dy->h; p.W = dy->w; p.Cin = dy->c;
+  p.w = (const __nv_bfloat16*)w_dgrad;
+  p.y = dx->ptr; p.ldy = dx->ld; p.Ho = dx->h; p.Wo = dx->w; p.Cout = dx->c; p.y_f32 = 0;
+  p.res = residual ? (const __nv_bfloat16*)residual->ptr : nullptr; p.ldr = residual ? residual->ld : 0;
+  p.bias = nullptr;
+  p.R = d->r; p.S = d->s;
+  // forward  y[o] = sum_r x[(o*stride - pad + r)/up]      (up==1 or stride==1)
+  // backward dx[i] = sum_r' dy[(i*up - (R-1-pad) + r')/stride]  with r' = R-1-r
+  p.stride = d->up; p.up = d->stride; p.pad_h = d->r - 1 - d->pad_h; p.pad_w = d->s - 1 - d->pad_w;
+  p.relu = 0;
+  p.M = pixels(dx); p.K = d->r * d->s * dy->c;
+  if (stp_tc_enabled() && tc_conv_supported(p)) return launch_tc_conv(p, (cudaStream_t)stream);
+  return launch_generic_conv(p, (cudaStream_t)stream);
+}
+
+extern "C" size_t stp_conv_wgrad_workspace(const stp_conv_desc* d, const stp_tensor* x, const stp_tensor* dy) {
+  if (!d || !x || !dy) return 0;
+  size_t a = generic_wgrad_workspace(pixels(dy), dy->c, d->r * d->s * x->c);
+  size_t b = tc_wgrad_workspace(pixels(dy), dy->c, d->r, d->s, x->c);
+  return a > b ? a : b;
+}
+
+extern "C" int stp_conv_wgrad(const stp_conv_desc* d, const stp_tensor* x, const stp_tensor* dy, float* dw,
+                              void* workspace, size_t workspace_bytes, stp_stream stream) {
+  int rc = check_conv_common(d, x, dy, "conv_wgrad");
+  if (rc) return rc;
+  STP_REQUIRE(vec_ok(dy) && dw, "conv_wgrad: dy must be bf16 NHWC c%%8==0; dw non-null");
+  WgradP p;
+  p.x = (const __nv_bfloat16*)x->ptr; p.ldx = x->ld; p.N = x->n; p.H = x->h; p.W = x->w; p.Cin = x->c;
+  p.dy = (const __nv_bfloat16*)dy->ptr; p.lddy = dy->ld; p.Ho = dy->h; p.Wo = dy->w; p.Cout = dy->c;
+  p.out = nullptr;
+  p.R = d->r; p.S = d->s; p.stride = d->stride; p.pad_h = d->pad_h; p.pad_w = d->pad_w; p.up = d->up;
+  p.M = pixels(dy); p.K = d->r * d->s * x->c;
+  p.chunks_per_split = 0;
+  if (stp_tc_enabled() && tc_wgrad_supported(p)) return launch_tc_wgrad(p, dw, workspace, workspace_bytes, (cudaStream_t)stream);
+  return launch_generic_wgrad(p, dw, workspace, workspace_bytes, (cudaStream_t)stream);
+}

@@ -1,0 +1,237 @@
+// K1: on-device augmentation of uint8 image + mask pairs: Fliplr, Flipud, Affine, Multiply, Add fused in ONE
+// gather pass (imgaug 0.3.0 Sequential semantics, reference schemas/augmenters.raml:43-133).
+// The affine sampling is cv2.warpAffine's fixed-point rule: fp64 rint of the
+// per-row / per-column terms (unfused mul/add, round-half-even), then pure integer math per pixel:
+// 1/32-pixel coordinates, 15-bit bilinear weights, (sum + 16384) >> 15.  Bit exact against cv2 4.13.
+// Integer/byte work, HBM/L2 bound: 4 output pixels per thread, 32-bit packed stores.
+#include "common.cuh"
+
+namespace stp {
+
+// ---- Philox4x32-10 (twin of oracle/philox.py) ------------------------------------------------
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                           uint32_t k1, uint32_t* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+  return (double)((((uint64_t)hi << 32) | lo) >> 11) * 1.1102230246251565e-16;  // 2^-53, exact
+}
+__device__ __forceinline__ double lerp_rn(double lo, double hi, double u) {
+  return __dadd_rn(lo, __dmul_rn(u, __dsub_rn(hi, lo)));
+}
+
+struct DevSample {  // == stp_aug_sample (include/stp.h)
+  double m[6];
+  double inv[6];
+  int32_t fliplr, flipud, has_affine, has_mul;
+  float mul;
+  int32_t add, src_index, _pad;
+};
+static_assert(sizeof(DevSample) == sizeof(stp_aug_sample), "stp_aug_sample layout");
+
+__global__ void augment_draw_kernel(stp_aug_spec spec, uint64_t seed, const int64_t* __restrict__ d_step, int n,
+                                    int pool, int H, int W, DevSample* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t step = *d_step;
+  const uint32_t sid = (uint32_t)((step * n + i) % pool);
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t r[5][4];
+#pragma unroll
+  for (int call = 0; call < 5; ++call) philox4x32((uint32_t)step, sid, call, (uint32_t)(step >> 32), k0, k1, r[call]);
+  const double u_lr = u53(r[0][0], r[0][1]), u_ud = u53(r[0][2], r[0][3]);
+  const double u_sc = u53(r[1][0], r[1][1]), u_rot = u53(r[1][2], r[1][3]);
+  const double u_sh = u53(r[2][0], r[2][1]), u_tx = u53(r[2][2], r[2][3]);
+  const double u_ty = u53(r[3][0], r[3][1]), u_mul = u53(r[3][2], r[3][3]);
+  const double u_add = u53(r[4][0], r[4][1]);
+  DevSample s;
+  s.fliplr = u_lr < (double)spec.fliplr_p;
+  s.flipud = u_ud < (double)spec.flipud_p;
+  s.has_affine = spec.affine;
+  s.m[0] = 1.0; s.m[1] = 0.0; s.m[2] = 0.0; s.m[3] = 0.0; s.m[4] = 1.0; s.m[5] = 0.0;
+  if (spec.affine) {
+    const double scale = lerp_rn(spec.scale_lo, spec.scale_hi, u_sc);
+    const double rotd = lerp_rn(spec.rot_lo, spec.rot_hi, u_rot);
+    const double shd = lerp_rn(spec.shear_lo, spec.shear_hi, u_sh);
+    const double tx = lerp_rn(spec.tx_lo, spec.tx_hi, u_tx);
+    const double ty = lerp_rn(spec.ty_lo, spec.ty_hi, u_ty);
+    const double tx_px = (double)__double2int_rn(__dmul_rn(tx, (double)W));
+    const double ty_px = (double)__double2int_rn(__dmul_rn(ty, (double)H));
+    const double d2r = 0.017453292519943295;  // math.pi / 180.0
+    const double rot = __dmul_rn(rotd, d2r), sh = __dmul_rn(shd, d2r);
+    const double rs = __dadd_rn(rot, sh);
+    const double a00 = __dmul_rn(scale, cos(rot));
+    const double a01 = -__dmul_rn(scale, sin(rs));
+    const double a10 = __dmul_rn(scale, sin(rot));
+    const double a11 = __dmul_rn(scale, cos(rs));
+    const double cx = __dsub_rn(__ddiv_rn((double)W, 2.0), 0.5), cy = __dsub_rn(__ddiv_rn((double)H, 2.0), 0.5);
+    const double b0 = __dadd_rn(__dadd_rn(__dmul_rn(a00, -cx), __dmul_rn(a01, -cy)), tx_px);
+    const double b1 = __dadd_rn(__dadd_rn(__dmul_rn(a10, -cx), __dmul_rn(a11, -cy)), ty_px);
+    s.m[0] = a00; s.m[1] = a01; s.m[2] = __dadd_rn(b0, cx);
+    s.m[3] = a10; s.m[4] = a11; s.m[5] = __dadd_rn(b1, cy);
+  }
+  // cv2.warpAffine's inversion (imgwarp.cpp), unfused fp64
+  {
+    double D = __dsub_rn(__dmul_rn(s.m[0], s.m[4]), __dmul_rn(s.m[1], s.m[3]));
+    D = D != 0.0 ? __ddiv_rn(1.0, D) : 0.0;
+    const double A11 = __dmul_rn(s.m[4], D), A22 = __dmul_rn(s.m[0], D);
+    const double i0 = A11, i1 = __dmul_rn(s.m[1], -D), i3 = __dmul_rn(s.m[3], -D), i4 = A22;
+    s.inv[0] = i0; s.inv[1] = i1; s.inv[3] = i3; s.inv[4] = i4;
+    s.inv[2] = __dsub_rn(__dmul_rn(-i0, s.m[2]), __dmul_rn(i1, s.m[5]));
+    s.inv[5] = __dsub_rn(__dmul_rn(-i3, s.m[2]), __dmul_rn(i4, s.m[5]));
+  }
+  s.has_mul = spec.has_mul;
+  s.mul = spec.has_mul ? (float)lerp_rn(spec.mul_lo, spec.mul_hi, u_mul) : 1.f;
+  s.add = 0;
+  if (spec.has_add) s.add = spec.add_lo + (int)floor(__dmul_rn(u_add, (double)(spec.add_hi - spec.add_lo + 1)));
+  s.src_index = (int32_t)sid;
+  s._pad = 0;
+  out[i] = s;
+}
+
+__device__ __forceinline__ int colour(int v, const DevSample& s, int mul_rint) {
+  if (s.has_mul) {
+    float f = __fmul_rn((float)v, s.mul);
+    f = fminf(fmaxf(f, 0.f), 255.f);
+    v = mul_rint ? __float2int_rn(f) : (int)f;
+  }
+  v += s.add;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// one thread = PX consecutive output pixels of one row
+template <int PX, int CI>
+__global__ void __launch_bounds__(256) augment_apply_kernel(const uint8_t* __restrict__ img_pool,
+                                                            const uint8_t* __restrict__ mask_pool,
+                                                            const DevSample* __restrict__ params,
+                                                            uint8_t* __restrict__ img_out,
+                                                            uint8_t* __restrict__ mask_out, int n, int H, int W,
+                                                            int cm, int mul_rint) {
+  const int wq = W / PX;
+  const int64_t total = (int64_t)n * H * wq;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int xq = (int)(idx % wq);
+    const int y = (int)((idx / wq) % H);
+    const int b = (int)(idx / ((int64_t)wq * H));
+    const DevSample s = params[b];
+    const uint8_t* simg = img_pool + (int64_t)s.src_index * H * W * CI;
+    const uint8_t* smsk = mask_pool ? mask_pool + (int64_t)s.src_index * H * W * cm : nullptr;
+    uint8_t oi[PX * CI];
+    uint8_t om[PX * 4];
+    long long X0n = 0, Y0n = 0, X0l = 0, Y0l = 0;
+    if (s.has_affine) {
+      const double yd = (double)y;
+      const long long xr = __double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(s.inv[1], yd), s.inv[2]), 1024.0));
+      const long long yr = __double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(s.inv[4], yd), s.inv[5]), 1024.0));
+      X0n = xr + 512; Y0n = yr + 512;
+      X0l = xr + 16;  Y0l = yr + 16;
+    }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      const int x = xq * PX + p;
+      if (!s.has_affine) {
+        const int sx = s.fliplr ? W - 1 - x : x, sy = s.flipud ? H - 1 - y : y;
+#pragma unroll
+        for (int c = 0; c < CI; ++c) oi[p * CI + c] = (uint8_t)colour(simg[((int64_t)sy * W + sx) * CI + c], s, mul_rint);
+        for (int c = 0; c < cm; ++c) om[p * cm + c] = smsk ? smsk[((int64_t)sy * W + sx) * cm + c] : 0;
+        continue;
+      }
+      const double xd = (double)x;
+      const long long ad = __double2ll_rn(__dmul_rn(__dmul_rn(s.inv[0], xd), 1024.0));
+      const long long bd = __double2ll_rn(__dmul_rn(__dmul_rn(s.inv[3], xd), 1024.0));
+      // mask: nearest
+      {
+        const long long sx = (X0n + ad) >> 10, sy = (Y0n + bd) >> 10;
+        const bool ok = sx >= 0 && sx < W && sy >= 0 && sy < H;
+        const int px = s.fliplr ? W - 1 - (int)sx : (int)sx, py = s.flipud ? H - 1 - (int)sy : (int)sy;
+        for (int c = 0; c < cm; ++c) om[p * cm + c] = (ok && smsk) ? smsk[((int64_t)py * W + px) * cm + c] : 0;
+      }
+      // image: bilinear, 5 fractional bits
+      {
+        const long long X = (X0l + ad) >> 5, Y = (Y0l + bd) >> 5;
+        const long long sx = X >> 5, sy = Y >> 5;
+        const int ax = (int)(X & 31), ay = (int)(Y & 31);
+        const int w00 = (32 - ay) * (32 - ax) * 32, w01 = (32 - ay) * ax * 32, w10 = ay * (32 - ax) * 32,
+                  w11 = ay * ax * 32;
+        const bool x0ok = sx >= 0 && sx < W, x1ok = sx + 1 >= 0 && sx + 1 < W;
+        const bool y0ok = sy >= 0 && sy < H, y1ok = sy + 1 >= 0 && sy + 1 < H;
+        const int px0 = s.fliplr ? W - 1 - (int)sx : (int)sx, px1 = s.fliplr ? px0 - 1 : px0 + 1;
+        const int py0 = s.flipud ? H - 1 - (int)sy : (int)sy, py1 = s.flipud ? py0 - 1 : py0 + 1;
+#pragma unroll
+        for (int c = 0; c < CI; ++c) {
+          const int v00 = (x0ok && y0ok) ? simg[((int64_t)py0 * W + px0) * CI + c] : 0;
+          const int v01 = (x1ok && y0ok) ? simg[((int64_t)py0 * W + px1) * CI + c] : 0;
+          const int v10 = (x0ok && y1ok) ? simg[((int64_t)py1 * W + px0) * CI + c] : 0;
+          const int v11 = (x1ok && y1ok) ? simg[((int64_t)py1 * W + px1) * CI + c] : 0;
+          const int v = (w00 * v00 + w01 * v01 + w10 * v10 + w11 * v11 + 16384) >> 15;
+          oi[p * CI + c] = (uint8_t)colour(v, s, mul_rint);
+        }
+      }
+    }
+    uint8_t* dst = img_out + (((int64_t)b * H + y) * W + (int64_t)xq * PX) * CI;
+    if ((PX * CI) % 4 == 0) {
+#pragma unroll
+      for (int k = 0; k < PX * CI / 4; ++k)
+        reinterpret_cast<uint32_t*>(dst)[k] =
+            (uint32_t)oi[4 * k] | ((uint32_t)oi[4 * k + 1] << 8) | ((uint32_t)oi[4 * k + 2] << 16) | ((uint32_t)oi[4 * k + 3] << 24);
+    } else {
+      for (int k = 0; k < PX * CI; ++k) dst[k] = oi[k];
+    }
+    if (mask_out) {
+      uint8_t* md = mask_out + (((int64_t)b * H + y) * W + (int64_t)xq * PX) * cm;
+      if (PX == 4 && cm == 1) {
+        *reinterpret_cast<uint32_t*>(md) =
+            (uint32_t)om[0] | ((uint32_t)om[1] << 8) | ((uint32_t)om[2] << 16) | ((uint32_t)om[3] << 24);
+      } else {
+        for (int k = 0; k < PX * cm; ++k) md[k] = om[k];
+      }
+    }
+  }
+}
+
+}  // namespace stp
+
+using namespace stp;
+
+extern "C" int stp_augment_draw(const stp_aug_spec* h_spec, uint64_t seed, const int64_t* d_step, int32_t n,
+                                int32_t pool, int32_t h, int32_t w, stp_aug_sample* d_out, stp_stream stream) {
+  STP_REQUIRE(h_spec && d_step && d_out && n > 0 && pool > 0, "augment_draw: bad args");
+  augment_draw_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(*h_spec, seed, d_step, n, pool, h, w,
+                                                                      (DevSample*)d_out);
+  return check_launch("augment_draw");
+}
+
+extern "C" int stp_augment_apply(const uint8_t* img_pool, const uint8_t* mask_pool, const stp_aug_sample* d_params,
+                                 uint8_t* img_out, uint8_t* mask_out, int32_t n, int32_t h, int32_t w, int32_t c_img,
+                                 int32_t c_mask, int32_t mul_rint, stp_stream stream) {
+  STP_REQUIRE(img_pool && d_params && img_out && n > 0, "augment_apply: bad args");
+  STP_REQUIRE(c_img == 3 || c_img == 1 || c_img == 4, "augment_apply: c_img must be 1, 3 or 4");
+  STP_REQUIRE(c_mask >= 0 && c_mask <= 4, "augment_apply: c_mask must be <= 4");
+  STP_REQUIRE((mask_pool == nullptr) == (mask_out == nullptr), "augment_apply: mask in/out must both be given");
+  const bool v4 = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(img_out) & 3) == 0) &&
+                  (!mask_out || (reinterpret_cast<uintptr_t>(mask_out) & 3) == 0);
+  int64_t total = (int64_t)n * h * (v4 ? w / 4 : w);
+  int64_t nb = (total + 255) / 256;
+  int grid = (int)(nb < (int64_t)kNumSMs * 16 ? nb : (int64_t)kNumSMs * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevSample* P = (const DevSample*)d_params;
+#define LAUNCH(PX, CI) \
+  augment_apply_kernel<PX, CI><<<grid, 256, 0, st>>>(img_pool, mask_pool, P, img_out, mask_out, n, h, w, c_mask, mul_rint)
+  if (v4) {
+    if (c_img == 3) LAUNCH(4, 3); else if (c_img == 1) LAUNCH(4, 1); else LAUNCH(4, 4);
+  } else {
+    if (c_img == 3) LAUNCH(1, 3); else if (c_img == 1) LAUNCH(1, 1); else LAUNCH(1, 4);
+  }
+#undef LAUNCH
+  return check_launch("augment_apply");
+}

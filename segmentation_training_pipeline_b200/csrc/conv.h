@@ -1,0 +1,46 @@
+// Shared parameter blocks + launchers of the convolution kernels (generic mma.sync and tcgen05 paths).
+#pragma once
+#include "common.cuh"
+
+namespace stp {
+
+struct ConvP {
+  const __nv_bfloat16* x;
+  int ldx, N, H, W, Cin;
+  const __nv_bfloat16* w;
+  void* y;
+  int ldy, Ho, Wo, Cout, y_f32;
+  const __nv_bfloat16* res;
+  int ldr;
+  const float* bias;
+  int R, S, stride, pad_h, pad_w, up, relu;
+  int64_t M;
+  int K;
+};
+
+struct WgradP {
+  const __nv_bfloat16* x;
+  int ldx, N, H, W, Cin;
+  const __nv_bfloat16* dy;
+  int lddy, Ho, Wo, Cout;
+  float* out;  // [splits][Cout][K]
+  int R, S, stride, pad_h, pad_w, up;
+  int64_t M;
+  int K;
+  int64_t chunks_per_split;  // in units of 32 pixels
+};
+
+
+// conv_generic.cu
+int launch_generic_conv(const ConvP& p, cudaStream_t st);
+int launch_generic_wgrad(WgradP p, float* dw, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t generic_wgrad_workspace(int64_t M, int Cout, int K);
+
+// conv_tc.cu (tcgen05 + TMA)
+bool tc_conv_supported(const ConvP& p);
+int launch_tc_conv(const ConvP& p, cudaStream_t st);
+bool tc_wgrad_supported(const WgradP& p);
+int launch_tc_wgrad(const WgradP& p, float* dw, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t tc_wgrad_workspace(int64_t M, int Cout, int R, int S, int Cin);
+
+}  // namespace stp

@@ -1,0 +1,223 @@
+// Segmentation head: final 3x3 'same' conv with classes <= 4 outputs (+bias).  AI ~ 8 FLOP/B -> HBM bound,
+// so it runs on CUDA cores with fp32 weights: one thread per output pixel, 16-byte channel vectors.
+// Replaces keras Conv2D(classes,(3,3),padding='same',name='final_conv') built by segmentation_models
+// (reference segmentation.py:155).  Backward computes dX, dW and dbias in two passes.
+#include "common.cuh"
+
+namespace stp {
+
+constexpr int kHeadMaxCin = 64;
+constexpr int kHeadMaxCls = 4;
+
+__global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int H, int W,
+                                                       int Cin, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, int classes,
+                                                       float* __restrict__ logits, int64_t M) {
+  __shared__ float ws[kHeadMaxCls * 9 * kHeadMaxCin];
+  for (int i = threadIdx.x; i < classes * 9 * Cin; i += blockDim.x) ws[i] = __bfloat162float(__float2bfloat16(w[i]));  // weights are bf16 in compute
+  __syncthreads();
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = m / ((int64_t)H * W);
+    int rem = (int)(m - n * (int64_t)H * W);
+    int h = rem / W, wq = rem - h * W;
+    float acc[kHeadMaxCls];
+#pragma unroll
+    for (int c = 0; c < kHeadMaxCls; ++c) acc[c] = (bias && c < classes) ? bias[c] : 0.f;
+    for (int r = 0; r < 3; ++r) {
+      int hi = h + r - 1;
+      if (hi < 0 || hi >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        int wi = wq + s - 1;
+        if (wi < 0 || wi >= W) continue;
+        const __nv_bfloat16* px = x + ((n * H + hi) * (int64_t)W + wi) * ldx;
+        for (int v = 0; v < Cin / 8; ++v) {
+          float f[8];
+          unpack8(ld8(px + v * 8), f);
+#pragma unroll
+          for (int c = 0; c < kHeadMaxCls; ++c) {
+            if (c < classes) {
+              const float* wp = ws + ((c * 3 + r) * 3 + s) * Cin + v * 8;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc[c] += f[k] * wp[k];
+            }
+          }
+        }
+      }
+    }
+    for (int c = 0; c < classes; ++c) logits[m * classes + c] = acc[c];
+  }
+}
+
+// dx[m][ci] = sum_{r,s,c} dl[m - off(r,s)][c] * w[c][r][s][ci]   (off = (r-1, s-1))
+__global__ void __launch_bounds__(256) head_dgrad_kernel(const float* __restrict__ dl, int H, int W, int Cin,
+                                                         const float* __restrict__ w, int classes,
+                                                         __nv_bfloat16* __restrict__ dx, int lddx, int64_t M) {
+  __shared__ float ws[kHeadMaxCls * 9 * kHeadMaxCin];
+  for (int i = threadIdx.x; i < classes * 9 * Cin; i += blockDim.x) ws[i] = __bfloat162float(__float2bfloat16(w[i]));  // weights are bf16 in compute
+  __syncthreads();
+  const int cv = Cin / 8;
+  const int64_t total = M * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t m = i / cv;
+    int v = (int)(i - m * cv);
+    int64_t n = m / ((int64_t)H * W);
+    int rem = (int)(m - n * (int64_t)H * W);
+    int h = rem / W, wq = rem - h * W;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int r = 0; r < 3; ++r) {
+      int ho = h - (r - 1);
+      if (ho < 0 || ho >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        int wo = wq - (s - 1);
+        if (wo < 0 || wo >= W) continue;
+        const float* g = dl + ((n * H + ho) * (int64_t)W + wo) * classes;
+        for (int c = 0; c < classes; ++c) {
+          float gc = g[c];
+          const float* wp = ws + ((c * 3 + r) * 3 + s) * Cin + v * 8;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] += gc * wp[k];
+        }
+      }
+    }
+    st8(dx + m * lddx + v * 8, pack8(acc));
+  }
+}
+
+// dw[c][r][s][ci] = sum_m dl[m][c] * x[m + off(r,s)][ci]  ==  sum_p x[p][ci] * dl[p - off][c]
+// each thread owns one 8-channel vector of one pixel per iteration and 9 taps x 8 accumulators.
+__global__ void __launch_bounds__(256) head_wgrad_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int H, int W,
+                                                         int Cin, const float* __restrict__ dl, int classes, int cls,
+                                                         float* __restrict__ partial, int64_t M) {
+  // partial[blk][9][Cin] for class `cls`, and [blk][9*Cin] slot for dbias at index 9*Cin
+  const int cv = Cin / 8;
+  const int v = threadIdx.x % cv;          // fixed channel vector per thread (blockDim % cv == 0)
+  const int lanes = blockDim.x / cv;       // pixels per block iteration
+  const int pl = threadIdx.x / cv;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
+  float bsum = 0.f;
+  for (int64_t p = (int64_t)blockIdx.x * lanes + pl; p < M; p += (int64_t)gridDim.x * lanes) {
+    int64_t n = p / ((int64_t)H * W);
+    int rem = (int)(p - n * (int64_t)H * W);
+    int h = rem / W, wq = rem - h * W;
+    float f[8];
+    unpack8(ld8(x + p * ldx + v * 8), f);
+    if (v == 0) bsum += dl[p * classes + cls];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      int ho = h - (r - 1);
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        int wo = wq - (s - 1);
+        float g = 0.f;
+        if (ho >= 0 && ho < H && wo >= 0 && wo < W) g = dl[((n * H + ho) * (int64_t)W + wo) * classes + cls];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[r * 3 + s][k] += f[k] * g;
+      }
+    }
+  }
+  extern __shared__ float sm[];  // [blockDim][73]
+  float* mine = sm + (size_t)threadIdx.x * 73;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mine[t * 8 + k] = acc[t][k];
+  mine[72] = bsum;
+  __syncthreads();
+  float* out = partial + (int64_t)blockIdx.x * (9 * Cin + 1);
+  for (int i = threadIdx.x; i < 9 * Cin + 1; i += blockDim.x) {
+    float a = 0.f;
+    if (i == 9 * Cin) {
+      for (int l = 0; l < lanes; ++l) a += sm[(size_t)(l * cv) * 73 + 72];
+    } else {
+      int t = i / Cin, ci = i - t * Cin;
+      int vv = ci / 8, k = ci - vv * 8;
+      for (int l = 0; l < lanes; ++l) a += sm[(size_t)(l * cv + vv) * 73 + t * 8 + k];
+    }
+    out[i] = a;
+  }
+}
+
+__global__ void head_wgrad_final_kernel(const float* __restrict__ partial, int nblk, int Cin, int cls,
+                                        float* __restrict__ dw, float* __restrict__ dbias) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = 9 * Cin + 1;
+  if (i >= n) return;
+  double a = 0.0;
+  for (int b = 0; b < nblk; ++b) a += (double)partial[(int64_t)b * n + i];
+  if (i == 9 * Cin) {
+    if (dbias) dbias[cls] = (float)a;
+  } else {
+    dw[(int64_t)cls * 9 * Cin + i] = (float)a;
+  }
+}
+
+constexpr int kHeadWgradBlocks = kNumSMs * 2;
+
+}  // namespace stp
+
+using namespace stp;
+
+extern "C" int stp_head_fwd(const stp_tensor* x, const float* w_krsc_f32, const float* bias, int32_t classes,
+                            float* logits, stp_stream stream) {
+  STP_REQUIRE(vec_ok(x) && w_krsc_f32 && logits, "head_fwd: bad args");
+  STP_REQUIRE(classes >= 1 && classes <= kHeadMaxCls && x->c <= kHeadMaxCin, "head_fwd: classes<=4, Cin<=64");
+  int64_t M = pixels(x);
+  int64_t nb = (M + 255) / 256;
+  head_fwd_kernel<<<(int)(nb < kNumSMs * 16 ? nb : kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x->ptr, x->ld, x->h, x->w, x->c, w_krsc_f32, bias, classes, logits, M);
+  return check_launch("head_fwd");
+}
+
+extern "C" size_t stp_head_bwd_workspace(const stp_tensor* x, int32_t classes) {
+  (void)classes;
+  return (size_t)kHeadWgradBlocks * (9 * (size_t)x->c + 1) * sizeof(float);
+}
+
+extern "C" int stp_head_bwd(const stp_tensor* x, const float* w_krsc_f32, const float* dlogits, int32_t classes,
+                            const stp_tensor* dx, float* dw, float* dbias, void* workspace, size_t workspace_bytes,
+                            stp_stream stream) {
+  STP_REQUIRE(vec_ok(x) && w_krsc_f32 && dlogits && dw, "head_bwd: bad args");
+  STP_REQUIRE(classes >= 1 && classes <= kHeadMaxCls && x->c <= kHeadMaxCin, "head_bwd: classes<=4, Cin<=64");
+  STP_REQUIRE(256 % (x->c / 8) == 0, "head_bwd: Cin/8 must divide 256");
+  if (workspace_bytes < stp_head_bwd_workspace(x, classes) || !workspace) {
+    set_error("head_bwd: workspace too small");
+    return STP_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t M = pixels(x);
+  if (dx) {
+    STP_REQUIRE(vec_ok(dx) && dx->c == x->c && pixels(dx) == M, "head_bwd: bad dx");
+    int64_t nb = (M * (x->c / 8) + 255) / 256;
+    head_dgrad_kernel<<<(int)(nb < kNumSMs * 16 ? nb : kNumSMs * 16), 256, 0, st>>>(
+        dlogits, x->h, x->w, x->c, w_krsc_f32, classes, (__nv_bfloat16*)dx->ptr, dx->ld, M);
+    int rc = check_launch("head_dgrad");
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(head_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(256 * 73 * sizeof(float)));
+    if (e != cudaSuccess) {
+      set_error("head_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return STP_E_CUDA;
+    }
+    attr_set = true;
+  }
+  for (int cls = 0; cls < classes; ++cls) {
+    head_wgrad_kernel<<<kHeadWgradBlocks, 256, 256 * 73 * sizeof(float), st>>>(
+        (const __nv_bfloat16*)x->ptr, x->ld, x->h, x->w, x->c, dlogits, classes, cls, (float*)workspace, M);
+    int rc = check_launch("head_wgrad");
+    if (rc) return rc;
+    head_wgrad_final_kernel<<<(9 * x->c + 1 + 127) / 128, 128, 0, st>>>((const float*)workspace, kHeadWgradBlocks,
+                                                                        x->c, cls, dw, dbias);
+    rc = check_launch("head_wgrad_final");
+    if (rc) return rc;
+  }
+  return STP_OK;
+}

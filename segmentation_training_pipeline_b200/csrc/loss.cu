@@ -1,0 +1,133 @@
+// K11/K14: fused sigmoid + binary_crossentropy + dice/iou loss + metrics, one pass over (logits, mask).
+// Formulas: keras.losses.binary_crossentropy (TF backend, from probabilities) and musket_core.losses
+// dice / iou_coef / iot_coef (reference segmentation.py:15-22).  fp32 math, precise
+// libm functions (no fast-math) so results track the fp32 oracle; deterministic two-stage reduction.
+#include "common.cuh"
+
+namespace stp {
+
+constexpr int kLossBlocks = kNumSMs * 8;
+constexpr int kLossSlots = 8;
+
+__device__ __forceinline__ float sigmoidf_precise(float z) { return 1.f / (1.f + expf(-z)); }
+
+__global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__ logits,
+                                                       const uint8_t* __restrict__ mask, int64_t count,
+                                                       float* __restrict__ partial) {
+  float s[kLossSlots];
+#pragma unroll
+  for (int i = 0; i < kLossSlots; ++i) s[i] = 0.f;
+  const float eps = 1e-7f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    float z = logits[i];
+    float t = (float)mask[i];
+    float p = sigmoidf_precise(z);
+    float pc = fminf(fmaxf(p, eps), 1.f - eps);
+    float x = logf(pc / (1.f - pc));
+    float l = fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
+    float hard = p > 0.5f ? 1.f : 0.f;
+    s[0] += l;
+    s[1] += p * t;
+    s[2] += p;
+    s[3] += t;
+    s[4] += (hard == t) ? 1.f : 0.f;
+    s[5] += hard * t;
+    s[6] += hard;
+  }
+  __shared__ float sm[kLossSlots][8];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < kLossSlots; ++i) {
+    float v = warp_sum(s[i]);
+    if (lane == 0) sm[i][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kLossSlots) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += sm[threadIdx.x][w];
+    partial[(int64_t)blockIdx.x * kLossSlots + threadIdx.x] = a;
+  }
+}
+
+__global__ void loss_finalize_kernel(const float* __restrict__ partial, int nblk, double count, float w_bce,
+                                     float w_dice, float w_iou, float* __restrict__ result) {
+  __shared__ double tot[kLossSlots];
+  if (threadIdx.x < kLossSlots) {
+    double a = 0.0;
+    for (int b = 0; b < nblk; ++b) a += (double)partial[(int64_t)b * kLossSlots + threadIdx.x];
+    tot[threadIdx.x] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double bce = tot[0] / count, I = tot[1], P = tot[2], T = tot[3];
+    double dice = (2.0 * I + 1.0) / (P + T + 1.0);
+    double iou = (I + 1.0) / (P + T - I + 1.0);
+    double Ih = tot[5], Ph = tot[6];
+    double iot = (Ih + 1.0) / (Ph + T - Ih + 1.0);
+    double loss = (double)w_bce * bce + (double)w_dice * (1.0 - dice) + (double)w_iou * (1.0 - iou);
+    result[STP_L_LOSS] = (float)loss;
+    result[STP_L_BCE] = (float)bce;
+    result[STP_L_DICE] = (float)dice;
+    result[STP_L_IOU] = (float)iou;
+    result[STP_L_ACC] = (float)(tot[4] / count);
+    result[STP_L_IOT] = (float)iot;
+    result[STP_L_SUM_P] = (float)P;
+    result[STP_L_SUM_T] = (float)T;
+    result[STP_L_SUM_PT] = (float)I;
+    result[STP_L_COUNT] = (float)count;
+    for (int i = 10; i < 16; ++i) result[i] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__ logits,
+                                                       const uint8_t* __restrict__ mask, int64_t count, float w_bce,
+                                                       float w_dice, float w_iou, const float* __restrict__ result,
+                                                       float* __restrict__ dlogits) {
+  const float eps = 1e-7f;
+  const float I = result[STP_L_SUM_PT], P = result[STP_L_SUM_P], T = result[STP_L_SUM_T];
+  const float inv_count = 1.f / (float)count;
+  const float S1 = P + T + 1.f;           // dice denominator
+  const float U1 = P + T - I + 1.f;       // iou denominator
+  const float dice_a = 2.f / S1, dice_b = (2.f * I + 1.f) / (S1 * S1);
+  const float iou_a = 1.f / U1, iou_b = (I + 1.f) / (U1 * U1);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    float z = logits[i];
+    float t = (float)mask[i];
+    float p = sigmoidf_precise(z);
+    float dp = 0.f;
+    if (w_bce != 0.f && p > eps && p < 1.f - eps) dp += w_bce * inv_count * (p - t) / (p * (1.f - p));
+    if (w_dice != 0.f) dp -= w_dice * (t * dice_a - dice_b);
+    if (w_iou != 0.f) dp -= w_iou * (t * iou_a - (1.f - t) * iou_b);
+    dlogits[i] = dp * p * (1.f - p);
+  }
+}
+
+}  // namespace stp
+
+using namespace stp;
+
+extern "C" size_t stp_loss_partial_floats(void) { return (size_t)kLossBlocks * kLossSlots; }
+
+extern "C" int stp_loss_fwd(const float* logits, const uint8_t* mask, int64_t count, const stp_loss_spec* h_spec,
+                            float* partial, float* result16, stp_stream stream) {
+  STP_REQUIRE(logits && mask && h_spec && partial && result16 && count > 0, "loss_fwd: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t nb = (count + 255) / 256;
+  int nblk = (int)(nb < kLossBlocks ? nb : kLossBlocks);
+  loss_fwd_kernel<<<nblk, 256, 0, st>>>(logits, mask, count, partial);
+  int rc = check_launch("loss_fwd");
+  if (rc) return rc;
+  loss_finalize_kernel<<<1, 32, 0, st>>>(partial, nblk, (double)count, h_spec->w_bce, h_spec->w_dice, h_spec->w_iou,
+                                         result16);
+  return check_launch("loss_finalize");
+}
+
+extern "C" int stp_loss_bwd(const float* logits, const uint8_t* mask, int64_t count, const stp_loss_spec* h_spec,
+                            const float* result16, float* dlogits, stp_stream stream) {
+  STP_REQUIRE(logits && mask && h_spec && result16 && dlogits && count > 0, "loss_bwd: bad args");
+  int64_t nb = (count + 255) / 256;
+  int nblk = (int)(nb < kLossBlocks ? nb : kLossBlocks);
+  loss_bwd_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(logits, mask, count, h_spec->w_bce, h_spec->w_dice,
+                                                          h_spec->w_iou, result16, dlogits);
+  return check_launch("loss_bwd");
+}

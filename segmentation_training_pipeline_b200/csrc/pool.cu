@@ -1,0 +1,141 @@
+// K7: MaxPooling2D forward (+argmax) / backward.  HBM-bound, 16-byte vectors over channels.
+// Semantics: ZeroPadding2D(pad) + MaxPooling2D(k, stride, 'valid') on post-ReLU data == max_pool(k, stride, pad)
+// with the FIRST maximum in (kh, kw) scan order taking the gradient.
+#include "common.cuh"
+
+namespace stp {
+
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int H, int W,
+                                                          int k, int stride, int pad, __nv_bfloat16* __restrict__ y,
+                                                          int ldy, int Ho, int Wo, uint8_t* __restrict__ argmax,
+                                                          int64_t rows_out, int C, int cv) {
+  int64_t total = rows_out * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / cv;
+    int v = (int)(i - r * cv);
+    int64_t n = r / ((int64_t)Ho * Wo);
+    int rem = (int)(r - n * (int64_t)Ho * Wo);
+    int ho = rem / Wo, wo = rem - ho * Wo;
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      best[c] = -INFINITY;
+      bi[c] = 0;
+    }
+    for (int a = 0; a < k; ++a) {
+      int hi = ho * stride - pad + a;
+      for (int b = 0; b < k; ++b) {
+        int wi = wo * stride - pad + b;
+        float f[8];
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+          unpack8(ld8(x + ((n * H + hi) * (int64_t)W + wi) * ldx + v * 8), f);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) f[c] = pad > 0 ? 0.f : -INFINITY;  // explicit ZeroPadding2D contributes zeros
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (f[c] > best[c]) {
+            best[c] = f[c];
+            bi[c] = a * k + b;
+          }
+      }
+    }
+    st8(y + r * ldy + v * 8, pack8(best));
+    if (argmax) {
+      uint2 pk;
+      pk.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+      pk.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+      *reinterpret_cast<uint2*>(argmax + r * C + v * 8) = pk;
+    }
+  }
+}
+
+// gather form: each input pixel looks at the <= ceil(k/stride)^2 windows covering it
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int Ho,
+                                                          int Wo, const uint8_t* __restrict__ argmax, int k,
+                                                          int stride, int pad, const __nv_bfloat16* __restrict__ res,
+                                                          int ldr, __nv_bfloat16* __restrict__ dx, int lddx, int H,
+                                                          int W, int64_t rows_in, int C, int cv) {
+  int64_t total = rows_in * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / cv;
+    int v = (int)(i - r * cv);
+    int64_t n = r / ((int64_t)H * W);
+    int rem = (int)(r - n * (int64_t)H * W);
+    int h = rem / W, w = rem - h * W;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    // windows ho with ho*stride - pad <= h <= ho*stride - pad + k - 1
+    int ho_hi = (h + pad) / stride;
+    int ho_lo = (h + pad - k + stride) / stride;  // ceil((h+pad-k+1)/stride) for non-negative numerators
+    if (h + pad - k + 1 <= 0) ho_lo = 0;
+    int wo_hi = (w + pad) / stride;
+    int wo_lo = (w + pad - k + stride) / stride;
+    if (w + pad - k + 1 <= 0) wo_lo = 0;
+    for (int ho = ho_lo; ho <= ho_hi && ho < Ho; ++ho) {
+      int a = h - (ho * stride - pad);
+      for (int wo = wo_lo; wo <= wo_hi && wo < Wo; ++wo) {
+        int b = w - (wo * stride - pad);
+        int idx = a * k + b;
+        int64_t ro = (n * Ho + ho) * (int64_t)Wo + wo;
+        uint2 pk = *reinterpret_cast<const uint2*>(argmax + ro * C + v * 8);
+        float g[8];
+        unpack8(ld8(dy + ro * lddy + v * 8), g);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t word = c < 4 ? pk.x : pk.y;
+          int am = (word >> (8 * (c & 3))) & 0xff;
+          if (am == idx) acc[c] += g[c];
+        }
+      }
+    }
+    if (res) {
+      float rf[8];
+      unpack8(ld8(res + r * ldr + v * 8), rf);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] += rf[c];
+    }
+    st8(dx + r * lddx + v * 8, pack8(acc));
+  }
+}
+
+static int ew_grid2(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace stp
+
+using namespace stp;
+
+extern "C" int stp_maxpool_fwd(const stp_tensor* x, int32_t k, int32_t stride, int32_t pad, const stp_tensor* y,
+                               uint8_t* argmax, stp_stream stream) {
+  STP_REQUIRE(vec_ok(x) && vec_ok(y), "maxpool_fwd: bad tensors");
+  STP_REQUIRE(k >= 1 && k <= 15 && stride >= 1 && y->c == x->c && y->n == x->n, "maxpool_fwd: bad args");
+  STP_REQUIRE(y->h == (x->h + 2 * pad - k) / stride + 1 && y->w == (x->w + 2 * pad - k) / stride + 1,
+              "maxpool_fwd: output size mismatch");
+  int64_t rows = pixels(y);
+  int cv = x->c / 8;
+  maxpool_fwd_kernel<<<ew_grid2(rows * cv), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x->ptr, x->ld, x->h, x->w, k, stride, pad, (__nv_bfloat16*)y->ptr, y->ld, y->h, y->w,
+      argmax, rows, x->c, cv);
+  return check_launch("maxpool_fwd");
+}
+
+extern "C" int stp_maxpool_bwd(const stp_tensor* dy, const uint8_t* argmax, int32_t k, int32_t stride, int32_t pad,
+                               const stp_tensor* residual, const stp_tensor* dx, stp_stream stream) {
+  STP_REQUIRE(vec_ok(dy) && vec_ok(dx) && argmax, "maxpool_bwd: bad tensors");
+  STP_REQUIRE(dy->c == dx->c && dy->n == dx->n, "maxpool_bwd: shape mismatch");
+  if (residual) STP_REQUIRE(vec_ok(residual) && residual->c == dx->c && pixels(residual) == pixels(dx), "maxpool_bwd: bad residual");
+  int64_t rows = pixels(dx);
+  int cv = dx->c / 8;
+  maxpool_bwd_kernel<<<ew_grid2(rows * cv), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy->ptr, dy->ld, dy->h, dy->w, argmax, k, stride, pad,
+      residual ? (const __nv_bfloat16*)residual->ptr : nullptr, residual ? residual->ld : 0, (__nv_bfloat16*)dx->ptr,
+      dx->ld, dx->h, dx->w, rows, dx->c, cv);
+  return check_launch("maxpool_bwd");
+}

@@ -1,0 +1,466 @@
+"""Static-graph training engine over libstp: explicit forward / backward op lists on preallocated NHWC bf16
+buffers, flat fp32 parameter / gradient / optimizer-state buffers, zero-copy concat (skip tensors are channel
+slices of the decoder's concat buffers), whole-step CUDA-graph capture.
+
+PyTorch is used for device memory, streams, CUDA graphs and torch.distributed only -- all arithmetic on the
+step path is libstp kernels (no autograd, no torch ops).  Mirrors what the reference reaches through
+keras Model.train_on_batch (reference segmentation.py:249-260 -> generic.Stage.execute -> fit_generator).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+
+BF16, F32, U8 = _lib.BF16, _lib.F32, _lib.U8
+_TORCH_DT = {BF16: torch.bfloat16, F32: torch.float32, U8: torch.uint8}
+_ESIZE = {BF16: 2, F32: 4, U8: 1}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Buf:
+    """NHWC device tensor, possibly a channel slice [c_off, c_off+c) of a wider root buffer (ld = root.c)."""
+
+    def __init__(self, net: "Net", n, h, w, c, dtype=BF16, root: Optional["Buf"] = None, c_off=0, name=""):
+        self.net, self.n, self.h, self.w, self.c, self.dtype, self.name = net, n, h, w, c, dtype, name
+        self.root = root.root if root is not None else self
+        self.c_off = c_off if root is None else root.c_off + c_off
+        if root is None:
+            self.storage = torch.zeros(n * h * w * c, dtype=_TORCH_DT[dtype], device=net.device)
+            self.ld = c
+        else:
+            self.storage = root.root.storage
+            self.ld = root.root.ld
+        ptr = self.storage.data_ptr() + self.c_off * _ESIZE[dtype]
+        self.st = _lib.Tensor(ptr, n, h, w, c, self.ld, dtype)
+        self.ref = C.byref(self.st)
+        self._grad: Optional[Buf] = None
+
+    @property
+    def rows(self):
+        return self.n * self.h * self.w
+
+    def slice(self, c_off, c, name="") -> "Buf":
+        return Buf(self.net, self.n, self.h, self.w, c, self.dtype, root=self, c_off=c_off, name=name)
+
+    def grad(self) -> "Buf":
+        if self._grad is None:
+            if self.root is self:
+                self._grad = Buf(self.net, self.n, self.h, self.w, self.c, self.dtype, name="d_" + self.name)
+            else:
+                self._grad = self.root.grad().slice(self.c_off, self.c, name="d_" + self.name)
+        return self._grad
+
+    def set_grad(self, g: "Buf"):
+        self._grad = g
+
+    def torch(self) -> torch.Tensor:
+        """[n,h,w,c] (strided) torch view, for tests / host access."""
+        full = self.storage.view(self.n, self.h, self.w, self.ld)
+        return full[..., self.c_off:self.c_off + self.c]
+
+    def key(self):
+        return (id(self.root), self.c_off, self.c)
+
+
+class Param:
+    def __init__(self, name, shape, kind, init):
+        self.name, self.shape, self.kind, self.init = name, tuple(shape), kind, init
+        self.size = int(np.prod(shape))
+        self.offset = -1  # in floats, into the flat buffers
+        self.trainable = True
+
+
+class Op:
+    acc: List[bool] = []
+
+    def prepare(self):
+        pass
+
+    def fwd(self):
+        pass
+
+    def bwd(self):
+        pass
+
+    def grad_writes(self) -> List[Buf]:
+        """grad buffers this op's bwd writes (in order), used to resolve first-writer vs accumulate."""
+        return []
+
+
+class Net:
+    def __init__(self, batch: int, device="cuda:0", seed: int = 0):
+        self.L = _lib.Lib()
+        self.device = torch.device(device)
+        self.batch = batch
+        self.ops: List[Op] = []
+        self.params: Dict[str, Param] = {}
+        self.buffers: Dict[str, torch.Tensor] = {}  # BN moving stats (fp32)
+        self.gen = np.random.default_rng(seed)
+        self.training = True
+        self.finalized = False
+        self._ws_bytes = 0
+        self._partial_floats = 2 * _lib.BN_MAX_PARTIALS * 8
+        self.encoder_param_names: List[str] = []
+
+    # ---- parameters ---------------------------------------------------------------------------
+    def add_param(self, name, shape, kind, init) -> Param:
+        assert name not in self.params, name
+        p = Param(name, shape, kind, init)
+        self.params[name] = p
+        return p
+
+    def need_ws(self, nbytes):
+        self._ws_bytes = max(self._ws_bytes, int(nbytes))
+
+    def need_partial(self, nfloats):
+        self._partial_floats = max(self._partial_floats, int(nfloats))
+
+    def finalize(self):
+        off = 0
+        for p in self.params.values():
+            p.offset = off
+            off += (p.size + 3) // 4 * 4
+        self.n_flat = max(off, 4)
+        dev = self.device
+        self.flat_p = torch.zeros(self.n_flat, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(self.n_flat, dtype=torch.float32, device=dev)
+        self.flat_wf = torch.zeros(self.n_flat, dtype=torch.bfloat16, device=dev)  # bf16 KRSC copies
+        self.flat_wd = torch.zeros(self.n_flat, dtype=torch.bfloat16, device=dev)  # bf16 dgrad-layout copies
+        self.ws = torch.zeros(max(self._ws_bytes, 16), dtype=torch.uint8, device=dev)
+        self.partial = torch.zeros(self._partial_floats, dtype=torch.float32, device=dev)
+        self.d_step = torch.zeros(1, dtype=torch.int64, device=dev)
+        host = np.zeros(self.n_flat, dtype=np.float32)
+        for p in self.params.values():
+            host[p.offset:p.offset + p.size] = p.init().reshape(-1)
+        self.flat_p.copy_(torch.from_numpy(host))
+        # resolve first-writer / accumulate for every grad buffer, in backward execution order
+        seen: List[Tuple[int, int, int]] = []
+
+        def covered(b: Buf):
+            rid, lo, c = b.key()
+            return any(r == rid and o <= lo and lo + c <= o + cc for (r, o, cc) in seen)
+
+        for op in reversed(self.ops):
+            acc = []
+            for g in op.grad_writes():
+                acc.append(covered(g))
+                seen.append(g.key())
+            op.acc = acc
+        for op in self.ops:
+            op.prepare()
+        self.finalized = True
+
+    # pointers into flat buffers
+    def pp(self, p: Param):
+        return self.flat_p.data_ptr() + 4 * p.offset
+
+    def pg(self, p: Param):
+        return self.flat_g.data_ptr() + 4 * p.offset
+
+    def pwf(self, p: Param):
+        return self.flat_wf.data_ptr() + 2 * p.offset
+
+    def pwd(self, p: Param):
+        return self.flat_wd.data_ptr() + 2 * p.offset
+
+    # ---- execution ----------------------------------------------------------------------------
+    def prep_weights(self):
+        st = _stream()
+        for op in self.ops:
+            if isinstance(op, Conv):
+                op.prep_weights(st)
+
+    def forward(self):
+        for op in self.ops:
+            op.fwd()
+
+    def backward(self):
+        for op in reversed(self.ops):
+            op.bwd()
+
+    # ---- weights in Keras layout ----------------------------------------------------------------
+    def get_grads(self) -> Dict[str, np.ndarray]:
+        """last backward's parameter gradients, Keras layouts (tests / debugging)."""
+        return self._export(self.flat_g, False)
+
+    def get_weights(self) -> Dict[str, np.ndarray]:
+        return self._export(self.flat_p, True)
+
+    def _export(self, flat, with_buffers) -> Dict[str, np.ndarray]:
+        host = flat.detach().cpu().numpy()
+        out = {}
+        for p in self.params.values():
+            a = host[p.offset:p.offset + p.size].reshape(p.shape)
+            if p.kind == "conv":  # KRSC(padded) -> Keras HWIO
+                cin = getattr(p, "cin_real", p.shape[3])
+                a = np.transpose(a[..., :cin], (1, 2, 3, 0))
+            out[p.name] = np.ascontiguousarray(a)
+        if with_buffers:
+            for k, v in self.buffers.items():
+                out[k] = v.detach().cpu().numpy().copy()
+        return out
+
+    def set_weights(self, d: Dict[str, np.ndarray], strict=True):
+        host = self.flat_p.detach().cpu().numpy().copy()
+        for p in self.params.values():
+            if p.name not in d:
+                if strict:
+                    raise KeyError(p.name)
+                continue
+            a = np.asarray(d[p.name], dtype=np.float32)
+            if p.kind == "conv":
+                a = np.transpose(a, (3, 0, 1, 2))  # HWIO -> KRSC
+                full = np.zeros(p.shape, dtype=np.float32)
+                full[..., :a.shape[3]] = a
+                a = full
+            host[p.offset:p.offset + p.size] = a.reshape(-1)
+        self.flat_p.copy_(torch.from_numpy(host))
+        for k, v in self.buffers.items():
+            if k in d:
+                v.copy_(torch.from_numpy(np.asarray(d[k], dtype=np.float32)))
+
+
+# -------------------------------------------------------------------------------------------------
+# ops
+# -------------------------------------------------------------------------------------------------
+class InputNorm(Op):
+    """bn_data (BatchNormalization(scale=False)) on the raw uint8 image fused with the bf16 cast and the
+    pad-to-8-channels; channel c_img is the constant-ones channel (see stp_stem_wgrad_post)."""
+
+    def __init__(self, net: Net, img: Buf, y: Buf, name: str, eps: float, momentum=0.99):
+        self.net, self.img, self.y, self.eps, self.momentum = net, img, y, eps, momentum
+        c = img.c
+        self.beta = net.add_param(name + "/beta", (c,), "beta", lambda: np.zeros(c, np.float32))
+        net.buffers[name + "/moving_mean"] = torch.zeros(c, device=net.device)
+        net.buffers[name + "/moving_variance"] = torch.ones(c, device=net.device)
+        self.mm, self.mv = net.buffers[name + "/moving_mean"], net.buffers[name + "/moving_variance"]
+        self.coef = torch.zeros(4 * c, device=net.device)
+        self.nblk = net.L.bn_nblk(img.rows, c)
+        net.need_partial(2 * self.nblk * 8)
+        net.ops.append(self)
+
+    def prepare(self):
+        pass
+
+    def fwd(self):
+        n, L, st = self.net, self.net.L, _stream()
+        c = self.img.c
+        if n.training:
+            L.bn_stats(self.img.ref, n.partial.data_ptr(), st)
+            L.bn_finalize(n.partial.data_ptr(), self.nblk, c, self.img.rows, None, n.pp(self.beta), self.eps,
+                          self.momentum, self.mm.data_ptr(), self.mv.data_ptr(), self.coef.data_ptr(), st)
+        else:
+            L.bn_coef_infer(None, n.pp(self.beta), self.mm.data_ptr(), self.mv.data_ptr(), self.eps, c,
+                            self.coef.data_ptr(), st)
+        L.stem_prep(self.img.storage.data_ptr(), self.img.n, self.img.h, self.img.w, c, self.coef.data_ptr(),
+                    self.y.ref, st)
+
+
+class Conv(Op):
+    def __init__(self, net: Net, x: Buf, y: Buf, name: str, k: int, stride=1, pad=0, residual: Optional[Buf] = None,
+                 bias=False, init="he_uniform", needs_dgrad=True, cin_real: Optional[int] = None,
+                 stem_beta: Optional[Param] = None, up=1):
+        self.net, self.x, self.y, self.name, self.k = net, x, y, name, k
+        self.residual, self.needs_dgrad = residual, needs_dgrad
+        self.desc = _lib.ConvDesc(k, k, stride, pad, pad, up, 0)
+        cin, cout = x.c, y.c
+        cr = cin_real or cin
+        fan_in, fan_out = k * k * cr, k * k * cout
+        lim = math.sqrt(6.0 / fan_in) if init == "he_uniform" else math.sqrt(6.0 / (fan_in + fan_out))
+
+        def mk():
+            # draw in Keras (kh,kw,Cin,Cout) order so the stream matches a Keras-layout initialiser, then -> KRSC
+            w = net.gen.uniform(-lim, lim, size=(k, k, cr, cout)).astype(np.float32)
+            full = np.zeros((cout, k, k, cin), np.float32)
+            full[..., :cr] = np.transpose(w, (3, 0, 1, 2))
+            return full
+
+        self.w = net.add_param(name + "/kernel", (cout, k, k, cin), "conv", mk)
+        self.w.cin_real = cr
+        self.b = net.add_param(name + "/bias", (cout,), "bias", lambda: np.zeros(cout, np.float32)) if bias else None
+        self.stem_beta = stem_beta
+        self.cin_real = cr
+        net.need_ws(net.L.conv_wgrad_workspace(C.byref(self.desc), x.ref, y.ref))
+        net.ops.append(self)
+
+    def grad_writes(self):
+        return [self.x.grad()] if self.needs_dgrad else []
+
+    def prepare(self):
+        n = self.net
+        self.dref = C.byref(self.desc)
+        self.res_ref = self.residual.ref if self.residual is not None else None
+        self.dy = self.y.grad()
+        if self.needs_dgrad:
+            self.dx = self.x.grad()
+            self.dx_res = self.dx.ref if self.acc[0] else None
+
+    def prep_weights(self, st):
+        n = self.net
+        c = self.w.shape
+        n.L.weight_prep(n.pp(self.w), n.pwf(self.w), n.pwd(self.w) if self.needs_dgrad else None, c[0], c[1], c[2],
+                        c[3], st)
+
+    def fwd(self):
+        n = self.net
+        n.L.conv_fwd(self.dref, self.x.ref, n.pwf(self.w), n.pp(self.b) if self.b else None, self.res_ref, self.y.ref,
+                     n.ws.data_ptr(), n.ws.numel(), _stream())
+
+    def bwd(self):
+        n, st = self.net, _stream()
+        if self.needs_dgrad:
+            n.L.conv_dgrad(self.dref, self.dy.ref, n.pwd(self.w), self.dx_res, self.dx.ref, n.ws.data_ptr(),
+                           n.ws.numel(), st)
+        n.L.conv_wgrad(self.dref, self.x.ref, self.dy.ref, n.pg(self.w), n.ws.data_ptr(), n.ws.numel(), st)
+        if self.stem_beta is not None:
+            c = self.w.shape
+            n.L.stem_wgrad_post(n.pg(self.w), n.pp(self.w), c[0], c[1], c[2], c[3], self.cin_real,
+                                n.pg(self.stem_beta), st)
+
+
+class BNRelu(Op):
+    """BatchNormalization (+ReLU) (+ fused UpSampling2D(2) on the output write)."""
+
+    def __init__(self, net: Net, x: Buf, y: Buf, name: str, eps: float, relu=True, up=1, momentum=0.99,
+                 extra_grad: Optional[Callable[[], Buf]] = None):
+        self.net, self.x, self.y, self.eps, self.relu, self.up, self.momentum = net, x, y, eps, relu, up, momentum
+        self.extra_grad = extra_grad
+        c = x.c
+        self.gamma = net.add_param(name + "/gamma", (c,), "gamma", lambda: np.ones(c, np.float32))
+        self.beta = net.add_param(name + "/beta", (c,), "beta", lambda: np.zeros(c, np.float32))
+        net.buffers[name + "/moving_mean"] = torch.zeros(c, device=net.device)
+        net.buffers[name + "/moving_variance"] = torch.ones(c, device=net.device)
+        self.mm, self.mv = net.buffers[name + "/moving_mean"], net.buffers[name + "/moving_variance"]
+        self.coef = torch.zeros(4 * c, device=net.device)
+        self.bcoef = torch.zeros(3 * c, device=net.device)
+        self.nblk = net.L.bn_nblk(x.rows, c)
+        net.need_partial(2 * self.nblk * c)
+        net.ops.append(self)
+
+    def grad_writes(self):
+        return [self.x.grad()]
+
+    def prepare(self):
+        self.dy = self.y.grad()
+        self.dx = self.x.grad()
+        extra = self.extra_grad() if self.extra_grad else None
+        if extra is not None and self.acc[0]:
+            raise RuntimeError("BNRelu: both identity-shortcut gradient and accumulate requested")
+        self.res_ref = extra.ref if extra is not None else (self.dx.ref if self.acc[0] else None)
+
+    def fwd(self):
+        n, L, st = self.net, self.net.L, _stream()
+        c = self.x.c
+        if n.training:
+            L.bn_stats(self.x.ref, n.partial.data_ptr(), st)
+            L.bn_finalize(n.partial.data_ptr(), self.nblk, c, self.x.rows, n.pp(self.gamma), n.pp(self.beta), self.eps,
+                          self.momentum, self.mm.data_ptr(), self.mv.data_ptr(), self.coef.data_ptr(), st)
+        else:
+            L.bn_coef_infer(n.pp(self.gamma), n.pp(self.beta), self.mm.data_ptr(), self.mv.data_ptr(), self.eps, c,
+                            self.coef.data_ptr(), st)
+        L.bn_apply(self.x.ref, self.coef.data_ptr(), int(self.relu), self.up, self.y.ref, st)
+
+    def bwd(self):
+        n, L, st = self.net, self.net.L, _stream()
+        c = self.x.c
+        L.bn_bwd_reduce(self.dy.ref, self.x.ref, self.coef.data_ptr(), int(self.relu), self.up, n.partial.data_ptr(), st)
+        L.bn_bwd_finalize(n.partial.data_ptr(), self.nblk, c, self.x.rows, self.coef.data_ptr(), n.pg(self.gamma),
+                          n.pg(self.beta), self.bcoef.data_ptr(), st)
+        L.bn_bwd_apply(self.dy.ref, self.x.ref, self.coef.data_ptr(), self.bcoef.data_ptr(), int(self.relu), self.up,
+                       self.res_ref, self.dx.ref, st)
+
+
+class MaxPool(Op):
+    def __init__(self, net: Net, x: Buf, y: Buf, k, stride, pad):
+        self.net, self.x, self.y, self.k, self.stride, self.pad = net, x, y, k, stride, pad
+        self.argmax = torch.zeros(y.rows * y.c, dtype=torch.uint8, device=net.device)
+        net.ops.append(self)
+
+    def grad_writes(self):
+        return [self.x.grad()]
+
+    def prepare(self):
+        self.dy, self.dx = self.y.grad(), self.x.grad()
+        self.res_ref = self.dx.ref if self.acc[0] else None
+
+    def fwd(self):
+        self.net.L.maxpool_fwd(self.x.ref, self.k, self.stride, self.pad, self.y.ref, self.argmax.data_ptr(), _stream())
+
+    def bwd(self):
+        self.net.L.maxpool_bwd(self.dy.ref, self.argmax.data_ptr(), self.k, self.stride, self.pad, self.res_ref,
+                               self.dx.ref, _stream())
+
+
+class Head(Op):
+    """final_conv (3x3 same, bias) -> logits f32 [M, classes]; sigmoid lives in the loss / predict kernels."""
+
+    def __init__(self, net: Net, x: Buf, classes: int, name="final_conv", init="glorot_uniform"):
+        self.net, self.x, self.classes = net, x, classes
+        cin = x.c
+        fan_in, fan_out = 9 * cin, 9 * classes
+        lim = math.sqrt(6.0 / (fan_in + fan_out)) if init == "glorot_uniform" else math.sqrt(6.0 / fan_in)
+
+        def mk():
+            w = net.gen.uniform(-lim, lim, size=(3, 3, cin, classes)).astype(np.float32)
+            return np.ascontiguousarray(np.transpose(w, (3, 0, 1, 2)))
+
+        self.w = net.add_param(name + "/kernel", (classes, 3, 3, cin), "conv", mk)
+        self.b = net.add_param(name + "/bias", (classes,), "bias", lambda: np.zeros(classes, np.float32))
+        self.logits = torch.zeros(x.rows * classes, dtype=torch.float32, device=net.device)
+        self.dlogits = torch.zeros(x.rows * classes, dtype=torch.float32, device=net.device)
+        net.need_ws(net.L.head_bwd_workspace(x.ref, classes))
+        net.ops.append(self)
+
+    def grad_writes(self):
+        return [self.x.grad()]
+
+    def prepare(self):
+        self.dx = self.x.grad()
+        if self.acc[0]:
+            raise RuntimeError("Head: accumulate into dx unsupported")
+
+    def fwd(self):
+        n = self.net
+        n.L.head_fwd(self.x.ref, n.pp(self.w), n.pp(self.b), self.classes, self.logits.data_ptr(), _stream())
+
+    def bwd(self):
+        n = self.net
+        n.L.head_bwd(self.x.ref, n.pp(self.w), self.dlogits.data_ptr(), self.classes, self.dx.ref, n.pg(self.w),
+                     n.pg(self.b), n.ws.data_ptr(), n.ws.numel(), _stream())
+
+
+class Loss(Op):
+    """w_bce*binary_crossentropy + w_dice*dice_loss + w_iou*iou_loss and the metrics, fused with the sigmoid."""
+
+    def __init__(self, net: Net, head: Head, mask: Buf, w_bce=1.0, w_dice=0.0, w_iou=0.0):
+        self.net, self.head, self.mask = net, head, mask
+        self.spec = _lib.LossSpec(w_bce, w_dice, w_iou)
+        self.result = torch.zeros(16, dtype=torch.float32, device=net.device)
+        self.lpartial = torch.zeros(net.L.loss_partial_floats(), dtype=torch.float32, device=net.device)
+        self.count = head.x.rows * head.classes
+        self.enabled = True
+        net.ops.append(self)
+
+    def prepare(self):
+        pass
+
+    def set_weights(self, w_bce, w_dice, w_iou):
+        self.spec = _lib.LossSpec(w_bce, w_dice, w_iou)
+
+    def fwd(self):
+        if self.enabled:
+            self.net.L.loss_fwd(self.head.logits.data_ptr(), self.mask.storage.data_ptr(), self.count,
+                                C.byref(self.spec), self.lpartial.data_ptr(), self.result.data_ptr(), _stream())
+
+    def bwd(self):
+        self.net.L.loss_bwd(self.head.logits.data_ptr(), self.mask.storage.data_ptr(), self.count, C.byref(self.spec),
+                            self.result.data_ptr(), self.head.dlogits.data_ptr(), _stream())

@@ -1,0 +1,144 @@
+"""ctypes binding of libstp.so (include/stp.h).  Fails LOUDLY when the CUDA library is missing: there is no
+CPU fallback for the product path (the oracle under /oracle is test infrastructure and is never imported here).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libstp.so")
+
+BF16, F32, U8 = 0, 1, 2
+OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_WORKSPACE = 0, -1, -2, -3, -4
+CONV_RELU, CONV_STATS = 1, 2
+L_LOSS, L_BCE, L_DICE, L_IOU, L_ACC, L_IOT, L_SUM_P, L_SUM_T, L_SUM_PT, L_COUNT = range(10)
+BN_MAX_PARTIALS = 1024
+
+
+class StpError(RuntimeError):
+    pass
+
+
+class Tensor(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+                ("ld", C.c_int32), ("dtype", C.c_int32)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("r", C.c_int32), ("s", C.c_int32), ("stride", C.c_int32), ("pad_h", C.c_int32),
+                ("pad_w", C.c_int32), ("up", C.c_int32), ("flags", C.c_int32)]
+
+
+class AugSpec(C.Structure):
+    _fields_ = [("fliplr_p", C.c_double), ("flipud_p", C.c_double), ("affine", C.c_int32),
+                ("scale_lo", C.c_double), ("scale_hi", C.c_double),
+                ("tx_lo", C.c_double), ("tx_hi", C.c_double), ("ty_lo", C.c_double), ("ty_hi", C.c_double),
+                ("rot_lo", C.c_double), ("rot_hi", C.c_double), ("shear_lo", C.c_double), ("shear_hi", C.c_double),
+                ("has_mul", C.c_int32), ("mul_lo", C.c_double), ("mul_hi", C.c_double),
+                ("has_add", C.c_int32), ("add_lo", C.c_int32), ("add_hi", C.c_int32), ("mul_rint", C.c_int32)]
+
+
+class AugSample(C.Structure):
+    _fields_ = [("m", C.c_double * 6), ("inv", C.c_double * 6), ("fliplr", C.c_int32), ("flipud", C.c_int32),
+                ("has_affine", C.c_int32), ("has_mul", C.c_int32), ("mul", C.c_float), ("add", C.c_int32),
+                ("src_index", C.c_int32), ("_pad", C.c_int32)]
+
+
+class LossSpec(C.Structure):
+    _fields_ = [("w_bce", C.c_float), ("w_dice", C.c_float), ("w_iou", C.c_float)]
+
+
+class GradXform(C.Structure):
+    _fields_ = [("scale", C.c_float), ("clipnorm", C.c_float), ("clipvalue", C.c_float), ("d_sumsq", C.c_void_p)]
+
+
+_P, _I32, _I64, _U64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
+_TP, _CDP = C.POINTER(Tensor), C.POINTER(ConvDesc)
+
+# name -> (restype, argtypes); every symbol include/stp.h declares
+SIGNATURES = {
+    "stp_version": (C.c_int, []),
+    "stp_last_error": (C.c_char_p, []),
+    "stp_launch_count": (_I64, []),
+    "stp_tc_enabled": (C.c_int, []),
+    "stp_set_tc_enabled": (None, [C.c_int]),
+    "stp_augment_draw": (C.c_int, [C.POINTER(AugSpec), _U64, _P, _I32, _I32, _I32, _I32, _P, _P]),
+    "stp_augment_apply": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "stp_conv_fwd": (C.c_int, [_CDP, _TP, _P, _P, _TP, _TP, _P, _SZ, _P]),
+    "stp_conv_dgrad": (C.c_int, [_CDP, _TP, _P, _TP, _TP, _P, _SZ, _P]),
+    "stp_conv_wgrad": (C.c_int, [_CDP, _TP, _TP, _P, _P, _SZ, _P]),
+    "stp_conv_wgrad_workspace": (_SZ, [_CDP, _TP, _TP]),
+    "stp_weight_prep": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    "stp_head_fwd": (C.c_int, [_TP, _P, _P, _I32, _P, _P]),
+    "stp_head_bwd": (C.c_int, [_TP, _P, _P, _I32, _TP, _P, _P, _P, _SZ, _P]),
+    "stp_head_bwd_workspace": (_SZ, [_TP, _I32]),
+    "stp_bn_nblk": (_I32, [_I64, _I32]),
+    "stp_bn_stats": (C.c_int, [_TP, _P, _P]),
+    "stp_bn_finalize": (C.c_int, [_P, _I32, _I32, _I64, _P, _P, _F, _F, _P, _P, _P, _P]),
+    "stp_bn_apply": (C.c_int, [_TP, _P, _I32, _I32, _TP, _P]),
+    "stp_bn_coef_infer": (C.c_int, [_P, _P, _P, _P, _F, _I32, _P, _P]),
+    "stp_bn_bwd_reduce": (C.c_int, [_TP, _TP, _P, _I32, _I32, _P, _P]),
+    "stp_bn_bwd_finalize": (C.c_int, [_P, _I32, _I32, _I64, _P, _P, _P, _P, _P]),
+    "stp_bn_bwd_apply": (C.c_int, [_TP, _TP, _P, _P, _I32, _I32, _TP, _TP, _P]),
+    "stp_relu_bwd": (C.c_int, [_TP, _TP, _I32, _TP, _TP, _P]),
+    "stp_stem_prep": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _TP, _P]),
+    "stp_stem_wgrad_post": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
+    "stp_maxpool_fwd": (C.c_int, [_TP, _I32, _I32, _I32, _TP, _P, _P]),
+    "stp_maxpool_bwd": (C.c_int, [_TP, _P, _I32, _I32, _I32, _TP, _TP, _P]),
+    "stp_copy_up": (C.c_int, [_TP, _I32, _TP, _P]),
+    "stp_add": (C.c_int, [_TP, _TP, _TP, _P]),
+    "stp_loss_fwd": (C.c_int, [_P, _P, _I64, C.POINTER(LossSpec), _P, _P, _P]),
+    "stp_loss_partial_floats": (_SZ, []),
+    "stp_loss_bwd": (C.c_int, [_P, _P, _I64, C.POINTER(LossSpec), _P, _P, _P]),
+    "stp_adam": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, C.POINTER(GradXform), _P, _P]),
+    "stp_sgd": (C.c_int, [_P, _P, _P, _I64, _F, _F, _I32, C.POINTER(GradXform), _P]),
+    "stp_rmsprop": (C.c_int, [_P, _P, _P, _I64, _F, _F, _F, C.POINTER(GradXform), _P]),
+    "stp_step_advance": (C.c_int, [_P, _P]),
+    "stp_sumsq": (C.c_int, [_P, _I64, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen libstp.so; raise if it was not built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise StpError("libstp.so not found at %s -- build it with `python -m segmentation_training_pipeline_b200.build` "
+                       "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().stp_last_error()
+        raise StpError("%s failed (%d): %s" % (what or "libstp call", rc, msg.decode() if msg else "?"))
+
+
+class Lib:
+    """Thin checked call layer: `L.conv_fwd(...)` == check(stp_conv_fwd(...))."""
+
+    def __init__(self):
+        self._lib = load()
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, "stp_" + name)
+        if fn.restype is C.c_int and name not in ("version", "tc_enabled"):
+            def wrapped(*a, _fn=fn, _name=name):
+                rc = _fn(*a)
+                if rc != 0:
+                    check(rc, "stp_" + _name)
+                return rc
+            setattr(self, name, wrapped)
+            return wrapped
+        setattr(self, name, fn)
+        return fn

@@ -1,0 +1,138 @@
+"""Model graph builders on the static-graph engine: what the reference builds at segmentation.py:96-155
+(createNet1 -> segmentation_models.Unet(backbone_name=..., ...)) [DEP segmentation_models==0.2.1,
+classification_models].  Layer / parameter names are the Keras names (weights exchangeable by name).
+
+Layout decisions: every skip tensor is written by its producer straight into the channel slice
+of the decoder's concat buffer, and every decoder stage output is written 2x-upsampled into the next
+concat buffer by its BN-apply kernel, so UpSampling2D + Concatenate cost no kernel and no extra traffic.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import engine as E
+
+ENC_BN_EPS = 2e-5   # classification_models get_bn_params()
+DEC_BN_EPS = 1e-3   # keras BatchNormalization default
+RESNET_REPS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3), "resnet50": (3, 4, 6, 3),
+               "resnet101": (3, 4, 23, 3), "resnet152": (3, 8, 36, 3)}
+RESNET_BOTTLENECK = {"resnet18": False, "resnet34": False, "resnet50": True, "resnet101": True, "resnet152": True}
+KNOWN_BACKBONES = sorted(RESNET_REPS)
+KNOWN_ARCHITECTURES = ["Unet"]
+
+
+class SegNet(E.Net):
+    """U-Net over a qubvel pre-activation ResNet; input uint8 NHWC image, target uint8 NHWC mask."""
+
+    def __init__(self, backbone="resnet34", classes=1, input_shape=(512, 512, 3), batch=16,
+                 decoder_filters=(256, 128, 64, 32, 16), device="cuda:0", seed=0,
+                 enc_init="he_uniform", dec_init="glorot_uniform", loss=(1.0, 0.0, 0.0)):
+        super().__init__(batch, device, seed)
+        backbone = backbone.lower()
+        if backbone not in RESNET_REPS:
+            print("Unknown backbone:" + backbone)
+            print("Known backbones:", KNOWN_BACKBONES)
+            raise ValueError("Unknown backbone")
+        H, W, CI = input_shape
+        if H % 32 or W % 32:
+            raise ValueError("input height/width must be divisible by 32")
+        if len(decoder_filters) != 5:
+            raise ValueError("decoder_filters must have 5 entries")
+        N = batch
+        reps, bott = RESNET_REPS[backbone], RESNET_BOTTLENECK[backbone]
+        exp = 4 if bott else 1
+        df = list(decoder_filters)
+        self.input_shape, self.classes, self.backbone = (H, W, CI), classes, backbone
+
+        self.img = E.Buf(self, N, H, W, CI, E.U8, name="image")
+        self.mask = E.Buf(self, N, H, W, classes, E.U8, name="mask")
+
+        # decoder concat buffers [up | skip]; skip channel counts per stage (0.2.1 skip names)
+        skip_c = [256 * exp, 128 * exp, 64 * exp, 64, 0]
+        up_c = [512 * exp] + df[:4]
+        cat: List[E.Buf] = []
+        for i in range(5):
+            s = 32 >> i  # input of stage i is at H/32 * 2^i after upsampling -> H / (16 >> i) ... computed below
+            hh, ww = H // (16 >> i) if i < 4 else H, W // (16 >> i) if i < 4 else W
+            cat.append(E.Buf(self, N, hh, ww, up_c[i] + skip_c[i], name="cat%d" % i))
+        skip_view = {  # keras layer name -> (stage index)
+            "stage4_unit1_relu1": 0, "stage3_unit1_relu1": 1, "stage2_unit1_relu1": 2, "relu0": 3}
+
+        def skip_buf(name, n, h, w, c):
+            if name in skip_view:
+                i = skip_view[name]
+                assert cat[i].h == h and cat[i].w == w and skip_c[i] == c, (name, cat[i].h, h, skip_c[i], c)
+                return cat[i].slice(up_c[i], c, name=name)
+            return E.Buf(self, n, h, w, c, name=name)
+
+        # ---- encoder ---------------------------------------------------------------------------
+        x0 = E.Buf(self, N, H, W, 8, name="bn_data")
+        inorm = E.InputNorm(self, self.img, x0, "bn_data", ENC_BN_EPS)
+        z = E.Buf(self, N, H // 2, W // 2, 64, name="conv0")
+        E.Conv(self, x0, z, "conv0", 7, stride=2, pad=3, init=enc_init, needs_dgrad=False, cin_real=CI,
+               stem_beta=inorm.beta)
+        relu0 = skip_buf("relu0", N, H // 2, W // 2, 64)
+        E.BNRelu(self, z, relu0, "bn0", ENC_BN_EPS)
+        x = E.Buf(self, N, H // 4, W // 4, 64, name="pooling0")
+        E.MaxPool(self, relu0, x, 3, 2, 1)
+        h, w = H // 4, W // 4
+        for stage, rep in enumerate(reps):
+            f = 64 * 2 ** stage
+            for block in range(rep):
+                pre = "stage%d_unit%d_" % (stage + 1, block + 1)
+                first = block == 0
+                stride = 2 if (first and stage > 0) else 1
+                ho, wo = h // stride, w // stride
+                y = skip_buf(pre + "relu1", N, h, w, x.c)
+                out = E.Buf(self, N, ho, wo, f * exp, name=pre + "add")
+                if first:
+                    E.BNRelu(self, x, y, pre + "bn1", ENC_BN_EPS)
+                    sc = E.Buf(self, N, ho, wo, f * exp, name=pre + "sc")
+                    E.Conv(self, y, sc, pre + "sc", 1, stride=stride, pad=0, init=enc_init)
+                    sc.set_grad(out.grad())  # d(shortcut) == d(sum)
+                    res = sc
+                else:
+                    E.BNRelu(self, x, y, pre + "bn1", ENC_BN_EPS, extra_grad=(lambda o=out: o.grad()))
+                    res = x
+                if bott:
+                    z1 = E.Buf(self, N, h, w, f, name=pre + "conv1")
+                    E.Conv(self, y, z1, pre + "conv1", 1, init=enc_init)
+                    a2 = E.Buf(self, N, h, w, f, name=pre + "relu2")
+                    E.BNRelu(self, z1, a2, pre + "bn2", ENC_BN_EPS)
+                    z2 = E.Buf(self, N, ho, wo, f, name=pre + "conv2")
+                    E.Conv(self, a2, z2, pre + "conv2", 3, stride=stride, pad=1, init=enc_init)
+                    a3 = E.Buf(self, N, ho, wo, f, name=pre + "relu3")
+                    E.BNRelu(self, z2, a3, pre + "bn3", ENC_BN_EPS)
+                    E.Conv(self, a3, out, pre + "conv3", 1, residual=res, init=enc_init)
+                else:
+                    z1 = E.Buf(self, N, ho, wo, f, name=pre + "conv1")
+                    E.Conv(self, y, z1, pre + "conv1", 3, stride=stride, pad=1, init=enc_init)
+                    a2 = E.Buf(self, N, ho, wo, f, name=pre + "relu2")
+                    E.BNRelu(self, z1, a2, pre + "bn2", ENC_BN_EPS)
+                    E.Conv(self, a2, out, pre + "conv2", 3, pad=1, residual=res, init=enc_init)
+                x, h, w = out, ho, wo
+        self.encoder_param_names = list(self.params.keys())
+        # bn1/relu1 written 2x-upsampled straight into the first concat buffer
+        E.BNRelu(self, x, cat[0].slice(0, up_c[0], name="relu1_up"), "bn1", ENC_BN_EPS, up=2)
+        self.encoder_param_names = list(self.params.keys())
+
+        # ---- decoder -----------------------------------------------------------------------------
+        for i, f in enumerate(df):
+            pre = "decoder_stage%d_" % i
+            cin = cat[i]
+            z1 = E.Buf(self, N, cin.h, cin.w, f, name=pre + "conv1")
+            E.Conv(self, cin, z1, pre + "conv1", 3, pad=1, init=dec_init)
+            a1 = E.Buf(self, N, cin.h, cin.w, f, name=pre + "relu1")
+            E.BNRelu(self, z1, a1, pre + "bn1", DEC_BN_EPS)
+            z2 = E.Buf(self, N, cin.h, cin.w, f, name=pre + "conv2")
+            E.Conv(self, a1, z2, pre + "conv2", 3, pad=1, init=dec_init)
+            if i < 4:
+                E.BNRelu(self, z2, cat[i + 1].slice(0, f, name=pre + "relu2_up"), pre + "bn2", DEC_BN_EPS, up=2)
+            else:
+                last = E.Buf(self, N, cin.h, cin.w, f, name=pre + "relu2")
+                E.BNRelu(self, z2, last, pre + "bn2", DEC_BN_EPS)
+        self.head = E.Head(self, last, classes, "final_conv", init=dec_init)
+        self.loss = E.Loss(self, self.head, self.mask, *loss)
+        self.finalize()

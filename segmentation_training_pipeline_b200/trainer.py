@@ -1,0 +1,195 @@
+"""One training step = [augment] -> weight prep -> forward -> loss -> backward -> [all-reduce] -> optimizer,
+all libstp kernels on one stream, captured once into a CUDA graph and replayed (no per-step host work, no
+host<->device copy on the step path when the sample pool is device resident).
+
+Replaces the reference's per-step path: imgaug BackgroundAugmenter queue -> np.array stack -> feed_dict H2D ->
+TF session.run (SURVEY.md 3.2 "HOT LOOP per step").
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .engine import _stream
+from .models import SegNet
+
+
+@dataclass
+class AugmentConfig:
+    """Device-fused subset of schemas/augmenters.raml: Fliplr, Flipud, Affine, Multiply, Add."""
+    fliplr: float = 0.0
+    flipud: float = 0.0
+    affine: bool = False
+    scale: Tuple[float, float] = (1.0, 1.0)
+    translate_x: Tuple[float, float] = (0.0, 0.0)
+    translate_y: Tuple[float, float] = (0.0, 0.0)
+    rotate: Tuple[float, float] = (0.0, 0.0)
+    shear: Tuple[float, float] = (0.0, 0.0)
+    multiply: Optional[Tuple[float, float]] = None
+    add: Optional[Tuple[int, int]] = None
+    mul_rint: bool = False
+    seed: int = 0
+
+    def enabled(self) -> bool:
+        return bool(self.fliplr or self.flipud or self.affine or self.multiply or self.add)
+
+    def to_c(self) -> _lib.AugSpec:
+        m = self.multiply or (1.0, 1.0)
+        a = self.add or (0, 0)
+        return _lib.AugSpec(self.fliplr, self.flipud, int(self.affine), self.scale[0], self.scale[1],
+                            self.translate_x[0], self.translate_x[1], self.translate_y[0], self.translate_y[1],
+                            self.rotate[0], self.rotate[1], self.shear[0], self.shear[1],
+                            int(self.multiply is not None), m[0], m[1], int(self.add is not None), int(a[0]), int(a[1]),
+                            int(self.mul_rint))
+
+
+class Trainer:
+    def __init__(self, net: SegNet, optimizer="Adam", lr=None, beta_1=0.9, beta_2=0.999, epsilon=1e-7, momentum=0.0,
+                 nesterov=False, rho=0.9, clipnorm=None, clipvalue=None, augment: Optional[AugmentConfig] = None,
+                 world_size=1, process_group=None):
+        self.net, self.L = net, net.L
+        self.opt = (optimizer or "Adam").lower()
+        if self.opt not in ("adam", "sgd", "rmsprop"):
+            raise ValueError("unknown optimizer " + str(optimizer))
+        self.lr = float(lr) if lr is not None else (0.01 if self.opt == "sgd" else 1e-3)
+        self.b1, self.b2, self.eps, self.mu, self.nesterov, self.rho = beta_1, beta_2, epsilon, momentum, nesterov, rho
+        self.clipnorm, self.clipvalue = clipnorm or 0.0, clipvalue or 0.0
+        dev = net.device
+        self.m = torch.zeros(net.n_flat, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(net.n_flat, dtype=torch.float32, device=dev) if self.opt == "adam" else None
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.sumsq_partial = torch.zeros(1024, dtype=torch.float32, device=dev)
+        self.world_size, self.pg = world_size, process_group
+        self.augment = augment if (augment is not None and augment.enabled()) else None
+        self.pool_img: Optional[torch.Tensor] = None
+        self.pool_mask: Optional[torch.Tensor] = None
+        self.aug_params = torch.zeros(net.batch * C.sizeof(_lib.AugSample), dtype=torch.uint8, device=dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._gx = _lib.GradXform(1.0 / world_size, self.clipnorm, self.clipvalue,
+                                  self.sumsq.data_ptr() if self.clipnorm > 0 else None)
+        self._ident = AugmentConfig()
+
+    # ---- data ---------------------------------------------------------------------------------
+    def set_pool(self, images: torch.Tensor, masks: torch.Tensor):
+        """Device-resident sample pool uint8 [P,H,W,C] / [P,H,W,classes]; step i draws samples (i*B+j) % P."""
+        H, W, CI = self.net.input_shape
+        assert images.dtype == torch.uint8 and masks.dtype == torch.uint8
+        assert tuple(images.shape[1:]) == (H, W, CI) and tuple(masks.shape[1:]) == (H, W, self.net.classes)
+        self.pool_img = images.to(self.net.device).contiguous()
+        self.pool_mask = masks.to(self.net.device).contiguous()
+
+    def set_batch(self, images: torch.Tensor, masks: torch.Tensor, non_blocking=True):
+        """Copy one (already augmented or raw) batch into the network's input buffers."""
+        self.net.img.storage.copy_(images.reshape(-1), non_blocking=non_blocking)
+        self.net.mask.storage.copy_(masks.reshape(-1), non_blocking=non_blocking)
+
+    # ---- pieces -------------------------------------------------------------------------------
+    def run_augment(self):
+        """pool -> (img, mask) input buffers through the fused K1 kernel (identity spec = plain gather)."""
+        net, st = self.net, _stream()
+        H, W, CI = net.input_shape
+        cfg = self.augment or self._ident
+        spec = cfg.to_c()
+        self.L.augment_draw(C.byref(spec), cfg.seed, net.d_step.data_ptr(), net.batch, self.pool_img.shape[0], H, W,
+                            self.aug_params.data_ptr(), st)
+        self.L.augment_apply(self.pool_img.data_ptr(), self.pool_mask.data_ptr(), self.aug_params.data_ptr(),
+                             net.img.storage.data_ptr(), net.mask.storage.data_ptr(), net.batch, H, W, CI, net.classes,
+                             int(cfg.mul_rint), st)
+
+    def allreduce(self):
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.net.flat_g, group=self.pg)
+
+    def run_optimizer(self):
+        net, st = self.net, _stream()
+        if self.clipnorm > 0:
+            self.L.sumsq(net.flat_g.data_ptr(), net.n_flat, self.sumsq_partial.data_ptr(), self.sumsq.data_ptr(), st)
+        gx = C.byref(self._gx)
+        if self.opt == "adam":
+            self.L.adam(net.flat_p.data_ptr(), net.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), net.n_flat,
+                        self.lr, self.b1, self.b2, self.eps, gx, net.d_step.data_ptr(), st)
+        elif self.opt == "sgd":
+            self.L.sgd(net.flat_p.data_ptr(), net.flat_g.data_ptr(), self.m.data_ptr(), net.n_flat, self.lr, self.mu,
+                       int(self.nesterov), gx, st)
+        else:
+            self.L.rmsprop(net.flat_p.data_ptr(), net.flat_g.data_ptr(), self.m.data_ptr(), net.n_flat, self.lr,
+                           self.rho, self.eps, gx, st)
+        self.L.step_advance(net.d_step.data_ptr(), st)
+
+    # ---- whole step ---------------------------------------------------------------------------
+    def step_eager(self, from_pool=True):
+        net = self.net
+        net.training = True
+        if from_pool and self.pool_img is not None:
+            self.run_augment()
+        net.prep_weights()
+        net.forward()
+        net.backward()
+        self.allreduce()
+        self.run_optimizer()
+
+    def capture(self, from_pool=True):
+        """Warm up eagerly once on a side stream, then capture the step into a CUDA graph."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        saved = self._snapshot()
+        with torch.cuda.stream(s):
+            self.step_eager(from_pool)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._restore(saved)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step_eager(from_pool)
+        self._restore(saved)  # capture does not execute, but be explicit
+        self.graph = g
+        return g
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.step_eager()
+
+    def loss_value(self) -> float:
+        return float(self.net.loss.result[_lib.L_LOSS].item())
+
+    def metrics(self) -> Dict[str, float]:
+        r = self.net.loss.result.detach().cpu().numpy()
+        return {"loss": float(r[_lib.L_LOSS]), "binary_crossentropy": float(r[_lib.L_BCE]), "dice": float(r[_lib.L_DICE]),
+                "iou": float(r[_lib.L_IOU]), "binary_accuracy": float(r[_lib.L_ACC]), "iot": float(r[_lib.L_IOT])}
+
+    # ---- state --------------------------------------------------------------------------------
+    def _snapshot(self):
+        n = self.net
+        return dict(p=n.flat_p.clone(), m=self.m.clone(), v=None if self.v is None else self.v.clone(),
+                    step=n.d_step.clone(), bufs={k: b.clone() for k, b in n.buffers.items()})
+
+    def _restore(self, s):
+        n = self.net
+        n.flat_p.copy_(s["p"])
+        self.m.copy_(s["m"])
+        if self.v is not None:
+            self.v.copy_(s["v"])
+        n.d_step.copy_(s["step"])
+        for k, b in n.buffers.items():
+            b.copy_(s["bufs"][k])
+
+    def state_dict(self):
+        n = self.net
+        return {"weights": n.get_weights(), "m": self.m.cpu().numpy(), "v": None if self.v is None else self.v.cpu().numpy(),
+                "step": int(n.d_step.item())}
+
+    def load_state_dict(self, d):
+        n = self.net
+        n.set_weights(d["weights"])
+        self.m.copy_(torch.from_numpy(d["m"]))
+        if self.v is not None and d.get("v") is not None:
+            self.v.copy_(torch.from_numpy(d["v"]))
+        n.d_step.fill_(int(d["step"]))

@@ -1,0 +1,142 @@
+"""CPU suite: pins the oracle against what CAN be pinned here (cv2 4.13, Random123 KATs, closed forms, sklearn)
+and checks graph bookkeeping.  The reference ships no tests/golden vectors."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import augment as OA
+from oracle import losses as OL
+from oracle import nn as ON
+from oracle import optim as OO
+from oracle import philox
+from oracle.models import SegModel
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_philox_random123_known_answers():
+    assert philox.philox4x32((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert philox.philox4x32((0xffffffff,) * 4, (0xffffffff,) * 2) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert philox.philox4x32((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+
+
+@pytest.mark.parametrize("hw", [(128, 128), (97, 131), (256, 256)])
+def test_fixedpoint_warp_equals_cv2(hw):
+    """the numpy restatement of cv2.warpAffine's fixed-point rule (what the CUDA kernel implements) is bit exact."""
+    H, W = hw
+    rng = np.random.default_rng(0)
+    spec = OA.AugSpec(affine=True, scale=(0.8, 1.5), translate_x=(-0.2, 0.2), translate_y=(-0.2, 0.2),
+                      rotate=(-16, 16), shear=(-16, 16))
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    msk = rng.integers(0, 2, (H, W, 1), dtype=np.uint8)
+    for s in range(10):
+        p = OA.draw_params(spec, 7, s, 3, H, W)
+        assert np.array_equal(OA.warp_cv2(img, p.matrix, False), OA.warp_fixedpoint(img, p.matrix, False))
+        assert np.array_equal(OA.warp_cv2(msk, p.matrix, True), OA.warp_fixedpoint(msk, p.matrix, True))
+
+
+def test_augment_golden_fixture():
+    """committed golden vectors (tests/golden/make_augment_golden.py) reproduce."""
+    d = np.load(os.path.join(GOLD, "augment_golden.npz"))
+    spec = OA.AugSpec(fliplr=0.5, flipud=0.5, affine=True, scale=(0.8, 1.5), translate_x=(-0.2, 0.2),
+                      translate_y=(-0.2, 0.2), rotate=(-16, 16), shear=(-16, 16), multiply=(0.8, 1.2), add=(-10, 10))
+    oi, om = OA.augment_batch(d["images"], d["masks"], spec, int(d["seed"]), int(d["step"]))
+    assert np.array_equal(oi, d["out_images"]) and np.array_equal(om, d["out_masks"])
+    for n in range(d["images"].shape[0]):
+        p = OA.draw_params(spec, int(d["seed"]), int(d["step"]), n, 64, 64)
+        assert np.allclose(p.matrix, d["matrices"][n], rtol=0, atol=1e-12)
+
+
+def test_identity_affine_is_identity():
+    img = np.random.default_rng(1).integers(0, 256, (33, 47, 3), dtype=np.uint8)
+    M = np.array([[1.0, 0, 0], [0, 1.0, 0]])
+    assert np.array_equal(OA.warp_fixedpoint(img, M, False), img)
+    assert np.array_equal(OA.warp_fixedpoint(img, M, True), img)
+
+
+def test_loss_known_answers():
+    t = torch.tensor([0.0, 1.0, 0.0, 1.0]).view(1, 2, 2, 1)
+    p = torch.full((1, 2, 2, 1), 0.5)
+    assert abs(float(OL.binary_crossentropy(t, p)) - math.log(2)) < 1e-6
+    assert abs(float(OL.dice_loss(t, t))) < 1e-6
+    assert abs(float(OL.dice(t, p)) - (2 * 1.0 + 1) / (2 + 2 + 1)) < 1e-6
+    assert abs(float(OL.iou(t, t)) - 1.0) < 1e-6
+    # Lovasz hinge, 4-pixel hand example (Berman, relu): labels 1,0,1,0 ; logits 2,-2,-0.5,0.5
+    lab = torch.tensor([1.0, 0.0, 1.0, 0.0])
+    lg = torch.tensor([2.0, -2.0, -0.5, 0.5])
+    # errors = 1 - lg*sign = [-1,-1,1.5,1.5]; sorted desc: 1.5(gt1),1.5(gt0),-1,-1 ; jaccard grads: 0.5, 1/6, ...
+    val = float(OL.lovasz_hinge_flat(lg, lab, act="relu"))
+    assert abs(val - (1.5 * 0.5 + 1.5 * (2.0 / 3 - 0.5))) < 1e-6
+    assert OL.parse_composite("binary_crossentropy+0.1*dice_loss") == [(1.0, "binary_crossentropy"), (0.1, "dice_loss")]
+
+
+def test_keras_adam_first_step():
+    p = {"w": torch.tensor([1.0, -2.0, 3.0])}
+    o = OO.Adam(p, lr=1e-3)
+    g = torch.tensor([0.5, -0.25, 1e-3])
+    o.step({"w": g})
+    lr_t = 1e-3 * math.sqrt(1 - 0.999) / (1 - 0.9)
+    expect = torch.tensor([1.0, -2.0, 3.0]) - lr_t * (0.1 * g) / (torch.sqrt(0.001 * g * g) + 1e-7)
+    assert torch.allclose(p["w"], expect, atol=1e-9)
+    assert abs(float(p["w"][0]) - (1.0 - 1e-3)) < 1e-6  # ~ lr * sign(g)
+
+
+def test_same_padding_rule_and_transpose():
+    assert ON.keras_same_pad(512, 3, 1) == (1, 1)
+    assert ON.keras_same_pad(512, 3, 2) == (0, 1)
+    assert ON.keras_same_pad(512, 7, 2) == (2, 3)
+    x = torch.randn(1, 4, 6, 6)
+    w4 = torch.randn(4, 4, 5, 4)  # (kh,kw,Cout,Cin)
+    assert ON.conv2d_transpose(x, w4, None, 2).shape == (1, 5, 12, 12)
+    w3 = torch.randn(3, 3, 5, 4)
+    assert ON.conv2d_transpose(x, w3, None, 2).shape == (1, 5, 12, 12)
+
+
+def test_tf1_bilinear_legacy_rule():
+    x = torch.arange(4.0).view(1, 1, 1, 4)
+    y = ON.resize_bilinear_tf1(x, 1, 8)
+    assert torch.allclose(y.flatten(), torch.tensor([0, 0.5, 1, 1.5, 2, 2.5, 3, 3]))
+    ya = ON.resize_bilinear_tf1(x, 1, 7, align_corners=True)
+    assert torch.allclose(ya.flatten(), torch.tensor([0, 0.5, 1, 1.5, 2, 2.5, 3]))
+
+
+@pytest.mark.parametrize("arch,bb,expected", [("Unet", "resnet34", 24421456), ("Unet", "vgg16", 19030608),
+                                              ("FPN", "resnet50", 28571328)])
+def test_model_conv_param_counts(arch, bb, expected):
+    """24.42 M / 19.03 M / 28.58 M conv parameters."""
+    m = SegModel(arch, bb, classes=1)
+    assert sum(p.numel() for k, p in m.params.items() if k.endswith("kernel")) == expected
+
+
+def test_unet_resnet34_layer_inventory():
+    m = SegModel("Unet", "resnet34", classes=1)
+    convs = [k for k in m.params if k.endswith("/kernel")]
+    assert len(convs) == 48
+    assert m.params["conv0/kernel"].shape == (7, 7, 3, 64)
+    assert m.params["decoder_stage0_conv1/kernel"].shape == (3, 3, 768, 256)
+    assert m.params["decoder_stage3_conv1/kernel"].shape == (3, 3, 128, 32)
+    assert m.params["decoder_stage4_conv1/kernel"].shape == (3, 3, 32, 16)
+    assert "bn_data/gamma" not in m.params and "bn_data/beta" in m.params
+
+
+def test_bf16_storage_mode_close_to_fp32():
+    torch.manual_seed(0)
+    a = SegModel("Unet", "resnet18", classes=1, storage="fp32")
+    b = SegModel("Unet", "resnet18", classes=1, storage="bf16")
+    b.load_numpy(a.state_numpy())
+    x = torch.rand(2, 64, 64, 3) * 255
+    with torch.no_grad():
+        ya, yb = a(x), b(x)
+    # bf16 storage is NOT within 1e-3 of fp32 through 40+ layers (tiny-batch BN amplifies it): this is why the
+    # engine is compared with the bf16-emulating oracle; here only a sanity bound on the mean deviation.
+    assert float((ya - yb).abs().mean()) < 0.02
+
+
+def test_kfold_split_is_sklearn():
+    from sklearn.model_selection import KFold
+    folds = list(KFold(n_splits=5, shuffle=True, random_state=33).split(np.arange(20)))
+    assert len(folds) == 5 and all(len(te) == 4 for _, te in folds)

@@ -1,0 +1,94 @@
+"""K1 augmentation parity: drawn parameters vs oracle/philox+augment (discrete draws exact, matrices to 1e-12),
+pixels/indices BIT EXACT vs cv2.warpAffine (the backend imgaug calls) given the device-drawn matrices."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from segmentation_training_pipeline_b200 import lib
+from tests.util import stream
+
+pytestmark = pytest.mark.gpu
+
+
+def _spec():
+    from oracle import augment as OA
+    o = OA.AugSpec(fliplr=0.5, flipud=0.5, affine=True, scale=(0.8, 1.5), translate_x=(-0.2, 0.2),
+                   translate_y=(-0.2, 0.2), rotate=(-16, 16), shear=(-16, 16), multiply=(0.8, 1.2), add=(-10, 10))
+    c = lib.AugSpec(0.5, 0.5, 1, 0.8, 1.5, -0.2, 0.2, -0.2, 0.2, -16, 16, -16, 16, 1, 0.8, 1.2, 1, -10, 10, 0)
+    return o, c
+
+
+def _draw(stp, cuda, cspec, seed, step, n, pool, h, w):
+    d_step = torch.tensor([step], dtype=torch.int64, device=cuda)
+    buf = torch.zeros(n * C.sizeof(lib.AugSample), dtype=torch.uint8, device=cuda)
+    stp.augment_draw(C.byref(cspec), seed, d_step.data_ptr(), n, pool, h, w, buf.data_ptr(), stream())
+    host = buf.cpu().numpy().tobytes()
+    return buf, [lib.AugSample.from_buffer_copy(host, i * C.sizeof(lib.AugSample)) for i in range(n)]
+
+
+@pytest.mark.parametrize("h,w", [(128, 128), (96, 132), (512, 512)])
+def test_draw_matches_oracle(stp, cuda, h, w):
+    from oracle import augment as OA
+    ospec, cspec = _spec()
+    n, pool, seed = 16, 64, 1234
+    for step in (0, 1, 7, 2 ** 33 + 5):
+        _, samples = _draw(stp, cuda, cspec, seed, step, n, pool, h, w)
+        for i, s in enumerate(samples):
+            sid = (step * n + i) % pool
+            p = OA.draw_params(ospec, seed, step, sid, h, w)
+            assert s.src_index == sid
+            assert bool(s.fliplr) == p.fliplr and bool(s.flipud) == p.flipud
+            assert s.add == p.add
+            assert np.float32(s.mul) == np.float32(p.mul)
+            m = np.array(list(s.m)).reshape(2, 3)
+            assert np.allclose(m, p.matrix, rtol=1e-12, atol=1e-10), (m, p.matrix)
+            inv = OA.invert_affine(m)
+            assert np.allclose(np.array(list(s.inv)), np.array(inv), rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("h,w", [(128, 128), (96, 132), (512, 512)])
+def test_apply_bit_exact_vs_cv2(stp, cuda, h, w):
+    from oracle import augment as OA
+    ospec, cspec = _spec()
+    n, pool, seed = 8, 8, 99
+    rng = np.random.default_rng(0)
+    imgs = rng.integers(0, 256, (pool, h, w, 3), dtype=np.uint8)
+    masks = (rng.random((pool, h, w, 1)) > 0.6).astype(np.uint8)
+    d_img, d_msk = torch.from_numpy(imgs).to(cuda), torch.from_numpy(masks).to(cuda)
+    total_bad = 0
+    for step in (0, 3):
+        buf, samples = _draw(stp, cuda, cspec, seed, step, n, pool, h, w)
+        out_i = torch.zeros((n, h, w, 3), dtype=torch.uint8, device=cuda)
+        out_m = torch.zeros((n, h, w, 1), dtype=torch.uint8, device=cuda)
+        stp.augment_apply(d_img.data_ptr(), d_msk.data_ptr(), buf.data_ptr(), out_i.data_ptr(), out_m.data_ptr(), n, h, w,
+                          3, 1, 0, stream())
+        gi, gm = out_i.cpu().numpy(), out_m.cpu().numpy()
+        for i, s in enumerate(samples):
+            p = OA.SampleParams(bool(s.fliplr), bool(s.flipud), np.array(list(s.m)).reshape(2, 3), True, float(s.mul),
+                                True, int(s.add))
+            ri, rm = OA.apply(imgs[s.src_index], masks[s.src_index], p, use_cv2=True)
+            total_bad += int((ri != gi[i]).sum()) + int((rm != gm[i]).sum())
+    assert total_bad == 0
+
+
+def test_identity_and_flip_only(stp, cuda):
+    from oracle import augment as OA
+    h, w, n = 40, 36, 4  # w % 4 == 0 vector path; also the scalar path below
+    rng = np.random.default_rng(1)
+    for ww in (w, 37):
+        imgs = rng.integers(0, 256, (n, h, ww, 3), dtype=np.uint8)
+        masks = rng.integers(0, 2, (n, h, ww, 1), dtype=np.uint8)
+        cspec = lib.AugSpec(0.5, 0.5, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 0, 0, 0, 0)
+        ospec = OA.AugSpec(fliplr=0.5, flipud=0.5)
+        buf, samples = _draw(stp, cuda, cspec, 5, 2, n, n, h, ww)
+        d_img, d_msk = torch.from_numpy(imgs).to(cuda), torch.from_numpy(masks).to(cuda)
+        out_i = torch.zeros((n, h, ww, 3), dtype=torch.uint8, device=cuda)
+        out_m = torch.zeros((n, h, ww, 1), dtype=torch.uint8, device=cuda)
+        stp.augment_apply(d_img.data_ptr(), d_msk.data_ptr(), buf.data_ptr(), out_i.data_ptr(), out_m.data_ptr(), n, h,
+                          ww, 3, 1, 0, stream())
+        for i, s in enumerate(samples):
+            p = OA.draw_params(ospec, 5, 2, s.src_index, h, ww)
+            ri, rm = OA.apply(imgs[s.src_index], masks[s.src_index], p)
+            assert np.array_equal(ri, out_i[i].cpu().numpy()) and np.array_equal(rm, out_m[i].cpu().numpy())

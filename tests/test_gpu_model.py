@@ -1,0 +1,129 @@
+"""End-to-end GPU parity: the engine's U-Net/ResNet forward, loss, gradients and training curve against the
+CPU oracle (bf16-storage emulation: the oracle rounds to bf16 exactly where the engine stores bf16)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, h, w, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randint(0, 256, (n, h, w, 3), generator=g, dtype=torch.uint8)
+    yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    mask = torch.zeros(n, h, w, 1, dtype=torch.uint8)
+    for i in range(n):
+        cy, cx, r = int(torch.randint(h // 4, 3 * h // 4, (1,), generator=g)), int(torch.randint(w // 4, 3 * w // 4, (1,), generator=g)), h // 4
+        mask[i, :, :, 0] = (((yy - cy) ** 2 + (xx - cx) ** 2) < r * r).to(torch.uint8)
+        img[i] = (img[i].float() * 0.5 + mask[i].float() * 100).clamp(0, 255).to(torch.uint8)
+    return img, mask
+
+
+def _perturb(weights, seed=1):
+    rng = np.random.default_rng(seed)
+    out = {}
+    for k, v in weights.items():
+        if k.endswith("/gamma"):
+            out[k] = (v + rng.uniform(-0.3, 0.3, v.shape)).astype(np.float32)
+        elif k.endswith("/beta") or k.endswith("/bias"):
+            out[k] = (v + rng.uniform(-0.2, 0.2, v.shape)).astype(np.float32)
+        else:
+            out[k] = v
+    return out
+
+
+@pytest.mark.parametrize("backbone,size,loss", [("resnet18", 64, (1.0, 1.0, 0.0)), ("resnet34", 64, (1.0, 1.0, 0.0)),
+                                                ("resnet50", 64, (1.0, 0.0, 0.0))])
+def test_forward_backward_parity(cuda, backbone, size, loss):
+    from oracle import losses as OL
+    from oracle.models import SegModel
+    from segmentation_training_pipeline_b200 import lib
+    from segmentation_training_pipeline_b200.models import SegNet
+    from segmentation_training_pipeline_b200.trainer import Trainer
+
+    n = 2
+    net = SegNet(backbone, classes=1, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=loss)
+    W = _perturb(net.get_weights())
+    net.set_weights(W)
+    tr = Trainer(net)
+    img, mask = _data(n, size, size)
+    tr.set_batch(img.cuda(), mask.cuda())
+    net.prep_weights()
+    net.forward()
+    net.backward()
+    torch.cuda.synchronize()
+    res = net.loss.result.cpu().numpy()
+    logits = net.head.logits.cpu().view(n, size, size, 1)
+    grads = net.get_grads()
+
+    om = SegModel("Unet", backbone, classes=1, input_shape=(size, size, 3), storage="bf16", update_moving=False)
+    assert set(om.params.keys()) == set(net.params.keys()), sorted(set(om.params.keys()) ^ set(net.params.keys()))
+    om.load_numpy(W)
+    y = om(img.float())
+    t = mask.float()
+    lo = loss[0] * OL.binary_crossentropy(t, y) + loss[1] * OL.dice_loss(t, y) + loss[2] * OL.iou_loss(t, y)
+    lo.backward()
+    ol = om.taps["logits"].detach().permute(0, 2, 3, 1)
+    err_logits = float((logits - ol).norm() / ol.norm())
+    print("logits rel err", err_logits, "loss", float(res[lib.L_LOSS]), float(lo))
+    assert err_logits < 2e-2
+    assert abs(float(res[lib.L_LOSS]) - float(lo)) < 1e-3 * max(1.0, abs(float(lo)))
+    worst = 0.0
+    for k, p in om.params.items():
+        go, ge = p.grad.numpy(), grads[k]
+        assert go.shape == ge.shape, (k, go.shape, ge.shape)
+        denom = np.linalg.norm(go) + 1e-12
+        e = float(np.linalg.norm(ge - go) / denom)
+        worst = max(worst, e)
+        assert e < 6e-2, (k, e, float(denom))
+    print("worst grad rel err", worst)
+
+
+def test_training_curve_parity(cuda):
+    """loss curve over 12 Adam steps (resnet18, 64x64, bs 4) vs the oracle with Keras Adam; also checks that
+    CUDA-graph replay == eager."""
+    from oracle import losses as OL, optim as OO
+    from oracle.models import SegModel
+    from segmentation_training_pipeline_b200.models import SegNet
+    from segmentation_training_pipeline_b200.trainer import Trainer
+
+    n, size, steps = 4, 64, 12
+    net = SegNet("resnet18", classes=1, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=(1.0, 1.0, 0.0))
+    W = net.get_weights()
+    img, mask = _data(n * 2, size, size, seed=3)
+    tr = Trainer(net, optimizer="Adam", lr=1e-3)
+    tr.set_pool(img, mask)
+    tr.capture()
+    curve = []
+    for s in range(steps):
+        tr.step()
+        curve.append(tr.loss_value())
+    om = SegModel("Unet", "resnet18", classes=1, input_shape=(size, size, 3), storage="bf16")
+    om.load_numpy(W)
+    opt = OO.Adam(om.params, lr=1e-3)
+    ocurve = []
+    for s in range(steps):
+        idx = [(s * n + j) % (2 * n) for j in range(n)]
+        y = om(img[idx].float())
+        t = mask[idx].float()
+        lo = OL.binary_crossentropy(t, y) + OL.dice_loss(t, y)
+        for p in om.params.values():
+            p.grad = None
+        lo.backward()
+        opt.step({k: p.grad for k, p in om.params.items()})
+        ocurve.append(float(lo))
+    print("engine", curve)
+    print("oracle", ocurve)
+    assert abs(curve[0] - ocurve[0]) < 1e-3 * max(1.0, abs(ocurve[0]))
+    for a, b in zip(curve, ocurve):
+        assert abs(a - b) < 3e-2 * max(1.0, abs(b)), (curve, ocurve)
+    # eager == graph replay on the same state
+    net2 = SegNet("resnet18", classes=1, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=(1.0, 1.0, 0.0))
+    net2.set_weights(W)
+    tr2 = Trainer(net2, optimizer="Adam", lr=1e-3)
+    tr2.set_pool(img, mask)
+    c2 = []
+    for s in range(3):
+        tr2.step_eager()
+        c2.append(tr2.loss_value())
+    assert c2 == curve[:3], (c2, curve[:3])

@@ -1,0 +1,360 @@
+"""GPU parity tests of every libstp kernel against the CPU oracle, called through the C ABI.
+
+Tolerances (stated per north_star: 1e-3 relative fp32; index work bit exact):
+  * f32 outputs (logits, dW, loss scalars): rel L2 error <= 1e-4 against fp32 math on the same bf16 operands
+  * bf16 outputs: rel L2 error <= 3e-3 (one bf16 rounding = 2^-9 max per element)
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from segmentation_training_pipeline_b200 import lib
+from tests.util import T, bf16_round, conv_ref, max_abs, rand_bf16, ref, rel_err, stream
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-4
+TOL_BF16 = 3e-3
+
+
+def _ws(nbytes, dev):
+    return torch.zeros(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+
+
+CONV_CASES = [
+    # n, h, w, cin, cout, k, stride, pad, up
+    (2, 16, 16, 64, 64, 3, 1, 1, 1),
+    (2, 16, 16, 64, 128, 3, 2, 1, 1),
+    (2, 16, 16, 64, 128, 1, 2, 0, 1),
+    (1, 32, 32, 8, 64, 7, 2, 3, 1),
+    (1, 24, 40, 32, 16, 3, 1, 1, 1),
+    (2, 8, 8, 128, 32, 3, 1, 1, 1),
+    (1, 8, 8, 256, 256, 3, 1, 1, 1),
+    (1, 9, 7, 16, 24, 3, 1, 1, 1),     # odd sizes, Cout not a tile multiple
+    (1, 8, 8, 64, 64, 1, 1, 0, 1),
+    (1, 8, 8, 32, 16, 4, 1, 2, 2),     # transposed-conv style zero insertion (k4 s2 'same': pad' = 2)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("tc", [0, 1])
+def test_conv_fwd_dgrad_wgrad(stp, cuda, case, tc):
+    n, h, w, cin, cout, k, stride, pad, up = case
+    stp.set_tc_enabled(tc)
+    try:
+        g = torch.Generator().manual_seed(hash(case) % 1000)
+        x = rand_bf16((n, h, w, cin), g)
+        wt = rand_bf16((cout, k, k, cin), g, scale=1.0 / math.sqrt(k * k * cin))
+        if up > 1:
+            ho, wo = h * up, w * up
+        else:
+            ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        res = rand_bf16((n, ho, wo, cout), g)
+        desc = lib.ConvDesc(k, k, stride, pad, pad, up, 0)
+        # ---- forward (bf16 out, with residual) ----
+        y = torch.zeros((n, ho, wo, cout), dtype=torch.bfloat16, device=cuda)
+        xs, ys, rs = T(x), T(y), T(res)
+        stp.conv_fwd(C.byref(desc), ref(xs), wt.data_ptr(), None, ref(rs), ref(ys), None, 0, stream())
+        yr = conv_ref(x, wt, stride, pad, up, (ho, wo)) + res.float().cpu()
+        assert rel_err(y, yr) < TOL_BF16
+        # ---- forward f32 out with bias ----
+        yf = torch.zeros((n, ho, wo, cout), dtype=torch.float32, device=cuda)
+        bias = torch.randn(cout, generator=g).to(cuda)
+        yfs = T(yf)
+        stp.conv_fwd(C.byref(desc), ref(xs), wt.data_ptr(), bias.data_ptr(), None, ref(yfs), None, 0, stream())
+        yr2 = conv_ref(x, wt, stride, pad, up, (ho, wo)) + bias.cpu()
+        assert rel_err(yf, yr2) < TOL_F32
+        # ---- autograd reference for dgrad / wgrad ----
+        xr = x.float().cpu().requires_grad_(True)
+        wr = wt.float().cpu().requires_grad_(True)
+        dy = rand_bf16((n, ho, wo, cout), g)
+        out = conv_ref_autograd(xr, wr, stride, pad, up, (ho, wo))
+        out.backward(dy.float().cpu())
+        # ---- dgrad ----
+        wm = wt.float().contiguous()
+        wf = torch.zeros_like(wt)
+        wd = torch.zeros_like(wt)
+        stp.weight_prep(wm.data_ptr(), wf.data_ptr(), wd.data_ptr(), cout, k, k, cin, stream())
+        assert torch.equal(wf, wt)
+        dx = torch.zeros_like(x)
+        dys, dxs = T(dy), T(dx)
+        stp.conv_dgrad(C.byref(desc), ref(dys), wd.data_ptr(), None, ref(dxs), None, 0, stream())
+        assert rel_err(dx, xr.grad) < TOL_BF16
+        # accumulate form (residual == output)
+        dx2 = x.clone()
+        dx2s = T(dx2)
+        stp.conv_dgrad(C.byref(desc), ref(dys), wd.data_ptr(), ref(dx2s), ref(dx2s), None, 0, stream())
+        assert rel_err(dx2, xr.grad + x.float().cpu()) < TOL_BF16
+        # ---- wgrad ----
+        nws = stp.conv_wgrad_workspace(C.byref(desc), ref(xs), ref(dys))
+        ws = _ws(nws, cuda)
+        dw = torch.zeros((cout, k, k, cin), dtype=torch.float32, device=cuda)
+        stp.conv_wgrad(C.byref(desc), ref(xs), ref(dys), dw.data_ptr(), ws.data_ptr(), ws.numel(), stream())
+        assert rel_err(dw, wr.grad) < TOL_F32
+        torch.cuda.synchronize()
+    finally:
+        stp.set_tc_enabled(1)
+
+
+def conv_ref_autograd(x_nhwc, w_krsc, stride, pad, up, out_hw):
+    x = x_nhwc.permute(0, 3, 1, 2)
+    w = w_krsc.permute(0, 3, 1, 2)
+    if up > 1:
+        n, c, h, ww = x.shape
+        z = torch.zeros(n, c, (h - 1) * up + 1, (ww - 1) * up + 1)
+        z[:, :, ::up, ::up] = x
+        x = z
+    R, S = w.shape[2], w.shape[3]
+    ho, wo = out_hw
+    pb = max((ho - 1) * stride + R - x.shape[2] - pad, 0)
+    pr = max((wo - 1) * stride + S - x.shape[3] - pad, 0)
+    x = F.pad(x, (pad, pr, pad, pb))
+    y = F.conv2d(x, w, None, stride=stride)[:, :, :ho, :wo]
+    return y.permute(0, 2, 3, 1)
+
+
+def test_conv_strided_views(stp, cuda):
+    """input and output as channel slices of wider buffers (zero-copy concat)."""
+    g = torch.Generator().manual_seed(5)
+    big_in = rand_bf16((2, 12, 12, 96), g)
+    big_out = torch.zeros((2, 12, 12, 80), dtype=torch.bfloat16, device=cuda)
+    wt = rand_bf16((32, 3, 3, 64), g, scale=0.05)
+    desc = lib.ConvDesc(3, 3, 1, 1, 1, 1, 0)
+    xs, ys = T(big_in, 32, 64), T(big_out, 16, 32)
+    stp.conv_fwd(C.byref(desc), ref(xs), wt.data_ptr(), None, None, ref(ys), None, 0, stream())
+    yr = conv_ref(big_in[..., 32:96], wt, 1, 1)
+    assert rel_err(big_out[..., 16:48], yr) < TOL_BF16
+    assert float(big_out[..., :16].abs().max()) == 0 and float(big_out[..., 48:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("shape,up", [((2, 16, 16, 64), 1), ((2, 8, 8, 128), 2), ((1, 12, 20, 16), 1), ((3, 4, 4, 512), 2)])
+def test_batchnorm_fwd_bwd(stp, cuda, shape, up):
+    from oracle import nn as ON
+    n, h, w, c = shape
+    g = torch.Generator().manual_seed(c + up)
+    x = rand_bf16(shape, g, scale=2.0)
+    x = (x.float() + torch.randn(c, generator=g).to(cuda) * 0.5).to(torch.bfloat16)
+    gamma = (torch.rand(c, generator=g) + 0.5).to(cuda)
+    beta = (torch.randn(c, generator=g) * 0.2).to(cuda)
+    eps, mom = 2e-5, 0.99
+    rows = n * h * w
+    nblk = stp.bn_nblk(rows, c)
+    partial = torch.zeros(2 * nblk * c, device=cuda)
+    coef = torch.zeros(4 * c, device=cuda)
+    mm, mv = torch.zeros(c, device=cuda), torch.ones(c, device=cuda)
+    y = torch.zeros((n, h * up, w * up, c), dtype=torch.bfloat16, device=cuda)
+    xs, ys = T(x), T(y)
+    stp.bn_stats(ref(xs), partial.data_ptr(), stream())
+    stp.bn_finalize(partial.data_ptr(), nblk, c, rows, gamma.data_ptr(), beta.data_ptr(), eps, mom, mm.data_ptr(),
+                    mv.data_ptr(), coef.data_ptr(), stream())
+    stp.bn_apply(ref(xs), coef.data_ptr(), 1, up, ref(ys), stream())
+    # oracle
+    xc = x.float().cpu().permute(0, 3, 1, 2).requires_grad_(True)
+    gc, bc = gamma.cpu().requires_grad_(True), beta.cpu().requires_grad_(True)
+    yo, mean, var = ON.batchnorm_train(xc, gc, bc, eps)
+    yo = torch.relu(yo)
+    if up == 2:
+        yo = ON.upsample_nearest(yo, 2)
+    assert max_abs(coef[:c], mean) < 1e-4 * (1 + float(mean.abs().max()))
+    assert rel_err(coef[c:2 * c], torch.rsqrt(var + eps)) < 1e-5
+    assert rel_err(y, yo.permute(0, 2, 3, 1)) < TOL_BF16
+    unb = var * rows / (rows - 1)
+    assert rel_err(mv, 0.99 * torch.ones(c) + 0.01 * unb.detach()) < 1e-5
+    assert max_abs(mm, 0.01 * mean.detach()) < 1e-5
+    # backward
+    dy = rand_bf16((n, h * up, w * up, c), g)
+    yo.backward(dy.float().cpu().permute(0, 3, 1, 2))
+    bcoef = torch.zeros(3 * c, device=cuda)
+    dgamma, dbeta = torch.zeros(c, device=cuda), torch.zeros(c, device=cuda)
+    dx = torch.zeros_like(x)
+    dys, dxs = T(dy), T(dx)
+    stp.bn_bwd_reduce(ref(dys), ref(xs), coef.data_ptr(), 1, up, partial.data_ptr(), stream())
+    stp.bn_bwd_finalize(partial.data_ptr(), nblk, c, rows, coef.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                        bcoef.data_ptr(), stream())
+    stp.bn_bwd_apply(ref(dys), ref(xs), coef.data_ptr(), bcoef.data_ptr(), 1, up, None, ref(dxs), stream())
+    assert rel_err(dgamma, gc.grad) < 1e-3
+    assert rel_err(dbeta, bc.grad) < 1e-3
+    assert rel_err(dx, xc.grad.permute(0, 2, 3, 1)) < 5e-3
+    # with residual
+    r = rand_bf16(shape, g)
+    dx2 = torch.zeros_like(x)
+    rs, dx2s = T(r), T(dx2)
+    stp.bn_bwd_apply(ref(dys), ref(xs), coef.data_ptr(), bcoef.data_ptr(), 1, up, ref(rs), ref(dx2s), stream())
+    assert rel_err(dx2, xc.grad.permute(0, 2, 3, 1) + r.float().cpu()) < 5e-3
+
+
+def test_input_norm_u8(stp, cuda):
+    g = torch.Generator().manual_seed(1)
+    img = torch.randint(0, 256, (2, 32, 32, 3), generator=g, dtype=torch.uint8).to(cuda)
+    rows, c = 2 * 32 * 32, 3
+    nblk = stp.bn_nblk(rows, c)
+    partial = torch.zeros(2 * nblk * 8, device=cuda)
+    coef = torch.zeros(4 * c, device=cuda)
+    beta = torch.tensor([0.1, -0.2, 0.3], device=cuda)
+    ims = T(img)
+    stp.bn_stats(ref(ims), partial.data_ptr(), stream())
+    stp.bn_finalize(partial.data_ptr(), nblk, c, rows, None, beta.data_ptr(), 2e-5, 0.99, None, None, coef.data_ptr(),
+                    stream())
+    y = torch.zeros((2, 32, 32, 8), dtype=torch.bfloat16, device=cuda)
+    ys = T(y)
+    stp.stem_prep(img.data_ptr(), 2, 32, 32, 3, coef.data_ptr(), ref(ys), stream())
+    x = img.float().cpu()
+    mean, var = x.mean(dim=(0, 1, 2)), x.var(dim=(0, 1, 2), unbiased=False)
+    yo = (x - mean) * torch.rsqrt(var + 2e-5) + beta.cpu()
+    assert rel_err(y[..., :3], yo) < TOL_BF16
+    assert float((y[..., 3].float() - 1).abs().max()) == 0
+    assert float(y[..., 4:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("shape,k,s,p", [((2, 16, 16, 64), 3, 2, 1), ((1, 10, 14, 16), 3, 2, 1), ((2, 8, 8, 32), 2, 2, 0)])
+def test_maxpool(stp, cuda, shape, k, s, p):
+    n, h, w, c = shape
+    g = torch.Generator().manual_seed(3)
+    x = torch.relu(rand_bf16(shape, g))  # post-ReLU data, with exact ties at 0
+    ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    y = torch.zeros((n, ho, wo, c), dtype=torch.bfloat16, device=cuda)
+    am = torch.zeros(n * ho * wo * c, dtype=torch.uint8, device=cuda)
+    xs, ys = T(x), T(y)
+    stp.maxpool_fwd(ref(xs), k, s, p, ref(ys), am.data_ptr(), stream())
+    xc = x.float().cpu().permute(0, 3, 1, 2).requires_grad_(True)
+    yo = F.max_pool2d(xc, k, s, p)
+    assert torch.equal(y.float().cpu(), yo.permute(0, 2, 3, 1).detach())
+    dy = rand_bf16((n, ho, wo, c), g)
+    yo.backward(dy.float().cpu().permute(0, 3, 1, 2))
+    dx = torch.zeros_like(x)
+    dys, dxs = T(dy), T(dx)
+    stp.maxpool_bwd(ref(dys), am.data_ptr(), k, s, p, None, ref(dxs), stream())
+    # gradients routed to zero-valued (tied) inputs are masked by the ReLU upstream: compare where x > 0
+    mask = (x.float().cpu() > 0)
+    ref_dx = xc.grad.permute(0, 2, 3, 1)
+    assert rel_err(dx.float().cpu() * mask, ref_dx * mask) < TOL_BF16
+
+
+@pytest.mark.parametrize("classes,cin", [(1, 16), (3, 32)])
+def test_head(stp, cuda, classes, cin):
+    g = torch.Generator().manual_seed(7)
+    n, h, w = 2, 24, 16
+    x = rand_bf16((n, h, w, cin), g)
+    wt = bf16_round(torch.randn((classes, 3, 3, cin), generator=g) * 0.1).to(cuda)
+    bias = torch.randn(classes, generator=g).to(cuda)
+    logits = torch.zeros(n * h * w * classes, device=cuda)
+    xs = T(x)
+    stp.head_fwd(ref(xs), wt.data_ptr(), bias.data_ptr(), classes, logits.data_ptr(), stream())
+    xr = x.float().cpu().requires_grad_(True)
+    wr = wt.cpu().requires_grad_(True)
+    out = conv_ref_autograd(xr, wr, 1, 1, 1, (h, w)) + bias.cpu()
+    assert rel_err(logits.view(n, h, w, classes), out) < TOL_F32
+    dl = torch.randn((n, h, w, classes), generator=g).to(cuda)
+    out.backward(dl.cpu())
+    dx = torch.zeros_like(x)
+    dw = torch.zeros_like(wt)
+    db = torch.zeros(classes, device=cuda)
+    ws = _ws(stp.head_bwd_workspace(ref(xs), classes), cuda)
+    dxs = T(dx)
+    stp.head_bwd(ref(xs), wt.data_ptr(), dl.data_ptr(), classes, ref(dxs), dw.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                 ws.numel(), stream())
+    assert rel_err(dx, xr.grad) < TOL_BF16
+    assert rel_err(dw, wr.grad) < TOL_F32
+    assert rel_err(db, dl.cpu().sum(dim=(0, 1, 2))) < TOL_F32
+
+
+@pytest.mark.parametrize("weights", [(1.0, 0.0, 0.0), (1.0, 1.0, 0.0), (0.5, 0.1, 0.3)])
+def test_loss(stp, cuda, weights):
+    from oracle import losses as OL
+    g = torch.Generator().manual_seed(11)
+    count = 2 * 40 * 36
+    logits = (torch.randn(count, generator=g) * 3).to(cuda)
+    logits[:5] = torch.tensor([40.0, -40.0, 0.0, 17.0, -17.0])  # exercise the 1e-7 clip
+    mask = (torch.rand(count, generator=g) > 0.7).to(torch.uint8).to(cuda)
+    spec = lib.LossSpec(*weights)
+    partial = torch.zeros(stp.loss_partial_floats(), device=cuda)
+    result = torch.zeros(16, device=cuda)
+    stp.loss_fwd(logits.data_ptr(), mask.data_ptr(), count, C.byref(spec), partial.data_ptr(), result.data_ptr(), stream())
+    z = logits.cpu().requires_grad_(True)
+    t = mask.float().cpu().view(2, 40, 36, 1)
+    p = torch.sigmoid(z).view(2, 40, 36, 1)
+    lo = weights[0] * OL.binary_crossentropy(t, p) + weights[1] * OL.dice_loss(t, p) + weights[2] * OL.iou_loss(t, p)
+    r = result.cpu()
+    assert abs(float(r[lib.L_LOSS]) - float(lo)) <= 1e-5 * max(1.0, abs(float(lo)))
+    assert abs(float(r[lib.L_DICE]) - float(OL.dice(t, p))) < 1e-5
+    assert abs(float(r[lib.L_IOU]) - float(OL.iou(t, p))) < 1e-5
+    assert abs(float(r[lib.L_ACC]) - float(OL.binary_accuracy(t, p))) < 1e-6
+    assert abs(float(r[lib.L_IOT]) - float(OL.iot(t, p))) < 1e-5
+    lo.backward()
+    dl = torch.zeros(count, device=cuda)
+    stp.loss_bwd(logits.data_ptr(), mask.data_ptr(), count, C.byref(spec), result.data_ptr(), dl.data_ptr(), stream())
+    assert rel_err(dl, z.grad) < 1e-4
+
+
+def test_loss_known_answers(stp, cuda):
+    """closed forms: BCE(p=0.5) = ln 2; dice of identical hard masks -> loss ~ 0."""
+    count = 4096
+    spec = lib.LossSpec(1.0, 0.0, 0.0)
+    partial = torch.zeros(stp.loss_partial_floats(), device=cuda)
+    result = torch.zeros(16, device=cuda)
+    logits = torch.zeros(count, device=cuda)
+    mask = (torch.arange(count) % 2).to(torch.uint8).to(cuda)
+    stp.loss_fwd(logits.data_ptr(), mask.data_ptr(), count, C.byref(spec), partial.data_ptr(), result.data_ptr(), stream())
+    assert abs(float(result[lib.L_LOSS]) - math.log(2.0)) < 1e-6
+    spec = lib.LossSpec(0.0, 1.0, 0.0)
+    logits = (mask.float() * 2 - 1) * 50.0
+    stp.loss_fwd(logits.data_ptr(), mask.data_ptr(), count, C.byref(spec), partial.data_ptr(), result.data_ptr(), stream())
+    assert abs(float(result[lib.L_LOSS])) < 1e-6 and abs(float(result[lib.L_DICE]) - 1.0) < 1e-6
+
+
+@pytest.mark.parametrize("opt", ["adam", "sgd", "rmsprop"])
+def test_optimizers(stp, cuda, opt):
+    from oracle import optim as OO
+    g = torch.Generator().manual_seed(13)
+    n = 4096 + 8
+    p0 = torch.randn(n, generator=g)
+    params = {"p": p0.clone()}
+    if opt == "adam":
+        o = OO.Adam(params, lr=1e-3, clipnorm=1.0)
+    elif opt == "sgd":
+        o = OO.SGD(params, lr=0.01, momentum=0.9, nesterov=True, clipvalue=0.5)
+    else:
+        o = OO.RMSprop(params, lr=1e-3)
+    p = p0.clone().to(cuda)
+    m, v = torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    d_step = torch.zeros(1, dtype=torch.int64, device=cuda)
+    sumsq, part = torch.zeros(1, device=cuda), torch.zeros(1024, device=cuda)
+    for it in range(5):
+        gr = torch.randn(n, generator=g) * (3.0 if it % 2 else 0.01)
+        o.step({"p": gr})
+        gd = gr.to(cuda)
+        if opt == "adam":
+            stp.sumsq(gd.data_ptr(), n, part.data_ptr(), sumsq.data_ptr(), stream())
+            gx = lib.GradXform(1.0, 1.0, 0.0, sumsq.data_ptr())
+            stp.adam(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-7, C.byref(gx),
+                     d_step.data_ptr(), stream())
+        elif opt == "sgd":
+            gx = lib.GradXform(1.0, 0.0, 0.5, None)
+            stp.sgd(p.data_ptr(), gd.data_ptr(), m.data_ptr(), n, 0.01, 0.9, 1, C.byref(gx), stream())
+        else:
+            gx = lib.GradXform(1.0, 0.0, 0.0, None)
+            stp.rmsprop(p.data_ptr(), gd.data_ptr(), m.data_ptr(), n, 1e-3, 0.9, 1e-7, C.byref(gx), stream())
+        stp.step_advance(d_step.data_ptr(), stream())
+        assert max_abs(p, params["p"]) < 2e-6
+    assert int(d_step.item()) == 5
+
+
+def test_adam_first_step_known_answer(stp, cuda):
+    """Keras Adam, t=1: m=(1-b1)g, v=(1-b2)g^2, lr_t=lr*sqrt(1-b2)/(1-b1) -> dp = lr*g/(|g| + eps*sqrt(1-b2))...
+    i.e. |dp| ~= lr for |g| >> eps."""
+    n = 16
+    p = torch.zeros(n, device=cuda)
+    gvals = torch.tensor([1.0, -1.0, 1e-3, -1e-3] * 4, device=cuda)
+    m, v = torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    d_step = torch.zeros(1, dtype=torch.int64, device=cuda)
+    gx = lib.GradXform(1.0, 0.0, 0.0, None)
+    stp.adam(p.data_ptr(), gvals.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-7, C.byref(gx),
+             d_step.data_ptr(), stream())
+    lr_t = 1e-3 * math.sqrt(1 - 0.999) / (1 - 0.9)
+    expect = -lr_t * (0.1 * gvals.cpu()) / (torch.sqrt(0.001 * gvals.cpu() ** 2) + 1e-7)
+    assert max_abs(p, expect) < 1e-8
+    assert abs(float(p[0]) + 1e-3) < 1e-6
