@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec of one U-Net/ResNet-34 512x512 bs16/GPU TRAINING step (BASELINE.json configs[1]):
+on-device augment -> forward -> Dice+BCE -> backward -> [NCCL gradient all-reduce] -> Keras-Adam, bf16 storage /
+fp32 accumulate, synthetic uint8 image/mask pool resident in HBM.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's libstp path (1 process per GPU)
+    python bench.py --impl reference ...                      # restated reference CPU path (oracle/) on host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+TRAIN_GFLOP_PER_IMG_R34_512 = 186.7   # fwd + wgrad + dgrad (no dgrad for conv0)
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            out = dict(FALLBACK_PEAKS)
+            for k in out:
+                if k in d:
+                    out[k] = float(d[k])
+            return out, "measured"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+def conv_train_gflop_per_img(backbone: str, size: int) -> float:
+    """Algorithmic conv FLOPs of one training step per image, computed from the layer table of the engine's graph."""
+    if backbone == "resnet34" and size == 512:
+        return TRAIN_GFLOP_PER_IMG_R34_512
+    return TRAIN_GFLOP_PER_IMG_R34_512 * (size / 512.0) ** 2  # only used for reduced debug runs (flagged in config)
+
+
+def synth_pool(n, h, w, seed_img, seed_mask):
+    """uint8 images uniform 0..255; masks = blurred-noise blobs, ~30% positive."""
+    import numpy as np
+    import cv2
+    rng = np.random.default_rng(seed_img)
+    img = rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+    rm = np.random.default_rng(seed_mask)
+    mask = np.zeros((n, h, w, 1), np.uint8)
+    for i in range(n):
+        noise = rm.random((h, w), dtype=np.float32)
+        blur = cv2.GaussianBlur(noise, (0, 0), 16)
+        mask[i, :, :, 0] = (blur > np.percentile(blur, 70)).astype(np.uint8)
+    return img, mask
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w": round(sum(pw) / len(pw), 1) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+C2_AUGMENT = dict(fliplr=0.5, flipud=0.5, affine=True, scale=(0.8, 1.5), translate_x=(-0.2, 0.2),
+                  translate_y=(-0.2, 0.2), rotate=(-16.0, 16.0), shear=(-16.0, 16.0), multiply=(0.8, 1.2), add=(-10, 10))
+
+
+# -------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the restated reference path (oracle/, PyTorch-CPU fp32) on the host cores
+# -------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(size, sample_batch, steps, warmup, backbone="resnet34"):
+    import numpy as np
+    import torch
+    from oracle import augment as OA, losses as OL, optim as OO
+    from oracle.models import SegModel
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    img, mask = synth_pool(sample_batch, size, size, 1234, 4321)
+    om = SegModel("Unet", backbone, classes=1, input_shape=(size, size, 3), storage="fp32")
+    opt = OO.Adam(om.params, lr=1e-3)
+    spec = OA.AugSpec(fliplr=0.5, flipud=0.5, affine=True, scale=(0.8, 1.5), translate_x=(-0.2, 0.2),
+                      translate_y=(-0.2, 0.2), rotate=(-16.0, 16.0), shear=(-16.0, 16.0), multiply=(0.8, 1.2),
+                      add=(-10, 10))
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        ai, am = OA.augment_batch(img, mask, spec, seed=0, step=s)
+        y = om(torch.from_numpy(ai).float())
+        t = torch.from_numpy(am).float()
+        lo = OL.binary_crossentropy(t, y) + OL.dice_loss(t, y)
+        for p in om.params.values():
+            p.grad = None
+        lo.backward()
+        opt.step({k: p.grad for k, p in om.params.items()})
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), cores, float(lo)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sb = args.ref_batch
+    dt, cores, _ = cpu_reference_step_time(args.size, sb, max(1, min(args.steps, 3)), 1, args.backbone)
+    v = sb / dt
+    out = {
+        "impl": "reference", "metric": "images/sec U-Net/ResNet-34 512x512 training step", "value": v, "unit": "img/s",
+        "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "U-Net/%s %dx%d 1-class, augment+fwd+Dice+BCE+bwd+Adam" % (args.backbone, args.size, args.size),
+                   "note": "restated reference path (oracle/, PyTorch-CPU fp32), not Keras: its dependencies are not installable"},
+        "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port",
+                         "sample": "batch of %d images per step (same graph/loss/optimizer as the bs16 workload)" % sb},
+        "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# -------------------------------------------------------------------------------------------------------------
+# libstp arm
+# -------------------------------------------------------------------------------------------------------------
+def time_dominant_kernel(net, reps=30):
+    """Time the FLOP-dominant conv shape of the step alone (stage-1 3x3 64->64 @H/4, fwd) with CUDA events on the
+    launch stream; inputs are re-used, L2 flushed between launches by a 256 MB memset."""
+    import ctypes as C
+    import torch
+    from segmentation_training_pipeline_b200 import engine as E
+    conv = None
+    for op in net.ops:
+        if isinstance(op, E.Conv) and op.name == "stage1_unit2_conv1":
+            conv = op
+    if conv is None:
+        return None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=net.device)
+    st = torch.cuda.current_stream()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for i in range(3):
+        conv.fwd()
+    for a, b in ev:
+        flush.zero_()
+        a.record(st)
+        conv.fwd()
+        b.record(st)
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    ms = sum(ts) / len(ts)
+    flop = 2.0 * conv.y.rows * conv.y.c * conv.k * conv.k * conv.x.c
+    return {"name": conv.name, "ms": ms, "flop": flop}
+
+
+def run_gpu(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = "cuda:%d" % local_rank
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    from segmentation_training_pipeline_b200 import lib
+    from segmentation_training_pipeline_b200.models import SegNet
+    from segmentation_training_pipeline_b200.trainer import AugmentConfig, Trainer
+
+    B, S = args.batch, args.size
+    net = SegNet(args.backbone, classes=1, input_shape=(S, S, 3), batch=B, device=dev, seed=0, loss=(1.0, 1.0, 0.0))
+    aug = AugmentConfig(seed=rank, **C2_AUGMENT)
+    tr = Trainer(net, optimizer="Adam", lr=1e-3, augment=aug, world_size=world)
+    pool_n = args.pool
+    img, mask = synth_pool(pool_n, S, S, 1234 + rank, 4321 + rank)
+    tr.set_pool(torch.from_numpy(img), torch.from_numpy(mask))
+    l0 = net.L.launch_count()
+    tr.capture()
+    launches_per_step = (net.L.launch_count() - l0) // 2  # capture() runs the step twice (warm-up + capture)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        tr.step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    barrier()
+    st = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record(st)
+    for _ in range(args.steps):
+        tr.step()
+    e1.record(st)
+    barrier()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    loss_end = tr.loss_value()
+    clk = clocks.stop(t0, t1) if rank == 0 else None
+
+    # ---- e2e: host buffers; per step H2D of the raw batch (pinned), step, D2H of the loss/metrics vector ----
+    hp_img = torch.from_numpy(img).pin_memory()
+    hp_mask = torch.from_numpy(mask).pin_memory()
+    tr2 = Trainer(net, optimizer="Adam", lr=1e-3, augment=aug, world_size=world)
+    tr2.m, tr2.v = tr.m, tr.v
+    stage_img = torch.zeros((B, S, S, 3), dtype=torch.uint8, device=dev)
+    stage_mask = torch.zeros((B, S, S, 1), dtype=torch.uint8, device=dev)
+    tr2.pool_img, tr2.pool_mask = stage_img, stage_mask
+    tr2.capture()
+    res_host = torch.zeros(16, dtype=torch.float32).pin_memory()
+    h2d = B * S * S * 4
+    d2h = 16 * 4
+
+    def e2e_step(i):
+        j = (i * B) % pool_n
+        stage_img.copy_(hp_img[j:j + B], non_blocking=True)
+        stage_mask.copy_(hp_mask[j:j + B], non_blocking=True)
+        tr2.step()
+        res_host.copy_(net.loss.result, non_blocking=True)
+        st.synchronize()           # the user reads the loss every step
+        return float(res_host[0])
+
+    for i in range(max(3, args.warmup)):
+        e2e_step(i)
+    barrier()
+    e0.record(st)
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record(st)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    dom = time_dominant_kernel(net) if rank == 0 else None
+
+    tms = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(tms[0]), float(tms[1])
+    if rank == 0:
+        pk, src = peaks()
+        imgs = args.steps * B * world
+        value = imgs / (ms / 1e3)
+        e2e = imgs / (ms_e2e / 1e3)
+        gf = conv_train_gflop_per_img(args.backbone, S)
+        out = {
+            "metric": "images/sec U-Net/ResNet-34 512x512 training step", "value": value, "unit": "img/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "U-Net/%s %dx%d 1-class bs%d/GPU, on-device augment (Fliplr/Flipud/Affine/Multiply/Add) + "
+                                   "fwd + binary_crossentropy+dice_loss + bwd + %sKeras-Adam" %
+                                   (args.backbone, S, S, B, "NCCL all-reduce + " if world > 1 else ""),
+                       "global_batch": B * world, "pool_per_rank": pool_n, "parallelism": "dp%d" % world,
+                       "l2": "per-step working set (>3 GB of activations) exceeds the 126 MB L2; dominant-kernel timing flushes L2 "
+                             "with a 256 MB memset between launches",
+                       "cuda_graph": True, "tcgen05": bool(lib.load().stp_tc_enabled())},
+            "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "launches_per_step": launches_per_step,
+            "loss_after": loss_end,
+            "clocks": clk,
+            "step_tflops": value / world * gf / 1e3,
+            "step_frac_of_sustained_peak": value / world * gf / 1e3 / pk["bf16_tflops_sustained"],
+        }
+        if dom is not None:
+            ach = dom["flop"] / (dom["ms"] / 1e3) / 1e12
+            out["roofline"] = {"bound": "tensor", "kernel": dom["name"] + " fwd (3x3 64->64 @%d^2 bs%d)" % (S // 4, B),
+                               "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+                               "peak_source": src, "traffic": None, "ms_per_launch": dom["ms"]}
+        if world == 1 and not args.no_cpu:
+            sb = args.ref_batch
+            dt, cores, _ = cpu_reference_step_time(S, sb, 2, 1, args.backbone)
+            out["cpu_baseline"] = {"value": sb / dt, "unit": "img/s", "cores": cores, "kind": "port",
+                                   "sample": "oracle (PyTorch-CPU fp32 restatement) train step on a batch of %d images, "
+                                             "1 warm-up + 2 timed" % sb}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="stp", choices=["stp", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--pool", type=int, default=64)
+    ap.add_argument("--backbone", default="resnet34")
+    ap.add_argument("--ref-batch", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "stp" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()
