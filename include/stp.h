@@ -54,6 +54,8 @@ const char* stp_last_error(void);
 int64_t stp_launch_count(void);
 /* 1 if the tcgen05/TMA conv path is compiled in and enabled, 0 if only the mma.sync path is used */
 int stp_tc_enabled(void);
+/* number of tcgen05/TMA kernels enqueued since load (evidence that the tensor-core path, not the mma.sync one, ran) */
+int64_t stp_tc_launch_count(void);
 void stp_set_tc_enabled(int on);
 
 /* ------------------------------------------------------------------------------------------------

@@ -1,9 +1,379 @@
-// placeholder until the tcgen05 path lands
+// tcgen05 / TMA implicit-GEMM convolution for sm_100a (stride 1, any RxS, NHWC bf16, fp32 accumulate in TMEM).
+//
+//   Y[(n,ho,wo), co] = sum_{r,s,ci} X[n, ho+r-pad_h, wo+s-pad_w, ci] * W[co, r, s, ci]
+//
+// GEMM view: M = output pixels, N = Cout, K = R*S*Cin.  One CTA computes a 128 x BN tile whose 128 rows are a
+// BH x BW RECTANGLE of output pixels of one image (BH*BW = 128).  For filter tap (r,s) and channel block c0 the A
+// operand is the input rectangle shifted by (r-pad_h, s-pad_w): ONE 4-D TMA box {BK ch, BW, BH, 1} whose out-of-
+// range rows/columns are zero filled by the TMA unit == the convolution's zero padding, landing in shared memory
+// directly in the K-major 128B/64B/32B-swizzled layout tcgen05.mma reads.  The B operand is a 2-D TMA box
+// {BK, BN} of the [Cout][R*S*Cin] weight matrix.  No im2col buffer, no index arithmetic in the main loop.
+//
+// Warp roles (192 threads, persistent over tiles, 1 CTA / SM):
+//   warp 0      TMA producer (one elected lane) : ring of NS stages, full/empty mbarriers
+//   warp 1      TMEM allocator + MMA issuer (one elected lane): tcgen05.mma M=128 N=BN K=16, commit -> empty / accum-full
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> (+bias, +residual, ReLU) -> bf16/f32 NHWC stores;
+//               the accumulator is double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// dgrad of a stride-1 conv is the same kernel on dY with tap-flipped [Cin][R][S][Cout] weights (stp_weight_prep).
+// Replaces TF Conv2D / Conv2DBackpropInput reached from keras Conv2D in the graph built at reference
+// segmentation.py:109-113,155.
 #include "conv.h"
+#include "tc_common.cuh"
+
 namespace stp {
-bool tc_conv_supported(const ConvP&) { return false; }
-int launch_tc_conv(const ConvP&, cudaStream_t) { set_error("tc conv not built"); return STP_E_UNSUPPORTED; }
+
+// ---- host: tensor maps ------------------------------------------------------------------------------
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+bool make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, uint32_t swizzle_bytes) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return false;
+  }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rank %d dims %llu,%llu box %u,%u swz %u", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1], swizzle_bytes);
+    return false;
+  }
+  return true;
+}
+
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 227 * 1024;
+
+struct TcConvArgs {
+  void* y;
+  const __nv_bfloat16* res;
+  const float* bias;
+  int ldy, ldr, y_f32, relu;
+  int Ho, Wo, Cout, Cin;
+  int R, S, pad_h, pad_w;
+  int BW, BH, log2BW;  // pixel rectangle of a tile, BW*BH = 128
+  int tilesW, tilesH, tilesN, n_img;
+  int num_tiles;
+};
+
+template <int BN, int BK>
+struct TcCfg {
+  static constexpr int kABytes = 128 * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesRaw = (kSmemBudget - 2048) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvArgs a) {
+  using Cfg = TcCfg<BN, BK>;
+  constexpr int NS = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-B aligned stage buffers (swizzle atoms), barriers after them
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + NS * Cfg::kABytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * Cfg::kStageBytes);
+  uint64_t* empty = full + NS;
+  uint64_t* acc_full = empty + NS;   // [2]
+  uint64_t* acc_empty = acc_full + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kcb = a.Cin / BK;            // channel blocks per tap
+  const int num_kb = a.R * a.S * kcb;    // k blocks per tile
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int tile, int& img, int& h0, int& w0, int& n0) {
+    int tn = tile % a.tilesN;
+    int t = tile / a.tilesN;
+    int tw = t % a.tilesW;
+    t /= a.tilesW;
+    int th = t % a.tilesH;
+    img = t / a.tilesH;
+    h0 = th * a.BH;
+    w0 = tw * a.BW;
+    n0 = tn * BN;
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        int img, h0, w0, n0;
+        decode(tile, img, h0, w0, n0);
+        for (int tap = 0; tap < a.R * a.S; ++tap) {
+          const int r = tap / a.S, s = tap - r * a.S;
+          for (int cb = 0; cb < kcb; ++cb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+            tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], cb * BK, w0 + s - a.pad_w, h0 + r - a.pad_h, img);
+            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], tap * a.Cin + cb * BK, n0);
+            if (++stage == NS) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(128, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++local) {
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(&acc_empty[as], aphase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = desc_kmajor(a_addr + k * 32, BK * 2);
+            const uint64_t bd = desc_kmajor(b_addr + k * 32, BK * 2);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == NS) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&acc_full[as]);  // accumulator complete
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;          // tile row == TMEM lane
+    const int hl = m >> a.log2BW, wl = m & (a.BW - 1);
+    int local = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++local) {
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      int img, h0, w0, n0;
+      decode(tile, img, h0, w0, n0);
+      const int ho = h0 + hl, wo = w0 + wl;
+      const bool valid = ho < a.Ho && wo < a.Wo;
+      const int64_t pix = ((int64_t)img * a.Ho + ho) * a.Wo + wo;
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      constexpr int CH = BN >= 32 ? 32 : 16;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        uint32_t rr[CH];
+        if constexpr (CH == 32) tmem_ld32(t_addr + c0, rr); else tmem_ld16(t_addr + c0, rr);
+        tmem_ld_wait();
+        if (valid) {
+          float v[CH];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(rr[i]);
+          const int n = n0 + c0;
+          if (a.bias) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] += __ldg(a.bias + n + i);
+          }
+          if (a.res) {
+            const __nv_bfloat16* rp = a.res + pix * a.ldr + n;
+#pragma unroll
+            for (int i = 0; i < CH; i += 8) {
+              float f[8];
+              unpack8(ld8(rp + i), f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[i + j] += f[j];
+            }
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (a.y_f32) {
+            float* yp = reinterpret_cast<float*>(a.y) + pix * a.ldy + n;
+#pragma unroll
+            for (int i = 0; i < CH; i += 4) *reinterpret_cast<float4*>(yp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + pix * a.ldy + n;
+#pragma unroll
+            for (int i = 0; i < CH; i += 8) st8(yp + i, pack8(v + i));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+int pick_bn(int cout) {
+  for (int bn : {256, 128, 64, 32, 16})
+    if (cout % bn == 0) return bn;
+  return 0;
+}
+int pick_bk(int cin) {
+  if (cin % 64 == 0) return 64;
+  if (cin == 32) return 32;
+  if (cin == 16) return 16;
+  return 0;
+}
+
+template <int BN, int BK>
+int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvArgs& a, cudaStream_t st) {
+  using Cfg = TcCfg<BN, BK>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("conv_tc: cudaFuncSetAttribute(%d B): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      return STP_E_CUDA;
+    }
+    attr_set = true;
+  }
+  int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
+  conv_tc_kernel<BN, BK><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
+  g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("conv_tc");
+}
+
+}  // namespace
+
+bool tc_conv_supported(const ConvP& p) {
+  if (p.stride != 1 || p.up != 1) return false;
+  if (pick_bn(p.Cout) == 0 || pick_bk(p.Cin) == 0) return false;
+  if (p.Wo < 8 || p.Ho < 1) return false;
+  if (p.ldx % 8 != 0 || !aligned16(p.x) || !aligned16(p.w)) return false;
+  if (p.y_f32 ? (p.ldy % 4 != 0) : (p.ldy % 8 != 0)) return false;
+  if (!aligned16(p.y)) return false;
+  if (p.res && (p.ldr % 8 != 0 || !aligned16(p.res))) return false;
+  if (p.K % 8 != 0) return false;
+  if (p.H > 65535 || p.W > 65535) return false;
+  return get_encode_tiled() != nullptr;
+}
+
+int launch_tc_conv(const ConvP& p, cudaStream_t st) {
+  const int BN = pick_bn(p.Cout), BK = pick_bk(p.Cin);
+  TcConvArgs a;
+  a.y = p.y; a.res = p.res; a.bias = p.bias; a.ldy = p.ldy; a.ldr = p.ldr; a.y_f32 = p.y_f32; a.relu = p.relu;
+  a.Ho = p.Ho; a.Wo = p.Wo; a.Cout = p.Cout; a.Cin = p.Cin; a.R = p.R; a.S = p.S; a.pad_h = p.pad_h; a.pad_w = p.pad_w;
+  int bw = 128;
+  while (bw > 8 && bw / 2 >= p.Wo) bw /= 2;  // smallest power of two >= Wo, clamped to [8,128]
+  a.BW = bw; a.BH = 128 / bw;
+  a.log2BW = 0;
+  while ((1 << a.log2BW) < bw) ++a.log2BW;
+  a.tilesW = (p.Wo + a.BW - 1) / a.BW;
+  a.tilesH = (p.Ho + a.BH - 1) / a.BH;
+  a.tilesN = p.Cout / BN;
+  a.n_img = p.N;
+  int64_t nt = (int64_t)p.N * a.tilesH * a.tilesW * a.tilesN;
+  if (nt > 0x7fffffff) {
+    set_error("conv_tc: too many tiles");
+    return STP_E_UNSUPPORTED;
+  }
+  a.num_tiles = (int)nt;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
+    uint64_t strides[3] = {(uint64_t)p.ldx * 2, (uint64_t)p.W * p.ldx * 2, (uint64_t)p.H * p.W * p.ldx * 2};
+    uint32_t box[4] = {(uint32_t)BK, (uint32_t)a.BW, (uint32_t)a.BH, 1};
+    if (!make_tmap_bf16(&tmA, p.x, 4, dims, strides, box, BK * 2)) return STP_E_CUDA;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.Cout};
+    uint64_t strides[1] = {(uint64_t)p.K * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    if (!make_tmap_bf16(&tmB, p.w, 2, dims, strides, box, BK * 2)) return STP_E_CUDA;
+  }
+#define STP_TC_CASE(bn, bk) \
+  if (BN == bn && BK == bk) return launch_cfg<bn, bk>(tmA, tmB, a, st);
+  STP_TC_CASE(256, 64) STP_TC_CASE(128, 64) STP_TC_CASE(64, 64) STP_TC_CASE(32, 64) STP_TC_CASE(16, 64)
+  STP_TC_CASE(256, 32) STP_TC_CASE(128, 32) STP_TC_CASE(64, 32) STP_TC_CASE(32, 32) STP_TC_CASE(16, 32)
+  STP_TC_CASE(256, 16) STP_TC_CASE(128, 16) STP_TC_CASE(64, 16) STP_TC_CASE(32, 16) STP_TC_CASE(16, 16)
+#undef STP_TC_CASE
+  set_error("conv_tc: no specialisation for BN=%d BK=%d", BN, BK);
+  return STP_E_UNSUPPORTED;
+}
+
 bool tc_wgrad_supported(const WgradP&) { return false; }
-int launch_tc_wgrad(const WgradP&, float*, void*, size_t, cudaStream_t) { set_error("tc wgrad not built"); return STP_E_UNSUPPORTED; }
+int launch_tc_wgrad(const WgradP&, float*, void*, size_t, cudaStream_t) {
+  set_error("tc wgrad not built");
+  return STP_E_UNSUPPORTED;
+}
 size_t tc_wgrad_workspace(int64_t, int, int, int, int) { return 0; }
+
 }  // namespace stp

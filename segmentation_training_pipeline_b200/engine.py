@@ -128,8 +128,8 @@ class Net:
         off = 0
         for p in self.params.values():
             p.offset = off
-            off += (p.size + 3) // 4 * 4
-        self.n_flat = max(off, 4)
+            off += (p.size + 7) // 8 * 8  # 8 elements: the bf16 copies stay 16-byte aligned
+        self.n_flat = max(off, 8)
         dev = self.device
         self.flat_p = torch.zeros(self.n_flat, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(self.n_flat, dtype=torch.float32, device=dev)

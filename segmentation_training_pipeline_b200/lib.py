@@ -62,6 +62,7 @@ SIGNATURES = {
     "stp_last_error": (C.c_char_p, []),
     "stp_launch_count": (_I64, []),
     "stp_tc_enabled": (C.c_int, []),
+    "stp_tc_launch_count": (_I64, []),
     "stp_set_tc_enabled": (None, [C.c_int]),
     "stp_augment_draw": (C.c_int, [C.POINTER(AugSpec), _U64, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "stp_augment_apply": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
@@ -124,6 +125,11 @@ def check(rc: int, what: str = ""):
         raise StpError("%s failed (%d): %s" % (what or "libstp call", rc, msg.decode() if msg else "?"))
 
 
+# functions whose int return value is a result, not a status code
+_UNCHECKED = ("version", "tc_enabled", "bn_nblk", "last_error", "launch_count", "tc_launch_count", "set_tc_enabled",
+              "conv_wgrad_workspace", "head_bwd_workspace", "loss_partial_floats")
+
+
 class Lib:
     """Thin checked call layer: `L.conv_fwd(...)` == check(stp_conv_fwd(...))."""
 
@@ -132,7 +138,7 @@ class Lib:
 
     def __getattr__(self, name):
         fn = getattr(self._lib, "stp_" + name)
-        if fn.restype is C.c_int and name not in ("version", "tc_enabled"):
+        if name not in _UNCHECKED and fn.restype is C.c_int:
             def wrapped(*a, _fn=fn, _name=name):
                 rc = _fn(*a)
                 if rc != 0:

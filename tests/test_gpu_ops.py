@@ -37,7 +37,15 @@ CONV_CASES = [
     (1, 9, 7, 16, 24, 3, 1, 1, 1),     # odd sizes, Cout not a tile multiple
     (1, 8, 8, 64, 64, 1, 1, 0, 1),
     (1, 8, 8, 32, 16, 4, 1, 2, 2),     # transposed-conv style zero insertion (k4 s2 'same': pad' = 2)
+    # shapes aimed at the tcgen05 path: wide N tiles, partial pixel rectangles, 64B / 32B swizzle K blocks
+    (1, 12, 24, 128, 256, 3, 1, 1, 1),
+    (1, 9, 40, 32, 32, 3, 1, 1, 1),
+    (2, 10, 136, 16, 16, 3, 1, 1, 1),
+    (1, 16, 16, 192, 64, 3, 1, 1, 1),
+    (1, 8, 8, 64, 384, 3, 1, 1, 1),
+    (2, 32, 32, 64, 128, 1, 1, 0, 1),
 ]
+TC_FWD_CASES = {0, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15}  # indices of CONV_CASES whose forward must take the tcgen05 kernel
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
@@ -58,7 +66,10 @@ def test_conv_fwd_dgrad_wgrad(stp, cuda, case, tc):
         # ---- forward (bf16 out, with residual) ----
         y = torch.zeros((n, ho, wo, cout), dtype=torch.bfloat16, device=cuda)
         xs, ys, rs = T(x), T(y), T(res)
+        tc0 = stp.tc_launch_count()
         stp.conv_fwd(C.byref(desc), ref(xs), wt.data_ptr(), None, ref(rs), ref(ys), None, 0, stream())
+        used_tc = stp.tc_launch_count() - tc0
+        assert used_tc == (1 if (tc and CONV_CASES.index(case) in TC_FWD_CASES) else 0), used_tc
         yr = conv_ref(x, wt, stride, pad, up, (ho, wo)) + res.float().cpu()
         assert rel_err(y, yr) < TOL_BF16
         # ---- forward f32 out with bias ----
@@ -268,7 +279,9 @@ def test_loss(stp, cuda, weights):
     g = torch.Generator().manual_seed(11)
     count = 2 * 40 * 36
     logits = (torch.randn(count, generator=g) * 3).to(cuda)
-    logits[:5] = torch.tensor([40.0, -40.0, 0.0, 17.0, -17.0])  # exercise the 1e-7 clip
+    # exercise the 1e-7 clip; a logit of exactly 0 is avoided: there autograd frameworks pick a SUBgradient of
+    # max(x,0)/|x| (torch 1/0, TF 0/0) while the kernel uses the analytic derivative sigmoid(x)-t
+    logits[:5] = torch.tensor([40.0, -40.0, 0.25, 17.0, -17.0])
     mask = (torch.rand(count, generator=g) > 0.7).to(torch.uint8).to(cuda)
     spec = lib.LossSpec(*weights)
     partial = torch.zeros(stp.loss_partial_floats(), device=cuda)
