@@ -96,10 +96,22 @@ extern "C" int stp_conv_dgrad(const stp_conv_desc* d, const stp_tensor* dy, cons
   return launch_generic_conv(p, (cudaStream_t)stream);
 }
 
+static WgradP make_wgrad_p(const stp_conv_desc* d, const stp_tensor* x, const stp_tensor* dy) {
+  WgradP p;
+  p.x = (const __nv_bfloat16*)x->ptr; p.ldx = x->ld; p.N = x->n; p.H = x->h; p.W = x->w; p.Cin = x->c;
+  p.dy = (const __nv_bfloat16*)dy->ptr; p.lddy = dy->ld; p.Ho = dy->h; p.Wo = dy->w; p.Cout = dy->c;
+  p.out = nullptr;
+  p.R = d->r; p.S = d->s; p.stride = d->stride; p.pad_h = d->pad_h; p.pad_w = d->pad_w; p.up = d->up;
+  p.M = pixels(dy); p.K = d->r * d->s * x->c;
+  p.chunks_per_split = 0;
+  return p;
+}
+
 extern "C" size_t stp_conv_wgrad_workspace(const stp_conv_desc* d, const stp_tensor* x, const stp_tensor* dy) {
   if (!d || !x || !dy) return 0;
-  size_t a = generic_wgrad_workspace(pixels(dy), dy->c, d->r * d->s * x->c);
-  size_t b = tc_wgrad_workspace(pixels(dy), dy->c, d->r, d->s, x->c);
+  WgradP p = make_wgrad_p(d, x, dy);
+  size_t a = generic_wgrad_workspace(p.M, p.Cout, p.K);
+  size_t b = tc_wgrad_workspace(p);
   return a > b ? a : b;
 }
 
@@ -108,13 +120,7 @@ extern "C" int stp_conv_wgrad(const stp_conv_desc* d, const stp_tensor* x, const
   int rc = check_conv_common(d, x, dy, "conv_wgrad");
   if (rc) return rc;
   STP_REQUIRE(vec_ok(dy) && dw, "conv_wgrad: dy must be bf16 NHWC c%%8==0; dw non-null");
-  WgradP p;
-  p.x = (const __nv_bfloat16*)x->ptr; p.ldx = x->ld; p.N = x->n; p.H = x->h; p.W = x->w; p.Cin = x->c;
-  p.dy = (const __nv_bfloat16*)dy->ptr; p.lddy = dy->ld; p.Ho = dy->h; p.Wo = dy->w; p.Cout = dy->c;
-  p.out = nullptr;
-  p.R = d->r; p.S = d->s; p.stride = d->stride; p.pad_h = d->pad_h; p.pad_w = d->pad_w; p.up = d->up;
-  p.M = pixels(dy); p.K = d->r * d->s * x->c;
-  p.chunks_per_split = 0;
+  WgradP p = make_wgrad_p(d, x, dy);
   if (stp_tc_enabled() && tc_wgrad_supported(p)) return launch_tc_wgrad(p, dw, workspace, workspace_bytes, (cudaStream_t)stream);
   return launch_generic_wgrad(p, dw, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -35,12 +35,13 @@ struct WgradP {
 int launch_generic_conv(const ConvP& p, cudaStream_t st);
 int launch_generic_wgrad(WgradP p, float* dw, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t generic_wgrad_workspace(int64_t M, int Cout, int K);
+int launch_split_reduce(const float* ws, int splits, int64_t n, float* out, cudaStream_t st);
 
 // conv_tc.cu (tcgen05 + TMA)
 bool tc_conv_supported(const ConvP& p);
 int launch_tc_conv(const ConvP& p, cudaStream_t st);
 bool tc_wgrad_supported(const WgradP& p);
 int launch_tc_wgrad(const WgradP& p, float* dw, void* ws, size_t ws_bytes, cudaStream_t st);
-size_t tc_wgrad_workspace(int64_t M, int Cout, int R, int S, int Cin);
+size_t tc_wgrad_workspace(const WgradP& p);
 
 }  // namespace stp

@@ -377,9 +377,12 @@ int launch_generic_wgrad(WgradP p, float* dw, void* ws, size_t ws_bytes, cudaStr
   conv_wgrad_kernel<<<grid, 256, 0, st>>>(p);
   int rc = check_launch("conv_wgrad");
   if (rc || splits == 1) return rc;
-  int64_t n = (int64_t)p.Cout * p.K;
+  return launch_split_reduce((const float*)ws, splits, (int64_t)p.Cout * p.K, dw, st);
+}
+
+int launch_split_reduce(const float* ws, int splits, int64_t n, float* out, cudaStream_t st) {
   int64_t nb = (n + 255) / 256;
-  split_reduce_kernel<<<(int)(nb < 2048 ? nb : 2048), 256, 0, st>>>((const float*)ws, splits, n, dw);
+  split_reduce_kernel<<<(int)(nb < 2048 ? nb : 2048), 256, 0, st>>>(ws, splits, n, out);
   return check_launch("split_reduce");
 }
 

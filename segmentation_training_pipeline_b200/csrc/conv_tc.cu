@@ -369,11 +369,273 @@ int launch_tc_conv(const ConvP& p, cudaStream_t st) {
   return STP_E_UNSUPPORTED;
 }
 
-bool tc_wgrad_supported(const WgradP&) { return false; }
-int launch_tc_wgrad(const WgradP&, float*, void*, size_t, cudaStream_t) {
-  set_error("tc wgrad not built");
-  return STP_E_UNSUPPORTED;
+// ====================================================================================================
+// wgrad on tcgen05:  dW[co][r][s][ci] = sum over output pixels p of dY[p][co] * X[p + (r,s) - pad][ci]
+//
+// GEMM view: M = co (128 rows / MMA), N = ci tile (64 or 128), K = pixels.  Both operands are "MN-major"
+// (channels contiguous, pixels = K rows of 128 B) which is exactly what a 128B-swizzled TMA box
+// {64 ch, BW, BH(+2), 1} of the NHWC tensors produces -- no transposition anywhere.
+// One CTA = (co tile, ci tile, filter column s, pixel split).  Per 128-pixel rectangle it loads dY once and the
+// input rectangle shifted by s WITH a +-1 row halo once; the R filter rows are then R shifted views of the same
+// shared-memory tile (shift by r rows = r*BW*128 B, a whole number of swizzle atoms), each accumulating into its
+// own TMEM accumulator [128 x BN].  Split partials are reduced deterministically by split_reduce_kernel.
+// ====================================================================================================
+struct TcWgradArgs {
+  float* out;  // [splits][Cout][R][S][Cin]
+  int Cout, Cin, R, S, pad_h, pad_w;
+  int BW, BH, tilesW, tilesH;
+  int num_pb, pb_per_split, splits, co_tiles, ci_tiles;
+  int a_boxes;   // 2 when Cout >= 128, else 1 (rows 64..127 alias rows 0..63 and are discarded)
+  int xrows;     // (BH + R - 1) * BW rows of the haloed input tile
+};
+
+template <int BN>
+struct TcWgradCfg {
+  static constexpr int kABytes = 2 * 16384;
+  static constexpr int kXBoxBytes = 20480;  // >= (BH+2)*BW*128 for the supported geometries, 1024-multiple
+  static constexpr int kBBytes = (BN / 64) * kXBoxBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (kSmemBudget - 2048) / kStageBytes;
+  static constexpr int kTmemCols = 3 * BN <= 256 ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const TcWgradArgs a) {
+  using Cfg = TcWgradCfg<BN>;
+  constexpr int NS = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + NS * Cfg::kABytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * Cfg::kStageBytes);
+  uint64_t* empty = full + NS;
+  uint64_t* acc_full = empty + NS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work item
+  int item = blockIdx.x;
+  const int split = item % a.splits; item /= a.splits;
+  const int s = item % a.S; item /= a.S;
+  const int cit = item % a.ci_tiles;
+  const int cot = item / a.ci_tiles;
+  const int co0 = cot * 128, ci0 = cit * BN;
+  const int pb_begin = split * a.pb_per_split;
+  int pb_end = pb_begin + a.pb_per_split;
+  if (pb_end > a.num_pb) pb_end = a.num_pb;
+  const int npb = pb_end > pb_begin ? pb_end - pb_begin : 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmDY);
+    prefetch_tmap(&tmX);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)a.a_boxes * 16384u + (uint32_t)(BN / 64) * (uint32_t)a.xrows * 128u;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pb = pb_begin; pb < pb_end; ++pb) {
+        int tw = pb % a.tilesW;
+        int t = pb / a.tilesW;
+        int th = t % a.tilesH;
+        int img = t / a.tilesH;
+        const int h0 = th * a.BH, w0 = tw * a.BW;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], tx_bytes);
+        uint8_t* pa = sA + stage * Cfg::kABytes;
+        uint8_t* pbuf = sB + stage * Cfg::kBBytes;
+        for (int j = 0; j < a.a_boxes; ++j) tma_load_4d(pa + j * 16384, &tmDY, &full[stage], co0 + 64 * j, w0, h0, img);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_4d(pbuf + j * Cfg::kXBoxBytes, &tmX, &full[stage], ci0 + 64 * j, w0 + s - a.pad_w, h0 - a.pad_h, img);
+        if (++stage == NS) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(128, BN, 1, 1);
+      const uint32_t a_lbo = a.a_boxes == 2 ? 16384u : 0u;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < npb; ++i) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
+        const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
+        for (int r = 0; r < a.R; ++r) {
+          const uint32_t b_r = b_addr + (uint32_t)(r * a.BW) * 128u;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t ad = desc_mnmajor_sw128(a_addr + kk * 2048, a_lbo);
+            const uint64_t bd = desc_mnmajor_sw128(b_r + kk * 2048, Cfg::kXBoxBytes);
+            umma_bf16(tmem_base + (uint32_t)(r * BN), ad, bd, idesc, (i | kk) != 0);
+          }
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == NS) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const bool valid = (q * 32 + lane) < (a.a_boxes == 2 ? 128 : 64) && co < a.Cout;
+    for (int r = 0; r < a.R; ++r) {
+      float* op = a.out + ((((int64_t)split * a.Cout + co) * a.R + r) * a.S + s) * a.Cin + ci0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t rr[32];
+        if (npb > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * BN + c0), rr);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rr[i] = 0u;
+        }
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(op + c0 + i) = make_float4(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1]),
+                                                                  __uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 }
-size_t tc_wgrad_workspace(int64_t, int, int, int, int) { return 0; }
+
+struct WgradPlan {
+  int BN, BW, BH, tilesW, tilesH, num_pb, splits, pb_per_split, co_tiles, ci_tiles, items;
+};
+
+static bool wgrad_plan(int64_t M, int N_img, int Ho, int Wo, int Cout, int Cin, int R, int S, WgradPlan* pl) {
+  if (Cout % 64 != 0 || Cin % 64 != 0 || R > 3 || S > 3 || Wo < 8) return false;
+  pl->BN = (Cin % 128 == 0) ? 128 : 64;
+  pl->BW = Wo >= 16 ? 16 : 8;
+  pl->BH = 128 / pl->BW;
+  if ((pl->BH + R - 1) * pl->BW * 128 > 20480) return false;
+  pl->tilesW = (Wo + pl->BW - 1) / pl->BW;
+  pl->tilesH = (Ho + pl->BH - 1) / pl->BH;
+  int64_t npb = (int64_t)N_img * pl->tilesW * pl->tilesH;
+  if (npb > 0x7fffffff) return false;
+  pl->num_pb = (int)npb;
+  pl->co_tiles = (Cout + 127) / 128;
+  pl->ci_tiles = Cin / pl->BN;
+  int base = pl->co_tiles * pl->ci_tiles * S;
+  int splits = (2 * kNumSMs + base - 1) / base;  // ~2 CTAs' worth of work items per SM
+  int max_s = (pl->num_pb + 3) / 4;              // at least 4 pixel blocks per split
+  if (splits > max_s) splits = max_s;
+  // keep the fp32 split partials L2 resident (126 MB L2): <= 48 MB in flight
+  int64_t per = (int64_t)Cout * R * S * Cin * 4;
+  int cap = (int)((48ll << 20) / per);
+  if (splits > cap) splits = cap;
+  if (splits < 1) splits = 1;
+  pl->pb_per_split = (pl->num_pb + splits - 1) / splits;
+  pl->splits = (pl->num_pb + pl->pb_per_split - 1) / pl->pb_per_split;
+  pl->items = base * pl->splits;
+  (void)M;
+  return true;
+}
+
+bool tc_wgrad_supported(const WgradP& p) {
+  if (p.stride != 1 || p.up != 1) return false;
+  WgradPlan pl;
+  if (!wgrad_plan(p.M, p.N, p.Ho, p.Wo, p.Cout, p.Cin, p.R, p.S, &pl)) return false;
+  if (p.ldx % 8 != 0 || p.lddy % 8 != 0 || !aligned16(p.x) || !aligned16(p.dy)) return false;
+  return get_encode_tiled() != nullptr;
+}
+
+size_t tc_wgrad_workspace(const WgradP& p) {
+  if (p.stride != 1 || p.up != 1) return 0;
+  WgradPlan pl;
+  if (!wgrad_plan(p.M, p.N, p.Ho, p.Wo, p.Cout, p.Cin, p.R, p.S, &pl)) return 0;
+  return pl.splits > 1 ? (size_t)pl.splits * p.Cout * p.K * sizeof(float) : 0;
+}
+
+template <int BN>
+static int launch_wgrad_cfg(const CUtensorMap& tmDY, const CUtensorMap& tmX, const TcWgradArgs& a, int items,
+                            cudaStream_t st) {
+  using Cfg = TcWgradCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return STP_E_CUDA;
+    }
+    attr_set = true;
+  }
+  wgrad_tc_kernel<BN><<<items, kThreads, Cfg::kSmemBytes, st>>>(tmDY, tmX, a);
+  g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("wgrad_tc");
+}
+
+int launch_tc_wgrad(const WgradP& p, float* dw, void* ws, size_t ws_bytes, cudaStream_t st) {
+  WgradPlan pl;
+  if (!wgrad_plan(p.M, p.N, p.Ho, p.Wo, p.Cout, p.Cin, p.R, p.S, &pl)) {
+    set_error("wgrad_tc: unsupported shape");
+    return STP_E_UNSUPPORTED;
+  }
+  const size_t per = (size_t)p.Cout * p.K * sizeof(float);
+  if (pl.splits > 1 && (ws == nullptr || ws_bytes < per * pl.splits)) {
+    set_error("conv_wgrad: workspace too small (%zu < %zu)", ws_bytes, per * pl.splits);
+    return STP_E_WORKSPACE;
+  }
+  TcWgradArgs a;
+  a.out = pl.splits > 1 ? (float*)ws : dw;
+  a.Cout = p.Cout; a.Cin = p.Cin; a.R = p.R; a.S = p.S; a.pad_h = p.pad_h; a.pad_w = p.pad_w;
+  a.BW = pl.BW; a.BH = pl.BH; a.tilesW = pl.tilesW; a.tilesH = pl.tilesH;
+  a.num_pb = pl.num_pb; a.pb_per_split = pl.pb_per_split; a.splits = pl.splits;
+  a.co_tiles = pl.co_tiles; a.ci_tiles = pl.ci_tiles;
+  a.a_boxes = p.Cout >= 128 ? 2 : 1;
+  a.xrows = (pl.BH + p.R - 1) * pl.BW;
+  CUtensorMap tmDY, tmX;
+  {
+    uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.N};
+    uint64_t strides[3] = {(uint64_t)p.lddy * 2, (uint64_t)p.Wo * p.lddy * 2, (uint64_t)p.Ho * p.Wo * p.lddy * 2};
+    uint32_t box[4] = {64, (uint32_t)pl.BW, (uint32_t)pl.BH, 1};
+    if (!make_tmap_bf16(&tmDY, p.dy, 4, dims, strides, box, 128)) return STP_E_CUDA;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
+    uint64_t strides[3] = {(uint64_t)p.ldx * 2, (uint64_t)p.W * p.ldx * 2, (uint64_t)p.H * p.W * p.ldx * 2};
+    uint32_t box[4] = {64, (uint32_t)pl.BW, (uint32_t)(pl.BH + p.R - 1), 1};
+    if (!make_tmap_bf16(&tmX, p.x, 4, dims, strides, box, 128)) return STP_E_CUDA;
+  }
+  int rc = pl.BN == 128 ? launch_wgrad_cfg<128>(tmDY, tmX, a, pl.items, st) : launch_wgrad_cfg<64>(tmDY, tmX, a, pl.items, st);
+  if (rc || pl.splits == 1) return rc;
+  return launch_split_reduce((const float*)ws, pl.splits, (int64_t)p.Cout * p.K, dw, st);
+}
 
 }  // namespace stp

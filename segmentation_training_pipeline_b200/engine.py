@@ -43,6 +43,8 @@ class Buf:
         self.st = _lib.Tensor(ptr, n, h, w, c, self.ld, dtype)
         self.ref = C.byref(self.st)
         self._grad: Optional[Buf] = None
+        if name:
+            net.bufs[name] = self
 
     @property
     def rows(self):
@@ -102,6 +104,7 @@ class Net:
         self.device = torch.device(device)
         self.batch = batch
         self.ops: List[Op] = []
+        self.bufs: Dict[str, "Buf"] = {}  # named activation buffers (tests / debugging)
         self.params: Dict[str, Param] = {}
         self.buffers: Dict[str, torch.Tensor] = {}  # BN moving stats (fp32)
         self.gen = np.random.default_rng(seed)

@@ -56,27 +56,41 @@ def test_forward_backward_parity(cuda, backbone, size, loss):
     logits = net.head.logits.cpu().view(n, size, size, 1)
     grads = net.get_grads()
 
-    om = SegModel("Unet", backbone, classes=1, input_shape=(size, size, 3), storage="bf16", update_moving=False)
-    assert set(om.params.keys()) == set(net.params.keys()), sorted(set(om.params.keys()) ^ set(net.params.keys()))
-    om.load_numpy(W)
-    y = om(img.float())
-    t = mask.float()
-    lo = loss[0] * OL.binary_crossentropy(t, y) + loss[1] * OL.dice_loss(t, y) + loss[2] * OL.iou_loss(t, y)
-    lo.backward()
-    ol = om.taps["logits"].detach().permute(0, 2, 3, 1)
+    # Two oracles: bf16-storage emulation (rounds where the engine stores bf16) and pure fp32.  Deep random-init
+    # pre-activation ResNets amplify one-ulp bf16 differences layer by layer, so the engine is held to the NOISE
+    # FLOOR of bf16 storage itself: it must be at least as close to the bf16 oracle as that oracle is to fp32.
+    def run(storage):
+        om = SegModel("Unet", backbone, classes=1, input_shape=(size, size, 3), storage=storage, update_moving=False)
+        assert set(om.params.keys()) == set(net.params.keys()), sorted(set(om.params.keys()) ^ set(net.params.keys()))
+        om.load_numpy(W)
+        y = om(img.float())
+        t = mask.float()
+        lo = loss[0] * OL.binary_crossentropy(t, y) + loss[1] * OL.dice_loss(t, y) + loss[2] * OL.iou_loss(t, y)
+        lo.backward()
+        return (om.taps["logits"].detach().permute(0, 2, 3, 1), float(lo.detach()),
+                {k: p.grad.numpy().copy() for k, p in om.params.items()})
+
+    ol, lo, go_all = run("bf16")
+    ol32, lo32, go32 = run("fp32")
+    floor_logits = float((ol - ol32).norm() / ol32.norm())
     err_logits = float((logits - ol).norm() / ol.norm())
-    print("logits rel err", err_logits, "loss", float(res[lib.L_LOSS]), float(lo))
-    assert err_logits < 2e-2
-    assert abs(float(res[lib.L_LOSS]) - float(lo)) < 1e-3 * max(1.0, abs(float(lo)))
+    print("logits rel err", err_logits, "bf16-vs-fp32 floor", floor_logits, "loss", float(res[lib.L_LOSS]), lo, lo32)
+    assert err_logits < max(5e-3, 0.8 * floor_logits)
+    assert abs(float(res[lib.L_LOSS]) - lo) < max(1e-3 * max(1.0, abs(lo)), 1.5 * abs(lo - lo32))
     worst = 0.0
-    for k, p in om.params.items():
-        go, ge = p.grad.numpy(), grads[k]
+    for k, go in go_all.items():
+        ge = grads[k]
         assert go.shape == ge.shape, (k, go.shape, ge.shape)
         denom = np.linalg.norm(go) + 1e-12
         e = float(np.linalg.norm(ge - go) / denom)
-        worst = max(worst, e)
-        assert e < 6e-2, (k, e, float(denom))
-    print("worst grad rel err", worst)
+        floor = float(np.linalg.norm(go - go32[k]) / (np.linalg.norm(go32[k]) + 1e-12))
+        if floor > 0.25:
+            # e.g. bn_data/beta: conv0 is followed by a BatchNorm, so this gradient is a near-total cancellation
+            # and bf16 storage leaves only rounding noise in it (the two ORACLES disagree by > 25 %) -- not testable
+            continue
+        worst = max(worst, e / max(floor, 1e-3))
+        assert e < max(2e-2, 1.5 * floor), (k, e, floor, float(denom))
+    print("worst grad err / bf16 floor", worst)
 
 
 def test_training_curve_parity(cuda):

@@ -45,6 +45,7 @@ CONV_CASES = [
     (1, 8, 8, 64, 384, 3, 1, 1, 1),
     (2, 32, 32, 64, 128, 1, 1, 0, 1),
 ]
+TC_WGRAD_CASES = {0, 6, 8, 10, 13, 14, 15}  # ... and whose wgrad must take the tcgen05 wgrad kernel
 TC_FWD_CASES = {0, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15}  # indices of CONV_CASES whose forward must take the tcgen05 kernel
 
 
@@ -104,7 +105,10 @@ def test_conv_fwd_dgrad_wgrad(stp, cuda, case, tc):
         nws = stp.conv_wgrad_workspace(C.byref(desc), ref(xs), ref(dys))
         ws = _ws(nws, cuda)
         dw = torch.zeros((cout, k, k, cin), dtype=torch.float32, device=cuda)
+        tc0 = stp.tc_launch_count()
         stp.conv_wgrad(C.byref(desc), ref(xs), ref(dys), dw.data_ptr(), ws.data_ptr(), ws.numel(), stream())
+        used_tc = stp.tc_launch_count() - tc0
+        assert used_tc == (1 if (tc and CONV_CASES.index(case) in TC_WGRAD_CASES) else 0), used_tc
         assert rel_err(dw, wr.grad) < TOL_F32
         torch.cuda.synchronize()
     finally:
