@@ -57,6 +57,8 @@ int stp_tc_enabled(void);
 /* number of tcgen05/TMA kernels enqueued since load (evidence that the tensor-core path, not the mma.sync one, ran) */
 int64_t stp_tc_launch_count(void);
 void stp_set_tc_enabled(int on);
+/* debugging / A-B knobs: "tc2_force_mt" (0 heuristic | 1,2,4,8), "tc_conv_version" (0 auto | 1 first-generation only) */
+int stp_set_option(const char* name, int32_t value);
 
 /* ------------------------------------------------------------------------------------------------
  * K1  augmentation  -- replaces imgaug.augmenters.{Fliplr,Flipud,Affine,Multiply,Add} run by

@@ -25,12 +25,35 @@ void set_error(const char* fmt, ...) {
 
 using namespace stp;
 
+namespace stp {
+static std::atomic<int> g_options[OPT_COUNT];
+int get_option(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key].load() : 0; }
+}  // namespace stp
+
+extern "C" int stp_set_option(const char* name, int32_t value) {
+  STP_REQUIRE(name, "set_option: null name");
+  int key = -1;
+  if (!strcmp(name, "tc2_force_mt")) key = OPT_TC2_FORCE_MT;        /* 0 = heuristic; 1,2,4,8 = force strip height */
+  else if (!strcmp(name, "tc_conv_version")) key = OPT_TC_CONV_VERSION; /* 0 = auto, 1 = first-generation kernel only */
+  STP_REQUIRE(key >= 0, "set_option: unknown option %s", name);
+  g_options[key].store(value);
+  return STP_OK;
+}
+
 extern "C" int stp_version(void) { return STP_VERSION; }
 extern "C" const char* stp_last_error(void) { return g_err; }
 extern "C" int64_t stp_launch_count(void) { return g_launches.load(); }
 extern "C" int64_t stp_tc_launch_count(void) { return g_tc_launches.load(); }
 extern "C" int stp_tc_enabled(void) { return g_tc_enabled.load(); }
 extern "C" void stp_set_tc_enabled(int on) { g_tc_enabled.store(on ? 1 : 0); }
+
+static int dispatch_conv(const ConvP& p, cudaStream_t st) {
+  if (stp_tc_enabled()) {
+    if (get_option(OPT_TC_CONV_VERSION) != 1 && tc2_conv_supported(p)) return launch_tc2_conv(p, st);
+    if (tc_conv_supported(p)) return launch_tc_conv(p, st);
+  }
+  return launch_generic_conv(p, st);
+}
 
 static int check_conv_common(const stp_conv_desc* d, const stp_tensor* in, const stp_tensor* out, const char* who) {
   STP_REQUIRE(d && in && out, "%s: null argument", who);
@@ -63,8 +86,7 @@ extern "C" int stp_conv_fwd(const stp_conv_desc* d, const stp_tensor* x, const v
   p.R = d->r; p.S = d->s; p.stride = d->stride; p.pad_h = d->pad_h; p.pad_w = d->pad_w; p.up = d->up;
   p.relu = (d->flags & STP_CONV_RELU) ? 1 : 0;
   p.M = pixels(y); p.K = d->r * d->s * x->c;
-  if (stp_tc_enabled() && tc_conv_supported(p)) return launch_tc_conv(p, (cudaStream_t)stream);
-  return launch_generic_conv(p, (cudaStream_t)stream);
+  return dispatch_conv(p, (cudaStream_t)stream);
 }
 
 extern "C" int stp_conv_dgrad(const stp_conv_desc* d, const stp_tensor* dy, const void* w_dgrad,
@@ -92,8 +114,7 @@ extern "C" int stp_conv_dgrad(const stp_conv_desc* d, const stp_tensor* dy, cons
   p.stride = d->up; p.up = d->stride; p.pad_h = d->r - 1 - d->pad_h; p.pad_w = d->s - 1 - d->pad_w;
   p.relu = 0;
   p.M = pixels(dx); p.K = d->r * d->s * dy->c;
-  if (stp_tc_enabled() && tc_conv_supported(p)) return launch_tc_conv(p, (cudaStream_t)stream);
-  return launch_generic_conv(p, (cudaStream_t)stream);
+  return dispatch_conv(p, (cudaStream_t)stream);
 }
 
 static WgradP make_wgrad_p(const stp_conv_desc* d, const stp_tensor* x, const stp_tensor* dy) {

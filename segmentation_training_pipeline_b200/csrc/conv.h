@@ -37,6 +37,12 @@ int launch_generic_wgrad(WgradP p, float* dw, void* ws, size_t ws_bytes, cudaStr
 size_t generic_wgrad_workspace(int64_t M, int Cout, int K);
 int launch_split_reduce(const float* ws, int splits, int64_t n, float* out, cudaStream_t st);
 
+// conv_tc2.cu (tcgen05 + TMA, halo kernel for RxS > 1)
+bool tc2_conv_supported(const ConvP& p);
+int launch_tc2_conv(const ConvP& p, cudaStream_t st);
+int get_option(int key);
+enum { OPT_TC2_FORCE_MT = 0, OPT_TC_CONV_VERSION = 1, OPT_COUNT = 8 };
+
 // conv_tc.cu (tcgen05 + TMA)
 bool tc_conv_supported(const ConvP& p);
 int launch_tc_conv(const ConvP& p, cudaStream_t st);

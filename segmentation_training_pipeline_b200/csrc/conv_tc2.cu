@@ -1,0 +1,375 @@
+// tcgen05 / TMA implicit-GEMM convolution, second generation ("halo" kernel) for RxS > 1x1, stride 1.
+//
+// The first-generation kernel (conv_tc.cu) issues one TMA box per filter tap, i.e. it pulls every input pixel R*S
+// times through L2 -- measured L2->SM bound on B200 (about 4.5-5 TB/s) long before the tensor pipe saturates.
+// Here one CTA owns a tall strip of MT sub-tiles (each BH x BW = 128 output pixels, stacked vertically) and, per
+// (filter column s, 64/32/16-channel block), loads
+//     ONE input box {BK ch, BW, MT*BH + R - 1 rows}  shifted horizontally by (s - pad_w)
+//     R weight boxes {BK, BN}                        (taps (0..R-1, s))
+// The R filter ROWS are then R shifted *views* of the same shared-memory tile: a shift by r image rows is r*BW
+// swizzled 8-row atoms, so only the UMMA descriptor start address changes.  Input traffic drops from R*S to
+// S*(1 + (R-1)/(MT*BH)) box loads per pixel and each weight box is reused by MT accumulators (MT*128 pixels).
+// Accumulators: MT tiles of [128 x BN] fp32 in TMEM, double buffered (2*MT*BN <= 512 columns) so the epilogue of
+// one strip overlaps the MMAs of the next.  Warp roles / barriers as in conv_tc.cu.
+#include "conv.h"
+#include "tc_common.cuh"
+
+namespace stp {
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads2 = 192;
+constexpr int kSmemBudget2 = 227 * 1024;
+
+struct Tc2Args {
+  void* y;
+  const __nv_bfloat16* res;
+  const float* bias;
+  int ldy, ldr, y_f32, relu;
+  int Ho, Wo, Cout, Cin;
+  int R, S, pad_h, pad_w;
+  int BW, BH, log2BW;
+  int tilesW, tilesH, tilesN;
+  int num_tiles;
+  int a_bytes, b_tap_bytes;  // runtime sizes of the A box and of one weight box
+};
+
+constexpr int align1k(int x) { return (x + 1023) / 1024 * 1024; }
+
+template <int BN, int BK, int MT>
+struct Tc2Cfg {
+  static constexpr int kRowBytes = BK * 2;
+  static constexpr int kMaxRows = (MT * 8 + 2) * 16 > (MT * 16 + 2) * 8 ? (MT * 8 + 2) * 16 : (MT * 16 + 2) * 8;
+  static constexpr int kABytes = align1k(kMaxRows * kRowBytes);   // BW=16/BH=8 or BW=8/BH=16, R<=3
+  static constexpr int kBTap = BN * BK * 2;
+  static constexpr int kBBytes = align1k(3 * kBTap);
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesRaw = (kSmemBudget2 - 2048) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemRaw = 2 * MT * BN;
+  static constexpr int kTmemCols = kTmemRaw <= 32 ? 32 : kTmemRaw <= 64 ? 64 : kTmemRaw <= 128 ? 128 : kTmemRaw <= 256 ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static_assert(kStages >= 2, "need at least two pipeline stages");
+  static_assert(kTmemRaw <= 512, "accumulators exceed TMEM");
+};
+
+template <int BN, int BK, int MT>
+__global__ void __launch_bounds__(kThreads2, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Tc2Args a) {
+  using Cfg = Tc2Cfg<BN, BK, MT>;
+  constexpr int NS = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + NS * Cfg::kABytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * Cfg::kStageBytes);
+  uint64_t* empty = full + NS;
+  uint64_t* acc_full = empty + NS;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kcb = a.Cin / BK;
+  const int num_st = a.S * kcb;  // pipeline stages' worth of work per tile
+  const int TH = MT * a.BH;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int tile, int& img, int& h0, int& w0, int& n0) {
+    int tn = tile % a.tilesN;
+    int t = tile / a.tilesN;
+    int tw = t % a.tilesW;
+    t /= a.tilesW;
+    int th = t % a.tilesH;
+    img = t / a.tilesH;
+    h0 = th * TH;
+    w0 = tw * a.BW;
+    n0 = tn * BN;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)a.a_bytes + (uint32_t)a.R * (uint32_t)a.b_tap_bytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        int img, h0, w0, n0;
+        decode(tile, img, h0, w0, n0);
+        for (int s = 0; s < a.S; ++s) {
+          for (int cb = 0; cb < kcb; ++cb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], tx);
+            tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], cb * BK, w0 + s - a.pad_w, h0 - a.pad_h, img);
+            for (int r = 0; r < a.R; ++r)
+              tma_load_2d(sB + stage * Cfg::kBBytes + r * Cfg::kBTap, &tmB, &full[stage],
+                          (r * a.S + s) * a.Cin + cb * BK, n0);
+            if (++stage == NS) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(128, BN, 0, 0);
+      const uint32_t sub_bytes = (uint32_t)(a.BH * a.BW) * Cfg::kRowBytes;  // one sub-tile's rows
+      const uint32_t row_bytes = (uint32_t)a.BW * Cfg::kRowBytes;           // one image row of the box
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++local) {
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(&acc_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(as * MT * BN);
+        for (int st = 0; st < num_st; ++st) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int j = 0; j < MT; ++j) {
+            for (int r = 0; r < a.R; ++r) {
+              const uint32_t aj = a_addr + j * sub_bytes + r * row_bytes;
+              const uint32_t br = b_addr + r * Cfg::kBTap;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                umma_bf16(d0 + (uint32_t)(j * BN), desc_kmajor(aj + k * 32, BK * 2), desc_kmajor(br + k * 32, BK * 2), idesc,
+                          (st | r | k) != 0);
+            }
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == NS) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int hl = m >> a.log2BW, wl = m & (a.BW - 1);
+    int local = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++local) {
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      int img, h0, w0, n0;
+      decode(tile, img, h0, w0, n0);
+      const int wo = w0 + wl;
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < MT; ++j) {
+        const int ho = h0 + j * a.BH + hl;
+        const bool valid = ho < a.Ho && wo < a.Wo;
+        const int64_t pix = ((int64_t)img * a.Ho + ho) * a.Wo + wo;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * MT + j) * BN);
+        constexpr int CH = BN >= 32 ? 32 : 16;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += CH) {
+          uint32_t rr[CH];
+          if constexpr (CH == 32) tmem_ld32(t_addr + c0, rr); else tmem_ld16(t_addr + c0, rr);
+          tmem_ld_wait();
+          if (valid) {
+            float v[CH];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(rr[i]);
+            const int n = n0 + c0;
+            if (a.bias) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) v[i] += __ldg(a.bias + n + i);
+            }
+            if (a.res) {
+              const __nv_bfloat16* rp = a.res + pix * a.ldr + n;
+#pragma unroll
+              for (int i = 0; i < CH; i += 8) {
+                float f[8];
+                unpack8(ld8(rp + i), f);
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) v[i + jj] += f[jj];
+              }
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (a.y_f32) {
+              float* yp = reinterpret_cast<float*>(a.y) + pix * a.ldy + n;
+#pragma unroll
+              for (int i = 0; i < CH; i += 4) *reinterpret_cast<float4*>(yp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+              __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + pix * a.ldy + n;
+#pragma unroll
+              for (int i = 0; i < CH; i += 8) st8(yp + i, pack8(v + i));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+struct Tc2Plan {
+  int BN, BK, MT;
+};
+
+bool tc2_plan(const ConvP& p, Tc2Plan* pl) {
+  if (p.stride != 1 || p.up != 1) return false;
+  if (p.R < 2 && p.S < 2) return false;  // 1x1: nothing to reuse, first-generation kernel
+  if (p.R > 3 || p.S > 3) return false;
+  int bk = (p.Cin % 64 == 0) ? 64 : (p.Cin == 32 ? 32 : (p.Cin == 16 ? 16 : 0));
+  if (!bk) return false;
+  int bn = 0;
+  for (int c : {128, 64, 32, 16})
+    if (p.Cout % c == 0) {
+      bn = c;
+      break;
+    }
+  if (!bn) return false;
+  int mt;
+  if (bn == 128) mt = 2;
+  else if (bn == 64) mt = 4;
+  else mt = (bk == 64) ? 4 : 8;
+  // do not make strips taller than the image needs; keep enough tiles to fill the GPU
+  const int bh = p.Wo >= 16 ? 8 : 16;
+  while (mt > 1 && (mt / 2) * bh >= p.Ho) mt /= 2;
+  const int bw = p.Wo >= 16 ? 16 : 8;
+  auto tiles = [&](int m) {
+    return (int64_t)p.N * ((p.Ho + m * bh - 1) / (m * bh)) * ((p.Wo + bw - 1) / bw) * (p.Cout / bn);
+  };
+  while (mt > 1 && tiles(mt) < kNumSMs) mt /= 2;
+  const int force = get_option(OPT_TC2_FORCE_MT);
+  if (force > 0) {
+    const int mt_max = bn == 128 ? 2 : (bn == 64 || bk == 64) ? 4 : 8;
+    mt = force < mt_max ? force : mt_max;
+  }
+  pl->BN = bn; pl->BK = bk; pl->MT = mt;
+  return true;
+}
+
+template <int BN, int BK, int MT>
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc2Args& a, cudaStream_t st) {
+  using Cfg = Tc2Cfg<BN, BK, MT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, BK, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("conv_tc2: cudaFuncSetAttribute(%d B): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      return STP_E_CUDA;
+    }
+    attr_set = true;
+  }
+  int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
+  conv_tc2_kernel<BN, BK, MT><<<grid, kThreads2, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
+  g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("conv_tc2");
+}
+
+}  // namespace
+
+bool tc2_conv_supported(const ConvP& p) {
+  Tc2Plan pl;
+  if (!tc2_plan(p, &pl)) return false;
+  if (p.Wo < 8 || p.Ho < 1) return false;
+  if (p.ldx % 8 != 0 || !aligned16(p.x) || !aligned16(p.w)) return false;
+  if (p.y_f32 ? (p.ldy % 4 != 0) : (p.ldy % 8 != 0)) return false;
+  if (!aligned16(p.y)) return false;
+  if (p.res && (p.ldr % 8 != 0 || !aligned16(p.res))) return false;
+  return get_encode_tiled() != nullptr;
+}
+
+int launch_tc2_conv(const ConvP& p, cudaStream_t st) {
+  Tc2Plan pl;
+  if (!tc2_plan(p, &pl)) {
+    set_error("conv_tc2: unsupported");
+    return STP_E_UNSUPPORTED;
+  }
+  Tc2Args a;
+  a.y = p.y; a.res = p.res; a.bias = p.bias; a.ldy = p.ldy; a.ldr = p.ldr; a.y_f32 = p.y_f32; a.relu = p.relu;
+  a.Ho = p.Ho; a.Wo = p.Wo; a.Cout = p.Cout; a.Cin = p.Cin; a.R = p.R; a.S = p.S; a.pad_h = p.pad_h; a.pad_w = p.pad_w;
+  a.BW = p.Wo >= 16 ? 16 : 8;
+  a.BH = 128 / a.BW;
+  a.log2BW = a.BW == 16 ? 4 : 3;
+  const int TH = pl.MT * a.BH;
+  a.tilesW = (p.Wo + a.BW - 1) / a.BW;
+  a.tilesH = (p.Ho + TH - 1) / TH;
+  a.tilesN = p.Cout / pl.BN;
+  int64_t nt = (int64_t)p.N * a.tilesH * a.tilesW * a.tilesN;
+  if (nt > 0x7fffffff) {
+    set_error("conv_tc2: too many tiles");
+    return STP_E_UNSUPPORTED;
+  }
+  a.num_tiles = (int)nt;
+  const int box_rows = TH + p.R - 1;
+  a.a_bytes = box_rows * a.BW * pl.BK * 2;
+  a.b_tap_bytes = pl.BN * pl.BK * 2;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
+    uint64_t strides[3] = {(uint64_t)p.ldx * 2, (uint64_t)p.W * p.ldx * 2, (uint64_t)p.H * p.W * p.ldx * 2};
+    uint32_t box[4] = {(uint32_t)pl.BK, (uint32_t)a.BW, (uint32_t)box_rows, 1};
+    if (!make_tmap_bf16(&tmA, p.x, 4, dims, strides, box, pl.BK * 2)) return STP_E_CUDA;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.Cout};
+    uint64_t strides[1] = {(uint64_t)p.K * 2};
+    uint32_t box[2] = {(uint32_t)pl.BK, (uint32_t)pl.BN};
+    if (!make_tmap_bf16(&tmB, p.w, 2, dims, strides, box, pl.BK * 2)) return STP_E_CUDA;
+  }
+#define STP_TC2_CASE(bn, bk, mt) \
+  if (pl.BN == bn && pl.BK == bk && pl.MT == mt) return launch2<bn, bk, mt>(tmA, tmB, a, st);
+  STP_TC2_CASE(128, 64, 2) STP_TC2_CASE(128, 64, 1)
+  STP_TC2_CASE(64, 64, 4) STP_TC2_CASE(64, 64, 2) STP_TC2_CASE(64, 64, 1)
+  STP_TC2_CASE(32, 64, 4) STP_TC2_CASE(32, 64, 2) STP_TC2_CASE(32, 64, 1)
+  STP_TC2_CASE(16, 64, 4) STP_TC2_CASE(16, 64, 2) STP_TC2_CASE(16, 64, 1)
+  STP_TC2_CASE(128, 32, 2) STP_TC2_CASE(128, 32, 1)
+  STP_TC2_CASE(64, 32, 4) STP_TC2_CASE(64, 32, 2) STP_TC2_CASE(64, 32, 1)
+  STP_TC2_CASE(32, 32, 8) STP_TC2_CASE(32, 32, 4) STP_TC2_CASE(32, 32, 2) STP_TC2_CASE(32, 32, 1)
+  STP_TC2_CASE(16, 32, 8) STP_TC2_CASE(16, 32, 4) STP_TC2_CASE(16, 32, 2) STP_TC2_CASE(16, 32, 1)
+  STP_TC2_CASE(128, 16, 2) STP_TC2_CASE(128, 16, 1)
+  STP_TC2_CASE(64, 16, 4) STP_TC2_CASE(64, 16, 2) STP_TC2_CASE(64, 16, 1)
+  STP_TC2_CASE(32, 16, 8) STP_TC2_CASE(32, 16, 4) STP_TC2_CASE(32, 16, 2) STP_TC2_CASE(32, 16, 1)
+  STP_TC2_CASE(16, 16, 8) STP_TC2_CASE(16, 16, 4) STP_TC2_CASE(16, 16, 2) STP_TC2_CASE(16, 16, 1)
+#undef STP_TC2_CASE
+  set_error("conv_tc2: no specialisation BN=%d BK=%d MT=%d", pl.BN, pl.BK, pl.MT);
+  return STP_E_UNSUPPORTED;
+}
+
+}  // namespace stp

@@ -64,6 +64,7 @@ SIGNATURES = {
     "stp_tc_enabled": (C.c_int, []),
     "stp_tc_launch_count": (_I64, []),
     "stp_set_tc_enabled": (None, [C.c_int]),
+    "stp_set_option": (C.c_int, [C.c_char_p, _I32]),
     "stp_augment_draw": (C.c_int, [C.POINTER(AugSpec), _U64, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "stp_augment_apply": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "stp_conv_fwd": (C.c_int, [_CDP, _TP, _P, _P, _TP, _TP, _P, _SZ, _P]),

@@ -375,3 +375,47 @@ def test_adam_first_step_known_answer(stp, cuda):
     expect = -lr_t * (0.1 * gvals.cpu()) / (torch.sqrt(0.001 * gvals.cpu() ** 2) + 1e-7)
     assert max_abs(p, expect) < 1e-8
     assert abs(float(p[0]) + 1e-3) < 1e-6
+
+
+@pytest.mark.parametrize("mt", [1, 2, 4, 8])
+@pytest.mark.parametrize("shape", [(1, 72, 24, 64, 64), (1, 40, 40, 16, 16), (2, 70, 16, 32, 32), (1, 40, 16, 128, 128),
+                                   (1, 33, 8, 64, 128), (1, 36, 20, 192, 32), (1, 20, 20, 32, 16)])
+def test_conv_tc2_strip_heights(stp, cuda, shape, mt):
+    """second-generation (halo) tcgen05 conv: every strip height MT, partial strips/rectangles, all swizzle widths,
+    fused bias / residual / ReLU epilogue; and the stride-1 dgrad through the same kernel."""
+    n, h, w, cin, cout = shape
+    stp.set_option(b"tc2_force_mt", mt)
+    try:
+        g = torch.Generator().manual_seed(n * 1000 + h + cin)
+        x = rand_bf16((n, h, w, cin), g)
+        wt = rand_bf16((cout, 3, 3, cin), g, scale=1.0 / math.sqrt(9 * cin))
+        res = rand_bf16((n, h, w, cout), g)
+        bias = torch.randn(cout, generator=g).to(cuda)
+        desc = lib.ConvDesc(3, 3, 1, 1, 1, 1, lib.CONV_RELU)
+        y = torch.zeros((n, h, w, cout), dtype=torch.bfloat16, device=cuda)
+        xs, ys, rs = T(x), T(y), T(res)
+        tc0 = stp.tc_launch_count()
+        stp.conv_fwd(C.byref(desc), ref(xs), wt.data_ptr(), bias.data_ptr(), ref(rs), ref(ys), None, 0, stream())
+        assert stp.tc_launch_count() - tc0 == 1
+        yr = torch.relu(conv_ref(x, wt, 1, 1, 1, (h, w)) + res.float().cpu() + bias.cpu())
+        assert rel_err(y, yr) < TOL_BF16
+        # f32 output, no epilogue extras
+        desc0 = lib.ConvDesc(3, 3, 1, 1, 1, 1, 0)
+        yf = torch.zeros((n, h, w, cout), dtype=torch.float32, device=cuda)
+        yfs = T(yf)
+        stp.conv_fwd(C.byref(desc0), ref(xs), wt.data_ptr(), None, None, ref(yfs), None, 0, stream())
+        assert rel_err(yf, conv_ref(x, wt, 1, 1, 1, (h, w))) < TOL_F32
+        # dgrad
+        wd = torch.zeros((cin, 3, 3, cout), dtype=torch.bfloat16, device=cuda)
+        wf = torch.zeros_like(wt)
+        stp.weight_prep(wt.float().contiguous().data_ptr(), wf.data_ptr(), wd.data_ptr(), cout, 3, 3, cin, stream())
+        dy = rand_bf16((n, h, w, cout), g)
+        dx = torch.zeros_like(x)
+        dys, dxs = T(dy), T(dx)
+        stp.conv_dgrad(C.byref(desc0), ref(dys), wd.data_ptr(), None, ref(dxs), None, 0, stream())
+        xr = x.float().cpu().requires_grad_(True)
+        conv_ref_autograd(xr, wt.float().cpu(), 1, 1, 1, (h, w)).backward(dy.float().cpu())
+        assert rel_err(dx, xr.grad) < TOL_BF16
+        torch.cuda.synchronize()
+    finally:
+        stp.set_option(b"tc2_force_mt", 0)
