@@ -35,6 +35,7 @@ extern "C" int stp_set_option(const char* name, int32_t value) {
   int key = -1;
   if (!strcmp(name, "tc2_force_mt")) key = OPT_TC2_FORCE_MT;        /* 0 = heuristic; 1,2,4,8 = force strip height */
   else if (!strcmp(name, "tc_conv_version")) key = OPT_TC_CONV_VERSION; /* 0 = auto, 1 = first-generation kernel only */
+  else if (!strcmp(name, "tc2_debug")) key = OPT_TC2_DEBUG;             /* timing experiments, see conv_tc2.cu */
   STP_REQUIRE(key >= 0, "set_option: unknown option %s", name);
   g_options[key].store(value);
   return STP_OK;

@@ -41,7 +41,7 @@ int launch_split_reduce(const float* ws, int splits, int64_t n, float* out, cuda
 bool tc2_conv_supported(const ConvP& p);
 int launch_tc2_conv(const ConvP& p, cudaStream_t st);
 int get_option(int key);
-enum { OPT_TC2_FORCE_MT = 0, OPT_TC_CONV_VERSION = 1, OPT_COUNT = 8 };
+enum { OPT_TC2_FORCE_MT = 0, OPT_TC_CONV_VERSION = 1, OPT_TC2_DEBUG = 2, OPT_COUNT = 8 };
 
 // conv_tc.cu (tcgen05 + TMA)
 bool tc_conv_supported(const ConvP& p);

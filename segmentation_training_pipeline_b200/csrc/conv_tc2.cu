@@ -33,6 +33,7 @@ struct Tc2Args {
   int tilesW, tilesH, tilesN;
   int num_tiles;
   int a_bytes, b_tap_bytes;  // runtime sizes of the A box and of one weight box
+  int dbg;                   // timing experiments only (results invalid): 1 skip A loads, 2 skip B loads, 4 skip epilogue memory ops, 8 skip MMAs
 };
 
 constexpr int align1k(int x) { return (x + 1023) / 1024 * 1024; }
@@ -45,18 +46,22 @@ struct Tc2Cfg {
   static constexpr int kBTap = BN * BK * 2;
   static constexpr int kBBytes = align1k(3 * kBTap);
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = (kSmemBudget2 - 2048) / kStageBytes;
+  static constexpr int kOutRowBytes = (BN < 64 ? BN : 64) * 2;       // one 64-channel (or narrower) slab of a pixel
+  static constexpr int kOutSlabs = BN < 64 ? 1 : BN / 64;
+  static constexpr int kOutBytes = align1k(128 * BN * 2);            // bf16 staging tile of one sub-tile
+  static constexpr int kStagesRaw = (kSmemBudget2 - 2048 - kOutBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemRaw = 2 * MT * BN;
   static constexpr int kTmemCols = kTmemRaw <= 32 ? 32 : kTmemRaw <= 64 ? 64 : kTmemRaw <= 128 ? 128 : kTmemRaw <= 256 ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 + 256;
   static_assert(kStages >= 2, "need at least two pipeline stages");
   static_assert(kTmemRaw <= 512, "accumulators exceed TMEM");
 };
 
 template <int BN, int BK, int MT>
 __global__ void __launch_bounds__(kThreads2, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Tc2Args a) {
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const Tc2Args a) {
   using Cfg = Tc2Cfg<BN, BK, MT>;
   constexpr int NS = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -64,11 +69,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + NS * Cfg::kABytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * Cfg::kStageBytes);
+  uint8_t* sOut = smem + NS * Cfg::kStageBytes;  // epilogue staging tile (TMA store source / residual landing zone)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sOut + Cfg::kOutBytes);
   uint64_t* empty = full + NS;
   uint64_t* acc_full = empty + NS;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* res_bar = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kcb = a.Cin / BK;
@@ -86,6 +93,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 4);
     }
+    mbar_init(res_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -120,8 +128,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int s = 0; s < a.S; ++s) {
           for (int cb = 0; cb < kcb; ++cb) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], tx);
+            if (a.dbg & 3) {
+              const uint32_t txd = ((a.dbg & 1) ? 0u : (uint32_t)a.a_bytes) + ((a.dbg & 2) ? 0u : (uint32_t)a.R * (uint32_t)a.b_tap_bytes);
+              if (txd) mbar_expect_tx(&full[stage], txd); else mbar_arrive(&full[stage]);
+            } else {
+              mbar_expect_tx(&full[stage], tx);
+            }
+            if (!(a.dbg & 1))
             tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], cb * BK, w0 + s - a.pad_w, h0 - a.pad_h, img);
+            if (!(a.dbg & 2))
             for (int r = 0; r < a.R; ++r)
               tma_load_2d(sB + stage * Cfg::kBBytes + r * Cfg::kBTap, &tmB, &full[stage],
                           (r * a.S + s) * a.Cin + cb * BK, n0);
@@ -152,6 +167,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
           const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
+          if (!(a.dbg & 8))
 #pragma unroll
           for (int j = 0; j < MT; ++j) {
             for (int r = 0; r < a.R; ++r) {
@@ -176,6 +192,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int hl = m >> a.log2BW, wl = m & (a.BW - 1);
+    const bool leader = (warp == 2 && lane == 0);
+    // 16-byte chunk swizzle of the staging tile == the TMA swizzle mode of its row width (128 / 64 / 32 B)
+    constexpr int RB = Cfg::kOutRowBytes;
+    const uint32_t swz = RB == 128 ? (uint32_t)(m & 7) : RB == 64 ? (uint32_t)((m >> 1) & 3) : (uint32_t)((m >> 2) & 1);
+    uint32_t res_phase = 0;
     int local = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++local) {
       const int as = local & 1;
@@ -187,55 +208,106 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < MT; ++j) {
-        const int ho = h0 + j * a.BH + hl;
-        const bool valid = ho < a.Ho && wo < a.Wo;
-        const int64_t pix = ((int64_t)img * a.Ho + ho) * a.Wo + wo;
+        const int hs = h0 + j * a.BH;  // first output row of this sub-tile
+        const int ho = hs + hl;
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * MT + j) * BN);
         constexpr int CH = BN >= 32 ? 32 : 16;
+        if (a.y_f32) {
+          // fp32 output (tests / small heads): direct stores
+          const bool valid = ho < a.Ho && wo < a.Wo && !(a.dbg & 4);
+          const int64_t pix = ((int64_t)img * a.Ho + ho) * a.Wo + wo;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += CH) {
+            uint32_t rr[CH];
+            if constexpr (CH == 32) tmem_ld32(t_addr + c0, rr); else tmem_ld16(t_addr + c0, rr);
+            tmem_ld_wait();
+            if (valid) {
+              float v[CH];
+#pragma unroll
+              for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(rr[i]);
+              const int n = n0 + c0;
+              if (a.bias) {
+#pragma unroll
+                for (int i = 0; i < CH; ++i) v[i] += __ldg(a.bias + n + i);
+              }
+              if (a.res) {
+                const __nv_bfloat16* rp = a.res + pix * a.ldr + n;
+#pragma unroll
+                for (int i = 0; i < CH; i += 8) {
+                  float f[8];
+                  unpack8(ld8(rp + i), f);
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) v[i + jj] += f[jj];
+                }
+              }
+              if (a.relu) {
+#pragma unroll
+                for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
+              }
+              float* yp = reinterpret_cast<float*>(a.y) + pix * a.ldy + n;
+#pragma unroll
+              for (int i = 0; i < CH; i += 4) *reinterpret_cast<float4*>(yp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+          }
+          continue;
+        }
+        // ---- bf16 output through the swizzled staging tile and TMA (coalesced, clipped at the image border) ----
+        if (hs >= a.Ho) continue;  // whole sub-tile below the image (uniform across the CTA)
+        if (leader) tma_store_wait_read();   // previous store no longer reads the staging tile
+        named_bar_sync(1, 128);
+        if (a.res) {
+          if (leader) {
+            mbar_expect_tx(res_bar, (uint32_t)(128 * BN * 2));
+#pragma unroll
+            for (int sl = 0; sl < Cfg::kOutSlabs; ++sl)
+              tma_load_4d(sOut + sl * 128 * RB, &tmR, res_bar, n0 + sl * 64, w0, hs, img);
+          }
+          mbar_wait(res_bar, res_phase);
+          res_phase ^= 1;
+        }
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += CH) {
           uint32_t rr[CH];
           if constexpr (CH == 32) tmem_ld32(t_addr + c0, rr); else tmem_ld16(t_addr + c0, rr);
           tmem_ld_wait();
-          if (valid) {
-            float v[CH];
+          float v[CH];
 #pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(rr[i]);
-            const int n = n0 + c0;
-            if (a.bias) {
+          for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(rr[i]);
+          if (a.bias) {
 #pragma unroll
-              for (int i = 0; i < CH; ++i) v[i] += __ldg(a.bias + n + i);
-            }
+            for (int i = 0; i < CH; ++i) v[i] += __ldg(a.bias + n0 + c0 + i);
+          }
+          uint8_t* slab = sOut + (c0 >> 6) * (128 * RB) + m * RB;
+          const uint32_t chunk0 = (uint32_t)((c0 & 63) >> 3);
+#pragma unroll
+          for (int i = 0; i < CH; i += 8) {
+            bf16x8* sp = reinterpret_cast<bf16x8*>(slab + (((chunk0 + (i >> 3)) ^ swz) << 4));
             if (a.res) {
-              const __nv_bfloat16* rp = a.res + pix * a.ldr + n;
+              float f[8];
+              unpack8(*sp, f);
 #pragma unroll
-              for (int i = 0; i < CH; i += 8) {
-                float f[8];
-                unpack8(ld8(rp + i), f);
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) v[i + jj] += f[jj];
-              }
+              for (int jj = 0; jj < 8; ++jj) v[i + jj] += f[jj];
             }
             if (a.relu) {
 #pragma unroll
-              for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
+              for (int jj = 0; jj < 8; ++jj) v[i + jj] = fmaxf(v[i + jj], 0.f);
             }
-            if (a.y_f32) {
-              float* yp = reinterpret_cast<float*>(a.y) + pix * a.ldy + n;
-#pragma unroll
-              for (int i = 0; i < CH; i += 4) *reinterpret_cast<float4*>(yp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-              __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + pix * a.ldy + n;
-#pragma unroll
-              for (int i = 0; i < CH; i += 8) st8(yp + i, pack8(v + i));
-            }
+            *sp = pack8(v + i);
           }
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 128);
+        if (leader && !(a.dbg & 4)) {
+#pragma unroll
+          for (int sl = 0; sl < Cfg::kOutSlabs; ++sl) tma_store_4d(&tmY, sOut + sl * 128 * RB, n0 + sl * 64, w0, hs, img);
+          tma_store_commit();
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
     }
+    if (leader) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -285,7 +357,8 @@ bool tc2_plan(const ConvP& p, Tc2Plan* pl) {
 }
 
 template <int BN, int BK, int MT>
-int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc2Args& a, cudaStream_t st) {
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR, const Tc2Args& a,
+            cudaStream_t st) {
   using Cfg = Tc2Cfg<BN, BK, MT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -297,7 +370,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc2Args& a, cu
     attr_set = true;
   }
   int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
-  conv_tc2_kernel<BN, BK, MT><<<grid, kThreads2, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
+  conv_tc2_kernel<BN, BK, MT><<<grid, kThreads2, Cfg::kSmemBytes, st>>>(tmA, tmB, tmY, tmR, a);
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("conv_tc2");
 }
@@ -340,6 +413,7 @@ int launch_tc2_conv(const ConvP& p, cudaStream_t st) {
   const int box_rows = TH + p.R - 1;
   a.a_bytes = box_rows * a.BW * pl.BK * 2;
   a.b_tap_bytes = pl.BN * pl.BK * 2;
+  a.dbg = get_option(OPT_TC2_DEBUG);
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
@@ -353,8 +427,20 @@ int launch_tc2_conv(const ConvP& p, cudaStream_t st) {
     uint32_t box[2] = {(uint32_t)pl.BK, (uint32_t)pl.BN};
     if (!make_tmap_bf16(&tmB, p.w, 2, dims, strides, box, pl.BK * 2)) return STP_E_CUDA;
   }
+  CUtensorMap tmY = tmA, tmR = tmA;  // placeholders when unused (fp32 output / no residual)
+  const uint32_t oc = pl.BN < 64 ? pl.BN : 64;
+  if (!p.y_f32) {
+    uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.N};
+    uint64_t strides[3] = {(uint64_t)p.ldy * 2, (uint64_t)p.Wo * p.ldy * 2, (uint64_t)p.Ho * p.Wo * p.ldy * 2};
+    uint32_t box[4] = {oc, (uint32_t)a.BW, (uint32_t)a.BH, 1};
+    if (!make_tmap_bf16(&tmY, p.y, 4, dims, strides, box, oc * 2)) return STP_E_CUDA;
+    if (p.res) {
+      uint64_t rstrides[3] = {(uint64_t)p.ldr * 2, (uint64_t)p.Wo * p.ldr * 2, (uint64_t)p.Ho * p.Wo * p.ldr * 2};
+      if (!make_tmap_bf16(&tmR, p.res, 4, dims, rstrides, box, oc * 2)) return STP_E_CUDA;
+    }
+  }
 #define STP_TC2_CASE(bn, bk, mt) \
-  if (pl.BN == bn && pl.BK == bk && pl.MT == mt) return launch2<bn, bk, mt>(tmA, tmB, a, st);
+  if (pl.BN == bn && pl.BK == bk && pl.MT == mt) return launch2<bn, bk, mt>(tmA, tmB, tmY, tmR, a, st);
   STP_TC2_CASE(128, 64, 2) STP_TC2_CASE(128, 64, 1)
   STP_TC2_CASE(64, 64, 4) STP_TC2_CASE(64, 64, 2) STP_TC2_CASE(64, 64, 1)
   STP_TC2_CASE(32, 64, 4) STP_TC2_CASE(32, 64, 2) STP_TC2_CASE(32, 64, 1)
