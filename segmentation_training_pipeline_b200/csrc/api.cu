@@ -134,7 +134,9 @@ extern "C" size_t stp_conv_wgrad_workspace(const stp_conv_desc* d, const stp_ten
   WgradP p = make_wgrad_p(d, x, dy);
   size_t a = generic_wgrad_workspace(p.M, p.Cout, p.K);
   size_t b = tc_wgrad_workspace(p);
-  return a > b ? a : b;
+  size_t c = narrow_wgrad_workspace(p);
+  if (b > a) a = b;
+  return a > c ? a : c;
 }
 
 extern "C" int stp_conv_wgrad(const stp_conv_desc* d, const stp_tensor* x, const stp_tensor* dy, float* dw,
@@ -143,6 +145,7 @@ extern "C" int stp_conv_wgrad(const stp_conv_desc* d, const stp_tensor* x, const
   if (rc) return rc;
   STP_REQUIRE(vec_ok(dy) && dw, "conv_wgrad: dy must be bf16 NHWC c%%8==0; dw non-null");
   WgradP p = make_wgrad_p(d, x, dy);
+  if (stp_tc_enabled() && narrow_wgrad_supported(p)) return launch_narrow_wgrad(p, dw, workspace, workspace_bytes, (cudaStream_t)stream);
   if (stp_tc_enabled() && tc_wgrad_supported(p)) return launch_tc_wgrad(p, dw, workspace, workspace_bytes, (cudaStream_t)stream);
   return launch_generic_wgrad(p, dw, workspace, workspace_bytes, (cudaStream_t)stream);
 }

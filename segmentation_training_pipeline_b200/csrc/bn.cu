@@ -144,16 +144,17 @@ __global__ void stats_u8_kernel(const uint8_t* __restrict__ x, int64_t rows, int
   }
 }
 
-// Sum the nblk block partials of 32 channels with 32 threads per channel (fixed order -> deterministic), in double.
-// blockDim = (32 channels, 32 partial groups); returns the two sums to the threads with ty == 0.
+// Sum the nblk block partials of 8 channels with 128 threads per channel (fixed order -> deterministic), in double.
+// blockDim = (8 channels, 128 partial groups); returns the two sums to the threads with ty == 0.
+constexpr int kFinCh = 8, kFinGroups = 128;
 __device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c, double& s,
                                                 double& ss) {
-  __shared__ double red[2][32][33];
+  __shared__ double red[2][kFinGroups][kFinCh + 1];
   const int tx = threadIdx.x, ty = threadIdx.y;
   double a = 0.0, b = 0.0;
   if (c < C) {
 #pragma unroll 4
-    for (int k = ty; k < nblk; k += 32) {
+    for (int k = ty; k < nblk; k += kFinGroups) {
       a += (double)partial[(int64_t)k * C + c];
       b += (double)partial[((int64_t)nblk + k) * C + c];
     }
@@ -161,15 +162,16 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
   red[0][ty][tx] = a;
   red[1][ty][tx] = b;
   __syncthreads();
-  s = 0.0;
-  ss = 0.0;
-  if (ty == 0) {
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      s += red[0][k][tx];
-      ss += red[1][k][tx];
+  // tree over the 128 groups (fixed shape -> deterministic)
+  for (int half = kFinGroups / 2; half >= 1; half >>= 1) {
+    if (ty < half) {
+      red[0][ty][tx] += red[0][ty + half][tx];
+      red[1][ty][tx] += red[1][ty + half][tx];
     }
+    __syncthreads();
   }
+  s = red[0][0][tx];
+  ss = red[1][0][tx];
 }
 
 __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partial, int nblk, int C,
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
                                                            const float* __restrict__ beta, float eps, float momentum,
                                                            float* __restrict__ mov_mean, float* __restrict__ mov_var,
                                                            float* __restrict__ coef) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int c = blockIdx.x * kFinCh + threadIdx.x;
   double s, ss;
   reduce_partials(partial, nblk, C, c, s, ss);
   if (threadIdx.y != 0 || c >= C) return;
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
                                                                double inv_count, const float* __restrict__ coef,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                float* __restrict__ bcoef) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int c = blockIdx.x * kFinCh + threadIdx.x;
   double s, ss;
   reduce_partials(partial, nblk, C, c, s, ss);
   if (threadIdx.y != 0 || c >= C) return;
@@ -407,7 +409,7 @@ extern "C" int stp_bn_finalize(const float* partial, int32_t nblk, int32_t c, in
                                float* coef, stp_stream stream) {
   STP_REQUIRE(partial && coef && nblk > 0 && c > 0 && count > 0, "bn_finalize: bad args");
   double bessel = count > 1 ? (double)count / (double)(count - 1) : 1.0;
-  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(partial, nblk, c, 1.0 / (double)count, bessel,
+  bn_finalize_kernel<<<(c + kFinCh - 1) / kFinCh, dim3(kFinCh, kFinGroups), 0, (cudaStream_t)stream>>>(partial, nblk, c, 1.0 / (double)count, bessel,
                                                                          gamma, beta, eps, momentum, moving_mean,
                                                                          moving_var, coef);
   return check_launch("bn_finalize");
@@ -452,7 +454,7 @@ extern "C" int stp_bn_bwd_reduce(const stp_tensor* dy, const stp_tensor* x, cons
 extern "C" int stp_bn_bwd_finalize(const float* partial, int32_t nblk, int32_t c, int64_t count, const float* coef,
                                    float* dgamma, float* dbeta, float* bcoef, stp_stream stream) {
   STP_REQUIRE(partial && coef && bcoef && nblk > 0, "bn_bwd_finalize: bad args");
-  bn_bwd_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(partial, nblk, c, 1.0 / (double)count,
+  bn_bwd_finalize_kernel<<<(c + kFinCh - 1) / kFinCh, dim3(kFinCh, kFinGroups), 0, (cudaStream_t)stream>>>(partial, nblk, c, 1.0 / (double)count,
                                                                              coef, dgamma, dbeta, bcoef);
   return check_launch("bn_bwd_finalize");
 }

@@ -43,6 +43,11 @@ int launch_tc2_conv(const ConvP& p, cudaStream_t st);
 int get_option(int key);
 enum { OPT_TC2_FORCE_MT = 0, OPT_TC_CONV_VERSION = 1, OPT_TC2_DEBUG = 2, OPT_COUNT = 8 };
 
+// wgrad_narrow.cu (mma.sync + TMA, Cin/Cout in {16,32})
+bool narrow_wgrad_supported(const WgradP& p);
+size_t narrow_wgrad_workspace(const WgradP& p);
+int launch_narrow_wgrad(const WgradP& p, float* dw, void* ws, size_t ws_bytes, cudaStream_t st);
+
 // conv_tc.cu (tcgen05 + TMA)
 bool tc_conv_supported(const ConvP& p);
 int launch_tc_conv(const ConvP& p, cudaStream_t st);

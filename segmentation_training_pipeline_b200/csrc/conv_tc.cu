@@ -385,26 +385,35 @@ struct TcWgradArgs {
   int Cout, Cin, R, S, pad_h, pad_w;
   int BW, BH, tilesW, tilesH;
   int num_pb, pb_per_split, splits, co_tiles, ci_tiles;
-  int a_boxes;   // 2 when Cout >= 128, else 1 (rows 64..127 alias rows 0..63 and are discarded)
-  int xrows;     // (BH + R - 1) * BW rows of the haloed input tile
+  int a_boxes;    // TMA boxes of dY per stage: 2 when Cout >= 128, else 1
+  int a_row;      // bytes per pixel row of a dY box: min(Cout,64)*2  (== its swizzle mode)
+  int a_lbo;      // byte distance between consecutive MN atoms of A (0: rows beyond the first atom alias it, discarded)
+  int m_valid;    // accumulator rows that hold real output channels
+  int b_row;      // bytes per pixel row of an X box: min(Cin,64)*2
+  int xrows;      // (BH + R - 1) * BW rows of the haloed input tile
 };
 
-template <int BN>
+// ANARROW: Cout <= 32 (dY rows of 32/64 B) -> small A stage; otherwise two 128-B-row boxes.
+template <int BN, int ANARROW>
 struct TcWgradCfg {
-  static constexpr int kABytes = 2 * 16384;
-  static constexpr int kXBoxBytes = 20480;  // >= (BH+2)*BW*128 for the supported geometries, 1024-multiple
-  static constexpr int kBBytes = (BN / 64) * kXBoxBytes;
+  static constexpr int kABytes = ANARROW ? 128 * 64 : 2 * 16384;
+  static constexpr int kBRow = (BN < 64 ? BN : 64) * 2;
+  static constexpr int kXBoxBytes = 160 * kBRow;  // >= (BH+2)*BW rows for the supported geometries; 1024-multiple
+  static constexpr int kBBytes = (BN < 64 ? 1 : BN / 64) * kXBoxBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (kSmemBudget - 2048) / kStageBytes;
-  static constexpr int kTmemCols = 3 * BN <= 256 ? 256 : 512;
+  static constexpr int kStagesRaw = (kSmemBudget - 2048) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
+  static constexpr int kTmemCols = 3 * BN <= 64 ? 64 : 3 * BN <= 128 ? 128 : 3 * BN <= 256 ? 256 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static_assert(kXBoxBytes % 1024 == 0, "stage buffers must stay swizzle-atom aligned");
 };
 
-template <int BN>
+template <int BN, int ANARROW>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const TcWgradArgs a) {
-  using Cfg = TcWgradCfg<BN>;
+  using Cfg = TcWgradCfg<BN, ANARROW>;
   constexpr int NS = Cfg::kStages;
+  constexpr int BBOX = BN < 64 ? 1 : BN / 64;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -427,6 +436,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   int pb_end = pb_begin + a.pb_per_split;
   if (pb_end > a.num_pb) pb_end = a.num_pb;
   const int npb = pb_end > pb_begin ? pb_end - pb_begin : 0;
+  const uint32_t a_box_bytes = 128u * (uint32_t)a.a_row;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmDY);
@@ -449,7 +459,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)a.a_boxes * 16384u + (uint32_t)(BN / 64) * (uint32_t)a.xrows * 128u;
+      const uint32_t tx_bytes = (uint32_t)a.a_boxes * a_box_bytes + (uint32_t)BBOX * (uint32_t)a.xrows * (uint32_t)a.b_row;
       int stage = 0;
       uint32_t phase = 0;
       for (int pb = pb_begin; pb < pb_end; ++pb) {
@@ -462,9 +472,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         mbar_expect_tx(&full[stage], tx_bytes);
         uint8_t* pa = sA + stage * Cfg::kABytes;
         uint8_t* pbuf = sB + stage * Cfg::kBBytes;
-        for (int j = 0; j < a.a_boxes; ++j) tma_load_4d(pa + j * 16384, &tmDY, &full[stage], co0 + 64 * j, w0, h0, img);
+        for (int j = 0; j < a.a_boxes; ++j) tma_load_4d(pa + j * a_box_bytes, &tmDY, &full[stage], co0 + 64 * j, w0, h0, img);
 #pragma unroll
-        for (int j = 0; j < BN / 64; ++j)
+        for (int j = 0; j < BBOX; ++j)
           tma_load_4d(pbuf + j * Cfg::kXBoxBytes, &tmX, &full[stage], ci0 + 64 * j, w0 + s - a.pad_w, h0 - a.pad_h, img);
         if (++stage == NS) {
           stage = 0;
@@ -475,7 +485,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = idesc_bf16(128, BN, 1, 1);
-      const uint32_t a_lbo = a.a_boxes == 2 ? 16384u : 0u;
+      const uint32_t a_step = 16u * (uint32_t)a.a_row, b_step = 16u * (uint32_t)a.b_row;  // 16 pixels (one MMA K) further
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < npb; ++i) {
@@ -484,11 +494,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
         const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
         for (int r = 0; r < a.R; ++r) {
-          const uint32_t b_r = b_addr + (uint32_t)(r * a.BW) * 128u;
+          const uint32_t b_r = b_addr + (uint32_t)(r * a.BW) * (uint32_t)a.b_row;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
-            const uint64_t ad = desc_mnmajor_sw128(a_addr + kk * 2048, a_lbo);
-            const uint64_t bd = desc_mnmajor_sw128(b_r + kk * 2048, Cfg::kXBoxBytes);
+            const uint64_t ad = desc_mnmajor(a_addr + kk * a_step, (uint32_t)a.a_lbo, (uint32_t)a.a_row);
+            const uint64_t bd = desc_mnmajor(b_r + kk * b_step, Cfg::kXBoxBytes, (uint32_t)a.b_row);
             umma_bf16(tmem_base + (uint32_t)(r * BN), ad, bd, idesc, (i | kk) != 0);
           }
         }
@@ -505,22 +515,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     const int co = co0 + q * 32 + lane;
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const bool valid = (q * 32 + lane) < (a.a_boxes == 2 ? 128 : 64) && co < a.Cout;
+    const bool valid = (q * 32 + lane) < a.m_valid && co < a.Cout;
+    constexpr int CH = BN >= 32 ? 32 : 16;
     for (int r = 0; r < a.R; ++r) {
       float* op = a.out + ((((int64_t)split * a.Cout + co) * a.R + r) * a.S + s) * a.Cin + ci0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t rr[32];
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        uint32_t rr[CH];
         if (npb > 0) {
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * BN + c0), rr);
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * BN + c0);
+          if constexpr (CH == 32) tmem_ld32(ta, rr); else tmem_ld16(ta, rr);
           tmem_ld_wait();
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) rr[i] = 0u;
+          for (int i = 0; i < CH; ++i) rr[i] = 0u;
         }
         if (valid) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
+          for (int i = 0; i < CH; i += 4)
             *reinterpret_cast<float4*>(op + c0 + i) = make_float4(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1]),
                                                                   __uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3]));
         }
@@ -540,11 +552,13 @@ struct WgradPlan {
 };
 
 static bool wgrad_plan(int64_t M, int N_img, int Ho, int Wo, int Cout, int Cin, int R, int S, WgradPlan* pl) {
-  if (Cout % 64 != 0 || Cin % 64 != 0 || R > 3 || S > 3 || Wo < 8) return false;
-  pl->BN = (Cin % 128 == 0) ? 128 : 64;
+  const bool co_ok = Cout % 64 == 0 || Cout == 32 || Cout == 16;
+  const bool ci_ok = Cin % 64 == 0 || Cin == 32 || Cin == 16;
+  if (!co_ok || !ci_ok || R > 3 || S > 3 || Wo < 8) return false;
+  pl->BN = (Cin % 128 == 0) ? 128 : (Cin % 64 == 0 ? 64 : Cin);
   pl->BW = Wo >= 16 ? 16 : 8;
   pl->BH = 128 / pl->BW;
-  if ((pl->BH + R - 1) * pl->BW * 128 > 20480) return false;
+  if ((pl->BH + R - 1) * pl->BW > 160) return false;
   pl->tilesW = (Wo + pl->BW - 1) / pl->BW;
   pl->tilesH = (Ho + pl->BH - 1) / pl->BH;
   int64_t npb = (int64_t)N_img * pl->tilesW * pl->tilesH;
@@ -583,20 +597,20 @@ size_t tc_wgrad_workspace(const WgradP& p) {
   return pl.splits > 1 ? (size_t)pl.splits * p.Cout * p.K * sizeof(float) : 0;
 }
 
-template <int BN>
+template <int BN, int ANARROW>
 static int launch_wgrad_cfg(const CUtensorMap& tmDY, const CUtensorMap& tmX, const TcWgradArgs& a, int items,
                             cudaStream_t st) {
-  using Cfg = TcWgradCfg<BN>;
+  using Cfg = TcWgradCfg<BN, ANARROW>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN, ANARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return STP_E_CUDA;
     }
     attr_set = true;
   }
-  wgrad_tc_kernel<BN><<<items, kThreads, Cfg::kSmemBytes, st>>>(tmDY, tmX, a);
+  wgrad_tc_kernel<BN, ANARROW><<<items, kThreads, Cfg::kSmemBytes, st>>>(tmDY, tmX, a);
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("wgrad_tc");
 }
@@ -619,21 +633,32 @@ int launch_tc_wgrad(const WgradP& p, float* dw, void* ws, size_t ws_bytes, cudaS
   a.num_pb = pl.num_pb; a.pb_per_split = pl.pb_per_split; a.splits = pl.splits;
   a.co_tiles = pl.co_tiles; a.ci_tiles = pl.ci_tiles;
   a.a_boxes = p.Cout >= 128 ? 2 : 1;
+  const int co_atom = p.Cout < 64 ? p.Cout : 64;  // channels per dY box / MN atom
+  a.a_row = co_atom * 2;
+  a.a_lbo = p.Cout >= 128 ? 128 * a.a_row : 0;
+  a.m_valid = p.Cout >= 128 ? 128 : p.Cout;
+  const int ci_atom = p.Cin < 64 ? p.Cin : 64;
+  a.b_row = ci_atom * 2;
   a.xrows = (pl.BH + p.R - 1) * pl.BW;
   CUtensorMap tmDY, tmX;
   {
     uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.N};
     uint64_t strides[3] = {(uint64_t)p.lddy * 2, (uint64_t)p.Wo * p.lddy * 2, (uint64_t)p.Ho * p.Wo * p.lddy * 2};
-    uint32_t box[4] = {64, (uint32_t)pl.BW, (uint32_t)pl.BH, 1};
-    if (!make_tmap_bf16(&tmDY, p.dy, 4, dims, strides, box, 128)) return STP_E_CUDA;
+    uint32_t box[4] = {(uint32_t)co_atom, (uint32_t)pl.BW, (uint32_t)pl.BH, 1};
+    if (!make_tmap_bf16(&tmDY, p.dy, 4, dims, strides, box, a.a_row)) return STP_E_CUDA;
   }
   {
     uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
     uint64_t strides[3] = {(uint64_t)p.ldx * 2, (uint64_t)p.W * p.ldx * 2, (uint64_t)p.H * p.W * p.ldx * 2};
-    uint32_t box[4] = {64, (uint32_t)pl.BW, (uint32_t)(pl.BH + p.R - 1), 1};
-    if (!make_tmap_bf16(&tmX, p.x, 4, dims, strides, box, 128)) return STP_E_CUDA;
+    uint32_t box[4] = {(uint32_t)ci_atom, (uint32_t)pl.BW, (uint32_t)(pl.BH + p.R - 1), 1};
+    if (!make_tmap_bf16(&tmX, p.x, 4, dims, strides, box, a.b_row)) return STP_E_CUDA;
   }
-  int rc = pl.BN == 128 ? launch_wgrad_cfg<128>(tmDY, tmX, a, pl.items, st) : launch_wgrad_cfg<64>(tmDY, tmX, a, pl.items, st);
+  const bool narrow = p.Cout <= 32;
+  int rc = STP_E_UNSUPPORTED;
+#define STP_WG_CASE(bn) \
+  if (pl.BN == bn) rc = narrow ? launch_wgrad_cfg<bn, 1>(tmDY, tmX, a, pl.items, st) : launch_wgrad_cfg<bn, 0>(tmDY, tmX, a, pl.items, st);
+  STP_WG_CASE(128) STP_WG_CASE(64) STP_WG_CASE(32) STP_WG_CASE(16)
+#undef STP_WG_CASE
   if (rc || pl.splits == 1) return rc;
   return launch_split_reduce((const float*)ws, pl.splits, (int64_t)p.Cout * p.K, dw, st);
 }

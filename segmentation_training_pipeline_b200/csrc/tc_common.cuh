@@ -155,6 +155,18 @@ __device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t saddr, uint32_t 
   d |= (uint64_t)LAYOUT_SW128 << 61;
   return d;
 }
+// MN-major operand with rows of row_bytes in {32, 64, 128} (= the TMA swizzle mode): 8-row K groups 8*row_bytes apart,
+// consecutive MN atoms (row_bytes/2 elements) lbo_bytes apart (0 = every atom aliases the first one).
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t row_bytes) {
+  const uint32_t layout = row_bytes == 128 ? LAYOUT_SW128 : (row_bytes == 64 ? LAYOUT_SW64 : LAYOUT_SW32);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((8u * row_bytes) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
 // kind::f16 instruction descriptor: bf16 x bf16 -> f32, M x N tile, majorness of A and B (0 = K-major, 1 = MN-major)
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |

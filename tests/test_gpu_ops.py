@@ -45,7 +45,7 @@ CONV_CASES = [
     (1, 8, 8, 64, 384, 3, 1, 1, 1),
     (2, 32, 32, 64, 128, 1, 1, 0, 1),
 ]
-TC_WGRAD_CASES = {0, 6, 8, 10, 13, 14, 15}  # ... and whose wgrad must take the tcgen05 wgrad kernel
+TC_WGRAD_CASES = {0, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15}  # ... and whose wgrad must take the tcgen05 wgrad kernel
 TC_FWD_CASES = {0, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15}  # indices of CONV_CASES whose forward must take the tcgen05 kernel
 
 
