@@ -204,6 +204,7 @@ def run_gpu(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = "cuda:%d" % local_rank
     if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(dev))
     from segmentation_training_pipeline_b200 import lib
     from segmentation_training_pipeline_b200.models import SegNet
@@ -216,6 +217,9 @@ def run_gpu(args, rank, local_rank, world):
     pool_n = args.pool
     img, mask = synth_pool(pool_n, S, S, 1234 + rank, 4321 + rank)
     tr.set_pool(torch.from_numpy(img), torch.from_numpy(mask))
+    if world > 1:
+        from segmentation_training_pipeline_b200 import ddp
+        ddp.broadcast_(net.flat_p, 0)
     l0 = net.L.launch_count()
     tr.capture()
     launches_per_step = (net.L.launch_count() - l0) // 2  # capture() runs the step twice (warm-up + capture)
@@ -246,27 +250,19 @@ def run_gpu(args, rank, local_rank, world):
     loss_end = tr.loss_value()
     clk = clocks.stop(t0, t1) if rank == 0 else None
 
-    # ---- e2e: host buffers; per step H2D of the raw batch (pinned), step, D2H of the loss/metrics vector ----
+    # ---- e2e: the public host-fed path (Trainer.step_from_host, what PipelineConfig.fit drives): per step H2D of the
+    # raw uint8 batch from pinned host memory, graph replay, D2H of the 16-float loss/metrics vector + stream sync ----
     hp_img = torch.from_numpy(img).pin_memory()
     hp_mask = torch.from_numpy(mask).pin_memory()
     tr2 = Trainer(net, optimizer="Adam", lr=1e-3, augment=aug, world_size=world)
     tr2.m, tr2.v = tr.m, tr.v
-    stage_img = torch.zeros((B, S, S, 3), dtype=torch.uint8, device=dev)
-    stage_mask = torch.zeros((B, S, S, 1), dtype=torch.uint8, device=dev)
-    tr2.pool_img, tr2.pool_mask = stage_img, stage_mask
-    tr2.capture()
-    res_host = torch.zeros(16, dtype=torch.float32).pin_memory()
+    tr2.enable_host_feed()
     h2d = B * S * S * 4
     d2h = 16 * 4
 
     def e2e_step(i):
         j = (i * B) % pool_n
-        stage_img.copy_(hp_img[j:j + B], non_blocking=True)
-        stage_mask.copy_(hp_mask[j:j + B], non_blocking=True)
-        tr2.step()
-        res_host.copy_(net.loss.result, non_blocking=True)
-        st.synchronize()           # the user reads the loss every step
-        return float(res_host[0])
+        return tr2.step_from_host(hp_img[j:j + B], hp_mask[j:j + B], read_metrics=True)["loss"]
 
     for i in range(max(3, args.warmup)):
         e2e_step(i)

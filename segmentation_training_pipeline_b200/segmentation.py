@@ -1,0 +1,248 @@
+"""Host-side mirror of the reference's experiment API for the training hot path.
+
+    from segmentation_pipeline import segmentation                      # alias package at the repo root
+    from segmentation_pipeline.impl.datasets import SimplePNGMaskDataSet
+    cfg = segmentation.parse("config.yaml"); cfg.fit(SimplePNGMaskDataSet(imgs, masks))
+
+Reference: segmentation_pipeline/segmentation.py -- parse :211-214, PipelineConfig :35-208, createNet1 :96-155,
+loss/metric registry :15-22, custom_models :31-33; schema keys schemas/segmentation.raml:26-136; augmenters
+schemas/augmenters.raml:43-133; inherited fit/kfold/stages from musket_core.generic_config [DEP] as documented in
+README.md:116-205 (5 shuffled folds, random_state, weights/, metrics/, summary.yaml next to the yaml).
+
+Everything numeric runs in libstp (CUDA, no CPU fallback): `fit` raises if the library / a GPU is missing.
+What is NOT mirrored (out of the hot-path scope): callbacks other than the best-weights checkpoint and CSV
+log, lr_find, negatives sampling, crops, DrawResults, FPN/Linknet/PSPNet/DeepLab graphs, lovasz/focal/jaccard losses
+(these raise NotImplementedError naming the key instead of being silently ignored).
+"""
+from __future__ import annotations
+
+import ast
+import csv
+import os
+import re
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import yaml
+
+from . import models as _models
+from .trainer import AugmentConfig
+
+# architecture plugins: name -> callable(**kwargs) returning a model object (reference segmentation.py:31-33)
+custom_models: Dict[str, Callable] = {}
+# custom loss/metric registry stand-in for keras.utils.get_custom_objects() (reference README.md:629-634)
+custom_objects: Dict[str, Callable] = {}
+extra_train: Dict[str, object] = {}
+dataset_augmenters: Dict[str, Callable] = {}
+
+_LOSS_TERMS = {"binary_crossentropy": 0, "dice_loss": 1, "iou_loss": 2}
+_UNFUSED_LOSSES = ("lovasz_loss", "focal_loss", "jaccard_loss", "categorical_crossentropy")
+_METRIC_ALIASES = {"binary_accuracy": "binary_accuracy", "dice": "dice", "iou": "iou", "iou_coef": "iou", "iot": "iot",
+                   "iot_coef": "iot", "loss": "loss", "binary_crossentropy": "binary_crossentropy"}
+
+
+def parse_loss(expr: str) -> Tuple[float, float, float]:
+    """'binary_crossentropy+0.1*dice_loss' (reference README.md:210-214) -> (w_bce, w_dice, w_iou)."""
+    if not isinstance(expr, str) or not expr.strip():
+        raise ValueError("loss must be a non-empty string")
+    w = [0.0, 0.0, 0.0]
+
+    def term(node, scale):
+        if isinstance(node, ast.BinOp) and isinstance(node.op, ast.Add):
+            term(node.left, scale)
+            term(node.right, scale)
+        elif isinstance(node, ast.BinOp) and isinstance(node.op, ast.Sub):
+            term(node.left, scale)
+            term(node.right, -scale)
+        elif isinstance(node, ast.BinOp) and isinstance(node.op, ast.Mult):
+            if isinstance(node.left, ast.Constant):
+                term(node.right, scale * float(node.left.value))
+            elif isinstance(node.right, ast.Constant):
+                term(node.left, scale * float(node.right.value))
+            else:
+                raise ValueError("loss expression: product needs a numeric factor: " + expr)
+        elif isinstance(node, ast.Name):
+            if node.id in _LOSS_TERMS:
+                w[_LOSS_TERMS[node.id]] += scale
+            elif node.id in _UNFUSED_LOSSES:
+                raise NotImplementedError("loss '%s' has no fused device kernel yet (DESIGN.md, out of scope rows)" % node.id)
+            else:
+                raise ValueError("unknown loss '%s'" % node.id)
+        else:
+            raise ValueError("cannot parse loss expression: " + expr)
+
+    term(ast.parse(expr.strip(), mode="eval").body, 1.0)
+    return w[0], w[1], w[2]
+
+
+def _rng(v, cast=float):
+    if isinstance(v, (list, tuple)):
+        if len(v) != 2:
+            raise ValueError("range needs 2 values: %r" % (v,))
+        return cast(v[0]), cast(v[1])
+    return cast(v), cast(v)
+
+
+def parse_augmentation(spec: Optional[dict], seed: int = 0) -> AugmentConfig:
+    """YAML `augmentation:` (reference README.md:249-268, augmenters.raml positional convention :24-40) -> the fused
+    device augmenter.  Only the augmenters the K1 kernel fuses are accepted; anything else raises."""
+    cfg = AugmentConfig(seed=seed)
+    if not spec:
+        return cfg
+    for name, val in spec.items():
+        if name == "Fliplr":
+            cfg.fliplr = float(val)
+        elif name == "Flipud":
+            cfg.flipud = float(val)
+        elif name == "Affine":
+            val = val or {}
+            cfg.affine = True
+            if "scale" in val:
+                cfg.scale = _rng(val["scale"])
+            tp = val.get("translate_percent")
+            if tp is not None:
+                if isinstance(tp, dict):
+                    cfg.translate_x = _rng(tp.get("x", 0.0))
+                    cfg.translate_y = _rng(tp.get("y", 0.0))
+                else:
+                    cfg.translate_x = cfg.translate_y = _rng(tp)
+            if "rotate" in val:
+                cfg.rotate = _rng(val["rotate"])
+            if "shear" in val:
+                cfg.shear = _rng(val["shear"])
+            bad = set(val) - {"scale", "translate_percent", "rotate", "shear"}
+            if bad:
+                raise NotImplementedError("Affine keys not fused on device: %s" % sorted(bad))
+        elif name == "Multiply":
+            cfg.multiply = _rng(val)
+        elif name == "Add":
+            cfg.add = _rng(val, int)
+        else:
+            raise NotImplementedError("augmenter '%s' is not fused on device (supported: Fliplr, Flipud, Affine, Multiply, Add)" % name)
+    return cfg
+
+
+class PipelineConfig:
+    """Mirrors the attributes/verbs of the reference PipelineConfig that the training path uses."""
+
+    def __init__(self, **atrs):
+        self.architecture = atrs.pop("architecture", None)
+        self.backbone = atrs.pop("backbone", "resnet34")
+        self.classes = int(atrs.pop("classes", 1))
+        self.activation = atrs.pop("activation", "sigmoid")
+        self.shape = list(atrs.pop("shape", [512, 512, 3]))
+        self.encoder_weights = atrs.pop("encoder_weights", None)
+        self.freeze_encoder = bool(atrs.pop("freeze_encoder", False))
+        self.augmentation = atrs.pop("augmentation", None) or {}
+        self.transforms = atrs.pop("transforms", None)
+        self.optimizer = atrs.pop("optimizer", "Adam")
+        self.lr = atrs.pop("lr", None)
+        self.clipnorm = atrs.pop("clipnorm", None)
+        self.clipvalue = atrs.pop("clipvalue", None)
+        self.loss = atrs.pop("loss", "binary_crossentropy")
+        self.batch = int(atrs.pop("batch", 16))                     # schema default, segmentation.raml:93-97
+        self.metrics = list(atrs.pop("metrics", []) or [])
+        self.primary_metric = atrs.pop("primary_metric", "val_loss")
+        self.primary_metric_mode = atrs.pop("primary_metric_mode", "auto")
+        self.stages = list(atrs.pop("stages", [{"epochs": 1}]) or [{"epochs": 1}])
+        self.folds_count = int(atrs.pop("folds_count", 5))
+        self.random_state = int(atrs.pop("random_state", 33))
+        self.testSplit = float(atrs.pop("testSplit", 0.0) or 0.0)
+        self.decoder_filters = tuple(atrs.pop("decoder_filters", (256, 128, 64, 32, 16)))
+        self.callbacks = atrs.pop("callbacks", None)
+        self.datasets = atrs.pop("datasets", None)
+        self.fit_with = atrs.pop("fit_with", None)
+        self.extra = atrs            # accepted, unused keys (kept so configs round-trip)
+        self.path: Optional[str] = None
+        self.gpus = 1                # FAQ.md:108-112 `cfg.gpus = N`; data parallel = 1 process / GPU here (see ddp.py)
+        self.showDataExamples = False
+        self.allowResume = False
+        self.device = "cuda:0"
+        self.device_augment = True
+
+    # -- reference verbs ---------------------------------------------------------------------------
+    def setAllowResume(self, v: bool = True):
+        self.allowResume = bool(v)
+
+    def createNet(self, batch: Optional[int] = None, loss: Optional[str] = None):
+        """YAML keys -> engine graph (reference createNet1, segmentation.py:96-155): unknown names raise the same
+        ValueErrors after printing the known lists."""
+        arch = self.architecture
+        if arch in custom_models:
+            return custom_models[arch](backbone=self.backbone, classes=self.classes, input_shape=tuple(self.shape),
+                                       activation=self.activation)
+        if arch not in _models.KNOWN_ARCHITECTURES:
+            print("Unknown architecture:" + str(arch))
+            print("Known architectures:", _models.KNOWN_ARCHITECTURES + sorted(custom_models))
+            raise ValueError("Unknown architecture")
+        bb = str(self.backbone).lower()
+        if bb not in _models.KNOWN_BACKBONES:
+            print("Unknown backbone:" + bb)
+            print("Known backbones:", _models.KNOWN_BACKBONES)
+            raise ValueError("Unknown backbone")
+        if self.classes != 1 or self.activation not in ("sigmoid", None, "none"):
+            raise NotImplementedError("only classes=1 / sigmoid heads have fused loss kernels so far")
+        if self.encoder_weights not in (None, "None", "none"):
+            raise NotImplementedError("encoder_weights: no network here -- load a local .npz with load_weights()")
+        return _models.SegNet(bb, classes=self.classes, input_shape=tuple(self.shape), batch=batch or self.batch,
+                              decoder_filters=self.decoder_filters, device=self.device, seed=self.random_state,
+                              loss=parse_loss(loss or self.loss))
+
+    def kfold(self, n: int) -> List[Tuple[np.ndarray, np.ndarray]]:
+        """sklearn KFold(folds_count, shuffle=True, random_state) as the reference's ImageKFoldedDataSet [DEP]."""
+        from sklearn.model_selection import KFold
+        idx = np.arange(n)
+        return [(tr, te) for tr, te in KFold(n_splits=self.folds_count, shuffle=True, random_state=self.random_state).split(idx)]
+
+    def _dir(self):
+        if self.path is None:
+            raise ValueError("cfg.path is not set (use segmentation.parse)")
+        return os.path.dirname(os.path.abspath(self.path))
+
+    def _resolve_dataset(self, d):
+        if d is not None:
+            return d
+        if self.fit_with and self.datasets and self.fit_with in self.datasets:
+            from .impl.datasets import SimplePNGMaskDataSet
+            spec = self.datasets[self.fit_with]
+            base = self._dir()
+            return SimplePNGMaskDataSet(os.path.join(base, spec["input_path"]), os.path.join(base, spec["output_path"]))
+        raise ValueError("fit() needs a dataset or `datasets:` + `fit_with:` in the config")
+
+    def fit(self, d=None, subsample=1.0, foldsToExecute: Optional[Sequence[int]] = None, start_from_stage=0):
+        from .fit import run_fit
+        return run_fit(self, self._resolve_dataset(d), subsample, foldsToExecute, start_from_stage)
+
+    def load_model(self, fold: int = 0, stage: int = -1):
+        """Engine graph with the best weights of (fold, stage) (reference README.md:553)."""
+        if stage < 0:
+            stage = len(self.stages) - 1
+        net = self.createNet()
+        p = os.path.join(self._dir(), "weights", "best-%d.%d.weights.npz" % (fold, stage))
+        w = dict(np.load(p))
+        net.set_weights(w)
+        return net
+
+    def info(self):
+        """aggregated best metric per fold/stage from metrics/*.csv (reference FAQ.md:63-70)."""
+        out = []
+        mdir = os.path.join(self._dir(), "metrics")
+        if not os.path.isdir(mdir):
+            return out
+        for f in sorted(os.listdir(mdir)):
+            m = re.match(r"metrics-(\d+)\.(\d+)\.csv$", f)
+            if not m:
+                continue
+            rows = list(csv.DictReader(open(os.path.join(mdir, f))))
+            if rows:
+                out.append({"fold": int(m.group(1)), "stage": int(m.group(2)), "epochs": len(rows), "last": rows[-1]})
+        return out
+
+
+def parse(path) -> PipelineConfig:
+    """reference segmentation.py:211-214."""
+    with open(path) as f:
+        atrs = yaml.safe_load(f) or {}
+    cfg = PipelineConfig(**atrs)
+    cfg.path = path
+    return cfg

@@ -70,6 +70,7 @@ class Trainer:
         self.pool_mask: Optional[torch.Tensor] = None
         self.aug_params = torch.zeros(net.batch * C.sizeof(_lib.AugSample), dtype=torch.uint8, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_opt: Optional[torch.cuda.CUDAGraph] = None
         self._gx = _lib.GradXform(1.0 / world_size, self.clipnorm, self.clipvalue,
                                   self.sumsq.data_ptr() if self.clipnorm > 0 else None)
         self._ident = AugmentConfig()
@@ -103,8 +104,8 @@ class Trainer:
 
     def allreduce(self):
         if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.net.flat_g, group=self.pg)
+            from . import ddp
+            ddp.allreduce_sum_(self.net.flat_g, self.pg)   # the 1/world mean is folded into the optimizer kernel
 
     def run_optimizer(self):
         net, st = self.net, _stream()
@@ -134,8 +135,21 @@ class Trainer:
         self.allreduce()
         self.run_optimizer()
 
+    def step_compute(self, from_pool=True):
+        net = self.net
+        net.training = True
+        if from_pool and self.pool_img is not None:
+            self.run_augment()
+        net.prep_weights()
+        net.forward()
+        net.backward()
+
     def capture(self, from_pool=True):
-        """Warm up eagerly once on a side stream, then capture the step into a CUDA graph."""
+        """Warm up eagerly once on a side stream, then capture the step into a CUDA graph.  With world_size > 1 the
+        step is TWO graphs (augment+forward+backward | optimizer) with the NCCL all-reduce enqueued between them on
+        the same stream, so no collective is captured."""
+        if self.world_size > 1:
+            return self._capture_ddp(from_pool)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         saved = self._snapshot()
@@ -151,11 +165,55 @@ class Trainer:
         self.graph = g
         return g
 
+    def _capture_ddp(self, from_pool=True):
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        saved = self._snapshot()
+        with torch.cuda.stream(s):
+            self.step_eager(from_pool)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._restore(saved)
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            self.step_compute(from_pool)
+        with torch.cuda.graph(g2, pool=g1.pool()):
+            self.run_optimizer()
+        self._restore(saved)
+        self.graph, self.graph_opt = g1, g2
+        return g1
+
     def step(self):
         if self.graph is not None:
             self.graph.replay()
+            if self.world_size > 1:
+                self.allreduce()
+                self.graph_opt.replay()
         else:
             self.step_eager()
+
+    # ---- host-fed steps (the public fit() path and bench.py's e2e number) -----------------------
+    def enable_host_feed(self):
+        """Device staging buffers for ONE batch + graph capture; afterwards step_from_host() is: async H2D of the raw
+        uint8 batch from pinned memory -> graph replay (augment .. optimizer) -> optional D2H of the 16-float result."""
+        net = self.net
+        H, W, CI = net.input_shape
+        self.pool_img = torch.zeros((net.batch, H, W, CI), dtype=torch.uint8, device=net.device)
+        self.pool_mask = torch.zeros((net.batch, H, W, net.classes), dtype=torch.uint8, device=net.device)
+        self._res_host = torch.zeros(16, dtype=torch.float32).pin_memory()
+        self.capture(from_pool=True)
+
+    def step_from_host(self, images: torch.Tensor, masks: torch.Tensor, read_metrics=True):
+        self.pool_img.copy_(images, non_blocking=True)
+        self.pool_mask.copy_(masks, non_blocking=True)
+        self.step()
+        if not read_metrics:
+            return None
+        self._res_host.copy_(self.net.loss.result, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        r = self._res_host
+        return {"loss": float(r[_lib.L_LOSS]), "binary_crossentropy": float(r[_lib.L_BCE]), "dice": float(r[_lib.L_DICE]),
+                "iou": float(r[_lib.L_IOU]), "binary_accuracy": float(r[_lib.L_ACC]), "iot": float(r[_lib.L_IOT])}
 
     def loss_value(self) -> float:
         return float(self.net.loss.result[_lib.L_LOSS].item())

@@ -1,0 +1,124 @@
+"""CPU suite: the reference-facing host API (config parsing, loss / augmentation mapping, dataset protocol, folds,
+rank sharding) -- no GPU, no libstp compute calls."""
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CFG = os.path.join(HERE, "golden", "configs")
+
+
+def test_import_paths_of_the_reference_work():
+    from segmentation_pipeline import segmentation
+    from segmentation_pipeline.impl.datasets import PredictionItem, SimplePNGMaskDataSet
+    assert callable(segmentation.parse) and isinstance(segmentation.custom_models, dict)
+    assert PredictionItem("a", 1, 2).id == "a" and SimplePNGMaskDataSet is not None
+
+
+def test_parse_baseline_config():
+    from segmentation_pipeline import segmentation
+    cfg = segmentation.parse(os.path.join(CFG, "c2_unet_resnet34.yaml"))
+    assert cfg.path.endswith("c2_unet_resnet34.yaml")
+    assert (cfg.architecture, cfg.backbone, cfg.classes, cfg.batch) == ("Unet", "resnet34", 1, 16)
+    assert cfg.shape == [512, 512, 3] and cfg.folds_count == 5 and cfg.random_state == 33
+    assert segmentation.parse_loss(cfg.loss) == (1.0, 1.0, 0.0)
+    a = segmentation.parse_augmentation(cfg.augmentation)
+    assert a.fliplr == 0.5 and a.flipud == 0.5 and a.affine and a.scale == (0.8, 1.5)
+    assert a.translate_x == (-0.2, 0.2) and a.rotate == (-16.0, 16.0) and a.multiply == (0.8, 1.2) and a.add == (-10, 10)
+    c = a.to_c()
+    assert c.affine == 1 and c.has_mul == 1 and c.has_add == 1 and abs(c.shear_hi - 16.0) < 1e-12
+
+
+@pytest.mark.parametrize("expr,want", [("binary_crossentropy", (1, 0, 0)), ("dice_loss", (0, 1, 0)),
+                                       ("binary_crossentropy+0.1*dice_loss", (1, 0.1, 0)),
+                                       ("0.5*binary_crossentropy + iou_loss*2", (0.5, 0, 2)),
+                                       ("binary_crossentropy+dice_loss+iou_loss", (1, 1, 1))])
+def test_composite_loss_strings(expr, want):
+    from segmentation_pipeline.segmentation import parse_loss
+    assert parse_loss(expr) == pytest.approx(want)
+
+
+def test_loss_and_augmenter_errors_are_loud():
+    from segmentation_pipeline.segmentation import parse_augmentation, parse_loss
+    with pytest.raises(NotImplementedError):
+        parse_loss("lovasz_loss")
+    with pytest.raises(ValueError):
+        parse_loss("no_such_loss")
+    with pytest.raises(NotImplementedError):
+        parse_augmentation({"GaussianBlur": 1.0})
+
+
+def test_unknown_architecture_and_backbone(tmp_path, capsys):
+    from segmentation_pipeline import segmentation
+    p = tmp_path / "c.yaml"
+    p.write_text("architecture: Nope\nbackbone: resnet34\nclasses: 1\nshape: [64,64,3]\n")
+    with pytest.raises(ValueError, match="Unknown architecture"):
+        segmentation.parse(str(p)).createNet()
+    p.write_text("architecture: Unet\nbackbone: nope\nclasses: 1\nshape: [64,64,3]\n")
+    with pytest.raises(ValueError, match="Unknown backbone"):
+        segmentation.parse(str(p)).createNet()
+    assert "Known backbones" in capsys.readouterr().out
+
+
+def test_custom_models_plugin_hook(tmp_path):
+    from segmentation_pipeline import segmentation
+    seen = {}
+
+    def factory(**kw):
+        seen.update(kw)
+        return "model"
+
+    segmentation.custom_models["MyNet"] = factory
+    try:
+        p = tmp_path / "c.yaml"
+        p.write_text("architecture: MyNet\nbackbone: resnet18\nclasses: 1\nshape: [64,64,3]\n")
+        assert segmentation.parse(str(p)).createNet() == "model"
+        assert seen["backbone"] == "resnet18" and seen["input_shape"] == (64, 64, 3)
+    finally:
+        del segmentation.custom_models["MyNet"]
+
+
+def test_simple_png_mask_dataset(tmp_path):
+    import cv2
+    from segmentation_pipeline.impl.datasets import SimplePNGMaskDataSet
+    (tmp_path / "i").mkdir()
+    (tmp_path / "m").mkdir()
+    rng = np.random.default_rng(0)
+    for k in range(3):
+        img = rng.integers(0, 256, (20, 24, 3), dtype=np.uint8)
+        m = np.zeros((20, 24), np.uint8)
+        m[5:10, 3:9] = 255 if k else 0
+        cv2.imwrite(str(tmp_path / "i" / ("%d.png" % k)), img)
+        cv2.imwrite(str(tmp_path / "m" / ("%d.png" % k)), m)
+    ds = SimplePNGMaskDataSet(str(tmp_path / "i"), str(tmp_path / "m"))
+    assert len(ds) == 3
+    it = ds[1]
+    assert it.x.shape == (20, 24, 3) and it.x.dtype == np.uint8 and it.y.shape == (20, 24, 1)
+    assert set(np.unique(it.y)) == {0, 1} and it.y.sum() == 30 and it.id == "1"
+    assert ds.isPositive(1) and not ds.isPositive(0)
+
+
+def test_kfold_is_sklearn_shuffled_and_seeded(tmp_path):
+    from sklearn.model_selection import KFold
+    from segmentation_pipeline import segmentation
+    cfg = segmentation.parse(os.path.join(CFG, "c1_plumbing.yaml"))
+    f1, f2 = cfg.kfold(11), cfg.kfold(11)
+    want = list(KFold(n_splits=2, shuffle=True, random_state=7).split(np.arange(11)))
+    for (a, b), (c, d), (e, f) in zip(f1, f2, want):
+        assert np.array_equal(a, c) and np.array_equal(b, d) and np.array_equal(a, e) and np.array_equal(b, f)
+
+
+def test_shard_indices_partitions_global_batches():
+    from segmentation_training_pipeline_b200.ddp import shard_indices
+    order = np.random.default_rng(1).permutation(103)
+    world, batch = 4, 5
+    shards = [shard_indices(order, r, world, batch) for r in range(world)]
+    assert all(len(s) == (103 // 20) * 5 for s in shards)
+    allv = np.concatenate(shards)
+    assert len(set(allv.tolist())) == len(allv)                      # disjoint
+    # global batch g of the single-process run == concatenation of the ranks' g-th batches
+    for g in range(103 // 20):
+        cat = np.concatenate([s[g * batch:(g + 1) * batch] for s in shards])
+        assert np.array_equal(cat, order[g * 20:(g + 1) * 20])
+    assert len(shard_indices(order[:7], 0, 4, 5)) == 0               # ragged tail dropped, empty is fine
