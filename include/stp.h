@@ -132,9 +132,18 @@ size_t stp_conv_wgrad_workspace(const stp_conv_desc* d, const stp_tensor* x, con
 int stp_weight_prep(const float* w_master, void* w_fwd, void* w_dgrad, int32_t cout, int32_t r, int32_t s,
                     int32_t cin, stp_stream stream);
 
+/* stp_weight_prep for every conv layer of a network in one launch over the flat buffers.  d_items: device int64 [n][8] =
+ * {element offset into the flat buffers, cout, r, s, cin, has_dgrad, first_tile, 0}; a layer owns
+ * r*s*ceil(cout/32)*ceil(cin/32) consecutive tiles starting at first_tile; total_tiles = their sum. */
+int stp_weight_prep_batched(const float* flat_master, void* flat_fwd, void* flat_dgrad, const int64_t* d_items,
+                            int32_t n_items, int64_t total_tiles, stp_stream stream);
+
 /* small-Cout head (final_conv + sigmoid, classes<=4): CUDA-core, HBM bound.  logits/probabilities f32 [M,classes] */
+/* workspace (stp_head_fwd_workspace bytes, 16-byte aligned) holds the bf16 zero-padded [16][3][3][Cin] weight copy of the
+ * tcgen05 path; with workspace == NULL (or an unsupported shape) the CUDA-core kernel runs instead */
 int stp_head_fwd(const stp_tensor* x, const float* w_krsc_f32, const float* bias, int32_t classes,
-                 float* logits, stp_stream stream);
+                 float* logits, void* workspace, size_t workspace_bytes, stp_stream stream);
+size_t stp_head_fwd_workspace(const stp_tensor* x, int32_t classes);
 /* dlogits f32 [M,classes] -> dx bf16, dw f32 [classes][3][3][Cin], dbias f32[classes] (workspace reduction) */
 int stp_head_bwd(const stp_tensor* x, const float* w_krsc_f32, const float* dlogits, int32_t classes,
                  const stp_tensor* dx, float* dw, float* dbias, void* workspace, size_t workspace_bytes,
@@ -154,6 +163,11 @@ int stp_bn_stats(const stp_tensor* x, float* partial, stp_stream stream);
 int stp_bn_finalize(const float* partial, int32_t nblk, int32_t c, int64_t count, const float* gamma,
                     const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
                     float* coef, stp_stream stream);
+/* stp_bn_stats + stp_bn_finalize in ONE launch: the last thread block to finish (device ticket in *sync, a
+ * zero-initialised uint32 the kernel returns to zero) reduces the partials and finalises. */
+int stp_bn_stats_fused(const stp_tensor* x, float* partial, uint32_t* sync, const float* gamma, const float* beta,
+                       float eps, float momentum, float* moving_mean, float* moving_var, float* coef,
+                       stp_stream stream);
 /* y = [relu](x*scale+shift); up=2 writes each value to the 2x2 block of y (UpSampling2D fused) */
 int stp_bn_apply(const stp_tensor* x, const float* coef, int32_t relu, int32_t up, const stp_tensor* y,
                  stp_stream stream);
@@ -167,6 +181,10 @@ int stp_bn_bwd_reduce(const stp_tensor* dy, const stp_tensor* x, const float* co
 /* partials -> dgamma, dbeta (f32, written; may be NULL for scale=False) and bcoef f32 [3][c] (a,b,cc) with dx = a*g + b*x + cc */
 int stp_bn_bwd_finalize(const float* partial, int32_t nblk, int32_t c, int64_t count, const float* coef,
                         float* dgamma, float* dbeta, float* bcoef, stp_stream stream);
+/* stp_bn_bwd_reduce + stp_bn_bwd_finalize in ONE launch (same last-block scheme as stp_bn_stats_fused) */
+int stp_bn_bwd_reduce_fused(const stp_tensor* dy, const stp_tensor* x, const float* coef, int32_t relu, int32_t pool,
+                            float* partial, uint32_t* sync, float* dgamma, float* dbeta, float* bcoef,
+                            stp_stream stream);
 /* dx = a*g + b*x + cc [+ residual] */
 int stp_bn_bwd_apply(const stp_tensor* dy, const stp_tensor* x, const float* coef, const float* bcoef,
                      int32_t relu, int32_t pool, const stp_tensor* residual, const stp_tensor* dx,

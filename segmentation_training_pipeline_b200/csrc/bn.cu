@@ -6,41 +6,190 @@
 
 namespace stp {
 
-// thread geometry for a [rows, C] tensor: CV = C/8 vectors per row, RPI rows per block iteration
+// Thread geometry for a [rows, C] tensor streamed row-wise: a thread owns ONE 8-channel vector (its per-channel
+// coefficients live in registers) and walks rows; a block covers `rpi` consecutive rows per step, so a block step
+// touches rpi*C*2 contiguous bytes (when ld == C).  Blocks own contiguous row ranges (deterministic partials).
 struct RowGeom {
-  int cv, rpi, threads, nblk;
-  int64_t rows_per_blk;
+  int cv, nv, rpi, threads, nblk;
+  int rows_per_blk;
 };
-static RowGeom geom(int64_t rows, int c) {
+static RowGeom geom(int64_t rows, int c, int unroll, int max_blk) {
   RowGeom g;
   g.cv = c / 8;
-  g.rpi = g.cv >= 256 ? 1 : 256 / g.cv;
-  g.threads = g.rpi * (g.cv > 256 ? 256 : g.cv);
-  int64_t nb = (rows + (int64_t)g.rpi * 8 - 1) / ((int64_t)g.rpi * 8);
+  g.nv = g.cv > 256 ? 256 : g.cv;
+  g.rpi = 256 / g.nv;
+  g.threads = g.rpi * g.nv;
+  const int64_t step = (int64_t)g.rpi * unroll;
+  int64_t nb = (rows + step - 1) / step;
   if (nb < 1) nb = 1;
-  if (nb > STP_BN_MAX_PARTIALS) nb = STP_BN_MAX_PARTIALS;
-  g.nblk = (int)nb;
-  g.rows_per_blk = (rows + nb - 1) / nb;
+  if (nb > max_blk) nb = max_blk;
+  int64_t rpb = (rows + nb - 1) / nb;
+  rpb = (rpb + g.rpi - 1) / g.rpi * g.rpi;
+  g.rows_per_blk = (int)rpb;
+  g.nblk = (int)((rows + rpb - 1) / rpb);
   return g;
+}
+// partial blocks of the reduction kernels: enough CTAs to fill the GPU, few enough that the last CTA can finalise
+// nblk x 2C partial sums in a couple of microseconds
+static int reduce_max_blk(int c) {
+  int m = 24576 / (c < 8 ? 8 : c);
+  if (m > 2 * kNumSMs) m = 2 * kNumSMs;
+  if (m < 32) m = 32;
+  return m;
+}
+static RowGeom reduce_geom(int64_t rows, int c) { return geom(rows, c, 4, reduce_max_blk(c)); }
+
+// What the LAST block of a reduction kernel does with the partial sums (mode 0: nothing, a separate finalize kernel runs)
+struct FinArgs {
+  int mode;  // 0 none | 1 forward statistics -> coef (+ moving stats) | 2 backward -> dgamma, dbeta, bcoef
+  unsigned int* sync;
+  double inv_count, bessel;
+  const float* gamma;
+  const float* beta;
+  float eps, momentum;
+  float* mov_mean;
+  float* mov_var;
+  float* coef;  // mode 1: output; mode 2: input
+  float* dgamma;
+  float* dbeta;
+  float* bcoef;
+};
+
+__device__ __forceinline__ void fin_forward(const FinArgs& f, int C, int c, double s, double ss) {
+  double mean = s * f.inv_count;
+  double var = ss * f.inv_count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  double invstd = rsqrt(var + (double)f.eps);
+  float g = f.gamma ? f.gamma[c] : 1.f;
+  float b = f.beta ? f.beta[c] : 0.f;
+  float scale = g * (float)invstd;
+  f.coef[c] = (float)mean;
+  f.coef[C + c] = (float)invstd;
+  f.coef[2 * C + c] = scale;
+  f.coef[3 * C + c] = b - (float)mean * scale;
+  if (f.mov_mean) {
+    f.mov_mean[c] = f.mov_mean[c] * f.momentum + (float)mean * (1.f - f.momentum);
+    f.mov_var[c] = f.mov_var[c] * f.momentum + (float)(var * f.bessel) * (1.f - f.momentum);
+  }
+}
+__device__ __forceinline__ void fin_backward(const FinArgs& f, int C, int c, double s, double ss) {
+  if (f.dbeta) f.dbeta[c] = (float)s;
+  if (f.dgamma) f.dgamma[c] = (float)ss;
+  double mean = f.coef[c], invstd = f.coef[C + c], a = f.coef[2 * C + c];
+  double b = -a * invstd * ss * f.inv_count;
+  double cc = -a * s * f.inv_count - b * mean;
+  f.bcoef[c] = (float)a;
+  f.bcoef[C + c] = (float)b;
+  f.bcoef[2 * C + c] = (float)cc;
+}
+
+// Executed by every thread of a reduction block after its partials are written: elects the last block of the grid
+// (threadfence + atomic ticket) which then sums the nblk partials per channel in a fixed order (deterministic), in
+// double, and finalises.  The ticket counter is returned to zero for the next launch / graph replay.
+__device__ void last_block_finalize(const FinArgs& f, const float* __restrict__ partial, int nblk, int C, float* smf) {
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(f.sync, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double* red = reinterpret_cast<double*>(smf);  // [2][blockDim]
+  const int nt = blockDim.x;
+  const int CC = C < nt ? C : nt;
+  const int G = nt / CC;
+  const int cl = threadIdx.x % CC, g = threadIdx.x / CC;
+  for (int c0 = 0; c0 < C; c0 += CC) {
+    const int c = c0 + cl;
+    double a = 0.0, b = 0.0;
+    if (g < G && c < C) {
+      // L2-coherent loads (other blocks wrote these), 16 independent loads in flight per thread
+      const float* p0 = partial + c;
+      const float* p1 = partial + (int64_t)nblk * C + c;
+      int k = g;
+      for (; k + 7 * G < nblk; k += 8 * G) {
+        float t0[8], t1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          t0[j] = __ldcg(p0 + (int64_t)(k + j * G) * C);
+          t1[j] = __ldcg(p1 + (int64_t)(k + j * G) * C);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a += (double)t0[j];
+          b += (double)t1[j];
+        }
+      }
+      for (; k < nblk; k += G) {
+        a += (double)__ldcg(p0 + (int64_t)k * C);
+        b += (double)__ldcg(p1 + (int64_t)k * C);
+      }
+    }
+    __syncthreads();
+    red[threadIdx.x] = a;
+    red[nt + threadIdx.x] = b;
+    __syncthreads();
+    if (g == 0 && c < C) {
+      for (int j = 1; j < G; ++j) {
+        a += red[j * CC + cl];
+        b += red[nt + j * CC + cl];
+      }
+      if (f.mode == 1) fin_forward(f, C, c, a, b); else fin_backward(f, C, c, a, b);
+    }
+  }
+  if (threadIdx.x == 0) *f.sync = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------
-// stats: partial[0][blk][c] = sum x, partial[1][blk][c] = sum x^2
-// MODE 0: plain stats of x.   MODE 1: bn backward reduce (sum g, sum g*xhat), dy optional 2x2 pooled.
+// row reductions: partial[0][blk][c], partial[1][blk][c]
+// MODE 0: sum x, sum x^2.   MODE 1: bn backward (sum g, sum g*xhat), g = dy masked by relu; dy optionally the
+// gradient of the 2x-upsampled tensor (2x2 summed on the fly).
 // ---------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(256) reduce_rows_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+__device__ __forceinline__ void load_g(const __nv_bfloat16* __restrict__ dy, int lddy, int pool, int H, int W, int r,
+                                       int v, float* g) {
+  if (pool == 2) {
+    unsigned n = (unsigned)r / (unsigned)(H * W);
+    unsigned rem = (unsigned)r - n * (unsigned)(H * W);
+    unsigned h = rem / (unsigned)W, w = rem - h * (unsigned)W;
+    const __nv_bfloat16* base = dy + (((int64_t)n * 2 * H + 2 * h) * (int64_t)(2 * W) + 2 * w) * lddy + v * 8;
+    bf16x8 a0 = ld8(base), a1 = ld8(base + lddy), a2 = ld8(base + (int64_t)2 * W * lddy),
+           a3 = ld8(base + (int64_t)2 * W * lddy + lddy);
+    float t[8];
+    unpack8(a0, g);
+    unpack8(a1, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] += t[i];
+    unpack8(a2, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] += t[i];
+    unpack8(a3, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] += t[i];
+  } else {
+    unpack8(ld8(dy + (int64_t)r * lddy + v * 8), g);
+  }
+}
+
+template <int MODE, int POOL>
+__global__ void __launch_bounds__(256, 2) reduce_rows_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                                           const __nv_bfloat16* __restrict__ dy, int lddy,
                                                           const float* __restrict__ coef, int relu, int pool,
-                                                          int H, int W, int64_t rows, int C, int cv, int rpi,
-                                                          int64_t rows_per_blk, float* __restrict__ partial) {
-  extern __shared__ float sm[];  // [2][rpi][C]
-  const int nv = cv > 256 ? 256 : cv;
+                                                          int H, int W, int rows, int C, int cv, int nv, int rpi,
+                                                          int rows_per_blk, float* __restrict__ partial,
+                                                          const FinArgs fin) {
+  extern __shared__ float sm[];  // [2][groups][C], groups <= 8 (>= 2*blockDim doubles for the finalize)
   const int v0 = threadIdx.x % nv;
   const int rl = threadIdx.x / nv;
-  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_blk;
-  int64_t r_end = r_begin + rows_per_blk;
+  const int r_begin = blockIdx.x * rows_per_blk;
+  int r_end = r_begin + rows_per_blk;
   if (r_end > rows) r_end = rows;
+  // rows of one warp can be pre-reduced with shuffles when a warp spans whole rows (nv a power of two <= 32)
+  const bool shfl = nv <= 32 && (nv & (nv - 1)) == 0 && (blockDim.x & 31) == 0;
+  const int groups = shfl ? (blockDim.x >> 5) : rpi;
+  const int grp = shfl ? (threadIdx.x >> 5) : rl;
   for (int v = v0; v < cv; v += nv) {
     float s0[8], s1[8];
 #pragma unroll
@@ -56,58 +205,83 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const __nv_bfloat16* _
         shift[i] = coef[3 * C + c];
       }
     }
-    for (int64_t r = r_begin + rl; r < r_end; r += rpi) {
-      float xf[8];
-      unpack8(ld8(x + r * ldx + v * 8), xf);
-      if (MODE == 0) {
+    if (MODE == 0) {
+      for (int r = r_begin + rl; r < r_end; r += 8 * rpi) {
+        bf16x8 q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (r + j * rpi < r_end) q[j] = ld8(x + (int64_t)(r + j * rpi) * ldx + v * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (r + j * rpi < r_end) {
+            float xf[8];
+            unpack8(q[j], xf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              s0[i] += xf[i];
+              s1[i] += xf[i] * xf[i];
+            }
+          }
+      }
+    } else {
+      constexpr int U = POOL == 2 ? 2 : 4;
+      for (int r = r_begin + rl; r < r_end; r += U * rpi) {
+        bf16x8 q[U];
+        bf16x8 qg[U];     // POOL == 1: raw dy vectors
+        float g2[POOL == 2 ? U : 1][8];  // POOL == 2: 2x2-summed dy
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+          if (r + j * rpi < r_end) {
+            q[j] = ld8(x + (int64_t)(r + j * rpi) * ldx + v * 8);
+            if (POOL == 2) load_g(dy, lddy, 2, H, W, r + j * rpi, v, g2[POOL == 2 ? j : 0]);
+            else qg[j] = ld8(dy + (int64_t)(r + j * rpi) * lddy + v * 8);
+          }
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+          if (r + j * rpi < r_end) {
+            float xf[8], g[8];
+            unpack8(q[j], xf);
+            if (POOL == 2) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) g[i] = g2[POOL == 2 ? j : 0][i];
+            } else {
+              unpack8(qg[j], g);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float gi = g[i];
+              if (relu && !(xf[i] * scale[i] + shift[i] > 0.f)) gi = 0.f;
+              s0[i] += gi;
+              s1[i] += gi * ((xf[i] - mean[i]) * invstd[i]);
+            }
+          }
+      }
+    }
+    if (shfl) {
+      for (int off = 16; off >= nv; off >>= 1) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          s0[i] += xf[i];
-          s1[i] += xf[i] * xf[i];
-        }
-      } else {
-        float g[8];
-        if (pool == 2) {
-          int64_t n = r / ((int64_t)H * W);
-          int rem = (int)(r - n * (int64_t)H * W);
-          int h = rem / W, w = rem - h * W;
-          const __nv_bfloat16* base = dy + ((n * 2 * H + 2 * h) * (int64_t)(2 * W) + 2 * w) * lddy + v * 8;
-          float t[8];
-          unpack8(ld8(base), g);
-          unpack8(ld8(base + lddy), t);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] += t[i];
-          unpack8(ld8(base + (int64_t)2 * W * lddy), t);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] += t[i];
-          unpack8(ld8(base + (int64_t)2 * W * lddy + lddy), t);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] += t[i];
-        } else {
-          unpack8(ld8(dy + r * lddy + v * 8), g);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float gi = g[i];
-          if (relu && !(xf[i] * scale[i] + shift[i] > 0.f)) gi = 0.f;
-          s0[i] += gi;
-          s1[i] += gi * ((xf[i] - mean[i]) * invstd[i]);
+          s0[i] += __shfl_xor_sync(0xffffffffu, s0[i], off);
+          s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], off);
         }
       }
     }
+    if (!shfl || (threadIdx.x & 31) < nv) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      sm[(0 * rpi + rl) * C + v * 8 + i] = s0[i];
-      sm[(1 * rpi + rl) * C + v * 8 + i] = s1[i];
+      for (int i = 0; i < 8; ++i) {
+        sm[(0 * groups + grp) * C + v * 8 + i] = s0[i];
+        sm[(1 * groups + grp) * C + v * 8 + i] = s1[i];
+      }
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
     int which = c / C, ch = c - which * C;
     float a = 0.f;
-    for (int r = 0; r < rpi; ++r) a += sm[(which * rpi + r) * C + ch];
+    for (int r = 0; r < groups; ++r) a += sm[(which * groups + r) * C + ch];
     partial[((int64_t)which * gridDim.x + blockIdx.x) * C + ch] = a;
   }
+  if (fin.mode != 0) last_block_finalize(fin, partial, gridDim.x, C, sm);
 }
 
 __global__ void stats_u8_kernel(const uint8_t* __restrict__ x, int64_t rows, int C, int64_t rows_per_blk,
@@ -231,90 +405,129 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
   bcoef[2 * C + c] = (float)cc;
 }
 
-// y = [relu](x*scale+shift), optional 2x nearest upsample on write
+// y = [relu](x*scale+shift), optional 2x nearest upsample on write.  Row-streamed (see RowGeom), 4 loads in flight.
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                                        const float* __restrict__ coef, int relu, int up,
                                                        __nv_bfloat16* __restrict__ y, int ldy, int H, int W,
-                                                       int64_t rows, int C, int cv) {
-  int64_t total = rows * cv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / cv;
-    int v = (int)(i - r * cv);
-    float f[8];
-    unpack8(ld8(x + r * ldx + v * 8), f);
+                                                       int rows, int C, int cv, int nv, int rpi, int rows_per_blk) {
+  const int v0 = threadIdx.x % nv;
+  const int rl = threadIdx.x / nv;
+  const int r_begin = blockIdx.x * rows_per_blk;
+  int r_end = r_begin + rows_per_blk;
+  if (r_end > rows) r_end = rows;
+  for (int v = v0; v < cv; v += nv) {
+    float scale[8], shift[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      int c = v * 8 + k;
-      float t = f[k] * __ldg(coef + 2 * C + c) + __ldg(coef + 3 * C + c);
-      f[k] = (relu && !(t > 0.f)) ? 0.f : t;
+    for (int i = 0; i < 8; ++i) {
+      scale[i] = coef[2 * C + v * 8 + i];
+      shift[i] = coef[3 * C + v * 8 + i];
     }
-    bf16x8 o = pack8(f);
-    if (up == 1) {
-      st8(y + r * ldy + v * 8, o);
-    } else {
-      int64_t n = r / ((int64_t)H * W);
-      int rem = (int)(r - n * (int64_t)H * W);
-      int h = rem / W, w = rem - h * W;
-      __nv_bfloat16* base = y + ((n * 2 * H + 2 * h) * (int64_t)(2 * W) + 2 * w) * ldy + v * 8;
-      st8(base, o);
-      st8(base + ldy, o);
-      st8(base + (int64_t)2 * W * ldy, o);
-      st8(base + (int64_t)2 * W * ldy + ldy, o);
+    for (int r = r_begin + rl; r < r_end; r += 4 * rpi) {
+      bf16x8 q[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (r + j * rpi < r_end) q[j] = ld8(x + (int64_t)(r + j * rpi) * ldx + v * 8);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = r + j * rpi;
+        if (rr < r_end) {
+          float f[8];
+          unpack8(q[j], f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float t = f[k] * scale[k] + shift[k];
+            f[k] = (relu && !(t > 0.f)) ? 0.f : t;
+          }
+          bf16x8 o = pack8(f);
+          if (up == 1) {
+            st8(y + (int64_t)rr * ldy + v * 8, o);
+          } else {
+            unsigned n = (unsigned)rr / (unsigned)(H * W);
+            unsigned rem = (unsigned)rr - n * (unsigned)(H * W);
+            unsigned h = rem / (unsigned)W, w = rem - h * (unsigned)W;
+            __nv_bfloat16* base = y + (((int64_t)n * 2 * H + 2 * h) * (int64_t)(2 * W) + 2 * w) * ldy + v * 8;
+            st8(base, o);
+            st8(base + ldy, o);
+            st8(base + (int64_t)2 * W * ldy, o);
+            st8(base + (int64_t)2 * W * ldy + ldy, o);
+          }
+        }
+      }
     }
   }
 }
 
 // MODE 0: dx = a*g + b*x + cc (+res) with g = dy masked by relu(bn(x)).  MODE 1: relu bwd, mask from y=x>0.
-template <int MODE>
-__global__ void __launch_bounds__(256) bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int lddy,
+template <int MODE, int POOL>
+__global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int lddy,
                                                         const __nv_bfloat16* __restrict__ x, int ldx,
                                                         const float* __restrict__ coef,
                                                         const float* __restrict__ bcoef, int relu, int pool,
                                                         const __nv_bfloat16* __restrict__ res, int ldr,
                                                         __nv_bfloat16* __restrict__ dx, int lddx, int H, int W,
-                                                        int64_t rows, int C, int cv) {
-  int64_t total = rows * cv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / cv;
-    int v = (int)(i - r * cv);
-    float xf[8], g[8];
-    unpack8(ld8(x + r * ldx + v * 8), xf);
-    if (pool == 2) {
-      int64_t n = r / ((int64_t)H * W);
-      int rem = (int)(r - n * (int64_t)H * W);
-      int h = rem / W, w = rem - h * W;
-      const __nv_bfloat16* base = dy + ((n * 2 * H + 2 * h) * (int64_t)(2 * W) + 2 * w) * lddy + v * 8;
-      float t[8];
-      unpack8(ld8(base), g);
-      unpack8(ld8(base + lddy), t);
+                                                        int rows, int C, int cv, int nv, int rpi, int rows_per_blk) {
+  const int v0 = threadIdx.x % nv;
+  const int rl = threadIdx.x / nv;
+  const int r_begin = blockIdx.x * rows_per_blk;
+  int r_end = r_begin + rows_per_blk;
+  if (r_end > rows) r_end = rows;
+  for (int v = v0; v < cv; v += nv) {
+    float scale[8], shift[8], ca[8], cb[8], cc[8];
+    if (MODE == 0) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] += t[k];
-      unpack8(ld8(base + (int64_t)2 * W * lddy), t);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] += t[k];
-      unpack8(ld8(base + (int64_t)2 * W * lddy + lddy), t);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] += t[k];
-    } else {
-      unpack8(ld8(dy + r * lddy + v * 8), g);
-    }
-    float rf[8];
-    if (res) unpack8(ld8(res + r * ldr + v * 8), rf);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      int c = v * 8 + k;
-      float o;
-      if (MODE == 0) {
-        float gi = g[k];
-        if (relu && !(xf[k] * __ldg(coef + 2 * C + c) + __ldg(coef + 3 * C + c) > 0.f)) gi = 0.f;
-        o = __ldg(bcoef + c) * gi + __ldg(bcoef + C + c) * xf[k] + __ldg(bcoef + 2 * C + c);
-      } else {
-        o = xf[k] > 0.f ? g[k] : 0.f;
+      for (int i = 0; i < 8; ++i) {
+        const int c = v * 8 + i;
+        scale[i] = coef[2 * C + c];
+        shift[i] = coef[3 * C + c];
+        ca[i] = bcoef[c];
+        cb[i] = bcoef[C + c];
+        cc[i] = bcoef[2 * C + c];
       }
-      if (res) o += rf[k];
-      g[k] = o;
     }
-    st8(dx + r * lddx + v * 8, pack8(g));
+    constexpr int U = POOL == 2 ? 2 : 4;
+    for (int r = r_begin + rl; r < r_end; r += U * rpi) {
+      bf16x8 qx[U], qr[U], qg[U];
+      float g2[POOL == 2 ? U : 1][8];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int rr = r + j * rpi;
+        if (rr < r_end) {
+          qx[j] = ld8(x + (int64_t)rr * ldx + v * 8);
+          if (res) qr[j] = ld8(res + (int64_t)rr * ldr + v * 8);
+          if (POOL == 2) load_g(dy, lddy, 2, H, W, rr, v, g2[POOL == 2 ? j : 0]);
+          else qg[j] = ld8(dy + (int64_t)rr * lddy + v * 8);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int rr = r + j * rpi;
+        if (rr < r_end) {
+          float xf[8], rf[8], g[8];
+          unpack8(qx[j], xf);
+          if (res) unpack8(qr[j], rf);
+          if (POOL == 2) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] = g2[POOL == 2 ? j : 0][k];
+          } else {
+            unpack8(qg[j], g);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float o;
+            if (MODE == 0) {
+              float gi = g[k];
+              if (relu && !(xf[k] * scale[k] + shift[k] > 0.f)) gi = 0.f;
+              o = ca[k] * gi + cb[k] * xf[k] + cc[k];
+            } else {
+              o = xf[k] > 0.f ? g[k] : 0.f;
+            }
+            if (res) o += rf[k];
+            g[k] = o;
+          }
+          st8(dx + (int64_t)rr * lddx + v * 8, pack8(g));
+        }
+      }
+    }
   }
 }
 
@@ -381,27 +594,73 @@ static int ew_grid(int64_t total) {
 
 using namespace stp;
 
-extern "C" int32_t stp_bn_nblk(int64_t rows, int32_t c) { return geom(rows, c < 8 ? 8 : c).nblk; }
+extern "C" int32_t stp_bn_nblk(int64_t rows, int32_t c) { return reduce_geom(rows, c < 8 ? 8 : c).nblk; }
 
-extern "C" int stp_bn_stats(const stp_tensor* x, float* partial, stp_stream stream) {
-  STP_REQUIRE(x && partial, "bn_stats: null");
-  cudaStream_t st = (cudaStream_t)stream;
+static size_t reduce_smem(const RowGeom& g, int c) {
+  const bool shfl = g.nv <= 32 && (g.nv & (g.nv - 1)) == 0 && (g.threads & 31) == 0;
+  const int groups = shfl ? g.threads / 32 : g.rpi;
+  size_t a = (size_t)2 * groups * c * sizeof(float);
+  size_t b = (size_t)2 * g.threads * sizeof(double);
+  return a > b ? a : b;
+}
+
+static int launch_stats(const stp_tensor* x, float* partial, const FinArgs& fin, cudaStream_t st) {
   int64_t rows = pixels(x);
   if (x->dtype == STP_U8) {
+    STP_REQUIRE(fin.mode == 0, "bn_stats u8: fused finalize unsupported");
     STP_REQUIRE(x->c <= 4 && x->ld == x->c, "bn_stats u8: c<=4 dense only");
-    int nblk = geom(rows, 8).nblk;  // same rule as stp_bn_nblk(rows, c<8)
+    int nblk = reduce_geom(rows, 8).nblk;  // same rule as stp_bn_nblk(rows, c<8)
     int64_t rpb = (rows + nblk - 1) / nblk;
     stats_u8_kernel<<<nblk, 256, 0, st>>>((const uint8_t*)x->ptr, rows, x->c, rpb, partial);
     return check_launch("stats_u8");
   }
   STP_REQUIRE(vec_ok(x), "bn_stats: tensor must be bf16, c%%8==0, ld%%8==0, 16B aligned");
-  STP_REQUIRE(x->c <= 2048, "bn_stats: c too large");
-  RowGeom g = geom(rows, x->c);
-  size_t smem = (size_t)2 * g.rpi * x->c * sizeof(float);
-  reduce_rows_kernel<0><<<g.nblk, g.threads, smem, st>>>((const __nv_bfloat16*)x->ptr, x->ld, nullptr, 0, nullptr, 0,
-                                                          1, x->h, x->w, rows, x->c, g.cv, g.rpi, g.rows_per_blk,
-                                                          partial);
+  STP_REQUIRE(x->c <= 2048 && rows < 0x7fffffff, "bn_stats: c or rows too large");
+  RowGeom g = reduce_geom(rows, x->c);
+  reduce_rows_kernel<0, 1><<<g.nblk, g.threads, reduce_smem(g, x->c), st>>>(
+      (const __nv_bfloat16*)x->ptr, x->ld, nullptr, 0, nullptr, 0, 1, x->h, x->w, (int)rows, x->c, g.cv, g.nv, g.rpi,
+      g.rows_per_blk, partial, fin);
   return check_launch("bn_stats");
+}
+
+static int launch_bwd_reduce(const stp_tensor* dy, const stp_tensor* x, const float* coef, int relu, int pool,
+                             float* partial, const FinArgs& fin, cudaStream_t st) {
+  STP_REQUIRE(vec_ok(dy) && vec_ok(x) && coef && partial, "bn_bwd_reduce: bad tensors");
+  STP_REQUIRE(pool == 1 || pool == 2, "bn_bwd_reduce: pool must be 1 or 2");
+  STP_REQUIRE(dy->c == x->c && dy->h == x->h * pool && dy->w == x->w * pool && dy->n == x->n,
+              "bn_bwd_reduce: shape mismatch");
+  int64_t rows = pixels(x);
+  STP_REQUIRE(x->c <= 2048 && rows < 0x7fffffff, "bn_bwd_reduce: c or rows too large");
+  RowGeom g = reduce_geom(rows, x->c);
+  if (pool == 2)
+    reduce_rows_kernel<1, 2><<<g.nblk, g.threads, reduce_smem(g, x->c), st>>>(
+        (const __nv_bfloat16*)x->ptr, x->ld, (const __nv_bfloat16*)dy->ptr, dy->ld, coef, relu, pool, x->h, x->w,
+        (int)rows, x->c, g.cv, g.nv, g.rpi, g.rows_per_blk, partial, fin);
+  else
+    reduce_rows_kernel<1, 1><<<g.nblk, g.threads, reduce_smem(g, x->c), st>>>(
+        (const __nv_bfloat16*)x->ptr, x->ld, (const __nv_bfloat16*)dy->ptr, dy->ld, coef, relu, pool, x->h, x->w,
+        (int)rows, x->c, g.cv, g.nv, g.rpi, g.rows_per_blk, partial, fin);
+  return check_launch("bn_bwd_reduce");
+}
+
+extern "C" int stp_bn_stats(const stp_tensor* x, float* partial, stp_stream stream) {
+  STP_REQUIRE(x && partial, "bn_stats: null");
+  FinArgs fin = {};
+  return launch_stats(x, partial, fin, (cudaStream_t)stream);
+}
+
+extern "C" int stp_bn_stats_fused(const stp_tensor* x, float* partial, uint32_t* sync, const float* gamma,
+                                  const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
+                                  float* coef, stp_stream stream) {
+  STP_REQUIRE(x && partial && sync && coef, "bn_stats_fused: null");
+  const int64_t count = pixels(x);
+  STP_REQUIRE(count > 0, "bn_stats_fused: empty tensor");
+  FinArgs fin = {};
+  fin.mode = 1; fin.sync = sync; fin.inv_count = 1.0 / (double)count;
+  fin.bessel = count > 1 ? (double)count / (double)(count - 1) : 1.0;
+  fin.gamma = gamma; fin.beta = beta; fin.eps = eps; fin.momentum = momentum;
+  fin.mov_mean = moving_mean; fin.mov_var = moving_var; fin.coef = coef;
+  return launch_stats(x, partial, fin, (cudaStream_t)stream);
 }
 
 extern "C" int stp_bn_finalize(const float* partial, int32_t nblk, int32_t c, int64_t count, const float* gamma,
@@ -429,26 +688,30 @@ extern "C" int stp_bn_apply(const stp_tensor* x, const float* coef, int32_t relu
   STP_REQUIRE(up == 1 || up == 2, "bn_apply: up must be 1 or 2");
   STP_REQUIRE(y->c == x->c && y->n == x->n && y->h == x->h * up && y->w == x->w * up, "bn_apply: shape mismatch");
   int64_t rows = pixels(x);
-  int cv = x->c / 8;
-  bn_apply_kernel<<<ew_grid(rows * cv), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x->ptr, x->ld, coef, relu, up, (__nv_bfloat16*)y->ptr, y->ld, x->h, x->w, rows, x->c, cv);
+  STP_REQUIRE(rows < 0x7fffffff, "bn_apply: too many rows");
+  RowGeom g = geom(rows, x->c, 4, kNumSMs * 8);
+  bn_apply_kernel<<<g.nblk, g.threads, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x->ptr, x->ld, coef, relu, up, (__nv_bfloat16*)y->ptr, y->ld, x->h, x->w, (int)rows, x->c,
+      g.cv, g.nv, g.rpi, g.rows_per_blk);
   return check_launch("bn_apply");
 }
 
 extern "C" int stp_bn_bwd_reduce(const stp_tensor* dy, const stp_tensor* x, const float* coef, int32_t relu,
                                  int32_t pool, float* partial, stp_stream stream) {
-  STP_REQUIRE(vec_ok(dy) && vec_ok(x) && coef && partial, "bn_bwd_reduce: bad tensors");
-  STP_REQUIRE(pool == 1 || pool == 2, "bn_bwd_reduce: pool must be 1 or 2");
-  STP_REQUIRE(dy->c == x->c && dy->h == x->h * pool && dy->w == x->w * pool && dy->n == x->n,
-              "bn_bwd_reduce: shape mismatch");
-  STP_REQUIRE(x->c <= 2048, "bn_bwd_reduce: c too large");
-  int64_t rows = pixels(x);
-  RowGeom g = geom(rows, x->c);
-  size_t smem = (size_t)2 * g.rpi * x->c * sizeof(float);
-  reduce_rows_kernel<1><<<g.nblk, g.threads, smem, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x->ptr, x->ld, (const __nv_bfloat16*)dy->ptr, dy->ld, coef, relu, pool, x->h, x->w, rows,
-      x->c, g.cv, g.rpi, g.rows_per_blk, partial);
-  return check_launch("bn_bwd_reduce");
+  FinArgs fin = {};
+  return launch_bwd_reduce(dy, x, coef, relu, pool, partial, fin, (cudaStream_t)stream);
+}
+
+extern "C" int stp_bn_bwd_reduce_fused(const stp_tensor* dy, const stp_tensor* x, const float* coef, int32_t relu,
+                                       int32_t pool, float* partial, uint32_t* sync, float* dgamma, float* dbeta,
+                                       float* bcoef, stp_stream stream) {
+  STP_REQUIRE(x && sync && bcoef, "bn_bwd_reduce_fused: null");
+  const int64_t count = pixels(x);
+  STP_REQUIRE(count > 0, "bn_bwd_reduce_fused: empty tensor");
+  FinArgs fin = {};
+  fin.mode = 2; fin.sync = sync; fin.inv_count = 1.0 / (double)count;
+  fin.coef = const_cast<float*>(coef); fin.dgamma = dgamma; fin.dbeta = dbeta; fin.bcoef = bcoef;
+  return launch_bwd_reduce(dy, x, coef, relu, pool, partial, fin, (cudaStream_t)stream);
 }
 
 extern "C" int stp_bn_bwd_finalize(const float* partial, int32_t nblk, int32_t c, int64_t count, const float* coef,
@@ -469,17 +732,20 @@ static int bwd_apply_common(int mode, const stp_tensor* dy, const stp_tensor* x,
               "bwd_apply: shape mismatch");
   if (residual) STP_REQUIRE(vec_ok(residual) && residual->c == x->c && pixels(residual) == pixels(x), "bwd_apply: bad residual");
   int64_t rows = pixels(x);
-  int cv = x->c / 8;
+  STP_REQUIRE(rows < 0x7fffffff, "bwd_apply: too many rows");
+  RowGeom g = geom(rows, x->c, pool == 2 ? 2 : 4, kNumSMs * 8);
   const __nv_bfloat16* rp = residual ? (const __nv_bfloat16*)residual->ptr : nullptr;
   int ldr = residual ? residual->ld : 0;
-  if (mode == 0)
-    bwd_apply_kernel<0><<<ew_grid(rows * cv), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dy->ptr, dy->ld, (const __nv_bfloat16*)x->ptr, x->ld, coef, bcoef, relu, pool, rp, ldr,
-        (__nv_bfloat16*)dx->ptr, dx->ld, x->h, x->w, rows, x->c, cv);
-  else
-    bwd_apply_kernel<1><<<ew_grid(rows * cv), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dy->ptr, dy->ld, (const __nv_bfloat16*)x->ptr, x->ld, coef, bcoef, relu, pool, rp, ldr,
-        (__nv_bfloat16*)dx->ptr, dx->ld, x->h, x->w, rows, x->c, cv);
+#define STP_BWD_APPLY(MODE, POOL)                                                                                      \
+  bwd_apply_kernel<MODE, POOL><<<g.nblk, g.threads, 0, (cudaStream_t)stream>>>(                                        \
+      (const __nv_bfloat16*)dy->ptr, dy->ld, (const __nv_bfloat16*)x->ptr, x->ld, coef, bcoef, relu, pool, rp, ldr,    \
+      (__nv_bfloat16*)dx->ptr, dx->ld, x->h, x->w, (int)rows, x->c, g.cv, g.nv, g.rpi, g.rows_per_blk)
+  if (mode == 0) {
+    if (pool == 2) STP_BWD_APPLY(0, 2); else STP_BWD_APPLY(0, 1);
+  } else {
+    if (pool == 2) STP_BWD_APPLY(1, 2); else STP_BWD_APPLY(1, 1);
+  }
+#undef STP_BWD_APPLY
   return check_launch("bwd_apply");
 }
 

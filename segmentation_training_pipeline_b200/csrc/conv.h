@@ -16,6 +16,7 @@ struct ConvP {
   int R, S, stride, pad_h, pad_w, up, relu;
   int64_t M;
   int K;
+  int ncls = 0;  // > 0: segmentation-head epilogue (tcgen05 halo kernel only): y = dense fp32 [M][ncls], Cout is padding
 };
 
 struct WgradP {

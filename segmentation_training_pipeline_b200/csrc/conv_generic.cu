@@ -328,6 +328,54 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
   }
 }
 
+// All conv layers of a network in ONE launch.  items: int64 [n][8] = {offset (elements, into the three flat buffers),
+// Cout, R, S, Cin, has_dgrad, first_tile, unused}; one block = one 32(co) x 32(ci) tile of one filter tap, transposed
+// through shared memory so that the KRSC read, the bf16 KRSC write and the tap-flipped [Cin][R][S][Cout] write are
+// all row-contiguous.
+__global__ void __launch_bounds__(256) weight_prep_batched_kernel(const float* __restrict__ wm,
+                                                                  __nv_bfloat16* __restrict__ wf,
+                                                                  __nv_bfloat16* __restrict__ wd,
+                                                                  const int64_t* __restrict__ items, int n_items) {
+  __shared__ float tile[32][33];
+  int lo = 0, hi = n_items - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (items[mid * 8 + 6] <= (int64_t)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const int64_t* it = items + lo * 8;
+  const int64_t off = it[0];
+  const int Cout = (int)it[1], R = (int)it[2], S = (int)it[3], Cin = (int)it[4];
+  const bool dg = it[5] != 0;
+  int t = (int)((int64_t)blockIdx.x - it[6]);
+  const int tci = (Cin + 31) / 32, tco = (Cout + 31) / 32;
+  const int ci0 = (t % tci) * 32;
+  t /= tci;
+  const int co0 = (t % tco) * 32;
+  const int tap = t / tco;
+  const int r = tap / S, sx = tap - r * S;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t K = (int64_t)R * S * Cin;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int co = co0 + ty + j * 8, ci = ci0 + tx;
+    if (co < Cout && ci < Cin) {
+      const int64_t i = off + (int64_t)co * K + (int64_t)tap * Cin + ci;
+      const float v = wm[i];
+      wf[i] = __float2bfloat16(v);
+      tile[ty + j * 8][tx] = v;
+    }
+  }
+  if (!dg) return;
+  __syncthreads();
+  const int tapf = (R - 1 - r) * S + (S - 1 - sx);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ci = ci0 + ty + j * 8, co = co0 + tx;
+    if (co < Cout && ci < Cin)
+      wd[off + ((int64_t)ci * R * S + tapf) * Cout + co] = __float2bfloat16(tile[tx][ty + j * 8]);
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 int launch_generic_conv(const ConvP& p, cudaStream_t st) {
   dim3 block(256);
@@ -389,6 +437,16 @@ int launch_split_reduce(const float* ws, int splits, int64_t n, float* out, cuda
 }  // namespace stp
 
 using namespace stp;
+
+extern "C" int stp_weight_prep_batched(const float* flat_master, void* flat_fwd, void* flat_dgrad,
+                                       const int64_t* d_items, int32_t n_items, int64_t total_tiles, stp_stream stream) {
+  STP_REQUIRE(flat_master && flat_fwd && flat_dgrad && d_items && n_items > 0 && total_tiles > 0 &&
+                  total_tiles < 0x7fffffff,
+              "weight_prep_batched: bad args");
+  weight_prep_batched_kernel<<<(unsigned)total_tiles, 256, 0, (cudaStream_t)stream>>>(
+      flat_master, (__nv_bfloat16*)flat_fwd, (__nv_bfloat16*)flat_dgrad, d_items, n_items);
+  return check_launch("weight_prep_batched");
+}
 
 extern "C" int stp_weight_prep(const float* w_master, void* w_fwd, void* w_dgrad, int32_t cout, int32_t r, int32_t s,
                                int32_t cin, stp_stream stream) {

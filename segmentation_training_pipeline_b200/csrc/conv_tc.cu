@@ -39,7 +39,7 @@ PFN_encodeTiled get_encode_tiled() {
 }
 
 bool make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, uint32_t swizzle_bytes) {
+                    const uint32_t* box, uint32_t swizzle_bytes, const uint32_t* elem_strides) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -50,7 +50,7 @@ bool make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t*
   for (int i = 0; i < rank; ++i) {
     gd[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -82,6 +82,7 @@ struct TcConvArgs {
   int ldy, ldr, y_f32, relu;
   int Ho, Wo, Cout, Cin;
   int R, S, pad_h, pad_w;
+  int stride;          // output stride (1 or 2): the A box is fetched with TMA element strides {1, stride, stride, 1}
   int BW, BH, log2BW;  // pixel rectangle of a tile, BW*BH = 128
   int tilesW, tilesH, tilesN, n_img;
   int num_tiles;
@@ -166,7 +167,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int cb = 0; cb < kcb; ++cb) {
             mbar_wait(&empty[stage], phase ^ 1);
             mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-            tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], cb * BK, w0 + s - a.pad_w, h0 + r - a.pad_h, img);
+            tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], cb * BK, w0 * a.stride + s - a.pad_w,
+                        h0 * a.stride + r - a.pad_h, img);
             tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], tap * a.Cin + cb * BK, n0);
             if (++stage == NS) {
               stage = 0;
@@ -313,7 +315,7 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvArgs&
 }  // namespace
 
 bool tc_conv_supported(const ConvP& p) {
-  if (p.stride != 1 || p.up != 1) return false;
+  if ((p.stride != 1 && p.stride != 2) || p.up != 1) return false;
   if (pick_bn(p.Cout) == 0 || pick_bk(p.Cin) == 0) return false;
   if (p.Wo < 8 || p.Ho < 1) return false;
   if (p.ldx % 8 != 0 || !aligned16(p.x) || !aligned16(p.w)) return false;
@@ -330,6 +332,7 @@ int launch_tc_conv(const ConvP& p, cudaStream_t st) {
   TcConvArgs a;
   a.y = p.y; a.res = p.res; a.bias = p.bias; a.ldy = p.ldy; a.ldr = p.ldr; a.y_f32 = p.y_f32; a.relu = p.relu;
   a.Ho = p.Ho; a.Wo = p.Wo; a.Cout = p.Cout; a.Cin = p.Cin; a.R = p.R; a.S = p.S; a.pad_h = p.pad_h; a.pad_w = p.pad_w;
+  a.stride = p.stride;
   int bw = 128;
   while (bw > 8 && bw / 2 >= p.Wo) bw /= 2;  // smallest power of two >= Wo, clamped to [8,128]
   a.BW = bw; a.BH = 128 / bw;
@@ -350,8 +353,10 @@ int launch_tc_conv(const ConvP& p, cudaStream_t st) {
   {
     uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
     uint64_t strides[3] = {(uint64_t)p.ldx * 2, (uint64_t)p.W * p.ldx * 2, (uint64_t)p.H * p.W * p.ldx * 2};
-    uint32_t box[4] = {(uint32_t)BK, (uint32_t)a.BW, (uint32_t)a.BH, 1};
-    if (!make_tmap_bf16(&tmA, p.x, 4, dims, strides, box, BK * 2)) return STP_E_CUDA;
+    // stride 2: the box spans stride*BW x stride*BH input pixels and the TMA unit keeps every stride-th one
+    uint32_t box[4] = {(uint32_t)BK, (uint32_t)(a.BW * p.stride), (uint32_t)(a.BH * p.stride), 1};
+    uint32_t es[4] = {1, (uint32_t)p.stride, (uint32_t)p.stride, 1};
+    if (!make_tmap_bf16(&tmA, p.x, 4, dims, strides, box, BK * 2, es)) return STP_E_CUDA;
   }
   {
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.Cout};
@@ -567,14 +572,32 @@ static bool wgrad_plan(int64_t M, int N_img, int Ho, int Wo, int Cout, int Cin, 
   pl->co_tiles = (Cout + 127) / 128;
   pl->ci_tiles = Cin / pl->BN;
   int base = pl->co_tiles * pl->ci_tiles * S;
-  int splits = (2 * kNumSMs + base - 1) / base;  // ~2 CTAs' worth of work items per SM
-  int max_s = (pl->num_pb + 3) / 4;              // at least 4 pixel blocks per split
-  if (splits > max_s) splits = max_s;
+  // One CTA per SM is resident (shared memory), so the grid should be a whole number of waves of (nearly) equal
+  // items: pick the split count whose item total fills k waves best (k = 1, 2), preferring fewer splits (less
+  // partial traffic, longer main loops) unless that leaves SMs idle.
+  int max_s = (pl->num_pb + 3) / 4;  // at least 4 pixel blocks per split
+  if (max_s < 1) max_s = 1;
   // keep the fp32 split partials L2 resident (126 MB L2): <= 48 MB in flight
   int64_t per = (int64_t)Cout * R * S * Cin * 4;
   int cap = (int)((48ll << 20) / per);
-  if (splits > cap) splits = cap;
-  if (splits < 1) splits = 1;
+  if (cap < 1) cap = 1;
+  if (max_s > cap) max_s = cap;
+  int splits = 1;
+  double best = -1.0;
+  for (int k = 1; k <= 2; ++k) {
+    int sp = (k * kNumSMs) / base;
+    if (sp < 1) sp = 1;
+    if (sp > max_s) sp = max_s;
+    const int items = sp * base;
+    const int waves = (items + kNumSMs - 1) / kNumSMs;
+    // efficiency of the wave fill, discounted by the fixed per-CTA cost (prologue + accumulator write-out ~ 3 blocks)
+    const double pb = (double)pl->num_pb / sp;
+    const double eff = ((double)items / (waves * kNumSMs)) * (pb / (pb + 3.0));
+    if (eff > best) {
+      best = eff;
+      splits = sp;
+    }
+  }
   pl->pb_per_split = (pl->num_pb + splits - 1) / splits;
   pl->splits = (pl->num_pb + pl->pb_per_split - 1) / pl->pb_per_split;
   pl->items = base * pl->splits;

@@ -33,6 +33,7 @@ struct Tc2Args {
   int tilesW, tilesH, tilesN;
   int num_tiles;
   int a_bytes, b_tap_bytes;  // runtime sizes of the A box and of one weight box
+  int ncls;                  // > 0: "head" epilogue -- only output channels [0, ncls) exist, fp32 [pixels][ncls] dense (+bias)
   int dbg;                   // timing experiments only (results invalid): 1 skip A loads, 2 skip B loads, 4 skip epilogue memory ops, 8 skip MMAs
 };
 
@@ -48,7 +49,12 @@ struct Tc2Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutRowBytes = (BN < 64 ? BN : 64) * 2;       // one 64-channel (or narrower) slab of a pixel
   static constexpr int kOutSlabs = BN < 64 ? 1 : BN / 64;
-  static constexpr int kOutBytes = align1k(128 * BN * 2);            // bf16 staging tile of one sub-tile
+  // Epilogue rounds: EP sub-tiles are converted into the staging buffer per barrier round.  Narrow-N kernels
+  // (BN <= 32: the HBM-bound decoder tail, short main loops) stage the whole strip so the ~1000-cycle round latency
+  // (store drain, two named barriers, proxy fence) is paid once per strip instead of once per 128 pixels.
+  static constexpr int EP = BN <= 32 ? MT : 1;
+  static constexpr int kSubBytes = align1k(128 * BN * 2);            // bf16 staging tile of one sub-tile
+  static constexpr int kOutBytes = EP * kSubBytes;
   static constexpr int kStagesRaw = (kSmemBudget2 - 2048 - kOutBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemRaw = 2 * MT * BN;
@@ -206,16 +212,29 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int wo = w0 + wl;
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
+      constexpr int CH = BN >= 32 ? 32 : 16;
+      if (a.ncls > 0 || a.y_f32) {
 #pragma unroll 1
-      for (int j = 0; j < MT; ++j) {
-        const int hs = h0 + j * a.BH;  // first output row of this sub-tile
-        const int ho = hs + hl;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * MT + j) * BN);
-        constexpr int CH = BN >= 32 ? 32 : 16;
-        if (a.y_f32) {
-          // fp32 output (tests / small heads): direct stores
+        for (int j = 0; j < MT; ++j) {
+          const int hs = h0 + j * a.BH;  // first output row of this sub-tile
+          const int ho = hs + hl;
+          const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * MT + j) * BN);
           const bool valid = ho < a.Ho && wo < a.Wo && !(a.dbg & 4);
           const int64_t pix = ((int64_t)img * a.Ho + ho) * a.Wo + wo;
+          if (a.ncls > 0) {
+            // segmentation head: Cout padded to BN, only the first ncls columns are real -> dense fp32 [pixels][ncls]
+            uint32_t rr[CH];
+            if constexpr (CH == 32) tmem_ld32(t_addr, rr); else tmem_ld16(t_addr, rr);
+            tmem_ld_wait();
+            if (valid && n0 == 0) {
+              float* yp = reinterpret_cast<float*>(a.y) + pix * a.ncls;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (i < a.ncls) yp[i] = __uint_as_float(rr[i]) + (a.bias ? __ldg(a.bias + i) : 0.f);
+            }
+            continue;
+          }
+          // fp32 output (tests): direct stores
 #pragma unroll 1
           for (int c0 = 0; c0 < BN; c0 += CH) {
             uint32_t rr[CH];
@@ -249,58 +268,74 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               for (int i = 0; i < CH; i += 4) *reinterpret_cast<float4*>(yp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             }
           }
-          continue;
         }
-        // ---- bf16 output through the swizzled staging tile and TMA (coalesced, clipped at the image border) ----
-        if (hs >= a.Ho) continue;  // whole sub-tile below the image (uniform across the CTA)
-        if (leader) tma_store_wait_read();   // previous store no longer reads the staging tile
-        named_bar_sync(1, 128);
-        if (a.res) {
-          if (leader) {
-            mbar_expect_tx(res_bar, (uint32_t)(128 * BN * 2));
-#pragma unroll
-            for (int sl = 0; sl < Cfg::kOutSlabs; ++sl)
-              tma_load_4d(sOut + sl * 128 * RB, &tmR, res_bar, n0 + sl * 64, w0, hs, img);
-          }
-          mbar_wait(res_bar, res_phase);
-          res_phase ^= 1;
-        }
+      } else {
+        // ---- bf16 output through the swizzled staging tiles and TMA (coalesced, clipped at the image border) ----
+        constexpr int EP = Cfg::EP;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += CH) {
-          uint32_t rr[CH];
-          if constexpr (CH == 32) tmem_ld32(t_addr + c0, rr); else tmem_ld16(t_addr + c0, rr);
-          tmem_ld_wait();
-          float v[CH];
+        for (int j0 = 0; j0 < MT; j0 += EP) {
+          if (h0 + j0 * a.BH >= a.Ho) break;  // rest of the strip is below the image (uniform across the CTA)
+          int nj = 0;                          // sub-tiles of this round that intersect the image
 #pragma unroll
-          for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(rr[i]);
-          if (a.bias) {
+          for (int e = 0; e < EP; ++e) nj += (j0 + e < MT && h0 + (j0 + e) * a.BH < a.Ho) ? 1 : 0;
+          if (leader) tma_store_wait_read();   // previous round's stores no longer read the staging tiles
+          named_bar_sync(1, 128);
+          if (a.res) {
+            if (leader) {
+              mbar_expect_tx(res_bar, (uint32_t)(nj * 128 * BN * 2));
+              for (int e = 0; e < nj; ++e)
 #pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] += __ldg(a.bias + n0 + c0 + i);
-          }
-          uint8_t* slab = sOut + (c0 >> 6) * (128 * RB) + m * RB;
-          const uint32_t chunk0 = (uint32_t)((c0 & 63) >> 3);
-#pragma unroll
-          for (int i = 0; i < CH; i += 8) {
-            bf16x8* sp = reinterpret_cast<bf16x8*>(slab + (((chunk0 + (i >> 3)) ^ swz) << 4));
-            if (a.res) {
-              float f[8];
-              unpack8(*sp, f);
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) v[i + jj] += f[jj];
+                for (int sl = 0; sl < Cfg::kOutSlabs; ++sl)
+                  tma_load_4d(sOut + e * Cfg::kSubBytes + sl * 128 * RB, &tmR, res_bar, n0 + sl * 64, w0,
+                              h0 + (j0 + e) * a.BH, img);
             }
-            if (a.relu) {
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) v[i + jj] = fmaxf(v[i + jj], 0.f);
-            }
-            *sp = pack8(v + i);
+            mbar_wait(res_bar, res_phase);
+            res_phase ^= 1;
           }
-        }
-        fence_proxy_async();
-        named_bar_sync(1, 128);
-        if (leader && !(a.dbg & 4)) {
+#pragma unroll 1
+          for (int e = 0; e < nj; ++e) {
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * MT + j0 + e) * BN);
+            uint8_t* sub = sOut + e * Cfg::kSubBytes;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += CH) {
+              uint32_t rr[CH];
+              if constexpr (CH == 32) tmem_ld32(t_addr + c0, rr); else tmem_ld16(t_addr + c0, rr);
+              tmem_ld_wait();
+              float v[CH];
 #pragma unroll
-          for (int sl = 0; sl < Cfg::kOutSlabs; ++sl) tma_store_4d(&tmY, sOut + sl * 128 * RB, n0 + sl * 64, w0, hs, img);
-          tma_store_commit();
+              for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(rr[i]);
+              if (a.bias) {
+#pragma unroll
+                for (int i = 0; i < CH; ++i) v[i] += __ldg(a.bias + n0 + c0 + i);
+              }
+              uint8_t* slab = sub + (c0 >> 6) * (128 * RB) + m * RB;
+              const uint32_t chunk0 = (uint32_t)((c0 & 63) >> 3);
+#pragma unroll
+              for (int i = 0; i < CH; i += 8) {
+                bf16x8* sp = reinterpret_cast<bf16x8*>(slab + (((chunk0 + (i >> 3)) ^ swz) << 4));
+                if (a.res) {
+                  float f[8];
+                  unpack8(*sp, f);
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) v[i + jj] += f[jj];
+                }
+                if (a.relu) {
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) v[i + jj] = fmaxf(v[i + jj], 0.f);
+                }
+                *sp = pack8(v + i);
+              }
+            }
+          }
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (leader && !(a.dbg & 4)) {
+            for (int e = 0; e < nj; ++e)
+#pragma unroll
+              for (int sl = 0; sl < Cfg::kOutSlabs; ++sl)
+                tma_store_4d(&tmY, sOut + e * Cfg::kSubBytes + sl * 128 * RB, n0 + sl * 64, w0, h0 + (j0 + e) * a.BH, img);
+            tma_store_commit();
+          }
         }
       }
       tc_fence_before();
@@ -322,37 +357,52 @@ struct Tc2Plan {
   int BN, BK, MT;
 };
 
+// Cycle estimate of one launch for a candidate tiling (B200: 148 SMs, ~40 B/clk/SM from L2, tcgen05 M=128 floor of
+// BN/2 cycles per K=16 MMA, 128 B/clk of shared-memory operand bandwidth).  Used only to RANK candidates: it captures
+// the three effects measured with ncu -- wave quantisation of the persistent grid, L2->SM bound stages when a weight
+// box is reused by too few pixels, and the per-strip epilogue latency.
+static double tc2_cost(const ConvP& p, int bn, int bk, int mt) {
+  const int bw = p.Wo >= 16 ? 16 : 8, bh = 128 / bw;
+  const int th = mt * bh;
+  const double tiles = (double)p.N * ((p.Ho + th - 1) / th) * ((p.Wo + bw - 1) / bw) * (p.Cout / bn);
+  const double waves = (double)(int64_t)((tiles + kNumSMs - 1) / kNumSMs);
+  const int num_st = p.S * (p.Cin / bk);
+  const double bytes = (double)(th + p.R - 1) * bw * bk * 2 + (double)p.R * bn * bk * 2;
+  const double load = bytes / 40.0;
+  const double mma_each = bn / 2.0 > 32.0 + bn / 4.0 ? bn / 2.0 : 32.0 + bn / 4.0;
+  const double mma = (double)mt * p.R * (bk / 16) * mma_each;
+  const double stage = (load > mma ? load : mma) + 150.0;
+  const double epi = 600.0 + mt * (bn >= 64 ? 500.0 : 350.0);
+  const double main = num_st * stage;
+  const double tile = main > epi ? main : epi;
+  return waves * tile + epi + 4000.0;
+}
+
 bool tc2_plan(const ConvP& p, Tc2Plan* pl) {
   if (p.stride != 1 || p.up != 1) return false;
   if (p.R < 2 && p.S < 2) return false;  // 1x1: nothing to reuse, first-generation kernel
   if (p.R > 3 || p.S > 3) return false;
   int bk = (p.Cin % 64 == 0) ? 64 : (p.Cin == 32 ? 32 : (p.Cin == 16 ? 16 : 0));
   if (!bk) return false;
-  int bn = 0;
-  for (int c : {128, 64, 32, 16})
-    if (p.Cout % c == 0) {
-      bn = c;
-      break;
-    }
-  if (!bn) return false;
-  int mt;
-  if (bn == 128) mt = 2;
-  else if (bn == 64) mt = 4;
-  else mt = (bk == 64) ? 4 : 8;
-  // do not make strips taller than the image needs; keep enough tiles to fill the GPU
-  const int bh = p.Wo >= 16 ? 8 : 16;
-  while (mt > 1 && (mt / 2) * bh >= p.Ho) mt /= 2;
-  const int bw = p.Wo >= 16 ? 16 : 8;
-  auto tiles = [&](int m) {
-    return (int64_t)p.N * ((p.Ho + m * bh - 1) / (m * bh)) * ((p.Wo + bw - 1) / bw) * (p.Cout / bn);
-  };
-  while (mt > 1 && tiles(mt) < kNumSMs) mt /= 2;
   const int force = get_option(OPT_TC2_FORCE_MT);
-  if (force > 0) {
+  double best = 0.0;
+  int best_bn = 0, best_mt = 0;
+  for (int bn : {128, 64, 32, 16}) {
+    if (p.Cout % bn != 0) continue;
+    if (best_bn != 0 && bn < 64) break;  // narrow N tiles only when Cout demands them
     const int mt_max = bn == 128 ? 2 : (bn == 64 || bk == 64) ? 4 : 8;
-    mt = force < mt_max ? force : mt_max;
+    for (int mt = 1; mt <= mt_max; mt *= 2) {
+      if (force > 0 && mt != (force < mt_max ? force : mt_max)) continue;
+      const double c = tc2_cost(p, bn, bk, mt);
+      if (best_bn == 0 || c < best) {
+        best = c;
+        best_bn = bn;
+        best_mt = mt;
+      }
+    }
   }
-  pl->BN = bn; pl->BK = bk; pl->MT = mt;
+  if (!best_bn) return false;
+  pl->BN = best_bn; pl->BK = bk; pl->MT = best_mt;
   return true;
 }
 
@@ -382,8 +432,12 @@ bool tc2_conv_supported(const ConvP& p) {
   if (!tc2_plan(p, &pl)) return false;
   if (p.Wo < 8 || p.Ho < 1) return false;
   if (p.ldx % 8 != 0 || !aligned16(p.x) || !aligned16(p.w)) return false;
-  if (p.y_f32 ? (p.ldy % 4 != 0) : (p.ldy % 8 != 0)) return false;
-  if (!aligned16(p.y)) return false;
+  if (p.ncls > 0) {
+    if (p.ncls > 4 || !p.y_f32 || p.res || p.relu) return false;
+  } else {
+    if (p.y_f32 ? (p.ldy % 4 != 0) : (p.ldy % 8 != 0)) return false;
+    if (!aligned16(p.y)) return false;
+  }
   if (p.res && (p.ldr % 8 != 0 || !aligned16(p.res))) return false;
   return get_encode_tiled() != nullptr;
 }
@@ -414,6 +468,7 @@ int launch_tc2_conv(const ConvP& p, cudaStream_t st) {
   a.a_bytes = box_rows * a.BW * pl.BK * 2;
   a.b_tap_bytes = pl.BN * pl.BK * 2;
   a.dbg = get_option(OPT_TC2_DEBUG);
+  a.ncls = p.ncls;
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};

@@ -3,6 +3,7 @@
 // Replaces keras Conv2D(classes,(3,3),padding='same',name='final_conv') built by segmentation_models
 // (reference segmentation.py:155).  Backward computes dX, dW and dbias in two passes.
 #include "common.cuh"
+#include "conv.h"
 
 namespace stp {
 
@@ -85,6 +86,50 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const float* __restrict
   }
 }
 
+// classes == 1 fast path: a thread owns one 8-channel vector (its 9x8 weights live in registers) and walks pixels, so a
+// pixel costs 9 L1-resident dlogit loads + 72 FMAs + one 16-byte store.
+__global__ void __launch_bounds__(256) head_dgrad1_kernel(const float* __restrict__ dl, int H, int W, int Cin,
+                                                          const float* __restrict__ w, __nv_bfloat16* __restrict__ dx,
+                                                          int lddx, int M, int cv, int ppi, int pix_per_blk) {
+  const int v = threadIdx.x % cv, pl = threadIdx.x / cv;
+  float wr[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wr[t][k] = __bfloat162float(__float2bfloat16(w[t * Cin + v * 8 + k]));
+  const int m_begin = blockIdx.x * pix_per_blk;
+  int m_end = m_begin + pix_per_blk;
+  if (m_end > M) m_end = M;
+  for (int m = m_begin + pl; m < m_end; m += ppi) {
+    unsigned n = (unsigned)m / (unsigned)(H * W);
+    unsigned rem = (unsigned)m - n * (unsigned)(H * W);
+    int h = (int)(rem / (unsigned)W), wq = (int)(rem - (unsigned)h * (unsigned)W);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ho = h - (r - 1);
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int wo = wq - (s - 1);
+        float g = 0.f;
+        if (ho >= 0 && ho < H && wo >= 0 && wo < W) g = __ldg(dl + ((int64_t)n * H + ho) * W + wo);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += g * wr[r * 3 + s][k];
+      }
+    }
+    st8(dx + (int64_t)m * lddx + v * 8, pack8(acc));
+  }
+}
+
+// f32 [classes][9][Cin] master weights -> bf16 [16][9][Cin], rows >= classes zero (operand of the tcgen05 head conv)
+__global__ void head_weight_pad_kernel(const float* __restrict__ w, int classes, int k, __nv_bfloat16* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 16 * k) return;
+  out[i] = __float2bfloat16(i < classes * k ? w[i] : 0.f);
+}
+
 // dw[c][r][s][ci] = sum_m dl[m][c] * x[m + off(r,s)][ci]  ==  sum_p x[p][ci] * dl[p - off][c]
 // each thread owns one 8-channel vector of one pixel per iteration and 9 taps x 8 accumulators.
 __global__ void __launch_bounds__(256) head_wgrad_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int H, int W,
@@ -163,13 +208,35 @@ constexpr int kHeadWgradBlocks = kNumSMs * 2;
 
 using namespace stp;
 
+extern "C" size_t stp_head_fwd_workspace(const stp_tensor* x, int32_t classes) {
+  (void)classes;
+  return x ? (size_t)16 * 9 * (size_t)x->c * sizeof(__nv_bfloat16) : 0;
+}
+
 extern "C" int stp_head_fwd(const stp_tensor* x, const float* w_krsc_f32, const float* bias, int32_t classes,
-                            float* logits, stp_stream stream) {
+                            float* logits, void* workspace, size_t workspace_bytes, stp_stream stream) {
   STP_REQUIRE(vec_ok(x) && w_krsc_f32 && logits, "head_fwd: bad args");
   STP_REQUIRE(classes >= 1 && classes <= kHeadMaxCls && x->c <= kHeadMaxCin, "head_fwd: classes<=4, Cin<=64");
   int64_t M = pixels(x);
+  cudaStream_t st = (cudaStream_t)stream;
+  // tcgen05 path: implicit GEMM with Cout padded to 16 (N = 16 MMA), only `classes` columns stored
+  ConvP p;
+  p.x = (const __nv_bfloat16*)x->ptr; p.ldx = x->ld; p.N = x->n; p.H = x->h; p.W = x->w; p.Cin = x->c;
+  p.w = (const __nv_bfloat16*)workspace;
+  p.y = logits; p.ldy = classes; p.Ho = x->h; p.Wo = x->w; p.Cout = 16; p.y_f32 = 1;
+  p.res = nullptr; p.ldr = 0; p.bias = bias;
+  p.R = 3; p.S = 3; p.stride = 1; p.pad_h = 1; p.pad_w = 1; p.up = 1; p.relu = 0;
+  p.M = M; p.K = 9 * x->c; p.ncls = classes;
+  if (stp_tc_enabled() && workspace && workspace_bytes >= stp_head_fwd_workspace(x, classes) && aligned16(workspace) &&
+      tc2_conv_supported(p)) {
+    const int k = 9 * x->c;
+    head_weight_pad_kernel<<<(16 * k + 255) / 256, 256, 0, st>>>(w_krsc_f32, classes, k, (__nv_bfloat16*)workspace);
+    int rc = check_launch("head_weight_pad");
+    if (rc) return rc;
+    return launch_tc2_conv(p, st);
+  }
   int64_t nb = (M + 255) / 256;
-  head_fwd_kernel<<<(int)(nb < kNumSMs * 16 ? nb : kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(
+  head_fwd_kernel<<<(int)(nb < kNumSMs * 16 ? nb : kNumSMs * 16), 256, 0, st>>>(
       (const __nv_bfloat16*)x->ptr, x->ld, x->h, x->w, x->c, w_krsc_f32, bias, classes, logits, M);
   return check_launch("head_fwd");
 }
@@ -193,9 +260,21 @@ extern "C" int stp_head_bwd(const stp_tensor* x, const float* w_krsc_f32, const 
   int64_t M = pixels(x);
   if (dx) {
     STP_REQUIRE(vec_ok(dx) && dx->c == x->c && pixels(dx) == M, "head_bwd: bad dx");
-    int64_t nb = (M * (x->c / 8) + 255) / 256;
-    head_dgrad_kernel<<<(int)(nb < kNumSMs * 16 ? nb : kNumSMs * 16), 256, 0, st>>>(
-        dlogits, x->h, x->w, x->c, w_krsc_f32, classes, (__nv_bfloat16*)dx->ptr, dx->ld, M);
+    const int cv = x->c / 8;
+    if (classes == 1 && M < 0x7fffffff) {
+      const int ppi = 256 / cv;
+      int64_t nb = (M + (int64_t)ppi * 8 - 1) / ((int64_t)ppi * 8);
+      if (nb > kNumSMs * 8) nb = kNumSMs * 8;
+      int64_t ppb = (M + nb - 1) / nb;
+      ppb = (ppb + ppi - 1) / ppi * ppi;
+      nb = (M + ppb - 1) / ppb;
+      head_dgrad1_kernel<<<(int)nb, ppi * cv, 0, st>>>(dlogits, x->h, x->w, x->c, w_krsc_f32,
+                                                       (__nv_bfloat16*)dx->ptr, dx->ld, (int)M, cv, ppi, (int)ppb);
+    } else {
+      int64_t nb = (M * cv + 255) / 256;
+      head_dgrad_kernel<<<(int)(nb < kNumSMs * 16 ? nb : kNumSMs * 16), 256, 0, st>>>(
+          dlogits, x->h, x->w, x->c, w_krsc_f32, classes, (__nv_bfloat16*)dx->ptr, dx->ld, M);
+    }
     int rc = check_launch("head_dgrad");
     if (rc) return rc;
   }

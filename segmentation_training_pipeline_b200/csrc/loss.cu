@@ -49,13 +49,18 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__
   }
 }
 
-__global__ void loss_finalize_kernel(const float* __restrict__ partial, int nblk, double count, float w_bce,
-                                     float w_dice, float w_iou, float* __restrict__ result) {
+// one warp per slot: lanes stride over the block partials (fixed order -> deterministic), double accumulation
+__global__ void __launch_bounds__(32 * kLossSlots) loss_finalize_kernel(const float* __restrict__ partial, int nblk,
+                                                                        double count, float w_bce, float w_dice,
+                                                                        float w_iou, float* __restrict__ result) {
   __shared__ double tot[kLossSlots];
-  if (threadIdx.x < kLossSlots) {
+  {
+    const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double a = 0.0;
-    for (int b = 0; b < nblk; ++b) a += (double)partial[(int64_t)b * kLossSlots + threadIdx.x];
-    tot[threadIdx.x] = a;
+    for (int b = lane; b < nblk; b += 32) a += (double)partial[(int64_t)b * kLossSlots + slot];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) tot[slot] = a;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -117,7 +122,7 @@ extern "C" int stp_loss_fwd(const float* logits, const uint8_t* mask, int64_t co
   loss_fwd_kernel<<<nblk, 256, 0, st>>>(logits, mask, count, partial);
   int rc = check_launch("loss_fwd");
   if (rc) return rc;
-  loss_finalize_kernel<<<1, 32, 0, st>>>(partial, nblk, (double)count, h_spec->w_bce, h_spec->w_dice, h_spec->w_iou,
+  loss_finalize_kernel<<<1, 32 * kLossSlots, 0, st>>>(partial, nblk, (double)count, h_spec->w_bce, h_spec->w_dice, h_spec->w_iou,
                                          result16);
   return check_launch("loss_finalize");
 }

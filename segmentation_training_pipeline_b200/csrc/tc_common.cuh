@@ -182,6 +182,6 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 PFN_encodeTiled get_encode_tiled();
 // bf16 tensor map, dims innermost-first; strides (bytes) for dims 1..rank-1; returns false + sets error on failure
 bool make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, uint32_t swizzle_bytes);
+                    const uint32_t* box, uint32_t swizzle_bytes, const uint32_t* elem_strides = nullptr);
 
 }  // namespace stp

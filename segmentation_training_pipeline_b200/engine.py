@@ -141,6 +141,7 @@ class Net:
         self.ws = torch.zeros(max(self._ws_bytes, 16), dtype=torch.uint8, device=dev)
         self.partial = torch.zeros(self._partial_floats, dtype=torch.float32, device=dev)
         self.d_step = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.sync = torch.zeros(4, dtype=torch.int32, device=dev)  # last-block tickets of the fused reduce+finalize kernels
         host = np.zeros(self.n_flat, dtype=np.float32)
         for p in self.params.values():
             host[p.offset:p.offset + p.size] = p.init().reshape(-1)
@@ -160,6 +161,15 @@ class Net:
             op.acc = acc
         for op in self.ops:
             op.prepare()
+        # table for the one-launch weight prep (bf16 KRSC + tap-flipped dgrad copies of every conv layer)
+        items, tile = [], 0
+        for op in self.ops:
+            if isinstance(op, Conv):
+                co, r, s_, ci = op.w.shape
+                items.append([op.w.offset, co, r, s_, ci, int(op.needs_dgrad), tile, 0])
+                tile += r * s_ * ((co + 31) // 32) * ((ci + 31) // 32)
+        self._wprep_tiles = tile
+        self._wprep_items = torch.tensor(items, dtype=torch.int64, device=dev) if items else None
         self.finalized = True
 
     # pointers into flat buffers
@@ -177,10 +187,10 @@ class Net:
 
     # ---- execution ----------------------------------------------------------------------------
     def prep_weights(self):
-        st = _stream()
-        for op in self.ops:
-            if isinstance(op, Conv):
-                op.prep_weights(st)
+        if self._wprep_items is not None:
+            self.L.weight_prep_batched(self.flat_p.data_ptr(), self.flat_wf.data_ptr(), self.flat_wd.data_ptr(),
+                                       self._wprep_items.data_ptr(), self._wprep_items.shape[0], self._wprep_tiles,
+                                       _stream())
 
     def forward(self):
         for op in self.ops:
@@ -364,9 +374,8 @@ class BNRelu(Op):
         n, L, st = self.net, self.net.L, _stream()
         c = self.x.c
         if n.training:
-            L.bn_stats(self.x.ref, n.partial.data_ptr(), st)
-            L.bn_finalize(n.partial.data_ptr(), self.nblk, c, self.x.rows, n.pp(self.gamma), n.pp(self.beta), self.eps,
-                          self.momentum, self.mm.data_ptr(), self.mv.data_ptr(), self.coef.data_ptr(), st)
+            L.bn_stats_fused(self.x.ref, n.partial.data_ptr(), n.sync.data_ptr(), n.pp(self.gamma), n.pp(self.beta),
+                             self.eps, self.momentum, self.mm.data_ptr(), self.mv.data_ptr(), self.coef.data_ptr(), st)
         else:
             L.bn_coef_infer(n.pp(self.gamma), n.pp(self.beta), self.mm.data_ptr(), self.mv.data_ptr(), self.eps, c,
                             self.coef.data_ptr(), st)
@@ -375,9 +384,9 @@ class BNRelu(Op):
     def bwd(self):
         n, L, st = self.net, self.net.L, _stream()
         c = self.x.c
-        L.bn_bwd_reduce(self.dy.ref, self.x.ref, self.coef.data_ptr(), int(self.relu), self.up, n.partial.data_ptr(), st)
-        L.bn_bwd_finalize(n.partial.data_ptr(), self.nblk, c, self.x.rows, self.coef.data_ptr(), n.pg(self.gamma),
-                          n.pg(self.beta), self.bcoef.data_ptr(), st)
+        L.bn_bwd_reduce_fused(self.dy.ref, self.x.ref, self.coef.data_ptr(), int(self.relu), self.up,
+                              n.partial.data_ptr(), n.sync.data_ptr(), n.pg(self.gamma), n.pg(self.beta),
+                              self.bcoef.data_ptr(), st)
         L.bn_bwd_apply(self.dy.ref, self.x.ref, self.coef.data_ptr(), self.bcoef.data_ptr(), int(self.relu), self.up,
                        self.res_ref, self.dx.ref, st)
 
@@ -421,6 +430,7 @@ class Head(Op):
         self.logits = torch.zeros(x.rows * classes, dtype=torch.float32, device=net.device)
         self.dlogits = torch.zeros(x.rows * classes, dtype=torch.float32, device=net.device)
         net.need_ws(net.L.head_bwd_workspace(x.ref, classes))
+        net.need_ws(net.L.head_fwd_workspace(x.ref, classes))
         net.ops.append(self)
 
     def grad_writes(self):
@@ -433,7 +443,8 @@ class Head(Op):
 
     def fwd(self):
         n = self.net
-        n.L.head_fwd(self.x.ref, n.pp(self.w), n.pp(self.b), self.classes, self.logits.data_ptr(), _stream())
+        n.L.head_fwd(self.x.ref, n.pp(self.w), n.pp(self.b), self.classes, self.logits.data_ptr(), n.ws.data_ptr(),
+                     n.ws.numel(), _stream())
 
     def bwd(self):
         n = self.net

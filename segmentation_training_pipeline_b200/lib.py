@@ -72,11 +72,15 @@ SIGNATURES = {
     "stp_conv_wgrad": (C.c_int, [_CDP, _TP, _TP, _P, _P, _SZ, _P]),
     "stp_conv_wgrad_workspace": (_SZ, [_CDP, _TP, _TP]),
     "stp_weight_prep": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
-    "stp_head_fwd": (C.c_int, [_TP, _P, _P, _I32, _P, _P]),
+    "stp_weight_prep_batched": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _P]),
+    "stp_head_fwd": (C.c_int, [_TP, _P, _P, _I32, _P, _P, _SZ, _P]),
+    "stp_head_fwd_workspace": (_SZ, [_TP, _I32]),
     "stp_head_bwd": (C.c_int, [_TP, _P, _P, _I32, _TP, _P, _P, _P, _SZ, _P]),
     "stp_head_bwd_workspace": (_SZ, [_TP, _I32]),
     "stp_bn_nblk": (_I32, [_I64, _I32]),
     "stp_bn_stats": (C.c_int, [_TP, _P, _P]),
+    "stp_bn_stats_fused": (C.c_int, [_TP, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P]),
+    "stp_bn_bwd_reduce_fused": (C.c_int, [_TP, _TP, _P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "stp_bn_finalize": (C.c_int, [_P, _I32, _I32, _I64, _P, _P, _F, _F, _P, _P, _P, _P]),
     "stp_bn_apply": (C.c_int, [_TP, _P, _I32, _I32, _TP, _P]),
     "stp_bn_coef_infer": (C.c_int, [_P, _P, _P, _P, _F, _I32, _P, _P]),
@@ -128,7 +132,7 @@ def check(rc: int, what: str = ""):
 
 # functions whose int return value is a result, not a status code
 _UNCHECKED = ("version", "tc_enabled", "bn_nblk", "last_error", "launch_count", "tc_launch_count", "set_tc_enabled",
-              "conv_wgrad_workspace", "head_bwd_workspace", "loss_partial_floats")
+              "conv_wgrad_workspace", "head_bwd_workspace", "head_fwd_workspace", "loss_partial_floats")
 
 
 class Lib:

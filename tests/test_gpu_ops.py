@@ -44,9 +44,13 @@ CONV_CASES = [
     (1, 16, 16, 192, 64, 3, 1, 1, 1),
     (1, 8, 8, 64, 384, 3, 1, 1, 1),
     (2, 32, 32, 64, 128, 1, 1, 0, 1),
+    # stride 2 on the tcgen05 path (TMA element strides): odd sizes, a 128-pixel-wide tile row, 1x1 shortcut
+    (1, 17, 23, 64, 64, 3, 2, 1, 1),
+    (1, 6, 260, 64, 32, 3, 2, 1, 1),
+    (2, 16, 16, 128, 256, 1, 2, 0, 1),
 ]
 TC_WGRAD_CASES = {0, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15}  # ... and whose wgrad must take the tcgen05 wgrad kernel
-TC_FWD_CASES = {0, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15}  # indices of CONV_CASES whose forward must take the tcgen05 kernel
+TC_FWD_CASES = {0, 1, 2, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15, 16, 17, 18}  # indices of CONV_CASES whose forward must take the tcgen05 kernel
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
@@ -146,7 +150,8 @@ def test_conv_strided_views(stp, cuda):
     assert float(big_out[..., :16].abs().max()) == 0 and float(big_out[..., 48:].abs().max()) == 0
 
 
-@pytest.mark.parametrize("shape,up", [((2, 16, 16, 64), 1), ((2, 8, 8, 128), 2), ((1, 12, 20, 16), 1), ((3, 4, 4, 512), 2)])
+@pytest.mark.parametrize("shape,up", [((2, 16, 16, 64), 1), ((2, 8, 8, 128), 2), ((1, 12, 20, 16), 1), ((3, 4, 4, 512), 2),
+                                      ((2, 40, 24, 192), 1), ((4, 128, 128, 16), 2), ((1, 3, 5, 2048), 1)])
 def test_batchnorm_fwd_bwd(stp, cuda, shape, up):
     from oracle import nn as ON
     n, h, w, c = shape
@@ -194,6 +199,21 @@ def test_batchnorm_fwd_bwd(stp, cuda, shape, up):
     assert rel_err(dgamma, gc.grad) < 1e-3
     assert rel_err(dbeta, bc.grad) < 1e-3
     assert rel_err(dx, xc.grad.permute(0, 2, 3, 1)) < 5e-3
+    # one-launch variants (last block finalises): same numbers, ticket returns to zero so they can be replayed
+    sync = torch.zeros(4, dtype=torch.int32, device=cuda)
+    for _ in range(2):
+        coef2, bcoef2 = torch.zeros(4 * c, device=cuda), torch.zeros(3 * c, device=cuda)
+        dg2, db2 = torch.zeros(c, device=cuda), torch.zeros(c, device=cuda)
+        mm2, mv2 = torch.zeros(c, device=cuda), torch.ones(c, device=cuda)
+        stp.bn_stats_fused(ref(xs), partial.data_ptr(), sync.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, mom,
+                           mm2.data_ptr(), mv2.data_ptr(), coef2.data_ptr(), stream())
+        stp.bn_bwd_reduce_fused(ref(dys), ref(xs), coef.data_ptr(), 1, up, partial.data_ptr(), sync.data_ptr(),
+                                dg2.data_ptr(), db2.data_ptr(), bcoef2.data_ptr(), stream())
+        assert int(sync[0]) == 0
+        assert max_abs(coef2, coef) <= 1e-6 * (1 + float(coef.abs().max()))
+        assert max_abs(mm2, mm) < 1e-7 and rel_err(mv2, mv) < 1e-6
+        assert max_abs(bcoef2, bcoef) <= 1e-6 * (1 + float(bcoef.abs().max()))
+        assert rel_err(dg2, dgamma) < 1e-6 and rel_err(db2, dbeta) < 1e-6
     # with residual
     r = rand_bf16(shape, g)
     dx2 = torch.zeros_like(x)
@@ -258,10 +278,17 @@ def test_head(stp, cuda, classes, cin):
     bias = torch.randn(classes, generator=g).to(cuda)
     logits = torch.zeros(n * h * w * classes, device=cuda)
     xs = T(x)
-    stp.head_fwd(ref(xs), wt.data_ptr(), bias.data_ptr(), classes, logits.data_ptr(), stream())
     xr = x.float().cpu().requires_grad_(True)
     wr = wt.cpu().requires_grad_(True)
     out = conv_ref_autograd(xr, wr, 1, 1, 1, (h, w)) + bias.cpu()
+    # CUDA-core kernel (no workspace) and the tcgen05 path (bf16 weight copy in the workspace) must both match
+    stp.head_fwd(ref(xs), wt.data_ptr(), bias.data_ptr(), classes, logits.data_ptr(), None, 0, stream())
+    assert rel_err(logits.view(n, h, w, classes), out) < TOL_F32
+    logits.zero_()
+    fws = _ws(stp.head_fwd_workspace(ref(xs), classes), cuda)
+    tc0 = stp.tc_launch_count()
+    stp.head_fwd(ref(xs), wt.data_ptr(), bias.data_ptr(), classes, logits.data_ptr(), fws.data_ptr(), fws.numel(), stream())
+    assert stp.tc_launch_count() == tc0 + 1
     assert rel_err(logits.view(n, h, w, classes), out) < TOL_F32
     dl = torch.randn((n, h, w, classes), generator=g).to(cuda)
     out.backward(dl.cpu())
@@ -419,3 +446,26 @@ def test_conv_tc2_strip_heights(stp, cuda, shape, mt):
         torch.cuda.synchronize()
     finally:
         stp.set_option(b"tc2_force_mt", 0)
+
+
+def test_weight_prep_batched_matches_per_layer(stp, cuda):
+    """one-launch weight prep over the flat buffers == the per-layer kernel, bit for bit (odd shapes included)"""
+    g = torch.Generator().manual_seed(5)
+    shapes = [(64, 7, 7, 8, 0), (64, 3, 3, 64, 1), (24, 3, 3, 16, 1), (128, 1, 1, 64, 1), (40, 4, 4, 72, 1)]
+    items, off, tile = [], 0, 0
+    for co, r, s_, ci, dg in shapes:
+        items.append([off, co, r, s_, ci, dg, tile, 0])
+        off += (co * r * s_ * ci + 7) // 8 * 8
+        tile += r * s_ * ((co + 31) // 32) * ((ci + 31) // 32)
+    flat = torch.randn(off, generator=g).to(cuda)
+    wf = torch.zeros(off, dtype=torch.bfloat16, device=cuda)
+    wd = torch.zeros(off, dtype=torch.bfloat16, device=cuda)
+    wf2, wd2 = torch.zeros_like(wf), torch.zeros_like(wd)
+    it = torch.tensor(items, dtype=torch.int64, device=cuda)
+    stp.weight_prep_batched(flat.data_ptr(), wf.data_ptr(), wd.data_ptr(), it.data_ptr(), len(items), tile, stream())
+    for o, co, r, s_, ci, dg, _, _ in items:
+        stp.weight_prep(flat.data_ptr() + 4 * o, wf2.data_ptr() + 2 * o, (wd2.data_ptr() + 2 * o) if dg else None, co, r,
+                        s_, ci, stream())
+        n = co * r * s_ * ci
+        assert torch.equal(wf[o:o + n], wf2[o:o + n])
+        assert torch.equal(wd[o:o + n], wd2[o:o + n])
