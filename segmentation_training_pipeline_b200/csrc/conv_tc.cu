@@ -79,7 +79,11 @@ struct TcConvArgs {
   void* y;
   const __nv_bfloat16* res;
   const float* bias;
-  int ldy, ldr, y_f32, relu;
+  int y_f32, relu;
+  int64_t y_sn, y_sh, y_sw;  // element strides of the output view (image, row, pixel) -- a parity class of a strided
+  int64_t r_sn, r_sh, r_sw;  // dgrad writes every other pixel; same for the residual view
+  int ntaps;                 // filter taps of this launch: A box offset (tap_dh, tap_dw), weight K block tap_k
+  int tap_dh[9], tap_dw[9], tap_k[9];
   int Ho, Wo, Cout, Cin;
   int R, S, pad_h, pad_w;
   int stride;          // output stride (1 or 2): the A box is fetched with TMA element strides {1, stride, stride, 1}
@@ -118,7 +122,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kcb = a.Cin / BK;            // channel blocks per tap
-  const int num_kb = a.R * a.S * kcb;    // k blocks per tile
+  const int num_kb = a.ntaps * kcb;      // k blocks per tile (0: a parity class no tap reaches -> zeros / residual)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -162,14 +166,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         int img, h0, w0, n0;
         decode(tile, img, h0, w0, n0);
-        for (int tap = 0; tap < a.R * a.S; ++tap) {
-          const int r = tap / a.S, s = tap - r * a.S;
+        for (int tap = 0; tap < a.ntaps; ++tap) {
           for (int cb = 0; cb < kcb; ++cb) {
             mbar_wait(&empty[stage], phase ^ 1);
             mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-            tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], cb * BK, w0 * a.stride + s - a.pad_w,
-                        h0 * a.stride + r - a.pad_h, img);
-            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], tap * a.Cin + cb * BK, n0);
+            tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], cb * BK, w0 * a.stride + a.tap_dw[tap],
+                        h0 * a.stride + a.tap_dh[tap], img);
+            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], a.tap_k[tap] * a.Cin + cb * BK, n0);
             if (++stage == NS) {
               stage = 0;
               phase ^= 1;
@@ -224,7 +227,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       decode(tile, img, h0, w0, n0);
       const int ho = h0 + hl, wo = w0 + wl;
       const bool valid = ho < a.Ho && wo < a.Wo;
-      const int64_t pix = ((int64_t)img * a.Ho + ho) * a.Wo + wo;
+      const int64_t yoff = (int64_t)img * a.y_sn + (int64_t)ho * a.y_sh + (int64_t)wo * a.y_sw;
+      const int64_t roff = (int64_t)img * a.r_sn + (int64_t)ho * a.r_sh + (int64_t)wo * a.r_sw;
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
@@ -232,8 +236,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
         uint32_t rr[CH];
-        if constexpr (CH == 32) tmem_ld32(t_addr + c0, rr); else tmem_ld16(t_addr + c0, rr);
-        tmem_ld_wait();
+        if (num_kb > 0) {
+          if constexpr (CH == 32) tmem_ld32(t_addr + c0, rr); else tmem_ld16(t_addr + c0, rr);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) rr[i] = 0u;
+        }
         if (valid) {
           float v[CH];
 #pragma unroll
@@ -244,7 +253,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < CH; ++i) v[i] += __ldg(a.bias + n + i);
           }
           if (a.res) {
-            const __nv_bfloat16* rp = a.res + pix * a.ldr + n;
+            const __nv_bfloat16* rp = a.res + roff + n;
 #pragma unroll
             for (int i = 0; i < CH; i += 8) {
               float f[8];
@@ -258,11 +267,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
           }
           if (a.y_f32) {
-            float* yp = reinterpret_cast<float*>(a.y) + pix * a.ldy + n;
+            float* yp = reinterpret_cast<float*>(a.y) + yoff + n;
 #pragma unroll
             for (int i = 0; i < CH; i += 4) *reinterpret_cast<float4*>(yp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           } else {
-            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + pix * a.ldy + n;
+            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + yoff + n;
 #pragma unroll
             for (int i = 0; i < CH; i += 8) st8(yp + i, pack8(v + i));
           }
@@ -314,10 +323,8 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvArgs&
 
 }  // namespace
 
-bool tc_conv_supported(const ConvP& p) {
-  if ((p.stride != 1 && p.stride != 2) || p.up != 1) return false;
+static bool tc_common_ok(const ConvP& p) {
   if (pick_bn(p.Cout) == 0 || pick_bk(p.Cin) == 0) return false;
-  if (p.Wo < 8 || p.Ho < 1) return false;
   if (p.ldx % 8 != 0 || !aligned16(p.x) || !aligned16(p.w)) return false;
   if (p.y_f32 ? (p.ldy % 4 != 0) : (p.ldy % 8 != 0)) return false;
   if (!aligned16(p.y)) return false;
@@ -327,19 +334,43 @@ bool tc_conv_supported(const ConvP& p) {
   return get_encode_tiled() != nullptr;
 }
 
-int launch_tc_conv(const ConvP& p, cudaStream_t st) {
+// stride 1 / 2 forward-type problems (one launch), and the zero-insertion (up == 2) problems that the dgrad of a
+// stride-2 convolution turns into (four launches, one per output parity class)
+bool tc_conv_supported(const ConvP& p) {
+  if (p.up == 1) {
+    if (p.stride != 1 && p.stride != 2) return false;
+    if (p.R * p.S > 9) return false;
+    if (p.Wo < 8 || p.Ho < 1) return false;
+  } else {
+    if (p.up != 2 || p.stride != 1 || p.R > 3 || p.S > 3) return false;
+    if (p.Wo < 16 || p.Ho < 2) return false;
+  }
+  return tc_common_ok(p);
+}
+
+// One launch over an output view of ho x wo pixels per image (element strides given), with an explicit tap list.
+static int launch_tc_view(const ConvP& p, int ho, int wo, void* y, int64_t y_sn, int64_t y_sh, int64_t y_sw,
+                          const __nv_bfloat16* res, int64_t r_sn, int64_t r_sh, int64_t r_sw, int in_stride, int ntaps,
+                          const int* dh, const int* dw, const int* tk, cudaStream_t st) {
   const int BN = pick_bn(p.Cout), BK = pick_bk(p.Cin);
   TcConvArgs a;
-  a.y = p.y; a.res = p.res; a.bias = p.bias; a.ldy = p.ldy; a.ldr = p.ldr; a.y_f32 = p.y_f32; a.relu = p.relu;
-  a.Ho = p.Ho; a.Wo = p.Wo; a.Cout = p.Cout; a.Cin = p.Cin; a.R = p.R; a.S = p.S; a.pad_h = p.pad_h; a.pad_w = p.pad_w;
-  a.stride = p.stride;
+  a.y = y; a.res = res; a.bias = p.bias; a.y_f32 = p.y_f32; a.relu = p.relu;
+  a.y_sn = y_sn; a.y_sh = y_sh; a.y_sw = y_sw; a.r_sn = r_sn; a.r_sh = r_sh; a.r_sw = r_sw;
+  a.ntaps = ntaps;
+  for (int t = 0; t < 9; ++t) {
+    a.tap_dh[t] = t < ntaps ? dh[t] : 0;
+    a.tap_dw[t] = t < ntaps ? dw[t] : 0;
+    a.tap_k[t] = t < ntaps ? tk[t] : 0;
+  }
+  a.Ho = ho; a.Wo = wo; a.Cout = p.Cout; a.Cin = p.Cin; a.R = p.R; a.S = p.S; a.pad_h = p.pad_h; a.pad_w = p.pad_w;
+  a.stride = in_stride;
   int bw = 128;
-  while (bw > 8 && bw / 2 >= p.Wo) bw /= 2;  // smallest power of two >= Wo, clamped to [8,128]
+  while (bw > 8 && bw / 2 >= wo) bw /= 2;  // smallest power of two >= Wo, clamped to [8,128]
   a.BW = bw; a.BH = 128 / bw;
   a.log2BW = 0;
   while ((1 << a.log2BW) < bw) ++a.log2BW;
-  a.tilesW = (p.Wo + a.BW - 1) / a.BW;
-  a.tilesH = (p.Ho + a.BH - 1) / a.BH;
+  a.tilesW = (wo + a.BW - 1) / a.BW;
+  a.tilesH = (ho + a.BH - 1) / a.BH;
   a.tilesN = p.Cout / BN;
   a.n_img = p.N;
   int64_t nt = (int64_t)p.N * a.tilesH * a.tilesW * a.tilesN;
@@ -354,8 +385,8 @@ int launch_tc_conv(const ConvP& p, cudaStream_t st) {
     uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
     uint64_t strides[3] = {(uint64_t)p.ldx * 2, (uint64_t)p.W * p.ldx * 2, (uint64_t)p.H * p.W * p.ldx * 2};
     // stride 2: the box spans stride*BW x stride*BH input pixels and the TMA unit keeps every stride-th one
-    uint32_t box[4] = {(uint32_t)BK, (uint32_t)(a.BW * p.stride), (uint32_t)(a.BH * p.stride), 1};
-    uint32_t es[4] = {1, (uint32_t)p.stride, (uint32_t)p.stride, 1};
+    uint32_t box[4] = {(uint32_t)BK, (uint32_t)(a.BW * in_stride), (uint32_t)(a.BH * in_stride), 1};
+    uint32_t es[4] = {1, (uint32_t)in_stride, (uint32_t)in_stride, 1};
     if (!make_tmap_bf16(&tmA, p.x, 4, dims, strides, box, BK * 2, es)) return STP_E_CUDA;
   }
   {
@@ -372,6 +403,52 @@ int launch_tc_conv(const ConvP& p, cudaStream_t st) {
 #undef STP_TC_CASE
   set_error("conv_tc: no specialisation for BN=%d BK=%d", BN, BK);
   return STP_E_UNSUPPORTED;
+}
+
+int launch_tc_conv(const ConvP& p, cudaStream_t st) {
+  const int64_t esz = 1;  // strides below are in elements of the output dtype
+  (void)esz;
+  if (p.up == 1) {
+    int dh[9], dw[9], tk[9];
+    if (p.R * p.S > 9) {
+      set_error("conv_tc: more than 9 taps");
+      return STP_E_UNSUPPORTED;
+    }
+    for (int r = 0; r < p.R; ++r)
+      for (int s = 0; s < p.S; ++s) {
+        dh[r * p.S + s] = r - p.pad_h;
+        dw[r * p.S + s] = s - p.pad_w;
+        tk[r * p.S + s] = r * p.S + s;
+      }
+    return launch_tc_view(p, p.Ho, p.Wo, p.y, (int64_t)p.Ho * p.Wo * p.ldy, (int64_t)p.Wo * p.ldy, p.ldy, p.res,
+                          (int64_t)p.Ho * p.Wo * p.ldr, (int64_t)p.Wo * p.ldr, p.ldr, p.stride, p.R * p.S, dh, dw, tk, st);
+  }
+  // up == 2:  y[i] = sum_r' xup[i - pad + r'] w[r'],  xup[2o] = x[o].  For the output parity class i = 2a + ph only the
+  // taps with (ph - pad + r') even contribute, reading x[a + (ph - pad + r')/2]: a stride-1 conv per class.
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      int dh[9], dw[9], tk[9], nt = 0;
+      for (int r = 0; r < p.R; ++r) {
+        if ((ph - p.pad_h + r) & 1) continue;
+        for (int s = 0; s < p.S; ++s) {
+          if ((pw - p.pad_w + s) & 1) continue;
+          dh[nt] = (ph - p.pad_h + r) / 2;  // numerator is even: exact for negatives too
+          dw[nt] = (pw - p.pad_w + s) / 2;
+          tk[nt] = r * p.S + s;
+          ++nt;
+        }
+      }
+      const int ho = (p.Ho - ph + 1) / 2, wo = (p.Wo - pw + 1) / 2;
+      if (ho <= 0 || wo <= 0) continue;
+      const int esize = p.y_f32 ? 4 : 2;
+      void* y = (char*)p.y + ((int64_t)ph * p.Wo + pw) * p.ldy * esize;
+      const __nv_bfloat16* res = p.res ? p.res + ((int64_t)ph * p.Wo + pw) * p.ldr : nullptr;
+      int rc = launch_tc_view(p, ho, wo, y, (int64_t)p.Ho * p.Wo * p.ldy, (int64_t)2 * p.Wo * p.ldy, (int64_t)2 * p.ldy,
+                              res, (int64_t)p.Ho * p.Wo * p.ldr, (int64_t)2 * p.Wo * p.ldr, (int64_t)2 * p.ldr, 1, nt,
+                              dh, dw, tk, st);
+      if (rc) return rc;
+    }
+  return STP_OK;
 }
 
 // ====================================================================================================
@@ -395,28 +472,31 @@ struct TcWgradArgs {
   int a_lbo;      // byte distance between consecutive MN atoms of A (0: rows beyond the first atom alias it, discarded)
   int m_valid;    // accumulator rows that hold real output channels
   int b_row;      // bytes per pixel row of an X box: min(Cin,64)*2
-  int xrows;      // (BH + R - 1) * BW rows of the haloed input tile
+  int xrows;      // (BH + R - 1) * BW rows of the haloed input tile (stride 2: 128, one box per filter row)
+  int stride;     // 1: the R filter rows are shifted views of ONE haloed box; 2: one element-strided TMA box per row
 };
 
 // ANARROW: Cout <= 32 (dY rows of 32/64 B) -> small A stage; otherwise two 128-B-row boxes.
-template <int BN, int ANARROW>
+template <int BN, int ANARROW, int STR>
 struct TcWgradCfg {
   static constexpr int kABytes = ANARROW ? 128 * 64 : 2 * 16384;
   static constexpr int kBRow = (BN < 64 ? BN : 64) * 2;
   static constexpr int kXBoxBytes = 160 * kBRow;  // >= (BH+2)*BW rows for the supported geometries; 1024-multiple
-  static constexpr int kBBytes = (BN < 64 ? 1 : BN / 64) * kXBoxBytes;
+  static constexpr int kRBytes = (BN < 64 ? 1 : BN / 64) * kXBoxBytes;  // input box(es) of one filter row
+  static constexpr int kBBytes = (STR ? 3 : 1) * kRBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagesRaw = (kSmemBudget - 2048) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
+  static_assert(kStages >= 2, "wgrad needs two pipeline stages");
   static constexpr int kTmemCols = 3 * BN <= 64 ? 64 : 3 * BN <= 128 ? 128 : 3 * BN <= 256 ? 256 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
   static_assert(kXBoxBytes % 1024 == 0, "stage buffers must stay swizzle-atom aligned");
 };
 
-template <int BN, int ANARROW>
+template <int BN, int ANARROW, int STR>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const TcWgradArgs a) {
-  using Cfg = TcWgradCfg<BN, ANARROW>;
+  using Cfg = TcWgradCfg<BN, ANARROW, STR>;
   constexpr int NS = Cfg::kStages;
   constexpr int BBOX = BN < 64 ? 1 : BN / 64;
   extern __shared__ uint8_t smem_raw[];
@@ -464,7 +544,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)a.a_boxes * a_box_bytes + (uint32_t)BBOX * (uint32_t)a.xrows * (uint32_t)a.b_row;
+      const uint32_t tx_bytes = (uint32_t)a.a_boxes * a_box_bytes +
+                                (uint32_t)(STR ? a.R : 1) * (uint32_t)BBOX * (uint32_t)a.xrows * (uint32_t)a.b_row;
       int stage = 0;
       uint32_t phase = 0;
       for (int pb = pb_begin; pb < pb_end; ++pb) {
@@ -478,9 +559,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         uint8_t* pa = sA + stage * Cfg::kABytes;
         uint8_t* pbuf = sB + stage * Cfg::kBBytes;
         for (int j = 0; j < a.a_boxes; ++j) tma_load_4d(pa + j * a_box_bytes, &tmDY, &full[stage], co0 + 64 * j, w0, h0, img);
+        if (STR) {
+          for (int r = 0; r < a.R; ++r)
 #pragma unroll
-        for (int j = 0; j < BBOX; ++j)
-          tma_load_4d(pbuf + j * Cfg::kXBoxBytes, &tmX, &full[stage], ci0 + 64 * j, w0 + s - a.pad_w, h0 - a.pad_h, img);
+            for (int j = 0; j < BBOX; ++j)
+              tma_load_4d(pbuf + r * Cfg::kRBytes + j * Cfg::kXBoxBytes, &tmX, &full[stage], ci0 + 64 * j,
+                          w0 * a.stride + s - a.pad_w, h0 * a.stride + r - a.pad_h, img);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BBOX; ++j)
+            tma_load_4d(pbuf + j * Cfg::kXBoxBytes, &tmX, &full[stage], ci0 + 64 * j, w0 + s - a.pad_w, h0 - a.pad_h, img);
+        }
         if (++stage == NS) {
           stage = 0;
           phase ^= 1;
@@ -499,7 +588,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
         const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
         for (int r = 0; r < a.R; ++r) {
-          const uint32_t b_r = b_addr + (uint32_t)(r * a.BW) * (uint32_t)a.b_row;
+          const uint32_t b_r = STR ? b_addr + (uint32_t)r * (uint32_t)Cfg::kRBytes
+                                   : b_addr + (uint32_t)(r * a.BW) * (uint32_t)a.b_row;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             const uint64_t ad = desc_mnmajor(a_addr + kk * a_step, (uint32_t)a.a_lbo, (uint32_t)a.a_row);
@@ -556,11 +646,11 @@ struct WgradPlan {
   int BN, BW, BH, tilesW, tilesH, num_pb, splits, pb_per_split, co_tiles, ci_tiles, items;
 };
 
-static bool wgrad_plan(int64_t M, int N_img, int Ho, int Wo, int Cout, int Cin, int R, int S, WgradPlan* pl) {
+static bool wgrad_plan(int64_t M, int N_img, int Ho, int Wo, int Cout, int Cin, int R, int S, int stride, WgradPlan* pl) {
   const bool co_ok = Cout % 64 == 0 || Cout == 32 || Cout == 16;
   const bool ci_ok = Cin % 64 == 0 || Cin == 32 || Cin == 16;
   if (!co_ok || !ci_ok || R > 3 || S > 3 || Wo < 8) return false;
-  pl->BN = (Cin % 128 == 0) ? 128 : (Cin % 64 == 0 ? 64 : Cin);
+  pl->BN = (Cin % 128 == 0 && stride == 1) ? 128 : (Cin % 64 == 0 ? 64 : Cin);
   pl->BW = Wo >= 16 ? 16 : 8;
   pl->BH = 128 / pl->BW;
   if ((pl->BH + R - 1) * pl->BW > 160) return false;
@@ -606,41 +696,41 @@ static bool wgrad_plan(int64_t M, int N_img, int Ho, int Wo, int Cout, int Cin, 
 }
 
 bool tc_wgrad_supported(const WgradP& p) {
-  if (p.stride != 1 || p.up != 1) return false;
+  if ((p.stride != 1 && p.stride != 2) || p.up != 1) return false;
   WgradPlan pl;
-  if (!wgrad_plan(p.M, p.N, p.Ho, p.Wo, p.Cout, p.Cin, p.R, p.S, &pl)) return false;
+  if (!wgrad_plan(p.M, p.N, p.Ho, p.Wo, p.Cout, p.Cin, p.R, p.S, p.stride, &pl)) return false;
   if (p.ldx % 8 != 0 || p.lddy % 8 != 0 || !aligned16(p.x) || !aligned16(p.dy)) return false;
   return get_encode_tiled() != nullptr;
 }
 
 size_t tc_wgrad_workspace(const WgradP& p) {
-  if (p.stride != 1 || p.up != 1) return 0;
+  if ((p.stride != 1 && p.stride != 2) || p.up != 1) return 0;
   WgradPlan pl;
-  if (!wgrad_plan(p.M, p.N, p.Ho, p.Wo, p.Cout, p.Cin, p.R, p.S, &pl)) return 0;
+  if (!wgrad_plan(p.M, p.N, p.Ho, p.Wo, p.Cout, p.Cin, p.R, p.S, p.stride, &pl)) return 0;
   return pl.splits > 1 ? (size_t)pl.splits * p.Cout * p.K * sizeof(float) : 0;
 }
 
-template <int BN, int ANARROW>
+template <int BN, int ANARROW, int STR>
 static int launch_wgrad_cfg(const CUtensorMap& tmDY, const CUtensorMap& tmX, const TcWgradArgs& a, int items,
                             cudaStream_t st) {
-  using Cfg = TcWgradCfg<BN, ANARROW>;
+  using Cfg = TcWgradCfg<BN, ANARROW, STR>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN, ANARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN, ANARROW, STR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return STP_E_CUDA;
     }
     attr_set = true;
   }
-  wgrad_tc_kernel<BN, ANARROW><<<items, kThreads, Cfg::kSmemBytes, st>>>(tmDY, tmX, a);
+  wgrad_tc_kernel<BN, ANARROW, STR><<<items, kThreads, Cfg::kSmemBytes, st>>>(tmDY, tmX, a);
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("wgrad_tc");
 }
 
 int launch_tc_wgrad(const WgradP& p, float* dw, void* ws, size_t ws_bytes, cudaStream_t st) {
   WgradPlan pl;
-  if (!wgrad_plan(p.M, p.N, p.Ho, p.Wo, p.Cout, p.Cin, p.R, p.S, &pl)) {
+  if (!wgrad_plan(p.M, p.N, p.Ho, p.Wo, p.Cout, p.Cin, p.R, p.S, p.stride, &pl)) {
     set_error("wgrad_tc: unsupported shape");
     return STP_E_UNSUPPORTED;
   }
@@ -662,7 +752,8 @@ int launch_tc_wgrad(const WgradP& p, float* dw, void* ws, size_t ws_bytes, cudaS
   a.m_valid = p.Cout >= 128 ? 128 : p.Cout;
   const int ci_atom = p.Cin < 64 ? p.Cin : 64;
   a.b_row = ci_atom * 2;
-  a.xrows = (pl.BH + p.R - 1) * pl.BW;
+  a.xrows = p.stride == 2 ? 128 : (pl.BH + p.R - 1) * pl.BW;
+  a.stride = p.stride;
   CUtensorMap tmDY, tmX;
   {
     uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.N};
@@ -673,15 +764,28 @@ int launch_tc_wgrad(const WgradP& p, float* dw, void* ws, size_t ws_bytes, cudaS
   {
     uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
     uint64_t strides[3] = {(uint64_t)p.ldx * 2, (uint64_t)p.W * p.ldx * 2, (uint64_t)p.H * p.W * p.ldx * 2};
-    uint32_t box[4] = {(uint32_t)ci_atom, (uint32_t)pl.BW, (uint32_t)(pl.BH + p.R - 1), 1};
-    if (!make_tmap_bf16(&tmX, p.x, 4, dims, strides, box, a.b_row)) return STP_E_CUDA;
+    if (p.stride == 2) {
+      uint32_t box[4] = {(uint32_t)ci_atom, (uint32_t)(2 * pl.BW), (uint32_t)(2 * pl.BH), 1};
+      uint32_t es[4] = {1, 2, 2, 1};
+      if (!make_tmap_bf16(&tmX, p.x, 4, dims, strides, box, a.b_row, es)) return STP_E_CUDA;
+    } else {
+      uint32_t box[4] = {(uint32_t)ci_atom, (uint32_t)pl.BW, (uint32_t)(pl.BH + p.R - 1), 1};
+      if (!make_tmap_bf16(&tmX, p.x, 4, dims, strides, box, a.b_row)) return STP_E_CUDA;
+    }
   }
   const bool narrow = p.Cout <= 32;
   int rc = STP_E_UNSUPPORTED;
+  if (p.stride == 2) {
 #define STP_WG_CASE(bn) \
-  if (pl.BN == bn) rc = narrow ? launch_wgrad_cfg<bn, 1>(tmDY, tmX, a, pl.items, st) : launch_wgrad_cfg<bn, 0>(tmDY, tmX, a, pl.items, st);
-  STP_WG_CASE(128) STP_WG_CASE(64) STP_WG_CASE(32) STP_WG_CASE(16)
+  if (pl.BN == bn) rc = narrow ? launch_wgrad_cfg<bn, 1, 1>(tmDY, tmX, a, pl.items, st) : launch_wgrad_cfg<bn, 0, 1>(tmDY, tmX, a, pl.items, st);
+    STP_WG_CASE(64) STP_WG_CASE(32) STP_WG_CASE(16)
 #undef STP_WG_CASE
+  } else {
+#define STP_WG_CASE(bn) \
+  if (pl.BN == bn) rc = narrow ? launch_wgrad_cfg<bn, 1, 0>(tmDY, tmX, a, pl.items, st) : launch_wgrad_cfg<bn, 0, 0>(tmDY, tmX, a, pl.items, st);
+    STP_WG_CASE(128) STP_WG_CASE(64) STP_WG_CASE(32) STP_WG_CASE(16)
+#undef STP_WG_CASE
+  }
   if (rc || pl.splits == 1) return rc;
   return launch_split_reduce((const float*)ws, pl.splits, (int64_t)p.Cout * p.K, dw, st);
 }

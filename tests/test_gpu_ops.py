@@ -49,7 +49,7 @@ CONV_CASES = [
     (1, 6, 260, 64, 32, 3, 2, 1, 1),
     (2, 16, 16, 128, 256, 1, 2, 0, 1),
 ]
-TC_WGRAD_CASES = {0, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15}  # ... and whose wgrad must take the tcgen05 wgrad kernel
+TC_WGRAD_CASES = {0, 1, 2, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15, 16, 17, 18}  # ... and whose wgrad must take the tcgen05 wgrad kernel
 TC_FWD_CASES = {0, 1, 2, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15, 16, 17, 18}  # indices of CONV_CASES whose forward must take the tcgen05 kernel
 
 
