@@ -198,6 +198,13 @@ int stp_relu_bwd(const stp_tensor* dy, const stp_tensor* y, int32_t pool, const 
 int stp_stem_prep(const uint8_t* img, int32_t n, int32_t h, int32_t w, int32_t c_img, const float* coef,
                   const stp_tensor* y, stp_stream stream);
 
+/* Space-to-depth stem (DESIGN.md "stem"): with stp_stem_prep writing y as [n, h/2, w/2, 32] (channel ((h&1)*2+(w&1))*8+c)
+ * the 7x7 stride-2 pad-3 stem convolution equals a 4x4 stride-1 convolution (pad 2 before) with the weights
+ * w2[co][r'][s'][q*8+c] = w[co][2r'+dy-1][2s'+dx-1][c], q = dy*2+dx.  stp_stem_weight_s2d builds the bf16 w2 from the
+ * f32 [cout][7][7][8] master; stp_stem_wgrad_s2d_gather maps the f32 gradient of w2 back to [cout][7][7][8]. */
+int stp_stem_weight_s2d(const float* w_master, void* w2, int32_t cout, stp_stream stream);
+int stp_stem_wgrad_s2d_gather(const float* dw2, float* dw, int32_t cout, stp_stream stream);
+
 /* after the stem wgrad (dw8 f32 [cout][r][s][cin_pad]): dbeta(bn_data)[c<c_img] from the ones-channel column,
  * then zero the padded columns c>=c_img in place (DESIGN.md "stem") */
 int stp_stem_wgrad_post(float* dw8, const float* w_master, int32_t cout, int32_t r, int32_t s, int32_t cin_pad,

@@ -531,9 +531,21 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const __nv_bfloat16* 
   }
 }
 
+// s2d == 0: y[n,h,w,C].  s2d == 1: space-to-depth output y[n,h/2,w/2,4*C8] with channel ((h&1)*2 + (w&1))*C8 + c, the
+// layout in which the 7x7/2 stem convolution is a stride-1 4x4 convolution (DESIGN.md "stem").
 __global__ void stem_prep_kernel(const uint8_t* __restrict__ img, int64_t rows, int cimg,
-                                 const float* __restrict__ coef, __nv_bfloat16* __restrict__ y, int ldy, int C) {
+                                 const float* __restrict__ coef, __nv_bfloat16* __restrict__ y, int ldy, int C, int s2d,
+                                 int H, int W) {
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    __nv_bfloat16* dst;
+    if (s2d) {
+      int64_t n = r / ((int64_t)H * W);
+      int rem = (int)(r - n * (int64_t)H * W);
+      int h = rem / W, w = rem - h * W;
+      dst = y + ((n * (H / 2) + (h >> 1)) * (int64_t)(W / 2) + (w >> 1)) * ldy + ((h & 1) * 2 + (w & 1)) * C;
+    } else {
+      dst = y + r * ldy;
+    }
     for (int v = 0; v < C / 8; ++v) {
       float f[8];
 #pragma unroll
@@ -544,7 +556,7 @@ __global__ void stem_prep_kernel(const uint8_t* __restrict__ img, int64_t rows, 
         else if (c == cimg) t = 1.f;
         f[k] = t;
       }
-      st8(y + r * ldy + v * 8, pack8(f));
+      st8(dst + v * 8, pack8(f));
     }
   }
 }
@@ -764,10 +776,18 @@ extern "C" int stp_relu_bwd(const stp_tensor* dy, const stp_tensor* y, int32_t p
 extern "C" int stp_stem_prep(const uint8_t* img, int32_t n, int32_t h, int32_t w, int32_t c_img, const float* coef,
                              const stp_tensor* y, stp_stream stream) {
   STP_REQUIRE(img && coef && vec_ok(y), "stem_prep: bad args");
-  STP_REQUIRE(c_img < y->c && y->n == n && y->h == h && y->w == w, "stem_prep: shape mismatch");
   int64_t rows = (int64_t)n * h * w;
-  stem_prep_kernel<<<ew_grid(rows), 256, 0, (cudaStream_t)stream>>>(img, rows, c_img, coef, (__nv_bfloat16*)y->ptr,
-                                                                    y->ld, y->c);
+  if (y->h == h && y->w == w) {
+    STP_REQUIRE(c_img < y->c && y->n == n, "stem_prep: shape mismatch");
+    stem_prep_kernel<<<ew_grid(rows), 256, 0, (cudaStream_t)stream>>>(img, rows, c_img, coef, (__nv_bfloat16*)y->ptr,
+                                                                      y->ld, y->c, 0, h, w);
+  } else {
+    // space-to-depth: y [n, h/2, w/2, 4*8]
+    STP_REQUIRE(h % 2 == 0 && w % 2 == 0 && y->h == h / 2 && y->w == w / 2 && y->c == 32 && y->n == n && c_img < 8,
+                "stem_prep: space-to-depth output must be [n, h/2, w/2, 32]");
+    stem_prep_kernel<<<ew_grid(rows), 256, 0, (cudaStream_t)stream>>>(img, rows, c_img, coef, (__nv_bfloat16*)y->ptr,
+                                                                      y->ld, 8, 1, h, w);
+  }
   return check_launch("stem_prep");
 }
 
@@ -820,6 +840,43 @@ __global__ void stem_wgrad_post_kernel(float* __restrict__ dw8, const float* __r
     for (int c = cimg; c < cpad; ++c) dw8[(int64_t)t * cpad + c] = 0.f;
 }
 }  // namespace stp
+
+// ---- space-to-depth stem: 7x7/2 over [H,W,8]  ==  4x4/1 (pad 2 before) over [H/2,W/2,32] ------------------------------
+// w2[co][r'][s'][(dy*2+dx)*8 + c] = w[co][2r'+dy-1][2s'+dx-1][c]  (zero where the 7x7 index falls outside)
+namespace stp {
+__global__ void stem_weight_s2d_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w2, int cout) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * 16 * 32) return;
+  int c = i & 7, q = (i >> 3) & 3, sp = (i >> 5) & 3, rp = (i >> 7) & 3, co = i >> 9;
+  int r = 2 * rp + (q >> 1) - 1, s = 2 * sp + (q & 1) - 1;
+  float v = 0.f;
+  if (r >= 0 && r < 7 && s >= 0 && s < 7) v = w[((co * 7 + r) * 7 + s) * 8 + c];
+  w2[i] = __float2bfloat16(v);
+}
+// inverse gather of the gradient: dw[co][r][s][c] = dw2[co][(r+1)/2][(s+1)/2][(((r+1)&1)*2 + ((s+1)&1))*8 + c]
+__global__ void stem_wgrad_s2d_gather_kernel(const float* __restrict__ dw2, float* __restrict__ dw, int cout) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * 49 * 8) return;
+  int c = i & 7, t = i >> 3;
+  int s = t % 7;
+  t /= 7;
+  int r = t % 7, co = t / 7;
+  int rp = (r + 1) >> 1, sp = (s + 1) >> 1, q = ((r + 1) & 1) * 2 + ((s + 1) & 1);
+  dw[i] = dw2[(((co * 4 + rp) * 4 + sp) * 4 + q) * 8 + c];
+}
+}  // namespace stp
+
+extern "C" int stp_stem_weight_s2d(const float* w_master, void* w2, int32_t cout, stp_stream stream) {
+  STP_REQUIRE(w_master && w2 && cout > 0, "stem_weight_s2d: bad args");
+  stp::stem_weight_s2d_kernel<<<(cout * 512 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_master, (__nv_bfloat16*)w2, cout);
+  return check_launch("stem_weight_s2d");
+}
+
+extern "C" int stp_stem_wgrad_s2d_gather(const float* dw2, float* dw, int32_t cout, stp_stream stream) {
+  STP_REQUIRE(dw2 && dw && cout > 0, "stem_wgrad_s2d_gather: bad args");
+  stp::stem_wgrad_s2d_gather_kernel<<<(cout * 392 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dw2, dw, cout);
+  return check_launch("stem_wgrad_s2d_gather");
+}
 
 extern "C" int stp_stem_wgrad_post(float* dw8, const float* w_master, int32_t cout, int32_t r, int32_t s,
                                    int32_t cin_pad, int32_t c_img, float* dbeta, stp_stream stream) {

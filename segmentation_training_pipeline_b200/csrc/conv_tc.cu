@@ -75,21 +75,30 @@ using namespace tc;
 constexpr int kThreads = 192;
 constexpr int kSmemBudget = 227 * 1024;
 
+// One output view + tap list.  A normal convolution has one; the dgrad of a stride-2 convolution has four (one per
+// output parity class, each a stride-1 convolution over dY with a subset of the taps), all served by ONE launch.
+struct TcClass {
+  int64_t y_off, r_off;  // element offset of the view's pixel (0,0) in the output / residual tensors
+  int Ho, Wo, tilesW, tilesH;
+  int tile_begin;        // first tile index of this class
+  int ntaps;             // 0: no tap reaches this class -> zeros (+ residual)
+  int tap_dh[9], tap_dw[9], tap_k[9];  // A box offset (rows, pixels) and weight K block of each tap
+};
+
 struct TcConvArgs {
   void* y;
   const __nv_bfloat16* res;
   const float* bias;
   int y_f32, relu;
-  int64_t y_sn, y_sh, y_sw;  // element strides of the output view (image, row, pixel) -- a parity class of a strided
-  int64_t r_sn, r_sh, r_sw;  // dgrad writes every other pixel; same for the residual view
-  int ntaps;                 // filter taps of this launch: A box offset (tap_dh, tap_dw), weight K block tap_k
-  int tap_dh[9], tap_dw[9], tap_k[9];
-  int Ho, Wo, Cout, Cin;
-  int R, S, pad_h, pad_w;
+  int64_t y_sn, y_sh, y_sw;  // element strides of the output views (image, row, pixel)
+  int64_t r_sn, r_sh, r_sw;  // ... and of the residual views
+  int Cout, Cin;
   int stride;          // output stride (1 or 2): the A box is fetched with TMA element strides {1, stride, stride, 1}
   int BW, BH, log2BW;  // pixel rectangle of a tile, BW*BH = 128
-  int tilesW, tilesH, tilesN, n_img;
+  int tilesN;
   int num_tiles;
+  int ncls;
+  TcClass cls[4];
 };
 
 template <int BN, int BK>
@@ -122,7 +131,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kcb = a.Cin / BK;            // channel blocks per tap
-  const int num_kb = a.ntaps * kcb;      // k blocks per tile (0: a parity class no tap reaches -> zeros / residual)
+  __shared__ TcClass s_cls[4];           // dynamic indexing of kernel parameters would go through local memory
+  if (threadIdx.x < 4) s_cls[threadIdx.x] = a.cls[threadIdx.x];
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -146,13 +156,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto decode = [&](int tile, int& img, int& h0, int& w0, int& n0) {
-    int tn = tile % a.tilesN;
-    int t = tile / a.tilesN;
-    int tw = t % a.tilesW;
-    t /= a.tilesW;
-    int th = t % a.tilesH;
-    img = t / a.tilesH;
+  auto decode = [&](int tile, int& c, int& img, int& h0, int& w0, int& n0) {
+    c = 0;
+    while (c + 1 < a.ncls && tile >= s_cls[c + 1].tile_begin) ++c;
+    int t = tile - s_cls[c].tile_begin;
+    int tn = t % a.tilesN;
+    t /= a.tilesN;
+    int tw = t % s_cls[c].tilesW;
+    t /= s_cls[c].tilesW;
+    int th = t % s_cls[c].tilesH;
+    img = t / s_cls[c].tilesH;
     h0 = th * a.BH;
     w0 = tw * a.BW;
     n0 = tn * BN;
@@ -164,15 +177,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        int img, h0, w0, n0;
-        decode(tile, img, h0, w0, n0);
-        for (int tap = 0; tap < a.ntaps; ++tap) {
+        int c, img, h0, w0, n0;
+        decode(tile, c, img, h0, w0, n0);
+        const TcClass& cl = s_cls[c];
+        for (int tap = 0; tap < cl.ntaps; ++tap) {
           for (int cb = 0; cb < kcb; ++cb) {
             mbar_wait(&empty[stage], phase ^ 1);
             mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-            tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], cb * BK, w0 * a.stride + a.tap_dw[tap],
-                        h0 * a.stride + a.tap_dh[tap], img);
-            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], a.tap_k[tap] * a.Cin + cb * BK, n0);
+            tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], cb * BK, w0 * a.stride + cl.tap_dw[tap],
+                        h0 * a.stride + cl.tap_dh[tap], img);
+            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], cl.tap_k[tap] * a.Cin + cb * BK, n0);
             if (++stage == NS) {
               stage = 0;
               phase ^= 1;
@@ -191,6 +205,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++local) {
         const int as = local & 1;
         const uint32_t aphase = (local >> 1) & 1;
+        int c, img_, h0_, w0_, n0_;
+        decode(tile, c, img_, h0_, w0_, n0_);
+        const int num_kb = s_cls[c].ntaps * kcb;
         mbar_wait(&acc_empty[as], aphase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
@@ -223,12 +240,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++local) {
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
-      int img, h0, w0, n0;
-      decode(tile, img, h0, w0, n0);
+      int c, img, h0, w0, n0;
+      decode(tile, c, img, h0, w0, n0);
+      const int num_kb = s_cls[c].ntaps * kcb;
       const int ho = h0 + hl, wo = w0 + wl;
-      const bool valid = ho < a.Ho && wo < a.Wo;
-      const int64_t yoff = (int64_t)img * a.y_sn + (int64_t)ho * a.y_sh + (int64_t)wo * a.y_sw;
-      const int64_t roff = (int64_t)img * a.r_sn + (int64_t)ho * a.r_sh + (int64_t)wo * a.r_sw;
+      const bool valid = ho < s_cls[c].Ho && wo < s_cls[c].Wo;
+      const int64_t yoff = s_cls[c].y_off + (int64_t)img * a.y_sn + (int64_t)ho * a.y_sh + (int64_t)wo * a.y_sw;
+      const int64_t roff = s_cls[c].r_off + (int64_t)img * a.r_sn + (int64_t)ho * a.r_sh + (int64_t)wo * a.r_sw;
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
@@ -291,10 +309,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-int pick_bn(int cout) {
+// widest N tile that divides Cout and still leaves at least ~one tile per SM (m_tiles = 128-pixel tiles of the launch)
+int pick_bn(int cout, int64_t m_tiles = 1 << 30) {
+  int fallback = 0;
   for (int bn : {256, 128, 64, 32, 16})
-    if (cout % bn == 0) return bn;
-  return 0;
+    if (cout % bn == 0) {
+      if (m_tiles * (cout / bn) >= kNumSMs - 20 || bn <= 64) return bn;
+      fallback = bn;
+    }
+  return fallback;
 }
 int pick_bk(int cin) {
   if (cin % 64 == 0) return 64;
@@ -348,35 +371,53 @@ bool tc_conv_supported(const ConvP& p) {
   return tc_common_ok(p);
 }
 
-// One launch over an output view of ho x wo pixels per image (element strides given), with an explicit tap list.
-static int launch_tc_view(const ConvP& p, int ho, int wo, void* y, int64_t y_sn, int64_t y_sh, int64_t y_sw,
-                          const __nv_bfloat16* res, int64_t r_sn, int64_t r_sh, int64_t r_sw, int in_stride, int ntaps,
-                          const int* dh, const int* dw, const int* tk, cudaStream_t st) {
-  const int BN = pick_bn(p.Cout), BK = pick_bk(p.Cin);
+struct ViewSpec {  // host description of one class
+  int ho, wo;
+  int64_t y_off, r_off;
+  int ntaps, dh[9], dw[9], tk[9];
+};
+
+// One launch over `ncls` output views (element strides shared), each with an explicit tap list.
+static int launch_tc_views(const ConvP& p, int ncls, const ViewSpec* v, int64_t y_sn, int64_t y_sh, int64_t y_sw,
+                           int64_t r_sn, int64_t r_sh, int64_t r_sw, int in_stride, cudaStream_t st) {
+  const int BK = pick_bk(p.Cin);
   TcConvArgs a;
-  a.y = y; a.res = res; a.bias = p.bias; a.y_f32 = p.y_f32; a.relu = p.relu;
+  a.y = p.y; a.res = p.res; a.bias = p.bias; a.y_f32 = p.y_f32; a.relu = p.relu;
   a.y_sn = y_sn; a.y_sh = y_sh; a.y_sw = y_sw; a.r_sn = r_sn; a.r_sh = r_sh; a.r_sw = r_sw;
-  a.ntaps = ntaps;
-  for (int t = 0; t < 9; ++t) {
-    a.tap_dh[t] = t < ntaps ? dh[t] : 0;
-    a.tap_dw[t] = t < ntaps ? dw[t] : 0;
-    a.tap_k[t] = t < ntaps ? tk[t] : 0;
-  }
-  a.Ho = ho; a.Wo = wo; a.Cout = p.Cout; a.Cin = p.Cin; a.R = p.R; a.S = p.S; a.pad_h = p.pad_h; a.pad_w = p.pad_w;
+  a.Cout = p.Cout; a.Cin = p.Cin;
   a.stride = in_stride;
+  int wmax = 0;
+  for (int c = 0; c < ncls; ++c) wmax = v[c].wo > wmax ? v[c].wo : wmax;
   int bw = 128;
-  while (bw > 8 && bw / 2 >= wo) bw /= 2;  // smallest power of two >= Wo, clamped to [8,128]
+  while (bw > 8 && bw / 2 >= wmax) bw /= 2;  // smallest power of two >= Wo, clamped to [8,128]
   a.BW = bw; a.BH = 128 / bw;
   a.log2BW = 0;
   while ((1 << a.log2BW) < bw) ++a.log2BW;
-  a.tilesW = (wo + a.BW - 1) / a.BW;
-  a.tilesH = (ho + a.BH - 1) / a.BH;
+  int64_t m_tiles = 0;
+  for (int c = 0; c < ncls; ++c)
+    m_tiles += (int64_t)p.N * ((v[c].wo + a.BW - 1) / a.BW) * ((v[c].ho + a.BH - 1) / a.BH);
+  const int BN = pick_bn(p.Cout, m_tiles);
   a.tilesN = p.Cout / BN;
-  a.n_img = p.N;
-  int64_t nt = (int64_t)p.N * a.tilesH * a.tilesW * a.tilesN;
-  if (nt > 0x7fffffff) {
-    set_error("conv_tc: too many tiles");
-    return STP_E_UNSUPPORTED;
+  a.ncls = ncls;
+  int64_t nt = 0;
+  for (int c = 0; c < 4; ++c) {
+    TcClass& k = a.cls[c];
+    const ViewSpec& s = v[c < ncls ? c : 0];
+    k.y_off = s.y_off; k.r_off = s.r_off; k.Ho = s.ho; k.Wo = s.wo;
+    k.tilesW = (s.wo + a.BW - 1) / a.BW;
+    k.tilesH = (s.ho + a.BH - 1) / a.BH;
+    k.tile_begin = (int)nt;
+    k.ntaps = s.ntaps;
+    for (int t = 0; t < 9; ++t) {
+      k.tap_dh[t] = t < s.ntaps ? s.dh[t] : 0;
+      k.tap_dw[t] = t < s.ntaps ? s.dw[t] : 0;
+      k.tap_k[t] = t < s.ntaps ? s.tk[t] : 0;
+    }
+    if (c < ncls) nt += (int64_t)p.N * k.tilesH * k.tilesW * a.tilesN;
+    if (nt > 0x7fffffff) {
+      set_error("conv_tc: too many tiles");
+      return STP_E_UNSUPPORTED;
+    }
   }
   a.num_tiles = (int)nt;
 
@@ -406,49 +447,53 @@ static int launch_tc_view(const ConvP& p, int ho, int wo, void* y, int64_t y_sn,
 }
 
 int launch_tc_conv(const ConvP& p, cudaStream_t st) {
-  const int64_t esz = 1;  // strides below are in elements of the output dtype
-  (void)esz;
   if (p.up == 1) {
-    int dh[9], dw[9], tk[9];
     if (p.R * p.S > 9) {
       set_error("conv_tc: more than 9 taps");
       return STP_E_UNSUPPORTED;
     }
+    ViewSpec v;
+    v.ho = p.Ho; v.wo = p.Wo; v.y_off = 0; v.r_off = 0; v.ntaps = p.R * p.S;
     for (int r = 0; r < p.R; ++r)
       for (int s = 0; s < p.S; ++s) {
-        dh[r * p.S + s] = r - p.pad_h;
-        dw[r * p.S + s] = s - p.pad_w;
-        tk[r * p.S + s] = r * p.S + s;
+        v.dh[r * p.S + s] = r - p.pad_h;
+        v.dw[r * p.S + s] = s - p.pad_w;
+        v.tk[r * p.S + s] = r * p.S + s;
       }
-    return launch_tc_view(p, p.Ho, p.Wo, p.y, (int64_t)p.Ho * p.Wo * p.ldy, (int64_t)p.Wo * p.ldy, p.ldy, p.res,
-                          (int64_t)p.Ho * p.Wo * p.ldr, (int64_t)p.Wo * p.ldr, p.ldr, p.stride, p.R * p.S, dh, dw, tk, st);
+    return launch_tc_views(p, 1, &v, (int64_t)p.Ho * p.Wo * p.ldy, (int64_t)p.Wo * p.ldy, p.ldy,
+                           (int64_t)p.Ho * p.Wo * p.ldr, (int64_t)p.Wo * p.ldr, p.ldr, p.stride, st);
   }
   // up == 2:  y[i] = sum_r' xup[i - pad + r'] w[r'],  xup[2o] = x[o].  For the output parity class i = 2a + ph only the
   // taps with (ph - pad + r') even contribute, reading x[a + (ph - pad + r')/2]: a stride-1 conv per class.
+  // A class no tap reaches is all zeros (+ residual): skipped when the call accumulates in place (residual == output).
+  const bool in_place = p.res && (const void*)p.res == (const void*)p.y && p.ldr == p.ldy && !p.y_f32;
+  ViewSpec v[4];
+  int ncls = 0;
   for (int ph = 0; ph < 2; ++ph)
     for (int pw = 0; pw < 2; ++pw) {
-      int dh[9], dw[9], tk[9], nt = 0;
+      ViewSpec& k = v[ncls];
+      k.ntaps = 0;
       for (int r = 0; r < p.R; ++r) {
         if ((ph - p.pad_h + r) & 1) continue;
         for (int s = 0; s < p.S; ++s) {
           if ((pw - p.pad_w + s) & 1) continue;
-          dh[nt] = (ph - p.pad_h + r) / 2;  // numerator is even: exact for negatives too
-          dw[nt] = (pw - p.pad_w + s) / 2;
-          tk[nt] = r * p.S + s;
-          ++nt;
+          k.dh[k.ntaps] = (ph - p.pad_h + r) / 2;  // numerator is even: exact for negatives too
+          k.dw[k.ntaps] = (pw - p.pad_w + s) / 2;
+          k.tk[k.ntaps] = r * p.S + s;
+          ++k.ntaps;
         }
       }
-      const int ho = (p.Ho - ph + 1) / 2, wo = (p.Wo - pw + 1) / 2;
-      if (ho <= 0 || wo <= 0) continue;
-      const int esize = p.y_f32 ? 4 : 2;
-      void* y = (char*)p.y + ((int64_t)ph * p.Wo + pw) * p.ldy * esize;
-      const __nv_bfloat16* res = p.res ? p.res + ((int64_t)ph * p.Wo + pw) * p.ldr : nullptr;
-      int rc = launch_tc_view(p, ho, wo, y, (int64_t)p.Ho * p.Wo * p.ldy, (int64_t)2 * p.Wo * p.ldy, (int64_t)2 * p.ldy,
-                              res, (int64_t)p.Ho * p.Wo * p.ldr, (int64_t)2 * p.Wo * p.ldr, (int64_t)2 * p.ldr, 1, nt,
-                              dh, dw, tk, st);
-      if (rc) return rc;
+      k.ho = (p.Ho - ph + 1) / 2;
+      k.wo = (p.Wo - pw + 1) / 2;
+      if (k.ho <= 0 || k.wo <= 0) continue;
+      if (k.ntaps == 0 && in_place && !p.relu && !p.bias) continue;
+      k.y_off = ((int64_t)ph * p.Wo + pw) * p.ldy;
+      k.r_off = ((int64_t)ph * p.Wo + pw) * p.ldr;
+      ++ncls;
     }
-  return STP_OK;
+  if (ncls == 0) return STP_OK;
+  return launch_tc_views(p, ncls, v, (int64_t)p.Ho * p.Wo * p.ldy, (int64_t)2 * p.Wo * p.ldy, (int64_t)2 * p.ldy,
+                         (int64_t)p.Ho * p.Wo * p.ldr, (int64_t)2 * p.Wo * p.ldr, (int64_t)2 * p.ldr, 1, st);
 }
 
 // ====================================================================================================
@@ -481,14 +526,15 @@ template <int BN, int ANARROW, int STR>
 struct TcWgradCfg {
   static constexpr int kABytes = ANARROW ? 128 * 64 : 2 * 16384;
   static constexpr int kBRow = (BN < 64 ? BN : 64) * 2;
-  static constexpr int kXBoxBytes = 160 * kBRow;  // >= (BH+2)*BW rows for the supported geometries; 1024-multiple
+  // >= (BH+R-1)*BW rows: 160 for R <= 3; the 32-channel variant also serves the 4x4 space-to-depth stem (176 rows)
+  static constexpr int kXBoxBytes = (BN == 32 ? 192 : 160) * kBRow;
   static constexpr int kRBytes = (BN < 64 ? 1 : BN / 64) * kXBoxBytes;  // input box(es) of one filter row
   static constexpr int kBBytes = (STR ? 3 : 1) * kRBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagesRaw = (kSmemBudget - 2048) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
   static_assert(kStages >= 2, "wgrad needs two pipeline stages");
-  static constexpr int kTmemCols = 3 * BN <= 64 ? 64 : 3 * BN <= 128 ? 128 : 3 * BN <= 256 ? 256 : 512;
+  static constexpr int kTmemCols = 4 * BN <= 64 ? 64 : 4 * BN <= 128 ? 128 : 4 * BN <= 256 ? 256 : 512;  // up to 4 filter rows
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
   static_assert(kXBoxBytes % 1024 == 0, "stage buffers must stay swizzle-atom aligned");
 };
@@ -649,11 +695,12 @@ struct WgradPlan {
 static bool wgrad_plan(int64_t M, int N_img, int Ho, int Wo, int Cout, int Cin, int R, int S, int stride, WgradPlan* pl) {
   const bool co_ok = Cout % 64 == 0 || Cout == 32 || Cout == 16;
   const bool ci_ok = Cin % 64 == 0 || Cin == 32 || Cin == 16;
-  if (!co_ok || !ci_ok || R > 3 || S > 3 || Wo < 8) return false;
+  const int rmax = (Cin == 32 && stride == 1) ? 4 : 3;
+  if (!co_ok || !ci_ok || R > rmax || S > rmax || Wo < 8) return false;
   pl->BN = (Cin % 128 == 0 && stride == 1) ? 128 : (Cin % 64 == 0 ? 64 : Cin);
   pl->BW = Wo >= 16 ? 16 : 8;
   pl->BH = 128 / pl->BW;
-  if ((pl->BH + R - 1) * pl->BW > 160) return false;
+  if ((pl->BH + R - 1) * pl->BW > (pl->BN == 32 ? 192 : 160)) return false;
   pl->tilesW = (Wo + pl->BW - 1) / pl->BW;
   pl->tilesH = (Ho + pl->BH - 1) / pl->BH;
   int64_t npb = (int64_t)N_img * pl->tilesW * pl->tilesH;

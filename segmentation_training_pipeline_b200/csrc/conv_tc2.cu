@@ -39,13 +39,14 @@ struct Tc2Args {
 
 constexpr int align1k(int x) { return (x + 1023) / 1024 * 1024; }
 
-template <int BN, int BK, int MT>
+// RMAX: largest filter height/width served (3; 4 for the space-to-depth stem).  Sizes the A halo and the weight boxes.
+template <int BN, int BK, int MT, int RMAX = 3>
 struct Tc2Cfg {
   static constexpr int kRowBytes = BK * 2;
-  static constexpr int kMaxRows = (MT * 8 + 2) * 16 > (MT * 16 + 2) * 8 ? (MT * 8 + 2) * 16 : (MT * 16 + 2) * 8;
-  static constexpr int kABytes = align1k(kMaxRows * kRowBytes);   // BW=16/BH=8 or BW=8/BH=16, R<=3
+  static constexpr int kMaxRows = (MT * 8 + RMAX - 1) * 16 > (MT * 16 + RMAX - 1) * 8 ? (MT * 8 + RMAX - 1) * 16 : (MT * 16 + RMAX - 1) * 8;
+  static constexpr int kABytes = align1k(kMaxRows * kRowBytes);   // BW=16/BH=8 or BW=8/BH=16, R<=RMAX
   static constexpr int kBTap = BN * BK * 2;
-  static constexpr int kBBytes = align1k(3 * kBTap);
+  static constexpr int kBBytes = align1k(RMAX * kBTap);
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutRowBytes = (BN < 64 ? BN : 64) * 2;       // one 64-channel (or narrower) slab of a pixel
   static constexpr int kOutSlabs = BN < 64 ? 1 : BN / 64;
@@ -64,11 +65,11 @@ struct Tc2Cfg {
   static_assert(kTmemRaw <= 512, "accumulators exceed TMEM");
 };
 
-template <int BN, int BK, int MT>
+template <int BN, int BK, int MT, int RMAX = 3>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const Tc2Args a) {
-  using Cfg = Tc2Cfg<BN, BK, MT>;
+  using Cfg = Tc2Cfg<BN, BK, MT, RMAX>;
   constexpr int NS = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -381,14 +382,16 @@ static double tc2_cost(const ConvP& p, int bn, int bk, int mt) {
 bool tc2_plan(const ConvP& p, Tc2Plan* pl) {
   if (p.stride != 1 || p.up != 1) return false;
   if (p.R < 2 && p.S < 2) return false;  // 1x1: nothing to reuse, first-generation kernel
-  if (p.R > 3 || p.S > 3) return false;
   int bk = (p.Cin % 64 == 0) ? 64 : (p.Cin == 32 ? 32 : (p.Cin == 16 ? 16 : 0));
   if (!bk) return false;
+  const bool r4 = p.R == 4 || p.S == 4;  // 4x4: only the stem shape (Cin 32 = 4 sub-pixels x 8 channels, Cout 64) is instantiated
+  if (p.R > 4 || p.S > 4 || (r4 && !(bk == 32 && p.Cout % 64 == 0))) return false;
   const int force = get_option(OPT_TC2_FORCE_MT);
   double best = 0.0;
   int best_bn = 0, best_mt = 0;
   for (int bn : {128, 64, 32, 16}) {
     if (p.Cout % bn != 0) continue;
+    if (r4 && bn != 64) continue;
     if (best_bn != 0 && bn < 64) break;  // narrow N tiles only when Cout demands them
     const int mt_max = bn == 128 ? 2 : (bn == 64 || bk == 64) ? 4 : 8;
     for (int mt = 1; mt <= mt_max; mt *= 2) {
@@ -406,13 +409,13 @@ bool tc2_plan(const ConvP& p, Tc2Plan* pl) {
   return true;
 }
 
-template <int BN, int BK, int MT>
+template <int BN, int BK, int MT, int RMAX = 3>
 int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR, const Tc2Args& a,
             cudaStream_t st) {
-  using Cfg = Tc2Cfg<BN, BK, MT>;
+  using Cfg = Tc2Cfg<BN, BK, MT, RMAX>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, BK, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, BK, MT, RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("conv_tc2: cudaFuncSetAttribute(%d B): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
       return STP_E_CUDA;
@@ -420,7 +423,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& t
     attr_set = true;
   }
   int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
-  conv_tc2_kernel<BN, BK, MT><<<grid, kThreads2, Cfg::kSmemBytes, st>>>(tmA, tmB, tmY, tmR, a);
+  conv_tc2_kernel<BN, BK, MT, RMAX><<<grid, kThreads2, Cfg::kSmemBytes, st>>>(tmA, tmB, tmY, tmR, a);
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("conv_tc2");
 }
@@ -493,6 +496,11 @@ int launch_tc2_conv(const ConvP& p, cudaStream_t st) {
       uint64_t rstrides[3] = {(uint64_t)p.ldr * 2, (uint64_t)p.Wo * p.ldr * 2, (uint64_t)p.Ho * p.Wo * p.ldr * 2};
       if (!make_tmap_bf16(&tmR, p.res, 4, dims, rstrides, box, oc * 2)) return STP_E_CUDA;
     }
+  }
+  if (p.R == 4 || p.S == 4) {
+    if (pl.BN == 64 && pl.BK == 32 && pl.MT == 4) return launch2<64, 32, 4, 4>(tmA, tmB, tmY, tmR, a, st);
+    if (pl.BN == 64 && pl.BK == 32 && pl.MT == 2) return launch2<64, 32, 2, 4>(tmA, tmB, tmY, tmR, a, st);
+    if (pl.BN == 64 && pl.BK == 32 && pl.MT == 1) return launch2<64, 32, 1, 4>(tmA, tmB, tmY, tmR, a, st);
   }
 #define STP_TC2_CASE(bn, bk, mt) \
   if (pl.BN == bn && pl.BK == bk && pl.MT == mt) return launch2<bn, bk, mt>(tmA, tmB, tmY, tmR, a, st);

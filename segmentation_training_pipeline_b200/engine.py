@@ -191,6 +191,9 @@ class Net:
             self.L.weight_prep_batched(self.flat_p.data_ptr(), self.flat_wf.data_ptr(), self.flat_wd.data_ptr(),
                                        self._wprep_items.data_ptr(), self._wprep_items.shape[0], self._wprep_tiles,
                                        _stream())
+        for op in self.ops:
+            if isinstance(op, StemConv):
+                op.prep_weights(_stream())
 
     def forward(self):
         for op in self.ops:
@@ -338,6 +341,54 @@ class Conv(Op):
             c = self.w.shape
             n.L.stem_wgrad_post(n.pg(self.w), n.pp(self.w), c[0], c[1], c[2], c[3], self.cin_real,
                                 n.pg(self.stem_beta), st)
+
+
+class StemConv(Op):
+    """conv0: 7x7 stride-2 pad-3 convolution of the (8-channel padded) bn_data output, executed as a 4x4 stride-1
+    convolution over the space-to-depth tensor [N, H/2, W/2, 32] that InputNorm writes (DESIGN.md "stem") so that it runs
+    on the tcgen05 halo kernel.  The parameter stays in Keras geometry ([64][7][7][8] master, exported as (7,7,3,64)); the
+    4x4x32 bf16 operand and the gradient mapping back are two tiny kernels."""
+
+    def __init__(self, net: Net, x_s2d: Buf, y: Buf, name: str, cin_real: int, stem_beta: Param, init="he_uniform"):
+        self.net, self.x, self.y, self.name = net, x_s2d, y, name
+        assert x_s2d.c == 32 and y.h == x_s2d.h and y.w == x_s2d.w
+        cout, k, cin = y.c, 7, 8
+        lim = math.sqrt(6.0 / (k * k * cin_real)) if init == "he_uniform" else math.sqrt(6.0 / (k * k * (cin_real + cout)))
+
+        def mk():
+            w = net.gen.uniform(-lim, lim, size=(k, k, cin_real, cout)).astype(np.float32)
+            full = np.zeros((cout, k, k, cin), np.float32)
+            full[..., :cin_real] = np.transpose(w, (3, 0, 1, 2))
+            return full
+
+        self.w = net.add_param(name + "/kernel", (cout, k, k, cin), "conv", mk)
+        self.w.cin_real = cin_real
+        self.cin_real, self.stem_beta = cin_real, stem_beta
+        self.desc = _lib.ConvDesc(4, 4, 1, 2, 2, 1, 0)
+        self.w2 = torch.zeros(cout * 16 * 32, dtype=torch.bfloat16, device=net.device)
+        self.dw2 = torch.zeros(cout * 16 * 32, dtype=torch.float32, device=net.device)
+        net.need_ws(net.L.conv_wgrad_workspace(C.byref(self.desc), x_s2d.ref, y.ref))
+        net.ops.append(self)
+
+    def prepare(self):
+        self.dref = C.byref(self.desc)
+        self.dy = self.y.grad()
+
+    def prep_weights(self, st):
+        n = self.net
+        n.L.stem_weight_s2d(n.pp(self.w), self.w2.data_ptr(), self.w.shape[0], st)
+
+    def fwd(self):
+        n = self.net
+        n.L.conv_fwd(self.dref, self.x.ref, self.w2.data_ptr(), None, None, self.y.ref, n.ws.data_ptr(), n.ws.numel(),
+                     _stream())
+
+    def bwd(self):
+        n, st = self.net, _stream()
+        c = self.w.shape
+        n.L.conv_wgrad(self.dref, self.x.ref, self.dy.ref, self.dw2.data_ptr(), n.ws.data_ptr(), n.ws.numel(), st)
+        n.L.stem_wgrad_s2d_gather(self.dw2.data_ptr(), n.pg(self.w), c[0], st)
+        n.L.stem_wgrad_post(n.pg(self.w), n.pp(self.w), c[0], c[1], c[2], c[3], self.cin_real, n.pg(self.stem_beta), st)
 
 
 class BNRelu(Op):

@@ -89,6 +89,8 @@ SIGNATURES = {
     "stp_bn_bwd_apply": (C.c_int, [_TP, _TP, _P, _P, _I32, _I32, _TP, _TP, _P]),
     "stp_relu_bwd": (C.c_int, [_TP, _TP, _I32, _TP, _TP, _P]),
     "stp_stem_prep": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _TP, _P]),
+    "stp_stem_weight_s2d": (C.c_int, [_P, _P, _I32, _P]),
+    "stp_stem_wgrad_s2d_gather": (C.c_int, [_P, _P, _I32, _P]),
     "stp_stem_wgrad_post": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "stp_maxpool_fwd": (C.c_int, [_TP, _I32, _I32, _I32, _TP, _P, _P]),
     "stp_maxpool_bwd": (C.c_int, [_TP, _P, _I32, _I32, _I32, _TP, _TP, _P]),

@@ -68,11 +68,11 @@ class SegNet(E.Net):
             return E.Buf(self, n, h, w, c, name=name)
 
         # ---- encoder ---------------------------------------------------------------------------
-        x0 = E.Buf(self, N, H, W, 8, name="bn_data")
+        # bn_data output in space-to-depth layout [N, H/2, W/2, 4 sub-pixels x 8 channels] (see engine.StemConv)
+        x0 = E.Buf(self, N, H // 2, W // 2, 32, name="bn_data_s2d")
         inorm = E.InputNorm(self, self.img, x0, "bn_data", ENC_BN_EPS)
         z = E.Buf(self, N, H // 2, W // 2, 64, name="conv0")
-        E.Conv(self, x0, z, "conv0", 7, stride=2, pad=3, init=enc_init, needs_dgrad=False, cin_real=CI,
-               stem_beta=inorm.beta)
+        E.StemConv(self, x0, z, "conv0", cin_real=CI, stem_beta=inorm.beta, init=enc_init)
         relu0 = skip_buf("relu0", N, H // 2, W // 2, 64)
         E.BNRelu(self, z, relu0, "bn0", ENC_BN_EPS)
         x = E.Buf(self, N, H // 4, W // 4, 64, name="pooling0")

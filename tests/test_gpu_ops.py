@@ -48,9 +48,10 @@ CONV_CASES = [
     (1, 17, 23, 64, 64, 3, 2, 1, 1),
     (1, 6, 260, 64, 32, 3, 2, 1, 1),
     (2, 16, 16, 128, 256, 1, 2, 0, 1),
+    (1, 16, 24, 32, 64, 4, 1, 2, 1),   # the space-to-depth stem shape: 4x4, Cin 32, Cout 64
 ]
-TC_WGRAD_CASES = {0, 1, 2, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15, 16, 17, 18}  # ... and whose wgrad must take the tcgen05 wgrad kernel
-TC_FWD_CASES = {0, 1, 2, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15, 16, 17, 18}  # indices of CONV_CASES whose forward must take the tcgen05 kernel
+TC_WGRAD_CASES = {0, 1, 2, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19}  # ... and whose wgrad must take the tcgen05 wgrad kernel
+TC_FWD_CASES = {0, 1, 2, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19}  # indices of CONV_CASES whose forward must take the tcgen05 kernel
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
@@ -469,3 +470,46 @@ def test_weight_prep_batched_matches_per_layer(stp, cuda):
         n = co * r * s_ * ci
         assert torch.equal(wf[o:o + n], wf2[o:o + n])
         assert torch.equal(wd[o:o + n], wd2[o:o + n])
+
+
+def test_stem_space_to_depth_equals_7x7_stride2(stp, cuda):
+    """conv0 as run by the engine (4x4/1 over the space-to-depth bn_data tensor, gradient gathered back) == the 7x7
+    stride-2 pad-3 convolution of the reference graph, forward and weight gradient."""
+    g = torch.Generator().manual_seed(3)
+    n, h, w, cout = 2, 32, 48, 64
+    img = torch.randint(0, 256, (n, h, w, 3), generator=g, dtype=torch.uint8).to(cuda)
+    coef = torch.cat([torch.full((3,), 120.0), torch.full((3,), 0.02), torch.tensor([0.02, 0.015, 0.025]),
+                      torch.tensor([-2.0, -1.5, -2.5])]).to(cuda)
+    x8 = torch.zeros((n, h, w, 8), dtype=torch.bfloat16, device=cuda)
+    xs = torch.zeros((n, h // 2, w // 2, 32), dtype=torch.bfloat16, device=cuda)
+    x8s, xss = T(x8), T(xs)
+    stp.stem_prep(img.data_ptr(), n, h, w, 3, coef.data_ptr(), ref(x8s), stream())
+    stp.stem_prep(img.data_ptr(), n, h, w, 3, coef.data_ptr(), ref(xss), stream())
+    # space-to-depth layout check
+    x8c = x8.float().cpu()
+    s2d = x8c.view(n, h // 2, 2, w // 2, 2, 8).permute(0, 1, 3, 2, 4, 5).reshape(n, h // 2, w // 2, 32)
+    assert torch.equal(xs.float().cpu(), s2d)
+    wm = torch.zeros((cout, 7, 7, 8))
+    wm[..., :4] = bf16_round(torch.randn((cout, 7, 7, 4), generator=g) * 0.08)
+    wm = wm.to(cuda)
+    w2 = torch.zeros(cout * 16 * 32, dtype=torch.bfloat16, device=cuda)
+    stp.stem_weight_s2d(wm.data_ptr(), w2.data_ptr(), cout, stream())
+    desc = lib.ConvDesc(4, 4, 1, 2, 2, 1, 0)
+    y = torch.zeros((n, h // 2, w // 2, cout), dtype=torch.bfloat16, device=cuda)
+    ys = T(y)
+    tc0 = stp.tc_launch_count()
+    stp.conv_fwd(C.byref(desc), ref(xss), w2.data_ptr(), None, None, ref(ys), None, 0, stream())
+    assert stp.tc_launch_count() == tc0 + 1
+    xr = x8c.clone().requires_grad_(True)
+    wr = wm.cpu().clone().requires_grad_(True)
+    yr = conv_ref_autograd(xr, wr, 2, 3, 1, (h // 2, w // 2))
+    assert rel_err(y, yr) < TOL_BF16
+    dy = rand_bf16((n, h // 2, w // 2, cout), g)
+    yr.backward(dy.float().cpu())
+    dys = T(dy)
+    ws = _ws(stp.conv_wgrad_workspace(C.byref(desc), ref(xss), ref(dys)), cuda)
+    dw2 = torch.zeros(cout * 16 * 32, device=cuda)
+    dw = torch.zeros((cout, 7, 7, 8), device=cuda)
+    stp.conv_wgrad(C.byref(desc), ref(xss), ref(dys), dw2.data_ptr(), ws.data_ptr(), ws.numel(), stream())
+    stp.stem_wgrad_s2d_gather(dw2.data_ptr(), dw.data_ptr(), cout, stream())
+    assert rel_err(dw, wr.grad) < TOL_F32
