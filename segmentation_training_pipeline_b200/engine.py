@@ -73,6 +73,29 @@ class Buf:
         return (id(self.root), self.c_off, self.c)
 
 
+class _NullCtx:
+    def __init__(self, ws):
+        self.ws = ws
+
+    def __enter__(self):
+        return self.ws
+
+    def __exit__(self, *a):
+        return False
+
+
+class _SideCtx:
+    def __init__(self, stream, ws):
+        self.ctx, self.ws = torch.cuda.stream(stream), ws
+
+    def __enter__(self):
+        self.ctx.__enter__()
+        return self.ws
+
+    def __exit__(self, *a):
+        return self.ctx.__exit__(*a)
+
+
 class Param:
     def __init__(self, name, shape, kind, init):
         self.name, self.shape, self.kind, self.init = name, tuple(shape), kind, init
@@ -139,6 +162,11 @@ class Net:
         self.flat_wf = torch.zeros(self.n_flat, dtype=torch.bfloat16, device=dev)  # bf16 KRSC copies
         self.flat_wd = torch.zeros(self.n_flat, dtype=torch.bfloat16, device=dev)  # bf16 dgrad-layout copies
         self.ws = torch.zeros(max(self._ws_bytes, 16), dtype=torch.uint8, device=dev)
+        # weight gradients run on a side stream (own workspace), overlapping the BatchNorm / dgrad chain of the layers
+        # below: nothing downstream of a wgrad reads its result before the optimizer
+        self.ws_side = torch.zeros(max(self._ws_bytes, 16), dtype=torch.uint8, device=dev)
+        self.side_stream = torch.cuda.Stream(device=dev) if self.device.type == "cuda" else None
+        self.overlap_wgrad = True
         self.partial = torch.zeros(self._partial_floats, dtype=torch.float32, device=dev)
         self.d_step = torch.zeros(1, dtype=torch.int64, device=dev)
         self.sync = torch.zeros(4, dtype=torch.int32, device=dev)  # last-block tickets of the fused reduce+finalize kernels
@@ -202,6 +230,16 @@ class Net:
     def backward(self):
         for op in reversed(self.ops):
             op.bwd()
+        if self.overlap_wgrad and self.side_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.side_stream)
+
+    def wgrad_stream(self):
+        """context in which a weight-gradient kernel is enqueued: the side stream, ordered after everything already on
+        the current stream (the layer's dY is complete), or the current stream when overlap is off."""
+        if not (self.overlap_wgrad and self.side_stream is not None):
+            return _NullCtx(self.ws)
+        self.side_stream.wait_stream(torch.cuda.current_stream())
+        return _SideCtx(self.side_stream, self.ws_side)
 
     # ---- weights in Keras layout ----------------------------------------------------------------
     def get_grads(self) -> Dict[str, np.ndarray]:
@@ -332,15 +370,17 @@ class Conv(Op):
                      n.ws.data_ptr(), n.ws.numel(), _stream())
 
     def bwd(self):
-        n, st = self.net, _stream()
+        n = self.net
+        with n.wgrad_stream() as ws:  # forked first: the wgrad overlaps this layer's dgrad and the BatchNorm backward below
+            st = _stream()
+            n.L.conv_wgrad(self.dref, self.x.ref, self.dy.ref, n.pg(self.w), ws.data_ptr(), ws.numel(), st)
+            if self.stem_beta is not None:
+                c = self.w.shape
+                n.L.stem_wgrad_post(n.pg(self.w), n.pp(self.w), c[0], c[1], c[2], c[3], self.cin_real,
+                                    n.pg(self.stem_beta), st)
         if self.needs_dgrad:
             n.L.conv_dgrad(self.dref, self.dy.ref, n.pwd(self.w), self.dx_res, self.dx.ref, n.ws.data_ptr(),
-                           n.ws.numel(), st)
-        n.L.conv_wgrad(self.dref, self.x.ref, self.dy.ref, n.pg(self.w), n.ws.data_ptr(), n.ws.numel(), st)
-        if self.stem_beta is not None:
-            c = self.w.shape
-            n.L.stem_wgrad_post(n.pg(self.w), n.pp(self.w), c[0], c[1], c[2], c[3], self.cin_real,
-                                n.pg(self.stem_beta), st)
+                           n.ws.numel(), _stream())
 
 
 class StemConv(Op):
@@ -384,11 +424,14 @@ class StemConv(Op):
                      _stream())
 
     def bwd(self):
-        n, st = self.net, _stream()
+        n = self.net
         c = self.w.shape
-        n.L.conv_wgrad(self.dref, self.x.ref, self.dy.ref, self.dw2.data_ptr(), n.ws.data_ptr(), n.ws.numel(), st)
-        n.L.stem_wgrad_s2d_gather(self.dw2.data_ptr(), n.pg(self.w), c[0], st)
-        n.L.stem_wgrad_post(n.pg(self.w), n.pp(self.w), c[0], c[1], c[2], c[3], self.cin_real, n.pg(self.stem_beta), st)
+        with n.wgrad_stream() as ws:
+            st = _stream()
+            n.L.conv_wgrad(self.dref, self.x.ref, self.dy.ref, self.dw2.data_ptr(), ws.data_ptr(), ws.numel(), st)
+            n.L.stem_wgrad_s2d_gather(self.dw2.data_ptr(), n.pg(self.w), c[0], st)
+            n.L.stem_wgrad_post(n.pg(self.w), n.pp(self.w), c[0], c[1], c[2], c[3], self.cin_real, n.pg(self.stem_beta),
+                                st)
 
 
 class BNRelu(Op):
