@@ -119,6 +119,24 @@ typedef struct stp_conv_desc {
 int stp_conv_fwd(const stp_conv_desc* d, const stp_tensor* x, const void* w_krsc, const float* bias,
                  const stp_tensor* residual, const stp_tensor* y, void* workspace, size_t workspace_bytes,
                  stp_stream stream);
+/* stp_conv_fwd that ALSO produces the training-mode BatchNorm statistics of its output y (the layer that follows a
+ * conv in every encoder/decoder block): sums are accumulated in the conv epilogue from the bf16 values it stores, the
+ * last thread block finalises into coef / moving statistics exactly like stp_bn_stats_fused (which is what runs as a
+ * second pass when no fused kernel serves the shape).  acc: 2*c zero-initialised device doubles, returned to zero. */
+typedef struct stp_bn_fwd {
+  float* partial;          /* as stp_bn_stats: 2*stp_bn_nblk(rows,c)*c floats (fallback pass) */
+  uint32_t* sync;          /* zero-initialised ticket */
+  double* acc;
+  const float* gamma;      /* may be NULL */
+  const float* beta;       /* may be NULL */
+  float eps, momentum;
+  float* moving_mean;      /* may be NULL */
+  float* moving_var;
+  float* coef;             /* out: f32 [4][c] mean, invstd, scale, shift */
+} stp_bn_fwd;
+int stp_conv_fwd_bn(const stp_conv_desc* d, const stp_tensor* x, const void* w_krsc, const float* bias,
+                    const stp_tensor* residual, const stp_tensor* y, const stp_bn_fwd* h_bn, void* workspace,
+                    size_t workspace_bytes, stp_stream stream);
 /* dx = conv_transpose(dy, w) [+ residual]  for the FORWARD descriptor `d`; `w_dgrad` is the
  * [Cin][R][S][Cout] tap-flipped copy made by stp_weight_prep. */
 int stp_conv_dgrad(const stp_conv_desc* d, const stp_tensor* dy, const void* w_dgrad,

@@ -65,9 +65,8 @@ static int check_conv_common(const stp_conv_desc* d, const stp_tensor* in, const
   return STP_OK;
 }
 
-extern "C" int stp_conv_fwd(const stp_conv_desc* d, const stp_tensor* x, const void* w_krsc, const float* bias,
-                            const stp_tensor* residual, const stp_tensor* y, void* workspace, size_t workspace_bytes,
-                            stp_stream stream) {
+static int conv_fwd_common(const stp_conv_desc* d, const stp_tensor* x, const void* w_krsc, const float* bias,
+                           const stp_tensor* residual, const stp_tensor* y, const stp_bn_fwd* h_bn, stp_stream stream) {
   int rc = check_conv_common(d, x, y, "conv_fwd");
   if (rc) return rc;
   STP_REQUIRE(w_krsc && y->ptr, "conv_fwd: null weights/output");
@@ -76,8 +75,6 @@ extern "C" int stp_conv_fwd(const stp_conv_desc* d, const stp_tensor* x, const v
   if (residual)
     STP_REQUIRE(residual->dtype == STP_BF16 && residual->c == y->c && pixels(residual) == pixels(y),
                 "conv_fwd: bad residual");
-  (void)workspace;
-  (void)workspace_bytes;
   ConvP p;
   p.x = (const __nv_bfloat16*)x->ptr; p.ldx = x->ld; p.N = x->n; p.H = x->h; p.W = x->w; p.Cin = x->c;
   p.w = (const __nv_bfloat16*)w_krsc;
@@ -87,7 +84,43 @@ extern "C" int stp_conv_fwd(const stp_conv_desc* d, const stp_tensor* x, const v
   p.R = d->r; p.S = d->s; p.stride = d->stride; p.pad_h = d->pad_h; p.pad_w = d->pad_w; p.up = d->up;
   p.relu = (d->flags & STP_CONV_RELU) ? 1 : 0;
   p.M = pixels(y); p.K = d->r * d->s * x->c;
-  return dispatch_conv(p, (cudaStream_t)stream);
+  if (!h_bn) return dispatch_conv(p, (cudaStream_t)stream);
+  // BatchNorm statistics of y: inside the conv epilogue when the halo kernel serves this shape, else one extra pass
+  STP_REQUIRE(h_bn->partial && h_bn->sync && h_bn->acc && h_bn->coef, "conv_fwd_bn: null statistics buffers");
+  STP_REQUIRE(y->dtype == STP_BF16 && pixels(y) > 0, "conv_fwd_bn: y must be a non-empty bf16 tensor");
+  if (stp_tc_enabled() && get_option(OPT_TC_CONV_VERSION) != 1 && tc2_conv_supported(p)) {
+    const int64_t count = pixels(y);
+    BnFuse bn;
+    bn.acc = h_bn->acc;
+    bn.fin = FinArgs{};
+    bn.fin.mode = 1; bn.fin.sync = h_bn->sync; bn.fin.inv_count = 1.0 / (double)count;
+    bn.fin.bessel = count > 1 ? (double)count / (double)(count - 1) : 1.0;
+    bn.fin.gamma = h_bn->gamma; bn.fin.beta = h_bn->beta; bn.fin.eps = h_bn->eps; bn.fin.momentum = h_bn->momentum;
+    bn.fin.mov_mean = h_bn->moving_mean; bn.fin.mov_var = h_bn->moving_var; bn.fin.coef = h_bn->coef;
+    p.bn = &bn;
+    return launch_tc2_conv(p, (cudaStream_t)stream);
+  }
+  rc = dispatch_conv(p, (cudaStream_t)stream);
+  if (rc) return rc;
+  return stp_bn_stats_fused(y, h_bn->partial, h_bn->sync, h_bn->gamma, h_bn->beta, h_bn->eps, h_bn->momentum,
+                            h_bn->moving_mean, h_bn->moving_var, h_bn->coef, stream);
+}
+
+extern "C" int stp_conv_fwd(const stp_conv_desc* d, const stp_tensor* x, const void* w_krsc, const float* bias,
+                            const stp_tensor* residual, const stp_tensor* y, void* workspace, size_t workspace_bytes,
+                            stp_stream stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  return conv_fwd_common(d, x, w_krsc, bias, residual, y, nullptr, stream);
+}
+
+extern "C" int stp_conv_fwd_bn(const stp_conv_desc* d, const stp_tensor* x, const void* w_krsc, const float* bias,
+                               const stp_tensor* residual, const stp_tensor* y, const stp_bn_fwd* h_bn, void* workspace,
+                               size_t workspace_bytes, stp_stream stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  STP_REQUIRE(h_bn, "conv_fwd_bn: null h_bn");
+  return conv_fwd_common(d, x, w_krsc, bias, residual, y, h_bn, stream);
 }
 
 extern "C" int stp_conv_dgrad(const stp_conv_desc* d, const stp_tensor* dy, const void* w_dgrad,

@@ -1,8 +1,17 @@
 // Shared parameter blocks + launchers of the convolution kernels (generic mma.sync and tcgen05 paths).
 #pragma once
+#include "bn_fin.cuh"
 #include "common.cuh"
 
 namespace stp {
+
+// Forward BatchNorm statistics of a convolution's OUTPUT, accumulated by the conv epilogue itself (conv_tc2.cu): per-CTA
+// fp32 sums of the bf16 values it stores -> double atomics into acc[2][Cout] -> the last CTA (ticket fin.sync)
+// finalises into fin.coef / moving statistics and returns acc to zero.
+struct BnFuse {
+  double* acc;
+  FinArgs fin;  // mode 1
+};
 
 struct ConvP {
   const __nv_bfloat16* x;
@@ -16,6 +25,7 @@ struct ConvP {
   int R, S, stride, pad_h, pad_w, up, relu;
   int64_t M;
   int K;
+  const BnFuse* bn = nullptr;  // non-null: also produce the BatchNorm statistics of y (halo kernel, bf16 output only)
   int ncls = 0;  // > 0: segmentation-head epilogue (tcgen05 halo kernel only): y = dense fp32 [M][ncls], Cout is padding
 };
 

@@ -33,6 +33,8 @@ struct Tc2Args {
   int tilesW, tilesH, tilesN;
   int num_tiles;
   int a_bytes, b_tap_bytes;  // runtime sizes of the A box and of one weight box
+  int bn_on;                 // accumulate BatchNorm statistics of the stored output (bf16 path)
+  BnFuse bn;
   int ncls;                  // > 0: "head" epilogue -- only output channels [0, ncls) exist, fp32 [pixels][ncls] dense (+bias)
   int dbg;                   // timing experiments only (results invalid): 1 skip A loads, 2 skip B loads, 4 skip epilogue memory ops, 8 skip MMAs
 };
@@ -56,11 +58,12 @@ struct Tc2Cfg {
   static constexpr int EP = BN <= 32 ? MT : 1;
   static constexpr int kSubBytes = align1k(128 * BN * 2);            // bf16 staging tile of one sub-tile
   static constexpr int kOutBytes = EP * kSubBytes;
-  static constexpr int kStagesRaw = (kSmemBudget2 - 2048 - kOutBytes) / kStageBytes;
+  static constexpr int kTailBytes = 256 /*barriers*/ + 2 * 128 * 4 /*sStat*/ + 4 * 2 * 128 * 4 /*sRed*/;
+  static constexpr int kStagesRaw = (kSmemBudget2 - 1024 - kTailBytes - 64 - kOutBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemRaw = 2 * MT * BN;
   static constexpr int kTmemCols = kTmemRaw <= 32 ? 32 : kTmemRaw <= 64 ? 64 : kTmemRaw <= 128 ? 128 : kTmemRaw <= 256 ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 + kTailBytes;
   static_assert(kStages >= 2, "need at least two pipeline stages");
   static_assert(kTmemRaw <= 512, "accumulators exceed TMEM");
 };
@@ -83,6 +86,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* res_bar = acc_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+  int* s_last = reinterpret_cast<int*>(tmem_slot + 1);
+  float* sStat = reinterpret_cast<float*>(sOut + Cfg::kOutBytes + 256);  // [2][128] per-CTA sums of the current N tile
+  float* sRed = sStat + 256;                                             // [2][128] cross-pixel-group combine
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kcb = a.Cin / BK;
@@ -205,11 +211,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t swz = RB == 128 ? (uint32_t)(m & 7) : RB == 64 ? (uint32_t)((m >> 1) & 3) : (uint32_t)((m >> 2) & 1);
     uint32_t res_phase = 0;
     int local = 0;
+    int cur_n0 = -1;  // N tile whose statistics sStat currently holds
+    auto bn_flush = [&]() {
+      if (cur_n0 >= 0 && m < BN) {
+        atomicAdd(a.bn.acc + cur_n0 + m, (double)sStat[m]);
+        atomicAdd(a.bn.acc + a.Cout + cur_n0 + m, (double)sStat[128 + m]);
+      }
+    };
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++local) {
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       int img, h0, w0, n0;
       decode(tile, img, h0, w0, n0);
+      if (a.bn_on && n0 != cur_n0) {  // thread m owns sStat[m], sStat[128+m]: no synchronisation needed
+        bn_flush();
+        cur_n0 = n0;
+        if (m < BN) sStat[m] = sStat[128 + m] = 0.f;
+      }
       const int wo = w0 + wl;
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
@@ -337,6 +355,62 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tma_store_4d(&tmY, sOut + e * Cfg::kSubBytes + sl * 128 * RB, n0 + sl * 64, w0, h0 + (j0 + e) * a.BH, img);
             tma_store_commit();
           }
+          if (a.bn_on) {
+            // BatchNorm statistics of exactly the bf16 values just staged.  Thread = (channel octet o, pixel group g):
+            // 16-byte conflict-free loads of the swizzled staging rows g, g+GP, ..., pixels outside the image masked;
+            // groups are combined by a fixed xor-shuffle tree inside the warp, then across the 4 warps through sRed.
+            constexpr int OCT = BN / 8;        // channel octets per pixel row
+            constexpr int GP = 128 / OCT;      // pixel groups (threads per octet)
+            const int o = m % OCT, g = m / OCT;
+            float s1[8], s2[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+            for (int e = 0; e < nj; ++e) {
+              const int hs = h0 + (j0 + e) * a.BH;
+              const uint8_t* sub = sOut + e * Cfg::kSubBytes + (o >> 3) * (128 * RB);
+#pragma unroll
+              for (int i = 0; i < OCT; ++i) {
+                const int mm = g + i * GP;
+                const int hh = hs + (mm >> a.log2BW), ww = w0 + (mm & (a.BW - 1));
+                if (hh < a.Ho && ww < a.Wo) {
+                  const uint32_t sw = RB == 128 ? (uint32_t)(mm & 7) : RB == 64 ? (uint32_t)((mm >> 1) & 3) : (uint32_t)((mm >> 2) & 1);
+                  float f[8];
+                  unpack8(*reinterpret_cast<const bf16x8*>(sub + mm * RB + ((((uint32_t)o & 7u) ^ sw) << 4)), f);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    s1[k] += f[k];
+                    s2[k] += f[k] * f[k];
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int off = 16; off >= OCT; off >>= 1) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], off);
+                s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], off);
+              }
+            }
+            if (lane < OCT) {  // lane == o for OCT <= 32
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                sRed[(q * 2 + 0) * 128 + lane * 8 + k] = s1[k];
+                sRed[(q * 2 + 1) * 128 + lane * 8 + k] = s2[k];
+              }
+            }
+            named_bar_sync(2, 128);
+            if (m < BN) {
+              float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+              for (int wq = 0; wq < 4; ++wq) {
+                t1 += sRed[(wq * 2 + 0) * 128 + m];
+                t2 += sRed[(wq * 2 + 1) * 128 + m];
+              }
+              sStat[m] += t1;
+              sStat[128 + m] += t2;
+            }
+          }
         }
       }
       tc_fence_before();
@@ -344,6 +418,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (lane == 0) mbar_arrive(&acc_empty[as]);
     }
     if (leader) tma_store_wait_all();
+    if (a.bn_on) {
+      bn_flush();
+      __threadfence();
+      named_bar_sync(1, 128);
+      if (leader) *s_last = (atomicAdd(a.bn.fin.sync, 1u) == gridDim.x - 1) ? 1 : 0;
+      named_bar_sync(1, 128);
+      if (*s_last) {  // every other CTA's sums have landed: finalise all channels, return the accumulators to zero
+        __threadfence();
+        for (int c = m; c < a.Cout; c += 128) {
+          const double s1 = __ldcg(a.bn.acc + c), s2 = __ldcg(a.bn.acc + a.Cout + c);
+          fin_forward(a.bn.fin, a.Cout, c, s1, s2);
+          a.bn.acc[c] = 0.0;
+          a.bn.acc[a.Cout + c] = 0.0;
+        }
+        if (leader) *a.bn.fin.sync = 0u;
+      }
+    }
   }
 
   tc_fence_before();
@@ -472,6 +563,8 @@ int launch_tc2_conv(const ConvP& p, cudaStream_t st) {
   a.b_tap_bytes = pl.BN * pl.BK * 2;
   a.dbg = get_option(OPT_TC2_DEBUG);
   a.ncls = p.ncls;
+  a.bn_on = (p.bn != nullptr && !p.y_f32 && p.ncls == 0) ? 1 : 0;
+  if (a.bn_on) a.bn = *p.bn; else a.bn = BnFuse{};
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};

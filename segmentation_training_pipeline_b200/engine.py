@@ -136,6 +136,7 @@ class Net:
         self._ws_bytes = 0
         self._partial_floats = 2 * _lib.BN_MAX_PARTIALS * 8
         self.encoder_param_names: List[str] = []
+        self.fuse_bn_stats = True
 
     # ---- parameters ---------------------------------------------------------------------------
     def add_param(self, name, shape, kind, init) -> Param:
@@ -170,6 +171,19 @@ class Net:
         self.partial = torch.zeros(self._partial_floats, dtype=torch.float32, device=dev)
         self.d_step = torch.zeros(1, dtype=torch.int64, device=dev)
         self.sync = torch.zeros(4, dtype=torch.int32, device=dev)  # last-block tickets of the fused reduce+finalize kernels
+        cmax = max([8] + [op.x.c for op in self.ops if isinstance(op, BNRelu)])
+        self.bn_acc = torch.zeros(2 * cmax, dtype=torch.float64, device=dev)  # conv-epilogue BatchNorm sums (returned to zero)
+        # a BatchNorm whose input is written by exactly one conv gets its statistics from that conv's epilogue
+        writers: Dict[int, List[Op]] = {}
+        for op in self.ops:
+            if isinstance(op, (Conv, StemConv, BNRelu, MaxPool)):
+                writers.setdefault(id(op.y), []).append(op)
+        for op in self.ops:
+            if isinstance(op, BNRelu):
+                w = writers.get(id(op.x), [])
+                if len(w) == 1 and isinstance(w[0], (Conv, StemConv)) and w[0].y.dtype == BF16 and self.fuse_bn_stats:
+                    w[0].bn_next = op
+                    op.stats_from_conv = True
         host = np.zeros(self.n_flat, dtype=np.float32)
         for p in self.params.values():
             host[p.offset:p.offset + p.size] = p.init().reshape(-1)
@@ -343,6 +357,7 @@ class Conv(Op):
         self.b = net.add_param(name + "/bias", (cout,), "bias", lambda: np.zeros(cout, np.float32)) if bias else None
         self.stem_beta = stem_beta
         self.cin_real = cr
+        self.bn_next: Optional["BNRelu"] = None
         net.need_ws(net.L.conv_wgrad_workspace(C.byref(self.desc), x.ref, y.ref))
         net.ops.append(self)
 
@@ -366,8 +381,12 @@ class Conv(Op):
 
     def fwd(self):
         n = self.net
-        n.L.conv_fwd(self.dref, self.x.ref, n.pwf(self.w), n.pp(self.b) if self.b else None, self.res_ref, self.y.ref,
-                     n.ws.data_ptr(), n.ws.numel(), _stream())
+        if self.bn_next is not None and n.training:
+            n.L.conv_fwd_bn(self.dref, self.x.ref, n.pwf(self.w), n.pp(self.b) if self.b else None, self.res_ref,
+                            self.y.ref, self.bn_next.bn_fwd_struct(), n.ws.data_ptr(), n.ws.numel(), _stream())
+        else:
+            n.L.conv_fwd(self.dref, self.x.ref, n.pwf(self.w), n.pp(self.b) if self.b else None, self.res_ref,
+                         self.y.ref, n.ws.data_ptr(), n.ws.numel(), _stream())
 
     def bwd(self):
         n = self.net
@@ -405,6 +424,7 @@ class StemConv(Op):
         self.w.cin_real = cin_real
         self.cin_real, self.stem_beta = cin_real, stem_beta
         self.desc = _lib.ConvDesc(4, 4, 1, 2, 2, 1, 0)
+        self.bn_next: Optional["BNRelu"] = None
         self.w2 = torch.zeros(cout * 16 * 32, dtype=torch.bfloat16, device=net.device)
         self.dw2 = torch.zeros(cout * 16 * 32, dtype=torch.float32, device=net.device)
         net.need_ws(net.L.conv_wgrad_workspace(C.byref(self.desc), x_s2d.ref, y.ref))
@@ -420,8 +440,12 @@ class StemConv(Op):
 
     def fwd(self):
         n = self.net
-        n.L.conv_fwd(self.dref, self.x.ref, self.w2.data_ptr(), None, None, self.y.ref, n.ws.data_ptr(), n.ws.numel(),
-                     _stream())
+        if self.bn_next is not None and n.training:
+            n.L.conv_fwd_bn(self.dref, self.x.ref, self.w2.data_ptr(), None, None, self.y.ref,
+                            self.bn_next.bn_fwd_struct(), n.ws.data_ptr(), n.ws.numel(), _stream())
+        else:
+            n.L.conv_fwd(self.dref, self.x.ref, self.w2.data_ptr(), None, None, self.y.ref, n.ws.data_ptr(),
+                         n.ws.numel(), _stream())
 
     def bwd(self):
         n = self.net
@@ -451,10 +475,21 @@ class BNRelu(Op):
         self.bcoef = torch.zeros(3 * c, device=net.device)
         self.nblk = net.L.bn_nblk(x.rows, c)
         net.need_partial(2 * self.nblk * c)
+        self.stats_from_conv = False
+        self._bn_fwd = None
         net.ops.append(self)
 
     def grad_writes(self):
         return [self.x.grad()]
+
+    def bn_fwd_struct(self):
+        """stp_bn_fwd for the conv that produces this layer's input (statistics come out of its epilogue)."""
+        if self._bn_fwd is None:
+            n = self.net
+            self._bn_fwd = _lib.BnFwd(n.partial.data_ptr(), n.sync.data_ptr(), n.bn_acc.data_ptr(), n.pp(self.gamma),
+                                      n.pp(self.beta), self.eps, self.momentum, self.mm.data_ptr(), self.mv.data_ptr(),
+                                      self.coef.data_ptr())
+        return C.byref(self._bn_fwd)
 
     def prepare(self):
         self.dy = self.y.grad()
@@ -468,8 +503,9 @@ class BNRelu(Op):
         n, L, st = self.net, self.net.L, _stream()
         c = self.x.c
         if n.training:
-            L.bn_stats_fused(self.x.ref, n.partial.data_ptr(), n.sync.data_ptr(), n.pp(self.gamma), n.pp(self.beta),
-                             self.eps, self.momentum, self.mm.data_ptr(), self.mv.data_ptr(), self.coef.data_ptr(), st)
+            if not self.stats_from_conv:
+                L.bn_stats_fused(self.x.ref, n.partial.data_ptr(), n.sync.data_ptr(), n.pp(self.gamma), n.pp(self.beta),
+                                 self.eps, self.momentum, self.mm.data_ptr(), self.mv.data_ptr(), self.coef.data_ptr(), st)
         else:
             L.bn_coef_infer(n.pp(self.gamma), n.pp(self.beta), self.mm.data_ptr(), self.mv.data_ptr(), self.eps, c,
                             self.coef.data_ptr(), st)

@@ -45,6 +45,12 @@ class AugSample(C.Structure):
                 ("src_index", C.c_int32), ("_pad", C.c_int32)]
 
 
+class BnFwd(C.Structure):
+    _fields_ = [("partial", C.c_void_p), ("sync", C.c_void_p), ("acc", C.c_void_p), ("gamma", C.c_void_p),
+                ("beta", C.c_void_p), ("eps", C.c_float), ("momentum", C.c_float), ("moving_mean", C.c_void_p),
+                ("moving_var", C.c_void_p), ("coef", C.c_void_p)]
+
+
 class LossSpec(C.Structure):
     _fields_ = [("w_bce", C.c_float), ("w_dice", C.c_float), ("w_iou", C.c_float)]
 
@@ -68,6 +74,7 @@ SIGNATURES = {
     "stp_augment_draw": (C.c_int, [C.POINTER(AugSpec), _U64, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "stp_augment_apply": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "stp_conv_fwd": (C.c_int, [_CDP, _TP, _P, _P, _TP, _TP, _P, _SZ, _P]),
+    "stp_conv_fwd_bn": (C.c_int, [_CDP, _TP, _P, _P, _TP, _TP, C.POINTER(BnFwd), _P, _SZ, _P]),
     "stp_conv_dgrad": (C.c_int, [_CDP, _TP, _P, _TP, _TP, _P, _SZ, _P]),
     "stp_conv_wgrad": (C.c_int, [_CDP, _TP, _TP, _P, _P, _SZ, _P]),
     "stp_conv_wgrad_workspace": (_SZ, [_CDP, _TP, _TP]),

@@ -513,3 +513,46 @@ def test_stem_space_to_depth_equals_7x7_stride2(stp, cuda):
     stp.conv_wgrad(C.byref(desc), ref(xss), ref(dys), dw2.data_ptr(), ws.data_ptr(), ws.numel(), stream())
     stp.stem_wgrad_s2d_gather(dw2.data_ptr(), dw.data_ptr(), cout, stream())
     assert rel_err(dw, wr.grad) < TOL_F32
+
+
+@pytest.mark.parametrize("case", [(2, 24, 40, 64, 64, 3, 1, 1), (1, 9, 17, 128, 256, 3, 1, 1), (2, 20, 36, 16, 16, 3, 1, 1),
+                                  (1, 12, 24, 32, 32, 3, 1, 1), (2, 16, 16, 64, 128, 3, 2, 1), (3, 8, 8, 256, 512, 3, 1, 1)])
+def test_conv_fwd_bn_epilogue_statistics(stp, cuda, case):
+    """stp_conv_fwd_bn (statistics accumulated in the conv epilogue, or the fallback pass) == conv + stp_bn_stats_fused,
+    with residual, partial tiles, several N tiles; accumulators and ticket return to zero (replayable)."""
+    n, h, w, cin, cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(cin + cout)
+    x = rand_bf16((n, h, w, cin), g)
+    wt = rand_bf16((cout, k, k, cin), g, scale=1.0 / math.sqrt(k * k * cin))
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    res = rand_bf16((n, ho, wo, cout), g)
+    desc = lib.ConvDesc(k, k, stride, pad, pad, 1, 0)
+    rows = n * ho * wo
+    nblk = stp.bn_nblk(rows, cout)
+    partial = torch.zeros(2 * nblk * cout, device=cuda)
+    sync = torch.zeros(4, dtype=torch.int32, device=cuda)
+    acc = torch.zeros(2 * cout, dtype=torch.float64, device=cuda)
+    gamma = (torch.rand(cout, generator=g) + 0.5).to(cuda)
+    beta = (torch.randn(cout, generator=g) * 0.2).to(cuda)
+    xs, rs = T(x), T(res)
+    # reference: plain conv, then the one-launch statistics kernel
+    y0 = torch.zeros((n, ho, wo, cout), dtype=torch.bfloat16, device=cuda)
+    y0s = T(y0)
+    coef0 = torch.zeros(4 * cout, device=cuda)
+    mm0, mv0 = torch.zeros(cout, device=cuda), torch.ones(cout, device=cuda)
+    stp.conv_fwd(C.byref(desc), ref(xs), wt.data_ptr(), None, ref(rs), ref(y0s), None, 0, stream())
+    stp.bn_stats_fused(ref(y0s), partial.data_ptr(), sync.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.99,
+                       mm0.data_ptr(), mv0.data_ptr(), coef0.data_ptr(), stream())
+    for _ in range(2):
+        y1 = torch.zeros_like(y0)
+        y1s = T(y1)
+        coef1 = torch.zeros(4 * cout, device=cuda)
+        mm1, mv1 = torch.zeros(cout, device=cuda), torch.ones(cout, device=cuda)
+        bn = lib.BnFwd(partial.data_ptr(), sync.data_ptr(), acc.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.99,
+                       mm1.data_ptr(), mv1.data_ptr(), coef1.data_ptr())
+        stp.conv_fwd_bn(C.byref(desc), ref(xs), wt.data_ptr(), None, ref(rs), ref(y1s), C.byref(bn), None, 0, stream())
+        assert torch.equal(y1, y0)
+        assert int(sync[0]) == 0 and float(acc.abs().max()) == 0.0
+        scale = 1 + float(coef0.abs().max())
+        assert max_abs(coef1, coef0) <= 2e-6 * scale, max_abs(coef1, coef0)
+        assert max_abs(mm1, mm0) < 1e-6 and rel_err(mv1, mv0) < 1e-6
