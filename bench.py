@@ -170,14 +170,15 @@ def run_reference(args, rank):
 # libstp arm
 # -------------------------------------------------------------------------------------------------------------
 def time_dominant_kernel(net, reps=30):
-    """Time the FLOP-dominant conv shape of the step alone (stage-1 3x3 64->64 @H/4, fwd) with CUDA events on the
-    launch stream; inputs are re-used, L2 flushed between launches by a 256 MB memset."""
+    """Time the kernel with the largest share of the step alone -- conv_tc2_kernel<128,64,2>, here the stage-2 3x3
+    128->128 @H/8 forward conv with its fused BatchNorm-statistics epilogue (profiles/r1_launches_*.summary.txt) -- with
+    CUDA events on the launch stream; inputs are re-used, L2 flushed between launches by a 256 MB memset."""
     import ctypes as C
     import torch
     from segmentation_training_pipeline_b200 import engine as E
     conv = None
     for op in net.ops:
-        if isinstance(op, E.Conv) and op.name == "stage1_unit2_conv1":
+        if isinstance(op, E.Conv) and op.name == "stage2_unit2_conv1":
             conv = op
     if conv is None:
         return None
@@ -195,7 +196,18 @@ def time_dominant_kernel(net, reps=30):
     ts = sorted(a.elapsed_time(b) for a, b in ev)
     ms = sum(ts) / len(ts)
     flop = 2.0 * conv.y.rows * conv.y.c * conv.k * conv.k * conv.x.c
-    return {"name": conv.name, "ms": ms, "flop": flop}
+    return {"name": conv.name, "ms": ms, "flop": flop,
+            "shape": "3x3 %d->%d @%dx%d bs%d" % (conv.x.c, conv.y.c, conv.y.h, conv.y.w, conv.y.n)}
+
+
+def dominant_kernel_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (None if absent)."""
+    p = os.path.join(ROOT, "profiles", "r1_dominant_kernel.json")
+    try:
+        d = json.load(open(p))
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except Exception:
+        return None
 
 
 def run_gpu(args, rank, local_rank, world):
@@ -308,9 +320,12 @@ def run_gpu(args, rank, local_rank, world):
         }
         if dom is not None:
             ach = dom["flop"] / (dom["ms"] / 1e3) / 1e12
-            out["roofline"] = {"bound": "tensor", "kernel": dom["name"] + " fwd (3x3 64->64 @%d^2 bs%d)" % (S // 4, B),
+            out["roofline"] = {"bound": "tensor", "kernel": "conv_tc2_kernel<128,64,2>: %s fwd (%s) + BN statistics epilogue" %
+                                                            (dom["name"], dom["shape"]),
                                "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
-                               "peak_source": src, "traffic": None, "ms_per_launch": dom["ms"]}
+                               "peak_source": src + (" (of measured)" if src == "measured" else " (of fallback, B200_PROFILING.md)"),
+                               "traffic": dominant_kernel_traffic(), "flop_per_launch": dom["flop"],
+                               "ms_per_launch": dom["ms"]}
         if world == 1 and not args.no_cpu:
             sb = args.ref_batch
             dt, cores, _ = cpu_reference_step_time(S, sb, 2, 1, args.backbone)
