@@ -182,9 +182,12 @@ int stp_bn_finalize(const float* partial, int32_t nblk, int32_t c, int64_t count
                     const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
                     float* coef, stp_stream stream);
 /* stp_bn_stats + stp_bn_finalize in ONE launch: the last thread block to finish (device ticket in *sync, a
- * zero-initialised uint32 the kernel returns to zero) reduces the partials and finalises. */
-int stp_bn_stats_fused(const stp_tensor* x, float* partial, uint32_t* sync, const float* gamma, const float* beta,
-                       float eps, float momentum, float* moving_mean, float* moving_var, float* coef,
+ * zero-initialised uint32 the kernel returns to zero) finalises.  acc == NULL: it reduces the per-block partials in a
+ * fixed order (bitwise reproducible).  acc != NULL (2*c zero-initialised doubles, returned to zero): blocks add their
+ * sums with double-precision atomics instead -- no serial reduction tail, many more blocks in flight; the summation
+ * order then varies at the 1e-16 relative level of the double accumulators. */
+int stp_bn_stats_fused(const stp_tensor* x, float* partial, uint32_t* sync, double* acc, const float* gamma,
+                       const float* beta, float eps, float momentum, float* moving_mean, float* moving_var, float* coef,
                        stp_stream stream);
 /* y = [relu](x*scale+shift); up=2 writes each value to the 2x2 block of y (UpSampling2D fused) */
 int stp_bn_apply(const stp_tensor* x, const float* coef, int32_t relu, int32_t up, const stp_tensor* y,
@@ -201,7 +204,7 @@ int stp_bn_bwd_finalize(const float* partial, int32_t nblk, int32_t c, int64_t c
                         float* dgamma, float* dbeta, float* bcoef, stp_stream stream);
 /* stp_bn_bwd_reduce + stp_bn_bwd_finalize in ONE launch (same last-block scheme as stp_bn_stats_fused) */
 int stp_bn_bwd_reduce_fused(const stp_tensor* dy, const stp_tensor* x, const float* coef, int32_t relu, int32_t pool,
-                            float* partial, uint32_t* sync, float* dgamma, float* dbeta, float* bcoef,
+                            float* partial, uint32_t* sync, double* acc, float* dgamma, float* dbeta, float* bcoef,
                             stp_stream stream);
 /* dx = a*g + b*x + cc [+ residual] */
 int stp_bn_bwd_apply(const stp_tensor* dy, const stp_tensor* x, const float* coef, const float* bcoef,

@@ -102,7 +102,7 @@ static int conv_fwd_common(const stp_conv_desc* d, const stp_tensor* x, const vo
   }
   rc = dispatch_conv(p, (cudaStream_t)stream);
   if (rc) return rc;
-  return stp_bn_stats_fused(y, h_bn->partial, h_bn->sync, h_bn->gamma, h_bn->beta, h_bn->eps, h_bn->momentum,
+  return stp_bn_stats_fused(y, h_bn->partial, h_bn->sync, h_bn->acc, h_bn->gamma, h_bn->beta, h_bn->eps, h_bn->momentum,
                             h_bn->moving_mean, h_bn->moving_var, h_bn->coef, stream);
 }
 

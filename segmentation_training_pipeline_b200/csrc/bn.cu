@@ -38,7 +38,15 @@ static int reduce_max_blk(int c) {
   if (m < 32) m = 32;
   return m;
 }
-static RowGeom reduce_geom(int64_t rows, int c) { return geom(rows, c, 4, reduce_max_blk(c)); }
+static RowGeom reduce_geom(int64_t rows, int c, bool atomic_acc = false) {
+  if (!atomic_acc) return geom(rows, c, 4, reduce_max_blk(c));
+  // atomic accumulation: every block issues 2*c double atomics + one ticket; keep the total (and the same-address
+  // contention, = the block count) bounded
+  int m = 16384 / (c < 8 ? 8 : c);
+  if (m > 2 * kNumSMs) m = 2 * kNumSMs;
+  if (m < 32) m = 32;
+  return geom(rows, c, 4, m);
+}
 
 // Executed by every thread of a reduction block after its partials are written: elects the last block of the grid
 // (threadfence + atomic ticket) which then sums the nblk partials per channel in a fixed order (deterministic), in
@@ -232,13 +240,33 @@ __global__ void __launch_bounds__(256, 2) reduce_rows_kernel(const __nv_bfloat16
     }
   }
   __syncthreads();
+  const bool atomic_acc = fin.mode != 0 && fin.acc != nullptr;
   for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
     int which = c / C, ch = c - which * C;
     float a = 0.f;
     for (int r = 0; r < groups; ++r) a += sm[(which * groups + r) * C + ch];
-    partial[((int64_t)which * gridDim.x + blockIdx.x) * C + ch] = a;
+    if (atomic_acc) atomicAdd(fin.acc + c, (double)a);
+    else partial[((int64_t)which * gridDim.x + blockIdx.x) * C + ch] = a;
   }
-  if (fin.mode != 0) last_block_finalize(fin, partial, gridDim.x, C, sm);
+  if (atomic_acc) {
+    // last block (ticket) finalises straight from the 2*C accumulated doubles and returns them to zero
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(fin.sync, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const double s = __ldcg(fin.acc + c), ss = __ldcg(fin.acc + C + c);
+      if (fin.mode == 1) fin_forward(fin, C, c, s, ss); else fin_backward(fin, C, c, s, ss);
+      fin.acc[c] = 0.0;
+      fin.acc[C + c] = 0.0;
+    }
+    if (threadIdx.x == 0) *fin.sync = 0u;
+  } else if (fin.mode != 0) {
+    last_block_finalize(fin, partial, gridDim.x, C, sm);
+  }
 }
 
 __global__ void stats_u8_kernel(const uint8_t* __restrict__ x, int64_t rows, int C, int64_t rows_per_blk,
@@ -585,7 +613,7 @@ static int launch_stats(const stp_tensor* x, float* partial, const FinArgs& fin,
   }
   STP_REQUIRE(vec_ok(x), "bn_stats: tensor must be bf16, c%%8==0, ld%%8==0, 16B aligned");
   STP_REQUIRE(x->c <= 2048 && rows < 0x7fffffff, "bn_stats: c or rows too large");
-  RowGeom g = reduce_geom(rows, x->c);
+  RowGeom g = reduce_geom(rows, x->c, fin.mode != 0 && fin.acc != nullptr);
   reduce_rows_kernel<0, 1><<<g.nblk, g.threads, reduce_smem(g, x->c), st>>>(
       (const __nv_bfloat16*)x->ptr, x->ld, nullptr, 0, nullptr, 0, 1, x->h, x->w, (int)rows, x->c, g.cv, g.nv, g.rpi,
       g.rows_per_blk, partial, fin);
@@ -600,7 +628,7 @@ static int launch_bwd_reduce(const stp_tensor* dy, const stp_tensor* x, const fl
               "bn_bwd_reduce: shape mismatch");
   int64_t rows = pixels(x);
   STP_REQUIRE(x->c <= 2048 && rows < 0x7fffffff, "bn_bwd_reduce: c or rows too large");
-  RowGeom g = reduce_geom(rows, x->c);
+  RowGeom g = reduce_geom(rows, x->c, fin.mode != 0 && fin.acc != nullptr);
   if (pool == 2)
     reduce_rows_kernel<1, 2><<<g.nblk, g.threads, reduce_smem(g, x->c), st>>>(
         (const __nv_bfloat16*)x->ptr, x->ld, (const __nv_bfloat16*)dy->ptr, dy->ld, coef, relu, pool, x->h, x->w,
@@ -618,14 +646,14 @@ extern "C" int stp_bn_stats(const stp_tensor* x, float* partial, stp_stream stre
   return launch_stats(x, partial, fin, (cudaStream_t)stream);
 }
 
-extern "C" int stp_bn_stats_fused(const stp_tensor* x, float* partial, uint32_t* sync, const float* gamma,
+extern "C" int stp_bn_stats_fused(const stp_tensor* x, float* partial, uint32_t* sync, double* acc, const float* gamma,
                                   const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
                                   float* coef, stp_stream stream) {
   STP_REQUIRE(x && partial && sync && coef, "bn_stats_fused: null");
   const int64_t count = pixels(x);
   STP_REQUIRE(count > 0, "bn_stats_fused: empty tensor");
   FinArgs fin = {};
-  fin.mode = 1; fin.sync = sync; fin.inv_count = 1.0 / (double)count;
+  fin.mode = 1; fin.sync = sync; fin.acc = acc; fin.inv_count = 1.0 / (double)count;
   fin.bessel = count > 1 ? (double)count / (double)(count - 1) : 1.0;
   fin.gamma = gamma; fin.beta = beta; fin.eps = eps; fin.momentum = momentum;
   fin.mov_mean = moving_mean; fin.mov_var = moving_var; fin.coef = coef;
@@ -672,13 +700,13 @@ extern "C" int stp_bn_bwd_reduce(const stp_tensor* dy, const stp_tensor* x, cons
 }
 
 extern "C" int stp_bn_bwd_reduce_fused(const stp_tensor* dy, const stp_tensor* x, const float* coef, int32_t relu,
-                                       int32_t pool, float* partial, uint32_t* sync, float* dgamma, float* dbeta,
-                                       float* bcoef, stp_stream stream) {
+                                       int32_t pool, float* partial, uint32_t* sync, double* acc, float* dgamma,
+                                       float* dbeta, float* bcoef, stp_stream stream) {
   STP_REQUIRE(x && sync && bcoef, "bn_bwd_reduce_fused: null");
   const int64_t count = pixels(x);
   STP_REQUIRE(count > 0, "bn_bwd_reduce_fused: empty tensor");
   FinArgs fin = {};
-  fin.mode = 2; fin.sync = sync; fin.inv_count = 1.0 / (double)count;
+  fin.mode = 2; fin.sync = sync; fin.acc = acc; fin.inv_count = 1.0 / (double)count;
   fin.coef = const_cast<float*>(coef); fin.dgamma = dgamma; fin.dbeta = dbeta; fin.bcoef = bcoef;
   return launch_bwd_reduce(dy, x, coef, relu, pool, partial, fin, (cudaStream_t)stream);
 }

@@ -10,6 +10,8 @@ namespace stp {
 struct FinArgs {
   int mode;  // 0 none | 1 forward statistics -> coef (+ moving stats) | 2 backward -> dgamma, dbeta, bcoef
   unsigned int* sync;
+  double* acc;  // non-null: blocks add their sums here with double atomics (2*C, zero on entry, returned to zero) and the
+                // last block finalises from 2*C values; null: deterministic fixed-order reduction of per-block partials
   double inv_count, bessel;
   const float* gamma;
   const float* beta;

@@ -504,7 +504,7 @@ class BNRelu(Op):
         c = self.x.c
         if n.training:
             if not self.stats_from_conv:
-                L.bn_stats_fused(self.x.ref, n.partial.data_ptr(), n.sync.data_ptr(), n.pp(self.gamma), n.pp(self.beta),
+                L.bn_stats_fused(self.x.ref, n.partial.data_ptr(), n.sync.data_ptr(), n.bn_acc.data_ptr(), n.pp(self.gamma), n.pp(self.beta),
                                  self.eps, self.momentum, self.mm.data_ptr(), self.mv.data_ptr(), self.coef.data_ptr(), st)
         else:
             L.bn_coef_infer(n.pp(self.gamma), n.pp(self.beta), self.mm.data_ptr(), self.mv.data_ptr(), self.eps, c,
@@ -515,7 +515,7 @@ class BNRelu(Op):
         n, L, st = self.net, self.net.L, _stream()
         c = self.x.c
         L.bn_bwd_reduce_fused(self.dy.ref, self.x.ref, self.coef.data_ptr(), int(self.relu), self.up,
-                              n.partial.data_ptr(), n.sync.data_ptr(), n.pg(self.gamma), n.pg(self.beta),
+                              n.partial.data_ptr(), n.sync.data_ptr(), n.bn_acc.data_ptr(), n.pg(self.gamma), n.pg(self.beta),
                               self.bcoef.data_ptr(), st)
         L.bn_bwd_apply(self.dy.ref, self.x.ref, self.coef.data_ptr(), self.bcoef.data_ptr(), int(self.relu), self.up,
                        self.res_ref, self.dx.ref, st)

@@ -202,15 +202,17 @@ def test_batchnorm_fwd_bwd(stp, cuda, shape, up):
     assert rel_err(dx, xc.grad.permute(0, 2, 3, 1)) < 5e-3
     # one-launch variants (last block finalises): same numbers, ticket returns to zero so they can be replayed
     sync = torch.zeros(4, dtype=torch.int32, device=cuda)
-    for _ in range(2):
+    acc = torch.zeros(2 * c, dtype=torch.float64, device=cuda)
+    for it in range(4):  # deterministic partial reduction (acc NULL) twice, double-atomic accumulation twice
+        accp = acc.data_ptr() if it >= 2 else None
         coef2, bcoef2 = torch.zeros(4 * c, device=cuda), torch.zeros(3 * c, device=cuda)
         dg2, db2 = torch.zeros(c, device=cuda), torch.zeros(c, device=cuda)
         mm2, mv2 = torch.zeros(c, device=cuda), torch.ones(c, device=cuda)
-        stp.bn_stats_fused(ref(xs), partial.data_ptr(), sync.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, mom,
+        stp.bn_stats_fused(ref(xs), partial.data_ptr(), sync.data_ptr(), accp, gamma.data_ptr(), beta.data_ptr(), eps, mom,
                            mm2.data_ptr(), mv2.data_ptr(), coef2.data_ptr(), stream())
-        stp.bn_bwd_reduce_fused(ref(dys), ref(xs), coef.data_ptr(), 1, up, partial.data_ptr(), sync.data_ptr(),
+        stp.bn_bwd_reduce_fused(ref(dys), ref(xs), coef.data_ptr(), 1, up, partial.data_ptr(), sync.data_ptr(), accp,
                                 dg2.data_ptr(), db2.data_ptr(), bcoef2.data_ptr(), stream())
-        assert int(sync[0]) == 0
+        assert int(sync[0]) == 0 and float(acc.abs().max()) == 0.0
         assert max_abs(coef2, coef) <= 1e-6 * (1 + float(coef.abs().max()))
         assert max_abs(mm2, mm) < 1e-7 and rel_err(mv2, mv) < 1e-6
         assert max_abs(bcoef2, bcoef) <= 1e-6 * (1 + float(bcoef.abs().max()))
@@ -541,7 +543,7 @@ def test_conv_fwd_bn_epilogue_statistics(stp, cuda, case):
     coef0 = torch.zeros(4 * cout, device=cuda)
     mm0, mv0 = torch.zeros(cout, device=cuda), torch.ones(cout, device=cuda)
     stp.conv_fwd(C.byref(desc), ref(xs), wt.data_ptr(), None, ref(rs), ref(y0s), None, 0, stream())
-    stp.bn_stats_fused(ref(y0s), partial.data_ptr(), sync.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.99,
+    stp.bn_stats_fused(ref(y0s), partial.data_ptr(), sync.data_ptr(), None, gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.99,
                        mm0.data_ptr(), mv0.data_ptr(), coef0.data_ptr(), stream())
     for _ in range(2):
         y1 = torch.zeros_like(y0)
