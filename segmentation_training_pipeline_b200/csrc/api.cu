@@ -13,6 +13,7 @@ static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 std::atomic<int64_t> g_tc_launches{0};
 static std::atomic<int> g_tc_enabled{1};
+std::atomic<int> g_pdl_enabled{1};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -36,6 +37,10 @@ extern "C" int stp_set_option(const char* name, int32_t value) {
   if (!strcmp(name, "tc2_force_mt")) key = OPT_TC2_FORCE_MT;        /* 0 = heuristic; 1,2,4,8 = force strip height */
   else if (!strcmp(name, "tc_conv_version")) key = OPT_TC_CONV_VERSION; /* 0 = auto, 1 = first-generation kernel only */
   else if (!strcmp(name, "tc2_debug")) key = OPT_TC2_DEBUG;             /* timing experiments, see conv_tc2.cu */
+  else if (!strcmp(name, "pdl")) {                                      /* programmatic dependent launch on/off */
+    g_pdl_enabled.store(value ? 1 : 0);
+    return STP_OK;
+  }
   STP_REQUIRE(key >= 0, "set_option: unknown option %s", name);
   g_options[key].store(value);
   return STP_OK;

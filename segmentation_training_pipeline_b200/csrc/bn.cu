@@ -146,6 +146,8 @@ __global__ void __launch_bounds__(256, 2) reduce_rows_kernel(const __nv_bfloat16
                                                           int rows_per_blk, float* __restrict__ partial,
                                                           const FinArgs fin) {
   extern __shared__ float sm[];  // [2][groups][C], groups <= 8 (>= 2*blockDim doubles for the finalize)
+  pdl_launch_dependents();
+  pdl_wait();
   const int v0 = threadIdx.x % nv;
   const int rl = threadIdx.x / nv;
   const int r_begin = blockIdx.x * rows_per_blk;
@@ -395,6 +397,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
                                                        const float* __restrict__ coef, int relu, int up,
                                                        __nv_bfloat16* __restrict__ y, int ldy, int H, int W,
                                                        int rows, int C, int cv, int nv, int rpi, int rows_per_blk) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int v0 = threadIdx.x % nv;
   const int rl = threadIdx.x / nv;
   const int r_begin = blockIdx.x * rows_per_blk;
@@ -451,6 +455,8 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const __nv_bfloat16* 
                                                         const __nv_bfloat16* __restrict__ res, int ldr,
                                                         __nv_bfloat16* __restrict__ dx, int lddx, int H, int W,
                                                         int rows, int C, int cv, int nv, int rpi, int rows_per_blk) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int v0 = threadIdx.x % nv;
   const int rl = threadIdx.x / nv;
   const int r_begin = blockIdx.x * rows_per_blk;
@@ -614,9 +620,9 @@ static int launch_stats(const stp_tensor* x, float* partial, const FinArgs& fin,
   STP_REQUIRE(vec_ok(x), "bn_stats: tensor must be bf16, c%%8==0, ld%%8==0, 16B aligned");
   STP_REQUIRE(x->c <= 2048 && rows < 0x7fffffff, "bn_stats: c or rows too large");
   RowGeom g = reduce_geom(rows, x->c, fin.mode != 0 && fin.acc != nullptr);
-  reduce_rows_kernel<0, 1><<<g.nblk, g.threads, reduce_smem(g, x->c), st>>>(
-      (const __nv_bfloat16*)x->ptr, x->ld, nullptr, 0, nullptr, 0, 1, x->h, x->w, (int)rows, x->c, g.cv, g.nv, g.rpi,
-      g.rows_per_blk, partial, fin);
+  launch_pdl(reduce_rows_kernel<0, 1>, dim3(g.nblk), dim3(g.threads), reduce_smem(g, x->c), st,
+             (const __nv_bfloat16*)x->ptr, x->ld, (const __nv_bfloat16*)nullptr, 0, (const float*)nullptr, 0, 1, x->h, x->w,
+             (int)rows, x->c, g.cv, g.nv, g.rpi, g.rows_per_blk, partial, fin);
   return check_launch("bn_stats");
 }
 
@@ -630,13 +636,13 @@ static int launch_bwd_reduce(const stp_tensor* dy, const stp_tensor* x, const fl
   STP_REQUIRE(x->c <= 2048 && rows < 0x7fffffff, "bn_bwd_reduce: c or rows too large");
   RowGeom g = reduce_geom(rows, x->c, fin.mode != 0 && fin.acc != nullptr);
   if (pool == 2)
-    reduce_rows_kernel<1, 2><<<g.nblk, g.threads, reduce_smem(g, x->c), st>>>(
-        (const __nv_bfloat16*)x->ptr, x->ld, (const __nv_bfloat16*)dy->ptr, dy->ld, coef, relu, pool, x->h, x->w,
-        (int)rows, x->c, g.cv, g.nv, g.rpi, g.rows_per_blk, partial, fin);
+    launch_pdl(reduce_rows_kernel<1, 2>, dim3(g.nblk), dim3(g.threads), reduce_smem(g, x->c), st,
+               (const __nv_bfloat16*)x->ptr, x->ld, (const __nv_bfloat16*)dy->ptr, dy->ld, coef, relu, pool, x->h, x->w,
+               (int)rows, x->c, g.cv, g.nv, g.rpi, g.rows_per_blk, partial, fin);
   else
-    reduce_rows_kernel<1, 1><<<g.nblk, g.threads, reduce_smem(g, x->c), st>>>(
-        (const __nv_bfloat16*)x->ptr, x->ld, (const __nv_bfloat16*)dy->ptr, dy->ld, coef, relu, pool, x->h, x->w,
-        (int)rows, x->c, g.cv, g.nv, g.rpi, g.rows_per_blk, partial, fin);
+    launch_pdl(reduce_rows_kernel<1, 1>, dim3(g.nblk), dim3(g.threads), reduce_smem(g, x->c), st,
+               (const __nv_bfloat16*)x->ptr, x->ld, (const __nv_bfloat16*)dy->ptr, dy->ld, coef, relu, pool, x->h, x->w,
+               (int)rows, x->c, g.cv, g.nv, g.rpi, g.rows_per_blk, partial, fin);
   return check_launch("bn_bwd_reduce");
 }
 
@@ -687,9 +693,9 @@ extern "C" int stp_bn_apply(const stp_tensor* x, const float* coef, int32_t relu
   int64_t rows = pixels(x);
   STP_REQUIRE(rows < 0x7fffffff, "bn_apply: too many rows");
   RowGeom g = geom(rows, x->c, 4, kNumSMs * 8);
-  bn_apply_kernel<<<g.nblk, g.threads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x->ptr, x->ld, coef, relu, up, (__nv_bfloat16*)y->ptr, y->ld, x->h, x->w, (int)rows, x->c,
-      g.cv, g.nv, g.rpi, g.rows_per_blk);
+  launch_pdl(bn_apply_kernel, dim3(g.nblk), dim3(g.threads), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x->ptr,
+             x->ld, coef, relu, up, (__nv_bfloat16*)y->ptr, y->ld, x->h, x->w, (int)rows, x->c, g.cv, g.nv, g.rpi,
+             g.rows_per_blk);
   return check_launch("bn_apply");
 }
 
@@ -734,9 +740,9 @@ static int bwd_apply_common(int mode, const stp_tensor* dy, const stp_tensor* x,
   const __nv_bfloat16* rp = residual ? (const __nv_bfloat16*)residual->ptr : nullptr;
   int ldr = residual ? residual->ld : 0;
 #define STP_BWD_APPLY(MODE, POOL)                                                                                      \
-  bwd_apply_kernel<MODE, POOL><<<g.nblk, g.threads, 0, (cudaStream_t)stream>>>(                                        \
-      (const __nv_bfloat16*)dy->ptr, dy->ld, (const __nv_bfloat16*)x->ptr, x->ld, coef, bcoef, relu, pool, rp, ldr,    \
-      (__nv_bfloat16*)dx->ptr, dx->ld, x->h, x->w, (int)rows, x->c, g.cv, g.nv, g.rpi, g.rows_per_blk)
+  launch_pdl(bwd_apply_kernel<MODE, POOL>, dim3(g.nblk), dim3(g.threads), 0, (cudaStream_t)stream,                     \
+             (const __nv_bfloat16*)dy->ptr, dy->ld, (const __nv_bfloat16*)x->ptr, x->ld, coef, bcoef, relu, pool, rp,  \
+             ldr, (__nv_bfloat16*)dx->ptr, dx->ld, x->h, x->w, (int)rows, x->c, g.cv, g.nv, g.rpi, g.rows_per_blk)
   if (mode == 0) {
     if (pool == 2) STP_BWD_APPLY(0, 2); else STP_BWD_APPLY(0, 1);
   } else {

@@ -44,6 +44,31 @@ inline bool vec_ok(const stp_tensor* t) {
 
 constexpr int kNumSMs = 148;
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------
+// Kernels launched through launch_pdl() may become resident while the previous kernel of the stream is still draining:
+// they signal launch_dependents at once, run their prologue (barrier init, TMEM allocation, descriptor prefetch) and
+// only then execute griddepcontrol.wait, which returns when every prerequisite grid has completed and flushed.  No
+// global memory written by an earlier kernel is touched before pdl_wait().  Hides launch latency and prologues
+// behind the previous kernel's tail inside the step graph; `stp_set_option("pdl", 0)` turns the attribute off.
+extern std::atomic<int> g_pdl_enabled;
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl_enabled.load(std::memory_order_relaxed) ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 struct alignas(16) bf16x8 {
   __nv_bfloat162 v[4];
 };

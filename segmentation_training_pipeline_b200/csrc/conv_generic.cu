@@ -302,9 +302,19 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradP p) {
 
 __global__ void __launch_bounds__(256) split_reduce_kernel(const float* __restrict__ ws, int splits, int64_t n,
                                                            float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float a = 0.f;
-    for (int s = 0; s < splits; ++s) a += ws[(int64_t)s * n + i];
+    int s = 0;
+    for (; s + 8 <= splits; s += 8) {  // 8 independent loads in flight, summed in split order (deterministic)
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = ws[(int64_t)(s + j) * n + i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a += t[j];
+    }
+    for (; s < splits; ++s) a += ws[(int64_t)s * n + i];
     out[i] = a;
   }
 }
@@ -430,7 +440,7 @@ int launch_generic_wgrad(WgradP p, float* dw, void* ws, size_t ws_bytes, cudaStr
 
 int launch_split_reduce(const float* ws, int splits, int64_t n, float* out, cudaStream_t st) {
   int64_t nb = (n + 255) / 256;
-  split_reduce_kernel<<<(int)(nb < 2048 ? nb : 2048), 256, 0, st>>>(ws, splits, n, out);
+  launch_pdl(split_reduce_kernel, dim3((unsigned)(nb < 2048 ? nb : 2048)), dim3(256), 0, st, ws, splits, n, out);
   return check_launch("split_reduce");
 }
 

@@ -151,10 +151,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   auto decode = [&](int tile, int& c, int& img, int& h0, int& w0, int& n0) {
     c = 0;
@@ -339,7 +341,7 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvArgs&
     attr_set = true;
   }
   int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
-  conv_tc_kernel<BN, BK><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
+  launch_pdl(conv_tc_kernel<BN, BK>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, tmA, tmB, a);
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("conv_tc");
 }
@@ -583,10 +585,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -770,7 +774,7 @@ static int launch_wgrad_cfg(const CUtensorMap& tmDY, const CUtensorMap& tmX, con
     }
     attr_set = true;
   }
-  wgrad_tc_kernel<BN, ANARROW, STR><<<items, kThreads, Cfg::kSmemBytes, st>>>(tmDY, tmX, a);
+  launch_pdl(wgrad_tc_kernel<BN, ANARROW, STR>, dim3(items), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, tmDY, tmX, a);
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("wgrad_tc");
 }

@@ -113,10 +113,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // prologue above touched no global data of earlier kernels; everything below may
 
   auto decode = [&](int tile, int& img, int& h0, int& w0, int& n0) {
     int tn = tile % a.tilesN;
@@ -514,7 +516,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& t
     attr_set = true;
   }
   int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
-  conv_tc2_kernel<BN, BK, MT, RMAX><<<grid, kThreads2, Cfg::kSmemBytes, st>>>(tmA, tmB, tmY, tmR, a);
+  launch_pdl(conv_tc2_kernel<BN, BK, MT, RMAX>, dim3(grid), dim3(kThreads2), (size_t)Cfg::kSmemBytes, st, tmA, tmB, tmY, tmR, a);
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("conv_tc2");
 }

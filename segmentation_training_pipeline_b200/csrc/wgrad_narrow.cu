@@ -73,7 +73,9 @@ wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
     fence_barrier_init();
   }
+  pdl_launch_dependents();
   __syncthreads();
+  pdl_wait();
 
   float acc[3][MT][NT][4];
 #pragma unroll
@@ -212,7 +214,7 @@ int launch_narrow(const WgradP& p, float* dw, void* ws, size_t ws_bytes, cudaStr
     uint32_t box[4] = {(uint32_t)COUT, TW, TH, 1};
     if (!make_tmap_bf16(&tmDY, p.dy, 4, dims, strides, box, 0)) return STP_E_CUDA;
   }
-  wgrad_narrow_kernel<CIN, COUT><<<grid, kNThreads, Cfg::kSmem, st>>>(tmX, tmDY, a);
+  launch_pdl(wgrad_narrow_kernel<CIN, COUT>, dim3(grid), dim3(kNThreads), (size_t)Cfg::kSmem, st, tmX, tmDY, a);
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);  // counted with the TMA-fed kernels
   int rc = check_launch("wgrad_narrow");
   if (rc) return rc;
