@@ -38,8 +38,22 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
+static bool make_tmap_any(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box, uint32_t swizzle_bytes,
+                          const uint32_t* elem_strides);
+
 bool make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, uint32_t swizzle_bytes, const uint32_t* elem_strides) {
+  return make_tmap_any(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swizzle_bytes, elem_strides);
+}
+bool make_tmap_f32(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, uint32_t swizzle_bytes) {
+  return make_tmap_any(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, swizzle_bytes, nullptr);
+}
+
+static bool make_tmap_any(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box, uint32_t swizzle_bytes,
+                          const uint32_t* elem_strides) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -57,7 +71,7 @@ bool make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t*
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                           : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = enc(tm, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -543,7 +557,8 @@ struct TcWgradCfg {
 
 template <int BN, int ANARROW, int STR>
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const TcWgradArgs a) {
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                const __grid_constant__ CUtensorMap tmOut, const TcWgradArgs a) {
   using Cfg = TcWgradCfg<BN, ANARROW, STR>;
   constexpr int NS = Cfg::kStages;
   constexpr int BBOX = BN < 64 ? 1 : BN / 64;
@@ -660,10 +675,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     const int co = co0 + q * 32 + lane;
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const bool valid = (q * 32 + lane) < a.m_valid && co < a.Cout;
+    // The accumulators leave through a swizzled per-warp staging tile [32 rows (co)][CH fp32] and 3-D TMA stores into
+    // out[split][co][K] (coalesced 128-byte rows; rows beyond Cout are clipped by the tensor map).  Direct per-thread
+    // stores would scatter 16-byte pieces over 32 rows K*4 bytes apart -- measured as ~half of this kernel's time.
+    // The pipeline stage buffers are idle by now (every MMA has completed) and serve as staging, double buffered.
     constexpr int CH = BN >= 32 ? 32 : 16;
+    constexpr int RBO = CH * 4;                       // bytes per staged row: 128 or 64 (== TMA swizzle span)
+    uint8_t* stg = sA + q * (2 * 32 * RBO);
+    const bool rows_live = co0 + q * 32 < a.Cout && q * 32 < a.m_valid;  // warp-uniform: any real output channel here?
+    const uint32_t swz = RBO == 128 ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+    int buf = 0;
+    (void)co;
     for (int r = 0; r < a.R; ++r) {
-      float* op = a.out + ((((int64_t)split * a.Cout + co) * a.R + r) * a.S + s) * a.Cin + ci0;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
         uint32_t rr[CH];
@@ -675,14 +698,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < CH; ++i) rr[i] = 0u;
         }
-        if (valid) {
+        if (!rows_live) continue;
+        if (lane == 0) tma_store_wait_read1();  // the store that used this buffer two rounds ago has drained it
+        __syncwarp();
+        uint8_t* row = stg + buf * (32 * RBO) + lane * RBO;
 #pragma unroll
-          for (int i = 0; i < CH; i += 4)
-            *reinterpret_cast<float4*>(op + c0 + i) = make_float4(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1]),
-                                                                  __uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3]));
+        for (int i = 0; i < CH; i += 4)
+          *reinterpret_cast<uint4*>(row + ((((uint32_t)i >> 2) ^ swz) << 4)) = make_uint4(rr[i], rr[i + 1], rr[i + 2], rr[i + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmOut, stg + buf * (32 * RBO), ((r * a.S + s) * a.Cin) + ci0 + c0, co0 + q * 32, split);
+          tma_store_commit();
         }
+        buf ^= 1;
       }
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -762,8 +794,8 @@ size_t tc_wgrad_workspace(const WgradP& p) {
 }
 
 template <int BN, int ANARROW, int STR>
-static int launch_wgrad_cfg(const CUtensorMap& tmDY, const CUtensorMap& tmX, const TcWgradArgs& a, int items,
-                            cudaStream_t st) {
+static int launch_wgrad_cfg(const CUtensorMap& tmDY, const CUtensorMap& tmX, const CUtensorMap& tmOut,
+                            const TcWgradArgs& a, int items, cudaStream_t st) {
   using Cfg = TcWgradCfg<BN, ANARROW, STR>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -774,7 +806,7 @@ static int launch_wgrad_cfg(const CUtensorMap& tmDY, const CUtensorMap& tmX, con
     }
     attr_set = true;
   }
-  launch_pdl(wgrad_tc_kernel<BN, ANARROW, STR>, dim3(items), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, tmDY, tmX, a);
+  launch_pdl(wgrad_tc_kernel<BN, ANARROW, STR>, dim3(items), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, tmDY, tmX, tmOut, a);
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("wgrad_tc");
 }
@@ -824,16 +856,25 @@ int launch_tc_wgrad(const WgradP& p, float* dw, void* ws, size_t ws_bytes, cudaS
       if (!make_tmap_bf16(&tmX, p.x, 4, dims, strides, box, a.b_row)) return STP_E_CUDA;
     }
   }
+  CUtensorMap tmOut;
+  {
+    // out[split][co][K] fp32; box = one staged tile [32 rows][CH columns]
+    const uint32_t ch = pl.BN >= 32 ? 32 : 16;
+    uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.Cout, (uint64_t)pl.splits};
+    uint64_t strides[2] = {(uint64_t)p.K * 4, (uint64_t)p.Cout * p.K * 4};
+    uint32_t box[3] = {ch, 32, 1};
+    if (!make_tmap_f32(&tmOut, a.out, 3, dims, strides, box, ch * 4)) return STP_E_CUDA;
+  }
   const bool narrow = p.Cout <= 32;
   int rc = STP_E_UNSUPPORTED;
   if (p.stride == 2) {
 #define STP_WG_CASE(bn) \
-  if (pl.BN == bn) rc = narrow ? launch_wgrad_cfg<bn, 1, 1>(tmDY, tmX, a, pl.items, st) : launch_wgrad_cfg<bn, 0, 1>(tmDY, tmX, a, pl.items, st);
+  if (pl.BN == bn) rc = narrow ? launch_wgrad_cfg<bn, 1, 1>(tmDY, tmX, tmOut, a, pl.items, st) : launch_wgrad_cfg<bn, 0, 1>(tmDY, tmX, tmOut, a, pl.items, st);
     STP_WG_CASE(64) STP_WG_CASE(32) STP_WG_CASE(16)
 #undef STP_WG_CASE
   } else {
 #define STP_WG_CASE(bn) \
-  if (pl.BN == bn) rc = narrow ? launch_wgrad_cfg<bn, 1, 0>(tmDY, tmX, a, pl.items, st) : launch_wgrad_cfg<bn, 0, 0>(tmDY, tmX, a, pl.items, st);
+  if (pl.BN == bn) rc = narrow ? launch_wgrad_cfg<bn, 1, 0>(tmDY, tmX, tmOut, a, pl.items, st) : launch_wgrad_cfg<bn, 0, 0>(tmDY, tmX, tmOut, a, pl.items, st);
     STP_WG_CASE(128) STP_WG_CASE(64) STP_WG_CASE(32) STP_WG_CASE(16)
 #undef STP_WG_CASE
   }

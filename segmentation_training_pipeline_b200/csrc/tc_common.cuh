@@ -66,6 +66,13 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* 
                "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// at most one committed bulk store still reading shared memory
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores have finished READING their shared-memory source (buffer reusable)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -193,5 +200,7 @@ PFN_encodeTiled get_encode_tiled();
 // bf16 tensor map, dims innermost-first; strides (bytes) for dims 1..rank-1; returns false + sets error on failure
 bool make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, uint32_t swizzle_bytes, const uint32_t* elem_strides = nullptr);
+bool make_tmap_f32(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, uint32_t swizzle_bytes);
 
 }  // namespace stp
