@@ -47,6 +47,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "dbg":
                 us, tf = bench(*shp)
                 print("shape", shp, "ver", "v1" if ver == 1 else "v2", "dbg", dbg, "us %.1f TF %.0f" % (us, tf), flush=True)
         L.set_option(b"tc2_debug", 0); L.set_option(b"tc_conv_version", 0)
+elif len(sys.argv) > 1 and sys.argv[1] == "wdbg":
+    for shp in shapes[:3]:
+        for dbg in [0, 1, 2, 3, 4, 8, 4 | 8, 1 | 2 | 4, 1 | 2 | 8, 15]:
+            L.set_option(b"tc2_debug", dbg)
+            us, tf = bench(*shp, what="wgrad")
+            print("wgrad shape", shp, "dbg", dbg, "us %.1f TF %.0f" % (us, tf), flush=True)
+        L.set_option(b"tc2_debug", 0)
 else:
     for shp in shapes:
         for what in ("fwd", "wgrad"):

@@ -535,6 +535,7 @@ struct TcWgradArgs {
   int b_row;      // bytes per pixel row of an X box: min(Cin,64)*2
   int xrows;      // (BH + R - 1) * BW rows of the haloed input tile (stride 2: 128, one box per filter row)
   int stride;     // 1: the R filter rows are shifted views of ONE haloed box; 2: one element-strided TMA box per row
+  int dbg;        // timing experiments only (results invalid): 1 skip dY loads, 2 skip X loads, 4 skip stores, 8 skip MMAs
 };
 
 // ANARROW: Cout <= 32 (dY rows of 32/64 B) -> small A stage; otherwise two 128-B-row boxes.
@@ -620,11 +621,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         int img = t / a.tilesH;
         const int h0 = th * a.BH, w0 = tw * a.BW;
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], tx_bytes);
         uint8_t* pa = sA + stage * Cfg::kABytes;
         uint8_t* pbuf = sB + stage * Cfg::kBBytes;
+        if (a.dbg & 3) {
+          const uint32_t txa = (a.dbg & 1) ? 0u : (uint32_t)a.a_boxes * a_box_bytes;
+          const uint32_t txb = (a.dbg & 2) ? 0u : tx_bytes - (uint32_t)a.a_boxes * a_box_bytes;
+          if (txa + txb) mbar_expect_tx(&full[stage], txa + txb); else mbar_arrive(&full[stage]);
+        } else {
+          mbar_expect_tx(&full[stage], tx_bytes);
+        }
+        if (!(a.dbg & 1))
         for (int j = 0; j < a.a_boxes; ++j) tma_load_4d(pa + j * a_box_bytes, &tmDY, &full[stage], co0 + 64 * j, w0, h0, img);
-        if (STR) {
+        if (a.dbg & 2) {
+        } else if (STR) {
           for (int r = 0; r < a.R; ++r)
 #pragma unroll
             for (int j = 0; j < BBOX; ++j)
@@ -652,6 +661,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         tc_fence_after();
         const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
         const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
+        if (!(a.dbg & 8))
         for (int r = 0; r < a.R; ++r) {
           const uint32_t b_r = STR ? b_addr + (uint32_t)r * (uint32_t)Cfg::kRBytes
                                    : b_addr + (uint32_t)(r * a.BW) * (uint32_t)a.b_row;
@@ -707,7 +717,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
           *reinterpret_cast<uint4*>(row + ((((uint32_t)i >> 2) ^ swz) << 4)) = make_uint4(rr[i], rr[i + 1], rr[i + 2], rr[i + 3]);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !(a.dbg & 4)) {
           tma_store_3d(&tmOut, stg + buf * (32 * RBO), ((r * a.S + s) * a.Cin) + ci0 + c0, co0 + q * 32, split);
           tma_store_commit();
         }
@@ -837,6 +847,7 @@ int launch_tc_wgrad(const WgradP& p, float* dw, void* ws, size_t ws_bytes, cudaS
   a.b_row = ci_atom * 2;
   a.xrows = p.stride == 2 ? 128 : (pl.BH + p.R - 1) * pl.BW;
   a.stride = p.stride;
+  a.dbg = get_option(OPT_TC2_DEBUG);
   CUtensorMap tmDY, tmX;
   {
     uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.N};
