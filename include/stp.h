@@ -59,6 +59,9 @@ int64_t stp_tc_launch_count(void);
 void stp_set_tc_enabled(int on);
 /* debugging / A-B knobs: "tc2_force_mt" (0 heuristic | 1,2,4,8), "tc_conv_version" (0 auto | 1 first-generation only) */
 int stp_set_option(const char* name, int32_t value);
+/* profiling aid: device buffer of >= 64 uint64 that the halo conv kernel's first and last thread blocks fill with
+ * %globaltimer stamps of their phases (scripts/trace_conv.py); NULL turns it off */
+void stp_set_trace_buffer(void* dev_ptr);
 
 /* ------------------------------------------------------------------------------------------------
  * K1  augmentation  -- replaces imgaug.augmenters.{Fliplr,Flipud,Affine,Multiply,Add} run by

@@ -31,12 +31,20 @@ static std::atomic<int> g_options[OPT_COUNT];
 int get_option(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key].load() : 0; }
 }  // namespace stp
 
+namespace stp {
+static std::atomic<unsigned long long*> g_trace{nullptr};
+unsigned long long* get_trace_buffer() { return g_trace.load(); }
+}  // namespace stp
+extern "C" void stp_set_trace_buffer(void* dev_ptr) { stp::g_trace.store((unsigned long long*)dev_ptr); }
+
 extern "C" int stp_set_option(const char* name, int32_t value) {
   STP_REQUIRE(name, "set_option: null name");
   int key = -1;
   if (!strcmp(name, "tc2_force_mt")) key = OPT_TC2_FORCE_MT;        /* 0 = heuristic; 1,2,4,8 = force strip height */
   else if (!strcmp(name, "tc_conv_version")) key = OPT_TC_CONV_VERSION; /* 0 = auto, 1 = first-generation kernel only */
   else if (!strcmp(name, "tc2_debug")) key = OPT_TC2_DEBUG;             /* timing experiments, see conv_tc2.cu */
+  else if (!strcmp(name, "tc2_cluster")) key = OPT_TC2_CLUSTER;         /* 0 auto | 1 no clusters | 2, 4 force that cluster size */
+  else if (!strcmp(name, "tc2_bk")) key = OPT_TC2_BK;                   /* 0 auto | 32: 32-channel K blocks even when Cin % 64 == 0 */
   else if (!strcmp(name, "pdl")) {                                      /* programmatic dependent launch on/off */
     g_pdl_enabled.store(value ? 1 : 0);
     return STP_OK;

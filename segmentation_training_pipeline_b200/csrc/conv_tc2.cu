@@ -19,6 +19,17 @@ namespace {
 
 using namespace tc;
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define STP_TRACE(slot)                                                                                   \
+  do {                                                                                                    \
+    if (a.trace && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))                                      \
+      a.trace[(blockIdx.x == 0 ? 0 : 16) + (slot)] = gtime();                                             \
+  } while (0)
+
 constexpr int kThreads2 = 192;
 constexpr int kSmemBudget2 = 227 * 1024;
 
@@ -31,11 +42,13 @@ struct Tc2Args {
   int R, S, pad_h, pad_w;
   int BW, BH, log2BW;
   int tilesW, tilesH, tilesN;
-  int num_tiles;
+  int num_tiles;             // work items: tiles (CL == 1) or cluster items = groups of CL pixel tiles x N tiles
+  int numPT, nimg;           // pixel tiles per N tile, images (cluster variants: ranks beyond numPT idle on an OOB image)
   int a_bytes, b_tap_bytes;  // runtime sizes of the A box and of one weight box
   int bn_on;                 // accumulate BatchNorm statistics of the stored output (bf16 path)
   BnFuse bn;
   int ncls;                  // > 0: "head" epilogue -- only output channels [0, ncls) exist, fp32 [pixels][ncls] dense (+bias)
+  unsigned long long* trace; // profiling aid (get_trace_buffer)
   int dbg;                   // timing experiments only (results invalid): 1 skip A loads, 2 skip B loads, 4 skip epilogue memory ops, 8 skip MMAs
 };
 
@@ -68,12 +81,19 @@ struct Tc2Cfg {
   static_assert(kTmemRaw <= 512, "accumulators exceed TMEM");
 };
 
-template <int BN, int BK, int MT, int RMAX = 3>
+// CL > 1: thread-block clusters of CL CTAs work on CL pixel tiles of the SAME N tile in lock step; every weight box is
+// fetched once per cluster -- each CTA loads 1/CL of its rows and TMA-multicasts them into all CL shared memories -- which
+// divides the dominant L2->SM stream of the deep encoder layers (weights re-read per pixel tile) by CL.
+template <int BN, int BK, int MT, int RMAX = 3, int CL = 1>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const Tc2Args a) {
   using Cfg = Tc2Cfg<BN, BK, MT, RMAX>;
   constexpr int NS = Cfg::kStages;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int w_first = CL > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int w_step = CL > 1 ? (int)cluster_count_x() : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -94,13 +114,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int kcb = a.Cin / BK;
   const int num_st = a.S * kcb;  // pipeline stages' worth of work per tile
   const int TH = MT * a.BH;
+  if (threadIdx.x == 0) STP_TRACE(0);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int i = 0; i < NS; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], CL);  // the MMA warp of every CTA of the cluster releases the stage everywhere
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -116,13 +137,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast / remote arrive reaches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) STP_TRACE(1);
   pdl_wait();  // prologue above touched no global data of earlier kernels; everything below may
+  if (threadIdx.x == 0) STP_TRACE(2);
 
   auto decode = [&](int tile, int& img, int& h0, int& w0, int& n0) {
     int tn = tile % a.tilesN;
     int t = tile / a.tilesN;
+    if (CL > 1) {
+      t = t * CL + crank;
+      if (t >= a.numPT) {  // no pixel tile left for this rank: run the item on an out-of-range image (zero fill, clipped stores)
+        img = a.nimg;
+        h0 = 0;
+        w0 = 0;
+        n0 = tn * BN;
+        return;
+      }
+    }
     int tw = t % a.tilesW;
     t /= a.tilesW;
     int th = t % a.tilesH;
@@ -137,7 +171,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t tx = (uint32_t)a.a_bytes + (uint32_t)a.R * (uint32_t)a.b_tap_bytes;
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      for (int tile = w_first; tile < a.num_tiles; tile += w_step) {
         int img, h0, w0, n0;
         decode(tile, img, h0, w0, n0);
         for (int s = 0; s < a.S; ++s) {
@@ -151,7 +185,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             if (!(a.dbg & 1))
             tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], cb * BK, w0 + s - a.pad_w, h0 - a.pad_h, img);
-            if (!(a.dbg & 2))
+            if (CL > 1) {
+              // this CTA's 1/CL slice of every tap's weight rows, multicast into all CTAs of the cluster
+              constexpr int kSliceRows = BN / CL;
+              for (int r = 0; r < a.R; ++r)
+                tma_load_2d_mc(sB + stage * Cfg::kBBytes + r * Cfg::kBTap + crank * (kSliceRows * BK * 2), &tmB, &full[stage],
+                               (r * a.S + s) * a.Cin + cb * BK, n0 + crank * kSliceRows, kMask);
+            } else if (!(a.dbg & 2))
             for (int r = 0; r < a.R; ++r)
               tma_load_2d(sB + stage * Cfg::kBBytes + r * Cfg::kBTap, &tmB, &full[stage],
                           (r * a.S + s) * a.Cin + cb * BK, n0);
@@ -171,7 +211,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++local) {
+      for (int tile = w_first; tile < a.num_tiles; tile += w_step, ++local) {
         const int as = local & 1;
         const uint32_t aphase = (local >> 1) & 1;
         mbar_wait(&acc_empty[as], aphase ^ 1);
@@ -179,6 +219,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t d0 = tmem_base + (uint32_t)(as * MT * BN);
         for (int st = 0; st < num_st; ++st) {
           mbar_wait(&full[stage], phase);
+          if (local == 0 && st == 0) STP_TRACE(3);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
           const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
@@ -194,7 +235,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                           (st | r | k) != 0);
             }
           }
-          umma_commit(&empty[stage]);
+          if (CL > 1) umma_commit_mc(&empty[stage], kMask); else umma_commit(&empty[stage]);
           if (++stage == NS) {
             stage = 0;
             phase ^= 1;
@@ -202,6 +243,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         umma_commit(&acc_full[as]);
       }
+      STP_TRACE(4);
     }
   } else {
     const int q = warp & 3;
@@ -220,7 +262,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         atomicAdd(a.bn.acc + a.Cout + cur_n0 + m, (double)sStat[128 + m]);
       }
     };
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++local) {
+    for (int tile = w_first; tile < a.num_tiles; tile += w_step, ++local) {
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       int img, h0, w0, n0;
@@ -232,6 +274,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       const int wo = w0 + wl;
       mbar_wait(&acc_full[as], aphase);
+      if (leader && local == 0) STP_TRACE(5);
       tc_fence_after();
       constexpr int CH = BN >= 32 ? 32 : 16;
       if (a.ncls > 0 || a.y_f32) {
@@ -357,7 +400,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tma_store_4d(&tmY, sOut + e * Cfg::kSubBytes + sl * 128 * RB, n0 + sl * 64, w0, h0 + (j0 + e) * a.BH, img);
             tma_store_commit();
           }
-          if (a.bn_on) {
+          if (a.bn_on && img < a.nimg) {
             // BatchNorm statistics of exactly the bf16 values just staged.  Thread = (channel octet o, pixel group g):
             // 16-byte conflict-free loads of the swizzled staging rows g, g+GP, ..., pixels outside the image masked;
             // groups are combined by a fixed xor-shuffle tree inside the warp, then across the 4 warps through sRed.
@@ -419,7 +462,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
     }
+    if (leader) STP_TRACE(6);
     if (leader) tma_store_wait_all();
+    if (leader) STP_TRACE(7);
     if (a.bn_on) {
       bn_flush();
       __threadfence();
@@ -439,8 +484,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   }
 
+  if (warp == 2 && lane == 0) STP_TRACE(8);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no peer still multicasts into / arrives on this CTA's shared memory
+  if (threadIdx.x == 0) STP_TRACE(9);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -448,20 +496,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 struct Tc2Plan {
-  int BN, BK, MT;
+  int BN, BK, MT, CL;
 };
 
 // Cycle estimate of one launch for a candidate tiling (B200: 148 SMs, ~40 B/clk/SM from L2, tcgen05 M=128 floor of
 // BN/2 cycles per K=16 MMA, 128 B/clk of shared-memory operand bandwidth).  Used only to RANK candidates: it captures
 // the three effects measured with ncu -- wave quantisation of the persistent grid, L2->SM bound stages when a weight
 // box is reused by too few pixels, and the per-strip epilogue latency.
-static double tc2_cost(const ConvP& p, int bn, int bk, int mt) {
+static double tc2_cost(const ConvP& p, int bn, int bk, int mt, int cl = 1) {
   const int bw = p.Wo >= 16 ? 16 : 8, bh = 128 / bw;
   const int th = mt * bh;
-  const double tiles = (double)p.N * ((p.Ho + th - 1) / th) * ((p.Wo + bw - 1) / bw) * (p.Cout / bn);
-  const double waves = (double)(int64_t)((tiles + kNumSMs - 1) / kNumSMs);
+  const int64_t pt = (int64_t)p.N * ((p.Ho + th - 1) / th) * ((p.Wo + bw - 1) / bw);
+  const double items = (double)((pt + cl - 1) / cl) * (p.Cout / bn);  // cluster work items (cl pixel tiles each)
+  const int slots = kNumSMs / cl;
+  const double waves = (double)(int64_t)((items + slots - 1) / slots);
   const int num_st = p.S * (p.Cin / bk);
-  const double bytes = (double)(th + p.R - 1) * bw * bk * 2 + (double)p.R * bn * bk * 2;
+  // weight boxes are fetched once per cluster (multicast): 1/cl of them per CTA
+  const double bytes = (double)(th + p.R - 1) * bw * bk * 2 + (double)p.R * bn * bk * 2 / cl;
   const double load = bytes / 40.0;
   const double mma_each = bn / 2.0 > 32.0 + bn / 4.0 ? bn / 2.0 : 32.0 + bn / 4.0;
   const double mma = (double)mt * p.R * (bk / 16) * mma_each;
@@ -477,11 +528,13 @@ bool tc2_plan(const ConvP& p, Tc2Plan* pl) {
   if (p.R < 2 && p.S < 2) return false;  // 1x1: nothing to reuse, first-generation kernel
   int bk = (p.Cin % 64 == 0) ? 64 : (p.Cin == 32 ? 32 : (p.Cin == 16 ? 16 : 0));
   if (!bk) return false;
+  if (bk == 64 && get_option(OPT_TC2_BK) == 32) bk = 32;  // experiment: smaller stages -> deeper pipeline
   const bool r4 = p.R == 4 || p.S == 4;  // 4x4: only the stem shape (Cin 32 = 4 sub-pixels x 8 channels, Cout 64) is instantiated
   if (p.R > 4 || p.S > 4 || (r4 && !(bk == 32 && p.Cout % 64 == 0))) return false;
   const int force = get_option(OPT_TC2_FORCE_MT);
+  const int clopt = get_option(OPT_TC2_CLUSTER);
   double best = 0.0;
-  int best_bn = 0, best_mt = 0;
+  int best_bn = 0, best_mt = 0, best_cl = 1;
   for (int bn : {128, 64, 32, 16}) {
     if (p.Cout % bn != 0) continue;
     if (r4 && bn != 64) continue;
@@ -489,34 +542,75 @@ bool tc2_plan(const ConvP& p, Tc2Plan* pl) {
     const int mt_max = bn == 128 ? 2 : (bn == 64 || bk == 64) ? 4 : 8;
     for (int mt = 1; mt <= mt_max; mt *= 2) {
       if (force > 0 && mt != (force < mt_max ? force : mt_max)) continue;
-      const double c = tc2_cost(p, bn, bk, mt);
-      if (best_bn == 0 || c < best) {
-        best = c;
-        best_bn = bn;
-        best_mt = mt;
+      for (int cl : {1, 2, 4}) {
+        // cluster (weight multicast) variants exist for the 128 x 64 tiles, bf16 TMA-store path.  Measured (profiles/
+        // README.md, s19): with only two pipeline stages in flight these layers are latency- rather than byte-bound, so
+        // multicast pays only where weights dominate outright (Cin, Cout >= 512: -17 %); elsewhere it is neutral and
+        // the automatic choice leaves it off.
+        if (cl > 1 && !(bn == 128 && bk == 64 && !r4 && !p.y_f32 && p.ncls == 0 && clopt != 1)) continue;
+        if (cl > 1 && clopt == 0 && !(p.Cin >= 512 && p.Cout >= 512)) continue;
+        if (clopt >= 2 && bn == 128 && bk == 64 && !r4 && !p.y_f32 && p.ncls == 0 && cl != clopt) continue;
+        const double c = tc2_cost(p, bn, bk, mt, cl);
+        if (best_bn == 0 || c < best) {
+          best = c;
+          best_bn = bn;
+          best_mt = mt;
+          best_cl = cl;
+        }
       }
     }
   }
   if (!best_bn) return false;
-  pl->BN = best_bn; pl->BK = bk; pl->MT = best_mt;
+  pl->BN = best_bn; pl->BK = bk; pl->MT = best_mt; pl->CL = best_cl;
   return true;
 }
 
-template <int BN, int BK, int MT, int RMAX = 3>
+template <int BN, int BK, int MT, int RMAX = 3, int CL = 1>
 int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR, const Tc2Args& a,
             cudaStream_t st) {
   using Cfg = Tc2Cfg<BN, BK, MT, RMAX>;
+  auto kernel = conv_tc2_kernel<BN, BK, MT, RMAX, CL>;
   static bool attr_set = false;
+  static int max_clusters = kNumSMs / CL;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, BK, MT, RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("conv_tc2: cudaFuncSetAttribute(%d B): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
       return STP_E_CUDA;
     }
+    if (CL > 1) {  // how many clusters can be co-resident (GPC granularity): the persistent grid must not exceed it
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(kNumSMs / CL * CL);
+      q.blockDim = dim3(kThreads2);
+      q.dynamicSmemBytes = Cfg::kSmemBytes;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kernel, &q) == cudaSuccess && n > 0 && n < max_clusters) max_clusters = n;
+      (void)cudaGetLastError();
+    }
     attr_set = true;
   }
-  int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
-  launch_pdl(conv_tc2_kernel<BN, BK, MT, RMAX>, dim3(grid), dim3(kThreads2), (size_t)Cfg::kSmemBytes, st, tmA, tmB, tmY, tmR, a);
+  cudaLaunchConfig_t cfg = {};
+  if (CL > 1) {
+    const int clusters = a.num_tiles < max_clusters ? a.num_tiles : max_clusters;
+    cfg.gridDim = dim3(clusters * CL);
+  } else {
+    cfg.gridDim = dim3(a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs);
+  }
+  cfg.blockDim = dim3(kThreads2);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl_enabled.load(std::memory_order_relaxed) ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = CL; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmY, tmR, a);
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("conv_tc2");
 }
@@ -560,10 +654,14 @@ int launch_tc2_conv(const ConvP& p, cudaStream_t st) {
     return STP_E_UNSUPPORTED;
   }
   a.num_tiles = (int)nt;
+  a.nimg = p.N;
+  a.numPT = p.N * a.tilesH * a.tilesW;
+  if (pl.CL > 1) a.num_tiles = ((a.numPT + pl.CL - 1) / pl.CL) * a.tilesN;
   const int box_rows = TH + p.R - 1;
   a.a_bytes = box_rows * a.BW * pl.BK * 2;
   a.b_tap_bytes = pl.BN * pl.BK * 2;
   a.dbg = get_option(OPT_TC2_DEBUG);
+  a.trace = get_trace_buffer();
   a.ncls = p.ncls;
   a.bn_on = (p.bn != nullptr && !p.y_f32 && p.ncls == 0) ? 1 : 0;
   if (a.bn_on) a.bn = *p.bn; else a.bn = BnFuse{};
@@ -577,7 +675,7 @@ int launch_tc2_conv(const ConvP& p, cudaStream_t st) {
   {
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.Cout};
     uint64_t strides[1] = {(uint64_t)p.K * 2};
-    uint32_t box[2] = {(uint32_t)pl.BK, (uint32_t)pl.BN};
+    uint32_t box[2] = {(uint32_t)pl.BK, (uint32_t)(pl.BN / pl.CL)};  // cluster variants: each CTA loads 1/CL of the rows
     if (!make_tmap_bf16(&tmB, p.w, 2, dims, strides, box, pl.BK * 2)) return STP_E_CUDA;
   }
   CUtensorMap tmY = tmA, tmR = tmA;  // placeholders when unused (fp32 output / no residual)
@@ -596,6 +694,13 @@ int launch_tc2_conv(const ConvP& p, cudaStream_t st) {
     if (pl.BN == 64 && pl.BK == 32 && pl.MT == 4) return launch2<64, 32, 4, 4>(tmA, tmB, tmY, tmR, a, st);
     if (pl.BN == 64 && pl.BK == 32 && pl.MT == 2) return launch2<64, 32, 2, 4>(tmA, tmB, tmY, tmR, a, st);
     if (pl.BN == 64 && pl.BK == 32 && pl.MT == 1) return launch2<64, 32, 1, 4>(tmA, tmB, tmY, tmR, a, st);
+  }
+  if (pl.CL == 2) {
+    if (pl.BN == 128 && pl.BK == 64 && pl.MT == 2) return launch2<128, 64, 2, 3, 2>(tmA, tmB, tmY, tmR, a, st);
+    if (pl.BN == 128 && pl.BK == 64 && pl.MT == 1) return launch2<128, 64, 1, 3, 2>(tmA, tmB, tmY, tmR, a, st);
+  } else if (pl.CL == 4) {
+    if (pl.BN == 128 && pl.BK == 64 && pl.MT == 2) return launch2<128, 64, 2, 3, 4>(tmA, tmB, tmY, tmR, a, st);
+    if (pl.BN == 128 && pl.BK == 64 && pl.MT == 1) return launch2<128, 64, 1, 3, 4>(tmA, tmB, tmY, tmR, a, st);
   }
 #define STP_TC2_CASE(bn, bk, mt) \
   if (pl.BN == bn && pl.BK == bk && pl.MT == mt) return launch2<bn, bk, mt>(tmA, tmB, tmY, tmR, a, st);

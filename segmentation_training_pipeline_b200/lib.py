@@ -71,6 +71,7 @@ SIGNATURES = {
     "stp_tc_launch_count": (_I64, []),
     "stp_set_tc_enabled": (None, [C.c_int]),
     "stp_set_option": (C.c_int, [C.c_char_p, _I32]),
+    "stp_set_trace_buffer": (None, [_P]),
     "stp_augment_draw": (C.c_int, [C.POINTER(AugSpec), _U64, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "stp_augment_apply": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "stp_conv_fwd": (C.c_int, [_CDP, _TP, _P, _P, _TP, _TP, _P, _SZ, _P]),
@@ -140,7 +141,7 @@ def check(rc: int, what: str = ""):
 
 
 # functions whose int return value is a result, not a status code
-_UNCHECKED = ("version", "tc_enabled", "bn_nblk", "last_error", "launch_count", "tc_launch_count", "set_tc_enabled",
+_UNCHECKED = ("set_trace_buffer", "version", "tc_enabled", "bn_nblk", "last_error", "launch_count", "tc_launch_count", "set_tc_enabled",
               "conv_wgrad_workspace", "head_bwd_workspace", "head_fwd_workspace", "loss_partial_floats")
 
 

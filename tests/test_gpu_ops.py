@@ -558,3 +558,43 @@ def test_conv_fwd_bn_epilogue_statistics(stp, cuda, case):
         scale = 1 + float(coef0.abs().max())
         assert max_abs(coef1, coef0) <= 2e-6 * scale, max_abs(coef1, coef0)
         assert max_abs(mm1, mm0) < 1e-6 and rel_err(mv1, mv0) < 1e-6
+
+
+@pytest.mark.parametrize("cl", [2, 4])
+@pytest.mark.parametrize("case", [(2, 24, 40, 128, 128), (1, 9, 17, 128, 256), (3, 8, 8, 256, 512), (5, 16, 16, 64, 128),
+                                  (16, 32, 32, 256, 256)])
+def test_conv_tc2_cluster_multicast(stp, cuda, case, cl):
+    """thread-block-cluster variants (weights TMA-multicast to CL CTAs): same results as the single-CTA kernel, incl.
+    ranks that idle on an out-of-range image, residual and fused BatchNorm statistics."""
+    n, h, w, cin, cout = case
+    g = torch.Generator().manual_seed(cin * 3 + cout + cl)
+    x = rand_bf16((n, h, w, cin), g)
+    wt = rand_bf16((cout, 3, 3, cin), g, scale=1.0 / math.sqrt(9 * cin))
+    res = rand_bf16((n, h, w, cout), g)
+    desc = lib.ConvDesc(3, 3, 1, 1, 1, 1, 0)
+    rows = n * h * w
+    partial = torch.zeros(2 * stp.bn_nblk(rows, cout) * cout, device=cuda)
+    sync = torch.zeros(4, dtype=torch.int32, device=cuda)
+    acc = torch.zeros(2 * cout, dtype=torch.float64, device=cuda)
+    gamma, beta = torch.ones(cout, device=cuda), torch.zeros(cout, device=cuda)
+    xs, rs = T(x), T(res)
+    outs = []
+    try:
+        for c in (1, cl):
+            stp.set_option(b"tc2_cluster", c)
+            y = torch.zeros((n, h, w, cout), dtype=torch.bfloat16, device=cuda)
+            ys = T(y)
+            coef = torch.zeros(4 * cout, device=cuda)
+            mm, mv = torch.zeros(cout, device=cuda), torch.ones(cout, device=cuda)
+            bn = lib.BnFwd(partial.data_ptr(), sync.data_ptr(), acc.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.99,
+                           mm.data_ptr(), mv.data_ptr(), coef.data_ptr())
+            for _ in range(2):
+                stp.conv_fwd_bn(C.byref(desc), ref(xs), wt.data_ptr(), None, ref(rs), ref(ys), C.byref(bn), None, 0, stream())
+            torch.cuda.synchronize()
+            outs.append((y, coef))
+    finally:
+        stp.set_option(b"tc2_cluster", 0)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert max_abs(outs[0][1], outs[1][1]) <= 2e-6 * (1 + float(outs[0][1].abs().max()))
+    yr = conv_ref(x, wt, 1, 1) + res.float().cpu()
+    assert rel_err(outs[1][0], yr) < TOL_BF16
