@@ -192,6 +192,9 @@ int stp_bn_finalize(const float* partial, int32_t nblk, int32_t c, int64_t count
 int stp_bn_stats_fused(const stp_tensor* x, float* partial, uint32_t* sync, double* acc, const float* gamma,
                        const float* beta, float eps, float momentum, float* moving_mean, float* moving_var, float* coef,
                        stp_stream stream);
+/* dbias[c] = sum over pixels of dz[.,c] (gradient of a conv bias; the conv+bias+ReLU layers of VGG-style encoders and of
+ * decoders without BatchNorm).  Same one-launch reduction as stp_bn_stats_fused (partial / sync / acc as there). */
+int stp_bias_grad(const stp_tensor* dz, float* partial, uint32_t* sync, double* acc, float* dbias, stp_stream stream);
 /* y = [relu](x*scale+shift); up=2 writes each value to the 2x2 block of y (UpSampling2D fused) */
 int stp_bn_apply(const stp_tensor* x, const float* coef, int32_t relu, int32_t up, const stp_tensor* y,
                  stp_stream stream);

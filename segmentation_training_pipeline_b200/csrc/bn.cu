@@ -102,7 +102,7 @@ __device__ void last_block_finalize(const FinArgs& f, const float* __restrict__ 
         a += red[j * CC + cl];
         b += red[nt + j * CC + cl];
       }
-      if (f.mode == 1) fin_forward(f, C, c, a, b); else fin_backward(f, C, c, a, b);
+      if (f.mode == 1) fin_forward(f, C, c, a, b); else if (f.mode == 2) fin_backward(f, C, c, a, b); else f.dbeta[c] = (float)a;
     }
   }
   if (threadIdx.x == 0) *f.sync = 0u;
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256, 2) reduce_rows_kernel(const __nv_bfloat16
     __threadfence();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const double s = __ldcg(fin.acc + c), ss = __ldcg(fin.acc + C + c);
-      if (fin.mode == 1) fin_forward(fin, C, c, s, ss); else fin_backward(fin, C, c, s, ss);
+      if (fin.mode == 1) fin_forward(fin, C, c, s, ss); else if (fin.mode == 2) fin_backward(fin, C, c, s, ss); else fin.dbeta[c] = (float)s;
       fin.acc[c] = 0.0;
       fin.acc[C + c] = 0.0;
     }
@@ -664,6 +664,14 @@ extern "C" int stp_bn_stats_fused(const stp_tensor* x, float* partial, uint32_t*
   fin.gamma = gamma; fin.beta = beta; fin.eps = eps; fin.momentum = momentum;
   fin.mov_mean = moving_mean; fin.mov_var = moving_var; fin.coef = coef;
   return launch_stats(x, partial, fin, (cudaStream_t)stream);
+}
+
+extern "C" int stp_bias_grad(const stp_tensor* dz, float* partial, uint32_t* sync, double* acc, float* dbias,
+                             stp_stream stream) {
+  STP_REQUIRE(dz && partial && sync && dbias, "bias_grad: null");
+  FinArgs fin = {};
+  fin.mode = 3; fin.sync = sync; fin.acc = acc; fin.dbeta = dbias;
+  return launch_stats(dz, partial, fin, (cudaStream_t)stream);
 }
 
 extern "C" int stp_bn_finalize(const float* partial, int32_t nblk, int32_t c, int64_t count, const float* gamma,

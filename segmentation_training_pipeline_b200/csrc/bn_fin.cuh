@@ -8,7 +8,7 @@ namespace stp {
 
 // What the LAST block of a reduction kernel does with the partial sums (mode 0: nothing, a separate finalize kernel runs)
 struct FinArgs {
-  int mode;  // 0 none | 1 forward statistics -> coef (+ moving stats) | 2 backward -> dgamma, dbeta, bcoef
+  int mode;  // 0 none | 1 forward statistics -> coef (+ moving stats) | 2 backward -> dgamma, dbeta, bcoef | 3 column sums -> dbeta
   unsigned int* sync;
   double* acc;  // non-null: blocks add their sums here with double atomics (2*C, zero on entry, returned to zero) and the
                 // last block finalises from 2*C values; null: deterministic fixed-order reduction of per-block partials

@@ -171,7 +171,8 @@ class Net:
         self.partial = torch.zeros(self._partial_floats, dtype=torch.float32, device=dev)
         self.d_step = torch.zeros(1, dtype=torch.int64, device=dev)
         self.sync = torch.zeros(4, dtype=torch.int32, device=dev)  # last-block tickets of the fused reduce+finalize kernels
-        cmax = max([8] + [op.x.c for op in self.ops if isinstance(op, BNRelu)])
+        cmax = max([8] + [op.x.c for op in self.ops if isinstance(op, BNRelu)] +
+                   [op.y.c for op in self.ops if isinstance(op, Conv) and op.b is not None])
         self.bn_acc = torch.zeros(2 * cmax, dtype=torch.float64, device=dev)  # conv-epilogue BatchNorm sums (returned to zero)
         # a BatchNorm whose input is written by exactly one conv gets its statistics from that conv's epilogue
         writers: Dict[int, List[Op]] = {}
@@ -333,13 +334,32 @@ class InputNorm(Op):
                     self.y.ref, st)
 
 
+class InputCast(Op):
+    """raw uint8 image -> bf16 with the channel count padded to 8 (keras.applications VGG16 has no input BatchNorm; the
+    reference feeds raw 0..255 pixels).  Padded channels meet zero weights (Conv zeroes their gradient columns)."""
+
+    def __init__(self, net: Net, img: Buf, y: Buf):
+        self.net, self.img, self.y = net, img, y
+        c = img.c
+        ident = np.zeros(4 * c, np.float32)
+        ident[c:3 * c] = 1.0  # mean 0, invstd 1, scale 1, shift 0
+        self.coef = torch.from_numpy(ident).to(net.device)
+        net.ops.append(self)
+
+    def fwd(self):
+        n = self.net
+        n.L.stem_prep(self.img.storage.data_ptr(), self.img.n, self.img.h, self.img.w, self.img.c, self.coef.data_ptr(),
+                      self.y.ref, _stream())
+
+
 class Conv(Op):
     def __init__(self, net: Net, x: Buf, y: Buf, name: str, k: int, stride=1, pad=0, residual: Optional[Buf] = None,
                  bias=False, init="he_uniform", needs_dgrad=True, cin_real: Optional[int] = None,
-                 stem_beta: Optional[Param] = None, up=1):
+                 stem_beta: Optional[Param] = None, up=1, relu=False):
         self.net, self.x, self.y, self.name, self.k = net, x, y, name, k
         self.residual, self.needs_dgrad = residual, needs_dgrad
-        self.desc = _lib.ConvDesc(k, k, stride, pad, pad, up, 0)
+        self.relu = relu  # conv + bias + ReLU in one kernel (VGG encoder, decoder without BatchNorm); y is post-ReLU
+        self.desc = _lib.ConvDesc(k, k, stride, pad, pad, up, _lib.CONV_RELU if relu else 0)
         cin, cout = x.c, y.c
         cr = cin_real or cin
         fan_in, fan_out = k * k * cr, k * k * cout
@@ -359,6 +379,8 @@ class Conv(Op):
         self.cin_real = cr
         self.bn_next: Optional["BNRelu"] = None
         net.need_ws(net.L.conv_wgrad_workspace(C.byref(self.desc), x.ref, y.ref))
+        if bias:
+            net.need_partial(2 * net.L.bn_nblk(y.rows, y.c) * y.c)
         net.ops.append(self)
 
     def grad_writes(self):
@@ -390,13 +412,18 @@ class Conv(Op):
 
     def bwd(self):
         n = self.net
+        if self.relu:
+            # dz = dy * (y > 0), in place in the gradient buffer of y (nothing else reads dy afterwards)
+            n.L.relu_bwd(self.dy.ref, self.y.ref, 1, None, self.dy.ref, _stream())
+        if self.b is not None:
+            n.L.bias_grad(self.dy.ref, n.partial.data_ptr(), n.sync.data_ptr(), n.bn_acc.data_ptr(), n.pg(self.b), _stream())
         with n.wgrad_stream() as ws:  # forked first: the wgrad overlaps this layer's dgrad and the BatchNorm backward below
             st = _stream()
             n.L.conv_wgrad(self.dref, self.x.ref, self.dy.ref, n.pg(self.w), ws.data_ptr(), ws.numel(), st)
-            if self.stem_beta is not None:
+            if self.stem_beta is not None or self.cin_real < self.w.shape[3]:
                 c = self.w.shape
                 n.L.stem_wgrad_post(n.pg(self.w), n.pp(self.w), c[0], c[1], c[2], c[3], self.cin_real,
-                                    n.pg(self.stem_beta), st)
+                                    n.pg(self.stem_beta) if self.stem_beta is not None else None, st)
         if self.needs_dgrad:
             n.L.conv_dgrad(self.dref, self.dy.ref, n.pwd(self.w), self.dx_res, self.dx.ref, n.ws.data_ptr(),
                            n.ws.numel(), _stream())
@@ -519,6 +546,30 @@ class BNRelu(Op):
                               self.bcoef.data_ptr(), st)
         L.bn_bwd_apply(self.dy.ref, self.x.ref, self.coef.data_ptr(), self.bcoef.data_ptr(), int(self.relu), self.up,
                        self.res_ref, self.dx.ref, st)
+
+
+class UpCopy(Op):
+    """UpSampling2D(2) of a post-ReLU tensor straight into (a channel slice of) a concat buffer.  Backward: 2x2 sum of
+    the upsampled gradient; positions where the (non-negative) source is exactly 0 receive 0, which the ReLU mask of
+    the producing layer would apply anyway."""
+
+    def __init__(self, net: Net, x: Buf, y: Buf):
+        self.net, self.x, self.y = net, x, y
+        net.ops.append(self)
+
+    def grad_writes(self):
+        return [self.x.grad()]
+
+    def prepare(self):
+        self.dy, self.dx = self.y.grad(), self.x.grad()
+        if self.acc[0]:
+            raise RuntimeError("UpCopy: accumulate into dx unsupported")
+
+    def fwd(self):
+        self.net.L.copy_up(self.x.ref, 2, self.y.ref, _stream())
+
+    def bwd(self):
+        self.net.L.relu_bwd(self.dy.ref, self.x.ref, 2, None, self.dx.ref, _stream())
 
 
 class MaxPool(Op):

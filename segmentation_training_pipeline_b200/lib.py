@@ -89,6 +89,7 @@ SIGNATURES = {
     "stp_bn_stats": (C.c_int, [_TP, _P, _P]),
     "stp_bn_stats_fused": (C.c_int, [_TP, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P]),
     "stp_bn_bwd_reduce_fused": (C.c_int, [_TP, _TP, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "stp_bias_grad": (C.c_int, [_TP, _P, _P, _P, _P, _P]),
     "stp_bn_finalize": (C.c_int, [_P, _I32, _I32, _I64, _P, _P, _F, _F, _P, _P, _P, _P]),
     "stp_bn_apply": (C.c_int, [_TP, _P, _I32, _I32, _TP, _P]),
     "stp_bn_coef_infer": (C.c_int, [_P, _P, _P, _P, _F, _I32, _P, _P]),

@@ -19,7 +19,8 @@ DEC_BN_EPS = 1e-3   # keras BatchNormalization default
 RESNET_REPS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3), "resnet50": (3, 4, 6, 3),
                "resnet101": (3, 4, 23, 3), "resnet152": (3, 8, 36, 3)}
 RESNET_BOTTLENECK = {"resnet18": False, "resnet34": False, "resnet50": True, "resnet101": True, "resnet152": True}
-KNOWN_BACKBONES = sorted(RESNET_REPS)
+VGG16_BLOCKS = ((64, 2), (128, 2), (256, 3), (512, 3), (512, 3))  # keras.applications.VGG16 [DEP]
+KNOWN_BACKBONES = sorted(RESNET_REPS) + ["vgg16"]
 KNOWN_ARCHITECTURES = ["Unet"]
 
 
@@ -31,6 +32,9 @@ class SegNet(E.Net):
                  enc_init="he_uniform", dec_init="glorot_uniform", loss=(1.0, 0.0, 0.0)):
         super().__init__(batch, device, seed)
         backbone = backbone.lower()
+        if backbone == "vgg16":
+            self._build_vgg16_unet(classes, input_shape, batch, decoder_filters, dec_init, loss)
+            return
         if backbone not in RESNET_REPS:
             print("Unknown backbone:" + backbone)
             print("Known backbones:", KNOWN_BACKBONES)
@@ -118,6 +122,10 @@ class SegNet(E.Net):
         E.BNRelu(self, x, cat[0].slice(0, up_c[0], name="relu1_up"), "bn1", ENC_BN_EPS, up=2)
         self.encoder_param_names = list(self.params.keys())
 
+        self._build_decoder(cat, df, classes, dec_init, loss)
+
+    def _build_decoder(self, cat, df, classes, dec_init, loss):
+        N = self.batch
         # ---- decoder -----------------------------------------------------------------------------
         for i, f in enumerate(df):
             pre = "decoder_stage%d_" % i
@@ -136,3 +144,43 @@ class SegNet(E.Net):
         self.head = E.Head(self, last, classes, "final_conv", init=dec_init)
         self.loss = E.Loss(self, self.head, self.mask, *loss)
         self.finalize()
+
+    def _build_vgg16_unet(self, classes, input_shape, batch, decoder_filters, dec_init, loss):
+        """U-Net over keras.applications.VGG16 (BASELINE.json configs[0]): 3x3 'same' conv + bias + ReLU blocks
+        (2,2,3,3,3), 2x2/2 max pooling, no BatchNorm, raw 0..255 input; skips block5_conv3 .. block1_conv2, decoder
+        input block5_pool.  Reference: segmentation.py:109-117 -> segmentation_models.Unet."""
+        H, W, CI = input_shape
+        if H % 32 or W % 32:
+            raise ValueError("input height/width must be divisible by 32")
+        if len(decoder_filters) != 5:
+            raise ValueError("decoder_filters must have 5 entries")
+        N = batch
+        df = list(decoder_filters)
+        self.input_shape, self.classes, self.backbone = (H, W, CI), classes, "vgg16"
+        self.img = E.Buf(self, N, H, W, CI, E.U8, name="image")
+        self.mask = E.Buf(self, N, H, W, classes, E.U8, name="mask")
+        skip_c = [512, 512, 256, 128, 64]
+        up_c = [512] + df[:4]
+        cat = []
+        for i in range(5):
+            hh, ww = (H // (16 >> i), W // (16 >> i)) if i < 4 else (H, W)
+            cat.append(E.Buf(self, N, hh, ww, up_c[i] + skip_c[i], name="cat%d" % i))
+        x = E.Buf(self, N, H, W, 8, name="input_bf16")
+        E.InputCast(self, self.img, x)
+        h, w = H, W
+        for bi, (f, reps) in enumerate(VGG16_BLOCKS):
+            for ci in range(reps):
+                name = "block%d_conv%d" % (bi + 1, ci + 1)
+                last_of_block = ci == reps - 1
+                ci_cat = 4 - bi  # block1 -> cat4 ... block5 -> cat0
+                y = cat[ci_cat].slice(up_c[ci_cat], f, name=name) if last_of_block else E.Buf(self, N, h, w, f, name=name)
+                first = bi == 0 and ci == 0
+                E.Conv(self, x, y, name, 3, pad=1, bias=True, relu=True, init="glorot_uniform", needs_dgrad=not first,
+                       cin_real=CI if first else None)
+                x = y
+            p = E.Buf(self, N, h // 2, w // 2, f, name="block%d_pool" % (bi + 1))
+            E.MaxPool(self, x, p, 2, 2, 0)
+            x, h, w = p, h // 2, w // 2
+        self.encoder_param_names = list(self.params.keys())
+        E.UpCopy(self, x, cat[0].slice(0, up_c[0], name="block5_pool_up"))
+        self._build_decoder(cat, df, classes, dec_init, loss)

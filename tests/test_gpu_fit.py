@@ -71,3 +71,23 @@ def test_loss_decreases_on_a_fixed_batch(cuda):
     losses = [tr.step_from_host(hi, hm)["loss"] for _ in range(30)]
     assert all(np.isfinite(losses))
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+def test_fit_config0_unet_vgg16(cuda, tmp_path):
+    """BASELINE.json configs[0] as written: 4 synthetic 128x128 png pairs, U-Net/VGG16, 2 folds x 2 epochs."""
+    from segmentation_pipeline import segmentation
+    from segmentation_pipeline.impl.datasets import SimplePNGMaskDataSet
+    _make_dataset(str(tmp_path), n=4, size=128)
+    cfgp = str(tmp_path / "exp" / "config.yaml")
+    os.makedirs(os.path.dirname(cfgp))
+    shutil.copy(os.path.join(HERE, "golden", "configs", "c1_unet_vgg16.yaml"), cfgp)
+    cfg = segmentation.parse(cfgp)
+    res = cfg.fit(SimplePNGMaskDataSet(str(tmp_path / "img"), str(tmp_path / "mask")))
+    exp = os.path.dirname(cfgp)
+    assert len(res) == 2 and os.path.exists(os.path.join(exp, "summary.yaml"))
+    for fold in range(2):
+        assert os.path.exists(os.path.join(exp, "weights", "best-%d.0.weights.npz" % fold))
+        rows = list(csv.DictReader(open(os.path.join(exp, "metrics", "metrics-%d.0.csv" % fold))))
+        assert len(rows) == 2 and all(np.isfinite(float(r["loss"])) and np.isfinite(float(r["val_loss"])) for r in rows)
+    w = cfg.load_model(0, 0).get_weights()
+    assert w["block1_conv1/kernel"].shape == (3, 3, 3, 64) and w["block5_conv3/bias"].shape == (512,)

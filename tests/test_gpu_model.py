@@ -33,7 +33,7 @@ def _perturb(weights, seed=1):
 
 
 @pytest.mark.parametrize("backbone,size,loss", [("resnet18", 64, (1.0, 1.0, 0.0)), ("resnet34", 64, (1.0, 1.0, 0.0)),
-                                                ("resnet50", 64, (1.0, 0.0, 0.0))])
+                                                ("resnet50", 64, (1.0, 0.0, 0.0)), ("vgg16", 64, (1.0, 1.0, 0.0))])
 def test_forward_backward_parity(cuda, backbone, size, loss):
     from oracle import losses as OL
     from oracle.models import SegModel
@@ -140,4 +140,5 @@ def test_training_curve_parity(cuda):
     for s in range(3):
         tr2.step_eager()
         c2.append(tr2.loss_value())
-    assert c2 == curve[:3], (c2, curve[:3])
+    # (BatchNorm sums are accumulated with double-precision atomics: equal up to the last fp32 bit, not bitwise)
+    assert all(abs(a - b) <= 1e-6 * max(1.0, abs(b)) for a, b in zip(c2, curve[:3])), (c2, curve[:3])
