@@ -260,7 +260,7 @@ typedef struct stp_loss_spec {
 } stp_loss_spec;
 enum { /* indices into the f32 result vector (16 floats) */
   STP_L_LOSS = 0, STP_L_BCE = 1, STP_L_DICE = 2, STP_L_IOU = 3, STP_L_ACC = 4, STP_L_IOT = 5,
-  STP_L_SUM_P = 6, STP_L_SUM_T = 7, STP_L_SUM_PT = 8, STP_L_COUNT = 9
+  STP_L_SUM_P = 6, STP_L_SUM_T = 7, STP_L_SUM_PT = 8, STP_L_COUNT = 9, STP_L_LOVASZ = 10
 };
 int stp_loss_fwd(const float* logits, const uint8_t* mask, int64_t count, const stp_loss_spec* h_spec,
                  float* partial, float* result16, stp_stream stream);
@@ -268,6 +268,18 @@ size_t stp_loss_partial_floats(void);
 /* dlogits f32 [count] = dL/dlogit using the sums in result16 */
 int stp_loss_bwd(const float* logits, const uint8_t* mask, int64_t count, const stp_loss_spec* h_spec,
                  const float* result16, float* dlogits, stp_stream stream);
+
+/* Lovasz hinge (binary, per image, on LOGITS; musket_core.losses.lovasz_loss -- the reference strips the trailing
+ * Activation when this loss is compiled).  act_elu: 1 = elu(e)+1 (Kaggle-TGS variant), 0 = relu (Berman).  fwd sorts the
+ * batch's hinge errors (one stable radix sort, images kept contiguous), writes result16[STP_L_LOVASZ] = mean over images
+ * and result16[STP_L_LOSS] (+)= weight * it, and leaves the per-element gradient in the workspace; bwd scatters
+ * weight * dL/dlogit into dlogits (accumulate: += ).  logits f32 [images*pixels_per_image], mask u8 same order. */
+size_t stp_lovasz_workspace(int32_t images, int64_t pixels_per_image);
+int stp_lovasz_fwd(const float* logits, const uint8_t* mask, int32_t images, int64_t pixels_per_image, int32_t act_elu,
+                   float weight, int32_t accumulate, void* workspace, size_t workspace_bytes, float* result16,
+                   stp_stream stream);
+int stp_lovasz_bwd(const void* workspace, size_t workspace_bytes, int32_t images, int64_t pixels_per_image, float weight,
+                   int32_t accumulate, float* dlogits, stp_stream stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K12  optimizer -- replaces keras.optimizers.Adam/SGD/RMSprop update ops (segmentation.raml:77-89)

@@ -634,28 +634,48 @@ class Head(Op):
 
 
 class Loss(Op):
-    """w_bce*binary_crossentropy + w_dice*dice_loss + w_iou*iou_loss and the metrics, fused with the sigmoid."""
+    """w_bce*binary_crossentropy + w_dice*dice_loss + w_iou*iou_loss and the metrics, fused with the sigmoid; or
+    w_lovasz*lovasz_loss on the logits (the reference's compile strips the final Activation for it)."""
 
-    def __init__(self, net: Net, head: Head, mask: Buf, w_bce=1.0, w_dice=0.0, w_iou=0.0):
+    def __init__(self, net: Net, head: Head, mask: Buf, w_bce=1.0, w_dice=0.0, w_iou=0.0, w_lovasz=0.0, lovasz_act="elu"):
         self.net, self.head, self.mask = net, head, mask
-        self.spec = _lib.LossSpec(w_bce, w_dice, w_iou)
         self.result = torch.zeros(16, dtype=torch.float32, device=net.device)
         self.lpartial = torch.zeros(net.L.loss_partial_floats(), dtype=torch.float32, device=net.device)
         self.count = head.x.rows * head.classes
         self.enabled = True
+        self.lov_ws: Optional[torch.Tensor] = None
+        self.lovasz_act = lovasz_act
+        self.set_weights(w_bce, w_dice, w_iou, w_lovasz)
         net.ops.append(self)
 
     def prepare(self):
         pass
 
-    def set_weights(self, w_bce, w_dice, w_iou):
+    def set_weights(self, w_bce, w_dice, w_iou, w_lovasz=0.0):
         self.spec = _lib.LossSpec(w_bce, w_dice, w_iou)
+        self.w_lovasz = float(w_lovasz)
+        if self.w_lovasz != 0.0:
+            if self.head.classes != 1:
+                raise NotImplementedError("lovasz_loss is defined by the reference for 1-class masks only (K.squeeze)")
+            if self.lov_ws is None:
+                x = self.head.x
+                nbytes = self.net.L.lovasz_workspace(x.n, x.h * x.w)
+                self.lov_ws = torch.zeros(max(int(nbytes), 16), dtype=torch.uint8, device=self.net.device)
 
     def fwd(self):
         if self.enabled:
-            self.net.L.loss_fwd(self.head.logits.data_ptr(), self.mask.storage.data_ptr(), self.count,
-                                C.byref(self.spec), self.lpartial.data_ptr(), self.result.data_ptr(), _stream())
+            L, x = self.net.L, self.head.x
+            L.loss_fwd(self.head.logits.data_ptr(), self.mask.storage.data_ptr(), self.count, C.byref(self.spec),
+                       self.lpartial.data_ptr(), self.result.data_ptr(), _stream())
+            if self.w_lovasz != 0.0:
+                L.lovasz_fwd(self.head.logits.data_ptr(), self.mask.storage.data_ptr(), x.n, x.h * x.w,
+                             int(self.lovasz_act == "elu"), self.w_lovasz, 1, self.lov_ws.data_ptr(), self.lov_ws.numel(),
+                             self.result.data_ptr(), _stream())
 
     def bwd(self):
-        self.net.L.loss_bwd(self.head.logits.data_ptr(), self.mask.storage.data_ptr(), self.count, C.byref(self.spec),
-                            self.result.data_ptr(), self.head.dlogits.data_ptr(), _stream())
+        L, x = self.net.L, self.head.x
+        L.loss_bwd(self.head.logits.data_ptr(), self.mask.storage.data_ptr(), self.count, C.byref(self.spec),
+                   self.result.data_ptr(), self.head.dlogits.data_ptr(), _stream())
+        if self.w_lovasz != 0.0:
+            L.lovasz_bwd(self.lov_ws.data_ptr(), self.lov_ws.numel(), x.n, x.h * x.w, self.w_lovasz, 1,
+                         self.head.dlogits.data_ptr(), _stream())

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libstp.so")
 BF16, F32, U8 = 0, 1, 2
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_WORKSPACE = 0, -1, -2, -3, -4
 CONV_RELU, CONV_STATS = 1, 2
-L_LOSS, L_BCE, L_DICE, L_IOU, L_ACC, L_IOT, L_SUM_P, L_SUM_T, L_SUM_PT, L_COUNT = range(10)
+L_LOSS, L_BCE, L_DICE, L_IOU, L_ACC, L_IOT, L_SUM_P, L_SUM_T, L_SUM_PT, L_COUNT, L_LOVASZ = range(11)
 BN_MAX_PARTIALS = 1024
 
 
@@ -108,6 +108,9 @@ SIGNATURES = {
     "stp_loss_fwd": (C.c_int, [_P, _P, _I64, C.POINTER(LossSpec), _P, _P, _P]),
     "stp_loss_partial_floats": (_SZ, []),
     "stp_loss_bwd": (C.c_int, [_P, _P, _I64, C.POINTER(LossSpec), _P, _P, _P]),
+    "stp_lovasz_workspace": (_SZ, [_I32, _I64]),
+    "stp_lovasz_fwd": (C.c_int, [_P, _P, _I32, _I64, _I32, _F, _I32, _P, _SZ, _P, _P]),
+    "stp_lovasz_bwd": (C.c_int, [_P, _SZ, _I32, _I64, _F, _I32, _P, _P]),
     "stp_adam": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, C.POINTER(GradXform), _P, _P]),
     "stp_sgd": (C.c_int, [_P, _P, _P, _I64, _F, _F, _I32, C.POINTER(GradXform), _P]),
     "stp_rmsprop": (C.c_int, [_P, _P, _P, _I64, _F, _F, _F, C.POINTER(GradXform), _P]),
@@ -143,7 +146,7 @@ def check(rc: int, what: str = ""):
 
 # functions whose int return value is a result, not a status code
 _UNCHECKED = ("set_trace_buffer", "version", "tc_enabled", "bn_nblk", "last_error", "launch_count", "tc_launch_count", "set_tc_enabled",
-              "conv_wgrad_workspace", "head_bwd_workspace", "head_fwd_workspace", "loss_partial_floats")
+              "conv_wgrad_workspace", "head_bwd_workspace", "head_fwd_workspace", "loss_partial_floats", "lovasz_workspace")
 
 
 class Lib:

@@ -11,7 +11,7 @@ README.md:116-205 (5 shuffled folds, random_state, weights/, metrics/, summary.y
 
 Everything numeric runs in libstp (CUDA, no CPU fallback): `fit` raises if the library / a GPU is missing.
 What is NOT mirrored (out of the hot-path scope): callbacks other than the best-weights checkpoint and CSV
-log, lr_find, negatives sampling, crops, DrawResults, FPN/Linknet/PSPNet/DeepLab graphs, lovasz/focal/jaccard losses
+log, lr_find, negatives sampling, crops, DrawResults, FPN/Linknet/PSPNet/DeepLab graphs, focal/jaccard losses
 (these raise NotImplementedError naming the key instead of being silently ignored).
 """
 from __future__ import annotations
@@ -35,17 +35,19 @@ custom_objects: Dict[str, Callable] = {}
 extra_train: Dict[str, object] = {}
 dataset_augmenters: Dict[str, Callable] = {}
 
-_LOSS_TERMS = {"binary_crossentropy": 0, "dice_loss": 1, "iou_loss": 2}
-_UNFUSED_LOSSES = ("lovasz_loss", "focal_loss", "jaccard_loss", "categorical_crossentropy")
+_LOSS_TERMS = {"binary_crossentropy": 0, "dice_loss": 1, "iou_loss": 2, "lovasz_loss": 3}
+_UNFUSED_LOSSES = ("focal_loss", "jaccard_loss", "categorical_crossentropy")
 _METRIC_ALIASES = {"binary_accuracy": "binary_accuracy", "dice": "dice", "iou": "iou", "iou_coef": "iou", "iot": "iot",
                    "iot_coef": "iot", "loss": "loss", "binary_crossentropy": "binary_crossentropy"}
 
 
-def parse_loss(expr: str) -> Tuple[float, float, float]:
-    """'binary_crossentropy+0.1*dice_loss' (reference README.md:210-214) -> (w_bce, w_dice, w_iou)."""
+def parse_loss(expr: str) -> Tuple[float, ...]:
+    """'binary_crossentropy+0.1*dice_loss' (reference README.md:210-214) -> (w_bce, w_dice, w_iou); with lovasz_loss
+    (segmentation.py:15-22 registry; computed on logits, the reference strips the final Activation) ->
+    (0, 0, 0, w_lovasz) -- mixing it with the probability-based terms is undefined in the reference and rejected."""
     if not isinstance(expr, str) or not expr.strip():
         raise ValueError("loss must be a non-empty string")
-    w = [0.0, 0.0, 0.0]
+    w = [0.0, 0.0, 0.0, 0.0]
 
     def term(node, scale):
         if isinstance(node, ast.BinOp) and isinstance(node.op, ast.Add):
@@ -72,6 +74,10 @@ def parse_loss(expr: str) -> Tuple[float, float, float]:
             raise ValueError("cannot parse loss expression: " + expr)
 
     term(ast.parse(expr.strip(), mode="eval").body, 1.0)
+    if w[3] != 0.0:
+        if any(w[:3]):
+            raise ValueError("lovasz_loss works on logits and cannot be combined with probability-based losses: " + expr)
+        return w[0], w[1], w[2], w[3]
     return w[0], w[1], w[2]
 
 

@@ -39,10 +39,18 @@ def test_composite_loss_strings(expr, want):
     assert parse_loss(expr) == pytest.approx(want)
 
 
+def test_lovasz_loss_string():
+    from segmentation_pipeline.segmentation import parse_loss
+    assert parse_loss("lovasz_loss") == (0.0, 0.0, 0.0, 1.0)
+    assert parse_loss("0.5*lovasz_loss") == (0.0, 0.0, 0.0, 0.5)
+    with pytest.raises(ValueError):
+        parse_loss("binary_crossentropy+lovasz_loss")
+
+
 def test_loss_and_augmenter_errors_are_loud():
     from segmentation_pipeline.segmentation import parse_augmentation, parse_loss
     with pytest.raises(NotImplementedError):
-        parse_loss("lovasz_loss")
+        parse_loss("focal_loss")
     with pytest.raises(ValueError):
         parse_loss("no_such_loss")
     with pytest.raises(NotImplementedError):

@@ -55,6 +55,27 @@ def test_fit_writes_reference_artifacts(cuda, tmp_path):
     assert len(cfg.info()) == 4
 
 
+def test_lovasz_step_in_cuda_graph(cuda):
+    """lovasz_loss (radix sort + scan + Jaccard-gradient kernels) inside the captured training step: loss goes down."""
+    import torch
+    from segmentation_training_pipeline_b200.models import SegNet
+    from segmentation_training_pipeline_b200.trainer import Trainer
+    n, size = 4, 64
+    g = torch.Generator().manual_seed(0)
+    yy, xx = torch.meshgrid(torch.arange(size), torch.arange(size), indexing="ij")
+    mask = (((yy - 30) ** 2 + (xx - 34) ** 2) < 220).to(torch.uint8)[None, :, :, None].repeat(n, 1, 1, 1)
+    img = (torch.randint(0, 100, (n, size, size, 3), generator=g) + mask * 120).to(torch.uint8)
+    net = SegNet("resnet18", classes=1, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=(0.0, 0.0, 0.0, 1.0))
+    tr = Trainer(net, optimizer="Adam", lr=1e-3)
+    tr.set_pool(img, mask)
+    tr.capture()
+    losses = []
+    for _ in range(30):
+        tr.step()
+        losses.append(tr.loss_value())
+    assert all(np.isfinite(losses)) and losses[-1] < 0.7 * losses[0], losses
+
+
 def test_loss_decreases_on_a_fixed_batch(cuda):
     import torch
     from segmentation_training_pipeline_b200.models import SegNet

@@ -33,7 +33,8 @@ def _perturb(weights, seed=1):
 
 
 @pytest.mark.parametrize("backbone,size,loss", [("resnet18", 64, (1.0, 1.0, 0.0)), ("resnet34", 64, (1.0, 1.0, 0.0)),
-                                                ("resnet50", 64, (1.0, 0.0, 0.0)), ("vgg16", 64, (1.0, 1.0, 0.0))])
+                                                ("resnet50", 64, (1.0, 0.0, 0.0)), ("vgg16", 64, (1.0, 1.0, 0.0)),
+                                                ("resnet18", 64, (0.0, 0.0, 0.0, 1.0))])
 def test_forward_backward_parity(cuda, backbone, size, loss):
     from oracle import losses as OL
     from oracle.models import SegModel
@@ -63,9 +64,12 @@ def test_forward_backward_parity(cuda, backbone, size, loss):
         om = SegModel("Unet", backbone, classes=1, input_shape=(size, size, 3), storage=storage, update_moving=False)
         assert set(om.params.keys()) == set(net.params.keys()), sorted(set(om.params.keys()) ^ set(net.params.keys()))
         om.load_numpy(W)
-        y = om(img.float())
         t = mask.float()
-        lo = loss[0] * OL.binary_crossentropy(t, y) + loss[1] * OL.dice_loss(t, y) + loss[2] * OL.iou_loss(t, y)
+        if len(loss) == 4 and loss[3]:  # lovasz_loss: on logits (the reference strips the final Activation)
+            lo = loss[3] * OL.lovasz_loss(t, om(img.float(), emit_logits=True))
+        else:
+            y = om(img.float())
+            lo = loss[0] * OL.binary_crossentropy(t, y) + loss[1] * OL.dice_loss(t, y) + loss[2] * OL.iou_loss(t, y)
         lo.backward()
         return (om.taps["logits"].detach().permute(0, 2, 3, 1), float(lo.detach()),
                 {k: p.grad.numpy().copy() for k, p in om.params.items()})

@@ -598,3 +598,33 @@ def test_conv_tc2_cluster_multicast(stp, cuda, case, cl):
     assert max_abs(outs[0][1], outs[1][1]) <= 2e-6 * (1 + float(outs[0][1].abs().max()))
     yr = conv_ref(x, wt, 1, 1) + res.float().cpu()
     assert rel_err(outs[1][0], yr) < TOL_BF16
+
+
+@pytest.mark.parametrize("act", ["elu", "relu"])
+@pytest.mark.parametrize("ties", [False, True])
+def test_lovasz_hinge(stp, cuda, act, ties):
+    """Lovasz hinge (per image, on logits) vs the oracle evaluated in float64; `ties` quantises the logits so that
+    many errors are equal (stable descending order must match torch.sort(stable=True)); image 1 has an empty mask."""
+    from oracle import losses as OL
+    g = torch.Generator().manual_seed(21)
+    n, h, w = 3, 40, 36
+    logits = torch.randn(n, h, w, 1, generator=g) * 2.0
+    if ties:
+        logits = (logits * 2).round() / 2
+    mask = (torch.rand(n, h, w, 1, generator=g) > 0.6).to(torch.uint8)
+    mask[1] = 0
+    lg = logits.to(cuda).contiguous()
+    mk = mask.to(cuda).contiguous()
+    ws = _ws(stp.lovasz_workspace(n, h * w), cuda)
+    result = torch.zeros(16, device=cuda)
+    result[lib.L_LOSS] = 0.25
+    dl = torch.full((n * h * w,), 0.5, device=cuda)
+    stp.lovasz_fwd(lg.data_ptr(), mk.data_ptr(), n, h * w, int(act == "elu"), 2.0, 1, ws.data_ptr(), ws.numel(), result.data_ptr(),
+                   stream())
+    stp.lovasz_bwd(ws.data_ptr(), ws.numel(), n, h * w, 2.0, 1, dl.data_ptr(), stream())
+    z = logits.double().requires_grad_(True)
+    lo = OL.lovasz_loss(mask.double(), z, act=act)
+    lo.backward()
+    assert abs(float(result[lib.L_LOVASZ]) - float(lo)) < 1e-5 * max(1.0, abs(float(lo)))
+    assert abs(float(result[lib.L_LOSS]) - (0.25 + 2.0 * float(lo))) < 1e-5 * max(1.0, abs(float(lo)))
+    assert rel_err(dl.view(n, h, w, 1) - 0.5, 2.0 * z.grad) < 1e-5
