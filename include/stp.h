@@ -291,6 +291,8 @@ typedef struct stp_grad_xform { /* g' = clipvalue(clipnorm(g * scale)) -- keras 
   float clipnorm;        /* <=0: off.  needs d_sumsq = sum(g^2) of the UNSCALED flat gradient */
   float clipvalue;       /* <=0: off */
   const float* d_sumsq;  /* device scalar or NULL */
+  const float* d_lr_scale; /* device scalar multiplying lr, or NULL: ReduceLROnPlateau / CyclicLR (callbacks.raml:22-48)
+                              change the rate between replays of the captured step without re-capturing it */
 } stp_grad_xform;
 int stp_adam(float* p, const float* g, float* m, float* v, int64_t count, float lr, float beta1, float beta2,
              float eps, const stp_grad_xform* h_gx, const int64_t* d_step, stp_stream stream);

@@ -10,7 +10,9 @@ namespace stp {
 struct GX {
   float scale, clipnorm, clipvalue;
   const float* sumsq;
+  const float* lr_scale;  // device scalar multiplying lr (learning-rate schedules without re-capturing the step graph)
 };
+__device__ __forceinline__ float gx_lr(float lr, const GX& gx) { return gx.lr_scale ? lr * (*gx.lr_scale) : lr; }
 
 __device__ __forceinline__ float gx_scale(const GX& gx) {
   float s = gx.scale;
@@ -32,7 +34,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
                                                    const int64_t* __restrict__ d_step) {
   // d_step holds the number of COMPLETED steps; this update is step t = *d_step + 1
   const double t = (double)(*d_step + 1);
-  const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+  const float lr_t = (float)((double)gx_lr(lr, gx) * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
   const float s = gx_scale(gx);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
                                                   float* __restrict__ v, int64_t n, float lr, float mu, int nesterov,
                                                   GX gx) {
   const float s = gx_scale(gx);
+  lr = gx_lr(lr, gx);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gk = gx_apply(g[i], s, gx);
     float vk = mu * v[i] - lr * gk;
@@ -69,6 +72,7 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ p, con
                                                       float* __restrict__ a, int64_t n, float lr, float rho,
                                                       float eps, GX gx) {
   const float s = gx_scale(gx);
+  lr = gx_lr(lr, gx);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gk = gx_apply(g[i], s, gx);
     float ak = rho * a[i] + (1.f - rho) * gk * gk;
@@ -103,12 +107,13 @@ __global__ void sumsq_final_kernel(const float* partial, int nblk, float* out) {
 }
 
 static GX make_gx(const stp_grad_xform* h) {
-  GX g{1.f, 0.f, 0.f, nullptr};
+  GX g{1.f, 0.f, 0.f, nullptr, nullptr};
   if (h) {
     g.scale = h->scale;
     g.clipnorm = h->clipnorm;
     g.clipvalue = h->clipvalue;
     g.sumsq = h->d_sumsq;
+    g.lr_scale = h->d_lr_scale;
   }
   return g;
 }

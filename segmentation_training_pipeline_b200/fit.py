@@ -15,6 +15,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import yaml
 
+from . import callbacks as _cb
 from .segmentation import _METRIC_ALIASES, parse_augmentation, parse_loss
 
 
@@ -88,8 +89,13 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
                           clipvalue=cfg.clipvalue,
                           augment=parse_augmentation(cfg.augmentation, seed=cfg.random_state + 1000 * fi + si))
             tr_.enable_host_feed()
+            # stage `callbacks:` replaces the config-level block, `extra_callbacks:` adds to it (StageConfig, segmentation.raml:124-136)
+            cbs = _cb.build(stage.get("callbacks", cfg.callbacks), stage.get("extra_callbacks"))
+            for cb in cbs:
+                cb.on_train_begin(tr_)
+            iteration = 0
             mpath = os.path.join(base, "metrics", "metrics-%d.%d.csv" % (fi, si))
-            fields = ["epoch", "loss"] + metric_names + ["val_loss"] + ["val_" + m for m in metric_names]
+            fields = ["epoch", "loss"] + metric_names + ["val_loss"] + ["val_" + m for m in metric_names] + ["lr"]
             rows: List[Dict] = []
             best = None
             pm = cfg.primary_metric
@@ -100,11 +106,14 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
                 for s in range(steps):
                     ids = [order[(s * B + j) % len(order)] for j in range(B)]
                     _stack(ds, ids, shape, himg, hmask)
+                    for cb in cbs:
+                        cb.on_batch_begin(tr_, iteration)
+                    iteration += 1
                     m = tr_.step_from_host(himg, hmask, read_metrics=True)
                     for k, v in m.items():
                         agg[k] = agg.get(k, 0.0) + v / steps          # Keras progress-bar averaging: equal weight per batch
                 val = evaluate(net, tr_, ds, va_idx, shape, himg, hmask)
-                row = {"epoch": epoch, "loss": agg.get("loss", float("nan"))}
+                row = {"epoch": epoch, "loss": agg.get("loss", float("nan")), "lr": tr_.get_lr()}
                 for mname in metric_names:
                     row[mname] = agg.get(mname, float("nan"))
                 row["val_loss"] = val.get("loss", float("nan"))
@@ -119,6 +128,10 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
                 if _better(cfg.primary_metric_mode, key, row[key], best):
                     best = row[key]
                     np.savez(os.path.join(base, "weights", "best-%d.%d.weights.npz" % (fi, si)), **net.get_weights())
+                for cb in cbs:
+                    cb.on_epoch_end(tr_, epoch, row)
+                if any(cb.stop_training for cb in cbs):
+                    break
             results.append({"fold": fi, "stage": si, "best_" + pm: None if best is None else float(best), "epochs": len(rows)})
     with open(summary, "w") as f:
         yaml.safe_dump({"completed": True, "folds": len(folds), "results": results,

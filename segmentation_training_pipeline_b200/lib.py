@@ -56,7 +56,8 @@ class LossSpec(C.Structure):
 
 
 class GradXform(C.Structure):
-    _fields_ = [("scale", C.c_float), ("clipnorm", C.c_float), ("clipvalue", C.c_float), ("d_sumsq", C.c_void_p)]
+    _fields_ = [("scale", C.c_float), ("clipnorm", C.c_float), ("clipvalue", C.c_float), ("d_sumsq", C.c_void_p),
+                ("d_lr_scale", C.c_void_p)]
 
 
 _P, _I32, _I64, _U64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_size_t

@@ -10,8 +10,8 @@ schemas/augmenters.raml:43-133; inherited fit/kfold/stages from musket_core.gene
 README.md:116-205 (5 shuffled folds, random_state, weights/, metrics/, summary.yaml next to the yaml).
 
 Everything numeric runs in libstp (CUDA, no CPU fallback): `fit` raises if the library / a GPU is missing.
-What is NOT mirrored (out of the hot-path scope): callbacks other than the best-weights checkpoint and CSV
-log, lr_find, negatives sampling, crops, DrawResults, FPN/Linknet/PSPNet/DeepLab graphs, focal/jaccard losses
+What is NOT mirrored (out of the hot-path scope): callbacks other than EarlyStopping / ReduceLROnPlateau /
+CyclicLR, the best-weights checkpoint and the CSV log; lr_find, negatives sampling, crops, DrawResults, FPN/Linknet/PSPNet/DeepLab graphs, focal/jaccard losses
 (these raise NotImplementedError naming the key instead of being silently ignored).
 """
 from __future__ import annotations

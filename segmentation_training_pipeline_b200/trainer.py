@@ -71,9 +71,22 @@ class Trainer:
         self.aug_params = torch.zeros(net.batch * C.sizeof(_lib.AugSample), dtype=torch.uint8, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_opt: Optional[torch.cuda.CUDAGraph] = None
+        self.lr_scale = torch.ones(1, dtype=torch.float32, device=dev)   # device-side lr multiplier (schedules)
+        self._lr_scale_host = torch.ones(1, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.ones(1)
         self._gx = _lib.GradXform(1.0 / world_size, self.clipnorm, self.clipvalue,
-                                  self.sumsq.data_ptr() if self.clipnorm > 0 else None)
+                                  self.sumsq.data_ptr() if self.clipnorm > 0 else None, self.lr_scale.data_ptr())
         self._ident = AugmentConfig()
+
+    # ---- learning-rate schedules ----------------------------------------------------------------
+    def set_lr(self, lr: float):
+        """Change the learning rate used by subsequent steps (also replays of the captured graph): the optimizer kernel
+        multiplies its captured base rate by a device scalar."""
+        self._lr_scale_host[0] = float(lr) / self.lr
+        self.lr_scale.copy_(self._lr_scale_host, non_blocking=True)
+        self.current_lr = float(lr)
+
+    def get_lr(self) -> float:
+        return getattr(self, "current_lr", self.lr)
 
     # ---- data ---------------------------------------------------------------------------------
     def set_pool(self, images: torch.Tensor, masks: torch.Tensor):

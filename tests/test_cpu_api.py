@@ -130,3 +130,54 @@ def test_shard_indices_partitions_global_batches():
         cat = np.concatenate([s[g * batch:(g + 1) * batch] for s in shards])
         assert np.array_equal(cat, order[g * 20:(g + 1) * 20])
     assert len(shard_indices(order[:7], 0, 4, 5)) == 0               # ragged tail dropped, empty is fine
+
+
+class _FakeTrainer:
+    def __init__(self, lr):
+        self.lr = lr
+
+    def set_lr(self, lr):
+        self.lr = lr
+
+    def get_lr(self):
+        return self.lr
+
+
+def test_callbacks_known_answers():
+    """keras 2.2.4 EarlyStopping / ReduceLROnPlateau and Kenstler's CyclicLR (reference callbacks.raml:22-48), by hand."""
+    from segmentation_training_pipeline_b200 import callbacks as CB
+    t = _FakeTrainer(0.01)
+    cyc = CB.CyclicLR(base_lr=0.001, max_lr=0.006, step_size=4, mode="triangular")
+    cyc.on_train_begin(t)
+    lrs = []
+    for it in range(17):
+        cyc.on_batch_begin(t, it)
+        lrs.append(t.lr)
+    assert lrs[0] == pytest.approx(0.001) and lrs[4] == pytest.approx(0.006) and lrs[8] == pytest.approx(0.001)
+    assert lrs[2] == pytest.approx(0.0035) and lrs[6] == pytest.approx(0.0035) and lrs[12] == pytest.approx(0.006)
+    cyc2 = CB.CyclicLR(base_lr=0.001, max_lr=0.006, step_size=4, mode="triangular2")
+    cyc2.on_train_begin(t)
+    l2 = []
+    for it in range(13):
+        cyc2.on_batch_begin(t, it)
+        l2.append(t.lr)
+    assert l2[4] == pytest.approx(0.006) and l2[12] == pytest.approx(0.001 + 0.005 / 2)
+    # ReduceLROnPlateau: patience 2, factor 0.5, cooldown 1, monitor val_loss (auto -> min, min_delta 1e-4)
+    t = _FakeTrainer(0.01)
+    rl = CB.ReduceLROnPlateau(monitor="val_loss", factor=0.5, patience=2, cooldown=1)
+    hist = []
+    for e, v in enumerate([1.0, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.5]):
+        rl.on_epoch_end(t, e, {"val_loss": v})
+        hist.append(t.lr)
+    assert hist == pytest.approx([0.01, 0.01, 0.01, 0.005, 0.005, 0.0025, 0.0025, 0.0025])
+    # EarlyStopping: auto mode is max for accuracies; stops after `patience` epochs without improvement
+    es = CB.EarlyStopping(monitor="val_binary_accuracy", patience=2)
+    es.on_train_begin(t)
+    stops = []
+    for e, v in enumerate([0.5, 0.6, 0.6, 0.55, 0.7]):
+        es.on_epoch_end(t, e, {"val_binary_accuracy": v})
+        stops.append(es.stop_training)
+    assert stops == [False, False, False, True, True]
+    assert [type(c).__name__ for c in CB.build({"EarlyStopping": {"patience": 3}}, {"CyclicLR": None})] == ["EarlyStopping", "CyclicLR"]
+    with pytest.raises(NotImplementedError):
+        CB.build({"LRVariator": {}})

@@ -628,3 +628,21 @@ def test_lovasz_hinge(stp, cuda, act, ties):
     assert abs(float(result[lib.L_LOVASZ]) - float(lo)) < 1e-5 * max(1.0, abs(float(lo)))
     assert abs(float(result[lib.L_LOSS]) - (0.25 + 2.0 * float(lo))) < 1e-5 * max(1.0, abs(float(lo)))
     assert rel_err(dl.view(n, h, w, 1) - 0.5, 2.0 * z.grad) < 1e-5
+
+
+def test_adam_device_lr_scale(stp, cuda):
+    """stp_grad_xform.d_lr_scale: the captured optimizer launch follows a learning rate changed on the device."""
+    n = 1024
+    g = torch.Generator().manual_seed(4)
+    grad = torch.randn(n, generator=g).to(cuda)
+    step = torch.zeros(1, dtype=torch.int64, device=cuda)
+    outs = []
+    for scale in (1.0, 0.25):
+        p = torch.zeros(n, device=cuda)
+        m, v = torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+        sc = torch.full((1,), scale, device=cuda)
+        gx = lib.GradXform(1.0, 0.0, 0.0, None, sc.data_ptr())
+        stp.adam(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-2, 0.9, 0.999, 1e-7, C.byref(gx),
+                 step.data_ptr(), stream())
+        outs.append(p.clone())
+    assert rel_err(outs[1], 0.25 * outs[0]) < 1e-6
