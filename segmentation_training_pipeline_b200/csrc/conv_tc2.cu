@@ -548,7 +548,7 @@ bool tc2_plan(const ConvP& p, Tc2Plan* pl) {
         // multicast pays only where weights dominate outright (Cin, Cout >= 512: -17 %); elsewhere it is neutral and
         // the automatic choice leaves it off.
         if (cl > 1 && !(bn == 128 && bk == 64 && !r4 && !p.y_f32 && p.ncls == 0 && clopt != 1)) continue;
-        if (cl > 1 && clopt == 0 && !(p.Cin >= 512 && p.Cout >= 512)) continue;
+        if (cl > 1 && clopt == 0) continue;  // automatic choice: off (neutral within noise in the full step, s19/s21)
         if (clopt >= 2 && bn == 128 && bk == 64 && !r4 && !p.y_f32 && p.ncls == 0 && cl != clopt) continue;
         const double c = tc2_cost(p, bn, bk, mt, cl);
         if (best_bn == 0 || c < best) {

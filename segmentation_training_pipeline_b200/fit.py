@@ -79,8 +79,10 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
         if subsample < 1.0:
             tr_idx = tr_idx[: max(1, int(len(tr_idx) * subsample))]
         net = cfg.createNet()
-        himg = torch.zeros((B, shape[0], shape[1], shape[2]), dtype=torch.uint8).pin_memory()
-        hmask = torch.zeros((B, shape[0], shape[1], cfg.classes), dtype=torch.uint8).pin_memory()
+        # two pinned host batches: the loader fills one while the previous one is still being copied / trained on
+        himgs = [torch.zeros((B, shape[0], shape[1], shape[2]), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        hmasks = [torch.zeros((B, shape[0], shape[1], cfg.classes), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        himg, hmask = himgs[0], hmasks[0]
         for si, stage in enumerate(cfg.stages):
             if si < start_from_stage:
                 continue
@@ -103,15 +105,18 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
                 order = rng.permutation(tr_idx)
                 steps = max(1, len(order) // B)
                 agg: Dict[str, float] = {}
+                def _acc(m):
+                    for k, v in (m or {}).items():
+                        agg[k] = agg.get(k, 0.0) + v / steps          # Keras progress-bar averaging: equal weight per batch
+
                 for s in range(steps):
                     ids = [order[(s * B + j) % len(order)] for j in range(B)]
-                    _stack(ds, ids, shape, himg, hmask)
+                    _stack(ds, ids, shape, himgs[s & 1], hmasks[s & 1])
                     for cb in cbs:
                         cb.on_batch_begin(tr_, iteration)
                     iteration += 1
-                    m = tr_.step_from_host(himg, hmask, read_metrics=True)
-                    for k, v in m.items():
-                        agg[k] = agg.get(k, 0.0) + v / steps          # Keras progress-bar averaging: equal weight per batch
+                    _acc(tr_.step_from_host_pipelined(himgs[s & 1], hmasks[s & 1]))   # metrics of the previous step
+                _acc(tr_.flush_host_pipeline())
                 val = evaluate(net, tr_, ds, va_idx, shape, himg, hmask)
                 row = {"epoch": epoch, "loss": agg.get("loss", float("nan")), "lr": tr_.get_lr()}
                 for mname in metric_names:

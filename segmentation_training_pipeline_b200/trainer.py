@@ -207,14 +207,33 @@ class Trainer:
 
     # ---- host-fed steps (the public fit() path and bench.py's e2e number) -----------------------
     def enable_host_feed(self):
-        """Device staging buffers for ONE batch + graph capture; afterwards step_from_host() is: async H2D of the raw
-        uint8 batch from pinned memory -> graph replay (augment .. optimizer) -> optional D2H of the 16-float result."""
+        """Device staging buffers + graph capture; afterwards a host-fed step is: async H2D of the raw uint8 batch from
+        pinned memory -> graph replay (augment .. optimizer) -> D2H of the 16-float result.
+
+        step_from_host() is synchronous (returns this step's metrics).  step_from_host_pipelined() double-buffers the
+        staging area on a copy stream so the H2D of step k overlaps the compute of step k-1 and returns the metrics of
+        the PREVIOUS step (flush_host_pipeline() returns the last one) -- what fit() and bench.py's e2e leg drive."""
         net = self.net
         H, W, CI = net.input_shape
-        self.pool_img = torch.zeros((net.batch, H, W, CI), dtype=torch.uint8, device=net.device)
-        self.pool_mask = torch.zeros((net.batch, H, W, net.classes), dtype=torch.uint8, device=net.device)
+        dev = net.device
+        self.pool_img = torch.zeros((net.batch, H, W, CI), dtype=torch.uint8, device=dev)
+        self.pool_mask = torch.zeros((net.batch, H, W, net.classes), dtype=torch.uint8, device=dev)
         self._res_host = torch.zeros(16, dtype=torch.float32).pin_memory()
+        self._stage_img = [torch.zeros_like(self.pool_img) for _ in range(2)]
+        self._stage_mask = [torch.zeros_like(self.pool_mask) for _ in range(2)]
+        self._res_ring = [torch.zeros(16, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._ev_copied = [torch.cuda.Event() for _ in range(2)]
+        self._ev_free = [torch.cuda.Event() for _ in range(2)]
+        self._ev_done = [torch.cuda.Event() for _ in range(2)]
+        self._pipe_k = 0
+        self._pipe_pending = None
         self.capture(from_pool=True)
+
+    @staticmethod
+    def _metrics_from(r) -> Dict[str, float]:
+        return {"loss": float(r[_lib.L_LOSS]), "binary_crossentropy": float(r[_lib.L_BCE]), "dice": float(r[_lib.L_DICE]),
+                "iou": float(r[_lib.L_IOU]), "binary_accuracy": float(r[_lib.L_ACC]), "iot": float(r[_lib.L_IOT])}
 
     def step_from_host(self, images: torch.Tensor, masks: torch.Tensor, read_metrics=True):
         self.pool_img.copy_(images, non_blocking=True)
@@ -224,17 +243,45 @@ class Trainer:
             return None
         self._res_host.copy_(self.net.loss.result, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        r = self._res_host
-        return {"loss": float(r[_lib.L_LOSS]), "binary_crossentropy": float(r[_lib.L_BCE]), "dice": float(r[_lib.L_DICE]),
-                "iou": float(r[_lib.L_IOU]), "binary_accuracy": float(r[_lib.L_ACC]), "iot": float(r[_lib.L_IOT])}
+        return self._metrics_from(self._res_host)
+
+    def step_from_host_pipelined(self, images: torch.Tensor, masks: torch.Tensor):
+        """Enqueue one host-fed step; returns the metrics of the previously enqueued step (None for the first call).
+        `images` / `masks` (pinned host tensors) may be overwritten once the NEXT call returns."""
+        b = self._pipe_k & 1
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._ev_free[b])          # staging slot b was drained by step k-2
+            self._stage_img[b].copy_(images, non_blocking=True)
+            self._stage_mask[b].copy_(masks, non_blocking=True)
+            self._ev_copied[b].record(self._copy_stream)
+        main.wait_event(self._ev_copied[b])
+        self.pool_img.copy_(self._stage_img[b], non_blocking=True)   # 17 MB device copy, ~5 us
+        self.pool_mask.copy_(self._stage_mask[b], non_blocking=True)
+        self._ev_free[b].record(main)
+        self.step()
+        self._res_ring[b].copy_(self.net.loss.result, non_blocking=True)
+        self._ev_done[b].record(main)
+        prev, self._pipe_pending = self._pipe_pending, b
+        self._pipe_k += 1
+        if prev is None:
+            return None
+        self._ev_done[prev].synchronize()
+        return self._metrics_from(self._res_ring[prev])
+
+    def flush_host_pipeline(self):
+        """Metrics of the last enqueued pipelined step (waits for it)."""
+        prev, self._pipe_pending = self._pipe_pending, None
+        if prev is None:
+            return None
+        self._ev_done[prev].synchronize()
+        return self._metrics_from(self._res_ring[prev])
 
     def loss_value(self) -> float:
         return float(self.net.loss.result[_lib.L_LOSS].item())
 
     def metrics(self) -> Dict[str, float]:
-        r = self.net.loss.result.detach().cpu().numpy()
-        return {"loss": float(r[_lib.L_LOSS]), "binary_crossentropy": float(r[_lib.L_BCE]), "dice": float(r[_lib.L_DICE]),
-                "iou": float(r[_lib.L_IOU]), "binary_accuracy": float(r[_lib.L_ACC]), "iot": float(r[_lib.L_IOT])}
+        return self._metrics_from(self.net.loss.result.detach().cpu().numpy())
 
     # ---- state --------------------------------------------------------------------------------
     def _snapshot(self):
