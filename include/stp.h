@@ -155,7 +155,7 @@ int stp_weight_prep(const float* w_master, void* w_fwd, void* w_dgrad, int32_t c
 
 /* stp_weight_prep for every conv layer of a network in one launch over the flat buffers.  d_items: device int64 [n][8] =
  * {element offset into the flat buffers, cout, r, s, cin, has_dgrad, first_tile, 0}; a layer owns
- * r*s*ceil(cout/32)*ceil(cin/32) consecutive tiles starting at first_tile; total_tiles = their sum. */
+ * ceil(cout/32)*ceil(cin/32) consecutive tiles (each covering all r*s taps) starting at first_tile; total_tiles = their sum. */
 int stp_weight_prep_batched(const float* flat_master, void* flat_fwd, void* flat_dgrad, const int64_t* d_items,
                             int32_t n_items, int64_t total_tiles, stp_stream stream);
 

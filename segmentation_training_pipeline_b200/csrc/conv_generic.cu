@@ -339,9 +339,9 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
 }
 
 // All conv layers of a network in ONE launch.  items: int64 [n][8] = {offset (elements, into the three flat buffers),
-// Cout, R, S, Cin, has_dgrad, first_tile, unused}; one block = one 32(co) x 32(ci) tile of one filter tap, transposed
-// through shared memory so that the KRSC read, the bf16 KRSC write and the tap-flipped [Cin][R][S][Cout] write are
-// all row-contiguous.
+// Cout, R, S, Cin, has_dgrad, first_tile, unused}; one block = one 32(co) x 32(ci) tile, looping over the layer's R*S
+// filter taps, each transposed through shared memory so that the KRSC read, the bf16 KRSC write and the tap-flipped
+// [Cin][R][S][Cout] write are all row-contiguous.
 __global__ void __launch_bounds__(256) weight_prep_batched_kernel(const float* __restrict__ wm,
                                                                   __nv_bfloat16* __restrict__ wf,
                                                                   __nv_bfloat16* __restrict__ wd,
@@ -357,32 +357,33 @@ __global__ void __launch_bounds__(256) weight_prep_batched_kernel(const float* _
   const int Cout = (int)it[1], R = (int)it[2], S = (int)it[3], Cin = (int)it[4];
   const bool dg = it[5] != 0;
   int t = (int)((int64_t)blockIdx.x - it[6]);
-  const int tci = (Cin + 31) / 32, tco = (Cout + 31) / 32;
+  const int tci = (Cin + 31) / 32;
   const int ci0 = (t % tci) * 32;
-  t /= tci;
-  const int co0 = (t % tco) * 32;
-  const int tap = t / tco;
-  const int r = tap / S, sx = tap - r * S;
+  const int co0 = (t / tci) * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t K = (int64_t)R * S * Cin;
+  for (int tap = 0; tap < R * S; ++tap) {
+    const int r = tap / S, sx = tap - r * S;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int co = co0 + ty + j * 8, ci = ci0 + tx;
-    if (co < Cout && ci < Cin) {
-      const int64_t i = off + (int64_t)co * K + (int64_t)tap * Cin + ci;
-      const float v = wm[i];
-      wf[i] = __float2bfloat16(v);
-      tile[ty + j * 8][tx] = v;
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + ty + j * 8, ci = ci0 + tx;
+      if (co < Cout && ci < Cin) {
+        const int64_t i = off + (int64_t)co * K + (int64_t)tap * Cin + ci;
+        const float v = wm[i];
+        wf[i] = __float2bfloat16(v);
+        tile[ty + j * 8][tx] = v;
+      }
     }
-  }
-  if (!dg) return;
-  __syncthreads();
-  const int tapf = (R - 1 - r) * S + (S - 1 - sx);
+    if (!dg) continue;
+    __syncthreads();
+    const int tapf = (R - 1 - r) * S + (S - 1 - sx);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int ci = ci0 + ty + j * 8, co = co0 + tx;
-    if (co < Cout && ci < Cin)
-      wd[off + ((int64_t)ci * R * S + tapf) * Cout + co] = __float2bfloat16(tile[tx][ty + j * 8]);
+    for (int j = 0; j < 4; ++j) {
+      const int ci = ci0 + ty + j * 8, co = co0 + tx;
+      if (co < Cout && ci < Cin)
+        wd[off + ((int64_t)ci * R * S + tapf) * Cout + co] = __float2bfloat16(tile[tx][ty + j * 8]);
+    }
+    __syncthreads();
   }
 }
 

@@ -131,14 +131,16 @@ __global__ void head_weight_pad_kernel(const float* __restrict__ w, int classes,
 }
 
 // dw[c][r][s][ci] = sum_m dl[m][c] * x[m + off(r,s)][ci]  ==  sum_p x[p][ci] * dl[p - off][c]
-// each thread owns one 8-channel vector of one pixel per iteration and 9 taps x 8 accumulators.
+// Thread = one 8-channel vector (fixed) walking pixels, 9 taps x 8 accumulators in registers.  Block reduction: xor
+// shuffles over the lanes that share the vector, then across the 8 warps through shared memory; one partial row per
+// block; a second kernel (one block per output element) sums the block partials in a fixed order.
 __global__ void __launch_bounds__(256) head_wgrad_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int H, int W,
                                                          int Cin, const float* __restrict__ dl, int classes, int cls,
-                                                         float* __restrict__ partial, int64_t M) {
-  // partial[blk][9][Cin] for class `cls`, and [blk][9*Cin] slot for dbias at index 9*Cin
-  const int cv = Cin / 8;
-  const int v = threadIdx.x % cv;          // fixed channel vector per thread (blockDim % cv == 0)
-  const int lanes = blockDim.x / cv;       // pixels per block iteration
+                                                         float* __restrict__ partial, int M, int pix_per_blk) {
+  // partial[blk][9][Cin] for class `cls`, and slot 9*Cin for dbias
+  const int cv = Cin / 8;                 // power of two <= 8 (checked by the launcher)
+  const int v = threadIdx.x % cv;
+  const int lanes = blockDim.x / cv;
   const int pl = threadIdx.x / cv;
   float acc[9][8];
 #pragma unroll
@@ -146,63 +148,85 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const __nv_bfloat16* __
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
   float bsum = 0.f;
-  for (int64_t p = (int64_t)blockIdx.x * lanes + pl; p < M; p += (int64_t)gridDim.x * lanes) {
-    int64_t n = p / ((int64_t)H * W);
-    int rem = (int)(p - n * (int64_t)H * W);
-    int h = rem / W, wq = rem - h * W;
+  const int m_begin = blockIdx.x * pix_per_blk;
+  int m_end = m_begin + pix_per_blk;
+  if (m_end > M) m_end = M;
+  for (int p = m_begin + pl; p < m_end; p += lanes) {
+    const unsigned n = (unsigned)p / (unsigned)(H * W);
+    const unsigned rem = (unsigned)p - n * (unsigned)(H * W);
+    const int h = (int)(rem / (unsigned)W), wq = (int)(rem - (unsigned)h * (unsigned)W);
     float f[8];
-    unpack8(ld8(x + p * ldx + v * 8), f);
-    if (v == 0) bsum += dl[p * classes + cls];
+    unpack8(ld8(x + (int64_t)p * ldx + v * 8), f);
+    if (v == 0) bsum += dl[(int64_t)p * classes + cls];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      int ho = h - (r - 1);
+      const int ho = h - (r - 1);
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
-        int wo = wq - (s - 1);
+        const int wo = wq - (s - 1);
         float g = 0.f;
-        if (ho >= 0 && ho < H && wo >= 0 && wo < W) g = dl[((n * H + ho) * (int64_t)W + wo) * classes + cls];
+        if (ho >= 0 && ho < H && wo >= 0 && wo < W) g = __ldg(dl + (((int64_t)n * H + ho) * W + wo) * classes + cls);
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[r * 3 + s][k] += f[k] * g;
       }
     }
   }
-  extern __shared__ float sm[];  // [blockDim][73]
-  float* mine = sm + (size_t)threadIdx.x * 73;
+  // lanes l, l^cv, l^2cv ... of a warp hold the same vector
+  for (int off = 16; off >= cv; off >>= 1) {
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+    for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) mine[t * 8 + k] = acc[t][k];
-  mine[72] = bsum;
+      for (int k = 0; k < 8; ++k) acc[t][k] += __shfl_xor_sync(0xffffffffu, acc[t][k], off);
+    bsum += __shfl_xor_sync(0xffffffffu, bsum, off);
+  }
+  __shared__ float sm[8][8 * 72 + 1];  // [warp][vector * 72 + tap * 8 + k], +1 for the bias sum
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < cv) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sm[warp][lane * 72 + t * 8 + k] = acc[t][k];
+    if (lane == 0) sm[warp][8 * 72] = bsum;
+  }
   __syncthreads();
   float* out = partial + (int64_t)blockIdx.x * (9 * Cin + 1);
   for (int i = threadIdx.x; i < 9 * Cin + 1; i += blockDim.x) {
     float a = 0.f;
     if (i == 9 * Cin) {
-      for (int l = 0; l < lanes; ++l) a += sm[(size_t)(l * cv) * 73 + 72];
+      for (int w = 0; w < 8; ++w) a += sm[w][8 * 72];
     } else {
-      int t = i / Cin, ci = i - t * Cin;
-      int vv = ci / 8, k = ci - vv * 8;
-      for (int l = 0; l < lanes; ++l) a += sm[(size_t)(l * cv + vv) * 73 + t * 8 + k];
+      const int t = i / Cin, ci = i - t * Cin;
+      const int vv = ci >> 3, k = ci & 7;
+      for (int w = 0; w < 8; ++w) a += sm[w][vv * 72 + t * 8 + k];
     }
     out[i] = a;
   }
 }
 
-__global__ void head_wgrad_final_kernel(const float* __restrict__ partial, int nblk, int Cin, int cls,
-                                        float* __restrict__ dw, float* __restrict__ dbias) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int n = 9 * Cin + 1;
-  if (i >= n) return;
+// one block per output element: strided partial sums in double, fixed tree -> deterministic
+__global__ void __launch_bounds__(128) head_wgrad_final_kernel(const float* __restrict__ partial, int nblk, int Cin, int cls,
+                                                               float* __restrict__ dw, float* __restrict__ dbias) {
+  const int i = blockIdx.x;
+  const int n = 9 * Cin + 1;
   double a = 0.0;
-  for (int b = 0; b < nblk; ++b) a += (double)partial[(int64_t)b * n + i];
-  if (i == 9 * Cin) {
-    if (dbias) dbias[cls] = (float)a;
-  } else {
-    dw[(int64_t)cls * 9 * Cin + i] = (float)a;
+  for (int b = threadIdx.x; b < nblk; b += 128) a += (double)partial[(int64_t)b * n + i];
+  __shared__ double red[128];
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int half = 64; half >= 1; half >>= 1) {
+    if (threadIdx.x < half) red[threadIdx.x] += red[threadIdx.x + half];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (i == 9 * Cin) {
+      if (dbias) dbias[cls] = (float)red[0];
+    } else {
+      dw[(int64_t)cls * 9 * Cin + i] = (float)red[0];
+    }
   }
 }
 
-constexpr int kHeadWgradBlocks = kNumSMs * 2;
+constexpr int kHeadWgradBlocks = kNumSMs * 8;
 
 }  // namespace stp
 
@@ -251,7 +275,7 @@ extern "C" int stp_head_bwd(const stp_tensor* x, const float* w_krsc_f32, const 
                             stp_stream stream) {
   STP_REQUIRE(vec_ok(x) && w_krsc_f32 && dlogits && dw, "head_bwd: bad args");
   STP_REQUIRE(classes >= 1 && classes <= kHeadMaxCls && x->c <= kHeadMaxCin, "head_bwd: classes<=4, Cin<=64");
-  STP_REQUIRE(256 % (x->c / 8) == 0, "head_bwd: Cin/8 must divide 256");
+  STP_REQUIRE(x->c == 8 || x->c == 16 || x->c == 32 || x->c == 64, "head_bwd: Cin must be 8, 16, 32 or 64");
   if (workspace_bytes < stp_head_bwd_workspace(x, classes) || !workspace) {
     set_error("head_bwd: workspace too small");
     return STP_E_WORKSPACE;
@@ -278,23 +302,19 @@ extern "C" int stp_head_bwd(const stp_tensor* x, const float* w_krsc_f32, const 
     int rc = check_launch("head_dgrad");
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(head_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(256 * 73 * sizeof(float)));
-    if (e != cudaSuccess) {
-      set_error("head_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return STP_E_CUDA;
-    }
-    attr_set = true;
-  }
+  STP_REQUIRE(M < 0x7fffffff, "head_bwd: too many pixels");
+  const int lanes = 256 / (x->c / 8);
+  int64_t nb = (M + (int64_t)lanes * 8 - 1) / ((int64_t)lanes * 8);
+  if (nb > kHeadWgradBlocks) nb = kHeadWgradBlocks;
+  int64_t ppb = (M + nb - 1) / nb;
+  ppb = (ppb + lanes - 1) / lanes * lanes;
+  nb = (M + ppb - 1) / ppb;
   for (int cls = 0; cls < classes; ++cls) {
-    head_wgrad_kernel<<<kHeadWgradBlocks, 256, 256 * 73 * sizeof(float), st>>>(
-        (const __nv_bfloat16*)x->ptr, x->ld, x->h, x->w, x->c, dlogits, classes, cls, (float*)workspace, M);
+    head_wgrad_kernel<<<(int)nb, 256, 0, st>>>((const __nv_bfloat16*)x->ptr, x->ld, x->h, x->w, x->c, dlogits, classes, cls,
+                                               (float*)workspace, (int)M, (int)ppb);
     int rc = check_launch("head_wgrad");
     if (rc) return rc;
-    head_wgrad_final_kernel<<<(9 * x->c + 1 + 127) / 128, 128, 0, st>>>((const float*)workspace, kHeadWgradBlocks,
-                                                                        x->c, cls, dw, dbias);
+    head_wgrad_final_kernel<<<9 * x->c + 1, 128, 0, st>>>((const float*)workspace, (int)nb, x->c, cls, dw, dbias);
     rc = check_launch("head_wgrad_final");
     if (rc) return rc;
   }

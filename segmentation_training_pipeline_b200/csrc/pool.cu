@@ -102,6 +102,76 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
   }
 }
 
+// 3x3 / stride 2 / pad 1 (the ResNet stem pool): an input row is covered by one window (even rows, offset 1) or two
+// (odd rows, offsets 2 and 0), likewise columns -> at most 4 windows, all loads issued before use; thread = fixed
+// 8-channel vector walking pixels (32-bit index math).
+__global__ void __launch_bounds__(256) maxpool_bwd_k3s2_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int Ho, int Wo,
+                                                               const uint8_t* __restrict__ argmax,
+                                                               const __nv_bfloat16* __restrict__ res, int ldr,
+                                                               __nv_bfloat16* __restrict__ dx, int lddx, int H, int W,
+                                                               int rows_in, int C, int cv, int ppi, int pix_per_blk) {
+  const int v = threadIdx.x % cv, pl = threadIdx.x / cv;
+  const int m_begin = blockIdx.x * pix_per_blk;
+  int m_end = m_begin + pix_per_blk;
+  if (m_end > rows_in) m_end = rows_in;
+  for (int m = m_begin + pl; m < m_end; m += ppi) {
+    const unsigned n = (unsigned)m / (unsigned)(H * W);
+    const unsigned rem = (unsigned)m - n * (unsigned)(H * W);
+    const int h = (int)(rem / (unsigned)W), w = (int)(rem - (unsigned)h * (unsigned)W);
+    // window candidates: (ho, row offset a) and (wo, column offset b)
+    int hos[2], as[2], nh = 0, wos[2], bs[2], nw = 0;
+    if (h & 1) {
+      hos[nh] = h >> 1; as[nh++] = 2;
+      if ((h >> 1) + 1 < Ho) { hos[nh] = (h >> 1) + 1; as[nh++] = 0; }
+    } else {
+      hos[nh] = h >> 1; as[nh++] = 1;
+    }
+    if (w & 1) {
+      wos[nw] = w >> 1; bs[nw++] = 2;
+      if ((w >> 1) + 1 < Wo) { wos[nw] = (w >> 1) + 1; bs[nw++] = 0; }
+    } else {
+      wos[nw] = w >> 1; bs[nw++] = 1;
+    }
+    uint2 pk[4];
+    bf16x8 gq[4];
+    int idx[4], cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (i < nh && j < nw && hos[i] < Ho && wos[j] < Wo) {
+          const int64_t ro = ((int64_t)n * Ho + hos[i]) * Wo + wos[j];
+          pk[cnt] = *reinterpret_cast<const uint2*>(argmax + ro * C + v * 8);
+          gq[cnt] = ld8(dy + ro * lddy + v * 8);
+          idx[cnt] = as[i] * 3 + bs[j];
+          ++cnt;
+        }
+    bf16x8 rq;
+    if (res) rq = ld8(res + (int64_t)m * ldr + v * 8);
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < cnt) {
+        float g[8];
+        unpack8(gq[q], g);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t word = c < 4 ? pk[q].x : pk[q].y;
+          if ((int)((word >> (8 * (c & 3))) & 0xff) == idx[q]) acc[c] += g[c];
+        }
+      }
+    if (res) {
+      float rf[8];
+      unpack8(rq, rf);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] += rf[c];
+    }
+    st8(dx + (int64_t)m * lddx + v * 8, pack8(acc));
+  }
+}
+
 static int ew_grid2(int64_t total) {
   int64_t b = (total + 255) / 256;
   int64_t cap = (int64_t)kNumSMs * 16;
@@ -133,6 +203,18 @@ extern "C" int stp_maxpool_bwd(const stp_tensor* dy, const uint8_t* argmax, int3
   if (residual) STP_REQUIRE(vec_ok(residual) && residual->c == dx->c && pixels(residual) == pixels(dx), "maxpool_bwd: bad residual");
   int64_t rows = pixels(dx);
   int cv = dx->c / 8;
+  if (k == 3 && stride == 2 && pad == 1 && rows < 0x7fffffff && cv <= 256 && 256 % cv == 0) {
+    const int ppi = 256 / cv;
+    int64_t nb = (rows + (int64_t)ppi * 4 - 1) / ((int64_t)ppi * 4);
+    if (nb > kNumSMs * 16) nb = kNumSMs * 16;
+    int64_t ppb = (rows + nb - 1) / nb;
+    ppb = (ppb + ppi - 1) / ppi * ppi;
+    nb = (rows + ppb - 1) / ppb;
+    maxpool_bwd_k3s2_kernel<<<(int)nb, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy->ptr, dy->ld, dy->h, dy->w, argmax, residual ? (const __nv_bfloat16*)residual->ptr : nullptr,
+        residual ? residual->ld : 0, (__nv_bfloat16*)dx->ptr, dx->ld, dx->h, dx->w, (int)rows, dx->c, cv, ppi, (int)ppb);
+    return check_launch("maxpool_bwd");
+  }
   maxpool_bwd_kernel<<<ew_grid2(rows * cv), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy->ptr, dy->ld, dy->h, dy->w, argmax, k, stride, pad,
       residual ? (const __nv_bfloat16*)residual->ptr : nullptr, residual ? residual->ld : 0, (__nv_bfloat16*)dx->ptr,

@@ -210,7 +210,7 @@ class Net:
             if isinstance(op, Conv):
                 co, r, s_, ci = op.w.shape
                 items.append([op.w.offset, co, r, s_, ci, int(op.needs_dgrad), tile, 0])
-                tile += r * s_ * ((co + 31) // 32) * ((ci + 31) // 32)
+                tile += ((co + 31) // 32) * ((ci + 31) // 32)
         self._wprep_tiles = tile
         self._wprep_items = torch.tensor(items, dtype=torch.int64, device=dev) if items else None
         self.finalized = True

@@ -248,7 +248,8 @@ def test_input_norm_u8(stp, cuda):
     assert float(y[..., 4:].abs().max()) == 0
 
 
-@pytest.mark.parametrize("shape,k,s,p", [((2, 16, 16, 64), 3, 2, 1), ((1, 10, 14, 16), 3, 2, 1), ((2, 8, 8, 32), 2, 2, 0)])
+@pytest.mark.parametrize("shape,k,s,p", [((2, 16, 16, 64), 3, 2, 1), ((1, 10, 14, 16), 3, 2, 1), ((2, 8, 8, 32), 2, 2, 0),
+                                         ((3, 11, 15, 24), 3, 2, 1)])
 def test_maxpool(stp, cuda, shape, k, s, p):
     n, h, w, c = shape
     g = torch.Generator().manual_seed(3)
@@ -270,6 +271,12 @@ def test_maxpool(stp, cuda, shape, k, s, p):
     mask = (x.float().cpu() > 0)
     ref_dx = xc.grad.permute(0, 2, 3, 1)
     assert rel_err(dx.float().cpu() * mask, ref_dx * mask) < TOL_BF16
+    # accumulate form
+    r = rand_bf16(shape, g)
+    dx2 = torch.zeros_like(x)
+    rs, dx2s = T(r), T(dx2)
+    stp.maxpool_bwd(ref(dys), am.data_ptr(), k, s, p, ref(rs), ref(dx2s), stream())
+    assert rel_err(dx2.float().cpu() * mask, (ref_dx + r.float().cpu()) * mask) < TOL_BF16
 
 
 @pytest.mark.parametrize("classes,cin", [(1, 16), (3, 32)])
@@ -459,7 +466,7 @@ def test_weight_prep_batched_matches_per_layer(stp, cuda):
     for co, r, s_, ci, dg in shapes:
         items.append([off, co, r, s_, ci, dg, tile, 0])
         off += (co * r * s_ * ci + 7) // 8 * 8
-        tile += r * s_ * ((co + 31) // 32) * ((ci + 31) // 32)
+        tile += ((co + 31) // 32) * ((ci + 31) // 32)
     flat = torch.randn(off, generator=g).to(cuda)
     wf = torch.zeros(off, dtype=torch.bfloat16, device=cuda)
     wd = torch.zeros(off, dtype=torch.bfloat16, device=cuda)
