@@ -257,10 +257,11 @@ int stp_add(const stp_tensor* a, const stp_tensor* b, const stp_tensor* y, stp_s
  * ---------------------------------------------------------------------------------------------- */
 typedef struct stp_loss_spec {
   float w_bce, w_dice, w_iou; /* composite loss weights: w_bce*binary_crossentropy + w_dice*dice_loss + w_iou*iou_loss */
+  float w_jaccard, w_focal;   /* + w_jaccard*jaccard_loss (smooth 100) + w_focal*focal_loss (gamma 2, alpha .75) */
 } stp_loss_spec;
 enum { /* indices into the f32 result vector (16 floats) */
   STP_L_LOSS = 0, STP_L_BCE = 1, STP_L_DICE = 2, STP_L_IOU = 3, STP_L_ACC = 4, STP_L_IOT = 5,
-  STP_L_SUM_P = 6, STP_L_SUM_T = 7, STP_L_SUM_PT = 8, STP_L_COUNT = 9, STP_L_LOVASZ = 10
+  STP_L_SUM_P = 6, STP_L_SUM_T = 7, STP_L_SUM_PT = 8, STP_L_COUNT = 9, STP_L_LOVASZ = 10, STP_L_JACCARD = 11, STP_L_FOCAL = 12
 };
 int stp_loss_fwd(const float* logits, const uint8_t* mask, int64_t count, const stp_loss_spec* h_spec,
                  float* partial, float* result16, stp_stream stream);

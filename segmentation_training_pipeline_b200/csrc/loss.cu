@@ -7,7 +7,8 @@
 namespace stp {
 
 constexpr int kLossBlocks = kNumSMs * 8;
-constexpr int kLossSlots = 8;
+constexpr int kLossSlots = 10;
+constexpr float kJaccardSmooth = 100.f, kFocalGamma = 2.f, kFocalAlpha = 0.75f;  // musket_core.losses defaults [DEP]
 
 __device__ __forceinline__ float sigmoidf_precise(float z) { return 1.f / (1.f + expf(-z)); }
 
@@ -33,6 +34,10 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__
     s[4] += (hard == t) ? 1.f : 0.f;
     s[5] += hard * t;
     s[6] += hard;
+    // jaccard_loss (per pixel over the 1-channel last axis, smooth = 100): (1 - (tp + S) / (t + p - tp + S)) * S
+    s[7] += (1.f - (t * p + kJaccardSmooth) / (t + p - t * p + kJaccardSmooth)) * kJaccardSmooth;
+    // focal_loss (gamma 2, alpha .75) on the clipped probability
+    s[8] += t != 0.f ? -kFocalAlpha * (1.f - pc) * (1.f - pc) * logf(pc) : -(1.f - kFocalAlpha) * pc * pc * logf(1.f - pc);
   }
   __shared__ float sm[kLossSlots][8];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -52,7 +57,8 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__
 // one warp per slot: lanes stride over the block partials (fixed order -> deterministic), double accumulation
 __global__ void __launch_bounds__(32 * kLossSlots) loss_finalize_kernel(const float* __restrict__ partial, int nblk,
                                                                         double count, float w_bce, float w_dice,
-                                                                        float w_iou, float* __restrict__ result) {
+                                                                        float w_iou, float w_jac, float w_focal,
+                                                                        float* __restrict__ result) {
   __shared__ double tot[kLossSlots];
   {
     const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -69,7 +75,9 @@ __global__ void __launch_bounds__(32 * kLossSlots) loss_finalize_kernel(const fl
     double iou = (I + 1.0) / (P + T - I + 1.0);
     double Ih = tot[5], Ph = tot[6];
     double iot = (Ih + 1.0) / (Ph + T - Ih + 1.0);
-    double loss = (double)w_bce * bce + (double)w_dice * (1.0 - dice) + (double)w_iou * (1.0 - iou);
+    const double jac = tot[7] / count, focal = tot[8] / count;
+    double loss = (double)w_bce * bce + (double)w_dice * (1.0 - dice) + (double)w_iou * (1.0 - iou) +
+                  (double)w_jac * jac + (double)w_focal * focal;
     result[STP_L_LOSS] = (float)loss;
     result[STP_L_BCE] = (float)bce;
     result[STP_L_DICE] = (float)dice;
@@ -80,14 +88,17 @@ __global__ void __launch_bounds__(32 * kLossSlots) loss_finalize_kernel(const fl
     result[STP_L_SUM_T] = (float)T;
     result[STP_L_SUM_PT] = (float)I;
     result[STP_L_COUNT] = (float)count;
-    for (int i = 10; i < 16; ++i) result[i] = 0.f;
+    result[STP_L_LOVASZ] = 0.f;
+    result[STP_L_JACCARD] = (float)jac;
+    result[STP_L_FOCAL] = (float)focal;
+    for (int i = 13; i < 16; ++i) result[i] = 0.f;
   }
 }
 
 __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__ logits,
                                                        const uint8_t* __restrict__ mask, int64_t count, float w_bce,
-                                                       float w_dice, float w_iou, const float* __restrict__ result,
-                                                       float* __restrict__ dlogits) {
+                                                       float w_dice, float w_iou, float w_jac, float w_focal,
+                                                       const float* __restrict__ result, float* __restrict__ dlogits) {
   const float eps = 1e-7f;
   const float I = result[STP_L_SUM_PT], P = result[STP_L_SUM_P], T = result[STP_L_SUM_T];
   const float inv_count = 1.f / (float)count;
@@ -103,6 +114,15 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
     if (w_bce != 0.f && p > eps && p < 1.f - eps) dp += w_bce * inv_count * (p - t) / (p * (1.f - p));
     if (w_dice != 0.f) dp -= w_dice * (t * dice_a - dice_b);
     if (w_iou != 0.f) dp -= w_iou * (t * iou_a - (1.f - t) * iou_b);
+    if (w_jac != 0.f) {
+      const float D = t + p - t * p + kJaccardSmooth;
+      dp -= w_jac * inv_count * kJaccardSmooth * (t * D - (t * p + kJaccardSmooth) * (1.f - t)) / (D * D);
+    }
+    if (w_focal != 0.f && p > eps && p < 1.f - eps) {
+      const float q = 1.f - p;
+      dp += w_focal * inv_count * (t != 0.f ? kFocalAlpha * (2.f * q * logf(p) - q * q / p)
+                                            : -(1.f - kFocalAlpha) * (2.f * p * logf(q) - p * p / q));
+    }
     dlogits[i] = dp * p * (1.f - p);
   }
 }
@@ -123,7 +143,7 @@ extern "C" int stp_loss_fwd(const float* logits, const uint8_t* mask, int64_t co
   int rc = check_launch("loss_fwd");
   if (rc) return rc;
   loss_finalize_kernel<<<1, 32 * kLossSlots, 0, st>>>(partial, nblk, (double)count, h_spec->w_bce, h_spec->w_dice, h_spec->w_iou,
-                                         result16);
+                                                     h_spec->w_jaccard, h_spec->w_focal, result16);
   return check_launch("loss_finalize");
 }
 
@@ -133,6 +153,6 @@ extern "C" int stp_loss_bwd(const float* logits, const uint8_t* mask, int64_t co
   int64_t nb = (count + 255) / 256;
   int nblk = (int)(nb < kLossBlocks ? nb : kLossBlocks);
   loss_bwd_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(logits, mask, count, h_spec->w_bce, h_spec->w_dice,
-                                                          h_spec->w_iou, result16, dlogits);
+                                                          h_spec->w_iou, h_spec->w_jaccard, h_spec->w_focal, result16, dlogits);
   return check_launch("loss_bwd");
 }

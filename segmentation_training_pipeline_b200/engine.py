@@ -637,7 +637,8 @@ class Loss(Op):
     """w_bce*binary_crossentropy + w_dice*dice_loss + w_iou*iou_loss and the metrics, fused with the sigmoid; or
     w_lovasz*lovasz_loss on the logits (the reference's compile strips the final Activation for it)."""
 
-    def __init__(self, net: Net, head: Head, mask: Buf, w_bce=1.0, w_dice=0.0, w_iou=0.0, w_lovasz=0.0, lovasz_act="elu"):
+    def __init__(self, net: Net, head: Head, mask: Buf, w_bce=1.0, w_dice=0.0, w_iou=0.0, w_lovasz=0.0, w_jaccard=0.0,
+                 w_focal=0.0, lovasz_act="elu"):
         self.net, self.head, self.mask = net, head, mask
         self.result = torch.zeros(16, dtype=torch.float32, device=net.device)
         self.lpartial = torch.zeros(net.L.loss_partial_floats(), dtype=torch.float32, device=net.device)
@@ -645,14 +646,14 @@ class Loss(Op):
         self.enabled = True
         self.lov_ws: Optional[torch.Tensor] = None
         self.lovasz_act = lovasz_act
-        self.set_weights(w_bce, w_dice, w_iou, w_lovasz)
+        self.set_weights(w_bce, w_dice, w_iou, w_lovasz, w_jaccard, w_focal)
         net.ops.append(self)
 
     def prepare(self):
         pass
 
-    def set_weights(self, w_bce, w_dice, w_iou, w_lovasz=0.0):
-        self.spec = _lib.LossSpec(w_bce, w_dice, w_iou)
+    def set_weights(self, w_bce, w_dice, w_iou, w_lovasz=0.0, w_jaccard=0.0, w_focal=0.0):
+        self.spec = _lib.LossSpec(w_bce, w_dice, w_iou, w_jaccard, w_focal)
         self.w_lovasz = float(w_lovasz)
         if self.w_lovasz != 0.0:
             if self.head.classes != 1:

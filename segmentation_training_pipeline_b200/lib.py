@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libstp.so")
 BF16, F32, U8 = 0, 1, 2
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_WORKSPACE = 0, -1, -2, -3, -4
 CONV_RELU, CONV_STATS = 1, 2
-L_LOSS, L_BCE, L_DICE, L_IOU, L_ACC, L_IOT, L_SUM_P, L_SUM_T, L_SUM_PT, L_COUNT, L_LOVASZ = range(11)
+L_LOSS, L_BCE, L_DICE, L_IOU, L_ACC, L_IOT, L_SUM_P, L_SUM_T, L_SUM_PT, L_COUNT, L_LOVASZ, L_JACCARD, L_FOCAL = range(13)
 BN_MAX_PARTIALS = 1024
 
 
@@ -52,7 +52,8 @@ class BnFwd(C.Structure):
 
 
 class LossSpec(C.Structure):
-    _fields_ = [("w_bce", C.c_float), ("w_dice", C.c_float), ("w_iou", C.c_float)]
+    _fields_ = [("w_bce", C.c_float), ("w_dice", C.c_float), ("w_iou", C.c_float), ("w_jaccard", C.c_float),
+                ("w_focal", C.c_float)]
 
 
 class GradXform(C.Structure):

@@ -11,7 +11,7 @@ README.md:116-205 (5 shuffled folds, random_state, weights/, metrics/, summary.y
 
 Everything numeric runs in libstp (CUDA, no CPU fallback): `fit` raises if the library / a GPU is missing.
 What is NOT mirrored (out of the hot-path scope): callbacks other than EarlyStopping / ReduceLROnPlateau /
-CyclicLR, the best-weights checkpoint and the CSV log; lr_find, negatives sampling, crops, DrawResults, FPN/Linknet/PSPNet/DeepLab graphs, focal/jaccard losses
+CyclicLR, the best-weights checkpoint and the CSV log; lr_find, negatives sampling, crops, DrawResults, FPN/Linknet/PSPNet/DeepLab graphs, categorical_crossentropy
 (these raise NotImplementedError naming the key instead of being silently ignored).
 """
 from __future__ import annotations
@@ -35,8 +35,8 @@ custom_objects: Dict[str, Callable] = {}
 extra_train: Dict[str, object] = {}
 dataset_augmenters: Dict[str, Callable] = {}
 
-_LOSS_TERMS = {"binary_crossentropy": 0, "dice_loss": 1, "iou_loss": 2, "lovasz_loss": 3}
-_UNFUSED_LOSSES = ("focal_loss", "jaccard_loss", "categorical_crossentropy")
+_LOSS_TERMS = {"binary_crossentropy": 0, "dice_loss": 1, "iou_loss": 2, "lovasz_loss": 3, "jaccard_loss": 4, "focal_loss": 5}
+_UNFUSED_LOSSES = ("categorical_crossentropy",)
 _METRIC_ALIASES = {"binary_accuracy": "binary_accuracy", "dice": "dice", "iou": "iou", "iou_coef": "iou", "iot": "iot",
                    "iot_coef": "iot", "loss": "loss", "binary_crossentropy": "binary_crossentropy"}
 
@@ -47,7 +47,7 @@ def parse_loss(expr: str) -> Tuple[float, ...]:
     (0, 0, 0, w_lovasz) -- mixing it with the probability-based terms is undefined in the reference and rejected."""
     if not isinstance(expr, str) or not expr.strip():
         raise ValueError("loss must be a non-empty string")
-    w = [0.0, 0.0, 0.0, 0.0]
+    w = [0.0, 0.0, 0.0, 0.0, 0.0, 0.0]
 
     def term(node, scale):
         if isinstance(node, ast.BinOp) and isinstance(node.op, ast.Add):
@@ -74,11 +74,12 @@ def parse_loss(expr: str) -> Tuple[float, ...]:
             raise ValueError("cannot parse loss expression: " + expr)
 
     term(ast.parse(expr.strip(), mode="eval").body, 1.0)
-    if w[3] != 0.0:
-        if any(w[:3]):
-            raise ValueError("lovasz_loss works on logits and cannot be combined with probability-based losses: " + expr)
-        return w[0], w[1], w[2], w[3]
-    return w[0], w[1], w[2]
+    if w[3] != 0.0 and (any(w[:3]) or any(w[4:])):
+        raise ValueError("lovasz_loss works on logits and cannot be combined with probability-based losses: " + expr)
+    n = 6
+    while n > 3 and w[n - 1] == 0.0:   # (w_bce, w_dice, w_iou[, w_lovasz[, w_jaccard[, w_focal]]])
+        n -= 1
+    return tuple(w[:n])
 
 
 def _rng(v, cast=float):

@@ -45,12 +45,14 @@ def test_lovasz_loss_string():
     assert parse_loss("0.5*lovasz_loss") == (0.0, 0.0, 0.0, 0.5)
     with pytest.raises(ValueError):
         parse_loss("binary_crossentropy+lovasz_loss")
+    assert parse_loss("binary_crossentropy+0.5*jaccard_loss") == (1.0, 0.0, 0.0, 0.0, 0.5)
+    assert parse_loss("focal_loss") == (0.0, 0.0, 0.0, 0.0, 0.0, 1.0)
 
 
 def test_loss_and_augmenter_errors_are_loud():
     from segmentation_pipeline.segmentation import parse_augmentation, parse_loss
     with pytest.raises(NotImplementedError):
-        parse_loss("focal_loss")
+        parse_loss("categorical_crossentropy")
     with pytest.raises(ValueError):
         parse_loss("no_such_loss")
     with pytest.raises(NotImplementedError):

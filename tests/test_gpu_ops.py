@@ -314,7 +314,8 @@ def test_head(stp, cuda, classes, cin):
     assert rel_err(db, dl.cpu().sum(dim=(0, 1, 2))) < TOL_F32
 
 
-@pytest.mark.parametrize("weights", [(1.0, 0.0, 0.0), (1.0, 1.0, 0.0), (0.5, 0.1, 0.3)])
+@pytest.mark.parametrize("weights", [(1.0, 0.0, 0.0), (1.0, 1.0, 0.0), (0.5, 0.1, 0.3), (0.0, 0.0, 0.0, 1.0, 0.0),
+                                     (0.0, 0.0, 0.0, 0.0, 1.0), (0.3, 0.2, 0.0, 0.5, 0.7)])
 def test_loss(stp, cuda, weights):
     from oracle import losses as OL
     g = torch.Generator().manual_seed(11)
@@ -324,6 +325,7 @@ def test_loss(stp, cuda, weights):
     # max(x,0)/|x| (torch 1/0, TF 0/0) while the kernel uses the analytic derivative sigmoid(x)-t
     logits[:5] = torch.tensor([40.0, -40.0, 0.25, 17.0, -17.0])
     mask = (torch.rand(count, generator=g) > 0.7).to(torch.uint8).to(cuda)
+    weights = tuple(weights) + (0.0,) * (5 - len(weights))   # (bce, dice, iou, jaccard, focal)
     spec = lib.LossSpec(*weights)
     partial = torch.zeros(stp.loss_partial_floats(), device=cuda)
     result = torch.zeros(16, device=cuda)
@@ -331,8 +333,11 @@ def test_loss(stp, cuda, weights):
     z = logits.cpu().requires_grad_(True)
     t = mask.float().cpu().view(2, 40, 36, 1)
     p = torch.sigmoid(z).view(2, 40, 36, 1)
-    lo = weights[0] * OL.binary_crossentropy(t, p) + weights[1] * OL.dice_loss(t, p) + weights[2] * OL.iou_loss(t, p)
+    lo = (weights[0] * OL.binary_crossentropy(t, p) + weights[1] * OL.dice_loss(t, p) + weights[2] * OL.iou_loss(t, p) +
+          weights[3] * OL.jaccard_loss(t, p) + weights[4] * OL.focal_loss(t, p))
     r = result.cpu()
+    assert abs(float(r[lib.L_JACCARD]) - float(OL.jaccard_loss(t, p))) < 1e-5 * max(1.0, float(OL.jaccard_loss(t, p)))
+    assert abs(float(r[lib.L_FOCAL]) - float(OL.focal_loss(t, p))) < 1e-5 * max(1.0, float(OL.focal_loss(t, p)))
     assert abs(float(r[lib.L_LOSS]) - float(lo)) <= 1e-5 * max(1.0, abs(float(lo)))
     assert abs(float(r[lib.L_DICE]) - float(OL.dice(t, p))) < 1e-5
     assert abs(float(r[lib.L_IOU]) - float(OL.iou(t, p))) < 1e-5
