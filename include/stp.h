@@ -301,6 +301,11 @@ int stp_sgd(float* p, const float* g, float* v, int64_t count, float lr, float m
             const stp_grad_xform* h_gx, stp_stream stream);
 int stp_rmsprop(float* p, const float* g, float* a, int64_t count, float lr, float rho, float eps,
                 const stp_grad_xform* h_gx, stp_stream stream);
+/* keras Nadam (schedule_decay 0.004): sched5 = device float[5], sched5[0] initialised to 1.0 (running momentum-schedule
+ * product), the rest scratch */
+int stp_nadam(float* p, const float* g, float* m, float* v, float* sched5, int64_t count, float lr, float beta1,
+              float beta2, float eps, float schedule_decay, const stp_grad_xform* h_gx, const int64_t* d_step,
+              stp_stream stream);
 int stp_step_advance(int64_t* d_step, stp_stream stream);
 /* sum of squares of g into out[0] (f32, deterministic two-pass through `partial`), for clipnorm */
 int stp_sumsq(const float* g, int64_t count, float* partial, float* out, stp_stream stream);

@@ -86,6 +86,41 @@ class RMSprop:
             p.sub_(self.lr * g / (self.a[k].sqrt() + self.eps))
 
 
+class Nadam:
+    """keras.optimizers.Nadam 2.2.4 [DEP] (segmentation.raml:77-89 optimizer enum): Nesterov Adam with the momentum
+    schedule mu_t = b1*(1 - 0.5*0.96^(t*schedule_decay)); lr 0.002, eps 1e-7, schedule_decay 0.004."""
+
+    def __init__(self, params, lr=0.002, beta_1=0.9, beta_2=0.999, epsilon=1e-7, schedule_decay=0.004, clipnorm=None,
+                 clipvalue=None):
+        self.params, self.lr, self.b1, self.b2, self.eps, self.sd = params, lr, beta_1, beta_2, epsilon, schedule_decay
+        self.clipnorm, self.clipvalue = clipnorm, clipvalue
+        self.t, self.m_schedule = 0, 1.0
+        self.m = {k: torch.zeros_like(p) for k, p in params.items()}
+        self.v = {k: torch.zeros_like(p) for k, p in params.items()}
+
+    @torch.no_grad()
+    def step(self, grads):
+        grads = _clip(grads, self.clipnorm, self.clipvalue)
+        self.t += 1
+        t = self.t
+        mu_t = self.b1 * (1.0 - 0.5 * 0.96 ** (t * self.sd))
+        mu_t1 = self.b1 * (1.0 - 0.5 * 0.96 ** ((t + 1) * self.sd))
+        ms_new = self.m_schedule * mu_t
+        ms_next = ms_new * mu_t1
+        self.m_schedule = ms_new
+        for k, p in self.params.items():
+            g = grads.get(k)
+            if g is None:
+                continue
+            g_prime = g / (1.0 - ms_new)
+            self.m[k].mul_(self.b1).add_(g, alpha=1 - self.b1)
+            m_prime = self.m[k] / (1.0 - ms_next)
+            self.v[k].mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
+            v_prime = self.v[k] / (1.0 - self.b2 ** t)
+            m_bar = (1.0 - mu_t) * g_prime + mu_t1 * m_prime
+            p.sub_(self.lr * m_bar / (v_prime.sqrt() + self.eps))
+
+
 def make(name: str, params, lr=None, **kw):
     name = (name or "Adam").lower()
     if name == "adam":
@@ -94,4 +129,6 @@ def make(name: str, params, lr=None, **kw):
         return SGD(params, lr=lr if lr is not None else 0.01, **kw)
     if name == "rmsprop":
         return RMSprop(params, lr=lr if lr is not None else 1e-3, **kw)
+    if name == "nadam":
+        return Nadam(params, lr=lr if lr is not None else 0.002, **kw)
     raise ValueError("unknown optimizer " + name)

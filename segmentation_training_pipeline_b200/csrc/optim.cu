@@ -81,6 +81,39 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ p, con
   }
 }
 
+// keras Nadam: sched[0] = running product of the momentum schedule (1.0 initially); this single-thread kernel, launched
+// before nadam_kernel, publishes {m_schedule_new, m_schedule_next, mu_t, mu_t1} in sched[1..4] and advances sched[0].
+__global__ void nadam_schedule_kernel(float* sched, const int64_t* d_step, float b1, float schedule_decay) {
+  const double t = (double)(*d_step + 1);
+  const double mu_t = (double)b1 * (1.0 - 0.5 * pow(0.96, t * (double)schedule_decay));
+  const double mu_t1 = (double)b1 * (1.0 - 0.5 * pow(0.96, (t + 1.0) * (double)schedule_decay));
+  const double ms_new = (double)sched[0] * mu_t;
+  sched[0] = (float)ms_new;
+  sched[1] = (float)ms_new;
+  sched[2] = (float)(ms_new * mu_t1);
+  sched[3] = (float)mu_t;
+  sched[4] = (float)mu_t1;
+}
+
+__global__ void __launch_bounds__(256) nadam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                                    GX gx, const int64_t* __restrict__ d_step, const float* __restrict__ sched) {
+  const double t = (double)(*d_step + 1);
+  const float ms_new = sched[1], ms_next = sched[2], mu_t = sched[3], mu_t1 = sched[4];
+  const float vcorr = (float)(1.0 - pow((double)b2, t));
+  const float s = gx_scale(gx);
+  lr = gx_lr(lr, gx);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gk = gx_apply(g[i], s, gx);
+    const float mk = b1 * m[i] + (1.f - b1) * gk;
+    const float vk = b2 * v[i] + (1.f - b2) * gk * gk;
+    m[i] = mk;
+    v[i] = vk;
+    const float m_bar = (1.f - mu_t) * (gk / (1.f - ms_new)) + mu_t1 * (mk / (1.f - ms_next));
+    p[i] -= lr * m_bar / (sqrtf(vk / vcorr) + eps);
+  }
+}
+
 __global__ void step_advance_kernel(int64_t* s) { *s += 1; }
 
 constexpr int kSumsqBlocks = 1024;
@@ -150,6 +183,18 @@ extern "C" int stp_rmsprop(float* p, const float* g, float* a, int64_t count, fl
   STP_REQUIRE(p && g && a && count > 0, "rmsprop: bad args");
   rmsprop_kernel<<<opt_grid(count), 256, 0, (cudaStream_t)stream>>>(p, g, a, count, lr, rho, eps, make_gx(h_gx));
   return check_launch("rmsprop");
+}
+
+extern "C" int stp_nadam(float* p, const float* g, float* m, float* v, float* sched5, int64_t count, float lr, float beta1,
+                         float beta2, float eps, float schedule_decay, const stp_grad_xform* h_gx, const int64_t* d_step,
+                         stp_stream stream) {
+  STP_REQUIRE(p && g && m && v && sched5 && d_step && count > 0, "nadam: bad args");
+  nadam_schedule_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sched5, d_step, beta1, schedule_decay);
+  int rc = check_launch("nadam_schedule");
+  if (rc) return rc;
+  nadam_kernel<<<opt_grid(count), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, count, lr, beta1, beta2, eps, make_gx(h_gx),
+                                                                  d_step, sched5);
+  return check_launch("nadam");
 }
 
 extern "C" int stp_step_advance(int64_t* d_step, stp_stream stream) {

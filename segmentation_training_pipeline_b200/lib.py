@@ -116,6 +116,7 @@ SIGNATURES = {
     "stp_adam": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, C.POINTER(GradXform), _P, _P]),
     "stp_sgd": (C.c_int, [_P, _P, _P, _I64, _F, _F, _I32, C.POINTER(GradXform), _P]),
     "stp_rmsprop": (C.c_int, [_P, _P, _P, _I64, _F, _F, _F, C.POINTER(GradXform), _P]),
+    "stp_nadam": (C.c_int, [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, C.POINTER(GradXform), _P, _P]),
     "stp_step_advance": (C.c_int, [_P, _P]),
     "stp_sumsq": (C.c_int, [_P, _I64, _P, _P, _P]),
 }

@@ -54,14 +54,15 @@ class Trainer:
                  world_size=1, process_group=None):
         self.net, self.L = net, net.L
         self.opt = (optimizer or "Adam").lower()
-        if self.opt not in ("adam", "sgd", "rmsprop"):
+        if self.opt not in ("adam", "sgd", "rmsprop", "nadam"):
             raise ValueError("unknown optimizer " + str(optimizer))
-        self.lr = float(lr) if lr is not None else (0.01 if self.opt == "sgd" else 1e-3)
+        self.lr = float(lr) if lr is not None else (0.01 if self.opt == "sgd" else 0.002 if self.opt == "nadam" else 1e-3)
         self.b1, self.b2, self.eps, self.mu, self.nesterov, self.rho = beta_1, beta_2, epsilon, momentum, nesterov, rho
         self.clipnorm, self.clipvalue = clipnorm or 0.0, clipvalue or 0.0
         dev = net.device
         self.m = torch.zeros(net.n_flat, dtype=torch.float32, device=dev)
-        self.v = torch.zeros(net.n_flat, dtype=torch.float32, device=dev) if self.opt == "adam" else None
+        self.v = torch.zeros(net.n_flat, dtype=torch.float32, device=dev) if self.opt in ("adam", "nadam") else None
+        self.nadam_sched = torch.tensor([1.0, 0.0, 0.0, 0.0, 0.0], dtype=torch.float32, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.sumsq_partial = torch.zeros(1024, dtype=torch.float32, device=dev)
         self.world_size, self.pg = world_size, process_group
@@ -128,6 +129,10 @@ class Trainer:
         if self.opt == "adam":
             self.L.adam(net.flat_p.data_ptr(), net.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), net.n_flat,
                         self.lr, self.b1, self.b2, self.eps, gx, net.d_step.data_ptr(), st)
+        elif self.opt == "nadam":
+            self.L.nadam(net.flat_p.data_ptr(), net.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                         self.nadam_sched.data_ptr(), net.n_flat, self.lr, self.b1, self.b2, self.eps, 0.004, gx,
+                         net.d_step.data_ptr(), st)
         elif self.opt == "sgd":
             self.L.sgd(net.flat_p.data_ptr(), net.flat_g.data_ptr(), self.m.data_ptr(), net.n_flat, self.lr, self.mu,
                        int(self.nesterov), gx, st)
@@ -287,7 +292,7 @@ class Trainer:
     def _snapshot(self):
         n = self.net
         return dict(p=n.flat_p.clone(), m=self.m.clone(), v=None if self.v is None else self.v.clone(),
-                    step=n.d_step.clone(), bufs={k: b.clone() for k, b in n.buffers.items()})
+                    step=n.d_step.clone(), sched=self.nadam_sched.clone(), bufs={k: b.clone() for k, b in n.buffers.items()})
 
     def _restore(self, s):
         n = self.net
@@ -296,6 +301,7 @@ class Trainer:
         if self.v is not None:
             self.v.copy_(s["v"])
         n.d_step.copy_(s["step"])
+        self.nadam_sched.copy_(s["sched"])
         for k, b in n.buffers.items():
             b.copy_(s["bufs"][k])
 

@@ -146,3 +146,56 @@ def test_training_curve_parity(cuda):
         c2.append(tr2.loss_value())
     # (BatchNorm sums are accumulated with double-precision atomics: equal up to the last fp32 bit, not bitwise)
     assert all(abs(a - b) <= 1e-6 * max(1.0, abs(b)) for a, b in zip(c2, curve[:3])), (c2, curve[:3])
+
+
+def test_full_size_step_properties(cuda):
+    """BASELINE.json configs[1] at FULL size (U-Net/ResNet-34, 512x512, bs 16, Dice+BCE, Adam): size-independent
+    properties -- identity augmentation is a bit-exact gather, flips are involutions, graph replay == eager, every
+    gradient / weight stays finite and the loss goes down on a fixed pool."""
+    import ctypes as C
+    from segmentation_training_pipeline_b200 import lib
+    from segmentation_training_pipeline_b200.models import SegNet
+    from segmentation_training_pipeline_b200.trainer import AugmentConfig, Trainer
+
+    n, size = 16, 512
+    g = torch.Generator().manual_seed(5)
+    img = torch.randint(0, 256, (n, size, size, 3), generator=g, dtype=torch.uint8)
+    yy, xx = torch.meshgrid(torch.arange(size), torch.arange(size), indexing="ij")
+    mask = (((yy - 250) ** 2 + (xx - 260) ** 2) < 150 ** 2).to(torch.uint8)[None, :, :, None].repeat(n, 1, 1, 1).contiguous()
+    img = (img.float() * 0.4 + mask.float() * 120).to(torch.uint8)
+    net = SegNet("resnet34", classes=1, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=(1.0, 1.0, 0.0))
+    # identity augmentation == bit-exact gather of the pool
+    tr = Trainer(net, optimizer="Adam", lr=1e-3, augment=AugmentConfig())
+    tr.set_pool(img, mask)
+    tr.run_augment()
+    torch.cuda.synchronize()
+    assert torch.equal(net.img.storage.view(n, size, size, 3).cpu(), img)
+    assert torch.equal(net.mask.storage.view(n, size, size, 1).cpu(), mask)
+    # always-flip twice == identity (index permutation, exact)
+    fl = Trainer(net, augment=AugmentConfig(fliplr=1.0, flipud=1.0))
+    fl.set_pool(img, mask)
+    fl.run_augment()
+    once = net.img.storage.view(n, size, size, 3).clone()
+    assert torch.equal(once.cpu(), img.flip(1).flip(2))
+    fl.set_pool(once, net.mask.storage.view(n, size, size, 1).clone())
+    fl.run_augment()
+    assert torch.equal(net.img.storage.view(n, size, size, 3).cpu(), img)
+    # eager step, then the same state through the captured graph
+    W0 = net.get_weights()
+    tr.step_eager()
+    l_eager = tr.loss_value()
+    grads = net.flat_g.clone()
+    assert bool(torch.isfinite(grads).all()) and float(grads.abs().max()) > 0
+    net2 = SegNet("resnet34", classes=1, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=(1.0, 1.0, 0.0))
+    net2.set_weights(W0)
+    tr2 = Trainer(net2, optimizer="Adam", lr=1e-3, augment=AugmentConfig())
+    tr2.set_pool(img, mask)
+    tr2.capture()
+    losses = []
+    for _ in range(8):
+        tr2.step()
+        losses.append(tr2.loss_value())
+    assert abs(losses[0] - l_eager) <= 1e-6 * max(1.0, abs(l_eager)), (losses[0], l_eager)
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    assert bool(torch.isfinite(net2.flat_p).all())
+    assert net2.L.tc_launch_count() > 0

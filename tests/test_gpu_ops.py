@@ -365,7 +365,7 @@ def test_loss_known_answers(stp, cuda):
     assert abs(float(result[lib.L_LOSS])) < 1e-6 and abs(float(result[lib.L_DICE]) - 1.0) < 1e-6
 
 
-@pytest.mark.parametrize("opt", ["adam", "sgd", "rmsprop"])
+@pytest.mark.parametrize("opt", ["adam", "sgd", "rmsprop", "nadam"])
 def test_optimizers(stp, cuda, opt):
     from oracle import optim as OO
     g = torch.Generator().manual_seed(13)
@@ -376,8 +376,11 @@ def test_optimizers(stp, cuda, opt):
         o = OO.Adam(params, lr=1e-3, clipnorm=1.0)
     elif opt == "sgd":
         o = OO.SGD(params, lr=0.01, momentum=0.9, nesterov=True, clipvalue=0.5)
+    elif opt == "nadam":
+        o = OO.Nadam(params, lr=0.002)
     else:
         o = OO.RMSprop(params, lr=1e-3)
+    sched = torch.tensor([1.0, 0, 0, 0, 0], device=cuda)
     p = p0.clone().to(cuda)
     m, v = torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
     d_step = torch.zeros(1, dtype=torch.int64, device=cuda)
@@ -391,6 +394,10 @@ def test_optimizers(stp, cuda, opt):
             gx = lib.GradXform(1.0, 1.0, 0.0, sumsq.data_ptr())
             stp.adam(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-7, C.byref(gx),
                      d_step.data_ptr(), stream())
+        elif opt == "nadam":
+            gx = lib.GradXform(1.0, 0.0, 0.0, None)
+            stp.nadam(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), sched.data_ptr(), n, 0.002, 0.9, 0.999, 1e-7,
+                      0.004, C.byref(gx), d_step.data_ptr(), stream())
         elif opt == "sgd":
             gx = lib.GradXform(1.0, 0.0, 0.5, None)
             stp.sgd(p.data_ptr(), gd.data_ptr(), m.data_ptr(), n, 0.01, 0.9, 1, C.byref(gx), stream())
