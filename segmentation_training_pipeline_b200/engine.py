@@ -548,6 +548,32 @@ class BNRelu(Op):
                        self.res_ref, self.dx.ref, st)
 
 
+class Add(Op):
+    """keras.layers.Add of a decoder branch and an encoder skip (Linknet).  Backward: the branch's gradient buffer IS
+    d(out) (aliased, no kernel); the skip receives d(out) as its first gradient contribution (copy) or accumulates it."""
+
+    def __init__(self, net: Net, a: Buf, skip: Buf, y: Buf):
+        self.net, self.a, self.skip, self.y = net, a, skip, y
+        a.set_grad(y.grad())
+        net.ops.append(self)
+
+    def grad_writes(self):
+        return [self.skip.grad()]
+
+    def prepare(self):
+        self.dy, self.ds = self.y.grad(), self.skip.grad()
+
+    def fwd(self):
+        self.net.L.add(self.a.ref, self.skip.ref, self.y.ref, _stream())
+
+    def bwd(self):
+        L = self.net.L
+        if self.acc[0]:
+            L.add(self.ds.ref, self.dy.ref, self.ds.ref, _stream())
+        else:
+            L.copy_up(self.dy.ref, 1, self.ds.ref, _stream())
+
+
 class UpCopy(Op):
     """UpSampling2D(2) of a post-ReLU tensor straight into (a channel slice of) a concat buffer.  Backward: 2x2 sum of
     the upsampled gradient; positions where the (non-negative) source is exactly 0 receive 0, which the ReLU mask of

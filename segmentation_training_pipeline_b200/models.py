@@ -21,7 +21,7 @@ RESNET_REPS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3), "resnet50": (
 RESNET_BOTTLENECK = {"resnet18": False, "resnet34": False, "resnet50": True, "resnet101": True, "resnet152": True}
 VGG16_BLOCKS = ((64, 2), (128, 2), (256, 3), (512, 3), (512, 3))  # keras.applications.VGG16 [DEP]
 KNOWN_BACKBONES = sorted(RESNET_REPS) + ["vgg16"]
-KNOWN_ARCHITECTURES = ["Unet"]
+KNOWN_ARCHITECTURES = ["Unet", "Linknet"]
 
 
 class SegNet(E.Net):
@@ -29,10 +29,18 @@ class SegNet(E.Net):
 
     def __init__(self, backbone="resnet34", classes=1, input_shape=(512, 512, 3), batch=16,
                  decoder_filters=(256, 128, 64, 32, 16), device="cuda:0", seed=0,
-                 enc_init="he_uniform", dec_init="glorot_uniform", loss=(1.0, 0.0, 0.0)):
+                 enc_init="he_uniform", dec_init="glorot_uniform", loss=(1.0, 0.0, 0.0), architecture="Unet"):
         super().__init__(batch, device, seed)
         backbone = backbone.lower()
+        if architecture not in KNOWN_ARCHITECTURES:
+            print("Unknown architecture:" + str(architecture))
+            print("Known architectures:", KNOWN_ARCHITECTURES)
+            raise ValueError("Unknown architecture")
+        self.architecture = architecture
+        linknet = architecture == "Linknet"
         if backbone == "vgg16":
+            if linknet:
+                raise NotImplementedError("Linknet is built over the ResNet encoders only")
             self._build_vgg16_unet(classes, input_shape, batch, decoder_filters, dec_init, loss)
             return
         if backbone not in RESNET_REPS:
@@ -57,12 +65,15 @@ class SegNet(E.Net):
         skip_c = [256 * exp, 128 * exp, 64 * exp, 64, 0]
         up_c = [512 * exp] + df[:4]
         cat: List[E.Buf] = []
-        for i in range(5):
+        for i in range(0 if linknet else 5):
             s = 32 >> i  # input of stage i is at H/32 * 2^i after upsampling -> H / (16 >> i) ... computed below
             hh, ww = H // (16 >> i) if i < 4 else H, W // (16 >> i) if i < 4 else W
             cat.append(E.Buf(self, N, hh, ww, up_c[i] + skip_c[i], name="cat%d" % i))
         skip_view = {  # keras layer name -> (stage index)
             "stage4_unit1_relu1": 0, "stage3_unit1_relu1": 1, "stage2_unit1_relu1": 2, "relu0": 3}
+        skip_names = list(skip_view)
+        if linknet:       # Linknet adds its skips instead of concatenating them: plain buffers, no concat layout
+            skip_view, cat = {}, []
 
         def skip_buf(name, n, h, w, c):
             if name in skip_view:
@@ -118,11 +129,49 @@ class SegNet(E.Net):
                     E.Conv(self, a2, out, pre + "conv2", 3, pad=1, residual=res, init=enc_init)
                 x, h, w = out, ho, wo
         self.encoder_param_names = list(self.params.keys())
+        if linknet:
+            top = E.Buf(self, N, h, w, x.c, name="relu1")
+            E.BNRelu(self, x, top, "bn1", ENC_BN_EPS)
+            self.encoder_param_names = list(self.params.keys())
+            self._build_linknet_decoder(top, [self.bufs[nm] for nm in skip_names], df, classes, dec_init, loss)
+            return
         # bn1/relu1 written 2x-upsampled straight into the first concat buffer
         E.BNRelu(self, x, cat[0].slice(0, up_c[0], name="relu1_up"), "bn1", ENC_BN_EPS, up=2)
         self.encoder_param_names = list(self.params.keys())
 
         self._build_decoder(cat, df, classes, dec_init, loss)
+
+    def _build_linknet_decoder(self, x, skips, df, classes, dec_init, loss):
+        """segmentation_models 0.2.1 Linknet decoder [DEP] (schema segmentation.raml:205-225): per stage
+        1x1 conv (C/4) + BN + ReLU -> UpSampling2D(2) -> 3x3 conv (C/4) + BN + ReLU -> 1x1 conv (C_skip | 16) + BN + ReLU
+        -> Add(skip); the nearest upsample is the `up=2` write mode of the first BatchNorm-apply."""
+        N = self.batch
+        for i in range(5):
+            pre = "decoder_stage%d_" % i
+            skip = skips[i] if i < len(skips) else None
+            cin = x.c
+            cout = skip.c if skip is not None else (df[i] if df[i] else 16)
+            z1 = E.Buf(self, N, x.h, x.w, cin // 4, name=pre + "conv1")
+            E.Conv(self, x, z1, pre + "conv1", 1, init=dec_init)
+            a1 = E.Buf(self, N, 2 * x.h, 2 * x.w, cin // 4, name=pre + "relu1_up")
+            E.BNRelu(self, z1, a1, pre + "bn1", DEC_BN_EPS, up=2)
+            z2 = E.Buf(self, N, a1.h, a1.w, cin // 4, name=pre + "conv2")
+            E.Conv(self, a1, z2, pre + "conv2", 3, pad=1, init=dec_init)
+            a2 = E.Buf(self, N, a1.h, a1.w, cin // 4, name=pre + "relu2")
+            E.BNRelu(self, z2, a2, pre + "bn2", DEC_BN_EPS)
+            z3 = E.Buf(self, N, a1.h, a1.w, cout, name=pre + "conv3")
+            E.Conv(self, a2, z3, pre + "conv3", 1, init=dec_init)
+            a3 = E.Buf(self, N, a1.h, a1.w, cout, name=pre + "relu3")
+            E.BNRelu(self, z3, a3, pre + "bn3", DEC_BN_EPS)
+            if skip is not None:
+                out = E.Buf(self, N, a1.h, a1.w, cout, name=pre + "add")
+                E.Add(self, a3, skip, out)
+                x = out
+            else:
+                x = a3
+        self.head = E.Head(self, x, classes, "final_conv", init=dec_init)
+        self.loss = E.Loss(self, self.head, self.mask, *loss)
+        self.finalize()
 
     def _build_decoder(self, cat, df, classes, dec_init, loss):
         N = self.batch

@@ -193,6 +193,7 @@ class PipelineConfig:
             raise NotImplementedError("encoder_weights: no network here -- load a local .npz with load_weights()")
         return _models.SegNet(bb, classes=self.classes, input_shape=tuple(self.shape), batch=batch or self.batch,
                               decoder_filters=self.decoder_filters, device=self.device, seed=self.random_state,
+                              architecture=arch,
                               loss=parse_loss(loss or self.loss))
 
     def kfold(self, n: int) -> List[Tuple[np.ndarray, np.ndarray]]:

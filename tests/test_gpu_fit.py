@@ -112,3 +112,22 @@ def test_fit_config0_unet_vgg16(cuda, tmp_path):
         assert len(rows) == 2 and all(np.isfinite(float(r["loss"])) and np.isfinite(float(r["val_loss"])) for r in rows)
     w = cfg.load_model(0, 0).get_weights()
     assert w["block1_conv1/kernel"].shape == (3, 3, 3, 64) and w["block5_conv3/bias"].shape == (512,)
+
+
+def test_fit_linknet_resnet34_cyclic_lr(cuda, tmp_path):
+    """Linknet / ResNet-34 through the YAML surface with the full device augmentation block and a CyclicLR callback."""
+    from segmentation_pipeline import segmentation
+    from segmentation_pipeline.impl.datasets import SimplePNGMaskDataSet
+    _make_dataset(str(tmp_path), n=8, size=64)
+    cfgp = str(tmp_path / "exp" / "config.yaml")
+    os.makedirs(os.path.dirname(cfgp))
+    shutil.copy(os.path.join(HERE, "golden", "configs", "c5_linknet_resnet34.yaml"), cfgp)
+    cfg = segmentation.parse(cfgp)
+    res = cfg.fit(SimplePNGMaskDataSet(str(tmp_path / "img"), str(tmp_path / "mask")))
+    assert len(res) == 2
+    rows = list(csv.DictReader(open(os.path.join(os.path.dirname(cfgp), "metrics", "metrics-0.0.csv"))))
+    assert len(rows) == 2 and all(np.isfinite(float(r["loss"])) for r in rows)
+    lrs = [float(r["lr"]) for r in rows]
+    assert all(0.0005 - 1e-9 <= v <= 0.002 + 1e-9 for v in lrs) and lrs[0] != lrs[1]
+    w = cfg.load_model(0, 0).get_weights()
+    assert "decoder_stage0_conv3/kernel" in w and w["decoder_stage4_conv3/kernel"].shape == (1, 1, 16, 16)
