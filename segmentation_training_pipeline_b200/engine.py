@@ -272,6 +272,8 @@ class Net:
             if p.kind == "conv":  # KRSC(padded) -> Keras HWIO
                 cin = getattr(p, "cin_real", p.shape[3])
                 a = np.transpose(a[..., :cin], (1, 2, 3, 0))
+            elif p.kind == "convT":  # internal [Cout][R][S][Cin], taps flipped -> Keras Conv2DTranspose (kh, kw, Cout, Cin)
+                a = np.transpose(a[:, ::-1, ::-1, :], (1, 2, 0, 3))
             out[p.name] = np.ascontiguousarray(a)
         if with_buffers:
             for k, v in self.buffers.items():
@@ -286,6 +288,8 @@ class Net:
                     raise KeyError(p.name)
                 continue
             a = np.asarray(d[p.name], dtype=np.float32)
+            if p.kind == "convT":
+                a = np.ascontiguousarray(np.transpose(a, (2, 0, 1, 3))[:, ::-1, ::-1, :])
             if p.kind == "conv":
                 a = np.transpose(a, (3, 0, 1, 2))  # HWIO -> KRSC
                 full = np.zeros(p.shape, dtype=np.float32)
@@ -355,7 +359,7 @@ class InputCast(Op):
 class Conv(Op):
     def __init__(self, net: Net, x: Buf, y: Buf, name: str, k: int, stride=1, pad=0, residual: Optional[Buf] = None,
                  bias=False, init="he_uniform", needs_dgrad=True, cin_real: Optional[int] = None,
-                 stem_beta: Optional[Param] = None, up=1, relu=False):
+                 stem_beta: Optional[Param] = None, up=1, relu=False, transposed=False):
         self.net, self.x, self.y, self.name, self.k = net, x, y, name, k
         self.residual, self.needs_dgrad = residual, needs_dgrad
         self.relu = relu  # conv + bias + ReLU in one kernel (VGG encoder, decoder without BatchNorm); y is post-ReLU
@@ -372,7 +376,9 @@ class Conv(Op):
             full[..., :cr] = np.transpose(w, (3, 0, 1, 2))
             return full
 
-        self.w = net.add_param(name + "/kernel", (cout, k, k, cin), "conv", mk)
+        # transposed=True: keras Conv2DTranspose(k, strides=up, 'same') run as a convolution of the zero-inserted input
+        # with the spatially flipped kernel (pad before = k-1-p); the parameter is exported in Keras (kh,kw,Cout,Cin) order
+        self.w = net.add_param(name + "/kernel", (cout, k, k, cin), "convT" if transposed else "conv", mk)
         self.w.cin_real = cr
         self.b = net.add_param(name + "/bias", (cout,), "bias", lambda: np.zeros(cout, np.float32)) if bias else None
         self.stem_beta = stem_beta

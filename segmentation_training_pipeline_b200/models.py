@@ -29,7 +29,8 @@ class SegNet(E.Net):
 
     def __init__(self, backbone="resnet34", classes=1, input_shape=(512, 512, 3), batch=16,
                  decoder_filters=(256, 128, 64, 32, 16), device="cuda:0", seed=0,
-                 enc_init="he_uniform", dec_init="glorot_uniform", loss=(1.0, 0.0, 0.0), architecture="Unet"):
+                 enc_init="he_uniform", dec_init="glorot_uniform", loss=(1.0, 0.0, 0.0), architecture="Unet",
+                 decoder_block_type="upsampling"):
         super().__init__(batch, device, seed)
         backbone = backbone.lower()
         if architecture not in KNOWN_ARCHITECTURES:
@@ -38,6 +39,11 @@ class SegNet(E.Net):
             raise ValueError("Unknown architecture")
         self.architecture = architecture
         linknet = architecture == "Linknet"
+        if decoder_block_type not in ("upsampling", "transpose"):
+            raise ValueError("decoder_block_type must be 'upsampling' or 'transpose'")
+        transpose = decoder_block_type == "transpose" and not linknet   # schema segmentation.raml:162-165 (Unet only)
+        if transpose and backbone == "vgg16":
+            raise NotImplementedError("decoder_block_type: transpose is built over the ResNet encoders only")
         if backbone == "vgg16":
             if linknet:
                 raise NotImplementedError("Linknet is built over the ResNet encoders only")
@@ -63,7 +69,7 @@ class SegNet(E.Net):
 
         # decoder concat buffers [up | skip]; skip channel counts per stage (0.2.1 skip names)
         skip_c = [256 * exp, 128 * exp, 64 * exp, 64, 0]
-        up_c = [512 * exp] + df[:4]
+        up_c = df[:] if transpose else [512 * exp] + df[:4]   # transpose blocks concat [ConvT output (f_i) | skip]
         cat: List[E.Buf] = []
         for i in range(0 if linknet else 5):
             s = 32 >> i  # input of stage i is at H/32 * 2^i after upsampling -> H / (16 >> i) ... computed below
@@ -129,17 +135,39 @@ class SegNet(E.Net):
                     E.Conv(self, a2, out, pre + "conv2", 3, pad=1, residual=res, init=enc_init)
                 x, h, w = out, ho, wo
         self.encoder_param_names = list(self.params.keys())
-        if linknet:
+        if linknet or transpose:
             top = E.Buf(self, N, h, w, x.c, name="relu1")
             E.BNRelu(self, x, top, "bn1", ENC_BN_EPS)
             self.encoder_param_names = list(self.params.keys())
-            self._build_linknet_decoder(top, [self.bufs[nm] for nm in skip_names], df, classes, dec_init, loss)
+            if linknet:
+                self._build_linknet_decoder(top, [self.bufs[nm] for nm in skip_names], df, classes, dec_init, loss)
+            else:
+                self._build_transpose_decoder(top, cat, df, classes, dec_init, loss)
             return
         # bn1/relu1 written 2x-upsampled straight into the first concat buffer
         E.BNRelu(self, x, cat[0].slice(0, up_c[0], name="relu1_up"), "bn1", ENC_BN_EPS, up=2)
         self.encoder_param_names = list(self.params.keys())
 
         self._build_decoder(cat, df, classes, dec_init, loss)
+
+    def _build_transpose_decoder(self, x, cat, df, classes, dec_init, loss):
+        """Unet `decoder_block_type: transpose` (segmentation.raml:162-165) [DEP segmentation_models 0.2.1]:
+        Conv2DTranspose(f, 4x4, strides 2, 'same') + BN + ReLU -> Concatenate(skip) -> 3x3 conv + BN + ReLU.  The
+        transposed conv runs as a convolution of the zero-inserted input with the flipped kernel (engine.Conv up=2)."""
+        N = self.batch
+        for i, f in enumerate(df):
+            pre = "decoder_stage%d_" % i
+            z = E.Buf(self, N, 2 * x.h, 2 * x.w, f, name=pre + "transpose")
+            E.Conv(self, x, z, pre + "transpose", 4, pad=2, up=2, transposed=True, init=dec_init)
+            E.BNRelu(self, z, cat[i].slice(0, f, name=pre + "relu1"), pre + "bn1", DEC_BN_EPS)
+            z2 = E.Buf(self, N, z.h, z.w, f, name=pre + "conv2")
+            E.Conv(self, cat[i], z2, pre + "conv2", 3, pad=1, init=dec_init)
+            a2 = E.Buf(self, N, z.h, z.w, f, name=pre + "relu2")
+            E.BNRelu(self, z2, a2, pre + "bn2", DEC_BN_EPS)
+            x = a2
+        self.head = E.Head(self, x, classes, "final_conv", init=dec_init)
+        self.loss = E.Loss(self, self.head, self.mask, *loss)
+        self.finalize()
 
     def _build_linknet_decoder(self, x, skips, df, classes, dec_init, loss):
         """segmentation_models 0.2.1 Linknet decoder [DEP] (schema segmentation.raml:205-225): per stage

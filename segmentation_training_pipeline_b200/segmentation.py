@@ -156,6 +156,7 @@ class PipelineConfig:
         self.random_state = int(atrs.pop("random_state", 33))
         self.testSplit = float(atrs.pop("testSplit", 0.0) or 0.0)
         self.decoder_filters = tuple(atrs.pop("decoder_filters", (256, 128, 64, 32, 16)))
+        self.decoder_block_type = atrs.pop("decoder_block_type", "upsampling")   # segmentation.raml:162-165
         self.callbacks = atrs.pop("callbacks", None)
         self.datasets = atrs.pop("datasets", None)
         self.fit_with = atrs.pop("fit_with", None)
@@ -193,7 +194,7 @@ class PipelineConfig:
             raise NotImplementedError("encoder_weights: no network here -- load a local .npz with load_weights()")
         return _models.SegNet(bb, classes=self.classes, input_shape=tuple(self.shape), batch=batch or self.batch,
                               decoder_filters=self.decoder_filters, device=self.device, seed=self.random_state,
-                              architecture=arch,
+                              architecture=arch, decoder_block_type=getattr(self, "decoder_block_type", None) or "upsampling",
                               loss=parse_loss(loss or self.loss))
 
     def kfold(self, n: int) -> List[Tuple[np.ndarray, np.ndarray]]:

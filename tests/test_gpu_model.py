@@ -32,7 +32,7 @@ def _perturb(weights, seed=1):
     return out
 
 
-@pytest.mark.parametrize("arch", ["Unet", "Linknet"])
+@pytest.mark.parametrize("arch", ["Unet", "Linknet", "Unet-transpose"])
 @pytest.mark.parametrize("backbone,size,loss", [("resnet18", 64, (1.0, 1.0, 0.0)), ("resnet34", 64, (1.0, 1.0, 0.0)),
                                                 ("resnet50", 64, (1.0, 0.0, 0.0)), ("vgg16", 64, (1.0, 1.0, 0.0)),
                                                 ("resnet18", 64, (0.0, 0.0, 0.0, 1.0))])
@@ -44,11 +44,17 @@ def test_forward_backward_parity(cuda, backbone, size, loss, arch):
     from segmentation_training_pipeline_b200.trainer import Trainer
 
     n = 2
+    block = "upsampling"
+    if arch == "Unet-transpose":
+        arch, block = "Unet", "transpose"
+        if backbone != "resnet18" or len(loss) == 4:
+            pytest.skip("the transposed-conv decoder parity is run on ResNet-18")
     if arch == "Linknet" and (backbone in ("vgg16", "resnet50") or len(loss) == 4):
         pytest.skip("Linknet parity is run on the basic-block ResNets")
     if arch == "Linknet":
         size = 128  # at 64x64 the deepest BatchNorm sees 2x2x2 samples per channel: pure rounding-noise amplification
-    net = SegNet(backbone, classes=1, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=loss, architecture=arch)
+    net = SegNet(backbone, classes=1, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=loss, architecture=arch,
+                 decoder_block_type=block)
     W = _perturb(net.get_weights())
     net.set_weights(W)
     tr = Trainer(net)
@@ -66,7 +72,8 @@ def test_forward_backward_parity(cuda, backbone, size, loss, arch):
     # pre-activation ResNets amplify one-ulp bf16 differences layer by layer, so the engine is held to the NOISE
     # FLOOR of bf16 storage itself: it must be at least as close to the bf16 oracle as that oracle is to fp32.
     def run(storage):
-        om = SegModel(arch, backbone, classes=1, input_shape=(size, size, 3), storage=storage, update_moving=False)
+        om = SegModel(arch, backbone, classes=1, input_shape=(size, size, 3), storage=storage, update_moving=False,
+                      decoder_block_type=block)
         assert set(om.params.keys()) == set(net.params.keys()), sorted(set(om.params.keys()) ^ set(net.params.keys()))
         om.load_numpy(W)
         t = mask.float()
