@@ -1,0 +1,142 @@
+"""Forward-only inference behind the reference's prediction verbs (reference segmentation.py:62-91
+predict_to_directory / predict_in_directory, :158-191 evaluateAll; README.md:493-534): images of a directory are resized
+to `shape`, run through the engine graph in inference mode (moving BatchNorm statistics), optionally averaged over the four
+flip variants (`ttflips`) and over several folds (`fold` may be a list: ensembling), thresholded at 0.5 and scaled back to
+the original size with nearest-neighbour sampling (imgaug Scale on segmentation maps)."""
+from __future__ import annotations
+
+import os
+from typing import Callable, Iterator, List, Optional, Sequence, Union
+
+import numpy as np
+
+IMG_EXT = (".jpg", ".jpeg", ".png", ".bmp")
+
+
+class PredictionBatch:
+    """What the reference yields per batch (an imgaug.Batch): ids, original images, probability maps and binary
+    segmentation maps at network resolution."""
+
+    def __init__(self, data, images, probs, shape):
+        self.data, self.images, self.probabilities = data, images, probs
+        self.segmentation_maps_aug = [(p > 0.5).astype(np.uint8) for p in probs]
+        self.shape = shape
+
+
+def _sigmoid(z):
+    return 1.0 / (1.0 + np.exp(-z))
+
+
+def predict_arrays(net, images_u8: np.ndarray, ttflips=False) -> np.ndarray:
+    """uint8 [n, H, W, 3] at network resolution -> float32 probabilities [n, H, W, classes]; n <= net.batch."""
+    import torch
+    n = images_u8.shape[0]
+    B = net.batch
+    H, W, CI = net.input_shape
+    assert n <= B and images_u8.shape[1:] == (H, W, CI), (images_u8.shape, net.input_shape, B)
+    variants = [(False, False)] + ([(True, False), (False, True), (True, True)] if ttflips else [])
+    acc = np.zeros((n, H, W, net.classes), np.float32)
+    was_training = net.training
+    net.training = False
+    try:
+        for fl, fu in variants:
+            x = images_u8
+            if fl:
+                x = x[:, :, ::-1]
+            if fu:
+                x = x[:, ::-1]
+            batch = np.zeros((B, H, W, CI), np.uint8)
+            batch[:n] = x
+            net.img.storage.copy_(torch.from_numpy(batch).reshape(-1).to(net.device))
+            net.prep_weights()
+            enabled, net.loss.enabled = net.loss.enabled, False
+            net.forward()
+            net.loss.enabled = enabled
+            p = _sigmoid(net.head.logits.detach().cpu().numpy().reshape(B, H, W, net.classes)[:n])
+            if fl:
+                p = p[:, :, ::-1]
+            if fu:
+                p = p[:, ::-1]
+            acc += p
+    finally:
+        net.training = was_training
+    return acc / len(variants)
+
+
+def _list_images(spath) -> List[str]:
+    return sorted(f for f in os.listdir(spath) if f.lower().endswith(IMG_EXT))
+
+
+def predict_on_directory(cfg, spath, fold: Union[int, Sequence[int]] = 0, stage=0, limit=-1, batch_size=32,
+                         ttflips=False) -> Iterator[PredictionBatch]:
+    import cv2
+    folds = list(fold) if isinstance(fold, (list, tuple)) else [fold]
+    nets = [cfg.load_model(f, stage) for f in folds]
+    B = min(int(batch_size), nets[0].batch)
+    H, W = int(cfg.shape[0]), int(cfg.shape[1])
+    names = _list_images(spath)
+    if limit is not None and limit > 0:
+        names = names[:limit]
+    for s in range(0, len(names), B):
+        ids = names[s:s + B]
+        origs, xs = [], []
+        for nm in ids:
+            img = cv2.cvtColor(cv2.imread(os.path.join(spath, nm), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+            origs.append(img)
+            xs.append(cv2.resize(img, (W, H), interpolation=cv2.INTER_CUBIC) if img.shape[:2] != (H, W) else img)
+        x = np.stack(xs).astype(np.uint8)
+        probs = sum(predict_arrays(net, x, ttflips) for net in nets) / len(nets)   # fold ensembling: mean probability
+        yield PredictionBatch(ids, origs, list(probs), (H, W))
+
+
+def _scale_back(seg: np.ndarray, orig) -> np.ndarray:
+    import cv2
+    h, w = orig.shape[:2]
+    if seg.shape[:2] == (h, w):
+        return seg
+    out = cv2.resize(seg, (w, h), interpolation=cv2.INTER_NEAREST)
+    return out[:, :, None] if out.ndim == 2 else out
+
+
+def predict_to_directory(cfg, spath, tpath, fold=0, stage=0, limit=-1, batchSize=32, binaryArray=False, ttflips=False):
+    import cv2
+    os.makedirs(tpath, exist_ok=True)
+    n = 0
+    for b in predict_on_directory(cfg, spath, fold, stage, limit, batchSize, ttflips):
+        for i, id_ in enumerate(b.data):
+            m = _scale_back(b.segmentation_maps_aug[i], b.images[i])
+            stem = id_[0:id_.index(".")]
+            if binaryArray:
+                np.save(os.path.join(tpath, stem), m)
+            else:
+                cv2.imwrite(os.path.join(tpath, stem + ".png"), (m[:, :, 0] * 255).astype(np.uint8))
+            n += 1
+    return n
+
+
+def predict_in_directory(cfg, spath, fold, stage, cb: Callable, data, limit=-1, batchSize=32, ttflips=False):
+    for b in predict_on_directory(cfg, spath, fold, stage, limit, batchSize, ttflips):
+        for i, id_ in enumerate(b.data):
+            cb(id_, _scale_back(b.segmentation_maps_aug[i], b.images[i]), data)
+
+
+def evaluate_all(cfg, ds, fold=None, stage=-1, negatives="real", ttflips=None, batchSize=32) -> Iterator[PredictionBatch]:
+    """Predictions for every item of a dataset (reference evaluateAll, segmentation.py:158-191): yields batches whose
+    `.data` are the PredictionItems and whose `.results` are the binary maps scaled back to each item's size."""
+    import cv2
+    folds = list(range(cfg.folds_count)) if fold is None else (list(fold) if isinstance(fold, (list, tuple)) else [fold])
+    nets = [cfg.load_model(f, stage) for f in folds]
+    B = min(int(batchSize), nets[0].batch)
+    H, W = int(cfg.shape[0]), int(cfg.shape[1])
+    idx = list(range(len(ds)))
+    if negatives == "none" and hasattr(ds, "isPositive"):
+        idx = [i for i in idx if ds.isPositive(i)]
+    for s in range(0, len(idx), B):
+        items = [ds[i] for i in idx[s:s + B]]
+        xs = [cv2.resize(np.asarray(it.x), (W, H), interpolation=cv2.INTER_CUBIC) if np.asarray(it.x).shape[:2] != (H, W)
+              else np.asarray(it.x) for it in items]
+        x = np.stack(xs).astype(np.uint8)
+        probs = sum(predict_arrays(net, x, bool(ttflips)) for net in nets) / len(nets)
+        b = PredictionBatch(items, [np.asarray(it.x) for it in items], list(probs), (H, W))
+        b.results = [_scale_back(m, np.asarray(it.x)) for m, it in zip(b.segmentation_maps_aug, items)]
+        yield b

@@ -232,6 +232,23 @@ class PipelineConfig:
         net.set_weights(w)
         return net
 
+    # -- inference verbs (reference segmentation.py:62-91, 158-191; README.md:493-534) ------------------------------
+    def predict_on_directory(self, spath, fold=0, stage=0, limit=-1, batch_size=32, ttflips=False):
+        from . import predict as _p
+        return _p.predict_on_directory(self, spath, fold, stage, limit, batch_size, ttflips)
+
+    def predict_to_directory(self, spath, tpath, fold=0, stage=0, limit=-1, batchSize=32, binaryArray=False, ttflips=False):
+        from . import predict as _p
+        return _p.predict_to_directory(self, spath, tpath, fold, stage, limit, batchSize, binaryArray, ttflips)
+
+    def predict_in_directory(self, spath, fold, stage, cb, data, limit=-1, batchSize=32, ttflips=False):
+        from . import predict as _p
+        return _p.predict_in_directory(self, spath, fold, stage, cb, data, limit, batchSize, ttflips)
+
+    def evaluateAll(self, ds, fold=None, stage=-1, negatives="real", ttflips=None, batchSize=32):
+        from . import predict as _p
+        return _p.evaluate_all(self, ds, fold, stage, negatives, ttflips, batchSize)
+
     def info(self):
         """aggregated best metric per fold/stage from metrics/*.csv (reference FAQ.md:63-70)."""
         out = []

@@ -183,3 +183,21 @@ def test_callbacks_known_answers():
     assert [type(c).__name__ for c in CB.build({"EarlyStopping": {"patience": 3}}, {"CyclicLR": None})] == ["EarlyStopping", "CyclicLR"]
     with pytest.raises(NotImplementedError):
         CB.build({"LRVariator": {}})
+
+
+def test_rle_known_answers_and_round_trip():
+    """Kaggle column-major RLE (reference impl/rle.py:10-35): 1-based starts, top-to-bottom then left-to-right."""
+    from segmentation_pipeline.impl.rle import masks_as_image, multi_rle_encode, rle_decode, rle_encode
+    m = np.zeros((4, 3), np.uint8)
+    m[0:3, 0] = 1          # pixels 1..3 (first column)
+    m[1:3, 2] = 1          # third column: pixels 10, 11
+    assert rle_encode(m) == "1 3 10 2"
+    assert np.array_equal(rle_decode("1 3 10 2", (4, 3)), m)
+    rng = np.random.default_rng(0)
+    for shape in ((1, 1), (5, 7), (64, 48)):
+        a = (rng.random(shape) > 0.6).astype(np.uint8)
+        assert np.array_equal(rle_decode(rle_encode(a), shape), a)
+    assert rle_encode(np.zeros((3, 3), np.uint8)) == "" and rle_decode("", (3, 3)).sum() == 0
+    parts = multi_rle_encode(m[:, :, None])
+    assert sorted(parts) == ["1 3", "10 2"]
+    assert np.array_equal(masks_as_image(parts, (4, 3))[:, :, 0], m)

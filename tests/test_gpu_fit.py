@@ -53,6 +53,28 @@ def test_fit_writes_reference_artifacts(cuda, tmp_path):
     net = cfg.load_model(0, 1)
     assert net.get_weights()["conv0/kernel"].shape == (7, 7, 3, 64)
     assert len(cfg.info()) == 4
+    # ---- inference verbs on the trained folds (reference segmentation.py:62-91): flip-TTA, fold ensembling, scale back
+    import cv2
+    big = str(tmp_path / "big")
+    os.makedirs(big)
+    src = cv2.imread(str(tmp_path / "img" / "00.png"))
+    cv2.imwrite(os.path.join(big, "a.png"), cv2.resize(src, (96, 80)))          # not the network resolution
+    cv2.imwrite(os.path.join(big, "b.png"), src)
+    out = str(tmp_path / "pred")
+    assert cfg.predict_to_directory(big, out, fold=[0, 1], stage=1, ttflips=True) == 2
+    pa, pb = cv2.imread(os.path.join(out, "a.png"), cv2.IMREAD_GRAYSCALE), cv2.imread(os.path.join(out, "b.png"), cv2.IMREAD_GRAYSCALE)
+    assert pa.shape == (80, 96) and pb.shape == (64, 64) and set(np.unique(pa)) <= {0, 255}
+    seen = {}
+    cfg.predict_in_directory(big, 0, 1, lambda id_, m, data: data.__setitem__(id_, m.shape), seen, ttflips=False)
+    assert seen == {"a.png": (80, 96, 1), "b.png": (64, 64, 1)}
+    # ttflips is an average over flips: a horizontally flipped image gives the flipped prediction
+    from segmentation_training_pipeline_b200.predict import predict_arrays
+    x = np.stack([cv2.cvtColor(src, cv2.COLOR_BGR2RGB)] * 2)
+    p0 = predict_arrays(net, x, ttflips=True)
+    p1 = predict_arrays(net, x[:, :, ::-1], ttflips=True)
+    assert np.allclose(p0, p1[:, :, ::-1], atol=2e-3)
+    batches = list(cfg.evaluateAll(ds, fold=0, stage=1))
+    assert sum(len(b.data) for b in batches) == len(ds) and batches[0].results[0].shape == (64, 64, 1)
 
 
 def test_lovasz_step_in_cuda_graph(cuda):
