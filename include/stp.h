@@ -250,6 +250,18 @@ int stp_maxpool_bwd(const stp_tensor* dy, const uint8_t* argmax, int32_t k, int3
 int stp_copy_up(const stp_tensor* x, int32_t up, const stp_tensor* y, stp_stream stream);
 /* y = a + b (Add layer; Linknet / FPN) */
 int stp_add(const stp_tensor* a, const stp_tensor* b, const stp_tensor* y, stp_stream stream);
+/* gradient of UpSampling2D(2, nearest) for a tensor that is NOT post-ReLU (the FPN top-down pathway, where the upsampled
+ * tensor is a linear 1x1-conv output): dx = 2x2 sum of dy [+ residual] */
+int stp_upsample2x_bwd(const stp_tensor* dy, const stp_tensor* residual, const stp_tensor* dx, stp_stream stream);
+
+/* K8b bilinear resize -- replaces keras UpSampling2D(interpolation='bilinear') -> tf.image.resize_bilinear (TF1 legacy:
+ * src = dst*in/out, no half-pixel offset, align_corners=False) in the FPN decoder built by segmentation_models.FPN
+ * (reference segmentation.py:109-113; schema segmentation.raml:179-204).  fwd: bf16 -> bf16 (equal channel counts; y may
+ * be a channel slice of a concat buffer) or f32 -> f32 (the first y.c channels of x: padded head logits -> dense
+ * [pixels][classes]).  bwd (up-scaling only, deterministic gather): bf16 dy -> bf16 dx [+ residual], or f32 dy ->
+ * bf16 dx whose channels >= dy.c are written as zero. */
+int stp_resize_bilinear_fwd(const stp_tensor* x, const stp_tensor* y, stp_stream stream);
+int stp_resize_bilinear_bwd(const stp_tensor* dy, const stp_tensor* residual, const stp_tensor* dx, stp_stream stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K11/K14  loss + metrics -- replaces keras binary_crossentropy, musket_core.losses.{dice,iou,...}
@@ -279,6 +291,13 @@ size_t stp_lovasz_workspace(int32_t images, int64_t pixels_per_image);
 int stp_lovasz_fwd(const float* logits, const uint8_t* mask, int32_t images, int64_t pixels_per_image, int32_t act_elu,
                    float weight, int32_t accumulate, void* workspace, size_t workspace_bytes, float* result16,
                    stp_stream stream);
+/* `classes` > 1: logits / mask are [image][pixel][class]; one hinge per (image, class), mean over all of them (the
+ * reference's K.squeeze(...,-1) is undefined for classes > 1 -- SURVEY.md 8 a-6 -- this is the definition the oracle
+ * uses).  Size the workspace with stp_lovasz_workspace(images*classes, pixels_per_image) and call stp_lovasz_bwd with
+ * images*classes. */
+int stp_lovasz_fwd_mc(const float* logits, const uint8_t* mask, int32_t images, int64_t pixels_per_image, int32_t classes,
+                      int32_t act_elu, float weight, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                      float* result16, stp_stream stream);
 int stp_lovasz_bwd(const void* workspace, size_t workspace_bytes, int32_t images, int64_t pixels_per_image, float weight,
                    int32_t accumulate, float* dlogits, stp_stream stream);
 

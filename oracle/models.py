@@ -202,10 +202,9 @@ class SegModel:
         p = None
         pyramid = []
         for i, c in enumerate(feats):
-            lat = self._conv(c, "pyramid_stage_%d_conv1x1" % i, 1, self.pyr, bias=True)
-            if p is not None:
-                lat = L.rb(L.upsample_nearest(p, 2) + lat, self.storage)
-            p = lat
+            # Add(UpSampling2D(2)(previous level), lateral): one rounding of the sum (the engine adds in the conv epilogue)
+            p = self._conv(c, "pyramid_stage_%d_conv1x1" % i, 1, self.pyr, bias=True,
+                           residual=L.upsample_nearest(p, 2) if p is not None else None)
             pyramid.append(p)
         outs = []
         rates = (8, 4, 2, 1)

@@ -149,9 +149,12 @@ def resize_bilinear_tf1(x, out_h, out_w, align_corners=False):
 
     ylo, yhi, wy = axis(H, out_h)
     xlo, xhi, wx = axis(W, out_w)
-    top = x[:, :, ylo][:, :, :, xlo] * (1 - wx) + x[:, :, ylo][:, :, :, xhi] * wx
-    bot = x[:, :, yhi][:, :, :, xlo] * (1 - wx) + x[:, :, yhi][:, :, :, xhi] * wx
-    return top * (1 - wy).view(1, 1, -1, 1) + bot * wy.view(1, 1, -1, 1)
+    # TF's compute_lerp (resize_bilinear_op.cc): top = tl + (tr - tl)*x_lerp; out = top + (bottom - top)*y_lerp
+    tl, tr = x[:, :, ylo][:, :, :, xlo], x[:, :, ylo][:, :, :, xhi]
+    bl, br = x[:, :, yhi][:, :, :, xlo], x[:, :, yhi][:, :, :, xhi]
+    top = tl + (tr - tl) * wx
+    bot = bl + (br - bl) * wx
+    return top + (bot - top) * wy.view(1, 1, -1, 1)
 
 
 # ----------------------------------------------------------------------------------------------

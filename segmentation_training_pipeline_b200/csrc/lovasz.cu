@@ -24,12 +24,14 @@ __device__ __forceinline__ uint32_t float_desc_key(float f) {
 }
 
 __global__ void __launch_bounds__(256) lovasz_keys_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ mask,
-                                                          int64_t total, int64_t per_img, uint64_t* __restrict__ keys,
-                                                          uint32_t* __restrict__ vals) {
+                                                          int64_t total, int64_t per_img, int classes,
+                                                          uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  // element i of the [image][pixel][class] tensor belongs to sort group image*classes + class (classes == 1: the image)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const float sign = mask[i] ? 1.f : -1.f;
     const float e = 1.f - logits[i] * sign;
-    keys[i] = ((uint64_t)(i / per_img) << 32) | float_desc_key(e);
+    const int64_t group = classes == 1 ? i / per_img : (i / (per_img * classes)) * classes + i % classes;
+    keys[i] = ((uint64_t)group << 32) | float_desc_key(e);
     vals[i] = (uint32_t)i;
   }
 }
@@ -143,7 +145,16 @@ extern "C" size_t stp_lovasz_workspace(int32_t images, int64_t pixels_per_image)
 extern "C" int stp_lovasz_fwd(const float* logits, const uint8_t* mask, int32_t images, int64_t pixels_per_image,
                               int32_t act_elu, float weight, int32_t accumulate, void* workspace, size_t workspace_bytes,
                               float* result16, stp_stream stream) {
-  STP_REQUIRE(logits && mask && workspace && result16 && images > 0 && pixels_per_image > 0, "lovasz_fwd: bad args");
+  return stp_lovasz_fwd_mc(logits, mask, images, pixels_per_image, 1, act_elu, weight, accumulate, workspace, workspace_bytes,
+                           result16, stream);
+}
+
+extern "C" int stp_lovasz_fwd_mc(const float* logits, const uint8_t* mask, int32_t n_images, int64_t pixels_per_image,
+                                 int32_t classes, int32_t act_elu, float weight, int32_t accumulate, void* workspace,
+                                 size_t workspace_bytes, float* result16, stp_stream stream) {
+  STP_REQUIRE(logits && mask && workspace && result16 && n_images > 0 && pixels_per_image > 0 && classes >= 1,
+              "lovasz_fwd: bad args");
+  const int32_t images = n_images * classes;  // sort groups: one hinge per (image, class)
   const int64_t total = (int64_t)images * pixels_per_image;
   STP_REQUIRE(total < 0x7fffffff, "lovasz_fwd: too many elements");
   LovLayout l = lov_layout(total);
@@ -162,7 +173,7 @@ extern "C" int stp_lovasz_fwd(const float* logits, const uint8_t* mask, int32_t 
   float* gs = (float*)(w + l.gs);
   float* partial = (float*)(w + l.partial);
   const int grid = (int)((total + 255) / 256 < kLovBlocks ? (total + 255) / 256 : kLovBlocks);
-  lovasz_keys_kernel<<<grid, 256, 0, st>>>(logits, mask, total, pixels_per_image, keys_a, vals_a);
+  lovasz_keys_kernel<<<grid, 256, 0, st>>>(logits, mask, total, pixels_per_image, classes, keys_a, vals_a);
   int rc = check_launch("lovasz_keys");
   if (rc) return rc;
   int img_bits = 1;

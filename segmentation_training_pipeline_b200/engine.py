@@ -271,7 +271,9 @@ class Net:
             a = host[p.offset:p.offset + p.size].reshape(p.shape)
             if p.kind == "conv":  # KRSC(padded) -> Keras HWIO
                 cin = getattr(p, "cin_real", p.shape[3])
-                a = np.transpose(a[..., :cin], (1, 2, 3, 0))
+                a = np.transpose(a[:getattr(p, "cout_real", p.shape[0]), ..., :cin], (1, 2, 3, 0))
+            elif p.kind == "bias":
+                a = a[:getattr(p, "cout_real", p.shape[0])]
             elif p.kind == "convT":  # internal [Cout][R][S][Cin], taps flipped -> Keras Conv2DTranspose (kh, kw, Cout, Cin)
                 a = np.transpose(a[:, ::-1, ::-1, :], (1, 2, 0, 3))
             out[p.name] = np.ascontiguousarray(a)
@@ -293,8 +295,10 @@ class Net:
             if p.kind == "conv":
                 a = np.transpose(a, (3, 0, 1, 2))  # HWIO -> KRSC
                 full = np.zeros(p.shape, dtype=np.float32)
-                full[..., :a.shape[3]] = a
+                full[:a.shape[0], ..., :a.shape[3]] = a
                 a = full
+            elif p.kind == "bias" and a.shape[0] < p.shape[0]:
+                a = np.concatenate([a, np.zeros(p.shape[0] - a.shape[0], np.float32)])
             host[p.offset:p.offset + p.size] = a.reshape(-1)
         self.flat_p.copy_(torch.from_numpy(host))
         for k, v in self.buffers.items():
@@ -359,28 +363,32 @@ class InputCast(Op):
 class Conv(Op):
     def __init__(self, net: Net, x: Buf, y: Buf, name: str, k: int, stride=1, pad=0, residual: Optional[Buf] = None,
                  bias=False, init="he_uniform", needs_dgrad=True, cin_real: Optional[int] = None,
-                 stem_beta: Optional[Param] = None, up=1, relu=False, transposed=False):
+                 stem_beta: Optional[Param] = None, up=1, relu=False, transposed=False, cout_real: Optional[int] = None):
         self.net, self.x, self.y, self.name, self.k = net, x, y, name, k
         self.residual, self.needs_dgrad = residual, needs_dgrad
         self.relu = relu  # conv + bias + ReLU in one kernel (VGG encoder, decoder without BatchNorm); y is post-ReLU
         self.desc = _lib.ConvDesc(k, k, stride, pad, pad, up, _lib.CONV_RELU if relu else 0)
         cin, cout = x.c, y.c
         cr = cin_real or cin
-        fan_in, fan_out = k * k * cr, k * k * cout
+        co_r = cout_real or cout  # output channels beyond cout_real are padding: zero weights, zero gradients
+        fan_in, fan_out = k * k * cr, k * k * co_r
         lim = math.sqrt(6.0 / fan_in) if init == "he_uniform" else math.sqrt(6.0 / (fan_in + fan_out))
 
         def mk():
             # draw in Keras (kh,kw,Cin,Cout) order so the stream matches a Keras-layout initialiser, then -> KRSC
-            w = net.gen.uniform(-lim, lim, size=(k, k, cr, cout)).astype(np.float32)
+            w = net.gen.uniform(-lim, lim, size=(k, k, cr, co_r)).astype(np.float32)
             full = np.zeros((cout, k, k, cin), np.float32)
-            full[..., :cr] = np.transpose(w, (3, 0, 1, 2))
+            full[:co_r, ..., :cr] = np.transpose(w, (3, 0, 1, 2))
             return full
 
         # transposed=True: keras Conv2DTranspose(k, strides=up, 'same') run as a convolution of the zero-inserted input
         # with the spatially flipped kernel (pad before = k-1-p); the parameter is exported in Keras (kh,kw,Cout,Cin) order
         self.w = net.add_param(name + "/kernel", (cout, k, k, cin), "convT" if transposed else "conv", mk)
         self.w.cin_real = cr
+        self.w.cout_real = co_r
         self.b = net.add_param(name + "/bias", (cout,), "bias", lambda: np.zeros(cout, np.float32)) if bias else None
+        if self.b is not None:
+            self.b.cout_real = co_r
         self.stem_beta = stem_beta
         self.cin_real = cr
         self.bn_next: Optional["BNRelu"] = None
@@ -604,6 +612,51 @@ class UpCopy(Op):
         self.net.L.relu_bwd(self.dy.ref, self.x.ref, 2, None, self.dx.ref, _stream())
 
 
+class Upsample2x(Op):
+    """UpSampling2D(2, nearest) of a LINEAR tensor (the FPN top-down pathway upsamples 1x1-conv outputs, so the ReLU mask
+    UpCopy applies in its backward would be wrong).  Backward: 2x2 sum of the gradient, accumulated into dx when another
+    consumer of x already wrote it."""
+
+    def __init__(self, net: Net, x: Buf, y: Buf):
+        self.net, self.x, self.y = net, x, y
+        net.ops.append(self)
+
+    def grad_writes(self):
+        return [self.x.grad()]
+
+    def prepare(self):
+        self.dy, self.dx = self.y.grad(), self.x.grad()
+        self.res_ref = self.dx.ref if self.acc[0] else None
+
+    def fwd(self):
+        self.net.L.copy_up(self.x.ref, 2, self.y.ref, _stream())
+
+    def bwd(self):
+        self.net.L.upsample2x_bwd(self.dy.ref, self.res_ref, self.dx.ref, _stream())
+
+
+class Resize(Op):
+    """keras UpSampling2D(rate, interpolation='bilinear') == TF1 legacy tf.image.resize_bilinear (FPN segmentation branches);
+    y is typically a channel slice of the concat buffer.  Backward: deterministic gather."""
+
+    def __init__(self, net: Net, x: Buf, y: Buf):
+        self.net, self.x, self.y = net, x, y
+        net.ops.append(self)
+
+    def grad_writes(self):
+        return [self.x.grad()]
+
+    def prepare(self):
+        self.dy, self.dx = self.y.grad(), self.x.grad()
+        self.res_ref = self.dx.ref if self.acc[0] else None
+
+    def fwd(self):
+        self.net.L.resize_bilinear_fwd(self.x.ref, self.y.ref, _stream())
+
+    def bwd(self):
+        self.net.L.resize_bilinear_bwd(self.dy.ref, self.res_ref, self.dx.ref, _stream())
+
+
 class MaxPool(Op):
     def __init__(self, net: Net, x: Buf, y: Buf, k, stride, pad):
         self.net, self.x, self.y, self.k, self.stride, self.pad = net, x, y, k, stride, pad
@@ -642,6 +695,7 @@ class Head(Op):
         self.b = net.add_param(name + "/bias", (classes,), "bias", lambda: np.zeros(classes, np.float32))
         self.logits = torch.zeros(x.rows * classes, dtype=torch.float32, device=net.device)
         self.dlogits = torch.zeros(x.rows * classes, dtype=torch.float32, device=net.device)
+        self.out_n, self.out_hw = x.n, x.h * x.w  # geometry of the logits the loss sees
         net.need_ws(net.L.head_bwd_workspace(x.ref, classes))
         net.need_ws(net.L.head_fwd_workspace(x.ref, classes))
         net.ops.append(self)
@@ -665,6 +719,37 @@ class Head(Op):
                      n.pg(self.b), n.ws.data_ptr(), n.ws.numel(), _stream())
 
 
+class UpHead(Conv):
+    """FPN head: Conv2D(classes, 3x3, same, bias) on the merged pyramid at H/4, then the x4 bilinear `last_upsample`
+    (schema segmentation.raml:179-204) -> logits f32 [N*H*W, classes] for the loss / predict kernels.  The conv runs on
+    the tensor-core conv path with the class dimension padded to 16 output channels (zero weights, zero gradients) and
+    fp32 output; the gradient of the small logits is materialised as bf16 like every other activation gradient."""
+
+    CPAD = 16
+
+    def __init__(self, net: Net, x: Buf, classes: int, name="head_conv", up=4, init="glorot_uniform"):
+        if classes > self.CPAD:
+            raise NotImplementedError("UpHead: classes <= %d" % self.CPAD)
+        small = Buf(net, x.n, x.h, x.w, self.CPAD, F32, name=name + "_out")
+        small.set_grad(Buf(net, x.n, x.h, x.w, self.CPAD, BF16, name="d_" + name + "_out"))
+        super().__init__(net, x, small, name, 3, pad=1, bias=True, init=init, cout_real=classes)
+        self.classes, self.small = classes, small
+        H, W = x.h * up, x.w * up
+        self.out_n, self.out_hw = x.n, H * W
+        self.logits = torch.zeros(x.n * H * W * classes, dtype=torch.float32, device=net.device)
+        self.dlogits = torch.zeros(x.n * H * W * classes, dtype=torch.float32, device=net.device)
+        self._lg = _lib.Tensor(self.logits.data_ptr(), x.n, H, W, classes, classes, F32)
+        self._dlg = _lib.Tensor(self.dlogits.data_ptr(), x.n, H, W, classes, classes, F32)
+
+    def fwd(self):
+        super().fwd()
+        self.net.L.resize_bilinear_fwd(self.small.ref, C.byref(self._lg), _stream())
+
+    def bwd(self):
+        self.net.L.resize_bilinear_bwd(C.byref(self._dlg), None, self.dy.ref, _stream())
+        super().bwd()
+
+
 class Loss(Op):
     """w_bce*binary_crossentropy + w_dice*dice_loss + w_iou*iou_loss and the metrics, fused with the sigmoid; or
     w_lovasz*lovasz_loss on the logits (the reference's compile strips the final Activation for it)."""
@@ -674,7 +759,7 @@ class Loss(Op):
         self.net, self.head, self.mask = net, head, mask
         self.result = torch.zeros(16, dtype=torch.float32, device=net.device)
         self.lpartial = torch.zeros(net.L.loss_partial_floats(), dtype=torch.float32, device=net.device)
-        self.count = head.x.rows * head.classes
+        self.count = head.out_n * head.out_hw * head.classes
         self.enabled = True
         self.lov_ws: Optional[torch.Tensor] = None
         self.lovasz_act = lovasz_act
@@ -688,27 +773,27 @@ class Loss(Op):
         self.spec = _lib.LossSpec(w_bce, w_dice, w_iou, w_jaccard, w_focal)
         self.w_lovasz = float(w_lovasz)
         if self.w_lovasz != 0.0:
-            if self.head.classes != 1:
-                raise NotImplementedError("lovasz_loss is defined by the reference for 1-class masks only (K.squeeze)")
+            # classes > 1: the reference's K.squeeze(..., -1) is undefined; one hinge per (image, class), averaged
+            # (oracle/losses.py lovasz_loss)
             if self.lov_ws is None:
-                x = self.head.x
-                nbytes = self.net.L.lovasz_workspace(x.n, x.h * x.w)
+                h = self.head
+                nbytes = self.net.L.lovasz_workspace(h.out_n * h.classes, h.out_hw)
                 self.lov_ws = torch.zeros(max(int(nbytes), 16), dtype=torch.uint8, device=self.net.device)
 
     def fwd(self):
         if self.enabled:
-            L, x = self.net.L, self.head.x
+            L, h = self.net.L, self.head
             L.loss_fwd(self.head.logits.data_ptr(), self.mask.storage.data_ptr(), self.count, C.byref(self.spec),
                        self.lpartial.data_ptr(), self.result.data_ptr(), _stream())
             if self.w_lovasz != 0.0:
-                L.lovasz_fwd(self.head.logits.data_ptr(), self.mask.storage.data_ptr(), x.n, x.h * x.w,
-                             int(self.lovasz_act == "elu"), self.w_lovasz, 1, self.lov_ws.data_ptr(), self.lov_ws.numel(),
-                             self.result.data_ptr(), _stream())
+                L.lovasz_fwd_mc(self.head.logits.data_ptr(), self.mask.storage.data_ptr(), h.out_n, h.out_hw, h.classes,
+                                int(self.lovasz_act == "elu"), self.w_lovasz, 1, self.lov_ws.data_ptr(),
+                                self.lov_ws.numel(), self.result.data_ptr(), _stream())
 
     def bwd(self):
-        L, x = self.net.L, self.head.x
+        L, h = self.net.L, self.head
         L.loss_bwd(self.head.logits.data_ptr(), self.mask.storage.data_ptr(), self.count, C.byref(self.spec),
                    self.result.data_ptr(), self.head.dlogits.data_ptr(), _stream())
         if self.w_lovasz != 0.0:
-            L.lovasz_bwd(self.lov_ws.data_ptr(), self.lov_ws.numel(), x.n, x.h * x.w, self.w_lovasz, 1,
+            L.lovasz_bwd(self.lov_ws.data_ptr(), self.lov_ws.numel(), h.out_n * h.classes, h.out_hw, self.w_lovasz, 1,
                          self.head.dlogits.data_ptr(), _stream())

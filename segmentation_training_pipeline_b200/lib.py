@@ -107,11 +107,15 @@ SIGNATURES = {
     "stp_maxpool_bwd": (C.c_int, [_TP, _P, _I32, _I32, _I32, _TP, _TP, _P]),
     "stp_copy_up": (C.c_int, [_TP, _I32, _TP, _P]),
     "stp_add": (C.c_int, [_TP, _TP, _TP, _P]),
+    "stp_upsample2x_bwd": (C.c_int, [_TP, _TP, _TP, _P]),
+    "stp_resize_bilinear_fwd": (C.c_int, [_TP, _TP, _P]),
+    "stp_resize_bilinear_bwd": (C.c_int, [_TP, _TP, _TP, _P]),
     "stp_loss_fwd": (C.c_int, [_P, _P, _I64, C.POINTER(LossSpec), _P, _P, _P]),
     "stp_loss_partial_floats": (_SZ, []),
     "stp_loss_bwd": (C.c_int, [_P, _P, _I64, C.POINTER(LossSpec), _P, _P, _P]),
     "stp_lovasz_workspace": (_SZ, [_I32, _I64]),
     "stp_lovasz_fwd": (C.c_int, [_P, _P, _I32, _I64, _I32, _F, _I32, _P, _SZ, _P, _P]),
+    "stp_lovasz_fwd_mc": (C.c_int, [_P, _P, _I32, _I64, _I32, _I32, _F, _I32, _P, _SZ, _P, _P]),
     "stp_lovasz_bwd": (C.c_int, [_P, _SZ, _I32, _I64, _F, _I32, _P, _P]),
     "stp_adam": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, C.POINTER(GradXform), _P, _P]),
     "stp_sgd": (C.c_int, [_P, _P, _P, _I64, _F, _F, _I32, C.POINTER(GradXform), _P]),

@@ -21,7 +21,7 @@ RESNET_REPS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3), "resnet50": (
 RESNET_BOTTLENECK = {"resnet18": False, "resnet34": False, "resnet50": True, "resnet101": True, "resnet152": True}
 VGG16_BLOCKS = ((64, 2), (128, 2), (256, 3), (512, 3), (512, 3))  # keras.applications.VGG16 [DEP]
 KNOWN_BACKBONES = sorted(RESNET_REPS) + ["vgg16"]
-KNOWN_ARCHITECTURES = ["Unet", "Linknet"]
+KNOWN_ARCHITECTURES = ["Unet", "FPN", "Linknet"]
 
 
 class SegNet(E.Net):
@@ -30,7 +30,8 @@ class SegNet(E.Net):
     def __init__(self, backbone="resnet34", classes=1, input_shape=(512, 512, 3), batch=16,
                  decoder_filters=(256, 128, 64, 32, 16), device="cuda:0", seed=0,
                  enc_init="he_uniform", dec_init="glorot_uniform", loss=(1.0, 0.0, 0.0), architecture="Unet",
-                 decoder_block_type="upsampling"):
+                 decoder_block_type="upsampling", pyramid_block_filters=256, segmentation_block_filters=128,
+                 dropout=None):
         super().__init__(batch, device, seed)
         backbone = backbone.lower()
         if architecture not in KNOWN_ARCHITECTURES:
@@ -39,6 +40,11 @@ class SegNet(E.Net):
             raise ValueError("Unknown architecture")
         self.architecture = architecture
         linknet = architecture == "Linknet"
+        fpn = architecture == "FPN"
+        if fpn and dropout:
+            raise NotImplementedError("FPN dropout (SpatialDropout2D) is not built; the schema default is None")
+        if fpn and backbone == "vgg16":
+            raise NotImplementedError("FPN is built over the ResNet encoders only")
         if decoder_block_type not in ("upsampling", "transpose"):
             raise ValueError("decoder_block_type must be 'upsampling' or 'transpose'")
         transpose = decoder_block_type == "transpose" and not linknet   # schema segmentation.raml:162-165 (Unet only)
@@ -71,14 +77,14 @@ class SegNet(E.Net):
         skip_c = [256 * exp, 128 * exp, 64 * exp, 64, 0]
         up_c = df[:] if transpose else [512 * exp] + df[:4]   # transpose blocks concat [ConvT output (f_i) | skip]
         cat: List[E.Buf] = []
-        for i in range(0 if linknet else 5):
+        for i in range(0 if (linknet or fpn) else 5):
             s = 32 >> i  # input of stage i is at H/32 * 2^i after upsampling -> H / (16 >> i) ... computed below
             hh, ww = H // (16 >> i) if i < 4 else H, W // (16 >> i) if i < 4 else W
             cat.append(E.Buf(self, N, hh, ww, up_c[i] + skip_c[i], name="cat%d" % i))
         skip_view = {  # keras layer name -> (stage index)
             "stage4_unit1_relu1": 0, "stage3_unit1_relu1": 1, "stage2_unit1_relu1": 2, "relu0": 3}
         skip_names = list(skip_view)
-        if linknet:       # Linknet adds its skips instead of concatenating them: plain buffers, no concat layout
+        if linknet or fpn:  # Linknet / FPN add their skips instead of concatenating them: plain buffers, no concat layout
             skip_view, cat = {}, []
 
         def skip_buf(name, n, h, w, c):
@@ -135,11 +141,14 @@ class SegNet(E.Net):
                     E.Conv(self, a2, out, pre + "conv2", 3, pad=1, residual=res, init=enc_init)
                 x, h, w = out, ho, wo
         self.encoder_param_names = list(self.params.keys())
-        if linknet or transpose:
+        if linknet or transpose or fpn:
             top = E.Buf(self, N, h, w, x.c, name="relu1")
             E.BNRelu(self, x, top, "bn1", ENC_BN_EPS)
             self.encoder_param_names = list(self.params.keys())
-            if linknet:
+            if fpn:
+                self._build_fpn_decoder(top, [self.bufs[nm] for nm in skip_names[:3]], pyramid_block_filters,
+                                        segmentation_block_filters, classes, dec_init, loss)
+            elif linknet:
                 self._build_linknet_decoder(top, [self.bufs[nm] for nm in skip_names], df, classes, dec_init, loss)
             else:
                 self._build_transpose_decoder(top, cat, df, classes, dec_init, loss)
@@ -166,6 +175,54 @@ class SegNet(E.Net):
             E.BNRelu(self, z2, a2, pre + "bn2", DEC_BN_EPS)
             x = a2
         self.head = E.Head(self, x, classes, "final_conv", init=dec_init)
+        self.loss = E.Loss(self, self.head, self.mask, *loss)
+        self.finalize()
+
+    def _build_fpn_decoder(self, top, skips, pyr, segf, classes, dec_init, loss):
+        """segmentation_models 0.2.1 FPN [DEP] (reference segmentation.py:109-113; schema segmentation.raml:179-204; SURVEY.md
+        8 a-5).  Top-down pyramid over relu1 (H/32) and the three deepest skips: 1x1 lateral conv (pyramid_block_filters,
+        bias) + Add(UpSampling2D(2)(previous level)) -- the Add is the residual input of the lateral conv's epilogue; per
+        level 2x [3x3 conv (segmentation_block_filters) + BN + ReLU], bilinear x8/x4/x2/x1 written straight into the channel
+        slices of the concat buffer at H/4; 3x3 conv (4*segmentation_block_filters) + BN + ReLU; head conv 3x3 (classes,
+        bias) and the x4 bilinear `last_upsample` of the logits (engine.UpHead)."""
+        N = self.batch
+        feats = [top] + list(skips)
+        p = None
+        pyramid = []
+        for i, c in enumerate(feats):
+            name = "pyramid_stage_%d_conv1x1" % i
+            lat = E.Buf(self, N, c.h, c.w, pyr, name="pyramid_stage_%d" % i)
+            if p is None:
+                E.Conv(self, c, lat, name, 1, bias=True, init=dec_init)
+            else:
+                up = E.Buf(self, N, c.h, c.w, pyr, name="pyramid_stage_%d_up" % i)
+                E.Upsample2x(self, p, up)
+                E.Conv(self, c, lat, name, 1, bias=True, residual=up, init=dec_init)
+                up.set_grad(lat.grad())  # d(Add)/d(upsampled) == d(lateral output)
+            p = lat
+            pyramid.append(p)
+        hq, wq = pyramid[-1].h, pyramid[-1].w
+        cat = E.Buf(self, N, hq, wq, 4 * segf, name="fpn_concat")
+        for i, p in enumerate(pyramid):
+            pre = "segm_stage_%d_" % i
+            z1 = E.Buf(self, N, p.h, p.w, segf, name=pre + "conv1")
+            E.Conv(self, p, z1, pre + "conv1", 3, pad=1, init=dec_init)
+            a1 = E.Buf(self, N, p.h, p.w, segf, name=pre + "relu1")
+            E.BNRelu(self, z1, a1, pre + "bn1", DEC_BN_EPS)
+            z2 = E.Buf(self, N, p.h, p.w, segf, name=pre + "conv2")
+            E.Conv(self, a1, z2, pre + "conv2", 3, pad=1, init=dec_init)
+            dst = cat.slice(i * segf, segf, name=pre + "out")
+            if p.h == hq:
+                E.BNRelu(self, z2, dst, pre + "bn2", DEC_BN_EPS)
+            else:
+                a2 = E.Buf(self, N, p.h, p.w, segf, name=pre + "relu2")
+                E.BNRelu(self, z2, a2, pre + "bn2", DEC_BN_EPS)
+                E.Resize(self, a2, dst)
+        zf = E.Buf(self, N, hq, wq, 4 * segf, name="final_stage_conv")
+        E.Conv(self, cat, zf, "final_stage_conv", 3, pad=1, init=dec_init)
+        af = E.Buf(self, N, hq, wq, 4 * segf, name="final_stage_relu")
+        E.BNRelu(self, zf, af, "final_stage_bn", DEC_BN_EPS)
+        self.head = E.UpHead(self, af, classes, "head_conv", up=4, init=dec_init)
         self.loss = E.Loss(self, self.head, self.mask, *loss)
         self.finalize()
 

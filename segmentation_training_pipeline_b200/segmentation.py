@@ -188,13 +188,19 @@ class PipelineConfig:
             print("Unknown backbone:" + bb)
             print("Known backbones:", _models.KNOWN_BACKBONES)
             raise ValueError("Unknown backbone")
-        if self.classes != 1 or self.activation not in ("sigmoid", None, "none"):
-            raise NotImplementedError("only classes=1 / sigmoid heads have fused loss kernels so far")
+        if self.activation not in ("sigmoid", None, "none"):
+            raise NotImplementedError("only sigmoid heads (per-class binary masks) have fused loss kernels so far; "
+                                      "softmax / categorical_crossentropy is not built")
+        if self.classes > 4:
+            raise NotImplementedError("classes <= 4 (mask channels of the on-device augmentation / head kernels)")
         if self.encoder_weights not in (None, "None", "none"):
             raise NotImplementedError("encoder_weights: no network here -- load a local .npz with load_weights()")
         return _models.SegNet(bb, classes=self.classes, input_shape=tuple(self.shape), batch=batch or self.batch,
                               decoder_filters=self.decoder_filters, device=self.device, seed=self.random_state,
                               architecture=arch, decoder_block_type=getattr(self, "decoder_block_type", None) or "upsampling",
+                              pyramid_block_filters=int(self.extra.get("pyramid_block_filters", 256)),
+                              segmentation_block_filters=int(self.extra.get("segmentation_block_filters", 128)),
+                              dropout=self.extra.get("dropout", None),
                               loss=parse_loss(loss or self.loss))
 
     def kfold(self, n: int) -> List[Tuple[np.ndarray, np.ndarray]]:

@@ -37,6 +37,20 @@ def _perturb(weights, seed=1):
                                                 ("resnet50", 64, (1.0, 0.0, 0.0)), ("vgg16", 64, (1.0, 1.0, 0.0)),
                                                 ("resnet18", 64, (0.0, 0.0, 0.0, 1.0))])
 def test_forward_backward_parity(cuda, backbone, size, loss, arch):
+    _run_parity(backbone, size, loss, arch)
+
+
+@pytest.mark.parametrize("backbone,size,loss,classes", [("resnet18", 128, (1.0, 1.0, 0.0), 1),
+                                                        ("resnet50", 128, (0.0, 0.0, 0.0, 1.0), 3),
+                                                        ("resnet34", 128, (1.0, 0.0, 0.0), 2)])
+def test_fpn_parity(cuda, backbone, size, loss, classes):
+    """FPN decoder (BASELINE.json configs[2]: FPN/ResNet-50, 3-class, Lovasz): top-down pyramid with the Add fused as the
+    lateral conv's residual, bilinear branch upsampling into the concat slices, padded-class head conv + x4 bilinear
+    logits; multi-class masks = independent sigmoid heads, Lovasz = one hinge per (image, class)."""
+    _run_parity(backbone, size, loss, "FPN", classes)
+
+
+def _run_parity(backbone, size, loss, arch, classes=1):
     from oracle import losses as OL
     from oracle.models import SegModel
     from segmentation_training_pipeline_b200 import lib
@@ -53,26 +67,28 @@ def test_forward_backward_parity(cuda, backbone, size, loss, arch):
         pytest.skip("Linknet parity is run on the basic-block ResNets")
     if arch == "Linknet":
         size = 128  # at 64x64 the deepest BatchNorm sees 2x2x2 samples per channel: pure rounding-noise amplification
-    net = SegNet(backbone, classes=1, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=loss, architecture=arch,
+    net = SegNet(backbone, classes=classes, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=loss, architecture=arch,
                  decoder_block_type=block)
     W = _perturb(net.get_weights())
     net.set_weights(W)
     tr = Trainer(net)
     img, mask = _data(n, size, size)
+    if classes > 1:  # class c: the disk shifted by c*size/8 columns (overlapping, independent binary masks)
+        mask = torch.cat([torch.roll(mask, c * size // 8, dims=2) for c in range(classes)], dim=3).contiguous()
     tr.set_batch(img.cuda(), mask.cuda())
     net.prep_weights()
     net.forward()
     net.backward()
     torch.cuda.synchronize()
     res = net.loss.result.cpu().numpy()
-    logits = net.head.logits.cpu().view(n, size, size, 1)
+    logits = net.head.logits.cpu().view(n, size, size, classes)
     grads = net.get_grads()
 
     # Two oracles: bf16-storage emulation (rounds where the engine stores bf16) and pure fp32.  Deep random-init
     # pre-activation ResNets amplify one-ulp bf16 differences layer by layer, so the engine is held to the NOISE
     # FLOOR of bf16 storage itself: it must be at least as close to the bf16 oracle as that oracle is to fp32.
     def run(storage):
-        om = SegModel(arch, backbone, classes=1, input_shape=(size, size, 3), storage=storage, update_moving=False,
+        om = SegModel(arch, backbone, classes=classes, input_shape=(size, size, 3), storage=storage, update_moving=False,
                       decoder_block_type=block)
         assert set(om.params.keys()) == set(net.params.keys()), sorted(set(om.params.keys()) ^ set(net.params.keys()))
         om.load_numpy(W)

@@ -665,3 +665,86 @@ def test_adam_device_lr_scale(stp, cuda):
                  step.data_ptr(), stream())
         outs.append(p.clone())
     assert rel_err(outs[1], 0.25 * outs[0]) < 1e-6
+
+
+@pytest.mark.parametrize("shape,rate", [((2, 4, 4, 16), 8), ((1, 8, 6, 32), 4), ((2, 16, 12, 8), 2), ((1, 5, 7, 8), 3)])
+def test_resize_bilinear_bf16(stp, cuda, shape, rate):
+    """TF1-legacy bilinear upsampling (FPN branches) into a channel slice of a wider buffer; backward = exact adjoint
+    (checked against autograd of the oracle restatement), residual accumulation."""
+    from oracle import nn as ON
+    g = torch.Generator().manual_seed(31)
+    n, h, w, c = shape
+    H, W = h * rate, w * rate
+    x = rand_bf16(shape, g, device=cuda)
+    ybuf = torch.zeros((n, H, W, c + 16), dtype=torch.bfloat16, device=cuda)
+    stp.resize_bilinear_fwd(ref(T(x)), ref(T(ybuf, 8, c)), stream())
+    xo = x.float().cpu().permute(0, 3, 1, 2).requires_grad_(True)
+    yo = ON.resize_bilinear_tf1(xo, H, W)
+    got = ybuf[..., 8:8 + c].float().cpu()
+    assert rel_err(got, yo.detach().permute(0, 2, 3, 1)) < TOL_BF16  # one bf16 rounding (fma contraction may move the last fp32 bit)
+    assert float(ybuf[..., :8].abs().max()) == 0.0 and float(ybuf[..., 8 + c:].abs().max()) == 0.0
+    dybuf = torch.zeros_like(ybuf)
+    dy = rand_bf16((n, H, W, c), g, device=cuda)
+    dybuf[..., 8:8 + c] = dy
+    res = rand_bf16(shape, g, device=cuda)
+    for use_res in (False, True):
+        dx = torch.zeros(shape, dtype=torch.bfloat16, device=cuda)
+        stp.resize_bilinear_bwd(ref(T(dybuf, 8, c)), ref(T(res)) if use_res else None, ref(T(dx)), stream())
+        (gx,) = torch.autograd.grad(yo, xo, dy.float().cpu().permute(0, 3, 1, 2), retain_graph=True)
+        want = gx.permute(0, 2, 3, 1) + (res.float().cpu() if use_res else 0.0)
+        assert rel_err(dx, want) < TOL_BF16
+
+
+def test_resize_bilinear_f32_logits(stp, cuda):
+    """x4 `last_upsample` of the padded FPN head logits: f32 [n,h,w,16] -> dense f32 [n,4h,4w,3]; backward f32 -> bf16 with
+    the padded channels written as zero."""
+    from oracle import nn as ON
+    g = torch.Generator().manual_seed(32)
+    n, h, w, cp, cls = 2, 8, 6, 16, 3
+    x = torch.randn(n, h, w, cp, generator=g).to(cuda)
+    y = torch.zeros(n, 4 * h, 4 * w, cls, device=cuda)
+    stp.resize_bilinear_fwd(ref(T(x)), ref(T(y)), stream())
+    xo = x[..., :cls].cpu().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    yo = ON.resize_bilinear_tf1(xo, 4 * h, 4 * w)
+    assert max_abs(y, yo.detach().permute(0, 2, 3, 1)) < 1e-6
+    dy = torch.randn(n, 4 * h, 4 * w, cls, generator=g).to(cuda)
+    dx = torch.full((n, h, w, cp), 7.0, dtype=torch.bfloat16, device=cuda)
+    stp.resize_bilinear_bwd(ref(T(dy)), None, ref(T(dx)), stream())
+    (gx,) = torch.autograd.grad(yo, xo, dy.cpu().permute(0, 3, 1, 2))
+    assert rel_err(dx[..., :cls], gx.permute(0, 2, 3, 1)) < TOL_BF16
+    assert float(dx[..., cls:].float().abs().max()) == 0.0
+
+
+def test_upsample2x_bwd(stp, cuda):
+    g = torch.Generator().manual_seed(33)
+    n, h, w, c = 2, 6, 10, 24
+    dy = rand_bf16((n, 2 * h, 2 * w, c), g, device=cuda)
+    res = rand_bf16((n, h, w, c), g, device=cuda)
+    dx = torch.zeros((n, h, w, c), dtype=torch.bfloat16, device=cuda)
+    want = dy.float().cpu().view(n, h, 2, w, 2, c).sum(dim=(2, 4))
+    stp.upsample2x_bwd(ref(T(dy)), None, ref(T(dx)), stream())
+    assert rel_err(dx, want) < TOL_BF16
+    stp.upsample2x_bwd(ref(T(dy)), ref(T(res)), ref(T(dx)), stream())
+    assert rel_err(dx, want + res.float().cpu()) < TOL_BF16
+
+
+def test_lovasz_hinge_multiclass(stp, cuda):
+    """classes > 1 ([image][pixel][class] logits): one hinge per (image, class), mean over all -- the oracle's definition
+    of the case the reference leaves undefined."""
+    from oracle import losses as OL
+    g = torch.Generator().manual_seed(22)
+    n, h, w, cls = 2, 24, 20, 3
+    logits = ((torch.randn(n, h, w, cls, generator=g) * 2.0) * 2).round() / 2
+    mask = (torch.rand(n, h, w, cls, generator=g) > 0.6).to(torch.uint8)
+    mask[1, :, :, 2] = 0
+    lg, mk = logits.to(cuda).contiguous(), mask.to(cuda).contiguous()
+    ws = _ws(stp.lovasz_workspace(n * cls, h * w), cuda)
+    result = torch.zeros(16, device=cuda)
+    dl = torch.zeros(n * h * w * cls, device=cuda)
+    stp.lovasz_fwd_mc(lg.data_ptr(), mk.data_ptr(), n, h * w, cls, 1, 1.0, 0, ws.data_ptr(), ws.numel(), result.data_ptr(), stream())
+    stp.lovasz_bwd(ws.data_ptr(), ws.numel(), n * cls, h * w, 1.0, 0, dl.data_ptr(), stream())
+    z = logits.double().requires_grad_(True)
+    lo = OL.lovasz_loss(mask.double(), z, act="elu")
+    lo.backward()
+    assert abs(float(result[lib.L_LOVASZ]) - float(lo)) < 1e-5 * max(1.0, abs(float(lo)))
+    assert rel_err(dl.view(n, h, w, cls), z.grad) < 1e-5
