@@ -42,7 +42,7 @@ def test_forward_backward_parity(cuda, backbone, size, loss, arch):
 
 @pytest.mark.parametrize("backbone,size,loss,classes", [("resnet18", 128, (1.0, 1.0, 0.0), 1),
                                                         ("resnet50", 128, (0.0, 0.0, 0.0, 1.0), 3),
-                                                        ("resnet34", 128, (1.0, 0.0, 0.0), 2)])
+                                                        ("resnet34", 192, (1.0, 0.0, 0.0), 2)])
 def test_fpn_parity(cuda, backbone, size, loss, classes):
     """FPN decoder (BASELINE.json configs[2]: FPN/ResNet-50, 3-class, Lovasz): top-down pyramid with the Add fused as the
     lateral conv's residual, bilinear branch upsampling into the concat slices, padded-class head conv + x4 bilinear
