@@ -52,7 +52,15 @@ def predict_arrays(net, images_u8: np.ndarray, ttflips=False) -> np.ndarray:
             enabled, net.loss.enabled = net.loss.enabled, False
             net.forward()
             net.loss.enabled = enabled
-            p = _sigmoid(net.head.logits.detach().cpu().numpy().reshape(B, H, W, net.classes)[:n])
+            z = net.head.logits.detach().cpu().numpy().reshape(B, H, W, net.classes)[:n]
+            act = getattr(net, "activation", "sigmoid")
+            if act == "softmax":
+                e = np.exp(z - z.max(axis=-1, keepdims=True))
+                p = e / e.sum(axis=-1, keepdims=True)
+            elif act in ("linear", "none"):
+                p = z
+            else:
+                p = _sigmoid(z)
             if fl:
                 p = p[:, :, ::-1]
             if fu:

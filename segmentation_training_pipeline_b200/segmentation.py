@@ -188,20 +188,28 @@ class PipelineConfig:
             print("Unknown backbone:" + bb)
             print("Known backbones:", _models.KNOWN_BACKBONES)
             raise ValueError("Unknown backbone")
-        if self.activation not in ("sigmoid", None, "none"):
-            raise NotImplementedError("only sigmoid heads (per-class binary masks) have fused loss kernels so far; "
-                                      "softmax / categorical_crossentropy is not built")
+        lw = parse_loss(loss or self.loss)
+        pure_lovasz = len(lw) == 4 and lw[3] != 0.0
+        if self.activation == "softmax" and not pure_lovasz:
+            # lovasz_loss is computed on LOGITS (the reference strips the final Activation), so `activation: softmax` only
+            # shapes predictions (BASELINE.json configs[2]); every other loss would need softmax inside the loss kernels
+            raise NotImplementedError("activation: softmax is built for lovasz_loss only (categorical_crossentropy and "
+                                      "softmax-probability losses have no fused kernels)")
+        if self.activation not in ("sigmoid", "softmax", None, "none"):
+            raise NotImplementedError("activation '%s' is not built" % self.activation)
         if self.classes > 4:
             raise NotImplementedError("classes <= 4 (mask channels of the on-device augmentation / head kernels)")
         if self.encoder_weights not in (None, "None", "none"):
             raise NotImplementedError("encoder_weights: no network here -- load a local .npz with load_weights()")
-        return _models.SegNet(bb, classes=self.classes, input_shape=tuple(self.shape), batch=batch or self.batch,
+        net = _models.SegNet(bb, classes=self.classes, input_shape=tuple(self.shape), batch=batch or self.batch,
                               decoder_filters=self.decoder_filters, device=self.device, seed=self.random_state,
                               architecture=arch, decoder_block_type=getattr(self, "decoder_block_type", None) or "upsampling",
                               pyramid_block_filters=int(self.extra.get("pyramid_block_filters", 256)),
                               segmentation_block_filters=int(self.extra.get("segmentation_block_filters", 128)),
                               dropout=self.extra.get("dropout", None),
-                              loss=parse_loss(loss or self.loss))
+                              loss=lw)
+        net.activation = self.activation or "linear"   # what predict applies to the logits
+        return net
 
     def kfold(self, n: int) -> List[Tuple[np.ndarray, np.ndarray]]:
         """sklearn KFold(folds_count, shuffle=True, random_state) as the reference's ImageKFoldedDataSet [DEP]."""

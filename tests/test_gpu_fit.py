@@ -153,3 +153,52 @@ def test_fit_linknet_resnet34_cyclic_lr(cuda, tmp_path):
     assert all(0.0005 - 1e-9 <= v <= 0.002 + 1e-9 for v in lrs) and lrs[0] != lrs[1]
     w = cfg.load_model(0, 0).get_weights()
     assert "decoder_stage0_conv3/kernel" in w and w["decoder_stage4_conv3/kernel"].shape == (1, 1, 16, 16)
+
+
+class _ThreeClassDisks:
+    """Dataset protocol (README.md:417-427): __len__, __getitem__ -> PredictionItem(id, x uint8 HxWx3, y uint8 HxWx3)."""
+
+    def __init__(self, n=8, size=128):
+        from segmentation_pipeline.impl.datasets import PredictionItem
+        rng = np.random.default_rng(7)
+        yy, xx = np.mgrid[0:size, 0:size]
+        self.items = []
+        for k in range(n):
+            y = np.zeros((size, size, 3), np.uint8)
+            x = rng.integers(0, 90, (size, size, 3)).astype(np.uint8)
+            for c in range(3):
+                cy, cx = rng.integers(size // 4, 3 * size // 4, 2).tolist()
+                y[:, :, c] = ((yy - cy) ** 2 + (xx - cx) ** 2) < (size // 6) ** 2
+                x[:, :, c] += y[:, :, c] * 150
+            self.items.append(PredictionItem("s%02d" % k, x, y))
+
+    def __len__(self):
+        return len(self.items)
+
+    def __getitem__(self, i):
+        return self.items[i]
+
+
+def test_fit_config2_fpn_resnet50_lovasz_3class(cuda, tmp_path):
+    """BASELINE.json configs[2] through the YAML surface (shape / batch / folds shrunk): FPN / ResNet-50, 3-class masks,
+    lovasz_loss on logits with `activation: softmax` shaping the predictions."""
+    import yaml
+    from segmentation_pipeline import segmentation
+    spec = yaml.safe_load(open(os.path.join(HERE, "golden", "configs", "c3_fpn_resnet50.yaml")))
+    spec.update({"shape": [128, 128, 3], "batch": 2, "folds_count": 2, "stages": [{"epochs": 3}]})
+    cfgp = str(tmp_path / "exp" / "config.yaml")
+    os.makedirs(os.path.dirname(cfgp))
+    yaml.safe_dump(spec, open(cfgp, "w"))
+    cfg = segmentation.parse(cfgp)
+    ds = _ThreeClassDisks()
+    res = cfg.fit(ds)
+    assert len(res) == 2
+    rows = list(csv.DictReader(open(os.path.join(os.path.dirname(cfgp), "metrics", "metrics-0.0.csv"))))
+    assert len(rows) == 3 and all(np.isfinite(float(r["loss"])) and np.isfinite(float(r["val_loss"])) for r in rows)
+    assert float(rows[-1]["loss"]) < float(rows[0]["loss"])
+    net = cfg.load_model(0, 0)
+    w = net.get_weights()
+    assert w["head_conv/kernel"].shape == (3, 3, 512, 3) and w["pyramid_stage_0_conv1x1/kernel"].shape == (1, 1, 2048, 256)
+    from segmentation_training_pipeline_b200.predict import predict_arrays
+    p = predict_arrays(net, np.stack([ds[0].x, ds[1].x]))
+    assert p.shape == (2, 128, 128, 3) and np.allclose(p.sum(axis=-1), 1.0, atol=1e-5)
