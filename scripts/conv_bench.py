@@ -38,7 +38,9 @@ def bench(n, h, w, cin, cout, k=3, reps=10, what="fwd", res=False):
     return ms * 1e3, fl / ms / 1e9
 
 shapes = [(16, 128, 128, 64, 64), (16, 64, 64, 128, 128), (16, 32, 32, 256, 256), (16, 16, 16, 512, 512), (16, 512, 512, 16, 16), (16, 256, 256, 32, 32)]
-if len(sys.argv) > 1 and sys.argv[1] == "dbg":
+if __name__ != "__main__":
+    pass
+elif len(sys.argv) > 1 and sys.argv[1] == "dbg":
     for shp in shapes[:4]:
         for ver in (1, 0):
             L.set_option(b"tc_conv_version", ver)

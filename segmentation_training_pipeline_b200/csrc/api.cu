@@ -45,6 +45,9 @@ extern "C" int stp_set_option(const char* name, int32_t value) {
   else if (!strcmp(name, "tc2_debug")) key = OPT_TC2_DEBUG;             /* timing experiments, see conv_tc2.cu */
   else if (!strcmp(name, "tc2_cluster")) key = OPT_TC2_CLUSTER;         /* 0 auto | 1 no clusters | 2, 4 force that cluster size */
   else if (!strcmp(name, "tc2_bk")) key = OPT_TC2_BK;                   /* 0 auto | 32: 32-channel K blocks even when Cin % 64 == 0 */
+  else if (!strcmp(name, "tc3")) key = OPT_TC3;                         /* 0 auto | 1 off | 2 CTA-pair kernel wherever it serves the shape */
+  else if (!strcmp(name, "tc3_force_bn")) key = OPT_TC3_FORCE_BN;       /* 0 heuristic | 128, 256 */
+  else if (!strcmp(name, "tc3_force_mt")) key = OPT_TC3_FORCE_MT;       /* 0 heuristic | 1, 2 */
   else if (!strcmp(name, "pdl")) {                                      /* programmatic dependent launch on/off */
     g_pdl_enabled.store(value ? 1 : 0);
     return STP_OK;
@@ -63,6 +66,7 @@ extern "C" void stp_set_tc_enabled(int on) { g_tc_enabled.store(on ? 1 : 0); }
 
 static int dispatch_conv(const ConvP& p, cudaStream_t st) {
   if (stp_tc_enabled()) {
+    if (get_option(OPT_TC_CONV_VERSION) != 1 && tc3_conv_supported(p)) return launch_tc3_conv(p, st);
     if (get_option(OPT_TC_CONV_VERSION) != 1 && tc2_conv_supported(p)) return launch_tc2_conv(p, st);
     if (tc_conv_supported(p)) return launch_tc_conv(p, st);
   }
@@ -101,7 +105,7 @@ static int conv_fwd_common(const stp_conv_desc* d, const stp_tensor* x, const vo
   // BatchNorm statistics of y: inside the conv epilogue when the halo kernel serves this shape, else one extra pass
   STP_REQUIRE(h_bn->partial && h_bn->sync && h_bn->acc && h_bn->coef, "conv_fwd_bn: null statistics buffers");
   STP_REQUIRE(y->dtype == STP_BF16 && pixels(y) > 0, "conv_fwd_bn: y must be a non-empty bf16 tensor");
-  if (stp_tc_enabled() && get_option(OPT_TC_CONV_VERSION) != 1 && tc2_conv_supported(p)) {
+  if (stp_tc_enabled() && get_option(OPT_TC_CONV_VERSION) != 1 && (tc3_conv_supported(p) || tc2_conv_supported(p))) {
     const int64_t count = pixels(y);
     BnFuse bn;
     bn.acc = h_bn->acc;
@@ -111,6 +115,7 @@ static int conv_fwd_common(const stp_conv_desc* d, const stp_tensor* x, const vo
     bn.fin.gamma = h_bn->gamma; bn.fin.beta = h_bn->beta; bn.fin.eps = h_bn->eps; bn.fin.momentum = h_bn->momentum;
     bn.fin.mov_mean = h_bn->moving_mean; bn.fin.mov_var = h_bn->moving_var; bn.fin.coef = h_bn->coef;
     p.bn = &bn;
+    if (tc3_conv_supported(p)) return launch_tc3_conv(p, (cudaStream_t)stream);
     return launch_tc2_conv(p, (cudaStream_t)stream);
   }
   rc = dispatch_conv(p, (cudaStream_t)stream);

@@ -52,10 +52,15 @@ int launch_split_reduce(const float* ws, int splits, int64_t n, float* out, cuda
 bool tc2_conv_supported(const ConvP& p);
 int launch_tc2_conv(const ConvP& p, cudaStream_t st);
 int get_option(int key);
-enum { OPT_TC2_FORCE_MT = 0, OPT_TC_CONV_VERSION = 1, OPT_TC2_DEBUG = 2, OPT_TC2_CLUSTER = 3, OPT_TC2_BK = 4, OPT_COUNT = 8 };
+enum { OPT_TC2_FORCE_MT = 0, OPT_TC_CONV_VERSION = 1, OPT_TC2_DEBUG = 2, OPT_TC2_CLUSTER = 3, OPT_TC2_BK = 4, OPT_TC3 = 5,
+       OPT_TC3_FORCE_BN = 6, OPT_TC3_FORCE_MT = 7, OPT_COUNT = 8 };
 // device buffer (>= 64 uint64) that CTA 0 and the last CTA of conv_tc2_kernel fill with %globaltimer stamps of their
 // phases (scripts/trace_conv.py); nullptr = off.  Profiling aid only.
 unsigned long long* get_trace_buffer();
+
+// conv_tc3.cu (tcgen05 cta_group::2 CTA-pair halo kernel: 3x3 stride 1, Cin % 64 == 0, Cout % 128 == 0, bf16 output)
+bool tc3_conv_supported(const ConvP& p);
+int launch_tc3_conv(const ConvP& p, cudaStream_t st);
 
 // wgrad_narrow.cu (mma.sync + TMA, Cin/Cout in {16,32})
 bool narrow_wgrad_supported(const WgradP& p);

@@ -748,3 +748,60 @@ def test_lovasz_hinge_multiclass(stp, cuda):
     lo.backward()
     assert abs(float(result[lib.L_LOVASZ]) - float(lo)) < 1e-5 * max(1.0, abs(float(lo)))
     assert rel_err(dl.view(n, h, w, cls), z.grad) < 1e-5
+
+
+@pytest.mark.parametrize("force", [(0, 0), (128, 1), (128, 2), (256, 1)])
+@pytest.mark.parametrize("case", [(2, 24, 40, 128, 128), (1, 9, 17, 128, 256), (3, 8, 8, 256, 512), (5, 16, 16, 64, 128),
+                                  (16, 32, 32, 256, 256), (1, 16, 16, 192, 256)])
+def test_conv_tc3_cta_pair(stp, cuda, case, force):
+    """tcgen05 cta_group::2 CTA-pair kernel (conv_tc3.cu) against the single-CTA halo kernel and the fp32 reference:
+    odd numbers of pixel tiles (a rank idling on an out-of-range image), partial tiles, residual, fused BatchNorm
+    statistics, every (BN, MT) specialisation, dgrad through the same kernel."""
+    n, h, w, cin, cout = case
+    fbn, fmt = force
+    if fbn == 256 and cout % 256:
+        pytest.skip("BN=256 needs Cout % 256 == 0")
+    g = torch.Generator().manual_seed(cin * 5 + cout + fbn + fmt)
+    x = rand_bf16((n, h, w, cin), g)
+    wt = rand_bf16((cout, 3, 3, cin), g, scale=1.0 / math.sqrt(9 * cin))
+    res = rand_bf16((n, h, w, cout), g)
+    desc = lib.ConvDesc(3, 3, 1, 1, 1, 1, 0)
+    rows = n * h * w
+    partial = torch.zeros(2 * stp.bn_nblk(rows, cout) * cout, device=cuda)
+    sync = torch.zeros(4, dtype=torch.int32, device=cuda)
+    acc = torch.zeros(2 * cout, dtype=torch.float64, device=cuda)
+    gamma, beta = torch.ones(cout, device=cuda), torch.zeros(cout, device=cuda)
+    xs, rs = T(x), T(res)
+    outs = []
+    try:
+        for mode in (1, 2):   # 1: single-CTA halo kernel, 2: CTA-pair kernel forced on
+            stp.set_option(b"tc3", mode)
+            stp.set_option(b"tc3_force_bn", fbn)
+            stp.set_option(b"tc3_force_mt", fmt)
+            before = stp.tc_launch_count()
+            y = torch.zeros((n, h, w, cout), dtype=torch.bfloat16, device=cuda)
+            ys = T(y)
+            coef = torch.zeros(4 * cout, device=cuda)
+            mm, mv = torch.zeros(cout, device=cuda), torch.ones(cout, device=cuda)
+            bn = lib.BnFwd(partial.data_ptr(), sync.data_ptr(), acc.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.99,
+                           mm.data_ptr(), mv.data_ptr(), coef.data_ptr())
+            for _ in range(2):
+                stp.conv_fwd_bn(C.byref(desc), ref(xs), wt.data_ptr(), None, ref(rs), ref(ys), C.byref(bn), None, 0, stream())
+            # plain conv (no residual / statistics)
+            y2 = torch.zeros((n, h, w, cout), dtype=torch.bfloat16, device=cuda)
+            stp.conv_fwd(C.byref(desc), ref(xs), wt.data_ptr(), None, None, ref(T(y2)), None, 0, stream())
+            torch.cuda.synchronize()
+            assert stp.tc_launch_count() - before == 3
+            outs.append((y, coef, y2))
+    finally:
+        stp.set_option(b"tc3", 0)
+        stp.set_option(b"tc3_force_bn", 0)
+        stp.set_option(b"tc3_force_mt", 0)
+    yr = conv_ref(x, wt, 1, 1)
+    assert rel_err(outs[1][2], yr) < TOL_BF16
+    assert rel_err(outs[1][0], yr + res.float().cpu()) < TOL_BF16
+    # same K order, fp32 accumulation in TMEM: the pair kernel reproduces the single-CTA kernel up to bf16 rounding ties
+    assert rel_err(outs[1][0], outs[0][0].float()) < 1e-3 and rel_err(outs[1][2], outs[0][2].float()) < 1e-3
+    assert int(sync[0]) == 0 and float(acc.abs().max()) == 0.0
+    scale = 1 + float(outs[0][1].abs().max())
+    assert max_abs(outs[1][1], outs[0][1]) <= 1e-3 * scale
