@@ -167,7 +167,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: warp-uniform loop, one elected lane issues (tc_common.cuh elect_one())
+    {
       const uint32_t tx = (uint32_t)a.a_bytes + (uint32_t)a.R * (uint32_t)a.b_tap_bytes;
       int stage = 0;
       uint32_t phase = 0;
@@ -177,24 +178,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int s = 0; s < a.S; ++s) {
           for (int cb = 0; cb < kcb; ++cb) {
             mbar_wait(&empty[stage], phase ^ 1);
-            if (a.dbg & 3) {
-              const uint32_t txd = ((a.dbg & 1) ? 0u : (uint32_t)a.a_bytes) + ((a.dbg & 2) ? 0u : (uint32_t)a.R * (uint32_t)a.b_tap_bytes);
-              if (txd) mbar_expect_tx(&full[stage], txd); else mbar_arrive(&full[stage]);
-            } else {
-              mbar_expect_tx(&full[stage], tx);
-            }
-            if (!(a.dbg & 1))
-            tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], cb * BK, w0 + s - a.pad_w, h0 - a.pad_h, img);
-            if (CL > 1) {
-              // this CTA's 1/CL slice of every tap's weight rows, multicast into all CTAs of the cluster
-              constexpr int kSliceRows = BN / CL;
+            if (elect_one()) {
+              if (a.dbg & 3) {
+                const uint32_t txd = ((a.dbg & 1) ? 0u : (uint32_t)a.a_bytes) + ((a.dbg & 2) ? 0u : (uint32_t)a.R * (uint32_t)a.b_tap_bytes);
+                if (txd) mbar_expect_tx(&full[stage], txd); else mbar_arrive(&full[stage]);
+              } else {
+                mbar_expect_tx(&full[stage], tx);
+              }
+              if (!(a.dbg & 1))
+              tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], cb * BK, w0 + s - a.pad_w, h0 - a.pad_h, img);
+              if (CL > 1) {
+                // this CTA's 1/CL slice of every tap's weight rows, multicast into all CTAs of the cluster
+                constexpr int kSliceRows = BN / CL;
+                for (int r = 0; r < a.R; ++r)
+                  tma_load_2d_mc(sB + stage * Cfg::kBBytes + r * Cfg::kBTap + crank * (kSliceRows * BK * 2), &tmB, &full[stage],
+                                 (r * a.S + s) * a.Cin + cb * BK, n0 + crank * kSliceRows, kMask);
+              } else if (!(a.dbg & 2))
               for (int r = 0; r < a.R; ++r)
-                tma_load_2d_mc(sB + stage * Cfg::kBBytes + r * Cfg::kBTap + crank * (kSliceRows * BK * 2), &tmB, &full[stage],
-                               (r * a.S + s) * a.Cin + cb * BK, n0 + crank * kSliceRows, kMask);
-            } else if (!(a.dbg & 2))
-            for (int r = 0; r < a.R; ++r)
-              tma_load_2d(sB + stage * Cfg::kBBytes + r * Cfg::kBTap, &tmB, &full[stage],
-                          (r * a.S + s) * a.Cin + cb * BK, n0);
+                tma_load_2d(sB + stage * Cfg::kBBytes + r * Cfg::kBTap, &tmB, &full[stage],
+                            (r * a.S + s) * a.Cin + cb * BK, n0);
+            }
+            __syncwarp();
             if (++stage == NS) {
               stage = 0;
               phase ^= 1;
@@ -204,10 +208,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issue: the whole warp runs the (warp-uniform) loop, one elected lane issues -- see tc_common.cuh elect_one()
+    {
       constexpr uint32_t idesc = idesc_bf16(128, BN, 0, 0);
-      const uint32_t sub_bytes = (uint32_t)(a.BH * a.BW) * Cfg::kRowBytes;  // one sub-tile's rows
-      const uint32_t row_bytes = (uint32_t)a.BW * Cfg::kRowBytes;           // one image row of the box
+      const uint32_t sub16 = ((uint32_t)(a.BH * a.BW) * Cfg::kRowBytes) >> 4;  // one sub-tile's rows, in descriptor units
+      const uint32_t row16 = ((uint32_t)a.BW * Cfg::kRowBytes) >> 4;           // one image row of the box
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -219,31 +224,34 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t d0 = tmem_base + (uint32_t)(as * MT * BN);
         for (int st = 0; st < num_st; ++st) {
           mbar_wait(&full[stage], phase);
-          if (local == 0 && st == 0) STP_TRACE(3);
+          if (local == 0 && st == 0 && lane == 0) STP_TRACE(3);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
-          const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
-          if (!(a.dbg & 8))
+          const uint64_t ad0 = desc_kmajor(smem_u32(sA + stage * Cfg::kABytes), BK * 2);
+          const uint64_t bd0 = desc_kmajor(smem_u32(sB + stage * Cfg::kBBytes), BK * 2);
+          if (elect_one()) {
+            if (!(a.dbg & 8))
 #pragma unroll
-          for (int j = 0; j < MT; ++j) {
-            for (int r = 0; r < a.R; ++r) {
-              const uint32_t aj = a_addr + j * sub_bytes + r * row_bytes;
-              const uint32_t br = b_addr + r * Cfg::kBTap;
+            for (int j = 0; j < MT; ++j) {
+              for (int r = 0; r < a.R; ++r) {
+                const uint64_t aj = ad0 + (uint64_t)(j * sub16 + r * row16);
+                const uint64_t br = bd0 + (uint64_t)(r * (Cfg::kBTap >> 4));
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                umma_bf16(d0 + (uint32_t)(j * BN), desc_kmajor(aj + k * 32, BK * 2), desc_kmajor(br + k * 32, BK * 2), idesc,
-                          (st | r | k) != 0);
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_bf16(d0 + (uint32_t)(j * BN), aj + (uint64_t)(k * 2), br + (uint64_t)(k * 2), idesc, (st | r | k) != 0);
+              }
             }
+            if (CL > 1) umma_commit_mc(&empty[stage], kMask); else umma_commit(&empty[stage]);
           }
-          if (CL > 1) umma_commit_mc(&empty[stage], kMask); else umma_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == NS) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&acc_full[as]);
+        if (elect_one()) umma_commit(&acc_full[as]);
+        __syncwarp();
       }
-      STP_TRACE(4);
+      if (lane == 0) STP_TRACE(4);
     }
   } else {
     const int q = warp & 3;

@@ -43,6 +43,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a CONVERGED warp.  The single-thread instructions (tcgen05.mma / commit, TMA) are issued as
+//     <all 32 lanes run the loop and compute the operands>;  if (elect_one()) { issue }
+// rather than from inside an `if (lane == 0)` region: in a divergent region ptxas cannot keep the descriptors in uniform
+// registers and wraps EVERY UTCHMMA in an ELECT / 5x R2UR.BROADCAST / BRA.U.ANY loop (~22 instructions, measured ~90 clk per
+// 64-clk MMA = the MMA-issue thread, not L2 or the tensor pipe, bounded the conv kernels: profiles/README.md s27); with
+// warp-uniform control flow the operands live in uniform registers and an MMA costs ~7 uniform-datapath instructions.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMA -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
