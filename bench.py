@@ -187,6 +187,9 @@ def time_dominant_kernel(net, reps=30):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
     for i in range(3):
         conv.fwd()
+    n3 = net.L.tc3_launch_count()
+    conv.fwd()
+    pair = net.L.tc3_launch_count() > n3  # which tcgen05 kernel serves this layer (CTA-pair kernel or single-CTA halo kernel)
     for a, b in ev:
         flush.zero_()
         a.record(st)
@@ -197,6 +200,7 @@ def time_dominant_kernel(net, reps=30):
     ms = sum(ts) / len(ts)
     flop = 2.0 * conv.y.rows * conv.y.c * conv.k * conv.k * conv.x.c
     return {"name": conv.name, "ms": ms, "flop": flop,
+            "kernel": "conv_tc3_kernel<128,2> (tcgen05 cta_group::2 CTA pair)" if pair else "conv_tc2_kernel<128,64,2>",
             "shape": "3x3 %d->%d @%dx%d bs%d" % (conv.x.c, conv.y.c, conv.y.h, conv.y.w, conv.y.n)}
 
 
@@ -325,7 +329,7 @@ def run_gpu(args, rank, local_rank, world):
         }
         if dom is not None:
             ach = dom["flop"] / (dom["ms"] / 1e3) / 1e12
-            out["roofline"] = {"bound": "tensor", "kernel": "conv_tc2_kernel<128,64,2>: %s fwd (%s) + BN statistics epilogue" %
+            out["roofline"] = {"bound": "tensor", "kernel": dom["kernel"] + ": %s fwd (%s) + BN statistics epilogue" %
                                                             (dom["name"], dom["shape"]),
                                "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
                                "peak_source": src + (" (of measured)" if src == "measured" else " (of fallback, B200_PROFILING.md)"),

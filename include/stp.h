@@ -56,8 +56,11 @@ int64_t stp_launch_count(void);
 int stp_tc_enabled(void);
 /* number of tcgen05/TMA kernels enqueued since load (evidence that the tensor-core path, not the mma.sync one, ran) */
 int64_t stp_tc_launch_count(void);
+/* ... of which launches of the tcgen05 cta_group::2 CTA-pair conv kernel (conv_tc3.cu) */
+int64_t stp_tc3_launch_count(void);
 void stp_set_tc_enabled(int on);
-/* debugging / A-B knobs: "tc2_force_mt" (0 heuristic | 1,2,4,8), "tc_conv_version" (0 auto | 1 first-generation only) */
+/* debugging / A-B knobs: "tc2_force_mt" (0 heuristic | 1,2,4,8), "tc_conv_version" (0 auto | 1 first-generation only),
+ * "tc3" (0 auto | 1 off | 2 CTA-pair kernel wherever it serves the shape), "tc3_force_bn" (128 | 256), "tc3_force_mt" (1 | 2) */
 int stp_set_option(const char* name, int32_t value);
 /* profiling aid: device buffer of >= 64 uint64 that the halo conv kernel's first and last thread blocks fill with
  * %globaltimer stamps of their phases (scripts/trace_conv.py); NULL turns it off */

@@ -12,6 +12,7 @@ namespace stp {
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 std::atomic<int64_t> g_tc_launches{0};
+std::atomic<int64_t> g_tc3_launches{0};
 static std::atomic<int> g_tc_enabled{1};
 std::atomic<int> g_pdl_enabled{1};
 
@@ -61,6 +62,7 @@ extern "C" int stp_version(void) { return STP_VERSION; }
 extern "C" const char* stp_last_error(void) { return g_err; }
 extern "C" int64_t stp_launch_count(void) { return g_launches.load(); }
 extern "C" int64_t stp_tc_launch_count(void) { return g_tc_launches.load(); }
+extern "C" int64_t stp_tc3_launch_count(void) { return g_tc3_launches.load(); }
 extern "C" int stp_tc_enabled(void) { return g_tc_enabled.load(); }
 extern "C" void stp_set_tc_enabled(int on) { g_tc_enabled.store(on ? 1 : 0); }
 

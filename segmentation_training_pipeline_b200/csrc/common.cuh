@@ -14,6 +14,7 @@ namespace stp {
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
 extern std::atomic<int64_t> g_tc_launches;
+extern std::atomic<int64_t> g_tc3_launches;
 
 inline int check_launch(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);

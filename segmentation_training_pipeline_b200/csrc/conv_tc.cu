@@ -188,8 +188,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   };
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+    // ================= TMA producer (warp-uniform loop, one elected lane issues: tc_common.cuh elect_one()) ==========
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
@@ -199,10 +199,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int tap = 0; tap < cl.ntaps; ++tap) {
           for (int cb = 0; cb < kcb; ++cb) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-            tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], cb * BK, w0 * a.stride + cl.tap_dw[tap],
-                        h0 * a.stride + cl.tap_dh[tap], img);
-            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], cl.tap_k[tap] * a.Cin + cb * BK, n0);
+            if (elect_one()) {
+              mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+              tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], cb * BK, w0 * a.stride + cl.tap_dw[tap],
+                          h0 * a.stride + cl.tap_dh[tap], img);
+              tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], cl.tap_k[tap] * a.Cin + cb * BK, n0);
+            }
+            __syncwarp();
             if (++stage == NS) {
               stage = 0;
               phase ^= 1;
@@ -212,8 +215,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (warp-uniform loop, one elected lane issues) =================
+    {
       constexpr uint32_t idesc = idesc_bf16(128, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -230,21 +233,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
-          const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
+          const uint64_t ad0 = desc_kmajor(smem_u32(sA + stage * Cfg::kABytes), BK * 2);
+          const uint64_t bd0 = desc_kmajor(smem_u32(sB + stage * Cfg::kBBytes), BK * 2);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = desc_kmajor(a_addr + k * 32, BK * 2);
-            const uint64_t bd = desc_kmajor(b_addr + k * 32, BK * 2);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
           }
-          umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          __syncwarp();
           if (++stage == NS) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&acc_full[as]);  // accumulator complete
+        if (elect_one()) umma_commit(&acc_full[as]);  // accumulator complete
+        __syncwarp();
       }
     }
   } else {
@@ -609,7 +612,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    {  // warp-uniform loop, one elected lane issues (tc_common.cuh elect_one())
       const uint32_t tx_bytes = (uint32_t)a.a_boxes * a_box_bytes +
                                 (uint32_t)(STR ? a.R : 1) * (uint32_t)BBOX * (uint32_t)a.xrows * (uint32_t)a.b_row;
       int stage = 0;
@@ -623,6 +626,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* pa = sA + stage * Cfg::kABytes;
         uint8_t* pbuf = sB + stage * Cfg::kBBytes;
+        if (elect_one()) {
         if (a.dbg & 3) {
           const uint32_t txa = (a.dbg & 1) ? 0u : (uint32_t)a.a_boxes * a_box_bytes;
           const uint32_t txb = (a.dbg & 2) ? 0u : tx_bytes - (uint32_t)a.a_boxes * a_box_bytes;
@@ -644,6 +648,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
           for (int j = 0; j < BBOX; ++j)
             tma_load_4d(pbuf + j * Cfg::kXBoxBytes, &tmX, &full[stage], ci0 + 64 * j, w0 + s - a.pad_w, h0 - a.pad_h, img);
         }
+        }
+        __syncwarp();
         if (++stage == NS) {
           stage = 0;
           phase ^= 1;
@@ -651,7 +657,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = idesc_bf16(128, BN, 1, 1);
       const uint32_t a_step = 16u * (uint32_t)a.a_row, b_step = 16u * (uint32_t)a.b_row;  // 16 pixels (one MMA K) further
       int stage = 0;
@@ -659,26 +665,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       for (int i = 0; i < npb; ++i) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
-        const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
-        if (!(a.dbg & 8))
-        for (int r = 0; r < a.R; ++r) {
-          const uint32_t b_r = STR ? b_addr + (uint32_t)r * (uint32_t)Cfg::kRBytes
-                                   : b_addr + (uint32_t)(r * a.BW) * (uint32_t)a.b_row;
+        // descriptors of the stage's first K step; later steps / filter rows only move the 14-bit start-address field
+        const uint64_t ad0 = desc_mnmajor(smem_u32(sA + stage * Cfg::kABytes), (uint32_t)a.a_lbo, (uint32_t)a.a_row);
+        const uint64_t bd0 = desc_mnmajor(smem_u32(sB + stage * Cfg::kBBytes), Cfg::kXBoxBytes, (uint32_t)a.b_row);
+        if (elect_one()) {
+          if (!(a.dbg & 8))
+          for (int r = 0; r < a.R; ++r) {
+            const uint64_t b_r = bd0 + (uint64_t)((STR ? (uint32_t)r * (uint32_t)Cfg::kRBytes
+                                                       : (uint32_t)(r * a.BW) * (uint32_t)a.b_row) >> 4);
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint64_t ad = desc_mnmajor(a_addr + kk * a_step, (uint32_t)a.a_lbo, (uint32_t)a.a_row);
-            const uint64_t bd = desc_mnmajor(b_r + kk * b_step, Cfg::kXBoxBytes, (uint32_t)a.b_row);
-            umma_bf16(tmem_base + (uint32_t)(r * BN), ad, bd, idesc, (i | kk) != 0);
+            for (int kk = 0; kk < 8; ++kk)
+              umma_bf16(tmem_base + (uint32_t)(r * BN), ad0 + (uint64_t)((kk * a_step) >> 4), b_r + (uint64_t)((kk * b_step) >> 4),
+                        idesc, (i | kk) != 0);
           }
+          umma_commit(&empty[stage]);
         }
-        umma_commit(&empty[stage]);
+        __syncwarp();
         if (++stage == NS) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(acc_full);
+      if (elect_one()) umma_commit(acc_full);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

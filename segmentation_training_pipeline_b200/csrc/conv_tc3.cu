@@ -162,7 +162,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {  // TMA producer: warp-uniform loop, one elected lane issues (tc_common.cuh elect_one())
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       for (int item = w_first; item < a.num_items; item += w_step) {
@@ -171,6 +171,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int s = 0; s < a.S; ++s) {
           for (int cb = 0; cb < kcb; ++cb) {
             mbar_wait(&emptyA[sa], pha ^ 1);
+            if (elect_one()) {
             if (a.dbg & 1) {
               if (leader) mbar_arrive(&fullA[sa]);
             } else {
@@ -178,12 +179,15 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma_load_4d_pair(sA + sa * Cfg::kABytes, &tmA, mapa_u32(smem_u32(&fullA[sa]), 0), cb * kBK3, w0 + s - a.pad_w,
                              h0 - a.pad_h, img);
             }
+            }
+            __syncwarp();
             if (++sa == NA) {
               sa = 0;
               pha ^= 1;
             }
             for (int r = 0; r < a.R; ++r) {
               mbar_wait(&emptyB[sb], phb ^ 1);
+              if (elect_one()) {
               if (a.dbg & 2) {
                 if (leader) mbar_arrive(&fullB[sb]);
               } else {
@@ -191,6 +195,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               tma_load_2d_pair(sB + sb * Cfg::kBTap, &tmB, mapa_u32(smem_u32(&fullB[sb]), 0),
                                (r * a.S + s) * a.Cin + cb * kBK3, n0 + (int)crank * (BN / 2));
               }
+              }
+              __syncwarp();
               if (++sb == NB) {
                 sb = 0;
                 phb ^= 1;
@@ -201,10 +207,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {  // MMA issue by the leader CTA: warp-uniform loop, one elected lane issues
       constexpr uint32_t idesc = idesc_bf16(256, BN, 0, 0);
-      const uint32_t sub_bytes = (uint32_t)(a.BH * a.BW) * Cfg::kRowBytes;
-      const uint32_t row_bytes = (uint32_t)a.BW * Cfg::kRowBytes;
+      const uint32_t sub16 = ((uint32_t)(a.BH * a.BW) * Cfg::kRowBytes) >> 4;
+      const uint32_t row16 = ((uint32_t)a.BW * Cfg::kRowBytes) >> 4;
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       int local = 0;
@@ -216,37 +222,41 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t d0 = tmem_base + (uint32_t)(as * MT * BN);
         for (int st = 0; st < a.S * kcb; ++st) {
           mbar_wait(&fullA[sa], pha);
-          const uint32_t a_addr = smem_u32(sA + sa * Cfg::kABytes);
+          const uint64_t ad0 = desc_kmajor(smem_u32(sA + sa * Cfg::kABytes), 128);
           for (int r = 0; r < a.R; ++r) {
             mbar_wait(&fullB[sb], phb);
-            if (local == 0 && st == 0 && r == 0) STP_TRACE3(3);
+            if (local == 0 && st == 0 && r == 0 && lane == 0) STP_TRACE3(3);
             tc_fence_after();
-            const uint32_t b_addr = smem_u32(sB + sb * Cfg::kBTap);
-            if (!(a.dbg & 8))
+            const uint64_t bd0 = desc_kmajor(smem_u32(sB + sb * Cfg::kBTap), 128);
+            if (elect_one()) {
+              if (!(a.dbg & 8))
 #pragma unroll
-            for (int j = 0; j < MT; ++j) {
-              const uint32_t aj = a_addr + j * sub_bytes + r * row_bytes;
+              for (int j = 0; j < MT; ++j) {
+                const uint64_t aj = ad0 + (uint64_t)(j * sub16 + r * row16);
 #pragma unroll
-              for (int k = 0; k < kBK3 / 16; ++k)
-                umma_bf16_pair(d0 + (uint32_t)(j * BN), desc_kmajor(aj + k * 32, 128), desc_kmajor(b_addr + k * 32, 128), idesc,
-                               (st | r | k) != 0);
+                for (int k = 0; k < kBK3 / 16; ++k)
+                  umma_bf16_pair(d0 + (uint32_t)(j * BN), aj + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), idesc, (st | r | k) != 0);
+              }
+              umma_commit_pair(&emptyB[sb], 3);
             }
-            umma_commit_pair(&emptyB[sb], 3);
+            __syncwarp();
             if (++sb == NB) {
               sb = 0;
               phb ^= 1;
             }
           }
-          umma_commit_pair(&emptyA[sa], 3);
+          if (elect_one()) umma_commit_pair(&emptyA[sa], 3);
+          __syncwarp();
           if (++sa == NA) {
             sa = 0;
             pha ^= 1;
           }
         }
-        umma_commit_pair(&acc_full[as], 3);
-        if (local == 0) STP_TRACE3(10);
+        if (elect_one()) umma_commit_pair(&acc_full[as], 3);
+        __syncwarp();
+        if (local == 0 && lane == 0) STP_TRACE3(10);
       }
-      STP_TRACE3(4);
+      if (lane == 0) STP_TRACE3(4);
     }
   } else {
     const int q = warp & 3;
@@ -451,7 +461,7 @@ bool tc3_plan(const ConvP& p, Tc3Plan* pl) {
   if (p.y_f32 || p.ncls > 0) return false;
   double best = 0.0;
   int bbn = 0, bmt = 0;
-  for (int bn : {128, 256}) {
+  for (int bn : {128}) {  // BN = 256 (no TMEM double buffering left for MT = 2, 64 KB staging) never won: only when forced
     if (p.Cout % bn != 0) continue;
     for (int mt = 1; mt <= (bn == 128 ? 2 : 1); ++mt) {
       const double c = tc3_cost(p, bn, mt);
@@ -514,18 +524,25 @@ int launch3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& t
   cfg.numAttrs = 2;
   cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmY, tmR, a);
   g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+  g_tc3_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("conv_tc3");
 }
 
 }  // namespace
 
 bool tc3_conv_supported(const ConvP& p) {
-  // option "tc3": 0 automatic | 1 off | 2 on wherever the shape is served.  Automatic is OFF for now: measured on B200
-  // (profiles/README.md, s27) the pair kernel matches or trails conv_tc2 on the U-Net shapes.
+  // option "tc3": 0 automatic | 1 off | 2 on wherever the shape is served.  Automatic: the pair kernel wins once every CTA
+  // pair has work (measured on B200, profiles/README.md s27: 128->128 @64^2 25.6 vs 27.6 us, 768->256 @32^2 48.1 vs 54.2 us,
+  // 384->128 @64^2 51.2 vs 58.4 us; 256->256 @32^2 equal; 512->512 @16^2 -- 32 work items -- 31.7 vs 29.7 us)
   const int opt = get_option(OPT_TC3);
-  if (opt != 2) return false;
+  if (opt == 1) return false;
   Tc3Plan pl;
   if (!tc3_plan(p, &pl)) return false;
+  if (opt == 0) {
+    const int bw = p.Wo >= 16 ? 16 : 8, th = pl.MT * (128 / bw);
+    const int64_t pt = (int64_t)p.N * ((p.Ho + th - 1) / th) * ((p.Wo + bw - 1) / bw);
+    if (((pt + 1) / 2) * (p.Cout / pl.BN) < kPairs) return false;
+  }
   if (p.Wo < 8 || p.Ho < 1) return false;
   if (p.ldx % 8 != 0 || !aligned16(p.x) || !aligned16(p.w)) return false;
   if (p.ldy % 8 != 0 || !aligned16(p.y)) return false;

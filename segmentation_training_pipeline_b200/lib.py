@@ -71,6 +71,7 @@ SIGNATURES = {
     "stp_launch_count": (_I64, []),
     "stp_tc_enabled": (C.c_int, []),
     "stp_tc_launch_count": (_I64, []),
+    "stp_tc3_launch_count": (_I64, []),
     "stp_set_tc_enabled": (None, [C.c_int]),
     "stp_set_option": (C.c_int, [C.c_char_p, _I32]),
     "stp_set_trace_buffer": (None, [_P]),
@@ -152,7 +153,7 @@ def check(rc: int, what: str = ""):
 
 
 # functions whose int return value is a result, not a status code
-_UNCHECKED = ("set_trace_buffer", "version", "tc_enabled", "bn_nblk", "last_error", "launch_count", "tc_launch_count", "set_tc_enabled",
+_UNCHECKED = ("set_trace_buffer", "version", "tc_enabled", "bn_nblk", "last_error", "launch_count", "tc_launch_count", "tc3_launch_count", "set_tc_enabled",
               "conv_wgrad_workspace", "head_bwd_workspace", "head_fwd_workspace", "loss_partial_floats", "lovasz_workspace")
 
 

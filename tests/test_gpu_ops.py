@@ -598,6 +598,7 @@ def test_conv_tc2_cluster_multicast(stp, cuda, case, cl):
     gamma, beta = torch.ones(cout, device=cuda), torch.zeros(cout, device=cuda)
     xs, rs = T(x), T(res)
     outs = []
+    stp.set_option(b"tc3", 1)  # this test is about the conv_tc2 cluster variants: keep the CTA-pair kernel out of the way
     try:
         for c in (1, cl):
             stp.set_option(b"tc2_cluster", c)
@@ -613,6 +614,7 @@ def test_conv_tc2_cluster_multicast(stp, cuda, case, cl):
             outs.append((y, coef))
     finally:
         stp.set_option(b"tc2_cluster", 0)
+        stp.set_option(b"tc3", 0)
     assert torch.equal(outs[0][0], outs[1][0])
     assert max_abs(outs[0][1], outs[1][1]) <= 2e-6 * (1 + float(outs[0][1].abs().max()))
     yr = conv_ref(x, wt, 1, 1) + res.float().cpu()
