@@ -4,6 +4,7 @@
 // variance, moving stats with Bessel-corrected variance.
 #include "common.cuh"
 #include "bn_fin.cuh"
+#include "conv.h"
 
 namespace stp {
 
@@ -42,8 +43,11 @@ static RowGeom reduce_geom(int64_t rows, int c, bool atomic_acc = false) {
   if (!atomic_acc) return geom(rows, c, 4, reduce_max_blk(c));
   // atomic accumulation: every block issues 2*c double atomics + one ticket; keep the total (and the same-address
   // contention, = the block count) bounded
-  int m = 16384 / (c < 8 ? 8 : c);
-  if (m > 2 * kNumSMs) m = 2 * kNumSMs;
+  const int budget = get_option(OPT_BN_BLOCKS) > 0 ? get_option(OPT_BN_BLOCKS) * 1024 : 16384;
+  int m = budget / (c < 8 ? 8 : c);
+  const int cap = get_option(OPT_BN_BLOCKS) > 0 ? 4 * kNumSMs : 2 * kNumSMs;
+  if (m > cap) m = cap;
+  if (get_option(OPT_BN_BLOCKS) > 0 && m < kNumSMs) m = kNumSMs;
   if (m < 32) m = 32;
   return geom(rows, c, 4, m);
 }

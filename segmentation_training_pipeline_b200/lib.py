@@ -142,6 +142,11 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
+    # A/B knobs from the environment: STP_OPTIONS="bn_blocks=64,tc3=1" -> stp_set_option for each pair
+    for kv in filter(None, os.environ.get("STP_OPTIONS", "").split(",")):
+        k, v = kv.split("=")
+        if lib.stp_set_option(k.strip().encode(), int(v)) != 0:
+            raise StpError("STP_OPTIONS: unknown option " + k)
     _lib = lib
     return lib
 
