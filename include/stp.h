@@ -148,6 +148,25 @@ int stp_conv_fwd_bn(const stp_conv_desc* d, const stp_tensor* x, const void* w_k
 int stp_conv_dgrad(const stp_conv_desc* d, const stp_tensor* dy, const void* w_dgrad,
                    const stp_tensor* residual, const stp_tensor* dx, void* workspace, size_t workspace_bytes,
                    stp_stream stream);
+/* stp_conv_dgrad that ALSO performs the BatchNorm-backward reduction of the BatchNorm(+ReLU) layer whose OUTPUT is this
+ * conv's input (keras BatchNormalization -> TF FusedBatchNormGrad reductions): with x = that layer's input and coef its
+ * forward coefficients, dx is stored as g = dx*[x*scale+shift > 0] (relu != 0; masking is idempotent, stp_bn_bwd_apply may
+ * mask again) and (sum g, sum g*xhat) -> dgamma, dbeta, bcoef exactly as stp_bn_bwd_reduce_fused -- one pass over (dx, x)
+ * removed.  The dgrad must deliver the COMPLETE gradient of that tensor (no residual).  Shapes the halo kernel does not
+ * serve run dgrad + stp_bn_bwd_reduce_fused. */
+typedef struct stp_bn_bwd {
+  const stp_tensor* x;  /* BatchNorm input (bf16, same pixels / channels as dx) */
+  const float* coef;    /* f32 [4][c] mean, invstd, scale, shift (stp_bn_finalize / stp_conv_fwd_bn) */
+  int32_t relu;
+  float* partial;       /* as stp_bn_bwd_reduce_fused (fallback pass) */
+  uint32_t* sync;       /* zero-initialised ticket */
+  double* acc;          /* 2*c zero-initialised doubles, returned to zero */
+  float* dgamma;        /* may be NULL */
+  float* dbeta;         /* may be NULL */
+  float* bcoef;         /* out: f32 [3][c] */
+} stp_bn_bwd;
+int stp_conv_dgrad_bn(const stp_conv_desc* d, const stp_tensor* dy, const void* w_dgrad, const stp_tensor* dx,
+                      const stp_bn_bwd* h_bnb, void* workspace, size_t workspace_bytes, stp_stream stream);
 /* dw[Cout][R][S][Cin] (f32) = sum_pixels dy (x) x ; deterministic split reduction through workspace */
 int stp_conv_wgrad(const stp_conv_desc* d, const stp_tensor* x, const stp_tensor* dy, float* dw,
                    void* workspace, size_t workspace_bytes, stp_stream stream);

@@ -49,6 +49,7 @@ extern "C" int stp_set_option(const char* name, int32_t value) {
   else if (!strcmp(name, "tc3")) key = OPT_TC3;                         /* 0 auto | 1 off | 2 CTA-pair kernel wherever it serves the shape */
   else if (!strcmp(name, "tc3_force_bn")) key = OPT_TC3_FORCE_BN;       /* 0 heuristic | 128, 256 */
   else if (!strcmp(name, "tc3_force_mt")) key = OPT_TC3_FORCE_MT;       /* 0 heuristic | 1, 2 */
+  else if (!strcmp(name, "bnb_fuse")) key = OPT_BNB_FUSE;               /* 0 auto | 1: never fuse the BatchNorm-backward reduction into the dgrad epilogue */
   else if (!strcmp(name, "bn_blocks")) key = OPT_BN_BLOCKS;             /* 0 default | n: atomic-mode BN reductions use up to n*1024/C blocks */
   else if (!strcmp(name, "pdl")) {                                      /* programmatic dependent launch on/off */
     g_pdl_enabled.store(value ? 1 : 0);
@@ -144,9 +145,8 @@ extern "C" int stp_conv_fwd_bn(const stp_conv_desc* d, const stp_tensor* x, cons
   return conv_fwd_common(d, x, w_krsc, bias, residual, y, h_bn, stream);
 }
 
-extern "C" int stp_conv_dgrad(const stp_conv_desc* d, const stp_tensor* dy, const void* w_dgrad,
-                              const stp_tensor* residual, const stp_tensor* dx, void* workspace,
-                              size_t workspace_bytes, stp_stream stream) {
+static int conv_dgrad_common(const stp_conv_desc* d, const stp_tensor* dy, const void* w_dgrad, const stp_tensor* residual,
+                             const stp_tensor* dx, const stp_bn_bwd* h_bnb, stp_stream stream) {
   int rc = check_conv_common(d, dy, dx, "conv_dgrad");
   if (rc) return rc;
   STP_REQUIRE(w_dgrad && dx->ptr && dx->dtype == STP_BF16 && dx->ld >= dx->c, "conv_dgrad: bad dx / weights");
@@ -155,8 +155,6 @@ extern "C" int stp_conv_dgrad(const stp_conv_desc* d, const stp_tensor* dy, cons
   if (residual)
     STP_REQUIRE(residual->dtype == STP_BF16 && residual->c == dx->c && pixels(residual) == pixels(dx),
                 "conv_dgrad: bad residual");
-  (void)workspace;
-  (void)workspace_bytes;
   ConvP p;
   p.x = (const __nv_bfloat16*)dy->ptr; p.ldx = dy->ld; p.N = dy->n; p.H = dy->h; p.W = dy->w; p.Cin = dy->c;
   p.w = (const __nv_bfloat16*)w_dgrad;
@@ -169,7 +167,44 @@ extern "C" int stp_conv_dgrad(const stp_conv_desc* d, const stp_tensor* dy, cons
   p.stride = d->up; p.up = d->stride; p.pad_h = d->r - 1 - d->pad_h; p.pad_w = d->s - 1 - d->pad_w;
   p.relu = 0;
   p.M = pixels(dx); p.K = d->r * d->s * dy->c;
-  return dispatch_conv(p, (cudaStream_t)stream);
+  if (!h_bnb) return dispatch_conv(p, (cudaStream_t)stream);
+  // BatchNorm-backward reduction of the layer that PRODUCED this conv's input: inside the dgrad epilogue when the halo
+  // kernel serves the shape (dx is then stored already masked by the ReLU), else one extra pass over (dx, x)
+  STP_REQUIRE(h_bnb->x && vec_ok(h_bnb->x) && h_bnb->x->c == dx->c && pixels(h_bnb->x) == pixels(dx) && h_bnb->coef &&
+                  h_bnb->sync && h_bnb->acc && h_bnb->bcoef && h_bnb->partial,
+              "conv_dgrad_bn: bad BatchNorm arguments");
+  STP_REQUIRE(!residual, "conv_dgrad_bn: the fused reduction needs the COMPLETE gradient (no residual accumulation)");
+  BnFuse bn;
+  bn.acc = h_bnb->acc;
+  bn.fin = FinArgs{};
+  bn.fin.mode = 2; bn.fin.sync = h_bnb->sync; bn.fin.acc = h_bnb->acc; bn.fin.inv_count = 1.0 / (double)pixels(dx);
+  bn.fin.coef = const_cast<float*>(h_bnb->coef); bn.fin.dgamma = h_bnb->dgamma; bn.fin.dbeta = h_bnb->dbeta;
+  bn.fin.bcoef = h_bnb->bcoef;
+  p.bn = &bn;
+  p.bnb_x = (const __nv_bfloat16*)h_bnb->x->ptr; p.bnb_ldx = h_bnb->x->ld; p.bnb_coef = h_bnb->coef; p.bnb_relu = h_bnb->relu;
+  if (stp_tc_enabled() && get_option(OPT_TC_CONV_VERSION) != 1 && get_option(OPT_BNB_FUSE) != 1 && tc2_conv_supported(p))
+    return launch_tc2_conv(p, (cudaStream_t)stream);
+  p.bn = nullptr;
+  rc = dispatch_conv(p, (cudaStream_t)stream);
+  if (rc) return rc;
+  return stp_bn_bwd_reduce_fused(dx, h_bnb->x, h_bnb->coef, h_bnb->relu, 1, h_bnb->partial, h_bnb->sync, h_bnb->acc,
+                                 h_bnb->dgamma, h_bnb->dbeta, h_bnb->bcoef, stream);
+}
+
+extern "C" int stp_conv_dgrad(const stp_conv_desc* d, const stp_tensor* dy, const void* w_dgrad,
+                              const stp_tensor* residual, const stp_tensor* dx, void* workspace,
+                              size_t workspace_bytes, stp_stream stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  return conv_dgrad_common(d, dy, w_dgrad, residual, dx, nullptr, stream);
+}
+
+extern "C" int stp_conv_dgrad_bn(const stp_conv_desc* d, const stp_tensor* dy, const void* w_dgrad, const stp_tensor* dx,
+                                 const stp_bn_bwd* h_bnb, void* workspace, size_t workspace_bytes, stp_stream stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  STP_REQUIRE(h_bnb, "conv_dgrad_bn: null h_bnb");
+  return conv_dgrad_common(d, dy, w_dgrad, nullptr, dx, h_bnb, stream);
 }
 
 static WgradP make_wgrad_p(const stp_conv_desc* d, const stp_tensor* x, const stp_tensor* dy) {

@@ -45,8 +45,12 @@ struct Tc2Args {
   int num_tiles;             // work items: tiles (CL == 1) or cluster items = groups of CL pixel tiles x N tiles
   int numPT, nimg;           // pixel tiles per N tile, images (cluster variants: ranks beyond numPT idle on an OOB image)
   int a_bytes, b_tap_bytes;  // runtime sizes of the A box and of one weight box
-  int bn_on;                 // accumulate BatchNorm statistics of the stored output (bf16 path)
+  int bn_on;                 // 1: accumulate the forward BatchNorm statistics of the stored output (bf16 path)
+                             // 2: this launch is a dgrad whose output is d(BatchNorm+ReLU output): tmR maps the BatchNorm INPUT x;
+                             //    store g = dy*[x*scale+shift > 0] and accumulate the BatchNorm-backward sums (sum g, sum g*x)
   BnFuse bn;
+  const float* bnb_coef;     // bn_on == 2: f32 [4][Cout] mean, invstd, scale, shift of that BatchNorm
+  int bnb_relu;
   int ncls;                  // > 0: "head" epilogue -- only output channels [0, ncls) exist, fp32 [pixels][ncls] dense (+bias)
   unsigned long long* trace; // profiling aid (get_trace_buffer)
   int dbg;                   // timing experiments only (results invalid): 1 skip A loads, 2 skip B loads, 4 skip epilogue memory ops, 8 skip MMAs
@@ -71,7 +75,7 @@ struct Tc2Cfg {
   static constexpr int EP = BN <= 32 ? MT : 1;
   static constexpr int kSubBytes = align1k(128 * BN * 2);            // bf16 staging tile of one sub-tile
   static constexpr int kOutBytes = EP * kSubBytes;
-  static constexpr int kTailBytes = 256 /*barriers*/ + 2 * 128 * 4 /*sStat*/ + 4 * 2 * 128 * 4 /*sRed*/;
+  static constexpr int kTailBytes = 256 /*barriers*/ + 2 * 128 * 4 /*sStat*/ + 4 * 2 * 128 * 4 /*sRed*/ + 2 * 128 * 4 /*sCoef*/;
   static constexpr int kStagesRaw = (kSmemBudget2 - 1024 - kTailBytes - 64 - kOutBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemRaw = 2 * MT * BN;
@@ -108,7 +112,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
   int* s_last = reinterpret_cast<int*>(tmem_slot + 1);
   float* sStat = reinterpret_cast<float*>(sOut + Cfg::kOutBytes + 256);  // [2][128] per-CTA sums of the current N tile
-  float* sRed = sStat + 256;                                             // [2][128] cross-pixel-group combine
+  float* sRed = sStat + 256;                                             // [4 warps][2][128] cross-warp combine
+  float* sCoef = sRed + 1024;                                            // [2][128] scale, shift of the current N tile (bn_on == 2)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kcb = a.Cin / BK;
@@ -279,6 +284,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         bn_flush();
         cur_n0 = n0;
         if (m < BN) sStat[m] = sStat[128 + m] = 0.f;
+        if (a.bn_on == 2 && m < BN) {  // read by every thread after the named barrier that opens each epilogue round
+          sCoef[m] = __ldg(a.bnb_coef + 2 * a.Cout + n0 + m);
+          sCoef[128 + m] = __ldg(a.bnb_coef + 3 * a.Cout + n0 + m);
+        }
       }
       const int wo = w0 + wl;
       mbar_wait(&acc_full[as], aphase);
@@ -352,7 +361,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int e = 0; e < EP; ++e) nj += (j0 + e < MT && h0 + (j0 + e) * a.BH < a.Ho) ? 1 : 0;
           if (leader) tma_store_wait_read();   // previous round's stores no longer read the staging tiles
           named_bar_sync(1, 128);
-          if (a.res) {
+          if (a.res || a.bn_on == 2) {  // residual tile, or (fused BatchNorm backward) the BatchNorm input x of the same pixels
             if (leader) {
               mbar_expect_tx(res_bar, (uint32_t)(nj * 128 * BN * 2));
               for (int e = 0; e < nj; ++e)
@@ -364,10 +373,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_wait(res_bar, res_phase);
             res_phase ^= 1;
           }
+          // fused BatchNorm backward, narrow tiles (BN <= 32): per-thread sums over the sub-tiles of the round, one
+          // warp transpose-reduction per round; wide tiles reduce every 32-channel chunk right away
+          float gacc[BN <= 32 ? BN : 1], xacc[BN <= 32 ? BN : 1];
+#pragma unroll
+          for (int i = 0; i < (BN <= 32 ? BN : 1); ++i) gacc[i] = xacc[i] = 0.f;
 #pragma unroll 1
           for (int e = 0; e < nj; ++e) {
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * MT + j0 + e) * BN);
             uint8_t* sub = sOut + e * Cfg::kSubBytes;
+            const bool pv = h0 + (j0 + e) * a.BH + hl < a.Ho && wo < a.Wo && img < a.nimg;  // this thread's pixel is real
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += CH) {
               uint32_t rr[CH];
@@ -382,6 +397,38 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
               uint8_t* slab = sub + (c0 >> 6) * (128 * RB) + m * RB;
               const uint32_t chunk0 = (uint32_t)((c0 & 63) >> 3);
+              if (a.bn_on == 2) {
+                float gx[CH];
+#pragma unroll
+                for (int i = 0; i < CH; i += 8) {
+                  bf16x8* sp = reinterpret_cast<bf16x8*>(slab + (((chunk0 + (i >> 3)) ^ swz) << 4));
+                  float xf[8];
+                  unpack8(*sp, xf);
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) {
+                    float val = __bfloat162float(__float2bfloat16_rn(v[i + jj]));  // the value that is stored
+                    const bool keep = pv && (!a.bnb_relu || xf[jj] * sCoef[c0 + i + jj] + sCoef[128 + c0 + i + jj] > 0.f);
+                    val = keep ? val : 0.f;
+                    v[i + jj] = val;
+                    gx[i + jj] = val * xf[jj];
+                  }
+                  *sp = pack8(v + i);
+                }
+                if constexpr (BN <= 32) {
+#pragma unroll
+                  for (int i = 0; i < CH; ++i) {
+                    gacc[c0 + i] += v[i];
+                    xacc[c0 + i] += gx[i];
+                  }
+                } else {
+                  const float sg = warp_transpose_sum<CH>(v, lane), sx = warp_transpose_sum<CH>(gx, lane);
+                  if (lane < CH) {
+                    sRed[(q * 2 + 0) * 128 + c0 + lane] = sg;
+                    sRed[(q * 2 + 1) * 128 + c0 + lane] = sx;
+                  }
+                }
+                continue;
+              }
 #pragma unroll
               for (int i = 0; i < CH; i += 8) {
                 bf16x8* sp = reinterpret_cast<bf16x8*>(slab + (((chunk0 + (i >> 3)) ^ swz) << 4));
@@ -399,6 +446,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
             }
           }
+          if constexpr (BN <= 32) {
+            if (a.bn_on == 2) {
+#pragma unroll
+              for (int c0 = 0; c0 < BN; c0 += CH) {
+                float tg[CH], tx[CH];
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                  tg[i] = gacc[c0 + i];
+                  tx[i] = xacc[c0 + i];
+                }
+                const float sg = warp_transpose_sum<CH>(tg, lane), sx = warp_transpose_sum<CH>(tx, lane);
+                if (lane < CH) {
+                  sRed[(q * 2 + 0) * 128 + c0 + lane] = sg;
+                  sRed[(q * 2 + 1) * 128 + c0 + lane] = sx;
+                }
+              }
+            }
+          }
           fence_proxy_async();
           named_bar_sync(1, 128);
           if (leader && !(a.dbg & 4)) {
@@ -408,7 +473,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tma_store_4d(&tmY, sOut + e * Cfg::kSubBytes + sl * 128 * RB, n0 + sl * 64, w0, h0 + (j0 + e) * a.BH, img);
             tma_store_commit();
           }
-          if (a.bn_on && img < a.nimg) {
+          if (a.bn_on == 2) {  // cross-warp combine of the round's (sum g, sum g*x); out-of-image pixels contributed zeros
+            named_bar_sync(2, 128);
+            if (m < BN) {
+              float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+              for (int wq = 0; wq < 4; ++wq) {
+                t1 += sRed[(wq * 2 + 0) * 128 + m];
+                t2 += sRed[(wq * 2 + 1) * 128 + m];
+              }
+              sStat[m] += t1;
+              sStat[128 + m] += t2;
+            }
+          }
+          if (a.bn_on == 1 && img < a.nimg) {
             // BatchNorm statistics of exactly the bf16 values just staged.  Thread = (channel octet o, pixel group g):
             // 16-byte conflict-free loads of the swizzled staging rows g, g+GP, ..., pixels outside the image masked;
             // groups are combined by a fixed xor-shuffle tree inside the warp, then across the 4 warps through sRed.
@@ -483,7 +561,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __threadfence();
         for (int c = m; c < a.Cout; c += 128) {
           const double s1 = __ldcg(a.bn.acc + c), s2 = __ldcg(a.bn.acc + a.Cout + c);
-          fin_forward(a.bn.fin, a.Cout, c, s1, s2);
+          if (a.bn_on == 2) {  // sum g*xhat = invstd * (sum g*x - mean * sum g)
+            const double mean = a.bn.fin.coef[c], invstd = a.bn.fin.coef[a.Cout + c];
+            fin_backward(a.bn.fin, a.Cout, c, s1, invstd * (s2 - mean * s1));
+          } else {
+            fin_forward(a.bn.fin, a.Cout, c, s1, s2);
+          }
           a.bn.acc[c] = 0.0;
           a.bn.acc[a.Cout + c] = 0.0;
         }
@@ -637,6 +720,9 @@ bool tc2_conv_supported(const ConvP& p) {
     if (!aligned16(p.y)) return false;
   }
   if (p.res && (p.ldr % 8 != 0 || !aligned16(p.res))) return false;
+  if (p.bn && p.bn->fin.mode == 2) {  // fused BatchNorm backward: bf16 output, no residual, x tensor TMA-mappable
+    if (p.res || p.y_f32 || p.ncls > 0 || !p.bnb_x || !p.bnb_coef || p.bnb_ldx % 8 != 0 || !aligned16(p.bnb_x)) return false;
+  }
   return get_encode_tiled() != nullptr;
 }
 
@@ -671,8 +757,10 @@ int launch_tc2_conv(const ConvP& p, cudaStream_t st) {
   a.dbg = get_option(OPT_TC2_DEBUG);
   a.trace = get_trace_buffer();
   a.ncls = p.ncls;
-  a.bn_on = (p.bn != nullptr && !p.y_f32 && p.ncls == 0) ? 1 : 0;
+  a.bn_on = (p.bn != nullptr && !p.y_f32 && p.ncls == 0) ? (p.bn->fin.mode == 2 ? 2 : 1) : 0;
   if (a.bn_on) a.bn = *p.bn; else a.bn = BnFuse{};
+  a.bnb_coef = p.bnb_coef;
+  a.bnb_relu = p.bnb_relu;
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
@@ -696,6 +784,9 @@ int launch_tc2_conv(const ConvP& p, cudaStream_t st) {
     if (p.res) {
       uint64_t rstrides[3] = {(uint64_t)p.ldr * 2, (uint64_t)p.Wo * p.ldr * 2, (uint64_t)p.Ho * p.Wo * p.ldr * 2};
       if (!make_tmap_bf16(&tmR, p.res, 4, dims, rstrides, box, oc * 2)) return STP_E_CUDA;
+    } else if (a.bn_on == 2) {  // the BatchNorm input of the same pixels travels through the residual slot
+      uint64_t rstrides[3] = {(uint64_t)p.bnb_ldx * 2, (uint64_t)p.Wo * p.bnb_ldx * 2, (uint64_t)p.Ho * p.Wo * p.bnb_ldx * 2};
+      if (!make_tmap_bf16(&tmR, p.bnb_x, 4, dims, rstrides, box, oc * 2)) return STP_E_CUDA;
     }
   }
   if (p.R == 4 || p.S == 4) {

@@ -61,6 +61,28 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// N (16 or 32) independent values per lane -> their sums over the 32 lanes of the warp, TRANSPOSED: on return lane l holds
+// the total of value (l & (N-1)).  Halving butterfly: N-1 (+N for N == 16) shuffles instead of 5*N.
+template <int N>
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[N], int lane) {
+  static_assert(N == 16 || N == 32, "16 or 32 values");
+  if (N == 16) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+  }
+#pragma unroll
+  for (int off = N / 2; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 // ---- TMA -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");

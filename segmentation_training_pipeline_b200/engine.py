@@ -137,6 +137,7 @@ class Net:
         self._partial_floats = 2 * _lib.BN_MAX_PARTIALS * 8
         self.encoder_param_names: List[str] = []
         self.fuse_bn_stats = True
+        self.fuse_bn_bwd = True
 
     # ---- parameters ---------------------------------------------------------------------------
     def add_param(self, name, shape, kind, init) -> Param:
@@ -185,6 +186,25 @@ class Net:
                 if len(w) == 1 and isinstance(w[0], (Conv, StemConv)) and w[0].y.dtype == BF16 and self.fuse_bn_stats:
                     w[0].bn_next = op
                     op.stats_from_conv = True
+        # a BatchNorm(+ReLU) whose output gradient is written by exactly ONE op, a convolution's dgrad that covers exactly
+        # that tensor, gets its backward reduction (dgamma, dbeta, bcoef) from that dgrad's epilogue (stp_conv_dgrad_bn)
+        if self.fuse_bn_bwd:
+            gwriters: Dict[Tuple[int, int, int], List[Op]] = {}
+            roots: Dict[int, int] = {}
+            for op in self.ops:
+                for g in op.grad_writes():
+                    gwriters.setdefault(g.key(), []).append(op)
+                    roots[id(g.root)] = roots.get(id(g.root), 0) + 1
+            for op in self.ops:
+                if isinstance(op, BNRelu) and op.up == 1:
+                    gk = op.y.grad().key()
+                    w = gwriters.get(gk, [])
+                    # no other op may write an overlapping slice of the same gradient buffer
+                    overlap = [k for k in gwriters if k[0] == gk[0] and k != gk and k[1] < gk[1] + gk[2] and gk[1] < k[1] + k[2]]
+                    if (len(w) == 1 and not overlap and type(w[0]) is Conv and w[0].needs_dgrad and w[0].x.key() == op.y.key()
+                            and w[0].desc.stride == 1 and w[0].desc.up == 1 and w[0].k > 1):
+                        w[0].bnb_prev = op
+                        op.reduce_from_dgrad = True
         host = np.zeros(self.n_flat, dtype=np.float32)
         for p in self.params.values():
             host[p.offset:p.offset + p.size] = p.init().reshape(-1)
@@ -392,6 +412,7 @@ class Conv(Op):
         self.stem_beta = stem_beta
         self.cin_real = cr
         self.bn_next: Optional["BNRelu"] = None
+        self.bnb_prev: Optional["BNRelu"] = None   # BatchNorm whose backward reduction this conv's dgrad performs
         net.need_ws(net.L.conv_wgrad_workspace(C.byref(self.desc), x.ref, y.ref))
         if bias:
             net.need_partial(2 * net.L.bn_nblk(y.rows, y.c) * y.c)
@@ -439,8 +460,12 @@ class Conv(Op):
                 n.L.stem_wgrad_post(n.pg(self.w), n.pp(self.w), c[0], c[1], c[2], c[3], self.cin_real,
                                     n.pg(self.stem_beta) if self.stem_beta is not None else None, st)
         if self.needs_dgrad:
-            n.L.conv_dgrad(self.dref, self.dy.ref, n.pwd(self.w), self.dx_res, self.dx.ref, n.ws.data_ptr(),
-                           n.ws.numel(), _stream())
+            if self.bnb_prev is not None and self.dx_res is None:
+                n.L.conv_dgrad_bn(self.dref, self.dy.ref, n.pwd(self.w), self.dx.ref, self.bnb_prev.bn_bwd_struct(),
+                                  n.ws.data_ptr(), n.ws.numel(), _stream())
+            else:
+                n.L.conv_dgrad(self.dref, self.dy.ref, n.pwd(self.w), self.dx_res, self.dx.ref, n.ws.data_ptr(),
+                               n.ws.numel(), _stream())
 
 
 class StemConv(Op):
@@ -517,7 +542,9 @@ class BNRelu(Op):
         self.nblk = net.L.bn_nblk(x.rows, c)
         net.need_partial(2 * self.nblk * c)
         self.stats_from_conv = False
+        self.reduce_from_dgrad = False
         self._bn_fwd = None
+        self._bn_bwd = None
         net.ops.append(self)
 
     def grad_writes(self):
@@ -531,6 +558,15 @@ class BNRelu(Op):
                                       n.pp(self.beta), self.eps, self.momentum, self.mm.data_ptr(), self.mv.data_ptr(),
                                       self.coef.data_ptr())
         return C.byref(self._bn_fwd)
+
+    def bn_bwd_struct(self):
+        """stp_bn_bwd for the conv whose dgrad writes this layer's output gradient (reduction in its epilogue)."""
+        if self._bn_bwd is None:
+            n = self.net
+            self._bn_bwd = _lib.BnBwd(C.pointer(self.x.st), self.coef.data_ptr(), int(self.relu), n.partial.data_ptr(),
+                                      n.sync.data_ptr(), n.bn_acc.data_ptr(), n.pg(self.gamma), n.pg(self.beta),
+                                      self.bcoef.data_ptr())
+        return C.byref(self._bn_bwd)
 
     def prepare(self):
         self.dy = self.y.grad()
@@ -555,9 +591,10 @@ class BNRelu(Op):
     def bwd(self):
         n, L, st = self.net, self.net.L, _stream()
         c = self.x.c
-        L.bn_bwd_reduce_fused(self.dy.ref, self.x.ref, self.coef.data_ptr(), int(self.relu), self.up,
-                              n.partial.data_ptr(), n.sync.data_ptr(), n.bn_acc.data_ptr(), n.pg(self.gamma), n.pg(self.beta),
-                              self.bcoef.data_ptr(), st)
+        if not self.reduce_from_dgrad:
+            L.bn_bwd_reduce_fused(self.dy.ref, self.x.ref, self.coef.data_ptr(), int(self.relu), self.up,
+                                  n.partial.data_ptr(), n.sync.data_ptr(), n.bn_acc.data_ptr(), n.pg(self.gamma), n.pg(self.beta),
+                                  self.bcoef.data_ptr(), st)
         L.bn_bwd_apply(self.dy.ref, self.x.ref, self.coef.data_ptr(), self.bcoef.data_ptr(), int(self.relu), self.up,
                        self.res_ref, self.dx.ref, st)
 

@@ -51,6 +51,11 @@ class BnFwd(C.Structure):
                 ("moving_var", C.c_void_p), ("coef", C.c_void_p)]
 
 
+class BnBwd(C.Structure):
+    _fields_ = [("x", C.POINTER(Tensor)), ("coef", C.c_void_p), ("relu", C.c_int32), ("partial", C.c_void_p),
+                ("sync", C.c_void_p), ("acc", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("bcoef", C.c_void_p)]
+
+
 class LossSpec(C.Structure):
     _fields_ = [("w_bce", C.c_float), ("w_dice", C.c_float), ("w_iou", C.c_float), ("w_jaccard", C.c_float),
                 ("w_focal", C.c_float)]
@@ -80,6 +85,7 @@ SIGNATURES = {
     "stp_conv_fwd": (C.c_int, [_CDP, _TP, _P, _P, _TP, _TP, _P, _SZ, _P]),
     "stp_conv_fwd_bn": (C.c_int, [_CDP, _TP, _P, _P, _TP, _TP, C.POINTER(BnFwd), _P, _SZ, _P]),
     "stp_conv_dgrad": (C.c_int, [_CDP, _TP, _P, _TP, _TP, _P, _SZ, _P]),
+    "stp_conv_dgrad_bn": (C.c_int, [_CDP, _TP, _P, _TP, C.POINTER(BnBwd), _P, _SZ, _P]),
     "stp_conv_wgrad": (C.c_int, [_CDP, _TP, _TP, _P, _P, _SZ, _P]),
     "stp_conv_wgrad_workspace": (_SZ, [_CDP, _TP, _TP]),
     "stp_weight_prep": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),

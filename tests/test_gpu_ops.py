@@ -807,3 +807,57 @@ def test_conv_tc3_cta_pair(stp, cuda, case, force):
     assert int(sync[0]) == 0 and float(acc.abs().max()) == 0.0
     scale = 1 + float(outs[0][1].abs().max())
     assert max_abs(outs[1][1], outs[0][1]) <= 1e-3 * scale
+
+
+@pytest.mark.parametrize("relu", [1, 0])
+@pytest.mark.parametrize("case", [(2, 24, 40, 64, 64), (1, 16, 16, 128, 128), (2, 32, 64, 16, 16), (1, 20, 36, 32, 32),
+                                  (3, 9, 17, 64, 128), (2, 16, 16, 256, 64), (1, 40, 24, 32, 16)])
+def test_conv_dgrad_with_fused_bn_backward_reduce(stp, cuda, case, relu):
+    """stp_conv_dgrad_bn: the BatchNorm-backward reduction of the layer that produced the conv's input, done in the dgrad
+    epilogue (dx stored ReLU-masked, sums of g and g*xhat -> dgamma, dbeta, bcoef), against dgrad + the separate reduction
+    pass; partial tiles, narrow (register-accumulated) and wide (per-chunk transpose-reduced) channel tiles."""
+    n, h, w, cin, cout = case   # forward conv: cin -> cout; the BatchNorm under test has cin channels
+    g = torch.Generator().manual_seed(cin * 7 + cout + relu)
+    x = rand_bf16((n, h, w, cin), g)                       # BatchNorm input
+    dy = rand_bf16((n, h, w, cout), g)                     # gradient of the conv output
+    wt = rand_bf16((cout, 3, 3, cin), g, scale=1.0 / math.sqrt(9 * cin))
+    wd = torch.zeros_like(wt).view(-1)
+    wf = torch.zeros_like(wt).view(-1)
+    stp.weight_prep(wt.float().contiguous().data_ptr(), wf.data_ptr(), wd.data_ptr(), cout, 3, 3, cin, stream())
+    desc = lib.ConvDesc(3, 3, 1, 1, 1, 1, 0)
+    rows = n * h * w
+    gamma = (torch.rand(cin, generator=g) + 0.5).to(cuda)
+    gamma[::3] *= -1.0                                       # negative scales flip the ReLU mask condition
+    beta = (torch.rand(cin, generator=g) - 0.5).to(cuda)
+    partial = torch.zeros(2 * stp.bn_nblk(rows, cin) * cin, device=cuda)
+    sync = torch.zeros(4, dtype=torch.int32, device=cuda)
+    acc = torch.zeros(2 * max(cin, cout), dtype=torch.float64, device=cuda)
+    coef = torch.zeros(4 * cin, device=cuda)
+    mm, mv = torch.zeros(cin, device=cuda), torch.ones(cin, device=cuda)
+    stp.bn_stats_fused(ref(T(x)), partial.data_ptr(), sync.data_ptr(), acc.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.99,
+                       mm.data_ptr(), mv.data_ptr(), coef.data_ptr(), stream())
+    outs = []
+    xs = T(x)
+    for fused in (0, 1):
+        dx = torch.zeros((n, h, w, cin), dtype=torch.bfloat16, device=cuda)
+        dgam, dbet, bco = torch.zeros(cin, device=cuda), torch.zeros(cin, device=cuda), torch.zeros(3 * cin, device=cuda)
+        if fused:
+            bnb = lib.BnBwd(C.pointer(xs), coef.data_ptr(), relu, partial.data_ptr(), sync.data_ptr(), acc.data_ptr(),
+                            dgam.data_ptr(), dbet.data_ptr(), bco.data_ptr())
+            before = stp.launch_count()
+            for _ in range(2):   # twice: the accumulators / ticket must come back to zero
+                stp.conv_dgrad_bn(C.byref(desc), ref(T(dy)), wd.data_ptr(), ref(T(dx)), C.byref(bnb), None, 0, stream())
+            assert stp.launch_count() - before == 2, "the reduction must run inside the dgrad kernel for these shapes"
+        else:
+            stp.conv_dgrad(C.byref(desc), ref(T(dy)), wd.data_ptr(), None, ref(T(dx)), None, 0, stream())
+            stp.bn_bwd_reduce_fused(ref(T(dx)), ref(xs), coef.data_ptr(), relu, 1, partial.data_ptr(), sync.data_ptr(), acc.data_ptr(),
+                                    dgam.data_ptr(), dbet.data_ptr(), bco.data_ptr(), stream())
+        torch.cuda.synchronize()
+        outs.append((dx, dgam, dbet, bco))
+    assert int(sync[0]) == 0 and float(acc.abs().max()) == 0.0
+    c4 = coef.view(4, cin)
+    mask = (x.float() * c4[2] + c4[3] > 0) if relu else torch.ones_like(x, dtype=torch.bool)
+    assert torch.equal(outs[1][0], torch.where(mask, outs[0][0], torch.zeros_like(outs[0][0])))
+    for k in (1, 2, 3):
+        scale = 1e-6 + float(outs[0][k].abs().max())
+        assert max_abs(outs[1][k], outs[0][k]) <= 2e-4 * scale, (k, max_abs(outs[1][k], outs[0][k]), scale)
