@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Callable, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -137,7 +138,11 @@ class Net:
         self._partial_floats = 2 * _lib.BN_MAX_PARTIALS * 8
         self.encoder_param_names: List[str] = []
         self.fuse_bn_stats = True
-        self.fuse_bn_bwd = True
+        # BatchNorm-backward reduction inside the producing dgrad's epilogue (stp_conv_dgrad_bn).  Parity green, 33 launches
+        # fewer per U-Net/ResNet-34 step, but measured 1.3 % SLOWER (9.06 vs 8.94 ms): the separate HBM-bound reduction
+        # kernels overlap the tensor-bound weight gradients of the side stream almost for free, while the fused epilogue
+        # (x tile load + transpose-reduction shuffles) lengthens the exposed last-tile epilogue of every dgrad.  Off by default.
+        self.fuse_bn_bwd = os.environ.get("STP_FUSE_BN_BWD", "0") == "1"
 
     # ---- parameters ---------------------------------------------------------------------------
     def add_param(self, name, shape, kind, init) -> Param:
