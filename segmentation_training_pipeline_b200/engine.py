@@ -240,6 +240,14 @@ class Net:
         self._wprep_items = torch.tensor(items, dtype=torch.int64, device=dev) if items else None
         self.finalized = True
 
+    def encoder_floats(self) -> int:
+        """Number of leading floats of the flat buffers that belong to encoder parameters (they are created first)."""
+        end = 0
+        for name in self.encoder_param_names:
+            p = self.params[name]
+            end = max(end, p.offset + (p.size + 7) // 8 * 8)
+        return end
+
     # pointers into flat buffers
     def pp(self, p: Param):
         return self.flat_p.data_ptr() + 4 * p.offset

@@ -51,6 +51,50 @@ def _better(mode: str, name: str, new: float, best: Optional[float]) -> bool:
     return new < best if mode == "min" else new > best
 
 
+class _Concat:
+    """`extra_train_data:` (reference FAQ.md:50-61, segmentation.py:29 `extra_train`): a registered dataset whose items are
+    appended to the TRAINING side of every fold (never to validation)."""
+
+    def __init__(self, a, b):
+        self.a, self.b = a, b
+
+    def __len__(self):
+        return len(self.a) + len(self.b)
+
+    def __getitem__(self, i):
+        i = int(i)
+        return self.a[i] if i < len(self.a) else self.b[i - len(self.a)]
+
+    def isPositive(self, i):
+        i = int(i)
+        d, j = (self.a, i) if i < len(self.a) else (self.b, i - len(self.a))
+        return d.isPositive(j) if hasattr(d, "isPositive") else bool(np.asarray(d[j].y).any())
+
+
+def _select_negatives(ds, idx, mode, rng):
+    """Stage keys `negatives` / `validation_negatives` (README.md:385-415): none = positives only, real = everything,
+    integer N = N negative examples per positive one (drawn without replacement)."""
+    if mode in (None, "real", "all"):
+        return idx
+    pos_fn = ds.isPositive if hasattr(ds, "isPositive") else (lambda i: bool(np.asarray(ds[int(i)].y).any()))
+    flags = np.array([bool(pos_fn(int(i))) for i in idx])
+    pos, neg = idx[flags], idx[~flags]
+    if mode == "none":
+        return pos
+    n = int(mode) * len(pos)
+    take = neg if n >= len(neg) else rng.choice(neg, size=n, replace=False)
+    return np.sort(np.concatenate([pos, take]))
+
+
+def _weights_file(base, spec):
+    """`initial_weights: ./exp/weights/best-0.1.weights` (README.md:382): path relative to the config, .npz appended if needed."""
+    p = spec if os.path.isabs(spec) else os.path.join(base, spec)
+    for cand in (p, p + ".npz"):
+        if os.path.exists(cand):
+            return cand
+    raise FileNotFoundError("initial_weights: " + p)
+
+
 def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
     import torch
     from .trainer import Trainer
@@ -62,6 +106,15 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
     for d in ("weights", "metrics"):
         os.makedirs(os.path.join(base, d), exist_ok=True)
     n_all = len(ds)
+    extra_name = cfg.extra.get("extra_train_data")
+    extra_idx = np.zeros(0, dtype=np.int64)
+    if extra_name:
+        from . import segmentation as _seg
+        if extra_name not in _seg.extra_train:
+            raise ValueError("extra_train_data '%s' is not registered in segmentation.extra_train" % extra_name)
+        extra = _seg.extra_train[extra_name]
+        extra_idx = np.arange(n_all, n_all + len(extra))
+        ds = _Concat(ds, extra)
     rng = np.random.default_rng(cfg.random_state)
     all_idx = np.arange(n_all)
     if cfg.testSplit > 0:
@@ -78,7 +131,9 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
         tr_idx, va_idx = all_idx[tr], all_idx[va]
         if subsample < 1.0:
             tr_idx = tr_idx[: max(1, int(len(tr_idx) * subsample))]
+        tr_idx = np.concatenate([tr_idx, extra_idx]).astype(np.int64)
         net = cfg.createNet()
+        frozen = bool(cfg.freeze_encoder)
         # two pinned host batches: the loader fills one while the previous one is still being copied / trained on
         himgs = [torch.zeros((B, shape[0], shape[1], shape[2]), dtype=torch.uint8).pin_memory() for _ in range(2)]
         hmasks = [torch.zeros((B, shape[0], shape[1], cfg.classes), dtype=torch.uint8).pin_memory() for _ in range(2)]
@@ -86,9 +141,33 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
         for si, stage in enumerate(cfg.stages):
             if si < start_from_stage:
                 continue
+            if stage.get("freeze_encoder") is not None:
+                frozen = bool(stage["freeze_encoder"])
+            if stage.get("unfreeze_encoder"):
+                frozen = False
+            wpath = os.path.join(base, "weights", "best-%d.%d.weights.npz" % (fi, si))
+            mpath = os.path.join(base, "metrics", "metrics-%d.%d.csv" % (fi, si))
+            if cfg.allowResume and os.path.exists(wpath) and os.path.exists(mpath):
+                # setAllowResume(True) (FAQ.md:3-12): a (fold, stage) whose best weights and full metrics log exist is not
+                # re-run; its best weights seed the next stage
+                done = list(csv.DictReader(open(mpath)))
+                if len(done) >= int(stage.get("epochs", 1)):
+                    net.set_weights(dict(np.load(wpath)))
+                    vals = [float(r[cfg.primary_metric]) for r in done if cfg.primary_metric in r]
+                    mode = cfg.primary_metric_mode if cfg.primary_metric_mode != "auto" else ("min" if "loss" in cfg.primary_metric else "max")
+                    best_done = (min(vals) if mode == "min" else max(vals)) if vals else None
+                    results.append({"fold": fi, "stage": si, "best_" + cfg.primary_metric: best_done, "epochs": len(done),
+                                    "resumed": True})
+                    continue
+            if stage.get("initial_weights"):
+                net.set_weights(dict(np.load(_weights_file(base, stage["initial_weights"]))), strict=False)
             net.loss.set_weights(*parse_loss(stage.get("loss", cfg.loss)))
+            st_tr = _select_negatives(ds, tr_idx, stage.get("negatives"), rng)
+            st_va = _select_negatives(ds, va_idx, stage.get("validation_negatives"), rng)
+            if len(st_tr) == 0:
+                raise ValueError("stage %d: no training samples left after `negatives: %s`" % (si, stage.get("negatives")))
             tr_ = Trainer(net, optimizer=cfg.optimizer, lr=stage.get("lr", cfg.lr), clipnorm=cfg.clipnorm,
-                          clipvalue=cfg.clipvalue,
+                          clipvalue=cfg.clipvalue, freeze_encoder=frozen,
                           augment=parse_augmentation(cfg.augmentation, seed=cfg.random_state + 1000 * fi + si))
             tr_.enable_host_feed()
             # stage `callbacks:` replaces the config-level block, `extra_callbacks:` adds to it (StageConfig, segmentation.raml:124-136)
@@ -96,13 +175,12 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
             for cb in cbs:
                 cb.on_train_begin(tr_)
             iteration = 0
-            mpath = os.path.join(base, "metrics", "metrics-%d.%d.csv" % (fi, si))
             fields = ["epoch", "loss"] + metric_names + ["val_loss"] + ["val_" + m for m in metric_names] + ["lr"]
             rows: List[Dict] = []
             best = None
             pm = cfg.primary_metric
             for epoch in range(int(stage.get("epochs", 1))):
-                order = rng.permutation(tr_idx)
+                order = rng.permutation(st_tr)
                 steps = max(1, len(order) // B)
                 agg: Dict[str, float] = {}
                 def _acc(m):
@@ -117,7 +195,7 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
                     iteration += 1
                     _acc(tr_.step_from_host_pipelined(himgs[s & 1], hmasks[s & 1]))   # metrics of the previous step
                 _acc(tr_.flush_host_pipeline())
-                val = evaluate(net, tr_, ds, va_idx, shape, himg, hmask)
+                val = evaluate(net, tr_, ds, st_va, shape, himg, hmask)
                 row = {"epoch": epoch, "loss": agg.get("loss", float("nan")), "lr": tr_.get_lr()}
                 for mname in metric_names:
                     row[mname] = agg.get(mname, float("nan"))
@@ -132,7 +210,7 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
                 key = pm if pm in row else "val_loss"
                 if _better(cfg.primary_metric_mode, key, row[key], best):
                     best = row[key]
-                    np.savez(os.path.join(base, "weights", "best-%d.%d.weights.npz" % (fi, si)), **net.get_weights())
+                    np.savez(wpath, **net.get_weights())
                 for cb in cbs:
                     cb.on_epoch_end(tr_, epoch, row)
                 if any(cb.stop_training for cb in cbs):
@@ -166,3 +244,72 @@ def evaluate(net, trainer, ds, idx, shape, himg, hmask) -> Dict[str, float]:
     finally:
         net.training = True
     return agg
+
+
+class LRFinder:
+    """Result of cfg.lr_find (README.md:455-470; Pavel Surmenok's keras_lr_finder as musket wraps it): the learning rate is
+    multiplied by a constant factor every batch from start_lr to end_lr; the sweep stops early once the loss explodes."""
+
+    def __init__(self):
+        self.lrs: List[float] = []
+        self.losses: List[float] = []
+
+    def best_lr(self, sma=1, n_skip_beginning=2, n_skip_end=1) -> float:
+        """learning rate at the steepest loss decrease (what plot_loss_change lets a user read off)."""
+        d = self.derivatives(sma)
+        lo, hi = n_skip_beginning, len(d) - n_skip_end
+        if hi <= lo:
+            return self.lrs[len(self.lrs) // 2]
+        return self.lrs[lo + int(np.argmin(d[lo:hi]))]
+
+    def derivatives(self, sma=1):
+        l = np.asarray(self.losses)
+        d = np.zeros_like(l)
+        d[sma:] = (l[sma:] - l[:-sma]) / sma
+        return d
+
+    def plot_loss(self, n_skip_beginning=10, n_skip_end=5):
+        import matplotlib.pyplot as plt
+        plt.ylabel("loss"); plt.xlabel("learning rate (log scale)")
+        plt.plot(self.lrs[n_skip_beginning:-n_skip_end], self.losses[n_skip_beginning:-n_skip_end]); plt.xscale("log")
+
+    def plot_loss_change(self, sma=1, n_skip_beginning=10, n_skip_end=5, y_lim=(-0.01, 0.01)):
+        import matplotlib.pyplot as plt
+        d = self.derivatives(sma)
+        plt.ylabel("rate of loss change"); plt.xlabel("learning rate (log scale)")
+        plt.plot(self.lrs[n_skip_beginning:-n_skip_end], d[n_skip_beginning:-n_skip_end]); plt.xscale("log"); plt.ylim(y_lim)
+
+
+def run_lr_find(cfg, ds, start_lr=1e-5, end_lr=1.0, epochs=1, stage=0) -> LRFinder:
+    import torch
+    from .trainer import Trainer
+
+    B, shape = cfg.batch, cfg.shape
+    net = cfg.createNet()
+    st = cfg.stages[stage] if cfg.stages else {}
+    net.loss.set_weights(*parse_loss(st.get("loss", cfg.loss)))
+    tr_ = Trainer(net, optimizer=cfg.optimizer, lr=start_lr, clipnorm=cfg.clipnorm, clipvalue=cfg.clipvalue,
+                  freeze_encoder=bool(cfg.freeze_encoder), augment=parse_augmentation(cfg.augmentation, seed=cfg.random_state))
+    tr_.enable_host_feed()
+    himg = torch.zeros((B, shape[0], shape[1], shape[2]), dtype=torch.uint8).pin_memory()
+    hmask = torch.zeros((B, shape[0], shape[1], cfg.classes), dtype=torch.uint8).pin_memory()
+    rng = np.random.default_rng(cfg.random_state)
+    steps = max(1, len(ds) // B)
+    total = max(2, steps * int(epochs))
+    factor = (float(end_lr) / float(start_lr)) ** (1.0 / (total - 1))
+    out, lr, best = LRFinder(), float(start_lr), None
+    for ep in range(int(epochs)):
+        order = rng.permutation(len(ds))
+        for s in range(steps):
+            ids = [order[(s * B + j) % len(order)] for j in range(B)]
+            _stack(ds, ids, shape, himg, hmask)
+            tr_.set_lr(lr)
+            m = tr_.step_from_host(himg, hmask)
+            loss = m["loss"]
+            out.lrs.append(lr)
+            out.losses.append(loss)
+            if not np.isfinite(loss) or (best is not None and loss > 4.0 * best):
+                return out
+            best = loss if best is None else min(best, loss)
+            lr *= factor
+    return out

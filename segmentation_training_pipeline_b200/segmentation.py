@@ -10,9 +10,11 @@ schemas/augmenters.raml:43-133; inherited fit/kfold/stages from musket_core.gene
 README.md:116-205 (5 shuffled folds, random_state, weights/, metrics/, summary.yaml next to the yaml).
 
 Everything numeric runs in libstp (CUDA, no CPU fallback): `fit` raises if the library / a GPU is missing.
-What is NOT mirrored (out of the hot-path scope): callbacks other than EarlyStopping / ReduceLROnPlateau /
-CyclicLR, the best-weights checkpoint and the CSV log; lr_find, negatives sampling, crops, DrawResults, FPN/Linknet/PSPNet/DeepLab graphs, categorical_crossentropy
-(these raise NotImplementedError naming the key instead of being silently ignored).
+Mirrored training controls: k-fold x stage loop, best-weights checkpoint + CSV log, callbacks EarlyStopping / ReduceLROnPlateau /
+CyclicLR, freeze_encoder / unfreeze_encoder, negatives / validation_negatives, initial_weights, extra_train_data,
+setAllowResume, lr_find.  NOT mirrored (out of the hot-path scope): other callbacks, crops, DrawResults,
+PSPNet / DeepLab graphs, categorical_crossentropy (these raise NotImplementedError naming the key instead of being
+silently ignored).
 """
 from __future__ import annotations
 
@@ -158,6 +160,8 @@ class PipelineConfig:
         self.decoder_filters = tuple(atrs.pop("decoder_filters", (256, 128, 64, 32, 16)))
         self.decoder_block_type = atrs.pop("decoder_block_type", "upsampling")   # segmentation.raml:162-165
         self.callbacks = atrs.pop("callbacks", None)
+        if atrs.get("crops"):
+            raise NotImplementedError("crops: training on image cells is not built (DESIGN.md section 7)")
         self.datasets = atrs.pop("datasets", None)
         self.fit_with = atrs.pop("fit_with", None)
         self.extra = atrs            # accepted, unused keys (kept so configs round-trip)
@@ -235,6 +239,12 @@ class PipelineConfig:
     def fit(self, d=None, subsample=1.0, foldsToExecute: Optional[Sequence[int]] = None, start_from_stage=0):
         from .fit import run_fit
         return run_fit(self, self._resolve_dataset(d), subsample, foldsToExecute, start_from_stage)
+
+    def lr_find(self, d=None, start_lr=0.00001, end_lr=1.0, epochs=1, stage=0):
+        """Learning-rate range test (reference README.md:455-470): returns an object with lrs / losses / plot_loss /
+        plot_loss_change."""
+        from .fit import run_lr_find
+        return run_lr_find(self, self._resolve_dataset(d), start_lr, end_lr, epochs, stage)
 
     def load_model(self, fold: int = 0, stage: int = -1):
         """Engine graph with the best weights of (fold, stage) (reference README.md:553)."""

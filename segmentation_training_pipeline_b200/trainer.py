@@ -51,11 +51,14 @@ class AugmentConfig:
 class Trainer:
     def __init__(self, net: SegNet, optimizer="Adam", lr=None, beta_1=0.9, beta_2=0.999, epsilon=1e-7, momentum=0.0,
                  nesterov=False, rho=0.9, clipnorm=None, clipvalue=None, augment: Optional[AugmentConfig] = None,
-                 world_size=1, process_group=None):
+                 world_size=1, process_group=None, freeze_encoder=False):
         self.net, self.L = net, net.L
         self.opt = (optimizer or "Adam").lower()
         if self.opt not in ("adam", "sgd", "rmsprop", "nadam"):
             raise ValueError("unknown optimizer " + str(optimizer))
+        # freeze_encoder (README.md:281-304): the encoder parameters come first in the flat buffers, so freezing them is an
+        # offset into the one optimizer launch (their gradients are still computed; nothing reads them)
+        self.opt_off = net.encoder_floats() if freeze_encoder else 0
         self.lr = float(lr) if lr is not None else (0.01 if self.opt == "sgd" else 0.002 if self.opt == "nadam" else 1e-3)
         self.b1, self.b2, self.eps, self.mu, self.nesterov, self.rho = beta_1, beta_2, epsilon, momentum, nesterov, rho
         self.clipnorm, self.clipvalue = clipnorm or 0.0, clipvalue or 0.0
@@ -123,22 +126,24 @@ class Trainer:
 
     def run_optimizer(self):
         net, st = self.net, _stream()
-        if self.clipnorm > 0:
-            self.L.sumsq(net.flat_g.data_ptr(), net.n_flat, self.sumsq_partial.data_ptr(), self.sumsq.data_ptr(), st)
+        off, cnt = self.opt_off, net.n_flat - self.opt_off
+        if cnt <= 0:
+            self.L.step_advance(net.d_step.data_ptr(), st)
+            return
+        p, g, m = net.flat_p.data_ptr() + 4 * off, net.flat_g.data_ptr() + 4 * off, self.m.data_ptr() + 4 * off
+        v = self.v.data_ptr() + 4 * off if self.v is not None else None
+        if self.clipnorm > 0:  # keras clipnorm: global norm over the TRAINABLE weights' gradients
+            self.L.sumsq(g, cnt, self.sumsq_partial.data_ptr(), self.sumsq.data_ptr(), st)
         gx = C.byref(self._gx)
         if self.opt == "adam":
-            self.L.adam(net.flat_p.data_ptr(), net.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), net.n_flat,
-                        self.lr, self.b1, self.b2, self.eps, gx, net.d_step.data_ptr(), st)
+            self.L.adam(p, g, m, v, cnt, self.lr, self.b1, self.b2, self.eps, gx, net.d_step.data_ptr(), st)
         elif self.opt == "nadam":
-            self.L.nadam(net.flat_p.data_ptr(), net.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                         self.nadam_sched.data_ptr(), net.n_flat, self.lr, self.b1, self.b2, self.eps, 0.004, gx,
+            self.L.nadam(p, g, m, v, self.nadam_sched.data_ptr(), cnt, self.lr, self.b1, self.b2, self.eps, 0.004, gx,
                          net.d_step.data_ptr(), st)
         elif self.opt == "sgd":
-            self.L.sgd(net.flat_p.data_ptr(), net.flat_g.data_ptr(), self.m.data_ptr(), net.n_flat, self.lr, self.mu,
-                       int(self.nesterov), gx, st)
+            self.L.sgd(p, g, m, cnt, self.lr, self.mu, int(self.nesterov), gx, st)
         else:
-            self.L.rmsprop(net.flat_p.data_ptr(), net.flat_g.data_ptr(), self.m.data_ptr(), net.n_flat, self.lr,
-                           self.rho, self.eps, gx, st)
+            self.L.rmsprop(p, g, m, cnt, self.lr, self.rho, self.eps, gx, st)
         self.L.step_advance(net.d_step.data_ptr(), st)
 
     # ---- whole step ---------------------------------------------------------------------------

@@ -201,3 +201,34 @@ def test_rle_known_answers_and_round_trip():
     parts = multi_rle_encode(m[:, :, None])
     assert sorted(parts) == ["1 3", "10 2"]
     assert np.array_equal(masks_as_image(parts, (4, 3))[:, :, 0], m)
+
+
+def test_negatives_selection_and_extra_train_concat():
+    """stage keys negatives / validation_negatives (README.md:385-415) and the extra_train_data concatenation (FAQ.md:50-61)."""
+    from segmentation_training_pipeline_b200.fit import _Concat, _select_negatives
+
+    class DS:
+        def __init__(self, flags):
+            self.flags = flags
+
+        def __len__(self):
+            return len(self.flags)
+
+        def isPositive(self, i):
+            return self.flags[i]
+
+        def __getitem__(self, i):
+            return ("item", i)
+
+    ds = DS([True, False, True, False, False, False, True, False])
+    idx = np.arange(8)
+    rng = np.random.default_rng(0)
+    assert list(_select_negatives(ds, idx, "real", rng)) == list(range(8))
+    assert list(_select_negatives(ds, idx, None, rng)) == list(range(8))
+    assert list(_select_negatives(ds, idx, "none", rng)) == [0, 2, 6]
+    one = _select_negatives(ds, idx, 1, rng)
+    assert len(one) == 6 and {0, 2, 6} <= set(one) and len(set(one)) == 6
+    assert list(_select_negatives(ds, idx, 5, rng)) == list(range(8))   # more negatives asked for than exist
+    cat = _Concat(ds, DS([False, True]))
+    assert len(cat) == 10 and cat[9] == ("item", 1) and cat[3] == ("item", 3)
+    assert cat.isPositive(9) and not cat.isPositive(8) and cat.isPositive(0)

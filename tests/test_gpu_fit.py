@@ -202,3 +202,54 @@ def test_fit_config2_fpn_resnet50_lovasz_3class(cuda, tmp_path):
     from segmentation_training_pipeline_b200.predict import predict_arrays
     p = predict_arrays(net, np.stack([ds[0].x, ds[1].x]))
     assert p.shape == (2, 128, 128, 3) and np.allclose(p.sum(axis=-1), 1.0, atol=1e-5)
+
+
+def test_fit_training_controls(cuda, tmp_path):
+    """freeze_encoder / unfreeze_encoder, negatives / validation_negatives, initial_weights, extra_train_data,
+    setAllowResume and lr_find through the YAML / API surface (reference README.md:281-304, 385-415, 455-470; FAQ.md:3-12, 50-61)."""
+    import cv2
+    import yaml
+    from segmentation_pipeline import segmentation
+    from segmentation_pipeline.impl.datasets import SimplePNGMaskDataSet
+    _make_dataset(str(tmp_path), n=10, size=64)
+    for k in (1, 4, 7):   # three negative examples
+        cv2.imwrite(str(tmp_path / "mask" / ("%02d.png" % k)), np.zeros((64, 64), np.uint8))
+    extra_root = tmp_path / "extra"
+    _make_dataset(str(extra_root), n=2, size=64)
+    ds = SimplePNGMaskDataSet(str(tmp_path / "img"), str(tmp_path / "mask"))
+    segmentation.extra_train["more"] = SimplePNGMaskDataSet(str(extra_root / "img"), str(extra_root / "mask"))
+    spec = {"architecture": "Unet", "backbone": "resnet18", "classes": 1, "activation": "sigmoid", "shape": [64, 64, 3],
+            "batch": 2, "folds_count": 2, "optimizer": "Adam", "lr": 0.001, "loss": "binary_crossentropy+dice_loss",
+            "metrics": ["binary_accuracy"], "primary_metric": "val_loss", "freeze_encoder": True, "extra_train_data": "more",
+            "stages": [{"epochs": 1, "negatives": "none", "validation_negatives": "real"},
+                       {"epochs": 1, "unfreeze_encoder": True, "negatives": 1, "initial_weights": "./weights/best-0.0.weights"}]}
+    cfgp = str(tmp_path / "exp" / "config.yaml")
+    os.makedirs(os.path.dirname(cfgp))
+    yaml.safe_dump(spec, open(cfgp, "w"))
+    cfg = segmentation.parse(cfgp)
+    w0 = cfg.createNet().get_weights()            # initial weights (same seed as the folds' networks)
+    res = cfg.fit(ds)
+    assert len(res) == 4
+    exp = os.path.dirname(cfgp)
+    wa = dict(np.load(os.path.join(exp, "weights", "best-0.0.weights.npz")))
+    wb = dict(np.load(os.path.join(exp, "weights", "best-0.1.weights.npz")))
+    enc = ["conv0/kernel", "stage2_unit1_conv1/kernel", "bn0/gamma", "stage4_unit2_bn1/beta"]
+    dec = ["decoder_stage0_conv1/kernel", "final_conv/kernel"]
+    for k in enc:
+        assert np.array_equal(wa[k], w0[k]), k            # frozen encoder: bit-identical after stage 0
+        assert not np.array_equal(wb[k], w0[k]), k        # unfrozen in stage 1
+    for k in dec:
+        assert not np.array_equal(wa[k], w0[k]), k
+    # resume: nothing is re-run once weights + metrics of every (fold, stage) exist
+    os.remove(os.path.join(exp, "summary.yaml"))
+    stamp = os.path.getmtime(os.path.join(exp, "weights", "best-1.1.weights.npz"))
+    cfg.setAllowResume(True)
+    res2 = cfg.fit(ds)
+    assert len(res2) == 4 and all(r.get("resumed") for r in res2)
+    assert os.path.getmtime(os.path.join(exp, "weights", "best-1.1.weights.npz")) == stamp
+    # learning-rate range test
+    finder = cfg.lr_find(ds, start_lr=1e-5, end_lr=1e-1, epochs=2)
+    assert len(finder.lrs) >= 3 and len(finder.lrs) == len(finder.losses)
+    assert abs(finder.lrs[0] - 1e-5) < 1e-12 and all(b > a for a, b in zip(finder.lrs, finder.lrs[1:]))
+    assert all(np.isfinite(v) for v in finder.losses[:-1]) and 1e-5 <= finder.best_lr() <= 1e-1
+    del segmentation.extra_train["more"]
