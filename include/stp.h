@@ -67,7 +67,7 @@ int stp_set_option(const char* name, int32_t value);
 void stp_set_trace_buffer(void* dev_ptr);
 
 /* ------------------------------------------------------------------------------------------------
- * K1  augmentation  -- replaces imgaug.augmenters.{Fliplr,Flipud,Affine,Multiply,Add} run by
+ * K1  augmentation  -- replaces imgaug.augmenters.{Fliplr,Flipud,Affine,Multiply,Add,Invert} and musket's Rotate90 run by
  *     musket_core.datasets.ImageKFoldedDataSet (segmentation.py:54; schemas/augmenters.raml:43-133).
  *     Sampling arithmetic == cv2.warpAffine fixed point, bit exact.
  * ---------------------------------------------------------------------------------------------- */
@@ -83,6 +83,11 @@ typedef struct stp_aug_spec {
   int32_t has_add;
   int32_t add_lo, add_hi;
   int32_t mul_rint; /* 0: imgaug-0.3.0 truncating LUT, 1: round-half-even */
+  int32_t rot90;    /* 0/1: musket `Rotate90: true` (reference ds_1.yaml:6): np.rot90 by a uniform k in {0,1,2,3}, applied FIRST;
+                       square images only */
+  double invert_p;  /* imgaug Invert(p): v -> 255 - v on the whole image with probability p */
+  int32_t color_order[3]; /* order in which the colour stage applies 0 = Multiply, 1 = Add, 2 = Invert (imgaug Sequential
+                             applies augmenters in YAML order; saturating uint8 ops do not commute) */
 } stp_aug_spec;
 
 typedef struct stp_aug_sample { /* per-sample drawn parameters, device resident, 128 bytes */
@@ -93,7 +98,7 @@ typedef struct stp_aug_sample { /* per-sample drawn parameters, device resident,
   float mul;
   int32_t add;
   int32_t src_index;           /* which pool sample this output is drawn from */
-  int32_t _pad;
+  int32_t flags2;              /* bits 0-1: rot90 k; bit 2: invert; bits 4-9: colour order (three 2-bit op ids, first op lowest) */
 } stp_aug_sample;
 
 /* draw parameters: Philox4x32-10(key=seed, ctr=(step, sample_id, call, step>>32)).  `d_step` is a device

@@ -36,6 +36,9 @@ class AugSpec:
     shear: Tuple[float, float] = (0.0, 0.0)  # degrees
     multiply: Optional[Tuple[float, float]] = None
     add: Optional[Tuple[int, int]] = None
+    rot90: bool = False            # musket Rotate90 (reference ds_1.yaml:6) [DEP, unpinned]: np.rot90 by uniform k, applied first
+    invert: float = 0.0            # imgaug Invert(p)
+    color_order: Tuple[int, int, int] = (0, 1, 2)   # 0 Multiply, 1 Add, 2 Invert in Sequential (YAML) order
 
 
 @dataclass
@@ -47,6 +50,9 @@ class SampleParams:
     mul: float  # float32-representable multiplier (1.0 = off)
     has_mul: bool
     add: int
+    rot90_k: int = 0
+    invert: bool = False
+    color_order: Tuple[int, int, int] = (0, 1, 2)
 
 
 def affine_matrix(scale, tx_px, ty_px, rot_deg, shear_deg, h, w) -> np.ndarray:
@@ -75,7 +81,8 @@ def draw_params(spec: AugSpec, seed: int, step: int, sample: int, h: int, w: int
     u_sc, u_rot = philox.uniforms(seed, step, sample, 1)
     u_sh, u_tx = philox.uniforms(seed, step, sample, 2)
     u_ty, u_mul = philox.uniforms(seed, step, sample, 3)
-    u_add, _ = philox.uniforms(seed, step, sample, 4)
+    u_add, u_r90 = philox.uniforms(seed, step, sample, 4)
+    u_inv, _ = philox.uniforms(seed, step, sample, 5)
     M = np.array([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]])
     if spec.affine:
         scale = _lerp(spec.scale[0], spec.scale[1], u_sc)
@@ -94,8 +101,9 @@ def draw_params(spec: AugSpec, seed: int, step: int, sample: int, h: int, w: int
     if spec.add is not None:
         lo, hi = int(spec.add[0]), int(spec.add[1])
         add = lo + int(math.floor(u_add * (hi - lo + 1)))
+    k90 = min(int(math.floor(u_r90 * 4.0)), 3) if spec.rot90 else 0
     return SampleParams(u_lr < spec.fliplr, u_ud < spec.flipud, M, spec.affine, float(mul),
-                        spec.multiply is not None, add)
+                        spec.multiply is not None, add, k90, bool(u_inv < spec.invert), tuple(spec.color_order))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -165,6 +173,8 @@ def multiply_lut(mul: float, rounding: str = "trunc") -> np.ndarray:
 def apply(image: np.ndarray, mask: np.ndarray, p: SampleParams, use_cv2: bool = True, mul_rounding="trunc"):
     """Sequential([Fliplr, Flipud, Affine, Multiply, Add]) on a uint8 HxWx3 image and HxWx1 mask."""
     img, msk = image, mask
+    if p.rot90_k:
+        img, msk = np.rot90(img, p.rot90_k), np.rot90(msk, p.rot90_k)
     if p.fliplr:
         img, msk = img[:, ::-1], msk[:, ::-1]
     if p.flipud:
@@ -174,10 +184,13 @@ def apply(image: np.ndarray, mask: np.ndarray, p: SampleParams, use_cv2: bool = 
         warp = warp_cv2 if (use_cv2 and cv2 is not None) else warp_fixedpoint
         img = warp(img, p.matrix, False)
         msk = warp(msk, p.matrix, True)
-    if p.has_mul:
-        img = multiply_lut(p.mul, mul_rounding)[img]
-    if p.add != 0:
-        img = np.clip(img.astype(np.int32) + p.add, 0, 255).astype(np.uint8)
+    for op in p.color_order:
+        if op == 0 and p.has_mul:
+            img = multiply_lut(p.mul, mul_rounding)[img]
+        elif op == 1 and p.add != 0:
+            img = np.clip(img.astype(np.int32) + p.add, 0, 255).astype(np.uint8)
+        elif op == 2 and p.invert:
+            img = (255 - img.astype(np.int32)).astype(np.uint8)
     return img, msk
 
 

@@ -34,7 +34,7 @@ struct DevSample {  // == stp_aug_sample (include/stp.h)
   double inv[6];
   int32_t fliplr, flipud, has_affine, has_mul;
   float mul;
-  int32_t add, src_index, _pad;
+  int32_t add, src_index, flags2;  // flags2: bits 0-1 rot90 k, bit 2 invert, bits 4-9 colour order
 };
 static_assert(sizeof(DevSample) == sizeof(stp_aug_sample), "stp_aug_sample layout");
 
@@ -45,9 +45,9 @@ __global__ void augment_draw_kernel(stp_aug_spec spec, uint64_t seed, const int6
   const int64_t step = *d_step;
   const uint32_t sid = (uint32_t)((step * n + i) % pool);
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  uint32_t r[5][4];
+  uint32_t r[6][4];
 #pragma unroll
-  for (int call = 0; call < 5; ++call) philox4x32((uint32_t)step, sid, call, (uint32_t)(step >> 32), k0, k1, r[call]);
+  for (int call = 0; call < 6; ++call) philox4x32((uint32_t)step, sid, call, (uint32_t)(step >> 32), k0, k1, r[call]);
   const double u_lr = u53(r[0][0], r[0][1]), u_ud = u53(r[0][2], r[0][3]);
   const double u_sc = u53(r[1][0], r[1][1]), u_rot = u53(r[1][2], r[1][3]);
   const double u_sh = u53(r[2][0], r[2][1]), u_tx = u53(r[2][2], r[2][3]);
@@ -94,18 +94,41 @@ __global__ void augment_draw_kernel(stp_aug_spec spec, uint64_t seed, const int6
   s.add = 0;
   if (spec.has_add) s.add = spec.add_lo + (int)floor(__dmul_rn(u_add, (double)(spec.add_hi - spec.add_lo + 1)));
   s.src_index = (int32_t)sid;
-  s._pad = 0;
+  const double u_r90 = u53(r[4][2], r[4][3]), u_inv = u53(r[5][0], r[5][1]);
+  int k90 = spec.rot90 ? (int)floor(__dmul_rn(u_r90, 4.0)) : 0;
+  if (k90 > 3) k90 = 3;
+  const int inv = u_inv < spec.invert_p ? 1 : 0;
+  s.flags2 = k90 | (inv << 2) | ((spec.color_order[0] & 3) << 4) | ((spec.color_order[1] & 3) << 6) | ((spec.color_order[2] & 3) << 8);
   out[i] = s;
 }
 
+// colour stage: Multiply / Add / Invert in the order of the YAML block (flags2 bits 4-9); each op saturates to uint8
 __device__ __forceinline__ int colour(int v, const DevSample& s, int mul_rint) {
-  if (s.has_mul) {
-    float f = __fmul_rn((float)v, s.mul);
-    f = fminf(fmaxf(f, 0.f), 255.f);
-    v = mul_rint ? __float2int_rn(f) : (int)f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int op = (s.flags2 >> (4 + 2 * k)) & 3;
+    if (op == 0) {
+      if (s.has_mul) {
+        float f = __fmul_rn((float)v, s.mul);
+        f = fminf(fmaxf(f, 0.f), 255.f);
+        v = mul_rint ? __float2int_rn(f) : (int)f;
+      }
+    } else if (op == 1) {
+      v += s.add;
+      v = v < 0 ? 0 : (v > 255 ? 255 : v);
+    } else if (op == 2) {
+      if (s.flags2 & 4) v = 255 - v;
+    }
   }
-  v += s.add;
-  return v < 0 ? 0 : (v > 255 ? 255 : v);
+  return v;
+}
+// pool coordinates of pixel (py, px) of the np.rot90(k)-rotated sample (square images): k = 1 is counter-clockwise
+__device__ __forceinline__ int64_t rot_off(int py, int px, int k, int H, int W) {
+  int sy = py, sx = px;
+  if (k == 1) { sy = px; sx = W - 1 - py; }
+  else if (k == 2) { sy = H - 1 - py; sx = W - 1 - px; }
+  else if (k == 3) { sy = H - 1 - px; sx = py; }
+  return (int64_t)sy * W + sx;
 }
 
 // one thread = PX consecutive output pixels of one row
@@ -124,6 +147,7 @@ __global__ void __launch_bounds__(256) augment_apply_kernel(const uint8_t* __res
     const int y = (int)((idx / wq) % H);
     const int b = (int)(idx / ((int64_t)wq * H));
     const DevSample s = params[b];
+    const int k90 = s.flags2 & 3;
     const uint8_t* simg = img_pool + (int64_t)s.src_index * H * W * CI;
     const uint8_t* smsk = mask_pool ? mask_pool + (int64_t)s.src_index * H * W * cm : nullptr;
     uint8_t oi[PX * CI];
@@ -142,8 +166,10 @@ __global__ void __launch_bounds__(256) augment_apply_kernel(const uint8_t* __res
       if (!s.has_affine) {
         const int sx = s.fliplr ? W - 1 - x : x, sy = s.flipud ? H - 1 - y : y;
 #pragma unroll
-        for (int c = 0; c < CI; ++c) oi[p * CI + c] = (uint8_t)colour(simg[((int64_t)sy * W + sx) * CI + c], s, mul_rint);
-        for (int c = 0; c < cm; ++c) om[p * cm + c] = smsk ? smsk[((int64_t)sy * W + sx) * cm + c] : 0;
+        const int64_t so = rot_off(sy, sx, k90, H, W);
+#pragma unroll
+        for (int c = 0; c < CI; ++c) oi[p * CI + c] = (uint8_t)colour(simg[so * CI + c], s, mul_rint);
+        for (int c = 0; c < cm; ++c) om[p * cm + c] = smsk ? smsk[so * cm + c] : 0;
         continue;
       }
       const double xd = (double)x;
@@ -154,7 +180,8 @@ __global__ void __launch_bounds__(256) augment_apply_kernel(const uint8_t* __res
         const long long sx = (X0n + ad) >> 10, sy = (Y0n + bd) >> 10;
         const bool ok = sx >= 0 && sx < W && sy >= 0 && sy < H;
         const int px = s.fliplr ? W - 1 - (int)sx : (int)sx, py = s.flipud ? H - 1 - (int)sy : (int)sy;
-        for (int c = 0; c < cm; ++c) om[p * cm + c] = (ok && smsk) ? smsk[((int64_t)py * W + px) * cm + c] : 0;
+        const int64_t so = ok ? rot_off(py, px, k90, H, W) : 0;
+        for (int c = 0; c < cm; ++c) om[p * cm + c] = (ok && smsk) ? smsk[so * cm + c] : 0;
       }
       // image: bilinear, 5 fractional bits
       {
@@ -167,12 +194,14 @@ __global__ void __launch_bounds__(256) augment_apply_kernel(const uint8_t* __res
         const bool y0ok = sy >= 0 && sy < H, y1ok = sy + 1 >= 0 && sy + 1 < H;
         const int px0 = s.fliplr ? W - 1 - (int)sx : (int)sx, px1 = s.fliplr ? px0 - 1 : px0 + 1;
         const int py0 = s.flipud ? H - 1 - (int)sy : (int)sy, py1 = s.flipud ? py0 - 1 : py0 + 1;
+        const int64_t o00 = (x0ok && y0ok) ? rot_off(py0, px0, k90, H, W) : 0, o01 = (x1ok && y0ok) ? rot_off(py0, px1, k90, H, W) : 0;
+        const int64_t o10 = (x0ok && y1ok) ? rot_off(py1, px0, k90, H, W) : 0, o11 = (x1ok && y1ok) ? rot_off(py1, px1, k90, H, W) : 0;
 #pragma unroll
         for (int c = 0; c < CI; ++c) {
-          const int v00 = (x0ok && y0ok) ? simg[((int64_t)py0 * W + px0) * CI + c] : 0;
-          const int v01 = (x1ok && y0ok) ? simg[((int64_t)py0 * W + px1) * CI + c] : 0;
-          const int v10 = (x0ok && y1ok) ? simg[((int64_t)py1 * W + px0) * CI + c] : 0;
-          const int v11 = (x1ok && y1ok) ? simg[((int64_t)py1 * W + px1) * CI + c] : 0;
+          const int v00 = (x0ok && y0ok) ? simg[o00 * CI + c] : 0;
+          const int v01 = (x1ok && y0ok) ? simg[o01 * CI + c] : 0;
+          const int v10 = (x0ok && y1ok) ? simg[o10 * CI + c] : 0;
+          const int v11 = (x1ok && y1ok) ? simg[o11 * CI + c] : 0;
           const int v = (w00 * v00 + w01 * v01 + w10 * v10 + w11 * v11 + 16384) >> 15;
           oi[p * CI + c] = (uint8_t)colour(v, s, mul_rint);
         }
@@ -206,6 +235,12 @@ using namespace stp;
 extern "C" int stp_augment_draw(const stp_aug_spec* h_spec, uint64_t seed, const int64_t* d_step, int32_t n,
                                 int32_t pool, int32_t h, int32_t w, stp_aug_sample* d_out, stp_stream stream) {
   STP_REQUIRE(h_spec && d_step && d_out && n > 0 && pool > 0, "augment_draw: bad args");
+  STP_REQUIRE(!h_spec->rot90 || h == w, "augment_draw: Rotate90 needs square images");
+  {
+    const int32_t* o = h_spec->color_order;
+    STP_REQUIRE(o[0] >= 0 && o[0] <= 2 && o[1] >= 0 && o[1] <= 2 && o[2] >= 0 && o[2] <= 2 && o[0] != o[1] && o[0] != o[2] && o[1] != o[2],
+                "augment_draw: color_order must be a permutation of {0, 1, 2}");
+  }
   augment_draw_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(*h_spec, seed, d_step, n, pool, h, w,
                                                                       (DevSample*)d_out);
   return check_launch("augment_draw");

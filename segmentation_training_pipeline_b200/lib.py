@@ -36,13 +36,19 @@ class AugSpec(C.Structure):
                 ("tx_lo", C.c_double), ("tx_hi", C.c_double), ("ty_lo", C.c_double), ("ty_hi", C.c_double),
                 ("rot_lo", C.c_double), ("rot_hi", C.c_double), ("shear_lo", C.c_double), ("shear_hi", C.c_double),
                 ("has_mul", C.c_int32), ("mul_lo", C.c_double), ("mul_hi", C.c_double),
-                ("has_add", C.c_int32), ("add_lo", C.c_int32), ("add_hi", C.c_int32), ("mul_rint", C.c_int32)]
+                ("has_add", C.c_int32), ("add_lo", C.c_int32), ("add_hi", C.c_int32), ("mul_rint", C.c_int32),
+                ("rot90", C.c_int32), ("invert_p", C.c_double), ("color_order", C.c_int32 * 3)]
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        if len(a) < 23 and "color_order" not in kw:   # default colour order: Multiply, Add, Invert
+            self.color_order[0], self.color_order[1], self.color_order[2] = 0, 1, 2
 
 
 class AugSample(C.Structure):
     _fields_ = [("m", C.c_double * 6), ("inv", C.c_double * 6), ("fliplr", C.c_int32), ("flipud", C.c_int32),
                 ("has_affine", C.c_int32), ("has_mul", C.c_int32), ("mul", C.c_float), ("add", C.c_int32),
-                ("src_index", C.c_int32), ("_pad", C.c_int32)]
+                ("src_index", C.c_int32), ("flags2", C.c_int32)]
 
 
 class BnFwd(C.Structure):

@@ -98,11 +98,30 @@ def parse_augmentation(spec: Optional[dict], seed: int = 0) -> AugmentConfig:
     cfg = AugmentConfig(seed=seed)
     if not spec:
         return cfg
+    # imgaug Sequential applies the augmenters in YAML order.  The fused kernel runs Rotate90 -> flips -> Affine -> colour
+    # stage (Multiply / Add / Invert in ANY order among themselves); a block in another order would silently compute
+    # something else, so it is rejected.
+    rank = {"Rotate90": 0, "Fliplr": 1, "Flipud": 1, "Affine": 2, "Multiply": 3, "Add": 3, "Invert": 3}
+    last, colour = -1, []
+    for name in spec:
+        if name not in rank:
+            raise NotImplementedError("augmenter '%s' is not fused on device (supported: %s)" % (name, ", ".join(rank)))
+        if rank[name] < last:
+            raise NotImplementedError("augmentation order %s is not the fused kernel's (Rotate90, Fliplr/Flipud, Affine, then "
+                                      "Multiply/Add/Invert)" % list(spec))
+        last = rank[name]
+        if rank[name] == 3:
+            colour.append({"Multiply": 0, "Add": 1, "Invert": 2}[name])
+    cfg.color_order = tuple(colour + [o for o in (0, 1, 2) if o not in colour])
     for name, val in spec.items():
         if name == "Fliplr":
             cfg.fliplr = float(val)
         elif name == "Flipud":
             cfg.flipud = float(val)
+        elif name == "Rotate90":
+            cfg.rot90 = bool(val)
+        elif name == "Invert":
+            cfg.invert = float(val["p"] if isinstance(val, dict) else val)
         elif name == "Affine":
             val = val or {}
             cfg.affine = True
@@ -126,8 +145,6 @@ def parse_augmentation(spec: Optional[dict], seed: int = 0) -> AugmentConfig:
             cfg.multiply = _rng(val)
         elif name == "Add":
             cfg.add = _rng(val, int)
-        else:
-            raise NotImplementedError("augmenter '%s' is not fused on device (supported: Fliplr, Flipud, Affine, Multiply, Add)" % name)
     return cfg
 
 

@@ -21,7 +21,7 @@ from .models import SegNet
 
 @dataclass
 class AugmentConfig:
-    """Device-fused subset of schemas/augmenters.raml: Fliplr, Flipud, Affine, Multiply, Add."""
+    """Device-fused subset of schemas/augmenters.raml: Fliplr, Flipud, Affine, Multiply, Add, Invert + musket's Rotate90."""
     fliplr: float = 0.0
     flipud: float = 0.0
     affine: bool = False
@@ -34,18 +34,24 @@ class AugmentConfig:
     add: Optional[Tuple[int, int]] = None
     mul_rint: bool = False
     seed: int = 0
+    rot90: bool = False
+    invert: float = 0.0
+    color_order: Tuple[int, int, int] = (0, 1, 2)   # 0 Multiply, 1 Add, 2 Invert, in YAML order
 
     def enabled(self) -> bool:
-        return bool(self.fliplr or self.flipud or self.affine or self.multiply or self.add)
+        return bool(self.fliplr or self.flipud or self.affine or self.multiply or self.add or self.rot90 or self.invert)
 
     def to_c(self) -> _lib.AugSpec:
         m = self.multiply or (1.0, 1.0)
         a = self.add or (0, 0)
-        return _lib.AugSpec(self.fliplr, self.flipud, int(self.affine), self.scale[0], self.scale[1],
+        spec = _lib.AugSpec(self.fliplr, self.flipud, int(self.affine), self.scale[0], self.scale[1],
                             self.translate_x[0], self.translate_x[1], self.translate_y[0], self.translate_y[1],
                             self.rotate[0], self.rotate[1], self.shear[0], self.shear[1],
                             int(self.multiply is not None), m[0], m[1], int(self.add is not None), int(a[0]), int(a[1]),
-                            int(self.mul_rint))
+                            int(self.mul_rint), int(self.rot90), float(self.invert))
+        for i, o in enumerate(self.color_order):
+            spec.color_order[i] = int(o)
+        return spec
 
 
 class Trainer:

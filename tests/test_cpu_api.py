@@ -232,3 +232,18 @@ def test_negatives_selection_and_extra_train_concat():
     cat = _Concat(ds, DS([False, True]))
     assert len(cat) == 10 and cat[9] == ("item", 1) and cat[3] == ("item", 3)
     assert cat.isPositive(9) and not cat.isPositive(8) and cat.isPositive(0)
+
+
+def test_augmentation_block_order_is_checked():
+    """imgaug Sequential runs augmenters in YAML order; the fused kernel's order is fixed for the geometric part and free
+    for the colour part -- anything else must raise instead of silently computing a different pipeline."""
+    from segmentation_training_pipeline_b200.segmentation import parse_augmentation
+    c = parse_augmentation({"Rotate90": True, "Fliplr": 0.5, "Affine": {"rotate": [-5, 5]}, "Invert": 0.25, "Add": [-3, 3], "Multiply": [0.9, 1.1]})
+    assert c.rot90 and c.invert == 0.25 and c.color_order == (2, 1, 0) and c.affine and c.enabled()
+    assert parse_augmentation({"Multiply": [0.9, 1.1]}).color_order == (0, 1, 2)
+    with pytest.raises(NotImplementedError, match="order"):
+        parse_augmentation({"Multiply": [0.9, 1.1], "Fliplr": 0.5})
+    with pytest.raises(NotImplementedError, match="order"):
+        parse_augmentation({"Affine": {}, "Flipud": 0.5})
+    with pytest.raises(NotImplementedError, match="not fused"):
+        parse_augmentation({"GaussianBlur": 1.0})

@@ -92,3 +92,41 @@ def test_identity_and_flip_only(stp, cuda):
             p = OA.draw_params(ospec, 5, 2, s.src_index, h, ww)
             ri, rm = OA.apply(imgs[s.src_index], masks[s.src_index], p)
             assert np.array_equal(ri, out_i[i].cpu().numpy()) and np.array_equal(rm, out_m[i].cpu().numpy())
+
+
+@pytest.mark.parametrize("order", [(0, 1, 2), (2, 1, 0), (1, 2, 0)])
+@pytest.mark.parametrize("affine", [0, 1])
+def test_rotate90_invert_and_colour_order(stp, cuda, order, affine):
+    """musket's Rotate90 (np.rot90 by a uniform k, applied first), imgaug Invert(p) and the colour stage in YAML order
+    (saturating uint8 ops do not commute): draws equal to the oracle's, pixels / mask indices bit exact."""
+    from oracle import augment as OA
+    h = w = 96
+    ospec = OA.AugSpec(fliplr=0.5, flipud=0.5, affine=bool(affine), scale=(0.8, 1.3), translate_x=(-0.1, 0.1), translate_y=(-0.1, 0.1),
+                       rotate=(-20, 20), shear=(-8, 8), multiply=(0.5, 1.9), add=(-60, 60), rot90=True, invert=0.5, color_order=order)
+    cspec = lib.AugSpec(0.5, 0.5, affine, 0.8, 1.3, -0.1, 0.1, -0.1, 0.1, -20, 20, -8, 8, 1, 0.5, 1.9, 1, -60, 60, 0, 1, 0.5)
+    for i, o in enumerate(order):
+        cspec.color_order[i] = o
+    n, pool, seed = 16, 16, 7
+    rng = np.random.default_rng(3)
+    imgs = rng.integers(0, 256, (pool, h, w, 3), dtype=np.uint8)
+    masks = (rng.random((pool, h, w, 1)) > 0.6).astype(np.uint8)
+    d_img, d_msk = torch.from_numpy(imgs).to(cuda), torch.from_numpy(masks).to(cuda)
+    ks, invs, bad = set(), set(), 0
+    for step in (0, 5):
+        buf, samples = _draw(stp, cuda, cspec, seed, step, n, pool, h, w)
+        out_i = torch.zeros((n, h, w, 3), dtype=torch.uint8, device=cuda)
+        out_m = torch.zeros((n, h, w, 1), dtype=torch.uint8, device=cuda)
+        stp.augment_apply(d_img.data_ptr(), d_msk.data_ptr(), buf.data_ptr(), out_i.data_ptr(), out_m.data_ptr(), n, h, w,
+                          3, 1, 0, stream())
+        gi, gm = out_i.cpu().numpy(), out_m.cpu().numpy()
+        for i, s in enumerate(samples):
+            p = OA.draw_params(ospec, seed, step, s.src_index, h, w)
+            assert (s.flags2 & 3) == p.rot90_k and bool(s.flags2 & 4) == p.invert
+            assert tuple((s.flags2 >> (4 + 2 * k)) & 3 for k in range(3)) == tuple(order)
+            ks.add(p.rot90_k)
+            invs.add(p.invert)
+            p.matrix = np.array(list(s.m)).reshape(2, 3)   # pixels are pinned given the device-drawn matrix
+            ri, rm = OA.apply(imgs[s.src_index], masks[s.src_index], p, use_cv2=True)
+            bad += int((ri != gi[i]).sum()) + int((rm != gm[i]).sum())
+    assert bad == 0
+    assert ks == {0, 1, 2, 3} and invs == {False, True}
