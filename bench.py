@@ -296,6 +296,13 @@ def run_gpu(args, rank, local_rank, world):
     ms_e2e = e0.elapsed_time(e1)
 
     dom = time_dominant_kernel(net) if rank == 0 else None
+    in_sync = None
+    if world > 1:  # data-parallel invariant: every rank holds bit-identical parameters after the timed steps
+        chk = torch.stack([net.flat_p.double().sum(), net.flat_p.double().abs().sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool(torch.equal(lo, hi))
 
     tms = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -323,6 +330,7 @@ def run_gpu(args, rank, local_rank, world):
             "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step,
             "loss_after": loss_end,
+            "params_in_sync": in_sync,
             "clocks": clk,
             "step_tflops": value / world * gf / 1e3,
             "step_frac_of_sustained_peak": value / world * gf / 1e3 / pk["bf16_tflops_sustained"],

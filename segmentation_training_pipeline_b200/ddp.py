@@ -56,6 +56,31 @@ def allreduce_sum_(flat: torch.Tensor, group=None) -> torch.Tensor:
     return flat
 
 
+def allreduce_sum_async(flat: torch.Tensor, group=None):
+    """Enqueue a SUM all-reduce that runs on the backend's own stream, ordered after what is already enqueued on the
+    current stream; returns a handle whose wait() orders the current stream after the collective (no host block on
+    NCCL).  None for world_size 1.  Lets the all-reduce of the late layers' gradients overlap the rest of the backward."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    return None
+
+
+def bucket_split(param_offsets_sizes, min_tail_fraction: float = 0.5) -> int:
+    """Float offset that cuts the flat gradient buffer (parameters in forward order) into [head | tail]: the tail holds at
+    least `min_tail_fraction` of the floats and starts at a parameter boundary.  The tail's gradients are complete first
+    (backward runs in reverse layer order), so its all-reduce can start while the head's layers are still back-propagating."""
+    items = sorted(param_offsets_sizes)
+    if not items:
+        return 0
+    end = max(off + sz for off, sz in items)
+    best = 0
+    for off, _ in items:
+        if end - off >= end * min_tail_fraction:
+            best = max(best, off)
+    return best
+
+
 def broadcast_(flat: torch.Tensor, src: int = 0, group=None) -> torch.Tensor:
     """Make every rank start from rank `src`'s parameters."""
     import torch.distributed as dist

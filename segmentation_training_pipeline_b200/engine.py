@@ -275,11 +275,37 @@ class Net:
         for op in self.ops:
             op.fwd()
 
-    def backward(self):
-        for op in reversed(self.ops):
+    def backward(self, lo: int = 0, hi: Optional[int] = None):
+        """back-propagate through ops[lo:hi] in reverse order (whole graph by default); joins the weight-gradient side
+        stream, so on return every gradient produced by these ops is complete on the current stream."""
+        ops = self.ops[lo:hi]
+        for op in reversed(ops):
             op.bwd()
         if self.overlap_wgrad and self.side_stream is not None:
             torch.cuda.current_stream().wait_stream(self.side_stream)
+
+    def split_for_overlap(self, min_tail_fraction: float = 0.5) -> Tuple[int, int]:
+        """(op index, float offset) cutting the network into an early part and a late part holding at least
+        `min_tail_fraction` of the parameters: ops[i:] own exactly the parameters at flat offsets >= off (parameters are
+        created in op order).  Used by the data-parallel step to all-reduce the late layers' gradients while the early
+        layers are still back-propagating."""
+        from . import ddp
+        off = ddp.bucket_split([(p.offset, (p.size + 7) // 8 * 8) for p in self.params.values()], min_tail_fraction)
+        first = None
+        for i, op in enumerate(self.ops):
+            ps = [getattr(op, a) for a in ("w", "b", "gamma", "beta") if isinstance(getattr(op, a, None), Param)]
+            if ps and min(p.offset for p in ps) >= off:
+                first = i
+                break
+        if first is None or off == 0:
+            return 0, 0
+        # every op from `first` on must own only tail parameters, every earlier op only head parameters
+        for i, op in enumerate(self.ops):
+            for a in ("w", "b", "gamma", "beta"):
+                p = getattr(op, a, None)
+                if isinstance(p, Param) and ((i >= first) != (p.offset >= off)):
+                    return 0, 0
+        return first, off
 
     def wgrad_stream(self):
         """context in which a weight-gradient kernel is enqueued: the side stream, ordered after everything already on

@@ -75,6 +75,8 @@ class Trainer:
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.sumsq_partial = torch.zeros(1024, dtype=torch.float32, device=dev)
         self.world_size, self.pg = world_size, process_group
+        self.overlap_allreduce = True   # bucketed all-reduce overlapping the early layers' backward (see _capture_ddp)
+        self.graph_bwd2: Optional[torch.cuda.CUDAGraph] = None
         self.augment = augment if (augment is not None and augment.enabled()) else None
         self.pool_img: Optional[torch.Tensor] = None
         self.pool_mask: Optional[torch.Tensor] = None
@@ -195,6 +197,14 @@ class Trainer:
         return g
 
     def _capture_ddp(self, from_pool=True):
+        """Data-parallel step = three graphs with two collectives between them:
+            G1  augment + forward + backward of the LATE layers (>= 90 % of the parameters: decoder + deep encoder stages)
+            --  all-reduce of their gradient range, asynchronous (NCCL stream), overlapping ...
+            G2  ... the backward of the early layers
+            --  all-reduce of the remaining range
+            G3  optimizer (waits for both collectives)."""
+        net = self.net
+        self._split_op, self._split_off = net.split_for_overlap(0.9) if self.overlap_allreduce else (0, 0)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         saved = self._snapshot()
@@ -203,21 +213,46 @@ class Trainer:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self._restore(saved)
-        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1):
-            self.step_compute(from_pool)
-        with torch.cuda.graph(g2, pool=g1.pool()):
+            net.training = True
+            if from_pool and self.pool_img is not None:
+                self.run_augment()
+            net.prep_weights()
+            net.forward()
+            net.backward(self._split_op, None)
+        if self._split_op > 0:
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                net.backward(0, self._split_op)
+        else:
+            g2 = None
+        with torch.cuda.graph(g3, pool=g1.pool()):
             self.run_optimizer()
         self._restore(saved)
-        self.graph, self.graph_opt = g1, g2
+        self.graph, self.graph_bwd2, self.graph_opt = g1, g2, g3
         return g1
+
+    def _ddp_step(self):
+        from . import ddp
+        g = self.net.flat_g
+        self.graph.replay()
+        if self.graph_bwd2 is None:
+            ddp.allreduce_sum_(g, self.pg)
+        else:
+            w1 = ddp.allreduce_sum_async(g[self._split_off:], self.pg)   # late layers: overlaps the early layers' backward
+            self.graph_bwd2.replay()
+            w2 = ddp.allreduce_sum_async(g[:self._split_off], self.pg)
+            for w in (w1, w2):
+                if w is not None:
+                    w.wait()
+        self.graph_opt.replay()
 
     def step(self):
         if self.graph is not None:
-            self.graph.replay()
             if self.world_size > 1:
-                self.allreduce()
-                self.graph_opt.replay()
+                self._ddp_step()
+            else:
+                self.graph.replay()
         else:
             self.step_eager()
 
