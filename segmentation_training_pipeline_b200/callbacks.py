@@ -107,7 +107,53 @@ class CyclicLR(Callback):
             trainer.set_lr(self.clr())
 
 
-_REGISTRY = {"EarlyStopping": EarlyStopping, "ReduceLROnPlateau": ReduceLROnPlateau, "CyclicLR": CyclicLR}
+class LRVariator(Callback):
+    """musket_core's LRVariator (reference README.md:454, listed with ReduceLROnPlateau as the way "to modify learning rate on
+    the fly") [DEP musket_core, unpinned]: the rate moves from `fromVal` to `toVal` over `relSize` epochs' worth of batches
+    (or `absSize` batches) following `style` -- linear, const, cos / cos+ / cos- or sin / sin+ / sin- -- and then stays at
+    `toVal`.  fromVal defaults to the rate the stage starts with."""
+
+    STYLES = ("linear", "const", "cos", "cos+", "cos-", "sin", "sin+", "sin-")
+
+    def __init__(self, relSize=1.0, toVal=0.0, fromVal=None, style="linear", absSize=None, steps_per_epoch=None, **_):
+        if style not in self.STYLES:
+            raise ValueError("LRVariator: unknown style %r (known: %s)" % (style, ", ".join(self.STYLES)))
+        self.relSize, self.toVal, self.fromVal, self.style = float(relSize), float(toVal), fromVal, style
+        self.absSize, self.steps_per_epoch = absSize, steps_per_epoch
+        self.total, self.it = None, 0
+
+    def shape(self, t: float) -> float:
+        """progress t in [0, 1] -> fraction of the way from fromVal to toVal"""
+        st = self.style
+        if st == "linear":
+            return t
+        if st == "const":
+            return 0.0 if t < 1.0 else 1.0
+        if st in ("cos", "cos+"):
+            return 0.5 * (1.0 - math.cos(math.pi * t))          # slow start, slow end
+        if st == "cos-":
+            return 1.0 - math.cos(0.5 * math.pi * t)            # slow start
+        if st in ("sin", "sin+"):
+            return math.sin(0.5 * math.pi * t)                  # fast start
+        return 1.0 - math.sin(0.5 * math.pi * (1.0 - t))        # sin-
+
+    def on_train_begin(self, trainer):
+        if self.fromVal is None:
+            self.fromVal = trainer.get_lr()
+        self.fromVal = float(self.fromVal)
+        spe = self.steps_per_epoch or getattr(trainer, "steps_per_epoch", None) or 1
+        self.total = int(self.absSize) if self.absSize else max(1, int(round(self.relSize * spe)))
+        self.it = 0
+        trainer.set_lr(self.fromVal)
+
+    def on_batch_begin(self, trainer, iteration):
+        t = min(1.0, self.it / float(self.total))
+        trainer.set_lr(self.fromVal + (self.toVal - self.fromVal) * self.shape(t))
+        self.it += 1
+
+
+_REGISTRY = {"EarlyStopping": EarlyStopping, "ReduceLROnPlateau": ReduceLROnPlateau, "CyclicLR": CyclicLR,
+             "LRVariator": LRVariator}
 
 
 def build(spec: Optional[dict], extra: Optional[dict] = None) -> List[Callback]:

@@ -172,6 +172,7 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
             tr_.enable_host_feed()
             # stage `callbacks:` replaces the config-level block, `extra_callbacks:` adds to it (StageConfig, segmentation.raml:124-136)
             cbs = _cb.build(stage.get("callbacks", cfg.callbacks), stage.get("extra_callbacks"))
+            tr_.steps_per_epoch = max(1, len(st_tr) // B)
             for cb in cbs:
                 cb.on_train_begin(tr_)
             iteration = 0

@@ -182,7 +182,7 @@ def test_callbacks_known_answers():
     assert stops == [False, False, False, True, True]
     assert [type(c).__name__ for c in CB.build({"EarlyStopping": {"patience": 3}}, {"CyclicLR": None})] == ["EarlyStopping", "CyclicLR"]
     with pytest.raises(NotImplementedError):
-        CB.build({"LRVariator": {}})
+        CB.build({"TensorBoard": {}})
 
 
 def test_rle_known_answers_and_round_trip():
@@ -247,3 +247,34 @@ def test_augmentation_block_order_is_checked():
         parse_augmentation({"Affine": {}, "Flipud": 0.5})
     with pytest.raises(NotImplementedError, match="not fused"):
         parse_augmentation({"GaussianBlur": 1.0})
+
+
+def test_lr_variator_schedule():
+    """musket's LRVariator (README.md:454): fromVal -> toVal over relSize epochs' worth of batches, then constant."""
+    from segmentation_training_pipeline_b200 import callbacks as CB
+
+    class T:
+        steps_per_epoch = 10
+        lr = 0.01
+
+        def get_lr(self):
+            return self.lr
+
+        def set_lr(self, v):
+            self.lr = v
+
+    t = T()
+    (cb,) = CB.build({"LRVariator": {"relSize": 0.5, "toVal": 0.001, "style": "linear"}})
+    cb.on_train_begin(t)
+    seen = []
+    for it in range(8):
+        cb.on_batch_begin(t, it)
+        seen.append(t.lr)
+    assert abs(seen[0] - 0.01) < 1e-12 and abs(seen[5] - 0.001) < 1e-12 and abs(seen[7] - 0.001) < 1e-12
+    assert all(b <= a + 1e-15 for a, b in zip(seen, seen[1:])) and abs(seen[1] - (0.01 - 0.009 / 5)) < 1e-12
+    for style in CB.LRVariator.STYLES:
+        v = CB.LRVariator(style=style)
+        assert abs(v.shape(0.0)) < 1e-12 and abs(v.shape(1.0) - 1.0) < 1e-12
+        assert all(0.0 <= v.shape(k / 10) <= 1.0 for k in range(11))
+    with pytest.raises(ValueError):
+        CB.LRVariator(style="zigzag")
