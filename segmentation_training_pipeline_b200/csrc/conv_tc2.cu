@@ -30,7 +30,12 @@ __device__ __forceinline__ unsigned long long gtime() {
       a.trace[(blockIdx.x == 0 ? 0 : 16) + (slot)] = gtime();                                             \
   } while (0)
 
-constexpr int kThreads2 = 192;
+// warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: EIGHT epilogue warps.  A warp may only read the TMEM lane quarter
+// (warp % 4), so the two warps of a quarter share its 32 pixel rows and split the work units (32-column chunks / sub-tiles)
+// by parity: the epilogue -- one dependent chain per warp, exposed after the last tile of every CTA and the pacing
+// resource of the HBM-bound narrow layers -- runs twice as wide as with one warp per quarter.
+constexpr int kEpiThreads2 = 256;
+constexpr int kThreads2 = 64 + kEpiThreads2;
 constexpr int kSmemBudget2 = 227 * 1024;
 
 struct Tc2Args {
@@ -75,7 +80,7 @@ struct Tc2Cfg {
   static constexpr int EP = BN <= 32 ? MT : 1;
   static constexpr int kSubBytes = align1k(128 * BN * 2);            // bf16 staging tile of one sub-tile
   static constexpr int kOutBytes = EP * kSubBytes;
-  static constexpr int kTailBytes = 256 /*barriers*/ + 2 * 128 * 4 /*sStat*/ + 4 * 2 * 128 * 4 /*sRed*/ + 2 * 128 * 4 /*sCoef*/;
+  static constexpr int kTailBytes = 256 /*barriers*/ + 2 * 128 * 4 /*sStat*/ + 8 * 2 * 128 * 4 /*sRed*/ + 2 * 128 * 4 /*sCoef*/;
   static constexpr int kStagesRaw = (kSmemBudget2 - 1024 - kTailBytes - 64 - kOutBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemRaw = 2 * MT * BN;
@@ -112,8 +117,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
   int* s_last = reinterpret_cast<int*>(tmem_slot + 1);
   float* sStat = reinterpret_cast<float*>(sOut + Cfg::kOutBytes + 256);  // [2][128] per-CTA sums of the current N tile
-  float* sRed = sStat + 256;                                             // [4 warps][2][128] cross-warp combine
-  float* sCoef = sRed + 1024;                                            // [2][128] scale, shift of the current N tile (bn_on == 2)
+  float* sRed = sStat + 256;                                             // [8 warps][2][128] cross-warp combine
+  float* sCoef = sRed + 2048;                                            // [2][128] scale, shift of the current N tile (bn_on == 2)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kcb = a.Cin / BK;
@@ -130,7 +135,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
+      mbar_init(&acc_empty[i], kEpiThreads2 / 32);
     }
     mbar_init(res_bar, 1);
     fence_barrier_init();
@@ -259,8 +264,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (lane == 0) STP_TRACE(4);
     }
   } else {
-    const int q = warp & 3;
-    const int m = q * 32 + lane;
+    const int q = warp & 3;               // TMEM lane quarter this warp may read
+    const int m = q * 32 + lane;          // pixel row of the sub-tile == TMEM lane
+    const int ew = warp - 2;              // epilogue warp 0..7
+    const int half = ew >> 2;             // which of the two warps of the quarter: owns the work units of this parity
+    const int t = half * 128 + m;         // epilogue thread id 0..255 (statistics mapping, per-channel ownership)
     const int hl = m >> a.log2BW, wl = m & (a.BW - 1);
     const bool leader = (warp == 2 && lane == 0);
     // 16-byte chunk swizzle of the staging tile == the TMA swizzle mode of its row width (128 / 64 / 32 B)
@@ -270,9 +278,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int local = 0;
     int cur_n0 = -1;  // N tile whose statistics sStat currently holds
     auto bn_flush = [&]() {
-      if (cur_n0 >= 0 && m < BN) {
-        atomicAdd(a.bn.acc + cur_n0 + m, (double)sStat[m]);
-        atomicAdd(a.bn.acc + a.Cout + cur_n0 + m, (double)sStat[128 + m]);
+      if (cur_n0 >= 0 && t < BN) {
+        atomicAdd(a.bn.acc + cur_n0 + t, (double)sStat[t]);
+        atomicAdd(a.bn.acc + a.Cout + cur_n0 + t, (double)sStat[128 + t]);
       }
     };
     for (int tile = w_first; tile < a.num_tiles; tile += w_step, ++local) {
@@ -280,13 +288,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t aphase = (local >> 1) & 1;
       int img, h0, w0, n0;
       decode(tile, img, h0, w0, n0);
-      if (a.bn_on && n0 != cur_n0) {  // thread m owns sStat[m], sStat[128+m]: no synchronisation needed
+      if (a.bn_on && n0 != cur_n0) {  // thread t < BN owns sStat[t], sStat[128+t]: no synchronisation needed
         bn_flush();
         cur_n0 = n0;
-        if (m < BN) sStat[m] = sStat[128 + m] = 0.f;
-        if (a.bn_on == 2 && m < BN) {  // read by every thread after the named barrier that opens each epilogue round
-          sCoef[m] = __ldg(a.bnb_coef + 2 * a.Cout + n0 + m);
-          sCoef[128 + m] = __ldg(a.bnb_coef + 3 * a.Cout + n0 + m);
+        if (t < BN) sStat[t] = sStat[128 + t] = 0.f;
+        if (a.bn_on == 2 && t < BN) {  // read by every thread after the named barrier that opens each epilogue round
+          sCoef[t] = __ldg(a.bnb_coef + 2 * a.Cout + n0 + t);
+          sCoef[128 + t] = __ldg(a.bnb_coef + 3 * a.Cout + n0 + t);
         }
       }
       const int wo = w0 + wl;
@@ -296,7 +304,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       constexpr int CH = BN >= 32 ? 32 : 16;
       if (a.ncls > 0 || a.y_f32) {
 #pragma unroll 1
-        for (int j = 0; j < MT; ++j) {
+        for (int j = half; j < MT; j += 2) {  // the two warps of a lane quarter take alternate sub-tiles
           const int hs = h0 + j * a.BH;  // first output row of this sub-tile
           const int ho = hs + hl;
           const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * MT + j) * BN);
@@ -360,7 +368,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int e = 0; e < EP; ++e) nj += (j0 + e < MT && h0 + (j0 + e) * a.BH < a.Ho) ? 1 : 0;
           if (leader) tma_store_wait_read();   // previous round's stores no longer read the staging tiles
-          named_bar_sync(1, 128);
+          named_bar_sync(1, kEpiThreads2);
           if (a.res || a.bn_on == 2) {  // residual tile, or (fused BatchNorm backward) the BatchNorm input x of the same pixels
             if (leader) {
               mbar_expect_tx(res_bar, (uint32_t)(nj * 128 * BN * 2));
@@ -385,6 +393,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const bool pv = h0 + (j0 + e) * a.BH + hl < a.Ho && wo < a.Wo && img < a.nimg;  // this thread's pixel is real
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += CH) {
+              if (((e * (BN / CH) + c0 / CH) & 1) != half) continue;  // the other warp of this lane quarter owns the unit
               uint32_t rr[CH];
               if constexpr (CH == 32) tmem_ld32(t_addr + c0, rr); else tmem_ld16(t_addr + c0, rr);
               tmem_ld_wait();
@@ -457,15 +466,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                   tx[i] = xacc[c0 + i];
                 }
                 const float sg = warp_transpose_sum<CH>(tg, lane), sx = warp_transpose_sum<CH>(tx, lane);
-                if (lane < CH) {
-                  sRed[(q * 2 + 0) * 128 + c0 + lane] = sg;
-                  sRed[(q * 2 + 1) * 128 + c0 + lane] = sx;
+                if (lane < CH) {  // narrow tiles: every one of the 8 warps holds partial sums of its own sub-tiles
+                  sRed[(ew * 2 + 0) * 128 + c0 + lane] = sg;
+                  sRed[(ew * 2 + 1) * 128 + c0 + lane] = sx;
                 }
               }
             }
           }
           fence_proxy_async();
-          named_bar_sync(1, 128);
+          named_bar_sync(1, kEpiThreads2);
           if (leader && !(a.dbg & 4)) {
             for (int e = 0; e < nj; ++e)
 #pragma unroll
@@ -474,16 +483,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma_store_commit();
           }
           if (a.bn_on == 2) {  // cross-warp combine of the round's (sum g, sum g*x); out-of-image pixels contributed zeros
-            named_bar_sync(2, 128);
-            if (m < BN) {
+            named_bar_sync(2, kEpiThreads2);
+            if (t < BN) {
+              // wide tiles: one warp per (lane quarter, chunk) wrote slot q; narrow tiles: all 8 warps wrote slot ew
+              constexpr int NW = BN <= 32 ? 8 : 4;
               float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-              for (int wq = 0; wq < 4; ++wq) {
-                t1 += sRed[(wq * 2 + 0) * 128 + m];
-                t2 += sRed[(wq * 2 + 1) * 128 + m];
+              for (int wq = 0; wq < NW; ++wq) {
+                t1 += sRed[(wq * 2 + 0) * 128 + t];
+                t2 += sRed[(wq * 2 + 1) * 128 + t];
               }
-              sStat[m] += t1;
-              sStat[128 + m] += t2;
+              sStat[t] += t1;
+              sStat[128 + t] += t2;
             }
           }
           if (a.bn_on == 1 && img < a.nimg) {
@@ -491,8 +502,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // 16-byte conflict-free loads of the swizzled staging rows g, g+GP, ..., pixels outside the image masked;
             // groups are combined by a fixed xor-shuffle tree inside the warp, then across the 4 warps through sRed.
             constexpr int OCT = BN / 8;        // channel octets per pixel row
-            constexpr int GP = 128 / OCT;      // pixel groups (threads per octet)
-            const int o = m % OCT, g = m / OCT;
+            constexpr int GP = kEpiThreads2 / OCT;  // pixel groups (threads per octet)
+            const int o = t % OCT, g = t / OCT;
             float s1[8], s2[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
@@ -500,7 +511,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const int hs = h0 + (j0 + e) * a.BH;
               const uint8_t* sub = sOut + e * Cfg::kSubBytes + (o >> 3) * (128 * RB);
 #pragma unroll
-              for (int i = 0; i < OCT; ++i) {
+              for (int i = 0; i < 128 / GP; ++i) {
                 const int mm = g + i * GP;
                 const int hh = hs + (mm >> a.log2BW), ww = w0 + (mm & (a.BW - 1));
                 if (hh < a.Ho && ww < a.Wo) {
@@ -526,20 +537,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (lane < OCT) {  // lane == o for OCT <= 32
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
-                sRed[(q * 2 + 0) * 128 + lane * 8 + k] = s1[k];
-                sRed[(q * 2 + 1) * 128 + lane * 8 + k] = s2[k];
+                sRed[(ew * 2 + 0) * 128 + lane * 8 + k] = s1[k];
+                sRed[(ew * 2 + 1) * 128 + lane * 8 + k] = s2[k];
               }
             }
-            named_bar_sync(2, 128);
-            if (m < BN) {
+            named_bar_sync(2, kEpiThreads2);
+            if (t < BN) {
               float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-              for (int wq = 0; wq < 4; ++wq) {
-                t1 += sRed[(wq * 2 + 0) * 128 + m];
-                t2 += sRed[(wq * 2 + 1) * 128 + m];
+              for (int wq = 0; wq < 8; ++wq) {
+                t1 += sRed[(wq * 2 + 0) * 128 + t];
+                t2 += sRed[(wq * 2 + 1) * 128 + t];
               }
-              sStat[m] += t1;
-              sStat[128 + m] += t2;
+              sStat[t] += t1;
+              sStat[128 + t] += t2;
             }
           }
         }
@@ -554,12 +565,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (a.bn_on) {
       bn_flush();
       __threadfence();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads2);
       if (leader) *s_last = (atomicAdd(a.bn.fin.sync, 1u) == gridDim.x - 1) ? 1 : 0;
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads2);
       if (*s_last) {  // every other CTA's sums have landed: finalise all channels, return the accumulators to zero
         __threadfence();
-        for (int c = m; c < a.Cout; c += 128) {
+        for (int c = t; c < a.Cout; c += kEpiThreads2) {
           const double s1 = __ldcg(a.bn.acc + c), s2 = __ldcg(a.bn.acc + a.Cout + c);
           if (a.bn_on == 2) {  // sum g*xhat = invstd * (sum g*x - mean * sum g)
             const double mean = a.bn.fin.coef[c], invstd = a.bn.fin.coef[a.Cout + c];
