@@ -115,6 +115,13 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
         extra = _seg.extra_train[extra_name]
         extra_idx = np.arange(n_all, n_all + len(extra))
         ds = _Concat(ds, extra)
+    cells = None
+    if getattr(cfg, "crops", 0) and cfg.crops > 1:
+        from .crops import CellDataSet
+        n_img = len(ds)                      # folds are split over IMAGES; every image contributes its N x N cells
+        cells = CellDataSet(ds, cfg.crops)
+        ds = cells
+        extra_idx = cells.expand(extra_idx)
     rng = np.random.default_rng(cfg.random_state)
     all_idx = np.arange(n_all)
     if cfg.testSplit > 0:
@@ -129,6 +136,8 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
         if foldsToExecute is not None and fi not in foldsToExecute:
             continue
         tr_idx, va_idx = all_idx[tr], all_idx[va]
+        if cells is not None:
+            tr_idx, va_idx = cells.expand(tr_idx), cells.expand(va_idx)
         if subsample < 1.0:
             tr_idx = tr_idx[: max(1, int(len(tr_idx) * subsample))]
         tr_idx = np.concatenate([tr_idx, extra_idx]).astype(np.int64)

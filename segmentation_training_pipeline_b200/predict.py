@@ -85,6 +85,14 @@ def predict_on_directory(cfg, spath, fold: Union[int, Sequence[int]] = 0, stage=
     names = _list_images(spath)
     if limit is not None and limit > 0:
         names = names[:limit]
+    crops = int(getattr(cfg, "crops", 0) or 0)
+    if crops > 1:   # `crops: N`: every image is predicted cell by cell and assembled back at its own size
+        from .crops import predict_image_by_cells
+        fn = lambda x: sum(predict_arrays(net, x, ttflips) for net in nets) / len(nets)
+        for nm in names:
+            img = cv2.cvtColor(cv2.imread(os.path.join(spath, nm), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+            yield PredictionBatch([nm], [img], [predict_image_by_cells(fn, img, crops, (H, W), B)], img.shape[:2])
+        return
     for s in range(0, len(names), B):
         ids = names[s:s + B]
         origs, xs = [], []
@@ -139,6 +147,17 @@ def evaluate_all(cfg, ds, fold=None, stage=-1, negatives="real", ttflips=None, b
     idx = list(range(len(ds)))
     if negatives == "none" and hasattr(ds, "isPositive"):
         idx = [i for i in idx if ds.isPositive(i)]
+    crops = int(getattr(cfg, "crops", 0) or 0)
+    if crops > 1:
+        from .crops import predict_image_by_cells
+        fn = lambda x: sum(predict_arrays(net, x, bool(ttflips)) for net in nets) / len(nets)
+        for i in idx:
+            it = ds[i]
+            img = np.asarray(it.x)
+            b = PredictionBatch([it], [img], [predict_image_by_cells(fn, img, crops, (H, W), B)], img.shape[:2])
+            b.results = list(b.segmentation_maps_aug)
+            yield b
+        return
     for s in range(0, len(idx), B):
         items = [ds[i] for i in idx[s:s + B]]
         xs = [cv2.resize(np.asarray(it.x), (W, H), interpolation=cv2.INTER_CUBIC) if np.asarray(it.x).shape[:2] != (H, W)

@@ -12,7 +12,7 @@ README.md:116-205 (5 shuffled folds, random_state, weights/, metrics/, summary.y
 Everything numeric runs in libstp (CUDA, no CPU fallback): `fit` raises if the library / a GPU is missing.
 Mirrored training controls: k-fold x stage loop, best-weights checkpoint + CSV log, callbacks EarlyStopping / ReduceLROnPlateau /
 CyclicLR, freeze_encoder / unfreeze_encoder, negatives / validation_negatives, initial_weights, extra_train_data,
-setAllowResume, lr_find.  NOT mirrored (out of the hot-path scope): other callbacks, crops, DrawResults,
+setAllowResume, lr_find, crops.  NOT mirrored (out of the hot-path scope): other callbacks, DrawResults,
 PSPNet / DeepLab graphs, categorical_crossentropy (these raise NotImplementedError naming the key instead of being
 silently ignored).
 """
@@ -177,8 +177,7 @@ class PipelineConfig:
         self.decoder_filters = tuple(atrs.pop("decoder_filters", (256, 128, 64, 32, 16)))
         self.decoder_block_type = atrs.pop("decoder_block_type", "upsampling")   # segmentation.raml:162-165
         self.callbacks = atrs.pop("callbacks", None)
-        if atrs.get("crops"):
-            raise NotImplementedError("crops: training on image cells is not built (DESIGN.md section 7)")
+        self.crops = int(atrs.pop("crops", 0) or 0)   # N: train / predict on the N x N cells of every image (README.md:471-491)
         self.datasets = atrs.pop("datasets", None)
         self.fit_with = atrs.pop("fit_with", None)
         self.extra = atrs            # accepted, unused keys (kept so configs round-trip)

@@ -278,3 +278,26 @@ def test_lr_variator_schedule():
         assert all(0.0 <= v.shape(k / 10) <= 1.0 for k in range(11))
     with pytest.raises(ValueError):
         CB.LRVariator(style="zigzag")
+
+
+def test_crops_cells_and_reassembly():
+    """`crops: N` (README.md:471-491): N x N cells per image for training, cell-wise prediction assembled back."""
+    from segmentation_pipeline.impl.datasets import PredictionItem
+    from segmentation_training_pipeline_b200.crops import CellDataSet, cell_bounds, predict_image_by_cells
+    b = cell_bounds(10, 7, 3)
+    assert len(b) == 9 and b[0][:2] == (0, 3) and b[-1] == (7, 10, 5, 7)
+    cover = np.zeros((10, 7), int)
+    for y0, y1, x0, x1 in b:
+        cover[y0:y1, x0:x1] += 1
+    assert (cover == 1).all()                     # the cells tile the image exactly
+    rng = np.random.default_rng(0)
+    items = [PredictionItem("a%d" % k, rng.integers(0, 255, (12, 12, 3), dtype=np.uint8),
+                            (rng.random((12, 12, 1)) > 0.5).astype(np.uint8)) for k in range(3)]
+    cd = CellDataSet(items, 2)
+    assert len(cd) == 12 and cd[5].id == "a1_1" and cd[5].x.shape == (6, 6, 3)
+    assert np.array_equal(cd[5].x, items[1].x[0:6, 6:12]) and np.array_equal(cd[7].y, items[1].y[6:12, 6:12])
+    assert list(cd.expand([2, 0])) == [8, 9, 10, 11, 0, 1, 2, 3]
+    # an "identity network" (probability = red channel / 255 at the network shape == cell size) is reassembled exactly
+    fn = lambda x: x[..., :1].astype(np.float32) / 255.0
+    p = predict_image_by_cells(fn, items[0].x, 2, (6, 6), batch=3)
+    assert p.shape == (12, 12, 1) and np.allclose(p[..., 0], items[0].x[..., 0] / 255.0)

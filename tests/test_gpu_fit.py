@@ -253,3 +253,31 @@ def test_fit_training_controls(cuda, tmp_path):
     assert abs(finder.lrs[0] - 1e-5) < 1e-12 and all(b > a for a, b in zip(finder.lrs, finder.lrs[1:]))
     assert all(np.isfinite(v) for v in finder.losses[:-1]) and 1e-5 <= finder.best_lr() <= 1e-1
     del segmentation.extra_train["more"]
+
+
+def test_fit_and_predict_on_crops(cuda, tmp_path):
+    """`crops: 2` (README.md:471-491): 128x128 images are trained on as four 64x64 cells and predicted cell by cell, the
+    assembled mask coming back at the image's own size."""
+    import cv2
+    import yaml
+    from segmentation_pipeline import segmentation
+    from segmentation_pipeline.impl.datasets import SimplePNGMaskDataSet
+    _make_dataset(str(tmp_path), n=4, size=128)
+    spec = {"architecture": "Unet", "backbone": "resnet18", "classes": 1, "activation": "sigmoid", "shape": [64, 64, 3],
+            "batch": 4, "folds_count": 2, "crops": 2, "loss": "binary_crossentropy+dice_loss", "metrics": ["binary_accuracy"],
+            "primary_metric": "val_loss", "stages": [{"epochs": 2}]}
+    cfgp = str(tmp_path / "exp" / "config.yaml")
+    os.makedirs(os.path.dirname(cfgp))
+    yaml.safe_dump(spec, open(cfgp, "w"))
+    cfg = segmentation.parse(cfgp)
+    ds = SimplePNGMaskDataSet(str(tmp_path / "img"), str(tmp_path / "mask"))
+    res = cfg.fit(ds)
+    assert len(res) == 2
+    rows = list(csv.DictReader(open(os.path.join(os.path.dirname(cfgp), "metrics", "metrics-0.0.csv"))))
+    assert len(rows) == 2 and all(np.isfinite(float(r["val_loss"])) for r in rows)
+    out = str(tmp_path / "pred")
+    assert cfg.predict_to_directory(str(tmp_path / "img"), out, fold=0, stage=0) == 4
+    m = cv2.imread(os.path.join(out, "00.png"), cv2.IMREAD_GRAYSCALE)
+    assert m.shape == (128, 128) and set(np.unique(m)) <= {0, 255}
+    b = next(iter(cfg.evaluateAll(ds, fold=0, stage=0)))
+    assert b.results[0].shape == (128, 128, 1)
