@@ -204,6 +204,42 @@ def time_dominant_kernel(net, reps=30):
             "shape": "3x3 %d->%d @%dx%d bs%d" % (conv.x.c, conv.y.c, conv.y.h, conv.y.w, conv.y.n)}
 
 
+def time_top_hbm_kernel(net, reps=20):
+    """The kernel with the largest single share of the step after the convolutions were sped up is HBM-bound:
+    reduce_rows_kernel<1,1>, the BatchNorm-backward reduction (profiles/r1_launches_s28.summary.txt).  Timed alone on the
+    stage-1 BatchNorm (x and dy: 16x128x128x64 bf16 each), L2 flushed between launches; algorithmic bytes = read x + read dy."""
+    import torch
+    from segmentation_training_pipeline_b200 import engine as E
+    from segmentation_training_pipeline_b200.engine import _stream
+    bn = None
+    for op in net.ops:
+        if isinstance(op, E.BNRelu) and op.up == 1 and op.x.c == 64 and op.x.h == net.input_shape[0] // 4:
+            bn = op
+            break
+    if bn is None:
+        return None
+    n, L = net, net.L
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=net.device)
+    st = torch.cuda.current_stream()
+
+    def run():
+        L.bn_bwd_reduce_fused(bn.dy.ref, bn.x.ref, bn.coef.data_ptr(), int(bn.relu), bn.up, n.partial.data_ptr(), n.sync.data_ptr(),
+                              n.bn_acc.data_ptr(), n.pg(bn.gamma), n.pg(bn.beta), bn.bcoef.data_ptr(), _stream())
+    for _ in range(3):
+        run()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        flush.zero_()
+        a.record(st)
+        run()
+        b.record(st)
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+    nbytes = 2.0 * bn.x.rows * bn.x.c * 2
+    return {"kernel": "reduce_rows_kernel<1,1>: BatchNorm-backward reduction of a 16x%dx%dx%d bf16 layer (reads x and dy)" %
+                      (bn.x.h, bn.x.w, bn.x.c), "ms": ms, "bytes": nbytes}
+
+
 def dominant_kernel_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (None if absent)."""
     p = os.path.join(ROOT, "profiles", "r1_dominant_kernel.json")
@@ -296,6 +332,7 @@ def run_gpu(args, rank, local_rank, world):
     ms_e2e = e0.elapsed_time(e1)
 
     dom = time_dominant_kernel(net) if rank == 0 else None
+    hbm = time_top_hbm_kernel(net) if rank == 0 else None
     in_sync = None
     if world > 1:  # data-parallel invariant: every rank holds bit-identical parameters after the timed steps
         chk = torch.stack([net.flat_p.double().sum(), net.flat_p.double().abs().sum()])
@@ -343,6 +380,10 @@ def run_gpu(args, rank, local_rank, world):
                                "peak_source": src + (" (of measured)" if src == "measured" else " (of fallback, B200_PROFILING.md)"),
                                "traffic": dominant_kernel_traffic(), "flop_per_launch": dom["flop"],
                                "ms_per_launch": dom["ms"]}
+        if hbm is not None:  # the largest single HBM-bound kernel of the step, against the measured copy bandwidth
+            gbs = hbm["bytes"] / (hbm["ms"] / 1e3) / 1e9
+            out["roofline_hbm"] = {"bound": "hbm", "kernel": hbm["kernel"], "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                   "frac": gbs / pk["hbm_gbs"], "bytes_per_launch": hbm["bytes"], "ms_per_launch": hbm["ms"]}
         if world == 1 and not args.no_cpu:
             sb = args.ref_batch
             dt, cores, _ = cpu_reference_step_time(S, sb, 2, 1, args.backbone)
