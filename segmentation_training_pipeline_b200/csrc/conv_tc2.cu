@@ -641,7 +641,9 @@ bool tc2_plan(const ConvP& p, Tc2Plan* pl) {
     if (p.Cout % bn != 0) continue;
     if (r4 && bn != 64) continue;
     if (best_bn != 0 && bn < 64) break;  // narrow N tiles only when Cout demands them
-    const int mt_max = bn == 128 ? 2 : (bn == 64 || bk == 64) ? 4 : 8;
+    // strip-height caps from the measured sweep (scripts/mt_sweep.py, profiles/r1_s38_mt_sweep.log): 64->64 @128^2 29.7 us at
+    // MT = 2 against 33.8 at MT = 4 (192->64: 68.6 vs 74.8); 32->32 @256^2 44.0 at MT = 4 against 48.2 at MT = 8
+    const int mt_max = bn == 128 ? 2 : (bn == 64 && bk == 64) ? 2 : (bn == 64 || bk == 64) ? 4 : (bn == 32 && bk == 32) ? 4 : 8;
     for (int mt = 1; mt <= mt_max; mt *= 2) {
       if (force > 0 && mt != (force < mt_max ? force : mt_max)) continue;
       for (int cl : {1, 2, 4}) {
