@@ -301,3 +301,71 @@ def test_crops_cells_and_reassembly():
     fn = lambda x: x[..., :1].astype(np.float32) / 255.0
     p = predict_image_by_cells(fn, items[0].x, 2, (6, 6), batch=3)
     assert p.shape == (12, 12, 1) and np.allclose(p[..., 0], items[0].x[..., 0] / 255.0)
+
+
+@pytest.mark.parametrize("arch,backbone,classes", [("Unet", "resnet34", 1), ("FPN", "resnet18", 1), ("FPN", "resnet50", 3),
+                                                   ("Linknet", "resnet18", 1), ("Unet", "vgg16", 1)])
+def test_engine_graph_matches_oracle_parameters(arch, backbone, classes):
+    """Graph construction needs no GPU (device='cpu' allocates the buffers on the host, nothing is launched): the engine's
+    parameter names / Keras-layout shapes must be exactly the oracle's, weights must round-trip through get/set_weights, and
+    the structural decisions the step relies on must hold."""
+    from oracle.models import SegModel
+    from segmentation_training_pipeline_b200 import engine as E
+    from segmentation_training_pipeline_b200.models import SegNet
+    net = SegNet(backbone, classes=classes, input_shape=(64, 64, 3), batch=2, device="cpu", seed=0, architecture=arch)
+    om = SegModel(arch, backbone, classes=classes, input_shape=(64, 64, 3))
+    W = net.get_weights()
+    assert set(om.params) == set(net.params)
+    for k, p in om.params.items():
+        assert tuple(p.shape) == W[k].shape, (k, tuple(p.shape), W[k].shape)
+    W2 = {k: (v + 1.0).astype(np.float32) for k, v in W.items()}
+    net.set_weights(W2)
+    W3 = net.get_weights()
+    assert all(np.array_equal(W3[k], W2[k]) for k in W2)
+    # encoder parameters form the leading range of the flat buffers (freeze_encoder = an offset into the optimizer launch)
+    enc_end = net.encoder_floats()
+    assert 0 < enc_end < net.n_flat
+    for name, p in net.params.items():
+        assert (name in net.encoder_param_names) == (p.offset < enc_end), name
+    # data-parallel bucket split: ops[i:] own exactly the parameters at offsets >= off, and that tail is >= 90 % of the floats
+    i, off = net.split_for_overlap(0.9)
+    if off:
+        assert (net.n_flat - off) >= 0.9 * net.n_flat * 0.99
+        for j, op in enumerate(net.ops):
+            for a in ("w", "b", "gamma", "beta"):
+                p = getattr(op, a, None)
+                if isinstance(p, E.Param):
+                    assert (j >= i) == (p.offset >= off), (j, a)
+    # every BatchNorm gets its forward statistics from the epilogue of the conv that feeds it (when exactly one conv does)
+    bns = [o for o in net.ops if isinstance(o, E.BNRelu)]
+    assert bns == [] or sum(o.stats_from_conv for o in bns) >= len(bns) - 2
+
+
+def test_create_net_key_validation(tmp_path):
+    """createNet (reference segmentation.py:96-155): unknown names raise the reference's ValueErrors; keys whose kernels are
+    not built raise NotImplementedError naming the key (nothing is silently ignored)."""
+    import yaml
+    from segmentation_pipeline import segmentation
+
+    def cfg(**kw):
+        spec = {"architecture": "Unet", "backbone": "resnet18", "classes": 1, "activation": "sigmoid", "shape": [64, 64, 3], "batch": 2}
+        spec.update(kw)
+        p = tmp_path / ("c%d.yaml" % len(list(tmp_path.iterdir())))
+        yaml.safe_dump(spec, open(p, "w"))
+        c = segmentation.parse(str(p))
+        c.device = "cpu"
+        return c
+
+    with pytest.raises(ValueError, match="Unknown architecture"):
+        cfg(architecture="PSPNet").createNet()
+    with pytest.raises(ValueError, match="Unknown backbone"):
+        cfg(backbone="efficientnetb4").createNet()
+    with pytest.raises(NotImplementedError, match="softmax"):
+        cfg(activation="softmax", classes=3).createNet()
+    with pytest.raises(NotImplementedError, match="classes"):
+        cfg(classes=7).createNet()
+    net = cfg(architecture="FPN", classes=3, activation="softmax", loss="lovasz_loss", pyramid_block_filters=64,
+              segmentation_block_filters=32).createNet()
+    assert net.activation == "softmax" and net.get_weights()["pyramid_stage_1_conv1x1/kernel"].shape == (1, 1, 256, 64)
+    assert net.get_weights()["head_conv/kernel"].shape == (3, 3, 128, 3)
+    assert cfg(crops=3).crops == 3
