@@ -64,3 +64,45 @@ def test_two_rank_gloo_allreduce_and_broadcast():
     assert e0 < 1e-6 and e1 < 1e-6                    # DP mean of shard gradients == global-batch gradient
     assert s0 == s1                                   # parameters identical after the broadcast
     assert m0 == m1 == [2.0, 5.0]                     # max over ranks (bench timing rule)
+
+
+def _worker_buckets(rank, world, port, out):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from segmentation_training_pipeline_b200 import ddp
+    ddp.init(backend="gloo")
+    # flat "gradient" of three layers in forward order; the late 90 % is reduced first (asynchronously), then the head --
+    # the order Trainer._ddp_step enqueues them in -- and the result must equal ONE all-reduce of the whole buffer
+    sizes = [(0, 8), (8, 40), (48, 120), (168, 832)]
+    off = ddp.bucket_split(sizes, 0.9)
+    g = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    whole = g.clone()
+    w1 = ddp.allreduce_sum_async(g[off:])
+    w2 = ddp.allreduce_sum_async(g[:off])
+    for w in (w1, w2):
+        w.wait()
+    ddp.allreduce_sum_(whole)
+    out.put((rank, off, bool(torch.equal(g, whole)), float(g[999])))
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_bucketed_allreduce_equals_single_allreduce():
+    """the two-bucket (late layers first, asynchronous) gradient all-reduce of the data-parallel step, world_size 2 on gloo."""
+    from segmentation_training_pipeline_b200 import ddp
+    assert ddp.bucket_split([(0, 8), (8, 40), (48, 120), (168, 832)], 0.9) == 48    # largest boundary with tail >= 90 %
+    assert ddp.bucket_split([(0, 8), (8, 40), (48, 120), (168, 832)], 0.5) == 168
+    assert ddp.bucket_split([], 0.9) == 0 and ddp.bucket_split([(0, 10)], 0.9) == 0
+    assert ddp.allreduce_sum_async(torch.zeros(4)) is None                           # single process: nothing to do
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_buckets, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=100) for _ in ps)
+    for p in ps:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for rank, off, same, last in res:
+        assert off == 48 and same and last == 999.0 * 3
