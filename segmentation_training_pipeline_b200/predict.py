@@ -1,8 +1,10 @@
 """Forward-only inference behind the reference's prediction verbs (reference segmentation.py:62-91
-predict_to_directory / predict_in_directory, :158-191 evaluateAll; README.md:493-534): images of a directory are resized
-to `shape`, run through the engine graph in inference mode (moving BatchNorm statistics), optionally averaged over the four
-flip variants (`ttflips`) and over several folds (`fold` may be a list: ensembling), thresholded at 0.5 and scaled back to
-the original size with nearest-neighbour sampling (imgaug Scale on segmentation maps)."""
+predict_to_directory / predict_in_directory, :158-191 evaluateAll; README.md:493-534, 745-754): images of a directory are
+resized to `shape`, run through the engine graph in inference mode (moving BatchNorm statistics), optionally averaged over
+the four flip variants (`ttflips`) and over several folds (`fold` may be a list: ensembling).  Like the reference, callbacks
+and writers get the FLOAT probability map scaled back to the image's own size as a SegmentationMapOnImage (`.arr`; users
+threshold it themselves, README.md:505-513); `PredictionBatch.segmentation_maps_aug` / evaluateAll's `.results` keep the
+0.5-thresholded masks (nearest-neighbour scale-back) for convenience."""
 from __future__ import annotations
 
 import os
@@ -11,6 +13,35 @@ from typing import Callable, Iterator, List, Optional, Sequence, Union
 import numpy as np
 
 IMG_EXT = (".jpg", ".jpeg", ".png", ".bmp")
+
+
+class SegmentationMapOnImage:
+    """What the reference hands to prediction callbacks and stores in its batches: an imgaug.SegmentationMapOnImage built from
+    the network's FLOAT output (reference segmentation.py:58-60 `update`, :62-91) -- user code reads `.arr` and thresholds it
+    itself (README.md:505-513 `img.arr > threshold`).  `.arr` = float32 probabilities [h, w, classes]; np.asarray(obj) and
+    get_arr_int() give the 0.5-thresholded mask."""
+
+    def __init__(self, arr, shape=None):
+        a = np.asarray(arr, dtype=np.float32)
+        self.arr = a[:, :, None] if a.ndim == 2 else a
+        self.shape = tuple(shape) if shape is not None else self.arr.shape
+
+    def get_arr_int(self, threshold=0.5):
+        return (self.arr > threshold).astype(np.int32)
+
+    def __array__(self, dtype=None, copy=None):
+        m = (self.arr > 0.5).astype(np.uint8)
+        return m.astype(dtype) if dtype is not None else m
+
+    def resize(self, sizes, interpolation="cubic"):
+        """imgaug 0.3.0 resizes float segmentation maps like heatmaps (cubic, clipped to [0, 1]) [DEP, unpinned]."""
+        import cv2
+        h, w = int(sizes[0]), int(sizes[1])
+        if self.arr.shape[:2] == (h, w):
+            return SegmentationMapOnImage(self.arr)
+        flag = {"cubic": cv2.INTER_CUBIC, "linear": cv2.INTER_LINEAR, "nearest": cv2.INTER_NEAREST}[interpolation]
+        out = cv2.resize(self.arr, (w, h), interpolation=flag)
+        return SegmentationMapOnImage(np.clip(out, 0.0, 1.0))
 
 
 class PredictionBatch:
@@ -114,26 +145,51 @@ def _scale_back(seg: np.ndarray, orig) -> np.ndarray:
     return out[:, :, None] if out.ndim == 2 else out
 
 
+def _scaled_map(prob: np.ndarray, orig) -> SegmentationMapOnImage:
+    """the probability map of one image as the reference's Scale({"height": orig.h, "width": orig.w}) leaves it"""
+    return SegmentationMapOnImage(prob).resize(np.asarray(orig).shape[:2])
+
+
 def predict_to_directory(cfg, spath, tpath, fold=0, stage=0, limit=-1, batchSize=32, binaryArray=False, ttflips=False):
+    """reference segmentation.py:62-79: per image the scaled map's `.arr` (float probabilities) is stored as <stem>.npy
+    (binaryArray=True; what ansemblePredictions sums) or as the 8-bit image arr*255."""
     import cv2
     os.makedirs(tpath, exist_ok=True)
     n = 0
     for b in predict_on_directory(cfg, spath, fold, stage, limit, batchSize, ttflips):
         for i, id_ in enumerate(b.data):
-            m = _scale_back(b.segmentation_maps_aug[i], b.images[i])
+            m = _scaled_map(b.probabilities[i], b.images[i]).arr
             stem = id_[0:id_.index(".")]
             if binaryArray:
                 np.save(os.path.join(tpath, stem), m)
             else:
-                cv2.imwrite(os.path.join(tpath, stem + ".png"), (m[:, :, 0] * 255).astype(np.uint8))
+                img8 = (m * 255).astype(np.uint8)
+                cv2.imwrite(os.path.join(tpath, stem + ".png"), img8[:, :, 0] if img8.shape[2] == 1 else img8)
             n += 1
     return n
 
 
 def predict_in_directory(cfg, spath, fold, stage, cb: Callable, data, limit=-1, batchSize=32, ttflips=False):
+    """reference segmentation.py:81-91: cb(file name, SegmentationMapOnImage scaled to the image's size, data)."""
     for b in predict_on_directory(cfg, spath, fold, stage, limit, batchSize, ttflips):
         for i, id_ in enumerate(b.data):
-            cb(id_, _scale_back(b.segmentation_maps_aug[i], b.images[i]), data)
+            cb(id_, _scaled_map(b.probabilities[i], b.images[i]), data)
+
+
+def ansemble_predictions(source_folder, folders: Sequence[str], cb: Callable, data, weights: Optional[Sequence[float]] = None):
+    """segmentation.ansemblePredictions (reference segmentation.py:27 -> musket_core.generic_config [DEP]; README.md:745-754):
+    for every image of `source_folder` the <stem>.npy probability arrays that predict_to_directory(..., binaryArray=True)
+    stored in each of `folders` are averaged (optionally weighted) and cb(file name, SegmentationMapOnImage, data) is called."""
+    ws = [1.0] * len(folders) if weights is None else [float(w) for w in weights]
+    if len(ws) != len(folders) or not folders:
+        raise ValueError("ansemblePredictions: one weight per folder")
+    for name in _list_images(source_folder):
+        stem = name[0:name.index(".")]
+        acc = None
+        for f, w in zip(folders, ws):
+            a = np.load(os.path.join(f, stem + ".npy")).astype(np.float32) * w
+            acc = a if acc is None else acc + a
+        cb(name, SegmentationMapOnImage(acc / sum(ws)), data)
 
 
 def evaluate_all(cfg, ds, fold=None, stage=-1, negatives="real", ttflips=None, batchSize=32) -> Iterator[PredictionBatch]:
@@ -156,6 +212,8 @@ def evaluate_all(cfg, ds, fold=None, stage=-1, negatives="real", ttflips=None, b
             img = np.asarray(it.x)
             b = PredictionBatch([it], [img], [predict_image_by_cells(fn, img, crops, (H, W), B)], img.shape[:2])
             b.results = list(b.segmentation_maps_aug)
+            b.predicted_maps_aug = [SegmentationMapOnImage(p) for p in b.probabilities]
+            b.segmentation_maps = [SegmentationMapOnImage(np.asarray(it.y, dtype=np.float32))]
             yield b
         return
     for s in range(0, len(idx), B):
@@ -166,4 +224,7 @@ def evaluate_all(cfg, ds, fold=None, stage=-1, negatives="real", ttflips=None, b
         probs = sum(predict_arrays(net, x, bool(ttflips)) for net in nets) / len(nets)
         b = PredictionBatch(items, [np.asarray(it.x) for it in items], list(probs), (H, W))
         b.results = [_scale_back(m, np.asarray(it.x)) for m, it in zip(b.segmentation_maps_aug, items)]
+        # the reference's batch fields (segmentation.py:182-184): ground-truth maps and the predicted maps scaled to each image
+        b.predicted_maps_aug = [_scaled_map(p, np.asarray(it.x)) for p, it in zip(b.probabilities, items)]
+        b.segmentation_maps = [SegmentationMapOnImage(np.asarray(it.y, dtype=np.float32)) for it in items]
         yield b

@@ -35,6 +35,12 @@ custom_models: Dict[str, Callable] = {}
 # custom loss/metric registry stand-in for keras.utils.get_custom_objects() (reference README.md:629-634)
 custom_objects: Dict[str, Callable] = {}
 extra_train: Dict[str, object] = {}
+
+
+def ansemblePredictions(sourceFolder, folders, cb, data, weights=None):
+    """reference segmentation.py:27 / README.md:745-754: average the per-file .npy predictions of several runs."""
+    from .predict import ansemble_predictions
+    return ansemble_predictions(sourceFolder, folders, cb, data, weights)
 dataset_augmenters: Dict[str, Callable] = {}
 
 _LOSS_TERMS = {"binary_crossentropy": 0, "dice_loss": 1, "iou_loss": 2, "lovasz_loss": 3, "jaccard_loss": 4, "focal_loss": 5}

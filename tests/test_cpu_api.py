@@ -369,3 +369,82 @@ def test_create_net_key_validation(tmp_path):
     assert net.activation == "softmax" and net.get_weights()["pyramid_stage_1_conv1x1/kernel"].shape == (1, 1, 256, 64)
     assert net.get_weights()["head_conv/kernel"].shape == (3, 3, 128, 3)
     assert cfg(crops=3).crops == 3
+
+
+def test_prediction_maps_and_ansemble_predictions(tmp_path):
+    """What prediction callbacks receive (reference segmentation.py:81-91, README.md:505-513: `img.arr > threshold`) and
+    segmentation.ansemblePredictions (README.md:745-754): averaging the .npy predictions of several runs."""
+    import cv2
+    from segmentation_pipeline import segmentation
+    from segmentation_training_pipeline_b200.predict import SegmentationMapOnImage, _scaled_map
+    p = np.linspace(0, 1, 64 * 64, dtype=np.float32).reshape(64, 64, 1)
+    m = SegmentationMapOnImage(p)
+    assert m.shape == (64, 64, 1) and m.arr.dtype == np.float32
+    assert np.array_equal(np.asarray(m), (p > 0.5).astype(np.uint8)) and m.get_arr_int(0.25).sum() > m.get_arr_int(0.75).sum()
+    big = _scaled_map(p, np.zeros((80, 96, 3), np.uint8))
+    assert big.shape == (80, 96, 1) and 0.0 <= big.arr.min() and big.arr.max() <= 1.0
+    assert _scaled_map(p, np.zeros((64, 64, 3), np.uint8)).arr is not None
+    # two runs' predictions of two files, weights 3:1
+    src, a, b = tmp_path / "src", tmp_path / "a", tmp_path / "b"
+    for d in (src, a, b):
+        d.mkdir()
+    for name, va, vb in (("x", 0.8, 0.0), ("y", 0.2, 0.6)):
+        cv2.imwrite(str(src / (name + ".png")), np.zeros((8, 8, 3), np.uint8))
+        np.save(str(a / name), np.full((8, 8, 1), va, np.float32))
+        np.save(str(b / name), np.full((8, 8, 1), vb, np.float32))
+    got = {}
+    segmentation.ansemblePredictions(str(src), [str(a), str(b)], lambda f, mm, data: data.__setitem__(f, float(mm.arr.mean())), got)
+    assert got == pytest.approx({"x.png": 0.4, "y.png": 0.4})
+    got2 = {}
+    segmentation.ansemblePredictions(str(src), [str(a), str(b)], lambda f, mm, data: data.__setitem__(f, float(mm.arr.mean())), got2,
+                                     weights=[3, 1])
+    assert got2 == pytest.approx({"x.png": 0.6, "y.png": 0.3})
+
+
+@pytest.mark.parametrize("crops", [0, 2])
+def test_prediction_verbs_host_logic(tmp_path, monkeypatch, crops):
+    """predict_to_directory / predict_in_directory / evaluateAll host logic (file walking, scale-back, writers, batch fields,
+    fold ensembling, crops reassembly) with the device forward replaced by a stand-in: probability = red channel / 255."""
+    import cv2
+    from segmentation_pipeline.impl.datasets import PredictionItem
+    from segmentation_training_pipeline_b200 import predict as P
+
+    class Net:
+        batch, classes, input_shape = 4, 1, (64, 64, 3)
+
+    class Cfg:
+        shape, folds_count = [64, 64, 3], 2
+
+        def load_model(self, fold, stage):
+            return Net()
+
+    cfg = Cfg()
+    cfg.crops = crops
+    monkeypatch.setattr(P, "predict_arrays", lambda net, x, ttflips=False: x[..., :1].astype(np.float32) / 255.0)
+    src = tmp_path / "src"
+    src.mkdir()
+    rng = np.random.default_rng(0)
+    imgs = {"a.png": rng.integers(0, 256, (80, 96, 3), dtype=np.uint8), "b.png": rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)}
+    for k, v in imgs.items():
+        cv2.imwrite(str(src / k), cv2.cvtColor(v, cv2.COLOR_RGB2BGR))
+    out = tmp_path / "out"
+    assert P.predict_to_directory(cfg, str(src), str(out), fold=[0, 1], stage=0) == 2
+    pb = cv2.imread(str(out / "b.png"), cv2.IMREAD_GRAYSCALE)
+    assert pb.shape == (64, 64)
+    if not crops:   # arr*255 of red/255; with crops every cell goes through a cubic up- and a bilinear down-sampling
+        assert np.abs(pb.astype(int) - imgs["b.png"][..., 0].astype(int)).max() <= 1
+    else:
+        assert np.corrcoef(pb.reshape(-1).astype(float), imgs["b.png"][..., 0].reshape(-1).astype(float))[0, 1] > 0.5
+    assert cv2.imread(str(out / "a.png"), cv2.IMREAD_GRAYSCALE).shape == (80, 96)
+    arrs = tmp_path / "arr"
+    assert P.predict_to_directory(cfg, str(src), str(arrs), binaryArray=True) == 2
+    assert np.load(str(arrs / "a.npy")).shape == (80, 96, 1) and np.load(str(arrs / "b.npy")).dtype == np.float32
+    seen = {}
+    P.predict_in_directory(cfg, str(src), 0, 0, lambda f, m, data: data.__setitem__(f, (m.shape, float((m.arr > 0.25).mean()))), seen)
+    assert seen["a.png"][0] == (80, 96, 1) and seen["b.png"][0] == (64, 64, 1) and 0.6 < seen["b.png"][1] < 0.9
+    ds = [PredictionItem("i%d" % k, v, (v[..., :1] > 127).astype(np.uint8)) for k, v in enumerate(imgs.values())]
+    batches = list(P.evaluate_all(cfg, ds, fold=0, stage=0))
+    assert sum(len(b.data) for b in batches) == 2
+    b0 = batches[0]
+    assert b0.results[0].shape == (80, 96, 1) and b0.predicted_maps_aug[0].shape == (80, 96, 1)
+    assert b0.segmentation_maps[0].arr.shape == (80, 96, 1) and b0.images[0].shape == (80, 96, 3)

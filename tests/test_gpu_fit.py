@@ -63,7 +63,7 @@ def test_fit_writes_reference_artifacts(cuda, tmp_path):
     out = str(tmp_path / "pred")
     assert cfg.predict_to_directory(big, out, fold=[0, 1], stage=1, ttflips=True) == 2
     pa, pb = cv2.imread(os.path.join(out, "a.png"), cv2.IMREAD_GRAYSCALE), cv2.imread(os.path.join(out, "b.png"), cv2.IMREAD_GRAYSCALE)
-    assert pa.shape == (80, 96) and pb.shape == (64, 64) and set(np.unique(pa)) <= {0, 255}
+    assert pa.shape == (80, 96) and pb.shape == (64, 64) and pa.dtype == np.uint8   # arr*255: an 8-bit probability image
     seen = {}
     cfg.predict_in_directory(big, 0, 1, lambda id_, m, data: data.__setitem__(id_, m.shape), seen, ttflips=False)
     assert seen == {"a.png": (80, 96, 1), "b.png": (64, 64, 1)}
@@ -278,6 +278,6 @@ def test_fit_and_predict_on_crops(cuda, tmp_path):
     out = str(tmp_path / "pred")
     assert cfg.predict_to_directory(str(tmp_path / "img"), out, fold=0, stage=0) == 4
     m = cv2.imread(os.path.join(out, "00.png"), cv2.IMREAD_GRAYSCALE)
-    assert m.shape == (128, 128) and set(np.unique(m)) <= {0, 255}
+    assert m.shape == (128, 128) and m.dtype == np.uint8
     b = next(iter(cfg.evaluateAll(ds, fold=0, stage=0)))
     assert b.results[0].shape == (128, 128, 1)
