@@ -95,3 +95,35 @@ def max_over_ranks(values: List[float], device="cpu", group=None) -> List[float]
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return [float(x) for x in t.cpu()]
+
+
+def mean_over_ranks_(t: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place mean over ranks (no-op for world_size 1)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t /= dist.get_world_size(group)
+    return t
+
+
+def sync_buffers_mean_(buffers, group=None):
+    """Average a dict of small fp32 tensors (the BatchNorm moving statistics, local per rank like the reference's per-tower
+    BatchNorm) across ranks through ONE flat all-reduce, so that every rank validates -- and therefore takes every
+    callback decision (EarlyStopping, ReduceLROnPlateau, best-weights checkpoint) -- on identical numbers."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1) or not buffers:
+        return
+    keys = sorted(buffers)
+    flat = torch.cat([buffers[k].reshape(-1).float() for k in keys])
+    mean_over_ranks_(flat, group)
+    off = 0
+    for k in keys:
+        n = buffers[k].numel()
+        buffers[k].copy_(flat[off:off + n].view_as(buffers[k]))
+        off += n
+
+
+def barrier(group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.barrier(group=group)

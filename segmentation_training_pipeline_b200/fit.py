@@ -97,7 +97,21 @@ def _weights_file(base, spec):
 
 def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
     import torch
+    from . import ddp
     from .trainer import Trainer
+
+    # `cfg.gpus = N` (reference FAQ.md:108-112 -> keras multi_gpu_model [DEP]) is one process per GPU here: launch the same
+    # script with `python -m torch.distributed.run --nproc-per-node N ...`; every rank trains on its shard of each global
+    # batch, gradients are all-reduced (ddp.py), rank 0 writes weights / metrics / summary.
+    rank, local_rank, world = ddp.env_world()
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        cfg.device = "cuda:%d" % local_rank
+        ddp.init(device=torch.device(cfg.device))
+    elif int(getattr(cfg, "gpus", 1) or 1) > 1:
+        raise NotImplementedError("cfg.gpus = %d: data-parallel training runs as one process per GPU -- launch this script with "
+                                  "`python -m torch.distributed.run --nproc-per-node %d <script>`" % (cfg.gpus, cfg.gpus))
+    is_main = rank == 0
 
     base = cfg._dir()
     summary = os.path.join(base, "summary.yaml")
@@ -105,6 +119,7 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
         raise ValueError("Experiment is already finished!")
     for d in ("weights", "metrics"):
         os.makedirs(os.path.join(base, d), exist_ok=True)
+    ddp.barrier()   # every rank has seen the same "finished / not finished" state before anything is written
     n_all = len(ds)
     extra_name = cfg.extra.get("extra_train_data")
     extra_idx = np.zeros(0, dtype=np.int64)
@@ -176,12 +191,14 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
             if len(st_tr) == 0:
                 raise ValueError("stage %d: no training samples left after `negatives: %s`" % (si, stage.get("negatives")))
             tr_ = Trainer(net, optimizer=cfg.optimizer, lr=stage.get("lr", cfg.lr), clipnorm=cfg.clipnorm,
-                          clipvalue=cfg.clipvalue, freeze_encoder=frozen,
-                          augment=parse_augmentation(cfg.augmentation, seed=cfg.random_state + 1000 * fi + si))
+                          clipvalue=cfg.clipvalue, freeze_encoder=frozen, world_size=world,
+                          augment=parse_augmentation(cfg.augmentation, seed=cfg.random_state + 1000 * fi + si + 7919 * rank))
+            if world > 1:
+                ddp.broadcast_(net.flat_p, 0)
             tr_.enable_host_feed()
             # stage `callbacks:` replaces the config-level block, `extra_callbacks:` adds to it (StageConfig, segmentation.raml:124-136)
             cbs = _cb.build(stage.get("callbacks", cfg.callbacks), stage.get("extra_callbacks"))
-            tr_.steps_per_epoch = max(1, len(st_tr) // B)
+            tr_.steps_per_epoch = max(1, len(st_tr) // (B * world))
             for cb in cbs:
                 cb.on_train_begin(tr_)
             iteration = 0
@@ -190,7 +207,10 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
             best = None
             pm = cfg.primary_metric
             for epoch in range(int(stage.get("epochs", 1))):
-                order = rng.permutation(st_tr)
+                order = rng.permutation(st_tr)            # same seed on every rank -> same permutation
+                if world > 1:
+                    mine = ddp.shard_indices(order, rank, world, B)
+                    order = mine if len(mine) >= B else order   # too few samples for one global batch: no sharding
                 steps = max(1, len(order) // B)
                 agg: Dict[str, float] = {}
                 def _acc(m):
@@ -205,6 +225,12 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
                     iteration += 1
                     _acc(tr_.step_from_host_pipelined(himgs[s & 1], hmasks[s & 1]))   # metrics of the previous step
                 _acc(tr_.flush_host_pipeline())
+                if world > 1:   # epoch metrics = mean over ranks; BatchNorm moving statistics averaged before validation
+                    keys = sorted(agg)
+                    t = torch.tensor([agg[k] for k in keys], dtype=torch.float64, device=net.device)
+                    ddp.mean_over_ranks_(t)
+                    agg = {k: float(v) for k, v in zip(keys, t.cpu())}
+                    ddp.sync_buffers_mean_(net.buffers)
                 val = evaluate(net, tr_, ds, st_va, shape, himg, hmask)
                 row = {"epoch": epoch, "loss": agg.get("loss", float("nan")), "lr": tr_.get_lr()}
                 for mname in metric_names:
@@ -213,22 +239,27 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
                 for mname in metric_names:
                     row["val_" + mname] = val.get(mname, float("nan"))
                 rows.append(row)
-                with open(mpath, "w", newline="") as f:
-                    w = csv.DictWriter(f, fieldnames=fields)
-                    w.writeheader()
-                    w.writerows(rows)
+                if is_main:
+                    with open(mpath, "w", newline="") as f:
+                        w = csv.DictWriter(f, fieldnames=fields)
+                        w.writeheader()
+                        w.writerows(rows)
                 key = pm if pm in row else "val_loss"
                 if _better(cfg.primary_metric_mode, key, row[key], best):
                     best = row[key]
-                    np.savez(wpath, **net.get_weights())
+                    if is_main:
+                        np.savez(wpath, **net.get_weights())
+                ddp.barrier()   # files of this epoch are complete before any rank may read them (initial_weights, resume)
                 for cb in cbs:
                     cb.on_epoch_end(tr_, epoch, row)
                 if any(cb.stop_training for cb in cbs):
                     break
             results.append({"fold": fi, "stage": si, "best_" + pm: None if best is None else float(best), "epochs": len(rows)})
-    with open(summary, "w") as f:
-        yaml.safe_dump({"completed": True, "folds": len(folds), "results": results,
-                        "finished_at": time.strftime("%Y-%m-%d %H:%M:%S")}, f)
+    if is_main:
+        with open(summary, "w") as f:
+            yaml.safe_dump({"completed": True, "folds": len(folds), "results": results, "world_size": world,
+                            "finished_at": time.strftime("%Y-%m-%d %H:%M:%S")}, f)
+    ddp.barrier()
     return results
 
 

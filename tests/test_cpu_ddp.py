@@ -82,7 +82,14 @@ def _worker_buckets(rank, world, port, out):
     for w in (w1, w2):
         w.wait()
     ddp.allreduce_sum_(whole)
-    out.put((rank, off, bool(torch.equal(g, whole)), float(g[999])))
+    # BatchNorm moving statistics (local per rank) averaged through one flat all-reduce before validation (fit.py)
+    bufs = {"bn1/moving_mean": torch.full((3,), float(rank)), "bn0/moving_variance": torch.full((2, 2), 10.0 * (rank + 1))}
+    ddp.sync_buffers_mean_(bufs)
+    ok_bufs = bool(torch.allclose(bufs["bn1/moving_mean"], torch.full((3,), 0.5)) and
+                   torch.allclose(bufs["bn0/moving_variance"], torch.full((2, 2), 15.0)))
+    m = ddp.mean_over_ranks_(torch.tensor([float(rank), 4.0], dtype=torch.float64))
+    ddp.barrier()
+    out.put((rank, off, bool(torch.equal(g, whole)) and ok_bufs and m.tolist() == [0.5, 4.0], float(g[999])))
     torch.distributed.destroy_process_group()
 
 
