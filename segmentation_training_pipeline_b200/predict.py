@@ -228,3 +228,28 @@ def evaluate_all(cfg, ds, fold=None, stage=-1, negatives="real", ttflips=None, b
         b.predicted_maps_aug = [_scaled_map(p, np.asarray(it.x)) for p, it in zip(b.probabilities, items)]
         b.segmentation_maps = [SegmentationMapOnImage(np.asarray(it.y, dtype=np.float32)) for it in items]
         yield b
+
+
+def evaluate(cfg, ds, fold: int, stage: int, negatives="all", limit=16, batchSize=32) -> Iterator[PredictionBatch]:
+    """reference PipelineConfig.evaluate (segmentation.py:37-47): heat maps of (at most `limit`) VALIDATION items of one fold at
+    network resolution -- yields batches with `.images_aug` (inputs as fed) and `.heatmaps_aug` (float probability maps)."""
+    import cv2
+    net = cfg.load_model(fold, stage)
+    B = min(int(batchSize), net.batch)
+    H, W = int(cfg.shape[0]), int(cfg.shape[1])
+    _, va = cfg.kfold(len(ds))[fold]
+    idx = [int(i) for i in va]
+    if negatives == "none" and hasattr(ds, "isPositive"):
+        idx = [i for i in idx if ds.isPositive(i)]
+    if limit is not None and limit > 0:
+        idx = idx[:limit]
+    for s in range(0, len(idx), B):
+        items = [ds[i] for i in idx[s:s + B]]
+        xs = [cv2.resize(np.asarray(it.x), (W, H), interpolation=cv2.INTER_CUBIC) if np.asarray(it.x).shape[:2] != (H, W)
+              else np.asarray(it.x) for it in items]
+        x = np.stack(xs).astype(np.uint8)
+        probs = predict_arrays(net, x, False)
+        b = PredictionBatch(items, [np.asarray(it.x) for it in items], list(probs), (H, W))
+        b.images_aug = list(x)
+        b.heatmaps_aug = [SegmentationMapOnImage(p) for p in probs]
+        yield b

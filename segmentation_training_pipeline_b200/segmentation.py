@@ -291,6 +291,10 @@ class PipelineConfig:
         from . import predict as _p
         return _p.predict_in_directory(self, spath, fold, stage, cb, data, limit, batchSize, ttflips)
 
+    def evaluate(self, d, fold, stage, negatives="all", limit=16):
+        from . import predict as _p
+        return _p.evaluate(self, d, fold, stage, negatives, limit)
+
     def evaluateAll(self, ds, fold=None, stage=-1, negatives="real", ttflips=None, batchSize=32):
         from . import predict as _p
         return _p.evaluate_all(self, ds, fold, stage, negatives, ttflips, batchSize)

@@ -448,3 +448,7 @@ def test_prediction_verbs_host_logic(tmp_path, monkeypatch, crops):
     b0 = batches[0]
     assert b0.results[0].shape == (80, 96, 1) and b0.predicted_maps_aug[0].shape == (80, 96, 1)
     assert b0.segmentation_maps[0].arr.shape == (80, 96, 1) and b0.images[0].shape == (80, 96, 3)
+    if not crops:   # PipelineConfig.evaluate: heat maps of the validation items of a fold at network resolution
+        cfg.kfold = lambda n: [(np.array([0]), np.array([1])), (np.array([1]), np.array([0]))]
+        ev = list(P.evaluate(cfg, ds, 0, 0, limit=16))
+        assert len(ev) == 1 and len(ev[0].data) == 1 and ev[0].heatmaps_aug[0].shape == (64, 64, 1) and ev[0].images_aug[0].shape == (64, 64, 3)
