@@ -74,6 +74,9 @@ def parse_loss(expr: str) -> Tuple[float, ...]:
         elif isinstance(node, ast.Name):
             if node.id in _LOSS_TERMS:
                 w[_LOSS_TERMS[node.id]] += scale
+            elif node.id in custom_objects:
+                raise NotImplementedError("loss '%s' is a Python callable registered in custom_objects: the training step runs as "
+                                          "fused device kernels, only the built-in loss names can be trained on" % node.id)
             elif node.id in _UNFUSED_LOSSES:
                 raise NotImplementedError("loss '%s' has no fused device kernel yet (DESIGN.md, out of scope rows)" % node.id)
             else:
@@ -258,8 +261,18 @@ class PipelineConfig:
             return SimplePNGMaskDataSet(os.path.join(base, spec["input_path"]), os.path.join(base, spec["output_path"]))
         raise ValueError("fit() needs a dataset or `datasets:` + `fit_with:` in the config")
 
+    def _check_training_keys(self):
+        """keys the training path does not implement must stop the run, not be silently ignored"""
+        if self.transforms:
+            raise NotImplementedError("transforms: (augmenters applied to every sample, also at validation / prediction time) is "
+                                      "not built; resize-to-shape is implicit")
+        for k in ("dataset_augmenter", "bgr", "manualResize", "compressPredictionsAsInts"):
+            if self.extra.get(k):
+                raise NotImplementedError("config key '%s' is not built (DESIGN.md section 7)" % k)
+
     def fit(self, d=None, subsample=1.0, foldsToExecute: Optional[Sequence[int]] = None, start_from_stage=0):
         from .fit import run_fit
+        self._check_training_keys()
         return run_fit(self, self._resolve_dataset(d), subsample, foldsToExecute, start_from_stage)
 
     def lr_find(self, d=None, start_lr=0.00001, end_lr=1.0, epochs=1, stage=0):

@@ -369,6 +369,16 @@ def test_create_net_key_validation(tmp_path):
     assert net.activation == "softmax" and net.get_weights()["pyramid_stage_1_conv1x1/kernel"].shape == (1, 1, 256, 64)
     assert net.get_weights()["head_conv/kernel"].shape == (3, 3, 128, 3)
     assert cfg(crops=3).crops == 3
+    with pytest.raises(NotImplementedError, match="transforms"):
+        cfg(transforms={"Fliplr": 1.0}).fit([])
+    with pytest.raises(NotImplementedError, match="dataset_augmenter"):
+        cfg(dataset_augmenter={"name": "x"}).fit([])
+    segmentation.custom_objects["my_loss"] = lambda t, p: 0.0
+    try:
+        with pytest.raises(NotImplementedError, match="custom_objects"):
+            segmentation.parse_loss("binary_crossentropy+0.5*my_loss")
+    finally:
+        del segmentation.custom_objects["my_loss"]
 
 
 def test_prediction_maps_and_ansemble_predictions(tmp_path):
