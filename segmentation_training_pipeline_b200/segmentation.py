@@ -228,8 +228,19 @@ class PipelineConfig:
             raise NotImplementedError("activation '%s' is not built" % self.activation)
         if self.classes > 4:
             raise NotImplementedError("classes <= 4 (mask channels of the on-device augmentation / head kernels)")
+        enc_file = None
         if self.encoder_weights not in (None, "None", "none"):
-            raise NotImplementedError("encoder_weights: no network here -- load a local .npz with load_weights()")
+            # `encoder_weights: imagenet` downloads a Keras checkpoint in the reference; there is no network here.  A path to a
+            # local .npz with Keras-named arrays (conv0/kernel, bn0/gamma, bn0/moving_mean, ...) is accepted instead.
+            cand = str(self.encoder_weights)
+            base = os.path.dirname(os.path.abspath(self.path)) if self.path else os.getcwd()
+            for c in (cand, cand + ".npz", os.path.join(base, cand), os.path.join(base, cand + ".npz")):
+                if os.path.isfile(c):
+                    enc_file = c
+                    break
+            if enc_file is None:
+                raise NotImplementedError("encoder_weights: '%s' cannot be downloaded here -- give the path of a local .npz with the "
+                                          "encoder's Keras-named arrays" % cand)
         net = _models.SegNet(bb, classes=self.classes, input_shape=tuple(self.shape), batch=batch or self.batch,
                               decoder_filters=self.decoder_filters, device=self.device, seed=self.random_state,
                               architecture=arch, decoder_block_type=getattr(self, "decoder_block_type", None) or "upsampling",
@@ -238,6 +249,12 @@ class PipelineConfig:
                               dropout=self.extra.get("dropout", None),
                               loss=lw)
         net.activation = self.activation or "linear"   # what predict applies to the logits
+        if enc_file is not None:
+            layers = {n.rsplit("/", 1)[0] for n in net.encoder_param_names}
+            w = {k: v for k, v in dict(np.load(enc_file)).items() if k.rsplit("/", 1)[0] in layers}
+            if not w:
+                raise ValueError("encoder_weights: %s holds no array of this encoder (%s, ...)" % (enc_file, sorted(layers)[:3]))
+            net.set_weights(w, strict=False)
         return net
 
     def kfold(self, n: int) -> List[Tuple[np.ndarray, np.ndarray]]:

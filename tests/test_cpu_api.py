@@ -369,6 +369,16 @@ def test_create_net_key_validation(tmp_path):
     assert net.activation == "softmax" and net.get_weights()["pyramid_stage_1_conv1x1/kernel"].shape == (1, 1, 256, 64)
     assert net.get_weights()["head_conv/kernel"].shape == (3, 3, 128, 3)
     assert cfg(crops=3).crops == 3
+    # encoder_weights: a local .npz of Keras-named encoder arrays (no download here); only encoder layers are taken from it
+    base = cfg().createNet()
+    w = base.get_weights()
+    np.savez(str(tmp_path / "enc.npz"), **{"conv0/kernel": w["conv0/kernel"] + 1.0, "bn0/moving_mean": w["bn0/moving_mean"] + 2.0,
+                                            "final_conv/kernel": w["final_conv/kernel"] + 3.0})
+    w2 = cfg(encoder_weights="enc.npz").createNet().get_weights()
+    assert np.array_equal(w2["conv0/kernel"], w["conv0/kernel"] + 1.0) and np.array_equal(w2["bn0/moving_mean"], w["bn0/moving_mean"] + 2.0)
+    assert np.array_equal(w2["final_conv/kernel"], w["final_conv/kernel"])          # decoder arrays of the file are ignored
+    with pytest.raises(NotImplementedError, match="encoder_weights"):
+        cfg(encoder_weights="imagenet").createNet()
     with pytest.raises(NotImplementedError, match="transforms"):
         cfg(transforms={"Fliplr": 1.0}).fit([])
     with pytest.raises(NotImplementedError, match="dataset_augmenter"):
