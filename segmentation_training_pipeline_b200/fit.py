@@ -162,6 +162,10 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
         himgs = [torch.zeros((B, shape[0], shape[1], shape[2]), dtype=torch.uint8).pin_memory() for _ in range(2)]
         hmasks = [torch.zeros((B, shape[0], shape[1], cfg.classes), dtype=torch.uint8).pin_memory() for _ in range(2)]
         himg, hmask = himgs[0], hmasks[0]
+        # decode + resize run in a thread pool a couple of batches ahead of the device (loader.py); `loader_workers: 0` in the
+        # config keeps everything on the calling thread (datasets whose __getitem__ is not thread safe)
+        from .loader import HostLoader
+        loader = HostLoader(ds, shape, cfg.classes, B, workers=int(cfg.extra.get("loader_workers", 4)))
         for si, stage in enumerate(cfg.stages):
             if si < start_from_stage:
                 continue
@@ -217,13 +221,12 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
                     for k, v in (m or {}).items():
                         agg[k] = agg.get(k, 0.0) + v / steps          # Keras progress-bar averaging: equal weight per batch
 
-                for s in range(steps):
-                    ids = [order[(s * B + j) % len(order)] for j in range(B)]
-                    _stack(ds, ids, shape, himgs[s & 1], hmasks[s & 1])
+                batches = [[order[(s * B + j) % len(order)] for j in range(B)] for s in range(steps)]
+                for bimg, bmask in loader.iterate(batches):
                     for cb in cbs:
                         cb.on_batch_begin(tr_, iteration)
                     iteration += 1
-                    _acc(tr_.step_from_host_pipelined(himgs[s & 1], hmasks[s & 1]))   # metrics of the previous step
+                    _acc(tr_.step_from_host_pipelined(bimg, bmask))   # metrics of the previous step
                 _acc(tr_.flush_host_pipeline())
                 if world > 1:   # epoch metrics = mean over ranks; BatchNorm moving statistics averaged before validation
                     keys = sorted(agg)
@@ -255,6 +258,7 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
                 if any(cb.stop_training for cb in cbs):
                     break
             results.append({"fold": fi, "stage": si, "best_" + pm: None if best is None else float(best), "epochs": len(rows)})
+        loader.close()
     if is_main:
         with open(summary, "w") as f:
             yaml.safe_dump({"completed": True, "folds": len(folds), "results": results, "world_size": world,

@@ -472,3 +472,38 @@ def test_prediction_verbs_host_logic(tmp_path, monkeypatch, crops):
         cfg.kfold = lambda n: [(np.array([0]), np.array([1])), (np.array([1]), np.array([0]))]
         ev = list(P.evaluate(cfg, ds, 0, 0, limit=16))
         assert len(ev) == 1 and len(ev[0].data) == 1 and ev[0].heatmaps_aug[0].shape == (64, 64, 1) and ev[0].images_aug[0].shape == (64, 64, 3)
+
+
+@pytest.mark.parametrize("workers", [0, 3])
+def test_host_loader_prefetch_ring(workers):
+    """loader.HostLoader: batches decoded / resized by a thread pool two batches ahead into a ring of four host buffers; every
+    yielded pair must hold exactly its batch (in order, ragged sizes resized) while the consumer still looks at the previous
+    one, and a worker's exception must surface in the consumer."""
+    from segmentation_pipeline.impl.datasets import PredictionItem
+    from segmentation_training_pipeline_b200.loader import HostLoader
+
+    class DS:
+        def __len__(self):
+            return 23
+
+        def __getitem__(self, i):
+            if i == 22:
+                raise IOError("broken file")
+            h, w = (16, 16) if i % 3 else (20, 12)                     # every third item has another size
+            x = np.full((h, w, 3), i, np.uint8)
+            y = np.full((h, w, 1), i % 2, np.uint8)
+            return PredictionItem(str(i), x, y)
+
+    ld = HostLoader(DS(), (16, 16, 3), 1, batch=4, workers=workers, pin=False)
+    batches = [[(4 * s + j) % 22 for j in range(4)] for s in range(9)]
+    prev = None
+    for k, (img, mask) in enumerate(ld.iterate(batches)):
+        assert img.shape == (4, 16, 16, 3) and mask.shape == (4, 16, 16, 1)
+        assert [int(img[j, 0, 0, 0]) for j in range(4)] == batches[k]
+        assert [int(mask[j, 5, 5, 0]) for j in range(4)] == [i % 2 for i in batches[k]]
+        if prev is not None:   # the previous pair is still intact while this one is being consumed
+            assert [int(prev[0][j, 0, 0, 0]) for j in range(4)] == batches[k - 1]
+        prev = (img, mask)
+    with pytest.raises(IOError):
+        list(ld.iterate([[0, 1, 2, 3], [4, 5, 22, 6]]))
+    ld.close()
