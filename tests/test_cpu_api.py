@@ -507,3 +507,109 @@ def test_host_loader_prefetch_ring(workers):
     with pytest.raises(IOError):
         list(ld.iterate([[0, 1, 2, 3], [4, 5, 22, 6]]))
     ld.close()
+
+
+def test_run_fit_control_flow_with_stub_engine(tmp_path, monkeypatch):
+    """The k-fold x stage loop of fit() (reference generic fit, README.md:116-205) end to end on the CPU with the device engine
+    replaced by a stub: files written, stage keys (negatives, initial_weights, freeze / unfreeze, callbacks), host loader,
+    resume -- everything except the kernels."""
+    import csv
+    import yaml
+    import torch
+    from segmentation_pipeline import segmentation
+    from segmentation_pipeline.impl.datasets import PredictionItem
+    from segmentation_training_pipeline_b200 import fit as F, trainer as TR
+
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    log = {"trainers": [], "steps": 0, "set_weights": 0}
+
+    class Net:
+        batch, classes, training = 2, 1, True
+        device = torch.device("cpu")
+        buffers = {}
+
+        class loss:
+            @staticmethod
+            def set_weights(*w):
+                log["loss_w"] = w
+
+        def __init__(self):
+            self.w = {"conv0/kernel": np.zeros(3, np.float32)}
+
+        def get_weights(self):
+            return {k: v.copy() for k, v in self.w.items()}
+
+        def set_weights(self, d, strict=True):
+            log["set_weights"] += 1
+            self.w.update({k: np.asarray(v) for k, v in d.items() if k in self.w})
+
+        def prep_weights(self):
+            pass
+
+        def forward(self):
+            pass
+
+    class StubTrainer:
+        def __init__(self, net, **kw):
+            self.net, self.kw, self.lr, self.k = net, kw, float(kw.get("lr") or 1e-3), 0
+            log["trainers"].append(kw)
+
+        def enable_host_feed(self):
+            pass
+
+        def set_lr(self, v):
+            self.lr = v
+
+        def get_lr(self):
+            return self.lr
+
+        def step_from_host_pipelined(self, img, mask):
+            assert img.shape == (2, 32, 32, 3) and mask.shape == (2, 32, 32, 1) and img.dtype == torch.uint8
+            log["steps"] += 1
+            self.net.w["conv0/kernel"] += 1.0
+            self.k += 1
+            return None if self.k == 1 else {"loss": 1.0 / self.k, "binary_accuracy": 0.5}
+
+        def flush_host_pipeline(self):
+            return {"loss": 0.25, "binary_accuracy": 0.75}
+
+        def set_batch(self, img, mask):
+            pass
+
+        def metrics(self):
+            return {"loss": 0.5 / (1 + log["steps"]), "binary_accuracy": 0.9}
+
+    monkeypatch.setattr(TR, "Trainer", StubTrainer)
+    spec = {"architecture": "Unet", "backbone": "resnet18", "classes": 1, "shape": [32, 32, 3], "batch": 2, "folds_count": 2,
+            "metrics": ["binary_accuracy"], "primary_metric": "val_loss", "freeze_encoder": True, "random_state": 3,
+            "callbacks": {"EarlyStopping": {"patience": 5, "monitor": "val_loss"}},
+            "stages": [{"epochs": 2, "negatives": "none"},
+                       {"epochs": 1, "unfreeze_encoder": True, "lr": 0.01, "initial_weights": "weights/best-0.0.weights",
+                        "extra_callbacks": {"LRVariator": {"relSize": 1.0, "toVal": 0.001}}}]}
+    cfgp = tmp_path / "exp" / "config.yaml"
+    cfgp.parent.mkdir()
+    yaml.safe_dump(spec, open(cfgp, "w"))
+    cfg = segmentation.parse(str(cfgp))
+    monkeypatch.setattr(cfg, "createNet", lambda *a, **k: Net())
+    rng = np.random.default_rng(0)
+    ds = [PredictionItem("s%d" % i, rng.integers(0, 255, (40, 36, 3), dtype=np.uint8),
+                         np.full((40, 36, 1), 0 if i in (2, 5) else 1, np.uint8)) for i in range(8)]
+    res = cfg.fit(ds)
+    exp = str(cfgp.parent)
+    assert len(res) == 4 and os.path.exists(os.path.join(exp, "summary.yaml"))
+    assert [t["freeze_encoder"] for t in log["trainers"]] == [True, False, True, False]
+    assert log["trainers"][1]["lr"] == 0.01 and log["set_weights"] == 2          # initial_weights loaded once per fold
+    rows = list(csv.DictReader(open(os.path.join(exp, "metrics", "metrics-0.0.csv"))))
+    assert len(rows) == 2 and set(rows[0]) >= {"epoch", "loss", "binary_accuracy", "val_loss", "val_binary_accuracy", "lr"}
+    # 8 items, 2 folds -> 4 training items per fold, minus the negatives of that fold ("negatives: none") -> 1 or 2 steps per epoch
+    assert 2 * 2 * 1 + 2 * 2 <= log["steps"] <= 2 * 2 * 2 + 2 * 2
+    rows1 = list(csv.DictReader(open(os.path.join(exp, "metrics", "metrics-1.1.csv"))))
+    assert len(rows1) == 1 and 0.001 <= float(rows1[0]["lr"]) <= 0.01
+    assert os.path.exists(os.path.join(exp, "weights", "best-1.1.weights.npz"))
+    with pytest.raises(ValueError, match="already finished"):
+        cfg.fit(ds)
+    os.remove(os.path.join(exp, "summary.yaml"))
+    steps_before = log["steps"]
+    cfg.setAllowResume(True)
+    res2 = cfg.fit(ds)
+    assert all(r.get("resumed") for r in res2) and log["steps"] == steps_before
