@@ -88,6 +88,10 @@ typedef struct stp_aug_spec {
   double invert_p;  /* imgaug Invert(p): v -> 255 - v on the whole image with probability p */
   int32_t color_order[3]; /* order in which the colour stage applies 0 = Multiply, 1 = Add, 2 = Invert (imgaug Sequential
                              applies augmenters in YAML order; saturating uint8 ops do not commute) */
+  int32_t flip_before_rot90; /* bit 0: Fliplr precedes Rotate90 in the YAML block, bit 1: Flipud does (reference
+                                examples/people/ds_1.yaml:3-6 lists Fliplr, Flipud, Rotate90).  All three are index permutations:
+                                a flip applied BEFORE an odd quarter turn equals the OTHER flip applied after it, so the kernel
+                                keeps its rot90 -> flips gather and the draw swaps the flags. */
 } stp_aug_spec;
 
 typedef struct stp_aug_sample { /* per-sample drawn parameters, device resident, 128 bytes */

@@ -39,6 +39,7 @@ class AugSpec:
     rot90: bool = False            # musket Rotate90 (reference ds_1.yaml:6) [DEP, unpinned]: np.rot90 by uniform k, applied first
     invert: float = 0.0            # imgaug Invert(p)
     color_order: Tuple[int, int, int] = (0, 1, 2)   # 0 Multiply, 1 Add, 2 Invert in Sequential (YAML) order
+    flip_before_rot90: int = 0     # bit 0: Fliplr is listed before Rotate90 (reference examples/people/ds_1.yaml:3-6), bit 1: Flipud
 
 
 @dataclass
@@ -53,6 +54,7 @@ class SampleParams:
     rot90_k: int = 0
     invert: bool = False
     color_order: Tuple[int, int, int] = (0, 1, 2)
+    flip_before_rot90: int = 0
 
 
 def affine_matrix(scale, tx_px, ty_px, rot_deg, shear_deg, h, w) -> np.ndarray:
@@ -103,7 +105,8 @@ def draw_params(spec: AugSpec, seed: int, step: int, sample: int, h: int, w: int
         add = lo + int(math.floor(u_add * (hi - lo + 1)))
     k90 = min(int(math.floor(u_r90 * 4.0)), 3) if spec.rot90 else 0
     return SampleParams(u_lr < spec.fliplr, u_ud < spec.flipud, M, spec.affine, float(mul),
-                        spec.multiply is not None, add, k90, bool(u_inv < spec.invert), tuple(spec.color_order))
+                        spec.multiply is not None, add, k90, bool(u_inv < spec.invert), tuple(spec.color_order),
+                        int(spec.flip_before_rot90))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -173,11 +176,17 @@ def multiply_lut(mul: float, rounding: str = "trunc") -> np.ndarray:
 def apply(image: np.ndarray, mask: np.ndarray, p: SampleParams, use_cv2: bool = True, mul_rounding="trunc"):
     """Sequential([Fliplr, Flipud, Affine, Multiply, Add]) on a uint8 HxWx3 image and HxWx1 mask."""
     img, msk = image, mask
+    # literal Sequential order: the flips listed before Rotate90, the quarter turns, the remaining flips
+    lr_pre, ud_pre = bool(p.flip_before_rot90 & 1), bool(p.flip_before_rot90 & 2)
+    if p.fliplr and lr_pre:
+        img, msk = img[:, ::-1], msk[:, ::-1]
+    if p.flipud and ud_pre:
+        img, msk = img[::-1], msk[::-1]
     if p.rot90_k:
         img, msk = np.rot90(img, p.rot90_k), np.rot90(msk, p.rot90_k)
-    if p.fliplr:
+    if p.fliplr and not lr_pre:
         img, msk = img[:, ::-1], msk[:, ::-1]
-    if p.flipud:
+    if p.flipud and not ud_pre:
         img, msk = img[::-1], msk[::-1]
     img, msk = np.ascontiguousarray(img), np.ascontiguousarray(msk)
     if p.has_affine:

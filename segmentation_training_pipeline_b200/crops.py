@@ -29,9 +29,14 @@ class CellDataSet:
         return len(self.ds) * self.n2
 
     def _item(self, k):
-        if self._last[0] != k:   # consecutive cells of one image: decode it once
-            self._last = (k, self.ds[k])
-        return self._last[1]
+        # consecutive cells of one image: decode it once.  `_last` is only a hint shared by the loader's worker threads: the
+        # pair is read ONCE into a local and the item returned is the one bound here, never a re-read of the shared slot
+        last = self._last
+        if last[0] == k:
+            return last[1]
+        it = self.ds[k]
+        self._last = (k, it)
+        return it
 
     def __getitem__(self, i) -> PredictionItem:
         i = int(i)

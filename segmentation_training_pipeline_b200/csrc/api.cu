@@ -49,6 +49,7 @@ extern "C" int stp_set_option(const char* name, int32_t value) {
   else if (!strcmp(name, "tc3")) key = OPT_TC3;                         /* 0 auto | 1 off | 2 CTA-pair kernel wherever it serves the shape */
   else if (!strcmp(name, "tc3_force_bn")) key = OPT_TC3_FORCE_BN;       /* 0 heuristic | 128, 256 */
   else if (!strcmp(name, "tc3_force_mt")) key = OPT_TC3_FORCE_MT;       /* 0 heuristic | 1, 2 */
+  else if (!strcmp(name, "tc3_halo")) key = OPT_TC3_HALO;               /* 0 on | 1 off: one A box per filter column (round-1 scheme) */
   else if (!strcmp(name, "bnb_fuse")) key = OPT_BNB_FUSE;               /* 0 auto | 1: never fuse the BatchNorm-backward reduction into the dgrad epilogue */
   else if (!strcmp(name, "bn_blocks")) key = OPT_BN_BLOCKS;             /* 0 default | n: atomic-mode BN reductions use up to n*1024/C blocks */
   else if (!strcmp(name, "pdl")) {                                      /* programmatic dependent launch on/off */

@@ -97,6 +97,11 @@ __global__ void augment_draw_kernel(stp_aug_spec spec, uint64_t seed, const int6
   const double u_r90 = u53(r[4][2], r[4][3]), u_inv = u53(r[5][0], r[5][1]);
   int k90 = spec.rot90 ? (int)floor(__dmul_rn(u_r90, 4.0)) : 0;
   if (k90 > 3) k90 = 3;
+  if (k90 & 1) {  // a flip listed before Rotate90 acts, after an odd quarter turn, as the other flip (stp.h flip_before_rot90)
+    const int a = s.fliplr, b = s.flipud, lr_pre = spec.flip_before_rot90 & 1, ud_pre = (spec.flip_before_rot90 >> 1) & 1;
+    s.fliplr = (lr_pre ? 0 : a) ^ (ud_pre ? b : 0);
+    s.flipud = (ud_pre ? 0 : b) ^ (lr_pre ? a : 0);
+  }
   const int inv = u_inv < spec.invert_p ? 1 : 0;
   s.flags2 = k90 | (inv << 2) | ((spec.color_order[0] & 3) << 4) | ((spec.color_order[1] & 3) << 6) | ((spec.color_order[2] & 3) << 8);
   out[i] = s;

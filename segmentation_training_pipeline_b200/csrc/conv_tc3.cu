@@ -46,6 +46,8 @@ struct Tc3Args {
   int Ho, Wo, Cout, Cin;
   int R, S, pad_h, pad_w;
   int BW, BH, log2BW;
+  int BWX;         // width (pixels) of the A halo box in shared memory: BW (one box per filter column) or BW + S - 1 (halo mode)
+  int halo;        // 1: ONE haloed box per channel block serves all R*S taps (filter columns = 1-pixel shifted descriptor views)
   int tilesW, tilesH, tilesN;
   int num_items;   // pair work items = ceil(numPT / 2) pixel-tile pairs x N tiles
   int numPT, nimg; // pixel tiles per N tile; images (a rank without a pixel tile runs on image index nimg: zero fill, clipped stores)
@@ -61,7 +63,9 @@ constexpr int align1k3(int x) { return (x + 1023) / 1024 * 1024; }
 template <int BN, int MT>
 struct Tc3Cfg {
   static constexpr int kRowBytes = kBK3 * 2;  // 128-byte swizzled rows
-  static constexpr int kMaxRows = (MT * 8 + 2) * 16 > (MT * 16 + 2) * 8 ? (MT * 8 + 2) * 16 : (MT * 16 + 2) * 8;
+  // largest A box in pixels: 16 x 8-row strips with a 2-row halo (one box per filter column), 8-wide x 16-row strips with a
+  // 2-row halo, or -- halo mode -- 8-wide x 16-row strips with a 2-row AND 2-column halo
+  static constexpr int kMaxRows = (MT * 16 + 2) * 10 > (MT * 8 + 2) * 16 ? (MT * 16 + 2) * 10 : (MT * 8 + 2) * 16;
   static constexpr int kABytes = align1k3(kMaxRows * kRowBytes);
   static constexpr int kBTap = (BN / 2) * kRowBytes;  // this CTA's half of one tap: BN/2 weight rows x 64 channels
   static constexpr int kOutSlabs = BN / 64;
@@ -168,8 +172,14 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int item = w_first; item < a.num_items; item += w_step) {
         int img, h0, w0, n0;
         decode(item, img, h0, w0, n0);
-        for (int s = 0; s < a.S; ++s) {
-          for (int cb = 0; cb < kcb; ++cb) {
+        // outer step = one A box: (filter column s, channel block cb) -- or, halo mode, one channel block whose haloed box
+        // serves all S columns; inner step = one weight tap (r [, s])
+        const int n_outer = a.halo ? kcb : a.S * kcb;
+        const int n_inner = a.halo ? a.R * a.S : a.R;
+        for (int o = 0; o < n_outer; ++o) {
+          const int s = a.halo ? 0 : o / kcb;
+          const int cb = a.halo ? o : o % kcb;
+          {
             mbar_wait(&emptyA[sa], pha ^ 1);
             if (elect_one()) {
             if (a.dbg & 1) {
@@ -185,7 +195,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               sa = 0;
               pha ^= 1;
             }
-            for (int r = 0; r < a.R; ++r) {
+            for (int t = 0; t < n_inner; ++t) {
+              const int tap = a.halo ? t : t * a.S + s;   // r * S + s
               mbar_wait(&emptyB[sb], phb ^ 1);
               if (elect_one()) {
               if (a.dbg & 2) {
@@ -193,7 +204,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               } else {
               if (leader) mbar_expect_tx(&fullB[sb], 2u * (uint32_t)Cfg::kBTap);
               tma_load_2d_pair(sB + sb * Cfg::kBTap, &tmB, mapa_u32(smem_u32(&fullB[sb]), 0),
-                               (r * a.S + s) * a.Cin + cb * kBK3, n0 + (int)crank * (BN / 2));
+                               tap * a.Cin + cb * kBK3, n0 + (int)crank * (BN / 2));
               }
               }
               __syncwarp();
@@ -209,8 +220,17 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     if (leader) {  // MMA issue by the leader CTA: warp-uniform loop, one elected lane issues
       constexpr uint32_t idesc = idesc_bf16(256, BN, 0, 0);
-      const uint32_t sub16 = ((uint32_t)(a.BH * a.BW) * Cfg::kRowBytes) >> 4;
-      const uint32_t row16 = ((uint32_t)a.BW * Cfg::kRowBytes) >> 4;
+      // A operand of sub-tile j, filter row r, filter column s (halo mode; 0 otherwise): the 128 pixel rows [BH][BW] of the box
+      // [rows][BWX][64 channels] starting at pixel ((j*BH + r)*BWX + s): 8-pixel groups are BWX*128 B apart (SBO).  The
+      // hardware applies the 128-byte swizzle to ABSOLUTE shared-memory address bits (scripts/umma_probe.cu, profiles/
+      // r2_umma_probe.txt), so a start address that is only 128-byte aligned and a group stride that is not a multiple of
+      // 1024 B address exactly the bytes TMA wrote -- base_offset stays 0.
+      const uint32_t px16 = (uint32_t)Cfg::kRowBytes >> 4;            // one pixel (128 B) in descriptor units
+      const uint32_t row16 = (uint32_t)a.BWX * px16;                  // one box row
+      const uint32_t sub16 = (uint32_t)a.BH * row16;                  // one 128-pixel sub-tile
+      const uint64_t sbo_field = (uint64_t)(((uint32_t)a.BW == 8u ? row16 : 8u * px16) & 0x3FFFu) << 32;
+      const int n_outer = a.halo ? kcb : a.S * kcb;
+      const int n_inner = a.halo ? a.R * a.S : a.R;
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       int local = 0;
@@ -220,22 +240,24 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(&acc_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(as * MT * BN);
-        for (int st = 0; st < a.S * kcb; ++st) {
+        for (int st = 0; st < n_outer; ++st) {
           mbar_wait(&fullA[sa], pha);
-          const uint64_t ad0 = desc_kmajor(smem_u32(sA + sa * Cfg::kABytes), 128);
-          for (int r = 0; r < a.R; ++r) {
+          const uint64_t ad0 = (desc_kmajor(smem_u32(sA + sa * Cfg::kABytes), 128) & ~((uint64_t)0x3FFF << 32)) | sbo_field;
+          for (int t = 0; t < n_inner; ++t) {
+            const uint32_t r = a.halo ? (uint32_t)(t / a.S) : (uint32_t)t;
+            const uint32_t sx = a.halo ? (uint32_t)(t % a.S) : 0u;
             mbar_wait(&fullB[sb], phb);
-            if (local == 0 && st == 0 && r == 0 && lane == 0) STP_TRACE3(3);
+            if (local == 0 && st == 0 && t == 0 && lane == 0) STP_TRACE3(3);
             tc_fence_after();
             const uint64_t bd0 = desc_kmajor(smem_u32(sB + sb * Cfg::kBTap), 128);
             if (elect_one()) {
               if (!(a.dbg & 8))
 #pragma unroll
               for (int j = 0; j < MT; ++j) {
-                const uint64_t aj = ad0 + (uint64_t)(j * sub16 + r * row16);
+                const uint64_t aj = ad0 + (uint64_t)(j * sub16 + r * row16 + sx * px16);
 #pragma unroll
                 for (int k = 0; k < kBK3 / 16; ++k)
-                  umma_bf16_pair(d0 + (uint32_t)(j * BN), aj + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), idesc, (st | r | k) != 0);
+                  umma_bf16_pair(d0 + (uint32_t)(j * BN), aj + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), idesc, (st | t | k) != 0);
               }
               umma_commit_pair(&emptyB[sb], 3);
             }
@@ -439,16 +461,23 @@ constexpr int kPairs = kNumSMs / 2;
 
 // cycle estimate used to rank (BN, MT): wave quantisation over the 74 CTA pairs, L2->SM bytes per CTA (~40 B/clk) against
 // the M=256 MMA floor (BN/2 clk per K=16 step), per-strip epilogue
+// halo mode (default; option "tc3_halo" = 1 turns it off): 8-wide x 16-row sub-tiles, ONE [TH+R-1][8+S-1] haloed A box per
+// channel block instead of one [TH+R-1][BW] box per filter column: L2->SM A bytes drop ~2.5x (profiles/README.md r2)
+static bool tc3_halo() { return get_option(OPT_TC3_HALO) != 1; }
+static int tc3_bw(const ConvP& p) { return tc3_halo() ? 8 : (p.Wo >= 16 ? 16 : 8); }
+
 static double tc3_cost(const ConvP& p, int bn, int mt) {
-  const int bw = p.Wo >= 16 ? 16 : 8, bh = 128 / bw;
+  const int bw = tc3_bw(p), bh = 128 / bw;
   const int th = mt * bh;
   const int64_t pt = (int64_t)p.N * ((p.Ho + th - 1) / th) * ((p.Wo + bw - 1) / bw);
   const double items = (double)((pt + 1) / 2) * (p.Cout / bn);
   const double waves = (double)(int64_t)((items + kPairs - 1) / kPairs);
-  const int num_st = p.S * (p.Cin / kBK3);
-  const double bytes = (double)(th + p.R - 1) * bw * 128 + (double)p.R * (bn / 2) * 128;
+  const bool halo = tc3_halo();
+  const int num_st = (halo ? 1 : p.S) * (p.Cin / kBK3);
+  const int taps = halo ? p.R * p.S : p.R;
+  const double bytes = (double)(th + p.R - 1) * (halo ? bw + p.S - 1 : bw) * 128 + (double)taps * (bn / 2) * 128;
   const double load = bytes / 40.0;
-  const double mma = (double)mt * p.R * 4 * (bn / 2.0);
+  const double mma = (double)mt * taps * 4 * (bn / 2.0);
   const double stage = (load > mma ? load : mma) + 100.0;
   const double epi = 600.0 + mt * (bn / 64) * 250.0;
   return waves * (num_st * stage + epi) + 4000.0;
@@ -539,7 +568,7 @@ bool tc3_conv_supported(const ConvP& p) {
   Tc3Plan pl;
   if (!tc3_plan(p, &pl)) return false;
   if (opt == 0) {
-    const int bw = p.Wo >= 16 ? 16 : 8, th = pl.MT * (128 / bw);
+    const int bw = tc3_bw(p), th = pl.MT * (128 / bw);
     const int64_t pt = (int64_t)p.N * ((p.Ho + th - 1) / th) * ((p.Wo + bw - 1) / bw);
     if (((pt + 1) / 2) * (p.Cout / pl.BN) < kPairs) return false;
   }
@@ -559,9 +588,11 @@ int launch_tc3_conv(const ConvP& p, cudaStream_t st) {
   Tc3Args a;
   a.res = p.res; a.bias = p.bias; a.relu = p.relu;
   a.Ho = p.Ho; a.Wo = p.Wo; a.Cout = p.Cout; a.Cin = p.Cin; a.R = p.R; a.S = p.S; a.pad_h = p.pad_h; a.pad_w = p.pad_w;
-  a.BW = p.Wo >= 16 ? 16 : 8;
+  a.halo = tc3_halo() ? 1 : 0;
+  a.BW = tc3_bw(p);
   a.BH = 128 / a.BW;
   a.log2BW = a.BW == 16 ? 4 : 3;
+  a.BWX = a.halo ? a.BW + p.S - 1 : a.BW;
   const int TH = pl.MT * a.BH;
   a.tilesW = (p.Wo + a.BW - 1) / a.BW;
   a.tilesH = (p.Ho + TH - 1) / TH;
@@ -576,7 +607,7 @@ int launch_tc3_conv(const ConvP& p, cudaStream_t st) {
   a.num_items = (int)items;
   a.nimg = p.N;
   const int box_rows = TH + p.R - 1;
-  a.a_bytes = box_rows * a.BW * kBK3 * 2;
+  a.a_bytes = box_rows * a.BWX * kBK3 * 2;
   a.trace = get_trace_buffer();
   a.dbg = get_option(OPT_TC2_DEBUG);
   a.bn_on = p.bn != nullptr ? 1 : 0;
@@ -585,7 +616,7 @@ int launch_tc3_conv(const ConvP& p, cudaStream_t st) {
   {
     uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
     uint64_t strides[3] = {(uint64_t)p.ldx * 2, (uint64_t)p.W * p.ldx * 2, (uint64_t)p.H * p.W * p.ldx * 2};
-    uint32_t box[4] = {(uint32_t)kBK3, (uint32_t)a.BW, (uint32_t)box_rows, 1};
+    uint32_t box[4] = {(uint32_t)kBK3, (uint32_t)a.BWX, (uint32_t)box_rows, 1};
     if (!make_tmap_bf16(&tmA, p.x, 4, dims, strides, box, 128)) return STP_E_CUDA;
   }
   {

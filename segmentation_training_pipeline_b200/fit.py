@@ -144,7 +144,7 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
         n_test = int(round(n_all * cfg.testSplit))
         all_idx = np.sort(perm[n_test:])
     folds = cfg.kfold(len(all_idx))
-    B, shape = cfg.batch, cfg.shape
+    B, shape = cfg.batch, cfg.net_shape()   # `crops: N`: the network (and every host buffer) has the CELL shape
     metric_names = [m for m in (_METRIC_ALIASES.get(m) for m in cfg.metrics) if m]
     results = []
     for fi, (tr, va) in enumerate(folds):
@@ -167,19 +167,27 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
         from .loader import HostLoader
         loader = HostLoader(ds, shape, cfg.classes, B, workers=int(cfg.extra.get("loader_workers", 4)))
         for si, stage in enumerate(cfg.stages):
-            if si < start_from_stage:
-                continue
+            # stage keys that change the encoder's trainability apply whether or not the stage is executed; an explicit
+            # `unfreeze_encoder: false` re-freezes (the reference's Stage sets trainability from the key's value)
             if stage.get("freeze_encoder") is not None:
                 frozen = bool(stage["freeze_encoder"])
-            if stage.get("unfreeze_encoder"):
-                frozen = False
+            if stage.get("unfreeze_encoder") is not None:
+                frozen = not bool(stage["unfreeze_encoder"])
             wpath = os.path.join(base, "weights", "best-%d.%d.weights.npz" % (fi, si))
             mpath = os.path.join(base, "metrics", "metrics-%d.%d.csv" % (fi, si))
+            dpath = os.path.join(base, "metrics", "metrics-%d.%d.done" % (fi, si))
+            if si < start_from_stage:
+                # fit(start_from_stage=k) (musket_core generic_config skip_stage [DEP]): a skipped stage contributes its best
+                # weights (when they exist) and its freeze / unfreeze keys; it is not trained
+                if os.path.exists(wpath):
+                    net.set_weights(dict(np.load(wpath)))
+                continue
             if cfg.allowResume and os.path.exists(wpath) and os.path.exists(mpath):
-                # setAllowResume(True) (FAQ.md:3-12): a (fold, stage) whose best weights and full metrics log exist is not
-                # re-run; its best weights seed the next stage
+                # setAllowResume(True) (FAQ.md:3-12): a (fold, stage) that ran to its end -- all epochs, or stopped early by a
+                # callback: the `.done` marker written when the epoch loop exits -- is not re-run; its best weights seed the
+                # next stage.  (Logs written before the marker existed count as finished when they hold every epoch.)
                 done = list(csv.DictReader(open(mpath)))
-                if len(done) >= int(stage.get("epochs", 1)):
+                if os.path.exists(dpath) or len(done) >= int(stage.get("epochs", 1)):
                     net.set_weights(dict(np.load(wpath)))
                     vals = [float(r[cfg.primary_metric]) for r in done if cfg.primary_metric in r]
                     mode = cfg.primary_metric_mode if cfg.primary_metric_mode != "auto" else ("min" if "loss" in cfg.primary_metric else "max")
@@ -187,6 +195,8 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
                     results.append({"fold": fi, "stage": si, "best_" + cfg.primary_metric: best_done, "epochs": len(done),
                                     "resumed": True})
                     continue
+            if is_main and os.path.exists(dpath):
+                os.remove(dpath)
             if stage.get("initial_weights"):
                 net.set_weights(dict(np.load(_weights_file(base, stage["initial_weights"]))), strict=False)
             net.loss.set_weights(*parse_loss(stage.get("loss", cfg.loss)))
@@ -257,6 +267,9 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
                     cb.on_epoch_end(tr_, epoch, row)
                 if any(cb.stop_training for cb in cbs):
                     break
+            if is_main:
+                with open(dpath, "w") as f:   # the stage ran to its end (all epochs or an early stop): resume skips it
+                    f.write("epochs: %d\n" % len(rows))
             results.append({"fold": fi, "stage": si, "best_" + pm: None if best is None else float(best), "epochs": len(rows)})
         loader.close()
     if is_main:
@@ -329,7 +342,7 @@ def run_lr_find(cfg, ds, start_lr=1e-5, end_lr=1.0, epochs=1, stage=0) -> LRFind
     import torch
     from .trainer import Trainer
 
-    B, shape = cfg.batch, cfg.shape
+    B, shape = cfg.batch, cfg.net_shape()
     net = cfg.createNet()
     st = cfg.stages[stage] if cfg.stages else {}
     net.loss.set_weights(*parse_loss(st.get("loss", cfg.loss)))

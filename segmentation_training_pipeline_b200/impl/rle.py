@@ -20,7 +20,21 @@ def rle_encode(img) -> str:
 
 
 def rle_decode(mask_rle: str, shape: Sequence[int]) -> np.ndarray:
-    """inverse of rle_encode; shape = (height, width); returns uint8 {0,1} of that shape"""
+    """inverse of rle_encode for SQUARE masks; shape = (height, width).  Bit-for-bit the reference (impl/rle.py:22-35):
+    `img.reshape(shape).T`, i.e. for a non-square shape the result is shape[1] x shape[0] with the runs laid out row-major in
+    a shape[0] x shape[1] grid before the transpose -- the reference's quirk is kept, not corrected (its Kaggle use,
+    768 x 768 Airbus masks, is square).  rle_decode_hw() below is the geometrically correct inverse for any shape."""
+    h, w = int(shape[0]), int(shape[1])
+    out = np.zeros(h * w, dtype=np.uint8)
+    tok = mask_rle.split() if isinstance(mask_rle, str) else []
+    for s, n in zip(tok[0::2], tok[1::2]):
+        s = int(s) - 1
+        out[s:s + int(n)] = 1
+    return out.reshape(h, w).T
+
+
+def rle_decode_hw(mask_rle: str, shape: Sequence[int]) -> np.ndarray:
+    """true inverse of rle_encode for any (height, width): returns uint8 {0,1} of exactly that shape."""
     h, w = int(shape[0]), int(shape[1])
     out = np.zeros(h * w, dtype=np.uint8)
     tok = mask_rle.split() if isinstance(mask_rle, str) else []

@@ -37,7 +37,8 @@ class AugSpec(C.Structure):
                 ("rot_lo", C.c_double), ("rot_hi", C.c_double), ("shear_lo", C.c_double), ("shear_hi", C.c_double),
                 ("has_mul", C.c_int32), ("mul_lo", C.c_double), ("mul_hi", C.c_double),
                 ("has_add", C.c_int32), ("add_lo", C.c_int32), ("add_hi", C.c_int32), ("mul_rint", C.c_int32),
-                ("rot90", C.c_int32), ("invert_p", C.c_double), ("color_order", C.c_int32 * 3)]
+                ("rot90", C.c_int32), ("invert_p", C.c_double), ("color_order", C.c_int32 * 3),
+                ("flip_before_rot90", C.c_int32)]
 
     def __init__(self, *a, **kw):
         super().__init__(*a, **kw)

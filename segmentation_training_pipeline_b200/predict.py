@@ -102,6 +102,13 @@ def predict_arrays(net, images_u8: np.ndarray, ttflips=False) -> np.ndarray:
     return acc / len(variants)
 
 
+def _net_hw(cfg):
+    """(H, W) the network runs at: `shape`, or the CELL shape under `crops: N` (reference createNet1, segmentation.py:131-132)."""
+    crops = int(getattr(cfg, "crops", 0) or 0)
+    H, W = int(cfg.shape[0]), int(cfg.shape[1])
+    return (H // crops, W // crops) if crops > 1 else (H, W)
+
+
 def _list_images(spath) -> List[str]:
     return sorted(f for f in os.listdir(spath) if f.lower().endswith(IMG_EXT))
 
@@ -112,7 +119,7 @@ def predict_on_directory(cfg, spath, fold: Union[int, Sequence[int]] = 0, stage=
     folds = list(fold) if isinstance(fold, (list, tuple)) else [fold]
     nets = [cfg.load_model(f, stage) for f in folds]
     B = min(int(batch_size), nets[0].batch)
-    H, W = int(cfg.shape[0]), int(cfg.shape[1])
+    H, W = _net_hw(cfg)
     names = _list_images(spath)
     if limit is not None and limit > 0:
         names = names[:limit]
@@ -199,7 +206,7 @@ def evaluate_all(cfg, ds, fold=None, stage=-1, negatives="real", ttflips=None, b
     folds = list(range(cfg.folds_count)) if fold is None else (list(fold) if isinstance(fold, (list, tuple)) else [fold])
     nets = [cfg.load_model(f, stage) for f in folds]
     B = min(int(batchSize), nets[0].batch)
-    H, W = int(cfg.shape[0]), int(cfg.shape[1])
+    H, W = _net_hw(cfg)
     idx = list(range(len(ds)))
     if negatives == "none" and hasattr(ds, "isPositive"):
         idx = [i for i in idx if ds.isPositive(i)]
@@ -236,7 +243,7 @@ def evaluate(cfg, ds, fold: int, stage: int, negatives="all", limit=16, batchSiz
     import cv2
     net = cfg.load_model(fold, stage)
     B = min(int(batchSize), net.batch)
-    H, W = int(cfg.shape[0]), int(cfg.shape[1])
+    H, W = _net_hw(cfg)
     _, va = cfg.kfold(len(ds))[fold]
     idx = [int(i) for i in va]
     if negatives == "none" and hasattr(ds, "isPositive"):

@@ -107,21 +107,27 @@ def parse_augmentation(spec: Optional[dict], seed: int = 0) -> AugmentConfig:
     cfg = AugmentConfig(seed=seed)
     if not spec:
         return cfg
-    # imgaug Sequential applies the augmenters in YAML order.  The fused kernel runs Rotate90 -> flips -> Affine -> colour
-    # stage (Multiply / Add / Invert in ANY order among themselves); a block in another order would silently compute
-    # something else, so it is rejected.
-    rank = {"Rotate90": 0, "Fliplr": 1, "Flipud": 1, "Affine": 2, "Multiply": 3, "Add": 3, "Invert": 3}
+    # imgaug Sequential applies the augmenters in YAML order.  The fused kernel runs {Rotate90, Fliplr, Flipud} (ANY order among
+    # themselves: they are index permutations, composed exactly -- AugmentConfig.flip_before_rot90) -> Affine -> colour stage
+    # (Multiply / Add / Invert in ANY order among themselves); a block in another order would silently compute something
+    # else, so it is rejected.
+    rank = {"Rotate90": 1, "Fliplr": 1, "Flipud": 1, "Affine": 2, "Multiply": 3, "Add": 3, "Invert": 3}
     last, colour = -1, []
     for name in spec:
         if name not in rank:
             raise NotImplementedError("augmenter '%s' is not fused on device (supported: %s)" % (name, ", ".join(rank)))
         if rank[name] < last:
-            raise NotImplementedError("augmentation order %s is not the fused kernel's (Rotate90, Fliplr/Flipud, Affine, then "
+            raise NotImplementedError("augmentation order %s is not the fused kernel's (Rotate90/Fliplr/Flipud, Affine, then "
                                       "Multiply/Add/Invert)" % list(spec))
         last = rank[name]
         if rank[name] == 3:
             colour.append({"Multiply": 0, "Add": 1, "Invert": 2}[name])
     cfg.color_order = tuple(colour + [o for o in (0, 1, 2) if o not in colour])
+    names = list(spec)
+    if "Rotate90" in names:   # reference examples/people/*.yaml list Fliplr, Flipud, Rotate90
+        r = names.index("Rotate90")
+        cfg.flip_before_rot90 = (1 if "Fliplr" in names and names.index("Fliplr") < r else 0) | \
+                                (2 if "Flipud" in names and names.index("Flipud") < r else 0)
     for name, val in spec.items():
         if name == "Fliplr":
             cfg.fliplr = float(val)
@@ -201,12 +207,19 @@ class PipelineConfig:
     def setAllowResume(self, v: bool = True):
         self.allowResume = bool(v)
 
+    def net_shape(self) -> List[int]:
+        """Input shape of the network: `shape`, or -- with `crops: N` -- the CELL shape (shape[0]//N, shape[1]//N, C), exactly
+        what the reference's createNet1 builds (segmentation.py:131-132): cells are trained and predicted at cell resolution."""
+        if self.crops and self.crops > 1:
+            return [int(self.shape[0]) // self.crops, int(self.shape[1]) // self.crops, int(self.shape[2])]
+        return list(self.shape)
+
     def createNet(self, batch: Optional[int] = None, loss: Optional[str] = None):
         """YAML keys -> engine graph (reference createNet1, segmentation.py:96-155): unknown names raise the same
         ValueErrors after printing the known lists."""
         arch = self.architecture
         if arch in custom_models:
-            return custom_models[arch](backbone=self.backbone, classes=self.classes, input_shape=tuple(self.shape),
+            return custom_models[arch](backbone=self.backbone, classes=self.classes, input_shape=tuple(self.net_shape()),
                                        activation=self.activation)
         if arch not in _models.KNOWN_ARCHITECTURES:
             print("Unknown architecture:" + str(arch))
@@ -241,7 +254,7 @@ class PipelineConfig:
             if enc_file is None:
                 raise NotImplementedError("encoder_weights: '%s' cannot be downloaded here -- give the path of a local .npz with the "
                                           "encoder's Keras-named arrays" % cand)
-        net = _models.SegNet(bb, classes=self.classes, input_shape=tuple(self.shape), batch=batch or self.batch,
+        net = _models.SegNet(bb, classes=self.classes, input_shape=tuple(self.net_shape()), batch=batch or self.batch,
                               decoder_filters=self.decoder_filters, device=self.device, seed=self.random_state,
                               architecture=arch, decoder_block_type=getattr(self, "decoder_block_type", None) or "upsampling",
                               pyramid_block_filters=int(self.extra.get("pyramid_block_filters", 256)),

@@ -37,6 +37,7 @@ class AugmentConfig:
     rot90: bool = False
     invert: float = 0.0
     color_order: Tuple[int, int, int] = (0, 1, 2)   # 0 Multiply, 1 Add, 2 Invert, in YAML order
+    flip_before_rot90: int = 0   # bit 0: Fliplr precedes Rotate90 in the YAML block, bit 1: Flipud does (stp.h)
 
     def enabled(self) -> bool:
         return bool(self.fliplr or self.flipud or self.affine or self.multiply or self.add or self.rot90 or self.invert)
@@ -51,6 +52,7 @@ class AugmentConfig:
                             int(self.mul_rint), int(self.rot90), float(self.invert))
         for i, o in enumerate(self.color_order):
             spec.color_order[i] = int(o)
+        spec.flip_before_rot90 = int(self.flip_before_rot90)
         return spec
 
 
@@ -72,6 +74,10 @@ class Trainer:
         self.m = torch.zeros(net.n_flat, dtype=torch.float32, device=dev)
         self.v = torch.zeros(net.n_flat, dtype=torch.float32, device=dev) if self.opt in ("adam", "nadam") else None
         self.nadam_sched = torch.tensor([1.0, 0.0, 0.0, 0.0, 0.0], dtype=torch.float32, device=dev)
+        # optimizer iteration counter (Keras `iterations`): belongs to THIS optimizer, starts at 0 with its zeroed moments -- the
+        # reference recompiles the model per stage, so bias correction restarts with every stage.  net.d_step keeps counting
+        # across stages: it only keys the augmentation RNG stream / the pool cursor.
+        self.d_opt_step = torch.zeros(1, dtype=torch.int64, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.sumsq_partial = torch.zeros(1024, dtype=torch.float32, device=dev)
         self.world_size, self.pg = world_size, process_group
@@ -137,6 +143,7 @@ class Trainer:
         off, cnt = self.opt_off, net.n_flat - self.opt_off
         if cnt <= 0:
             self.L.step_advance(net.d_step.data_ptr(), st)
+            self.L.step_advance(self.d_opt_step.data_ptr(), st)
             return
         p, g, m = net.flat_p.data_ptr() + 4 * off, net.flat_g.data_ptr() + 4 * off, self.m.data_ptr() + 4 * off
         v = self.v.data_ptr() + 4 * off if self.v is not None else None
@@ -144,15 +151,16 @@ class Trainer:
             self.L.sumsq(g, cnt, self.sumsq_partial.data_ptr(), self.sumsq.data_ptr(), st)
         gx = C.byref(self._gx)
         if self.opt == "adam":
-            self.L.adam(p, g, m, v, cnt, self.lr, self.b1, self.b2, self.eps, gx, net.d_step.data_ptr(), st)
+            self.L.adam(p, g, m, v, cnt, self.lr, self.b1, self.b2, self.eps, gx, self.d_opt_step.data_ptr(), st)
         elif self.opt == "nadam":
             self.L.nadam(p, g, m, v, self.nadam_sched.data_ptr(), cnt, self.lr, self.b1, self.b2, self.eps, 0.004, gx,
-                         net.d_step.data_ptr(), st)
+                         self.d_opt_step.data_ptr(), st)
         elif self.opt == "sgd":
             self.L.sgd(p, g, m, cnt, self.lr, self.mu, int(self.nesterov), gx, st)
         else:
             self.L.rmsprop(p, g, m, cnt, self.lr, self.rho, self.eps, gx, st)
         self.L.step_advance(net.d_step.data_ptr(), st)
+        self.L.step_advance(self.d_opt_step.data_ptr(), st)
 
     # ---- whole step ---------------------------------------------------------------------------
     def step_eager(self, from_pool=True):
@@ -338,7 +346,8 @@ class Trainer:
     def _snapshot(self):
         n = self.net
         return dict(p=n.flat_p.clone(), m=self.m.clone(), v=None if self.v is None else self.v.clone(),
-                    step=n.d_step.clone(), sched=self.nadam_sched.clone(), bufs={k: b.clone() for k, b in n.buffers.items()})
+                    step=n.d_step.clone(), opt_step=self.d_opt_step.clone(), sched=self.nadam_sched.clone(),
+                    bufs={k: b.clone() for k, b in n.buffers.items()})
 
     def _restore(self, s):
         n = self.net
@@ -347,6 +356,7 @@ class Trainer:
         if self.v is not None:
             self.v.copy_(s["v"])
         n.d_step.copy_(s["step"])
+        self.d_opt_step.copy_(s["opt_step"])
         self.nadam_sched.copy_(s["sched"])
         for k, b in n.buffers.items():
             b.copy_(s["bufs"][k])
@@ -354,7 +364,7 @@ class Trainer:
     def state_dict(self):
         n = self.net
         return {"weights": n.get_weights(), "m": self.m.cpu().numpy(), "v": None if self.v is None else self.v.cpu().numpy(),
-                "step": int(n.d_step.item())}
+                "step": int(n.d_step.item()), "opt_step": int(self.d_opt_step.item())}
 
     def load_state_dict(self, d):
         n = self.net
@@ -363,3 +373,4 @@ class Trainer:
         if self.v is not None and d.get("v") is not None:
             self.v.copy_(torch.from_numpy(d["v"]))
         n.d_step.fill_(int(d["step"]))
+        self.d_opt_step.fill_(int(d.get("opt_step", d["step"])))

@@ -191,16 +191,44 @@ def test_rle_known_answers_and_round_trip():
     m = np.zeros((4, 3), np.uint8)
     m[0:3, 0] = 1          # pixels 1..3 (first column)
     m[1:3, 2] = 1          # third column: pixels 10, 11
+    from segmentation_pipeline.impl.rle import rle_decode_hw
     assert rle_encode(m) == "1 3 10 2"
-    assert np.array_equal(rle_decode("1 3 10 2", (4, 3)), m)
+    assert np.array_equal(rle_decode_hw("1 3 10 2", (4, 3)), m)
     rng = np.random.default_rng(0)
     for shape in ((1, 1), (5, 7), (64, 48)):
+        a = (rng.random(shape) > 0.6).astype(np.uint8)
+        assert np.array_equal(rle_decode_hw(rle_encode(a), shape), a)
+    for shape in ((1, 1), (7, 7), (32, 32)):   # square: the reference-exact decode is the true inverse as well
         a = (rng.random(shape) > 0.6).astype(np.uint8)
         assert np.array_equal(rle_decode(rle_encode(a), shape), a)
     assert rle_encode(np.zeros((3, 3), np.uint8)) == "" and rle_decode("", (3, 3)).sum() == 0
     parts = multi_rle_encode(m[:, :, None])
     assert sorted(parts) == ["1 3", "10 2"]
-    assert np.array_equal(masks_as_image(parts, (4, 3))[:, :, 0], m)
+    sq = np.zeros((4, 4), np.uint8)
+    sq[0:3, 0] = 1
+    sq[1:3, 2] = 1
+    assert np.array_equal(masks_as_image(multi_rle_encode(sq[:, :, None]), (4, 4))[:, :, 0], sq)
+
+
+def test_rle_matches_reference_golden_vectors():
+    """tests/golden/rle_golden.npz holds outputs of the REFERENCE's own impl/rle.py (generated by make_rle_golden.py, which
+    imports it): encode strings, decode arrays -- including the reference's (w, h)-shaped result for non-square shapes --
+    masks_as_image / masks_as_images.  Integer work: bit exact."""
+    import os
+    from segmentation_pipeline.impl.rle import masks_as_image, masks_as_images, rle_decode, rle_encode
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rle_golden.npz"))
+    for k in range(int(g["n"])):
+        a, enc, shape = g["mask_%d" % k], str(g["enc_%d" % k]), tuple(int(v) for v in g["shape_%d" % k])
+        assert rle_encode(a) == enc, (k, shape)
+        if "dec_%d" % k in g.files:
+            d = rle_decode(enc, shape)
+            want = g["dec_%d" % k]
+            assert d.shape == want.shape and d.dtype == want.dtype and np.array_equal(d, want), (k, shape, d.shape, want.shape)
+    l = [str(g["mai_in_0"]), str(g["mai_in_1"]), float("nan")]
+    got = masks_as_image(l, (9, 9))
+    assert got.shape == g["mai_out"].shape and got.dtype == g["mai_out"].dtype and np.array_equal(got, g["mai_out"])
+    gots = np.stack(masks_as_images(l, (9, 9)))
+    assert gots.dtype == g["mais_out"].dtype and np.array_equal(gots, g["mais_out"])
 
 
 def test_negatives_selection_and_extra_train_concat():
@@ -247,6 +275,57 @@ def test_augmentation_block_order_is_checked():
         parse_augmentation({"Affine": {}, "Flipud": 0.5})
     with pytest.raises(NotImplementedError, match="not fused"):
         parse_augmentation({"GaussianBlur": 1.0})
+    # Rotate90 / Fliplr / Flipud in any order among themselves (the reference's examples list the flips first)
+    c = parse_augmentation({"Fliplr": 0.5, "Flipud": 0.5, "Rotate90": True})
+    assert c.rot90 and c.fliplr == 0.5 and c.flipud == 0.5 and c.flip_before_rot90 == 3
+    assert parse_augmentation({"Fliplr": 0.5, "Rotate90": True, "Flipud": 0.5}).flip_before_rot90 == 1
+    assert parse_augmentation({"Rotate90": True, "Fliplr": 0.5, "Flipud": 0.5}).flip_before_rot90 == 0
+    assert parse_augmentation({"Flipud": 0.5, "Rotate90": True}).to_c().flip_before_rot90 == 2
+
+
+def test_oracle_flip_rotate_composition_is_the_literal_sequence():
+    """the algebra behind stp_aug_spec.flip_before_rot90, checked on the CPU oracle: flips listed before an odd np.rot90
+    equal the OTHER flips applied after it."""
+    from oracle import augment as OA
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (6, 6, 3), dtype=np.uint8)
+    msk = rng.integers(0, 2, (6, 6, 1), dtype=np.uint8)
+    for pre in range(4):
+        for k in range(4):
+            for a in (False, True):
+                for b in (False, True):
+                    lit = OA.SampleParams(a, b, np.eye(2, 3), False, 1.0, False, 0, k, False, (0, 1, 2), pre)
+                    lr_pre, ud_pre = bool(pre & 1), bool(pre & 2)
+                    if k & 1:
+                        a2 = (False if lr_pre else a) ^ (b if ud_pre else False)
+                        b2 = (False if ud_pre else b) ^ (a if lr_pre else False)
+                    else:
+                        a2, b2 = a, b
+                    dev = OA.SampleParams(a2, b2, np.eye(2, 3), False, 1.0, False, 0, k, False, (0, 1, 2), 0)
+                    li, lm = OA.apply(img, msk, lit)
+                    di, dm = OA.apply(img, msk, dev)
+                    assert np.array_equal(li, di) and np.array_equal(lm, dm), (pre, k, a, b)
+
+
+def test_reference_example_configs_parse_and_build_their_augmenter():
+    """all five experiment files the reference ships (examples/people/*.yaml, copied verbatim as fixtures under
+    tests/golden/configs/reference_examples/) parse, expose the reference's keys and build the fused device augmenter --
+    their block order is Fliplr, Flipud, Rotate90."""
+    import glob
+    import os
+    from segmentation_pipeline import segmentation
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "configs", "reference_examples", "*.yaml")))
+    assert len(files) == 5
+    for f in files:
+        cfg = segmentation.parse(f)
+        assert cfg.architecture == "DeepLabV3" and cfg.backbone == "mobilenetv2" and cfg.classes == 1
+        assert cfg.shape == [320, 320, 3] and cfg.activation == "sigmoid" and cfg.optimizer == "Adam"
+        aug = segmentation.parse_augmentation(cfg.augmentation)
+        assert aug.fliplr == 0.5 and aug.enabled()
+        if "Rotate90" in cfg.augmentation:
+            assert aug.rot90 and aug.flipud == 0.5 and aug.flip_before_rot90 == 3
+        from segmentation_training_pipeline_b200 import callbacks as CB
+        assert isinstance(CB.build(cfg.callbacks, None), list)
 
 
 def test_lr_variator_schedule():

@@ -94,18 +94,23 @@ def test_identity_and_flip_only(stp, cuda):
             assert np.array_equal(ri, out_i[i].cpu().numpy()) and np.array_equal(rm, out_m[i].cpu().numpy())
 
 
+@pytest.mark.parametrize("pre", [0, 3, 1, 2])
 @pytest.mark.parametrize("order", [(0, 1, 2), (2, 1, 0), (1, 2, 0)])
 @pytest.mark.parametrize("affine", [0, 1])
-def test_rotate90_invert_and_colour_order(stp, cuda, order, affine):
-    """musket's Rotate90 (np.rot90 by a uniform k, applied first), imgaug Invert(p) and the colour stage in YAML order
-    (saturating uint8 ops do not commute): draws equal to the oracle's, pixels / mask indices bit exact."""
+def test_rotate90_invert_and_colour_order(stp, cuda, order, affine, pre):
+    """musket's Rotate90 (np.rot90 by a uniform k), imgaug Invert(p) and the colour stage in YAML order (saturating uint8
+    ops do not commute): draws equal to the oracle's, pixels / mask indices bit exact.  pre = which flips are listed BEFORE
+    Rotate90 in the YAML block (bit 0 Fliplr, bit 1 Flipud; the reference's examples list both first): the oracle applies the
+    literal Sequential order, the kernel its rot90 -> flips gather with the flags swapped on odd quarter turns."""
     from oracle import augment as OA
     h = w = 96
     ospec = OA.AugSpec(fliplr=0.5, flipud=0.5, affine=bool(affine), scale=(0.8, 1.3), translate_x=(-0.1, 0.1), translate_y=(-0.1, 0.1),
-                       rotate=(-20, 20), shear=(-8, 8), multiply=(0.5, 1.9), add=(-60, 60), rot90=True, invert=0.5, color_order=order)
+                       rotate=(-20, 20), shear=(-8, 8), multiply=(0.5, 1.9), add=(-60, 60), rot90=True, invert=0.5, color_order=order,
+                       flip_before_rot90=pre)
     cspec = lib.AugSpec(0.5, 0.5, affine, 0.8, 1.3, -0.1, 0.1, -0.1, 0.1, -20, 20, -8, 8, 1, 0.5, 1.9, 1, -60, 60, 0, 1, 0.5)
     for i, o in enumerate(order):
         cspec.color_order[i] = o
+    cspec.flip_before_rot90 = pre
     n, pool, seed = 16, 16, 7
     rng = np.random.default_rng(3)
     imgs = rng.integers(0, 256, (pool, h, w, 3), dtype=np.uint8)

@@ -752,13 +752,15 @@ def test_lovasz_hinge_multiclass(stp, cuda):
     assert rel_err(dl.view(n, h, w, cls), z.grad) < 1e-5
 
 
+@pytest.mark.parametrize("halo", [0, 1])
 @pytest.mark.parametrize("force", [(0, 0), (128, 1), (128, 2), (256, 1)])
 @pytest.mark.parametrize("case", [(2, 24, 40, 128, 128), (1, 9, 17, 128, 256), (3, 8, 8, 256, 512), (5, 16, 16, 64, 128),
                                   (16, 32, 32, 256, 256), (1, 16, 16, 192, 256)])
-def test_conv_tc3_cta_pair(stp, cuda, case, force):
+def test_conv_tc3_cta_pair(stp, cuda, case, force, halo):
     """tcgen05 cta_group::2 CTA-pair kernel (conv_tc3.cu) against the single-CTA halo kernel and the fp32 reference:
     odd numbers of pixel tiles (a rank idling on an out-of-range image), partial tiles, residual, fused BatchNorm
-    statistics, every (BN, MT) specialisation, dgrad through the same kernel."""
+    statistics, every (BN, MT) specialisation, dgrad through the same kernel.  halo = 1 (default): ONE haloed A box per
+    channel block, the three filter columns are 1-pixel shifted descriptor views; halo = 0: one box per filter column."""
     n, h, w, cin, cout = case
     fbn, fmt = force
     if fbn == 256 and cout % 256:
@@ -778,6 +780,7 @@ def test_conv_tc3_cta_pair(stp, cuda, case, force):
     try:
         for mode in (1, 2):   # 1: single-CTA halo kernel, 2: CTA-pair kernel forced on
             stp.set_option(b"tc3", mode)
+            stp.set_option(b"tc3_halo", 0 if halo else 1)
             stp.set_option(b"tc3_force_bn", fbn)
             stp.set_option(b"tc3_force_mt", fmt)
             before = stp.tc_launch_count()
@@ -797,6 +800,7 @@ def test_conv_tc3_cta_pair(stp, cuda, case, force):
             outs.append((y, coef, y2))
     finally:
         stp.set_option(b"tc3", 0)
+        stp.set_option(b"tc3_halo", 0)
         stp.set_option(b"tc3_force_bn", 0)
         stp.set_option(b"tc3_force_mt", 0)
     yr = conv_ref(x, wt, 1, 1)
