@@ -147,20 +147,38 @@ def cpu_reference_step_time(size, sample_batch, steps, warmup, backbone="resnet3
     return sum(times) / len(times), cores, float(lo)
 
 
+def workload_config(args, world, tc=True):
+    """`config` of the JSON line: identical for the libstp arm and the reference arm (same workload, same batch)."""
+    B, S = args.batch, args.size
+    return {"workload": "U-Net/%s %dx%d 1-class bs%d/GPU, on-device augment (Fliplr/Flipud/Affine/Multiply/Add) + "
+                        "fwd + binary_crossentropy+dice_loss + bwd + %sKeras-Adam" %
+                        (args.backbone, S, S, B, "NCCL all-reduce + " if world > 1 else ""),
+            "global_batch": B * world, "pool_per_rank": args.pool, "parallelism": "dp%d" % world,
+            "l2": "per-step working set (>3 GB of activations) exceeds the 126 MB L2; dominant-kernel timing flushes L2 "
+                  "with a 256 MB memset between launches",
+            "cuda_graph": True, "tcgen05": tc}
+
+
 def run_reference(args, rank):
+    """Reference arm: the restated reference path (oracle/, PyTorch-CPU fp32 with Keras semantics -- the Keras/TF1 stack itself
+    is not installable) on this box's host cores, one bs16 batch per step = the libstp arm's per-GPU
+    workload.  Under torchrun only rank 0 works."""
     if rank != 0:
         return
-    sb = args.ref_batch
-    dt, cores, _ = cpu_reference_step_time(args.size, sb, max(1, min(args.steps, 3)), 1, args.backbone)
+    sb = args.ref_batch if args.ref_batch > 0 else args.batch
+    steps = max(1, min(args.steps, 2))
+    dt, cores, _ = cpu_reference_step_time(args.size, sb, steps, 1, args.backbone)
     v = sb / dt
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     out = {
         "impl": "reference", "metric": "images/sec U-Net/ResNet-34 512x512 training step", "value": v, "unit": "img/s",
-        "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": dt * 1e3,
+        "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "U-Net/%s %dx%d 1-class, augment+fwd+Dice+BCE+bwd+Adam" % (args.backbone, args.size, args.size),
-                   "note": "restated reference path (oracle/, PyTorch-CPU fp32), not Keras: its dependencies are not installable"},
+        "config": workload_config(args, world),
+        "note": "restated reference path (oracle/, PyTorch-CPU fp32), not Keras: its dependencies are not installable; the "
+                "CPU path is one process whatever --gpus says",
         "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port",
-                         "sample": "batch of %d images per step (same graph/loss/optimizer as the bs16 workload)" % sb},
+                         "sample": "%d timed steps of one batch of %d images (the per-GPU batch of the workload), 1 warm-up" % (steps, sb)},
         "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
@@ -391,13 +409,7 @@ def run_gpu(args, rank, local_rank, world):
             "metric": "images/sec U-Net/ResNet-34 512x512 training step", "value": value, "unit": "img/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "U-Net/%s %dx%d 1-class bs%d/GPU, on-device augment (Fliplr/Flipud/Affine/Multiply/Add) + "
-                                   "fwd + binary_crossentropy+dice_loss + bwd + %sKeras-Adam" %
-                                   (args.backbone, S, S, B, "NCCL all-reduce + " if world > 1 else ""),
-                       "global_batch": B * world, "pool_per_rank": pool_n, "parallelism": "dp%d" % world,
-                       "l2": "per-step working set (>3 GB of activations) exceeds the 126 MB L2; dominant-kernel timing flushes L2 "
-                             "with a 256 MB memset between launches",
-                       "cuda_graph": True, "tcgen05": bool(lib.load().stp_tc_enabled())},
+            "config": workload_config(args, world, bool(lib.load().stp_tc_enabled())),
             "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
@@ -429,11 +441,11 @@ def run_gpu(args, rank, local_rank, world):
                                    "frac": gbs / pk["hbm_gbs"], "bytes_per_launch": hbm["bytes"], "ms_per_launch": hbm["ms"],
                                    "note": "isolated launch after an L2 flush: ~10 us of launch / ramp / drain are inside a <30 us figure"}
         if world == 1 and not args.no_cpu:
-            sb = args.ref_batch
+            sb = args.ref_batch if args.ref_batch > 0 else B
             dt, cores, _ = cpu_reference_step_time(S, sb, 2, 1, args.backbone)
             out["cpu_baseline"] = {"value": sb / dt, "unit": "img/s", "cores": cores, "kind": "port",
-                                   "sample": "oracle (PyTorch-CPU fp32 restatement) train step on a batch of %d images, "
-                                             "1 warm-up + 2 timed" % sb}
+                                   "sample": "oracle (PyTorch-CPU fp32 restatement) train step on one batch of %d images (the "
+                                             "workload's per-GPU batch), 1 warm-up + 2 timed" % sb}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -449,7 +461,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--pool", type=int, default=64)
     ap.add_argument("--backbone", default="resnet34")
-    ap.add_argument("--ref-batch", type=int, default=2)
+    ap.add_argument("--ref-batch", type=int, default=0, help="images per CPU reference step; 0 = --batch (bs16, BASELINE.md section 4)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "stp" else args.warmup

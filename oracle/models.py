@@ -86,6 +86,13 @@ class SegModel:
         with torch.no_grad():
             self.forward(torch.zeros(1, h, h, input_shape[2]), emit_logits=False)
         self.update_moving = um
+        # storage="fp64": the same graph in double precision -- the ANCHOR against which both the fp32 oracle and the engine's
+        # fp32 parity mode are measured (how far apart two correct fp32 implementations of this training run can be)
+        self.dtype = torch.float64 if storage == "fp64" else torch.float32
+        if self.dtype is torch.float64:
+            for d in (self.P.params, self.P.buffers):
+                for k in list(d):
+                    d[k] = d[k].double()
         for p in self.P.params.values():
             p.requires_grad_(True)
 
@@ -238,7 +245,7 @@ class SegModel:
 
         emit_logits=True strips the trailing Activation (what musket compile does for lovasz_loss)."""
         self.P._in_encoder = True
-        x = x_nhwc.permute(0, 3, 1, 2).contiguous().float()
+        x = x_nhwc.permute(0, 3, 1, 2).contiguous().to(getattr(self, "dtype", torch.float32))
         if self.backbone == "vgg16":
             x, skips = self._vgg16(x)
         else:

@@ -6,8 +6,8 @@ from scripts.tc3_halo_bench import L, bench  # noqa
 
 shapes = [(16, 64, 64, 128, 128), (16, 64, 64, 384, 128)]
 for shp in shapes:
-    for name, opts in (("3-box mt2", {b"tc3": 2, b"tc3_halo": 1, b"tc3_force_mt": 2}), ("halo mt2", {b"tc3": 2, b"tc3_force_mt": 2}),
-                       ("halo mt1", {b"tc3": 2, b"tc3_force_mt": 1}), ("3-box mt1", {b"tc3": 2, b"tc3_halo": 1, b"tc3_force_mt": 1})):
+    for name, opts in (("3-box mt2", {b"tc3": 2, b"tc3_halo": 0, b"tc3_force_mt": 2}), ("halo mt2", {b"tc3": 2, b"tc3_halo": 1, b"tc3_force_mt": 2}),
+                       ("halo mt1", {b"tc3": 2, b"tc3_halo": 1, b"tc3_force_mt": 1}), ("3-box mt1", {b"tc3": 2, b"tc3_halo": 0, b"tc3_force_mt": 1})):
         for dbg in (0, 3, 1, 2, 8):
             for k in (b"tc3", b"tc3_force_bn", b"tc3_force_mt", b"tc3_halo"):
                 L.set_option(k, 0)

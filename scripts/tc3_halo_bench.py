@@ -1,4 +1,4 @@
-"""A/B of conv_tc3's single-halo-box mode (option tc3_halo: 0 on, 1 off): isolated launches (L2 flushed) and 30 launches back
+"""A/B of conv_tc3's single-halo-box mode (option tc3_halo: 1 on, 0 off): isolated launches (L2 flushed) and 30 launches back
 to back over rotating input/output sets larger than L2 (how the layer runs inside the step graph)."""
 import ctypes as C, math, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -46,9 +46,9 @@ if __name__ == "__main__":
     shapes = [(16, 64, 64, 128, 128), (16, 32, 32, 256, 256), (16, 16, 16, 512, 512), (16, 32, 32, 768, 256), (16, 64, 64, 384, 128),
               (16, 128, 128, 64, 128)]
     for shp in shapes:
-        for name, opts in (("tc2", {b"tc3": 1}), ("tc3 3-box mt2", {b"tc3": 2, b"tc3_halo": 1, b"tc3_force_mt": 2}),
-                           ("tc3 halo mt1", {b"tc3": 2, b"tc3_force_mt": 1}), ("tc3 halo mt2", {b"tc3": 2, b"tc3_force_mt": 2}),
-                           ("tc3 halo bn256", {b"tc3": 2, b"tc3_force_bn": 256})):
+        for name, opts in (("tc2", {b"tc3": 1}), ("tc3 3-box mt2", {b"tc3": 2, b"tc3_halo": 0, b"tc3_force_mt": 2}),
+                           ("tc3 halo mt1", {b"tc3": 2, b"tc3_halo": 1, b"tc3_force_mt": 1}), ("tc3 halo mt2", {b"tc3": 2, b"tc3_halo": 1, b"tc3_force_mt": 2}),
+                           ("tc3 halo bn256", {b"tc3": 2, b"tc3_halo": 1, b"tc3_force_bn": 256})):
             for k in (b"tc3", b"tc3_force_bn", b"tc3_force_mt", b"tc3_halo"):
                 L.set_option(k, 0)
             for k, v in opts.items():

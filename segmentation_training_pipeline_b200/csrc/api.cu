@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "conv.h"
+#include "f32_path.h"
 
 namespace stp {
 
@@ -49,7 +50,7 @@ extern "C" int stp_set_option(const char* name, int32_t value) {
   else if (!strcmp(name, "tc3")) key = OPT_TC3;                         /* 0 auto | 1 off | 2 CTA-pair kernel wherever it serves the shape */
   else if (!strcmp(name, "tc3_force_bn")) key = OPT_TC3_FORCE_BN;       /* 0 heuristic | 128, 256 */
   else if (!strcmp(name, "tc3_force_mt")) key = OPT_TC3_FORCE_MT;       /* 0 heuristic | 1, 2 */
-  else if (!strcmp(name, "tc3_halo")) key = OPT_TC3_HALO;               /* 0 on | 1 off: one A box per filter column (round-1 scheme) */
+  else if (!strcmp(name, "tc3_halo")) key = OPT_TC3_HALO;               /* 0 off | 1 on: ONE haloed A box per channel block (measured slower, see conv_tc3.cu) */
   else if (!strcmp(name, "bnb_fuse")) key = OPT_BNB_FUSE;               /* 0 auto | 1: never fuse the BatchNorm-backward reduction into the dgrad epilogue */
   else if (!strcmp(name, "bn_blocks")) key = OPT_BN_BLOCKS;             /* 0 default | n: atomic-mode BN reductions use up to n*1024/C blocks */
   else if (!strcmp(name, "pdl")) {                                      /* programmatic dependent launch on/off */
@@ -87,8 +88,33 @@ static int check_conv_common(const stp_conv_desc* d, const stp_tensor* in, const
   return STP_OK;
 }
 
+// ---- parity mode (fp32 tensors): CUDA-core kernels of f32_path.cu -------------------------------------------------
+static f32::ConvF make_conv_f(const stp_conv_desc* d, const stp_tensor* x, const void* w, const float* bias,
+                              const stp_tensor* residual, const stp_tensor* y) {
+  f32::ConvF p;
+  p.x = (const float*)x->ptr; p.ldx = x->ld; p.N = x->n; p.H = x->h; p.W = x->w; p.Cin = x->c;
+  p.w = (const float*)w;
+  p.y = (float*)y->ptr; p.ldy = y->ld; p.Ho = y->h; p.Wo = y->w; p.Cout = y->c;
+  p.res = residual ? (const float*)residual->ptr : nullptr; p.ldr = residual ? residual->ld : 0;
+  p.bias = bias;
+  p.R = d->r; p.S = d->s; p.stride = d->stride; p.pad_h = d->pad_h; p.pad_w = d->pad_w; p.up = d->up;
+  p.relu = (d->flags & STP_CONV_RELU) ? 1 : 0; p.dgrad = 0;
+  p.M = pixels(y); p.K = d->r * d->s * x->c;
+  return p;
+}
+static int conv_fwd_f32(const stp_conv_desc* d, const stp_tensor* x, const void* w, const float* bias, const stp_tensor* residual,
+                        const stp_tensor* y, const stp_bn_fwd* h_bn, stp_stream stream) {
+  STP_REQUIRE(d && f32::f32_ok(x) && f32::f32_ok(y) && w && x->n == y->n, "conv_fwd (fp32 parity mode): bad tensors");
+  if (residual) STP_REQUIRE(f32::f32_ok(residual) && residual->c == y->c && pixels(residual) == pixels(y), "conv_fwd (fp32): bad residual");
+  int rc = f32::launch_conv(make_conv_f(d, x, w, bias, residual, y), (cudaStream_t)stream);
+  if (rc || !h_bn) return rc;
+  return stp_bn_stats_fused(y, h_bn->partial, h_bn->sync, h_bn->acc, h_bn->gamma, h_bn->beta, h_bn->eps, h_bn->momentum,
+                            h_bn->moving_mean, h_bn->moving_var, h_bn->coef, stream);
+}
+
 static int conv_fwd_common(const stp_conv_desc* d, const stp_tensor* x, const void* w_krsc, const float* bias,
                            const stp_tensor* residual, const stp_tensor* y, const stp_bn_fwd* h_bn, stp_stream stream) {
+  if (x && x->dtype == STP_F32) return conv_fwd_f32(d, x, w_krsc, bias, residual, y, h_bn, stream);
   int rc = check_conv_common(d, x, y, "conv_fwd");
   if (rc) return rc;
   STP_REQUIRE(w_krsc && y->ptr, "conv_fwd: null weights/output");
@@ -148,6 +174,16 @@ extern "C" int stp_conv_fwd_bn(const stp_conv_desc* d, const stp_tensor* x, cons
 
 static int conv_dgrad_common(const stp_conv_desc* d, const stp_tensor* dy, const void* w_dgrad, const stp_tensor* residual,
                              const stp_tensor* dx, const stp_bn_bwd* h_bnb, stp_stream stream) {
+  if (dy && dy->dtype == STP_F32) {
+    // parity mode: w_dgrad is the FORWARD fp32 KRSC tensor (flipped / transposed inside the kernel)
+    STP_REQUIRE(d && f32::f32_ok(dy) && f32::f32_ok(dx) && w_dgrad && dx->n == dy->n && !h_bnb, "conv_dgrad (fp32 parity mode): bad args");
+    STP_REQUIRE(d->up == 1 || d->stride == 1, "conv_dgrad: stride and up cannot both be > 1");
+    STP_REQUIRE(d->r - 1 - d->pad_h >= 0 && d->s - 1 - d->pad_w >= 0, "conv_dgrad: pad > filter-1 unsupported");
+    if (residual) STP_REQUIRE(f32::f32_ok(residual) && residual->c == dx->c && pixels(residual) == pixels(dx), "conv_dgrad (fp32): bad residual");
+    f32::ConvF p = make_conv_f(d, dy, w_dgrad, nullptr, residual, dx);
+    p.stride = d->up; p.up = d->stride; p.pad_h = d->r - 1 - d->pad_h; p.pad_w = d->s - 1 - d->pad_w; p.relu = 0; p.dgrad = 1;
+    return f32::launch_conv(p, (cudaStream_t)stream);
+  }
   int rc = check_conv_common(d, dy, dx, "conv_dgrad");
   if (rc) return rc;
   STP_REQUIRE(w_dgrad && dx->ptr && dx->dtype == STP_BF16 && dx->ld >= dx->c, "conv_dgrad: bad dx / weights");
@@ -231,6 +267,11 @@ extern "C" size_t stp_conv_wgrad_workspace(const stp_conv_desc* d, const stp_ten
 
 extern "C" int stp_conv_wgrad(const stp_conv_desc* d, const stp_tensor* x, const stp_tensor* dy, float* dw,
                               void* workspace, size_t workspace_bytes, stp_stream stream) {
+  if (x && x->dtype == STP_F32) {
+    STP_REQUIRE(d && f32::f32_ok(x) && f32::f32_ok(dy) && dw && x->n == dy->n, "conv_wgrad (fp32 parity mode): bad tensors");
+    f32::ConvF p = make_conv_f(d, x, nullptr, nullptr, nullptr, dy);   // geometry: x gathered at the positions of dy's pixels
+    return f32::launch_wgrad(p, (const float*)dy->ptr, dy->ld, dy->c, dw, (cudaStream_t)stream);
+  }
   int rc = check_conv_common(d, x, dy, "conv_wgrad");
   if (rc) return rc;
   STP_REQUIRE(vec_ok(dy) && dw, "conv_wgrad: dy must be bf16 NHWC c%%8==0; dw non-null");

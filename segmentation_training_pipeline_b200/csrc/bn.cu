@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "bn_fin.cuh"
 #include "conv.h"
+#include "f32_path.h"
 
 namespace stp {
 
@@ -613,6 +614,10 @@ static size_t reduce_smem(const RowGeom& g, int c) {
 
 static int launch_stats(const stp_tensor* x, float* partial, const FinArgs& fin, cudaStream_t st) {
   int64_t rows = pixels(x);
+  if (x->dtype == STP_F32) {   // parity mode
+    STP_REQUIRE(f32::f32_ok(x) && fin.mode != 0, "bn_stats (fp32 parity mode): fused finalize only");
+    return f32::launch_reduce(0, x, nullptr, nullptr, 0, 1, fin, st);
+  }
   if (x->dtype == STP_U8) {
     STP_REQUIRE(fin.mode == 0, "bn_stats u8: fused finalize unsupported");
     STP_REQUIRE(x->c <= 4 && x->ld == x->c, "bn_stats u8: c<=4 dense only");
@@ -632,6 +637,11 @@ static int launch_stats(const stp_tensor* x, float* partial, const FinArgs& fin,
 
 static int launch_bwd_reduce(const stp_tensor* dy, const stp_tensor* x, const float* coef, int relu, int pool,
                              float* partial, const FinArgs& fin, cudaStream_t st) {
+  if (x && x->dtype == STP_F32) {   // parity mode
+    STP_REQUIRE(f32::f32_ok(x) && f32::f32_ok(dy) && coef && fin.mode == 2 && (pool == 1 || pool == 2), "bn_bwd_reduce (fp32): bad args");
+    STP_REQUIRE(dy->c == x->c && dy->h == x->h * pool && dy->w == x->w * pool && dy->n == x->n, "bn_bwd_reduce (fp32): shape mismatch");
+    return f32::launch_reduce(1, x, dy, coef, relu, pool, fin, st);
+  }
   STP_REQUIRE(vec_ok(dy) && vec_ok(x) && coef && partial, "bn_bwd_reduce: bad tensors");
   STP_REQUIRE(pool == 1 || pool == 2, "bn_bwd_reduce: pool must be 1 or 2");
   STP_REQUIRE(dy->c == x->c && dy->h == x->h * pool && dy->w == x->w * pool && dy->n == x->n,
@@ -699,6 +709,11 @@ extern "C" int stp_bn_coef_infer(const float* gamma, const float* beta, const fl
 
 extern "C" int stp_bn_apply(const stp_tensor* x, const float* coef, int32_t relu, int32_t up, const stp_tensor* y,
                             stp_stream stream) {
+  if (x && x->dtype == STP_F32) {   // parity mode
+    STP_REQUIRE(f32::f32_ok(x) && f32::f32_ok(y) && coef && (up == 1 || up == 2), "bn_apply (fp32): bad tensors");
+    STP_REQUIRE(y->c == x->c && y->n == x->n && y->h == x->h * up && y->w == x->w * up, "bn_apply (fp32): shape mismatch");
+    return f32::bn_apply(x, coef, relu, up, y, (cudaStream_t)stream);
+  }
   STP_REQUIRE(vec_ok(x) && vec_ok(y) && coef, "bn_apply: bad tensors");
   STP_REQUIRE(up == 1 || up == 2, "bn_apply: up must be 1 or 2");
   STP_REQUIRE(y->c == x->c && y->n == x->n && y->h == x->h * up && y->w == x->w * up, "bn_apply: shape mismatch");
@@ -740,6 +755,13 @@ extern "C" int stp_bn_bwd_finalize(const float* partial, int32_t nblk, int32_t c
 static int bwd_apply_common(int mode, const stp_tensor* dy, const stp_tensor* x, const float* coef,
                             const float* bcoef, int relu, int pool, const stp_tensor* residual, const stp_tensor* dx,
                             stp_stream stream) {
+  if (x && x->dtype == STP_F32) {   // parity mode
+    STP_REQUIRE(f32::f32_ok(x) && f32::f32_ok(dy) && f32::f32_ok(dx) && (pool == 1 || pool == 2), "bwd_apply (fp32): bad tensors");
+    STP_REQUIRE(dy->c == x->c && dx->c == x->c && dy->h == x->h * pool && dy->w == x->w * pool && dx->h == x->h && dx->w == x->w &&
+                    dx->n == x->n && dy->n == x->n, "bwd_apply (fp32): shape mismatch");
+    if (residual) STP_REQUIRE(f32::f32_ok(residual) && residual->c == x->c && pixels(residual) == pixels(x), "bwd_apply (fp32): bad residual");
+    return f32::bwd_apply(mode, dy, x, coef, bcoef, relu, pool, residual, dx, (cudaStream_t)stream);
+  }
   STP_REQUIRE(vec_ok(dy) && vec_ok(x) && vec_ok(dx), "bwd_apply: bad tensors");
   STP_REQUIRE(pool == 1 || pool == 2, "bwd_apply: pool must be 1 or 2");
   STP_REQUIRE(dy->c == x->c && dx->c == x->c && dy->h == x->h * pool && dy->w == x->w * pool && dx->h == x->h &&
@@ -778,6 +800,10 @@ extern "C" int stp_relu_bwd(const stp_tensor* dy, const stp_tensor* y, int32_t p
 
 extern "C" int stp_stem_prep(const uint8_t* img, int32_t n, int32_t h, int32_t w, int32_t c_img, const float* coef,
                              const stp_tensor* y, stp_stream stream) {
+  if (y && y->dtype == STP_F32) {   // parity mode: plain [n, h, w, C] output (no space-to-depth form)
+    STP_REQUIRE(img && coef && f32::f32_ok(y) && y->h == h && y->w == w && y->n == n && c_img < y->c, "stem_prep (fp32): bad args");
+    return f32::stem_prep(img, (int64_t)n * h * w, c_img, coef, y, (cudaStream_t)stream);
+  }
   STP_REQUIRE(img && coef && vec_ok(y), "stem_prep: bad args");
   int64_t rows = (int64_t)n * h * w;
   if (y->h == h && y->w == w) {
@@ -795,6 +821,11 @@ extern "C" int stp_stem_prep(const uint8_t* img, int32_t n, int32_t h, int32_t w
 }
 
 extern "C" int stp_copy_up(const stp_tensor* x, int32_t up, const stp_tensor* y, stp_stream stream) {
+  if (x && x->dtype == STP_F32) {   // parity mode
+    STP_REQUIRE(f32::f32_ok(x) && f32::f32_ok(y) && up >= 1 && y->c == x->c && y->n == x->n && y->h == x->h * up && y->w == x->w * up,
+                "copy_up (fp32): bad tensors");
+    return f32::copy_up(x, up, y, (cudaStream_t)stream);
+  }
   STP_REQUIRE(vec_ok(x) && vec_ok(y) && up >= 1, "copy_up: bad tensors");
   STP_REQUIRE(y->c == x->c && y->n == x->n && y->h == x->h * up && y->w == x->w * up, "copy_up: shape mismatch");
   int64_t rows = pixels(x);
@@ -806,6 +837,11 @@ extern "C" int stp_copy_up(const stp_tensor* x, int32_t up, const stp_tensor* y,
 }
 
 extern "C" int stp_add(const stp_tensor* a, const stp_tensor* b, const stp_tensor* y, stp_stream stream) {
+  if (a && a->dtype == STP_F32) {   // parity mode
+    STP_REQUIRE(f32::f32_ok(a) && f32::f32_ok(b) && f32::f32_ok(y) && a->c == b->c && a->c == y->c && pixels(a) == pixels(b) &&
+                    pixels(a) == pixels(y), "add (fp32): bad tensors");
+    return f32::add(a, b, y, (cudaStream_t)stream);
+  }
   STP_REQUIRE(vec_ok(a) && vec_ok(b) && vec_ok(y), "add: bad tensors");
   STP_REQUIRE(a->c == b->c && a->c == y->c && pixels(a) == pixels(b) && pixels(a) == pixels(y), "add: shape mismatch");
   int64_t rows = pixels(a);
@@ -884,6 +920,9 @@ extern "C" int stp_stem_wgrad_s2d_gather(const float* dw2, float* dw, int32_t co
 extern "C" int stp_stem_wgrad_post(float* dw8, const float* w_master, int32_t cout, int32_t r, int32_t s,
                                    int32_t cin_pad, int32_t c_img, float* dbeta, stp_stream stream) {
   STP_REQUIRE(dw8 && w_master && c_img >= 1 && c_img <= 4 && c_img < cin_pad, "stem_wgrad_post: bad args");
+  if (r < 0) {   // parity mode (engine passes -r): the conv ran on the fp32 weights themselves, not on a bf16 copy
+    return stp::f32::stem_wgrad_post(dw8, w_master, cout * (-r) * s, cin_pad, c_img, dbeta, (cudaStream_t)stream);
+  }
   stp::stem_wgrad_post_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(dw8, w_master, cout * r * s, cin_pad, c_img, dbeta);
   return check_launch("stem_wgrad_post");
 }

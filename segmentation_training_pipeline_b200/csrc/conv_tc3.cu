@@ -461,9 +461,12 @@ constexpr int kPairs = kNumSMs / 2;
 
 // cycle estimate used to rank (BN, MT): wave quantisation over the 74 CTA pairs, L2->SM bytes per CTA (~40 B/clk) against
 // the M=256 MMA floor (BN/2 clk per K=16 step), per-strip epilogue
-// halo mode (default; option "tc3_halo" = 1 turns it off): 8-wide x 16-row sub-tiles, ONE [TH+R-1][8+S-1] haloed A box per
-// channel block instead of one [TH+R-1][BW] box per filter column: L2->SM A bytes drop ~2.5x (profiles/README.md r2)
-static bool tc3_halo() { return get_option(OPT_TC3_HALO) != 1; }
+// halo mode (option "tc3_halo" = 1; OFF by default): 8-wide x 16-row sub-tiles, ONE [TH+R-1][8+S-1] haloed A box per channel
+// block instead of one [TH+R-1][BW] box per filter column.  L2->SM A bytes drop ~2.5x and parity is green, but the MMAs
+// themselves run ~1.45x SLOWER when the 8-row groups of the A descriptor are not 1024-byte aligned / SBO is not a multiple of
+// 1024 B (pure-MMA loop, all loads skipped: 56.1 vs 38.8 us on 384->128 @64^2; profiles/r2_tc3_dbg_bench.txt), so the layer
+// loses (26.6 vs 21.9 us on 128->128 @64^2).  Kept as a measured negative result (profiles/README.md r2).
+static bool tc3_halo() { return get_option(OPT_TC3_HALO) == 1; }
 static int tc3_bw(const ConvP& p) { return tc3_halo() ? 8 : (p.Wo >= 16 ? 16 : 8); }
 
 static double tc3_cost(const ConvP& p, int bn, int mt) {

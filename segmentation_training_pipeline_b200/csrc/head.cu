@@ -4,6 +4,7 @@
 // (reference segmentation.py:155).  Backward computes dX, dW and dbias in two passes.
 #include "common.cuh"
 #include "conv.h"
+#include "f32_path.h"
 
 namespace stp {
 
@@ -239,6 +240,16 @@ extern "C" size_t stp_head_fwd_workspace(const stp_tensor* x, int32_t classes) {
 
 extern "C" int stp_head_fwd(const stp_tensor* x, const float* w_krsc_f32, const float* bias, int32_t classes,
                             float* logits, void* workspace, size_t workspace_bytes, stp_stream stream) {
+  if (x && x->dtype == STP_F32) {   // parity mode: the same 3x3 'same' convolution + bias on the CUDA-core fp32 kernel
+    STP_REQUIRE(f32::f32_ok(x) && w_krsc_f32 && logits && classes >= 1, "head_fwd (fp32): bad args");
+    f32::ConvF p;
+    p.x = (const float*)x->ptr; p.ldx = x->ld; p.N = x->n; p.H = x->h; p.W = x->w; p.Cin = x->c;
+    p.w = w_krsc_f32; p.y = logits; p.ldy = classes; p.Ho = x->h; p.Wo = x->w; p.Cout = classes;
+    p.res = nullptr; p.ldr = 0; p.bias = bias;
+    p.R = 3; p.S = 3; p.stride = 1; p.pad_h = 1; p.pad_w = 1; p.up = 1; p.relu = 0; p.dgrad = 0;
+    p.M = pixels(x); p.K = 9 * x->c;
+    return f32::launch_conv(p, (cudaStream_t)stream);
+  }
   STP_REQUIRE(vec_ok(x) && w_krsc_f32 && logits, "head_fwd: bad args");
   STP_REQUIRE(classes >= 1 && classes <= kHeadMaxCls && x->c <= kHeadMaxCin, "head_fwd: classes<=4, Cin<=64");
   int64_t M = pixels(x);
@@ -273,6 +284,31 @@ extern "C" size_t stp_head_bwd_workspace(const stp_tensor* x, int32_t classes) {
 extern "C" int stp_head_bwd(const stp_tensor* x, const float* w_krsc_f32, const float* dlogits, int32_t classes,
                             const stp_tensor* dx, float* dw, float* dbias, void* workspace, size_t workspace_bytes,
                             stp_stream stream) {
+  if (x && x->dtype == STP_F32) {   // parity mode: dgrad + wgrad of the same convolution; db = column sums of dlogits
+    STP_REQUIRE(f32::f32_ok(x) && w_krsc_f32 && dlogits && dw && classes >= 1 && workspace && workspace_bytes >= 2 * sizeof(double) * classes,
+                "head_bwd (fp32): bad args / workspace");
+    cudaStream_t st = (cudaStream_t)stream;
+    f32::ConvF p;
+    p.R = 3; p.S = 3; p.bias = nullptr; p.res = nullptr; p.ldr = 0; p.relu = 0;
+    if (dx) {
+      STP_REQUIRE(f32::f32_ok(dx) && dx->c == x->c && pixels(dx) == pixels(x), "head_bwd (fp32): bad dx");
+      p.x = dlogits; p.ldx = classes; p.N = x->n; p.H = x->h; p.W = x->w; p.Cin = classes;
+      p.w = w_krsc_f32; p.y = (float*)dx->ptr; p.ldy = dx->ld; p.Ho = x->h; p.Wo = x->w; p.Cout = x->c;
+      p.stride = 1; p.up = 1; p.pad_h = 1; p.pad_w = 1; p.dgrad = 1; p.M = pixels(x); p.K = 9 * classes;
+      int rc = f32::launch_conv(p, st);
+      if (rc) return rc;
+    }
+    p.x = (const float*)x->ptr; p.ldx = x->ld; p.N = x->n; p.H = x->h; p.W = x->w; p.Cin = x->c;
+    p.w = nullptr; p.y = nullptr; p.ldy = classes; p.Ho = x->h; p.Wo = x->w; p.Cout = classes;
+    p.stride = 1; p.up = 1; p.pad_h = 1; p.pad_w = 1; p.dgrad = 0; p.M = pixels(x); p.K = 9 * x->c;
+    int rc = f32::launch_wgrad(p, dlogits, classes, classes, dw, st);
+    if (rc || !dbias) return rc;
+    stp_tensor dl = {const_cast<float*>(dlogits), x->n, x->h, x->w, classes, classes, STP_F32};
+    cudaMemsetAsync(workspace, 0, 2 * sizeof(double) * classes, st);
+    FinArgs fin = {};
+    fin.mode = 3; fin.acc = (double*)workspace; fin.dbeta = dbias;
+    return f32::launch_reduce(0, &dl, nullptr, nullptr, 0, 1, fin, st);
+  }
   STP_REQUIRE(vec_ok(x) && w_krsc_f32 && dlogits && dw, "head_bwd: bad args");
   STP_REQUIRE(classes >= 1 && classes <= kHeadMaxCls && x->c <= kHeadMaxCin, "head_bwd: classes<=4, Cin<=64");
   STP_REQUIRE(x->c == 8 || x->c == 16 || x->c == 32 || x->c == 64, "head_bwd: Cin must be 8, 16, 32 or 64");

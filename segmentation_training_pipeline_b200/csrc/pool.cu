@@ -2,6 +2,7 @@
 // Semantics: ZeroPadding2D(pad) + MaxPooling2D(k, stride, 'valid') on post-ReLU data == max_pool(k, stride, pad)
 // with the FIRST maximum in (kh, kw) scan order taking the gradient.
 #include "common.cuh"
+#include "f32_path.h"
 
 namespace stp {
 
@@ -184,6 +185,11 @@ using namespace stp;
 
 extern "C" int stp_maxpool_fwd(const stp_tensor* x, int32_t k, int32_t stride, int32_t pad, const stp_tensor* y,
                                uint8_t* argmax, stp_stream stream) {
+  if (x && x->dtype == STP_F32) {   // parity mode
+    STP_REQUIRE(f32::f32_ok(x) && f32::f32_ok(y) && k >= 1 && k <= 15 && stride >= 1 && y->c == x->c && y->n == x->n &&
+                    y->h == (x->h + 2 * pad - k) / stride + 1 && y->w == (x->w + 2 * pad - k) / stride + 1, "maxpool_fwd (fp32): bad args");
+    return f32::maxpool_fwd(x, k, stride, pad, y, argmax, (cudaStream_t)stream);
+  }
   STP_REQUIRE(vec_ok(x) && vec_ok(y), "maxpool_fwd: bad tensors");
   STP_REQUIRE(k >= 1 && k <= 15 && stride >= 1 && y->c == x->c && y->n == x->n, "maxpool_fwd: bad args");
   STP_REQUIRE(y->h == (x->h + 2 * pad - k) / stride + 1 && y->w == (x->w + 2 * pad - k) / stride + 1,
@@ -198,6 +204,11 @@ extern "C" int stp_maxpool_fwd(const stp_tensor* x, int32_t k, int32_t stride, i
 
 extern "C" int stp_maxpool_bwd(const stp_tensor* dy, const uint8_t* argmax, int32_t k, int32_t stride, int32_t pad,
                                const stp_tensor* residual, const stp_tensor* dx, stp_stream stream) {
+  if (dy && dy->dtype == STP_F32) {   // parity mode
+    STP_REQUIRE(f32::f32_ok(dy) && f32::f32_ok(dx) && argmax && dy->c == dx->c && dy->n == dx->n, "maxpool_bwd (fp32): bad tensors");
+    if (residual) STP_REQUIRE(f32::f32_ok(residual) && residual->c == dx->c && pixels(residual) == pixels(dx), "maxpool_bwd (fp32): bad residual");
+    return f32::maxpool_bwd(dy, argmax, k, stride, pad, residual, dx, (cudaStream_t)stream);
+  }
   STP_REQUIRE(vec_ok(dy) && vec_ok(dx) && argmax, "maxpool_bwd: bad tensors");
   STP_REQUIRE(dy->c == dx->c && dy->n == dx->n, "maxpool_bwd: shape mismatch");
   if (residual) STP_REQUIRE(vec_ok(residual) && residual->c == dx->c && pixels(residual) == pixels(dx), "maxpool_bwd: bad residual");

@@ -30,7 +30,9 @@ def _stream() -> int:
 class Buf:
     """NHWC device tensor, possibly a channel slice [c_off, c_off+c) of a wider root buffer (ld = root.c)."""
 
-    def __init__(self, net: "Net", n, h, w, c, dtype=BF16, root: Optional["Buf"] = None, c_off=0, name=""):
+    def __init__(self, net: "Net", n, h, w, c, dtype=None, root: Optional["Buf"] = None, c_off=0, name=""):
+        if dtype is None:   # activations / gradients: bf16, or fp32 in parity mode (Net.precision)
+            dtype = root.dtype if root is not None else net.act_dtype
         self.net, self.n, self.h, self.w, self.c, self.dtype, self.name = net, n, h, w, c, dtype, name
         self.root = root.root if root is not None else self
         self.c_off = c_off if root is None else root.c_off + c_off
@@ -123,7 +125,15 @@ class Op:
 
 
 class Net:
-    def __init__(self, batch: int, device="cuda:0", seed: int = 0):
+    def __init__(self, batch: int, device="cuda:0", seed: int = 0, precision: str = "bf16"):
+        """precision = "bf16" (product path: bf16 activations / gradients / weight copies on the tcgen05 kernels, fp32
+        accumulation, fp32 master weights) or "fp32" (PARITY MODE, csrc/f32_path.cu: fp32 activations, gradients and weights,
+        CUDA-core FFMA convolutions, double-precision reductions -- the mode in which the 100-step loss curve is held to the
+        1e-3 of north_star; same graph, same ops, same C ABI entry points)."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = precision
+        self.act_dtype = F32 if precision == "fp32" else BF16
         self.L = _lib.Lib()
         self.device = torch.device(device)
         self.batch = batch
@@ -137,12 +147,12 @@ class Net:
         self._ws_bytes = 0
         self._partial_floats = 2 * _lib.BN_MAX_PARTIALS * 8
         self.encoder_param_names: List[str] = []
-        self.fuse_bn_stats = True
+        self.fuse_bn_stats = precision == "bf16"
         # BatchNorm-backward reduction inside the producing dgrad's epilogue (stp_conv_dgrad_bn).  Parity green, 33 launches
         # fewer per U-Net/ResNet-34 step, but measured 1.3 % SLOWER (9.06 vs 8.94 ms): the separate HBM-bound reduction
         # kernels overlap the tensor-bound weight gradients of the side stream almost for free, while the fused epilogue
         # (x tile load + transpose-reduction shuffles) lengthens the exposed last-tile epilogue of every dgrad.  Off by default.
-        self.fuse_bn_bwd = os.environ.get("STP_FUSE_BN_BWD", "0") == "1"
+        self.fuse_bn_bwd = os.environ.get("STP_FUSE_BN_BWD", "0") == "1" and precision == "bf16"
 
     # ---- parameters ---------------------------------------------------------------------------
     def add_param(self, name, shape, kind, init) -> Param:
@@ -256,13 +266,21 @@ class Net:
         return self.flat_g.data_ptr() + 4 * p.offset
 
     def pwf(self, p: Param):
+        """forward conv operand: the bf16 KRSC copy (parity mode: the fp32 master itself)"""
+        if self.precision == "fp32":
+            return self.pp(p)
         return self.flat_wf.data_ptr() + 2 * p.offset
 
     def pwd(self, p: Param):
+        """dgrad conv operand: the tap-flipped bf16 copy (parity mode: the fp32 master, flipped inside the kernel)"""
+        if self.precision == "fp32":
+            return self.pp(p)
         return self.flat_wd.data_ptr() + 2 * p.offset
 
     # ---- execution ----------------------------------------------------------------------------
     def prep_weights(self):
+        if self.precision == "fp32":   # parity mode: the kernels read the fp32 master weights directly
+            return
         if self._wprep_items is not None:
             self.L.weight_prep_batched(self.flat_p.data_ptr(), self.flat_wf.data_ptr(), self.flat_wd.data_ptr(),
                                        self._wprep_items.data_ptr(), self._wprep_items.shape[0], self._wprep_tiles,
@@ -496,8 +514,9 @@ class Conv(Op):
             n.L.conv_wgrad(self.dref, self.x.ref, self.dy.ref, n.pg(self.w), ws.data_ptr(), ws.numel(), st)
             if self.stem_beta is not None or self.cin_real < self.w.shape[3]:
                 c = self.w.shape
-                n.L.stem_wgrad_post(n.pg(self.w), n.pp(self.w), c[0], c[1], c[2], c[3], self.cin_real,
-                                    n.pg(self.stem_beta) if self.stem_beta is not None else None, st)
+                # (parity mode passes -R: d(beta) is then formed with the fp32 weights instead of their bf16 rounding)
+                n.L.stem_wgrad_post(n.pg(self.w), n.pp(self.w), c[0], -c[1] if n.precision == "fp32" else c[1], c[2], c[3],
+                                    self.cin_real, n.pg(self.stem_beta) if self.stem_beta is not None else None, st)
         if self.needs_dgrad:
             if self.bnb_prev is not None and self.dx_res is None:
                 n.L.conv_dgrad_bn(self.dref, self.dy.ref, n.pwd(self.w), self.dx.ref, self.bnb_prev.bn_bwd_struct(),

@@ -31,8 +31,9 @@ class SegNet(E.Net):
                  decoder_filters=(256, 128, 64, 32, 16), device="cuda:0", seed=0,
                  enc_init="he_uniform", dec_init="glorot_uniform", loss=(1.0, 0.0, 0.0), architecture="Unet",
                  decoder_block_type="upsampling", pyramid_block_filters=256, segmentation_block_filters=128,
-                 dropout=None):
-        super().__init__(batch, device, seed)
+                 dropout=None, precision="bf16", decoder_use_batchnorm=True):
+        super().__init__(batch, device, seed, precision)
+        self.dec_bn = bool(decoder_use_batchnorm)
         backbone = backbone.lower()
         if architecture not in KNOWN_ARCHITECTURES:
             print("Unknown architecture:" + str(architecture))
@@ -41,12 +42,16 @@ class SegNet(E.Net):
         self.architecture = architecture
         linknet = architecture == "Linknet"
         fpn = architecture == "FPN"
+        if fpn and precision == "fp32":
+            raise NotImplementedError("precision: fp32 (parity mode) is built for the Unet / Linknet graphs")
         if fpn and dropout:
             raise NotImplementedError("FPN dropout (SpatialDropout2D) is not built; the schema default is None")
         if fpn and backbone == "vgg16":
             raise NotImplementedError("FPN is built over the ResNet encoders only")
         if decoder_block_type not in ("upsampling", "transpose"):
             raise ValueError("decoder_block_type must be 'upsampling' or 'transpose'")
+        if not self.dec_bn and (linknet or fpn or decoder_block_type == "transpose"):
+            raise NotImplementedError("decoder_use_batchnorm: false is built for the Unet upsampling decoder only")
         transpose = decoder_block_type == "transpose" and not linknet   # schema segmentation.raml:162-165 (Unet only)
         if transpose and backbone == "vgg16":
             raise NotImplementedError("decoder_block_type: transpose is built over the ResNet encoders only")
@@ -96,10 +101,15 @@ class SegNet(E.Net):
 
         # ---- encoder ---------------------------------------------------------------------------
         # bn_data output in space-to-depth layout [N, H/2, W/2, 4 sub-pixels x 8 channels] (see engine.StemConv)
-        x0 = E.Buf(self, N, H // 2, W // 2, 32, name="bn_data_s2d")
-        inorm = E.InputNorm(self, self.img, x0, "bn_data", ENC_BN_EPS)
         z = E.Buf(self, N, H // 2, W // 2, 64, name="conv0")
-        E.StemConv(self, x0, z, "conv0", cin_real=CI, stem_beta=inorm.beta, init=enc_init)
+        if precision == "fp32":   # parity mode: the plain 7x7/2 convolution over the 8-channel padded bn_data output
+            x0 = E.Buf(self, N, H, W, 8, name="bn_data")
+            inorm = E.InputNorm(self, self.img, x0, "bn_data", ENC_BN_EPS)
+            E.Conv(self, x0, z, "conv0", 7, stride=2, pad=3, init=enc_init, needs_dgrad=False, cin_real=CI, stem_beta=inorm.beta)
+        else:
+            x0 = E.Buf(self, N, H // 2, W // 2, 32, name="bn_data_s2d")
+            inorm = E.InputNorm(self, self.img, x0, "bn_data", ENC_BN_EPS)
+            E.StemConv(self, x0, z, "conv0", cin_real=CI, stem_beta=inorm.beta, init=enc_init)
         relu0 = skip_buf("relu0", N, H // 2, W // 2, 64)
         E.BNRelu(self, z, relu0, "bn0", ENC_BN_EPS)
         x = E.Buf(self, N, H // 4, W // 4, 64, name="pooling0")
@@ -264,6 +274,18 @@ class SegNet(E.Net):
         for i, f in enumerate(df):
             pre = "decoder_stage%d_" % i
             cin = cat[i]
+            if not self.dec_bn:
+                # `use_batchnorm: false` (schema segmentation.raml:173-176 -> decoder_use_batchnorm): Conv2D with bias + ReLU,
+                # no BatchNormalization; the post-ReLU output is copied 2x-upsampled into the next concat buffer
+                a1 = E.Buf(self, N, cin.h, cin.w, f, name=pre + "relu1")
+                E.Conv(self, cin, a1, pre + "conv1", 3, pad=1, bias=True, relu=True, init=dec_init)
+                a2 = E.Buf(self, N, cin.h, cin.w, f, name=pre + "relu2")
+                E.Conv(self, a1, a2, pre + "conv2", 3, pad=1, bias=True, relu=True, init=dec_init)
+                if i < 4:
+                    E.UpCopy(self, a2, cat[i + 1].slice(0, f, name=pre + "relu2_up"))
+                else:
+                    last = a2
+                continue
             z1 = E.Buf(self, N, cin.h, cin.w, f, name=pre + "conv1")
             E.Conv(self, cin, z1, pre + "conv1", 3, pad=1, init=dec_init)
             a1 = E.Buf(self, N, cin.h, cin.w, f, name=pre + "relu1")

@@ -254,12 +254,15 @@ class PipelineConfig:
             if enc_file is None:
                 raise NotImplementedError("encoder_weights: '%s' cannot be downloaded here -- give the path of a local .npz with the "
                                           "encoder's Keras-named arrays" % cand)
+        mk = self._model_kwargs(arch)
         net = _models.SegNet(bb, classes=self.classes, input_shape=tuple(self.net_shape()), batch=batch or self.batch,
                               decoder_filters=self.decoder_filters, device=self.device, seed=self.random_state,
                               architecture=arch, decoder_block_type=getattr(self, "decoder_block_type", None) or "upsampling",
-                              pyramid_block_filters=int(self.extra.get("pyramid_block_filters", 256)),
-                              segmentation_block_filters=int(self.extra.get("segmentation_block_filters", 128)),
-                              dropout=self.extra.get("dropout", None),
+                              pyramid_block_filters=int(mk.get("pyramid_block_filters") or 256),
+                              segmentation_block_filters=int(mk.get("segmentation_block_filters") or 128),
+                              dropout=mk.get("dropout") or None,
+                              decoder_use_batchnorm=bool(mk.get("use_batchnorm", True)),
+                              precision=str(self.extra.get("precision", "bf16")),
                               loss=lw)
         net.activation = self.activation or "linear"   # what predict applies to the logits
         if enc_file is not None:
@@ -269,6 +272,39 @@ class PipelineConfig:
                 raise ValueError("encoder_weights: %s holds no array of this encoder (%s, ...)" % (enc_file, sorted(layers)[:3]))
             net.set_weights(w, strict=False)
         return net
+
+    def _model_kwargs(self, arch: str) -> Dict[str, object]:
+        """The architecture's schema-typed keyword arguments (schemas/segmentation.raml:158-248) as the reference's createNet1
+        would forward them (segmentation.py:119-129), each one either honoured by the engine graph or rejected BY NAME:
+        nothing the schema types as a model argument is dropped silently."""
+        from . import schema as _schema
+        given = dict(self.extra)
+        given["decoder_filters"], given["decoder_block_type"] = list(self.decoder_filters), self.decoder_block_type
+        mk = _schema.resolve(arch, given)
+
+        def only(key, allowed, what):
+            v = mk.get(key)
+            if v is not None and v not in allowed:
+                raise NotImplementedError("%s: %r is not built for %s (%s; schema default %r)" %
+                                          (key, v, arch, what, _schema.model_keys(arch)[key][1]))
+
+        if arch == "Unet":
+            only("n_upsample_blocks", (5,), "the decoder has one block per encoder stage")
+            only("upsample_rates", ([2, 2, 2, 2, 2], (2, 2, 2, 2, 2)), "every decoder block upsamples x2")
+            if mk.get("use_batchnorm") is False and self.decoder_block_type == "transpose":
+                raise NotImplementedError("use_batchnorm / decoder_use_batchnorm: false is built for decoder_block_type: upsampling only")
+        elif arch == "FPN":
+            only("upsample_rates", ([2, 2, 2], (2, 2, 2)), "the top-down pathway upsamples x2 per level")
+            only("last_upsample", (4,), "logits are upsampled x4")
+            only("interpolation", ("bilinear",), "segmentation branches use TF1 bilinear resize")
+            only("use_batchnorm", (True,), "the FPN blocks are conv + BatchNorm + ReLU")
+            only("dropout", (0, 0.0, None), "SpatialDropout2D is not built")
+        elif arch == "Linknet":
+            only("use_batchnorm", (True,), "the Linknet blocks are conv + BatchNorm + ReLU")
+            only("n_upsample_blocks", (5,), "the decoder has one block per encoder stage")
+            only("upsample_layer", ("upsampling",), "decoder blocks use UpSampling2D")
+            only("upsample_kernel_size", ([3, 3], (3, 3)), "only used by upsample_layer: transpose")
+        return mk
 
     def kfold(self, n: int) -> List[Tuple[np.ndarray, np.ndarray]]:
         """sklearn KFold(folds_count, shuffle=True, random_state) as the reference's ImageKFoldedDataSet [DEP]."""

@@ -712,3 +712,42 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config"):
         assert k in d, k
+
+
+def test_schema_typed_model_kwargs_are_honoured_or_rejected_by_name():
+    """reference createNet1 (segmentation.py:119-129) forwards every non-custom schema property to the architecture's
+    constructor; here each such key (schemas/segmentation.raml:158-248, read by schema.py) is either built or raises naming
+    the key -- none is dropped silently (Linknet + upsample_layer: transpose used to pass)."""
+    from segmentation_training_pipeline_b200 import schema
+    from segmentation_training_pipeline_b200.segmentation import PipelineConfig
+    assert schema.architectures() == ["Unet", "FPN", "Linknet", "PSPNet", "DeepLabV3"]
+    mk = schema.model_keys("Unet")
+    assert mk["use_batchnorm"] == ("decoder_use_batchnorm", True) and mk["shape"][0] == "input_shape" and mk["backbone"][0] == "backbone_name"
+    assert "loss" not in mk and "batch" not in mk and "augmentation" not in mk      # (meta.custom) keys never reach the constructor
+    assert schema.model_keys("FPN")["last_upsample"] == ("last_upsample", 4)
+    base = dict(backbone="resnet18", classes=1, activation="sigmoid", shape=[64, 64, 3])
+    ok = PipelineConfig(architecture="Linknet", **base)._model_kwargs("Linknet")
+    assert ok["upsample_layer"] == "upsampling" and ok["use_batchnorm"] is True
+    for arch, key, val in [("Linknet", "upsample_layer", "transpose"), ("Linknet", "decoder_use_batchnorm", False),
+                           ("Linknet", "n_upsample_blocks", 4), ("Linknet", "upsample_kernel_size", [2, 2]),
+                           ("Unet", "n_upsample_blocks", 4), ("Unet", "upsample_rates", [2, 2, 2, 2, 4]),
+                           ("FPN", "interpolation", "nearest"), ("FPN", "last_upsample", 2), ("FPN", "upsample_rates", [2, 2, 4]),
+                           ("FPN", "use_batchnorm", False), ("FPN", "dropout", 0.3)]:
+        cfg = PipelineConfig(architecture=arch, **base, **{key: val})
+        name = {"decoder_use_batchnorm": "use_batchnorm"}.get(key, key)
+        with pytest.raises(NotImplementedError, match=name):
+            cfg._model_kwargs(arch)
+    # schema defaults / supported values pass; decoder_use_batchnorm: false is BUILT for the Unet upsampling decoder
+    assert PipelineConfig(architecture="Unet", **base, decoder_use_batchnorm=False)._model_kwargs("Unet")["use_batchnorm"] is False
+    assert PipelineConfig(architecture="Unet", **base, use_batchnorm=False, n_upsample_blocks=5)._model_kwargs("Unet")["use_batchnorm"] is False
+    with pytest.raises(NotImplementedError, match="use_batchnorm"):
+        PipelineConfig(architecture="Unet", **base, use_batchnorm=False, decoder_block_type="transpose")._model_kwargs("Unet")
+    assert PipelineConfig(architecture="FPN", **base, dropout=0, interpolation="bilinear")._model_kwargs("FPN")["last_upsample"] == 4
+
+
+def test_crops_build_the_network_at_cell_resolution():
+    """reference createNet1 (segmentation.py:131-132): with `crops: N` the model's input_shape is (H//N, W//N, C)."""
+    from segmentation_training_pipeline_b200.segmentation import PipelineConfig
+    cfg = PipelineConfig(architecture="Unet", backbone="resnet18", classes=1, shape=[256, 384, 3], crops=2)
+    assert cfg.net_shape() == [128, 192, 3]
+    assert PipelineConfig(architecture="Unet", shape=[256, 256, 3]).net_shape() == [256, 256, 3]

@@ -759,8 +759,8 @@ def test_lovasz_hinge_multiclass(stp, cuda):
 def test_conv_tc3_cta_pair(stp, cuda, case, force, halo):
     """tcgen05 cta_group::2 CTA-pair kernel (conv_tc3.cu) against the single-CTA halo kernel and the fp32 reference:
     odd numbers of pixel tiles (a rank idling on an out-of-range image), partial tiles, residual, fused BatchNorm
-    statistics, every (BN, MT) specialisation, dgrad through the same kernel.  halo = 1 (default): ONE haloed A box per
-    channel block, the three filter columns are 1-pixel shifted descriptor views; halo = 0: one box per filter column."""
+    statistics, every (BN, MT) specialisation, dgrad through the same kernel.  halo = 1 (option tc3_halo): ONE haloed A box per
+    channel block, the three filter columns are 1-pixel shifted descriptor views; halo = 0 (default): one box per filter column."""
     n, h, w, cin, cout = case
     fbn, fmt = force
     if fbn == 256 and cout % 256:
@@ -780,7 +780,7 @@ def test_conv_tc3_cta_pair(stp, cuda, case, force, halo):
     try:
         for mode in (1, 2):   # 1: single-CTA halo kernel, 2: CTA-pair kernel forced on
             stp.set_option(b"tc3", mode)
-            stp.set_option(b"tc3_halo", 0 if halo else 1)
+            stp.set_option(b"tc3_halo", 1 if halo else 0)
             stp.set_option(b"tc3_force_bn", fbn)
             stp.set_option(b"tc3_force_mt", fmt)
             before = stp.tc_launch_count()
