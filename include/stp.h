@@ -304,7 +304,8 @@ typedef struct stp_loss_spec {
 } stp_loss_spec;
 enum { /* indices into the f32 result vector (16 floats) */
   STP_L_LOSS = 0, STP_L_BCE = 1, STP_L_DICE = 2, STP_L_IOU = 3, STP_L_ACC = 4, STP_L_IOT = 5,
-  STP_L_SUM_P = 6, STP_L_SUM_T = 7, STP_L_SUM_PT = 8, STP_L_COUNT = 9, STP_L_LOVASZ = 10, STP_L_JACCARD = 11, STP_L_FOCAL = 12
+  STP_L_SUM_P = 6, STP_L_SUM_T = 7, STP_L_SUM_PT = 8, STP_L_COUNT = 9, STP_L_LOVASZ = 10, STP_L_JACCARD = 11, STP_L_FOCAL = 12,
+  STP_L_CCE = 13, STP_L_CACC = 14 /* categorical_crossentropy / categorical accuracy (stp_softmax_cce_fwd) */
 };
 int stp_loss_fwd(const float* logits, const uint8_t* mask, int64_t count, const stp_loss_spec* h_spec,
                  float* partial, float* result16, stp_stream stream);
@@ -312,6 +313,17 @@ size_t stp_loss_partial_floats(void);
 /* dlogits f32 [count] = dL/dlogit using the sums in result16 */
 int stp_loss_bwd(const float* logits, const uint8_t* mask, int64_t count, const stp_loss_spec* h_spec,
                  const float* result16, float* dlogits, stp_stream stream);
+
+/* `activation: softmax` + `loss: categorical_crossentropy` (schema segmentation.raml:12-21, 62-63): keras categorical_crossentropy
+ * on probabilities [DEP]: p = softmax(logits); p /= sum(p); clip(p, 1e-7, 1-1e-7); -sum_c t_c log p_c; mean over pixels.
+ * logits f32 [pixels][classes], mask u8 [pixels][classes] (one-hot or multi-hot), 2 <= classes <= 4.  fwd writes
+ * result16[STP_L_CCE], result16[STP_L_CACC] (argmax agreement) and result16[STP_L_LOSS] (+)= weight * cce (run it AFTER
+ * stp_loss_fwd, which fills the other slots); partial: stp_loss_partial_floats() floats.  bwd writes (accumulate: adds)
+ * weight * dL/dlogit. */
+int stp_softmax_cce_fwd(const float* logits, const uint8_t* mask, int64_t pixels, int32_t classes, float weight,
+                        int32_t accumulate, float* partial, float* result16, stp_stream stream);
+int stp_softmax_cce_bwd(const float* logits, const uint8_t* mask, int64_t pixels, int32_t classes, float weight,
+                        int32_t accumulate, float* dlogits, stp_stream stream);
 
 /* Lovasz hinge (binary, per image, on LOGITS; musket_core.losses.lovasz_loss -- the reference strips the trailing
  * Activation when this loss is compiled).  act_elu: 1 = elu(e)+1 (Kaggle-TGS variant), 0 = relu (Berman).  fwd sorts the

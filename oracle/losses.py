@@ -61,13 +61,19 @@ def jaccard_loss(y_true, y_pred, smooth=100.0):
     return ((1 - jac) * smooth).mean()
 
 
-def focal_loss(y_true, y_pred, gamma=2.0, alpha=0.75):
+def focal_loss(y_true, y_pred, gamma=2.0, alpha=0.75, reduction="mean"):
+    """musket_core.losses.focal_loss [DEP, unpinned].  reduction: "mean" (TAKEN by the engine and by lookup("focal_loss"):
+    Keras reduces a per-pixel loss by mean, consistent with every other loss here) or "sum" (the Keras-RetinaNet-style
+    K.sum() form some musket_core versions use: same gradient direction, scaled by the element count) -- the doubtful [DEP]
+    choice is this named flag."""
     p = torch.clamp(y_pred, EPS, 1 - EPS)
     pt1 = torch.where(y_true == 1, p, torch.ones_like(p))
     pt0 = torch.where(y_true == 0, p, torch.zeros_like(p))
-    # musket_core (Keras RetinaNet-style) sums rather than means [DEP]; keep the mean-normalised form
-    # behind a flag so the choice is visible (README states which was taken).
     l = -(alpha * (1 - pt1) ** gamma * torch.log(pt1)) - ((1 - alpha) * pt0 ** gamma * torch.log(1 - pt0))
+    if reduction == "sum":
+        return l.sum()
+    if reduction != "mean":
+        raise ValueError("reduction must be 'mean' or 'sum'")
     return l.mean(dim=-1).mean()
 
 

@@ -112,7 +112,8 @@ class SegModel:
             if self.update_moving:
                 with torch.no_grad():
                     m = x.numel() // x.shape[1]
-                    unbiased = var * (m / max(m - 1, 1))
+                    # keras 2.2.x normalization.py: variance *= sample_size / (sample_size - (1.0 + epsilon))
+                    unbiased = var * (m / (m - (1.0 + eps))) if m > 1 else var
                     mm, mv = self.P.buffers[name + "/moving_mean"], self.P.buffers[name + "/moving_variance"]
                     mm.mul_(BN_MOMENTUM).add_(mean.detach() * (1 - BN_MOMENTUM))
                     mv.mul_(BN_MOMENTUM).add_(unbiased.detach() * (1 - BN_MOMENTUM))

@@ -142,7 +142,7 @@ static int conv_fwd_common(const stp_conv_desc* d, const stp_tensor* x, const vo
     bn.acc = h_bn->acc;
     bn.fin = FinArgs{};
     bn.fin.mode = 1; bn.fin.sync = h_bn->sync; bn.fin.inv_count = 1.0 / (double)count;
-    bn.fin.bessel = count > 1 ? (double)count / (double)(count - 1) : 1.0;
+    bn.fin.bessel = keras_bessel(count, h_bn->eps);
     bn.fin.gamma = h_bn->gamma; bn.fin.beta = h_bn->beta; bn.fin.eps = h_bn->eps; bn.fin.momentum = h_bn->momentum;
     bn.fin.mov_mean = h_bn->moving_mean; bn.fin.mov_var = h_bn->moving_var; bn.fin.coef = h_bn->coef;
     p.bn = &bn;

@@ -674,7 +674,7 @@ extern "C" int stp_bn_stats_fused(const stp_tensor* x, float* partial, uint32_t*
   STP_REQUIRE(count > 0, "bn_stats_fused: empty tensor");
   FinArgs fin = {};
   fin.mode = 1; fin.sync = sync; fin.acc = acc; fin.inv_count = 1.0 / (double)count;
-  fin.bessel = count > 1 ? (double)count / (double)(count - 1) : 1.0;
+  fin.bessel = keras_bessel(count, eps);
   fin.gamma = gamma; fin.beta = beta; fin.eps = eps; fin.momentum = momentum;
   fin.mov_mean = moving_mean; fin.mov_var = moving_var; fin.coef = coef;
   return launch_stats(x, partial, fin, (cudaStream_t)stream);
@@ -692,7 +692,7 @@ extern "C" int stp_bn_finalize(const float* partial, int32_t nblk, int32_t c, in
                                const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
                                float* coef, stp_stream stream) {
   STP_REQUIRE(partial && coef && nblk > 0 && c > 0 && count > 0, "bn_finalize: bad args");
-  double bessel = count > 1 ? (double)count / (double)(count - 1) : 1.0;
+  double bessel = keras_bessel(count, eps);
   bn_finalize_kernel<<<(c + kFinCh - 1) / kFinCh, dim3(kFinCh, kFinGroups), 0, (cudaStream_t)stream>>>(partial, nblk, c, 1.0 / (double)count, bessel,
                                                                          gamma, beta, eps, momentum, moving_mean,
                                                                          moving_var, coef);

@@ -24,6 +24,13 @@ struct FinArgs {
   float* bcoef;
 };
 
+// keras.layers.BatchNormalization (2.2.x, normalization.py) turns the biased batch variance into the moving-average update with
+//   variance *= sample_size / (sample_size - (1.0 + epsilon))
+// -- Bessel's correction with the layer's epsilon in the denominator [DEP keras>=2.2.4].
+inline double keras_bessel(int64_t count, float eps) {
+  return count > 1 ? (double)count / ((double)count - (1.0 + (double)eps)) : 1.0;
+}
+
 __device__ __forceinline__ void fin_forward(const FinArgs& f, int C, int c, double s, double ss) {
   double mean = s * f.inv_count;
   double var = ss * f.inv_count - mean * mean;

@@ -5,7 +5,8 @@
 // noise that training dynamics amplify to ~1e-2 (tests/test_gpu_model.py::test_loss_curve_100_steps_fp32_parity_mode).
 //
 // Semantics are those of the bf16 kernels they shadow (same formulas, keras.layers semantics per SURVEY.md Appendix B);
-// reductions run in double, convolutions accumulate each output in ONE thread in a fixed k order (deterministic).
+// reductions and convolution accumulators run in double; each conv output is summed by ONE thread in a fixed k order
+// (deterministic).
 #include "bn_fin.cuh"
 #include "common.cuh"
 #include "f32_path.h"
@@ -71,11 +72,13 @@ __global__ void __launch_bounds__(256) conv_kernel(const ConvF p) {
     hi0[j] = ho * p.stride - p.pad_h;
     wi0[j] = wo * p.stride - p.pad_w;
   }
-  float acc[4][4];
+  // fp32 operands, products and sums in DOUBLE (DFMA): a K = 4608 dot product then carries one final rounding instead of
+  // ~sqrt(K) fp32 ones -- the parity mode's job is to sit as close to exact arithmetic as the fp32 storage allows
+  double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
   for (int k0 = 0; k0 < p.K; k0 += TK) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(256) conv_kernel(const ConvF p) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma((double)a[i], (double)b[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(256) conv_kernel(const ConvF p) {
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= p.Cout) continue;
-      float v = acc[i][j];
+      float v = (float)acc[i][j];
       if (p.bias) v += p.bias[n];
       if (p.res) v += p.res[m * p.ldr + n];
       if (p.relu) v = fmaxf(v, 0.f);
@@ -124,11 +127,11 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const ConvF p, const float* 
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int co0 = blockIdx.x * TM, k0 = blockIdx.y * TN;
-  float acc[4][4];
+  double acc[4][4];   // sums over up to millions of pixels: double accumulation (see conv_kernel)
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
   for (int64_t mb = 0; mb < p.M; mb += TK) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const ConvF p, const float* 
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma((double)a[i], (double)b[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const ConvF p, const float* 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int k = k0 + tx * 4 + j;
-      if (k < p.K) dw[(int64_t)co * p.K + k] = acc[i][j];
+      if (k < p.K) dw[(int64_t)co * p.K + k] = (float)acc[i][j];
     }
   }
 }

@@ -101,26 +101,39 @@ __global__ void __launch_bounds__(256) head_dgrad1_kernel(const float* __restric
   const int m_begin = blockIdx.x * pix_per_blk;
   int m_end = m_begin + pix_per_blk;
   if (m_end > M) m_end = M;
-  for (int m = m_begin + pl; m < m_end; m += ppi) {
-    unsigned n = (unsigned)m / (unsigned)(H * W);
-    unsigned rem = (unsigned)m - n * (unsigned)(H * W);
-    int h = (int)(rem / (unsigned)W), wq = (int)(rem - (unsigned)h * (unsigned)W);
-    float acc[8];
+  // U pixels per iteration: their 9 dlogit loads each are independent, so U*9 loads are in flight per thread instead of 9
+  constexpr int U = 4;
+  for (int m0 = m_begin + pl; m0 < m_end; m0 += U * ppi) {
+    float g[U][9];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int m = m0 + u * ppi;
+      const unsigned n = (unsigned)m / (unsigned)(H * W);
+      const unsigned rem = (unsigned)m - n * (unsigned)(H * W);
+      const int h = (int)(rem / (unsigned)W), wq = (int)(rem - (unsigned)h * (unsigned)W);
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int ho = h - (r - 1);
+      for (int r = 0; r < 3; ++r) {
+        const int ho = h - (r - 1);
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int wo = wq - (s - 1);
-        float g = 0.f;
-        if (ho >= 0 && ho < H && wo >= 0 && wo < W) g = __ldg(dl + ((int64_t)n * H + ho) * W + wo);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += g * wr[r * 3 + s][k];
+        for (int s = 0; s < 3; ++s) {
+          const int wo = wq - (s - 1);
+          g[u][r * 3 + s] = (m < m_end && ho >= 0 && ho < H && wo >= 0 && wo < W) ? __ldg(dl + ((int64_t)n * H + ho) * W + wo) : 0.f;
+        }
       }
     }
-    st8(dx + (int64_t)m * lddx + v * 8, pack8(acc));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int m = m0 + u * ppi;
+      if (m >= m_end) break;
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += g[u][t] * wr[t][k];
+      st8(dx + (int64_t)m * lddx + v * 8, pack8(acc));
+    }
   }
 }
 
@@ -152,24 +165,43 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const __nv_bfloat16* __
   const int m_begin = blockIdx.x * pix_per_blk;
   int m_end = m_begin + pix_per_blk;
   if (m_end > M) m_end = M;
-  for (int p = m_begin + pl; p < m_end; p += lanes) {
-    const unsigned n = (unsigned)p / (unsigned)(H * W);
-    const unsigned rem = (unsigned)p - n * (unsigned)(H * W);
-    const int h = (int)(rem / (unsigned)W), wq = (int)(rem - (unsigned)h * (unsigned)W);
-    float f[8];
-    unpack8(ld8(x + (int64_t)p * ldx + v * 8), f);
-    if (v == 0) bsum += dl[(int64_t)p * classes + cls];
+  // U pixels per iteration: U independent 16-byte activation loads (+ 9 L1-resident dlogit loads each) in flight per thread;
+  // the accumulation order over a thread's pixels is unchanged (u = 0..U-1 in sequence) -> same partial sums as before
+  constexpr int U = 4;
+  for (int p0 = m_begin + pl; p0 < m_end; p0 += U * lanes) {
+    bf16x8 q[U];
+    float g[U][9];
+    float gb[U];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int ho = h - (r - 1);
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * lanes;
+      const bool ok = p < m_end;
+      if (ok) q[u] = ld8(x + (int64_t)p * ldx + v * 8);
+      const unsigned n = (unsigned)p / (unsigned)(H * W);
+      const unsigned rem = (unsigned)p - n * (unsigned)(H * W);
+      const int h = (int)(rem / (unsigned)W), wq = (int)(rem - (unsigned)h * (unsigned)W);
+      gb[u] = (ok && v == 0) ? dl[(int64_t)p * classes + cls] : 0.f;
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int wo = wq - (s - 1);
-        float g = 0.f;
-        if (ho >= 0 && ho < H && wo >= 0 && wo < W) g = __ldg(dl + (((int64_t)n * H + ho) * W + wo) * classes + cls);
+      for (int r = 0; r < 3; ++r) {
+        const int ho = h - (r - 1);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[r * 3 + s][k] += f[k] * g;
+        for (int s = 0; s < 3; ++s) {
+          const int wo = wq - (s - 1);
+          g[u][r * 3 + s] = (ok && ho >= 0 && ho < H && wo >= 0 && wo < W)
+                                ? __ldg(dl + (((int64_t)n * H + ho) * W + wo) * classes + cls) : 0.f;
+        }
       }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (p0 + u * lanes >= m_end) break;
+      float f[8];
+      unpack8(q[u], f);
+      bsum += gb[u];
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[t][k] += f[k] * g[u][t];
     }
   }
   // lanes l, l^cv, l^2cv ... of a warp hold the same vector

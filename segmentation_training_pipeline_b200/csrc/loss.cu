@@ -127,9 +127,147 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
   }
 }
 
+// ---- softmax + categorical_crossentropy (schema segmentation.raml:12-21 `categorical_crossentropy`, :62-63 `activation: softmax`)
+// keras.losses.categorical_crossentropy on PROBABILITIES with the TF backend [DEP]: p = softmax(z); p /= sum(p); p = clip(p,
+// eps, 1-eps); l = -sum_c t_c*log(p_c); mean over pixels.  Also the categorical accuracy (argmax match, first maximum wins).
+constexpr int kMaxCls = 4;
+template <int C>
+__device__ __forceinline__ void softmax_c(const float* __restrict__ z, float* p) {
+  float m = z[0];
+#pragma unroll
+  for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    p[c] = expf(z[c] - m);
+    s += p[c];
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) p[c] /= s;
+}
+template <int C>
+__global__ void __launch_bounds__(256) cce_fwd_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ mask, int64_t M,
+                                                      float* __restrict__ partial) {
+  const float eps = 1e-7f;
+  float s0 = 0.f, s1 = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+    float p[C];
+    softmax_c<C>(logits + i * C, p);
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) sum += p[c];
+    float l = 0.f;
+    int ap = 0, at = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float t = (float)mask[i * C + c];
+      const float q = fminf(fmaxf(p[c] / sum, eps), 1.f - eps);
+      l -= t * logf(q);
+      if (p[c] > p[ap]) ap = c;
+      if (mask[i * C + c] > mask[i * C + at]) at = c;
+    }
+    s0 += l;
+    s1 += ap == at ? 1.f : 0.f;
+  }
+  __shared__ float sm[2][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  if (lane == 0) {
+    sm[0][warp] = s0;
+    sm[1][warp] = s1;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += sm[threadIdx.x][w];
+    partial[(int64_t)blockIdx.x * 2 + threadIdx.x] = a;
+  }
+}
+__global__ void __launch_bounds__(64) cce_finalize_kernel(const float* __restrict__ partial, int nblk, double count, float weight,
+                                                          int accumulate, float* __restrict__ result) {
+  __shared__ double tot[2];
+  const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double a = 0.0;
+  for (int b = lane; b < nblk; b += 32) a += (double)partial[(int64_t)b * 2 + slot];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) tot[slot] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float cce = (float)(tot[0] / count);
+    result[STP_L_CCE] = cce;
+    result[STP_L_CACC] = (float)(tot[1] / count);
+    result[STP_L_LOSS] = (accumulate ? result[STP_L_LOSS] : 0.f) + weight * cce;
+  }
+}
+template <int C>
+__global__ void __launch_bounds__(256) cce_bwd_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ mask, int64_t M,
+                                                      float scale, int accumulate, float* __restrict__ dlogits) {
+  const float eps = 1e-7f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+    float p[C], dq[C], dp[C];
+    softmax_c<C>(logits + i * C, p);
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) sum += p[c];
+    // l = -sum_c t_c log(clip(p_c / sum)):  dl/dq_c = -t_c / q_c inside the clip range, 0 outside
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float q = p[c] / sum;
+      dq[c] = (q > eps && q < 1.f - eps) ? -(float)mask[i * C + c] / q : 0.f;
+      dot += dq[c] * p[c];
+    }
+    // q_c = p_c / sum:  dl/dp_k = dq_k / sum - dot / sum^2
+    float dot2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      dp[c] = dq[c] / sum - dot / (sum * sum);
+      dot2 += dp[c] * p[c];
+    }
+    // softmax:  dl/dz_j = p_j (dp_j - sum_k p_k dp_k)
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float g = scale * p[c] * (dp[c] - dot2);
+      dlogits[i * C + c] = accumulate ? dlogits[i * C + c] + g : g;
+    }
+  }
+}
+
 }  // namespace stp
 
 using namespace stp;
+
+extern "C" int stp_softmax_cce_fwd(const float* logits, const uint8_t* mask, int64_t pixels, int32_t classes, float weight,
+                                   int32_t accumulate, float* partial, float* result16, stp_stream stream) {
+  STP_REQUIRE(logits && mask && partial && result16 && pixels > 0, "softmax_cce_fwd: bad args");
+  STP_REQUIRE(classes >= 2 && classes <= kMaxCls, "softmax_cce_fwd: 2 <= classes <= 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nb = (pixels + 255) / 256;
+  const int nblk = (int)(nb < kLossBlocks ? nb : kLossBlocks);
+  if (classes == 2) cce_fwd_kernel<2><<<nblk, 256, 0, st>>>(logits, mask, pixels, partial);
+  else if (classes == 3) cce_fwd_kernel<3><<<nblk, 256, 0, st>>>(logits, mask, pixels, partial);
+  else cce_fwd_kernel<4><<<nblk, 256, 0, st>>>(logits, mask, pixels, partial);
+  int rc = check_launch("softmax_cce_fwd");
+  if (rc) return rc;
+  cce_finalize_kernel<<<1, 64, 0, st>>>(partial, nblk, (double)pixels, weight, accumulate, result16);
+  return check_launch("softmax_cce_finalize");
+}
+
+extern "C" int stp_softmax_cce_bwd(const float* logits, const uint8_t* mask, int64_t pixels, int32_t classes, float weight,
+                                   int32_t accumulate, float* dlogits, stp_stream stream) {
+  STP_REQUIRE(logits && mask && dlogits && pixels > 0, "softmax_cce_bwd: bad args");
+  STP_REQUIRE(classes >= 2 && classes <= kMaxCls, "softmax_cce_bwd: 2 <= classes <= 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nb = (pixels + 255) / 256;
+  const int nblk = (int)(nb < kLossBlocks ? nb : kLossBlocks);
+  const float scale = weight / (float)pixels;
+  if (classes == 2) cce_bwd_kernel<2><<<nblk, 256, 0, st>>>(logits, mask, pixels, scale, accumulate, dlogits);
+  else if (classes == 3) cce_bwd_kernel<3><<<nblk, 256, 0, st>>>(logits, mask, pixels, scale, accumulate, dlogits);
+  else cce_bwd_kernel<4><<<nblk, 256, 0, st>>>(logits, mask, pixels, scale, accumulate, dlogits);
+  return check_launch("softmax_cce_bwd");
+}
 
 extern "C" size_t stp_loss_partial_floats(void) { return (size_t)kLossBlocks * kLossSlots; }
 

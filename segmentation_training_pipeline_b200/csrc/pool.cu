@@ -115,64 +115,70 @@ __global__ void __launch_bounds__(256) maxpool_bwd_k3s2_kernel(const __nv_bfloat
   const int m_begin = blockIdx.x * pix_per_blk;
   int m_end = m_begin + pix_per_blk;
   if (m_end > rows_in) m_end = rows_in;
-  for (int m = m_begin + pl; m < m_end; m += ppi) {
-    const unsigned n = (unsigned)m / (unsigned)(H * W);
-    const unsigned rem = (unsigned)m - n * (unsigned)(H * W);
-    const int h = (int)(rem / (unsigned)W), w = (int)(rem - (unsigned)h * (unsigned)W);
-    // window candidates: (ho, row offset a) and (wo, column offset b)
-    int hos[2], as[2], nh = 0, wos[2], bs[2], nw = 0;
-    if (h & 1) {
-      hos[nh] = h >> 1; as[nh++] = 2;
-      if ((h >> 1) + 1 < Ho) { hos[nh] = (h >> 1) + 1; as[nh++] = 0; }
-    } else {
-      hos[nh] = h >> 1; as[nh++] = 1;
-    }
-    if (w & 1) {
-      wos[nw] = w >> 1; bs[nw++] = 2;
-      if ((w >> 1) + 1 < Wo) { wos[nw] = (w >> 1) + 1; bs[nw++] = 0; }
-    } else {
-      wos[nw] = w >> 1; bs[nw++] = 1;
-    }
-    uint2 pk[4];
-    bf16x8 gq[4];
-    int idx[4], cnt = 0;
+  // U pixels per iteration, all indices compile-time (registers, no local-memory arrays): up to U*4 argmax words + dy vectors
+  // (+ U residual vectors) are in flight per thread before the first use
+  constexpr int U = 2;
+  for (int m0 = m_begin + pl; m0 < m_end; m0 += U * ppi) {
+    uint2 pk[U][4];
+    bf16x8 gq[U][4], rq[U];
+    int idx[U][4];
+    bool ok[U][4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int u = 0; u < U; ++u) {
+      const int m = m0 + u * ppi;
+      const bool live = m < m_end;
+      const unsigned n = (unsigned)m / (unsigned)(H * W);
+      const unsigned rem = (unsigned)m - n * (unsigned)(H * W);
+      const int h = (int)(rem / (unsigned)W), w = (int)(rem - (unsigned)h * (unsigned)W);
+      // window candidates: an even row is covered by one window (offset 1), an odd row by two (offsets 2 and 0)
+      const int ho0 = h >> 1, a0 = (h & 1) ? 2 : 1, ho1 = (h >> 1) + 1;
+      const bool vh1 = (h & 1) && ho1 < Ho;
+      const int wo0 = w >> 1, b0 = (w & 1) ? 2 : 1, wo1 = (w >> 1) + 1;
+      const bool vw1 = (w & 1) && wo1 < Wo;
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
-        if (i < nh && j < nw && hos[i] < Ho && wos[j] < Wo) {
-          const int64_t ro = ((int64_t)n * Ho + hos[i]) * Wo + wos[j];
-          pk[cnt] = *reinterpret_cast<const uint2*>(argmax + ro * C + v * 8);
-          gq[cnt] = ld8(dy + ro * lddy + v * 8);
-          idx[cnt] = as[i] * 3 + bs[j];
-          ++cnt;
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int ho = i ? ho1 : ho0, wo = j ? wo1 : wo0;
+          const bool valid = live && (i ? vh1 : ho0 < Ho) && (j ? vw1 : wo0 < Wo);
+          ok[u][i * 2 + j] = valid;
+          idx[u][i * 2 + j] = (i ? 0 : a0) * 3 + (j ? 0 : b0);
+          if (valid) {
+            const int64_t ro = ((int64_t)n * Ho + ho) * Wo + wo;
+            pk[u][i * 2 + j] = *reinterpret_cast<const uint2*>(argmax + ro * C + v * 8);
+            gq[u][i * 2 + j] = ld8(dy + ro * lddy + v * 8);
+          }
         }
-    bf16x8 rq;
-    if (res) rq = ld8(res + (int64_t)m * ldr + v * 8);
-    float acc[8];
+      if (res && live) rq[u] = ld8(res + (int64_t)m * ldr + v * 8);
+    }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int m = m0 + u * ppi;
+      if (m >= m_end) break;
+      float acc[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (q < cnt) {
-        float g[8];
-        unpack8(gq[q], g);
+      for (int c = 0; c < 8; ++c) acc[c] = 0.f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t word = c < 4 ? pk[q].x : pk[q].y;
-          if ((int)((word >> (8 * (c & 3))) & 0xff) == idx[q]) acc[c] += g[c];
+      for (int q = 0; q < 4; ++q)
+        if (ok[u][q]) {
+          float g[8];
+          unpack8(gq[u][q], g);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t word = c < 4 ? pk[u][q].x : pk[u][q].y;
+            if ((int)((word >> (8 * (c & 3))) & 0xff) == idx[u][q]) acc[c] += g[c];
+          }
         }
+      if (res) {
+        float rf[8];
+        unpack8(rq[u], rf);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] += rf[c];
       }
-    if (res) {
-      float rf[8];
-      unpack8(rq, rf);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) acc[c] += rf[c];
+      st8(dx + (int64_t)m * lddx + v * 8, pack8(acc));
     }
-    st8(dx + (int64_t)m * lddx + v * 8, pack8(acc));
   }
 }
-
 static int ew_grid2(int64_t total) {
   int64_t b = (total + 255) / 256;
   int64_t cap = (int64_t)kNumSMs * 16;

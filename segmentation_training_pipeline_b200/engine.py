@@ -27,6 +27,12 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# Critical-path experiments ONLY (results are invalid): STP_SKIP="wgrad,bn_apply,bn_bwd_reduce,bn_bwd_apply,dgrad,conv_fwd"
+# drops whole kernel categories from the step so that scripts/knockout.py can measure how much of the captured step each
+# category actually costs once overlap (side-stream weight gradients, PDL) is accounted for.
+_SKIP = set(filter(None, os.environ.get("STP_SKIP", "").split(",")))
+
+
 class Buf:
     """NHWC device tensor, possibly a channel slice [c_off, c_off+c) of a wider root buffer (ld = root.c)."""
 
@@ -495,6 +501,8 @@ class Conv(Op):
 
     def fwd(self):
         n = self.net
+        if "conv_fwd" in _SKIP:
+            return
         if self.bn_next is not None and n.training:
             n.L.conv_fwd_bn(self.dref, self.x.ref, n.pwf(self.w), n.pp(self.b) if self.b else None, self.res_ref,
                             self.y.ref, self.bn_next.bn_fwd_struct(), n.ws.data_ptr(), n.ws.numel(), _stream())
@@ -511,13 +519,14 @@ class Conv(Op):
             n.L.bias_grad(self.dy.ref, n.partial.data_ptr(), n.sync.data_ptr(), n.bn_acc.data_ptr(), n.pg(self.b), _stream())
         with n.wgrad_stream() as ws:  # forked first: the wgrad overlaps this layer's dgrad and the BatchNorm backward below
             st = _stream()
-            n.L.conv_wgrad(self.dref, self.x.ref, self.dy.ref, n.pg(self.w), ws.data_ptr(), ws.numel(), st)
+            if "wgrad" not in _SKIP:
+                n.L.conv_wgrad(self.dref, self.x.ref, self.dy.ref, n.pg(self.w), ws.data_ptr(), ws.numel(), st)
             if self.stem_beta is not None or self.cin_real < self.w.shape[3]:
                 c = self.w.shape
                 # (parity mode passes -R: d(beta) is then formed with the fp32 weights instead of their bf16 rounding)
                 n.L.stem_wgrad_post(n.pg(self.w), n.pp(self.w), c[0], -c[1] if n.precision == "fp32" else c[1], c[2], c[3],
                                     self.cin_real, n.pg(self.stem_beta) if self.stem_beta is not None else None, st)
-        if self.needs_dgrad:
+        if self.needs_dgrad and "dgrad" not in _SKIP:
             if self.bnb_prev is not None and self.dx_res is None:
                 n.L.conv_dgrad_bn(self.dref, self.dy.ref, n.pwd(self.w), self.dx.ref, self.bnb_prev.bn_bwd_struct(),
                                   n.ws.data_ptr(), n.ws.numel(), _stream())
@@ -644,17 +653,21 @@ class BNRelu(Op):
         else:
             L.bn_coef_infer(n.pp(self.gamma), n.pp(self.beta), self.mm.data_ptr(), self.mv.data_ptr(), self.eps, c,
                             self.coef.data_ptr(), st)
-        L.bn_apply(self.x.ref, self.coef.data_ptr(), int(self.relu), self.up, self.y.ref, st)
+        if "bn_apply" not in _SKIP:
+            L.bn_apply(self.x.ref, self.coef.data_ptr(), int(self.relu), self.up, self.y.ref, st)
 
     def bwd(self):
         n, L, st = self.net, self.net.L, _stream()
         c = self.x.c
-        if not self.reduce_from_dgrad:
+        if "bn_bwd_apply" in _SKIP and "bn_bwd_reduce" in _SKIP:
+            return
+        if not self.reduce_from_dgrad and "bn_bwd_reduce" not in _SKIP:
             L.bn_bwd_reduce_fused(self.dy.ref, self.x.ref, self.coef.data_ptr(), int(self.relu), self.up,
                                   n.partial.data_ptr(), n.sync.data_ptr(), n.bn_acc.data_ptr(), n.pg(self.gamma), n.pg(self.beta),
                                   self.bcoef.data_ptr(), st)
-        L.bn_bwd_apply(self.dy.ref, self.x.ref, self.coef.data_ptr(), self.bcoef.data_ptr(), int(self.relu), self.up,
-                       self.res_ref, self.dx.ref, st)
+        if "bn_bwd_apply" not in _SKIP:
+            L.bn_bwd_apply(self.dy.ref, self.x.ref, self.coef.data_ptr(), self.bcoef.data_ptr(), int(self.relu), self.up,
+                           self.res_ref, self.dx.ref, st)
 
 
 class Add(Op):
@@ -850,7 +863,7 @@ class Loss(Op):
     w_lovasz*lovasz_loss on the logits (the reference's compile strips the final Activation for it)."""
 
     def __init__(self, net: Net, head: Head, mask: Buf, w_bce=1.0, w_dice=0.0, w_iou=0.0, w_lovasz=0.0, w_jaccard=0.0,
-                 w_focal=0.0, lovasz_act="elu"):
+                 w_focal=0.0, w_cce=0.0, lovasz_act="elu"):
         self.net, self.head, self.mask = net, head, mask
         self.result = torch.zeros(16, dtype=torch.float32, device=net.device)
         self.lpartial = torch.zeros(net.L.loss_partial_floats(), dtype=torch.float32, device=net.device)
@@ -858,15 +871,18 @@ class Loss(Op):
         self.enabled = True
         self.lov_ws: Optional[torch.Tensor] = None
         self.lovasz_act = lovasz_act
-        self.set_weights(w_bce, w_dice, w_iou, w_lovasz, w_jaccard, w_focal)
+        self.set_weights(w_bce, w_dice, w_iou, w_lovasz, w_jaccard, w_focal, w_cce)
         net.ops.append(self)
 
     def prepare(self):
         pass
 
-    def set_weights(self, w_bce, w_dice, w_iou, w_lovasz=0.0, w_jaccard=0.0, w_focal=0.0):
+    def set_weights(self, w_bce, w_dice, w_iou, w_lovasz=0.0, w_jaccard=0.0, w_focal=0.0, w_cce=0.0):
         self.spec = _lib.LossSpec(w_bce, w_dice, w_iou, w_jaccard, w_focal)
         self.w_lovasz = float(w_lovasz)
+        self.w_cce = float(w_cce)   # categorical_crossentropy on softmax probabilities (stp_softmax_cce_fwd)
+        if self.w_cce != 0.0 and self.head.classes < 2:
+            raise ValueError("categorical_crossentropy needs classes >= 2")
         if self.w_lovasz != 0.0:
             # classes > 1: the reference's K.squeeze(..., -1) is undefined; one hinge per (image, class), averaged
             # (oracle/losses.py lovasz_loss)
@@ -884,6 +900,9 @@ class Loss(Op):
                 L.lovasz_fwd_mc(self.head.logits.data_ptr(), self.mask.storage.data_ptr(), h.out_n, h.out_hw, h.classes,
                                 int(self.lovasz_act == "elu"), self.w_lovasz, 1, self.lov_ws.data_ptr(),
                                 self.lov_ws.numel(), self.result.data_ptr(), _stream())
+            if self.w_cce != 0.0:
+                L.softmax_cce_fwd(self.head.logits.data_ptr(), self.mask.storage.data_ptr(), h.out_n * h.out_hw, h.classes,
+                                  self.w_cce, 1, self.lpartial.data_ptr(), self.result.data_ptr(), _stream())
 
     def bwd(self):
         L, h = self.net.L, self.head
@@ -892,3 +911,6 @@ class Loss(Op):
         if self.w_lovasz != 0.0:
             L.lovasz_bwd(self.lov_ws.data_ptr(), self.lov_ws.numel(), h.out_n * h.classes, h.out_hw, self.w_lovasz, 1,
                          self.head.dlogits.data_ptr(), _stream())
+        if self.w_cce != 0.0:
+            L.softmax_cce_bwd(self.head.logits.data_ptr(), self.mask.storage.data_ptr(), h.out_n * h.out_hw, h.classes,
+                              self.w_cce, 1, self.head.dlogits.data_ptr(), _stream())

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libstp.so")
 BF16, F32, U8 = 0, 1, 2
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_WORKSPACE = 0, -1, -2, -3, -4
 CONV_RELU, CONV_STATS = 1, 2
-L_LOSS, L_BCE, L_DICE, L_IOU, L_ACC, L_IOT, L_SUM_P, L_SUM_T, L_SUM_PT, L_COUNT, L_LOVASZ, L_JACCARD, L_FOCAL = range(13)
+L_LOSS, L_BCE, L_DICE, L_IOU, L_ACC, L_IOT, L_SUM_P, L_SUM_T, L_SUM_PT, L_COUNT, L_LOVASZ, L_JACCARD, L_FOCAL, L_CCE, L_CACC = range(15)
 BN_MAX_PARTIALS = 1024
 
 
@@ -127,6 +127,8 @@ SIGNATURES = {
     "stp_loss_fwd": (C.c_int, [_P, _P, _I64, C.POINTER(LossSpec), _P, _P, _P]),
     "stp_loss_partial_floats": (_SZ, []),
     "stp_loss_bwd": (C.c_int, [_P, _P, _I64, C.POINTER(LossSpec), _P, _P, _P]),
+    "stp_softmax_cce_fwd": (C.c_int, [_P, _P, _I64, _I32, _F, _I32, _P, _P, _P]),
+    "stp_softmax_cce_bwd": (C.c_int, [_P, _P, _I64, _I32, _F, _I32, _P, _P]),
     "stp_lovasz_workspace": (_SZ, [_I32, _I64]),
     "stp_lovasz_fwd": (C.c_int, [_P, _P, _I32, _I64, _I32, _F, _I32, _P, _SZ, _P, _P]),
     "stp_lovasz_fwd_mc": (C.c_int, [_P, _P, _I32, _I64, _I32, _I32, _F, _I32, _P, _SZ, _P, _P]),

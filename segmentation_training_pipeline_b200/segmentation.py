@@ -43,10 +43,13 @@ def ansemblePredictions(sourceFolder, folders, cb, data, weights=None):
     return ansemble_predictions(sourceFolder, folders, cb, data, weights)
 dataset_augmenters: Dict[str, Callable] = {}
 
-_LOSS_TERMS = {"binary_crossentropy": 0, "dice_loss": 1, "iou_loss": 2, "lovasz_loss": 3, "jaccard_loss": 4, "focal_loss": 5}
-_UNFUSED_LOSSES = ("categorical_crossentropy",)
+_LOSS_TERMS = {"binary_crossentropy": 0, "dice_loss": 1, "iou_loss": 2, "lovasz_loss": 3, "jaccard_loss": 4, "focal_loss": 5,
+               "categorical_crossentropy": 6}
+_UNFUSED_LOSSES = ()
 _METRIC_ALIASES = {"binary_accuracy": "binary_accuracy", "dice": "dice", "iou": "iou", "iou_coef": "iou", "iot": "iot",
-                   "iot_coef": "iot", "loss": "loss", "binary_crossentropy": "binary_crossentropy"}
+                   "iot_coef": "iot", "loss": "loss", "binary_crossentropy": "binary_crossentropy",
+                   "categorical_crossentropy": "categorical_crossentropy", "categorical_accuracy": "categorical_accuracy",
+                   "accuracy": "categorical_accuracy", "acc": "categorical_accuracy"}
 
 
 def parse_loss(expr: str) -> Tuple[float, ...]:
@@ -55,7 +58,7 @@ def parse_loss(expr: str) -> Tuple[float, ...]:
     (0, 0, 0, w_lovasz) -- mixing it with the probability-based terms is undefined in the reference and rejected."""
     if not isinstance(expr, str) or not expr.strip():
         raise ValueError("loss must be a non-empty string")
-    w = [0.0, 0.0, 0.0, 0.0, 0.0, 0.0]
+    w = [0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]
 
     def term(node, scale):
         if isinstance(node, ast.BinOp) and isinstance(node.op, ast.Add):
@@ -87,8 +90,11 @@ def parse_loss(expr: str) -> Tuple[float, ...]:
     term(ast.parse(expr.strip(), mode="eval").body, 1.0)
     if w[3] != 0.0 and (any(w[:3]) or any(w[4:])):
         raise ValueError("lovasz_loss works on logits and cannot be combined with probability-based losses: " + expr)
-    n = 6
-    while n > 3 and w[n - 1] == 0.0:   # (w_bce, w_dice, w_iou[, w_lovasz[, w_jaccard[, w_focal]]])
+    if w[6] != 0.0 and any(w[:6]):
+        raise ValueError("categorical_crossentropy works on softmax probabilities and cannot be combined with the sigmoid-based "
+                         "losses: " + expr)
+    n = 7
+    while n > 3 and w[n - 1] == 0.0:   # (w_bce, w_dice, w_iou[, w_lovasz[, w_jaccard[, w_focal[, w_cce]]]])
         n -= 1
     return tuple(w[:n])
 
@@ -232,11 +238,14 @@ class PipelineConfig:
             raise ValueError("Unknown backbone")
         lw = parse_loss(loss or self.loss)
         pure_lovasz = len(lw) == 4 and lw[3] != 0.0
-        if self.activation == "softmax" and not pure_lovasz:
-            # lovasz_loss is computed on LOGITS (the reference strips the final Activation), so `activation: softmax` only
-            # shapes predictions (BASELINE.json configs[2]); every other loss would need softmax inside the loss kernels
-            raise NotImplementedError("activation: softmax is built for lovasz_loss only (categorical_crossentropy and "
-                                      "softmax-probability losses have no fused kernels)")
+        pure_cce = len(lw) == 7 and lw[6] != 0.0
+        if pure_cce and (self.activation != "softmax" or self.classes < 2):
+            raise ValueError("categorical_crossentropy needs `activation: softmax` and classes >= 2 (schema segmentation.raml:12-21, 62-63)")
+        if self.activation == "softmax" and not (pure_lovasz or pure_cce):
+            # lovasz_loss is computed on LOGITS (the reference strips the final Activation) and categorical_crossentropy has its
+            # own fused softmax kernel; the sigmoid-based loss kernels (binary_crossentropy, dice, ...) do not apply to softmax
+            raise NotImplementedError("activation: softmax is built for categorical_crossentropy and lovasz_loss (the dice / iou / "
+                                      "jaccard / focal / binary_crossentropy kernels fuse a sigmoid)")
         if self.activation not in ("sigmoid", "softmax", None, "none"):
             raise NotImplementedError("activation '%s' is not built" % self.activation)
         if self.classes > 4:
@@ -321,10 +330,11 @@ class PipelineConfig:
         if d is not None:
             return d
         if self.fit_with and self.datasets and self.fit_with in self.datasets:
-            from .impl.datasets import SimplePNGMaskDataSet
+            from .impl.datasets import dataset_from_spec
             spec = self.datasets[self.fit_with]
-            base = self._dir()
-            return SimplePNGMaskDataSet(os.path.join(base, spec["input_path"]), os.path.join(base, spec["output_path"]))
+            if not isinstance(spec, dict):   # e.g. `composite: ["default"]` (ds_2.yaml:41): a list of tensor names, not a dataset
+                raise ValueError("datasets: '%s' is not a dataset declaration" % self.fit_with)
+            return dataset_from_spec(spec, self._dir())
         raise ValueError("fit() needs a dataset or `datasets:` + `fit_with:` in the config")
 
     def _check_training_keys(self):

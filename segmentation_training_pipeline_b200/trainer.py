@@ -292,7 +292,8 @@ class Trainer:
     @staticmethod
     def _metrics_from(r) -> Dict[str, float]:
         return {"loss": float(r[_lib.L_LOSS]), "binary_crossentropy": float(r[_lib.L_BCE]), "dice": float(r[_lib.L_DICE]),
-                "iou": float(r[_lib.L_IOU]), "binary_accuracy": float(r[_lib.L_ACC]), "iot": float(r[_lib.L_IOT])}
+                "iou": float(r[_lib.L_IOU]), "binary_accuracy": float(r[_lib.L_ACC]), "iot": float(r[_lib.L_IOT]),
+                "categorical_crossentropy": float(r[_lib.L_CCE]), "categorical_accuracy": float(r[_lib.L_CACC])}
 
     def step_from_host(self, images: torch.Tensor, masks: torch.Tensor, read_metrics=True):
         self.pool_img.copy_(images, non_blocking=True)

@@ -51,8 +51,9 @@ def test_lovasz_loss_string():
 
 def test_loss_and_augmenter_errors_are_loud():
     from segmentation_pipeline.segmentation import parse_augmentation, parse_loss
-    with pytest.raises(NotImplementedError):
-        parse_loss("categorical_crossentropy")
+    assert parse_loss("categorical_crossentropy") == (0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0)    # fused softmax kernel (round 2)
+    with pytest.raises(ValueError, match="cannot be combined"):
+        parse_loss("categorical_crossentropy+dice_loss")                                     # dice fuses a sigmoid
     with pytest.raises(ValueError):
         parse_loss("no_such_loss")
     with pytest.raises(NotImplementedError):
@@ -751,3 +752,70 @@ def test_crops_build_the_network_at_cell_resolution():
     cfg = PipelineConfig(architecture="Unet", backbone="resnet18", classes=1, shape=[256, 384, 3], crops=2)
     assert cfg.net_shape() == [128, 192, 3]
     assert PipelineConfig(architecture="Unet", shape=[256, 256, 3]).net_shape() == [256, 256, 3]
+
+
+def test_declarative_datasets_with_bindings(tmp_path):
+    """`datasets:` entries in the bindings form of the reference's examples (ds_2.yaml:43-66, ds_3.yaml:43-76): channels picked
+    from several folders / readers, binary masks, colour-keyed masks; the short {input_path, output_path} form yields the same
+    items; fit_with resolves either."""
+    import cv2
+    import shutil
+    import yaml
+    from segmentation_pipeline import segmentation
+    from segmentation_pipeline.impl.datasets import BoundDataSet, SimplePNGMaskDataSet, dataset_from_spec
+    rng = np.random.default_rng(0)
+    img_dir, mask_dir, rgba_dir = tmp_path / "img", tmp_path / "mask", tmp_path / "rgba"
+    for d in (img_dir, mask_dir, rgba_dir):
+        d.mkdir()
+    colors = [[56, 37, 13], [123, 12, 11], [56, 56, 68], [255, 255, 255], [43, 37, 21]]
+    imgs = {}
+    for i in range(3):
+        rgb = rng.integers(0, 256, (24, 20, 3), dtype=np.uint8)
+        m = (rng.random((24, 20)) > 0.6).astype(np.uint8) * 255
+        cm = np.zeros((24, 20, 3), np.uint8)
+        cm[:, :] = [1, 2, 3]
+        cm[2:6, 3:9] = colors[3]
+        cm[10:12, 0:4] = colors[1]
+        cv2.imwrite(str(img_dir / ("s%d.png" % i)), rgb[:, :, ::-1])
+        cv2.imwrite(str(mask_dir / ("s%d.png" % i)), m)
+        cv2.imwrite(str(rgba_dir / ("s%d.png" % i)), cm[:, :, ::-1])
+        imgs[i] = (rgb, m, cm)
+    # ds_2.yaml form: identical to the short form
+    spec2 = {"inputs": [{"name": "default", "data_type": "uint8", "bindings": [
+                {"reader": "RGBA", "path": "img", "bind": [0, 1, 2], "treat": {'type"': "as_is"}}]}],
+             "outputs": [{"name": "default", "data_type": "bool", "bindings": [
+                {"reader": "monochrome", "path": "mask", "bind": [0], "treat": {"type": "binary_mask"}}]}]}
+    a = dataset_from_spec(spec2, str(tmp_path))
+    b = dataset_from_spec({"input_path": "img", "output_path": "mask"}, str(tmp_path))
+    assert isinstance(a, BoundDataSet) and isinstance(b, SimplePNGMaskDataSet) and len(a) == len(b) == 3
+    for i in range(3):
+        assert a[i].id == b[i].id == "s%d" % i
+        assert np.array_equal(a[i].x, imgs[i][0]) and np.array_equal(b[i].x, imgs[i][0])
+        assert np.array_equal(a[i].y, (imgs[i][1] > 0).astype(np.uint8)[:, :, None]) and np.array_equal(a[i].y, b[i].y)
+    assert a.isPositive(0)
+    # ds_3.yaml form: channels 0,1 from one binding, channel 2 from another; output = 4th channel of the colour-keyed tensor
+    spec3 = {"inputs": [{"name": "default", "data_type": "uint8", "bindings": [
+                {"reader": "RGBA", "path": "img", "bind": [0, 1], "treat": {'type"': "as_is"}},
+                {"reader": "RGBA", "path": "img", "bind": [2], "treat": {'type"': "as_is"}}]}],
+             "outputs": [{"name": "default", "data_type": "bool", "bindings": [
+                {"reader": "RGBA", "path": "rgba", "bind": [3], "treat": {"type": "binary_mask", "colors": colors}}]}]}
+    c = dataset_from_spec(spec3, str(tmp_path))
+    assert np.array_equal(c[1].x, imgs[1][0])
+    want = np.zeros((24, 20, 1), np.uint8)
+    want[2:6, 3:9] = 1
+    assert np.array_equal(c[1].y, want)
+    with pytest.raises(IndexError):
+        dataset_from_spec({**spec3, "outputs": [{"bindings": [{"reader": "monochrome", "path": "mask", "bind": [2]}]}]}, str(tmp_path))[0]
+    with pytest.raises(NotImplementedError, match="reader"):
+        dataset_from_spec({**spec3, "outputs": [{"bindings": [{"reader": "hsv", "path": "mask", "bind": [0]}]}]}, str(tmp_path))[0]
+    # fit_with picks the entry by name; the list-valued `composite:` key of the examples is not a dataset
+    cfgd = {"architecture": "Unet", "backbone": "resnet18", "classes": 1, "shape": [32, 32, 3], "fit_with": "simple_1",
+            "datasets": {"simple": {"input_path": "img", "output_path": "mask"}, "composite": ["default"], "simple_1": spec2}}
+    (tmp_path / "c.yaml").write_text(yaml.safe_dump(cfgd))
+    cfg = segmentation.parse(str(tmp_path / "c.yaml"))
+    assert isinstance(cfg._resolve_dataset(None), BoundDataSet)
+    cfg.fit_with = "simple"
+    assert isinstance(cfg._resolve_dataset(None), SimplePNGMaskDataSet)
+    cfg.fit_with = "composite"
+    with pytest.raises(ValueError, match="not a dataset"):
+        cfg._resolve_dataset(None)

@@ -103,7 +103,7 @@ def test_conv_at_baseline_shape_bs16(stp, cuda, layer):
     assert float(((cf[1] - invstd) / invstd).abs().max()) <= 1e-4, name
     assert float(((cf[2] - gamma.cpu().double() * invstd) / invstd).abs().max()) <= 1e-4, name
     assert float((mm.cpu().double() - 0.01 * mean).abs().max()) <= 1e-6 * (1 + float(mean.abs().max())), name
-    unb = var * (rows / (rows - 1.0))
+    unb = var * (rows / (rows - (1.0 + eps)))   # keras: sample_size / (sample_size - (1 + epsilon))
     assert float((mv.cpu().double() - (0.99 + 0.01 * unb)).abs().max()) <= 1e-5 * (1 + float(unb.max())), name
     assert int(sync[0]) == 0 and float(acc.abs().max()) == 0.0
     del flat, yc

@@ -125,7 +125,7 @@ def conv_ref_autograd(x_nhwc, w_krsc, stride, pad, up, out_hw):
     w = w_krsc.permute(0, 3, 1, 2)
     if up > 1:
         n, c, h, ww = x.shape
-        z = torch.zeros(n, c, (h - 1) * up + 1, (ww - 1) * up + 1)
+        z = torch.zeros(n, c, (h - 1) * up + 1, (ww - 1) * up + 1, dtype=x.dtype)
         z[:, :, ::up, ::up] = x
         x = z
     R, S = w.shape[2], w.shape[3]
@@ -183,7 +183,7 @@ def test_batchnorm_fwd_bwd(stp, cuda, shape, up):
     assert max_abs(coef[:c], mean) < 1e-4 * (1 + float(mean.abs().max()))
     assert rel_err(coef[c:2 * c], torch.rsqrt(var + eps)) < 1e-5
     assert rel_err(y, yo.permute(0, 2, 3, 1)) < TOL_BF16
-    unb = var * rows / (rows - 1)
+    unb = var * rows / (rows - (1.0 + eps))   # keras: sample_size / (sample_size - (1 + epsilon))
     assert rel_err(mv, 0.99 * torch.ones(c) + 0.01 * unb.detach()) < 1e-5
     assert max_abs(mm, 0.01 * mean.detach()) < 1e-5
     # backward
@@ -750,6 +750,41 @@ def test_lovasz_hinge_multiclass(stp, cuda):
     lo.backward()
     assert abs(float(result[lib.L_LOVASZ]) - float(lo)) < 1e-5 * max(1.0, abs(float(lo)))
     assert rel_err(dl.view(n, h, w, cls), z.grad) < 1e-5
+
+
+@pytest.mark.parametrize("classes", [2, 3, 4])
+def test_softmax_categorical_crossentropy(stp, cuda, classes):
+    """`activation: softmax` + `loss: categorical_crossentropy` (schema segmentation.raml:12-21, 62-63): keras
+    categorical_crossentropy on probabilities (renormalise, clip 1e-7, -sum t log p, mean) fused with the softmax; value,
+    categorical accuracy and dL/dlogits against autograd of the oracle formula, incl. saturated logits (clip region) and the
+    accumulate form."""
+    from oracle import losses as OL
+    g = torch.Generator().manual_seed(100 + classes)
+    n, h, w = 2, 20, 28
+    logits = torch.randn(n, h, w, classes, generator=g) * 3
+    logits[0, 0, 0] = torch.tensor([30.0] + [-30.0] * (classes - 1))      # p saturates: clipped, zero gradient there
+    logits[0, 0, 1] = torch.tensor([-30.0] * (classes - 1) + [30.0])
+    cls = torch.randint(0, classes, (n, h, w), generator=g)
+    mask = torch.nn.functional.one_hot(cls, classes).to(torch.uint8)
+    mask[1, 3, 3] = 0                                                     # an unlabeled pixel (all-zero target row)
+    lg, mk = logits.to(cuda).contiguous(), mask.to(cuda).contiguous()
+    partial = torch.zeros(stp.loss_partial_floats(), device=cuda)
+    result = torch.zeros(16, device=cuda)
+    result[lib.L_LOSS] = 0.25
+    wgt = 0.7
+    stp.softmax_cce_fwd(lg.data_ptr(), mk.data_ptr(), n * h * w, classes, wgt, 1, partial.data_ptr(), result.data_ptr(), stream())
+    z = logits.double().requires_grad_(True)
+    lo = OL.categorical_crossentropy(mask.double(), torch.softmax(z, dim=-1))
+    lo.backward()
+    assert abs(float(result[lib.L_CCE]) - float(lo)) < 1e-5 * max(1.0, abs(float(lo)))
+    assert abs(float(result[lib.L_LOSS]) - (0.25 + wgt * float(lo))) < 1e-5 * max(1.0, abs(float(lo)))
+    acc = float((logits.argmax(-1) == mask.argmax(-1)).float().mean())
+    assert abs(float(result[lib.L_CACC]) - acc) < 1e-6
+    dl = torch.ones(n * h * w * classes, device=cuda)
+    stp.softmax_cce_bwd(lg.data_ptr(), mk.data_ptr(), n * h * w, classes, wgt, 1, dl.data_ptr(), stream())
+    assert rel_err(dl.view(n, h, w, classes) - 1.0, (wgt * z.grad).float()) < 1e-4
+    stp.softmax_cce_bwd(lg.data_ptr(), mk.data_ptr(), n * h * w, classes, 1.0, 0, dl.data_ptr(), stream())
+    assert rel_err(dl.view(n, h, w, classes), z.grad.float()) < 1e-4
 
 
 @pytest.mark.parametrize("halo", [0, 1])
