@@ -105,6 +105,45 @@ typedef struct stp_aug_sample { /* per-sample drawn parameters, device resident,
   int32_t flags2;              /* bits 0-1: rot90 k; bit 2: invert; bits 4-9: colour order (three 2-bit op ids, first op lowest) */
 } stp_aug_sample;
 
+/* ---- uint8 resize with OpenCV's arithmetic (csrc/resize_u8.cu) -- replaces the `Resize -> shape` tail of the reference's
+ * input pipeline (imgaug Resize = cv2.resize: INTER_CUBIC for images, INTER_NEAREST for masks; musket_core.datasets via
+ * segmentation.py:54) and serves the crop / pad augmenters (schemas/augmenters.raml:72-87, 113-116).  Each of the n items
+ * describes a stored image [sh][sw][c] at byte offset src_off of `d_arena` and a VIRTUAL window of it (origin vy0/vx0 may be
+ * negative, size vh x vw may exceed the stored image: pixels outside read 0 = constant padding); the window is resized to
+ * [h][w][c] and written to image i of d_dst [n][h][w][c].  A window that already is h x w is copied. */
+enum { STP_RESIZE_NEAREST = 0, STP_RESIZE_CUBIC = 1 };
+typedef struct stp_resize_item {
+  int64_t src_off;
+  int32_t sh, sw;
+  int32_t vy0, vx0;
+  int32_t vh, vw;
+} stp_resize_item;
+int stp_resize_u8(const uint8_t* d_arena, const stp_resize_item* d_items, int32_t n, int32_t c, uint8_t* d_dst, int32_t h,
+                  int32_t w, int32_t mode, stp_stream stream);
+
+/* Crop / pad augmenters (schemas/augmenters.raml:72-87, 113-116 -> imgaug 0.3.0 Pad / PadToFixedSize / CropToFixedSize /
+ * CropAndPad [DEP]): each is a window of the sample, possibly extending beyond it (constant zero padding), that the pipeline's
+ * final Resize brings back to `shape`.  The ops of the YAML block are composed into ONE window per sample (exact: none of them
+ * resamples before the final Resize when `keep_size` ops come last), drawn on the device from Philox calls 6-7 of the
+ * sample's stream, and written as stp_resize_item tables for stp_resize_u8 (cubic for the image, nearest for the mask).
+ *   STP_CP_PAD            a,b,c,d = px (top, right, bottom, left)
+ *   STP_CP_PAD_TO_FIXED   a = width, b = height; pads only a smaller side; left = floor((1 - u) * total)  [position uniform]
+ *   STP_CP_CROP_TO_FIXED  a = width, b = height; crops only a larger side; left = floor(u * total)
+ *   STP_CP_CROP_AND_PAD   percent: a,b,c,d = (top, right, bottom, left), or ranged = 1: a,b = range, one draw per side;
+ *                         pixels = round(percent * size): positive pads, negative crops */
+enum { STP_CP_PAD = 1, STP_CP_PAD_TO_FIXED = 2, STP_CP_CROP_TO_FIXED = 3, STP_CP_CROP_AND_PAD = 4, STP_CP_MAX_OPS = 4 };
+typedef struct stp_croppad_op {
+  int32_t kind, ranged;
+  float a, b, c, d;
+} stp_croppad_op;
+typedef struct stp_croppad_spec {
+  int32_t n_ops;
+  stp_croppad_op ops[4];
+} stp_croppad_spec;
+int stp_croppad_draw(const stp_croppad_spec* h_spec, uint64_t seed, const int64_t* d_step, int32_t n, int32_t pool, int32_t h,
+                     int32_t w, int32_t c_img, int32_t c_mask, stp_resize_item* d_img_items, stp_resize_item* d_mask_items,
+                     stp_stream stream);
+
 /* draw parameters: Philox4x32-10(key=seed, ctr=(step, sample_id, call, step>>32)).  `d_step` is a device
  * int64 so the call is CUDA-graph replayable; sample_id = (step*n + i) % pool (src_index likewise). */
 int stp_augment_draw(const stp_aug_spec* h_spec, uint64_t seed, const int64_t* d_step, int32_t n,

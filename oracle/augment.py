@@ -212,3 +212,58 @@ def augment_batch(images: np.ndarray, masks: np.ndarray, spec: AugSpec, seed: in
         p = draw_params(spec, seed, step, sid, H, W)
         oi[n], om[n] = apply(images[n], masks[n], p, use_cv2)
     return oi, om
+
+
+# ----------------------------------------------------------------------------------------------
+# crop / pad family (schemas/augmenters.raml:72-87, 113-116 -> imgaug 0.3.0 Pad / PadToFixedSize / CropToFixedSize /
+# CropAndPad [DEP, recalled -- parity unpinned]): window composition, then the pipeline's final Resize -> shape with cv2
+# arithmetic (oracle/resize.py, pinned against the real cv2).  Choices taken where imgaug's source could not be consulted:
+# PadToFixedSize puts floor((1 - u) * total) pixels before the image, CropToFixedSize removes floor(u * total) before it
+# (position="uniform"); CropAndPad rounds percent * size half-to-even; Pad / CropAndPad keep_size=True.
+# ----------------------------------------------------------------------------------------------
+def crop_pad_window(ops, seed: int, step: int, sample: int, h: int, w: int):
+    """ops: sequence of (kind, ranged, a, b, c, d) as in include/stp.h stp_croppad_op -> (vy0, vx0, vh, vw)"""
+    u0, u1 = philox.uniforms(seed, step, sample, 6)
+    u2, u3 = philox.uniforms(seed, step, sample, 7)
+    u = (u0, u1, u2, u3)
+    vy0, vx0, vh, vw = 0, 0, h, w
+    for kind, ranged, a, b, c, d in ops:
+        if kind == 1:
+            vy0 -= int(a); vh += int(a) + int(c)
+            vx0 -= int(d); vw += int(d) + int(b)
+        elif kind == 2:
+            if vw < int(a):
+                tot = int(a) - vw
+                vx0 -= int(math.floor((1.0 - u[0]) * tot)); vw = int(a)
+            if vh < int(b):
+                tot = int(b) - vh
+                vy0 -= int(math.floor((1.0 - u[1]) * tot)); vh = int(b)
+        elif kind == 3:
+            if vw > int(a):
+                tot = vw - int(a)
+                vx0 += int(math.floor(u[2] * tot)); vw = int(a)
+            if vh > int(b):
+                tot = vh - int(b)
+                vy0 += int(math.floor(u[3] * tot)); vh = int(b)
+        elif kind == 4:
+            f32 = lambda v: float(np.float32(v))     # the C struct carries the percentages as float32
+            if ranged:
+                lo, hi = f32(a), f32(b)
+                pt, pr, pb, pl = (lo + u[k] * (hi - lo) for k in range(4))
+            else:
+                pt, pr, pb, pl = f32(a), f32(b), f32(c), f32(d)
+            t, bb = int(np.rint(pt * vh)), int(np.rint(pb * vh))
+            l, r = int(np.rint(pl * vw)), int(np.rint(pr * vw))
+            nh, nw = vh + t + bb, vw + l + r
+            if nh >= 1 and nw >= 1:
+                vy0 -= t; vx0 -= l; vh, vw = nh, nw
+        else:
+            raise ValueError("unknown crop / pad kind %r" % (kind,))
+    return vy0, vx0, vh, vw
+
+
+def apply_crop_pad(image: np.ndarray, mask: np.ndarray, win, H: int, W: int):
+    """window of (image, mask), zeros outside, resized to (H, W): cubic for the image, nearest for the mask"""
+    from . import resize as R
+    vi, vm = R.window(image, *win), R.window(mask, *win)
+    return R.resize_cubic_u8(vi, H, W), R.resize_nearest_u8(vm, H, W)

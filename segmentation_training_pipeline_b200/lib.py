@@ -46,6 +46,23 @@ class AugSpec(C.Structure):
             self.color_order[0], self.color_order[1], self.color_order[2] = 0, 1, 2
 
 
+class ResizeItem(C.Structure):             # include/stp.h: stp_resize_item
+    _fields_ = [("src_off", C.c_int64), ("sh", C.c_int32), ("sw", C.c_int32), ("vy0", C.c_int32), ("vx0", C.c_int32),
+                ("vh", C.c_int32), ("vw", C.c_int32)]
+
+
+RESIZE_NEAREST, RESIZE_CUBIC = 0, 1
+CP_PAD, CP_PAD_TO_FIXED, CP_CROP_TO_FIXED, CP_CROP_AND_PAD = 1, 2, 3, 4
+
+
+class CropPadOp(C.Structure):              # include/stp.h: stp_croppad_op
+    _fields_ = [("kind", C.c_int32), ("ranged", C.c_int32), ("a", C.c_float), ("b", C.c_float), ("c", C.c_float), ("d", C.c_float)]
+
+
+class CropPadSpec(C.Structure):            # include/stp.h: stp_croppad_spec
+    _fields_ = [("n_ops", C.c_int32), ("ops", CropPadOp * 4)]
+
+
 class AugSample(C.Structure):
     _fields_ = [("m", C.c_double * 6), ("inv", C.c_double * 6), ("fliplr", C.c_int32), ("flipud", C.c_int32),
                 ("has_affine", C.c_int32), ("has_mul", C.c_int32), ("mul", C.c_float), ("add", C.c_int32),
@@ -127,6 +144,8 @@ SIGNATURES = {
     "stp_loss_fwd": (C.c_int, [_P, _P, _I64, C.POINTER(LossSpec), _P, _P, _P]),
     "stp_loss_partial_floats": (_SZ, []),
     "stp_loss_bwd": (C.c_int, [_P, _P, _I64, C.POINTER(LossSpec), _P, _P, _P]),
+    "stp_resize_u8": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _I32, _I32, _P]),
+    "stp_croppad_draw": (C.c_int, [C.POINTER(CropPadSpec), C.c_uint64, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "stp_softmax_cce_fwd": (C.c_int, [_P, _P, _I64, _I32, _F, _I32, _P, _P, _P]),
     "stp_softmax_cce_bwd": (C.c_int, [_P, _P, _I64, _I32, _F, _I32, _P, _P]),
     "stp_lovasz_workspace": (_SZ, [_I32, _I64]),

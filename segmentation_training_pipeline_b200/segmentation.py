@@ -117,14 +117,17 @@ def parse_augmentation(spec: Optional[dict], seed: int = 0) -> AugmentConfig:
     # themselves: they are index permutations, composed exactly -- AugmentConfig.flip_before_rot90) -> Affine -> colour stage
     # (Multiply / Add / Invert in ANY order among themselves); a block in another order would silently compute something
     # else, so it is rejected.
-    rank = {"Rotate90": 1, "Fliplr": 1, "Flipud": 1, "Affine": 2, "Multiply": 3, "Add": 3, "Invert": 3}
+    # The crop / pad family (Pad, PadToFixedSize, CropToFixedSize, CropAndPad) leads the block: the ops are composed into one
+    # window per sample that the cv2-arithmetic resize brings back to `shape` (trainer.run_augment).
+    rank = {"Pad": 0, "PadToFixedSize": 0, "CropToFixedSize": 0, "CropAndPad": 0,
+            "Rotate90": 1, "Fliplr": 1, "Flipud": 1, "Affine": 2, "Multiply": 3, "Add": 3, "Invert": 3}
     last, colour = -1, []
     for name in spec:
         if name not in rank:
             raise NotImplementedError("augmenter '%s' is not fused on device (supported: %s)" % (name, ", ".join(rank)))
         if rank[name] < last:
-            raise NotImplementedError("augmentation order %s is not the fused kernel's (Rotate90/Fliplr/Flipud, Affine, then "
-                                      "Multiply/Add/Invert)" % list(spec))
+            raise NotImplementedError("augmentation order %s is not the fused kernel's (Pad/PadToFixedSize/CropToFixedSize/"
+                                      "CropAndPad, Rotate90/Fliplr/Flipud, Affine, then Multiply/Add/Invert)" % list(spec))
         last = rank[name]
         if rank[name] == 3:
             colour.append({"Multiply": 0, "Add": 1, "Invert": 2}[name])
@@ -134,6 +137,44 @@ def parse_augmentation(spec: Optional[dict], seed: int = 0) -> AugmentConfig:
         r = names.index("Rotate90")
         cfg.flip_before_rot90 = (1 if "Fliplr" in names and names.index("Fliplr") < r else 0) | \
                                 (2 if "Flipud" in names and names.index("Flipud") < r else 0)
+    cp, keep_size_seen = [], False
+    for name, val in spec.items():
+        if rank.get(name) != 0:
+            continue
+        if keep_size_seen:
+            # imgaug Pad / CropAndPad default to keep_size=True (resample back to the input size); composed with the final
+            # Resize that is exact only when nothing else of the family follows
+            raise NotImplementedError("augmentation: %s after Pad / CropAndPad (keep_size resampling between crop / pad ops is "
+                                      "not built)" % name)
+        if len(cp) >= 4:
+            raise NotImplementedError("augmentation: at most 4 crop / pad augmenters")
+        val = val if isinstance(val, dict) else ({"px": val} if name == "Pad" else {"percent": val} if name == "CropAndPad" else val)
+        if name == "Pad":
+            px = val.get("px")
+            px = [px] * 4 if isinstance(px, int) else list(px or [])
+            if len(px) != 4 or any(int(v) < 0 for v in px):
+                raise ValueError("Pad: px must be one non-negative integer or [top, right, bottom, left]")
+            cp.append((1, 0, int(px[0]), int(px[1]), int(px[2]), int(px[3])))
+            keep_size_seen = True
+        elif name in ("PadToFixedSize", "CropToFixedSize"):
+            if not isinstance(val, dict) or "width" not in val or "height" not in val:
+                raise ValueError("%s needs width and height" % name)
+            cp.append((2 if name == "PadToFixedSize" else 3, 0, int(val["width"]), int(val["height"]), 0, 0))
+        else:
+            pc = val.get("percent")
+            pc = [pc] if isinstance(pc, (int, float)) else list(pc or [])
+            if len(pc) == 1:
+                cp.append((4, 0, float(pc[0]), float(pc[0]), float(pc[0]), float(pc[0])))
+            elif len(pc) == 2:
+                cp.append((4, 1, float(pc[0]), float(pc[1]), 0.0, 0.0))     # a range: one draw per side and sample
+            elif len(pc) == 4:
+                cp.append((4, 0, float(pc[0]), float(pc[1]), float(pc[2]), float(pc[3])))
+            else:
+                raise ValueError("CropAndPad: percent must hold 1, 2 (range) or 4 (top, right, bottom, left) numbers")
+            if min(pc) <= -0.5:
+                raise ValueError("CropAndPad: crops of 50 % or more per side leave no image")
+            keep_size_seen = True
+    cfg.crop_pad = tuple(cp)
     for name, val in spec.items():
         if name == "Fliplr":
             cfg.fliplr = float(val)

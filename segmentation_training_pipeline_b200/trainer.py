@@ -38,9 +38,19 @@ class AugmentConfig:
     invert: float = 0.0
     color_order: Tuple[int, int, int] = (0, 1, 2)   # 0 Multiply, 1 Add, 2 Invert, in YAML order
     flip_before_rot90: int = 0   # bit 0: Fliplr precedes Rotate90 in the YAML block, bit 1: Flipud does (stp.h)
+    # leading crop / pad augmenters, in YAML order: (kind, ranged, a, b, c, d) per include/stp.h stp_croppad_op
+    crop_pad: Tuple[Tuple[int, int, float, float, float, float], ...] = ()
 
     def enabled(self) -> bool:
-        return bool(self.fliplr or self.flipud or self.affine or self.multiply or self.add or self.rot90 or self.invert)
+        return bool(self.fliplr or self.flipud or self.affine or self.multiply or self.add or self.rot90 or self.invert or
+                    self.crop_pad)
+
+    def croppad_c(self) -> _lib.CropPadSpec:
+        spec = _lib.CropPadSpec()
+        spec.n_ops = len(self.crop_pad)
+        for i, (kind, ranged, a, b, c, d) in enumerate(self.crop_pad):
+            spec.ops[i] = _lib.CropPadOp(int(kind), int(ranged), float(a), float(b), float(c), float(d))
+        return spec
 
     def to_c(self) -> _lib.AugSpec:
         m = self.multiply or (1.0, 1.0)
@@ -94,6 +104,7 @@ class Trainer:
         self._gx = _lib.GradXform(1.0 / world_size, self.clipnorm, self.clipvalue,
                                   self.sumsq.data_ptr() if self.clipnorm > 0 else None, self.lr_scale.data_ptr())
         self._ident = AugmentConfig()
+        self._cp_img = self._cp_mask = self._cp_items = None   # staging of the crop / pad augmenter stage (run_augment)
 
     # ---- learning-rate schedules ----------------------------------------------------------------
     def set_lr(self, lr: float):
@@ -127,9 +138,27 @@ class Trainer:
         H, W, CI = net.input_shape
         cfg = self.augment or self._ident
         spec = cfg.to_c()
-        self.L.augment_draw(C.byref(spec), cfg.seed, net.d_step.data_ptr(), net.batch, self.pool_img.shape[0], H, W,
+        src_img, src_mask, pool_n = self.pool_img, self.pool_mask, self.pool_img.shape[0]
+        if cfg.crop_pad:
+            # leading Pad / PadToFixedSize / CropToFixedSize / CropAndPad: one window per sample (drawn on the device), brought
+            # back to `shape` by the cv2-arithmetic resize (cubic for the image, nearest for the mask) into a staging batch that
+            # the fused flip / affine / colour kernel then reads in batch order
+            if self._cp_img is None:
+                dev = net.device
+                self._cp_img = torch.zeros((net.batch, H, W, CI), dtype=torch.uint8, device=dev)
+                self._cp_mask = torch.zeros((net.batch, H, W, net.classes), dtype=torch.uint8, device=dev)
+                self._cp_items = torch.zeros(2 * net.batch * C.sizeof(_lib.ResizeItem), dtype=torch.uint8, device=dev)
+            cps = cfg.croppad_c()
+            it_img = self._cp_items.data_ptr()
+            it_mask = it_img + net.batch * C.sizeof(_lib.ResizeItem)
+            self.L.croppad_draw(C.byref(cps), cfg.seed, net.d_step.data_ptr(), net.batch, pool_n, H, W, CI, net.classes, it_img, it_mask, st)
+            self.L.resize_u8(self.pool_img.data_ptr(), it_img, net.batch, CI, self._cp_img.data_ptr(), H, W, _lib.RESIZE_CUBIC, st)
+            self.L.resize_u8(self.pool_mask.data_ptr(), it_mask, net.batch, net.classes, self._cp_mask.data_ptr(), H, W,
+                             _lib.RESIZE_NEAREST, st)
+            src_img, src_mask, pool_n = self._cp_img, self._cp_mask, net.batch   # sample i of the staging batch is batch item i
+        self.L.augment_draw(C.byref(spec), cfg.seed, net.d_step.data_ptr(), net.batch, pool_n, H, W,
                             self.aug_params.data_ptr(), st)
-        self.L.augment_apply(self.pool_img.data_ptr(), self.pool_mask.data_ptr(), self.aug_params.data_ptr(),
+        self.L.augment_apply(src_img.data_ptr(), src_mask.data_ptr(), self.aug_params.data_ptr(),
                              net.img.storage.data_ptr(), net.mask.storage.data_ptr(), net.batch, H, W, CI, net.classes,
                              int(cfg.mul_rint), st)
 

@@ -819,3 +819,35 @@ def test_declarative_datasets_with_bindings(tmp_path):
     cfg.fit_with = "composite"
     with pytest.raises(ValueError, match="not a dataset"):
         cfg._resolve_dataset(None)
+
+
+def test_crop_pad_augmenters_parse():
+    """Pad / PadToFixedSize / CropToFixedSize / CropAndPad (schemas/augmenters.raml:72-87, 113-116) lead the block and are
+    composed into one window; keep_size ops must come last of the family."""
+    from segmentation_training_pipeline_b200.segmentation import parse_augmentation
+    c = parse_augmentation({"PadToFixedSize": {"width": 600, "height": 600}, "CropToFixedSize": {"width": 512, "height": 512},
+                            "Fliplr": 0.5, "Multiply": [0.9, 1.1]})
+    assert c.crop_pad == ((2, 0, 600, 600, 0, 0), (3, 0, 512, 512, 0, 0)) and c.fliplr == 0.5 and c.enabled()
+    assert parse_augmentation({"Pad": {"px": [1, 2, 3, 4]}}).crop_pad == ((1, 0, 1, 2, 3, 4),)
+    assert parse_augmentation({"Pad": 5}).crop_pad == ((1, 0, 5, 5, 5, 5),)
+    assert parse_augmentation({"CropAndPad": {"percent": [-0.1, 0.2]}}).crop_pad == ((4, 1, -0.1, 0.2, 0.0, 0.0),)
+    assert parse_augmentation({"CropAndPad": {"percent": [0.1, 0.0, -0.1, 0.05]}}).crop_pad[0][:2] == (4, 0)
+    spec = parse_augmentation({"CropToFixedSize": {"width": 8, "height": 8}, "CropAndPad": {"percent": 0.1}}).croppad_c()
+    assert spec.n_ops == 2 and spec.ops[0].kind == 3 and spec.ops[1].kind == 4 and abs(spec.ops[1].a - 0.1) < 1e-7
+    with pytest.raises(NotImplementedError, match="order"):
+        parse_augmentation({"Fliplr": 0.5, "CropToFixedSize": {"width": 8, "height": 8}})
+    with pytest.raises(NotImplementedError, match="keep_size"):
+        parse_augmentation({"Pad": 3, "CropToFixedSize": {"width": 8, "height": 8}})
+    with pytest.raises(ValueError):
+        parse_augmentation({"CropAndPad": {"percent": [0.1, 0.2, 0.3]}})
+
+
+def test_oracle_crop_pad_window_composition():
+    from oracle import augment as OA
+    # PadToFixedSize then CropToFixedSize back to the original size: a pure shift, never larger than the pad
+    for sample in range(6):
+        vy0, vx0, vh, vw = OA.crop_pad_window([(2, 0, 80, 80, 0, 0), (3, 0, 64, 64, 0, 0)], 1, 0, sample, 64, 64)
+        assert (vh, vw) == (64, 64) and -16 <= vy0 <= 16 and -16 <= vx0 <= 16
+    assert OA.crop_pad_window([(1, 0, 1, 2, 3, 4)], 0, 0, 0, 10, 20) == (-1, -4, 14, 26)
+    assert OA.crop_pad_window([(4, 0, 0.1, 0.1, 0.1, 0.1)], 0, 0, 0, 100, 50) == (-10, -5, 120, 60)
+    assert OA.crop_pad_window([(4, 0, -0.25, 0.0, 0.0, 0.0)], 0, 0, 0, 100, 50) == (25, 0, 75, 50)

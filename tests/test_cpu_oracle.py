@@ -140,3 +140,36 @@ def test_kfold_split_is_sklearn():
     from sklearn.model_selection import KFold
     folds = list(KFold(n_splits=5, shuffle=True, random_state=33).split(np.arange(20)))
     assert len(folds) == 5 and all(len(te) == 4 for _, te in folds)
+
+
+def test_resize_oracle_is_pinned_against_real_cv2():
+    """oracle/resize.py restates cv::resize's scalar arithmetic; the real cv2 of this image (IPP off) agrees except at rounding
+    ties of its SIMD vertical pass (fp32, round-half-even vs integer round-half-up): <= 0.05 % of pixels, |d| <= 1.  Nearest is
+    bit exact."""
+    import cv2
+    from oracle import resize as OR
+    rng = np.random.default_rng(5)
+    prev = cv2.ipp.useIPP() if hasattr(cv2, "ipp") else None
+    try:
+        if prev is not None:
+            cv2.ipp.setUseIPP(False)
+        tot = bad = 0
+        for (h, w, H, W) in [(37, 53, 64, 64), (300, 200, 128, 160), (64, 64, 200, 333), (100, 100, 37, 41), (96, 96, 192, 192),
+                             (128, 96, 64, 48), (33, 65, 512, 512)]:
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            ref = cv2.resize(img, (W, H), interpolation=cv2.INTER_CUBIC)
+            got = OR.resize_cubic_u8(img, H, W)
+            d = np.abs(got.astype(int) - ref.astype(int))
+            assert d.max() <= 1, (h, w, H, W, d.max())
+            tot += d.size
+            bad += int((d != 0).sum())
+            m = (rng.random((h, w)) > 0.6).astype(np.uint8)
+            assert np.array_equal(OR.resize_nearest_u8(m, H, W), cv2.resize(m, (W, H), interpolation=cv2.INTER_NEAREST)), (h, w, H, W)
+        assert bad <= 5e-4 * tot, (bad, tot)
+        # smooth images (photographs, not noise) hit fewer ties still; padding window helper == np.pad / slicing
+        img = rng.integers(0, 256, (20, 30, 3), dtype=np.uint8)
+        assert np.array_equal(OR.window(img, -3, -2, 28, 40), np.pad(img, ((3, 5), (2, 8), (0, 0)))[:28, :40])
+        assert np.array_equal(OR.window(img, 4, 5, 10, 12), img[4:14, 5:17])
+    finally:
+        if prev is not None:
+            cv2.ipp.setUseIPP(prev)
