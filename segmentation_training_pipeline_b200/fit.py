@@ -165,7 +165,9 @@ def run_fit(cfg, ds, subsample=1.0, foldsToExecute=None, start_from_stage=0):
         # decode + resize run in a thread pool a couple of batches ahead of the device (loader.py); `loader_workers: 0` in the
         # config keeps everything on the calling thread (datasets whose __getitem__ is not thread safe)
         from .loader import HostLoader
-        loader = HostLoader(ds, shape, cfg.classes, B, workers=int(cfg.extra.get("loader_workers", 4)))
+        # `device_resize: true`: workers only decode; the resize to `shape` (cv2 arithmetic) runs on the device (loader.RawBatch)
+        loader = HostLoader(ds, shape, cfg.classes, B, workers=int(cfg.extra.get("loader_workers", 4)),
+                            device_resize=bool(cfg.extra.get("device_resize", False)))
         for si, stage in enumerate(cfg.stages):
             # stage keys that change the encoder's trainability apply whether or not the stage is executed; an explicit
             # `unfreeze_encoder: false` re-freezes (the reference's Stage sets trainability from the key's value)

@@ -339,15 +339,19 @@ class Trainer:
         `images` / `masks` (pinned host tensors) may be overwritten once the NEXT call returns."""
         b = self._pipe_k & 1
         main = torch.cuda.current_stream()
-        with torch.cuda.stream(self._copy_stream):
-            self._copy_stream.wait_event(self._ev_free[b])          # staging slot b was drained by step k-2
-            self._stage_img[b].copy_(images, non_blocking=True)
-            self._stage_mask[b].copy_(masks, non_blocking=True)
-            self._ev_copied[b].record(self._copy_stream)
-        main.wait_event(self._ev_copied[b])
-        self.pool_img.copy_(self._stage_img[b], non_blocking=True)   # 17 MB device copy, ~5 us
-        self.pool_mask.copy_(self._stage_mask[b], non_blocking=True)
-        self._ev_free[b].record(main)
+        raw = images if masks is None and hasattr(images, "arena_img") else None   # loader.RawBatch: on-device ingest
+        if raw is not None:
+            self._ingest_raw(raw, b, main)
+        else:
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._ev_free[b])          # staging slot b was drained by step k-2
+                self._stage_img[b].copy_(images, non_blocking=True)
+                self._stage_mask[b].copy_(masks, non_blocking=True)
+                self._ev_copied[b].record(self._copy_stream)
+            main.wait_event(self._ev_copied[b])
+            self.pool_img.copy_(self._stage_img[b], non_blocking=True)   # 17 MB device copy, ~5 us
+            self.pool_mask.copy_(self._stage_mask[b], non_blocking=True)
+            self._ev_free[b].record(main)
         self.step()
         self._res_ring[b].copy_(self.net.loss.result, non_blocking=True)
         self._ev_done[b].record(main)
@@ -357,6 +361,37 @@ class Trainer:
             return None
         self._ev_done[prev].synchronize()
         return self._metrics_from(self._res_ring[prev])
+
+    def _ingest_raw(self, raw, b: int, main):
+        """on-device ingest: H2D of the UNRESIZED samples (loader.RawBatch: byte arenas + one
+        stp_resize_item per sample) on the copy stream, then stp_resize_u8 -- cv2.resize arithmetic, cubic for images / nearest
+        for masks -- writes the network-shape batch straight into the step's input pool."""
+        net = self.net
+        H, W, CI = net.input_shape
+        if not hasattr(self, "_raw_dev"):
+            self._raw_dev = [None, None]
+        need = (raw.arena_img.numel(), raw.arena_mask.numel())
+        cur = self._raw_dev[b]
+        if cur is None or cur[0].numel() < need[0] or cur[1].numel() < need[1]:
+            dev = net.device
+            torch.cuda.current_stream().synchronize()   # (re)allocation of a staging arena: rare, not on the steady-state path
+            cur = (torch.zeros(need[0], dtype=torch.uint8, device=dev), torch.zeros(need[1], dtype=torch.uint8, device=dev),
+                   torch.zeros(raw.items_img.numel(), dtype=torch.uint8, device=dev),
+                   torch.zeros(raw.items_mask.numel(), dtype=torch.uint8, device=dev))
+            self._raw_dev[b] = cur
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._ev_free[b])
+            cur[0][:raw.used_img].copy_(raw.arena_img[:raw.used_img], non_blocking=True)
+            cur[1][:raw.used_mask].copy_(raw.arena_mask[:raw.used_mask], non_blocking=True)
+            cur[2].copy_(raw.items_img, non_blocking=True)
+            cur[3].copy_(raw.items_mask, non_blocking=True)
+            self._ev_copied[b].record(self._copy_stream)
+        main.wait_event(self._ev_copied[b])
+        st = main.cuda_stream
+        self.L.resize_u8(cur[0].data_ptr(), cur[2].data_ptr(), raw.n, CI, self.pool_img.data_ptr(), H, W, _lib.RESIZE_CUBIC, st)
+        self.L.resize_u8(cur[1].data_ptr(), cur[3].data_ptr(), raw.n, net.classes, self.pool_mask.data_ptr(), H, W, _lib.RESIZE_NEAREST, st)
+        self._ev_free[b].record(main)
+        self.last_h2d_bytes = raw.used_img + raw.used_mask + 2 * raw.items_img.numel()
 
     def flush_host_pipeline(self):
         """Metrics of the last enqueued pipelined step (waits for it)."""

@@ -851,3 +851,36 @@ def test_oracle_crop_pad_window_composition():
     assert OA.crop_pad_window([(1, 0, 1, 2, 3, 4)], 0, 0, 0, 10, 20) == (-1, -4, 14, 26)
     assert OA.crop_pad_window([(4, 0, 0.1, 0.1, 0.1, 0.1)], 0, 0, 0, 100, 50) == (-10, -5, 120, 60)
     assert OA.crop_pad_window([(4, 0, -0.25, 0.0, 0.0, 0.0)], 0, 0, 0, 100, 50) == (25, 0, 75, 50)
+
+
+def test_raw_batch_packing_for_device_ingest():
+    """loader.RawBatch (on-device ingest, `device_resize: true`): samples of different sizes packed back to back, one
+    stp_resize_item each; HostLoader hands them out through the same iterate() contract (no GPU needed: unpinned)."""
+    import ctypes as C
+    from segmentation_training_pipeline_b200 import lib
+    from segmentation_training_pipeline_b200.impl.datasets import PredictionItem
+    from segmentation_training_pipeline_b200.loader import HostLoader, RawBatch
+    rng = np.random.default_rng(0)
+    samples = [(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), rng.integers(0, 2, (h, w, 1), dtype=np.uint8)) for h, w in [(5, 7), (8, 8), (3, 11)]]
+    rb = RawBatch(64, 16, 4, pin=False)       # deliberately too small: grows
+    rb.pack(samples, 3, 1)
+    assert rb.n == 3 and rb.used_img >= sum(x.size for x, _ in samples)
+    host = bytes(rb.items_img.numpy())
+    hostm = bytes(rb.items_mask.numpy())
+    for j, (x, y) in enumerate(samples):
+        it = lib.ResizeItem.from_buffer_copy(host, j * C.sizeof(lib.ResizeItem))
+        assert (it.sh, it.sw, it.vy0, it.vx0, it.vh, it.vw) == (x.shape[0], x.shape[1], 0, 0, x.shape[0], x.shape[1]) and it.src_off % 16 == 0
+        assert np.array_equal(rb.arena_img.numpy()[it.src_off:it.src_off + x.size].reshape(x.shape), x)
+        im = lib.ResizeItem.from_buffer_copy(hostm, j * C.sizeof(lib.ResizeItem))
+        assert np.array_equal(rb.arena_mask.numpy()[im.src_off:im.src_off + y.size].reshape(y.shape), y)
+
+    class DS:
+        def __len__(self):
+            return 3
+
+        def __getitem__(self, i):
+            return PredictionItem(str(i), samples[i][0], samples[i][1][:, :, 0])
+
+    ld = HostLoader(DS(), (32, 32, 3), 1, 2, workers=0, pin=False, device_resize=True)
+    out = list(ld.iterate([[0, 1], [2, 0]]))
+    assert len(out) == 2 and all(m is None and b.n == 2 for b, m in out)

@@ -153,3 +153,48 @@ def test_crop_pad_stage_in_the_training_step(cuda):
         win = OA.crop_pad_window(cfg.crop_pad, 77, 5, sid, size, size)
         ri, rm = OA.apply_crop_pad(imgs[sid], masks[sid], win, size, size)
         assert np.array_equal(gi[i], ri[:, ::-1]) and np.array_equal(gm[i], rm[:, ::-1]), i
+
+
+def test_on_device_ingest_of_unresized_samples(cuda, tmp_path):
+    """`device_resize: true` -- HostLoader hands out UNRESIZED decoded samples (loader.RawBatch), the
+    trainer copies them and stp_resize_u8 writes the network-shape batch into the step's input pool: bit exact against the
+    restated cv2 arithmetic, and the host-fed step runs on it."""
+    from oracle import resize as OR
+    from segmentation_training_pipeline_b200.impl.datasets import PredictionItem
+    from segmentation_training_pipeline_b200.loader import HostLoader
+    from segmentation_training_pipeline_b200.models import SegNet
+    from segmentation_training_pipeline_b200.trainer import Trainer
+
+    rng = np.random.default_rng(3)
+    sizes = [(50, 70), (64, 64), (120, 90), (33, 200), (64, 64), (80, 80)]
+
+    class DS:
+        def __len__(self):
+            return len(sizes)
+
+        def __getitem__(self, i):
+            h, w = sizes[i]
+            r = np.random.default_rng(100 + i)
+            return PredictionItem("s%d" % i, r.integers(0, 256, (h, w, 3), dtype=np.uint8), (r.random((h, w)) > 0.5).astype(np.uint8))
+
+    ds, n, size = DS(), 4, 64
+    net = SegNet("resnet18", classes=1, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=(1.0, 1.0, 0.0))
+    tr = Trainer(net, optimizer="SGD", lr=1e-3)
+    tr.enable_host_feed()
+    loader = HostLoader(ds, (size, size, 3), 1, n, workers=2, device_resize=True)
+    batches = [[0, 1, 2, 3], [4, 5, 0, 2], [3, 1, 5, 4]]
+    seen = 0
+    for k, (rb, none) in enumerate(loader.iterate(batches)):
+        assert none is None and rb.n == n
+        tr.step_from_host_pipelined(rb, None)
+        torch.cuda.synchronize()
+        gi, gm = tr.pool_img.cpu().numpy(), tr.pool_mask.cpu().numpy()
+        for j, idx in enumerate(batches[k]):
+            it = ds[idx]
+            assert np.array_equal(gi[j], OR.resize_cubic_u8(it.x, size, size)), (k, j)
+            assert np.array_equal(gm[j][:, :, 0], OR.resize_nearest_u8(it.y, size, size)), (k, j)
+        seen += 1
+    m = tr.flush_host_pipeline()
+    loader.close()
+    assert seen == 3 and m is not None and np.isfinite(m["loss"])
+    assert tr.last_h2d_bytes > 0
