@@ -41,8 +41,13 @@ def peaks():
     return dict(FALLBACK_PEAKS), "fallback"
 
 
-def conv_train_gflop_per_img(backbone: str, size: int) -> float:
+TRAIN_GFLOP_PER_IMG_FPN_R50_512 = 430.0   # FPN/ResNet-50 512x512, fwd + dgrad + wgrad
+
+
+def conv_train_gflop_per_img(backbone: str, size: int, architecture: str = "Unet") -> float:
     """Algorithmic conv FLOPs of one training step per image, computed from the layer table of the engine's graph."""
+    if architecture == "FPN" and backbone == "resnet50":
+        return TRAIN_GFLOP_PER_IMG_FPN_R50_512 * (size / 512.0) ** 2
     if backbone == "resnet34" and size == 512:
         return TRAIN_GFLOP_PER_IMG_R34_512
     return TRAIN_GFLOP_PER_IMG_R34_512 * (size / 512.0) ** 2  # only used for reduced debug runs (flagged in config)
@@ -150,9 +155,10 @@ def cpu_reference_step_time(size, sample_batch, steps, warmup, backbone="resnet3
 def workload_config(args, world, tc=True):
     """`config` of the JSON line: identical for the libstp arm and the reference arm (same workload, same batch)."""
     B, S = args.batch, args.size
-    return {"workload": "U-Net/%s %dx%d 1-class bs%d/GPU, on-device augment (Fliplr/Flipud/Affine/Multiply/Add) + "
-                        "fwd + binary_crossentropy+dice_loss + bwd + %sKeras-Adam" %
-                        (args.backbone, S, S, B, "NCCL all-reduce + " if world > 1 else ""),
+    arch, classes, loss = ("FPN", 3, "lovasz_loss") if getattr(args, "config", "c2") == "c3" else ("U-Net", 1, "binary_crossentropy+dice_loss")
+    return {"workload": "%s/%s %dx%d %d-class bs%d/GPU, on-device augment (Fliplr/Flipud/Affine/Multiply/Add) + "
+                        "fwd + %s + bwd + %sKeras-Adam" %
+                        (arch, args.backbone, S, S, classes, B, loss, "NCCL all-reduce + " if world > 1 else ""),
             "global_batch": B * world, "pool_per_rank": args.pool, "parallelism": "dp%d" % world,
             "l2": "per-step working set (>3 GB of activations) exceeds the 126 MB L2; dominant-kernel timing flushes L2 "
                   "with a 256 MB memset between launches",
@@ -195,8 +201,9 @@ def time_dominant_kernel(net, reps=30):
     import torch
     from segmentation_training_pipeline_b200 import engine as E
     conv = None
-    for op in net.ops:
-        if isinstance(op, E.Conv) and op.name == "stage2_unit2_conv1":
+    want = "final_stage_conv" if getattr(net, "architecture", "Unet") == "FPN" else "stage2_unit2_conv1"
+    for op in net.ops:   # FPN: the FLOP-dominant layer is the 512->512 3x3 over the merged pyramid (54 % of the network's FLOPs)
+        if isinstance(op, E.Conv) and op.name == want:
             conv = op
     if conv is None:
         return None
@@ -317,11 +324,19 @@ def run_gpu(args, rank, local_rank, world):
     from segmentation_training_pipeline_b200.trainer import AugmentConfig, Trainer
 
     B, S = args.batch, args.size
-    net = SegNet(args.backbone, classes=1, input_shape=(S, S, 3), batch=B, device=dev, seed=0, loss=(1.0, 1.0, 0.0))
+    c3 = args.config == "c3"     # BASELINE.json configs[2]: FPN/ResNet-50, 3-class, Lovasz (secondary; the headline is configs[1])
+    if c3:
+        net = SegNet(args.backbone, classes=3, input_shape=(S, S, 3), batch=B, device=dev, seed=0, loss=(0.0, 0.0, 0.0, 1.0),
+                     architecture="FPN")
+    else:
+        net = SegNet(args.backbone, classes=1, input_shape=(S, S, 3), batch=B, device=dev, seed=0, loss=(1.0, 1.0, 0.0))
     aug = AugmentConfig(seed=rank, **C2_AUGMENT)
     tr = Trainer(net, optimizer="Adam", lr=1e-3, augment=aug, world_size=world)
     pool_n = args.pool
     img, mask = synth_pool(pool_n, S, S, 1234 + rank, 4321 + rank)
+    if c3:   # three independent blob masks (the engine treats classes as independent sigmoid heads under lovasz_loss)
+        import numpy as np
+        mask = np.concatenate([mask, np.roll(mask, S // 8, axis=2), np.roll(mask, S // 4, axis=1)], axis=3)
     tr.set_pool(torch.from_numpy(img), torch.from_numpy(mask))
     if world > 1:
         from segmentation_training_pipeline_b200 import ddp
@@ -363,7 +378,7 @@ def run_gpu(args, rank, local_rank, world):
     tr2 = Trainer(net, optimizer="Adam", lr=1e-3, augment=aug, world_size=world)
     tr2.m, tr2.v = tr.m, tr.v
     tr2.enable_host_feed()
-    h2d = B * S * S * 4
+    h2d = B * S * S * (3 + net.classes)
     d2h = 16 * 4
 
     def e2e_step(i):
@@ -404,9 +419,10 @@ def run_gpu(args, rank, local_rank, world):
         imgs = args.steps * B * world
         value = imgs / (ms / 1e3)
         e2e = imgs / (ms_e2e / 1e3)
-        gf = conv_train_gflop_per_img(args.backbone, S)
+        gf = conv_train_gflop_per_img(args.backbone, S, "FPN" if c3 else "Unet")
         out = {
-            "metric": "images/sec U-Net/ResNet-34 512x512 training step", "value": value, "unit": "img/s",
+            "metric": "images/sec FPN/ResNet-50 512x512 3-class training step" if c3 else "images/sec U-Net/ResNet-34 512x512 training step",
+            "value": value, "unit": "img/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, world, bool(lib.load().stp_tc_enabled())),
@@ -463,7 +479,13 @@ def main():
     ap.add_argument("--backbone", default="resnet34")
     ap.add_argument("--ref-batch", type=int, default=0, help="images per CPU reference step; 0 = --batch (bs16, BASELINE.md section 4)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3"],
+                    help="c2 (default, the headline): BASELINE.json configs[1] U-Net/ResNet-34 Dice+BCE; c3: configs[2] FPN/ResNet-50 "
+                         "3-class Lovasz (implies --backbone resnet50; libstp arm only)")
     args = ap.parse_args()
+    if args.config == "c3":
+        args.backbone = "resnet50"
+        args.no_cpu = True
     args.warmup = max(args.warmup, 3) if args.impl == "stp" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

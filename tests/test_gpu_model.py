@@ -204,7 +204,7 @@ def test_loss_curve_100_steps(cuda):
     net = SegNet("resnet18", classes=1, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=(1.0, 1.0, 0.0))
     W = net.get_weights()
     img, mask = _data(pool, size, size, seed=11)
-    tr = Trainer(net, optimizer=optimizer, lr=lr, momentum=momentum)
+    tr = Trainer(net, optimizer="Adam", lr=1e-3)
     tr.set_pool(img, mask)
     tr.capture()
     curve = []
@@ -215,7 +215,7 @@ def test_loss_curve_100_steps(cuda):
     def oracle_curve(storage):
         om = SegModel("Unet", "resnet18", classes=1, input_shape=(size, size, 3), storage=storage)
         om.load_numpy(W)
-        opt = OO.Adam(om.params, lr=lr) if optimizer == "Adam" else OO.SGD(om.params, lr=lr, momentum=momentum)
+        opt = OO.Adam(om.params, lr=1e-3)
         out = []
         for s in range(steps):
             idx = [(s * n + j) % pool for j in range(n)]
