@@ -437,20 +437,24 @@ def run_gpu(args, rank, local_rank, world):
             "step_frac_of_sustained_peak": value / world * gf / 1e3 / pk["bf16_tflops_sustained"],
         }
         if dom is not None:
-            ach = dom["flop"] / (dom["ms"] / 1e3) / 1e12
+            # Headline figure: the launch as it runs INSIDE the step -- 30 launches back to back over 10 rotating input /
+            # output sets (335 MB > 126 MB L2: every launch reads its activations from HBM; no flush kernel, so programmatic
+            # dependent launch hides the launch gap exactly as in the captured step).  The isolated launch after an explicit L2
+            # flush (launch gap + prologue + cold descriptors inside a < 35 us figure) is kept beside it.
+            ms_main = dom.get("ms_b2b") or dom["ms"]
+            ach = dom["flop"] / (ms_main / 1e3) / 1e12
             out["roofline"] = {"bound": "tensor", "kernel": dom["kernel"] + ": %s fwd (%s) + BN statistics epilogue" %
                                                             (dom["name"], dom["shape"]),
                                "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
                                "peak_source": src + (" (of measured)" if src == "measured" else " (of fallback, B200_PROFILING.md)"),
                                "traffic": dominant_kernel_traffic(), "flop_per_launch": dom["flop"],
-                               "ms_per_launch": dom["ms"],
-                               "timing": "isolated launch, L2 flushed by a 256 MB memset before each (launch gap + prologue inside)"}
-            if dom.get("ms_b2b"):
-                out["roofline"]["back_to_back"] = {
-                    "ms_per_launch": dom["ms_b2b"], "achieved": dom["flop"] / (dom["ms_b2b"] / 1e3) / 1e12,
-                    "frac": dom["flop"] / (dom["ms_b2b"] / 1e3) / 1e12 / pk["bf16_tflops"],
-                    "timing": "30 launches back to back over 10 rotating input/output sets (335 MB > 126 MB L2), no flush "
-                              "kernel: how the launch runs inside the step graph"}
+                               "ms_per_launch": ms_main,
+                               "timing": ("CUDA events around 30 launches back to back over 10 rotating input/output sets (335 MB > 126 MB "
+                                          "L2, no flush kernel): the launch as it runs inside the step graph") if dom.get("ms_b2b") else
+                                         "isolated launch, L2 flushed by a 256 MB memset before each",
+                               "isolated": {"ms_per_launch": dom["ms"], "achieved": dom["flop"] / (dom["ms"] / 1e3) / 1e12,
+                                            "frac": dom["flop"] / (dom["ms"] / 1e3) / 1e12 / pk["bf16_tflops"],
+                                            "timing": "one launch after an L2 flush (256 MB memset): launch gap + prologue inside"}}
         if hbm is not None:  # the largest single HBM-bound kernel of the step, against the measured copy bandwidth
             gbs = hbm["bytes"] / (hbm["ms"] / 1e3) / 1e9
             out["roofline_hbm"] = {"bound": "hbm", "kernel": hbm["kernel"], "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",

@@ -314,6 +314,10 @@ int stp_maxpool_fwd(const stp_tensor* x, int32_t k, int32_t stride, int32_t pad,
                     uint8_t* argmax, stp_stream stream);
 int stp_maxpool_bwd(const stp_tensor* dy, const uint8_t* argmax, int32_t k, int32_t stride, int32_t pad,
                     const stp_tensor* residual, const stp_tensor* dx, stp_stream stream);
+/* AveragePooling2D(k, strides k) over windows that tile the input exactly (PSPNet pyramid pooling, schema
+ * segmentation.raml:226-248 -> segmentation_models PSPNet [DEP]); backward: dx = dy / k^2 per window (+ residual). */
+int stp_avgpool_fwd(const stp_tensor* x, int32_t k, const stp_tensor* y, stp_stream stream);
+int stp_avgpool_bwd(const stp_tensor* dy, int32_t k, const stp_tensor* residual, const stp_tensor* dx, stp_stream stream);
 
 /* K8 copy / nearest-upsample a tensor into a (strided) destination: UpSampling2D + Concatenate when the
  * producer could not write in place */

@@ -68,7 +68,7 @@ class SegModel:
                  decoder_filters=(256, 128, 64, 32, 16), decoder_use_batchnorm=True,
                  decoder_block_type="upsampling", enc_init="he_uniform", dec_init="glorot_uniform",
                  pyramid_block_filters=256, segmentation_block_filters=128, fpn_dropout=None,
-                 update_moving=True):
+                 update_moving=True, downsample_factor=8, psp_conv_filters=512):
         self.arch, self.backbone = architecture, backbone.lower()
         self.classes, self.activation = classes, activation
         self.storage = storage
@@ -76,12 +76,15 @@ class SegModel:
         self.dec_bn = decoder_use_batchnorm
         self.block_type = decoder_block_type
         self.pyr, self.segf = pyramid_block_filters, segmentation_block_filters
+        self.psp_factor, self.psp_filters = int(downsample_factor), int(psp_conv_filters)
         self.P = ParamStore(seed, enc_init, dec_init)
         self.training = True
         self.update_moving = update_moving
         self.taps: Dict[str, torch.Tensor] = {}
         # materialise parameters with a dry run on a tiny input of the right channel count
         h = 64 if self.backbone != "vgg16" else 32
+        if self.arch == "PSPNet":
+            h = 6 * self.psp_factor
         um, self.update_moving = self.update_moving, False
         with torch.no_grad():
             self.forward(torch.zeros(1, h, h, input_shape[2]), emit_logits=False)
@@ -141,6 +144,8 @@ class SegModel:
         x = self._conv(x, "conv0", 7, 64, stride=2, padding=3)
         x = self._bn_relu(x, "bn0", ENC_BN_EPS, tap="relu0")
         x = L.maxpool(x, 3, 2, 1)
+        psp_tap = {4: "stage2_unit1_relu1", 8: "stage3_unit1_relu1", 16: "stage4_unit1_relu1"}.get(self.psp_factor) \
+            if self.arch == "PSPNet" else None
         for stage, rep in enumerate(reps):
             f = 64 * 2 ** stage
             for block in range(rep):
@@ -148,6 +153,8 @@ class SegModel:
                 first = block == 0
                 stride = 2 if (first and stage > 0) else 1
                 y = self._bn_relu(x, pre + "bn1", ENC_BN_EPS, tap=pre + "relu1")
+                if psp_tap == pre + "relu1":
+                    return y, []   # PSPNet: the Keras Model ends the encoder at the feature layer (later layers are not in the graph)
                 if bott:
                     sc = self._conv(y, pre + "sc", 1, 4 * f, stride) if first else x
                     z = self._conv(y, pre + "conv1", 1, f)
@@ -240,6 +247,21 @@ class SegModel:
             x = L.rb(z + skip, self.storage) if skip is not None else z
         return x
 
+    def _pspnet_decoder(self, feat):
+        """segmentation_models 0.2.1 PSPNet [DEP, recalled] (schema segmentation.raml:226-248): pyramid pooling over the
+        feature map at 1/downsample_factor -- for level in (1, 2, 3, 6): AveragePooling2D(size/level) -> 1x1 conv
+        (psp_conv_filters) + BN + ReLU -> bilinear resize back (TF1 legacy); Concatenate([features, levels...]); 1x1 conv (512)
+        + BN + ReLU; then final_conv 3x3 and a bilinear x downsample_factor upsample of the logits (in forward())."""
+        h, w = feat.shape[2], feat.shape[3]
+        outs = [feat]
+        for level in (1, 2, 3, 6):
+            k = h // level
+            z = L.rb(torch.nn.functional.avg_pool2d(feat, k, k), self.storage)
+            z = self._conv_bn_relu(z, "psp_level%d_conv" % level, "psp_level%d_bn" % level, 1, self.psp_filters, True)
+            outs.append(L.rb(L.resize_bilinear_tf1(z, h, w), self.storage))
+        x = torch.cat(outs, dim=1)
+        return self._conv_bn_relu(x, "psp_conv", "psp_bn", 1, 512, True)
+
     # -- full graph ------------------------------------------------------------------------
     def forward(self, x_nhwc: torch.Tensor, emit_logits: bool = False) -> torch.Tensor:
         """x: float NHWC raw 0..255 (no preprocessing call anywhere in the reference).
@@ -265,6 +287,11 @@ class SegModel:
             x = self._linknet_decoder(x, skips)
             w, b = self.P.conv("final_conv", 3, 3, x.shape[1], self.classes, True)
             logits = L.conv2d(x, w, b, 1, "same", self.storage)
+        elif self.arch == "PSPNet":
+            x = self._pspnet_decoder(x)
+            w, b = self.P.conv("final_conv", 3, 3, x.shape[1], self.classes, True)
+            logits = L.conv2d(x, w, b, 1, "same", self.storage)
+            logits = L.resize_bilinear_tf1(logits, logits.shape[2] * self.psp_factor, logits.shape[3] * self.psp_factor)
         else:
             raise ValueError("Unknown architecture")
         self.taps["logits"] = logits

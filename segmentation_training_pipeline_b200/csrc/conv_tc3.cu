@@ -489,12 +489,20 @@ static double tc3_cost(const ConvP& p, int bn, int mt) {
 bool tc3_plan(const ConvP& p, Tc3Plan* pl) {
   if (p.stride != 1 || p.up != 1) return false;
   if (p.R > 3 || p.S > 3 || (p.R < 2 && p.S < 2)) return false;
-  if (p.Cin % kBK3 != 0 || p.Cout % 128 != 0) return false;
+  if (p.Cin % kBK3 != 0 || p.Cout % 64 != 0) return false;
   if (p.y_f32 || p.ncls > 0) return false;
+  // N = 64 pair tiles (Cout = 64 / 192 layers) only on request (option "tc3_bn64" = 1): parity green, but measured SLOWER than
+  // the single-CTA kernel on every such layer (64->64 @128^2 29.9 vs 24.7 us back to back, 192->64 69.1 vs 57.7 us,
+  // 64->192 73.9 vs 60.3 us; profiles/README.md r2): a weight tap then feeds only 8 MMAs of 32 clk between two commits
+  if (p.Cout % 128 != 0 && get_option(OPT_TC3_BN64) != 1) return false;
   double best = 0.0;
   int bbn = 0, bmt = 0;
-  for (int bn : {128}) {  // BN = 256 (no TMEM double buffering left for MT = 2, 64 KB staging) never won: only when forced
+  // BN = 256 (no TMEM double buffering left for MT = 2, 64 KB staging) never won: only when forced.  BN = 64 serves the
+  // Cout = 64 / 192 layers (stage 1, dec2, dgrad of dec2_conv1): an M = 256 x N = 64 pair MMA reads 5 KB of shared memory
+  // per CTA per 32-clk MMA where the single-CTA M = 128 x N = 64 MMA of conv_tc2 reads 6 KB (operand-bandwidth bound).
+  for (int bn : {128, 64}) {
     if (p.Cout % bn != 0) continue;
+    if (bn == 64 && p.Cout % 128 == 0) continue;
     for (int mt = 1; mt <= (bn == 128 ? 2 : 1); ++mt) {
       const double c = tc3_cost(p, bn, mt);
       if (!bbn || c < best) {
@@ -505,7 +513,7 @@ bool tc3_plan(const ConvP& p, Tc3Plan* pl) {
     }
   }
   const int fbn = get_option(OPT_TC3_FORCE_BN), fmt = get_option(OPT_TC3_FORCE_MT);
-  if (fbn == 128 || (fbn == 256 && p.Cout % 256 == 0)) {
+  if ((fbn == 128 && p.Cout % 128 == 0) || (fbn == 256 && p.Cout % 256 == 0) || fbn == 64) {
     bbn = fbn;
     if (bbn == 256) bmt = 1;
   }
@@ -639,6 +647,7 @@ int launch_tc3_conv(const ConvP& p, cudaStream_t st) {
       if (!make_tmap_bf16(&tmR, p.res, 4, dims, rstrides, box, 128)) return STP_E_CUDA;
     }
   }
+  if (pl.BN == 64) return pl.MT == 2 ? launch3<64, 2>(tmA, tmB, tmY, tmR, a, st) : launch3<64, 1>(tmA, tmB, tmY, tmR, a, st);
   if (pl.BN == 256) return launch3<256, 1>(tmA, tmB, tmY, tmR, a, st);
   if (pl.MT == 2) return launch3<128, 2>(tmA, tmB, tmY, tmR, a, st);
   return launch3<128, 1>(tmA, tmB, tmY, tmR, a, st);

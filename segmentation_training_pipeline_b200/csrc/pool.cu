@@ -179,6 +179,59 @@ __global__ void __launch_bounds__(256) maxpool_bwd_k3s2_kernel(const __nv_bfloat
     }
   }
 }
+// AveragePooling2D(pool_size k, strides k) over exact windows (PSPNet pyramid pooling, schema segmentation.raml:226-248 ->
+// segmentation_models PSPNet InterpBlock [DEP]): y = mean of the k x k window, fp32 accumulation.  Backward: every input
+// pixel receives dy / k^2 of its window (+ residual: the feature map feeds four pyramid levels and the concat).
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int H, int W, int k,
+                                                          __nv_bfloat16* __restrict__ y, int ldy, int Ho, int Wo, int64_t rows_out, int cv) {
+  const int64_t total = rows_out * cv;
+  const float inv = 1.f / (float)(k * k);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cv;
+    const int v = (int)(i - r * cv);
+    const int64_t n = r / ((int64_t)Ho * Wo);
+    const int rem = (int)(r - n * (int64_t)Ho * Wo);
+    const int ho = rem / Wo, wo = rem - ho * Wo;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    for (int a = 0; a < k; ++a)
+      for (int b = 0; b < k; ++b) {
+        float f[8];
+        unpack8(ld8(x + ((n * H + ho * k + a) * (int64_t)W + wo * k + b) * ldx + v * 8), f);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] += f[c];
+      }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] *= inv;
+    st8(y + r * ldy + v * 8, pack8(acc));
+  }
+}
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int Ho, int Wo, int k,
+                                                          const __nv_bfloat16* __restrict__ res, int ldr, __nv_bfloat16* __restrict__ dx,
+                                                          int lddx, int H, int W, int64_t rows_in, int cv) {
+  const int64_t total = rows_in * cv;
+  const float inv = 1.f / (float)(k * k);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cv;
+    const int v = (int)(i - r * cv);
+    const int64_t n = r / ((int64_t)H * W);
+    const int rem = (int)(r - n * (int64_t)H * W);
+    const int h = rem / W, w = rem - h * W;
+    float g[8];
+    unpack8(ld8(dy + ((n * Ho + h / k) * (int64_t)Wo + w / k) * lddy + v * 8), g);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) g[c] *= inv;
+    if (res) {
+      float rf[8];
+      unpack8(ld8(res + r * ldr + v * 8), rf);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) g[c] += rf[c];
+    }
+    st8(dx + r * lddx + v * 8, pack8(g));
+  }
+}
+
 static int ew_grid2(int64_t total) {
   int64_t b = (total + 255) / 256;
   int64_t cap = (int64_t)kNumSMs * 16;
@@ -237,4 +290,25 @@ extern "C" int stp_maxpool_bwd(const stp_tensor* dy, const uint8_t* argmax, int3
       residual ? (const __nv_bfloat16*)residual->ptr : nullptr, residual ? residual->ld : 0, (__nv_bfloat16*)dx->ptr,
       dx->ld, dx->h, dx->w, rows, dx->c, cv);
   return check_launch("maxpool_bwd");
+}
+
+extern "C" int stp_avgpool_fwd(const stp_tensor* x, int32_t k, const stp_tensor* y, stp_stream stream) {
+  STP_REQUIRE(vec_ok(x) && vec_ok(y), "avgpool_fwd: bad tensors");
+  STP_REQUIRE(k >= 1 && y->c == x->c && y->n == x->n && x->h == y->h * k && x->w == y->w * k, "avgpool_fwd: windows must tile the input exactly");
+  const int64_t rows = pixels(y);
+  const int cv = x->c / 8;
+  avgpool_fwd_kernel<<<ew_grid2(rows * cv), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x->ptr, x->ld, x->h, x->w, k,
+                                                                            (__nv_bfloat16*)y->ptr, y->ld, y->h, y->w, rows, cv);
+  return check_launch("avgpool_fwd");
+}
+extern "C" int stp_avgpool_bwd(const stp_tensor* dy, int32_t k, const stp_tensor* residual, const stp_tensor* dx, stp_stream stream) {
+  STP_REQUIRE(vec_ok(dy) && vec_ok(dx), "avgpool_bwd: bad tensors");
+  STP_REQUIRE(k >= 1 && dy->c == dx->c && dy->n == dx->n && dx->h == dy->h * k && dx->w == dy->w * k, "avgpool_bwd: shape mismatch");
+  if (residual) STP_REQUIRE(vec_ok(residual) && residual->c == dx->c && pixels(residual) == pixels(dx), "avgpool_bwd: bad residual");
+  const int64_t rows = pixels(dx);
+  const int cv = dx->c / 8;
+  avgpool_bwd_kernel<<<ew_grid2(rows * cv), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy->ptr, dy->ld, dy->h, dy->w, k, residual ? (const __nv_bfloat16*)residual->ptr : nullptr,
+      residual ? residual->ld : 0, (__nv_bfloat16*)dx->ptr, dx->ld, dx->h, dx->w, rows, cv);
+  return check_launch("avgpool_bwd");
 }

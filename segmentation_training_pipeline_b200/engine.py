@@ -786,6 +786,28 @@ class MaxPool(Op):
                                self.dx.ref, _stream())
 
 
+class AvgPool(Op):
+    """keras AveragePooling2D(k, strides k) over windows that tile the input exactly (PSPNet pyramid pooling)."""
+
+    def __init__(self, net: Net, x: Buf, y: Buf, k: int):
+        assert x.h == y.h * k and x.w == y.w * k and x.c == y.c
+        self.net, self.x, self.y, self.k = net, x, y, int(k)
+        net.ops.append(self)
+
+    def grad_writes(self):
+        return [self.x.grad()]
+
+    def prepare(self):
+        self.dy, self.dx = self.y.grad(), self.x.grad()
+        self.res_ref = self.dx.ref if self.acc[0] else None
+
+    def fwd(self):
+        self.net.L.avgpool_fwd(self.x.ref, self.k, self.y.ref, _stream())
+
+    def bwd(self):
+        self.net.L.avgpool_bwd(self.dy.ref, self.k, self.res_ref, self.dx.ref, _stream())
+
+
 class Head(Op):
     """final_conv (3x3 same, bias) -> logits f32 [M, classes]; sigmoid lives in the loss / predict kernels."""
 

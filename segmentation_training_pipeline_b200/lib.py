@@ -136,6 +136,8 @@ SIGNATURES = {
     "stp_stem_wgrad_post": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "stp_maxpool_fwd": (C.c_int, [_TP, _I32, _I32, _I32, _TP, _P, _P]),
     "stp_maxpool_bwd": (C.c_int, [_TP, _P, _I32, _I32, _I32, _TP, _TP, _P]),
+    "stp_avgpool_fwd": (C.c_int, [_TP, _I32, _TP, _P]),
+    "stp_avgpool_bwd": (C.c_int, [_TP, _I32, _TP, _TP, _P]),
     "stp_copy_up": (C.c_int, [_TP, _I32, _TP, _P]),
     "stp_add": (C.c_int, [_TP, _TP, _TP, _P]),
     "stp_upsample2x_bwd": (C.c_int, [_TP, _TP, _TP, _P]),

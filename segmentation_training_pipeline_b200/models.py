@@ -21,7 +21,7 @@ RESNET_REPS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3), "resnet50": (
 RESNET_BOTTLENECK = {"resnet18": False, "resnet34": False, "resnet50": True, "resnet101": True, "resnet152": True}
 VGG16_BLOCKS = ((64, 2), (128, 2), (256, 3), (512, 3), (512, 3))  # keras.applications.VGG16 [DEP]
 KNOWN_BACKBONES = sorted(RESNET_REPS) + ["vgg16"]
-KNOWN_ARCHITECTURES = ["Unet", "FPN", "Linknet"]
+KNOWN_ARCHITECTURES = ["Unet", "FPN", "Linknet", "PSPNet"]
 
 
 class SegNet(E.Net):
@@ -31,7 +31,7 @@ class SegNet(E.Net):
                  decoder_filters=(256, 128, 64, 32, 16), device="cuda:0", seed=0,
                  enc_init="he_uniform", dec_init="glorot_uniform", loss=(1.0, 0.0, 0.0), architecture="Unet",
                  decoder_block_type="upsampling", pyramid_block_filters=256, segmentation_block_filters=128,
-                 dropout=None, precision="bf16", decoder_use_batchnorm=True):
+                 dropout=None, precision="bf16", decoder_use_batchnorm=True, downsample_factor=8, psp_conv_filters=512):
         super().__init__(batch, device, seed, precision)
         self.dec_bn = bool(decoder_use_batchnorm)
         backbone = backbone.lower()
@@ -42,15 +42,20 @@ class SegNet(E.Net):
         self.architecture = architecture
         linknet = architecture == "Linknet"
         fpn = architecture == "FPN"
-        if fpn and precision == "fp32":
+        psp = architecture == "PSPNet"
+        if (fpn or psp) and precision == "fp32":
             raise NotImplementedError("precision: fp32 (parity mode) is built for the Unet / Linknet graphs")
+        if psp and backbone.lower() == "vgg16":
+            raise NotImplementedError("PSPNet is built over the ResNet encoders only")
+        if psp and downsample_factor not in (4, 8, 16):
+            raise ValueError("PSPNet: downsample_factor must be 4, 8 or 16")
         if fpn and dropout:
             raise NotImplementedError("FPN dropout (SpatialDropout2D) is not built; the schema default is None")
         if fpn and backbone == "vgg16":
             raise NotImplementedError("FPN is built over the ResNet encoders only")
         if decoder_block_type not in ("upsampling", "transpose"):
             raise ValueError("decoder_block_type must be 'upsampling' or 'transpose'")
-        if not self.dec_bn and (linknet or fpn or decoder_block_type == "transpose"):
+        if not self.dec_bn and (linknet or fpn or psp or decoder_block_type == "transpose"):
             raise NotImplementedError("decoder_use_batchnorm: false is built for the Unet upsampling decoder only")
         transpose = decoder_block_type == "transpose" and not linknet   # schema segmentation.raml:162-165 (Unet only)
         if transpose and backbone == "vgg16":
@@ -65,8 +70,14 @@ class SegNet(E.Net):
             print("Known backbones:", KNOWN_BACKBONES)
             raise ValueError("Unknown backbone")
         H, W, CI = input_shape
-        if H % 32 or W % 32:
+        if psp:
+            if H % (6 * downsample_factor) or W % (6 * downsample_factor):
+                # segmentation_models' own check: the pyramid levels (1, 2, 3, 6) must tile the feature map exactly
+                raise ValueError("PSPNet: input height/width must be divisible by 6 * downsample_factor = %d" % (6 * downsample_factor))
+        elif H % 32 or W % 32:
             raise ValueError("input height/width must be divisible by 32")
+        if not 1 <= CI <= 4:
+            raise NotImplementedError("input channels: 1..4 are built (uint8 augmentation / stem kernels); shape[2] = %d" % CI)
         if len(decoder_filters) != 5:
             raise ValueError("decoder_filters must have 5 entries")
         N = batch
@@ -82,15 +93,18 @@ class SegNet(E.Net):
         skip_c = [256 * exp, 128 * exp, 64 * exp, 64, 0]
         up_c = df[:] if transpose else [512 * exp] + df[:4]   # transpose blocks concat [ConvT output (f_i) | skip]
         cat: List[E.Buf] = []
-        for i in range(0 if (linknet or fpn) else 5):
+        for i in range(0 if (linknet or fpn or psp) else 5):
             s = 32 >> i  # input of stage i is at H/32 * 2^i after upsampling -> H / (16 >> i) ... computed below
             hh, ww = H // (16 >> i) if i < 4 else H, W // (16 >> i) if i < 4 else W
             cat.append(E.Buf(self, N, hh, ww, up_c[i] + skip_c[i], name="cat%d" % i))
         skip_view = {  # keras layer name -> (stage index)
             "stage4_unit1_relu1": 0, "stage3_unit1_relu1": 1, "stage2_unit1_relu1": 2, "relu0": 3}
         skip_names = list(skip_view)
-        if linknet or fpn:  # Linknet / FPN add their skips instead of concatenating them: plain buffers, no concat layout
+        if linknet or fpn or psp:  # Linknet / FPN add their skips instead of concatenating them: plain buffers, no concat layout
             skip_view, cat = {}, []
+        psp_tap, psp_cat = None, None
+        if psp:   # the feature map the pyramid pools is written straight into channel slice 0 of the PSP concat buffer
+            psp_tap = {4: "stage2_unit1_relu1", 8: "stage3_unit1_relu1", 16: "stage4_unit1_relu1"}[downsample_factor]
 
         def skip_buf(name, n, h, w, c):
             if name in skip_view:
@@ -122,6 +136,13 @@ class SegNet(E.Net):
                 first = block == 0
                 stride = 2 if (first and stage > 0) else 1
                 ho, wo = h // stride, w // stride
+                if psp and pre + "relu1" == psp_tap:
+                    psp_cat = E.Buf(self, N, h, w, x.c + 4 * psp_conv_filters, name="psp_concat")
+                    feat = psp_cat.slice(0, x.c, name=psp_tap)
+                    E.BNRelu(self, x, feat, pre + "bn1", ENC_BN_EPS)
+                    self.encoder_param_names = list(self.params.keys())
+                    self._build_pspnet_decoder(feat, psp_cat, psp_conv_filters, downsample_factor, classes, dec_init, loss)
+                    return   # the Keras Model ends the encoder here: later encoder layers are not part of the graph
                 y = skip_buf(pre + "relu1", N, h, w, x.c)
                 out = E.Buf(self, N, ho, wo, f * exp, name=pre + "add")
                 if first:
@@ -233,6 +254,30 @@ class SegNet(E.Net):
         af = E.Buf(self, N, hq, wq, 4 * segf, name="final_stage_relu")
         E.BNRelu(self, zf, af, "final_stage_bn", DEC_BN_EPS)
         self.head = E.UpHead(self, af, classes, "head_conv", up=4, init=dec_init)
+        self.loss = E.Loss(self, self.head, self.mask, *loss)
+        self.finalize()
+
+    def _build_pspnet_decoder(self, feat, cat, filters, factor, classes, dec_init, loss):
+        """segmentation_models 0.2.1 PSPNet [DEP, recalled] (reference segmentation.py:109-113; schema segmentation.raml:226-248):
+        for level in (1, 2, 3, 6): AveragePooling2D(size / level) -> 1x1 conv (psp_conv_filters) + BN + ReLU -> bilinear resize
+        (TF1 legacy) back to the feature size, written into its channel slice of the concat buffer whose slice 0 IS the feature
+        map; 1x1 conv (512) + BN + ReLU; final_conv 3x3 (classes, bias) and the bilinear x downsample_factor upsample of the
+        logits (engine.UpHead)."""
+        N, h, w = self.batch, feat.h, feat.w
+        for li, level in enumerate((1, 2, 3, 6)):
+            pre = "psp_level%d_" % level
+            pooled = E.Buf(self, N, level, level, feat.c, name=pre + "pool")
+            E.AvgPool(self, feat, pooled, h // level)
+            z = E.Buf(self, N, level, level, filters, name=pre + "conv")
+            E.Conv(self, pooled, z, pre + "conv", 1, init=dec_init)
+            a = E.Buf(self, N, level, level, filters, name=pre + "relu")
+            E.BNRelu(self, z, a, pre + "bn", DEC_BN_EPS)
+            E.Resize(self, a, cat.slice(feat.c + li * filters, filters, name=pre + "up"))
+        z = E.Buf(self, N, h, w, 512, name="psp_conv")
+        E.Conv(self, cat, z, "psp_conv", 1, init=dec_init)
+        a = E.Buf(self, N, h, w, 512, name="psp_relu")
+        E.BNRelu(self, z, a, "psp_bn", DEC_BN_EPS)
+        self.head = E.UpHead(self, a, classes, "final_conv", up=factor, init=dec_init)
         self.loss = E.Loss(self, self.head, self.mask, *loss)
         self.finalize()
 

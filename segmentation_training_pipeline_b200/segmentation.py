@@ -311,7 +311,9 @@ class PipelineConfig:
                               pyramid_block_filters=int(mk.get("pyramid_block_filters") or 256),
                               segmentation_block_filters=int(mk.get("segmentation_block_filters") or 128),
                               dropout=mk.get("dropout") or None,
-                              decoder_use_batchnorm=bool(mk.get("use_batchnorm", True)),
+                              decoder_use_batchnorm=bool(mk.get("use_batchnorm", True)) if arch != "PSPNet" else True,
+                              downsample_factor=int(mk.get("downsample_factor") or 8),
+                              psp_conv_filters=int(mk.get("psp_conv_filters") or 512),
                               precision=str(self.extra.get("precision", "bf16")),
                               loss=lw)
         net.activation = self.activation or "linear"   # what predict applies to the logits
@@ -320,8 +322,44 @@ class PipelineConfig:
             w = {k: v for k, v in dict(np.load(enc_file)).items() if k.rsplit("/", 1)[0] in layers}
             if not w:
                 raise ValueError("encoder_weights: %s holds no array of this encoder (%s, ...)" % (enc_file, sorted(layers)[:3]))
+            w = self._adapt_input_channels(net, w)
             net.set_weights(w, strict=False)
         return net
+
+    def _adapt_input_channels(self, net, w: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+        """More than 3 input channels with pretrained 3-channel encoder weights (reference createNet1, segmentation.py:138-153):
+        the reference builds the 3-channel model WITH weights and the N-channel one without, copies every layer across
+        (`adaptNet` / `copyWeights`, musket_core [DEP, unpinned]) and caches the result in `<config>.mdl-nchannel`.  Here: every
+        array whose shape matches is taken as is; a first-layer kernel (kh, kw, 3, f) is widened to (kh, kw, C, f) -- the RGB
+        planes are copied and every extra plane is their mean (config key `nchannel_fill: mean | zero`); the per-channel
+        arrays of the input BatchNorm (bn_data) are extended the same way.  The adapted dict is cached as
+        `<config>.mdl-nchannel.npz` and reused on the next build."""
+        C = int(self.shape[2])
+        if C <= 3:
+            return w
+        cache = (self.path + ".mdl-nchannel.npz") if self.path else None
+        if cache and os.path.exists(cache):
+            return dict(np.load(cache))
+        fill = str(self.extra.get("nchannel_fill", "mean"))
+        if fill not in ("mean", "zero"):
+            raise ValueError("nchannel_fill must be 'mean' or 'zero'")
+        cur = net.get_weights()
+        out = {}
+        for k, v in w.items():
+            tgt = cur.get(k)
+            if tgt is None or tgt.shape == v.shape:
+                out[k] = v
+            elif v.ndim == 4 and tgt.ndim == 4 and v.shape[:2] == tgt.shape[:2] and v.shape[3] == tgt.shape[3] and v.shape[2] == 3:
+                extra = v.mean(axis=2, keepdims=True) if fill == "mean" else np.zeros_like(v[:, :, :1])
+                out[k] = np.concatenate([v] + [extra] * (tgt.shape[2] - 3), axis=2).astype(np.float32)
+            elif v.ndim == 1 and tgt.ndim == 1 and v.shape[0] == 3 and tgt.shape[0] == C:
+                ext = np.full(C - 3, v.mean() if fill == "mean" else (1.0 if k.endswith("moving_variance") else 0.0), np.float32)
+                out[k] = np.concatenate([v, ext]).astype(np.float32)
+            else:
+                raise ValueError("encoder_weights: %s has shape %s, the %d-channel encoder needs %s" % (k, v.shape, C, tgt.shape))
+        if cache:
+            np.savez(cache, **out)
+        return out
 
     def _model_kwargs(self, arch: str) -> Dict[str, object]:
         """The architecture's schema-typed keyword arguments (schemas/segmentation.raml:158-248) as the reference's createNet1
@@ -349,6 +387,12 @@ class PipelineConfig:
             only("interpolation", ("bilinear",), "segmentation branches use TF1 bilinear resize")
             only("use_batchnorm", (True,), "the FPN blocks are conv + BatchNorm + ReLU")
             only("dropout", (0, 0.0, None), "SpatialDropout2D is not built")
+        elif arch == "PSPNet":
+            only("psp_pooling_type", ("avg",), "pyramid levels use average pooling")
+            only("use_batchnorm", (True,), "the PSP blocks are conv + BatchNorm + ReLU")
+            only("dropout", (0, 0.0, None), "SpatialDropout2D is not built")
+            only("final_interpolation", ("bilinear",), "logits are upsampled bilinearly")
+            only("downsample_factor", (4, 8, 16), "feature layers at 1/4, 1/8 or 1/16")
         elif arch == "Linknet":
             only("use_batchnorm", (True,), "the Linknet blocks are conv + BatchNorm + ReLU")
             only("n_upsample_blocks", (5,), "the decoder has one block per encoder stage")

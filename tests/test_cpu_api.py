@@ -437,7 +437,16 @@ def test_create_net_key_validation(tmp_path):
         return c
 
     with pytest.raises(ValueError, match="Unknown architecture"):
-        cfg(architecture="PSPNet").createNet()
+        cfg(architecture="DeepLabV3").createNet()
+    with pytest.raises(ValueError, match="divisible by 6"):
+        cfg(architecture="PSPNet").createNet()                       # 64 is not a multiple of 6 * downsample_factor
+    with pytest.raises(NotImplementedError, match="psp_pooling_type"):
+        cfg(architecture="PSPNet", shape=[96, 96, 3], psp_pooling_type="max").createNet()
+    psp = cfg(architecture="PSPNet", shape=[96, 96, 3], psp_conv_filters=64).createNet()
+    wp = psp.get_weights()
+    assert wp["psp_level6_conv/kernel"].shape == (1, 1, 128, 64) and wp["psp_conv/kernel"].shape == (1, 1, 128 + 4 * 64, 512)
+    assert "stage3_unit1_bn1/gamma" in wp and "stage3_unit1_conv1/kernel" not in wp and "stage4_unit1_bn1/gamma" not in wp
+    assert wp["final_conv/kernel"].shape == (3, 3, 512, 1)
     with pytest.raises(ValueError, match="Unknown backbone"):
         cfg(backbone="efficientnetb4").createNet()
     with pytest.raises(NotImplementedError, match="softmax"):
@@ -884,3 +893,31 @@ def test_raw_batch_packing_for_device_ingest():
     ld = HostLoader(DS(), (32, 32, 3), 1, 2, workers=0, pin=False, device_resize=True)
     out = list(ld.iterate([[0, 1], [2, 0]]))
     assert len(out) == 2 and all(m is None and b.n == 2 for b, m in out)
+
+
+def test_nchannel_encoder_weight_adaptation(tmp_path):
+    """reference createNet1 (segmentation.py:138-153): a >3-channel input with pretrained 3-channel encoder weights -- first
+    conv widened (RGB planes copied, extra planes = their mean), result cached next to the config as .mdl-nchannel."""
+    from segmentation_training_pipeline_b200.segmentation import PipelineConfig
+    cfg = PipelineConfig(architecture="Unet", backbone="resnet18", classes=1, shape=[64, 64, 4])
+    cfg.path = str(tmp_path / "c.yaml")
+
+    class FakeNet:
+        def get_weights(self):
+            return {"conv0/kernel": np.zeros((7, 7, 4, 64), np.float32), "bn_data/beta": np.zeros(4, np.float32),
+                    "bn_data/moving_variance": np.ones(4, np.float32), "bn0/gamma": np.ones(64, np.float32)}
+
+    rng = np.random.default_rng(0)
+    w3 = {"conv0/kernel": rng.normal(size=(7, 7, 3, 64)).astype(np.float32), "bn_data/beta": np.array([1, 2, 3], np.float32),
+          "bn_data/moving_variance": np.array([4, 5, 6], np.float32), "bn0/gamma": rng.normal(size=64).astype(np.float32)}
+    out = cfg._adapt_input_channels(FakeNet(), w3)
+    assert out["conv0/kernel"].shape == (7, 7, 4, 64)
+    assert np.array_equal(out["conv0/kernel"][:, :, :3], w3["conv0/kernel"])
+    assert np.allclose(out["conv0/kernel"][:, :, 3], w3["conv0/kernel"].mean(axis=2))
+    assert np.allclose(out["bn_data/beta"], [1, 2, 3, 2]) and np.allclose(out["bn_data/moving_variance"], [4, 5, 6, 5])
+    assert np.array_equal(out["bn0/gamma"], w3["bn0/gamma"])
+    assert (tmp_path / "c.yaml.mdl-nchannel.npz").exists()
+    again = cfg._adapt_input_channels(FakeNet(), {})           # served from the cache
+    assert np.array_equal(again["conv0/kernel"], out["conv0/kernel"])
+    cfg3 = PipelineConfig(architecture="Unet", backbone="resnet18", classes=1, shape=[64, 64, 3])
+    assert cfg3._adapt_input_channels(FakeNet(), w3) is w3

@@ -55,7 +55,22 @@ def test_softmax_cce_model_parity(cuda):
     _run_parity("resnet18", 128, (0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0), "Unet", classes=3, onehot=True)
 
 
-def _run_parity(backbone, size, loss, arch, classes=1, onehot=False):
+@pytest.mark.parametrize("backbone,size,factor,classes", [("resnet18", 96, 8, 1), ("resnet34", 192, 16, 2), ("resnet50", 96, 4, 1)])
+def test_pspnet_parity(cuda, backbone, size, factor, classes):
+    """PSPNet (schema segmentation.raml:226-248; the reference's report.csv lists a PSPNet run): encoder cut at the feature
+    layer, pyramid average pooling (levels 1, 2, 3, 6) -> 1x1 conv + BN + ReLU -> bilinear resize into the concat slices, 1x1
+    conv block, final_conv and the bilinear x downsample_factor logits upsample; forward / loss / gradients vs the oracle."""
+    _run_parity(backbone, size, (1.0, 1.0, 0.0), "PSPNet", classes=classes, net_kw=dict(downsample_factor=factor),
+                oracle_kw=dict(downsample_factor=factor))
+
+
+def test_four_channel_input_parity(cuda):
+    """More than 3 input channels (reference createNet1, segmentation.py:138-153 handles `shape: [H, W, C > 3]`): the stem
+    (bn_data + conv0) runs on 4-channel images; forward / loss / gradients against the oracle built with 4 input channels."""
+    _run_parity("resnet18", 128, (1.0, 1.0, 0.0), "Unet", channels=4)   # (64x64 with 2 images: 8-sample BatchNorms, pure noise amplification)
+
+
+def _run_parity(backbone, size, loss, arch, classes=1, onehot=False, channels=3, net_kw=None, oracle_kw=None):
     from oracle import losses as OL
     from oracle.models import SegModel
     from segmentation_training_pipeline_b200 import lib
@@ -72,12 +87,15 @@ def _run_parity(backbone, size, loss, arch, classes=1, onehot=False):
         pytest.skip("Linknet parity is run on the basic-block ResNets")
     if arch == "Linknet":
         size = 128  # at 64x64 the deepest BatchNorm sees 2x2x2 samples per channel: pure rounding-noise amplification
-    net = SegNet(backbone, classes=classes, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=loss, architecture=arch,
-                 decoder_block_type=block)
+    net = SegNet(backbone, classes=classes, input_shape=(size, size, channels), batch=n, device="cuda:0", seed=0, loss=loss, architecture=arch,
+                 decoder_block_type=block, **(net_kw or {}))
     W = _perturb(net.get_weights())
     net.set_weights(W)
     tr = Trainer(net)
     img, mask = _data(n, size, size)
+    if channels > 3:
+        g4 = torch.Generator().manual_seed(9)
+        img = torch.cat([img, torch.randint(0, 256, (n, size, size, channels - 3), generator=g4, dtype=torch.uint8)], dim=3).contiguous()
     if classes > 1:  # class c: the disk shifted by c*size/8 columns (overlapping, independent binary masks)
         mask = torch.cat([torch.roll(mask, c * size // 8, dims=2) for c in range(classes)], dim=3).contiguous()
     if onehot:       # exclusive labels: background = class 0, then the first disk that covers the pixel
@@ -98,8 +116,8 @@ def _run_parity(backbone, size, loss, arch, classes=1, onehot=False):
     # pre-activation ResNets amplify one-ulp bf16 differences layer by layer, so the engine is held to the NOISE
     # FLOOR of bf16 storage itself: it must be at least as close to the bf16 oracle as that oracle is to fp32.
     def run(storage):
-        om = SegModel(arch, backbone, classes=classes, input_shape=(size, size, 3), storage=storage, update_moving=False,
-                      decoder_block_type=block)
+        om = SegModel(arch, backbone, classes=classes, input_shape=(size, size, channels), storage=storage, update_moving=False,
+                      decoder_block_type=block, **(oracle_kw or {}))
         assert set(om.params.keys()) == set(net.params.keys()), sorted(set(om.params.keys()) ^ set(net.params.keys()))
         om.load_numpy(W)
         t = mask.float()

@@ -790,7 +790,7 @@ def test_softmax_categorical_crossentropy(stp, cuda, classes):
 @pytest.mark.parametrize("halo", [0, 1])
 @pytest.mark.parametrize("force", [(0, 0), (128, 1), (128, 2), (256, 1)])
 @pytest.mark.parametrize("case", [(2, 24, 40, 128, 128), (1, 9, 17, 128, 256), (3, 8, 8, 256, 512), (5, 16, 16, 64, 128),
-                                  (16, 32, 32, 256, 256), (1, 16, 16, 192, 256)])
+                                  (16, 32, 32, 256, 256), (1, 16, 16, 192, 256), (3, 24, 24, 64, 64), (2, 16, 40, 128, 192)])
 def test_conv_tc3_cta_pair(stp, cuda, case, force, halo):
     """tcgen05 cta_group::2 CTA-pair kernel (conv_tc3.cu) against the single-CTA halo kernel and the fp32 reference:
     odd numbers of pixel tiles (a rank idling on an out-of-range image), partial tiles, residual, fused BatchNorm
@@ -800,6 +800,10 @@ def test_conv_tc3_cta_pair(stp, cuda, case, force, halo):
     fbn, fmt = force
     if fbn == 256 and cout % 256:
         pytest.skip("BN=256 needs Cout % 256 == 0")
+    if cout % 128:   # Cout = 64 / 192: the N = 64 pair tiles (option tc3_bn64)
+        if fbn in (128, 256):
+            pytest.skip("Cout % 128 != 0 is served by BN = 64 only")
+        stp.set_option(b"tc3_bn64", 1)
     g = torch.Generator().manual_seed(cin * 5 + cout + fbn + fmt)
     x = rand_bf16((n, h, w, cin), g)
     wt = rand_bf16((cout, 3, 3, cin), g, scale=1.0 / math.sqrt(9 * cin))
@@ -836,6 +840,7 @@ def test_conv_tc3_cta_pair(stp, cuda, case, force, halo):
     finally:
         stp.set_option(b"tc3", 0)
         stp.set_option(b"tc3_halo", 0)
+        stp.set_option(b"tc3_bn64", 0)
         stp.set_option(b"tc3_force_bn", 0)
         stp.set_option(b"tc3_force_mt", 0)
     yr = conv_ref(x, wt, 1, 1)
