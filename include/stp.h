@@ -153,6 +153,27 @@ int stp_augment_apply(const uint8_t* img_pool, const uint8_t* mask_pool, const s
                       uint8_t* img_out, uint8_t* mask_out, int32_t n, int32_t h, int32_t w,
                       int32_t c_img, int32_t c_mask, int32_t mul_rint, stp_stream stream);
 
+/* Pixel-wise augmenters in YAML order, in place on the augmented batch (run AFTER stp_augment_apply called with mul_rint | 2,
+ * which leaves the colour stage to this kernel): Multiply / Add / Invert use the per-sample draws of stp_augment_draw;
+ * AddElementwise (a..b integers), MultiplyElementwise (a..b), Dropout (p ~ U(a, b) per image), AdditiveGaussianNoise
+ * (scale ~ U(a, b) per image) draw per pixel -- per channel with probability `per_channel` per image; Grayscale blends
+ * 0.299 R + 0.587 G + 0.114 B with alpha ~ U(a, b) per image.  group_size > 0: the op is member `group_member` of OneOf
+ * group `group_id` and runs only for the samples that drew it.  imgaug 0.3.0 semantics as recalled [DEP]. */
+enum { STP_PIX_MULTIPLY = 0, STP_PIX_ADD = 1, STP_PIX_INVERT = 2, STP_PIX_ADD_ELEMENTWISE = 3, STP_PIX_MULTIPLY_ELEMENTWISE = 4,
+       STP_PIX_DROPOUT = 5, STP_PIX_GAUSSIAN_NOISE = 6, STP_PIX_GRAYSCALE = 7, STP_PIX_MAX_OPS = 8 };
+typedef struct stp_aug_pix_op {
+  int32_t kind;
+  float per_channel;
+  float a, b;
+  int32_t group_id, group_size, group_member;
+} stp_aug_pix_op;
+typedef struct stp_aug_pix_spec {
+  int32_t n_ops, mul_rint;
+  stp_aug_pix_op ops[8];
+} stp_aug_pix_spec;
+int stp_augment_pixel_ops(uint8_t* d_img, const stp_aug_sample* d_params, const stp_aug_pix_spec* h_spec, uint64_t seed,
+                          const int64_t* d_step, int32_t n, int32_t h, int32_t w, int32_t c_img, stp_stream stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K2/K4/K5/K9  convolution -- replaces keras.layers.Conv2D / Conv2DTranspose -> TF Conv2D,
  *     Conv2DBackpropInput, Conv2DBackpropFilter (graph built by segmentation_models.Unet etc. at

@@ -267,3 +267,66 @@ def apply_crop_pad(image: np.ndarray, mask: np.ndarray, win, H: int, W: int):
     from . import resize as R
     vi, vm = R.window(image, *win), R.window(mask, *win)
     return R.resize_cubic_u8(vi, H, W), R.resize_nearest_u8(vm, H, W)
+
+
+# ----------------------------------------------------------------------------------------------
+# pixel-wise augmenters (schemas/augmenters.raml:43-60, 88-96, 120-122 -> imgaug 0.3.0 [DEP, recalled -- parity unpinned]):
+# the CPU twin of csrc/augment.cu augment_pixel_ops_kernel: same Philox counters, same fp32 operation order.
+# ops: (kind, per_channel, a, b, group_id, group_size, group_member); kinds per include/stp.h STP_PIX_*.
+# ----------------------------------------------------------------------------------------------
+def apply_pixel_ops(img: np.ndarray, ops, seed: int, step: int, sid: int, p: SampleParams, mul_rint: bool = False) -> np.ndarray:
+    f32 = np.float32
+    H, W, CI = img.shape
+    v = img.astype(np.int64).reshape(-1, CI)
+    pix = np.arange(H * W, dtype=np.uint64)
+    key = (seed & philox.MASK, (seed >> 32) & philox.MASK)
+    s_lo, s_hi = step & philox.MASK, (step >> 32) & philox.MASK
+    u24 = lambda w: ((w >> np.uint64(8)).astype(np.float32) * f32(5.9604644775390625e-08)).astype(np.float32)
+    for k, (kind, per_channel, a, b, gid, gsz, gm) in enumerate(ops):
+        ri = philox.philox4x32((s_lo, sid, 32 + k, s_hi), key)
+        if gsz > 0:
+            rg = philox.philox4x32((s_lo, sid, 32 + 16 + gid, s_hi), key)
+            pick = min(int(math.floor(philox.u53(rg[0], rg[1]) * gsz)), gsz - 1)
+            if pick != gm:
+                continue
+        pc = philox.u53(ri[0], ri[1]) < float(f32(per_channel))
+        a32, b32 = f32(a), f32(b)
+        par = f32(a32 + f32(f32(philox.u53(ri[2], ri[3])) * f32(b32 - a32)))
+        if kind == 0:
+            if p.has_mul:
+                fv = np.clip((v.astype(np.float32) * f32(p.mul)).astype(np.float32), 0, 255)
+                v = (np.rint(fv) if mul_rint else np.trunc(fv)).astype(np.int64)
+        elif kind == 1:
+            v = np.clip(v + int(p.add), 0, 255)
+        elif kind == 2:
+            if p.invert:
+                v = 255 - v
+        elif kind == 7:
+            if CI >= 3:
+                vf = v.astype(np.float32)
+                g = (f32(0.299) * vf[:, 0] + f32(0.587) * vf[:, 1]).astype(np.float32) + f32(0.114) * vf[:, 2]
+                for c in range(3):
+                    fv = (f32(1.0) - par) * vf[:, c] + par * g
+                    v[:, c] = np.clip(np.rint(fv.astype(np.float32)), 0, 255).astype(np.int64)
+        else:
+            rp = philox.philox4x32_vec(s_lo, sid, (pix << np.uint64(8)) | np.uint64(64 + k), s_hi, *key)
+            rq = philox.philox4x32_vec(s_lo, sid, (pix << np.uint64(8)) | np.uint64(64 + 128 + k), s_hi, *key) if kind == 6 else None
+            for c in range(CI):
+                wi = (c & 3) if pc else 0
+                u = u24(rp[wi])
+                if kind == 3:
+                    lo, hi = int(a32), int(b32)
+                    v[:, c] = np.clip(v[:, c] + lo + np.floor((u * f32(hi - lo + 1)).astype(np.float32)).astype(np.int64), 0, 255)
+                elif kind == 4:
+                    m = (a32 + (u * f32(b32 - a32)).astype(np.float32)).astype(np.float32)
+                    fv = np.clip((v[:, c].astype(np.float32) * m).astype(np.float32), 0, 255)
+                    v[:, c] = (np.rint(fv) if mul_rint else np.trunc(fv)).astype(np.int64)
+                elif kind == 5:
+                    v[:, c] = np.where(u < par, 0, v[:, c])
+                elif kind == 6:
+                    u2 = u24(rq[wi])
+                    z = (np.sqrt((f32(-2.0) * np.log((f32(1.0) - u).astype(np.float32)).astype(np.float32)).astype(np.float32)).astype(np.float32)
+                         * np.cos((f32(6.283185307179586) * u2).astype(np.float32)).astype(np.float32)).astype(np.float32)
+                    fv = (v[:, c].astype(np.float32) + (z * par).astype(np.float32)).astype(np.float32)
+                    v[:, c] = np.clip(np.rint(fv), 0, 255).astype(np.int64)
+    return v.reshape(H, W, CI).astype(np.uint8)

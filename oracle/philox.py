@@ -31,3 +31,16 @@ def u53(hi: int, lo: int) -> float:
 def uniforms(seed: int, step: int, sample: int, call: int):
     x = philox4x32((step & MASK, sample & MASK, call & MASK, (step >> 32) & MASK), (seed & MASK, (seed >> 32) & MASK))
     return u53(x[0], x[1]), u53(x[2], x[3])
+
+
+def philox4x32_vec(c0, c1, c2, c3, k0, k1):
+    """vectorised Philox4x32-10: counters are uint64 numpy arrays (values < 2^32) or scalars; returns four uint64 arrays"""
+    c0, c1, c2, c3 = [np.asarray(c, dtype=np.uint64) & np.uint64(MASK) for c in (c0, c1, c2, c3)]
+    c0, c1, c2, c3 = np.broadcast_arrays(c0, c1, c2, c3)
+    k0, k1 = np.uint64(int(k0) & MASK), np.uint64(int(k1) & MASK)
+    m = np.uint64(MASK)
+    for _ in range(10):
+        p0, p1 = np.uint64(M0) * c0, np.uint64(M1) * c2
+        c0, c1, c2, c3 = ((p1 >> np.uint64(32)) ^ c1 ^ k0) & m, p1 & m, ((p0 >> np.uint64(32)) ^ c3 ^ k1) & m, p0 & m
+        k0, k1 = (k0 + np.uint64(W0)) & m, (k1 + np.uint64(W1)) & m
+    return c0, c1, c2, c3

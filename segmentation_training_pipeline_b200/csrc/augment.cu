@@ -109,6 +109,7 @@ __global__ void augment_draw_kernel(stp_aug_spec spec, uint64_t seed, const int6
 
 // colour stage: Multiply / Add / Invert in the order of the YAML block (flags2 bits 4-9); each op saturates to uint8
 __device__ __forceinline__ int colour(int v, const DevSample& s, int mul_rint) {
+  if (mul_rint & 2) return v;   // the colour stage runs in augment_pixel_ops_kernel (extended pixel-wise augmenters present)
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int op = (s.flags2 >> (4 + 2 * k)) & 3;
@@ -116,7 +117,7 @@ __device__ __forceinline__ int colour(int v, const DevSample& s, int mul_rint) {
       if (s.has_mul) {
         float f = __fmul_rn((float)v, s.mul);
         f = fminf(fmaxf(f, 0.f), 255.f);
-        v = mul_rint ? __float2int_rn(f) : (int)f;
+        v = (mul_rint & 1) ? __float2int_rn(f) : (int)f;
       }
     } else if (op == 1) {
       v += s.add;
@@ -233,9 +234,123 @@ __global__ void __launch_bounds__(256) augment_apply_kernel(const uint8_t* __res
   }
 }
 
+// ---- pixel-wise augmenters in YAML order (schemas/augmenters.raml:43-60, 88-96, 120-122 -> imgaug 0.3.0 [DEP, recalled]) --------
+// Multiply / Add / Invert (per-sample draws of stp_augment_draw) and AddElementwise, MultiplyElementwise, Dropout,
+// AdditiveGaussianNoise (per-pixel draws), Grayscale (per-sample alpha), optionally gated by OneOf groups.  One thread per
+// pixel, in place on the augmented batch.  Randomness: Philox4x32-10, key = seed, counter = (step, sample id, call, step >> 32)
+// with call = 32 + op for per-image draws and call = ((pixel << 8) | (64 + op)) [| 128 for the second Gaussian word set] for
+// per-pixel draws -- the CPU oracle (oracle/augment.py apply_pixel_ops) draws the same numbers.
+__device__ __forceinline__ float u24(uint32_t w) { return (float)(w >> 8) * 5.9604644775390625e-08f; }   // [0, 1), exact
+
+template <int CI>
+__global__ void __launch_bounds__(256) augment_pixel_ops_kernel(uint8_t* __restrict__ img, const DevSample* __restrict__ params,
+                                                                const stp_aug_pix_spec spec, uint64_t seed,
+                                                                const int64_t* __restrict__ d_step, int n, int H, int W) {
+  const int64_t step = *d_step;
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), s_lo = (uint32_t)step, s_hi = (uint32_t)(step >> 32);
+  const int64_t total = (int64_t)n * H * W;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / ((int64_t)H * W));
+    const uint32_t pix = (uint32_t)(idx - (int64_t)b * H * W);
+    const DevSample s = params[b];
+    const uint32_t sid = (uint32_t)s.src_index;
+    int v[CI];
+#pragma unroll
+    for (int c = 0; c < CI; ++c) v[c] = img[idx * CI + c];
+    for (int k = 0; k < spec.n_ops; ++k) {
+      const stp_aug_pix_op op = spec.ops[k];
+      uint32_t ri[4];
+      philox4x32(s_lo, sid, 32u + (uint32_t)k, s_hi, k0, k1, ri);                  // per-image draws of this op
+      if (op.group_size > 0) {                                                     // OneOf: one member per sample
+        uint32_t rg[4];
+        philox4x32(s_lo, sid, 32u + 16u + (uint32_t)op.group_id, s_hi, k0, k1, rg);
+        int pick = (int)floor(__dmul_rn(u53(rg[0], rg[1]), (double)op.group_size));
+        if (pick >= op.group_size) pick = op.group_size - 1;
+        if (pick != op.group_member) continue;
+      }
+      const bool pc = u53(ri[0], ri[1]) < (double)op.per_channel;
+      const float par = __fadd_rn(op.a, __fmul_rn((float)u53(ri[2], ri[3]), __fsub_rn(op.b, op.a)));   // per-image parameter
+      if (op.kind == STP_PIX_MULTIPLY) {
+        if (s.has_mul) {
+#pragma unroll
+          for (int c = 0; c < CI; ++c) {
+            float f = fminf(fmaxf(__fmul_rn((float)v[c], s.mul), 0.f), 255.f);
+            v[c] = spec.mul_rint ? __float2int_rn(f) : (int)f;
+          }
+        }
+      } else if (op.kind == STP_PIX_ADD) {
+#pragma unroll
+        for (int c = 0; c < CI; ++c) { int t = v[c] + s.add; v[c] = t < 0 ? 0 : (t > 255 ? 255 : t); }
+      } else if (op.kind == STP_PIX_INVERT) {
+        if (s.flags2 & 4) {
+#pragma unroll
+          for (int c = 0; c < CI; ++c) v[c] = 255 - v[c];
+        }
+      } else if (op.kind == STP_PIX_GRAYSCALE) {
+        if (CI >= 3) {
+          const float g = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, (float)v[0]), __fmul_rn(0.587f, (float)v[1])), __fmul_rn(0.114f, (float)v[2]));
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float f = __fadd_rn(__fmul_rn(__fsub_rn(1.f, par), (float)v[c]), __fmul_rn(par, g));
+            const int t = __float2int_rn(f);
+            v[c] = t < 0 ? 0 : (t > 255 ? 255 : t);
+          }
+        }
+      } else {
+        uint32_t rp[4], rq[4];
+        philox4x32(s_lo, sid, (pix << 8) | (64u + (uint32_t)k), s_hi, k0, k1, rp);
+        if (op.kind == STP_PIX_GAUSSIAN_NOISE) philox4x32(s_lo, sid, (pix << 8) | (64u + 128u + (uint32_t)k), s_hi, k0, k1, rq);
+#pragma unroll
+        for (int c = 0; c < CI; ++c) {
+          const int wi = pc ? (c & 3) : 0;
+          const float u = u24(rp[wi]);
+          if (op.kind == STP_PIX_ADD_ELEMENTWISE) {
+            const int lo = (int)op.a, hi = (int)op.b;
+            const int t = v[c] + lo + (int)floorf(__fmul_rn(u, (float)(hi - lo + 1)));
+            v[c] = t < 0 ? 0 : (t > 255 ? 255 : t);
+          } else if (op.kind == STP_PIX_MULTIPLY_ELEMENTWISE) {
+            const float m = __fadd_rn(op.a, __fmul_rn(u, __fsub_rn(op.b, op.a)));
+            const float f = fminf(fmaxf(__fmul_rn((float)v[c], m), 0.f), 255.f);
+            v[c] = spec.mul_rint ? __float2int_rn(f) : (int)f;
+          } else if (op.kind == STP_PIX_DROPOUT) {
+            if (u < par) v[c] = 0;
+          } else if (op.kind == STP_PIX_GAUSSIAN_NOISE) {
+            const float u2 = u24(rq[wi]);
+            const float z = __fmul_rn(sqrtf(__fmul_rn(-2.f, logf(__fsub_rn(1.f, u)))), cosf(__fmul_rn(6.283185307179586f, u2)));
+            const int t = __float2int_rn(__fadd_rn((float)v[c], __fmul_rn(z, par)));
+            v[c] = t < 0 ? 0 : (t > 255 ? 255 : t);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CI; ++c) img[idx * CI + c] = (uint8_t)v[c];
+  }
+}
+
 }  // namespace stp
 
 using namespace stp;
+
+extern "C" int stp_augment_pixel_ops(uint8_t* d_img, const stp_aug_sample* d_params, const stp_aug_pix_spec* h_spec, uint64_t seed,
+                                     const int64_t* d_step, int32_t n, int32_t h, int32_t w, int32_t c_img, stp_stream stream) {
+  STP_REQUIRE(d_img && d_params && h_spec && d_step && n > 0 && h > 0 && w > 0, "augment_pixel_ops: bad args");
+  STP_REQUIRE(c_img == 1 || c_img == 3 || c_img == 4, "augment_pixel_ops: c_img must be 1, 3 or 4");
+  STP_REQUIRE(h_spec->n_ops >= 0 && h_spec->n_ops <= STP_PIX_MAX_OPS, "augment_pixel_ops: at most %d ops", STP_PIX_MAX_OPS);
+  STP_REQUIRE((int64_t)h * w <= (1 << 24), "augment_pixel_ops: at most 2^24 pixels per image");
+  for (int k = 0; k < h_spec->n_ops; ++k)
+    STP_REQUIRE(h_spec->ops[k].kind >= STP_PIX_MULTIPLY && h_spec->ops[k].kind <= STP_PIX_GRAYSCALE, "augment_pixel_ops: unknown op kind");
+  if (h_spec->n_ops == 0) return STP_OK;
+  const int64_t total = (int64_t)n * h * w;
+  int64_t nb = (total + 255) / 256;
+  const int grid = (int)(nb < (int64_t)kNumSMs * 16 ? nb : (int64_t)kNumSMs * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevSample* P = (const DevSample*)d_params;
+  if (c_img == 3) augment_pixel_ops_kernel<3><<<grid, 256, 0, st>>>(d_img, P, *h_spec, seed, d_step, n, h, w);
+  else if (c_img == 1) augment_pixel_ops_kernel<1><<<grid, 256, 0, st>>>(d_img, P, *h_spec, seed, d_step, n, h, w);
+  else augment_pixel_ops_kernel<4><<<grid, 256, 0, st>>>(d_img, P, *h_spec, seed, d_step, n, h, w);
+  return check_launch("augment_pixel_ops");
+}
 
 extern "C" int stp_augment_draw(const stp_aug_spec* h_spec, uint64_t seed, const int64_t* d_step, int32_t n,
                                 int32_t pool, int32_t h, int32_t w, stp_aug_sample* d_out, stp_stream stream) {

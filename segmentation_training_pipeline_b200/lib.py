@@ -55,6 +55,19 @@ RESIZE_NEAREST, RESIZE_CUBIC = 0, 1
 CP_PAD, CP_PAD_TO_FIXED, CP_CROP_TO_FIXED, CP_CROP_AND_PAD = 1, 2, 3, 4
 
 
+PIX_KINDS = {"Multiply": 0, "Add": 1, "Invert": 2, "AddElementwise": 3, "MultiplyElementwise": 4, "Dropout": 5,
+             "AdditiveGaussianNoise": 6, "Grayscale": 7}
+
+
+class AugPixOp(C.Structure):               # include/stp.h: stp_aug_pix_op
+    _fields_ = [("kind", C.c_int32), ("per_channel", C.c_float), ("a", C.c_float), ("b", C.c_float), ("group_id", C.c_int32),
+                ("group_size", C.c_int32), ("group_member", C.c_int32)]
+
+
+class AugPixSpec(C.Structure):             # include/stp.h: stp_aug_pix_spec
+    _fields_ = [("n_ops", C.c_int32), ("mul_rint", C.c_int32), ("ops", AugPixOp * 8)]
+
+
 class CropPadOp(C.Structure):              # include/stp.h: stp_croppad_op
     _fields_ = [("kind", C.c_int32), ("ranged", C.c_int32), ("a", C.c_float), ("b", C.c_float), ("c", C.c_float), ("d", C.c_float)]
 
@@ -146,6 +159,7 @@ SIGNATURES = {
     "stp_loss_fwd": (C.c_int, [_P, _P, _I64, C.POINTER(LossSpec), _P, _P, _P]),
     "stp_loss_partial_floats": (_SZ, []),
     "stp_loss_bwd": (C.c_int, [_P, _P, _I64, C.POINTER(LossSpec), _P, _P, _P]),
+    "stp_augment_pixel_ops": (C.c_int, [_P, _P, C.POINTER(AugPixSpec), C.c_uint64, _P, _I32, _I32, _I32, _I32, _P]),
     "stp_resize_u8": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _I32, _I32, _P]),
     "stp_croppad_draw": (C.c_int, [C.POINTER(CropPadSpec), C.c_uint64, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "stp_softmax_cce_fwd": (C.c_int, [_P, _P, _I64, _I32, _F, _I32, _P, _P, _P]),

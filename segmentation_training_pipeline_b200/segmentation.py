@@ -113,6 +113,7 @@ def parse_augmentation(spec: Optional[dict], seed: int = 0) -> AugmentConfig:
     cfg = AugmentConfig(seed=seed)
     if not spec:
         return cfg
+    spec, groups = _flatten_augmentation(spec)
     # imgaug Sequential applies the augmenters in YAML order.  The fused kernel runs {Rotate90, Fliplr, Flipud} (ANY order among
     # themselves: they are index permutations, composed exactly -- AugmentConfig.flip_before_rot90) -> Affine -> colour stage
     # (Multiply / Add / Invert in ANY order among themselves); a block in another order would silently compute something
@@ -120,7 +121,12 @@ def parse_augmentation(spec: Optional[dict], seed: int = 0) -> AugmentConfig:
     # The crop / pad family (Pad, PadToFixedSize, CropToFixedSize, CropAndPad) leads the block: the ops are composed into one
     # window per sample that the cv2-arithmetic resize brings back to `shape` (trainer.run_augment).
     rank = {"Pad": 0, "PadToFixedSize": 0, "CropToFixedSize": 0, "CropAndPad": 0,
-            "Rotate90": 1, "Fliplr": 1, "Flipud": 1, "Affine": 2, "Multiply": 3, "Add": 3, "Invert": 3}
+            "Rotate90": 1, "Fliplr": 1, "Flipud": 1, "Affine": 2, "Multiply": 3, "Add": 3, "Invert": 3,
+            "AddElementwise": 3, "MultiplyElementwise": 3, "Dropout": 3, "AdditiveGaussianNoise": 3, "Grayscale": 3}
+    for name in groups:
+        if rank.get(name) != 3:
+            raise NotImplementedError("OneOf over '%s': only the pixel-wise augmenters (Multiply, Add, Invert, AddElementwise, "
+                                      "MultiplyElementwise, Dropout, AdditiveGaussianNoise, Grayscale) can be OneOf members" % name)
     last, colour = -1, []
     for name in spec:
         if name not in rank:
@@ -129,9 +135,36 @@ def parse_augmentation(spec: Optional[dict], seed: int = 0) -> AugmentConfig:
             raise NotImplementedError("augmentation order %s is not the fused kernel's (Pad/PadToFixedSize/CropToFixedSize/"
                                       "CropAndPad, Rotate90/Fliplr/Flipud, Affine, then Multiply/Add/Invert)" % list(spec))
         last = rank[name]
-        if rank[name] == 3:
+        if rank[name] == 3 and name in ("Multiply", "Add", "Invert"):
             colour.append({"Multiply": 0, "Add": 1, "Invert": 2}[name])
     cfg.color_order = tuple(colour + [o for o in (0, 1, 2) if o not in colour])
+    extended = [n for n in spec if rank.get(n) == 3 and n not in ("Multiply", "Add", "Invert")]
+    if extended or groups:
+        # pixel-wise colour stage in YAML order (csrc/augment.cu augment_pixel_ops_kernel)
+        from . import lib as _lib
+        ops = []
+        for name, val in spec.items():
+            if rank.get(name) != 3:
+                continue
+            v = val if isinstance(val, dict) else {}
+            pc = float(v.get("per_channel", 0.0) or 0.0)
+            if name in ("Multiply", "Add", "Invert"):
+                a = b = 0.0
+            elif name in ("AddElementwise", "MultiplyElementwise"):
+                a, b = _rng(v.get("range", val) if isinstance(val, dict) else val, int if name == "AddElementwise" else float)
+            elif name == "Dropout":
+                a, b = _rng(v.get("p", 0.0) if isinstance(val, dict) else val)
+                if not 0.0 <= a <= b <= 1.0:
+                    raise ValueError("Dropout: p must lie in [0, 1]")
+            elif name == "AdditiveGaussianNoise":
+                a, b = _rng(v.get("scale", 0.0) if isinstance(val, dict) else val)
+            else:   # Grayscale
+                a, b = _rng(v.get("alpha", 1.0) if isinstance(val, dict) else val)
+            gid, gsz, gm = groups.get(name, (0, 0, 0))
+            ops.append((_lib.PIX_KINDS[name], pc, float(a), float(b), gid, gsz, gm))
+        if len(ops) > 8:
+            raise NotImplementedError("augmentation: at most 8 pixel-wise augmenters")
+        cfg.pix_ops = tuple(ops)
     names = list(spec)
     if "Rotate90" in names:   # reference examples/people/*.yaml list Fliplr, Flipud, Rotate90
         r = names.index("Rotate90")
@@ -204,10 +237,54 @@ def parse_augmentation(spec: Optional[dict], seed: int = 0) -> AugmentConfig:
             if bad:
                 raise NotImplementedError("Affine keys not fused on device: %s" % sorted(bad))
         elif name == "Multiply":
-            cfg.multiply = _rng(val)
+            cfg.multiply = _rng(val.get("range", val.get("mul")) if isinstance(val, dict) else val)
         elif name == "Add":
-            cfg.add = _rng(val, int)
+            cfg.add = _rng(val.get("range", val.get("value")) if isinstance(val, dict) else val, int)
     return cfg
+
+
+def _flatten_augmentation(spec):
+    """`Sequential` (schemas/augmenters.raml:56, ControlFlow: a list of augmenters) is spliced into the block in place; `OneOf`
+    (:72) likewise, its members recorded as a group (group id, size, member index) so that exactly one of them runs per sample.
+    Children are written as a list of one-key mappings or as one mapping.  Returns (ordered dict, {name: group})."""
+    out, groups, gid = {}, {}, [0]
+
+    def children(val):
+        if isinstance(val, dict):
+            return list(val.items())
+        items = []
+        for c in val or []:
+            if not isinstance(c, dict) or len(c) != 1:
+                raise ValueError("Sequential / OneOf children must be one-key mappings, got %r" % (c,))
+            items.extend(c.items())
+        return items
+
+    def walk(items, group=None):
+        for name, val in items:
+            if name == "Sequential":
+                if group is not None:
+                    raise NotImplementedError("Sequential inside OneOf is not built")
+                walk(children(val))
+            elif name == "OneOf":
+                if group is not None:
+                    raise NotImplementedError("nested OneOf is not built")
+                ch = children(val)
+                if not ch:
+                    continue
+                g = gid[0]
+                gid[0] += 1
+                if g >= 16:
+                    raise NotImplementedError("at most 16 OneOf groups")
+                walk([(n, v) for n, v in ch], group=(g, len(ch)))
+            else:
+                if name in out:
+                    raise NotImplementedError("augmentation: '%s' appears twice (each augmenter can be used once per block)" % name)
+                out[name] = val
+                if group is not None:
+                    groups[name] = (group[0], group[1], sum(1 for n in groups if groups[n][0] == group[0]))
+
+    walk(list(spec.items()) if isinstance(spec, dict) else children(spec))
+    return out, groups
 
 
 class PipelineConfig:

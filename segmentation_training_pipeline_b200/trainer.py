@@ -40,10 +40,21 @@ class AugmentConfig:
     flip_before_rot90: int = 0   # bit 0: Fliplr precedes Rotate90 in the YAML block, bit 1: Flipud does (stp.h)
     # leading crop / pad augmenters, in YAML order: (kind, ranged, a, b, c, d) per include/stp.h stp_croppad_op
     crop_pad: Tuple[Tuple[int, int, float, float, float, float], ...] = ()
+    # pixel-wise colour stage in YAML order when an extended augmenter (AddElementwise, MultiplyElementwise, Dropout,
+    # AdditiveGaussianNoise, Grayscale) or a OneOf group is present: (kind, per_channel, a, b, group_id, group_size, group_member)
+    # per include/stp.h stp_aug_pix_op; Multiply / Add / Invert entries use the per-sample draws configured above
+    pix_ops: Tuple[Tuple[int, float, float, float, int, int, int], ...] = ()
 
     def enabled(self) -> bool:
         return bool(self.fliplr or self.flipud or self.affine or self.multiply or self.add or self.rot90 or self.invert or
-                    self.crop_pad)
+                    self.crop_pad or self.pix_ops)
+
+    def pix_c(self) -> _lib.AugPixSpec:
+        spec = _lib.AugPixSpec()
+        spec.n_ops, spec.mul_rint = len(self.pix_ops), int(self.mul_rint)
+        for i, (kind, pc, a, b, gid, gsz, gm) in enumerate(self.pix_ops):
+            spec.ops[i] = _lib.AugPixOp(int(kind), float(pc), float(a), float(b), int(gid), int(gsz), int(gm))
+        return spec
 
     def croppad_c(self) -> _lib.CropPadSpec:
         spec = _lib.CropPadSpec()
@@ -160,7 +171,11 @@ class Trainer:
                             self.aug_params.data_ptr(), st)
         self.L.augment_apply(src_img.data_ptr(), src_mask.data_ptr(), self.aug_params.data_ptr(),
                              net.img.storage.data_ptr(), net.mask.storage.data_ptr(), net.batch, H, W, CI, net.classes,
-                             int(cfg.mul_rint), st)
+                             int(cfg.mul_rint) | (2 if cfg.pix_ops else 0), st)
+        if cfg.pix_ops:   # the colour stage (incl. Multiply / Add / Invert) runs pixel-wise in YAML order, in place
+            ps = cfg.pix_c()
+            self.L.augment_pixel_ops(net.img.storage.data_ptr(), self.aug_params.data_ptr(), C.byref(ps), cfg.seed,
+                                     net.d_step.data_ptr(), net.batch, H, W, CI, st)
 
     def allreduce(self):
         if self.world_size > 1:

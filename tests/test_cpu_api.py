@@ -921,3 +921,28 @@ def test_nchannel_encoder_weight_adaptation(tmp_path):
     assert np.array_equal(again["conv0/kernel"], out["conv0/kernel"])
     cfg3 = PipelineConfig(architecture="Unet", backbone="resnet18", classes=1, shape=[64, 64, 3])
     assert cfg3._adapt_input_channels(FakeNet(), w3) is w3
+
+
+def test_pixelwise_augmenters_and_control_flow_parse():
+    """AddElementwise / MultiplyElementwise / Dropout / AdditiveGaussianNoise / Grayscale (schemas/augmenters.raml:54-60, 88-96,
+    120-122), Sequential (spliced in place) and OneOf (one member per sample) build the pixel-wise colour stage in YAML order."""
+    from segmentation_training_pipeline_b200 import lib
+    from segmentation_training_pipeline_b200.segmentation import parse_augmentation
+    c = parse_augmentation({"Fliplr": 0.5, "Sequential": [{"Multiply": [0.9, 1.1]}, {"AdditiveGaussianNoise": {"scale": [0, 12.75], "per_channel": 0.5}}],
+                            "OneOf": [{"Dropout": {"p": [0, 0.1]}}, {"Grayscale": {"alpha": [0, 1]}}, {"AddElementwise": [-10, 10]}]})
+    kinds = [o[0] for o in c.pix_ops]
+    assert kinds == [lib.PIX_KINDS[n] for n in ("Multiply", "AdditiveGaussianNoise", "Dropout", "Grayscale", "AddElementwise")]
+    assert c.multiply == (0.9, 1.1) and c.fliplr == 0.5 and c.enabled()
+    assert [o[4:] for o in c.pix_ops[2:]] == [(0, 3, 0), (0, 3, 1), (0, 3, 2)] and c.pix_ops[1][1] == 0.5
+    spec = c.pix_c()
+    assert spec.n_ops == 5 and spec.ops[1].kind == 6 and abs(spec.ops[1].b - 12.75) < 1e-6 and spec.ops[4].group_member == 2
+    assert parse_augmentation({"Multiply": [0.9, 1.1], "Add": [-3, 3]}).pix_ops == ()        # the fused colour stage serves these alone
+    assert parse_augmentation({"Dropout": 0.1}).pix_ops == ((5, 0.0, 0.1, 0.1, 0, 0, 0),)
+    with pytest.raises(NotImplementedError, match="OneOf"):
+        parse_augmentation({"OneOf": [{"Fliplr": 0.5}, {"Flipud": 0.5}]})
+    with pytest.raises(NotImplementedError, match="twice"):
+        parse_augmentation({"Add": [-3, 3], "Sequential": [{"Add": [-1, 1]}]})
+    with pytest.raises(NotImplementedError, match="not fused"):
+        parse_augmentation({"Sequential": [{"GaussianBlur": 1.0}]})
+    with pytest.raises(NotImplementedError, match="order"):
+        parse_augmentation({"Dropout": 0.1, "Fliplr": 0.5})

@@ -135,3 +135,58 @@ def test_rotate90_invert_and_colour_order(stp, cuda, order, affine, pre):
             bad += int((ri != gi[i]).sum()) + int((rm != gm[i]).sum())
     assert bad == 0
     assert ks == {0, 1, 2, 3} and invs == {False, True}
+
+
+PIX_BLOCKS = [
+    {"AddElementwise": {"range": [-20, 20], "per_channel": 0.5}},
+    {"Multiply": [0.5, 1.5], "MultiplyElementwise": {"range": [0.5, 1.5], "per_channel": 1.0}, "Add": [-30, 30]},
+    {"Dropout": {"p": [0.0, 0.3], "per_channel": 0.5}, "Invert": 0.5},
+    {"Grayscale": {"alpha": [0.0, 1.0]}, "AdditiveGaussianNoise": {"scale": [0.0, 25.0], "per_channel": 0.5}},
+    {"Fliplr": 0.5, "Sequential": [{"Add": [-5, 5]}, {"OneOf": [{"Dropout": 0.2}, {"Grayscale": 1.0}, {"AddElementwise": [-40, 40]}]}]},
+]
+
+
+@pytest.mark.parametrize("block", PIX_BLOCKS, ids=[str(i) for i in range(len(PIX_BLOCKS))])
+def test_pixelwise_augmenters_match_oracle(cuda, block):
+    """AddElementwise / MultiplyElementwise / Dropout / AdditiveGaussianNoise / Grayscale, Sequential and OneOf, mixed with
+    Multiply / Add / Invert in YAML order, through Trainer.run_augment: every pixel against oracle.augment.apply_pixel_ops
+    (same Philox counters, same fp32 operation order).  Bit exact except AdditiveGaussianNoise, whose logf / cosf differ from
+    numpy's in the last ulp: there at most 1e-4 of the values may differ, by 1."""
+    from oracle import augment as OA
+    from segmentation_training_pipeline_b200.models import SegNet
+    from segmentation_training_pipeline_b200.segmentation import parse_augmentation
+    from segmentation_training_pipeline_b200.trainer import Trainer
+    n, size, pool, seed = 4, 64, 8, 31
+    net = SegNet("resnet18", classes=1, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0)
+    cfg = parse_augmentation(block, seed=seed)
+    assert cfg.pix_ops
+    rng = np.random.default_rng(5)
+    imgs = rng.integers(0, 256, (pool, size, size, 3), dtype=np.uint8)
+    masks = (rng.random((pool, size, size, 1)) > 0.5).astype(np.uint8)
+    tr = Trainer(net, augment=cfg)
+    tr.set_pool(torch.from_numpy(imgs), torch.from_numpy(masks))
+    ospec = OA.AugSpec(fliplr=cfg.fliplr, flipud=cfg.flipud, multiply=cfg.multiply, add=cfg.add, invert=cfg.invert)
+    bad = tot = changed = 0
+    picks = set()
+    for step in (0, 3):
+        net.d_step.fill_(step)
+        tr.run_augment()
+        torch.cuda.synchronize()
+        gi = net.img.storage.view(n, size, size, 3).cpu().numpy()
+        gm = net.mask.storage.view(n, size, size, 1).cpu().numpy()
+        for i in range(n):
+            sid = (step * n + i) % pool
+            p = OA.draw_params(ospec, seed, step, sid, size, size)
+            geo = OA.SampleParams(p.fliplr, p.flipud, p.matrix, False, 1.0, False, 0, 0, False, (0, 1, 2), 0)
+            base, bm = OA.apply(imgs[sid], masks[sid], geo)                    # geometric part only (flips)
+            ref = OA.apply_pixel_ops(base, cfg.pix_ops, seed, step, sid, p)
+            d = np.abs(ref.astype(int) - gi[i].astype(int))
+            assert d.max() <= 1, (step, i, d.max())
+            bad += int((d != 0).sum())
+            tot += d.size
+            changed += int((gi[i] != base).sum())
+            assert np.array_equal(gm[i], bm)
+            picks.add(bytes(gi[i][:2, :2].tobytes()))
+    has_gauss = any(o[0] == 6 for o in cfg.pix_ops)
+    assert bad <= (1e-4 * tot if has_gauss else 0), (bad, tot)
+    assert changed > 0.05 * tot          # the block really changes pixels
