@@ -436,6 +436,19 @@ int stp_step_advance(int64_t* d_step, stp_stream stream);
 /* sum of squares of g into out[0] (f32, deterministic two-pass through `partial`), for clipnorm */
 int stp_sumsq(const float* g, int64_t count, float* partial, float* out, stp_stream stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K13  data-parallel exchange -- the one collective of the path: SUM all-reduce of the flat fp32 gradient over the GPUs of a
+ *      box (replaces keras.utils.multi_gpu_model's CPU-side merge, reference FAQ.md:108-112).  Thin wrappers over NCCL, bound
+ *      at run time (dlopen): one process per GPU; rank 0 creates the 128-byte id with stp_comm_unique_id and hands it to the
+ *      other ranks out of band; every rank calls stp_comm_init AFTER selecting its device; stp_allreduce is asynchronous on
+ *      `stream` (in place, count floats).  STP_E_UNSUPPORTED when libnccl.so.2 cannot be loaded.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct stp_comm stp_comm;
+int stp_comm_unique_id(void* out128);
+int stp_comm_init(int32_t world, int32_t rank, const void* id128, stp_comm** out);
+int stp_allreduce(stp_comm* comm, float* d_buf, int64_t count, stp_stream stream);
+int stp_comm_destroy(stp_comm* comm);
+
 #ifdef __cplusplus
 }
 #endif

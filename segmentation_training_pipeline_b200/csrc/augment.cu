@@ -108,8 +108,10 @@ __global__ void augment_draw_kernel(stp_aug_spec spec, uint64_t seed, const int6
 }
 
 // colour stage: Multiply / Add / Invert in the order of the YAML block (flags2 bits 4-9); each op saturates to uint8
+// SKIP = true: the colour stage runs in augment_pixel_ops_kernel instead (extended pixel-wise augmenters present)
+template <bool SKIP>
 __device__ __forceinline__ int colour(int v, const DevSample& s, int mul_rint) {
-  if (mul_rint & 2) return v;   // the colour stage runs in augment_pixel_ops_kernel (extended pixel-wise augmenters present)
+  if (SKIP) return v;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int op = (s.flags2 >> (4 + 2 * k)) & 3;
@@ -117,7 +119,7 @@ __device__ __forceinline__ int colour(int v, const DevSample& s, int mul_rint) {
       if (s.has_mul) {
         float f = __fmul_rn((float)v, s.mul);
         f = fminf(fmaxf(f, 0.f), 255.f);
-        v = (mul_rint & 1) ? __float2int_rn(f) : (int)f;
+        v = mul_rint ? __float2int_rn(f) : (int)f;
       }
     } else if (op == 1) {
       v += s.add;
@@ -138,7 +140,7 @@ __device__ __forceinline__ int64_t rot_off(int py, int px, int k, int H, int W) 
 }
 
 // one thread = PX consecutive output pixels of one row
-template <int PX, int CI>
+template <int PX, int CI, bool SKIPC = false>
 __global__ void __launch_bounds__(256) augment_apply_kernel(const uint8_t* __restrict__ img_pool,
                                                             const uint8_t* __restrict__ mask_pool,
                                                             const DevSample* __restrict__ params,
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(256) augment_apply_kernel(const uint8_t* __res
 #pragma unroll
         const int64_t so = rot_off(sy, sx, k90, H, W);
 #pragma unroll
-        for (int c = 0; c < CI; ++c) oi[p * CI + c] = (uint8_t)colour(simg[so * CI + c], s, mul_rint);
+        for (int c = 0; c < CI; ++c) oi[p * CI + c] = (uint8_t)colour<SKIPC>(simg[so * CI + c], s, mul_rint);
         for (int c = 0; c < cm; ++c) om[p * cm + c] = smsk ? smsk[so * cm + c] : 0;
         continue;
       }
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(256) augment_apply_kernel(const uint8_t* __res
           const int v10 = (x0ok && y1ok) ? simg[o10 * CI + c] : 0;
           const int v11 = (x1ok && y1ok) ? simg[o11 * CI + c] : 0;
           const int v = (w00 * v00 + w01 * v01 + w10 * v10 + w11 * v11 + 16384) >> 15;
-          oi[p * CI + c] = (uint8_t)colour(v, s, mul_rint);
+          oi[p * CI + c] = (uint8_t)colour<SKIPC>(v, s, mul_rint);
         }
       }
     }
@@ -380,8 +382,15 @@ extern "C" int stp_augment_apply(const uint8_t* img_pool, const uint8_t* mask_po
   int grid = (int)(nb < (int64_t)kNumSMs * 16 ? nb : (int64_t)kNumSMs * 16);
   cudaStream_t st = (cudaStream_t)stream;
   const DevSample* P = (const DevSample*)d_params;
-#define LAUNCH(PX, CI) \
-  augment_apply_kernel<PX, CI><<<grid, 256, 0, st>>>(img_pool, mask_pool, P, img_out, mask_out, n, h, w, c_mask, mul_rint)
+  const bool skipc = (mul_rint & 2) != 0;   // bit 1: leave the colour stage to stp_augment_pixel_ops
+  mul_rint &= 1;
+#define LAUNCH(PX, CI)                                                                                                          \
+  do {                                                                                                                          \
+    if (skipc)                                                                                                                  \
+      augment_apply_kernel<PX, CI, true><<<grid, 256, 0, st>>>(img_pool, mask_pool, P, img_out, mask_out, n, h, w, c_mask, mul_rint); \
+    else                                                                                                                        \
+      augment_apply_kernel<PX, CI, false><<<grid, 256, 0, st>>>(img_pool, mask_pool, P, img_out, mask_out, n, h, w, c_mask, mul_rint); \
+  } while (0)
   if (v4) {
     if (c_img == 3) LAUNCH(4, 3); else if (c_img == 1) LAUNCH(4, 1); else LAUNCH(4, 4);
   } else {

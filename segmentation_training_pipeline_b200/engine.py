@@ -154,11 +154,10 @@ class Net:
         self._partial_floats = 2 * _lib.BN_MAX_PARTIALS * 8
         self.encoder_param_names: List[str] = []
         self.fuse_bn_stats = precision == "bf16"
-        # BatchNorm-backward reduction inside the producing dgrad's epilogue (stp_conv_dgrad_bn).  Parity green, 33 launches
-        # fewer per U-Net/ResNet-34 step, but measured 1.3 % SLOWER (9.06 vs 8.94 ms): the separate HBM-bound reduction
-        # kernels overlap the tensor-bound weight gradients of the side stream almost for free, while the fused epilogue
-        # (x tile load + transpose-reduction shuffles) lengthens the exposed last-tile epilogue of every dgrad.  Off by default.
-        self.fuse_bn_bwd = os.environ.get("STP_FUSE_BN_BWD", "0") == "1" and precision == "bf16"
+        # BatchNorm-backward reduction inside the producing dgrad's epilogue (stp_conv_dgrad_bn): 33 launches fewer per
+        # U-Net/ResNet-34 step.  Round 1 (4 epilogue warps) measured it 1.3 % slower; with the 8-warp epilogue it is 1 % FASTER
+        # (round 2, same box: 8.826 vs 8.911 ms, profiles/r2_s4_bench*.json.log) -> on by default; STP_FUSE_BN_BWD=0 turns it off.
+        self.fuse_bn_bwd = os.environ.get("STP_FUSE_BN_BWD", "1") == "1" and precision == "bf16"
 
     # ---- parameters ---------------------------------------------------------------------------
     def add_param(self, name, shape, kind, init) -> Param:

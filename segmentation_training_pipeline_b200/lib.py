@@ -173,6 +173,10 @@ SIGNATURES = {
     "stp_rmsprop": (C.c_int, [_P, _P, _P, _I64, _F, _F, _F, C.POINTER(GradXform), _P]),
     "stp_nadam": (C.c_int, [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, C.POINTER(GradXform), _P, _P]),
     "stp_step_advance": (C.c_int, [_P, _P]),
+    "stp_comm_unique_id": (C.c_int, [_P]),
+    "stp_comm_init": (C.c_int, [_I32, _I32, _P, C.POINTER(C.c_void_p)]),
+    "stp_allreduce": (C.c_int, [_P, _P, _I64, _P]),
+    "stp_comm_destroy": (C.c_int, [_P]),
     "stp_sumsq": (C.c_int, [_P, _I64, _P, _P, _P]),
 }
 

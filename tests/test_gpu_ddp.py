@@ -101,3 +101,49 @@ def test_two_rank_step_equals_oracle_with_per_slice_batchnorm(tmp_path, precisio
             tol = max(3e-2, 2.0 * floor) + 2e-7 * float(np.linalg.norm(W0[k])) / (lr * den)
         assert e < tol, (k, e, tol, floor)
     print("2-rank %s step: losses %s vs oracle %s; worst averaged-gradient error %s" % (precision, z["losses"], l_ref, worst))
+
+
+def _comm_worker(rank, world, id_path, out_path):
+    import ctypes as C
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from segmentation_training_pipeline_b200 import lib
+    torch.cuda.set_device(rank)
+    L = lib.Lib()
+    if rank == 0:
+        buf = (C.c_ubyte * 128)()
+        L.comm_unique_id(buf)
+        with open(id_path + ".tmp", "wb") as f:
+            f.write(bytes(buf))
+        os.replace(id_path + ".tmp", id_path)
+    else:
+        for _ in range(600):
+            if os.path.exists(id_path):
+                break
+            time.sleep(0.05)
+    uid = open(id_path, "rb").read()
+    comm = C.c_void_p()
+    L.comm_init(world, rank, uid, C.byref(comm))
+    x = torch.full((1 << 20,), float(rank + 1), device="cuda:%d" % rank)
+    x[:8] = torch.arange(8, device=x.device, dtype=torch.float32) * (rank + 1)
+    L.allreduce(comm, x.data_ptr(), x.numel(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    L.comm_destroy(comm)
+    np.save(out_path % rank, x[:16].cpu().numpy())
+
+
+def test_c_abi_nccl_wrappers(tmp_path):
+    """stp_comm_unique_id / stp_comm_init / stp_allreduce / stp_comm_destroy (include/stp.h K13): one process per GPU, the
+    id handed over out of band (a file), in-place SUM all-reduce of an fp32 buffer."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world = 2
+    out = str(tmp_path / "r%d.npy")
+    mp.spawn(_comm_worker, args=(world, str(tmp_path / "nccl.id"), out), nprocs=world, join=True)
+    want = np.full(16, 3.0, np.float32)
+    want[:8] = np.arange(8) * 3.0
+    for r in range(world):
+        assert np.array_equal(np.load(out % r), want), r
