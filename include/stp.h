@@ -436,6 +436,43 @@ int stp_step_advance(int64_t* d_step, stp_stream stream);
 /* sum of squares of g into out[0] (f32, deterministic two-pass through `partial`), for clipnorm */
 int stp_sumsq(const float* g, int64_t count, float* partial, float* out, stp_stream stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * K14  depthwise convolution (keras DepthwiseConv2D, depth_multiplier 1) of the reference's in-tree DeepLabV3+ /
+ *      MobileNetV2 (impl/deeplab/model.py:236-275 `_inverted_res_block`, :104-142 `SepConv_BN`): k x k filter per channel,
+ *      stride, atrous rate.  x / y / dy / dx bf16 NHWC (c % 8 == 0), weights f32 [k][k][c] (= the keras (k,k,c,1) kernel),
+ *      rounded to bf16 in compute like every other conv operand.  pad_* = padding BEFORE; the output size implies the rest
+ *      (TF 'same' with stride 2 on an even size pads 0 before / 1 after).  wgrad: per-block partials + fixed-order reduction.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct stp_dwconv_desc {
+  int32_t k, stride, dilation, pad_h, pad_w;
+} stp_dwconv_desc;
+int stp_dwconv_fwd(const stp_dwconv_desc* d, const stp_tensor* x, const float* w_kkc, const stp_tensor* y, stp_stream stream);
+int stp_dwconv_dgrad(const stp_dwconv_desc* d, const stp_tensor* dy, const float* w_kkc, const stp_tensor* residual,
+                     const stp_tensor* dx, stp_stream stream);
+int stp_dwconv_wgrad(const stp_dwconv_desc* d, const stp_tensor* x, const stp_tensor* dy, float* dw_kkc, void* workspace,
+                     size_t workspace_bytes, stp_stream stream);
+size_t stp_dwconv_wgrad_workspace(const stp_dwconv_desc* d, const stp_tensor* x, const stp_tensor* dy);
+
+/* ----------------------------------------------------------------------------------------------
+ * K15  the other pieces of the DeepLabV3+ graph (impl/deeplab/model.py): whole-map mean + broadcast (image-pooling branch,
+ *      :462-469), training-mode Dropout (:486) and the probability head (:494-500: activation at 1/8 resolution, THEN
+ *      align_corners bilinear resize to the input size).
+ *      stp_prob_head_fwd: z f32 [n,h,w,>=classes] (1x1 conv output) -> logits f32 dense [n,H,W,classes] such that
+ *      activation(logits) == resize(activation(z)): the loss / predict kernels consume it unchanged.  activation 1 sigmoid,
+ *      2 softmax.  stp_prob_head_bwd: gradient wrt those logits -> dz bf16 [n,h,w,dz.c] (channels >= classes zero).
+ *      stp_dropout: y = x * keep / (1-rate); the mask is a function of (seed, salt, *d_step, element), so the backward is the
+ *      same call on the gradient.  x == y allowed.
+ * ---------------------------------------------------------------------------------------------- */
+int stp_global_avgpool_fwd(const stp_tensor* x, const stp_tensor* y, stp_stream stream);
+int stp_global_avgpool_bwd(const stp_tensor* dy, const stp_tensor* residual, const stp_tensor* dx, stp_stream stream);
+int stp_broadcast_fwd(const stp_tensor* x, const stp_tensor* y, stp_stream stream);
+int stp_broadcast_bwd(const stp_tensor* dy, const stp_tensor* dx, stp_stream stream);
+int stp_dropout(const stp_tensor* x, float rate, uint64_t seed, uint32_t salt, const int64_t* d_step, const stp_tensor* y,
+                stp_stream stream);
+int stp_prob_head_fwd(const stp_tensor* z, int32_t classes, int32_t activation, const stp_tensor* logits, stp_stream stream);
+int stp_prob_head_bwd(const stp_tensor* dlogits, const stp_tensor* logits, const stp_tensor* z, int32_t classes,
+                      int32_t activation, const stp_tensor* dz, stp_stream stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K13  data-parallel exchange -- the one collective of the path: SUM all-reduce of the flat fp32 gradient over the GPUs of a
  *      box (replaces keras.utils.multi_gpu_model's CPU-side merge, reference FAQ.md:108-112).  Thin wrappers over NCCL, bound

@@ -44,3 +44,19 @@ def philox4x32_vec(c0, c1, c2, c3, k0, k1):
         c0, c1, c2, c3 = ((p1 >> np.uint64(32)) ^ c1 ^ k0) & m, p1 & m, ((p0 >> np.uint64(32)) ^ c3 ^ k1) & m, p0 & m
         k0, k1 = (k0 + np.uint64(W0)) & m, (k1 + np.uint64(W1)) & m
     return c0, c1, c2, c3
+
+
+def dropout_keep_mask(rows: int, channels: int, rate: float, seed: int, salt: int, step: int) -> np.ndarray:
+    """keep mask [rows, channels] (bool) of the engine's Dropout (csrc/dropout.cu): element (row, 8*v + j) keeps iff word j%4 of
+    Philox(counter=(step lo, i lo, (i hi << 1) | (j >= 4), step hi), key=(seed lo, seed hi ^ salt)) >= rate * 2^32, i = row*(C/8)+v."""
+    assert channels % 8 == 0
+    cv = channels // 8
+    i = np.arange(rows * cv, dtype=np.uint64)
+    thresh = min(int(float(np.float32(rate)) * 4294967296.0), 0xFFFFFFFF)
+    k0, k1 = seed & MASK, ((seed >> 32) & MASK) ^ (salt & MASK)
+    words = []
+    for half in (0, 1):
+        w = philox4x32_vec(step & MASK, i & np.uint64(MASK), ((i >> np.uint64(32)) << np.uint64(1)) | np.uint64(half), (step >> 32) & MASK, k0, k1)
+        words.extend(w)
+    m = np.stack(words, axis=1) >= np.uint64(thresh)        # [rows*cv, 8]
+    return m.reshape(rows, channels)

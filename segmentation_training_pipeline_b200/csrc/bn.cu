@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256, 2) reduce_rows_kernel(const __nv_bfloat16
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               float gi = g[i];
-              if (relu && !(xf[i] * scale[i] + shift[i] > 0.f)) gi = 0.f;
+              if (relu && !relu_pass(xf[i] * scale[i] + shift[i], relu)) gi = 0.f;
               s0[i] += gi;
               s1[i] += gi * ((xf[i] - mean[i]) * invstd[i]);
             }
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             float t = f[k] * scale[k] + shift[k];
-            f[k] = (relu && !(t > 0.f)) ? 0.f : t;
+            f[k] = relu_act(t, relu);
           }
           bf16x8 o = pack8(f);
           if (up == 1) {
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const __nv_bfloat16* 
             float o;
             if (MODE == 0) {
               float gi = g[k];
-              if (relu && !(xf[k] * scale[k] + shift[k] > 0.f)) gi = 0.f;
+              if (relu && !relu_pass(xf[k] * scale[k] + shift[k], relu)) gi = 0.f;
               o = ca[k] * gi + cb[k] * xf[k] + cc[k];
             } else {
               o = xf[k] > 0.f ? g[k] : 0.f;

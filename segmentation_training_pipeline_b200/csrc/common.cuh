@@ -91,6 +91,17 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
 __device__ __forceinline__ bf16x8 ld8(const __nv_bfloat16* p) { return *reinterpret_cast<const bf16x8*>(p); }
 __device__ __forceinline__ void st8(__nv_bfloat16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
 
+// activation codes of the BatchNorm(+activation) kernels: 0 none, 1 ReLU, 2 ReLU6 (keras relu(max_value=6), MobileNetV2 blocks of
+// the reference's DeepLabV3+, impl/deeplab/model.py:38-39 / :248-262).  Gradient passes on 0 < t <= 6 (tf.clip_by_value's
+// gradient includes the upper boundary; ReLU's excludes 0).
+constexpr int kActRelu6 = 2;
+__device__ __forceinline__ float relu_act(float t, int act) {
+  if (act == 0) return t;
+  if (!(t > 0.f)) return 0.f;
+  return (act == kActRelu6 && t > 6.f) ? 6.f : t;
+}
+__device__ __forceinline__ bool relu_pass(float t, int act) { return t > 0.f && (act != kActRelu6 || t <= 6.f); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

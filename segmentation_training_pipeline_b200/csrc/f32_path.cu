@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(const float* __restrict__ x
           s1 += (double)xv * (double)xv;
         } else {
           float g = pooled(dy, lddy, pool, H, W, r, c);
-          if (relu && !(xv * scale + shift > 0.f)) g = 0.f;
+          if (relu && !relu_pass(xv * scale + shift, relu)) g = 0.f;
           s0 += (double)g;
           s1 += (double)g * (double)((xv - mean) * invstd);
         }
@@ -283,7 +283,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, int ldx, const floa
     const int64_t r = i / C;
     const int c = (int)(i - r * C);
     float t = x[r * ldx + c] * coef[2 * C + c] + coef[3 * C + c];
-    if (relu && !(t > 0.f)) t = 0.f;
+    t = relu_act(t, relu);
     if (up == 1) {
       y[r * ldy + c] = t;
     } else {
@@ -309,7 +309,7 @@ __global__ void bwd_apply_kernel(const float* __restrict__ dy, int lddy, const f
     float g = pooled(dy, lddy, pool, H, W, r, c);
     float o;
     if (MODE == 0) {
-      if (relu && !(xv * coef[2 * C + c] + coef[3 * C + c] > 0.f)) g = 0.f;
+      if (relu && !relu_pass(xv * coef[2 * C + c] + coef[3 * C + c], relu)) g = 0.f;
       o = bcoef[c] * g + bcoef[C + c] * xv + bcoef[2 * C + c];
     } else {
       o = xv > 0.f ? g : 0.f;

@@ -232,6 +232,57 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const __nv_bfloat16* _
   }
 }
 
+// ---- whole-map mean and its inverse (DeepLabV3+ image-pooling branch, impl/deeplab/model.py:462-469: AveragePooling2D over
+// the whole 1/8 map -> 1x1 conv -> BN -> ReLU -> BilinearUpsampling back to the map, which from a single pixel is a broadcast).
+// spatial_reduce: y[n,c] = scale * sum_{h,w} x[n,h,w,c];  block = (image, 8 channel octets) x 32 pixel lanes.
+// spatial_bcast : y[n,h,w,c] = scale * x[n,c] (+ residual).
+__global__ void __launch_bounds__(256) spatial_reduce_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int cv, float scale,
+                                                             __nv_bfloat16* __restrict__ y, int ldy) {
+  __shared__ float sm[32][8][9];
+  const int n = blockIdx.y;
+  const int vl = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int v = blockIdx.x * 8 + vl;
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+  if (v < cv)
+    for (int p = pl; p < HW; p += 32) {
+      float f[8];
+      unpack8(ld8(x + ((int64_t)n * HW + p) * ldx + v * 8), f);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] += f[c];
+    }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) sm[pl][vl][c] = acc[c];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int vv = threadIdx.x >> 3, c = threadIdx.x & 7;
+    float s = 0.f;
+    for (int l = 0; l < 32; ++l) s += sm[l][vv][c];
+    if (blockIdx.x * 8 + vv < cv) y[(int64_t)n * ldy + (blockIdx.x * 8 + vv) * 8 + c] = __float2bfloat16_rn(s * scale);
+  }
+}
+__global__ void __launch_bounds__(256) spatial_bcast_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int cv, float scale,
+                                                            const __nv_bfloat16* __restrict__ res, int ldr, __nv_bfloat16* __restrict__ y,
+                                                            int ldy, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cv;
+    const int v = (int)(i - r * cv);
+    const int64_t n = r / HW;
+    float f[8];
+    unpack8(ld8(x + n * ldx + v * 8), f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) f[c] *= scale;
+    if (res) {
+      float rf[8];
+      unpack8(ld8(res + r * ldr + v * 8), rf);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) f[c] += rf[c];
+    }
+    st8(y + r * ldy + v * 8, pack8(f));
+  }
+}
+
 static int ew_grid2(int64_t total) {
   int64_t b = (total + 255) / 256;
   int64_t cap = (int64_t)kNumSMs * 16;
@@ -311,4 +362,43 @@ extern "C" int stp_avgpool_bwd(const stp_tensor* dy, int32_t k, const stp_tensor
       (const __nv_bfloat16*)dy->ptr, dy->ld, dy->h, dy->w, k, residual ? (const __nv_bfloat16*)residual->ptr : nullptr,
       residual ? residual->ld : 0, (__nv_bfloat16*)dx->ptr, dx->ld, dx->h, dx->w, rows, cv);
   return check_launch("avgpool_bwd");
+}
+
+static int spatial_check(const stp_tensor* small, const stp_tensor* big, const char* who) {
+  STP_REQUIRE(vec_ok(small) && vec_ok(big) && small->c == big->c && small->n == big->n && small->h == 1 && small->w == 1,
+              "%s: [n,1,1,c] against [n,h,w,c], bf16, c %% 8 == 0", who);
+  return STP_OK;
+}
+static int spatial_reduce(const stp_tensor* x, float scale, const stp_tensor* y, stp_stream stream, const char* who) {
+  const int cv = x->c / 8;
+  dim3 grid((cv + 7) / 8, x->n);
+  spatial_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x->ptr, x->ld, x->h * x->w, cv, scale,
+                                                                (__nv_bfloat16*)y->ptr, y->ld);
+  return check_launch(who);
+}
+static int spatial_bcast(const stp_tensor* x, float scale, const stp_tensor* residual, const stp_tensor* y, stp_stream stream, const char* who) {
+  if (residual) STP_REQUIRE(vec_ok(residual) && residual->c == y->c && pixels(residual) == pixels(y), "%s: bad residual", who);
+  const int cv = y->c / 8;
+  const int64_t total = pixels(y) * cv;
+  spatial_bcast_kernel<<<ew_grid2(total), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x->ptr, x->ld, y->h * y->w, cv, scale, residual ? (const __nv_bfloat16*)residual->ptr : nullptr,
+      residual ? residual->ld : 0, (__nv_bfloat16*)y->ptr, y->ld, total);
+  return check_launch(who);
+}
+
+extern "C" int stp_global_avgpool_fwd(const stp_tensor* x, const stp_tensor* y, stp_stream stream) {
+  int rc = spatial_check(y, x, "global_avgpool_fwd");
+  return rc ? rc : spatial_reduce(x, 1.f / (float)(x->h * x->w), y, stream, "global_avgpool_fwd");
+}
+extern "C" int stp_global_avgpool_bwd(const stp_tensor* dy, const stp_tensor* residual, const stp_tensor* dx, stp_stream stream) {
+  int rc = spatial_check(dy, dx, "global_avgpool_bwd");
+  return rc ? rc : spatial_bcast(dy, 1.f / (float)(dx->h * dx->w), residual, dx, stream, "global_avgpool_bwd");
+}
+extern "C" int stp_broadcast_fwd(const stp_tensor* x, const stp_tensor* y, stp_stream stream) {
+  int rc = spatial_check(x, y, "broadcast_fwd");
+  return rc ? rc : spatial_bcast(x, 1.f, nullptr, y, stream, "broadcast_fwd");
+}
+extern "C" int stp_broadcast_bwd(const stp_tensor* dy, const stp_tensor* dx, stp_stream stream) {
+  int rc = spatial_check(dx, dy, "broadcast_bwd");
+  return rc ? rc : spatial_reduce(dy, 1.f, dx, stream, "broadcast_bwd");
 }

@@ -197,6 +197,120 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16
   }
 }
 
+// ---- probability head of the reference's DeepLabV3+ (impl/deeplab/model.py:494-500): Conv2D(classes, 1x1, activation)
+// at 1/8 resolution, THEN BilinearUpsampling(output_size = input size) with align_corners=True (:81-83) -- the network's
+// output is the bilinear blend of low-resolution PROBABILITIES.  The loss / predict kernels of this library consume logits
+// and apply the activation themselves, so the forward emits  l = log(p/(1-p))  (sigmoid; p clipped to [1e-7, 1-1e-7] exactly
+// where keras binary_crossentropy clips before turning its probability input back into logits)  or  l = log(p)  (softmax:
+// softmax(log p) = p because the blended probability vectors still sum to 1).  The backward undoes that map
+// (dp = dl / (p(1-p)) resp. dl / p), gathers through the resize like resize_bwd_f32_kernel and applies the activation
+// derivative at low resolution; the result is the bf16 gradient of the padded 1x1 conv output.
+constexpr int kProbMaxClasses = 16;
+constexpr float kProbEps = 1e-7f;
+__device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + __expf(-z)); }
+
+__global__ void __launch_bounds__(256) prob_head_fwd_kernel(const float* __restrict__ z, int ldz, int h, int w, int classes, int act,
+                                                             float* __restrict__ logits, int H, int W, int64_t total, float sy, float sx) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = r / ((int64_t)H * W);
+    const int rem = (int)(r - n * (int64_t)H * W);
+    const int oy = rem / W, ox = rem - oy * W;
+    const Axis ay = src_of(oy, sy, h), ax = src_of(ox, sx, w);
+    const float* base = z + n * (int64_t)h * w * ldz;
+    const float* c4[4] = {base + ((int64_t)ay.lo * w + ax.lo) * ldz, base + ((int64_t)ay.lo * w + ax.hi) * ldz,
+                          base + ((int64_t)ay.hi * w + ax.lo) * ldz, base + ((int64_t)ay.hi * w + ax.hi) * ldz};
+    float mx[4], inv[4];
+    if (act == 2) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float m = -INFINITY, s = 0.f;
+        for (int c = 0; c < classes; ++c) m = fmaxf(m, c4[q][c]);
+        for (int c = 0; c < classes; ++c) s += __expf(c4[q][c] - m);
+        mx[q] = m; inv[q] = 1.f / s;
+      }
+    }
+    for (int c = 0; c < classes; ++c) {
+      float pq[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pq[q] = act == 2 ? __expf(c4[q][c] - mx[q]) * inv[q] : sigmoidf_(c4[q][c]);
+      const float top = pq[0] + (pq[1] - pq[0]) * ax.t;
+      const float bot = pq[2] + (pq[3] - pq[2]) * ax.t;
+      float p = top + (bot - top) * ay.t;
+      if (act == 2) {
+        logits[r * classes + c] = __logf(fmaxf(p, kProbEps));
+      } else {
+        p = fminf(fmaxf(p, kProbEps), 1.f - kProbEps);
+        logits[r * classes + c] = __logf(p / (1.f - p));
+      }
+    }
+  }
+}
+
+// thread = (low-resolution pixel); dz bf16 [n,h,w,cx] (channels >= classes zero)
+__global__ void __launch_bounds__(128) prob_head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ logits, int H, int W,
+                                                             int classes, int act, const float* __restrict__ z, int ldz,
+                                                             __nv_bfloat16* __restrict__ dz, int lddz, int cx, int h, int w, int64_t total,
+                                                             float sy, float sx, float isy, float isx) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = r / ((int64_t)h * w);
+    const int rem = (int)(r - n * (int64_t)h * w);
+    const int iy = rem / w, ix = rem - iy * w;
+    int y0, y1, x0, x1;
+    cand_range(iy, isy, H, y0, y1);
+    cand_range(ix, isx, W, x0, x1);
+    float acc[kProbMaxClasses];
+#pragma unroll
+    for (int c = 0; c < kProbMaxClasses; ++c) acc[c] = 0.f;
+    for (int oy = y0; oy <= y1; ++oy) {
+      const float wy = axis_weight(oy, iy, sy, h);
+      if (wy == 0.f) continue;
+      for (int ox = x0; ox <= x1; ++ox) {
+        const float wx = axis_weight(ox, ix, sx, w);
+        if (wx == 0.f) continue;
+        const int64_t o = ((n * H + oy) * (int64_t)W + ox) * classes;
+        const float ww = wy * wx;
+#pragma unroll
+        for (int c = 0; c < kProbMaxClasses; ++c) {
+          if (c >= classes) break;
+          const float l = logits[o + c], g = dlogits[o + c];
+          float dp;
+          if (act == 2) {
+            const float p = __expf(l);
+            dp = p > kProbEps ? g / p : 0.f;       // clipped probabilities carry no gradient
+          } else {
+            const float p = sigmoidf_(l);
+            const float q = p * (1.f - p);
+            dp = (p > kProbEps * 1.0001f && p < 1.f - kProbEps * 1.0001f) ? g / q : 0.f;
+          }
+          acc[c] += ww * dp;
+        }
+      }
+    }
+    const float* zr = z + r * ldz;
+    __nv_bfloat16* out = dz + r * lddz;
+    if (act == 2) {
+      float m = -INFINITY, s = 0.f, dot = 0.f;
+      for (int c = 0; c < classes; ++c) m = fmaxf(m, zr[c]);
+      for (int c = 0; c < classes; ++c) s += __expf(zr[c] - m);
+      const float inv = 1.f / s;
+#pragma unroll
+      for (int c = 0; c < kProbMaxClasses; ++c)
+        if (c < classes) dot += acc[c] * __expf(zr[c] - m) * inv;
+#pragma unroll
+      for (int c = 0; c < kProbMaxClasses; ++c)
+        if (c < classes) out[c] = __float2bfloat16_rn(__expf(zr[c] - m) * inv * (acc[c] - dot));
+    } else {
+#pragma unroll
+      for (int c = 0; c < kProbMaxClasses; ++c)
+        if (c < classes) {
+          const float sg = sigmoidf_(zr[c]);
+          out[c] = __float2bfloat16_rn(acc[c] * sg * (1.f - sg));
+        }
+    }
+    for (int c = classes; c < cx; ++c) out[c] = __float2bfloat16_rn(0.f);
+  }
+}
+
 int grid_for(int64_t total) {
   int64_t b = (total + 255) / 256;
   const int64_t cap = (int64_t)kNumSMs * 16;
@@ -265,4 +379,45 @@ extern "C" int stp_upsample2x_bwd(const stp_tensor* dy, const stp_tensor* residu
       (const __nv_bfloat16*)dy->ptr, dy->ld, residual ? (const __nv_bfloat16*)residual->ptr : nullptr,
       residual ? residual->ld : 0, (__nv_bfloat16*)dx->ptr, dx->ld, dx->h, dx->w, total, cv);
   return check_launch("upsample2x_bwd");
+}
+
+static void align_scales(int in_h, int in_w, int out_h, int out_w, float& sy, float& sx, float& isy, float& isx) {
+  // tf.image.resize_bilinear(align_corners=True): scale = (in-1)/(out-1) when out > 1 [DEP tensorflow==1.15 CalculateResizeScale]
+  sy = out_h > 1 ? (float)(in_h - 1) / (float)(out_h - 1) : (float)in_h / (float)out_h;
+  sx = out_w > 1 ? (float)(in_w - 1) / (float)(out_w - 1) : (float)in_w / (float)out_w;
+  isy = in_h > 1 ? (float)(out_h - 1) / (float)(in_h - 1) : (float)out_h;
+  isx = in_w > 1 ? (float)(out_w - 1) / (float)(in_w - 1) : (float)out_w;
+}
+
+extern "C" int stp_prob_head_fwd(const stp_tensor* z, int32_t classes, int32_t activation, const stp_tensor* logits, stp_stream stream) {
+  STP_REQUIRE(z && logits && f32_ok(z) && f32_ok(logits) && z->n == logits->n, "prob_head_fwd: f32 tensors of one batch");
+  STP_REQUIRE(classes >= 1 && classes <= kProbMaxClasses && classes <= z->c && logits->c == classes && logits->ld == classes,
+              "prob_head_fwd: 1 <= classes <= 16 <= z.c; logits dense [n,H,W,classes]");
+  STP_REQUIRE(activation == 1 || (activation == 2 && classes >= 2), "prob_head_fwd: activation 1 (sigmoid) or 2 (softmax, classes >= 2)");
+  float sy, sx, isy, isx;
+  align_scales(z->h, z->w, logits->h, logits->w, sy, sx, isy, isx);
+  const int64_t total = pixels(logits);
+  prob_head_fwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const float*)z->ptr, z->ld, z->h, z->w, classes, activation,
+                                                                          (float*)logits->ptr, logits->h, logits->w, total, sy, sx);
+  return check_launch("prob_head_fwd");
+}
+
+extern "C" int stp_prob_head_bwd(const stp_tensor* dlogits, const stp_tensor* logits, const stp_tensor* z, int32_t classes,
+                                 int32_t activation, const stp_tensor* dz, stp_stream stream) {
+  STP_REQUIRE(dlogits && logits && z && dz && f32_ok(dlogits) && f32_ok(logits) && f32_ok(z), "prob_head_bwd: f32 dlogits / logits / z");
+  STP_REQUIRE(dz->ptr && dz->dtype == STP_BF16 && dz->ld >= dz->c && dz->c >= classes && pixels(dz) == pixels(z) && dz->n == z->n &&
+                  dz->h == z->h && dz->w == z->w, "prob_head_bwd: dz bf16 with z's geometry");
+  STP_REQUIRE(classes >= 1 && classes <= kProbMaxClasses && classes <= z->c && logits->c == classes && logits->ld == classes &&
+                  dlogits->c == classes && dlogits->ld == classes && pixels(dlogits) == pixels(logits) && logits->n == z->n,
+              "prob_head_bwd: dense [n,H,W,classes] logits and gradient");
+  STP_REQUIRE(logits->h >= z->h && logits->w >= z->w, "prob_head_bwd: up-scaling only");
+  STP_REQUIRE(activation == 1 || (activation == 2 && classes >= 2), "prob_head_bwd: activation 1 (sigmoid) or 2 (softmax)");
+  float sy, sx, isy, isx;
+  align_scales(z->h, z->w, logits->h, logits->w, sy, sx, isy, isx);
+  const int64_t total = pixels(z);
+  const int64_t nb = (total + 127) / 128;
+  prob_head_bwd_kernel<<<(int)(nb < 1 ? 1 : nb), 128, 0, (cudaStream_t)stream>>>(
+      (const float*)dlogits->ptr, (const float*)logits->ptr, logits->h, logits->w, classes, activation, (const float*)z->ptr, z->ld,
+      (__nv_bfloat16*)dz->ptr, dz->ld, dz->c, z->h, z->w, total, sy, sx, isy, isx);
+  return check_launch("prob_head_bwd");
 }

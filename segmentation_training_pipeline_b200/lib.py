@@ -30,6 +30,10 @@ class ConvDesc(C.Structure):
                 ("pad_w", C.c_int32), ("up", C.c_int32), ("flags", C.c_int32)]
 
 
+class DwConvDesc(C.Structure):              # include/stp.h: stp_dwconv_desc
+    _fields_ = [("k", C.c_int32), ("stride", C.c_int32), ("dilation", C.c_int32), ("pad_h", C.c_int32), ("pad_w", C.c_int32)]
+
+
 class AugSpec(C.Structure):
     _fields_ = [("fliplr_p", C.c_double), ("flipud_p", C.c_double), ("affine", C.c_int32),
                 ("scale_lo", C.c_double), ("scale_hi", C.c_double),
@@ -104,7 +108,7 @@ class GradXform(C.Structure):
 
 
 _P, _I32, _I64, _U64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
-_TP, _CDP = C.POINTER(Tensor), C.POINTER(ConvDesc)
+_TP, _CDP, _DDP = C.POINTER(Tensor), C.POINTER(ConvDesc), C.POINTER(DwConvDesc)
 
 # name -> (restype, argtypes); every symbol include/stp.h declares
 SIGNATURES = {
@@ -151,6 +155,17 @@ SIGNATURES = {
     "stp_maxpool_bwd": (C.c_int, [_TP, _P, _I32, _I32, _I32, _TP, _TP, _P]),
     "stp_avgpool_fwd": (C.c_int, [_TP, _I32, _TP, _P]),
     "stp_avgpool_bwd": (C.c_int, [_TP, _I32, _TP, _TP, _P]),
+    "stp_global_avgpool_fwd": (C.c_int, [_TP, _TP, _P]),
+    "stp_global_avgpool_bwd": (C.c_int, [_TP, _TP, _TP, _P]),
+    "stp_broadcast_fwd": (C.c_int, [_TP, _TP, _P]),
+    "stp_broadcast_bwd": (C.c_int, [_TP, _TP, _P]),
+    "stp_dropout": (C.c_int, [_TP, _F, _U64, C.c_uint32, _P, _TP, _P]),
+    "stp_prob_head_fwd": (C.c_int, [_TP, _I32, _I32, _TP, _P]),
+    "stp_prob_head_bwd": (C.c_int, [_TP, _TP, _TP, _I32, _I32, _TP, _P]),
+    "stp_dwconv_fwd": (C.c_int, [_DDP, _TP, _P, _TP, _P]),
+    "stp_dwconv_dgrad": (C.c_int, [_DDP, _TP, _P, _TP, _TP, _P]),
+    "stp_dwconv_wgrad": (C.c_int, [_DDP, _TP, _TP, _P, _P, _SZ, _P]),
+    "stp_dwconv_wgrad_workspace": (_SZ, [_DDP, _TP, _TP]),
     "stp_copy_up": (C.c_int, [_TP, _I32, _TP, _P]),
     "stp_add": (C.c_int, [_TP, _TP, _TP, _P]),
     "stp_upsample2x_bwd": (C.c_int, [_TP, _TP, _TP, _P]),
