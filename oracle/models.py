@@ -48,6 +48,16 @@ class ParamStore:
                 self.encoder_names.append(name)
         return self.params[name + "/kernel"], self.params.get(name + "/bias")
 
+    def depthwise(self, name, k, c):
+        """keras DepthwiseConv2D kernel (k, k, C, 1), glorot_uniform (fan_in k*k*C, fan_out k*k)"""
+        key = name + "/depthwise_kernel"
+        if key not in self.params:
+            lim = float(np.sqrt(6.0 / (k * k * c + k * k)))
+            self.params[key] = torch.from_numpy(self.gen.uniform(-lim, lim, size=(k, k, c)).astype(np.float32)[..., None])
+            if self._in_encoder:
+                self.encoder_names.append(name)
+        return self.params[key]
+
     def bn(self, name, c, scale=True):
         if name + "/beta" not in self.params:
             if scale:
@@ -68,7 +78,7 @@ class SegModel:
                  decoder_filters=(256, 128, 64, 32, 16), decoder_use_batchnorm=True,
                  decoder_block_type="upsampling", enc_init="he_uniform", dec_init="glorot_uniform",
                  pyramid_block_filters=256, segmentation_block_filters=128, fpn_dropout=None,
-                 update_moving=True, downsample_factor=8, psp_conv_filters=512):
+                 update_moving=True, downsample_factor=8, psp_conv_filters=512, dropout=None):
         self.arch, self.backbone = architecture, backbone.lower()
         self.classes, self.activation = classes, activation
         self.storage = storage
@@ -77,6 +87,10 @@ class SegModel:
         self.block_type = decoder_block_type
         self.pyr, self.segf = pyramid_block_filters, segmentation_block_filters
         self.psp_factor, self.psp_filters = int(downsample_factor), int(psp_conv_filters)
+        # DeepLabV3 only: None (no dropout) or (rate, seed, salt, step) -- the engine's Philox mask (oracle/philox.py)
+        self.dropout = dropout
+        if self.arch == "DeepLabV3":
+            enc_init = dec_init = "glorot_uniform"   # keras defaults of impl/deeplab/model.py
         self.P = ParamStore(seed, enc_init, dec_init)
         self.training = True
         self.update_moving = update_moving
@@ -85,6 +99,8 @@ class SegModel:
         h = 64 if self.backbone != "vgg16" else 32
         if self.arch == "PSPNet":
             h = 6 * self.psp_factor
+        if self.arch == "DeepLabV3":
+            h = 16
         um, self.update_moving = self.update_moving, False
         with torch.no_grad():
             self.forward(torch.zeros(1, h, h, input_shape[2]), emit_logits=False)
@@ -108,7 +124,7 @@ class SegModel:
     def buffers(self):
         return self.P.buffers
 
-    def _bn(self, x, name, eps, scale=True):
+    def _bn(self, x, name, eps, scale=True, momentum=BN_MOMENTUM):
         gamma, beta = self.P.bn(name, x.shape[1], scale)
         if self.training:
             y, mean, var = L.batchnorm_train(x, gamma, beta, eps)
@@ -118,8 +134,8 @@ class SegModel:
                     # keras 2.2.x normalization.py: variance *= sample_size / (sample_size - (1.0 + epsilon))
                     unbiased = var * (m / (m - (1.0 + eps))) if m > 1 else var
                     mm, mv = self.P.buffers[name + "/moving_mean"], self.P.buffers[name + "/moving_variance"]
-                    mm.mul_(BN_MOMENTUM).add_(mean.detach() * (1 - BN_MOMENTUM))
-                    mv.mul_(BN_MOMENTUM).add_(unbiased.detach() * (1 - BN_MOMENTUM))
+                    mm.mul_(momentum).add_(mean.detach() * (1 - momentum))
+                    mv.mul_(momentum).add_(unbiased.detach() * (1 - momentum))
             return y
         return L.batchnorm_infer(x, gamma, beta, self.P.buffers[name + "/moving_mean"],
                                  self.P.buffers[name + "/moving_variance"], eps)
@@ -262,6 +278,74 @@ class SegModel:
         x = torch.cat(outs, dim=1)
         return self._conv_bn_relu(x, "psp_conv", "psp_bn", 1, 512, True)
 
+    # -- DeepLabV3+ / MobileNetV2 (reference impl/deeplab/model.py, in-tree) -------------------
+    MOBILENETV2_BLOCKS = (
+        (16, 1, 1, 0, False, 1),
+        (24, 2, 6, 1, False, 1), (24, 1, 6, 2, True, 1),
+        (32, 2, 6, 3, False, 1), (32, 1, 6, 4, True, 1), (32, 1, 6, 5, True, 1),
+        (64, 1, 6, 6, False, 1), (64, 1, 6, 7, True, 2), (64, 1, 6, 8, True, 2), (64, 1, 6, 9, True, 2),
+        (96, 1, 6, 10, False, 2), (96, 1, 6, 11, True, 2), (96, 1, 6, 12, True, 2),
+        (160, 1, 6, 13, False, 2), (160, 1, 6, 14, True, 4), (160, 1, 6, 15, True, 4),
+        (320, 1, 6, 16, False, 4),
+    )
+
+    def _bn_act(self, x, name, eps, act, momentum=BN_MOMENTUM, tap=None):
+        y = self._bn(x, name, eps, momentum=momentum)
+        if act == "relu6":      # keras relu(max_value=6) (model.py:38-39)
+            y = torch.clamp(y, 0.0, 6.0)
+        elif act == "relu":
+            y = torch.relu(y)
+        y = L.rb(y, self.storage)
+        if tap:
+            self.taps[tap] = y
+        return y
+
+    def _mobilenetv2(self, x):
+        """model.py:386-433 (feature extractor, output stride 8) with `_inverted_res_block` :236-275"""
+        EPS, MOM = 1e-3, 0.999
+        x = self._conv(x, "Conv", 3, 32, stride=2, padding="same")
+        x = self._bn_act(x, "Conv_BN", EPS, "relu6", MOM, tap="Conv_Relu6")
+        for filters, stride, expansion, bid, skip, rate in self.MOBILENETV2_BLOCKS:
+            pre = "expanded_conv_%d_" % bid if bid else "expanded_conv_"
+            inp, t = x, x
+            if bid:
+                t = self._conv(t, pre + "expand", 1, expansion * inp.shape[1])
+                t = self._bn_act(t, pre + "expand_BN", EPS, "relu6", MOM)
+            wd = self.P.depthwise(pre + "depthwise", 3, t.shape[1])
+            t = L.rb(L.depthwise_conv2d(t, wd, stride, rate, self.storage), self.storage)
+            t = self._bn_act(t, pre + "depthwise_BN", EPS, "relu6", MOM)
+            t = self._conv(t, pre + "project", 1, filters)
+            t = self._bn_act(t, pre + "project_BN", EPS, None, MOM)
+            x = L.rb(inp + t, self.storage) if skip else t
+            self.taps[pre + ("add" if skip else "project_BN")] = x
+        return x
+
+    def _deeplab_head(self, x):
+        """model.py:457-500: image pooling + 1x1 ASPP branches, concat_projection, Dropout(0.1), Conv2D(classes, 1x1,
+        activation), BilinearUpsampling(align_corners=True) to the input size.  Returns the network OUTPUT (probabilities)."""
+        EPS = 1e-5
+        h, w = x.shape[2], x.shape[3]
+        b4 = L.rb(x.mean(dim=(2, 3), keepdim=True), self.storage)        # AveragePooling2D over the whole map
+        b4 = self._conv(b4, "image_pooling", 1, 256)
+        b4 = self._bn_act(b4, "image_pooling_BN", EPS, "relu")
+        b4 = L.resize_bilinear_tf1(b4, h, w, align_corners=True)         # from 1x1: a broadcast
+        b0 = self._conv(x, "aspp0", 1, 256)
+        b0 = self._bn_act(b0, "aspp0_BN", EPS, "relu")
+        y = torch.cat([b4, b0], dim=1)
+        y = self._conv(y, "concat_projection", 1, 256)
+        y = self._bn_act(y, "concat_projection_BN", EPS, "relu")
+        if self.training and self.dropout is not None and self.dropout[0] > 0:
+            from .philox import dropout_keep_mask
+            rate, seed, salt, step = self.dropout
+            n, c = y.shape[0], y.shape[1]
+            keep = dropout_keep_mask(n * h * w, c, rate, seed, salt, step).reshape(n, h, w, c)
+            keep = torch.from_numpy(keep).permute(0, 3, 1, 2).to(y.dtype)
+            y = L.rb(y * keep * float(np.float32(1.0) / (np.float32(1.0) - np.float32(rate))), self.storage)
+        self.taps["concat_projection_relu"] = y
+        name = "logits_semantic" if self.classes == 21 else "custom_logits_semantic"
+        wk, b = self.P.conv(name, 1, 1, y.shape[1], self.classes, True)
+        return L.conv2d(y, wk, b, 1, "same", self.storage)
+
     # -- full graph ------------------------------------------------------------------------
     def forward(self, x_nhwc: torch.Tensor, emit_logits: bool = False) -> torch.Tensor:
         """x: float NHWC raw 0..255 (no preprocessing call anywhere in the reference).
@@ -269,6 +353,20 @@ class SegModel:
         emit_logits=True strips the trailing Activation (what musket compile does for lovasz_loss)."""
         self.P._in_encoder = True
         x = x_nhwc.permute(0, 3, 1, 2).contiguous().to(getattr(self, "dtype", torch.float32))
+        if self.arch == "DeepLabV3":
+            H, W = x.shape[2], x.shape[3]
+            x = self._mobilenetv2(x)
+            self.P._in_encoder = False
+            z = self._deeplab_head(x)
+            self.taps["logits_small"] = z
+            if emit_logits or self.activation in (None, "none", "linear"):
+                p = z
+            elif self.activation == "sigmoid":
+                p = torch.sigmoid(z)
+            else:
+                p = torch.softmax(z, dim=1)
+            # the activation sits INSIDE the 1x1 Conv2D; the upsampling acts on its output (model.py:499-500)
+            return L.resize_bilinear_tf1(p, H, W, align_corners=True).permute(0, 2, 3, 1)
         if self.backbone == "vgg16":
             x, skips = self._vgg16(x)
         else:

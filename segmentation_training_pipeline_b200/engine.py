@@ -148,6 +148,7 @@ class Net:
         self.params: Dict[str, Param] = {}
         self.buffers: Dict[str, torch.Tensor] = {}  # BN moving stats (fp32)
         self.gen = np.random.default_rng(seed)
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.training = True
         self.finalized = False
         self._ws_bytes = 0
@@ -354,6 +355,8 @@ class Net:
             if p.kind == "conv":  # KRSC(padded) -> Keras HWIO
                 cin = getattr(p, "cin_real", p.shape[3])
                 a = np.transpose(a[:getattr(p, "cout_real", p.shape[0]), ..., :cin], (1, 2, 3, 0))
+            elif p.kind == "dwconv":  # [k][k][C] -> Keras DepthwiseConv2D (k, k, C, 1)
+                a = a[..., None]
             elif p.kind == "bias":
                 a = a[:getattr(p, "cout_real", p.shape[0])]
             elif p.kind == "convT":  # internal [Cout][R][S][Cin], taps flipped -> Keras Conv2DTranspose (kh, kw, Cout, Cin)
@@ -374,6 +377,8 @@ class Net:
             a = np.asarray(d[p.name], dtype=np.float32)
             if p.kind == "convT":
                 a = np.ascontiguousarray(np.transpose(a, (2, 0, 1, 3))[:, ::-1, ::-1, :])
+            if p.kind == "dwconv":
+                a = a.reshape(p.shape)
             if p.kind == "conv":
                 a = np.transpose(a, (3, 0, 1, 2))  # HWIO -> KRSC
                 full = np.zeros(p.shape, dtype=np.float32)
@@ -876,6 +881,154 @@ class UpHead(Conv):
 
     def bwd(self):
         self.net.L.resize_bilinear_bwd(C.byref(self._dlg), None, self.dy.ref, _stream())
+        super().bwd()
+
+
+class DWConv(Op):
+    """keras DepthwiseConv2D(k, strides, 'same', dilation_rate, use_bias=False) (MobileNetV2 blocks of the reference's
+    DeepLabV3+, impl/deeplab/model.py:252-255).  Parameter `<name>/depthwise_kernel`, Keras shape (k, k, C, 1); internal
+    [k][k][C] fp32, read directly by the kernels (rounded to bf16 in compute)."""
+
+    def __init__(self, net: Net, x: Buf, y: Buf, name: str, k=3, stride=1, dilation=1, init="glorot_uniform"):
+        if net.precision != "bf16":
+            raise NotImplementedError("DWConv: bf16 path only")
+        self.net, self.x, self.y, self.name = net, x, y, name
+        c = x.c
+        assert y.c == c
+
+        def same(size):   # TF 'same': padding before = total // 2
+            out = -(-size // stride)
+            return max((out - 1) * stride + (k - 1) * dilation + 1 - size, 0) // 2, out
+
+        (ph, ho), (pw, wo) = same(x.h), same(x.w)
+        assert (ho, wo) == (y.h, y.w), ((ho, wo), (y.h, y.w))
+        self.desc = _lib.DwConvDesc(k, stride, dilation, ph, pw)
+        lim = math.sqrt(6.0 / (k * k * c + k * k)) if init == "glorot_uniform" else math.sqrt(6.0 / (k * k * c))
+        self.w = net.add_param(name + "/depthwise_kernel", (k, k, c), "dwconv",
+                               lambda: net.gen.uniform(-lim, lim, size=(k, k, c)).astype(np.float32))
+        net.need_ws(net.L.dwconv_wgrad_workspace(C.byref(self.desc), x.ref, y.ref))
+        net.ops.append(self)
+
+    def grad_writes(self):
+        return [self.x.grad()]
+
+    def prepare(self):
+        self.dref = C.byref(self.desc)
+        self.dy, self.dx = self.y.grad(), self.x.grad()
+        self.dx_res = self.dx.ref if self.acc[0] else None
+
+    def fwd(self):
+        n = self.net
+        n.L.dwconv_fwd(self.dref, self.x.ref, n.pp(self.w), self.y.ref, _stream())
+
+    def bwd(self):
+        n = self.net
+        with n.wgrad_stream() as ws:
+            n.L.dwconv_wgrad(self.dref, self.x.ref, self.dy.ref, n.pg(self.w), ws.data_ptr(), ws.numel(), _stream())
+        n.L.dwconv_dgrad(self.dref, self.dy.ref, n.pp(self.w), self.dx_res, self.dx.ref, _stream())
+
+
+class GlobalAvgPool(Op):
+    """AveragePooling2D over the whole map (DeepLabV3+ image-pooling branch, impl/deeplab/model.py:462): [N,h,w,C] -> [N,1,1,C]."""
+
+    def __init__(self, net: Net, x: Buf, y: Buf):
+        self.net, self.x, self.y = net, x, y
+        assert (y.h, y.w, y.c) == (1, 1, x.c)
+        net.ops.append(self)
+
+    def grad_writes(self):
+        return [self.x.grad()]
+
+    def prepare(self):
+        self.dy, self.dx = self.y.grad(), self.x.grad()
+        self.res_ref = self.dx.ref if self.acc[0] else None
+
+    def fwd(self):
+        self.net.L.global_avgpool_fwd(self.x.ref, self.y.ref, _stream())
+
+    def bwd(self):
+        self.net.L.global_avgpool_bwd(self.dy.ref, self.res_ref, self.dx.ref, _stream())
+
+
+class Broadcast(Op):
+    """BilinearUpsampling of a 1x1 map (impl/deeplab/model.py:469): every output pixel is the one input pixel; y is typically
+    a channel slice of the ASPP concat buffer.  Backward: spatial sum."""
+
+    def __init__(self, net: Net, x: Buf, y: Buf):
+        self.net, self.x, self.y = net, x, y
+        assert (x.h, x.w, x.c) == (1, 1, y.c)
+        net.ops.append(self)
+
+    def grad_writes(self):
+        return [self.x.grad()]
+
+    def prepare(self):
+        self.dy, self.dx = self.y.grad(), self.x.grad()
+        if self.acc[0]:
+            raise RuntimeError("Broadcast: accumulate into dx unsupported")
+
+    def fwd(self):
+        self.net.L.broadcast_fwd(self.x.ref, self.y.ref, _stream())
+
+    def bwd(self):
+        self.net.L.broadcast_bwd(self.dy.ref, self.dx.ref, _stream())
+
+
+class Dropout(Op):
+    """keras Dropout(rate), in place on a post-activation buffer (impl/deeplab/model.py:486).  Training: x *= keep/(1-rate) with
+    the Philox mask of (net.seed, salt, net.d_step, element); inference: identity.  Backward: the same mask on the gradient."""
+
+    def __init__(self, net: Net, x: Buf, rate: float, salt: int):
+        self.net, self.x, self.rate, self.salt = net, x, float(rate), int(salt)
+        net.ops.append(self)
+
+    def grad_writes(self):
+        return []
+
+    def prepare(self):
+        self.dx = self.x.grad()
+
+    def fwd(self):
+        n = self.net
+        if n.training and self.rate > 0.0:
+            n.L.dropout(self.x.ref, self.rate, n.seed, self.salt, n.d_step.data_ptr(), self.x.ref, _stream())
+
+    def bwd(self):
+        n = self.net
+        if self.rate > 0.0:
+            n.L.dropout(self.dx.ref, self.rate, n.seed, self.salt, n.d_step.data_ptr(), self.dx.ref, _stream())
+
+
+class ProbHead(Conv):
+    """DeepLabV3+ head (impl/deeplab/model.py:494-500): Conv2D(classes, 1x1, bias, activation) at 1/8 resolution, then the
+    align_corners BilinearUpsampling of the PROBABILITIES to the input size.  `logits` is what the loss / predict kernels
+    read: activation(logits) == resize(activation(conv)) (stp_prob_head_fwd).  Class dimension padded to 16 like UpHead."""
+
+    CPAD = 16
+    ACT = {"sigmoid": 1, "softmax": 2}
+
+    def __init__(self, net: Net, x: Buf, classes: int, out_hw, activation: str, name: str, init="glorot_uniform"):
+        if classes > self.CPAD:
+            raise NotImplementedError("ProbHead: classes <= %d" % self.CPAD)
+        if activation not in self.ACT:
+            raise NotImplementedError("DeepLabV3 head: activation sigmoid or softmax (got %r)" % (activation,))
+        small = Buf(net, x.n, x.h, x.w, self.CPAD, F32, name=name + "_out")
+        small.set_grad(Buf(net, x.n, x.h, x.w, self.CPAD, BF16, name="d_" + name + "_out"))
+        super().__init__(net, x, small, name, 1, pad=0, bias=True, init=init, cout_real=classes)
+        self.classes, self.small, self.act = classes, small, self.ACT[activation]
+        H, W = out_hw
+        self.out_n, self.out_hw = x.n, H * W
+        self.logits = torch.zeros(x.n * H * W * classes, dtype=torch.float32, device=net.device)
+        self.dlogits = torch.zeros(x.n * H * W * classes, dtype=torch.float32, device=net.device)
+        self._lg = _lib.Tensor(self.logits.data_ptr(), x.n, H, W, classes, classes, F32)
+        self._dlg = _lib.Tensor(self.dlogits.data_ptr(), x.n, H, W, classes, classes, F32)
+
+    def fwd(self):
+        super().fwd()
+        self.net.L.prob_head_fwd(self.small.ref, self.classes, self.act, C.byref(self._lg), _stream())
+
+    def bwd(self):
+        self.net.L.prob_head_bwd(C.byref(self._dlg), C.byref(self._lg), self.small.ref, self.classes, self.act, self.dy.ref, _stream())
         super().bwd()
 
 

@@ -21,7 +21,28 @@ RESNET_REPS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3), "resnet50": (
 RESNET_BOTTLENECK = {"resnet18": False, "resnet34": False, "resnet50": True, "resnet101": True, "resnet152": True}
 VGG16_BLOCKS = ((64, 2), (128, 2), (256, 3), (512, 3), (512, 3))  # keras.applications.VGG16 [DEP]
 KNOWN_BACKBONES = sorted(RESNET_REPS) + ["vgg16"]
-KNOWN_ARCHITECTURES = ["Unet", "FPN", "Linknet", "PSPNet"]
+KNOWN_ARCHITECTURES = ["Unet", "FPN", "Linknet", "PSPNet", "DeepLabV3"]
+DEEPLAB_BACKBONES = ["mobilenetv2"]   # impl/deeplab/model.py:324-326 also names 'xception' (not built)
+# MobileNetV2 feature extractor of the reference's DeepLabV3+ (impl/deeplab/model.py:386-433): (filters, stride, expansion,
+# block_id, skip_connection, atrous rate); strides after block 3 are replaced by rates (output stride 8)
+MOBILENETV2_BLOCKS = (
+    (16, 1, 1, 0, False, 1),
+    (24, 2, 6, 1, False, 1), (24, 1, 6, 2, True, 1),
+    (32, 2, 6, 3, False, 1), (32, 1, 6, 4, True, 1), (32, 1, 6, 5, True, 1),
+    (64, 1, 6, 6, False, 1), (64, 1, 6, 7, True, 2), (64, 1, 6, 8, True, 2), (64, 1, 6, 9, True, 2),
+    (96, 1, 6, 10, False, 2), (96, 1, 6, 11, True, 2), (96, 1, 6, 12, True, 2),
+    (160, 1, 6, 13, False, 2), (160, 1, 6, 14, True, 4), (160, 1, 6, 15, True, 4),
+    (320, 1, 6, 16, False, 4),
+)
+
+
+def _make_divisible(v, divisor=8, min_value=None):
+    """impl/deeplab/model.py:225-233"""
+    min_value = divisor if min_value is None else min_value
+    new_v = max(min_value, int(v + divisor / 2) // divisor * divisor)
+    if new_v < 0.9 * v:
+        new_v += divisor
+    return new_v
 
 
 class SegNet(E.Net):
@@ -31,10 +52,15 @@ class SegNet(E.Net):
                  decoder_filters=(256, 128, 64, 32, 16), device="cuda:0", seed=0,
                  enc_init="he_uniform", dec_init="glorot_uniform", loss=(1.0, 0.0, 0.0), architecture="Unet",
                  decoder_block_type="upsampling", pyramid_block_filters=256, segmentation_block_filters=128,
-                 dropout=None, precision="bf16", decoder_use_batchnorm=True, downsample_factor=8, psp_conv_filters=512):
+                 dropout=None, precision="bf16", decoder_use_batchnorm=True, downsample_factor=8, psp_conv_filters=512,
+                 activation="sigmoid"):
         super().__init__(batch, device, seed, precision)
         self.dec_bn = bool(decoder_use_batchnorm)
         backbone = backbone.lower()
+        if architecture == "DeepLabV3":
+            self._build_deeplabv3(backbone, classes, input_shape, batch, activation, loss,
+                                  0.1 if dropout is None else float(dropout))
+            return
         if architecture not in KNOWN_ARCHITECTURES:
             print("Unknown architecture:" + str(architecture))
             print("Known architectures:", KNOWN_ARCHITECTURES)
@@ -343,6 +369,85 @@ class SegNet(E.Net):
                 last = E.Buf(self, N, cin.h, cin.w, f, name=pre + "relu2")
                 E.BNRelu(self, z2, last, pre + "bn2", DEC_BN_EPS)
         self.head = E.Head(self, last, classes, "final_conv", init=dec_init)
+        self.loss = E.Loss(self, self.head, self.mask, *loss)
+        self.finalize()
+
+    def _build_deeplabv3(self, backbone, classes, input_shape, batch, activation, loss, dropout):
+        """DeepLabV3+ over MobileNetV2, the model the reference ships in-tree and registers as architecture `DeepLabV3`
+        (impl/deeplab/model.py:278-505, segmentation.py:31-33; all five example configs use it): Conv 3x3/2 + BN + ReLU6, 17
+        inverted-residual blocks (1x1 expand -> 3x3 depthwise (stride / atrous rate) -> 1x1 project, BatchNorm eps 1e-3
+        momentum 0.999, ReLU6, identity Add) at output stride 8, ASPP with the image-pooling branch and the 1x1 branch only
+        (:462-481), concat_projection + BN + ReLU + Dropout(0.1), then Conv2D(classes, 1x1, activation) at 1/8 resolution and
+        the align_corners bilinear resize of the PROBABILITIES to the input size (:494-500).  Raw 0..255 input like every model
+        of the pipeline.  Layer names are the Keras names of that file (weights exchangeable by name)."""
+        if self.precision != "bf16":
+            raise NotImplementedError("precision: fp32 (parity mode) is built for the Unet / Linknet graphs")
+        if backbone not in DEEPLAB_BACKBONES:
+            print("Unknown backbone:" + backbone)
+            print("Known backbones:", DEEPLAB_BACKBONES)
+            raise ValueError("Unknown backbone" if backbone != "xception" else "DeepLabV3: the xception backbone is not built")
+        H, W, CI = input_shape
+        if H % 8 or W % 8:
+            raise ValueError("DeepLabV3: input height/width must be divisible by 8 (output stride of the feature extractor)")
+        if not 1 <= CI <= 4:
+            raise NotImplementedError("input channels: 1..4 are built (uint8 augmentation / stem kernels); shape[2] = %d" % CI)
+        N = batch
+        self.architecture, self.input_shape, self.classes, self.backbone = "DeepLabV3", (H, W, CI), classes, backbone
+        self.img = E.Buf(self, N, H, W, CI, E.U8, name="image")
+        self.mask = E.Buf(self, N, H, W, classes, E.U8, name="mask")
+        BN_EPS, BN_MOM, RELU6, init = 1e-3, 0.999, 2, "glorot_uniform"
+        x0 = E.Buf(self, N, H, W, 8, name="input_bf16")
+        E.InputCast(self, self.img, x0)
+        h, w = H // 2, W // 2
+        z = E.Buf(self, N, h, w, _make_divisible(32), name="Conv")
+        E.Conv(self, x0, z, "Conv", 3, stride=2, pad=0, init=init, needs_dgrad=False, cin_real=CI)   # TF 'same', even size: pad 0 / 1
+        x = E.Buf(self, N, h, w, z.c, name="Conv_Relu6")
+        E.BNRelu(self, z, x, "Conv_BN", BN_EPS, relu=RELU6, momentum=BN_MOM)
+        for filters, stride, expansion, bid, skip, rate in MOBILENETV2_BLOCKS:
+            pre = "expanded_conv_%d_" % bid if bid else "expanded_conv_"
+            t = x
+            if bid:
+                e = E.Buf(self, N, h, w, expansion * x.c, name=pre + "expand")
+                E.Conv(self, x, e, pre + "expand", 1, init=init)
+                t = E.Buf(self, N, h, w, e.c, name=pre + "expand_relu")
+                E.BNRelu(self, e, t, pre + "expand_BN", BN_EPS, relu=RELU6, momentum=BN_MOM)
+            ho, wo = -(-h // stride), -(-w // stride)
+            d = E.Buf(self, N, ho, wo, t.c, name=pre + "depthwise")
+            E.DWConv(self, t, d, pre + "depthwise", 3, stride=stride, dilation=rate, init=init)
+            dr = E.Buf(self, N, ho, wo, t.c, name=pre + "depthwise_relu")
+            E.BNRelu(self, d, dr, pre + "depthwise_BN", BN_EPS, relu=RELU6, momentum=BN_MOM)
+            pj = E.Buf(self, N, ho, wo, _make_divisible(filters), name=pre + "project")
+            E.Conv(self, dr, pj, pre + "project", 1, init=init)
+            pb = E.Buf(self, N, ho, wo, pj.c, name=pre + "project_BN")
+            E.BNRelu(self, pj, pb, pre + "project_BN", BN_EPS, relu=False, momentum=BN_MOM)
+            if skip:
+                out = E.Buf(self, N, ho, wo, pj.c, name=pre + "add")
+                E.Add(self, pb, x, out)
+                x = out
+            else:
+                x = pb
+            h, w = ho, wo
+        self.encoder_param_names = list(self.params.keys())   # "# end of feature extractor" (model.py:455)
+        # ---- ASPP: image pooling branch (whole-map mean -> 1x1 -> BN -> ReLU -> broadcast) | 1x1 branch --------------------
+        ASPP_EPS = 1e-5
+        cat = E.Buf(self, N, h, w, 512, name="aspp_concat")
+        gp = E.Buf(self, N, 1, 1, x.c, name="image_pooling_avg")
+        E.GlobalAvgPool(self, x, gp)
+        ip = E.Buf(self, N, 1, 1, 256, name="image_pooling")
+        E.Conv(self, gp, ip, "image_pooling", 1, init=init)
+        ipr = E.Buf(self, N, 1, 1, 256, name="image_pooling_relu")
+        E.BNRelu(self, ip, ipr, "image_pooling_BN", ASPP_EPS)
+        E.Broadcast(self, ipr, cat.slice(0, 256, name="image_pooling_up"))
+        a0 = E.Buf(self, N, h, w, 256, name="aspp0")
+        E.Conv(self, x, a0, "aspp0", 1, init=init)
+        E.BNRelu(self, a0, cat.slice(256, 256, name="aspp0_activation"), "aspp0_BN", ASPP_EPS)
+        cp = E.Buf(self, N, h, w, 256, name="concat_projection")
+        E.Conv(self, cat, cp, "concat_projection", 1, init=init)
+        cpr = E.Buf(self, N, h, w, 256, name="concat_projection_relu")
+        E.BNRelu(self, cp, cpr, "concat_projection_BN", ASPP_EPS)
+        self.dropout = E.Dropout(self, cpr, dropout, salt=0xD0)
+        self.head = E.ProbHead(self, cpr, classes, (H, W), activation or "none",
+                               "logits_semantic" if classes == 21 else "custom_logits_semantic", init=init)
         self.loss = E.Loss(self, self.head, self.mask, *loss)
         self.finalize()
 

@@ -1,0 +1,175 @@
+"""End-to-end GPU parity of the DeepLabV3+ / MobileNetV2 graph (the reference's in-tree impl/deeplab/model.py, architecture
+`DeepLabV3` of every example config) against the CPU oracle: forward probabilities, loss, every parameter gradient, with the
+engine's dropout mask reproduced by the oracle; inference mode; a short training run under the whole-step CUDA graph.
+Tolerance model as tests/test_gpu_model.py: the engine must be as close to the bf16-storage oracle as bf16 storage itself is
+to fp32 (the deviation between the two oracles is the noise floor)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.test_gpu_model import _data, _perturb
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(n, size, classes, loss, activation, dropout=None, channels=3):
+    from segmentation_training_pipeline_b200.models import SegNet
+    return SegNet("mobilenetv2", classes=classes, input_shape=(size, size, channels), batch=n, device="cuda:0", seed=0, loss=loss,
+                  architecture="DeepLabV3", activation=activation, dropout=dropout)
+
+
+def _masks(mask, classes, onehot, size):
+    if classes > 1:
+        mask = torch.cat([torch.roll(mask, c * size // 8, dims=2) for c in range(classes)], dim=3).contiguous()
+    if onehot:
+        lab = torch.zeros(mask.shape[:3], dtype=torch.long)
+        for c in range(classes - 1, 0, -1):
+            lab[mask[..., c] > 0] = c
+        mask = torch.nn.functional.one_hot(lab, classes).to(torch.uint8).contiguous()
+    return mask
+
+
+@pytest.mark.parametrize("size,classes,loss,activation,dropout", [
+    (64, 1, (1.0, 1.0, 0.0), "sigmoid", 0.1),
+    (96, 2, (1.0, 0.0, 0.0), "sigmoid", 0.0),
+    (64, 3, (0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0), "softmax", 0.1),
+])
+def test_deeplab_forward_backward_parity(cuda, size, classes, loss, activation, dropout):
+    from oracle import losses as OL
+    from oracle.models import SegModel
+    from segmentation_training_pipeline_b200 import lib
+    from segmentation_training_pipeline_b200.trainer import Trainer
+
+    n = 4
+    onehot = activation == "softmax"
+    net = _build(n, size, classes, loss, activation, dropout)
+    W = _perturb(net.get_weights())
+    net.set_weights(W)
+    tr = Trainer(net)
+    img, mask = _data(n, size, size)
+    mask = _masks(mask, classes, onehot, size)
+    tr.set_batch(img.cuda(), mask.cuda())
+    net.d_step.fill_(5)
+    net.prep_weights()
+    net.forward()
+    net.backward()
+    torch.cuda.synchronize()
+    res = net.loss.result.cpu().numpy()
+    lg = net.head.logits.cpu().view(n, size, size, classes)
+    prob = torch.sigmoid(lg) if activation == "sigmoid" else torch.softmax(lg, dim=-1)
+    grads = net.get_grads()
+
+    def run(storage):
+        om = SegModel("DeepLabV3", "mobilenetv2", classes=classes, activation=activation, input_shape=(size, size, 3), storage=storage,
+                      update_moving=False, dropout=(dropout, net.seed, 0xD0, 5) if dropout else None)
+        assert set(om.params.keys()) == set(net.params.keys()), sorted(set(om.params.keys()) ^ set(net.params.keys()))
+        om.load_numpy(W)
+        y = om(img.float())
+        t = mask.float()
+        if onehot:
+            lo = loss[6] * OL.categorical_crossentropy(t, y)
+        else:
+            lo = loss[0] * OL.binary_crossentropy(t, y) + loss[1] * OL.dice_loss(t, y) + loss[2] * OL.iou_loss(t, y)
+        lo.backward()
+        return y.detach(), float(lo.detach()), {k: p.grad.numpy().copy() for k, p in om.params.items()}
+
+    y, lo, go_all = run("bf16")
+    y32, lo32, go32 = run("fp32")
+    floor = float((y - y32).norm() / y32.norm())
+    err = float((prob - y).norm() / y.norm())
+    print("probabilities rel err", err, "bf16-vs-fp32 floor", floor, "loss", float(res[lib.L_LOSS]), lo, lo32)
+    assert err < max(5e-3, 0.8 * floor)
+    assert abs(float(res[lib.L_LOSS]) - lo) < max(1e-3 * max(1.0, abs(lo)), 1.5 * abs(lo - lo32))
+    worst = ("", 0.0)
+    for k, go in go_all.items():
+        ge = grads[k]
+        assert go.shape == ge.shape, (k, go.shape, ge.shape)
+        e = float(np.linalg.norm(ge - go) / (np.linalg.norm(go) + 1e-12))
+        fl = float(np.linalg.norm(go - go32[k]) / (np.linalg.norm(go32[k]) + 1e-12))
+        if fl > 0.25:     # gradients that are near-total cancellations (e.g. a bias / beta in front of a BatchNorm)
+            continue
+        if e / max(fl, 1e-3) > worst[1]:
+            worst = (k, e / max(fl, 1e-3))
+        assert e < max(2e-2, 1.5 * fl), (k, e, fl)
+    print("worst grad err / bf16 floor", worst)
+
+
+def test_deeplab_weight_names_match_keras_layers(cuda):
+    """parameter names / Keras layouts of impl/deeplab/model.py (weights exchangeable by name with model.load_weights(by_name))"""
+    net = _build(2, 64, 1, (1.0, 0.0, 0.0), "sigmoid")
+    w = net.get_weights()
+    assert w["Conv/kernel"].shape == (3, 3, 3, 32)
+    assert w["expanded_conv_depthwise/depthwise_kernel"].shape == (3, 3, 32, 1)
+    assert w["expanded_conv_1_expand/kernel"].shape == (1, 1, 16, 96)
+    assert w["expanded_conv_16_project/kernel"].shape == (1, 1, 960, 320)
+    assert w["image_pooling/kernel"].shape == (1, 1, 320, 256)
+    assert w["concat_projection/kernel"].shape == (1, 1, 512, 256)
+    assert w["custom_logits_semantic/kernel"].shape == (1, 1, 256, 1) and w["custom_logits_semantic/bias"].shape == (1,)
+    assert w["Conv_BN/moving_variance"].shape == (32,)
+    assert sum(v.size for k, v in w.items() if not k.startswith(("Conv_BN/moving", )) and "moving_" not in k) == 2108417 + 0
+    w2 = {k: (v + 0.01).astype(np.float32) for k, v in w.items()}
+    net.set_weights(w2)
+    w3 = net.get_weights()
+    for k in w2:
+        assert np.array_equal(w2[k], w3[k]), k
+    enc = set(net.encoder_param_names)
+    assert "expanded_conv_16_project_BN/beta" in enc and "aspp0/kernel" not in enc
+
+
+def test_deeplab_inference_matches_oracle(cuda):
+    from oracle.models import SegModel
+    from segmentation_training_pipeline_b200.trainer import Trainer
+    n, size = 2, 64
+    net = _build(n, size, 1, (1.0, 0.0, 0.0), "sigmoid")
+    rng = np.random.default_rng(3)
+    W = _perturb(net.get_weights())
+    for k in W:
+        if k.endswith("moving_mean"):
+            W[k] = rng.normal(0, 0.2, W[k].shape).astype(np.float32)
+        if k.endswith("moving_variance"):
+            W[k] = rng.uniform(0.5, 1.5, W[k].shape).astype(np.float32)
+    net.set_weights(W)
+    tr = Trainer(net)
+    img, mask = _data(n, size, size)
+    tr.set_batch(img.cuda(), mask.cuda())
+    net.training = False
+    net.prep_weights()
+    net.forward()
+    torch.cuda.synchronize()
+    prob = torch.sigmoid(net.head.logits.cpu().view(n, size, size, 1))
+    outs = {}
+    for storage in ("bf16", "fp32"):
+        om = SegModel("DeepLabV3", "mobilenetv2", classes=1, input_shape=(size, size, 3), storage=storage)
+        om.load_numpy(W)
+        om.training = False
+        with torch.no_grad():
+            outs[storage] = om(img.float())
+    floor = float((outs["bf16"] - outs["fp32"]).norm() / outs["fp32"].norm())
+    err = float((prob - outs["bf16"]).norm() / outs["bf16"].norm())
+    print("inference rel err", err, "floor", floor)
+    assert err < max(5e-3, 1.5 * floor)
+
+
+def test_deeplab_trains_under_cuda_graph(cuda):
+    """the reference example's shape of run (architecture DeepLabV3, backbone mobilenetv2, binary_crossentropy, Adam) at small
+    size: loss decreases; whole-step CUDA graph replay == eager (the dropout mask follows the device step counter)."""
+    from segmentation_training_pipeline_b200.trainer import Trainer
+    n, size, steps = 4, 64, 30
+    img, mask = _data(n * 2, size, size, seed=3)
+    curves = []
+    for graph in (True, False):
+        net = _build(n, size, 1, (1.0, 0.0, 0.0), "sigmoid")
+        tr = Trainer(net, optimizer="Adam", lr=1e-3)
+        tr.set_pool(img, mask)
+        if graph:
+            tr.capture()
+        c = []
+        for s in range(steps if graph else 6):
+            tr.step()
+            c.append(tr.loss_value())
+        curves.append(c)
+    print(curves[0])
+    assert curves[0][-1] < 0.8 * curves[0][0]
+    assert np.isfinite(curves[0]).all()
+    for a, b in zip(curves[0][:6], curves[1]):
+        assert abs(a - b) < 1e-5 * max(1.0, abs(b)), (curves[0][:6], curves[1])
