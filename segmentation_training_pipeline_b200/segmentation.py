@@ -13,8 +13,7 @@ Everything numeric runs in libstp (CUDA, no CPU fallback): `fit` raises if the l
 Mirrored training controls: k-fold x stage loop, best-weights checkpoint + CSV log, callbacks EarlyStopping / ReduceLROnPlateau /
 CyclicLR, freeze_encoder / unfreeze_encoder, negatives / validation_negatives, initial_weights, extra_train_data,
 setAllowResume, lr_find, crops.  NOT mirrored (out of the hot-path scope): other callbacks, DrawResults,
-PSPNet / DeepLab graphs, categorical_crossentropy (these raise NotImplementedError naming the key instead of being
-silently ignored).
+the xception DeepLab backbone (these raise NotImplementedError naming the key instead of being silently ignored).
 """
 from __future__ import annotations
 
@@ -350,9 +349,13 @@ class PipelineConfig:
             print("Known architectures:", _models.KNOWN_ARCHITECTURES + sorted(custom_models))
             raise ValueError("Unknown architecture")
         bb = str(self.backbone).lower()
-        if bb not in _models.KNOWN_BACKBONES:
+        deeplab = arch == "DeepLabV3"   # the reference's in-tree model (custom_models, segmentation.py:31-33; impl/deeplab/model.py)
+        if deeplab and bb == "xception":
+            raise NotImplementedError("backbone: xception is not built for DeepLabV3 (mobilenetv2 is; impl/deeplab/model.py:324-326)")
+        known = _models.DEEPLAB_BACKBONES if deeplab else _models.KNOWN_BACKBONES
+        if bb not in known:
             print("Unknown backbone:" + bb)
-            print("Known backbones:", _models.KNOWN_BACKBONES)
+            print("Known backbones:", known)
             raise ValueError("Unknown backbone")
         lw = parse_loss(loss or self.loss)
         pure_lovasz = len(lw) == 4 and lw[3] != 0.0
@@ -368,13 +371,24 @@ class PipelineConfig:
             raise NotImplementedError("activation '%s' is not built" % self.activation)
         if self.classes > 4:
             raise NotImplementedError("classes <= 4 (mask channels of the on-device augmentation / head kernels)")
+        if deeplab and pure_lovasz:
+            raise NotImplementedError("lovasz_loss with DeepLabV3: the activation sits inside the last Conv2D there, the reference's "
+                                      "compile cannot strip it; not built")
+        if deeplab and self.activation not in ("sigmoid", "softmax"):
+            raise NotImplementedError("DeepLabV3: activation sigmoid or softmax (the head resizes probabilities)")
         enc_file = None
         if self.encoder_weights not in (None, "None", "none"):
             # `encoder_weights: imagenet` downloads a Keras checkpoint in the reference; there is no network here.  A path to a
             # local .npz with Keras-named arrays (conv0/kernel, bn0/gamma, bn0/moving_mean, ...) is accepted instead.
             cand = str(self.encoder_weights)
             base = os.path.dirname(os.path.abspath(self.path)) if self.path else os.getcwd()
-            for c in (cand, cand + ".npz", os.path.join(base, cand), os.path.join(base, cand + ".npz")):
+            names = [cand, cand + ".npz", os.path.join(base, cand), os.path.join(base, cand + ".npz")]
+            if deeplab and cand == "pascal_voc":
+                # the reference fetches this file into ~/.keras/models (impl/deeplab/model.py:505-512) and loads it by layer
+                # name; the same arrays as .npz (scripts/keras_h5_to_npz.py converts) are looked up in the same places
+                stem = "deeplabv3_mobilenetv2_tf_dim_ordering_tf_kernels.npz"
+                names += [os.path.join(base, stem), os.path.join(os.path.expanduser("~"), ".keras", "models", stem)]
+            for c in names:
                 if os.path.isfile(c):
                     enc_file = c
                     break
@@ -392,9 +406,17 @@ class PipelineConfig:
                               downsample_factor=int(mk.get("downsample_factor") or 8),
                               psp_conv_filters=int(mk.get("psp_conv_filters") or 512),
                               precision=str(self.extra.get("precision", "bf16")),
-                              loss=lw)
+                              activation=self.activation, loss=lw)
         net.activation = self.activation or "linear"   # what predict applies to the logits
-        if enc_file is not None:
+        if enc_file is not None and deeplab:
+            # model.load_weights(path, by_name=True): every layer whose name and shapes match, ASPP included; the class layer
+            # only when classes == 21 (its name differs otherwise)
+            cur = net.get_weights()
+            w = {k: v for k, v in dict(np.load(enc_file)).items() if k in cur}
+            if not w:
+                raise ValueError("encoder_weights: %s holds no array of this model" % enc_file)
+            net.set_weights(self._adapt_input_channels(net, w), strict=False)
+        elif enc_file is not None:
             layers = {n.rsplit("/", 1)[0] for n in net.encoder_param_names}
             w = {k: v for k, v in dict(np.load(enc_file)).items() if k.rsplit("/", 1)[0] in layers}
             if not w:
@@ -470,6 +492,8 @@ class PipelineConfig:
             only("dropout", (0, 0.0, None), "SpatialDropout2D is not built")
             only("final_interpolation", ("bilinear",), "logits are upsampled bilinearly")
             only("downsample_factor", (4, 8, 16), "feature layers at 1/4, 1/8 or 1/16")
+        elif arch == "DeepLabV3":
+            only("alpha", (1, 1.0), "MobileNetV2 width multiplier 1")   # OS is xception-only in the reference (model.py:384-385)
         elif arch == "Linknet":
             only("use_batchnorm", (True,), "the Linknet blocks are conv + BatchNorm + ReLU")
             only("n_upsample_blocks", (5,), "the decoder has one block per encoder stage")

@@ -437,7 +437,28 @@ def test_create_net_key_validation(tmp_path):
         return c
 
     with pytest.raises(ValueError, match="Unknown architecture"):
+        cfg(architecture="DeepLabV4").createNet()
+    # DeepLabV3: the reference's in-tree model over mobilenetv2 (impl/deeplab/model.py); segmentation backbones do not apply
+    with pytest.raises(ValueError, match="Unknown backbone"):
         cfg(architecture="DeepLabV3").createNet()
+    with pytest.raises(NotImplementedError, match="xception"):
+        cfg(architecture="DeepLabV3", backbone="xception").createNet()
+    with pytest.raises(NotImplementedError, match="alpha"):
+        cfg(architecture="DeepLabV3", backbone="mobilenetv2", alpha=0.5).createNet()
+    with pytest.raises(NotImplementedError, match="cannot be downloaded"):
+        cfg(architecture="DeepLabV3", backbone="mobilenetv2", encoder_weights="pascal_voc").createNet()
+    dl = cfg(architecture="DeepLabV3", backbone="mobilenetv2").createNet()
+    wd = dl.get_weights()
+    assert wd["expanded_conv_16_project/kernel"].shape == (1, 1, 960, 320) and wd["custom_logits_semantic/kernel"].shape == (1, 1, 256, 1)
+    assert wd["expanded_conv_3_depthwise/depthwise_kernel"].shape == (3, 3, 144, 1) and dl.activation == "sigmoid"
+    assert sum(v.size for k, v in wd.items() if "moving_" not in k) == 2108417      # == the Keras model's trainable parameter count
+    # `encoder_weights: pascal_voc`: the .npz twin of the reference's download, found next to the config, is loaded by layer name
+    pv = {k: np.full_like(v, 0.25) for k, v in wd.items() if not k.startswith("custom_logits")}
+    np.savez(str(tmp_path / "deeplabv3_mobilenetv2_tf_dim_ordering_tf_kernels.npz"), **pv)
+    dl2 = cfg(architecture="DeepLabV3", backbone="mobilenetv2", encoder_weights="pascal_voc").createNet()
+    wd2 = dl2.get_weights()
+    assert float(wd2["aspp0/kernel"].min()) == 0.25 and float(wd2["Conv_BN/moving_mean"].max()) == 0.25
+    assert not np.allclose(wd2["custom_logits_semantic/kernel"], 0.25)
     with pytest.raises(ValueError, match="divisible by 6"):
         cfg(architecture="PSPNet").createNet()                       # 64 is not a multiple of 6 * downsample_factor
     with pytest.raises(NotImplementedError, match="psp_pooling_type"):

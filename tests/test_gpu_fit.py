@@ -281,3 +281,56 @@ def test_fit_and_predict_on_crops(cuda, tmp_path):
     assert m.shape == (128, 128) and m.dtype == np.uint8
     b = next(iter(cfg.evaluateAll(ds, fold=0, stage=0)))
     assert b.results[0].shape == (128, 128, 1)
+
+
+def test_fit_reference_example_config_verbatim(cuda, tmp_path):
+    """The reference's own example experiment examples/people/ds_1.yaml, VERBATIM (DeepLabV3 / mobilenetv2, shape 320, batch 10,
+    Fliplr+Flipud+Rotate90, binary_crossentropy, Adam, EarlyStopping + ReduceLROnPlateau on val_iou_coef, `datasets:` +
+    `fit_with:` pointing at ../../picsart/train): parsed, built, trained and validated through cfg.fit() with no dataset
+    argument, then used for prediction.  Only deviations: the stage's 100 epochs are cut to 2 after parsing (test time) and
+    `encoder_weights: pascal_voc` is served by a local .npz twin of the file the reference downloads (no network)."""
+    import cv2
+    from segmentation_pipeline import segmentation
+    root = tmp_path
+    exp = root / "examples" / "people"
+    os.makedirs(exp)
+    cfgp = str(exp / "ds_1.yaml")
+    shutil.copy(os.path.join(HERE, "golden", "configs", "reference_examples", "ds_1.yaml"), cfgp)
+    os.makedirs(root / "picsart" / "train")
+    os.makedirs(root / "picsart" / "train_mask")
+    rng = np.random.default_rng(0)
+    for k in range(25):
+        h, w = int(rng.integers(90, 140)), int(rng.integers(90, 140))          # ragged sizes: "everything will be resized to fit"
+        yy, xx = np.mgrid[0:h, 0:w]
+        cy, cx, r = int(rng.integers(h // 4, 3 * h // 4)), int(rng.integers(w // 4, 3 * w // 4)), min(h, w) // 4
+        m = (((yy - cy) ** 2 + (xx - cx) ** 2) < r * r).astype(np.uint8)
+        img = (rng.integers(0, 120, (h, w, 3)) + m[:, :, None] * 120).astype(np.uint8)
+        cv2.imwrite(str(root / "picsart" / "train" / ("%02d.jpg" % k)), img)
+        cv2.imwrite(str(root / "picsart" / "train_mask" / ("%02d.png" % k)), m * 255)
+    # the .npz twin of deeplabv3_mobilenetv2_tf_dim_ordering_tf_kernels.h5 (by-name load; the class layer is not in it)
+    probe = segmentation.parse(cfgp)
+    probe.encoder_weights = None
+    w0 = probe.createNet(batch=2).get_weights()
+    marker = {k: v for k, v in w0.items() if not k.startswith("custom_logits")}
+    marker["Conv_BN/moving_mean"] = np.full_like(marker["Conv_BN/moving_mean"], 0.125)
+    np.savez(str(exp / "deeplabv3_mobilenetv2_tf_dim_ordering_tf_kernels.npz"), **marker)
+    del probe
+
+    cfg = segmentation.parse(cfgp)
+    assert cfg.architecture == "DeepLabV3" and cfg.backbone == "mobilenetv2" and cfg.batch == 10 and cfg.encoder_weights == "pascal_voc"
+    assert float(cfg.createNet(batch=2).get_weights()["Conv_BN/moving_mean"][0]) == 0.125       # pascal_voc twin was loaded by name
+    cfg.stages[0]["epochs"] = 2
+    res = cfg.fit(foldsToExecute=[0])
+    assert len(res) == 1
+    rows = list(csv.DictReader(open(str(exp / "metrics" / "metrics-0.0.csv"))))
+    assert len(rows) == 2
+    for r in rows:
+        for k in ("loss", "val_loss", "binary_accuracy", "val_binary_accuracy", "iou", "val_iou"):
+            assert np.isfinite(float(r[k])), (k, r)
+    assert float(rows[-1]["loss"]) < float(rows[0]["loss"])
+    assert os.path.exists(str(exp / "weights" / "best-0.0.weights.npz"))
+    out = str(root / "pred")
+    assert cfg.predict_to_directory(str(root / "picsart" / "train"), out, fold=0, stage=0, ttflips=True) == 25
+    p = cv2.imread(os.path.join(out, "00.png"), cv2.IMREAD_GRAYSCALE)
+    src = cv2.imread(str(root / "picsart" / "train" / "00.jpg"))
+    assert p.shape == src.shape[:2]
