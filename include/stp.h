@@ -439,15 +439,15 @@ int stp_sumsq(const float* g, int64_t count, float* partial, float* out, stp_str
 /* ----------------------------------------------------------------------------------------------
  * K14  depthwise convolution (keras DepthwiseConv2D, depth_multiplier 1) of the reference's in-tree DeepLabV3+ /
  *      MobileNetV2 (impl/deeplab/model.py:236-275 `_inverted_res_block`, :104-142 `SepConv_BN`): k x k filter per channel,
- *      stride, atrous rate.  x / y / dy / dx bf16 NHWC (c % 8 == 0), weights f32 [k][k][c] (= the keras (k,k,c,1) kernel),
- *      rounded to bf16 in compute like every other conv operand.  pad_* = padding BEFORE; the output size implies the rest
+ *      stride, atrous rate.  x / y / dy / dx bf16 NHWC (c % 8 == 0); weights bf16 [k][k][c] (= the keras (k,k,c,1) kernel;
+ *      stp_weight_prep(master, w, NULL, 1, k, k, c) makes the copy); dw f32 [k][k][c].  pad_* = padding BEFORE; the output size implies the rest
  *      (TF 'same' with stride 2 on an even size pads 0 before / 1 after).  wgrad: per-block partials + fixed-order reduction.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct stp_dwconv_desc {
   int32_t k, stride, dilation, pad_h, pad_w;
 } stp_dwconv_desc;
-int stp_dwconv_fwd(const stp_dwconv_desc* d, const stp_tensor* x, const float* w_kkc, const stp_tensor* y, stp_stream stream);
-int stp_dwconv_dgrad(const stp_dwconv_desc* d, const stp_tensor* dy, const float* w_kkc, const stp_tensor* residual,
+int stp_dwconv_fwd(const stp_dwconv_desc* d, const stp_tensor* x, const void* w_kkc, const stp_tensor* y, stp_stream stream);
+int stp_dwconv_dgrad(const stp_dwconv_desc* d, const stp_tensor* dy, const void* w_kkc, const stp_tensor* residual,
                      const stp_tensor* dx, stp_stream stream);
 int stp_dwconv_wgrad(const stp_dwconv_desc* d, const stp_tensor* x, const stp_tensor* dy, float* dw_kkc, void* workspace,
                      size_t workspace_bytes, stp_stream stream);

@@ -50,6 +50,9 @@ static RowGeom reduce_geom(int64_t rows, int c, bool atomic_acc = false) {
   if (m > cap) m = cap;
   if (get_option(OPT_BN_BLOCKS) > 0 && m < kNumSMs) m = kNumSMs;
   if (m < 32) m = 32;
+  // wide AND large tensors (MobileNetV2 expansions: 960 channels x 25600 pixels = 49 MB): the atomic budget above would leave
+  // 32 CTAs for the whole GPU; one CTA per SM measured 12.1 -> 10.4 ms on the DeepLabV3 step (profiles/r2_deeplab_bench.txt)
+  if (m < kNumSMs && rows * (int64_t)c * 2 >= ((int64_t)16 << 20)) m = kNumSMs;
   return geom(rows, c, 4, m);
 }
 

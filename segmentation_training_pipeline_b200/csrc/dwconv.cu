@@ -1,8 +1,8 @@
 // Depthwise 3x3 (k x k) convolution, NHWC bf16, stride 1 / 2, dilation (atrous rate) >= 1 -- keras DepthwiseConv2D of the in-tree
 // DeepLabV3+ / MobileNetV2 model the reference registers as architecture `DeepLabV3` (impl/deeplab/model.py:236-275,
 // registration segmentation.py:31-33; every example config of the reference uses it).  2 * k^2 FLOP per output element against
-// 4 bytes of traffic: HBM-bound byte work on the CUDA cores -- thread = (pixel, 8-channel vector), 16-byte accesses, weights
-// (k*k*C fp32, rounded to bf16 in compute like every other conv operand) through the read-only path.
+// 4 bytes of traffic: HBM-bound byte work on the CUDA cores -- thread = (pixel pair, 8-channel vector), 16-byte accesses, weights
+// bf16 [k][k][C] (the bf16 copy stp_weight_prep makes of the fp32 master with Cout = 1, like every other conv operand).
 //   fwd  : y[n,ho,wo,c]  = sum_{r,s} x[n, ho*stride - pad_h + r*dil, wo*stride - pad_w + s*dil, c] * w[r][s][c]
 //   dgrad: dx[n,h,w,c]   = sum_{r,s} dy[n, (h + pad_h - r*dil)/stride, (w + pad_w - s*dil)/stride, c] * w[r][s][c]  (divisible taps)
 //   wgrad: dw[r][s][c]   = sum_{n,ho,wo} dy[n,ho,wo,c] * x[...]    per-block partials + fixed-order double reduction
@@ -17,122 +17,185 @@ constexpr int kDwMaxTaps = 25;
 struct DwP {
   const __nv_bfloat16* x;
   int ldx, N, H, W, C;
-  const float* w;   // [k][k][C] fp32 master
   __nv_bfloat16* y;
   int ldy, Ho, Wo;
   int k, stride, dil, pad_h, pad_w;
 };
 
-__device__ __forceinline__ float bfr(float v) { return __bfloat162float(__float2bfloat16(v)); }
+__device__ __forceinline__ bf16x8 ld8_or_zero(const __nv_bfloat16* p, bool ok) {
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (ok) v = *reinterpret_cast<const uint4*>(p);   // predicated load, no branch
+  return *reinterpret_cast<bf16x8*>(&v);
+}
 
-__global__ void __launch_bounds__(256) dwconv_fwd_kernel(const DwP p) {
+// thread = (8-channel octet, kDwP adjacent output pixels along W).  Every tap is a predicated 16-byte load (no branches, so
+// all loads of a thread are in flight together); the bf16 weights of a tap are one 16-byte load shared by the kDwP pixels.
+// (First version: fp32 weights re-rounded per pixel behind branchy bounds checks, 630 instructions per output octet, issue- and
+// latency-bound at 0.9 TB/s -- profiles/r2_dwconv_probe.txt.)
+constexpr int kDwP = 2;
+
+template <int K>
+__global__ void __launch_bounds__(256) dwconv_fwd_kernel(const DwP p, const __nv_bfloat16* __restrict__ wq, int total, int strips) {
   const int cv = p.C / 8;
-  const int64_t total = (int64_t)p.N * p.Ho * p.Wo * cv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int v = (int)(i % cv);
-    const int64_t r = i / cv;
-    const int64_t n = r / ((int64_t)p.Ho * p.Wo);
-    const int rem = (int)(r - n * (int64_t)p.Ho * p.Wo);
-    const int ho = rem / p.Wo, wo = rem - ho * p.Wo;
-    float acc[8];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = i % cv;
+    int r = i / cv;
+    const int sw = r % strips;
+    r /= strips;
+    const int ho = r % p.Ho;
+    const int n = r / p.Ho;
+    const int wo0 = sw * kDwP;
+    const __nv_bfloat16* xb = p.x + (int64_t)n * p.H * p.W * p.ldx + v * 8;
+    float acc[kDwP][8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-    for (int a = 0; a < p.k; ++a) {
+    for (int q = 0; q < kDwP; ++q)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[q][c] = 0.f;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
       const int hi = ho * p.stride - p.pad_h + a * p.dil;
-      if (hi < 0 || hi >= p.H) continue;
-      for (int b = 0; b < p.k; ++b) {
-        const int wi = wo * p.stride - p.pad_w + b * p.dil;
-        if (wi < 0 || wi >= p.W) continue;
-        float f[8];
-        unpack8(ld8(p.x + ((n * p.H + hi) * (int64_t)p.W + wi) * p.ldx + v * 8), f);
-        const float* wp = p.w + (a * p.k + b) * p.C + v * 8;
+      const bool okh = (unsigned)hi < (unsigned)p.H;
+      const __nv_bfloat16* row = xb + (int64_t)(okh ? hi : 0) * p.W * p.ldx;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] += f[c] * bfr(__ldg(wp + c));
+      for (int b = 0; b < K; ++b) {
+        float w[8];
+        unpack8(ld8(wq + (a * K + b) * p.C + v * 8), w);
+#pragma unroll
+        for (int q = 0; q < kDwP; ++q) {
+          const int wi = (wo0 + q) * p.stride - p.pad_w + b * p.dil;
+          const bool ok = okh && (unsigned)wi < (unsigned)p.W;
+          float f[8];
+          unpack8(ld8_or_zero(row + (int64_t)(ok ? wi : 0) * p.ldx, ok), f);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[q][c] += f[c] * w[c];
+        }
       }
     }
-    st8(p.y + r * p.ldy + v * 8, pack8(acc));
+    __nv_bfloat16* yb = p.y + ((int64_t)(n * p.Ho + ho) * p.Wo) * p.ldy + v * 8;
+#pragma unroll
+    for (int q = 0; q < kDwP; ++q)
+      if (wo0 + q < p.Wo) st8(yb + (int64_t)(wo0 + q) * p.ldy, pack8(acc[q]));
   }
 }
 
-// x := dy (Ho x Wo), y := dx (H x W) in DwP terms of the FORWARD conv geometry
-__global__ void __launch_bounds__(256) dwconv_dgrad_kernel(const DwP p, const __nv_bfloat16* __restrict__ dy, int lddy,
+// p describes the FORWARD conv geometry (x: H x W input, y: Ho x Wo output); the pixel pairs run along W of dx
+template <int K>
+__global__ void __launch_bounds__(256) dwconv_dgrad_kernel(const DwP p, const __nv_bfloat16* __restrict__ wq,
+                                                           const __nv_bfloat16* __restrict__ dy, int lddy,
                                                            const __nv_bfloat16* __restrict__ res, int ldr, __nv_bfloat16* __restrict__ dx,
-                                                           int lddx) {
+                                                           int lddx, int total, int strips) {
   const int cv = p.C / 8;
-  const int64_t total = (int64_t)p.N * p.H * p.W * cv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int v = (int)(i % cv);
-    const int64_t r = i / cv;
-    const int64_t n = r / ((int64_t)p.H * p.W);
-    const int rem = (int)(r - n * (int64_t)p.H * p.W);
-    const int h = rem / p.W, w = rem - h * p.W;
-    float acc[8];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = i % cv;
+    int r = i / cv;
+    const int sw = r % strips;
+    r /= strips;
+    const int h = r % p.H;
+    const int n = r / p.H;
+    const int w0 = sw * kDwP;
+    const __nv_bfloat16* gb = dy + (int64_t)n * p.Ho * p.Wo * lddy + v * 8;
+    float acc[kDwP][8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-    for (int a = 0; a < p.k; ++a) {
+    for (int q = 0; q < kDwP; ++q)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[q][c] = 0.f;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
       const int th = h + p.pad_h - a * p.dil;
-      if (th < 0 || th % p.stride != 0) continue;
       const int ho = th / p.stride;
-      if (ho >= p.Ho) continue;
-      for (int b = 0; b < p.k; ++b) {
-        const int tw = w + p.pad_w - b * p.dil;
-        if (tw < 0 || tw % p.stride != 0) continue;
-        const int wo = tw / p.stride;
-        if (wo >= p.Wo) continue;
-        float g[8];
-        unpack8(ld8(dy + ((n * p.Ho + ho) * (int64_t)p.Wo + wo) * lddy + v * 8), g);
-        const float* wp = p.w + (a * p.k + b) * p.C + v * 8;
+      const bool okh = th >= 0 && ho * p.stride == th && ho < p.Ho;
+      const __nv_bfloat16* row = gb + (int64_t)(okh ? ho : 0) * p.Wo * lddy;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] += g[c] * bfr(__ldg(wp + c));
+      for (int b = 0; b < K; ++b) {
+        float wt[8];
+        unpack8(ld8(wq + (a * K + b) * p.C + v * 8), wt);
+#pragma unroll
+        for (int q = 0; q < kDwP; ++q) {
+          const int tw = w0 + q + p.pad_w - b * p.dil;
+          const int wo = tw / p.stride;
+          const bool ok = okh && tw >= 0 && wo * p.stride == tw && wo < p.Wo;
+          float g[8];
+          unpack8(ld8_or_zero(row + (int64_t)(ok ? wo : 0) * lddy, ok), g);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[q][c] += g[c] * wt[c];
+        }
       }
     }
-    if (res) {
-      float rf[8];
-      unpack8(ld8(res + r * ldr + v * 8), rf);
+    const int64_t rowpix = (int64_t)(n * p.H + h) * p.W;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) acc[c] += rf[c];
+    for (int q = 0; q < kDwP; ++q) {
+      if (w0 + q >= p.W) continue;
+      if (res) {
+        float rf[8];
+        unpack8(ld8(res + (rowpix + w0 + q) * ldr + v * 8), rf);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[q][c] += rf[c];
+      }
+      st8(dx + (rowpix + w0 + q) * lddx + v * 8, pack8(acc[q]));
     }
-    st8(dx + r * lddx + v * 8, pack8(acc));
   }
 }
 
-// partial[blk][tap][C]: thread = (8-channel vector, pixel lane) walking this block's output pixels
+// partial[chunk][tap][C]: block = (pixel chunk, group of up to 32 channel octets); thread = (octet, pixel lane).  Every thread
+// keeps all K*K tap sums of its 8 channels in registers, so dy is read once and x K*K times (L1/L2 hits: neighbouring taps).
+template <int K>
 __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const DwP p, const __nv_bfloat16* __restrict__ dy, int lddy,
-                                                           float* __restrict__ partial, int64_t pix_per_blk) {
-  extern __shared__ float sm[];   // [lanes][C] per tap pass
+                                                           float* __restrict__ partial, int ppb, int cvb, int lanes) {
+  extern __shared__ float sm[];   // [lanes][cvb*8]
+  constexpr int T = K * K;
   const int cv = p.C / 8;
-  const int lanes = blockDim.x / cv;             // launcher: cv divides blockDim
-  const int v = threadIdx.x % cv, pl = threadIdx.x / cv;
-  const int64_t M = (int64_t)p.N * p.Ho * p.Wo;
-  const int64_t m_begin = (int64_t)blockIdx.x * pix_per_blk;
-  int64_t m_end = m_begin + pix_per_blk;
-  if (m_end > M) m_end = M;
-  const int taps = p.k * p.k;
-  for (int t = 0; t < taps; ++t) {
-    const int a = t / p.k, b = t - a * p.k;
-    float acc[8];
+  const int vl = threadIdx.x % cvb, pl = threadIdx.x / cvb;
+  const int v = blockIdx.y * cvb + vl;
+  const bool active = v < cv && pl < lanes;
+  const int HoWo = p.Ho * p.Wo;
+  const int M = p.N * HoWo;
+  const int m_begin = blockIdx.x * ppb;
+  const int m_end = min(m_begin + ppb, M);
+  float acc[T][8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-    for (int64_t m = m_begin + pl; m < m_end; m += lanes) {
-      const int64_t n = m / ((int64_t)p.Ho * p.Wo);
-      const int rem = (int)(m - n * (int64_t)p.Ho * p.Wo);
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[t][c] = 0.f;
+  if (active)
+    for (int m = m_begin + pl; m < m_end; m += lanes) {
+      const int n = m / HoWo;
+      const int rem = m - n * HoWo;
       const int ho = rem / p.Wo, wo = rem - ho * p.Wo;
-      const int hi = ho * p.stride - p.pad_h + a * p.dil, wi = wo * p.stride - p.pad_w + b * p.dil;
-      if (hi < 0 || hi >= p.H || wi < 0 || wi >= p.W) continue;
-      float g[8], f[8];
-      unpack8(ld8(dy + m * lddy + v * 8), g);
-      unpack8(ld8(p.x + ((n * p.H + hi) * (int64_t)p.W + wi) * p.ldx + v * 8), f);
+      float g[8];
+      unpack8(ld8(dy + (int64_t)m * lddy + v * 8), g);
+      const __nv_bfloat16* xb = p.x + (int64_t)n * p.H * p.W * p.ldx + v * 8;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) acc[c] += g[c] * f[c];
+      for (int a = 0; a < K; ++a) {
+        const int hi = ho * p.stride - p.pad_h + a * p.dil;
+        const bool okh = (unsigned)hi < (unsigned)p.H;
+        const __nv_bfloat16* row = xb + (int64_t)(okh ? hi : 0) * p.W * p.ldx;
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+          const int wi = wo * p.stride - p.pad_w + b * p.dil;
+          const bool ok = okh && (unsigned)wi < (unsigned)p.W;
+          float f[8];
+          unpack8(ld8_or_zero(row + (int64_t)(ok ? wi : 0) * p.ldx, ok), f);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[a * K + b][c] += g[c] * f[c];
+        }
+      }
+    }
+  const int row = cvb * 8;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    __syncthreads();
+    if (pl < lanes) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) sm[pl * row + vl * 8 + c] = acc[t][c];
     }
     __syncthreads();
-#pragma unroll
-    for (int c = 0; c < 8; ++c) sm[pl * p.C + v * 8 + c] = acc[c];
-    __syncthreads();
-    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-      float s = 0.f;
-      for (int l = 0; l < lanes; ++l) s += sm[l * p.C + c];
-      partial[((int64_t)blockIdx.x * taps + t) * p.C + c] = s;
+    for (int c = threadIdx.x; c < row; c += blockDim.x) {
+      const int ch = blockIdx.y * row + c;
+      if (ch < p.C) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += sm[l * row + c];
+        partial[((int64_t)blockIdx.x * T + t) * p.C + ch] = s;
+      }
     }
   }
 }
@@ -149,9 +212,15 @@ static int dw_grid(int64_t total) {
   const int64_t cap = (int64_t)kNumSMs * 16;
   return (int)(b < 1 ? 1 : (b < cap ? b : cap));
 }
+// pixel chunks of the wgrad: 128 pixels per block, at most 512 chunks (workspace = chunks * K*K * C floats)
+static int dw_ppb(int64_t M) {
+  int64_t ppb = 128;
+  while ((M + ppb - 1) / ppb > 512) ppb *= 2;
+  return (int)ppb;
+}
 static int dw_blocks(int64_t M) {
-  int64_t nb = (M + 2047) / 2048;
-  if (nb > kNumSMs * 4) nb = kNumSMs * 4;
+  const int ppb = dw_ppb(M);
+  const int64_t nb = (M + ppb - 1) / ppb;
   return (int)(nb < 1 ? 1 : nb);
 }
 
@@ -162,39 +231,54 @@ using namespace stp;
 static int dw_check(const stp_dwconv_desc* d, const stp_tensor* x, const stp_tensor* y, const char* who) {
   STP_REQUIRE(d && x && y, "%s: null argument", who);
   STP_REQUIRE(vec_ok(x) && vec_ok(y) && x->c == y->c && x->n == y->n, "%s: tensors must be bf16 NHWC with equal channel counts (c%%8==0)", who);
-  STP_REQUIRE(d->k >= 1 && d->k * d->k <= kDwMaxTaps && d->stride >= 1 && d->dilation >= 1 && d->pad_h >= 0 && d->pad_w >= 0,
-              "%s: square filter up to 5x5, stride >= 1, dilation >= 1", who);
+  STP_REQUIRE((d->k == 1 || d->k == 3 || d->k == 5) && d->stride >= 1 && d->dilation >= 1 && d->pad_h >= 0 && d->pad_w >= 0,
+              "%s: filter 1x1, 3x3 or 5x5, stride >= 1, dilation >= 1", who);
   STP_REQUIRE(x->c <= 2048, "%s: at most 2048 channels", who);
   return STP_OK;
 }
-static DwP make_dw(const stp_dwconv_desc* d, const stp_tensor* x, const float* w, const stp_tensor* y) {
+static DwP make_dw(const stp_dwconv_desc* d, const stp_tensor* x, const stp_tensor* y) {
   DwP p;
   p.x = (const __nv_bfloat16*)x->ptr; p.ldx = x->ld; p.N = x->n; p.H = x->h; p.W = x->w; p.C = x->c;
-  p.w = w;
   p.y = (__nv_bfloat16*)y->ptr; p.ldy = y->ld; p.Ho = y->h; p.Wo = y->w;
   p.k = d->k; p.stride = d->stride; p.dil = d->dilation; p.pad_h = d->pad_h; p.pad_w = d->pad_w;
   return p;
 }
 
-extern "C" int stp_dwconv_fwd(const stp_dwconv_desc* d, const stp_tensor* x, const float* w_rsc, const stp_tensor* y, stp_stream stream) {
+extern "C" int stp_dwconv_fwd(const stp_dwconv_desc* d, const stp_tensor* x, const void* w_kkc, const stp_tensor* y, stp_stream stream) {
   int rc = dw_check(d, x, y, "dwconv_fwd");
   if (rc) return rc;
-  STP_REQUIRE(w_rsc, "dwconv_fwd: null weights");
-  DwP p = make_dw(d, x, w_rsc, y);
-  dwconv_fwd_kernel<<<dw_grid(pixels(y) * (x->c / 8)), 256, 0, (cudaStream_t)stream>>>(p);
+  STP_REQUIRE(w_kkc && aligned16(w_kkc), "dwconv_fwd: weights (bf16 [k][k][c]) must be 16-byte aligned");
+  DwP p = make_dw(d, x, y);
+  const __nv_bfloat16* wq = (const __nv_bfloat16*)w_kkc;
+  const int strips = (y->w + kDwP - 1) / kDwP;
+  const int64_t total = (int64_t)y->n * y->h * strips * (x->c / 8);
+  STP_REQUIRE(total < (int64_t)1 << 31 && pixels(x) < (int64_t)1 << 31, "dwconv_fwd: tensor too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->k == 3) dwconv_fwd_kernel<3><<<dw_grid(total), 256, 0, st>>>(p, wq, (int)total, strips);
+  else if (d->k == 5) dwconv_fwd_kernel<5><<<dw_grid(total), 256, 0, st>>>(p, wq, (int)total, strips);
+  else dwconv_fwd_kernel<1><<<dw_grid(total), 256, 0, st>>>(p, wq, (int)total, strips);
   return check_launch("dwconv_fwd");
 }
 
-extern "C" int stp_dwconv_dgrad(const stp_dwconv_desc* d, const stp_tensor* dy, const float* w_rsc, const stp_tensor* residual,
+extern "C" int stp_dwconv_dgrad(const stp_dwconv_desc* d, const stp_tensor* dy, const void* w_kkc, const stp_tensor* residual,
                                 const stp_tensor* dx, stp_stream stream) {
   int rc = dw_check(d, dx, dy, "dwconv_dgrad");
   if (rc) return rc;
-  STP_REQUIRE(w_rsc, "dwconv_dgrad: null weights");
+  STP_REQUIRE(w_kkc && aligned16(w_kkc), "dwconv_dgrad: weights (bf16 [k][k][c]) must be 16-byte aligned");
   if (residual) STP_REQUIRE(vec_ok(residual) && residual->c == dx->c && pixels(residual) == pixels(dx), "dwconv_dgrad: bad residual");
-  DwP p = make_dw(d, dx, w_rsc, dy);   // forward geometry: input = dx's tensor, output = dy's tensor
-  dwconv_dgrad_kernel<<<dw_grid(pixels(dx) * (dx->c / 8)), 256, 0, (cudaStream_t)stream>>>(
-      p, (const __nv_bfloat16*)dy->ptr, dy->ld, residual ? (const __nv_bfloat16*)residual->ptr : nullptr, residual ? residual->ld : 0,
-      (__nv_bfloat16*)dx->ptr, dx->ld);
+  DwP p = make_dw(d, dx, dy);   // forward geometry: input = dx's tensor, output = dy's tensor
+  const __nv_bfloat16* wq = (const __nv_bfloat16*)w_kkc;
+  const int strips = (dx->w + kDwP - 1) / kDwP;
+  const int64_t total = (int64_t)dx->n * dx->h * strips * (dx->c / 8);
+  STP_REQUIRE(total < (int64_t)1 << 31 && pixels(dx) < (int64_t)1 << 31, "dwconv_dgrad: tensor too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16* dyp = (const __nv_bfloat16*)dy->ptr;
+  const __nv_bfloat16* rp = residual ? (const __nv_bfloat16*)residual->ptr : nullptr;
+  const int ldr = residual ? residual->ld : 0;
+  __nv_bfloat16* dxp = (__nv_bfloat16*)dx->ptr;
+  if (d->k == 3) dwconv_dgrad_kernel<3><<<dw_grid(total), 256, 0, st>>>(p, wq, dyp, dy->ld, rp, ldr, dxp, dx->ld, (int)total, strips);
+  else if (d->k == 5) dwconv_dgrad_kernel<5><<<dw_grid(total), 256, 0, st>>>(p, wq, dyp, dy->ld, rp, ldr, dxp, dx->ld, (int)total, strips);
+  else dwconv_dgrad_kernel<1><<<dw_grid(total), 256, 0, st>>>(p, wq, dyp, dy->ld, rp, ldr, dxp, dx->ld, (int)total, strips);
   return check_launch("dwconv_dgrad");
 }
 
@@ -212,16 +296,25 @@ extern "C" int stp_dwconv_wgrad(const stp_dwconv_desc* d, const stp_tensor* x, c
     set_error("dwconv_wgrad: workspace too small");
     return STP_E_WORKSPACE;
   }
-  DwP p = make_dw(d, x, nullptr, dy);
+  DwP p = make_dw(d, x, dy);
   const int cv = x->c / 8;
-  const int lanes = 256 / cv > 0 ? 256 / cv : 1;   // cv <= 256 (C <= 2048)
-  const int threads = cv * lanes;
   const int64_t M = pixels(dy);
+  STP_REQUIRE(M < (int64_t)1 << 31, "dwconv_wgrad: fewer than 2^31 output pixels");
+  const int cvb = cv < 32 ? cv : 32;
+  const int lanes = 256 / cvb;
   const int nblk = dw_blocks(M);
-  const int64_t ppb = (M + nblk - 1) / nblk;
+  const int ppb = dw_ppb(M);
   cudaStream_t st = (cudaStream_t)stream;
-  dwconv_wgrad_kernel<<<nblk, threads, (size_t)lanes * x->c * sizeof(float), st>>>(p, (const __nv_bfloat16*)dy->ptr, dy->ld,
-                                                                                    (float*)workspace, ppb);
+  dim3 grid(nblk, (cv + cvb - 1) / cvb);
+  const size_t smem = (size_t)lanes * cvb * 8 * sizeof(float);
+  const __nv_bfloat16* dyp = (const __nv_bfloat16*)dy->ptr;
+  if (d->k == 3) dwconv_wgrad_kernel<3><<<grid, 256, smem, st>>>(p, dyp, dy->ld, (float*)workspace, ppb, cvb, lanes);
+  else if (d->k == 5) dwconv_wgrad_kernel<5><<<grid, 256, smem, st>>>(p, dyp, dy->ld, (float*)workspace, ppb, cvb, lanes);
+  else if (d->k == 1) dwconv_wgrad_kernel<1><<<grid, 256, smem, st>>>(p, dyp, dy->ld, (float*)workspace, ppb, cvb, lanes);
+  else {
+    set_error("dwconv_wgrad: filter sizes 1, 3 and 5 are built");
+    return STP_E_UNSUPPORTED;
+  }
   rc = check_launch("dwconv_wgrad");
   if (rc) return rc;
   const int n_out = d->k * d->k * x->c;

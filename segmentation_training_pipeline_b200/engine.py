@@ -252,6 +252,10 @@ class Net:
                 co, r, s_, ci = op.w.shape
                 items.append([op.w.offset, co, r, s_, ci, int(op.needs_dgrad), tile, 0])
                 tile += ((co + 31) // 32) * ((ci + 31) // 32)
+            elif isinstance(op, DWConv):   # [k][k][C] == a Cout = 1 conv weight: bf16 copy only
+                k, _, ci = op.w.shape
+                items.append([op.w.offset, 1, k, k, ci, 0, tile, 0])
+                tile += (ci + 31) // 32
         self._wprep_tiles = tile
         self._wprep_items = torch.tensor(items, dtype=torch.int64, device=dev) if items else None
         self.finalized = True
@@ -887,7 +891,8 @@ class UpHead(Conv):
 class DWConv(Op):
     """keras DepthwiseConv2D(k, strides, 'same', dilation_rate, use_bias=False) (MobileNetV2 blocks of the reference's
     DeepLabV3+, impl/deeplab/model.py:252-255).  Parameter `<name>/depthwise_kernel`, Keras shape (k, k, C, 1); internal
-    [k][k][C] fp32, read directly by the kernels (rounded to bf16 in compute)."""
+    [k][k][C] fp32 master with a bf16 copy in the flat forward-weight buffer (made by the batched weight prep as a Cout = 1
+    item)."""
 
     def __init__(self, net: Net, x: Buf, y: Buf, name: str, k=3, stride=1, dilation=1, init="glorot_uniform"):
         if net.precision != "bf16":
@@ -919,13 +924,13 @@ class DWConv(Op):
 
     def fwd(self):
         n = self.net
-        n.L.dwconv_fwd(self.dref, self.x.ref, n.pp(self.w), self.y.ref, _stream())
+        n.L.dwconv_fwd(self.dref, self.x.ref, n.pwf(self.w), self.y.ref, _stream())
 
     def bwd(self):
         n = self.net
         with n.wgrad_stream() as ws:
             n.L.dwconv_wgrad(self.dref, self.x.ref, self.dy.ref, n.pg(self.w), ws.data_ptr(), ws.numel(), _stream())
-        n.L.dwconv_dgrad(self.dref, self.dy.ref, n.pp(self.w), self.dx_res, self.dx.ref, _stream())
+        n.L.dwconv_dgrad(self.dref, self.dy.ref, n.pwf(self.w), self.dx_res, self.dx.ref, _stream())
 
 
 class GlobalAvgPool(Op):

@@ -44,8 +44,8 @@ def test_dwconv(stp, cuda, case):
     g = torch.Generator().manual_seed(sum(case))
     (ph, ho), (pw, wo) = _same_pad(h, k, stride, dil), _same_pad(w, k, stride, dil)
     x = rand_bf16((n, h, w, c), g)
-    wt = (torch.randn((k, k, c), generator=g) / k).to(cuda)                      # f32 master [k][k][C]
-    wb = wt.to(torch.bfloat16).float()
+    wt = (torch.randn((k, k, c), generator=g) / k).to(torch.bfloat16).to(cuda)   # bf16 [k][k][C]
+    wb = wt.float()
     dy = rand_bf16((n, ho, wo, c), g)
     res = rand_bf16((n, h, w, c), g)
     desc = lib.DwConvDesc(k, stride, dil, ph, pw)
@@ -85,12 +85,12 @@ def test_dwconv_concat_slices(stp, cuda):
     n, h, w, c = 1, 8, 8, 16
     big = rand_bf16((n, h, w, 48), g)
     out = torch.zeros((n, h, w, 32), dtype=torch.bfloat16, device=cuda)
-    wt = torch.randn((3, 3, c), generator=g).to(cuda) / 3
+    wt = (torch.randn((3, 3, c), generator=g) / 3).to(torch.bfloat16).to(cuda)
     desc = lib.DwConvDesc(3, 1, 1, 1, 1)
     xs, ys = T(big, 16, c), T(out, 8, c)
     stp.dwconv_fwd(C.byref(desc), ref(xs), wt.data_ptr(), ref(ys), stream())
     xr = big[..., 16:32].float().cpu().permute(0, 3, 1, 2)
-    wr = wt.to(torch.bfloat16).float().cpu().permute(2, 0, 1).unsqueeze(1)
+    wr = wt.float().cpu().permute(2, 0, 1).unsqueeze(1)
     yr = F.conv2d(xr, wr, None, padding=1, groups=c).permute(0, 2, 3, 1)
     assert rel_err(out[..., 8:24], yr) < TOL_BF16
     assert float(out[..., :8].abs().max()) == 0 and float(out[..., 24:].abs().max()) == 0
@@ -99,7 +99,7 @@ def test_dwconv_concat_slices(stp, cuda):
 def test_dwconv_rejects_bad_arguments(stp, cuda):
     x = torch.zeros((1, 8, 8, 12), dtype=torch.bfloat16, device=cuda)     # c % 8 != 0
     y = torch.zeros((1, 8, 8, 12), dtype=torch.bfloat16, device=cuda)
-    wt = torch.zeros(9 * 12, device=cuda)
+    wt = torch.zeros(9 * 16, dtype=torch.bfloat16, device=cuda)
     desc = lib.DwConvDesc(3, 1, 1, 1, 1)
     xs, ys = T(x), T(y)
     with pytest.raises(lib.StpError):

@@ -49,6 +49,12 @@ CONV_CASES = [
     (1, 6, 260, 64, 32, 3, 2, 1, 1),
     (2, 16, 16, 128, 256, 1, 2, 0, 1),
     (1, 16, 24, 32, 64, 4, 1, 2, 1),   # the space-to-depth stem shape: 4x4, Cin 32, Cout 64
+    # MobileNetV2 widths (DeepLabV3): Cin a multiple of 32 / 16 but not of 64 (generic kernel; routing them to the first-generation
+    # tcgen05 kernel with 32- / 16-channel K blocks measured SLOWER on the DeepLabV3 step: 11.6 vs 10.4 ms)
+    (2, 20, 20, 96, 576, 1, 1, 0, 1),
+    (1, 20, 20, 160, 960, 1, 1, 0, 1),
+    (1, 16, 16, 144, 32, 1, 1, 0, 1),
+    (1, 16, 16, 48, 64, 3, 1, 1, 1),
 ]
 TC_WGRAD_CASES = {0, 1, 2, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19}  # ... and whose wgrad must take the tcgen05 wgrad kernel
 TC_FWD_CASES = {0, 1, 2, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19}  # indices of CONV_CASES whose forward must take the tcgen05 kernel
