@@ -22,10 +22,12 @@ def main():
     ap.add_argument("--top", type=int, default=25)
     ap.add_argument("--opt", action="append", default=[], help="libstp option name=value (stp_set_option), repeatable")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--tc", type=int, default=1, help="0: disable the tcgen05 conv kernels (generic mma.sync everywhere)")
     a = ap.parse_args()
     S, B = a.size, a.batch
     net = SegNet("mobilenetv2", classes=1, input_shape=(S, S, 3), batch=B, device="cuda:0", seed=0, loss=(1.0, 0.0, 0.0),
                  architecture="DeepLabV3")
+    net.L.set_tc_enabled(a.tc)
     for o in a.opt:
         k, v = o.split("=")
         net.L.set_option(k.encode(), int(v))

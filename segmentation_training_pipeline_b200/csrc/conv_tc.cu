@@ -379,6 +379,11 @@ static bool tc_common_ok(const ConvP& p) {
 // stride 1 / 2 forward-type problems (one launch), and the zero-insertion (up == 2) problems that the dgrad of a
 // stride-2 convolution turns into (four launches, one per output parity class)
 bool tc_conv_supported(const ConvP& p) {
+  // 1x1 convolutions with a tiny reduction dimension and many output channels (MobileNetV2 "expand" layers and the dgrads of
+  // its "project" layers: 16->96, 32->192, 64->384): one 16/32/64-deep MMA per 128 x BN tile, so the per-tile TMA -> MMA ->
+  // TMEM -> store latency chain is all there is; the mma.sync kernel measured 0.090 vs 0.345 ms (16->96 @160^2 bs16), 0.021 vs
+  // 0.046 (32->192 @40^2), 0.037 vs 0.053 (64->384 @40^2) -- profiles/r2_deeplab_bench.txt
+  if (p.R * p.S == 1 && p.up == 1 && (p.Cin <= 32 || (p.Cin == 64 && p.Cout > 256)) && p.Cout >= 3 * p.Cin) return false;
   if (p.up == 1) {
     if (p.stride != 1 && p.stride != 2) return false;
     if (p.R * p.S > 9) return false;

@@ -136,6 +136,75 @@ __global__ void __launch_bounds__(256) dwconv_dgrad_kernel(const DwP p, const __
   }
 }
 
+// Stride-1 correlation with tap reuse: out[h][w] = sum_{a,b} in[h + oh + a*dil][w + ow + b*dil] * wsel(a, b).  A thread owns kDwS
+// output pixels of one row spaced by the atrous rate (w_q = wbase + q*dil), so tap b of pixel q reads column q + b of a window
+// of kDwS + K - 1 columns: K * (kDwS + K - 1) predicated loads for kDwS outputs (18 for 4 with K = 3, against 36), each unpacked
+// once.  FLIP selects w[K-1-a][K-1-b]: the dgrad of a stride-1 depthwise conv is the same correlation over dy with the flipped
+// filter and offsets (pad - (K-1)*dil).  The L1 data path, not DRAM, bounds these kernels (profiles/r2_dwconv_probe.txt).
+constexpr int kDwS = 4;
+
+template <int K, bool FLIP>
+__global__ void __launch_bounds__(256, 2) dwconv_s1_kernel(const __nv_bfloat16* __restrict__ in, int ldi, int Hi, int Wi,
+                                                        const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ res,
+                                                        int ldr, __nv_bfloat16* __restrict__ out, int ldo, int Ho, int Wo, int C,
+                                                        int dil, int oh, int ow, int total, int groups) {
+  const int cv = C / 8;
+  constexpr int NC = kDwS + K - 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = i % cv;
+    int r = i / cv;
+    const int gidx = r % groups;          // (residue class j, group g): wbase = j + g * kDwS * dil
+    r /= groups;
+    const int h = r % Ho;
+    const int n = r / Ho;
+    const int j = gidx % dil, g = gidx / dil;
+    const int wbase = j + g * kDwS * dil;
+    if (wbase >= Wo) continue;
+    const __nv_bfloat16* ib = in + (int64_t)n * Hi * Wi * ldi + v * 8;
+    float acc[kDwS][8];
+#pragma unroll
+    for (int q = 0; q < kDwS; ++q)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[q][c] = 0.f;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+      const int hi = h + oh + a * dil;
+      const bool okh = (unsigned)hi < (unsigned)Hi;
+      const __nv_bfloat16* row = ib + (int64_t)(okh ? hi : 0) * Wi * ldi;
+      float col[NC][8];
+#pragma unroll
+      for (int m = 0; m < NC; ++m) {
+        const int wi = wbase + ow + m * dil;
+        const bool ok = okh && (unsigned)wi < (unsigned)Wi;
+        unpack8(ld8_or_zero(row + (int64_t)(ok ? wi : 0) * ldi, ok), col[m]);
+      }
+#pragma unroll
+      for (int b = 0; b < K; ++b) {
+        const int t = FLIP ? (K - 1 - a) * K + (K - 1 - b) : a * K + b;
+        float w[8];
+        unpack8(ld8(wq + t * C + v * 8), w);
+#pragma unroll
+        for (int q = 0; q < kDwS; ++q)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[q][c] += col[q + b][c] * w[c];
+      }
+    }
+    const int64_t rowpix = (int64_t)(n * Ho + h) * Wo;
+#pragma unroll
+    for (int q = 0; q < kDwS; ++q) {
+      const int w = wbase + q * dil;
+      if (w >= Wo) continue;
+      if (res) {
+        float rf[8];
+        unpack8(ld8(res + (rowpix + w) * ldr + v * 8), rf);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[q][c] += rf[c];
+      }
+      st8(out + (rowpix + w) * ldo + v * 8, pack8(acc[q]));
+    }
+  }
+}
+
 // partial[chunk][tap][C]: block = (pixel chunk, group of up to 32 channel octets); thread = (octet, pixel lane).  Every thread
 // keeps all K*K tap sums of its 8 channels in registers, so dy is read once and x K*K times (L1/L2 hits: neighbouring taps).
 template <int K>
@@ -254,6 +323,14 @@ extern "C" int stp_dwconv_fwd(const stp_dwconv_desc* d, const stp_tensor* x, con
   const int64_t total = (int64_t)y->n * y->h * strips * (x->c / 8);
   STP_REQUIRE(total < (int64_t)1 << 31 && pixels(x) < (int64_t)1 << 31, "dwconv_fwd: tensor too large");
   cudaStream_t st = (cudaStream_t)stream;
+  if (d->k == 3 && d->stride == 1) {
+    const int groups = d->dilation * (((y->w + d->dilation - 1) / d->dilation + kDwS - 1) / kDwS);
+    const int64_t tot = (int64_t)y->n * y->h * groups * (x->c / 8);
+    STP_REQUIRE(tot < (int64_t)1 << 31, "dwconv_fwd: tensor too large");
+    dwconv_s1_kernel<3, false><<<dw_grid(tot), 256, 0, st>>>(p.x, p.ldx, p.H, p.W, wq, nullptr, 0, p.y, p.ldy, p.Ho, p.Wo, p.C, p.dil,
+                                                             -p.pad_h, -p.pad_w, (int)tot, groups);
+    return check_launch("dwconv_fwd");
+  }
   if (d->k == 3) dwconv_fwd_kernel<3><<<dw_grid(total), 256, 0, st>>>(p, wq, (int)total, strips);
   else if (d->k == 5) dwconv_fwd_kernel<5><<<dw_grid(total), 256, 0, st>>>(p, wq, (int)total, strips);
   else dwconv_fwd_kernel<1><<<dw_grid(total), 256, 0, st>>>(p, wq, (int)total, strips);
@@ -276,6 +353,15 @@ extern "C" int stp_dwconv_dgrad(const stp_dwconv_desc* d, const stp_tensor* dy, 
   const __nv_bfloat16* rp = residual ? (const __nv_bfloat16*)residual->ptr : nullptr;
   const int ldr = residual ? residual->ld : 0;
   __nv_bfloat16* dxp = (__nv_bfloat16*)dx->ptr;
+  if (d->k == 3 && d->stride == 1) {
+    // dx[h][w] = sum_{a,b} dy[h + pad_h - a*dil][w + pad_w - b*dil] w[a][b]: correlation over dy with the flipped filter
+    const int groups = d->dilation * (((dx->w + d->dilation - 1) / d->dilation + kDwS - 1) / kDwS);
+    const int64_t tot = (int64_t)dx->n * dx->h * groups * (dx->c / 8);
+    STP_REQUIRE(tot < (int64_t)1 << 31, "dwconv_dgrad: tensor too large");
+    dwconv_s1_kernel<3, true><<<dw_grid(tot), 256, 0, st>>>(dyp, dy->ld, p.Ho, p.Wo, wq, rp, ldr, dxp, dx->ld, p.H, p.W, p.C, p.dil,
+                                                            p.pad_h - 2 * p.dil, p.pad_w - 2 * p.dil, (int)tot, groups);
+    return check_launch("dwconv_dgrad");
+  }
   if (d->k == 3) dwconv_dgrad_kernel<3><<<dw_grid(total), 256, 0, st>>>(p, wq, dyp, dy->ld, rp, ldr, dxp, dx->ld, (int)total, strips);
   else if (d->k == 5) dwconv_dgrad_kernel<5><<<dw_grid(total), 256, 0, st>>>(p, wq, dyp, dy->ld, rp, ldr, dxp, dx->ld, (int)total, strips);
   else dwconv_dgrad_kernel<1><<<dw_grid(total), 256, 0, st>>>(p, wq, dyp, dy->ld, rp, ldr, dxp, dx->ld, (int)total, strips);

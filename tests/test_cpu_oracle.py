@@ -173,3 +173,51 @@ def test_resize_oracle_is_pinned_against_real_cv2():
     finally:
         if prev is not None:
             cv2.ipp.setUseIPP(prev)
+
+
+def test_deeplab_oracle_graph_follows_the_reference_source():
+    """DeepLabV3+/MobileNetV2 restated from the reference's IN-TREE impl/deeplab/model.py: Keras layer names, the Keras model's
+    trainable parameter count, output = align_corners resize of the low-resolution probabilities, every parameter reached by the
+    gradient."""
+    import torch
+    from oracle.models import SegModel
+    m = SegModel("DeepLabV3", "mobilenetv2", classes=1, input_shape=(64, 64, 3), seed=1)
+    assert sum(p.numel() for p in m.params.values()) == 2108417
+    for k, shape in {"Conv/kernel": (3, 3, 3, 32), "expanded_conv_depthwise/depthwise_kernel": (3, 3, 32, 1),
+                     "expanded_conv_1_expand/kernel": (1, 1, 16, 96), "expanded_conv_16_project/kernel": (1, 1, 960, 320),
+                     "image_pooling/kernel": (1, 1, 320, 256), "aspp0/kernel": (1, 1, 320, 256),
+                     "concat_projection/kernel": (1, 1, 512, 256), "custom_logits_semantic/kernel": (1, 1, 256, 1)}.items():
+        assert tuple(m.params[k].shape) == shape, k
+    assert "expanded_conv_expand/kernel" not in m.params            # block 0 has no expansion (model.py:241-251)
+    assert "expanded_conv_16_project_BN" in m.P.encoder_names and "aspp0" not in m.P.encoder_names
+    x = torch.rand(2, 64, 64, 3) * 255
+    y = m(x)
+    assert y.shape == (2, 64, 64, 1) and float(y.min()) > 0 and float(y.max()) < 1
+    z = m.taps["logits_small"]
+    assert z.shape == (2, 1, 8, 8)                                   # output stride 8
+    ref = torch.nn.functional.interpolate(torch.sigmoid(z), size=(64, 64), mode="bilinear", align_corners=True)
+    assert float((y.permute(0, 3, 1, 2) - ref).abs().max()) < 1e-6   # activation BEFORE the resize (model.py:499-500)
+    y.mean().backward()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.params.values())
+    # moving statistics use momentum 0.999 in the backbone, 0.99 in the ASPP head
+    assert abs(float(m.buffers["Conv_BN/moving_variance"].mean()) - 1.0) > 1e-6
+    m2 = SegModel("DeepLabV3", "mobilenetv2", classes=3, activation="softmax", input_shape=(32, 48, 3))
+    p = m2(torch.rand(1, 32, 48, 3) * 255)
+    assert p.shape == (1, 32, 48, 3) and float((p.sum(-1) - 1).abs().max()) < 1e-5
+
+
+def test_depthwise_same_padding_and_dropout_mask():
+    import torch
+    from oracle import nn as L
+    from oracle.philox import dropout_keep_mask
+    w = torch.ones(3, 3, 8, 1)
+    for size, stride, rate, out in ((16, 2, 1, 8), (15, 2, 1, 8), (12, 1, 4, 12)):
+        y = L.depthwise_conv2d(torch.ones(1, 8, size, size), w, stride, rate)
+        assert y.shape[-1] == out
+    # even size, stride 2: TF pads 0 before / 1 after -> the first output sees the full 3x3 window, the last one loses a row+column
+    y = L.depthwise_conv2d(torch.ones(1, 8, 16, 16), w, 2, 1)
+    assert float(y[0, 0, 0, 0]) == 9.0 and float(y[0, 0, -1, -1]) == 4.0
+    a = dropout_keep_mask(50, 16, 0.1, 7, 0xD0, 3)
+    assert np.array_equal(a, dropout_keep_mask(50, 16, 0.1, 7, 0xD0, 3))
+    assert not np.array_equal(a, dropout_keep_mask(50, 16, 0.1, 7, 0xD0, 4))
+    assert abs(dropout_keep_mask(4000, 16, 0.1, 1, 2, 3).mean() - 0.9) < 0.01
