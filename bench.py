@@ -122,7 +122,7 @@ C2_AUGMENT = dict(fliplr=0.5, flipud=0.5, affine=True, scale=(0.8, 1.5), transla
 # -------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the restated reference path (oracle/, PyTorch-CPU fp32) on the host cores
 # -------------------------------------------------------------------------------------------------------------
-def cpu_reference_step_time(size, sample_batch, steps, warmup, backbone="resnet34"):
+def cpu_reference_step_time(size, sample_batch, steps, warmup, backbone="resnet34", config="c2"):
     import numpy as np
     import torch
     from oracle import augment as OA, losses as OL, optim as OO
@@ -130,18 +130,21 @@ def cpu_reference_step_time(size, sample_batch, steps, warmup, backbone="resnet3
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     img, mask = synth_pool(sample_batch, size, size, 1234, 4321)
-    om = SegModel("Unet", backbone, classes=1, input_shape=(size, size, 3), storage="fp32")
+    people = config == "people"   # the reference's examples/people/people.yaml: DeepLabV3/mobilenetv2, Fliplr, binary_crossentropy
+    om = SegModel("DeepLabV3" if people else "Unet", backbone, classes=1, input_shape=(size, size, 3), storage="fp32",
+                  dropout=(0.1, 0, 0xD0, 0) if people else None)
     opt = OO.Adam(om.params, lr=1e-3)
-    spec = OA.AugSpec(fliplr=0.5, flipud=0.5, affine=True, scale=(0.8, 1.5), translate_x=(-0.2, 0.2),
-                      translate_y=(-0.2, 0.2), rotate=(-16.0, 16.0), shear=(-16.0, 16.0), multiply=(0.8, 1.2),
-                      add=(-10, 10))
+    spec = OA.AugSpec(fliplr=0.5) if people else \
+        OA.AugSpec(fliplr=0.5, flipud=0.5, affine=True, scale=(0.8, 1.5), translate_x=(-0.2, 0.2),
+                   translate_y=(-0.2, 0.2), rotate=(-16.0, 16.0), shear=(-16.0, 16.0), multiply=(0.8, 1.2),
+                   add=(-10, 10))
     times = []
     for s in range(warmup + steps):
         t0 = time.perf_counter()
         ai, am = OA.augment_batch(img, mask, spec, seed=0, step=s)
         y = om(torch.from_numpy(ai).float())
         t = torch.from_numpy(am).float()
-        lo = OL.binary_crossentropy(t, y) + OL.dice_loss(t, y)
+        lo = OL.binary_crossentropy(t, y) + (0.0 if people else OL.dice_loss(t, y))
         for p in om.params.values():
             p.grad = None
         lo.backward()
@@ -155,10 +158,13 @@ def cpu_reference_step_time(size, sample_batch, steps, warmup, backbone="resnet3
 def workload_config(args, world, tc=True):
     """`config` of the JSON line: identical for the libstp arm and the reference arm (same workload, same batch)."""
     B, S = args.batch, args.size
-    arch, classes, loss = ("FPN", 3, "lovasz_loss") if getattr(args, "config", "c2") == "c3" else ("U-Net", 1, "binary_crossentropy+dice_loss")
-    return {"workload": "%s/%s %dx%d %d-class bs%d/GPU, on-device augment (Fliplr/Flipud/Affine/Multiply/Add) + "
+    cfgname = getattr(args, "config", "c2")
+    arch, classes, loss = ("FPN", 3, "lovasz_loss") if cfgname == "c3" else ("DeepLabV3", 1, "binary_crossentropy") if cfgname == "people" \
+        else ("U-Net", 1, "binary_crossentropy+dice_loss")
+    augs = "Fliplr" if cfgname == "people" else "Fliplr/Flipud/Affine/Multiply/Add"
+    return {"workload": "%s/%s %dx%d %d-class bs%d/GPU, on-device augment (%s) + "
                         "fwd + %s + bwd + %sKeras-Adam" %
-                        (arch, args.backbone, S, S, classes, B, loss, "NCCL all-reduce + " if world > 1 else ""),
+                        (arch, args.backbone, S, S, classes, B, augs, loss, "NCCL all-reduce + " if world > 1 else ""),
             "global_batch": B * world, "pool_per_rank": args.pool, "parallelism": "dp%d" % world,
             "l2": "per-step working set (>3 GB of activations) exceeds the 126 MB L2; dominant-kernel timing flushes L2 "
                   "with a 256 MB memset between launches",
@@ -173,11 +179,12 @@ def run_reference(args, rank):
         return
     sb = args.ref_batch if args.ref_batch > 0 else args.batch
     steps = max(1, min(args.steps, 2))
-    dt, cores, _ = cpu_reference_step_time(args.size, sb, steps, 1, args.backbone)
+    dt, cores, _ = cpu_reference_step_time(args.size, sb, steps, 1, args.backbone, args.config)
     v = sb / dt
     world = int(os.environ.get("WORLD_SIZE", "1"))
     out = {
-        "impl": "reference", "metric": "images/sec U-Net/ResNet-34 512x512 training step", "value": v, "unit": "img/s",
+        "impl": "reference", "metric": "images/sec DeepLabV3/MobileNetV2 320x320 training step (reference examples/people/people.yaml)"
+        if args.config == "people" else "images/sec U-Net/ResNet-34 512x512 training step", "value": v, "unit": "img/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world),
@@ -301,6 +308,33 @@ def time_top_hbm_kernel(net, reps=20):
                       (bn.x.h, bn.x.w, bn.x.c), "ms": ms, "bytes": nbytes}
 
 
+def time_dwconv_kernel(net, reps=20):
+    """`--config people`: the dominant kernel family of the DeepLabV3/MobileNetV2 step is HBM-bound -- the widest depthwise 3x3
+    layer (expanded_conv_14_depthwise, 16x40x40x960, atrous rate 4) timed alone, L2 flushed between launches; algorithmic
+    bytes = read x + write y."""
+    import torch
+    from segmentation_training_pipeline_b200 import engine as E
+    from segmentation_training_pipeline_b200.engine import _stream
+    ops = [op for op in net.ops if isinstance(op, E.DWConv)]
+    if not ops:
+        return None
+    op = max(ops, key=lambda o: o.x.rows * o.x.c)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=net.device)
+    st = torch.cuda.current_stream()
+    for _ in range(3):
+        op.fwd()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        flush.zero_()
+        a.record(st)
+        op.fwd()
+        b.record(st)
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+    return {"kernel": "dwconv_s1_kernel<3>: depthwise 3x3 forward of %s (%dx%dx%dx%d bf16, atrous rate %d; reads x, writes y)" %
+                      (op.name, op.x.n, op.x.h, op.x.w, op.x.c, op.desc.dilation), "ms": ms, "bytes": 2.0 * op.x.rows * op.x.c * 2}
+
+
 def dominant_kernel_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (None if absent)."""
     p = os.path.join(ROOT, "profiles", "r1_dominant_kernel.json")
@@ -325,12 +359,16 @@ def run_gpu(args, rank, local_rank, world):
 
     B, S = args.batch, args.size
     c3 = args.config == "c3"     # BASELINE.json configs[2]: FPN/ResNet-50, 3-class, Lovasz (secondary; the headline is configs[1])
-    if c3:
+    people = args.config == "people"   # the reference's own example experiment (examples/people/people.yaml), secondary
+    if people:
+        net = SegNet("mobilenetv2", classes=1, input_shape=(S, S, 3), batch=B, device=dev, seed=0, loss=(1.0, 0.0, 0.0),
+                     architecture="DeepLabV3")
+    elif c3:
         net = SegNet(args.backbone, classes=3, input_shape=(S, S, 3), batch=B, device=dev, seed=0, loss=(0.0, 0.0, 0.0, 1.0),
                      architecture="FPN")
     else:
         net = SegNet(args.backbone, classes=1, input_shape=(S, S, 3), batch=B, device=dev, seed=0, loss=(1.0, 1.0, 0.0))
-    aug = AugmentConfig(seed=rank, **C2_AUGMENT)
+    aug = AugmentConfig(seed=rank, fliplr=0.5) if people else AugmentConfig(seed=rank, **C2_AUGMENT)
     tr = Trainer(net, optimizer="Adam", lr=1e-3, augment=aug, world_size=world)
     pool_n = args.pool
     img, mask = synth_pool(pool_n, S, S, 1234 + rank, 4321 + rank)
@@ -400,8 +438,8 @@ def run_gpu(args, rank, local_rank, world):
     assert last is not None and last["loss"] == last["loss"]
     ms_e2e = e0.elapsed_time(e1)
 
-    dom = time_dominant_kernel(net) if rank == 0 else None
-    hbm = time_top_hbm_kernel(net) if rank == 0 else None
+    dom = time_dominant_kernel(net) if rank == 0 and not people else None
+    hbm = (time_dwconv_kernel(net) if people else time_top_hbm_kernel(net)) if rank == 0 else None
     in_sync = None
     if world > 1:  # data-parallel invariant: every rank holds bit-identical parameters after the timed steps
         chk = torch.stack([net.flat_p.double().sum(), net.flat_p.double().abs().sum()])
@@ -419,9 +457,10 @@ def run_gpu(args, rank, local_rank, world):
         imgs = args.steps * B * world
         value = imgs / (ms / 1e3)
         e2e = imgs / (ms_e2e / 1e3)
-        gf = conv_train_gflop_per_img(args.backbone, S, "FPN" if c3 else "Unet")
+        gf = 0.0 if people else conv_train_gflop_per_img(args.backbone, S, "FPN" if c3 else "Unet")
         out = {
-            "metric": "images/sec FPN/ResNet-50 512x512 3-class training step" if c3 else "images/sec U-Net/ResNet-34 512x512 training step",
+            "metric": "images/sec DeepLabV3/MobileNetV2 320x320 training step (reference examples/people/people.yaml)" if people else
+                      "images/sec FPN/ResNet-50 512x512 3-class training step" if c3 else "images/sec U-Net/ResNet-34 512x512 training step",
             "value": value, "unit": "img/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -455,14 +494,16 @@ def run_gpu(args, rank, local_rank, world):
                                "isolated": {"ms_per_launch": dom["ms"], "achieved": dom["flop"] / (dom["ms"] / 1e3) / 1e12,
                                             "frac": dom["flop"] / (dom["ms"] / 1e3) / 1e12 / pk["bf16_tflops"],
                                             "timing": "one launch after an L2 flush (256 MB memset): launch gap + prologue inside"}}
+        if people:
+            out.pop("step_tflops"), out.pop("step_frac_of_sustained_peak")
         if hbm is not None:  # the largest single HBM-bound kernel of the step, against the measured copy bandwidth
             gbs = hbm["bytes"] / (hbm["ms"] / 1e3) / 1e9
-            out["roofline_hbm"] = {"bound": "hbm", "kernel": hbm["kernel"], "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            out["roofline" if people else "roofline_hbm"] = {"bound": "hbm", "kernel": hbm["kernel"], "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                    "frac": gbs / pk["hbm_gbs"], "bytes_per_launch": hbm["bytes"], "ms_per_launch": hbm["ms"],
                                    "note": "isolated launch after an L2 flush: ~10 us of launch / ramp / drain are inside a <30 us figure"}
         if world == 1 and not args.no_cpu:
             sb = args.ref_batch if args.ref_batch > 0 else B
-            dt, cores, _ = cpu_reference_step_time(S, sb, 2, 1, args.backbone)
+            dt, cores, _ = cpu_reference_step_time(S, sb, 2, 1, args.backbone, args.config)
             out["cpu_baseline"] = {"value": sb / dt, "unit": "img/s", "cores": cores, "kind": "port",
                                    "sample": "oracle (PyTorch-CPU fp32 restatement) train step on one batch of %d images (the "
                                              "workload's per-GPU batch), 1 warm-up + 2 timed" % sb}
@@ -483,13 +524,15 @@ def main():
     ap.add_argument("--backbone", default="resnet34")
     ap.add_argument("--ref-batch", type=int, default=0, help="images per CPU reference step; 0 = --batch (bs16, BASELINE.md section 4)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--config", default="c2", choices=["c2", "c3"],
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "people"],
                     help="c2 (default, the headline): BASELINE.json configs[1] U-Net/ResNet-34 Dice+BCE; c3: configs[2] FPN/ResNet-50 "
                          "3-class Lovasz (implies --backbone resnet50; libstp arm only)")
     args = ap.parse_args()
     if args.config == "c3":
         args.backbone = "resnet50"
         args.no_cpu = True
+    if args.config == "people":   # examples/people/people.yaml: DeepLabV3 / mobilenetv2, shape 320, batch 16 (secondary workload)
+        args.backbone, args.size = "mobilenetv2", 320
     args.warmup = max(args.warmup, 3) if args.impl == "stp" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -220,7 +220,8 @@ static int conv_dgrad_common(const stp_conv_desc* d, const stp_tensor* dy, const
   bn.fin.bcoef = h_bnb->bcoef;
   p.bn = &bn;
   p.bnb_x = (const __nv_bfloat16*)h_bnb->x->ptr; p.bnb_ldx = h_bnb->x->ld; p.bnb_coef = h_bnb->coef; p.bnb_relu = h_bnb->relu;
-  if (stp_tc_enabled() && get_option(OPT_TC_CONV_VERSION) != 1 && get_option(OPT_BNB_FUSE) != 1 && tc2_conv_supported(p))
+  // (the fused epilogue masks ReLU only: a ReLU6 layer, relu == 2, takes the two-pass path below)
+  if (stp_tc_enabled() && get_option(OPT_TC_CONV_VERSION) != 1 && get_option(OPT_BNB_FUSE) != 1 && h_bnb->relu != 2 && tc2_conv_supported(p))
     return launch_tc2_conv(p, (cudaStream_t)stream);
   p.bn = nullptr;
   rc = dispatch_conv(p, (cudaStream_t)stream);

@@ -416,7 +416,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                   for (int jj = 0; jj < 8; ++jj) {
                     float val = __bfloat162float(__float2bfloat16_rn(v[i + jj]));  // the value that is stored
-                    const bool keep = pv && (!a.bnb_relu || relu_pass(xf[jj] * sCoef[c0 + i + jj] + sCoef[128 + c0 + i + jj], a.bnb_relu));
+                    const bool keep = pv && (!a.bnb_relu || xf[jj] * sCoef[c0 + i + jj] + sCoef[128 + c0 + i + jj] > 0.f);
                     val = keep ? val : 0.f;
                     v[i + jj] = val;
                     gx[i + jj] = val * xf[jj];

@@ -217,7 +217,7 @@ class Net:
                     gwriters.setdefault(g.key(), []).append(op)
                     roots[id(g.root)] = roots.get(id(g.root), 0) + 1
             for op in self.ops:
-                if isinstance(op, BNRelu) and op.up == 1:
+                if isinstance(op, BNRelu) and op.up == 1 and int(op.relu) != 2:   # (the fused epilogue masks ReLU, not ReLU6)
                     gk = op.y.grad().key()
                     w = gwriters.get(gk, [])
                     # no other op may write an overlapping slice of the same gradient buffer
