@@ -318,7 +318,7 @@ def time_dwconv_kernel(net, reps=20):
     ops = [op for op in net.ops if isinstance(op, E.DWConv)]
     if not ops:
         return None
-    op = max(ops, key=lambda o: o.x.rows * o.x.c)
+    op = max([o for o in ops if o.desc.stride == 1] or ops, key=lambda o: o.x.rows * o.x.c)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=net.device)
     st = torch.cuda.current_stream()
     for _ in range(3):
@@ -332,7 +332,7 @@ def time_dwconv_kernel(net, reps=20):
     torch.cuda.synchronize()
     ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
     return {"kernel": "dwconv_s1_kernel<3>: depthwise 3x3 forward of %s (%dx%dx%dx%d bf16, atrous rate %d; reads x, writes y)" %
-                      (op.name, op.x.n, op.x.h, op.x.w, op.x.c, op.desc.dilation), "ms": ms, "bytes": 2.0 * op.x.rows * op.x.c * 2}
+                      (op.name, op.x.n, op.x.h, op.x.w, op.x.c, op.desc.dilation), "ms": ms, "bytes": 2.0 * (op.x.rows + op.y.rows) * op.x.c}
 
 
 def dominant_kernel_traffic():
@@ -357,6 +357,9 @@ def run_gpu(args, rank, local_rank, world):
     from segmentation_training_pipeline_b200.models import SegNet
     from segmentation_training_pipeline_b200.trainer import AugmentConfig, Trainer
 
+    for o in args.opt:
+        k, v = o.split("=")
+        lib.Lib().set_option(k.encode(), int(v))
     B, S = args.batch, args.size
     c3 = args.config == "c3"     # BASELINE.json configs[2]: FPN/ResNet-50, 3-class, Lovasz (secondary; the headline is configs[1])
     people = args.config == "people"   # the reference's own example experiment (examples/people/people.yaml), secondary
@@ -524,6 +527,7 @@ def main():
     ap.add_argument("--backbone", default="resnet34")
     ap.add_argument("--ref-batch", type=int, default=0, help="images per CPU reference step; 0 = --batch (bs16, BASELINE.md section 4)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="libstp option name=value (stp_set_option; A/B experiments), repeatable")
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "people"],
                     help="c2 (default, the headline): BASELINE.json configs[1] U-Net/ResNet-34 Dice+BCE; c3: configs[2] FPN/ResNet-50 "
                          "3-class Lovasz (implies --backbone resnet50; libstp arm only)")

@@ -11,6 +11,10 @@ timeout 200 python bench.py --config c3 --steps 10 --warmup 3 > gpurun_out/${TAG
 tail -1 gpurun_out/${TAG}_bench_c3.json.log | cut -c1-200
 PYTHONPATH=. timeout 200 python scripts/deeplab_bench.py --top 40 > gpurun_out/${TAG}_deeplab_bench.txt 2>&1
 head -1 gpurun_out/${TAG}_deeplab_bench.txt
+timeout 300 python bench.py --config people --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_people.json.log 2>&1
+tail -1 gpurun_out/${TAG}_bench_people.json.log | cut -c1-300
+timeout 300 python bench.py --config people --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_people_reference.json.log 2>&1
+tail -1 gpurun_out/${TAG}_bench_people_reference.json.log | cut -c1-200
 LPS=$(timeout 300 python scripts/profile_step.py --steps 1 2>/dev/null | awk '/launches_per_step/{print $2}')
 echo "launches_per_step=$LPS" > gpurun_out/${TAG}_prof.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s $((2*LPS)) -c $LPS --csv --log-file gpurun_out/${TAG}_launches.csv python scripts/profile_step.py --steps 3 >> gpurun_out/${TAG}_prof.log 2>&1

@@ -51,6 +51,7 @@ extern "C" int stp_set_option(const char* name, int32_t value) {
   else if (!strcmp(name, "tc3_force_bn")) key = OPT_TC3_FORCE_BN;       /* 0 heuristic | 128, 256 */
   else if (!strcmp(name, "tc3_force_mt")) key = OPT_TC3_FORCE_MT;       /* 0 heuristic | 1, 2 */
   else if (!strcmp(name, "tc3_halo")) key = OPT_TC3_HALO;               /* 0 off | 1 on: ONE haloed A box per channel block (measured slower, see conv_tc3.cu) */
+  else if (!strcmp(name, "head_strip")) key = OPT_HEAD_STRIP;           /* 0 on | 1 off: column-strip head backward kernels (sliding dlogit window) */
   else if (!strcmp(name, "tc3_bn64")) key = OPT_TC3_BN64;               /* 0 off | 1 on: N = 64 CTA-pair tiles for Cout = 64 / 192 layers (measured slower) */
   else if (!strcmp(name, "bnb_fuse")) key = OPT_BNB_FUSE;               /* 0 auto | 1: never fuse the BatchNorm-backward reduction into the dgrad epilogue */
   else if (!strcmp(name, "bn_blocks")) key = OPT_BN_BLOCKS;             /* 0 default | n: atomic-mode BN reductions use up to n*1024/C blocks */

@@ -144,6 +144,41 @@ __global__ void head_weight_pad_kernel(const float* __restrict__ w, int classes,
   out[i] = __float2bfloat16(i < classes * k ? w[i] : 0.f);
 }
 
+// Block reduction shared by the head wgrad kernels: xor shuffles over the lanes of a warp that hold the same 8-channel vector
+// (threadIdx.x % cv), then across the 8 warps through shared memory; one partial row [9][Cin] (+ the bias sum) per block.
+__device__ __forceinline__ void head_wgrad_block_reduce(float (&acc)[9][8], float bsum, int cv, int Cin, float* __restrict__ partial) {
+  // lanes l, l^cv, l^2cv ... of a warp hold the same vector
+  for (int off = 16; off >= cv; off >>= 1) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[t][k] += __shfl_xor_sync(0xffffffffu, acc[t][k], off);
+    bsum += __shfl_xor_sync(0xffffffffu, bsum, off);
+  }
+  __shared__ float sm[8][8 * 72 + 1];  // [warp][vector * 72 + tap * 8 + k], +1 for the bias sum
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < cv) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sm[warp][lane * 72 + t * 8 + k] = acc[t][k];
+    if (lane == 0) sm[warp][8 * 72] = bsum;
+  }
+  __syncthreads();
+  float* out = partial + (int64_t)blockIdx.x * (9 * Cin + 1);
+  for (int i = threadIdx.x; i < 9 * Cin + 1; i += blockDim.x) {
+    float a = 0.f;
+    if (i == 9 * Cin) {
+      for (int w = 0; w < 8; ++w) a += sm[w][8 * 72];
+    } else {
+      const int t = i / Cin, ci = i - t * Cin;
+      const int vv = ci >> 3, k = ci & 7;
+      for (int w = 0; w < 8; ++w) a += sm[w][vv * 72 + t * 8 + k];
+    }
+    out[i] = a;
+  }
+}
+
 // dw[c][r][s][ci] = sum_m dl[m][c] * x[m + off(r,s)][ci]  ==  sum_p x[p][ci] * dl[p - off][c]
 // Thread = one 8-channel vector (fixed) walking pixels, 9 taps x 8 accumulators in registers.  Block reduction: xor
 // shuffles over the lanes that share the vector, then across the 8 warps through shared memory; one partial row per
@@ -204,35 +239,133 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const __nv_bfloat16* __
         for (int k = 0; k < 8; ++k) acc[t][k] += f[k] * g[u][t];
     }
   }
-  // lanes l, l^cv, l^2cv ... of a warp hold the same vector
-  for (int off = 16; off >= cv; off >>= 1) {
+  head_wgrad_block_reduce(acc, bsum, cv, Cin, partial);
+}
+
+// Column-strip variants (H % strip == 0): a thread owns one 8-channel vector of ONE image column and walks `strip` rows down,
+// with a 3x3 sliding window over the dlogits -- 3 new dlogit loads per pixel instead of 9, no per-pixel index divisions, and
+// the lanes of a warp cover consecutive (pixel, vector) pairs of a row, so every load / store instruction is one contiguous
+// 512-byte segment.  History (profiles/r2_ncu_full_tail_head*.metrics.txt): the per-pixel kernels ran 365 instructions per
+// (pixel, vector) at 12 % occupancy (167 / 107 us for 134 MB of activations); ROW strips cut the instructions 2.2x but every
+// warp load then touched 16 different 128-byte lines and the L1 pipe saturated (82 %, 143 / 114 us).
+__global__ void __launch_bounds__(256, 2) head_wgrad_strip_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int H, int W, int Cin,
+                                                                  const float* __restrict__ dl, int classes, int cls,
+                                                                  float* __restrict__ partial, int items, int strip) {
+  const int cv = Cin / 8;
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = threadIdx.x % cv;           // == item % cv (256 % cv == 0)
+  float acc[9][8];
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[t][k] += __shfl_xor_sync(0xffffffffu, acc[t][k], off);
-    bsum += __shfl_xor_sync(0xffffffffu, bsum, off);
-  }
-  __shared__ float sm[8][8 * 72 + 1];  // [warp][vector * 72 + tap * 8 + k], +1 for the bias sum
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane < cv) {
+    for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
+  float bsum = 0.f;
+  if (item < items) {
+    int q = item / cv;
+    const int w = q % W;
+    q /= W;                                  // n * (H / strip) + hb
+    const int hbs = H / strip;
+    const int n = q / hbs;
+    const int h0 = (q - n * hbs) * strip;
+    // d[r][s] = dl[h - (r-1)][w - (s-1)]  (tap (r, s) of the forward conv pairs x[p] with dl at p - off(r, s))
+    const float* col[3];
+    bool okc[3];
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) sm[warp][lane * 72 + t * 8 + k] = acc[t][k];
-    if (lane == 0) sm[warp][8 * 72] = bsum;
-  }
-  __syncthreads();
-  float* out = partial + (int64_t)blockIdx.x * (9 * Cin + 1);
-  for (int i = threadIdx.x; i < 9 * Cin + 1; i += blockDim.x) {
-    float a = 0.f;
-    if (i == 9 * Cin) {
-      for (int w = 0; w < 8; ++w) a += sm[w][8 * 72];
-    } else {
-      const int t = i / Cin, ci = i - t * Cin;
-      const int vv = ci >> 3, k = ci & 7;
-      for (int w = 0; w < 8; ++w) a += sm[w][vv * 72 + t * 8 + k];
+    for (int sx = 0; sx < 3; ++sx) {
+      const int wo = w - (sx - 1);
+      okc[sx] = wo >= 0 && wo < W;
+      col[sx] = dl + ((int64_t)n * H * W + (okc[sx] ? wo : 0)) * classes + cls;
     }
-    out[i] = a;
+    float d[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ho = h0 - (r - 1);
+#pragma unroll
+      for (int sx = 0; sx < 3; ++sx)
+        d[r][sx] = (okc[sx] && ho >= 0 && ho < H) ? __ldg(col[sx] + (int64_t)ho * W * classes) : 0.f;
+    }
+    const __nv_bfloat16* xp = x + (((int64_t)n * H + h0) * W + w) * ldx + v * 8;
+    const int64_t xstep = (int64_t)W * ldx;
+#pragma unroll 2
+    for (int i = 0; i < strip; ++i) {
+      float f[8];
+      unpack8(ld8(xp), f);
+      xp += xstep;
+      if (v == 0) bsum += d[1][1];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int sx = 0; sx < 3; ++sx)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[r * 3 + sx][k] += f[k] * d[r][sx];
+      const int hn = h0 + i + 2;             // the row that enters the window as r = 0 of the next pixel
+#pragma unroll
+      for (int sx = 0; sx < 3; ++sx) {
+        d[2][sx] = d[1][sx];
+        d[1][sx] = d[0][sx];
+        d[0][sx] = (okc[sx] && hn < H) ? __ldg(col[sx] + (int64_t)hn * W * classes) : 0.f;
+      }
+    }
+  }
+  head_wgrad_block_reduce(acc, bsum, cv, Cin, partial);
+}
+
+// classes == 1: dx[p][ci] = sum_{r,s} dl[h-(r-1)][w-(s-1)] * w[r][s][ci]
+__global__ void __launch_bounds__(256, 2) head_dgrad1_strip_kernel(const float* __restrict__ dl, int H, int W, int Cin,
+                                                                   const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, int lddx,
+                                                                   int items, int strip) {
+  const int cv = Cin / 8;
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= items) return;
+  const int v = item % cv;
+  int q = item / cv;
+  const int wq = q % W;
+  q /= W;
+  const int hbs = H / strip;
+  const int n = q / hbs;
+  const int h0 = (q - n * hbs) * strip;
+  float wr[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wr[t][k] = __bfloat162float(__float2bfloat16(w[t * Cin + v * 8 + k]));
+  const float* col[3];
+  bool okc[3];
+#pragma unroll
+  for (int sx = 0; sx < 3; ++sx) {
+    const int wo = wq - (sx - 1);
+    okc[sx] = wo >= 0 && wo < W;
+    col[sx] = dl + (int64_t)n * H * W + (okc[sx] ? wo : 0);
+  }
+  float d[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int ho = h0 - (r - 1);
+#pragma unroll
+    for (int sx = 0; sx < 3; ++sx) d[r][sx] = (okc[sx] && ho >= 0 && ho < H) ? __ldg(col[sx] + (int64_t)ho * W) : 0.f;
+  }
+  __nv_bfloat16* op = dx + (((int64_t)n * H + h0) * W + wq) * lddx + v * 8;
+  const int64_t ostep = (int64_t)W * lddx;
+#pragma unroll 2
+  for (int i = 0; i < strip; ++i) {
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int sx = 0; sx < 3; ++sx)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += d[r][sx] * wr[r * 3 + sx][k];
+    st8(op, pack8(acc));
+    op += ostep;
+    const int hn = h0 + i + 2;
+#pragma unroll
+    for (int sx = 0; sx < 3; ++sx) {
+      d[2][sx] = d[1][sx];
+      d[1][sx] = d[0][sx];
+      d[0][sx] = (okc[sx] && hn < H) ? __ldg(col[sx] + (int64_t)hn * W) : 0.f;
+    }
   }
 }
 
@@ -308,6 +441,18 @@ extern "C" int stp_head_fwd(const stp_tensor* x, const float* w_krsc_f32, const 
   return check_launch("head_fwd");
 }
 
+// strip height of the column-strip backward kernels: the smallest of 16, 32, 64, ... that divides H and keeps the block count
+// (one partial row per block) within `max_blocks`; 0 = not applicable (the per-pixel kernels run)
+static int head_strip(const stp_tensor* x, int64_t max_blocks) {
+  const int cv = x->c / 8;
+  for (int L = 16; L <= x->h; L *= 2) {
+    if (x->h % L != 0) return 0;
+    const int64_t items = pixels(x) / L * cv;
+    if ((items + 255) / 256 <= max_blocks) return L;
+  }
+  return 0;
+}
+
 extern "C" size_t stp_head_bwd_workspace(const stp_tensor* x, int32_t classes) {
   (void)classes;
   return (size_t)kHeadWgradBlocks * (9 * (size_t)x->c + 1) * sizeof(float);
@@ -353,7 +498,12 @@ extern "C" int stp_head_bwd(const stp_tensor* x, const float* w_krsc_f32, const 
   if (dx) {
     STP_REQUIRE(vec_ok(dx) && dx->c == x->c && pixels(dx) == M, "head_bwd: bad dx");
     const int cv = x->c / 8;
-    if (classes == 1 && M < 0x7fffffff) {
+    const int dstrip = head_strip(x, 0x7fffffff);
+    if (classes == 1 && M < 0x7fffffff && dstrip && get_option(OPT_HEAD_STRIP) != 1) {
+      const int items = (int)(M / dstrip) * cv;
+      head_dgrad1_strip_kernel<<<(items + 255) / 256, 256, 0, st>>>(dlogits, x->h, x->w, x->c, w_krsc_f32, (__nv_bfloat16*)dx->ptr,
+                                                                    dx->ld, items, dstrip);
+    } else if (classes == 1 && M < 0x7fffffff) {
       const int ppi = 256 / cv;
       int64_t nb = (M + (int64_t)ppi * 8 - 1) / ((int64_t)ppi * 8);
       if (nb > kNumSMs * 8) nb = kNumSMs * 8;
@@ -371,6 +521,21 @@ extern "C" int stp_head_bwd(const stp_tensor* x, const float* w_krsc_f32, const 
     if (rc) return rc;
   }
   STP_REQUIRE(M < 0x7fffffff, "head_bwd: too many pixels");
+  const int wstrip = head_strip(x, kHeadWgradBlocks);
+  if (wstrip && get_option(OPT_HEAD_STRIP) != 1) {
+    const int items = (int)(M / wstrip) * (x->c / 8);
+    const int nbs = (items + 255) / 256;
+    for (int cls = 0; cls < classes; ++cls) {
+      head_wgrad_strip_kernel<<<nbs, 256, 0, st>>>((const __nv_bfloat16*)x->ptr, x->ld, x->h, x->w, x->c, dlogits, classes, cls,
+                                                   (float*)workspace, items, wstrip);
+      int rc = check_launch("head_wgrad_strip");
+      if (rc) return rc;
+      head_wgrad_final_kernel<<<9 * x->c + 1, 128, 0, st>>>((const float*)workspace, nbs, x->c, cls, dw, dbias);
+      rc = check_launch("head_wgrad_final");
+      if (rc) return rc;
+    }
+    return STP_OK;
+  }
   const int lanes = 256 / (x->c / 8);
   int64_t nb = (M + (int64_t)lanes * 8 - 1) / ((int64_t)lanes * 8);
   if (nb > kHeadWgradBlocks) nb = kHeadWgradBlocks;

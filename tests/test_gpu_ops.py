@@ -285,10 +285,11 @@ def test_maxpool(stp, cuda, shape, k, s, p):
     assert rel_err(dx2.float().cpu() * mask, (ref_dx + r.float().cpu()) * mask) < TOL_BF16
 
 
+@pytest.mark.parametrize("h,w", [(16, 24), (48, 20), (24, 16)])   # one column strip / three strips per column / per-pixel kernels (24 % 16 != 0)
 @pytest.mark.parametrize("classes,cin", [(1, 16), (3, 32)])
-def test_head(stp, cuda, classes, cin):
+def test_head(stp, cuda, classes, cin, h, w):
     g = torch.Generator().manual_seed(7)
-    n, h, w = 2, 24, 16
+    n = 2
     x = rand_bf16((n, h, w, cin), g)
     wt = bf16_round(torch.randn((classes, 3, 3, cin), generator=g) * 0.1).to(cuda)
     bias = torch.randn(classes, generator=g).to(cuda)
