@@ -2,6 +2,7 @@
 // Semantics: ZeroPadding2D(pad) + MaxPooling2D(k, stride, 'valid') on post-ReLU data == max_pool(k, stride, pad)
 // with the FIRST maximum in (kh, kw) scan order taking the gradient.
 #include "common.cuh"
+#include "conv.h"
 #include "f32_path.h"
 
 namespace stp {
@@ -179,6 +180,77 @@ __global__ void __launch_bounds__(256) maxpool_bwd_k3s2_kernel(const __nv_bfloat
     }
   }
 }
+// 3x3 / stride 2 / pad 1, even H and W: thread = (8-channel vector, 2x2 block of input pixels).  The block (2i..2i+1, 2j..2j+1)
+// is covered by the windows (i, j) [all four pixels], (i+1, j) [odd row], (i, j+1) [odd column] and (i+1, j+1) [odd, odd]:
+// four (argmax word, dy vector) loads serve four pixels (the per-pixel kernel above issues nine for them), no index divisions
+// per pixel.  ncu on the per-pixel kernel: 108 registers, 24 % occupancy, 135 us for 134 MB in + 134 MB out + 50 MB of dy /
+// argmax (profiles/r2_ncu_full_tail_mpb.metrics.txt).
+__global__ void __launch_bounds__(256) maxpool_bwd_k3s2_block_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int Ho, int Wo,
+                                                                     const uint8_t* __restrict__ argmax,
+                                                                     const __nv_bfloat16* __restrict__ res, int ldr,
+                                                                     __nv_bfloat16* __restrict__ dx, int lddx, int H, int W, int C, int cv,
+                                                                     int total) {
+  const int Wb = W / 2, Hb = H / 2;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int v = t % cv;
+    int q = t / cv;
+    const int j = q % Wb;
+    q /= Wb;
+    const int i = q % Hb;
+    const int n = q / Hb;
+    float g[4][8];
+    uint2 pk[4];
+    bool ok[4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int ho = i + a, wo = j + b;
+        const bool valid = ho < Ho && wo < Wo;
+        ok[a * 2 + b] = valid;
+        const int64_t ro = ((int64_t)n * Ho + (valid ? ho : 0)) * Wo + (valid ? wo : 0);
+        uint2 w2 = make_uint2(0xffffffffu, 0xffffffffu);
+        uint4 d4 = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) {
+          w2 = *reinterpret_cast<const uint2*>(argmax + ro * C + v * 8);
+          d4 = *reinterpret_cast<const uint4*>(dy + ro * lddy + v * 8);
+        }
+        pk[a * 2 + b] = w2;
+        unpack8(*reinterpret_cast<bf16x8*>(&d4), g[a * 2 + b]);
+      }
+#pragma unroll
+    for (int pa = 0; pa < 2; ++pa)
+#pragma unroll
+      for (int pb = 0; pb < 2; ++pb) {
+        float acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+        // pixel (2i+pa, 2j+pb): window rows {i} (offset 1) for pa = 0, {i (offset 2), i+1 (offset 0)} for pa = 1; columns alike
+#pragma unroll
+        for (int a = 0; a <= pa; ++a)
+#pragma unroll
+          for (int b = 0; b <= pb; ++b) {
+            const int roff = pa == 0 ? 1 : (a == 0 ? 2 : 0), coff = pb == 0 ? 1 : (b == 0 ? 2 : 0);
+            const uint32_t idx = (uint32_t)(roff * 3 + coff);
+            const uint2 w2 = pk[a * 2 + b];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t word = c < 4 ? w2.x : w2.y;
+              if (((word >> (8 * (c & 3))) & 0xffu) == idx) acc[c] += g[a * 2 + b][c];
+            }
+          }
+        const int64_t m = ((int64_t)n * H + 2 * i + pa) * W + 2 * j + pb;
+        if (res) {
+          float rf[8];
+          unpack8(ld8(res + m * ldr + v * 8), rf);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[c] += rf[c];
+        }
+        st8(dx + m * lddx + v * 8, pack8(acc));
+      }
+  }
+}
+
 // AveragePooling2D(pool_size k, strides k) over exact windows (PSPNet pyramid pooling, schema segmentation.raml:226-248 ->
 // segmentation_models PSPNet InterpBlock [DEP]): y = mean of the k x k window, fp32 accumulation.  Backward: every input
 // pixel receives dy / k^2 of its window (+ residual: the feature map feeds four pyramid levels and the concat).
@@ -324,6 +396,14 @@ extern "C" int stp_maxpool_bwd(const stp_tensor* dy, const uint8_t* argmax, int3
   if (residual) STP_REQUIRE(vec_ok(residual) && residual->c == dx->c && pixels(residual) == pixels(dx), "maxpool_bwd: bad residual");
   int64_t rows = pixels(dx);
   int cv = dx->c / 8;
+  if (k == 3 && stride == 2 && pad == 1 && rows < 0x7fffffff && dx->h % 2 == 0 && dx->w % 2 == 0 && dy->h == dx->h / 2 &&
+      dy->w == dx->w / 2 && get_option(OPT_HEAD_STRIP) != 1) {
+    const int64_t total = rows / 4 * cv;
+    maxpool_bwd_k3s2_block_kernel<<<ew_grid2(total), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy->ptr, dy->ld, dy->h, dy->w, argmax, residual ? (const __nv_bfloat16*)residual->ptr : nullptr,
+        residual ? residual->ld : 0, (__nv_bfloat16*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, cv, (int)total);
+    return check_launch("maxpool_bwd");
+  }
   if (k == 3 && stride == 2 && pad == 1 && rows < 0x7fffffff && cv <= 256 && 256 % cv == 0) {
     const int ppi = 256 / cv;
     int64_t nb = (rows + (int64_t)ppi * 4 - 1) / ((int64_t)ppi * 4);
