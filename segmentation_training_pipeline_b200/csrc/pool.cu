@@ -54,6 +54,61 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* _
   }
 }
 
+// 3x3 / stride 2 / pad 1 (the ResNet stem pool) with packed bf16x2 compares: per tap and channel PAIR one HMNMX2, one compare
+// mask and one LOP3 for the argmax index (the generic kernel above spends ~107 instructions per output channel on unpack /
+// compare / select and is issue-bound: 56 M warp instructions, 69 % issue active, 85 us for 134 MB in --
+// profiles/r2_ncu_full_tail_mpf.metrics.txt).  Same semantics: zero padding takes part in the max (explicit ZeroPadding2D),
+// the first maximum in tap order wins (strict >).  The output is the selected bf16 value itself, bit exact.
+__global__ void __launch_bounds__(256) maxpool_fwd_k3s2_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int H, int W,
+                                                               __nv_bfloat16* __restrict__ y, int ldy, int Ho, int Wo,
+                                                               uint8_t* __restrict__ argmax, int total, int C, int cv) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = i % cv;
+    int q = i / cv;
+    const int wo = q % Wo;
+    q /= Wo;
+    const int ho = q % Ho;
+    const int n = q / Ho;
+    const __nv_bfloat16* xb = x + (int64_t)n * H * W * ldx + v * 8;
+    uint32_t best[4], idx[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      best[c] = 0xFF80FF80u;   // (-inf, -inf)
+      idx[c] = 0u;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int hi = 2 * ho - 1 + a;
+      const bool okh = (unsigned)hi < (unsigned)H;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const int wi = 2 * wo - 1 + b;
+        const bool ok = okh && (unsigned)wi < (unsigned)W;
+        uint4 f = make_uint4(0u, 0u, 0u, 0u);   // padded taps are zeros
+        if (ok) f = *reinterpret_cast<const uint4*>(xb + ((int64_t)hi * W + wi) * ldx);
+        const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
+        const uint32_t tap = (uint32_t)(a * 3 + b) * 0x00010001u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const __nv_bfloat162 fv = *reinterpret_cast<const __nv_bfloat162*>(&fw[c]);
+          const __nv_bfloat162 bv = *reinterpret_cast<const __nv_bfloat162*>(&best[c]);
+          const uint32_t m = __hgt2_mask(fv, bv);            // 0xFFFF per half where f > best
+          best[c] = (fw[c] & m) | (best[c] & ~m);
+          idx[c] = (tap & m) | (idx[c] & ~m);
+        }
+      }
+    }
+    const int64_t r = ((int64_t)n * Ho + ho) * Wo + wo;
+    *reinterpret_cast<uint4*>(y + r * ldy + v * 8) = make_uint4(best[0], best[1], best[2], best[3]);
+    if (argmax) {
+      uint2 pk;
+      pk.x = __byte_perm(idx[0], idx[1], 0x6420);
+      pk.y = __byte_perm(idx[2], idx[3], 0x6420);
+      *reinterpret_cast<uint2*>(argmax + r * C + v * 8) = pk;
+    }
+  }
+}
+
 // gather form: each input pixel looks at the <= ceil(k/stride)^2 windows covering it
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int Ho,
                                                           int Wo, const uint8_t* __restrict__ argmax, int k,
@@ -378,6 +433,11 @@ extern "C" int stp_maxpool_fwd(const stp_tensor* x, int32_t k, int32_t stride, i
               "maxpool_fwd: output size mismatch");
   int64_t rows = pixels(y);
   int cv = x->c / 8;
+  if (k == 3 && stride == 2 && pad == 1 && rows * cv < 0x7fffffff && pixels(x) < 0x7fffffff && get_option(OPT_HEAD_STRIP) != 1) {
+    maxpool_fwd_k3s2_kernel<<<ew_grid2(rows * cv), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x->ptr, x->ld, x->h, x->w, (__nv_bfloat16*)y->ptr, y->ld, y->h, y->w, argmax, (int)(rows * cv), x->c, cv);
+    return check_launch("maxpool_fwd");
+  }
   maxpool_fwd_kernel<<<ew_grid2(rows * cv), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x->ptr, x->ld, x->h, x->w, k, stride, pad, (__nv_bfloat16*)y->ptr, y->ld, y->h, y->w,
       argmax, rows, x->c, cv);
