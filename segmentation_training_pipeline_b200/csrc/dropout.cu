@@ -6,6 +6,7 @@
 //   counter = (step lo, octet index lo, (octet index hi << 1) | half, step hi);  key = (seed lo, seed hi ^ salt)
 //   half 0 -> channels 0..3 of the 8-channel octet, half 1 -> channels 4..7;  keep  <=>  word >= rate * 2^32
 #include "common.cuh"
+#include "f32_path.h"
 
 namespace stp {
 
@@ -47,8 +48,14 @@ using namespace stp;
 
 extern "C" int stp_dropout(const stp_tensor* x, float rate, uint64_t seed, uint32_t salt, const int64_t* d_step, const stp_tensor* y,
                            stp_stream stream) {
-  STP_REQUIRE(vec_ok(x) && vec_ok(y) && x->c == y->c && pixels(x) == pixels(y) && d_step, "dropout: bf16 tensors of one shape, device step");
   STP_REQUIRE(rate >= 0.f && rate < 1.f, "dropout: 0 <= rate < 1");
+  if (x && x->dtype == STP_F32) {   // parity mode: the same mask on fp32 tensors
+    STP_REQUIRE(f32::f32_ok(x) && f32::f32_ok(y) && x->c == y->c && x->c % 8 == 0 && pixels(x) == pixels(y) && d_step,
+                "dropout (fp32): tensors of one shape, c %% 8 == 0, device step");
+    const double tf = (double)rate * 4294967296.0;
+    return f32::dropout(x, tf >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)tf, 1.f / (1.f - rate), seed, salt, d_step, y, (cudaStream_t)stream);
+  }
+  STP_REQUIRE(vec_ok(x) && vec_ok(y) && x->c == y->c && pixels(x) == pixels(y) && d_step, "dropout: bf16 tensors of one shape, device step");
   const int cv = x->c / 8;
   const int64_t total = pixels(x) * cv;
   const double t = (double)rate * 4294967296.0;

@@ -9,6 +9,7 @@
 // pad_h / pad_w are the padding BEFORE (TF 'same' with stride 2 on even sizes pads 0 before, 1 after: the output size implies
 // the padding after).
 #include "common.cuh"
+#include "f32_path.h"
 
 namespace stp {
 
@@ -297,6 +298,12 @@ static int dw_blocks(int64_t M) {
 
 using namespace stp;
 
+// parity mode: fp32 tensors, fp32 master weights
+static bool dw_f32(const stp_dwconv_desc* d, const stp_tensor* x, const stp_tensor* y) {
+  return d && x && y && x->dtype == STP_F32 && f32::f32_ok(x) && f32::f32_ok(y) && x->c == y->c && x->n == y->n && d->k >= 1 && d->k <= 5 &&
+         d->stride >= 1 && d->dilation >= 1 && d->pad_h >= 0 && d->pad_w >= 0;
+}
+
 static int dw_check(const stp_dwconv_desc* d, const stp_tensor* x, const stp_tensor* y, const char* who) {
   STP_REQUIRE(d && x && y, "%s: null argument", who);
   STP_REQUIRE(vec_ok(x) && vec_ok(y) && x->c == y->c && x->n == y->n, "%s: tensors must be bf16 NHWC with equal channel counts (c%%8==0)", who);
@@ -314,6 +321,10 @@ static DwP make_dw(const stp_dwconv_desc* d, const stp_tensor* x, const stp_tens
 }
 
 extern "C" int stp_dwconv_fwd(const stp_dwconv_desc* d, const stp_tensor* x, const void* w_kkc, const stp_tensor* y, stp_stream stream) {
+  if (x && x->dtype == STP_F32) {
+    STP_REQUIRE(dw_f32(d, x, y) && w_kkc, "dwconv_fwd (fp32): bad arguments");
+    return f32::dwconv_fwd(d, x, (const float*)w_kkc, y, (cudaStream_t)stream);
+  }
   int rc = dw_check(d, x, y, "dwconv_fwd");
   if (rc) return rc;
   STP_REQUIRE(w_kkc && aligned16(w_kkc), "dwconv_fwd: weights (bf16 [k][k][c]) must be 16-byte aligned");
@@ -339,6 +350,11 @@ extern "C" int stp_dwconv_fwd(const stp_dwconv_desc* d, const stp_tensor* x, con
 
 extern "C" int stp_dwconv_dgrad(const stp_dwconv_desc* d, const stp_tensor* dy, const void* w_kkc, const stp_tensor* residual,
                                 const stp_tensor* dx, stp_stream stream) {
+  if (dx && dx->dtype == STP_F32) {
+    STP_REQUIRE(dw_f32(d, dx, dy) && w_kkc && (!residual || (f32::f32_ok(residual) && residual->c == dx->c && pixels(residual) == pixels(dx))),
+                "dwconv_dgrad (fp32): bad arguments");
+    return f32::dwconv_dgrad(d, dy, (const float*)w_kkc, residual, dx, (cudaStream_t)stream);
+  }
   int rc = dw_check(d, dx, dy, "dwconv_dgrad");
   if (rc) return rc;
   STP_REQUIRE(w_kkc && aligned16(w_kkc), "dwconv_dgrad: weights (bf16 [k][k][c]) must be 16-byte aligned");
@@ -375,6 +391,10 @@ extern "C" size_t stp_dwconv_wgrad_workspace(const stp_dwconv_desc* d, const stp
 
 extern "C" int stp_dwconv_wgrad(const stp_dwconv_desc* d, const stp_tensor* x, const stp_tensor* dy, float* dw_rsc, void* workspace,
                                 size_t workspace_bytes, stp_stream stream) {
+  if (x && x->dtype == STP_F32) {
+    STP_REQUIRE(dw_f32(d, x, dy) && dw_rsc, "dwconv_wgrad (fp32): bad arguments");
+    return f32::dwconv_wgrad(d, x, dy, dw_rsc, (cudaStream_t)stream);
+  }
   int rc = dw_check(d, x, dy, "dwconv_wgrad");
   if (rc) return rc;
   STP_REQUIRE(dw_rsc && workspace, "dwconv_wgrad: null output / workspace");

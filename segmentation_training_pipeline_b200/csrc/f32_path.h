@@ -38,6 +38,14 @@ int maxpool_fwd(const stp_tensor* x, int k, int stride, int pad, const stp_tenso
 int maxpool_bwd(const stp_tensor* dy, const uint8_t* argmax, int k, int stride, int pad, const stp_tensor* res, const stp_tensor* dx,
                 cudaStream_t st);
 int stem_wgrad_post(float* dw8, const float* w, int taps, int cpad, int cimg, float* dbeta, cudaStream_t st);
+// DeepLabV3 graph (f32_deeplab.cu): depthwise conv (weights = the fp32 master [k][k][C]), whole-map mean / broadcast, dropout
+int dwconv_fwd(const stp_dwconv_desc* d, const stp_tensor* x, const float* w, const stp_tensor* y, cudaStream_t st);
+int dwconv_dgrad(const stp_dwconv_desc* d, const stp_tensor* dy, const float* w, const stp_tensor* res, const stp_tensor* dx, cudaStream_t st);
+int dwconv_wgrad(const stp_dwconv_desc* d, const stp_tensor* x, const stp_tensor* dy, float* dw, cudaStream_t st);
+int spatial_reduce(const stp_tensor* x, double scale, const stp_tensor* y, cudaStream_t st);
+int spatial_bcast(const stp_tensor* x, float scale, const stp_tensor* res, const stp_tensor* y, cudaStream_t st);
+int dropout(const stp_tensor* x, uint32_t thresh, float scale, uint64_t seed, uint32_t salt, const int64_t* d_step, const stp_tensor* y,
+            cudaStream_t st);
 
 }  // namespace f32
 }  // namespace stp

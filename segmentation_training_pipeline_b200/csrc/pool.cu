@@ -504,6 +504,10 @@ extern "C" int stp_avgpool_bwd(const stp_tensor* dy, int32_t k, const stp_tensor
   return check_launch("avgpool_bwd");
 }
 
+static bool spatial_f32(const stp_tensor* small, const stp_tensor* big) {
+  return small && big && big->dtype == STP_F32 && f32::f32_ok(small) && f32::f32_ok(big) && small->c == big->c && small->n == big->n &&
+         small->h == 1 && small->w == 1;
+}
 static int spatial_check(const stp_tensor* small, const stp_tensor* big, const char* who) {
   STP_REQUIRE(vec_ok(small) && vec_ok(big) && small->c == big->c && small->n == big->n && small->h == 1 && small->w == 1,
               "%s: [n,1,1,c] against [n,h,w,c], bf16, c %% 8 == 0", who);
@@ -527,18 +531,35 @@ static int spatial_bcast(const stp_tensor* x, float scale, const stp_tensor* res
 }
 
 extern "C" int stp_global_avgpool_fwd(const stp_tensor* x, const stp_tensor* y, stp_stream stream) {
+  if (x && x->dtype == STP_F32) {
+    STP_REQUIRE(spatial_f32(y, x), "global_avgpool_fwd (fp32): bad tensors");
+    return f32::spatial_reduce(x, 1.0 / (double)(x->h * x->w), y, (cudaStream_t)stream);
+  }
   int rc = spatial_check(y, x, "global_avgpool_fwd");
   return rc ? rc : spatial_reduce(x, 1.f / (float)(x->h * x->w), y, stream, "global_avgpool_fwd");
 }
 extern "C" int stp_global_avgpool_bwd(const stp_tensor* dy, const stp_tensor* residual, const stp_tensor* dx, stp_stream stream) {
+  if (dx && dx->dtype == STP_F32) {
+    STP_REQUIRE(spatial_f32(dy, dx) && (!residual || (f32::f32_ok(residual) && residual->c == dx->c && pixels(residual) == pixels(dx))),
+                "global_avgpool_bwd (fp32): bad tensors");
+    return f32::spatial_bcast(dy, 1.f / (float)(dx->h * dx->w), residual, dx, (cudaStream_t)stream);
+  }
   int rc = spatial_check(dy, dx, "global_avgpool_bwd");
   return rc ? rc : spatial_bcast(dy, 1.f / (float)(dx->h * dx->w), residual, dx, stream, "global_avgpool_bwd");
 }
 extern "C" int stp_broadcast_fwd(const stp_tensor* x, const stp_tensor* y, stp_stream stream) {
+  if (y && y->dtype == STP_F32) {
+    STP_REQUIRE(spatial_f32(x, y), "broadcast_fwd (fp32): bad tensors");
+    return f32::spatial_bcast(x, 1.f, nullptr, y, (cudaStream_t)stream);
+  }
   int rc = spatial_check(x, y, "broadcast_fwd");
   return rc ? rc : spatial_bcast(x, 1.f, nullptr, y, stream, "broadcast_fwd");
 }
 extern "C" int stp_broadcast_bwd(const stp_tensor* dy, const stp_tensor* dx, stp_stream stream) {
+  if (dy && dy->dtype == STP_F32) {
+    STP_REQUIRE(spatial_f32(dx, dy), "broadcast_bwd (fp32): bad tensors");
+    return f32::spatial_reduce(dy, 1.0, dx, (cudaStream_t)stream);
+  }
   int rc = spatial_check(dx, dy, "broadcast_bwd");
   return rc ? rc : spatial_reduce(dy, 1.f, dx, stream, "broadcast_bwd");
 }

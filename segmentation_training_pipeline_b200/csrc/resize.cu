@@ -247,9 +247,13 @@ __global__ void __launch_bounds__(256) prob_head_fwd_kernel(const float* __restr
 }
 
 // thread = (low-resolution pixel); dz bf16 [n,h,w,cx] (channels >= classes zero)
+__device__ __forceinline__ void store_dz(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void store_dz(float* p, float v) { *p = v; }
+
+template <typename TZ>
 __global__ void __launch_bounds__(128) prob_head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ logits, int H, int W,
                                                              int classes, int act, const float* __restrict__ z, int ldz,
-                                                             __nv_bfloat16* __restrict__ dz, int lddz, int cx, int h, int w, int64_t total,
+                                                             TZ* __restrict__ dz, int lddz, int cx, int h, int w, int64_t total,
                                                              float sy, float sx, float isy, float isx) {
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (int64_t)gridDim.x * blockDim.x) {
     const int64_t n = r / ((int64_t)h * w);
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(128) prob_head_bwd_kernel(const float* __restr
       }
     }
     const float* zr = z + r * ldz;
-    __nv_bfloat16* out = dz + r * lddz;
+    TZ* out = dz + r * lddz;
     if (act == 2) {
       float m = -INFINITY, s = 0.f, dot = 0.f;
       for (int c = 0; c < classes; ++c) m = fmaxf(m, zr[c]);
@@ -298,16 +302,16 @@ __global__ void __launch_bounds__(128) prob_head_bwd_kernel(const float* __restr
         if (c < classes) dot += acc[c] * __expf(zr[c] - m) * inv;
 #pragma unroll
       for (int c = 0; c < kProbMaxClasses; ++c)
-        if (c < classes) out[c] = __float2bfloat16_rn(__expf(zr[c] - m) * inv * (acc[c] - dot));
+        if (c < classes) store_dz(out + c, __expf(zr[c] - m) * inv * (acc[c] - dot));
     } else {
 #pragma unroll
       for (int c = 0; c < kProbMaxClasses; ++c)
         if (c < classes) {
           const float sg = sigmoidf_(zr[c]);
-          out[c] = __float2bfloat16_rn(acc[c] * sg * (1.f - sg));
+          store_dz(out + c, acc[c] * sg * (1.f - sg));
         }
     }
-    for (int c = classes; c < cx; ++c) out[c] = __float2bfloat16_rn(0.f);
+    for (int c = classes; c < cx; ++c) store_dz(out + c, 0.f);
   }
 }
 
@@ -405,8 +409,8 @@ extern "C" int stp_prob_head_fwd(const stp_tensor* z, int32_t classes, int32_t a
 extern "C" int stp_prob_head_bwd(const stp_tensor* dlogits, const stp_tensor* logits, const stp_tensor* z, int32_t classes,
                                  int32_t activation, const stp_tensor* dz, stp_stream stream) {
   STP_REQUIRE(dlogits && logits && z && dz && f32_ok(dlogits) && f32_ok(logits) && f32_ok(z), "prob_head_bwd: f32 dlogits / logits / z");
-  STP_REQUIRE(dz->ptr && dz->dtype == STP_BF16 && dz->ld >= dz->c && dz->c >= classes && pixels(dz) == pixels(z) && dz->n == z->n &&
-                  dz->h == z->h && dz->w == z->w, "prob_head_bwd: dz bf16 with z's geometry");
+  STP_REQUIRE(dz->ptr && (dz->dtype == STP_BF16 || dz->dtype == STP_F32) && dz->ld >= dz->c && dz->c >= classes && pixels(dz) == pixels(z) && dz->n == z->n &&
+                  dz->h == z->h && dz->w == z->w, "prob_head_bwd: dz bf16 (or f32 in parity mode) with z's geometry");
   STP_REQUIRE(classes >= 1 && classes <= kProbMaxClasses && classes <= z->c && logits->c == classes && logits->ld == classes &&
                   dlogits->c == classes && dlogits->ld == classes && pixels(dlogits) == pixels(logits) && logits->n == z->n,
               "prob_head_bwd: dense [n,H,W,classes] logits and gradient");
@@ -416,8 +420,13 @@ extern "C" int stp_prob_head_bwd(const stp_tensor* dlogits, const stp_tensor* lo
   align_scales(z->h, z->w, logits->h, logits->w, sy, sx, isy, isx);
   const int64_t total = pixels(z);
   const int64_t nb = (total + 127) / 128;
-  prob_head_bwd_kernel<<<(int)(nb < 1 ? 1 : nb), 128, 0, (cudaStream_t)stream>>>(
-      (const float*)dlogits->ptr, (const float*)logits->ptr, logits->h, logits->w, classes, activation, (const float*)z->ptr, z->ld,
-      (__nv_bfloat16*)dz->ptr, dz->ld, dz->c, z->h, z->w, total, sy, sx, isy, isx);
+  if (dz->dtype == STP_F32)
+    prob_head_bwd_kernel<float><<<(int)(nb < 1 ? 1 : nb), 128, 0, (cudaStream_t)stream>>>(
+        (const float*)dlogits->ptr, (const float*)logits->ptr, logits->h, logits->w, classes, activation, (const float*)z->ptr, z->ld,
+        (float*)dz->ptr, dz->ld, dz->c, z->h, z->w, total, sy, sx, isy, isx);
+  else
+    prob_head_bwd_kernel<__nv_bfloat16><<<(int)(nb < 1 ? 1 : nb), 128, 0, (cudaStream_t)stream>>>(
+        (const float*)dlogits->ptr, (const float*)logits->ptr, logits->h, logits->w, classes, activation, (const float*)z->ptr, z->ld,
+        (__nv_bfloat16*)dz->ptr, dz->ld, dz->c, z->h, z->w, total, sy, sx, isy, isx);
   return check_launch("prob_head_bwd");
 }

@@ -895,8 +895,6 @@ class DWConv(Op):
     item)."""
 
     def __init__(self, net: Net, x: Buf, y: Buf, name: str, k=3, stride=1, dilation=1, init="glorot_uniform"):
-        if net.precision != "bf16":
-            raise NotImplementedError("DWConv: bf16 path only")
         self.net, self.x, self.y, self.name = net, x, y, name
         c = x.c
         assert y.c == c
@@ -1018,7 +1016,7 @@ class ProbHead(Conv):
         if activation not in self.ACT:
             raise NotImplementedError("DeepLabV3 head: activation sigmoid or softmax (got %r)" % (activation,))
         small = Buf(net, x.n, x.h, x.w, self.CPAD, F32, name=name + "_out")
-        small.set_grad(Buf(net, x.n, x.h, x.w, self.CPAD, BF16, name="d_" + name + "_out"))
+        small.set_grad(Buf(net, x.n, x.h, x.w, self.CPAD, net.act_dtype, name="d_" + name + "_out"))
         super().__init__(net, x, small, name, 1, pad=0, bias=True, init=init, cout_real=classes)
         self.classes, self.small, self.act = classes, small, self.ACT[activation]
         H, W = out_hw

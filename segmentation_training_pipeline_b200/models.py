@@ -380,8 +380,6 @@ class SegNet(E.Net):
         (:462-481), concat_projection + BN + ReLU + Dropout(0.1), then Conv2D(classes, 1x1, activation) at 1/8 resolution and
         the align_corners bilinear resize of the PROBABILITIES to the input size (:494-500).  Raw 0..255 input like every model
         of the pipeline.  Layer names are the Keras names of that file (weights exchangeable by name)."""
-        if self.precision != "bf16":
-            raise NotImplementedError("precision: fp32 (parity mode) is built for the Unet / Linknet graphs")
         if backbone not in DEEPLAB_BACKBONES:
             print("Unknown backbone:" + backbone)
             print("Known backbones:", DEEPLAB_BACKBONES)

@@ -212,3 +212,73 @@ def test_deeplab_depth_profile(cuda):
     assert seen >= 18
     first = net.bufs["Conv_Relu6"].torch().float().cpu()
     assert float((first - oms["bf16"].taps["Conv_Relu6"].permute(0, 2, 3, 1)).norm() / first.norm()) < 1e-3
+
+
+@pytest.mark.parametrize("size,n,classes,activation,dropout", [(64, 4, 1, "sigmoid", 0.1), (96, 4, 3, "softmax", 0.0)])
+def test_deeplab_fp32_parity_mode(cuda, size, n, classes, activation, dropout):
+    """PARITY MODE of the DeepLabV3 graph (SegNet(precision="fp32"): fp32 activations / gradients / weights, CUDA-core kernels
+    with double accumulators behind the same C-ABI entry points, csrc/f32_path.cu + f32_deeplab.cu).  Anchor: the oracle in DOUBLE
+    precision.  The output probabilities within 1e-4 relative L2 (or twice the fp32 oracle's own distance from the anchor), the
+    loss within 1e-5, every parameter gradient as close to the anchor as the fp32 oracle is (each tensor within x5, median ratio
+    below 2) -- where bf16 storage is 30-40 % away (test_deeplab_depth_profile)."""
+    from oracle import losses as OL
+    from oracle.models import SegModel
+    from segmentation_training_pipeline_b200 import lib
+    from segmentation_training_pipeline_b200.models import SegNet
+    from segmentation_training_pipeline_b200.trainer import Trainer
+
+    onehot = activation == "softmax"
+    loss = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0) if onehot else (1.0, 1.0, 0.0)
+    net = SegNet("mobilenetv2", classes=classes, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=loss,
+                 architecture="DeepLabV3", activation=activation, dropout=dropout, precision="fp32")
+    W = _perturb(net.get_weights())
+    net.set_weights(W)
+    tr = Trainer(net)
+    img, mask = _data(n, size, size)
+    mask = _masks(mask, classes, onehot, size)
+    tr.set_batch(img.cuda(), mask.cuda())
+    net.d_step.fill_(3)
+    before = net.L.tc_launch_count()
+    net.prep_weights()
+    net.forward()
+    net.backward()
+    torch.cuda.synchronize()
+    assert net.L.tc_launch_count() == before      # no bf16 tensor-core kernel ran
+    res = net.loss.result.cpu().numpy()
+    lg = net.head.logits.cpu().view(n, size, size, classes).double()
+    prob = torch.sigmoid(lg) if activation == "sigmoid" else torch.softmax(lg, dim=-1)
+    grads = net.get_grads()
+
+    def run(storage):
+        om = SegModel("DeepLabV3", "mobilenetv2", classes=classes, activation=activation, input_shape=(size, size, 3), storage=storage,
+                      update_moving=False, dropout=(dropout, net.seed, 0xD0, 3) if dropout else None)
+        om.load_numpy(W)
+        y = om(img.float())
+        t = mask.float()
+        lo = loss[6] * OL.categorical_crossentropy(t, y) if onehot else OL.binary_crossentropy(t, y) + OL.dice_loss(t, y)
+        lo.backward()
+        return y.detach().double(), float(lo.detach()), {k: p.grad.double().numpy().copy() for k, p in om.params.items()}
+
+    y64, lo64, g64 = run("fp64")
+    y32, lo32, g32 = run("fp32")
+    err = float((prob - y64).norm() / y64.norm())
+    err32 = float((y32 - y64).norm() / y64.norm())
+    print("DeepLabV3 fp32 parity mode vs fp64 anchor: probabilities rel err %.3e (fp32 oracle %.3e), loss %.7f vs %.7f" %
+          (err, err32, float(res[lib.L_LOSS]), lo64))
+    assert err < max(1e-4, 2.0 * err32)
+    assert abs(float(res[lib.L_LOSS]) - lo64) < 1e-5 * max(1.0, abs(lo64))
+    worst, ratios = ("", 0.0, 0.0), []
+    for k, go in g64.items():
+        ge = grads[k].astype(np.float64)
+        assert go.shape == ge.shape, (k, go.shape, ge.shape)
+        if np.linalg.norm(go) < 1e-9 * go.size ** 0.5:
+            continue
+        den = np.linalg.norm(go) + 1e-30
+        e, floor = float(np.linalg.norm(ge - go) / den), float(np.linalg.norm(g32[k] - go) / den)
+        if e > worst[1]:
+            worst = (k, e, floor)
+        ratios.append(e / max(floor, 1e-7))
+        assert e < max(2e-4, 5.0 * floor), (k, e, floor)
+    print("worst gradient: %s engine-vs-fp64 %.3e, fp32-oracle-vs-fp64 %.3e; median engine/oracle error ratio %.2f" %
+          (worst + (float(np.median(ratios)),)))
+    assert float(np.median(ratios)) < 2.0, float(np.median(ratios))
