@@ -136,6 +136,33 @@ __global__ void dropout_kernel(const float* __restrict__ x, int ldx, float* __re
   }
 }
 
+// AveragePooling2D(k, k) over exact windows (PSPNet pyramid) and its gradient
+__global__ void avgpool_fwd_kernel(const float* __restrict__ x, int ldx, int H, int W, int k, float* __restrict__ y, int ldy, int Ho, int Wo,
+                                   int C, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t r = i / C;
+    const int wo = (int)(r % Wo), ho = (int)((r / Wo) % Ho);
+    const int64_t n = r / ((int64_t)Wo * Ho);
+    double acc = 0.0;
+    for (int a = 0; a < k; ++a)
+      for (int b = 0; b < k; ++b) acc += (double)x[((n * H + ho * k + a) * (int64_t)W + wo * k + b) * ldx + c];
+    y[r * ldy + c] = (float)(acc / (double)(k * k));
+  }
+}
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dy, int lddy, int Ho, int Wo, int k, const float* __restrict__ res, int ldr,
+                                   float* __restrict__ dx, int lddx, int H, int W, int C, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t r = i / C;
+    const int w = (int)(r % W), h = (int)((r / W) % H);
+    const int64_t n = r / ((int64_t)W * H);
+    float g = dy[((n * Ho + h / k) * (int64_t)Wo + w / k) * lddy + c] / (float)(k * k);
+    if (res) g += res[r * ldr + c];
+    dx[r * lddx + c] = g;
+  }
+}
+
 DwF make(const stp_dwconv_desc* d, const stp_tensor* x, const stp_tensor* y) {
   DwF p;
   p.N = x->n; p.H = x->h; p.W = x->w; p.C = x->c; p.Ho = y->h; p.Wo = y->w;
@@ -168,6 +195,17 @@ int spatial_bcast(const stp_tensor* x, float scale, const stp_tensor* res, const
   spatial_bcast_kernel<<<grid1(total), 256, 0, st>>>((const float*)x->ptr, x->ld, y->h * y->w, y->c, scale,
                                                     res ? (const float*)res->ptr : nullptr, res ? res->ld : 0, (float*)y->ptr, y->ld, total);
   return check_launch("spatial_bcast (fp32)");
+}
+int avgpool_fwd(const stp_tensor* x, int k, const stp_tensor* y, cudaStream_t st) {
+  const int64_t total = pixels(y) * y->c;
+  avgpool_fwd_kernel<<<grid1(total), 256, 0, st>>>((const float*)x->ptr, x->ld, x->h, x->w, k, (float*)y->ptr, y->ld, y->h, y->w, y->c, total);
+  return check_launch("avgpool_fwd (fp32)");
+}
+int avgpool_bwd(const stp_tensor* dy, int k, const stp_tensor* res, const stp_tensor* dx, cudaStream_t st) {
+  const int64_t total = pixels(dx) * dx->c;
+  avgpool_bwd_kernel<<<grid1(total), 256, 0, st>>>((const float*)dy->ptr, dy->ld, dy->h, dy->w, k, res ? (const float*)res->ptr : nullptr,
+                                                  res ? res->ld : 0, (float*)dx->ptr, dx->ld, dx->h, dx->w, dx->c, total);
+  return check_launch("avgpool_bwd (fp32)");
 }
 int dropout(const stp_tensor* x, uint32_t thresh, float scale, uint64_t seed, uint32_t salt, const int64_t* d_step, const stp_tensor* y,
             cudaStream_t st) {

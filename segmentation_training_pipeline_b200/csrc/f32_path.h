@@ -44,6 +44,8 @@ int dwconv_dgrad(const stp_dwconv_desc* d, const stp_tensor* dy, const float* w,
 int dwconv_wgrad(const stp_dwconv_desc* d, const stp_tensor* x, const stp_tensor* dy, float* dw, cudaStream_t st);
 int spatial_reduce(const stp_tensor* x, double scale, const stp_tensor* y, cudaStream_t st);
 int spatial_bcast(const stp_tensor* x, float scale, const stp_tensor* res, const stp_tensor* y, cudaStream_t st);
+int avgpool_fwd(const stp_tensor* x, int k, const stp_tensor* y, cudaStream_t st);
+int avgpool_bwd(const stp_tensor* dy, int k, const stp_tensor* res, const stp_tensor* dx, cudaStream_t st);
 int dropout(const stp_tensor* x, uint32_t thresh, float scale, uint64_t seed, uint32_t salt, const int64_t* d_step, const stp_tensor* y,
             cudaStream_t st);
 

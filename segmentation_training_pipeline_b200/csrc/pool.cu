@@ -484,6 +484,11 @@ extern "C" int stp_maxpool_bwd(const stp_tensor* dy, const uint8_t* argmax, int3
 }
 
 extern "C" int stp_avgpool_fwd(const stp_tensor* x, int32_t k, const stp_tensor* y, stp_stream stream) {
+  if (x && x->dtype == STP_F32) {   // parity mode
+    STP_REQUIRE(f32::f32_ok(x) && f32::f32_ok(y) && k >= 1 && y->c == x->c && y->n == x->n && x->h == y->h * k && x->w == y->w * k,
+                "avgpool_fwd (fp32): windows must tile the input exactly");
+    return f32::avgpool_fwd(x, k, y, (cudaStream_t)stream);
+  }
   STP_REQUIRE(vec_ok(x) && vec_ok(y), "avgpool_fwd: bad tensors");
   STP_REQUIRE(k >= 1 && y->c == x->c && y->n == x->n && x->h == y->h * k && x->w == y->w * k, "avgpool_fwd: windows must tile the input exactly");
   const int64_t rows = pixels(y);
@@ -493,6 +498,12 @@ extern "C" int stp_avgpool_fwd(const stp_tensor* x, int32_t k, const stp_tensor*
   return check_launch("avgpool_fwd");
 }
 extern "C" int stp_avgpool_bwd(const stp_tensor* dy, int32_t k, const stp_tensor* residual, const stp_tensor* dx, stp_stream stream) {
+  if (dx && dx->dtype == STP_F32) {   // parity mode
+    STP_REQUIRE(f32::f32_ok(dy) && f32::f32_ok(dx) && k >= 1 && dy->c == dx->c && dy->n == dx->n && dx->h == dy->h * k && dx->w == dy->w * k &&
+                    (!residual || (f32::f32_ok(residual) && residual->c == dx->c && pixels(residual) == pixels(dx))),
+                "avgpool_bwd (fp32): shape mismatch");
+    return f32::avgpool_bwd(dy, k, residual, dx, (cudaStream_t)stream);
+  }
   STP_REQUIRE(vec_ok(dy) && vec_ok(dx), "avgpool_bwd: bad tensors");
   STP_REQUIRE(k >= 1 && dy->c == dx->c && dy->n == dx->n && dx->h == dy->h * k && dx->w == dy->w * k, "avgpool_bwd: shape mismatch");
   if (residual) STP_REQUIRE(vec_ok(residual) && residual->c == dx->c && pixels(residual) == pixels(dx), "avgpool_bwd: bad residual");

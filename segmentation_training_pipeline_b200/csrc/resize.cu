@@ -163,6 +163,39 @@ __global__ void __launch_bounds__(256) resize_bwd_f32_kernel(const float* __rest
   }
 }
 
+// parity mode: dy f32 [n,H,W,c] -> dx f32 [n,h,w,c] (+ residual), double accumulation in the forward's index arithmetic
+__global__ void __launch_bounds__(256) resize_bwd_f32f32_kernel(const float* __restrict__ dy, int lddy, int H, int W, const float* __restrict__ res,
+                                                                 int ldr, float* __restrict__ dx, int lddx, int h, int w, int64_t total, int c,
+                                                                 int cy, float sy, float sx, float isy, float isx) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c;
+    const int ch = (int)(i - r * c);
+    if (ch >= cy) {   // padded channels of the head conv output carry no gradient
+      dx[r * lddx + ch] = res ? res[r * ldr + ch] : 0.f;
+      continue;
+    }
+    const int64_t n = r / ((int64_t)h * w);
+    const int rem = (int)(r - n * (int64_t)h * w);
+    const int iy = rem / w, ix = rem - iy * w;
+    int y0, y1, x0, x1;
+    cand_range(iy, isy, H, y0, y1);
+    cand_range(ix, isx, W, x0, x1);
+    const float* base = dy + n * (int64_t)H * W * lddy + ch;
+    double acc = 0.0;
+    for (int oy = y0; oy <= y1; ++oy) {
+      const float wy = axis_weight(oy, iy, sy, h);
+      if (wy == 0.f) continue;
+      for (int ox = x0; ox <= x1; ++ox) {
+        const float wx = axis_weight(ox, ix, sx, w);
+        if (wx == 0.f) continue;
+        acc += (double)wy * (double)wx * (double)base[((int64_t)oy * W + ox) * lddy];
+      }
+    }
+    if (res) acc += (double)res[r * ldr + ch];
+    dx[r * lddx + ch] = (float)acc;
+  }
+}
+
 // gradient of UpSampling2D(2): dx = 2x2 sum of dy (+ residual), no activation mask
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy,
                                                               const __nv_bfloat16* __restrict__ res, int ldr,
@@ -315,6 +348,22 @@ __global__ void __launch_bounds__(128) prob_head_bwd_kernel(const float* __restr
   }
 }
 
+// parity mode: f32 2x2 sum (+ residual)
+__global__ void __launch_bounds__(256) upsample2x_bwd_f32_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ res, int ldr,
+                                                                  float* __restrict__ dx, int lddx, int h, int w, int64_t total, int c) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c;
+    const int ch = (int)(i - r * c);
+    const int64_t n = r / ((int64_t)h * w);
+    const int rem = (int)(r - n * (int64_t)h * w);
+    const int iy = rem / w, ix = rem - iy * w;
+    const float* base = dy + ((n * 2 * h + 2 * iy) * (int64_t)(2 * w) + 2 * ix) * lddy + ch;
+    double g = (double)base[0] + (double)base[lddy] + (double)base[(int64_t)2 * w * lddy] + (double)base[(int64_t)2 * w * lddy + lddy];
+    if (res) g += (double)res[r * ldr + ch];
+    dx[r * lddx + ch] = (float)g;
+  }
+}
+
 int grid_for(int64_t total) {
   int64_t b = (total + 255) / 256;
   const int64_t cap = (int64_t)kNumSMs * 16;
@@ -349,7 +398,7 @@ extern "C" int stp_resize_bilinear_fwd(const stp_tensor* x, const stp_tensor* y,
 
 extern "C" int stp_resize_bilinear_bwd(const stp_tensor* dy, const stp_tensor* residual, const stp_tensor* dx,
                                        stp_stream stream) {
-  STP_REQUIRE(dy && dx && dy->n == dx->n && vec_ok(dx), "resize_bilinear_bwd: bad tensors");
+  STP_REQUIRE(dy && dx && dy->n == dx->n && (vec_ok(dx) || (dx->dtype == STP_F32 && f32_ok(dx))), "resize_bilinear_bwd: bad tensors");
   STP_REQUIRE(dy->h >= dx->h && dy->w >= dx->w, "resize_bilinear_bwd: only up-scaling resizes have a gather backward here");
   const float sy = (float)((double)dx->h / (double)dy->h), sx = (float)((double)dx->w / (double)dy->w);
   const float isy = (float)((double)dy->h / (double)dx->h), isx = (float)((double)dy->w / (double)dx->w);
@@ -362,6 +411,13 @@ extern "C" int stp_resize_bilinear_bwd(const stp_tensor* dy, const stp_tensor* r
     resize_bwd_bf16_kernel<<<grid_for(total), 256, 0, st>>>(
         (const __nv_bfloat16*)dy->ptr, dy->ld, dy->h, dy->w, residual ? (const __nv_bfloat16*)residual->ptr : nullptr,
         residual ? residual->ld : 0, (__nv_bfloat16*)dx->ptr, dx->ld, dx->h, dx->w, total, cv, sy, sx, isy, isx);
+  } else if (dx->dtype == STP_F32) {   // parity mode
+    STP_REQUIRE(f32_ok(dy) && f32_ok(dx) && dy->c <= dx->c, "resize_bilinear_bwd (fp32): dy.c <= dx.c");
+    if (residual) STP_REQUIRE(f32_ok(residual) && residual->c == dx->c && pixels(residual) == pixels(dx), "resize_bilinear_bwd (fp32): bad residual");
+    const int64_t total = pixels(dx) * dx->c;
+    resize_bwd_f32f32_kernel<<<grid_for(total), 256, 0, st>>>((const float*)dy->ptr, dy->ld, dy->h, dy->w,
+                                                              residual ? (const float*)residual->ptr : nullptr, residual ? residual->ld : 0,
+                                                              (float*)dx->ptr, dx->ld, dx->h, dx->w, total, dx->c, dy->c, sy, sx, isy, isx);
   } else {
     STP_REQUIRE(f32_ok(dy) && dy->c <= dx->c && !residual, "resize_bilinear_bwd: f32 dy needs dy.c <= dx.c and no residual");
     const int64_t total = pixels(dx) * dx->c;
@@ -374,6 +430,16 @@ extern "C" int stp_resize_bilinear_bwd(const stp_tensor* dy, const stp_tensor* r
 
 extern "C" int stp_upsample2x_bwd(const stp_tensor* dy, const stp_tensor* residual, const stp_tensor* dx,
                                   stp_stream stream) {
+  if (dx && dx->dtype == STP_F32) {   // parity mode
+    STP_REQUIRE(f32_ok(dy) && f32_ok(dx) && dy->c == dx->c && dy->n == dx->n && dy->h == 2 * dx->h && dy->w == 2 * dx->w &&
+                    (!residual || (f32_ok(residual) && residual->c == dx->c && pixels(residual) == pixels(dx))),
+                "upsample2x_bwd (fp32): shape mismatch");
+    const int64_t total = pixels(dx) * dx->c;
+    upsample2x_bwd_f32_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+        (const float*)dy->ptr, dy->ld, residual ? (const float*)residual->ptr : nullptr, residual ? residual->ld : 0, (float*)dx->ptr,
+        dx->ld, dx->h, dx->w, total, dx->c);
+    return check_launch("upsample2x_bwd (fp32)");
+  }
   STP_REQUIRE(vec_ok(dy) && vec_ok(dx) && dy->c == dx->c && dy->n == dx->n && dy->h == 2 * dx->h && dy->w == 2 * dx->w,
               "upsample2x_bwd: shape mismatch");
   if (residual) STP_REQUIRE(vec_ok(residual) && residual->c == dx->c && pixels(residual) == pixels(dx), "upsample2x_bwd: bad residual");

@@ -869,7 +869,7 @@ class UpHead(Conv):
         if classes > self.CPAD:
             raise NotImplementedError("UpHead: classes <= %d" % self.CPAD)
         small = Buf(net, x.n, x.h, x.w, self.CPAD, F32, name=name + "_out")
-        small.set_grad(Buf(net, x.n, x.h, x.w, self.CPAD, BF16, name="d_" + name + "_out"))
+        small.set_grad(Buf(net, x.n, x.h, x.w, self.CPAD, net.act_dtype, name="d_" + name + "_out"))
         super().__init__(net, x, small, name, 3, pad=1, bias=True, init=init, cout_real=classes)
         self.classes, self.small = classes, small
         H, W = x.h * up, x.w * up

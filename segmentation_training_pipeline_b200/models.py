@@ -69,8 +69,6 @@ class SegNet(E.Net):
         linknet = architecture == "Linknet"
         fpn = architecture == "FPN"
         psp = architecture == "PSPNet"
-        if (fpn or psp) and precision == "fp32":
-            raise NotImplementedError("precision: fp32 (parity mode) is built for the Unet / Linknet graphs")
         if psp and backbone.lower() == "vgg16":
             raise NotImplementedError("PSPNet is built over the ResNet encoders only")
         if psp and downsample_factor not in (4, 8, 16):

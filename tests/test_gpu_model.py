@@ -264,7 +264,8 @@ def test_loss_curve_100_steps(cuda):
 
 
 @pytest.mark.parametrize("arch,backbone,size", [("Unet", "resnet18", 64), ("Unet", "resnet34", 128), ("Linknet", "resnet18", 128),
-                                                ("Unet", "vgg16", 64)])
+                                                ("Unet", "vgg16", 64), ("FPN", "resnet18", 128), ("FPN", "resnet50", 128),
+                                                ("PSPNet", "resnet18", 96)])
 def test_fp32_parity_mode_forward_backward(cuda, arch, backbone, size):
     """PARITY MODE (SegNet(precision="fp32"), csrc/f32_path.cu: fp32 activations / weights / FFMA accumulation, double
     reductions).  Anchor: the oracle in DOUBLE precision (storage="fp64").  Logits within 1e-4 rel-L2 and the loss within 1e-5
