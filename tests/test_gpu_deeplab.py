@@ -282,3 +282,63 @@ def test_deeplab_fp32_parity_mode(cuda, size, n, classes, activation, dropout):
     print("worst gradient: %s engine-vs-fp64 %.3e, fp32-oracle-vs-fp64 %.3e; median engine/oracle error ratio %.2f" %
           (worst + (float(np.median(ratios)),)))
     assert float(np.median(ratios)) < 2.0, float(np.median(ratios))
+
+
+@pytest.mark.parametrize("lr,mom", [(3e-3, 0.9)])
+def test_deeplab_loss_curve_fp32_parity_mode(cuda, lr, mom):
+    """Loss curve of the DeepLabV3 graph in the fp32 parity mode: 40 SGD-momentum steps under the whole-step CUDA graph with
+    Dropout(0.1) ON (the oracle regenerates each step's mask from the device step counter) against the fp32 and fp64 oracles from
+    the same weights and batches.  The first step (pure forward parity) agrees to 1e-7.  After that THIS run is chaotic for any fp32
+    implementation: the fp32 ORACLE is 4e-3 from the fp64 oracle at step 2 and 8e-2 by step 40 (batch 4: the image-pooling
+    BatchNorm normalises over four values per channel, and every block re-normalises), so north_star's 1e-3 cannot be asserted
+    between two fp32 runs of it; asserted instead: the engine stays as close to the fp64 anchor as the fp32 oracle does (x2).
+    Measured: engine 6.6e-2, fp32 oracle 8.2e-2 (lr 3e-3, momentum 0.9); 6.1e-2 vs 9.8e-2 with plain SGD lr 1e-3."""
+    from oracle import losses as OL, optim as OO
+    from oracle.models import SegModel
+    from segmentation_training_pipeline_b200.models import SegNet
+    from segmentation_training_pipeline_b200.trainer import Trainer
+
+    n, size, steps, pool = 4, 64, 40, 8
+    net = SegNet("mobilenetv2", classes=1, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=(1.0, 0.0, 0.0),
+                 architecture="DeepLabV3", precision="fp32")
+    W = net.get_weights()
+    img, mask = _data(pool, size, size, seed=11)
+    tr = Trainer(net, optimizer="SGD", lr=lr, momentum=mom)
+    tr.set_pool(img, mask)
+    tr.capture()
+    curve, dsteps = [], []
+    for s in range(steps):
+        dsteps.append(int(net.d_step.item()))
+        tr.step()
+        curve.append(tr.loss_value())
+
+    def oracle_curve(storage):
+        om = SegModel("DeepLabV3", "mobilenetv2", classes=1, input_shape=(size, size, 3), storage=storage)
+        om.load_numpy(W)
+        opt = OO.SGD(om.params, lr=lr, momentum=mom)
+        out = []
+        for s in range(steps):
+            idx = [(s * n + j) % pool for j in range(n)]
+            om.dropout = (0.1, net.seed, 0xD0, dsteps[s])
+            y = om(img[idx].float())
+            lo = OL.binary_crossentropy(mask[idx].float(), y)
+            for p in om.params.values():
+                p.grad = None
+            lo.backward()
+            opt.step({k: p.grad for k, p in om.params.items()})
+            out.append(float(lo.detach()))
+        return np.array(out)
+
+    c, r32, r64 = np.array(curve), oracle_curve("fp32"), oracle_curve("fp64")
+    dev = lambda a, b: np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    d_engine, d_oracle, d_pair = dev(c, r64), dev(r32, r64), dev(c, r32)
+    print("engine fp32", np.round(c[::5], 5))
+    print("oracle fp32", np.round(r32[::5], 5))
+    print("oracle fp64", np.round(r64[::5], 5))
+    print("max deviation from the fp64 anchor: engine %.3e, fp32 oracle %.3e; engine vs fp32 oracle %.3e" %
+          (d_engine.max(), d_oracle.max(), d_pair.max()))
+    print("per-step deviation engine vs fp32 oracle", np.round(d_pair[:6], 6), "fp32 oracle vs fp64", np.round(d_oracle[:6], 6))
+    assert d_pair[0] < 1e-5, d_pair[0]                 # the first step is pure forward parity
+    assert d_engine.max() < max(1e-3, 2.0 * d_oracle.max()), (d_engine.max(), d_oracle.max())
+    assert d_pair.max() < max(1e-3, 2.0 * d_oracle.max()), (d_pair.max(), d_oracle.max())
+    assert c[-5:].mean() < c[:3].mean()
