@@ -469,6 +469,10 @@ int stp_broadcast_fwd(const stp_tensor* x, const stp_tensor* y, stp_stream strea
 int stp_broadcast_bwd(const stp_tensor* dy, const stp_tensor* dx, stp_stream stream);
 int stp_dropout(const stp_tensor* x, float rate, uint64_t seed, uint32_t salt, const int64_t* d_step, const stp_tensor* y,
                 stp_stream stream);
+/* stp_resize_bilinear_fwd/bwd with tf.image.resize_bilinear(align_corners=True) index arithmetic: the BilinearUpsampling layer of
+ * impl/deeplab/model.py:81-100 on feature maps (xception decoder, :488-490) */
+int stp_resize_bilinear_ac_fwd(const stp_tensor* x, const stp_tensor* y, stp_stream stream);
+int stp_resize_bilinear_ac_bwd(const stp_tensor* dy, const stp_tensor* residual, const stp_tensor* dx, stp_stream stream);
 int stp_prob_head_fwd(const stp_tensor* z, int32_t classes, int32_t activation, const stp_tensor* logits, stp_stream stream);
 int stp_prob_head_bwd(const stp_tensor* dlogits, const stp_tensor* logits, const stp_tensor* z, int32_t classes,
                       int32_t activation, const stp_tensor* dz, stp_stream stream);

@@ -78,7 +78,7 @@ class SegModel:
                  decoder_filters=(256, 128, 64, 32, 16), decoder_use_batchnorm=True,
                  decoder_block_type="upsampling", enc_init="he_uniform", dec_init="glorot_uniform",
                  pyramid_block_filters=256, segmentation_block_filters=128, fpn_dropout=None,
-                 update_moving=True, downsample_factor=8, psp_conv_filters=512, dropout=None):
+                 update_moving=True, downsample_factor=8, psp_conv_filters=512, dropout=None, OS=16):
         self.arch, self.backbone = architecture, backbone.lower()
         self.classes, self.activation = classes, activation
         self.storage = storage
@@ -89,6 +89,7 @@ class SegModel:
         self.psp_factor, self.psp_filters = int(downsample_factor), int(psp_conv_filters)
         # DeepLabV3 only: None (no dropout) or (rate, seed, salt, step) -- the engine's Philox mask (oracle/philox.py)
         self.dropout = dropout
+        self.OS = int(OS)   # DeepLabV3 / xception only (model.py:339-349); mobilenetv2 is always output stride 8
         if self.arch == "DeepLabV3":
             enc_init = dec_init = "glorot_uniform"   # keras defaults of impl/deeplab/model.py
         self.P = ParamStore(seed, enc_init, dec_init)
@@ -320,7 +321,56 @@ class SegModel:
             self.taps[pre + ("add" if skip else "project_BN")] = x
         return x
 
-    def _deeplab_head(self, x):
+    # -- DeepLabV3+ / modified aligned Xception (model.py:110-224, 339-383, 457-500) -----------
+    def _sepconv_bn(self, x, filters, prefix, stride=1, rate=1, depth_activation=False, eps=1e-3):
+        """model.py:110-147"""
+        if not depth_activation:
+            x = L.rb(torch.relu(x), self.storage)
+        wd = self.P.depthwise(prefix + "_depthwise", 3, x.shape[1])
+        ke = 3 + 2 * (rate - 1)
+        pad = None if stride == 1 else ((ke - 1) // 2, (ke - 1) - (ke - 1) // 2)
+        x = L.rb(L.depthwise_conv2d(x, wd, stride, rate, self.storage, explicit_pad=pad), self.storage)
+        x = self._bn_act(x, prefix + "_depthwise_BN", eps, "relu" if depth_activation else None)
+        x = self._conv(x, prefix + "_pointwise", 1, filters)
+        return self._bn_act(x, prefix + "_pointwise_BN", eps, "relu" if depth_activation else None)
+
+    def _xception_block(self, inputs, depth_list, prefix, skip_type, stride, rate=1, depth_activation=False):
+        """model.py:177-216; returns (outputs, skip = the tensor after the second SepConv)"""
+        residual, skip = inputs, None
+        for i in range(3):
+            residual = self._sepconv_bn(residual, depth_list[i], prefix + "_separable_conv%d" % (i + 1),
+                                        stride=stride if i == 2 else 1, rate=rate, depth_activation=depth_activation)
+            if i == 1:
+                skip = residual
+        if skip_type == "conv":
+            sc = self._conv(inputs, prefix + "_shortcut", 1, depth_list[-1], stride=stride)   # k = 1: _conv2d_same pads nothing
+            sc = self._bn_act(sc, prefix + "_shortcut_BN", 1e-3, None)
+            out = L.rb(residual + sc, self.storage)
+        elif skip_type == "sum":
+            out = L.rb(residual + inputs, self.storage)
+        else:
+            out = residual
+        self.taps[prefix] = out
+        return out, skip
+
+    def _xception(self, x):
+        """model.py:339-383: entry / middle (16 units) / exit flow; OS 16: strides 2-2-2 then rates (1, (1, 2)); OS 8: the third
+        entry stride becomes 1 with rates (2, (2, 4))"""
+        s3, mid, ex = (1, 2, (2, 4)) if self.OS == 8 else (2, 1, (1, 2))
+        x = self._conv(x, "entry_flow_conv1_1", 3, 32, stride=2, padding="same")
+        x = self._bn_act(x, "entry_flow_conv1_1_BN", 1e-3, "relu")
+        x = self._conv(x, "entry_flow_conv1_2", 3, 64, stride=1, padding="same")
+        x = self._bn_act(x, "entry_flow_conv1_2_BN", 1e-3, "relu")
+        x, _ = self._xception_block(x, [128, 128, 128], "entry_flow_block1", "conv", 2)
+        x, skip1 = self._xception_block(x, [256, 256, 256], "entry_flow_block2", "conv", 2)
+        x, _ = self._xception_block(x, [728, 728, 728], "entry_flow_block3", "conv", s3)
+        for i in range(16):
+            x, _ = self._xception_block(x, [728, 728, 728], "middle_flow_unit_%d" % (i + 1), "sum", 1, rate=mid)
+        x, _ = self._xception_block(x, [728, 1024, 1024], "exit_flow_block1", "conv", 1, rate=ex[0])
+        x, _ = self._xception_block(x, [1536, 1536, 2048], "exit_flow_block2", "none", 1, rate=ex[1], depth_activation=True)
+        return x, skip1
+
+    def _deeplab_head(self, x, skip1=None, input_hw=None):
         """model.py:457-500: image pooling + 1x1 ASPP branches, concat_projection, Dropout(0.1), Conv2D(classes, 1x1,
         activation), BilinearUpsampling(align_corners=True) to the input size.  Returns the network OUTPUT (probabilities)."""
         EPS = 1e-5
@@ -331,7 +381,12 @@ class SegModel:
         b4 = L.resize_bilinear_tf1(b4, h, w, align_corners=True)         # from 1x1: a broadcast
         b0 = self._conv(x, "aspp0", 1, 256)
         b0 = self._bn_act(b0, "aspp0_BN", EPS, "relu")
-        y = torch.cat([b4, b0], dim=1)
+        if skip1 is not None:   # xception: three atrous separable branches as well (model.py:472-481)
+            rates = (12, 24, 36) if self.OS == 8 else (6, 12, 18)
+            bs = [self._sepconv_bn(x, 256, "aspp%d" % (k + 1), rate=r, depth_activation=True, eps=EPS) for k, r in enumerate(rates)]
+            y = torch.cat([b4, b0] + bs, dim=1)
+        else:
+            y = torch.cat([b4, b0], dim=1)
         y = self._conv(y, "concat_projection", 1, 256)
         y = self._bn_act(y, "concat_projection_BN", EPS, "relu")
         if self.training and self.dropout is not None and self.dropout[0] > 0:
@@ -342,6 +397,15 @@ class SegModel:
             keep = torch.from_numpy(keep).permute(0, 3, 1, 2).to(y.dtype)
             y = L.rb(y * keep * float(np.float32(1.0) / (np.float32(1.0) - np.float32(rate))), self.storage)
         self.taps["concat_projection_relu"] = y
+        if skip1 is not None:   # DeepLab v3+ decoder (model.py:488-500)
+            H, W = input_hw
+            y = L.rb(L.resize_bilinear_tf1(y, -(-H // 4), -(-W // 4), align_corners=True), self.storage)
+            d = self._conv(skip1, "feature_projection0", 1, 48)
+            d = self._bn_act(d, "feature_projection0_BN", EPS, "relu")
+            y = torch.cat([y, d], dim=1)
+            y = self._sepconv_bn(y, 256, "decoder_conv0", depth_activation=True, eps=EPS)
+            y = self._sepconv_bn(y, 256, "decoder_conv1", depth_activation=True, eps=EPS)
+            self.taps["decoder_conv1"] = y
         name = "logits_semantic" if self.classes == 21 else "custom_logits_semantic"
         wk, b = self.P.conv(name, 1, 1, y.shape[1], self.classes, True)
         return L.conv2d(y, wk, b, 1, "same", self.storage)
@@ -355,9 +419,14 @@ class SegModel:
         x = x_nhwc.permute(0, 3, 1, 2).contiguous().to(getattr(self, "dtype", torch.float32))
         if self.arch == "DeepLabV3":
             H, W = x.shape[2], x.shape[3]
-            x = self._mobilenetv2(x)
-            self.P._in_encoder = False
-            z = self._deeplab_head(x)
+            if self.backbone == "xception":
+                x, skip1 = self._xception(x)
+                self.P._in_encoder = False
+                z = self._deeplab_head(x, skip1, (H, W))
+            else:
+                x = self._mobilenetv2(x)
+                self.P._in_encoder = False
+                z = self._deeplab_head(x)
             self.taps["logits_small"] = z
             if emit_logits or self.activation in (None, "none", "linear"):
                 p = z

@@ -81,13 +81,17 @@ def conv2d(x, kernel_hwio, bias=None, stride=1, padding="valid", storage="fp32")
     return y
 
 
-def depthwise_conv2d(x, kernel_hwc1, stride=1, dilation=1, storage="fp32"):
+def depthwise_conv2d(x, kernel_hwc1, stride=1, dilation=1, storage="fp32", explicit_pad=None):
     """keras.layers.DepthwiseConv2D(padding='same', dilation_rate, use_bias=False) [DEP]; kernel (kh, kw, C, 1).
     TF 'SAME' with the dilated extent (k-1)*rate+1 (reference impl/deeplab/model.py:252-255)."""
     kh, kw, c, _ = kernel_hwc1.shape
     w = rw(kernel_hwc1, storage).permute(2, 3, 0, 1)  # -> (C, 1, kh, kw)
-    pt, pb = keras_same_pad(x.shape[2], (kh - 1) * dilation + 1, stride)
-    pl, pr = keras_same_pad(x.shape[3], (kw - 1) * dilation + 1, stride)
+    if explicit_pad is not None:   # ZeroPadding2D((beg, end)) + padding='valid' (SepConv_BN with stride > 1, model.py:125-131)
+        pt, pb = explicit_pad
+        pl, pr = explicit_pad
+    else:
+        pt, pb = keras_same_pad(x.shape[2], (kh - 1) * dilation + 1, stride)
+        pl, pr = keras_same_pad(x.shape[3], (kw - 1) * dilation + 1, stride)
     return F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, None, stride=stride, dilation=dilation, groups=c)
 
 

@@ -377,9 +377,18 @@ bool f32_ok(const stp_tensor* t) { return t && t->ptr && t->dtype == STP_F32 && 
 
 using namespace stp;
 
-extern "C" int stp_resize_bilinear_fwd(const stp_tensor* x, const stp_tensor* y, stp_stream stream) {
+static void align_scales(int in_h, int in_w, int out_h, int out_w, float& sy, float& sx, float& isy, float& isx) {
+  // tf.image.resize_bilinear(align_corners=True): scale = (in-1)/(out-1) when out > 1 [DEP tensorflow==1.15 CalculateResizeScale]
+  sy = out_h > 1 ? (float)(in_h - 1) / (float)(out_h - 1) : (float)in_h / (float)out_h;
+  sx = out_w > 1 ? (float)(in_w - 1) / (float)(out_w - 1) : (float)in_w / (float)out_w;
+  isy = in_h > 1 ? (float)(out_h - 1) / (float)(in_h - 1) : (float)out_h;
+  isx = in_w > 1 ? (float)(out_w - 1) / (float)(in_w - 1) : (float)out_w;
+}
+
+static int resize_fwd_impl(const stp_tensor* x, const stp_tensor* y, bool align, stp_stream stream) {
   STP_REQUIRE(x && y && x->n == y->n && x->h >= 1 && x->w >= 1 && y->h >= 1 && y->w >= 1, "resize_bilinear_fwd: bad shapes");
-  const float sy = (float)((double)x->h / (double)y->h), sx = (float)((double)x->w / (double)y->w);
+  float sy = (float)((double)x->h / (double)y->h), sx = (float)((double)x->w / (double)y->w), isy_, isx_;
+  if (align) align_scales(x->h, x->w, y->h, y->w, sy, sx, isy_, isx_);
   cudaStream_t st = (cudaStream_t)stream;
   if (x->dtype == STP_BF16) {
     STP_REQUIRE(vec_ok(x) && vec_ok(y) && x->c == y->c, "resize_bilinear_fwd: bf16 tensors must have equal channel counts");
@@ -395,13 +404,19 @@ extern "C" int stp_resize_bilinear_fwd(const stp_tensor* x, const stp_tensor* y,
   }
   return check_launch("resize_bilinear_fwd");
 }
+extern "C" int stp_resize_bilinear_fwd(const stp_tensor* x, const stp_tensor* y, stp_stream stream) {
+  return resize_fwd_impl(x, y, false, stream);
+}
+extern "C" int stp_resize_bilinear_ac_fwd(const stp_tensor* x, const stp_tensor* y, stp_stream stream) {
+  return resize_fwd_impl(x, y, true, stream);
+}
 
-extern "C" int stp_resize_bilinear_bwd(const stp_tensor* dy, const stp_tensor* residual, const stp_tensor* dx,
-                                       stp_stream stream) {
+static int resize_bwd_impl(const stp_tensor* dy, const stp_tensor* residual, const stp_tensor* dx, bool align, stp_stream stream) {
   STP_REQUIRE(dy && dx && dy->n == dx->n && (vec_ok(dx) || (dx->dtype == STP_F32 && f32_ok(dx))), "resize_bilinear_bwd: bad tensors");
   STP_REQUIRE(dy->h >= dx->h && dy->w >= dx->w, "resize_bilinear_bwd: only up-scaling resizes have a gather backward here");
-  const float sy = (float)((double)dx->h / (double)dy->h), sx = (float)((double)dx->w / (double)dy->w);
-  const float isy = (float)((double)dy->h / (double)dx->h), isx = (float)((double)dy->w / (double)dx->w);
+  float sy = (float)((double)dx->h / (double)dy->h), sx = (float)((double)dx->w / (double)dy->w);
+  float isy = (float)((double)dy->h / (double)dx->h), isx = (float)((double)dy->w / (double)dx->w);
+  if (align) align_scales(dx->h, dx->w, dy->h, dy->w, sy, sx, isy, isx);
   cudaStream_t st = (cudaStream_t)stream;
   if (dy->dtype == STP_BF16) {
     STP_REQUIRE(vec_ok(dy) && dy->c == dx->c, "resize_bilinear_bwd: bf16 tensors must have equal channel counts");
@@ -427,6 +442,12 @@ extern "C" int stp_resize_bilinear_bwd(const stp_tensor* dy, const stp_tensor* r
   }
   return check_launch("resize_bilinear_bwd");
 }
+extern "C" int stp_resize_bilinear_bwd(const stp_tensor* dy, const stp_tensor* residual, const stp_tensor* dx, stp_stream stream) {
+  return resize_bwd_impl(dy, residual, dx, false, stream);
+}
+extern "C" int stp_resize_bilinear_ac_bwd(const stp_tensor* dy, const stp_tensor* residual, const stp_tensor* dx, stp_stream stream) {
+  return resize_bwd_impl(dy, residual, dx, true, stream);
+}
 
 extern "C" int stp_upsample2x_bwd(const stp_tensor* dy, const stp_tensor* residual, const stp_tensor* dx,
                                   stp_stream stream) {
@@ -449,14 +470,6 @@ extern "C" int stp_upsample2x_bwd(const stp_tensor* dy, const stp_tensor* residu
       (const __nv_bfloat16*)dy->ptr, dy->ld, residual ? (const __nv_bfloat16*)residual->ptr : nullptr,
       residual ? residual->ld : 0, (__nv_bfloat16*)dx->ptr, dx->ld, dx->h, dx->w, total, cv);
   return check_launch("upsample2x_bwd");
-}
-
-static void align_scales(int in_h, int in_w, int out_h, int out_w, float& sy, float& sx, float& isy, float& isx) {
-  // tf.image.resize_bilinear(align_corners=True): scale = (in-1)/(out-1) when out > 1 [DEP tensorflow==1.15 CalculateResizeScale]
-  sy = out_h > 1 ? (float)(in_h - 1) / (float)(out_h - 1) : (float)in_h / (float)out_h;
-  sx = out_w > 1 ? (float)(in_w - 1) / (float)(out_w - 1) : (float)in_w / (float)out_w;
-  isy = in_h > 1 ? (float)(out_h - 1) / (float)(in_h - 1) : (float)out_h;
-  isx = in_w > 1 ? (float)(out_w - 1) / (float)(in_w - 1) : (float)out_w;
 }
 
 extern "C" int stp_prob_head_fwd(const stp_tensor* z, int32_t classes, int32_t activation, const stp_tensor* logits, stp_stream stream) {

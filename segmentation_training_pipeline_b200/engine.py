@@ -755,8 +755,9 @@ class Resize(Op):
     """keras UpSampling2D(rate, interpolation='bilinear') == TF1 legacy tf.image.resize_bilinear (FPN segmentation branches);
     y is typically a channel slice of the concat buffer.  Backward: deterministic gather."""
 
-    def __init__(self, net: Net, x: Buf, y: Buf):
-        self.net, self.x, self.y = net, x, y
+    def __init__(self, net: Net, x: Buf, y: Buf, align_corners=False):
+        # align_corners=True: the BilinearUpsampling layer of the reference's DeepLabV3+ (impl/deeplab/model.py:81-100)
+        self.net, self.x, self.y, self.align = net, x, y, bool(align_corners)
         net.ops.append(self)
 
     def grad_writes(self):
@@ -767,10 +768,12 @@ class Resize(Op):
         self.res_ref = self.dx.ref if self.acc[0] else None
 
     def fwd(self):
-        self.net.L.resize_bilinear_fwd(self.x.ref, self.y.ref, _stream())
+        L = self.net.L
+        (L.resize_bilinear_ac_fwd if self.align else L.resize_bilinear_fwd)(self.x.ref, self.y.ref, _stream())
 
     def bwd(self):
-        self.net.L.resize_bilinear_bwd(self.dy.ref, self.res_ref, self.dx.ref, _stream())
+        L = self.net.L
+        (L.resize_bilinear_ac_bwd if self.align else L.resize_bilinear_bwd)(self.dy.ref, self.res_ref, self.dx.ref, _stream())
 
 
 class MaxPool(Op):
@@ -894,7 +897,7 @@ class DWConv(Op):
     [k][k][C] fp32 master with a bf16 copy in the flat forward-weight buffer (made by the batched weight prep as a Cout = 1
     item)."""
 
-    def __init__(self, net: Net, x: Buf, y: Buf, name: str, k=3, stride=1, dilation=1, init="glorot_uniform"):
+    def __init__(self, net: Net, x: Buf, y: Buf, name: str, k=3, stride=1, dilation=1, init="glorot_uniform", pad=None):
         self.net, self.x, self.y, self.name = net, x, y, name
         c = x.c
         assert y.c == c
@@ -903,7 +906,11 @@ class DWConv(Op):
             out = -(-size // stride)
             return max((out - 1) * stride + (k - 1) * dilation + 1 - size, 0) // 2, out
 
-        (ph, ho), (pw, wo) = same(x.h), same(x.w)
+        def explicit(size):   # ZeroPadding2D((pad, pad_end)) + 'valid' (SepConv_BN with stride > 1, model.py:125-131)
+            ke = (k - 1) * dilation + 1
+            return pad, (size + (ke - 1) - ke) // stride + 1
+
+        (ph, ho), (pw, wo) = (same(x.h), same(x.w)) if pad is None else (explicit(x.h), explicit(x.w))
         assert (ho, wo) == (y.h, y.w), ((ho, wo), (y.h, y.w))
         self.desc = _lib.DwConvDesc(k, stride, dilation, ph, pw)
         lim = math.sqrt(6.0 / (k * k * c + k * k)) if init == "glorot_uniform" else math.sqrt(6.0 / (k * k * c))
@@ -929,6 +936,32 @@ class DWConv(Op):
         with n.wgrad_stream() as ws:
             n.L.dwconv_wgrad(self.dref, self.x.ref, self.dy.ref, n.pg(self.w), ws.data_ptr(), ws.numel(), _stream())
         n.L.dwconv_dgrad(self.dref, self.dy.ref, n.pwf(self.w), self.dx_res, self.dx.ref, _stream())
+
+
+class Relu(Op):
+    """Stand-alone Activation('relu') (the pre-activation of SepConv_BN with depth_activation=False, impl/deeplab/model.py:133-134):
+    the BatchNorm-apply kernel with identity coefficients; backward masks by y > 0."""
+
+    def __init__(self, net: Net, x: Buf, y: Buf):
+        self.net, self.x, self.y = net, x, y
+        c = x.c
+        ident = np.zeros(4 * c, np.float32)
+        ident[c:3 * c] = 1.0   # mean 0, invstd 1, scale 1, shift 0
+        self.coef = torch.from_numpy(ident).to(net.device)
+        net.ops.append(self)
+
+    def grad_writes(self):
+        return [self.x.grad()]
+
+    def prepare(self):
+        self.dy, self.dx = self.y.grad(), self.x.grad()
+        self.res_ref = self.dx.ref if self.acc[0] else None
+
+    def fwd(self):
+        self.net.L.bn_apply(self.x.ref, self.coef.data_ptr(), 1, 1, self.y.ref, _stream())
+
+    def bwd(self):
+        self.net.L.relu_bwd(self.dy.ref, self.y.ref, 1, self.res_ref, self.dx.ref, _stream())
 
 
 class GlobalAvgPool(Op):

@@ -171,6 +171,8 @@ SIGNATURES = {
     "stp_upsample2x_bwd": (C.c_int, [_TP, _TP, _TP, _P]),
     "stp_resize_bilinear_fwd": (C.c_int, [_TP, _TP, _P]),
     "stp_resize_bilinear_bwd": (C.c_int, [_TP, _TP, _TP, _P]),
+    "stp_resize_bilinear_ac_fwd": (C.c_int, [_TP, _TP, _P]),
+    "stp_resize_bilinear_ac_bwd": (C.c_int, [_TP, _TP, _TP, _P]),
     "stp_loss_fwd": (C.c_int, [_P, _P, _I64, C.POINTER(LossSpec), _P, _P, _P]),
     "stp_loss_partial_floats": (_SZ, []),
     "stp_loss_bwd": (C.c_int, [_P, _P, _I64, C.POINTER(LossSpec), _P, _P, _P]),

@@ -22,7 +22,7 @@ RESNET_BOTTLENECK = {"resnet18": False, "resnet34": False, "resnet50": True, "re
 VGG16_BLOCKS = ((64, 2), (128, 2), (256, 3), (512, 3), (512, 3))  # keras.applications.VGG16 [DEP]
 KNOWN_BACKBONES = sorted(RESNET_REPS) + ["vgg16"]
 KNOWN_ARCHITECTURES = ["Unet", "FPN", "Linknet", "PSPNet", "DeepLabV3"]
-DEEPLAB_BACKBONES = ["mobilenetv2"]   # impl/deeplab/model.py:324-326 also names 'xception' (not built)
+DEEPLAB_BACKBONES = ["mobilenetv2", "xception"]   # impl/deeplab/model.py:324-326
 # MobileNetV2 feature extractor of the reference's DeepLabV3+ (impl/deeplab/model.py:386-433): (filters, stride, expansion,
 # block_id, skip_connection, atrous rate); strides after block 3 are replaced by rates (output stride 8)
 MOBILENETV2_BLOCKS = (
@@ -53,13 +53,13 @@ class SegNet(E.Net):
                  enc_init="he_uniform", dec_init="glorot_uniform", loss=(1.0, 0.0, 0.0), architecture="Unet",
                  decoder_block_type="upsampling", pyramid_block_filters=256, segmentation_block_filters=128,
                  dropout=None, precision="bf16", decoder_use_batchnorm=True, downsample_factor=8, psp_conv_filters=512,
-                 activation="sigmoid"):
+                 activation="sigmoid", OS=16):
         super().__init__(batch, device, seed, precision)
         self.dec_bn = bool(decoder_use_batchnorm)
         backbone = backbone.lower()
         if architecture == "DeepLabV3":
             self._build_deeplabv3(backbone, classes, input_shape, batch, activation, loss,
-                                  0.1 if dropout is None else float(dropout))
+                                  0.1 if dropout is None else float(dropout), int(OS))
             return
         if architecture not in KNOWN_ARCHITECTURES:
             print("Unknown architecture:" + str(architecture))
@@ -370,7 +370,7 @@ class SegNet(E.Net):
         self.loss = E.Loss(self, self.head, self.mask, *loss)
         self.finalize()
 
-    def _build_deeplabv3(self, backbone, classes, input_shape, batch, activation, loss, dropout):
+    def _build_deeplabv3(self, backbone, classes, input_shape, batch, activation, loss, dropout, OS=16):
         """DeepLabV3+ over MobileNetV2, the model the reference ships in-tree and registers as architecture `DeepLabV3`
         (impl/deeplab/model.py:278-505, segmentation.py:31-33; all five example configs use it): Conv 3x3/2 + BN + ReLU6, 17
         inverted-residual blocks (1x1 expand -> 3x3 depthwise (stride / atrous rate) -> 1x1 project, BatchNorm eps 1e-3
@@ -381,7 +381,9 @@ class SegNet(E.Net):
         if backbone not in DEEPLAB_BACKBONES:
             print("Unknown backbone:" + backbone)
             print("Known backbones:", DEEPLAB_BACKBONES)
-            raise ValueError("Unknown backbone" if backbone != "xception" else "DeepLabV3: the xception backbone is not built")
+            raise ValueError("Unknown backbone")
+        if backbone == "xception":
+            return self._build_deeplabv3_xception(classes, input_shape, batch, activation, loss, dropout, OS)
         H, W, CI = input_shape
         if H % 8 or W % 8:
             raise ValueError("DeepLabV3: input height/width must be divisible by 8 (output stride of the feature extractor)")
@@ -443,6 +445,120 @@ class SegNet(E.Net):
         E.BNRelu(self, cp, cpr, "concat_projection_BN", ASPP_EPS)
         self.dropout = E.Dropout(self, cpr, dropout, salt=0xD0)
         self.head = E.ProbHead(self, cpr, classes, (H, W), activation or "none",
+                               "logits_semantic" if classes == 21 else "custom_logits_semantic", init=init)
+        self.loss = E.Loss(self, self.head, self.mask, *loss)
+        self.finalize()
+
+    def _sepconv_bn(self, x, filters, prefix, stride=1, rate=1, depth_activation=False, eps=1e-3, out=None):
+        """SepConv_BN of impl/deeplab/model.py:110-147: [ReLU] -> depthwise 3x3 (stride > 1: explicit padding + 'valid') -> BN
+        [-> ReLU] -> 1x1 -> BN [-> ReLU]; `out` = destination of the last BatchNorm (e.g. a concat slice)."""
+        N = self.batch
+        t = x
+        if not depth_activation:
+            t = E.Buf(self, N, x.h, x.w, x.c, name=prefix + "_relu")
+            E.Relu(self, x, t)
+        ho, wo = -(-x.h // stride), -(-x.w // stride)
+        d = E.Buf(self, N, ho, wo, x.c, name=prefix + "_depthwise")
+        E.DWConv(self, t, d, prefix + "_depthwise", 3, stride=stride, dilation=rate, pad=None if stride == 1 else rate)
+        db = E.Buf(self, N, ho, wo, x.c, name=prefix + "_depthwise_BN")
+        E.BNRelu(self, d, db, prefix + "_depthwise_BN", eps, relu=depth_activation)
+        p = E.Buf(self, N, ho, wo, filters, name=prefix + "_pointwise")
+        E.Conv(self, db, p, prefix + "_pointwise", 1, init="glorot_uniform")
+        pb = out if out is not None else E.Buf(self, N, ho, wo, filters, name=prefix + "_pointwise_BN")
+        E.BNRelu(self, p, pb, prefix + "_pointwise_BN", eps, relu=depth_activation)
+        return pb
+
+    def _xception_block(self, x, depth_list, prefix, skip_type, stride, rate=1, depth_activation=False):
+        """_xception_block of impl/deeplab/model.py:177-216; returns (outputs, skip = tensor after the second SepConv)"""
+        N = self.batch
+        r, skip = x, None
+        for i in range(3):
+            r = self._sepconv_bn(r, depth_list[i], prefix + "_separable_conv%d" % (i + 1), stride=stride if i == 2 else 1, rate=rate,
+                                 depth_activation=depth_activation)
+            if i == 1:
+                skip = r
+        if skip_type == "none":
+            return r, skip
+        out = E.Buf(self, N, r.h, r.w, r.c, name=prefix)
+        if skip_type == "conv":
+            sc = E.Buf(self, N, r.h, r.w, r.c, name=prefix + "_shortcut")
+            E.Conv(self, x, sc, prefix + "_shortcut", 1, stride=stride, pad=0, init="glorot_uniform")
+            scb = E.Buf(self, N, r.h, r.w, r.c, name=prefix + "_shortcut_BN")
+            E.BNRelu(self, sc, scb, prefix + "_shortcut_BN", 1e-3, relu=False)
+            E.Add(self, r, scb, out)
+        else:
+            E.Add(self, r, x, out)
+        return out, skip
+
+    def _build_deeplabv3_xception(self, classes, input_shape, batch, activation, loss, dropout, OS):
+        """DeepLabV3+ over the modified aligned Xception of the reference's in-tree model (impl/deeplab/model.py:339-383 entry /
+        middle (16 units) / exit flow; ASPP with image pooling, 1x1 and three atrous separable branches :457-481; decoder with the
+        1/4-resolution skip :488-498; probability head :494-500).  OS = 16 (schema default) or 8 (:340-349)."""
+        if OS not in (8, 16):
+            raise ValueError("DeepLabV3 / xception: OS must be 8 or 16")
+        H, W, CI = input_shape
+        if H % 16 or W % 16:
+            raise ValueError("DeepLabV3 / xception: input height/width must be divisible by 16")
+        if not 1 <= CI <= 4:
+            raise NotImplementedError("input channels: 1..4 are built (uint8 augmentation / stem kernels); shape[2] = %d" % CI)
+        N = batch
+        self.architecture, self.input_shape, self.classes, self.backbone = "DeepLabV3", (H, W, CI), classes, "xception"
+        self.img = E.Buf(self, N, H, W, CI, E.U8, name="image")
+        self.mask = E.Buf(self, N, H, W, classes, E.U8, name="mask")
+        s3, mid, ex = (1, 2, (2, 4)) if OS == 8 else (2, 1, (1, 2))
+        rates = (12, 24, 36) if OS == 8 else (6, 12, 18)
+        init = "glorot_uniform"
+        x0 = E.Buf(self, N, H, W, 8, name="input_bf16")
+        E.InputCast(self, self.img, x0)
+        h, w = H // 2, W // 2
+        z = E.Buf(self, N, h, w, 32, name="entry_flow_conv1_1")
+        E.Conv(self, x0, z, "entry_flow_conv1_1", 3, stride=2, pad=0, init=init, needs_dgrad=False, cin_real=CI)   # TF 'same', even size
+        a = E.Buf(self, N, h, w, 32, name="entry_flow_conv1_1_relu")
+        E.BNRelu(self, z, a, "entry_flow_conv1_1_BN", 1e-3)
+        z = E.Buf(self, N, h, w, 64, name="entry_flow_conv1_2")
+        E.Conv(self, a, z, "entry_flow_conv1_2", 3, pad=1, init=init)
+        x = E.Buf(self, N, h, w, 64, name="entry_flow_conv1_2_relu")
+        E.BNRelu(self, z, x, "entry_flow_conv1_2_BN", 1e-3)
+        x, _ = self._xception_block(x, [128, 128, 128], "entry_flow_block1", "conv", 2)
+        x, skip1 = self._xception_block(x, [256, 256, 256], "entry_flow_block2", "conv", 2)
+        x, _ = self._xception_block(x, [728, 728, 728], "entry_flow_block3", "conv", s3)
+        for i in range(16):
+            x, _ = self._xception_block(x, [728, 728, 728], "middle_flow_unit_%d" % (i + 1), "sum", 1, rate=mid)
+        x, _ = self._xception_block(x, [728, 1024, 1024], "exit_flow_block1", "conv", 1, rate=ex[0])
+        x, _ = self._xception_block(x, [1536, 1536, 2048], "exit_flow_block2", "none", 1, rate=ex[1], depth_activation=True)
+        self.encoder_param_names = list(self.params.keys())
+        EPS = 1e-5
+        h, w = x.h, x.w
+        cat = E.Buf(self, N, h, w, 5 * 256, name="aspp_concat")
+        gp = E.Buf(self, N, 1, 1, x.c, name="image_pooling_avg")
+        E.GlobalAvgPool(self, x, gp)
+        ip = E.Buf(self, N, 1, 1, 256, name="image_pooling")
+        E.Conv(self, gp, ip, "image_pooling", 1, init=init)
+        ipr = E.Buf(self, N, 1, 1, 256, name="image_pooling_relu")
+        E.BNRelu(self, ip, ipr, "image_pooling_BN", EPS)
+        E.Broadcast(self, ipr, cat.slice(0, 256, name="image_pooling_up"))
+        a0 = E.Buf(self, N, h, w, 256, name="aspp0")
+        E.Conv(self, x, a0, "aspp0", 1, init=init)
+        E.BNRelu(self, a0, cat.slice(256, 256, name="aspp0_activation"), "aspp0_BN", EPS)
+        for k, r in enumerate(rates):
+            self._sepconv_bn(x, 256, "aspp%d" % (k + 1), rate=r, depth_activation=True, eps=EPS,
+                             out=cat.slice(512 + 256 * k, 256, name="aspp%d_out" % (k + 1)))
+        cp = E.Buf(self, N, h, w, 256, name="concat_projection")
+        E.Conv(self, cat, cp, "concat_projection", 1, init=init)
+        cpr = E.Buf(self, N, h, w, 256, name="concat_projection_relu")
+        E.BNRelu(self, cp, cpr, "concat_projection_BN", EPS)
+        self.dropout = E.Dropout(self, cpr, dropout, salt=0xD0)
+        # DeepLab v3+ decoder at 1/4 resolution
+        h4, w4 = H // 4, W // 4
+        cat2 = E.Buf(self, N, h4, w4, 256 + 48, name="decoder_concat")
+        E.Resize(self, cpr, cat2.slice(0, 256, name="decoder_up"), align_corners=True)
+        fp = E.Buf(self, N, h4, w4, 48, name="feature_projection0")
+        E.Conv(self, skip1, fp, "feature_projection0", 1, init=init)
+        E.BNRelu(self, fp, cat2.slice(256, 48, name="feature_projection0_relu"), "feature_projection0_BN", EPS)
+        y = self._sepconv_bn(cat2, 256, "decoder_conv0", depth_activation=True, eps=EPS)
+        y = self._sepconv_bn(y, 256, "decoder_conv1", depth_activation=True, eps=EPS)
+        self.bufs.setdefault("decoder_conv1", y)
+        self.head = E.ProbHead(self, y, classes, (H, W), activation or "none",
                                "logits_semantic" if classes == 21 else "custom_logits_semantic", init=init)
         self.loss = E.Loss(self, self.head, self.mask, *loss)
         self.finalize()

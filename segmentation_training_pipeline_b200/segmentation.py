@@ -350,8 +350,6 @@ class PipelineConfig:
             raise ValueError("Unknown architecture")
         bb = str(self.backbone).lower()
         deeplab = arch == "DeepLabV3"   # the reference's in-tree model (custom_models, segmentation.py:31-33; impl/deeplab/model.py)
-        if deeplab and bb == "xception":
-            raise NotImplementedError("backbone: xception is not built for DeepLabV3 (mobilenetv2 is; impl/deeplab/model.py:324-326)")
         known = _models.DEEPLAB_BACKBONES if deeplab else _models.KNOWN_BACKBONES
         if bb not in known:
             print("Unknown backbone:" + bb)
@@ -386,7 +384,7 @@ class PipelineConfig:
             if deeplab and cand == "pascal_voc":
                 # the reference fetches this file into ~/.keras/models (impl/deeplab/model.py:505-512) and loads it by layer
                 # name; the same arrays as .npz (scripts/keras_h5_to_npz.py converts) are looked up in the same places
-                stem = "deeplabv3_mobilenetv2_tf_dim_ordering_tf_kernels.npz"
+                stem = "deeplabv3_%s_tf_dim_ordering_tf_kernels.npz" % bb
                 names += [os.path.join(base, stem), os.path.join(os.path.expanduser("~"), ".keras", "models", stem)]
             for c in names:
                 if os.path.isfile(c):
@@ -406,7 +404,7 @@ class PipelineConfig:
                               downsample_factor=int(mk.get("downsample_factor") or 8),
                               psp_conv_filters=int(mk.get("psp_conv_filters") or 512),
                               precision=str(self.extra.get("precision", "bf16")),
-                              activation=self.activation, loss=lw)
+                              activation=self.activation, OS=int(mk.get("OS") or 16), loss=lw)
         net.activation = self.activation or "linear"   # what predict applies to the logits
         if enc_file is not None and deeplab:
             # model.load_weights(path, by_name=True): every layer whose name and shapes match, ASPP included; the class layer
@@ -493,7 +491,8 @@ class PipelineConfig:
             only("final_interpolation", ("bilinear",), "logits are upsampled bilinearly")
             only("downsample_factor", (4, 8, 16), "feature layers at 1/4, 1/8 or 1/16")
         elif arch == "DeepLabV3":
-            only("alpha", (1, 1.0), "MobileNetV2 width multiplier 1")   # OS is xception-only in the reference (model.py:384-385)
+            only("alpha", (1, 1.0), "MobileNetV2 width multiplier 1")   # OS applies to xception only (model.py:339-349, 384-385)
+            only("OS", (8, 16), "output stride 8 or 16")
         elif arch == "Linknet":
             only("use_batchnorm", (True,), "the Linknet blocks are conv + BatchNorm + ReLU")
             only("n_upsample_blocks", (5,), "the decoder has one block per encoder stage")

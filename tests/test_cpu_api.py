@@ -441,8 +441,14 @@ def test_create_net_key_validation(tmp_path):
     # DeepLabV3: the reference's in-tree model over mobilenetv2 (impl/deeplab/model.py); segmentation backbones do not apply
     with pytest.raises(ValueError, match="Unknown backbone"):
         cfg(architecture="DeepLabV3").createNet()
-    with pytest.raises(NotImplementedError, match="xception"):
-        cfg(architecture="DeepLabV3", backbone="xception").createNet()
+    with pytest.raises(NotImplementedError, match="OS"):
+        cfg(architecture="DeepLabV3", backbone="xception", OS=32).createNet()
+    xc = cfg(architecture="DeepLabV3", backbone="xception", OS=8).createNet()     # the other backbone of impl/deeplab/model.py
+    wx = xc.get_weights()
+    assert wx["middle_flow_unit_16_separable_conv3_pointwise/kernel"].shape == (1, 1, 728, 728)
+    assert wx["exit_flow_block2_separable_conv3_depthwise/depthwise_kernel"].shape == (3, 3, 1536, 1)
+    assert wx["feature_projection0/kernel"].shape == (1, 1, 256, 48) and wx["decoder_conv1_pointwise/kernel"].shape == (1, 1, 256, 256)
+    assert sum(v.size for k, v in wx.items() if "moving_" not in k) == 41050273
     with pytest.raises(NotImplementedError, match="alpha"):
         cfg(architecture="DeepLabV3", backbone="mobilenetv2", alpha=0.5).createNet()
     with pytest.raises(NotImplementedError, match="cannot be downloaded"):

@@ -206,6 +206,25 @@ def test_deeplab_oracle_graph_follows_the_reference_source():
     assert p.shape == (1, 32, 48, 3) and float((p.sum(-1) - 1).abs().max()) < 1e-5
 
 
+def test_deeplab_xception_oracle_graph():
+    """modified aligned Xception + ASPP + decoder (impl/deeplab/model.py:339-383, 457-500): parameter count of the Keras model
+    (41 050 273 trainable for one class), Keras layer names, explicit (1, 1) padding of the stride-2 separable convs"""
+    import torch
+    from oracle.models import SegModel
+    m = SegModel("DeepLabV3", "xception", classes=1, input_shape=(64, 64, 3), seed=1)
+    assert sum(p.numel() for p in m.params.values()) == 41050273
+    for k in ("entry_flow_conv1_1/kernel", "entry_flow_block2_shortcut/kernel", "middle_flow_unit_16_separable_conv3_pointwise/kernel",
+              "exit_flow_block2_separable_conv3_pointwise_BN/gamma", "aspp3_depthwise/depthwise_kernel", "feature_projection0_BN/beta",
+              "decoder_conv1_pointwise/kernel", "custom_logits_semantic/bias"):
+        assert k in m.params, k
+    y = m(torch.rand(1, 64, 64, 3) * 255)
+    assert y.shape == (1, 64, 64, 1) and m.taps["logits_small"].shape == (1, 1, 16, 16)      # decoder works at 1/4 resolution
+    assert m.taps["exit_flow_block1"].shape[-1] == 4                                           # output stride 16
+    m8 = SegModel("DeepLabV3", "xception", classes=1, input_shape=(64, 64, 3), OS=8)
+    m8(torch.rand(1, 64, 64, 3) * 255)
+    assert m8.taps["exit_flow_block1"].shape[-1] == 8
+
+
 def test_depthwise_same_padding_and_dropout_mask():
     import torch
     from oracle import nn as L

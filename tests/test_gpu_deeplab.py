@@ -342,3 +342,103 @@ def test_deeplab_loss_curve_fp32_parity_mode(cuda, lr, mom):
     assert d_engine.max() < max(1e-3, 2.0 * d_oracle.max()), (d_engine.max(), d_oracle.max())
     assert d_pair.max() < max(1e-3, 2.0 * d_oracle.max()), (d_pair.max(), d_oracle.max())
     assert c[-5:].mean() < c[:3].mean()
+
+
+@pytest.mark.parametrize("OS", [16, 8])
+def test_deeplab_xception_fp32_parity_mode(cuda, OS):
+    """The other backbone of the reference's in-tree model (impl/deeplab/model.py:339-383: modified aligned Xception, 41 M
+    parameters; ASPP with three atrous separable branches, decoder with the 1/4-resolution skip): fp32 parity mode against the fp64
+    oracle -- probabilities, loss, every parameter gradient -- for output stride 16 (schema default) and 8."""
+    from oracle import losses as OL
+    from oracle.models import SegModel
+    from segmentation_training_pipeline_b200 import lib
+    from segmentation_training_pipeline_b200.models import SegNet
+    from segmentation_training_pipeline_b200.trainer import Trainer
+
+    n, size, dropout = 2, 64, 0.1
+    net = SegNet("xception", classes=1, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=(1.0, 1.0, 0.0),
+                 architecture="DeepLabV3", dropout=dropout, precision="fp32", OS=OS)
+    W = _perturb(net.get_weights())
+    net.set_weights(W)
+    tr = Trainer(net)
+    img, mask = _data(n, size, size)
+    tr.set_batch(img.cuda(), mask.cuda())
+    net.prep_weights()
+    net.forward()
+    net.backward()
+    torch.cuda.synchronize()
+    res = net.loss.result.cpu().numpy()
+    prob = torch.sigmoid(net.head.logits.cpu().view(n, size, size, 1).double())
+    grads = net.get_grads()
+
+    def run(storage):
+        om = SegModel("DeepLabV3", "xception", classes=1, input_shape=(size, size, 3), storage=storage, update_moving=False,
+                      dropout=(dropout, net.seed, 0xD0, 0), OS=OS)
+        assert set(om.params.keys()) == set(net.params.keys())
+        om.load_numpy(W)
+        y = om(img.float())
+        lo = OL.binary_crossentropy(mask.float(), y) + OL.dice_loss(mask.float(), y)
+        lo.backward()
+        return y.detach().double(), float(lo.detach()), {k: p.grad.double().numpy().copy() for k, p in om.params.items()}
+
+    y64, lo64, g64 = run("fp64")
+    y32, lo32, g32 = run("fp32")
+    err, err32 = float((prob - y64).norm() / y64.norm()), float((y32 - y64).norm() / y64.norm())
+    print("xception OS%d fp32 parity mode vs fp64 anchor: probabilities rel err %.3e (fp32 oracle %.3e), loss %.7f vs %.7f" %
+          (OS, err, err32, float(res[lib.L_LOSS]), lo64))
+    assert err < max(1e-4, 2.0 * err32)
+    assert abs(float(res[lib.L_LOSS]) - lo64) < 1e-5 * max(1.0, abs(lo64))
+    ratios, worst = [], ("", 0.0, 0.0)
+    for k, go in g64.items():
+        ge = grads[k].astype(np.float64)
+        if np.linalg.norm(go) < 1e-9 * go.size ** 0.5:
+            continue
+        den = np.linalg.norm(go) + 1e-30
+        e, floor = float(np.linalg.norm(ge - go) / den), float(np.linalg.norm(g32[k] - go) / den)
+        if e > worst[1]:
+            worst = (k, e, floor)
+        ratios.append(e / max(floor, 1e-7))
+        assert e < max(2e-4, 5.0 * floor), (k, e, floor)
+    print("worst gradient: %s engine-vs-fp64 %.3e, fp32-oracle-vs-fp64 %.3e; median ratio %.2f" % (worst + (float(np.median(ratios)),)))
+    assert float(np.median(ratios)) < 2.0
+
+
+def test_deeplab_xception_bf16_step(cuda):
+    """product path (bf16, tcgen05 where the shapes allow): forward / loss against the bf16-storage oracle within the bf16 floor,
+    and a few Adam steps under the CUDA graph reduce the loss"""
+    from oracle import losses as OL
+    from oracle.models import SegModel
+    from segmentation_training_pipeline_b200 import lib
+    from segmentation_training_pipeline_b200.models import SegNet
+    from segmentation_training_pipeline_b200.trainer import Trainer
+    n, size = 4, 64
+    net = SegNet("xception", classes=1, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0, loss=(1.0, 0.0, 0.0),
+                 architecture="DeepLabV3", dropout=0.0)
+    W = _perturb(net.get_weights())
+    net.set_weights(W)
+    tr = Trainer(net, optimizer="Adam", lr=1e-3)
+    img, mask = _data(n, size, size)
+    tr.set_batch(img.cuda(), mask.cuda())
+    net.prep_weights()
+    net.forward()
+    torch.cuda.synchronize()
+    prob = torch.sigmoid(net.head.logits.cpu().view(n, size, size, 1))
+    loss0 = float(net.loss.result.cpu()[lib.L_LOSS])
+    ys = {}
+    for st in ("bf16", "fp32"):
+        om = SegModel("DeepLabV3", "xception", classes=1, input_shape=(size, size, 3), storage=st, update_moving=False)
+        om.load_numpy(W)
+        with torch.no_grad():
+            ys[st] = om(img.float())
+    floor = float((ys["bf16"] - ys["fp32"]).norm() / ys["fp32"].norm())
+    err = float((prob - ys["bf16"]).norm() / ys["bf16"].norm())
+    lo = float(OL.binary_crossentropy(mask.float(), ys["bf16"]))
+    print("xception bf16: probabilities rel err %.4f, bf16-vs-fp32 floor %.4f, loss %.5f vs %.5f" % (err, floor, loss0, lo))
+    assert err < max(5e-3, 0.8 * floor)
+    tr.set_pool(img, mask)
+    tr.capture()
+    c = []
+    for _ in range(25):
+        tr.step()
+        c.append(tr.loss_value())
+    assert np.isfinite(c).all() and c[-1] < 0.9 * c[0], c
