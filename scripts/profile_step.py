@@ -13,10 +13,17 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--size", type=int, default=512)
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--backbone", default="resnet34")
+ap.add_argument("--config", default="c2", choices=["c2", "people"], help="people: DeepLabV3/mobilenetv2 320x320 (examples/people/people.yaml)")
 a = ap.parse_args()
 torch.cuda.set_device(0)
-net = SegNet(a.backbone, classes=1, input_shape=(a.size, a.size, 3), batch=a.batch, device="cuda:0", seed=0, loss=(1.0, 1.0, 0.0))
-tr = Trainer(net, optimizer="Adam", lr=1e-3, augment=AugmentConfig(seed=0, **C2_AUGMENT))
+if a.config == "people":
+    a.size = 320
+    net = SegNet("mobilenetv2", classes=1, input_shape=(a.size, a.size, 3), batch=a.batch, device="cuda:0", seed=0, loss=(1.0, 0.0, 0.0),
+                 architecture="DeepLabV3")
+    tr = Trainer(net, optimizer="Adam", lr=1e-3, augment=AugmentConfig(seed=0, fliplr=0.5))
+else:
+    net = SegNet(a.backbone, classes=1, input_shape=(a.size, a.size, 3), batch=a.batch, device="cuda:0", seed=0, loss=(1.0, 1.0, 0.0))
+    tr = Trainer(net, optimizer="Adam", lr=1e-3, augment=AugmentConfig(seed=0, **C2_AUGMENT))
 img, mask = synth_pool(a.batch, a.size, a.size, 1234, 4321)
 tr.set_pool(torch.from_numpy(img), torch.from_numpy(mask))
 l0 = net.L.launch_count()

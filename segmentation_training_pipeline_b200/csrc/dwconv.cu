@@ -269,12 +269,24 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const DwP p, const __
     }
   }
 }
-__global__ void dwconv_wgrad_final_kernel(const float* __restrict__ partial, int nblk, int n_out, float* __restrict__ dw) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_out) return;
+// dw[i] = sum over the pixel chunks of partial[chunk][i], fixed order, double.  Block = 32 outputs x 8 chunk lanes (coalesced
+// 128-byte reads of the partial rows); the first version had ONE thread walk all chunks of an output: 20 us per layer, 3 % of the
+// DeepLabV3 step (profiles/r2_people_launches.summary.txt).
+__global__ void __launch_bounds__(256) dwconv_wgrad_final_kernel(const float* __restrict__ partial, int nblk, int n_out, float* __restrict__ dw) {
+  __shared__ double sm[8][33];
+  const int ol = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + ol;
   double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += (double)partial[(int64_t)b * n_out + i];
-  dw[i] = (float)s;
+  if (i < n_out)
+    for (int b = lane; b < nblk; b += 8) s += (double)partial[(int64_t)b * n_out + i];
+  sm[lane][ol] = s;
+  __syncthreads();
+  if (lane == 0 && i < n_out) {
+    double t = 0.0;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) t += sm[l][ol];
+    dw[i] = (float)t;
+  }
 }
 
 static int dw_grid(int64_t total) {
@@ -424,6 +436,6 @@ extern "C" int stp_dwconv_wgrad(const stp_dwconv_desc* d, const stp_tensor* x, c
   rc = check_launch("dwconv_wgrad");
   if (rc) return rc;
   const int n_out = d->k * d->k * x->c;
-  dwconv_wgrad_final_kernel<<<(n_out + 255) / 256, 256, 0, st>>>((const float*)workspace, nblk, n_out, dw_rsc);
+  dwconv_wgrad_final_kernel<<<(n_out + 31) / 32, 256, 0, st>>>((const float*)workspace, nblk, n_out, dw_rsc);
   return check_launch("dwconv_wgrad_final");
 }
