@@ -274,7 +274,8 @@ def apply_crop_pad(image: np.ndarray, mask: np.ndarray, win, H: int, W: int):
 # the CPU twin of csrc/augment.cu augment_pixel_ops_kernel: same Philox counters, same fp32 operation order.
 # ops: (kind, per_channel, a, b, group_id, group_size, group_member); kinds per include/stp.h STP_PIX_*.
 # ----------------------------------------------------------------------------------------------
-def apply_pixel_ops(img: np.ndarray, ops, seed: int, step: int, sid: int, p: SampleParams, mul_rint: bool = False) -> np.ndarray:
+def apply_pixel_ops(img: np.ndarray, ops, seed: int, step: int, sid: int, p: SampleParams, mul_rint: bool = False,
+                    k_base: int = 0) -> np.ndarray:
     f32 = np.float32
     H, W, CI = img.shape
     v = img.astype(np.int64).reshape(-1, CI)
@@ -282,7 +283,7 @@ def apply_pixel_ops(img: np.ndarray, ops, seed: int, step: int, sid: int, p: Sam
     key = (seed & philox.MASK, (seed >> 32) & philox.MASK)
     s_lo, s_hi = step & philox.MASK, (step >> 32) & philox.MASK
     u24 = lambda w: ((w >> np.uint64(8)).astype(np.float32) * f32(5.9604644775390625e-08)).astype(np.float32)
-    for k, (kind, per_channel, a, b, gid, gsz, gm) in enumerate(ops):
+    for k, (kind, per_channel, a, b, gid, gsz, gm) in enumerate(ops, start=k_base):   # k = position in the whole colour block
         ri = philox.philox4x32((s_lo, sid, 32 + k, s_hi), key)
         if gsz > 0:
             rg = philox.philox4x32((s_lo, sid, 32 + 16 + gid, s_hi), key)
@@ -330,3 +331,140 @@ def apply_pixel_ops(img: np.ndarray, ops, seed: int, step: int, sid: int, p: Sam
                     fv = (v[:, c].astype(np.float32) + (z * par).astype(np.float32)).astype(np.float32)
                     v[:, c] = np.clip(np.rint(fv), 0, 255).astype(np.int64)
     return v.reshape(H, W, CI).astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------------------------
+# Neighbourhood augmenters (schemas/augmenters.raml:97-112, 117-119 -> imgaug 0.3.0 GaussianBlur / AverageBlur / MedianBlur /
+# Sharpen / Emboss / EdgeDetect [DEP, recalled] -> cv2.GaussianBlur / cv2.blur / cv2.medianBlur / cv2.filter2D): the CPU twin of
+# csrc/augment_nb.cu.  The cv2 ARITHMETIC restated below is pinned against the real cv2 of this image (tests/test_cpu_oracle.py
+# ::test_neighbourhood_arithmetic_is_pinned_against_real_cv2); the imgaug parameter conventions are recalled.
+# op: (kind, a, b, c, d, k_index, group_id, group_size, group_member); kinds per include/stp.h STP_NB_*.
+# ----------------------------------------------------------------------------------------------
+def gaussian_ksize_imgaug(sigma: float) -> int:
+    k = 3.3 * sigma if sigma < 3.0 else (2.9 * sigma if sigma < 5.0 else 2.6 * sigma)
+    k = int(max(k, 5))
+    return k + 1 if k % 2 == 0 else k
+
+
+def gaussian_kernel_fixed(ksize: int, sigma: float) -> np.ndarray:
+    """cv2's 8.8 fixed-point Gaussian kernel for uint8 images: round(k_i * 256) with error diffusion from the border inwards,
+    the centre takes the remainder (sum == 256)."""
+    x = np.arange(ksize, dtype=np.float64) - (ksize - 1) * 0.5
+    kd = np.exp((-0.5 / (sigma * sigma)) * x * x)
+    kd = kd * (1.0 / kd.sum())
+    out = np.zeros(ksize, np.int64)
+    err, s2 = 0.0, 0
+    for i in range(ksize // 2):
+        adj = kd[i] * 256.0 + err
+        v = int(math.floor(adj + 0.5))
+        err = adj - v
+        out[i] = out[ksize - 1 - i] = v
+        s2 += 2 * v
+    out[ksize // 2] = 256 - s2
+    return out
+
+
+def _window_stack(img2d: np.ndarray, kh: int, kw: int, ay: int, ax: int, mode: str):
+    p = np.pad(img2d, ((ay, kh - 1 - ay), (ax, kw - 1 - ax)), mode=mode)
+    h, w = img2d.shape
+    return [[p[a:a + h, b:b + w] for b in range(kw)] for a in range(kh)]
+
+
+def gaussian_blur_u8(img: np.ndarray, ksize: int, sigma: float) -> np.ndarray:
+    k = gaussian_kernel_fixed(ksize, sigma)
+    out = np.empty_like(img)
+    for c in range(img.shape[2]):
+        win = _window_stack(img[..., c].astype(np.int64), ksize, ksize, ksize // 2, ksize // 2, "reflect")
+        acc = sum(k[a] * sum(k[b] * win[a][b] for b in range(ksize)) for a in range(ksize))
+        out[..., c] = np.clip((acc + 32768) >> 16, 0, 255)
+    return out
+
+
+def average_blur_round_up_from(k: int) -> int:
+    """smallest residue of the window sum modulo k^2 that cv2.blur rounds UP (measured on OpenCV 4.13 for k = 2..17, every pixel
+    of random images consistent): round half up, except for k a power of two where the shift path rounds up one residue earlier
+    (out = (sum + k^2/2 + 1) >> log2(k^2))"""
+    kk = k * k
+    return kk // 2 - 1 if (k & (k - 1)) == 0 else (kk + 1) // 2
+
+
+def average_blur_u8(img: np.ndarray, k: int) -> np.ndarray:
+    out = np.empty_like(img)
+    for c in range(img.shape[2]):
+        win = _window_stack(img[..., c].astype(np.int64), k, k, k // 2, k // 2, "reflect")
+        acc = sum(win[a][b] for a in range(k) for b in range(k))
+        out[..., c] = acc // (k * k) + (acc % (k * k) >= average_blur_round_up_from(k))
+    return out
+
+
+def median_blur_u8(img: np.ndarray, k: int) -> np.ndarray:
+    out = np.empty_like(img)
+    for c in range(img.shape[2]):
+        win = _window_stack(img[..., c], k, k, k // 2, k // 2, "edge")
+        st = np.stack([win[a][b] for a in range(k) for b in range(k)], 0)
+        out[..., c] = np.sort(st, axis=0)[(k * k) // 2]
+    return out
+
+
+def filter2d_3x3_u8(img: np.ndarray, mat: np.ndarray) -> np.ndarray:
+    """cv2.filter2D(uint8 image, -1, float32 3x3 kernel): acc = fma(k, x, acc) in float32, row-major over the non-zero taps (the
+    AVX2 / FMA3 build of OpenCV 4.13 fuses the multiply-add; separate multiply and add differs by 1 on ~0.1 % of the pixels).
+    The fused operation is emulated in float64: a float32 product is exact there."""
+    f32 = np.float32
+    out = np.empty_like(img)
+    for c in range(img.shape[2]):
+        win = _window_stack(img[..., c].astype(np.float32), 3, 3, 1, 1, "reflect")
+        acc = np.zeros(img.shape[:2], np.float32)
+        for a in range(3):
+            for b in range(3):
+                if f32(mat[a, b]) != 0:
+                    acc = (acc.astype(np.float64) + np.float64(f32(mat[a, b])) * win[a][b].astype(np.float64)).astype(np.float32)
+        out[..., c] = np.clip(np.rint(acc), 0, 255)
+    return out
+
+
+def neighbourhood_params(op, seed: int, step: int, sid: int):
+    """(active, kind-specific parameters) of one sample: the draws of csrc/augment_nb.cu nb_prep_kernel"""
+    kind, a, b, c, d, k_index, gid, gsz, gm = op
+    f32 = np.float32
+    key = (seed & philox.MASK, (seed >> 32) & philox.MASK)
+    s_lo, s_hi = step & philox.MASK, (step >> 32) & philox.MASK
+    if gsz > 0:
+        rg = philox.philox4x32((s_lo, sid, 32 + 16 + gid, s_hi), key)
+        if min(int(math.floor(philox.u53(rg[0], rg[1]) * gsz)), gsz - 1) != gm:
+            return False, None
+    ri = philox.philox4x32((s_lo, sid, 32 + k_index, s_hi), key)
+    u1, u2 = philox.u53(ri[0], ri[1]), philox.u53(ri[2], ri[3])
+    a, b, c, d = float(f32(a)), float(f32(b)), float(f32(c)), float(f32(d))
+    p1, p2 = a + u1 * (b - a), c + u2 * (d - c)
+    if kind == 0:
+        return (p1 >= 1e-3), ("gauss", min(gaussian_ksize_imgaug(p1), 25), p1)
+    if kind in (1, 2):
+        lo, hi = int(a), int(b)
+        k = min(lo + int(math.floor(u1 * (hi - lo + 1))), hi)
+        if kind == 2 and k % 2 == 0:
+            k += 1
+        return (k > 1), ("avg" if kind == 1 else "median", k)
+    alpha, c1 = f32(p1), f32(1.0 - p1)
+    if kind == 3:
+        eff = np.array([[-1, -1, -1], [-1, f32(8.0 + p2), -1], [-1, -1, -1]], np.float32)
+    elif kind == 4:
+        eff = np.array([[f32(-1.0 - p2), f32(0.0 - p2), 0], [f32(0.0 - p2), 1, f32(0.0 + p2)], [0, f32(0.0 + p2), f32(1.0 + p2)]], np.float32)
+    else:
+        eff = np.array([[0, 1, 0], [1, -4, 1], [0, 1, 0]], np.float32)
+    ident = np.array([[0, 0, 0], [0, 1, 0], [0, 0, 0]], np.float32)
+    mat = ((c1 * ident).astype(np.float32) + (alpha * eff).astype(np.float32)).astype(np.float32)
+    return True, ("filter", mat)
+
+
+def apply_neighbourhood_op(img: np.ndarray, op, seed: int, step: int, sid: int) -> np.ndarray:
+    active, par = neighbourhood_params(op, seed, step, sid)
+    if not active:
+        return img.copy()
+    if par[0] == "gauss":
+        return gaussian_blur_u8(img, par[1], par[2])
+    if par[0] == "avg":
+        return average_blur_u8(img, par[1])
+    if par[0] == "median":
+        return median_blur_u8(img, par[1])
+    return filter2d_3x3_u8(img, par[1])

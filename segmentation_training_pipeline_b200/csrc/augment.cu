@@ -262,7 +262,8 @@ __global__ void __launch_bounds__(256) augment_pixel_ops_kernel(uint8_t* __restr
     for (int k = 0; k < spec.n_ops; ++k) {
       const stp_aug_pix_op op = spec.ops[k];
       uint32_t ri[4];
-      philox4x32(s_lo, sid, 32u + (uint32_t)k, s_hi, k0, k1, ri);                  // per-image draws of this op
+      const uint32_t kk = (uint32_t)(spec.k_base + k);                             // position in the whole colour block
+      philox4x32(s_lo, sid, 32u + kk, s_hi, k0, k1, ri);                           // per-image draws of this op
       if (op.group_size > 0) {                                                     // OneOf: one member per sample
         uint32_t rg[4];
         philox4x32(s_lo, sid, 32u + 16u + (uint32_t)op.group_id, s_hi, k0, k1, rg);
@@ -300,8 +301,8 @@ __global__ void __launch_bounds__(256) augment_pixel_ops_kernel(uint8_t* __restr
         }
       } else {
         uint32_t rp[4], rq[4];
-        philox4x32(s_lo, sid, (pix << 8) | (64u + (uint32_t)k), s_hi, k0, k1, rp);
-        if (op.kind == STP_PIX_GAUSSIAN_NOISE) philox4x32(s_lo, sid, (pix << 8) | (64u + 128u + (uint32_t)k), s_hi, k0, k1, rq);
+        philox4x32(s_lo, sid, (pix << 8) | (64u + kk), s_hi, k0, k1, rp);
+        if (op.kind == STP_PIX_GAUSSIAN_NOISE) philox4x32(s_lo, sid, (pix << 8) | (64u + 128u + kk), s_hi, k0, k1, rq);
 #pragma unroll
         for (int c = 0; c < CI; ++c) {
           const int wi = pc ? (c & 3) : 0;
@@ -339,6 +340,7 @@ extern "C" int stp_augment_pixel_ops(uint8_t* d_img, const stp_aug_sample* d_par
   STP_REQUIRE(d_img && d_params && h_spec && d_step && n > 0 && h > 0 && w > 0, "augment_pixel_ops: bad args");
   STP_REQUIRE(c_img == 1 || c_img == 3 || c_img == 4, "augment_pixel_ops: c_img must be 1, 3 or 4");
   STP_REQUIRE(h_spec->n_ops >= 0 && h_spec->n_ops <= STP_PIX_MAX_OPS, "augment_pixel_ops: at most %d ops", STP_PIX_MAX_OPS);
+  STP_REQUIRE(h_spec->k_base >= 0 && h_spec->k_base + h_spec->n_ops <= 16, "augment_pixel_ops: k_base + n_ops <= 16");
   STP_REQUIRE((int64_t)h * w <= (1 << 24), "augment_pixel_ops: at most 2^24 pixels per image");
   for (int k = 0; k < h_spec->n_ops; ++k)
     STP_REQUIRE(h_spec->ops[k].kind >= STP_PIX_MULTIPLY && h_spec->ops[k].kind <= STP_PIX_GRAYSCALE, "augment_pixel_ops: unknown op kind");

@@ -69,7 +69,15 @@ class AugPixOp(C.Structure):               # include/stp.h: stp_aug_pix_op
 
 
 class AugPixSpec(C.Structure):             # include/stp.h: stp_aug_pix_spec
-    _fields_ = [("n_ops", C.c_int32), ("mul_rint", C.c_int32), ("ops", AugPixOp * 8)]
+    _fields_ = [("n_ops", C.c_int32), ("mul_rint", C.c_int32), ("ops", AugPixOp * 8), ("k_base", C.c_int32)]
+
+
+class AugNbOp(C.Structure):                # include/stp.h: stp_aug_nb_op
+    _fields_ = [("kind", C.c_int32), ("a", C.c_float), ("b", C.c_float), ("c", C.c_float), ("d", C.c_float), ("k_index", C.c_int32),
+                ("group_id", C.c_int32), ("group_size", C.c_int32), ("group_member", C.c_int32)]
+
+
+NB_KINDS = {"GaussianBlur": 0, "AverageBlur": 1, "MedianBlur": 2, "Sharpen": 3, "Emboss": 4, "EdgeDetect": 5}
 
 
 class CropPadOp(C.Structure):              # include/stp.h: stp_croppad_op
@@ -177,6 +185,8 @@ SIGNATURES = {
     "stp_loss_partial_floats": (_SZ, []),
     "stp_loss_bwd": (C.c_int, [_P, _P, _I64, C.POINTER(LossSpec), _P, _P, _P]),
     "stp_augment_pixel_ops": (C.c_int, [_P, _P, C.POINTER(AugPixSpec), C.c_uint64, _P, _I32, _I32, _I32, _I32, _P]),
+    "stp_augment_neighbourhood_workspace": (_SZ, [_I32]),
+    "stp_augment_neighbourhood": (C.c_int, [_P, _P, _P, C.POINTER(AugNbOp), C.c_uint64, _P, _I32, _I32, _I32, _I32, _P, _SZ, _P]),
     "stp_resize_u8": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _I32, _I32, _P]),
     "stp_croppad_draw": (C.c_int, [C.POINTER(CropPadSpec), C.c_uint64, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "stp_softmax_cce_fwd": (C.c_int, [_P, _P, _I64, _I32, _F, _I32, _P, _P, _P]),

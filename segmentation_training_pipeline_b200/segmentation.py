@@ -121,11 +121,14 @@ def parse_augmentation(spec: Optional[dict], seed: int = 0) -> AugmentConfig:
     # window per sample that the cv2-arithmetic resize brings back to `shape` (trainer.run_augment).
     rank = {"Pad": 0, "PadToFixedSize": 0, "CropToFixedSize": 0, "CropAndPad": 0,
             "Rotate90": 1, "Fliplr": 1, "Flipud": 1, "Affine": 2, "Multiply": 3, "Add": 3, "Invert": 3,
-            "AddElementwise": 3, "MultiplyElementwise": 3, "Dropout": 3, "AdditiveGaussianNoise": 3, "Grayscale": 3}
+            "AddElementwise": 3, "MultiplyElementwise": 3, "Dropout": 3, "AdditiveGaussianNoise": 3, "Grayscale": 3,
+            "GaussianBlur": 3, "AverageBlur": 3, "MedianBlur": 3, "Sharpen": 3, "Emboss": 3, "EdgeDetect": 3}
+    NB = ("GaussianBlur", "AverageBlur", "MedianBlur", "Sharpen", "Emboss", "EdgeDetect")
     for name in groups:
         if rank.get(name) != 3:
-            raise NotImplementedError("OneOf over '%s': only the pixel-wise augmenters (Multiply, Add, Invert, AddElementwise, "
-                                      "MultiplyElementwise, Dropout, AdditiveGaussianNoise, Grayscale) can be OneOf members" % name)
+            raise NotImplementedError("OneOf over '%s': only the colour-block augmenters (Multiply, Add, Invert, AddElementwise, "
+                                      "MultiplyElementwise, Dropout, AdditiveGaussianNoise, Grayscale, GaussianBlur, AverageBlur, "
+                                      "MedianBlur, Sharpen, Emboss, EdgeDetect) can be OneOf members" % name)
     last, colour = -1, []
     for name in spec:
         if name not in rank:
@@ -137,16 +140,40 @@ def parse_augmentation(spec: Optional[dict], seed: int = 0) -> AugmentConfig:
         if rank[name] == 3 and name in ("Multiply", "Add", "Invert"):
             colour.append({"Multiply": 0, "Add": 1, "Invert": 2}[name])
     cfg.color_order = tuple(colour + [o for o in (0, 1, 2) if o not in colour])
-    extended = [n for n in spec if rank.get(n) == 3 and n not in ("Multiply", "Add", "Invert")]
+    extended = [n for n in spec if rank.get(n) == 3 and n not in ("Multiply", "Add", "Invert")]   # incl. the neighbourhood augmenters
     if extended or groups:
         # pixel-wise colour stage in YAML order (csrc/augment.cu augment_pixel_ops_kernel)
         from . import lib as _lib
-        ops = []
+        ops, seq = [], []
         for name, val in spec.items():
             if rank.get(name) != 3:
                 continue
             v = val if isinstance(val, dict) else {}
             pc = float(v.get("per_channel", 0.0) or 0.0)
+            gid, gsz, gm = groups.get(name, (0, 0, 0))
+            if name in NB:
+                # neighbourhood augmenters (csrc/augment_nb.cu): (kind, a, b, c, d, group...) -- first / second parameter ranges
+                one = (lambda key, default: _rng(v.get(key, default) if isinstance(val, dict) else (val if val is not None else default)))
+                c = d = 0.0
+                if name == "GaussianBlur":
+                    a, b = one("sigma", 0.0)
+                    if not 0.0 <= a <= b or 2.6 * b >= 25:
+                        raise ValueError("GaussianBlur: sigma must lie in [0, 9.6)")
+                elif name in ("AverageBlur", "MedianBlur"):
+                    a, b = _rng(v.get("k", 1) if isinstance(val, dict) else val, int)
+                    if not 0 <= a <= b or b > (7 if name == "MedianBlur" else 31):
+                        raise ValueError("%s: k must lie in [0, %d]" % (name, 7 if name == "MedianBlur" else 31))
+                    a, b = (max(a, 1), max(b, 1)) if name == "MedianBlur" else (a, b)
+                else:
+                    a, b = _rng(v.get("alpha", 0.0) if isinstance(val, dict) else val)
+                    if not 0.0 <= a <= b <= 1.0:
+                        raise ValueError("%s: alpha must lie in [0, 1]" % name)
+                    if name == "Sharpen":
+                        c, d = _rng(v.get("lightness", 1.0))
+                    elif name == "Emboss":
+                        c, d = _rng(v.get("strength", 1.0))
+                seq.append(("nb", (_lib.NB_KINDS[name], float(a), float(b), float(c), float(d), gid, gsz, gm)))
+                continue
             if name in ("Multiply", "Add", "Invert"):
                 a = b = 0.0
             elif name in ("AddElementwise", "MultiplyElementwise"):
@@ -159,11 +186,13 @@ def parse_augmentation(spec: Optional[dict], seed: int = 0) -> AugmentConfig:
                 a, b = _rng(v.get("scale", 0.0) if isinstance(val, dict) else val)
             else:   # Grayscale
                 a, b = _rng(v.get("alpha", 1.0) if isinstance(val, dict) else val)
-            gid, gsz, gm = groups.get(name, (0, 0, 0))
             ops.append((_lib.PIX_KINDS[name], pc, float(a), float(b), gid, gsz, gm))
-        if len(ops) > 8:
-            raise NotImplementedError("augmentation: at most 8 pixel-wise augmenters")
+            seq.append(("pix", ops[-1]))
+        if len(ops) > 8 or len(seq) > 16:
+            raise NotImplementedError("augmentation: at most 8 pixel-wise and 16 colour-block augmenters in total")
         cfg.pix_ops = tuple(ops)
+        if any(t == "nb" for t, _ in seq):
+            cfg.colour_seq = tuple(seq)
     names = list(spec)
     if "Rotate90" in names:   # reference examples/people/*.yaml list Fliplr, Flipud, Rotate90
         r = names.index("Rotate90")

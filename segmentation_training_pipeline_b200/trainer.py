@@ -44,17 +44,35 @@ class AugmentConfig:
     # AdditiveGaussianNoise, Grayscale) or a OneOf group is present: (kind, per_channel, a, b, group_id, group_size, group_member)
     # per include/stp.h stp_aug_pix_op; Multiply / Add / Invert entries use the per-sample draws configured above
     pix_ops: Tuple[Tuple[int, float, float, float, int, int, int], ...] = ()
+    # neighbourhood augmenters (GaussianBlur, AverageBlur, MedianBlur, Sharpen, Emboss, EdgeDetect) interleaved with the pixel-wise
+    # ones: the colour block in YAML order as ("pix", op) / ("nb", (kind, a, b, c, d, group_id, group_size, group_member)) entries;
+    # empty = the block is `pix_ops` alone.  Position in this sequence = the op's Philox call index.
+    colour_seq: Tuple[Tuple[str, tuple], ...] = ()
 
     def enabled(self) -> bool:
         return bool(self.fliplr or self.flipud or self.affine or self.multiply or self.add or self.rot90 or self.invert or
-                    self.crop_pad or self.pix_ops)
+                    self.crop_pad or self.pix_ops or self.colour_seq)
 
-    def pix_c(self) -> _lib.AugPixSpec:
+    def pix_c(self, ops=None, k_base=0) -> _lib.AugPixSpec:
+        ops = self.pix_ops if ops is None else ops
         spec = _lib.AugPixSpec()
-        spec.n_ops, spec.mul_rint = len(self.pix_ops), int(self.mul_rint)
-        for i, (kind, pc, a, b, gid, gsz, gm) in enumerate(self.pix_ops):
+        spec.n_ops, spec.mul_rint, spec.k_base = len(ops), int(self.mul_rint), int(k_base)
+        for i, (kind, pc, a, b, gid, gsz, gm) in enumerate(ops):
             spec.ops[i] = _lib.AugPixOp(int(kind), float(pc), float(a), float(b), int(gid), int(gsz), int(gm))
         return spec
+
+    def colour_runs(self):
+        """the colour block as launches: ("pix", k_base, [ops]) runs of consecutive pixel-wise ops and ("nb", k_index, op) entries"""
+        seq = self.colour_seq or tuple(("pix", op) for op in self.pix_ops)
+        runs = []
+        for k, (typ, op) in enumerate(seq):
+            if typ == "pix" and runs and runs[-1][0] == "pix":
+                runs[-1][2].append(op)
+            elif typ == "pix":
+                runs.append(("pix", k, [op]))
+            else:
+                runs.append(("nb", k, op))
+        return runs
 
     def croppad_c(self) -> _lib.CropPadSpec:
         spec = _lib.CropPadSpec()
@@ -116,6 +134,7 @@ class Trainer:
                                   self.sumsq.data_ptr() if self.clipnorm > 0 else None, self.lr_scale.data_ptr())
         self._ident = AugmentConfig()
         self._cp_img = self._cp_mask = self._cp_items = None   # staging of the crop / pad augmenter stage (run_augment)
+        self._nb_img = self._nb_work = None                    # scratch batch / tap tables of the neighbourhood augmenters
 
     # ---- learning-rate schedules ----------------------------------------------------------------
     def set_lr(self, lr: float):
@@ -169,13 +188,31 @@ class Trainer:
             src_img, src_mask, pool_n = self._cp_img, self._cp_mask, net.batch   # sample i of the staging batch is batch item i
         self.L.augment_draw(C.byref(spec), cfg.seed, net.d_step.data_ptr(), net.batch, pool_n, H, W,
                             self.aug_params.data_ptr(), st)
+        runs = cfg.colour_runs() if (cfg.pix_ops or cfg.colour_seq) else []
+        n_nb = sum(1 for r in runs if r[0] == "nb")
+        if n_nb and self._nb_img is None:
+            self._nb_img = torch.zeros(net.batch * H * W * CI, dtype=torch.uint8, device=net.device)
+            self._nb_work = torch.zeros(max(int(self.L.augment_neighbourhood_workspace(net.batch)), 16), dtype=torch.uint8,
+                                        device=net.device)
+        # neighbourhood ops (blur / sharpen / emboss / edge-detect) ping-pong between the network's image buffer and a scratch
+        # batch; the gather kernel starts in whichever of the two makes the LAST op land in the network's buffer
+        cur = self._nb_img if n_nb % 2 else net.img.storage
         self.L.augment_apply(src_img.data_ptr(), src_mask.data_ptr(), self.aug_params.data_ptr(),
-                             net.img.storage.data_ptr(), net.mask.storage.data_ptr(), net.batch, H, W, CI, net.classes,
-                             int(cfg.mul_rint) | (2 if cfg.pix_ops else 0), st)
-        if cfg.pix_ops:   # the colour stage (incl. Multiply / Add / Invert) runs pixel-wise in YAML order, in place
-            ps = cfg.pix_c()
-            self.L.augment_pixel_ops(net.img.storage.data_ptr(), self.aug_params.data_ptr(), C.byref(ps), cfg.seed,
-                                     net.d_step.data_ptr(), net.batch, H, W, CI, st)
+                             cur.data_ptr(), net.mask.storage.data_ptr(), net.batch, H, W, CI, net.classes,
+                             int(cfg.mul_rint) | (2 if runs else 0), st)
+        for typ, k, payload in runs:   # the colour stage in YAML order (incl. Multiply / Add / Invert), pixel-wise runs in place
+            if typ == "pix":
+                ps = cfg.pix_c(payload, k)
+                self.L.augment_pixel_ops(cur.data_ptr(), self.aug_params.data_ptr(), C.byref(ps), cfg.seed,
+                                         net.d_step.data_ptr(), net.batch, H, W, CI, st)
+            else:
+                other = net.img.storage if cur is self._nb_img else self._nb_img
+                kind, a, b, c, d, gid, gsz, gm = payload
+                op = _lib.AugNbOp(int(kind), float(a), float(b), float(c), float(d), int(k), int(gid), int(gsz), int(gm))
+                self.L.augment_neighbourhood(cur.data_ptr(), other.data_ptr(), self.aug_params.data_ptr(), C.byref(op), cfg.seed,
+                                             net.d_step.data_ptr(), net.batch, H, W, CI, self._nb_work.data_ptr(),
+                                             self._nb_work.numel(), st)
+                cur = other
 
     def allreduce(self):
         if self.world_size > 1:

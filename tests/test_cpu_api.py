@@ -57,7 +57,7 @@ def test_loss_and_augmenter_errors_are_loud():
     with pytest.raises(ValueError):
         parse_loss("no_such_loss")
     with pytest.raises(NotImplementedError):
-        parse_augmentation({"GaussianBlur": 1.0})
+        parse_augmentation({"ElasticTransformation": {"alpha": 1.0}})
 
 
 def test_unknown_architecture_and_backbone(tmp_path, capsys):
@@ -275,7 +275,23 @@ def test_augmentation_block_order_is_checked():
     with pytest.raises(NotImplementedError, match="order"):
         parse_augmentation({"Affine": {}, "Flipud": 0.5})
     with pytest.raises(NotImplementedError, match="not fused"):
-        parse_augmentation({"GaussianBlur": 1.0})
+        parse_augmentation({"DirectedEdgeDetect": {"alpha": 0.5, "direction": 0.25}})
+    # neighbourhood augmenters (csrc/augment_nb.cu) join the colour block in YAML order, interleaved with the pixel-wise ones
+    nb = parse_augmentation({"Fliplr": 0.5, "Multiply": [0.9, 1.1], "GaussianBlur": {"sigma": [0.0, 3.0]}, "Add": [-5, 5],
+                             "OneOf": {"AverageBlur": {"k": [2, 7]}, "MedianBlur": {"k": [3, 5]}},
+                             "Sharpen": {"alpha": [0, 1.0], "lightness": [0.75, 1.5]}, "Emboss": {"alpha": 0.5, "strength": [0, 2.0]},
+                             "EdgeDetect": 0.25})
+    assert [t for t, _ in nb.colour_seq] == ["pix", "nb", "pix", "nb", "nb", "nb", "nb", "nb"]
+    runs = nb.colour_runs()
+    assert [(r[0], r[1]) for r in runs] == [("pix", 0), ("nb", 1), ("pix", 2), ("nb", 3), ("nb", 4), ("nb", 5), ("nb", 6), ("nb", 7)]
+    assert runs[1][2][:3] == (0, 0.0, 3.0) and runs[3][2][5:] == (0, 2, 0) and runs[4][2][5:] == (0, 2, 1)     # OneOf group 0, 2 members
+    assert runs[5][2][:5] == (3, 0.0, 1.0, 0.75, 1.5) and runs[7][2][:3] == (5, 0.25, 0.25)
+    with pytest.raises(ValueError, match="sigma"):
+        parse_augmentation({"GaussianBlur": {"sigma": [0.0, 12.0]}})
+    with pytest.raises(ValueError, match="MedianBlur"):
+        parse_augmentation({"MedianBlur": {"k": [3, 11]}})
+    with pytest.raises(ValueError, match="alpha"):
+        parse_augmentation({"Sharpen": {"alpha": [0.0, 1.5]}})
     # Rotate90 / Fliplr / Flipud in any order among themselves (the reference's examples list the flips first)
     c = parse_augmentation({"Fliplr": 0.5, "Flipud": 0.5, "Rotate90": True})
     assert c.rot90 and c.fliplr == 0.5 and c.flipud == 0.5 and c.flip_before_rot90 == 3
@@ -970,6 +986,7 @@ def test_pixelwise_augmenters_and_control_flow_parse():
     with pytest.raises(NotImplementedError, match="twice"):
         parse_augmentation({"Add": [-3, 3], "Sequential": [{"Add": [-1, 1]}]})
     with pytest.raises(NotImplementedError, match="not fused"):
-        parse_augmentation({"Sequential": [{"GaussianBlur": 1.0}]})
+        parse_augmentation({"Sequential": [{"PiecewiseAffine": 0.05}]})
+    assert parse_augmentation({"Sequential": [{"GaussianBlur": 1.0}]}).colour_seq[0][0] == "nb"
     with pytest.raises(NotImplementedError, match="order"):
         parse_augmentation({"Dropout": 0.1, "Fliplr": 0.5})

@@ -240,3 +240,38 @@ def test_depthwise_same_padding_and_dropout_mask():
     assert np.array_equal(a, dropout_keep_mask(50, 16, 0.1, 7, 0xD0, 3))
     assert not np.array_equal(a, dropout_keep_mask(50, 16, 0.1, 7, 0xD0, 4))
     assert abs(dropout_keep_mask(4000, 16, 0.1, 1, 2, 3).mean() - 0.9) < 0.01
+
+
+def test_neighbourhood_arithmetic_is_pinned_against_real_cv2():
+    """The cv2 calls behind imgaug's GaussianBlur / AverageBlur / MedianBlur / Sharpen / Emboss / EdgeDetect, restated in
+    oracle/augment.py (and in csrc/augment_nb.cu), are bit exact against the real cv2 of this image, with Intel IPP on and off:
+    cv2.GaussianBlur's 8.8 fixed-point separable kernel (error-diffused coefficients, (sum + 2^15) >> 16), cv2.blur for k = 2..17
+    (round half up, one residue earlier for powers of two), cv2.medianBlur (k = 3, 5, 7; replicated border), cv2.filter2D with
+    a float32 3x3 matrix (row-major float32 accumulation, rint)."""
+    import cv2
+    from oracle import augment as OA
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (61, 83, 3), dtype=np.uint8)
+    img[:8, :8] = 255
+    img[-8:, -8:] = 0
+    ipp0 = cv2.ipp.useIPP()
+    try:
+        for ipp in (True, False):
+            cv2.ipp.setUseIPP(ipp)
+            for sigma in (0.4, 1.0, 1.9, 2.99, 3.0, 3.5, 4.99, 5.5, 8.8):
+                ks = OA.gaussian_ksize_imgaug(sigma)
+                ref = cv2.GaussianBlur(img, (ks, ks), sigmaX=sigma, sigmaY=sigma, borderType=cv2.BORDER_REFLECT_101)
+                assert np.array_equal(OA.gaussian_blur_u8(img, ks, sigma), ref), ("gauss", sigma, ks, ipp)
+            for k in range(2, 18):
+                assert np.array_equal(OA.average_blur_u8(img, k), cv2.blur(img, (k, k))), ("blur", k, ipp)
+            for k in (3, 5, 7):
+                assert np.array_equal(OA.median_blur_u8(img, k), cv2.medianBlur(img, k)), ("median", k, ipp)
+            for kind, alpha, second in ((3, 0.3, 1.2), (3, 1.0, 0.75), (4, 0.8, 1.7), (4, 0.05, 0.3), (5, 0.55, 0.0), (5, 0.0, 0.0)):
+                act, par = OA.neighbourhood_params((kind, alpha, alpha, second, second, 2, 0, 0, 0), 1, 2, 3)
+                assert act and par[0] == "filter"
+                ref = np.stack([cv2.filter2D(np.ascontiguousarray(img[..., c]), -1, par[1]) for c in range(3)], -1)
+                assert np.array_equal(OA.filter2d_3x3_u8(img, par[1]), ref), ("filter2D", kind, alpha, ipp)
+    finally:
+        cv2.ipp.setUseIPP(ipp0)
+    assert OA.gaussian_kernel_fixed(5, 1.0).tolist() == [14, 62, 104, 62, 14]      # sum 256, centre takes the remainder
+    assert [OA.gaussian_ksize_imgaug(s) for s in (0.5, 2.0, 3.0, 4.0, 6.0)] == [5, 7, 9, 11, 15]

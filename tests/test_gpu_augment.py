@@ -190,3 +190,83 @@ def test_pixelwise_augmenters_match_oracle(cuda, block):
     has_gauss = any(o[0] == 6 for o in cfg.pix_ops)
     assert bad <= (1e-4 * tot if has_gauss else 0), (bad, tot)
     assert changed > 0.05 * tot          # the block really changes pixels
+
+
+NB_BLOCKS = [
+    {"GaussianBlur": {"sigma": [0.0, 3.0]}},
+    {"Fliplr": 0.5, "AverageBlur": {"k": [2, 9]}},
+    {"MedianBlur": {"k": [3, 7]}},
+    {"Sharpen": {"alpha": [0.0, 1.0], "lightness": [0.75, 1.5]}},
+    {"Emboss": {"alpha": [0.0, 1.0], "strength": [0.0, 2.0]}, "EdgeDetect": {"alpha": [0.0, 0.7]}},
+    {"Fliplr": 0.5, "Multiply": [0.8, 1.2], "GaussianBlur": {"sigma": [0.5, 5.5]}, "Add": [-10, 10],
+     "OneOf": {"AverageBlur": {"k": [2, 7]}, "MedianBlur": {"k": [3, 5]}, "Sharpen": {"alpha": [0.2, 1.0], "lightness": [0.75, 1.5]}},
+     "Dropout": {"p": [0.0, 0.05]}, "Emboss": {"alpha": [0.1, 1.0], "strength": [0.5, 1.5]}},
+]
+
+
+@pytest.mark.parametrize("block", NB_BLOCKS, ids=[str(i) for i in range(len(NB_BLOCKS))])
+@pytest.mark.parametrize("channels", [3, 1])
+def test_neighbourhood_augmenters_match_oracle(cuda, block, channels):
+    """GaussianBlur / AverageBlur / MedianBlur / Sharpen / Emboss / EdgeDetect, alone, inside OneOf and interleaved with pixel-wise
+    augmenters in YAML order, through Trainer.run_augment: EVERY pixel equals the oracle twin (oracle.augment.apply_neighbourhood_op,
+    whose arithmetic is pinned against the real cv2 in tests/test_cpu_oracle.py); masks untouched."""
+    from oracle import augment as OA
+    from segmentation_training_pipeline_b200.models import SegNet
+    from segmentation_training_pipeline_b200.segmentation import parse_augmentation
+    from segmentation_training_pipeline_b200.trainer import Trainer
+    n, size, pool, seed = 4, 64, 8, 77
+    net = SegNet("resnet18", classes=1, input_shape=(size, size, channels), batch=n, device="cuda:0", seed=0)
+    cfg = parse_augmentation(block, seed=seed)
+    assert cfg.colour_seq
+    rng = np.random.default_rng(9)
+    imgs = rng.integers(0, 256, (pool, size, size, channels), dtype=np.uint8)
+    imgs[:, 20:40, 10:30] //= 4                                  # some structure for the edge / median filters
+    masks = (rng.random((pool, size, size, 1)) > 0.5).astype(np.uint8)
+    tr = Trainer(net, augment=cfg)
+    tr.set_pool(torch.from_numpy(imgs), torch.from_numpy(masks))
+    ospec = OA.AugSpec(fliplr=cfg.fliplr, flipud=cfg.flipud, multiply=cfg.multiply, add=cfg.add, invert=cfg.invert)
+    changed = tot = 0
+    for step in (0, 5):
+        net.d_step.fill_(step)
+        tr.run_augment()
+        torch.cuda.synchronize()
+        gi = net.img.storage.view(n, size, size, channels).cpu().numpy()
+        gm = net.mask.storage.view(n, size, size, 1).cpu().numpy()
+        for i in range(n):
+            sid = (step * n + i) % pool
+            p = OA.draw_params(ospec, seed, step, sid, size, size)
+            geo = OA.SampleParams(p.fliplr, p.flipud, p.matrix, False, 1.0, False, 0, 0, False, (0, 1, 2), 0)
+            ref, bm = OA.apply(imgs[sid], masks[sid], geo)
+            base = ref
+            for typ, k, payload in cfg.colour_runs():
+                if typ == "pix":
+                    ref = OA.apply_pixel_ops(ref, payload, seed, step, sid, p, k_base=k)
+                else:
+                    kind, a, b, c, d, gid, gsz, gm_ = payload
+                    ref = OA.apply_neighbourhood_op(ref, (kind, a, b, c, d, k, gid, gsz, gm_), seed, step, sid)
+            assert np.array_equal(gi[i], ref), (step, i, int((gi[i] != ref).sum()), int(np.abs(gi[i].astype(int) - ref.astype(int)).max()))
+            assert np.array_equal(gm[i], bm)
+            changed += int((gi[i] != base).sum())
+            tot += base.size
+    assert changed > 0.05 * tot
+
+
+def test_neighbourhood_augmenter_in_the_captured_step(cuda):
+    """a blur inside the whole-step CUDA graph: the step runs, the loss is finite and differs from the un-blurred run"""
+    from segmentation_training_pipeline_b200.models import SegNet
+    from segmentation_training_pipeline_b200.segmentation import parse_augmentation
+    from segmentation_training_pipeline_b200.trainer import Trainer
+    n, size = 4, 64
+    rng = np.random.default_rng(1)
+    imgs = torch.from_numpy(rng.integers(0, 256, (8, size, size, 3), dtype=np.uint8))
+    masks = torch.from_numpy((rng.random((8, size, size, 1)) > 0.5).astype(np.uint8))
+    losses = []
+    for block in ({"Fliplr": 0.5}, {"Fliplr": 0.5, "GaussianBlur": {"sigma": [1.0, 2.0]}, "Sharpen": {"alpha": 0.5}}):
+        net = SegNet("resnet18", classes=1, input_shape=(size, size, 3), batch=n, device="cuda:0", seed=0)
+        tr = Trainer(net, optimizer="Adam", lr=1e-3, augment=parse_augmentation(block, seed=3))
+        tr.set_pool(imgs, masks)
+        tr.capture()
+        for _ in range(3):
+            tr.step()
+        losses.append(tr.loss_value())
+    assert np.isfinite(losses).all() and abs(losses[0] - losses[1]) > 1e-6, losses
