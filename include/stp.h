@@ -178,17 +178,19 @@ int stp_augment_pixel_ops(uint8_t* d_img, const stp_aug_sample* d_params, const 
 
 /* Neighbourhood augmenters (schemas/augmenters.raml:97-112, 117-119): imgaug GaussianBlur (sigma ~ U(a, b)), AverageBlur
  * (k ~ integers a..b), MedianBlur (k ~ odd integers a..b <= 7), Sharpen (alpha ~ U(a, b), lightness ~ U(c, d)), Emboss (alpha,
- * strength), EdgeDetect (alpha) with the arithmetic of the cv2 calls they make (cv2.GaussianBlur's 8.8 fixed point, cv2.blur,
+ * strength), EdgeDetect (alpha), DirectedEdgeDetect (alpha, direction) with the arithmetic of the cv2 calls they make (cv2.GaussianBlur's 8.8 fixed point, cv2.blur,
  * cv2.medianBlur, cv2.filter2D; bit exact, see csrc/augment_nb.cu).  One op per call, d_src -> d_dst (different buffers),
  * images only.  k_index = position of the op in the colour block (Philox call 32 + k_index); group_* as in stp_aug_pix_op.
  * d_work: stp_augment_neighbourhood_workspace(n) bytes of device memory. */
 enum { STP_NB_GAUSSIAN_BLUR = 0, STP_NB_AVERAGE_BLUR = 1, STP_NB_MEDIAN_BLUR = 2, STP_NB_SHARPEN = 3, STP_NB_EMBOSS = 4,
-       STP_NB_EDGE_DETECT = 5 };
+       STP_NB_EDGE_DETECT = 5, STP_NB_DIRECTED_EDGE_DETECT = 6 };
 typedef struct stp_aug_nb_op {
   int32_t kind;
   float a, b, c, d;
   int32_t k_index;
   int32_t group_id, group_size, group_member;
+  const void* d_table;   /* DirectedEdgeDetect (alpha ~ U(a, b), direction ~ U(c, d)): device float32 [360][9], the effect matrix per
+                            integer degree (imgaug computes it with double-precision trigonometry; tabulated by the host) */
 } stp_aug_nb_op;
 size_t stp_augment_neighbourhood_workspace(int32_t n);
 int stp_augment_neighbourhood(const uint8_t* d_src, uint8_t* d_dst, const stp_aug_sample* d_params, const stp_aug_nb_op* h_op,

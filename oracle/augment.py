@@ -423,6 +423,32 @@ def filter2d_3x3_u8(img: np.ndarray, mat: np.ndarray) -> np.ndarray:
     return out
 
 
+def directed_edge_table() -> np.ndarray:
+    """imgaug 0.3.0 DirectedEdgeDetect [DEP, recalled]: effect matrix per integer degree (deg = int(direction * 360) % 360):
+    the direction vector is (cos, sin)(rad - pi/2); every non-centre cell (x, y) of the 3x3 matrix gets (1 - angle/180deg)^4 with
+    the angle between the cell vector and the direction vector; normalised to sum 1, negated, centre 1.  float32 [360][3][3]."""
+    tab = np.zeros((360, 3, 3), np.float32)
+    for deg in range(360):
+        rad = np.deg2rad(deg)
+        dv = np.array([np.cos(rad - 0.5 * np.pi), np.sin(rad - 0.5 * np.pi)])
+        m = np.zeros((3, 3), np.float32)
+        for x in (-1, 0, 1):
+            for y in (-1, 0, 1):
+                if (x, y) != (0, 0):
+                    cv = np.array([x, y], np.float64)
+                    cos_a = np.clip(np.dot(cv / np.linalg.norm(cv), dv / np.linalg.norm(dv)), -1.0, 1.0)
+                    distance = np.rad2deg(np.arccos(cos_a)) / 180.0
+                    m[y + 1, x + 1] = (1.0 - distance) ** 4
+        m = m / np.sum(m)
+        m = m * np.float32(-1)
+        m[1, 1] = 1
+        tab[deg] = m
+    return tab
+
+
+_DIRECTED_TABLE = None
+
+
 def neighbourhood_params(op, seed: int, step: int, sid: int):
     """(active, kind-specific parameters) of one sample: the draws of csrc/augment_nb.cu nb_prep_kernel"""
     kind, a, b, c, d, k_index, gid, gsz, gm = op
@@ -450,6 +476,11 @@ def neighbourhood_params(op, seed: int, step: int, sid: int):
         eff = np.array([[-1, -1, -1], [-1, f32(8.0 + p2), -1], [-1, -1, -1]], np.float32)
     elif kind == 4:
         eff = np.array([[f32(-1.0 - p2), f32(0.0 - p2), 0], [f32(0.0 - p2), 1, f32(0.0 + p2)], [0, f32(0.0 + p2), f32(1.0 + p2)]], np.float32)
+    elif kind == 6:   # DirectedEdgeDetect: second parameter = direction in [0, 1] -> integer degree -> table row
+        global _DIRECTED_TABLE
+        if _DIRECTED_TABLE is None:
+            _DIRECTED_TABLE = directed_edge_table()
+        eff = _DIRECTED_TABLE[int(p2 * 360.0) % 360]
     else:
         eff = np.array([[0, 1, 0], [1, -4, 1], [0, 1, 0]], np.float32)
     ident = np.array([[0, 0, 0], [0, 1, 0], [0, 0, 0]], np.float32)

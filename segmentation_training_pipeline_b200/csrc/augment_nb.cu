@@ -1,5 +1,5 @@
 // Neighbourhood augmenters on the uint8 image batch (schemas/augmenters.raml:97-112, 117-119 -> imgaug 0.3.0 GaussianBlur /
-// AverageBlur / MedianBlur / Sharpen / Emboss / EdgeDetect, which call cv2.GaussianBlur / cv2.blur / cv2.medianBlur /
+// AverageBlur / MedianBlur / Sharpen / Emboss / EdgeDetect / DirectedEdgeDetect, which call cv2.GaussianBlur / cv2.blur / cv2.medianBlur /
 // cv2.filter2D [DEP]).  The cv2 arithmetic is restated exactly and pinned against the real cv2 (tests/test_cpu_oracle.py):
 //   GaussianBlur (uint8): 8.8 fixed-point separable kernel -- coefficients round(k_i * 256) with error diffusion from the border
 //       inwards, the centre taking the remainder so that the sum is 256 -- integer products, out = (sum + 2^15) >> 16;
@@ -117,6 +117,13 @@ __global__ void nb_prep_kernel(const stp_aug_nb_op op, const stp_aug_sample* __r
       const float e[9] = {(float)(-1.0 - p2), (float)(0.0 - p2), 0.f, (float)(0.0 - p2), 1.f, (float)(0.0 + p2), 0.f, (float)(0.0 + p2), (float)(1.0 + p2)};
       (void)s;
       for (int i = 0; i < 9; ++i) eff[i] = e[i];
+    } else if (op.kind == STP_NB_DIRECTED_EDGE_DETECT) {
+      // imgaug computes the effect matrix from deg = int(direction * 360) % 360 with double-precision trigonometry: the 360
+      // possible float32 matrices are tabulated on the host (no libm / CUDA libdevice last-bit differences)
+      int deg = (int)(p2 * 360.0) % 360;
+      if (deg < 0) deg += 360;
+      const float* t = (const float*)op.d_table + deg * 9;
+      for (int i = 0; i < 9; ++i) eff[i] = t[i];
     } else {
       const float e[9] = {0.f, 1.f, 0.f, 1.f, -4.f, 1.f, 0.f, 1.f, 0.f};
       for (int i = 0; i < 9; ++i) eff[i] = e[i];
@@ -247,7 +254,8 @@ extern "C" int stp_augment_neighbourhood(const uint8_t* d_src, uint8_t* d_dst, c
   STP_REQUIRE(d_src && d_dst && d_src != d_dst && d_params && h_op && d_step && d_work && n > 0 && h > 0 && w > 0,
               "augment_neighbourhood: bad args (src and dst must differ)");
   STP_REQUIRE(c_img == 1 || c_img == 3 || c_img == 4, "augment_neighbourhood: c_img must be 1, 3 or 4");
-  STP_REQUIRE(h_op->kind >= STP_NB_GAUSSIAN_BLUR && h_op->kind <= STP_NB_EDGE_DETECT, "augment_neighbourhood: unknown op kind");
+  STP_REQUIRE(h_op->kind >= STP_NB_GAUSSIAN_BLUR && h_op->kind <= STP_NB_DIRECTED_EDGE_DETECT, "augment_neighbourhood: unknown op kind");
+  STP_REQUIRE(h_op->kind != STP_NB_DIRECTED_EDGE_DETECT || h_op->d_table, "augment_neighbourhood: DirectedEdgeDetect needs d_table (360 x 9 floats)");
   STP_REQUIRE(h_op->k_index >= 0 && h_op->k_index < 16, "augment_neighbourhood: k_index in [0, 16)");
   if (h_op->kind == STP_NB_GAUSSIAN_BLUR)
     STP_REQUIRE(h_op->a >= 0.f && h_op->b >= h_op->a && 2.6 * h_op->b < (double)kNbMaxK, "augment_neighbourhood: GaussianBlur sigma in [0, %.1f)", kNbMaxK / 2.6);

@@ -74,10 +74,33 @@ class AugPixSpec(C.Structure):             # include/stp.h: stp_aug_pix_spec
 
 class AugNbOp(C.Structure):                # include/stp.h: stp_aug_nb_op
     _fields_ = [("kind", C.c_int32), ("a", C.c_float), ("b", C.c_float), ("c", C.c_float), ("d", C.c_float), ("k_index", C.c_int32),
-                ("group_id", C.c_int32), ("group_size", C.c_int32), ("group_member", C.c_int32)]
+                ("group_id", C.c_int32), ("group_size", C.c_int32), ("group_member", C.c_int32), ("d_table", C.c_void_p)]
 
 
-NB_KINDS = {"GaussianBlur": 0, "AverageBlur": 1, "MedianBlur": 2, "Sharpen": 3, "Emboss": 4, "EdgeDetect": 5}
+NB_KINDS = {"GaussianBlur": 0, "AverageBlur": 1, "MedianBlur": 2, "Sharpen": 3, "Emboss": 4, "EdgeDetect": 5, "DirectedEdgeDetect": 6}
+
+
+def directed_edge_table():
+    """float32 [360][3][3]: imgaug 0.3.0 DirectedEdgeDetect's effect matrix per integer degree [DEP, recalled] (deg = int(direction *
+    360) % 360; direction vector (cos, sin)(rad - pi/2); cell (x, y) != centre gets (1 - angle / 180deg)^4, normalised to sum 1,
+    negated, centre 1) -- tabulated on the host because imgaug evaluates it with double-precision numpy trigonometry."""
+    import numpy as np
+    tab = np.zeros((360, 3, 3), np.float32)
+    for deg in range(360):
+        rad = np.deg2rad(deg)
+        dv = np.array([np.cos(rad - 0.5 * np.pi), np.sin(rad - 0.5 * np.pi)])
+        m = np.zeros((3, 3), np.float32)
+        for x in (-1, 0, 1):
+            for y in (-1, 0, 1):
+                if (x, y) != (0, 0):
+                    cv = np.array([x, y], np.float64)
+                    cos_a = np.clip(np.dot(cv / np.linalg.norm(cv), dv / np.linalg.norm(dv)), -1.0, 1.0)
+                    m[y + 1, x + 1] = (1.0 - np.rad2deg(np.arccos(cos_a)) / 180.0) ** 4
+        m = m / np.sum(m)
+        m = m * np.float32(-1)
+        m[1, 1] = 1
+        tab[deg] = m
+    return tab
 
 
 class CropPadOp(C.Structure):              # include/stp.h: stp_croppad_op

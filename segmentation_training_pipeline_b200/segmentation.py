@@ -122,8 +122,8 @@ def parse_augmentation(spec: Optional[dict], seed: int = 0) -> AugmentConfig:
     rank = {"Pad": 0, "PadToFixedSize": 0, "CropToFixedSize": 0, "CropAndPad": 0,
             "Rotate90": 1, "Fliplr": 1, "Flipud": 1, "Affine": 2, "Multiply": 3, "Add": 3, "Invert": 3,
             "AddElementwise": 3, "MultiplyElementwise": 3, "Dropout": 3, "AdditiveGaussianNoise": 3, "Grayscale": 3,
-            "GaussianBlur": 3, "AverageBlur": 3, "MedianBlur": 3, "Sharpen": 3, "Emboss": 3, "EdgeDetect": 3}
-    NB = ("GaussianBlur", "AverageBlur", "MedianBlur", "Sharpen", "Emboss", "EdgeDetect")
+            "GaussianBlur": 3, "AverageBlur": 3, "MedianBlur": 3, "Sharpen": 3, "Emboss": 3, "EdgeDetect": 3, "DirectedEdgeDetect": 3}
+    NB = ("GaussianBlur", "AverageBlur", "MedianBlur", "Sharpen", "Emboss", "EdgeDetect", "DirectedEdgeDetect")
     for name in groups:
         if rank.get(name) != 3:
             raise NotImplementedError("OneOf over '%s': only the colour-block augmenters (Multiply, Add, Invert, AddElementwise, "
@@ -172,6 +172,8 @@ def parse_augmentation(spec: Optional[dict], seed: int = 0) -> AugmentConfig:
                         c, d = _rng(v.get("lightness", 1.0))
                     elif name == "Emboss":
                         c, d = _rng(v.get("strength", 1.0))
+                    elif name == "DirectedEdgeDetect":
+                        c, d = _rng(v.get("direction", [0.0, 1.0]))
                 seq.append(("nb", (_lib.NB_KINDS[name], float(a), float(b), float(c), float(d), gid, gsz, gm)))
                 continue
             if name in ("Multiply", "Add", "Invert"):

@@ -134,7 +134,7 @@ class Trainer:
                                   self.sumsq.data_ptr() if self.clipnorm > 0 else None, self.lr_scale.data_ptr())
         self._ident = AugmentConfig()
         self._cp_img = self._cp_mask = self._cp_items = None   # staging of the crop / pad augmenter stage (run_augment)
-        self._nb_img = self._nb_work = None                    # scratch batch / tap tables of the neighbourhood augmenters
+        self._nb_img = self._nb_work = self._nb_table = None   # scratch batch / tap tables of the neighbourhood augmenters
 
     # ---- learning-rate schedules ----------------------------------------------------------------
     def set_lr(self, lr: float):
@@ -208,7 +208,12 @@ class Trainer:
             else:
                 other = net.img.storage if cur is self._nb_img else self._nb_img
                 kind, a, b, c, d, gid, gsz, gm = payload
-                op = _lib.AugNbOp(int(kind), float(a), float(b), float(c), float(d), int(k), int(gid), int(gsz), int(gm))
+                table = None
+                if int(kind) == _lib.NB_KINDS["DirectedEdgeDetect"]:
+                    if self._nb_table is None:
+                        self._nb_table = torch.from_numpy(_lib.directed_edge_table()).to(net.device).contiguous()
+                    table = self._nb_table.data_ptr()
+                op = _lib.AugNbOp(int(kind), float(a), float(b), float(c), float(d), int(k), int(gid), int(gsz), int(gm), table)
                 self.L.augment_neighbourhood(cur.data_ptr(), other.data_ptr(), self.aug_params.data_ptr(), C.byref(op), cfg.seed,
                                              net.d_step.data_ptr(), net.batch, H, W, CI, self._nb_work.data_ptr(),
                                              self._nb_work.numel(), st)

@@ -275,7 +275,8 @@ def test_augmentation_block_order_is_checked():
     with pytest.raises(NotImplementedError, match="order"):
         parse_augmentation({"Affine": {}, "Flipud": 0.5})
     with pytest.raises(NotImplementedError, match="not fused"):
-        parse_augmentation({"DirectedEdgeDetect": {"alpha": 0.5, "direction": 0.25}})
+        parse_augmentation({"ElasticTransformation": {"alpha": 0.5, "sigma": 0.25}})
+    assert parse_augmentation({"DirectedEdgeDetect": {"alpha": 0.5, "direction": [0.0, 0.5]}}).colour_seq[0][1][:5] == (6, 0.5, 0.5, 0.0, 0.5)
     # neighbourhood augmenters (csrc/augment_nb.cu) join the colour block in YAML order, interleaved with the pixel-wise ones
     nb = parse_augmentation({"Fliplr": 0.5, "Multiply": [0.9, 1.1], "GaussianBlur": {"sigma": [0.0, 3.0]}, "Add": [-5, 5],
                              "OneOf": {"AverageBlur": {"k": [2, 7]}, "MedianBlur": {"k": [3, 5]}},

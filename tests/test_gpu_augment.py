@@ -198,6 +198,7 @@ NB_BLOCKS = [
     {"MedianBlur": {"k": [3, 7]}},
     {"Sharpen": {"alpha": [0.0, 1.0], "lightness": [0.75, 1.5]}},
     {"Emboss": {"alpha": [0.0, 1.0], "strength": [0.0, 2.0]}, "EdgeDetect": {"alpha": [0.0, 0.7]}},
+    {"DirectedEdgeDetect": {"alpha": [0.2, 1.0], "direction": [0.0, 1.0]}},
     {"Fliplr": 0.5, "Multiply": [0.8, 1.2], "GaussianBlur": {"sigma": [0.5, 5.5]}, "Add": [-10, 10],
      "OneOf": {"AverageBlur": {"k": [2, 7]}, "MedianBlur": {"k": [3, 5]}, "Sharpen": {"alpha": [0.2, 1.0], "lightness": [0.75, 1.5]}},
      "Dropout": {"p": [0.0, 0.05]}, "Emboss": {"alpha": [0.1, 1.0], "strength": [0.5, 1.5]}},
