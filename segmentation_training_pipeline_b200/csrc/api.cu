@@ -51,6 +51,7 @@ extern "C" int stp_set_option(const char* name, int32_t value) {
   else if (!strcmp(name, "tc3_force_bn")) key = OPT_TC3_FORCE_BN;       /* 0 heuristic | 128, 256 */
   else if (!strcmp(name, "tc3_force_mt")) key = OPT_TC3_FORCE_MT;       /* 0 heuristic | 1, 2 */
   else if (!strcmp(name, "tc3_halo")) key = OPT_TC3_HALO;               /* 0 off | 1 on: ONE haloed A box per channel block (measured slower, see conv_tc3.cu) */
+  else if (!strcmp(name, "gemm1x1")) key = OPT_GEMM1X1;                 /* 0 auto: every eligible 1x1 stride-1 conv (no fused BatchNorm epilogue) on the streaming GEMM kernel | 1 off | 2 only where no tcgen05 kernel serves the shape */
   else if (!strcmp(name, "head_strip")) key = OPT_HEAD_STRIP;           /* 0 on | 1 off: column-strip head backward kernels (sliding dlogit window) */
   else if (!strcmp(name, "tc3_bn64")) key = OPT_TC3_BN64;               /* 0 off | 1 on: N = 64 CTA-pair tiles for Cout = 64 / 192 layers (measured slower) */
   else if (!strcmp(name, "bnb_fuse")) key = OPT_BNB_FUSE;               /* 0 auto | 1: never fuse the BatchNorm-backward reduction into the dgrad epilogue */
@@ -73,11 +74,17 @@ extern "C" int stp_tc_enabled(void) { return g_tc_enabled.load(); }
 extern "C" void stp_set_tc_enabled(int on) { g_tc_enabled.store(on ? 1 : 0); }
 
 static int dispatch_conv(const ConvP& p, cudaStream_t st) {
+  // 1x1 stride-1 convolutions without a fused BatchNorm epilogue (dgrads, FPN laterals, MobileNetV2 projections) are HBM-bound
+  // GEMMs: the streaming mma.sync kernel beat the tcgen05 tiles on both graphs that have them (profiles/r2_s8_gemm1x1_ab.txt:
+  // FPN/ResNet-50 782 -> 854 img/s, DeepLabV3 8.66 -> 8.09 ms), so it is the automatic choice.  1 = off, 2 = fallback only.
+  const int g1 = get_option(OPT_GEMM1X1);
+  if (g1 == 0 && gemm1x1_supported(p)) return launch_gemm1x1(p, st);
   if (stp_tc_enabled()) {
     if (get_option(OPT_TC_CONV_VERSION) != 1 && tc3_conv_supported(p)) return launch_tc3_conv(p, st);
     if (get_option(OPT_TC_CONV_VERSION) != 1 && tc2_conv_supported(p)) return launch_tc2_conv(p, st);
     if (tc_conv_supported(p)) return launch_tc_conv(p, st);
   }
+  if (g1 != 1 && gemm1x1_supported(p)) return launch_gemm1x1(p, st);
   return launch_generic_conv(p, st);
 }
 

@@ -1,0 +1,189 @@
+// 1x1 stride-1 convolution = plain GEMM  Y[M][N] = X[M][K] * W[N][K]^T (+ bias, + residual, ReLU)  for the channel counts the
+// tcgen05 kernels do not tile (MobileNetV2 / Xception widths: 24, 96, 144, 160, 728 ...) and for the tiny-K layers where one
+// 16/32/64-deep MMA per 128 x BN tile leaves the tcgen05 pipeline latency-bound.  These GEMMs are HBM-bound (K <= 960: 2*K FLOP
+// per 2*(1 + N/K)-byte... a few hundred FLOP per byte at most is never reached: the tensors are read and written once), so the
+// design goal is streaming, not tensor throughput: 16-byte cp.async into a 4-stage XOR-swizzled shared-memory ring, ldmatrix +
+// mma.sync.m16n8k16 (bf16 in, fp32 accumulate), the epilogue staged through shared memory so that every global store is a
+// row-contiguous 16-byte vector.  The dgrad of such a layer is the same GEMM over dY with the [Cin][Cout] weight copy.
+// The implicit-GEMM generic kernel (conv_generic.cu) spends its time on im2col index arithmetic that a 1x1 filter does not need:
+// 160 -> 960 @40x40 bs16 took 101 us there (profiles/r2_s7_deeplab_bench.txt).
+#include "conv.h"
+
+namespace stp {
+namespace {
+
+constexpr int kBM = 128, kBK = 32, kStages = 4, kThreads = 256;
+
+struct G1Args {
+  const __nv_bfloat16* A;
+  int lda;
+  const __nv_bfloat16* B;   // [N][K]
+  __nv_bfloat16* Y;
+  int ldy;
+  const __nv_bfloat16* res;
+  int ldr;
+  const float* bias;
+  int relu, M, N, K, tiles_n;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(bytes));
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// byte offset of (row, 16-byte chunk c in 0..3) inside a [rows][32] bf16 tile: chunk index XORed with (row >> 1) & 3
+__device__ __forceinline__ uint32_t swz(int row, int c) { return (uint32_t)(row * 64 + ((c ^ ((row >> 1) & 3)) << 4)); }
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads) gemm1x1_kernel(const G1Args a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int kABytes = kBM * kBK * 2, kBBytes = BN * kBK * 2, kStage = kABytes + kBBytes;
+  constexpr int WM = BN == 128 ? 2 : 4, WN = 8 / WM;           // warp grid
+  constexpr int TM = kBM / WM / 16, TN = BN / WN / 8;           // mma tiles per warp: (4 x 4) for BN = 128, (2 x 4) for BN = 64
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tn = blockIdx.x % a.tiles_n, tm = blockIdx.x / a.tiles_n;
+  const int m0 = tm * kBM, n0 = tn * BN;
+  const int wm = warp % WM, wn = warp / WM;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+  const int KT = (a.K + kBK - 1) / kBK;
+
+  auto load_stage = [&](int kt, int stage) {
+    const uint32_t sa = sbase + stage * kStage, sb = sa + kABytes;
+    const int k0 = kt * kBK;
+#pragma unroll
+    for (int i = 0; i < kBM * 4 / kThreads; ++i) {
+      const int q = tid + i * kThreads, row = q >> 2, c = q & 3;
+      const int m = m0 + row, k = k0 + c * 8;
+      const bool ok = m < a.M && k < a.K;
+      cp_async16(sa + swz(row, c), ok ? (const void*)(a.A + (int64_t)m * a.lda + k) : (const void*)a.A, ok ? 16 : 0);
+    }
+#pragma unroll
+    for (int i = 0; i < (BN * 4 + kThreads - 1) / kThreads; ++i) {
+      const int q = tid + i * kThreads, row = q >> 2, c = q & 3;
+      if (row < BN) {
+        const int n = n0 + row, k = k0 + c * 8;
+        const bool ok = n < a.N && k < a.K;
+        cp_async16(sb + swz(row, c), ok ? (const void*)(a.B + (int64_t)n * a.K + k) : (const void*)a.B, ok ? 16 : 0);
+      }
+    }
+  };
+
+  float acc[TM][TN][4];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+
+#pragma unroll
+  for (int s = 0; s < kStages - 1; ++s) {
+    if (s < KT) load_stage(s, s);
+    cp_commit();
+  }
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_wait<kStages - 2>();
+    __syncthreads();
+    if (kt + kStages - 1 < KT) load_stage(kt + kStages - 1, (kt + kStages - 1) % kStages);
+    cp_commit();
+    const uint32_t sa = sbase + (kt % kStages) * kStage, sb = sa + kABytes;
+#pragma unroll
+    for (int ks = 0; ks < kBK / 16; ++ks) {
+      uint32_t af[TM][4], bf[TN][2];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        const int row = wm * (kBM / WM) + i * 16 + (lane & 15);
+        ldsm4(sa + swz(row, ks * 2 + (lane >> 4)), af[i][0], af[i][1], af[i][2], af[i][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < TN; j += 2) {
+        const int row = wn * (BN / WN) + j * 8 + (lane & 7) + ((lane >> 4) << 3);
+        ldsm4(sb + swz(row, ks * 2 + ((lane >> 3) & 1)), bf[j][0], bf[j][1], bf[j + 1][0], bf[j + 1][1]);
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) mma16816(acc[i][j], af[i], bf[j][0], bf[j][1]);
+    }
+  }
+  cp_wait<0>();
+  __syncthreads();
+
+  // epilogue: bias / residual / ReLU on the fragments (one rounding), staged as bf16 [128][BN + 8], then 16-byte row stores
+  constexpr int LDS = BN + 8;
+  __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(smem);
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int row = wm * (kBM / WM) + i * 16 + (lane >> 2) + hh * 8;
+        const int col = wn * (BN / WN) + j * 8 + (lane & 3) * 2;
+        float v0 = acc[i][j][hh * 2], v1 = acc[i][j][hh * 2 + 1];
+        const int m = m0 + row, n = n0 + col;
+        if (a.bias && n < a.N) { v0 += a.bias[n]; v1 += a.bias[n + 1]; }
+        if (a.res && m < a.M && n < a.N) {
+          const __nv_bfloat162 r = *reinterpret_cast<const __nv_bfloat162*>(a.res + (int64_t)m * a.ldr + n);
+          v0 += __bfloat162float(r.x); v1 += __bfloat162float(r.y);
+        }
+        if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+        *reinterpret_cast<__nv_bfloat162*>(st + row * LDS + col) = __floats2bfloat162_rn(v0, v1);
+      }
+  __syncthreads();
+  constexpr int CV = BN / 8;
+  for (int q = tid; q < kBM * CV; q += kThreads) {
+    const int row = q / CV, c = q - row * CV;
+    const int m = m0 + row, n = n0 + c * 8;
+    if (m < a.M && n < a.N)
+      *reinterpret_cast<uint4*>(a.Y + (int64_t)m * a.ldy + n) = *reinterpret_cast<const uint4*>(st + row * LDS + c * 8);
+  }
+}
+
+template <int BN>
+int launch_bn(const G1Args& a, cudaStream_t stv) {
+  constexpr int smem = kStages * (kBM * kBK * 2 + BN * kBK * 2);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gemm1x1_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  const int tiles_m = (a.M + kBM - 1) / kBM;
+  gemm1x1_kernel<BN><<<tiles_m * a.tiles_n, kThreads, smem, stv>>>(a);
+  return check_launch("gemm1x1");
+}
+
+}  // namespace
+
+bool gemm1x1_supported(const ConvP& p) {
+  if (p.R != 1 || p.S != 1 || p.stride != 1 || p.up != 1 || p.pad_h != 0 || p.pad_w != 0) return false;
+  if (p.y_f32 || p.bn != nullptr || p.ncls != 0 || p.bnb_x != nullptr) return false;
+  if (p.Cin % 8 != 0 || p.Cout % 8 != 0 || p.ldx % 8 != 0 || p.ldy % 8 != 0) return false;
+  if (!aligned16(p.x) || !aligned16(p.w) || !aligned16(p.y)) return false;
+  if (p.res && (p.ldr % 2 != 0)) return false;
+  if (p.M >= ((int64_t)1 << 31) - kBM) return false;
+  return true;
+}
+
+int launch_gemm1x1(const ConvP& p, cudaStream_t st) {
+  G1Args a;
+  a.A = p.x; a.lda = p.ldx; a.B = p.w; a.Y = (__nv_bfloat16*)p.y; a.ldy = p.ldy; a.res = p.res; a.ldr = p.ldr; a.bias = p.bias;
+  a.relu = p.relu; a.M = (int)p.M; a.N = p.Cout; a.K = p.Cin;
+  if (p.Cout > 64) {
+    a.tiles_n = (p.Cout + 127) / 128;
+    return launch_bn<128>(a, st);
+  }
+  a.tiles_n = 1;
+  return launch_bn<64>(a, st);
+}
+
+}  // namespace stp

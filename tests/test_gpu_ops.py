@@ -912,3 +912,65 @@ def test_conv_dgrad_with_fused_bn_backward_reduce(stp, cuda, case, relu):
     for k in (1, 2, 3):
         scale = 1e-6 + float(outs[0][k].abs().max())
         assert max_abs(outs[1][k], outs[0][k]) <= 2e-4 * scale, (k, max_abs(outs[1][k], outs[0][k]), scale)
+
+
+G1_CASES = [
+    # n, h, w, cin, cout: 1x1 stride-1 convolutions as plain GEMMs (csrc/gemm1x1.cu)
+    (2, 20, 20, 96, 576),     # MobileNetV2 expand, K = 3 x 32
+    (1, 20, 20, 160, 960),    # N = 7.5 x 128: partial last N tile
+    (1, 9, 7, 24, 144),       # K tail (24 = 16 + 8), M = 63 (partial M tile)
+    (1, 9, 7, 144, 24),       # N = 24 < 64
+    (2, 16, 16, 728, 728),    # Xception middle flow
+    (1, 12, 12, 16, 96),      # the tiny-K case the tcgen05 kernel loses
+    (2, 32, 32, 64, 128),     # a shape the tcgen05 kernel also serves (gemm1x1 = 0, the default, prefers this kernel)
+    (1, 8, 8, 960, 320),
+]
+
+
+@pytest.mark.parametrize("case", G1_CASES)
+def test_gemm1x1(stp, cuda, case):
+    """forward (+ residual, + bias + ReLU), forward into / out of channel slices (ld > c), and dgrad (plain and accumulate in
+    place) of 1x1 stride-1 convolutions on the streaming GEMM kernel, against fp32 math on the same bf16 operands"""
+    n, h, w, cin, cout = case
+    stp.set_option(b"gemm1x1", 0)
+    try:
+        g = torch.Generator().manual_seed(sum(case))
+        x = rand_bf16((n, h, w, cin), g)
+        wt = rand_bf16((cout, 1, 1, cin), g, scale=1.0 / math.sqrt(cin))
+        res = rand_bf16((n, h, w, cout), g)
+        desc = lib.ConvDesc(1, 1, 1, 0, 0, 1, 0)
+        xs, rs = T(x), T(res)
+        y = torch.zeros((n, h, w, cout), dtype=torch.bfloat16, device=cuda)
+        ys = T(y)
+        tc0, l0 = stp.tc_launch_count(), stp.launch_count()
+        stp.conv_fwd(C.byref(desc), ref(xs), wt.data_ptr(), None, ref(rs), ref(ys), None, 0, stream())
+        assert stp.tc_launch_count() == tc0 and stp.launch_count() == l0 + 1
+        yr = conv_ref(x, wt, 1, 0, 1, (h, w))
+        assert rel_err(y, yr + res.float().cpu()) < TOL_BF16
+        # bias + ReLU (keras Conv2D(activation='relu') of the decoders without BatchNorm)
+        bias = torch.randn(cout, generator=g).to(cuda)
+        drelu = lib.ConvDesc(1, 1, 1, 0, 0, 1, lib.CONV_RELU)
+        stp.conv_fwd(C.byref(drelu), ref(xs), wt.data_ptr(), bias.data_ptr(), None, ref(ys), None, 0, stream())
+        assert rel_err(y, torch.relu(yr + bias.cpu())) < TOL_BF16
+        # channel slices of wider buffers on both sides
+        xbig = rand_bf16((n, h, w, cin + 16), g)
+        ybig = torch.zeros((n, h, w, cout + 24), dtype=torch.bfloat16, device=cuda)
+        xbs, ybs = T(xbig, 8, cin), T(ybig, 16, cout)
+        stp.conv_fwd(C.byref(desc), ref(xbs), wt.data_ptr(), None, None, ref(ybs), None, 0, stream())
+        assert rel_err(ybig[..., 16:16 + cout], conv_ref(xbig[..., 8:8 + cin], wt, 1, 0, 1, (h, w))) < TOL_BF16
+        assert float(ybig[..., :16].abs().max()) == 0 and float(ybig[..., 16 + cout:].abs().max()) == 0
+        # dgrad = the same GEMM over dy with the [Cin][Cout] weight copy
+        wf, wd = torch.zeros_like(wt), torch.zeros_like(wt)
+        stp.weight_prep(wt.float().contiguous().data_ptr(), wf.data_ptr(), wd.data_ptr(), cout, 1, 1, cin, stream())
+        dy = rand_bf16((n, h, w, cout), g)
+        dx = torch.zeros_like(x)
+        dys, dxs = T(dy), T(dx)
+        stp.conv_dgrad(C.byref(desc), ref(dys), wd.data_ptr(), None, ref(dxs), None, 0, stream())
+        dxr = torch.einsum("nhwo,oi->nhwi", dy.float().cpu(), wt.float().cpu().view(cout, cin))
+        assert rel_err(dx, dxr) < TOL_BF16
+        dx2 = x.clone()
+        dx2s = T(dx2)
+        stp.conv_dgrad(C.byref(desc), ref(dys), wd.data_ptr(), ref(dx2s), ref(dx2s), None, 0, stream())
+        assert rel_err(dx2, dxr + x.float().cpu()) < TOL_BF16
+    finally:
+        stp.set_option(b"gemm1x1", 0)
