@@ -51,7 +51,9 @@ extern "C" int stp_set_option(const char* name, int32_t value) {
   else if (!strcmp(name, "tc3_force_bn")) key = OPT_TC3_FORCE_BN;       /* 0 heuristic | 128, 256 */
   else if (!strcmp(name, "tc3_force_mt")) key = OPT_TC3_FORCE_MT;       /* 0 heuristic | 1, 2 */
   else if (!strcmp(name, "tc3_halo")) key = OPT_TC3_HALO;               /* 0 off | 1 on: ONE haloed A box per channel block (measured slower, see conv_tc3.cu) */
-  else if (!strcmp(name, "gemm1x1")) key = OPT_GEMM1X1;                 /* 0 auto: every eligible 1x1 stride-1 conv (no fused BatchNorm epilogue) on the streaming GEMM kernel | 1 off | 2 only where no tcgen05 kernel serves the shape */
+  else if (!strcmp(name, "gemm1x1")) key = OPT_GEMM1X1;                 /* 0 auto: 1x1 stride-1 convs the tcgen05 halo kernel does not tile (MobileNetV2 / Xception widths) on the streaming mma.sync GEMM | 1 off | 2 every eligible 1x1 conv */
+  else if (!strcmp(name, "nconv")) key = OPT_NCONV;                     /* 0 off (measured slower than the tcgen05 halo kernel, conv_narrow.cu) | 1: 3x3 convs with Cin, Cout in {16, 32} on the mma.sync narrow-channel kernel */
+  else if (!strcmp(name, "tc2_1x1")) key = OPT_TC2_1X1;                 /* 0 auto: 1x1 stride-1 convs take the halo kernel conv_tc2 (a plain GEMM over pixel strips) where it tiles the shape | 1 off */
   else if (!strcmp(name, "head_strip")) key = OPT_HEAD_STRIP;           /* 0 on | 1 off: column-strip head backward kernels (sliding dlogit window) */
   else if (!strcmp(name, "tc3_bn64")) key = OPT_TC3_BN64;               /* 0 off | 1 on: N = 64 CTA-pair tiles for Cout = 64 / 192 layers (measured slower) */
   else if (!strcmp(name, "bnb_fuse")) key = OPT_BNB_FUSE;               /* 0 auto | 1: never fuse the BatchNorm-backward reduction into the dgrad epilogue */
@@ -74,17 +76,25 @@ extern "C" int stp_tc_enabled(void) { return g_tc_enabled.load(); }
 extern "C" void stp_set_tc_enabled(int on) { g_tc_enabled.store(on ? 1 : 0); }
 
 static int dispatch_conv(const ConvP& p, cudaStream_t st) {
-  // 1x1 stride-1 convolutions without a fused BatchNorm epilogue (dgrads, FPN laterals, MobileNetV2 projections) are HBM-bound
-  // GEMMs: the streaming mma.sync kernel beat the tcgen05 tiles on both graphs that have them (profiles/r2_s8_gemm1x1_ab.txt:
-  // FPN/ResNet-50 782 -> 854 img/s, DeepLabV3 8.66 -> 8.09 ms), so it is the automatic choice.  1 = off, 2 = fallback only.
+  // 1x1 stride-1 convolutions (profiles/r2_s10_g1_bench.txt, bs16 back to back): the tcgen05 halo kernel conv_tc2 run as a plain
+  // GEMM wins wherever it tiles the shape (64 -> 256 @128^2: 42.6 us against 72.5 us streaming mma.sync GEMM and 193 us first-
+  // generation tcgen05 kernel); the streaming GEMM (legacy tensor path, ~290 TF/s ceiling) serves the widths it does not tile
+  // (24, 96, 144, 160, 728 ...); the first-generation kernel keeps the few-pixel long-K corner (2048 -> 512 @16^2: 16.3 vs 23.0 us).
   const int g1 = get_option(OPT_GEMM1X1);
-  if (g1 == 0 && gemm1x1_supported(p)) return launch_gemm1x1(p, st);
-  if (stp_tc_enabled()) {
+  const bool tc = stp_tc_enabled() != 0;
+  bool long_k_few_pixels = false;
+  if (p.R == 1 && p.S == 1 && p.stride == 1 && p.up == 1) {
+    if (g1 == 2 && gemm1x1_supported(p)) return launch_gemm1x1(p, st);
+    long_k_few_pixels = p.M <= 8192 && p.Cin >= 1024 && tc && tc_conv_supported(p);
+    if (tc && get_option(OPT_TC_CONV_VERSION) != 1 && !long_k_few_pixels && tc2_conv_supported(p)) return launch_tc2_conv(p, st);
+    if (g1 == 0 && !long_k_few_pixels && gemm1x1_supported(p)) return launch_gemm1x1(p, st);
+  }
+  if (get_option(OPT_NCONV) == 1 && narrow_conv_supported(p)) return launch_narrow_conv(p, st);
+  if (tc) {
     if (get_option(OPT_TC_CONV_VERSION) != 1 && tc3_conv_supported(p)) return launch_tc3_conv(p, st);
-    if (get_option(OPT_TC_CONV_VERSION) != 1 && tc2_conv_supported(p)) return launch_tc2_conv(p, st);
+    if (get_option(OPT_TC_CONV_VERSION) != 1 && !long_k_few_pixels && tc2_conv_supported(p)) return launch_tc2_conv(p, st);
     if (tc_conv_supported(p)) return launch_tc_conv(p, st);
   }
-  if (g1 != 1 && gemm1x1_supported(p)) return launch_gemm1x1(p, st);
   return launch_generic_conv(p, st);
 }
 
@@ -145,7 +155,8 @@ static int conv_fwd_common(const stp_conv_desc* d, const stp_tensor* x, const vo
   // BatchNorm statistics of y: inside the conv epilogue when the halo kernel serves this shape, else one extra pass
   STP_REQUIRE(h_bn->partial && h_bn->sync && h_bn->acc && h_bn->coef, "conv_fwd_bn: null statistics buffers");
   STP_REQUIRE(y->dtype == STP_BF16 && pixels(y) > 0, "conv_fwd_bn: y must be a non-empty bf16 tensor");
-  if (stp_tc_enabled() && get_option(OPT_TC_CONV_VERSION) != 1 && (tc3_conv_supported(p) || tc2_conv_supported(p))) {
+  const bool nconv = get_option(OPT_NCONV) == 1 && narrow_conv_supported(p);
+  if (nconv || (stp_tc_enabled() && get_option(OPT_TC_CONV_VERSION) != 1 && (tc3_conv_supported(p) || tc2_conv_supported(p)))) {
     const int64_t count = pixels(y);
     BnFuse bn;
     bn.acc = h_bn->acc;
@@ -155,6 +166,7 @@ static int conv_fwd_common(const stp_conv_desc* d, const stp_tensor* x, const vo
     bn.fin.gamma = h_bn->gamma; bn.fin.beta = h_bn->beta; bn.fin.eps = h_bn->eps; bn.fin.momentum = h_bn->momentum;
     bn.fin.mov_mean = h_bn->moving_mean; bn.fin.mov_var = h_bn->moving_var; bn.fin.coef = h_bn->coef;
     p.bn = &bn;
+    if (nconv) return launch_narrow_conv(p, (cudaStream_t)stream);
     if (tc3_conv_supported(p)) return launch_tc3_conv(p, (cudaStream_t)stream);
     return launch_tc2_conv(p, (cudaStream_t)stream);
   }
@@ -229,6 +241,8 @@ static int conv_dgrad_common(const stp_conv_desc* d, const stp_tensor* dy, const
   p.bn = &bn;
   p.bnb_x = (const __nv_bfloat16*)h_bnb->x->ptr; p.bnb_ldx = h_bnb->x->ld; p.bnb_coef = h_bnb->coef; p.bnb_relu = h_bnb->relu;
   // (the fused epilogue masks ReLU only: a ReLU6 layer, relu == 2, takes the two-pass path below)
+  if (get_option(OPT_BNB_FUSE) != 1 && h_bnb->relu != 2 && get_option(OPT_NCONV) == 1 && narrow_conv_supported(p))
+    return launch_narrow_conv(p, (cudaStream_t)stream);
   if (stp_tc_enabled() && get_option(OPT_TC_CONV_VERSION) != 1 && get_option(OPT_BNB_FUSE) != 1 && h_bnb->relu != 2 && tc2_conv_supported(p))
     return launch_tc2_conv(p, (cudaStream_t)stream);
   p.bn = nullptr;

@@ -55,6 +55,23 @@ __global__ void __launch_bounds__(kThreads) gemm1x1_kernel(const G1Args a) {
   const int wm = warp % WM, wn = warp / WM;
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
   const int KT = (a.K + kBK - 1) / kBK;
+  // residual tile [128][BN + 8] bf16 behind the ring: fetched as coalesced 16-byte row chunks by the first cp.async group (it
+  // lands under the whole K loop) and read back in fragment layout by the epilogue.  Per-fragment 4-byte global loads (8 rows
+  // x 16 B per warp instruction, half of every sector wasted) made the accumulate-in-place dgrads of the ResNet-50 bottlenecks
+  // the slowest launches of the FPN step (256 ch @128^2: 134 us for a 46 us HBM floor, profiles/r2_c3_launches.csv).
+  constexpr int LDR = BN + 8;
+  __nv_bfloat16* sres = reinterpret_cast<__nv_bfloat16*>(smem + kStages * kStage);
+  if (a.res) {
+    constexpr int CVR = BN / 8;
+    const uint32_t sr = sbase + kStages * kStage;
+    for (int q = tid; q < kBM * CVR; q += kThreads) {
+      const int row = q / CVR, c = q - row * CVR;
+      const int m = m0 + row, n = n0 + c * 8;
+      const bool ok = m < a.M && n < a.N;
+      cp_async16(sr + (uint32_t)(row * LDR + c * 8) * 2, ok ? (const void*)(a.res + (int64_t)m * a.ldr + n) : (const void*)a.res, ok ? 16 : 0);
+    }
+    cp_commit();
+  }
 
   auto load_stage = [&](int kt, int stage) {
     const uint32_t sa = sbase + stage * kStage, sb = sa + kABytes;
@@ -151,14 +168,14 @@ __global__ void __launch_bounds__(kThreads) gemm1x1_kernel(const G1Args a) {
 
 template <int BN>
 int launch_bn(const G1Args& a, cudaStream_t stv) {
-  constexpr int smem = kStages * (kBM * kBK * 2 + BN * kBK * 2);
+  constexpr int ring = kStages * (kBM * kBK * 2 + BN * kBK * 2), rtile = kBM * (BN + 8) * 2;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(gemm1x1_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(gemm1x1_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring + rtile);
     attr = true;
   }
   const int tiles_m = (a.M + kBM - 1) / kBM;
-  gemm1x1_kernel<BN><<<tiles_m * a.tiles_n, kThreads, smem, stv>>>(a);
+  gemm1x1_kernel<BN><<<tiles_m * a.tiles_n, kThreads, ring + (a.res ? rtile : 0), stv>>>(a);
   return check_launch("gemm1x1");
 }
 
@@ -169,7 +186,7 @@ bool gemm1x1_supported(const ConvP& p) {
   if (p.y_f32 || p.bn != nullptr || p.ncls != 0 || p.bnb_x != nullptr) return false;
   if (p.Cin % 8 != 0 || p.Cout % 8 != 0 || p.ldx % 8 != 0 || p.ldy % 8 != 0) return false;
   if (!aligned16(p.x) || !aligned16(p.w) || !aligned16(p.y)) return false;
-  if (p.res && (p.ldr % 2 != 0)) return false;
+  if (p.res && (p.ldr % 8 != 0 || !aligned16(p.res))) return false;
   if (p.M >= ((int64_t)1 << 31) - kBM) return false;
   return true;
 }

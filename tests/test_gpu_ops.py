@@ -544,7 +544,9 @@ def test_stem_space_to_depth_equals_7x7_stride2(stp, cuda):
 
 
 @pytest.mark.parametrize("case", [(2, 24, 40, 64, 64, 3, 1, 1), (1, 9, 17, 128, 256, 3, 1, 1), (2, 20, 36, 16, 16, 3, 1, 1),
-                                  (1, 12, 24, 32, 32, 3, 1, 1), (2, 16, 16, 64, 128, 3, 2, 1), (3, 8, 8, 256, 512, 3, 1, 1)])
+                                  (1, 12, 24, 32, 32, 3, 1, 1), (2, 16, 16, 64, 128, 3, 2, 1), (3, 8, 8, 256, 512, 3, 1, 1),
+                                  # 1x1 stride-1 layers on the halo kernel (plain GEMM over pixel strips): ResNet-50 bottleneck forms
+                                  (2, 24, 40, 64, 256, 1, 1, 0), (1, 9, 17, 256, 64, 1, 1, 0), (3, 16, 16, 512, 128, 1, 1, 0)])
 def test_conv_fwd_bn_epilogue_statistics(stp, cuda, case):
     """stp_conv_fwd_bn (statistics accumulated in the conv epilogue, or the fallback pass) == conv + stp_bn_stats_fused,
     with residual, partial tiles, several N tiles; accumulators and ticket return to zero (replayable)."""
@@ -922,7 +924,7 @@ G1_CASES = [
     (1, 9, 7, 144, 24),       # N = 24 < 64
     (2, 16, 16, 728, 728),    # Xception middle flow
     (1, 12, 12, 16, 96),      # the tiny-K case the tcgen05 kernel loses
-    (2, 32, 32, 64, 128),     # a shape the tcgen05 kernel also serves (gemm1x1 = 0, the default, prefers this kernel)
+    (2, 32, 32, 64, 128),     # a shape the tcgen05 kernel also serves (option gemm1x1 = 2 forces this kernel)
     (1, 8, 8, 960, 320),
 ]
 
@@ -932,7 +934,7 @@ def test_gemm1x1(stp, cuda, case):
     """forward (+ residual, + bias + ReLU), forward into / out of channel slices (ld > c), and dgrad (plain and accumulate in
     place) of 1x1 stride-1 convolutions on the streaming GEMM kernel, against fp32 math on the same bf16 operands"""
     n, h, w, cin, cout = case
-    stp.set_option(b"gemm1x1", 0)
+    stp.set_option(b"gemm1x1", 2)
     try:
         g = torch.Generator().manual_seed(sum(case))
         x = rand_bf16((n, h, w, cin), g)
@@ -974,3 +976,128 @@ def test_gemm1x1(stp, cuda, case):
         assert rel_err(dx2, dxr + x.float().cpu()) < TOL_BF16
     finally:
         stp.set_option(b"gemm1x1", 0)
+
+
+NC_CASES = [
+    # n, h, w, cin, cout: 3x3 stride-1 'same' convolutions of the decoder tail on the narrow-channel kernel (csrc/conv_narrow.cu)
+    (4, 100, 300, 16, 16),    # 520 tiles > 2 x 148 CTAs: the persistent loop, both ring stages, partial right / bottom tiles
+    (2, 37, 70, 32, 16),
+    (2, 40, 33, 16, 32),
+    (3, 64, 96, 32, 32),
+    (1, 5, 9, 16, 16),        # smaller than one tile
+]
+
+
+@pytest.mark.parametrize("case", NC_CASES)
+def test_conv_narrow(stp, cuda, case):
+    """forward (plain, bias + ReLU, into / out of channel slices), forward with the BatchNorm-statistics epilogue and dgrad on the
+    narrow-channel mma.sync kernel (opt-in, option nconv = 1: measured slower than the tcgen05 halo kernel on every shape,
+    profiles/r2_s9_nconv_bench.txt): against fp32 math on the same bf16 operands, and against the halo kernel (nconv = 0)"""
+    n, h, w, cin, cout = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = rand_bf16((n, h, w, cin), g)
+    wt = rand_bf16((cout, 3, 3, cin), g, scale=1.0 / math.sqrt(9 * cin))
+    desc = lib.ConvDesc(3, 3, 1, 1, 1, 1, 0)
+    xs = T(x)
+    yr = conv_ref(x, wt, 1, 1)
+    ys_by_path = []
+    for on in (1, 0):
+        stp.set_option(b"nconv", on)
+        y = torch.zeros((n, h, w, cout), dtype=torch.bfloat16, device=cuda)
+        tc0, l0 = stp.tc_launch_count(), stp.launch_count()
+        stp.conv_fwd(C.byref(desc), ref(xs), wt.data_ptr(), None, None, ref(T(y)), None, 0, stream())
+        assert stp.launch_count() == l0 + 1 and stp.tc_launch_count() - tc0 == 1 - on   # which kernel served it
+        assert rel_err(y, yr) < TOL_BF16
+        ys_by_path.append(y)
+    assert rel_err(ys_by_path[0], ys_by_path[1].float()) < 1e-3
+    stp.set_option(b"nconv", 1)
+    try:
+        _conv_narrow_rest(stp, cuda, case, g, x, wt, desc, xs, yr, ys_by_path[0])
+    finally:
+        stp.set_option(b"nconv", 0)
+
+
+def _conv_narrow_rest(stp, cuda, case, g, x, wt, desc, xs, yr, y_narrow):
+    n, h, w, cin, cout = case
+    # bias + ReLU
+    bias = torch.randn(cout, generator=g).to(cuda)
+    drelu = lib.ConvDesc(3, 3, 1, 1, 1, 1, lib.CONV_RELU)
+    y = torch.zeros((n, h, w, cout), dtype=torch.bfloat16, device=cuda)
+    stp.conv_fwd(C.byref(drelu), ref(xs), wt.data_ptr(), bias.data_ptr(), None, ref(T(y)), None, 0, stream())
+    assert rel_err(y, torch.relu(yr + bias.cpu())) < TOL_BF16
+    # channel slices of wider buffers on both sides (zero-copy concat)
+    xbig = rand_bf16((n, h, w, cin + 24), g)
+    ybig = torch.zeros((n, h, w, cout + 16), dtype=torch.bfloat16, device=cuda)
+    l0 = stp.launch_count()
+    stp.conv_fwd(C.byref(desc), ref(T(xbig, 16, cin)), wt.data_ptr(), None, None, ref(T(ybig, 8, cout)), None, 0, stream())
+    assert stp.launch_count() == l0 + 1
+    assert rel_err(ybig[..., 8:8 + cout], conv_ref(xbig[..., 16:16 + cin], wt, 1, 1)) < TOL_BF16
+    assert float(ybig[..., :8].abs().max()) == 0 and float(ybig[..., 8 + cout:].abs().max()) == 0
+    # BatchNorm statistics in the epilogue == conv + the one-launch statistics kernel (twice: accumulators / ticket return to zero)
+    rows = n * h * w
+    partial = torch.zeros(2 * stp.bn_nblk(rows, cout) * cout, device=cuda)
+    sync = torch.zeros(4, dtype=torch.int32, device=cuda)
+    acc = torch.zeros(2 * cout, dtype=torch.float64, device=cuda)
+    gamma = (torch.rand(cout, generator=g) + 0.5).to(cuda)
+    beta = (torch.randn(cout, generator=g) * 0.2).to(cuda)
+    y0 = y_narrow
+    coef0 = torch.zeros(4 * cout, device=cuda)
+    mm0, mv0 = torch.zeros(cout, device=cuda), torch.ones(cout, device=cuda)
+    stp.bn_stats_fused(ref(T(y0)), partial.data_ptr(), sync.data_ptr(), None, gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.99,
+                       mm0.data_ptr(), mv0.data_ptr(), coef0.data_ptr(), stream())
+    for _ in range(2):
+        y1 = torch.zeros_like(y0)
+        coef1 = torch.zeros(4 * cout, device=cuda)
+        mm1, mv1 = torch.zeros(cout, device=cuda), torch.ones(cout, device=cuda)
+        bn = lib.BnFwd(partial.data_ptr(), sync.data_ptr(), acc.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.99,
+                       mm1.data_ptr(), mv1.data_ptr(), coef1.data_ptr())
+        l0 = stp.launch_count()
+        stp.conv_fwd_bn(C.byref(desc), ref(xs), wt.data_ptr(), None, None, ref(T(y1)), C.byref(bn), None, 0, stream())
+        assert stp.launch_count() == l0 + 1, "the statistics must come out of the conv kernel's epilogue"
+        assert torch.equal(y1, y0)
+        assert int(sync[0]) == 0 and float(acc.abs().max()) == 0.0
+        scale = 1 + float(coef0.abs().max())
+        assert max_abs(coef1, coef0) <= 2e-6 * scale, max_abs(coef1, coef0)
+        assert max_abs(mm1, mm0) < 1e-6 and rel_err(mv1, mv0) < 1e-6
+    # dgrad = the same kernel over dy with the tap-flipped [Cin][3][3][Cout] weight copy
+    wf, wd = torch.zeros_like(wt), torch.zeros_like(wt)
+    stp.weight_prep(wt.float().contiguous().data_ptr(), wf.data_ptr(), wd.data_ptr(), cout, 3, 3, cin, stream())
+    dy = rand_bf16((n, h, w, cout), g)
+    dx = torch.zeros_like(x)
+    tc0 = stp.tc_launch_count()
+    stp.conv_dgrad(C.byref(desc), ref(T(dy)), wd.data_ptr(), None, ref(T(dx)), None, 0, stream())
+    assert stp.tc_launch_count() == tc0
+    xr = x.float().cpu().requires_grad_(True)
+    conv_ref_autograd(xr, wt.float().cpu(), 1, 1, 1, (h, w)).backward(dy.float().cpu())
+    assert rel_err(dx, xr.grad) < TOL_BF16
+    # fused BatchNorm-backward masking + reduction in the dgrad epilogue == dgrad, then the separate reduction pass
+    gam = (torch.rand(cin, generator=g) + 0.5).to(cuda)
+    gam[::3] *= -1.0
+    bet = (torch.rand(cin, generator=g) - 0.5).to(cuda)
+    rows = n * h * w
+    partial = torch.zeros(2 * stp.bn_nblk(rows, max(cin, cout)) * max(cin, cout), device=cuda)
+    sync = torch.zeros(4, dtype=torch.int32, device=cuda)
+    acc = torch.zeros(2 * max(cin, cout), dtype=torch.float64, device=cuda)
+    coef = torch.zeros(4 * cin, device=cuda)
+    mm, mv = torch.zeros(cin, device=cuda), torch.ones(cin, device=cuda)
+    stp.bn_stats_fused(ref(xs), partial.data_ptr(), sync.data_ptr(), acc.data_ptr(), gam.data_ptr(), bet.data_ptr(), 1e-3, 0.99,
+                       mm.data_ptr(), mv.data_ptr(), coef.data_ptr(), stream())
+    d0, b0, c0 = torch.zeros(cin, device=cuda), torch.zeros(cin, device=cuda), torch.zeros(3 * cin, device=cuda)
+    stp.bn_bwd_reduce_fused(ref(T(dx)), ref(xs), coef.data_ptr(), 1, 1, partial.data_ptr(), sync.data_ptr(), acc.data_ptr(),
+                            d0.data_ptr(), b0.data_ptr(), c0.data_ptr(), stream())
+    d1, b1, c1 = torch.zeros(cin, device=cuda), torch.zeros(cin, device=cuda), torch.zeros(3 * cin, device=cuda)
+    dxm = torch.zeros_like(x)
+    bnb = lib.BnBwd(C.pointer(xs), coef.data_ptr(), 1, partial.data_ptr(), sync.data_ptr(), acc.data_ptr(),
+                    d1.data_ptr(), b1.data_ptr(), c1.data_ptr())
+    l0, tc0 = stp.launch_count(), stp.tc_launch_count()
+    for _ in range(2):
+        stp.conv_dgrad_bn(C.byref(desc), ref(T(dy)), wd.data_ptr(), ref(T(dxm)), C.byref(bnb), None, 0, stream())
+    assert stp.launch_count() == l0 + 2 and stp.tc_launch_count() == tc0
+    torch.cuda.synchronize()
+    assert int(sync[0]) == 0 and float(acc.abs().max()) == 0.0
+    c4 = coef.view(4, cin)
+    mask = x.float() * c4[2] + c4[3] > 0
+    assert torch.equal(dxm, torch.where(mask, dx, torch.zeros_like(dx)))
+    for got, want in ((d1, d0), (b1, b0), (c1, c0)):
+        scale = 1e-6 + float(want.abs().max())
+        assert max_abs(got, want) <= 2e-4 * scale, (max_abs(got, want), scale)
