@@ -53,7 +53,7 @@ extern "C" int stp_set_option(const char* name, int32_t value) {
   else if (!strcmp(name, "tc3_halo")) key = OPT_TC3_HALO;               /* 0 off | 1 on: ONE haloed A box per channel block (measured slower, see conv_tc3.cu) */
   else if (!strcmp(name, "gemm1x1")) key = OPT_GEMM1X1;                 /* 0 auto: 1x1 stride-1 convs the tcgen05 halo kernel does not tile (MobileNetV2 / Xception widths) on the streaming mma.sync GEMM | 1 off | 2 every eligible 1x1 conv */
   else if (!strcmp(name, "nconv")) key = OPT_NCONV;                     /* 0 off (measured slower than the tcgen05 halo kernel, conv_narrow.cu) | 1: 3x3 convs with Cin, Cout in {16, 32} on the mma.sync narrow-channel kernel */
-  else if (!strcmp(name, "tc2_1x1")) key = OPT_TC2_1X1;                 /* 0 auto: 1x1 stride-1 convs take the halo kernel conv_tc2 (a plain GEMM over pixel strips) where it tiles the shape | 1 off */
+  else if (!strcmp(name, "tc2_1x1")) key = OPT_TC2_1X1;                 /* 0 auto: 1x1 stride-1 convs take the halo kernel conv_tc2 (a plain GEMM over pixel strips) where it tiles the shape | 1 off | 2 only Cin % 64 == 0 */
   else if (!strcmp(name, "head_strip")) key = OPT_HEAD_STRIP;           /* 0 on | 1 off: column-strip head backward kernels (sliding dlogit window) */
   else if (!strcmp(name, "tc3_bn64")) key = OPT_TC3_BN64;               /* 0 off | 1 on: N = 64 CTA-pair tiles for Cout = 64 / 192 layers (measured slower) */
   else if (!strcmp(name, "bnb_fuse")) key = OPT_BNB_FUSE;               /* 0 auto | 1: never fuse the BatchNorm-backward reduction into the dgrad epilogue */
@@ -155,8 +155,7 @@ static int conv_fwd_common(const stp_conv_desc* d, const stp_tensor* x, const vo
   // BatchNorm statistics of y: inside the conv epilogue when the halo kernel serves this shape, else one extra pass
   STP_REQUIRE(h_bn->partial && h_bn->sync && h_bn->acc && h_bn->coef, "conv_fwd_bn: null statistics buffers");
   STP_REQUIRE(y->dtype == STP_BF16 && pixels(y) > 0, "conv_fwd_bn: y must be a non-empty bf16 tensor");
-  const bool nconv = get_option(OPT_NCONV) == 1 && narrow_conv_supported(p);
-  if (nconv || (stp_tc_enabled() && get_option(OPT_TC_CONV_VERSION) != 1 && (tc3_conv_supported(p) || tc2_conv_supported(p)))) {
+  {
     const int64_t count = pixels(y);
     BnFuse bn;
     bn.acc = h_bn->acc;
@@ -166,9 +165,12 @@ static int conv_fwd_common(const stp_conv_desc* d, const stp_tensor* x, const vo
     bn.fin.gamma = h_bn->gamma; bn.fin.beta = h_bn->beta; bn.fin.eps = h_bn->eps; bn.fin.momentum = h_bn->momentum;
     bn.fin.mov_mean = h_bn->moving_mean; bn.fin.mov_var = h_bn->moving_var; bn.fin.coef = h_bn->coef;
     p.bn = &bn;
-    if (nconv) return launch_narrow_conv(p, (cudaStream_t)stream);
-    if (tc3_conv_supported(p)) return launch_tc3_conv(p, (cudaStream_t)stream);
-    return launch_tc2_conv(p, (cudaStream_t)stream);
+    if (get_option(OPT_NCONV) == 1 && narrow_conv_supported(p)) return launch_narrow_conv(p, (cudaStream_t)stream);
+    if (stp_tc_enabled() && get_option(OPT_TC_CONV_VERSION) != 1) {
+      if (tc3_conv_supported(p)) return launch_tc3_conv(p, (cudaStream_t)stream);
+      if (tc2_conv_supported(p)) return launch_tc2_conv(p, (cudaStream_t)stream);
+    }
+    p.bn = nullptr;
   }
   rc = dispatch_conv(p, (cudaStream_t)stream);
   if (rc) return rc;

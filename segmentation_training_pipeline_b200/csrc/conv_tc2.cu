@@ -630,7 +630,7 @@ bool tc2_plan(const ConvP& p, Tc2Plan* pl) {
   // 1x1 stride-1 convolutions run here as plain GEMMs over pixel strips (no halo, one weight box per stage): the 8-warp TMA-store
   // epilogue and the MT-stacked accumulators make this kernel ~2x faster than the streaming mma.sync GEMM (gemm1x1.cu) and 2-4x
   // faster than the first-generation kernel on the ResNet-50 bottleneck shapes (profiles/r2_s10_g1_bench.txt).  tc2_1x1 = 1: off.
-  if (p.R < 2 && p.S < 2 && get_option(OPT_TC2_1X1) == 1) return false;
+  if (p.R < 2 && p.S < 2 && (get_option(OPT_TC2_1X1) == 1 || (get_option(OPT_TC2_1X1) == 2 && p.Cin % 64 != 0))) return false;
   int bk = (p.Cin % 64 == 0) ? 64 : (p.Cin == 32 ? 32 : (p.Cin == 16 ? 16 : 0));
   if (!bk) return false;
   if (bk == 64 && get_option(OPT_TC2_BK) == 32) bk = 32;  // experiment: smaller stages -> deeper pipeline

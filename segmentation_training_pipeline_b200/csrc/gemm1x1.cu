@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(kThreads) gemm1x1_kernel(const G1Args a) {
         float v0 = acc[i][j][hh * 2], v1 = acc[i][j][hh * 2 + 1];
         const int m = m0 + row, n = n0 + col;
         if (a.bias && n < a.N) { v0 += a.bias[n]; v1 += a.bias[n + 1]; }
-        if (a.res && m < a.M && n < a.N) {
-          const __nv_bfloat162 r = *reinterpret_cast<const __nv_bfloat162*>(a.res + (int64_t)m * a.ldr + n);
+        if (a.res) {
+          const __nv_bfloat162 r = *reinterpret_cast<const __nv_bfloat162*>(sres + row * LDR + col);
           v0 += __bfloat162float(r.x); v1 += __bfloat162float(r.y);
         }
         if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }

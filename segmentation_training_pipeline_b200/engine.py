@@ -159,6 +159,9 @@ class Net:
         # U-Net/ResNet-34 step.  Round 1 (4 epilogue warps) measured it 1.3 % slower; with the 8-warp epilogue it is 1 % FASTER
         # (round 2, same box: 8.826 vs 8.911 ms, profiles/r2_s4_bench*.json.log) -> on by default; STP_FUSE_BN_BWD=0 turns it off.
         self.fuse_bn_bwd = os.environ.get("STP_FUSE_BN_BWD", "1") == "1" and precision == "bf16"
+        # 1x1 stride-1 dgrads (ResNet-50 bottlenecks, MobileNetV2 expansions) run on the same halo kernel since it serves them as
+        # plain GEMMs, so their BatchNorm-backward reductions can ride its epilogue too; STP_FUSE_BN_BWD_1X1=0 turns that off.
+        self.fuse_bn_bwd_1x1 = os.environ.get("STP_FUSE_BN_BWD_1X1", "1") == "1"
 
     # ---- parameters ---------------------------------------------------------------------------
     def add_param(self, name, shape, kind, init) -> Param:
@@ -223,7 +226,7 @@ class Net:
                     # no other op may write an overlapping slice of the same gradient buffer
                     overlap = [k for k in gwriters if k[0] == gk[0] and k != gk and k[1] < gk[1] + gk[2] and gk[1] < k[1] + k[2]]
                     if (len(w) == 1 and not overlap and type(w[0]) is Conv and w[0].needs_dgrad and w[0].x.key() == op.y.key()
-                            and w[0].desc.stride == 1 and w[0].desc.up == 1 and w[0].k > 1):
+                            and w[0].desc.stride == 1 and w[0].desc.up == 1 and (w[0].k > 1 or self.fuse_bn_bwd_1x1)):
                         w[0].bnb_prev = op
                         op.reduce_from_dgrad = True
         host = np.zeros(self.n_flat, dtype=np.float32)
