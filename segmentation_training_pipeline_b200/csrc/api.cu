@@ -54,6 +54,7 @@ extern "C" int stp_set_option(const char* name, int32_t value) {
   else if (!strcmp(name, "gemm1x1")) key = OPT_GEMM1X1;                 /* 0 auto: 1x1 stride-1 convs the tcgen05 halo kernel does not tile (MobileNetV2 / Xception widths) on the streaming mma.sync GEMM | 1 off | 2 every eligible 1x1 conv */
   else if (!strcmp(name, "nconv")) key = OPT_NCONV;                     /* 0 off (measured slower than the tcgen05 halo kernel, conv_narrow.cu) | 1: 3x3 convs with Cin, Cout in {16, 32} on the mma.sync narrow-channel kernel */
   else if (!strcmp(name, "tc2_1x1")) key = OPT_TC2_1X1;                 /* 0 auto: 1x1 stride-1 convs take the halo kernel conv_tc2 (a plain GEMM over pixel strips) where it tiles the shape | 1 off | 2 only Cin % 64 == 0 */
+  else if (!strcmp(name, "tc2_up2")) key = OPT_TC2_UP2;                 /* 0 auto: zero-insertion convs (stride-2 dgrads) as four halo-kernel launches, one per output parity class | 1 off */
   else if (!strcmp(name, "head_strip")) key = OPT_HEAD_STRIP;           /* 0 on | 1 off: column-strip head backward kernels (sliding dlogit window) */
   else if (!strcmp(name, "tc3_bn64")) key = OPT_TC3_BN64;               /* 0 off | 1 on: N = 64 CTA-pair tiles for Cout = 64 / 192 layers (measured slower) */
   else if (!strcmp(name, "bnb_fuse")) key = OPT_BNB_FUSE;               /* 0 auto | 1: never fuse the BatchNorm-backward reduction into the dgrad epilogue */
@@ -91,6 +92,7 @@ static int dispatch_conv(const ConvP& p, cudaStream_t st) {
   }
   if (get_option(OPT_NCONV) == 1 && narrow_conv_supported(p)) return launch_narrow_conv(p, st);
   if (tc) {
+    if (get_option(OPT_TC_CONV_VERSION) != 1 && get_option(OPT_TC2_UP2) != 1 && tc2_up2_supported(p)) return launch_tc2_up2(p, st);
     if (get_option(OPT_TC_CONV_VERSION) != 1 && tc3_conv_supported(p)) return launch_tc3_conv(p, st);
     if (get_option(OPT_TC_CONV_VERSION) != 1 && !long_k_few_pixels && tc2_conv_supported(p)) return launch_tc2_conv(p, st);
     if (tc_conv_supported(p)) return launch_tc_conv(p, st);

@@ -33,6 +33,11 @@ struct ConvP {
   const float* bnb_coef = nullptr;
   int bnb_relu = 0;
   int ncls = 0;  // > 0: segmentation-head epilogue (tcgen05 halo kernel only): y = dense fp32 [M][ncls], Cout is padding
+  // conv_tc2 only -- one output parity class of a zero-insertion (up == 2) problem run as a stride-1 convolution (launch_tc2_up2):
+  // element strides of the output / residual VIEW (0: dense, ldy / Wo*ldy / Ho*Wo*ldy) and the tap subset of the weight tensor
+  // [Cout][R0][w_S][Cin] it uses: filter tap (r, s) of this launch is tap (w_r0 + r*w_rs, w_s0 + s*w_ss) of the original
+  int64_t y_sw = 0, y_sh = 0, y_sn = 0, r_sw = 0, r_sh = 0, r_sn = 0;
+  int w_r0 = 0, w_rs = 1, w_s0 = 0, w_ss = 1, w_S = 0, w_K = 0;  // w_S / w_K == 0: S / K
 };
 
 struct WgradP {
@@ -57,9 +62,13 @@ int launch_split_reduce(const float* ws, int splits, int64_t n, float* out, cuda
 // conv_tc2.cu (tcgen05 + TMA, halo kernel for RxS > 1)
 bool tc2_conv_supported(const ConvP& p);
 int launch_tc2_conv(const ConvP& p, cudaStream_t st);
+// zero-insertion problems (p.up == 2: the dgrad of a stride-2 convolution, Conv2DTranspose): four stride-1 launches, one per
+// output parity class, each with its tap subset and a strided output view
+bool tc2_up2_supported(const ConvP& p);
+int launch_tc2_up2(const ConvP& p, cudaStream_t st);
 int get_option(int key);
 enum { OPT_TC2_FORCE_MT = 0, OPT_TC_CONV_VERSION = 1, OPT_TC2_DEBUG = 2, OPT_TC2_CLUSTER = 3, OPT_TC2_BK = 4, OPT_TC3 = 5,
-       OPT_TC3_FORCE_BN = 6, OPT_TC3_FORCE_MT = 7, OPT_BN_BLOCKS = 8, OPT_BNB_FUSE = 9, OPT_TC3_HALO = 10, OPT_TC3_BN64 = 11, OPT_HEAD_STRIP = 12, OPT_GEMM1X1 = 13, OPT_NCONV = 14, OPT_TC2_1X1 = 15, OPT_COUNT = 16 };
+       OPT_TC3_FORCE_BN = 6, OPT_TC3_FORCE_MT = 7, OPT_BN_BLOCKS = 8, OPT_BNB_FUSE = 9, OPT_TC3_HALO = 10, OPT_TC3_BN64 = 11, OPT_HEAD_STRIP = 12, OPT_GEMM1X1 = 13, OPT_NCONV = 14, OPT_TC2_1X1 = 15, OPT_TC2_UP2 = 16, OPT_COUNT = 24 };
 // device buffer (>= 64 uint64) that CTA 0 and the last CTA of conv_tc2_kernel fill with %globaltimer stamps of their
 // phases (scripts/trace_conv.py); nullptr = off.  Profiling aid only.
 unsigned long long* get_trace_buffer();

@@ -45,6 +45,7 @@ struct Tc2Args {
   int ldy, ldr, y_f32, relu;
   int Ho, Wo, Cout, Cin;
   int R, S, pad_h, pad_w;
+  int wr0, wrs, ws0, wss, wS;  // weight tap remap (ConvP::w_*): tap (r, s) reads tap (wr0 + r*wrs, ws0 + s*wss) of a [..][wS] filter
   int BW, BH, log2BW;
   int tilesW, tilesH, tilesN;
   int num_tiles;             // work items: tiles (CL == 1) or cluster items = groups of CL pixel tiles x N tiles
@@ -202,11 +203,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 constexpr int kSliceRows = BN / CL;
                 for (int r = 0; r < a.R; ++r)
                   tma_load_2d_mc(sB + stage * Cfg::kBBytes + r * Cfg::kBTap + crank * (kSliceRows * BK * 2), &tmB, &full[stage],
-                                 (r * a.S + s) * a.Cin + cb * BK, n0 + crank * kSliceRows, kMask);
+                                 ((a.wr0 + r * a.wrs) * a.wS + a.ws0 + s * a.wss) * a.Cin + cb * BK, n0 + crank * kSliceRows, kMask);
               } else if (!(a.dbg & 2))
               for (int r = 0; r < a.R; ++r)
                 tma_load_2d(sB + stage * Cfg::kBBytes + r * Cfg::kBTap, &tmB, &full[stage],
-                            (r * a.S + s) * a.Cin + cb * BK, n0);
+                            ((a.wr0 + r * a.wrs) * a.wS + a.ws0 + s * a.wss) * a.Cin + cb * BK, n0);
             }
             __syncwarp();
             if (++stage == NS) {
@@ -751,6 +752,7 @@ int launch_tc2_conv(const ConvP& p, cudaStream_t st) {
   Tc2Args a;
   a.y = p.y; a.res = p.res; a.bias = p.bias; a.ldy = p.ldy; a.ldr = p.ldr; a.y_f32 = p.y_f32; a.relu = p.relu;
   a.Ho = p.Ho; a.Wo = p.Wo; a.Cout = p.Cout; a.Cin = p.Cin; a.R = p.R; a.S = p.S; a.pad_h = p.pad_h; a.pad_w = p.pad_w;
+  a.wr0 = p.w_r0; a.wrs = p.w_rs; a.ws0 = p.w_s0; a.wss = p.w_ss; a.wS = p.w_S ? p.w_S : p.S;
   a.BW = p.Wo >= 16 ? 16 : 8;
   a.BH = 128 / a.BW;
   a.log2BW = a.BW == 16 ? 4 : 3;
@@ -785,8 +787,9 @@ int launch_tc2_conv(const ConvP& p, cudaStream_t st) {
     if (!make_tmap_bf16(&tmA, p.x, 4, dims, strides, box, pl.BK * 2)) return STP_E_CUDA;
   }
   {
-    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.Cout};
-    uint64_t strides[1] = {(uint64_t)p.K * 2};
+    const uint64_t wk = (uint64_t)(p.w_K ? p.w_K : p.K);
+    uint64_t dims[2] = {wk, (uint64_t)p.Cout};
+    uint64_t strides[1] = {wk * 2};
     uint32_t box[2] = {(uint32_t)pl.BK, (uint32_t)(pl.BN / pl.CL)};  // cluster variants: each CTA loads 1/CL of the rows
     if (!make_tmap_bf16(&tmB, p.w, 2, dims, strides, box, pl.BK * 2)) return STP_E_CUDA;
   }
@@ -795,10 +798,12 @@ int launch_tc2_conv(const ConvP& p, cudaStream_t st) {
   if (!p.y_f32) {
     uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.N};
     uint64_t strides[3] = {(uint64_t)p.ldy * 2, (uint64_t)p.Wo * p.ldy * 2, (uint64_t)p.Ho * p.Wo * p.ldy * 2};
+    if (p.y_sw) { strides[0] = (uint64_t)p.y_sw * 2; strides[1] = (uint64_t)p.y_sh * 2; strides[2] = (uint64_t)p.y_sn * 2; }
     uint32_t box[4] = {oc, (uint32_t)a.BW, (uint32_t)a.BH, 1};
     if (!make_tmap_bf16(&tmY, p.y, 4, dims, strides, box, oc * 2)) return STP_E_CUDA;
     if (p.res) {
       uint64_t rstrides[3] = {(uint64_t)p.ldr * 2, (uint64_t)p.Wo * p.ldr * 2, (uint64_t)p.Ho * p.Wo * p.ldr * 2};
+      if (p.r_sw) { rstrides[0] = (uint64_t)p.r_sw * 2; rstrides[1] = (uint64_t)p.r_sh * 2; rstrides[2] = (uint64_t)p.r_sn * 2; }
       if (!make_tmap_bf16(&tmR, p.res, 4, dims, rstrides, box, oc * 2)) return STP_E_CUDA;
     } else if (a.bn_on == 2) {  // the BatchNorm input of the same pixels travels through the residual slot
       uint64_t rstrides[3] = {(uint64_t)p.bnb_ldx * 2, (uint64_t)p.Wo * p.bnb_ldx * 2, (uint64_t)p.Ho * p.Wo * p.bnb_ldx * 2};
@@ -834,6 +839,61 @@ int launch_tc2_conv(const ConvP& p, cudaStream_t st) {
 #undef STP_TC2_CASE
   set_error("conv_tc2: no specialisation BN=%d BK=%d MT=%d", pl.BN, pl.BK, pl.MT);
   return STP_E_UNSUPPORTED;
+}
+
+// ---- zero-insertion (up == 2) problems as four stride-1 launches --------------------------------------------------------
+// y[i] = sum_r' xup[i - pad + r'] w[r'],  xup[2o] = x[o]: for the output parity class i = 2a + ph only the taps with
+// (ph - pad + r') even contribute, reading x[a + (ph - pad + r')/2] -- consecutive input rows for consecutive kept taps, i.e. a
+// stride-1 convolution with every second filter tap, written to every second output pixel (a strided TMA-store view).  The
+// first-generation kernel serves all four classes in one launch with per-thread strided stores (conv_tc.cu); here each class
+// gets the halo kernel's operand reuse and TMA-store epilogue: dgrad of 3x3/2 64 -> 128 @128^2 bs16 107 us -> see profiles/.
+static bool tc2_up2_class(const ConvP& p, int ph, int pw, ConvP* q) {
+  *q = p;
+  const int r0 = ((p.pad_h - ph) % 2 + 2) % 2, s0 = ((p.pad_w - pw) % 2 + 2) % 2;
+  const int rc = r0 < p.R ? (p.R - r0 + 1) / 2 : 0, sc = s0 < p.S ? (p.S - s0 + 1) / 2 : 0;
+  q->Ho = (p.Ho - ph + 1) / 2;
+  q->Wo = (p.Wo - pw + 1) / 2;
+  if (rc == 0 || sc == 0 || q->Ho <= 0 || q->Wo <= 0) return false;
+  q->up = 1; q->stride = 1;
+  q->R = rc; q->S = sc;
+  q->pad_h = -((ph - p.pad_h + r0) / 2);  // numerator even: exact for negatives
+  q->pad_w = -((pw - p.pad_w + s0) / 2);
+  q->w_r0 = r0; q->w_rs = 2; q->w_s0 = s0; q->w_ss = 2; q->w_S = p.S; q->w_K = p.K;
+  q->K = rc * sc * p.Cin;
+  q->M = (int64_t)p.N * q->Ho * q->Wo;
+  const int64_t yo = ((int64_t)ph * p.Wo + pw) * p.ldy;
+  q->y = (__nv_bfloat16*)p.y + yo;
+  q->y_sw = (int64_t)2 * p.ldy; q->y_sh = (int64_t)2 * p.Wo * p.ldy; q->y_sn = (int64_t)p.Ho * p.Wo * p.ldy;
+  if (p.res) {
+    q->res = p.res + ((int64_t)ph * p.Wo + pw) * p.ldr;
+    q->r_sw = (int64_t)2 * p.ldr; q->r_sh = (int64_t)2 * p.Wo * p.ldr; q->r_sn = (int64_t)p.Ho * p.Wo * p.ldr;
+  }
+  return true;
+}
+
+bool tc2_up2_supported(const ConvP& p) {
+  if (p.up != 2 || p.stride != 1 || p.y_f32 || p.ncls != 0 || p.bn || p.R > 4 || p.S > 4 || p.R < 2 || p.S < 2) return false;
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      ConvP q;
+      if (!tc2_up2_class(p, ph, pw, &q)) return false;  // a class no tap reaches (zeros + residual): first-generation kernel
+      if (!tc2_conv_supported(q)) return false;
+    }
+  return true;
+}
+
+int launch_tc2_up2(const ConvP& p, cudaStream_t st) {
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      ConvP q;
+      if (!tc2_up2_class(p, ph, pw, &q)) {
+        set_error("conv_tc2 (up 2): empty class");
+        return STP_E_UNSUPPORTED;
+      }
+      const int rc = launch_tc2_conv(q, st);
+      if (rc) return rc;
+    }
+  return STP_OK;
 }
 
 }  // namespace stp

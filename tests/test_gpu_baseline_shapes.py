@@ -126,7 +126,8 @@ def test_conv_at_baseline_shape_bs16(stp, cuda, layer):
         tc0 = stp.tc_launch_count()
         stp.conv_dgrad(C.byref(desc), ref(dys), wd.data_ptr(), None, ref(dxs), None, 0, stream())
         torch.cuda.synchronize()
-        assert stp.tc_launch_count() - tc0 == 1, "dgrad of %s did not run on a tcgen05 kernel" % name
+        # one tcgen05 launch, or four for the dgrad of a 3x3 stride-2 layer (one halo-kernel launch per output parity class)
+        assert stp.tc_launch_count() - tc0 == (4 if (stride == 2 and k == 3) else 1), "dgrad of %s did not run on a tcgen05 kernel" % name
         assert _rel(dx.float().cpu(), xr.grad.permute(0, 2, 3, 1)) < TOL_BF16, name
     nws = stp.conv_wgrad_workspace(C.byref(desc), ref(xs), ref(dys))
     ws = torch.zeros(max(int(nws), 16), dtype=torch.uint8, device=cuda)
