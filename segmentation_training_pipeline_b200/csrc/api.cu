@@ -55,6 +55,7 @@ extern "C" int stp_set_option(const char* name, int32_t value) {
   else if (!strcmp(name, "nconv")) key = OPT_NCONV;                     /* 0 off (measured slower than the tcgen05 halo kernel, conv_narrow.cu) | 1: 3x3 convs with Cin, Cout in {16, 32} on the mma.sync narrow-channel kernel */
   else if (!strcmp(name, "tc2_1x1")) key = OPT_TC2_1X1;                 /* 0 auto: 1x1 stride-1 convs take the halo kernel conv_tc2 (a plain GEMM over pixel strips) where it tiles the shape | 1 off | 2 only Cin % 64 == 0 */
   else if (!strcmp(name, "tc2_up2")) key = OPT_TC2_UP2;                 /* 0 auto: zero-insertion convs (stride-2 dgrads) as four halo-kernel launches, one per output parity class | 1 off */
+  else if (!strcmp(name, "g1_bn")) key = OPT_G1_BN;                     /* 0 auto | 1: no BatchNorm epilogues in the streaming 1x1 GEMM (conv + separate reduction pass) */
   else if (!strcmp(name, "head_strip")) key = OPT_HEAD_STRIP;           /* 0 on | 1 off: column-strip head backward kernels (sliding dlogit window) */
   else if (!strcmp(name, "tc3_bn64")) key = OPT_TC3_BN64;               /* 0 off | 1 on: N = 64 CTA-pair tiles for Cout = 64 / 192 layers (measured slower) */
   else if (!strcmp(name, "bnb_fuse")) key = OPT_BNB_FUSE;               /* 0 auto | 1: never fuse the BatchNorm-backward reduction into the dgrad epilogue */
@@ -172,6 +173,8 @@ static int conv_fwd_common(const stp_conv_desc* d, const stp_tensor* x, const vo
       if (tc3_conv_supported(p)) return launch_tc3_conv(p, (cudaStream_t)stream);
       if (tc2_conv_supported(p)) return launch_tc2_conv(p, (cudaStream_t)stream);
     }
+    // 1x1 layers the halo kernel does not tile (MobileNetV2 / Xception widths): statistics in the streaming GEMM's epilogue
+    if (get_option(OPT_GEMM1X1) != 1 && get_option(OPT_G1_BN) != 1 && gemm1x1_supported(p)) return launch_gemm1x1(p, (cudaStream_t)stream);
     p.bn = nullptr;
   }
   rc = dispatch_conv(p, (cudaStream_t)stream);
@@ -249,6 +252,9 @@ static int conv_dgrad_common(const stp_conv_desc* d, const stp_tensor* dy, const
     return launch_narrow_conv(p, (cudaStream_t)stream);
   if (stp_tc_enabled() && get_option(OPT_TC_CONV_VERSION) != 1 && get_option(OPT_BNB_FUSE) != 1 && h_bnb->relu != 2 && tc2_conv_supported(p))
     return launch_tc2_conv(p, (cudaStream_t)stream);
+  // 1x1 dgrads the halo kernel does not serve (MobileNetV2 / Xception widths, ReLU6 masks): the streaming GEMM's epilogue
+  if (get_option(OPT_BNB_FUSE) != 1 && get_option(OPT_GEMM1X1) != 1 && get_option(OPT_G1_BN) != 1 && gemm1x1_supported(p))
+    return launch_gemm1x1(p, (cudaStream_t)stream);
   p.bn = nullptr;
   rc = dispatch_conv(p, (cudaStream_t)stream);
   if (rc) return rc;

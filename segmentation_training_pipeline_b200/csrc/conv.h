@@ -68,7 +68,7 @@ bool tc2_up2_supported(const ConvP& p);
 int launch_tc2_up2(const ConvP& p, cudaStream_t st);
 int get_option(int key);
 enum { OPT_TC2_FORCE_MT = 0, OPT_TC_CONV_VERSION = 1, OPT_TC2_DEBUG = 2, OPT_TC2_CLUSTER = 3, OPT_TC2_BK = 4, OPT_TC3 = 5,
-       OPT_TC3_FORCE_BN = 6, OPT_TC3_FORCE_MT = 7, OPT_BN_BLOCKS = 8, OPT_BNB_FUSE = 9, OPT_TC3_HALO = 10, OPT_TC3_BN64 = 11, OPT_HEAD_STRIP = 12, OPT_GEMM1X1 = 13, OPT_NCONV = 14, OPT_TC2_1X1 = 15, OPT_TC2_UP2 = 16, OPT_COUNT = 24 };
+       OPT_TC3_FORCE_BN = 6, OPT_TC3_FORCE_MT = 7, OPT_BN_BLOCKS = 8, OPT_BNB_FUSE = 9, OPT_TC3_HALO = 10, OPT_TC3_BN64 = 11, OPT_HEAD_STRIP = 12, OPT_GEMM1X1 = 13, OPT_NCONV = 14, OPT_TC2_1X1 = 15, OPT_TC2_UP2 = 16, OPT_G1_BN = 17, OPT_COUNT = 24 };
 // device buffer (>= 64 uint64) that CTA 0 and the last CTA of conv_tc2_kernel fill with %globaltimer stamps of their
 // phases (scripts/trace_conv.py); nullptr = off.  Profiling aid only.
 unsigned long long* get_trace_buffer();

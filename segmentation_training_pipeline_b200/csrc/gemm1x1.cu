@@ -24,6 +24,10 @@ struct G1Args {
   int ldr;
   const float* bias;
   int relu, M, N, K, tiles_n;
+  int bn_on;  // 0 | 1 forward BatchNorm statistics of Y | 2 fused BatchNorm backward: res = the BatchNorm input x (mask + reduce)
+  BnFuse bn;
+  const float* bnb_coef;
+  int bnb_relu;
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int bytes) {
@@ -43,7 +47,9 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b
 // byte offset of (row, 16-byte chunk c in 0..3) inside a [rows][32] bf16 tile: chunk index XORed with (row >> 1) & 3
 __device__ __forceinline__ uint32_t swz(int row, int c) { return (uint32_t)(row * 64 + ((c ^ ((row >> 1) & 3)) << 4)); }
 
-template <int BN>
+// BNM: 0 plain | 1 forward BatchNorm statistics | 2 fused BatchNorm backward -- compile-time, so the plain GEMM carries none of the
+// epilogue's registers / instructions (with a run-time switch the plain launches of the DeepLabV3 step were 3 % slower)
+template <int BN, int BNM>
 __global__ void __launch_bounds__(kThreads) gemm1x1_kernel(const G1Args a) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int kABytes = kBM * kBK * 2, kBBytes = BN * kBK * 2, kStage = kABytes + kBBytes;
@@ -135,9 +141,19 @@ __global__ void __launch_bounds__(kThreads) gemm1x1_kernel(const G1Args a) {
   cp_wait<0>();
   __syncthreads();
 
-  // epilogue: bias / residual / ReLU on the fragments (one rounding), staged as bf16 [128][BN + 8], then 16-byte row stores
+  // epilogue: bias / residual / ReLU on the fragments (one rounding), staged as bf16 [128][BN + 8], then 16-byte row stores.
+  // bn_on == 1: per-channel (sum y, sum y^2) of exactly the stored bf16 values (BatchNorm forward statistics); bn_on == 2 (a dgrad
+  // launch): the residual slot carries the BatchNorm INPUT x of the same pixels, the stored value is g = y*[act'(x*scale+shift)]
+  // and the sums are (sum g, sum g*x) -- conv_tc2's epilogue contract.  The sums leave as fire-and-forget double reductions and
+  // g1_bn_finalize_kernel turns them into coefficients: with ~1600 short-lived CTAs per launch a per-CTA fence + ticket (the
+  // last-CTA protocol of the persistent tcgen05 kernels) added ~2 us to every wave and made the fused form a net loss.
   constexpr int LDS = BN + 8;
   __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(smem);
+  float* sRed = reinterpret_cast<float*>(smem + 40 * 1024);  // [WM][2][BN] behind the staging tile, inside the (now idle) ring
+  static_assert(kBM * LDS * 2 <= 40 * 1024 && 40 * 1024 + WM * 2 * BN * 4 <= kStages * kStage, "epilogue scratch must fit the ring");
+  float s1[TN][2], s2[TN][2];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) s1[j][0] = s1[j][1] = s2[j][0] = s2[j][1] = 0.f;
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -148,15 +164,62 @@ __global__ void __launch_bounds__(kThreads) gemm1x1_kernel(const G1Args a) {
         const int col = wn * (BN / WN) + j * 8 + (lane & 3) * 2;
         float v0 = acc[i][j][hh * 2], v1 = acc[i][j][hh * 2 + 1];
         const int m = m0 + row, n = n0 + col;
+        const bool pv = m < a.M && n < a.N;
         if (a.bias && n < a.N) { v0 += a.bias[n]; v1 += a.bias[n + 1]; }
-        if (a.res) {
-          const __nv_bfloat162 r = *reinterpret_cast<const __nv_bfloat162*>(sres + row * LDR + col);
-          v0 += __bfloat162float(r.x); v1 += __bfloat162float(r.y);
-        }
+        float2 rf = make_float2(0.f, 0.f);
+        if (a.res) rf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sres + row * LDR + col));
+        if (BNM != 2) { v0 += rf.x; v1 += rf.y; }
         if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-        *reinterpret_cast<__nv_bfloat162*>(st + row * LDS + col) = __floats2bfloat162_rn(v0, v1);
+        __nv_bfloat162 o = __floats2bfloat162_rn(v0, v1);
+        if constexpr (BNM == 1) {
+          if (pv) {
+            const float2 of = __bfloat1622float2(o);
+            s1[j][0] += of.x; s1[j][1] += of.y;
+            s2[j][0] += of.x * of.x; s2[j][1] += of.y * of.y;
+          }
+        } else if constexpr (BNM == 2) {
+          float2 of = __bfloat1622float2(o);
+          bool k0 = pv, k1 = pv;
+          if (pv && a.bnb_relu) {
+            k0 = relu_pass(rf.x * __ldg(a.bnb_coef + 2 * a.N + n) + __ldg(a.bnb_coef + 3 * a.N + n), a.bnb_relu);
+            k1 = relu_pass(rf.y * __ldg(a.bnb_coef + 2 * a.N + n + 1) + __ldg(a.bnb_coef + 3 * a.N + n + 1), a.bnb_relu);
+          }
+          of.x = k0 ? of.x : 0.f;
+          of.y = k1 ? of.y : 0.f;
+          o = __floats2bfloat162_rn(of.x, of.y);
+          s1[j][0] += of.x; s1[j][1] += of.y;
+          s2[j][0] += of.x * rf.x; s2[j][1] += of.y * rf.y;
+        }
+        *reinterpret_cast<__nv_bfloat162*>(st + row * LDS + col) = o;
       }
+  if constexpr (BNM != 0) {  // lanes sharing (lane & 3) hold the same channel pair: xor tree over lane bits 2..4, then the WM warps of a column
+#pragma unroll
+    for (int j = 0; j < TN; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float t1 = s1[j][e], t2 = s2[j][e];
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) {
+          t1 += __shfl_xor_sync(0xffffffffu, t1, off);
+          t2 += __shfl_xor_sync(0xffffffffu, t2, off);
+        }
+        if (lane < 4) {
+          const int col = wn * (BN / WN) + j * 8 + lane * 2 + e;
+          sRed[(wm * 2 + 0) * BN + col] = t1;
+          sRed[(wm * 2 + 1) * BN + col] = t2;
+        }
+      }
+  }
   __syncthreads();
+  if (BNM != 0 && tid < 2 * BN) {
+    const int which = tid / BN, c = tid - which * BN;
+    if (n0 + c < a.N) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < WM; ++w) t += sRed[(w * 2 + which) * BN + c];
+      atomicAdd(a.bn.acc + which * a.N + n0 + c, (double)t);
+    }
+  }
   constexpr int CV = BN / 8;
   for (int q = tid; q < kBM * CV; q += kThreads) {
     const int row = q / CV, c = q - row * CV;
@@ -166,24 +229,54 @@ __global__ void __launch_bounds__(kThreads) gemm1x1_kernel(const G1Args a) {
   }
 }
 
-template <int BN>
+// sums of a finished gemm1x1 launch -> BatchNorm coefficients (mode 1) / dgamma, dbeta, bcoef (mode 2); accumulators back to zero
+__global__ void g1_bn_finalize_kernel(const BnFuse bn, int C, int mode) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double t1 = __ldcg(bn.acc + c), t2 = __ldcg(bn.acc + C + c);
+  if (mode == 2) {  // sum g*xhat = invstd * (sum g*x - mean * sum g)
+    const double mean = bn.fin.coef[c], invstd = bn.fin.coef[C + c];
+    fin_backward(bn.fin, C, c, t1, invstd * (t2 - mean * t1));
+  } else {
+    fin_forward(bn.fin, C, c, t1, t2);
+  }
+  bn.acc[c] = 0.0;
+  bn.acc[C + c] = 0.0;
+}
+
+template <int BN, int BNM>
 int launch_bn(const G1Args& a, cudaStream_t stv) {
   constexpr int ring = kStages * (kBM * kBK * 2 + BN * kBK * 2), rtile = kBM * (BN + 8) * 2;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(gemm1x1_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring + rtile);
+    cudaFuncSetAttribute(gemm1x1_kernel<BN, BNM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring + rtile);
     attr = true;
   }
   const int tiles_m = (a.M + kBM - 1) / kBM;
-  gemm1x1_kernel<BN><<<tiles_m * a.tiles_n, kThreads, ring + (a.res ? rtile : 0), stv>>>(a);
-  return check_launch("gemm1x1");
+  gemm1x1_kernel<BN, BNM><<<tiles_m * a.tiles_n, kThreads, ring + (a.res ? rtile : 0), stv>>>(a);
+  const int rc = check_launch("gemm1x1");
+  if (rc || !a.bn_on) return rc;
+  if (launch_pdl(g1_bn_finalize_kernel, dim3((a.N + 127) / 128), dim3(128), 0, stv, a.bn, a.N, a.bn_on) != cudaSuccess) {
+    set_error("gemm1x1: finalize launch failed");
+    return STP_E_CUDA;
+  }
+  return check_launch("g1_bn_finalize");
 }
 
 }  // namespace
 
 bool gemm1x1_supported(const ConvP& p) {
   if (p.R != 1 || p.S != 1 || p.stride != 1 || p.up != 1 || p.pad_h != 0 || p.pad_w != 0) return false;
-  if (p.y_f32 || p.bn != nullptr || p.ncls != 0 || p.bnb_x != nullptr) return false;
+  if (p.y_f32 || p.ncls != 0) return false;
+  if (p.bn) {  // BatchNorm epilogues: forward statistics (mode 1), fused backward reduction (mode 2: x travels in the residual slot)
+    if (p.bn->fin.mode == 2) {
+      if (p.res || !p.bnb_x || !p.bnb_coef || p.bnb_ldx % 8 != 0 || !aligned16(p.bnb_x)) return false;
+    } else if (p.bn->fin.mode != 1) {
+      return false;
+    }
+  }
   if (p.Cin % 8 != 0 || p.Cout % 8 != 0 || p.ldx % 8 != 0 || p.ldy % 8 != 0) return false;
   if (!aligned16(p.x) || !aligned16(p.w) || !aligned16(p.y)) return false;
   if (p.res && (p.ldr % 8 != 0 || !aligned16(p.res))) return false;
@@ -195,12 +288,16 @@ int launch_gemm1x1(const ConvP& p, cudaStream_t st) {
   G1Args a;
   a.A = p.x; a.lda = p.ldx; a.B = p.w; a.Y = (__nv_bfloat16*)p.y; a.ldy = p.ldy; a.res = p.res; a.ldr = p.ldr; a.bias = p.bias;
   a.relu = p.relu; a.M = (int)p.M; a.N = p.Cout; a.K = p.Cin;
+  a.bn_on = p.bn ? (p.bn->fin.mode == 2 ? 2 : 1) : 0;
+  if (a.bn_on) a.bn = *p.bn; else a.bn = BnFuse{};
+  a.bnb_coef = p.bnb_coef; a.bnb_relu = p.bnb_relu;
+  if (a.bn_on == 2) { a.res = p.bnb_x; a.ldr = p.bnb_ldx; }
   if (p.Cout > 64) {
     a.tiles_n = (p.Cout + 127) / 128;
-    return launch_bn<128>(a, st);
+    return a.bn_on == 0 ? launch_bn<128, 0>(a, st) : a.bn_on == 1 ? launch_bn<128, 1>(a, st) : launch_bn<128, 2>(a, st);
   }
   a.tiles_n = 1;
-  return launch_bn<64>(a, st);
+  return a.bn_on == 0 ? launch_bn<64, 0>(a, st) : a.bn_on == 1 ? launch_bn<64, 1>(a, st) : launch_bn<64, 2>(a, st);
 }
 
 }  // namespace stp

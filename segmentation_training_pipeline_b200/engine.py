@@ -220,13 +220,14 @@ class Net:
                     gwriters.setdefault(g.key(), []).append(op)
                     roots[id(g.root)] = roots.get(id(g.root), 0) + 1
             for op in self.ops:
-                if isinstance(op, BNRelu) and op.up == 1 and int(op.relu) != 2:   # (the fused epilogue masks ReLU, not ReLU6)
+                if isinstance(op, BNRelu) and op.up == 1:   # (ReLU6 masks: only in the streaming 1x1 GEMM's epilogue, see below)
                     gk = op.y.grad().key()
                     w = gwriters.get(gk, [])
                     # no other op may write an overlapping slice of the same gradient buffer
                     overlap = [k for k in gwriters if k[0] == gk[0] and k != gk and k[1] < gk[1] + gk[2] and gk[1] < k[1] + k[2]]
                     if (len(w) == 1 and not overlap and type(w[0]) is Conv and w[0].needs_dgrad and w[0].x.key() == op.y.key()
-                            and w[0].desc.stride == 1 and w[0].desc.up == 1 and (w[0].k > 1 or self.fuse_bn_bwd_1x1)):
+                            and w[0].desc.stride == 1 and w[0].desc.up == 1 and (w[0].k > 1 or self.fuse_bn_bwd_1x1)
+                            and (int(op.relu) != 2 or (w[0].k == 1 and self.fuse_bn_bwd_1x1))):
                         w[0].bnb_prev = op
                         op.reduce_from_dgrad = True
         host = np.zeros(self.n_flat, dtype=np.float32)

@@ -975,6 +975,65 @@ def test_gemm1x1(stp, cuda, case):
         dx2s = T(dx2)
         stp.conv_dgrad(C.byref(desc), ref(dys), wd.data_ptr(), ref(dx2s), ref(dx2s), None, 0, stream())
         assert rel_err(dx2, dxr + x.float().cpu()) < TOL_BF16
+        # ---- BatchNorm epilogues (forward statistics; fused backward masking + reduction with ReLU / ReLU6 / no activation) ----
+        rows = n * h * w
+        cmax = max(cin, cout)
+        partial = torch.zeros(2 * stp.bn_nblk(rows, cmax) * cmax, device=cuda)
+        sync = torch.zeros(4, dtype=torch.int32, device=cuda)
+        acc = torch.zeros(2 * cmax, dtype=torch.float64, device=cuda)
+        gamma = (torch.rand(cout, generator=g) + 0.5).to(cuda)
+        beta = (torch.randn(cout, generator=g) * 0.2).to(cuda)
+        y0 = torch.zeros((n, h, w, cout), dtype=torch.bfloat16, device=cuda)
+        stp.conv_fwd(C.byref(desc), ref(xs), wt.data_ptr(), None, None, ref(T(y0)), None, 0, stream())
+        coef0 = torch.zeros(4 * cout, device=cuda)
+        mm0, mv0 = torch.zeros(cout, device=cuda), torch.ones(cout, device=cuda)
+        stp.bn_stats_fused(ref(T(y0)), partial.data_ptr(), sync.data_ptr(), None, gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.99,
+                           mm0.data_ptr(), mv0.data_ptr(), coef0.data_ptr(), stream())
+        for _ in range(2):   # twice: accumulators / ticket return to zero
+            y1 = torch.zeros_like(y0)
+            coef1 = torch.zeros(4 * cout, device=cuda)
+            mm1, mv1 = torch.zeros(cout, device=cuda), torch.ones(cout, device=cuda)
+            bn = lib.BnFwd(partial.data_ptr(), sync.data_ptr(), acc.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.99,
+                           mm1.data_ptr(), mv1.data_ptr(), coef1.data_ptr())
+            l0 = stp.launch_count()
+            stp.conv_fwd_bn(C.byref(desc), ref(xs), wt.data_ptr(), None, None, ref(T(y1)), C.byref(bn), None, 0, stream())
+            # one launch (tcgen05 halo kernel where it tiles the shape) or GEMM + its 1-block finalize -- never a pass over y
+            assert stp.launch_count() - l0 in (1, 2)
+            assert rel_err(y1, y0.float()) < 1e-3   # (same math; fp32 summation order differs between the two kernels)
+            assert int(sync[0]) == 0 and float(acc.abs().max()) == 0.0
+            scale = 1 + float(coef0.abs().max())
+            assert max_abs(coef1, coef0) <= 1e-3 * scale, max_abs(coef1, coef0)
+            assert max_abs(mm1, mm0) < 1e-5 and rel_err(mv1, mv0) < 1e-4
+        # BatchNorm(+activation) over x (cin channels) feeding this conv: its backward reduction inside the dgrad GEMM
+        gam = (torch.rand(cin, generator=g) + 0.5).to(cuda)
+        gam[::3] *= -1.0
+        bet = (torch.rand(cin, generator=g) - 0.5).to(cuda)
+        coef = torch.zeros(4 * cin, device=cuda)
+        mm, mv = torch.zeros(cin, device=cuda), torch.ones(cin, device=cuda)
+        stp.bn_stats_fused(ref(xs), partial.data_ptr(), sync.data_ptr(), acc.data_ptr(), gam.data_ptr(), bet.data_ptr(), 1e-3, 0.99,
+                           mm.data_ptr(), mv.data_ptr(), coef.data_ptr(), stream())
+        c4 = coef.view(4, cin)
+        tpre = x.float() * c4[2] + c4[3]
+        for act in (1, 2, 0):
+            d0, b0, c0 = torch.zeros(cin, device=cuda), torch.zeros(cin, device=cuda), torch.zeros(3 * cin, device=cuda)
+            stp.conv_dgrad(C.byref(desc), ref(dys), wd.data_ptr(), None, ref(dxs), None, 0, stream())
+            stp.bn_bwd_reduce_fused(ref(dxs), ref(xs), coef.data_ptr(), act, 1, partial.data_ptr(), sync.data_ptr(), acc.data_ptr(),
+                                    d0.data_ptr(), b0.data_ptr(), c0.data_ptr(), stream())
+            d1, b1, c1 = torch.zeros(cin, device=cuda), torch.zeros(cin, device=cuda), torch.zeros(3 * cin, device=cuda)
+            dxm = torch.zeros_like(x)
+            bnb = lib.BnBwd(C.pointer(xs), coef.data_ptr(), act, partial.data_ptr(), sync.data_ptr(), acc.data_ptr(),
+                            d1.data_ptr(), b1.data_ptr(), c1.data_ptr())
+            l0 = stp.launch_count()
+            for _ in range(2):
+                stp.conv_dgrad_bn(C.byref(desc), ref(dys), wd.data_ptr(), ref(T(dxm)), C.byref(bnb), None, 0, stream())
+            assert stp.launch_count() - l0 in (2, 4), "the reduction must run inside the dgrad kernel (+ its 1-block finalize)"
+            torch.cuda.synchronize()
+            assert int(sync[0]) == 0 and float(acc.abs().max()) == 0.0
+            mask = (tpre > 0) if act == 1 else ((tpre > 0) & (tpre <= 6)) if act == 2 else torch.ones_like(tpre, dtype=torch.bool)
+            assert rel_err(dxm, torch.where(mask, dx, torch.zeros_like(dx)).float()) < 1e-3
+            for got, want in ((d1, d0), (b1, b0), (c1, c0)):
+                scale = 1e-6 + float(want.abs().max())
+                assert max_abs(got, want) <= 1e-3 * scale, (act, max_abs(got, want), scale)
     finally:
         stp.set_option(b"gemm1x1", 0)
 
