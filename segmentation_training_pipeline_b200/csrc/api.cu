@@ -56,6 +56,7 @@ extern "C" int stp_set_option(const char* name, int32_t value) {
   else if (!strcmp(name, "tc2_1x1")) key = OPT_TC2_1X1;                 /* 0 auto: 1x1 stride-1 convs take the halo kernel conv_tc2 (a plain GEMM over pixel strips) where it tiles the shape | 1 off | 2 only Cin % 64 == 0 */
   else if (!strcmp(name, "tc2_up2")) key = OPT_TC2_UP2;                 /* 0 auto: zero-insertion convs (stride-2 dgrads) as four halo-kernel launches, one per output parity class | 1 off */
   else if (!strcmp(name, "g1_bn")) key = OPT_G1_BN;                     /* 0 auto | 1: no BatchNorm epilogues in the streaming 1x1 GEMM (conv + separate reduction pass) */
+  else if (!strcmp(name, "wgrad1x1")) key = OPT_WGRAD1X1;               /* 0 auto | 1 off: 1x1 weight gradients the tcgen05 kernel does not tile stay on the generic kernel */
   else if (!strcmp(name, "head_strip")) key = OPT_HEAD_STRIP;           /* 0 on | 1 off: column-strip head backward kernels (sliding dlogit window) */
   else if (!strcmp(name, "tc3_bn64")) key = OPT_TC3_BN64;               /* 0 off | 1 on: N = 64 CTA-pair tiles for Cout = 64 / 192 layers (measured slower) */
   else if (!strcmp(name, "bnb_fuse")) key = OPT_BNB_FUSE;               /* 0 auto | 1: never fuse the BatchNorm-backward reduction into the dgrad epilogue */
@@ -295,7 +296,9 @@ extern "C" size_t stp_conv_wgrad_workspace(const stp_conv_desc* d, const stp_ten
   size_t a = generic_wgrad_workspace(p.M, p.Cout, p.K);
   size_t b = tc_wgrad_workspace(p);
   size_t c = narrow_wgrad_workspace(p);
+  size_t e = wgrad1x1_workspace(p);
   if (b > a) a = b;
+  if (e > a) a = e;
   return a > c ? a : c;
 }
 
@@ -312,5 +315,7 @@ extern "C" int stp_conv_wgrad(const stp_conv_desc* d, const stp_tensor* x, const
   WgradP p = make_wgrad_p(d, x, dy);
   if (stp_tc_enabled() && narrow_wgrad_supported(p)) return launch_narrow_wgrad(p, dw, workspace, workspace_bytes, (cudaStream_t)stream);
   if (stp_tc_enabled() && tc_wgrad_supported(p)) return launch_tc_wgrad(p, dw, workspace, workspace_bytes, (cudaStream_t)stream);
+  // 1x1 layers of MobileNetV2 / Xception widths: a pixel-reduction GEMM instead of the generic im2col kernel
+  if (get_option(OPT_WGRAD1X1) != 1 && wgrad1x1_supported(p)) return launch_wgrad1x1(p, dw, workspace, workspace_bytes, (cudaStream_t)stream);
   return launch_generic_wgrad(p, dw, workspace, workspace_bytes, (cudaStream_t)stream);
 }

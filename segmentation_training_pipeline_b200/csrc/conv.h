@@ -68,7 +68,7 @@ bool tc2_up2_supported(const ConvP& p);
 int launch_tc2_up2(const ConvP& p, cudaStream_t st);
 int get_option(int key);
 enum { OPT_TC2_FORCE_MT = 0, OPT_TC_CONV_VERSION = 1, OPT_TC2_DEBUG = 2, OPT_TC2_CLUSTER = 3, OPT_TC2_BK = 4, OPT_TC3 = 5,
-       OPT_TC3_FORCE_BN = 6, OPT_TC3_FORCE_MT = 7, OPT_BN_BLOCKS = 8, OPT_BNB_FUSE = 9, OPT_TC3_HALO = 10, OPT_TC3_BN64 = 11, OPT_HEAD_STRIP = 12, OPT_GEMM1X1 = 13, OPT_NCONV = 14, OPT_TC2_1X1 = 15, OPT_TC2_UP2 = 16, OPT_G1_BN = 17, OPT_COUNT = 24 };
+       OPT_TC3_FORCE_BN = 6, OPT_TC3_FORCE_MT = 7, OPT_BN_BLOCKS = 8, OPT_BNB_FUSE = 9, OPT_TC3_HALO = 10, OPT_TC3_BN64 = 11, OPT_HEAD_STRIP = 12, OPT_GEMM1X1 = 13, OPT_NCONV = 14, OPT_TC2_1X1 = 15, OPT_TC2_UP2 = 16, OPT_G1_BN = 17, OPT_WGRAD1X1 = 18, OPT_COUNT = 24 };
 // device buffer (>= 64 uint64) that CTA 0 and the last CTA of conv_tc2_kernel fill with %globaltimer stamps of their
 // phases (scripts/trace_conv.py); nullptr = off.  Profiling aid only.
 unsigned long long* get_trace_buffer();
@@ -81,6 +81,11 @@ int launch_tc3_conv(const ConvP& p, cudaStream_t st);
 bool narrow_wgrad_supported(const WgradP& p);
 size_t narrow_wgrad_workspace(const WgradP& p);
 int launch_narrow_wgrad(const WgradP& p, float* dw, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// wgrad1x1.cu (cp.async + ldmatrix.trans + mma.sync: weight gradient of 1x1 stride-1 convs the tcgen05 wgrad kernel does not tile)
+bool wgrad1x1_supported(const WgradP& p);
+size_t wgrad1x1_workspace(const WgradP& p);
+int launch_wgrad1x1(const WgradP& p, float* dw, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // conv_narrow.cu (cp.async halo tiles + ldmatrix + mma.sync: 3x3 stride-1 "same" conv, Cin / Cout in {16, 32}, HBM-bound decoder tail)
 bool narrow_conv_supported(const ConvP& p);
