@@ -60,7 +60,13 @@ int64_t stp_tc_launch_count(void);
 int64_t stp_tc3_launch_count(void);
 void stp_set_tc_enabled(int on);
 /* debugging / A-B knobs: "tc2_force_mt" (0 heuristic | 1,2,4,8), "tc_conv_version" (0 auto | 1 first-generation only),
- * "tc3" (0 auto | 1 off | 2 CTA-pair kernel wherever it serves the shape), "tc3_force_bn" (128 | 256), "tc3_force_mt" (1 | 2) */
+ * "tc3" (0 auto | 1 off | 2 CTA-pair kernel wherever it serves the shape), "tc3_force_bn" (128 | 256), "tc3_force_mt" (1 | 2);
+ * kernel selection of the 1x1 / narrow / strided layers (each with its measurement in csrc/api.cu dispatch_conv):
+ * "tc2_1x1" (0 auto: 1x1 stride-1 convs on the tcgen05 halo kernel as plain GEMMs | 1 off | 2 only Cin % 64 == 0),
+ * "gemm1x1" (0 auto: streaming mma.sync GEMM where the halo kernel does not tile the widths | 1 off | 2 every eligible 1x1),
+ * "g1_bn" (1: no BatchNorm epilogues in that GEMM), "tc2_up2" (1: stride-2 dgrads stay on the first-generation kernel),
+ * "wgrad1x1" (1: 1x1 weight gradients of untiled widths stay on the generic kernel), "nconv" (1: narrow-channel mma.sync conv,
+ * an opt-in negative result), "bnb_fuse" (1: never fuse the BatchNorm-backward reduction into a dgrad epilogue) */
 int stp_set_option(const char* name, int32_t value);
 /* profiling aid: device buffer of >= 64 uint64 that the halo conv kernel's first and last thread blocks fill with
  * %globaltimer stamps of their phases (scripts/trace_conv.py); NULL turns it off */
