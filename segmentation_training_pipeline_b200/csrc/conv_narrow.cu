@@ -1,15 +1,19 @@
-// 3x3 stride-1 "same" convolution (forward and dgrad) for the narrow decoder layers: Cin, Cout in {16, 32} at 256^2 / 512^2.
+// OPT-IN EXPERIMENT (option nconv = 1), MEASURED SLOWER than the tcgen05 halo kernel -- kept as a recorded negative result.
 //
-// These layers are HBM-bound (16 -> 16 @512^2 bs16: 134 MB in + 134 MB out, 19 GFLOP) and a tcgen05 tile is mostly padding for
-// them: the halo kernel (conv_tc2.cu) feeds its UMMA operands with 32/64-byte TMA box rows and is paced by the TMA request rate
-// (~3 clk per 32-byte row, profiles/README.md s15/s16), 0.31-0.46 of the copy bandwidth.  Here the operand path is built for
-// the byte stream instead: a persistent CTA walks 8 x 32-pixel output tiles; the haloed 10 x 34-pixel input tile arrives as
-// coalesced 16-byte cp.async copies (zero-filled outside the image) into a two-stage XOR-swizzled ring, one tile ahead of the
-// math; each warp owns one output row (two m16 tiles) and takes its nine taps as shifted ldmatrix views of the same tile
-// (mma.sync.m16n8k16 bf16 -> fp32); weights stay resident in shared memory (registers for 16 -> 16) for the CTA's lifetime; the
-// result leaves through a padded staging tile as 16-byte row-contiguous stores.  Epilogues match conv_tc2's contract:
-// bias / ReLU, forward BatchNorm statistics of the stored bf16 values (bn mode 1), or the fused BatchNorm-backward masking +
-// (sum g, sum g*x) reduction of a dgrad launch (mode 2), both finalised by the last CTA (ticket) exactly as conv_tc2 does.
+// 3x3 stride-1 "same" convolution (forward and dgrad) for the narrow decoder layers: Cin, Cout in {16, 32} at 256^2 / 512^2.
+// These layers run at 0.31-0.46 of the copy bandwidth on the halo kernel (conv_tc2.cu), which feeds its UMMA operands with
+// 32/64-byte TMA box rows and is paced by the TMA request rate (~3 clk per 32-byte row, profiles/README.md s15/s16).  The
+// hypothesis tested here: build the operand path for the byte stream instead and take the math on the legacy tensor path -- a
+// persistent CTA walks 8 x 32-pixel output tiles; the haloed 10 x 34-pixel input tile arrives as coalesced 16-byte cp.async
+// copies (zero-filled outside the image) into a two-stage XOR-swizzled ring, one tile ahead of the math; each warp owns one
+// output row (two m16 tiles) and takes its nine taps as shifted ldmatrix views of the same tile (mma.sync.m16n8k16 bf16 -> fp32);
+// weights stay resident in shared memory (registers for 16 -> 16); the result leaves through a padded staging tile as 16-byte
+// row-contiguous stores; epilogues follow conv_tc2's contract (bias / ReLU, forward BatchNorm statistics, fused BatchNorm
+// backward, last-CTA finalize).  Result (profiles/r2_s9_nconv_bench.txt, bs16 back to back): 16 -> 16 @512^2 105.8 us against
+// 108.4 us, every other shape slower (32 -> 32 @256^2 74.6 vs 39.4 us), the step 8.70 vs 8.53 ms.  Reason: mma.sync.m16n8k16
+// issues at ~16 clk per SM sub-partition on sm_100a (~290 TF/s for the whole chip, one fifth of tcgen05), and these layers need
+// 4.7 M of them per launch -- 65 us of issue time before any load or store.  The remedy for the narrow tail has to stay on
+// tcgen05 (wider TMA rows through a pixel-merged view).
 #include "conv.h"
 
 namespace stp {

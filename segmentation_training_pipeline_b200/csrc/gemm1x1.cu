@@ -1,12 +1,15 @@
 // 1x1 stride-1 convolution = plain GEMM  Y[M][N] = X[M][K] * W[N][K]^T (+ bias, + residual, ReLU)  for the channel counts the
-// tcgen05 kernels do not tile (MobileNetV2 / Xception widths: 24, 96, 144, 160, 728 ...) and for the tiny-K layers where one
-// 16/32/64-deep MMA per 128 x BN tile leaves the tcgen05 pipeline latency-bound.  These GEMMs are HBM-bound (K <= 960: 2*K FLOP
-// per 2*(1 + N/K)-byte... a few hundred FLOP per byte at most is never reached: the tensors are read and written once), so the
-// design goal is streaming, not tensor throughput: 16-byte cp.async into a 4-stage XOR-swizzled shared-memory ring, ldmatrix +
-// mma.sync.m16n8k16 (bf16 in, fp32 accumulate), the epilogue staged through shared memory so that every global store is a
-// row-contiguous 16-byte vector.  The dgrad of such a layer is the same GEMM over dY with the [Cin][Cout] weight copy.
-// The implicit-GEMM generic kernel (conv_generic.cu) spends its time on im2col index arithmetic that a 1x1 filter does not need:
-// 160 -> 960 @40x40 bs16 took 101 us there (profiles/r2_s7_deeplab_bench.txt).
+// tcgen05 halo kernel does not tile (MobileNetV2 / Xception widths: 24, 96, 144, 160, 728 ...).  Where that kernel does tile the
+// shape it is ~2x faster and takes the layer (csrc/api.cu dispatch_conv, profiles/r2_s10_g1_bench.txt): this kernel runs on the
+// legacy tensor path, whose ceiling on sm_100a is ~290 TF/s (K-heavy shapes measure 219-257 TF/s here).
+// Design: 16-byte cp.async into a 4-stage XOR-swizzled shared-memory ring, ldmatrix + mma.sync.m16n8k16 (bf16 in, fp32
+// accumulate), three short-lived CTAs per SM (a persistent variant with one continuous cp.async stream measured 20 % slower),
+// the residual tile prefetched by the first cp.async group, the epilogue staged through shared memory so that every global
+// store is a row-contiguous 16-byte vector.  The dgrad of such a layer is the same GEMM over dY with the [Cin][Cout] weight copy.
+// BatchNorm epilogues are compile-time variants (BNM): forward statistics of the stored values, or -- for a dgrad -- masking by
+// the producing BatchNorm's activation (ReLU or ReLU6) + the (sum g, sum g*x) reduction, finalised by g1_bn_finalize_kernel.
+// It replaced the implicit-GEMM generic kernel (conv_generic.cu), which spends its time on im2col index arithmetic that a 1x1
+// filter does not need: 160 -> 960 @40x40 bs16 took 101 us there (profiles/r2_s7_deeplab_bench.txt).
 #include "conv.h"
 
 namespace stp {

@@ -134,8 +134,10 @@ __global__ void __launch_bounds__(kWThreads) wgrad1x1_kernel(const W1Args a) {
       for (int hh = 0; hh < 2; ++hh) {
         const int co = n0 + wn * 32 + i * 16 + (lane >> 2) + hh * 8;
         const int ci = k0 + wk * 32 + j * 8 + (lane & 3) * 2;
-        if (co < a.Cout && ci < a.Cin)
-          *reinterpret_cast<float2*>(o + (int64_t)co * a.Cin + ci) = make_float2(acc[i][j][hh * 2], acc[i][j][hh * 2 + 1]);
+        if (co < a.Cout && ci < a.Cin) {   // (scalar stores: with one split `o` is the caller's dw, which need not be 8-byte aligned)
+          o[(int64_t)co * a.Cin + ci] = acc[i][j][hh * 2];
+          o[(int64_t)co * a.Cin + ci + 1] = acc[i][j][hh * 2 + 1];
+        }
       }
 }
 

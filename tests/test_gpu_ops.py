@@ -1164,7 +1164,7 @@ def _conv_narrow_rest(stp, cuda, case, g, x, wt, desc, xs, yr, y_narrow):
 
 
 @pytest.mark.parametrize("case", [(4, 80, 80, 24, 144), (4, 80, 80, 144, 24), (2, 33, 47, 96, 576), (1, 20, 20, 960, 160),
-                                  (3, 40, 40, 192, 32), (1, 7, 9, 8, 8), (2, 64, 64, 728, 728)])
+                                  (3, 40, 40, 192, 32), (1, 7, 9, 8, 8), (2, 64, 64, 728, 728), (16, 1, 1, 320, 256)])
 def test_wgrad1x1(stp, cuda, case):
     """weight gradient of 1x1 stride-1 convolutions at MobileNetV2 / Xception widths on the pixel-reduction GEMM (csrc/wgrad1x1.cu):
     many pixel splits, partial channel tiles, a pixel count that is not a multiple of the stage depth, channel slices of wider
@@ -1178,10 +1178,12 @@ def test_wgrad1x1(stp, cuda, case):
     ws = _ws(stp.conv_wgrad_workspace(C.byref(desc), ref(xs), ref(dys)), cuda)
     outs = []
     for _ in range(2):
-        dw = torch.zeros((cout, 1, 1, cin), dtype=torch.float32, device=cuda)
+        flat = torch.zeros(cout * cin + 1, dtype=torch.float32, device=cuda)
+        dw = flat[1:].view(cout, 1, 1, cin)     # a 4-byte aligned destination, as inside a flat gradient buffer
         tc0, l0 = stp.tc_launch_count(), stp.launch_count()
         stp.conv_wgrad(C.byref(desc), ref(xs), ref(dys), dw.data_ptr(), ws.data_ptr(), ws.numel(), stream())
         torch.cuda.synchronize()
+        assert float(flat[0]) == 0.0
         outs.append(dw)
     want = torch.einsum("nhwo,nhwi->oi", dybig[..., :cout].float().cpu().double(), xbig[..., 8:].float().cpu().double())
     if stp.tc_launch_count() == tc0:      # (shapes the tcgen05 wgrad kernel tiles keep it: nothing to check here)
