@@ -601,6 +601,33 @@ static int ew_grid(int64_t total) {
   return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 
+// Sums that a producing kernel left in bn.acc ([2][C] doubles, fire-and-forget reductions) -> BatchNorm coefficients (mode 1) or
+// dgamma / dbeta / bcoef (mode 2); the accumulators return to zero.  One small launch instead of a fence + ticket in every CTA of
+// a kernel with thousands of short-lived CTAs (gemm1x1.cu, dwconv.cu).
+__global__ void bn_acc_finalize_kernel(const BnFuse bn, int C, int mode) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double t1 = __ldcg(bn.acc + c), t2 = __ldcg(bn.acc + C + c);
+  if (mode == 2) {  // sum g*xhat = invstd * (sum g*x - mean * sum g)
+    const double mean = bn.fin.coef[c], invstd = bn.fin.coef[C + c];
+    fin_backward(bn.fin, C, c, t1, invstd * (t2 - mean * t1));
+  } else {
+    fin_forward(bn.fin, C, c, t1, t2);
+  }
+  bn.acc[c] = 0.0;
+  bn.acc[C + c] = 0.0;
+}
+
+int launch_bn_acc_finalize(const BnFuse& bn, int C, int mode, cudaStream_t st) {
+  if (launch_pdl(bn_acc_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, st, bn, C, mode) != cudaSuccess) {
+    set_error("bn_acc_finalize: launch failed");
+    return STP_E_CUDA;
+  }
+  return check_launch("bn_acc_finalize");
+}
+
 }  // namespace stp
 
 using namespace stp;

@@ -13,6 +13,9 @@ struct BnFuse {
   FinArgs fin;  // mode 1
 };
 
+// bn.cu: bn.acc ([2][C] sums left by a producing kernel) -> coefficients (mode 1) / backward terms (mode 2), accumulators re-zeroed
+int launch_bn_acc_finalize(const BnFuse& bn, int C, int mode, cudaStream_t st);
+
 struct ConvP {
   const __nv_bfloat16* x;
   int ldx, N, H, W, Cin;

@@ -7,7 +7,7 @@
 // the residual tile prefetched by the first cp.async group, the epilogue staged through shared memory so that every global
 // store is a row-contiguous 16-byte vector.  The dgrad of such a layer is the same GEMM over dY with the [Cin][Cout] weight copy.
 // BatchNorm epilogues are compile-time variants (BNM): forward statistics of the stored values, or -- for a dgrad -- masking by
-// the producing BatchNorm's activation (ReLU or ReLU6) + the (sum g, sum g*x) reduction, finalised by g1_bn_finalize_kernel.
+// the producing BatchNorm's activation (ReLU or ReLU6) + the (sum g, sum g*x) reduction, finalised by bn_acc_finalize_kernel (bn.cu).
 // It replaced the implicit-GEMM generic kernel (conv_generic.cu), which spends its time on im2col index arithmetic that a 1x1
 // filter does not need: 160 -> 960 @40x40 bs16 took 101 us there (profiles/r2_s7_deeplab_bench.txt).
 #include "conv.h"
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kThreads) gemm1x1_kernel(const G1Args a) {
   // bn_on == 1: per-channel (sum y, sum y^2) of exactly the stored bf16 values (BatchNorm forward statistics); bn_on == 2 (a dgrad
   // launch): the residual slot carries the BatchNorm INPUT x of the same pixels, the stored value is g = y*[act'(x*scale+shift)]
   // and the sums are (sum g, sum g*x) -- conv_tc2's epilogue contract.  The sums leave as fire-and-forget double reductions and
-  // g1_bn_finalize_kernel turns them into coefficients: with ~1600 short-lived CTAs per launch a per-CTA fence + ticket (the
+  // bn_acc_finalize_kernel (bn.cu) turns them into coefficients: with ~1600 short-lived CTAs per launch a per-CTA fence + ticket (the
   // last-CTA protocol of the persistent tcgen05 kernels) added ~2 us to every wave and made the fused form a net loss.
   constexpr int LDS = BN + 8;
   __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(smem);
@@ -232,23 +232,6 @@ __global__ void __launch_bounds__(kThreads) gemm1x1_kernel(const G1Args a) {
   }
 }
 
-// sums of a finished gemm1x1 launch -> BatchNorm coefficients (mode 1) / dgamma, dbeta, bcoef (mode 2); accumulators back to zero
-__global__ void g1_bn_finalize_kernel(const BnFuse bn, int C, int mode) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double t1 = __ldcg(bn.acc + c), t2 = __ldcg(bn.acc + C + c);
-  if (mode == 2) {  // sum g*xhat = invstd * (sum g*x - mean * sum g)
-    const double mean = bn.fin.coef[c], invstd = bn.fin.coef[C + c];
-    fin_backward(bn.fin, C, c, t1, invstd * (t2 - mean * t1));
-  } else {
-    fin_forward(bn.fin, C, c, t1, t2);
-  }
-  bn.acc[c] = 0.0;
-  bn.acc[C + c] = 0.0;
-}
-
 template <int BN, int BNM>
 int launch_bn(const G1Args& a, cudaStream_t stv) {
   constexpr int ring = kStages * (kBM * kBK * 2 + BN * kBK * 2), rtile = kBM * (BN + 8) * 2;
@@ -261,11 +244,7 @@ int launch_bn(const G1Args& a, cudaStream_t stv) {
   gemm1x1_kernel<BN, BNM><<<tiles_m * a.tiles_n, kThreads, ring + (a.res ? rtile : 0), stv>>>(a);
   const int rc = check_launch("gemm1x1");
   if (rc || !a.bn_on) return rc;
-  if (launch_pdl(g1_bn_finalize_kernel, dim3((a.N + 127) / 128), dim3(128), 0, stv, a.bn, a.N, a.bn_on) != cudaSuccess) {
-    set_error("gemm1x1: finalize launch failed");
-    return STP_E_CUDA;
-  }
-  return check_launch("g1_bn_finalize");
+  return launch_bn_acc_finalize(a.bn, a.N, a.bn_on, stv);
 }
 
 }  // namespace
