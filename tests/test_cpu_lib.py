@@ -42,3 +42,17 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 s = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", s, flags=re.M), os.path.join(dp, f)
+
+
+def test_kernel_selection_options_are_known_and_unknown_names_fail():
+    """every A/B knob include/stp.h documents is accepted by stp_set_option (no GPU involved), anything else is an error that names it"""
+    from segmentation_training_pipeline_b200 import lib
+    l = lib.load()
+    hdr = open(os.path.join(ROOT, "include", "stp.h")).read()
+    doc = hdr[hdr.index("debugging / A-B knobs"):hdr.index("int stp_set_option")]
+    names = set(re.findall(r'"([a-z0-9_]+)"', doc))
+    assert {"tc3", "gemm1x1", "tc2_1x1", "tc2_up2", "wgrad1x1", "nconv", "g1_bn", "bnb_fuse"} <= names
+    for n in sorted(names):
+        assert l.stp_set_option(n.encode(), 0) == 0, n
+    assert l.stp_set_option(b"no_such_option", 1) != 0
+    assert b"no_such_option" in l.stp_last_error()
