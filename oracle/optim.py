@@ -1,5 +1,7 @@
 """keras.optimizers (2.2.4) restated [DEP]; reference selects them via `optimizer:`/`lr:`/`clipnorm:`/`clipvalue:`
-(schemas/segmentation.raml:77-89).  TEST INFRASTRUCTURE, parity unpinned.  SURVEY.md 8 a-9.
+(schemas/segmentation.raml:77-89).  TEST INFRASTRUCTURE.  SURVEY.md 8 a-9.  The Keras source is absent, so the rules are restated
+from its published formulation; they are pinned against torch.optim's independent implementations of the same algorithms
+(tests/test_cpu_oracle_optim.py: SGD / Nesterov, RMSprop, Nadam equal; Adam equal up to Keras' documented epsilon placement).
 """
 from __future__ import annotations
 

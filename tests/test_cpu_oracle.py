@@ -275,3 +275,47 @@ def test_neighbourhood_arithmetic_is_pinned_against_real_cv2():
         cv2.ipp.setUseIPP(ipp0)
     assert OA.gaussian_kernel_fixed(5, 1.0).tolist() == [14, 62, 104, 62, 14]      # sum 256, centre takes the remainder
     assert [OA.gaussian_ksize_imgaug(s) for s in (0.5, 2.0, 3.0, 4.0, 6.0)] == [5, 7, 9, 11, 15]
+
+
+@pytest.mark.parametrize("shape,out", [((2, 3, 7, 9), (20, 31)), ((1, 4, 40, 40), (320, 320)), ((1, 2, 33, 17), (9, 5)), ((2, 1, 1, 1), (6, 4))])
+def test_align_corners_resize_is_torch_interpolate(shape, out):
+    """the align_corners=True bilinear resize of impl/deeplab/model.py:92-100 (the network's final upsampling) against torch's
+    independent implementation of the same published rule (scale = (in - 1) / (out - 1))"""
+    import torch.nn.functional as F
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(sum(shape)))
+    got = ON.resize_bilinear_tf1(x, out[0], out[1], align_corners=True)
+    want = F.interpolate(x, size=out, mode="bilinear", align_corners=True)
+    assert float((got - want).abs().max()) < 2e-6 * (1 + float(want.abs().max()))
+
+
+def test_batchnorm_restatement_is_torch_batch_norm():
+    """training mode normalises with the BIASED batch variance, inference mode with the moving statistics: torch.nn.functional.batch_norm"""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(4, 12, 9, 7, generator=g) * 2 + 0.5
+    gamma, beta = torch.rand(12, generator=g) + 0.5, torch.randn(12, generator=g)
+    y, mean, var = ON.batchnorm_train(x, gamma, beta, 1e-3)
+    want = F.batch_norm(x, None, None, gamma, beta, training=True, eps=1e-3)
+    assert float((y - want).abs().max()) < 2e-6 * (1 + float(want.abs().max()))
+    assert torch.allclose(mean, x.mean(dim=(0, 2, 3)), atol=1e-6) and torch.allclose(var, x.var(dim=(0, 2, 3), unbiased=False), atol=1e-6)
+    mm, mv = torch.randn(12, generator=g), torch.rand(12, generator=g) + 0.5
+    yi = ON.batchnorm_infer(x, gamma, beta, mm, mv, 1e-5)
+    wi = F.batch_norm(x, mm, mv, gamma, beta, training=False, eps=1e-5)
+    assert float((yi - wi).abs().max()) < 2e-6 * (1 + float(wi.abs().max()))
+
+
+def test_tf_same_padding_rule_is_the_one_hf_transformers_ports():
+    """keras 'same' padding (total = max((ceil(n/s) - 1)*s + k_eff - n, 0), the smaller half BEFORE) against the rule Hugging Face
+    ported from TensorFlow for its TF-checkpoint models (apply_tf_padding), on even / odd sizes, strides and atrous rates"""
+    mod = pytest.importorskip("transformers.models.mobilenet_v2.modeling_mobilenet_v2")
+    import torch.nn as nn
+    for n in (7, 8, 15, 16, 33, 64):
+        for k, s, d in ((3, 1, 1), (3, 2, 1), (3, 1, 2), (3, 1, 4), (1, 1, 1), (1, 2, 1)):
+            conv = nn.Conv2d(1, 1, k, stride=s, dilation=d)
+            padded = mod.apply_tf_padding(torch.zeros(1, 1, n, n), conv)
+            x = torch.zeros(1, 1, n, n)
+            x[0, 0, 0, 0] = 1.0                                   # where the first input pixel lands = the padding BEFORE
+            first = int(torch.nonzero(mod.apply_tf_padding(x, conv))[0][2])
+            total = padded.shape[2] - n
+            before, after = ON.keras_same_pad(n, (k - 1) * d + 1, s)
+            assert (first, total - first) == (before, after), (n, k, s, d, (first, total - first), (before, after))
