@@ -122,3 +122,36 @@ def test_parameter_count_matches_hf_minus_the_unused_classifier_stem():
     om = SegModel("DeepLabV3", "mobilenetv2", classes=1, activation="sigmoid", input_shape=(64, 64, 3), storage="fp32")
     hf_n = sum(p.numel() for nme, p in m.named_parameters() if not nme.startswith("mobilenet_v2.conv_1x1"))
     assert hf_n == sum(p.numel() for p in om.params.values()) == 2108417   # == the Keras model's trainable count
+
+
+def test_oracle_vgg16_encoder_matches_torchvision():
+    """BASELINE configs[0] (U-Net / VGG16): the restated keras.applications.VGG16 feature extractor -- 13 biased 3x3 'same' convolutions
+    + ReLU in five blocks (64-64, 128-128, 256x3, 512x3, 512x3), a 2x2/2 max pool after each, the last activation of every block
+    as a decoder skip -- against torchvision.models.vgg16's independent definition of the same network, with identical weights"""
+    tv = pytest.importorskip("torchvision")
+    from oracle.models import SegModel
+    net = tv.models.vgg16(weights=None).features.eval()
+    g = torch.Generator().manual_seed(7)
+    convs = [m for m in net if isinstance(m, torch.nn.Conv2d)]
+    assert len(convs) == 13
+    with torch.no_grad():
+        for c in convs:
+            c.weight.copy_(torch.randn(c.weight.shape, generator=g) * (1.4 / np.sqrt(c.weight.shape[1] * 9)))
+            c.bias.copy_(torch.randn(c.bias.shape, generator=g) * 0.05)
+    om = SegModel("Unet", "vgg16", classes=1, activation="sigmoid", input_shape=(64, 96, 3), storage="fp32")
+    names = ["block%d_conv%d" % (b + 1, i + 1) for b, n in enumerate((2, 2, 3, 3, 3)) for i in range(n)]
+    for name, c in zip(names, convs):
+        assert tuple(om.params[name + "/kernel"].shape) == tuple(c.weight.permute(2, 3, 1, 0).shape), name
+        om.params[name + "/kernel"].data.copy_(c.weight.detach().permute(2, 3, 1, 0))
+        om.params[name + "/bias"].data.copy_(c.bias.detach())
+    x = torch.rand(2, 64, 96, 3, generator=g) * 255.0            # raw 0..255, as the reference feeds it
+    with torch.no_grad():
+        feat, skips = om._vgg16(x.permute(0, 3, 1, 2).contiguous())
+        want_skips, h = [], x.permute(0, 3, 1, 2).contiguous()
+        for m in net:
+            if isinstance(m, torch.nn.MaxPool2d):
+                want_skips.append(h)
+            h = m(h)
+    assert len(skips) == 5 and _rel(feat, h) < 1e-5
+    for got, want in zip(skips, want_skips[::-1]):                # the oracle lists skips deepest first
+        assert tuple(got.shape) == tuple(want.shape) and _rel(got, want) < 1e-5
