@@ -95,3 +95,28 @@ def test_adam_is_torch_adam_up_to_the_epsilon_placement():
     # and with torch's own (fixed) epsilon the trajectories DO separate on such gradients -- the placement is not a no-op
     fixed = _run_torch(lambda q: torch.optim.Adam(q, lr=1e-3, betas=(0.9, 0.999), eps=1e-7), p0, small)
     assert max(float((fixed[k] - oparams[k]).abs().max()) for k in fixed) > 1e-4
+
+
+def test_loss_formulas_against_independent_implementations():
+    """binary / categorical cross-entropy against torch's own losses on Keras-clipped probabilities (clip 1e-7), and the focal-loss
+    FORMULA -alpha*(1-p)^gamma*t*log p - (1-alpha)*p^gamma*(1-t)*log(1-p) against torchvision.ops.sigmoid_focal_loss (what stays a
+    named flag is only the reduction the absent musket_core applies, oracle/losses.py)"""
+    import torch.nn.functional as F
+    from oracle import losses as OL
+    g = torch.Generator().manual_seed(5)
+    logits = torch.randn(3, 16, 20, 1, generator=g) * 3
+    p = torch.sigmoid(logits)
+    t = (torch.rand(3, 16, 20, 1, generator=g) > 0.6).float()
+    pc = p.clamp(1e-7, 1 - 1e-7)
+    assert abs(float(OL.binary_crossentropy(t, p)) - float(F.binary_cross_entropy(pc, t))) < 1e-6
+    z = torch.randn(3, 16, 20, 4, generator=g)
+    pm = torch.softmax(z, dim=-1)
+    onehot = F.one_hot(torch.randint(0, 4, (3, 16, 20), generator=g), 4).float()
+    want = F.nll_loss(torch.log(pm.clamp(1e-7, 1.0)).reshape(-1, 4), onehot.argmax(-1).reshape(-1))
+    assert abs(float(OL.categorical_crossentropy(onehot, pm)) - float(want)) < 1e-6
+    tvo = pytest.importorskip("torchvision.ops")
+    for alpha, gamma in ((0.75, 2.0), (0.25, 2.0), (0.5, 1.0)):
+        for red in ("mean", "sum"):
+            want = tvo.sigmoid_focal_loss(logits, t, alpha=alpha, gamma=gamma, reduction=red)
+            got = OL.focal_loss(t, p, gamma=gamma, alpha=alpha, reduction=red)
+            assert abs(float(got) - float(want)) <= 2e-5 * (1.0 + abs(float(want))), (alpha, gamma, red, float(got), float(want))
