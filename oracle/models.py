@@ -4,7 +4,7 @@
 are un-vendored [DEP]; the graphs below follow SURVEY.md section 8 a-4/a-5 and Appendix A/B.
 TEST INFRASTRUCTURE -- parity unpinned (no reference test pins these graphs), with one exception: the DeepLabV3 / MobileNetV2
 graph (restated from the reference's in-tree impl/deeplab/model.py) is pinned block by block against Hugging Face transformers'
-independent MobileNetV2 + DeepLabV3 implementation, and the VGG16 encoder against torchvision.models.vgg16 (tests/test_cpu_oracle_hf.py).
+independent MobileNetV2 + DeepLabV3 implementation, and the VGG16 encoder against torchvision.models.vgg16 (tests/test_cpu_oracle_independent.py).
 
 A model is (params: Dict[str, Tensor in Keras layout], forward(x_nhwc_float, training) -> y_nhwc).
 Layer names are the Keras names so weight dicts are exchangeable with the engine.
