@@ -120,3 +120,43 @@ def test_loss_formulas_against_independent_implementations():
             want = tvo.sigmoid_focal_loss(logits, t, alpha=alpha, gamma=gamma, reduction=red)
             got = OL.focal_loss(t, p, gamma=gamma, alpha=alpha, reduction=red)
             assert abs(float(got) - float(want)) <= 2e-5 * (1.0 + abs(float(want))), (alpha, gamma, red, float(got), float(want))
+
+
+def test_lovasz_hinge_is_the_lovasz_extension_of_the_jaccard_loss():
+    """Berman et al. 2018 (eq. 8-9) by its DEFINITION, with Python sets: sort the hinge errors m decreasingly (permutation pi); the loss
+    is sum_i m_pi(i) * [Delta_J({pi_1..pi_i}) - Delta_J({pi_1..pi_(i-1)})] with Delta_J(M) = 1 - |P \\ M| / |P u (M n N)| the Jaccard
+    loss when exactly the pixels in M are mispredicted (P / N: ground-truth positives / negatives).  The oracle's cumulative-sum form
+    (`_lovasz_grad`) must give the same number; act='relu' is the paper's hinge, act='elu' only changes m -> elu(m) + 1."""
+    from oracle import losses as OL
+    g = torch.Generator().manual_seed(9)
+    for trial in range(6):
+        n = 14
+        logits = torch.randn(n, generator=g) * 2
+        labels = (torch.rand(n, generator=g) > (0.3 + 0.1 * trial)).float()
+        if trial == 5:
+            labels.zero_()                                   # no positive pixel at all
+        signs = 2 * labels - 1
+        errors = (1 - logits * signs)
+        order = sorted(range(n), key=lambda i: -float(errors[i]))
+        P = {i for i in range(n) if labels[i] == 1}
+        N = set(range(n)) - P
+
+        def delta(M):
+            union = len(P | (M & N))
+            return 1.0 - (len(P - M) / union) if union else 0.0   # (empty union only for M = {} and no positives)
+        want, M, prev = 0.0, set(), 0.0
+        for i in order:
+            M = M | {i}
+            d = delta(M)
+            want += max(float(errors[i]), 0.0) * (d - prev)
+            prev = d
+        got = float(OL.lovasz_hinge_flat(logits, labels, act="relu"))
+        assert abs(got - want) < 1e-5 * (1 + abs(want)), (trial, got, want)
+        e = torch.tensor([float(errors[i]) for i in order])
+        want_elu, M, prev = 0.0, set(), 0.0
+        for k, i in enumerate(order):
+            M = M | {i}
+            d = delta(M)
+            want_elu += float(torch.nn.functional.elu(e[k]) + 1.0) * (d - prev)
+            prev = d
+        assert abs(float(OL.lovasz_hinge_flat(logits, labels, act="elu")) - want_elu) < 1e-5 * (1 + abs(want_elu))
