@@ -1,6 +1,9 @@
 """Losses / metrics registered by the reference at segmentation.py:15-22 -> musket_core.losses + Keras [DEP].
 
-TEST INFRASTRUCTURE, parity unpinned.  Formulas per SURVEY.md section 8 a-6 / Appendix B.  All take
+TEST INFRASTRUCTURE.  Formulas per SURVEY.md section 8 a-6 / Appendix B; musket_core is absent, so the reference's exact choices
+(smoothing constants, focal reduction, the Lovasz activation) are parity unpinned and kept as named flags.  What IS pinned
+(tests/test_cpu_oracle_optim.py): the cross-entropies against torch's losses on Keras-clipped probabilities, the focal formula
+against torchvision.ops.sigmoid_focal_loss, the Lovasz hinge against the set-based definition of the Lovasz extension.  All take
 (y_true, y_pred) as float NHWC tensors like the Keras callables, and return a scalar (Keras reduces
 per-sample losses by mean over every remaining axis and over the batch).
 """
