@@ -12,10 +12,8 @@ import numpy as np
 import pytest
 import torch
 
-transformers = pytest.importorskip("transformers")
-
-
 def _hf_model(num_labels, train):
+    pytest.importorskip("transformers")   # (imported lazily: collecting this module for a `-m gpu` run must stay cheap)
     from transformers import MobileNetV2Config, MobileNetV2ForSemanticSegmentation
     cfg = MobileNetV2Config(output_stride=8, num_labels=num_labels, classifier_dropout_prob=0.0, tf_padding=True, hidden_act="relu6",
                             depth_multiplier=1.0, first_layer_is_expansion=True, layer_norm_eps=1e-3)
