@@ -319,3 +319,17 @@ def test_tf_same_padding_rule_is_the_one_hf_transformers_ports():
             total = padded.shape[2] - n
             before, after = ON.keras_same_pad(n, (k - 1) * d + 1, s)
             assert (first, total - first) == (before, after), (n, k, s, d, (first, total - first), (before, after))
+
+
+@pytest.mark.parametrize("cin,cout,G,w", [(16, 16, 4, 16), (32, 16, 4, 24), (16, 32, 4, 8), (32, 32, 2, 10)])
+def test_pixel_merged_view_prototype(cin, cout, G, w):
+    """the block-sparse expanded weights of the planned narrow-layer kernel (scripts/quadview_proto.py): a 3x3 'same' conv
+    equals the 3x3 conv over the [N, H, W/G, G*C] VIEW with them; every K = 16 step feeds a contiguous run of output-pixel blocks"""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("quadview_proto", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "quadview_proto.py"))
+    qp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(qp)
+    assert qp.check(n=2, h=7, w=w, cin=cin, cout=cout, G=G, seed=cin + cout) < 1e-10
+    sched = qp.mma_schedule(cin, cout, G)
+    assert all(1 <= nb <= 3 for steps in sched.values() for _, _, nb in steps)
+    assert len(sched[-1]) == len(sched[1]) == cin // 16        # only the nearest pixel of a neighbouring group contributes
